@@ -1,0 +1,110 @@
+"""ctypes declarations matching include/dav1d_cuda.h one to one."""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libdav1d_cuda.so")
+
+N_2D_FILTERS = 10
+N_RECT_TX_SIZES = 19
+N_TX_TYPES_PLUS_LL = 17
+
+# enum RectTxfmSize -> (w, h)   (reference src/levels.h:44-78)
+TX_DIMS = [(4, 4), (8, 8), (16, 16), (32, 32), (64, 64), (4, 8), (8, 4), (8, 16), (16, 8),
+           (16, 32), (32, 16), (32, 64), (64, 32), (4, 16), (16, 4), (8, 32), (32, 8),
+           (16, 64), (64, 16)]
+
+
+class MCDSPContext(C.Structure):
+    _fields_ = [("mc", C.c_void_p * N_2D_FILTERS), ("mc_scaled", C.c_void_p * N_2D_FILTERS),
+                ("mct", C.c_void_p * N_2D_FILTERS), ("mct_scaled", C.c_void_p * N_2D_FILTERS),
+                ("avg", C.c_void_p), ("w_avg", C.c_void_p), ("mask", C.c_void_p),
+                ("w_mask", C.c_void_p * 3), ("blend", C.c_void_p), ("blend_v", C.c_void_p),
+                ("blend_h", C.c_void_p), ("warp8x8", C.c_void_p), ("warp8x8t", C.c_void_p),
+                ("emu_edge", C.c_void_p), ("resize", C.c_void_p)]
+
+
+class InvTxfmDSPContext(C.Structure):
+    _fields_ = [("itxfm_add", (C.c_void_p * N_TX_TYPES_PLUS_LL) * N_RECT_TX_SIZES)]
+
+
+class IntraPredDSPContext(C.Structure):
+    _fields_ = [("intra_pred", C.c_void_p * 14), ("cfl_ac", C.c_void_p * 3),
+                ("cfl_pred", C.c_void_p * 6), ("pal_pred", C.c_void_p)]
+
+
+class ItxDesc(C.Structure):
+    _fields_ = [("coef_off", C.c_uint32), ("x", C.c_uint16), ("y", C.c_uint16),
+                ("eob", C.c_int16), ("plane", C.c_uint8), ("tx", C.c_uint8),
+                ("txtp", C.c_uint8), ("pad", C.c_uint8 * 3)]
+
+
+class McSrc(C.Structure):
+    _fields_ = [("x", C.c_int32), ("y", C.c_int32), ("ref", C.c_uint8),
+                ("filter_2d", C.c_uint8), ("mx", C.c_uint8), ("my", C.c_uint8)]
+
+
+class McDesc(C.Structure):
+    _fields_ = [("x", C.c_uint16), ("y", C.c_uint16), ("w", C.c_uint8), ("h", C.c_uint8),
+                ("plane", C.c_uint8), ("kind", C.c_uint8), ("src", McSrc * 2),
+                ("weight", C.c_uint8), ("mask_ss", C.c_uint8), ("pad", C.c_uint16),
+                ("aux_off", C.c_uint32)]
+
+
+class IntraDesc(C.Structure):
+    _fields_ = [("x4", C.c_uint16), ("y4", C.c_uint16), ("tile_x4_start", C.c_uint16),
+                ("tile_y4_start", C.c_uint16), ("tile_x4_end", C.c_uint16),
+                ("tile_y4_end", C.c_uint16), ("plane", C.c_uint8), ("tw4", C.c_uint8),
+                ("th4", C.c_uint8), ("mode", C.c_uint8), ("angle_delta", C.c_int8),
+                ("edge_flags", C.c_uint8), ("flags", C.c_uint16), ("eob", C.c_int16),
+                ("tx", C.c_uint8), ("txtp", C.c_uint8), ("coef_off", C.c_uint32),
+                ("level", C.c_uint32)]
+
+
+class Plane(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("stride", C.c_ssize_t), ("w", C.c_int32), ("h", C.c_int32)]
+
+
+class Picture(C.Structure):
+    _fields_ = [("p", Plane * 3), ("bitdepth_max", C.c_int32), ("ss_hor", C.c_int32),
+                ("ss_ver", C.c_int32)]
+
+
+assert C.sizeof(ItxDesc) == 16 and C.sizeof(McDesc) == 40 and C.sizeof(IntraDesc) == 32
+
+_lib = None
+
+
+def lib():
+    """Load libdav1d_cuda.so. Raises if the CUDA library was not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `make -C dav1d-mirror_b200` "
+            "(there is no CPU fallback for the ported operators)")
+    L = C.CDLL(LIB_PATH)
+    L.dav1d_cuda_last_error.restype = C.c_int
+    L.dav1d_cuda_last_error_string.restype = C.c_char_p
+    L.dav1d_cuda_launch_count.restype = C.c_uint64
+    L.dav1d_cuda_available.restype = C.c_int
+    L.dav1d_cuda_open.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_void_p]
+    L.dav1d_cuda_close.argtypes = [C.c_void_p]
+    L.dav1d_cuda_synchronize.argtypes = [C.c_void_p]
+    L.dav1d_cuda_picture_alloc.argtypes = [C.c_void_p, C.POINTER(Picture)] + [C.c_int] * 5
+    L.dav1d_cuda_picture_free.argtypes = [C.c_void_p, C.POINTER(Picture)]
+    L.dav1d_cuda_picture_upload.argtypes = [C.c_void_p, C.POINTER(Picture), C.c_int, C.c_void_p, C.c_ssize_t]
+    L.dav1d_cuda_picture_download.argtypes = [C.c_void_p, C.POINTER(Picture), C.c_int, C.c_void_p, C.c_ssize_t]
+    L.dav1d_cuda_itx_batch.argtypes = [C.c_void_p, C.POINTER(Picture), C.c_void_p, C.c_void_p,
+                                       C.POINTER(C.c_int32), C.c_int]
+    _lib = L
+    return L
+
+
+def check_error():
+    L = lib()
+    e = L.dav1d_cuda_last_error()
+    if e:
+        msg = L.dav1d_cuda_last_error_string().decode()
+        raise RuntimeError(f"dav1d_cuda error {e}: {msg}")

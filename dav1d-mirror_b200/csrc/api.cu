@@ -1,0 +1,184 @@
+// Context, error channel, HBM picture allocation and the per-call staging
+// arena of libdav1d_cuda.so.
+#include <stdio.h>
+#include <string.h>
+#include <atomic>
+#include "ctx.h"
+
+namespace d1 {
+
+static std::atomic<int> g_err{0};
+static char g_err_msg[512] = "";
+static std::mutex g_err_mu;
+static std::atomic<uint64_t> g_launches{0};
+
+void set_error(int code, const char *what, const char *detail) {
+    std::lock_guard<std::mutex> lk(g_err_mu);
+    if (g_err.load() == 0) {   // sticky: first error wins
+        g_err.store(code);
+        snprintf(g_err_msg, sizeof(g_err_msg), "%s: %s", what, detail ? detail : "");
+        fprintf(stderr, "[dav1d_cuda] error %d: %s\n", code, g_err_msg);
+    }
+}
+
+bool cuda_ok(cudaError_t e, const char *what) {
+    if (e == cudaSuccess) return true;
+    set_error((int)e, what, cudaGetErrorString(e));
+    return false;
+}
+
+void count_launch(int n) { g_launches.fetch_add((uint64_t)n); }
+
+Staging &staging() {
+    static Staging s;
+    return s;
+}
+
+bool Staging::ensure(size_t bytes) {
+    if (!ok) {
+        int n = 0;
+        if (!cuda_ok(cudaGetDeviceCount(&n), "cudaGetDeviceCount") || n < 1) {
+            set_error(-19, "no CUDA device", "the DSP-table overrides have no CPU fallback");
+            return false;
+        }
+        if (!cuda_ok(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking), "cudaStreamCreate"))
+            return false;
+        ok = true;
+    }
+    if (bytes <= dev_size) return true;
+    size_t want = dev_size ? dev_size : (size_t)4 << 20;
+    while (want < bytes) want <<= 1;
+    if (dev) cudaFree(dev);
+    if (host) cudaFreeHost(host);
+    dev = nullptr; host = nullptr; dev_size = 0;
+    if (!cuda_ok(cudaMalloc(&dev, want), "cudaMalloc(staging)")) return false;
+    if (!cuda_ok(cudaMallocHost(&host, want), "cudaMallocHost(staging)")) return false;
+    dev_size = want;
+    return true;
+}
+
+}  // namespace d1
+
+using namespace d1;
+
+extern "C" {
+
+int dav1d_cuda_last_error(void) { return g_err.load(); }
+const char *dav1d_cuda_last_error_string(void) { return g_err_msg; }
+void dav1d_cuda_clear_error(void) {
+    std::lock_guard<std::mutex> lk(g_err_mu);
+    g_err.store(0);
+    g_err_msg[0] = 0;
+    cudaGetLastError();
+}
+uint64_t dav1d_cuda_launch_count(void) { return g_launches.load(); }
+
+int dav1d_cuda_available(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n < 1) {
+        cudaGetLastError();
+        return 0;
+    }
+    return 1;
+}
+
+int dav1d_cuda_open(Dav1dCudaContext **out, int device, void *stream) {
+    if (!out) return -22;
+    *out = nullptr;
+    int n = 0;
+    D1_CHECK(cudaGetDeviceCount(&n));
+    if (device < 0 || device >= n) {
+        set_error(-22, "dav1d_cuda_open", "no such device");
+        return -22;
+    }
+    D1_CHECK(cudaSetDevice(device));
+    Dav1dCudaContext *c = new Dav1dCudaContext();
+    c->device = device;
+    c->own_stream = false;
+    c->stream = (cudaStream_t)stream;
+    c->tmp_pool = nullptr;
+    c->tmp_pool_bytes = 0;
+    cudaDeviceProp prop;
+    D1_CHECK(cudaGetDeviceProperties(&prop, device));
+    c->num_sms = prop.multiProcessorCount;
+    *out = c;
+    return 0;
+}
+
+void dav1d_cuda_close(Dav1dCudaContext *c) {
+    if (!c) return;
+    cudaStreamSynchronize(c->stream);
+    if (c->tmp_pool) cudaFree(c->tmp_pool);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int dav1d_cuda_synchronize(Dav1dCudaContext *c) {
+    D1_CHECK(cudaStreamSynchronize(c->stream));
+    D1_CHECK(cudaGetLastError());
+    return 0;
+}
+
+// Geometry of the reference's default allocator, src/picture.c:46-84.
+int dav1d_cuda_picture_alloc(Dav1dCudaContext *c, Dav1dCudaPicture *pic,
+                             int w, int h, int ss_hor, int ss_ver, int bitdepth_max)
+{
+    (void)c;
+    if (!pic || w <= 0 || h <= 0) return -22;
+    memset(pic, 0, sizeof(*pic));
+    const int hbd = bitdepth_max > 0xff;
+    const int aligned_w = (w + 127) & ~127;
+    const int aligned_h = (h + 127) & ~127;
+    ptrdiff_t y_stride = (ptrdiff_t)aligned_w << hbd;
+    ptrdiff_t uv_stride = y_stride >> ss_hor;
+    if (!(y_stride & 1023)) y_stride += 64;
+    if (!(uv_stride & 1023)) uv_stride += 64;
+    const size_t y_sz = (size_t)y_stride * aligned_h;
+    const size_t uv_sz = (size_t)uv_stride * (aligned_h >> ss_ver);
+    uint8_t *buf = nullptr;
+    D1_CHECK(cudaMalloc(&buf, y_sz + 2 * uv_sz + 64));
+    D1_CHECK(cudaMemset(buf, 0, y_sz + 2 * uv_sz + 64));
+    pic->p[0].data = buf;
+    pic->p[0].stride = y_stride;
+    pic->p[0].w = w;
+    pic->p[0].h = h;
+    for (int i = 1; i < 3; i++) {
+        pic->p[i].data = buf + y_sz + (i - 1) * uv_sz;
+        pic->p[i].stride = uv_stride;
+        pic->p[i].w = (w + ss_hor) >> ss_hor;
+        pic->p[i].h = (h + ss_ver) >> ss_ver;
+    }
+    pic->bitdepth_max = bitdepth_max;
+    pic->ss_hor = ss_hor;
+    pic->ss_ver = ss_ver;
+    return 0;
+}
+
+void dav1d_cuda_picture_free(Dav1dCudaContext *c, Dav1dCudaPicture *pic) {
+    (void)c;
+    if (pic && pic->p[0].data) cudaFree(pic->p[0].data);
+    if (pic) memset(pic, 0, sizeof(*pic));
+}
+
+int dav1d_cuda_picture_upload(Dav1dCudaContext *c, const Dav1dCudaPicture *pic, int plane,
+                              const void *host, ptrdiff_t host_stride)
+{
+    const int hbd = pic->bitdepth_max > 0xff;
+    const Dav1dCudaPlane *p = &pic->p[plane];
+    D1_CHECK(cudaMemcpy2DAsync(p->data, p->stride, host, host_stride, (size_t)p->w << hbd, p->h,
+                               cudaMemcpyHostToDevice, c->stream));
+    return 0;
+}
+
+int dav1d_cuda_picture_download(Dav1dCudaContext *c, const Dav1dCudaPicture *pic, int plane,
+                                void *host, ptrdiff_t host_stride)
+{
+    const int hbd = pic->bitdepth_max > 0xff;
+    const Dav1dCudaPlane *p = &pic->p[plane];
+    D1_CHECK(cudaMemcpy2DAsync(host, host_stride, p->data, p->stride, (size_t)p->w << hbd, p->h,
+                               cudaMemcpyDeviceToHost, c->stream));
+    return 0;
+}
+
+}  // extern "C"

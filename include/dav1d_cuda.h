@@ -1,0 +1,259 @@
+/*
+ * dav1d_cuda.h - C ABI of the B200 (sm_100a) backend for dav1d's
+ * pixel-reconstruction DSP: motion compensation, inverse transforms and
+ * intra prediction, 8/10/12 bit.
+ *
+ * Two surfaces, both plain C (pointers + sizes, no C++/torch types):
+ *
+ *  (1) DSP-table overrides.  dav1d_cuda_{mc,itx,intra_pred}_dsp_init_{8,16}bpc
+ *      fill the reference's own struct-of-function-pointers
+ *      (Dav1dMCDSPContext  src/mc.h:116-132,
+ *       Dav1dInvTxfmDSPContext src/itx.h:42-44,
+ *       Dav1dIntraPredDSPContext src/ipred.h:81-90) exactly like a per-arch
+ *      `*_dsp_init_x86(c)` does (src/mc_tmpl.c:948-956, src/itx_tmpl.c:270-283,
+ *      src/ipred_tmpl.c:767-773, src/x86/mc.h:113-118).  Every entry keeps the
+ *      reference signature (decl_*_fn in src/mc.h:38-114, src/itx.h:37-40,
+ *      src/ipred.h:44-79) and the reference semantics: caller-owned HOST
+ *      buffers, byte strides, synchronous, void return.  Each call stages its
+ *      operands to the GPU, runs the same kernel the batched path uses with a
+ *      single descriptor, and copies the result back.  This surface exists
+ *      for checkasm-style bit-exact comparison, not for speed.
+ *
+ *  (2) Batched entry points.  The caller (recon_tmpl.c turned into a
+ *      descriptor recorder: pass 2 of the frame-threading split,
+ *      src/decode.c:741-830, src/recon_tmpl.c:1195-2036) hands over
+ *      device-resident arrays of block descriptors; one kernel launch per
+ *      operator class consumes them against pictures that live in HBM.
+ *
+ * Errors: the reference DSP functions return void and cannot fail
+ * (src/recon_tmpl.c:1068,1131,1192).  Failures of this backend are therefore
+ * reported out of band through dav1d_cuda_last_error(); batched entry points
+ * additionally return 0 / a negative errno-style value like the reference's
+ * public API (include/dav1d/common.h DAV1D_ERR).  There is no CPU fallback
+ * for any ported operator: without a usable device the init functions leave
+ * the table untouched and set the sticky error.
+ */
+#ifndef DAV1D_CUDA_H
+#define DAV1D_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define DAV1D_CUDA_API __attribute__((visibility("default")))
+#else
+#define DAV1D_CUDA_API
+#endif
+
+/* ------------------------------------------------------------------ enums
+ * Values are the reference's (src/levels.h:44-133,184-196); restated so the
+ * header stands alone. */
+enum { DAV1D_CUDA_N_2D_FILTERS = 10 };        /* enum Filter2d, levels.h:184-196 */
+enum { DAV1D_CUDA_N_RECT_TX_SIZES = 19 };     /* enum RectTxfmSize, levels.h:44-78 */
+enum { DAV1D_CUDA_N_TX_TYPES_PLUS_LL = 17 };  /* enum TxfmType, levels.h:80-100 */
+enum { DAV1D_CUDA_N_IMPL_INTRA_PRED_MODES = 14 }; /* levels.h:108-133 */
+
+enum Dav1dCudaIntraMode {                     /* DSP-table index, levels.h:108-133 */
+    DAV1D_CUDA_DC_PRED = 0, DAV1D_CUDA_VERT_PRED, DAV1D_CUDA_HOR_PRED,
+    DAV1D_CUDA_LEFT_DC_PRED, DAV1D_CUDA_TOP_DC_PRED, DAV1D_CUDA_DC_128_PRED,
+    DAV1D_CUDA_Z1_PRED, DAV1D_CUDA_Z2_PRED, DAV1D_CUDA_Z3_PRED,
+    DAV1D_CUDA_SMOOTH_PRED, DAV1D_CUDA_SMOOTH_V_PRED, DAV1D_CUDA_SMOOTH_H_PRED,
+    DAV1D_CUDA_PAETH_PRED, DAV1D_CUDA_FILTER_PRED,
+    DAV1D_CUDA_CFL_PRED = 13                  /* bitstream uv mode, same value */
+};
+
+/* ------------------------------------------------- (1) DSP-table overrides
+ * Layout-compatible mirrors of the reference structs.  Slots are typed
+ * void* here because the 8 bpc and 16 bpc variants differ by a trailing
+ * `int bitdepth_max` argument (include/common/bitdepth.h:72); the exact
+ * signatures are the reference typedefs named beside each slot. */
+typedef struct Dav1dCudaMCDSPContext {        /* == Dav1dMCDSPContext */
+    void *mc[DAV1D_CUDA_N_2D_FILTERS];        /* mc_fn          */
+    void *mc_scaled[DAV1D_CUDA_N_2D_FILTERS]; /* mc_scaled_fn   */
+    void *mct[DAV1D_CUDA_N_2D_FILTERS];       /* mct_fn         */
+    void *mct_scaled[DAV1D_CUDA_N_2D_FILTERS];/* mct_scaled_fn  */
+    void *avg;                                /* avg_fn         */
+    void *w_avg;                              /* w_avg_fn       */
+    void *mask;                               /* mask_fn        */
+    void *w_mask[3];                          /* w_mask_fn: 444, 422, 420 */
+    void *blend;                              /* blend_fn       */
+    void *blend_v;                            /* blend_dir_fn   */
+    void *blend_h;                            /* blend_dir_fn   */
+    void *warp8x8;                            /* warp8x8_fn     */
+    void *warp8x8t;                           /* warp8x8t_fn    */
+    void *emu_edge;                           /* emu_edge_fn    */
+    void *resize;                             /* resize_fn - NOT overridden (super-res is a post-filter) */
+} Dav1dCudaMCDSPContext;
+
+typedef struct Dav1dCudaInvTxfmDSPContext {   /* == Dav1dInvTxfmDSPContext */
+    void *itxfm_add[DAV1D_CUDA_N_RECT_TX_SIZES][DAV1D_CUDA_N_TX_TYPES_PLUS_LL]; /* itxfm_fn */
+} Dav1dCudaInvTxfmDSPContext;
+
+typedef struct Dav1dCudaIntraPredDSPContext { /* == Dav1dIntraPredDSPContext */
+    void *intra_pred[DAV1D_CUDA_N_IMPL_INTRA_PRED_MODES]; /* angular_ipred_fn */
+    void *cfl_ac[3];                          /* cfl_ac_fn: 420, 422, 444 */
+    void *cfl_pred[6];                        /* cfl_pred_fn: DC, -, -, LEFT_DC, TOP_DC, DC_128 */
+    void *pal_pred;                           /* pal_pred_fn */
+} Dav1dCudaIntraPredDSPContext;
+
+/* Replace dav1d_mc_dsp_init_{8,16}bpc's arch tail (src/mc_tmpl.c:948-956). */
+DAV1D_CUDA_API void dav1d_cuda_mc_dsp_init_8bpc(Dav1dCudaMCDSPContext *c);
+DAV1D_CUDA_API void dav1d_cuda_mc_dsp_init_16bpc(Dav1dCudaMCDSPContext *c);
+/* Replace dav1d_itx_dsp_init_{8,16}bpc's arch tail (src/itx_tmpl.c:270-283). */
+DAV1D_CUDA_API void dav1d_cuda_itx_dsp_init_8bpc(Dav1dCudaInvTxfmDSPContext *c, int bpc);
+DAV1D_CUDA_API void dav1d_cuda_itx_dsp_init_16bpc(Dav1dCudaInvTxfmDSPContext *c, int bpc);
+/* Replace dav1d_intra_pred_dsp_init_{8,16}bpc's arch tail (src/ipred_tmpl.c:767-773). */
+DAV1D_CUDA_API void dav1d_cuda_intra_pred_dsp_init_8bpc(Dav1dCudaIntraPredDSPContext *c);
+DAV1D_CUDA_API void dav1d_cuda_intra_pred_dsp_init_16bpc(Dav1dCudaIntraPredDSPContext *c);
+
+/* On-device counterpart of dav1d_prepare_intra_edges_{8,16}bpc
+ * (src/ipred_prepare_tmpl.c:77-204, declared src/ipred_prepare.h:77-84):
+ * same arguments, same return value (the DSP-table mode index), HOST buffers.
+ * `prefilter_toplevel_sb_edge` may be NULL. */
+DAV1D_CUDA_API int dav1d_cuda_prepare_intra_edges_8bpc(
+    int x, int have_left, int y, int have_top, int w, int h, int edge_flags,
+    const uint8_t *dst, ptrdiff_t stride, const uint8_t *prefilter_toplevel_sb_edge,
+    int mode, int *angle, int tw, int th, int filter_edge, uint8_t *topleft_out);
+DAV1D_CUDA_API int dav1d_cuda_prepare_intra_edges_16bpc(
+    int x, int have_left, int y, int have_top, int w, int h, int edge_flags,
+    const uint16_t *dst, ptrdiff_t stride, const uint16_t *prefilter_toplevel_sb_edge,
+    int mode, int *angle, int tw, int th, int filter_edge, uint16_t *topleft_out,
+    int bitdepth_max);
+
+/* Sticky out-of-band error (0 = none).  Cleared by dav1d_cuda_clear_error(). */
+DAV1D_CUDA_API int dav1d_cuda_last_error(void);
+DAV1D_CUDA_API const char *dav1d_cuda_last_error_string(void);
+DAV1D_CUDA_API void dav1d_cuda_clear_error(void);
+/* Number of kernels this library has launched so far (all surfaces). */
+DAV1D_CUDA_API uint64_t dav1d_cuda_launch_count(void);
+/* 1 if a CUDA device is usable by this process, else 0 (sets the error). */
+DAV1D_CUDA_API int dav1d_cuda_available(void);
+
+/* ------------------------------------------------- (2) batched entry points */
+
+/* One plane / picture resident in HBM.  Same geometry rules as the
+ * reference's default allocator (src/picture.c:46-84): planar Y,U,V, byte
+ * strides, 64-byte aligned rows. `data` is a DEVICE pointer. */
+typedef struct Dav1dCudaPlane {
+    void     *data;
+    ptrdiff_t stride;      /* bytes */
+    int32_t   w, h;        /* visible size in pixels (edge clamp uses these) */
+} Dav1dCudaPlane;
+
+typedef struct Dav1dCudaPicture {
+    Dav1dCudaPlane p[3];
+    int32_t bitdepth_max;  /* 0xff, 0x3ff or 0xfff */
+    int32_t ss_hor, ss_ver;/* chroma subsampling (4:2:0 = 1,1) */
+} Dav1dCudaPicture;
+
+/* -- inverse transform + add (itxfm_add call sites: recon_tmpl.c:816,1347,1567,2017)
+ * 16 bytes.  `coef_off` indexes the device cf stream in coef units (int16 for
+ * 8 bpc, int32 for 10/12 bpc); the block's coefficients are stored exactly as
+ * the reference stores them: column-major, min(w,32) x min(h,32)
+ * (itx_tmpl.c:79-87).  Blocks with eob < 0 are not recorded. */
+typedef struct Dav1dCudaItxDesc {
+    uint32_t coef_off;
+    uint16_t x, y;         /* top-left of the tx block in `plane`, pixels */
+    int16_t  eob;
+    uint8_t  plane;
+    uint8_t  tx;           /* enum RectTxfmSize */
+    uint8_t  txtp;         /* enum TxfmType (incl. WHT_WHT = 16) */
+    uint8_t  pad[3];
+} Dav1dCudaItxDesc;
+
+/* -- motion compensation (mc()/obmc() call sites: recon_tmpl.c:957-1069).
+ * One descriptor = one prediction block of one plane.  Sources are
+ * (ref picture, integer position, sub-pel phase, filter); positions may lie
+ * outside the reference plane - the kernel clamps coordinates, which is what
+ * emu_edge (mc_tmpl.c:827-875) followed by a normal read amounts to. */
+enum Dav1dCudaMcKind {
+    DAV1D_CUDA_MC_PUT    = 0,  /* dsp->mc.mc[filter]                       */
+    DAV1D_CUDA_MC_AVG    = 1,  /* 2x mct + avg     (recon_tmpl.c:1843-1846) */
+    DAV1D_CUDA_MC_W_AVG  = 2,  /* 2x mct + w_avg   (:1847-1851)             */
+    DAV1D_CUDA_MC_MASK   = 3,  /* 2x mct + mask    (:1859-1868, wedge/chroma seg) */
+    DAV1D_CUDA_MC_W_MASK = 4,  /* 2x mct + w_mask  (:1852-1858) writes seg mask */
+    DAV1D_CUDA_MC_PREP   = 5   /* dsp->mc.mct[filter] into the int16 tmp pool */
+};
+
+typedef struct Dav1dCudaMcSrc {
+    int32_t  x, y;         /* integer sample position of the block's top-left in the ref plane */
+    uint8_t  ref;          /* index into Dav1dCudaReconBatch.refs[] */
+    uint8_t  filter_2d;    /* enum Filter2d */
+    uint8_t  mx, my;       /* 1/16 sample phase, 0..15 */
+} Dav1dCudaMcSrc;
+
+typedef struct Dav1dCudaMcDesc {   /* 40 bytes */
+    uint16_t x, y;         /* destination position in `plane`, pixels */
+    uint8_t  w, h;         /* 2..128 */
+    uint8_t  plane;
+    uint8_t  kind;         /* enum Dav1dCudaMcKind */
+    Dav1dCudaMcSrc src[2]; /* src[1] unused for PUT/PREP */
+    uint8_t  weight;       /* W_AVG: jnt weight 1..15; W_MASK: sign */
+    uint8_t  mask_ss;      /* W_MASK: 0=444 1=422 2=420 layout of the emitted mask */
+    uint16_t pad;
+    uint32_t aux_off;      /* MASK: byte offset of the w*h mask in `masks`;
+                              W_MASK: byte offset the emitted mask is written to in `masks`;
+                              PREP: int16 offset into the tmp pool */
+} Dav1dCudaMcDesc;
+
+/* -- intra prediction, one descriptor per transform block in decode order
+ * (recon_tmpl.c:1259-1300, 1503-1576), optionally fused with its residual.
+ * The fields are the arguments of dav1d_prepare_intra_edges +
+ * intra_pred[m]; mode/angle resolution happens on the device. */
+typedef struct Dav1dCudaIntraDesc {  /* 32 bytes */
+    uint16_t x4, y4;       /* position in 4-px units of THIS plane */
+    uint16_t tile_x4_start;/* have_left = x4 > tile_x4_start */
+    uint16_t tile_y4_start;/* have_top  = y4 > tile_y4_start */
+    uint16_t tile_x4_end, tile_y4_end;   /* w, h arguments (tile end, frame end) */
+    uint8_t  plane;
+    uint8_t  tw4, th4;     /* transform size in 4-px units */
+    uint8_t  mode;         /* bitstream enum IntraPredMode 0..12, or FILTER_PRED=13 */
+    int8_t   angle_delta;  /* -3..3; FILTER_PRED: filter index 0..4 */
+    uint8_t  edge_flags;   /* bit0 top-has-right, bit3 left-has-bottom (EDGE_I444_*) */
+    uint16_t flags;        /* bit9 smooth neighbour, bit10 edge filter (ipred_prepare.h:87-93) */
+    int16_t  eob;          /* < 0: no residual */
+    uint8_t  tx, txtp;     /* residual transform, if any */
+    uint32_t coef_off;
+    uint32_t level;        /* dependency level (filled by the recorder) */
+} Dav1dCudaIntraDesc;
+
+typedef struct Dav1dCudaContext Dav1dCudaContext;
+
+/* `stream` is a cudaStream_t (or NULL for the legacy default stream): the
+ * caller may pass the stream it already orders its own work on. */
+DAV1D_CUDA_API int  dav1d_cuda_open(Dav1dCudaContext **out, int device, void *stream);
+DAV1D_CUDA_API void dav1d_cuda_close(Dav1dCudaContext *c);
+DAV1D_CUDA_API int  dav1d_cuda_synchronize(Dav1dCudaContext *c);
+
+/* HBM picture allocation with the reference's geometry (src/picture.c:46-84:
+ * width/height padded to 128, stride = aligned width << hbd, +64 B when the
+ * stride is a multiple of 1024). */
+DAV1D_CUDA_API int  dav1d_cuda_picture_alloc(Dav1dCudaContext *c, Dav1dCudaPicture *pic,
+                                             int w, int h, int ss_hor, int ss_ver, int bitdepth_max);
+DAV1D_CUDA_API void dav1d_cuda_picture_free(Dav1dCudaContext *c, Dav1dCudaPicture *pic);
+DAV1D_CUDA_API int  dav1d_cuda_picture_upload(Dav1dCudaContext *c, const Dav1dCudaPicture *pic, int plane,
+                                              const void *host, ptrdiff_t host_stride);
+DAV1D_CUDA_API int  dav1d_cuda_picture_download(Dav1dCudaContext *c, const Dav1dCudaPicture *pic, int plane,
+                                                void *host, ptrdiff_t host_stride);
+
+/* Operator-class launches.  All pointers inside the argument list that are
+ * documented as "device" must be device pointers; the calls are asynchronous
+ * on the context's stream. */
+
+/* itxfm_add over `n` descriptors (device array).  `cf` = device coefficient
+ * stream.  Descriptors must be grouped by `tx` (class_count[t] of them for
+ * each tx size t, in increasing t).  If `zero_coefs` the consumed coefficient
+ * blocks are cleared like the per-call contract requires (itx_tmpl.c:89). */
+DAV1D_CUDA_API int dav1d_cuda_itx_batch(Dav1dCudaContext *c, const Dav1dCudaPicture *dst,
+                                        void *cf, const Dav1dCudaItxDesc *descs,
+                                        const int32_t class_count[DAV1D_CUDA_N_RECT_TX_SIZES],
+                                        int zero_coefs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DAV1D_CUDA_H */
