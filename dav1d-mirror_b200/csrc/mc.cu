@@ -1,0 +1,629 @@
+// Motion-compensation operator classes: batched kernels (put/prep, fused
+// compound, warp, blend, scaled) and the Dav1dMCDSPContext overrides that run
+// the same kernels on one staged block.  Reference: src/mc_tmpl.c.
+#include <string.h>
+#include <vector>
+#include <type_traits>
+#include "ctx.h"
+#include "stage.h"
+#include "mc.cuh"
+
+namespace d1 {
+
+constexpr int MC_WARPS = 4;
+
+struct McArgs {
+    PicView dst;
+    PicView refs[7];
+    const Dav1dCudaMcDesc *descs;
+    const uint32_t *tiles;      // desc_index * 16 + (ty * 4 + tx), 32x32 tiles
+    int n_tiles;
+    uint8_t *masks;             // wedge / segmentation masks (device)
+    int16_t *tmp;               // int16 pool for PREP output
+};
+
+struct TileGeo { int x0, y0, tw, th; };
+DEV TileGeo tile_geo(const Dav1dCudaMcDesc &d, const int t) {
+    TileGeo g;
+    g.x0 = (t & 3) * MC_T;
+    g.y0 = (t >> 2) * MC_T;
+    g.tw = imin(MC_T, d.w - g.x0);
+    g.th = imin(MC_T, d.h - g.y0);
+    return g;
+}
+
+// ---- put / prep: one warp per 32x32 tile
+template <typename pixel>
+__global__ void __launch_bounds__(MC_WARPS * 32) mc_put_kernel(const __grid_constant__ McArgs a) {
+    extern __shared__ __align__(16) uint8_t mc_smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ti = blockIdx.x * MC_WARPS + warp;
+    if (ti >= a.n_tiles) return;
+    McSmem<pixel> *sm = (McSmem<pixel> *)mc_smem_raw + warp;
+    const uint32_t tcode = a.tiles[ti];
+    const Dav1dCudaMcDesc d = a.descs[tcode >> 4];
+    const TileGeo g = tile_geo(d, tcode & 15);
+    const Dav1dCudaMcSrc s = d.src[0];
+    const PlaneView &ref = a.refs[s.ref].p[d.plane];
+    if (d.kind == DAV1D_CUDA_MC_PREP) {
+        int16_t *out = a.tmp + d.aux_off + g.y0 * d.w + g.x0;
+        mc_tile<pixel, true>(ref, s.x + g.x0, s.y + g.y0, g.tw, g.th, d.w, d.h, s.mx, s.my, s.filter_2d,
+                             a.dst.bdmax, sm, out, d.w, lane);
+    } else {
+        const PlaneView &dp = a.dst.p[d.plane];
+        const int dstride = (int)(dp.stride / (int)sizeof(pixel));
+        pixel *out = (pixel *)dp.data + (int64_t)(d.y + g.y0) * dstride + d.x + g.x0;
+        mc_tile<pixel, false>(ref, s.x + g.x0, s.y + g.y0, g.tw, g.th, d.w, d.h, s.mx, s.my, s.filter_2d,
+                              a.dst.bdmax, sm, out, dstride, lane);
+    }
+}
+
+// ---- fused compound: two preps into shared int16 tiles, then the combine
+template <typename pixel>
+__global__ void __launch_bounds__(MC_WARPS * 32) mc_compound_kernel(const __grid_constant__ McArgs a) {
+    extern __shared__ __align__(16) uint8_t mc_smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ti = blockIdx.x * MC_WARPS + warp;
+    if (ti >= a.n_tiles) return;
+    McSmemCompound<pixel> *sm = (McSmemCompound<pixel> *)mc_smem_raw + warp;
+    const uint32_t tcode = a.tiles[ti];
+    const Dav1dCudaMcDesc d = a.descs[tcode >> 4];
+    const TileGeo g = tile_geo(d, tcode & 15);
+    for (int i = 0; i < 2; i++) {
+        const Dav1dCudaMcSrc s = d.src[i];
+        const PlaneView &ref = a.refs[s.ref].p[d.plane];
+        mc_tile<pixel, true>(ref, s.x + g.x0, s.y + g.y0, g.tw, g.th, d.w, d.h, s.mx, s.my, s.filter_2d,
+                             a.dst.bdmax, &sm->s, i ? sm->tb : sm->ta, MC_T, lane);
+    }
+    const PlaneView &dp = a.dst.p[d.plane];
+    const int dstride = (int)(dp.stride / (int)sizeof(pixel));
+    pixel *out = (pixel *)dp.data + (int64_t)(d.y + g.y0) * dstride + d.x + g.x0;
+    uint8_t *mask = nullptr;
+    int ms = 0;
+    if (d.kind == DAV1D_CUDA_MC_MASK) {
+        ms = d.w;
+        mask = a.masks + d.aux_off + g.y0 * ms + g.x0;
+    } else if (d.kind == DAV1D_CUDA_MC_W_MASK) {
+        const int ssh = d.mask_ss >= 1, ssv = d.mask_ss == 2;
+        ms = d.w >> ssh;
+        mask = a.masks + d.aux_off + (g.y0 >> ssv) * ms + (g.x0 >> ssh);
+    }
+    mc_combine<pixel>(d.kind, sm->ta, sm->tb, MC_T, out, dstride, g.tw, g.th, d.weight, mask, ms, d.mask_ss,
+                      a.dst.bdmax, lane, 32);
+}
+
+// ---- stand-alone ops on one block (per-call surface + unfused batch use)
+struct BlockOp {
+    int kind;                 // combine: Dav1dCudaMcKind; blend: 0/1/2
+    int w, h;
+    int weight, mask_ss;
+    void *dst; int dstride;   // pixels
+    const void *a, *b;        // combine: int16 tmp1/tmp2 (stride w); blend: a = pixel tmp (stride w)
+    uint8_t *mask;
+    int bdmax;
+};
+
+template <typename pixel> __global__ void mc_combine_kernel(const BlockOp op) {
+    const int ssh = op.mask_ss >= 1;
+    const int ms = op.kind == DAV1D_CUDA_MC_W_MASK ? op.w >> ssh : op.w;
+    mc_combine<pixel>(op.kind, (const int16_t *)op.a, (const int16_t *)op.b, op.w, (pixel *)op.dst, op.dstride,
+                      op.w, op.h, op.weight, op.mask, ms, op.mask_ss, op.bdmax, threadIdx.x, blockDim.x);
+}
+
+template <typename pixel> __global__ void mc_blend_kernel(const BlockOp op) {
+    mc_blend<pixel>(op.kind, (pixel *)op.dst, op.dstride, (const pixel *)op.a, op.w, op.h, op.mask,
+                    threadIdx.x, blockDim.x);
+}
+
+struct WarpArgs {
+    PlaneView ref;
+    int sx, sy;
+    int16_t abcd[4];
+    int mx, my;
+    void *out; int ostride;
+    int bdmax;
+};
+template <typename pixel, bool PREP> __global__ void mc_warp_kernel(const WarpArgs w) {
+    __shared__ int16_t mid[15 * 8];
+    mc_warp8x8<pixel, PREP>(w.ref, w.sx, w.sy, w.abcd, w.mx, w.my, w.bdmax, mid,
+                            (typename McOut<pixel, PREP>::type *)w.out, w.ostride, threadIdx.x);
+}
+
+struct EmuArgs { PlaneView ref; int x, y, bw, bh; void *dst; int dstride; };
+template <typename pixel> __global__ void mc_emu_edge_kernel(const EmuArgs e) {
+    const pixel *rp = (const pixel *)e.ref.data;
+    const int64_t rs = e.ref.stride / (int64_t)sizeof(pixel);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < e.bw * e.bh; i += gridDim.x * blockDim.x) {
+        const int y = i / e.bw, x = i % e.bw;
+        ((pixel *)e.dst)[y * e.dstride + x] =
+            rp[iclip(e.y + y, 0, e.ref.h - 1) * rs + iclip(e.x + x, 0, e.ref.w - 1)];
+    }
+}
+
+// ---- scaled put/prep (reference scaling), one warp per 32x32 tile.
+// mc_tmpl.c:173-221 (put_8tap_scaled), :284-328 (prep), :452-491,548-585 (bilin)
+struct ScaledArgs {
+    PlaneView ref;
+    int sx, sy;               // integer position of the block's top-left
+    int w, h, mx, my, dx, dy; // mx,my in 1/1024
+    int filter_2d;
+    void *out; int ostride;
+    int bdmax;
+};
+
+constexpr int SC_MAX_ROWS = 72;
+
+template <typename pixel, bool PREP>
+__global__ void __launch_bounds__(MC_WARPS * 32) mc_scaled_kernel(const ScaledArgs a) {
+    __shared__ int16_t mid_all[MC_WARPS][SC_MAX_ROWS * MC_T];
+    typedef typename McOut<pixel, PREP>::type out_t;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tiles_x = (a.w + MC_T - 1) / MC_T, tiles_y = (a.h + MC_T - 1) / MC_T;
+    const int t = blockIdx.x * MC_WARPS + warp;
+    if (t >= tiles_x * tiles_y) return;
+    int16_t *mid = mid_all[warp];
+    const int x0 = (t % tiles_x) * MC_T, y0 = (t / tiles_x) * MC_T;
+    const int tw = imin(MC_T, a.w - x0), th = imin(MC_T, a.h - y0);
+    const bool bilin = a.filter_2d == 9;
+    const int ib = PxTraits<pixel>::inter_bits(a.bdmax);
+    const int th_t = (0x15A80 >> (2 * a.filter_2d)) & 3, tv_t = a.filter_2d % 3;
+    const int hset = a.w > 4 ? th_t : 3 + (th_t & 1);
+    const int vset = a.h > 4 ? tv_t : 3 + (tv_t & 1);
+    const pixel *rp = (const pixel *)a.ref.data;
+    const int64_t rs = a.ref.stride / (int64_t)sizeof(pixel);
+
+    // rows of `mid` this tile needs, relative to the block's first mid row
+    const int ypos0 = a.my + y0 * a.dy;
+    const int row_first = ypos0 >> 10;
+    const int row_last = ((a.my + (y0 + th - 1) * a.dy) >> 10) + (bilin ? 1 : 7);
+    const int nrows = row_last - row_first + 1;
+    const int roff = bilin ? 0 : -3;      // mid row r <-> source row sy + roff + r
+    for (int i = lane; i < nrows * tw; i += 32) {
+        const int r = i / tw, x = i % tw;
+        const int pos = a.mx + (x0 + x) * a.dx;
+        const int ioff = pos >> 10, fx = (pos & 0x3ff) >> 6;
+        const int yy = iclip(a.sy + roff + row_first + r, 0, a.ref.h - 1);
+        const pixel *row = rp + yy * rs;
+        int v;
+        if (bilin) {
+            const int p0 = row[iclip(a.sx + ioff, 0, a.ref.w - 1)];
+            const int p1 = row[iclip(a.sx + ioff + 1, 0, a.ref.w - 1)];
+            const int sh = 4 - ib;
+            v = (16 * p0 + fx * (p1 - p0) + ((1 << sh) >> 1)) >> sh;
+        } else if (fx) {
+            const int8_t *f = g_subpel_filters + (hset * 15 + fx - 1) * 8;
+            int sum = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) sum += f[k] * row[iclip(a.sx + ioff + k - 3, 0, a.ref.w - 1)];
+            const int sh = 6 - ib;
+            v = (sum + ((1 << sh) >> 1)) >> sh;
+        } else {
+            v = row[iclip(a.sx + ioff, 0, a.ref.w - 1)] << ib;
+        }
+        mid[r * MC_T + x] = (int16_t)v;
+    }
+    __syncwarp();
+    out_t *out = (out_t *)a.out + y0 * a.ostride + x0;
+    for (int i = lane; i < tw * th; i += 32) {
+        const int y = i / tw, x = i % tw;
+        const int ypos = a.my + (y0 + y) * a.dy;
+        const int r = (ypos >> 10) - row_first, fy = (ypos & 0x3ff) >> 6;
+        const int16_t *m = mid + r * MC_T + x;
+        int res;
+        if (bilin) {
+            const int s = 16 * m[0] + fy * (m[MC_T] - m[0]);
+            if (PREP) res = ((s + 8) >> 4) - PxTraits<pixel>::prep_bias;
+            else res = clip_px<pixel>((s + ((1 << (4 + ib)) >> 1)) >> (4 + ib), a.bdmax);
+        } else if (fy) {
+            const int8_t *f = g_subpel_filters + (vset * 15 + fy - 1) * 8;
+            int sum = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) sum += f[k] * m[k * MC_T];
+            if (PREP) res = ((sum + 32) >> 6) - PxTraits<pixel>::prep_bias;
+            else res = clip_px<pixel>((sum + ((1 << (6 + ib)) >> 1)) >> (6 + ib), a.bdmax);
+        } else {
+            const int c = m[3 * MC_T];
+            if (PREP) res = c - PxTraits<pixel>::prep_bias;
+            else res = clip_px<pixel>((c + ((1 << ib) >> 1)) >> ib, a.bdmax);
+        }
+        out[y * a.ostride + x] = (out_t)res;
+    }
+}
+
+// ------------------------------------------------------------------ launchers
+static std::vector<uint32_t> tiles_for(int desc_idx, int w, int h) {
+    std::vector<uint32_t> t;
+    for (int ty = 0; ty * MC_T < h; ty++)
+        for (int tx = 0; tx * MC_T < w; tx++)
+            t.push_back((uint32_t)desc_idx * 16 + ty * 4 + tx);
+    return t;
+}
+
+template <typename pixel>
+static int launch_put(const McArgs &a, cudaStream_t st) {
+    const int grid = (a.n_tiles + MC_WARPS - 1) / MC_WARPS;
+    mc_put_kernel<pixel><<<grid, MC_WARPS * 32, MC_WARPS * sizeof(McSmem<pixel>), st>>>(a);
+    count_launch();
+    return cuda_ok(cudaGetLastError(), "mc_put_kernel") ? 0 : -5;
+}
+template <typename pixel>
+static int launch_compound(const McArgs &a, cudaStream_t st) {
+    static bool attr_done = false;
+    const size_t smem = MC_WARPS * sizeof(McSmemCompound<pixel>);
+    if (!attr_done) {
+        cudaFuncSetAttribute(mc_compound_kernel<pixel>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_done = true;
+    }
+    const int grid = (a.n_tiles + MC_WARPS - 1) / MC_WARPS;
+    mc_compound_kernel<pixel><<<grid, MC_WARPS * 32, smem, st>>>(a);
+    count_launch();
+    return cuda_ok(cudaGetLastError(), "mc_compound_kernel") ? 0 : -5;
+}
+
+int mc_put_launch(const McArgs &a, cudaStream_t st) {
+    if (a.n_tiles <= 0) return 0;
+    return a.dst.bdmax > 0xff ? launch_put<uint16_t>(a, st) : launch_put<uint8_t>(a, st);
+}
+int mc_compound_launch(const McArgs &a, cudaStream_t st) {
+    if (a.n_tiles <= 0) return 0;
+    return a.dst.bdmax > 0xff ? launch_compound<uint16_t>(a, st) : launch_compound<uint8_t>(a, st);
+}
+
+// ------------------------------------------------------------ per-call surface
+static void plane_of(PlaneView &p, void *data, size_t stride, int w, int h) {
+    p.data = data; p.stride = (int64_t)stride; p.w = w; p.h = h;
+}
+
+// mc_fn / mct_fn (src/mc.h:38-63)
+template <typename pixel, bool PREP>
+static void mc_single(const int filter, void *out_host, const ptrdiff_t out_stride_bytes,
+                      const pixel *src, const ptrdiff_t src_stride, const int w, const int h,
+                      const int mx, const int my, const int bdmax)
+{
+    const bool bil = filter == 9;
+    const int cl = mx ? (bil ? 0 : 3) : 0, cr = mx ? (bil ? 1 : 4) : 0;
+    const int rl = my ? (bil ? 0 : 3) : 0, rb = my ? (bil ? 1 : 4) : 0;
+    const int ww = w + cl + cr, wh = h + rl + rb;
+    const size_t sstride = ((size_t)ww * sizeof(pixel) + 63) & ~(size_t)63;
+    const size_t ostride = PREP ? (size_t)w * 2 : (((size_t)w * sizeof(pixel) + 63) & ~(size_t)63);
+    Staging &sg = staging();
+    std::lock_guard<std::mutex> lk(sg.mu);
+    Stage st(sg);
+    const size_t o_src = st.reserve(sstride * wh);
+    const size_t o_desc = st.reserve(sizeof(Dav1dCudaMcDesc));
+    std::vector<uint32_t> tiles = tiles_for(0, w, h);
+    const size_t o_tiles = st.reserve(tiles.size() * 4);
+    const size_t o_out = st.reserve(ostride * h);
+    if (!st.commit()) return;
+    const ptrdiff_t spx = src_stride / (ptrdiff_t)sizeof(pixel);
+    st.put2d(o_src, sstride, src - rl * spx - cl, src_stride, (size_t)ww * sizeof(pixel), wh);
+    Dav1dCudaMcDesc d;
+    memset(&d, 0, sizeof(d));
+    d.w = (uint8_t)w; d.h = (uint8_t)h;
+    d.kind = PREP ? DAV1D_CUDA_MC_PREP : DAV1D_CUDA_MC_PUT;
+    d.src[0].x = cl; d.src[0].y = rl;
+    d.src[0].filter_2d = (uint8_t)filter; d.src[0].mx = (uint8_t)mx; d.src[0].my = (uint8_t)my;
+    memcpy(st.host(o_desc), &d, sizeof(d));
+    memcpy(st.host(o_tiles), tiles.data(), tiles.size() * 4);
+    if (!st.upload()) return;
+    McArgs a;
+    memset(&a, 0, sizeof(a));
+    plane_of(a.refs[0].p[0], st.dev(o_src), sstride, ww, wh);
+    plane_of(a.dst.p[0], st.dev(o_out), ostride, w, h);
+    a.dst.bdmax = bdmax;
+    a.descs = (const Dav1dCudaMcDesc *)st.dev(o_desc);
+    a.tiles = (const uint32_t *)st.dev(o_tiles);
+    a.n_tiles = (int)tiles.size();
+    a.tmp = (int16_t *)st.dev(o_out);
+    if (mc_put_launch(a, st.stream())) return;
+    if (!st.download(o_out, ostride * h) || !st.sync()) return;
+    st.get2d(o_out, ostride, out_host, PREP ? (ptrdiff_t)w * 2 : out_stride_bytes,
+             PREP ? (size_t)w * 2 : (size_t)w * sizeof(pixel), h);
+}
+
+// mc_scaled_fn / mct_scaled_fn (src/mc.h:45-69)
+template <typename pixel, bool PREP>
+static void mc_scaled_single(const int filter, void *out_host, const ptrdiff_t out_stride_bytes,
+                             const pixel *src, const ptrdiff_t src_stride, const int w, const int h,
+                             const int mx, const int my, const int dx, const int dy, const int bdmax)
+{
+    const bool bil = filter == 9;
+    // extent the reference touches (mc_tmpl.c:182-201, 459-478)
+    const int cl = bil ? 0 : 3, rl = bil ? 0 : 3;
+    const int last_x = ((mx + (w - 1) * dx) >> 10) + (bil ? 1 : 4);
+    const int last_y = ((my + (h - 1) * dy) >> 10) + (bil ? 1 : 4);
+    const int ww = cl + last_x + 1, wh = rl + last_y + 1;
+    const size_t sstride = ((size_t)ww * sizeof(pixel) + 63) & ~(size_t)63;
+    const size_t ostride = PREP ? (size_t)w * 2 : (((size_t)w * sizeof(pixel) + 63) & ~(size_t)63);
+    Staging &sg = staging();
+    std::lock_guard<std::mutex> lk(sg.mu);
+    Stage st(sg);
+    const size_t o_src = st.reserve(sstride * wh);
+    const size_t o_out = st.reserve(ostride * h);
+    if (!st.commit()) return;
+    const ptrdiff_t spx = src_stride / (ptrdiff_t)sizeof(pixel);
+    st.put2d(o_src, sstride, src - rl * spx - cl, src_stride, (size_t)ww * sizeof(pixel), wh);
+    if (!st.upload()) return;
+    ScaledArgs a;
+    plane_of(a.ref, st.dev(o_src), sstride, ww, wh);
+    a.sx = cl; a.sy = rl;
+    a.w = w; a.h = h; a.mx = mx; a.my = my; a.dx = dx; a.dy = dy;
+    a.filter_2d = filter;
+    a.out = st.dev(o_out);
+    a.ostride = (int)(PREP ? w : ostride / sizeof(pixel));
+    a.bdmax = bdmax;
+    const int ntiles = ((w + MC_T - 1) / MC_T) * ((h + MC_T - 1) / MC_T);
+    mc_scaled_kernel<pixel, PREP><<<(ntiles + MC_WARPS - 1) / MC_WARPS, MC_WARPS * 32, 0, st.stream()>>>(a);
+    count_launch();
+    if (!cuda_ok(cudaGetLastError(), "mc_scaled_kernel")) return;
+    if (!st.download(o_out, ostride * h) || !st.sync()) return;
+    st.get2d(o_out, ostride, out_host, PREP ? (ptrdiff_t)w * 2 : out_stride_bytes,
+             PREP ? (size_t)w * 2 : (size_t)w * sizeof(pixel), h);
+}
+
+// avg_fn / w_avg_fn / mask_fn / w_mask_fn (src/mc.h:71-93)
+template <typename pixel>
+static void combine_single(const int kind, pixel *dst, const ptrdiff_t dst_stride, const int16_t *t1,
+                           const int16_t *t2, const int w, const int h, const int weight_or_sign,
+                           uint8_t *mask, const int mask_ss, const int bdmax)
+{
+    const size_t tb = (size_t)w * h * 2;
+    const size_t ostride = ((size_t)w * sizeof(pixel) + 63) & ~(size_t)63;
+    const int ssh = mask_ss >= 1, ssv = mask_ss == 2;
+    const size_t mbytes = kind == DAV1D_CUDA_MC_MASK ? (size_t)w * h
+                        : kind == DAV1D_CUDA_MC_W_MASK ? (size_t)(w >> ssh) * (h >> ssv) : 0;
+    Staging &sg = staging();
+    std::lock_guard<std::mutex> lk(sg.mu);
+    Stage st(sg);
+    const size_t o1 = st.reserve(tb), o2 = st.reserve(tb);
+    const size_t om = st.reserve(mbytes ? mbytes : 1);
+    const size_t o_out = st.reserve(ostride * h);
+    if (!st.commit()) return;
+    memcpy(st.host(o1), t1, tb);
+    memcpy(st.host(o2), t2, tb);
+    if (kind == DAV1D_CUDA_MC_MASK) memcpy(st.host(om), mask, mbytes);
+    if (!st.upload()) return;
+    BlockOp op;
+    memset(&op, 0, sizeof(op));
+    op.kind = kind; op.w = w; op.h = h; op.weight = weight_or_sign; op.mask_ss = mask_ss;
+    op.dst = st.dev(o_out); op.dstride = (int)(ostride / sizeof(pixel));
+    op.a = st.dev(o1); op.b = st.dev(o2);
+    op.mask = st.dev(om);
+    op.bdmax = bdmax;
+    mc_combine_kernel<pixel><<<1, 256, 0, st.stream()>>>(op);
+    count_launch();
+    if (!cuda_ok(cudaGetLastError(), "mc_combine_kernel")) return;
+    if (!st.download(om, (size_t)(o_out - om) + ostride * h) || !st.sync()) return;
+    st.get2d(o_out, ostride, dst, dst_stride, (size_t)w * sizeof(pixel), h);
+    if (kind == DAV1D_CUDA_MC_W_MASK) memcpy(mask, st.host(om), mbytes);
+}
+
+// blend_fn / blend_dir_fn (src/mc.h:95-102)
+template <typename pixel>
+static void blend_single(const int kind, pixel *dst, const ptrdiff_t dst_stride, const pixel *tmp,
+                         const int w, const int h, const uint8_t *mask)
+{
+    const size_t tbytes = (size_t)w * h * sizeof(pixel);
+    const size_t ostride = ((size_t)w * sizeof(pixel) + 63) & ~(size_t)63;
+    Staging &sg = staging();
+    std::lock_guard<std::mutex> lk(sg.mu);
+    Stage st(sg);
+    const size_t ot = st.reserve(tbytes), om = st.reserve((size_t)w * h);
+    const size_t o_out = st.reserve(ostride * h);
+    if (!st.commit()) return;
+    memcpy(st.host(ot), tmp, tbytes);
+    if (kind == 0) memcpy(st.host(om), mask, (size_t)w * h);
+    st.put2d(o_out, ostride, dst, dst_stride, (size_t)w * sizeof(pixel), h);
+    if (!st.upload()) return;
+    BlockOp op;
+    memset(&op, 0, sizeof(op));
+    op.kind = kind; op.w = w; op.h = h;
+    op.dst = st.dev(o_out); op.dstride = (int)(ostride / sizeof(pixel));
+    op.a = st.dev(ot);
+    op.mask = st.dev(om);
+    mc_blend_kernel<pixel><<<1, 256, 0, st.stream()>>>(op);
+    count_launch();
+    if (!cuda_ok(cudaGetLastError(), "mc_blend_kernel")) return;
+    if (!st.download(o_out, ostride * h) || !st.sync()) return;
+    st.get2d(o_out, ostride, dst, dst_stride, (size_t)w * sizeof(pixel), h);
+}
+
+// warp8x8_fn / warp8x8t_fn (src/mc.h:52-69)
+template <typename pixel, bool PREP>
+static void warp_single(void *out_host, const ptrdiff_t out_stride_bytes, const pixel *src,
+                        const ptrdiff_t src_stride, const int16_t *abcd, const int mx, const int my,
+                        const int bdmax)
+{
+    const size_t sstride = 64;   // 15 pixels
+    const size_t obytes = PREP ? 2 : sizeof(pixel);
+    Staging &sg = staging();
+    std::lock_guard<std::mutex> lk(sg.mu);
+    Stage st(sg);
+    const size_t o_src = st.reserve(sstride * 15);
+    const size_t o_out = st.reserve(8 * 8 * obytes);
+    if (!st.commit()) return;
+    const ptrdiff_t spx = src_stride / (ptrdiff_t)sizeof(pixel);
+    st.put2d(o_src, sstride, src - 3 * spx - 3, src_stride, 15 * sizeof(pixel), 15);
+    if (!st.upload()) return;
+    WarpArgs w;
+    plane_of(w.ref, st.dev(o_src), sstride, 15, 15);
+    w.sx = 3; w.sy = 3;
+    memcpy(w.abcd, abcd, sizeof(w.abcd));
+    w.mx = mx; w.my = my;
+    w.out = st.dev(o_out); w.ostride = 8;
+    w.bdmax = bdmax;
+    mc_warp_kernel<pixel, PREP><<<1, 32, 0, st.stream()>>>(w);
+    count_launch();
+    if (!cuda_ok(cudaGetLastError(), "mc_warp_kernel")) return;
+    if (!st.download(o_out, 8 * 8 * obytes) || !st.sync()) return;
+    st.get2d(o_out, 8 * obytes, out_host, out_stride_bytes, 8 * obytes, 8);
+}
+
+// emu_edge_fn (src/mc.h:104-107)
+template <typename pixel>
+static void emu_edge_single(const intptr_t bw, const intptr_t bh, const intptr_t iw, const intptr_t ih,
+                            const intptr_t x, const intptr_t y, pixel *dst, const ptrdiff_t dst_stride,
+                            const pixel *ref, const ptrdiff_t ref_stride)
+{
+    // visible sub-rectangle of the reference that the block maps to
+    const int cx0 = iclip((int)x, 0, (int)iw - 1), cx1 = iclip((int)(x + bw - 1), 0, (int)iw - 1);
+    const int cy0 = iclip((int)y, 0, (int)ih - 1), cy1 = iclip((int)(y + bh - 1), 0, (int)ih - 1);
+    const int rw = cx1 - cx0 + 1, rh = cy1 - cy0 + 1;
+    const size_t sstride = ((size_t)rw * sizeof(pixel) + 63) & ~(size_t)63;
+    const size_t ostride = ((size_t)bw * sizeof(pixel) + 63) & ~(size_t)63;
+    Staging &sg = staging();
+    std::lock_guard<std::mutex> lk(sg.mu);
+    Stage st(sg);
+    const size_t o_src = st.reserve(sstride * rh);
+    const size_t o_out = st.reserve(ostride * bh);
+    if (!st.commit()) return;
+    const ptrdiff_t rpx = ref_stride / (ptrdiff_t)sizeof(pixel);
+    st.put2d(o_src, sstride, ref + cy0 * rpx + cx0, ref_stride, (size_t)rw * sizeof(pixel), rh);
+    if (!st.upload()) return;
+    EmuArgs e;
+    plane_of(e.ref, st.dev(o_src), sstride, rw, rh);
+    e.x = (int)x - cx0; e.y = (int)y - cy0;
+    e.bw = (int)bw; e.bh = (int)bh;
+    e.dst = st.dev(o_out); e.dstride = (int)(ostride / sizeof(pixel));
+    mc_emu_edge_kernel<pixel><<<8, 256, 0, st.stream()>>>(e);
+    count_launch();
+    if (!cuda_ok(cudaGetLastError(), "mc_emu_edge_kernel")) return;
+    if (!st.download(o_out, ostride * bh) || !st.sync()) return;
+    st.get2d(o_out, ostride, dst, dst_stride, (size_t)bw * sizeof(pixel), (int)bh);
+}
+
+// ---- typed entry points filled into the table
+#define HBD_ARGS , int bitdepth_max
+template <int F> static void put8(uint8_t *d, ptrdiff_t ds, const uint8_t *s, ptrdiff_t ss, int w, int h, int mx, int my)
+{ mc_single<uint8_t, false>(F, d, ds, s, ss, w, h, mx, my, 0xff); }
+template <int F> static void put16(uint16_t *d, ptrdiff_t ds, const uint16_t *s, ptrdiff_t ss, int w, int h, int mx, int my HBD_ARGS)
+{ mc_single<uint16_t, false>(F, d, ds, s, ss, w, h, mx, my, bitdepth_max); }
+template <int F> static void prep8(int16_t *t, const uint8_t *s, ptrdiff_t ss, int w, int h, int mx, int my)
+{ mc_single<uint8_t, true>(F, t, 0, s, ss, w, h, mx, my, 0xff); }
+template <int F> static void prep16(int16_t *t, const uint16_t *s, ptrdiff_t ss, int w, int h, int mx, int my HBD_ARGS)
+{ mc_single<uint16_t, true>(F, t, 0, s, ss, w, h, mx, my, bitdepth_max); }
+template <int F> static void puts8(uint8_t *d, ptrdiff_t ds, const uint8_t *s, ptrdiff_t ss, int w, int h, int mx, int my, int dx, int dy)
+{ mc_scaled_single<uint8_t, false>(F, d, ds, s, ss, w, h, mx, my, dx, dy, 0xff); }
+template <int F> static void puts16(uint16_t *d, ptrdiff_t ds, const uint16_t *s, ptrdiff_t ss, int w, int h, int mx, int my, int dx, int dy HBD_ARGS)
+{ mc_scaled_single<uint16_t, false>(F, d, ds, s, ss, w, h, mx, my, dx, dy, bitdepth_max); }
+template <int F> static void preps8(int16_t *t, const uint8_t *s, ptrdiff_t ss, int w, int h, int mx, int my, int dx, int dy)
+{ mc_scaled_single<uint8_t, true>(F, t, 0, s, ss, w, h, mx, my, dx, dy, 0xff); }
+template <int F> static void preps16(int16_t *t, const uint16_t *s, ptrdiff_t ss, int w, int h, int mx, int my, int dx, int dy HBD_ARGS)
+{ mc_scaled_single<uint16_t, true>(F, t, 0, s, ss, w, h, mx, my, dx, dy, bitdepth_max); }
+
+static void avg8(uint8_t *d, ptrdiff_t ds, const int16_t *a, const int16_t *b, int w, int h)
+{ combine_single<uint8_t>(DAV1D_CUDA_MC_AVG, d, ds, a, b, w, h, 0, nullptr, 0, 0xff); }
+static void avg16(uint16_t *d, ptrdiff_t ds, const int16_t *a, const int16_t *b, int w, int h HBD_ARGS)
+{ combine_single<uint16_t>(DAV1D_CUDA_MC_AVG, d, ds, a, b, w, h, 0, nullptr, 0, bitdepth_max); }
+static void wavg8(uint8_t *d, ptrdiff_t ds, const int16_t *a, const int16_t *b, int w, int h, int wt)
+{ combine_single<uint8_t>(DAV1D_CUDA_MC_W_AVG, d, ds, a, b, w, h, wt, nullptr, 0, 0xff); }
+static void wavg16(uint16_t *d, ptrdiff_t ds, const int16_t *a, const int16_t *b, int w, int h, int wt HBD_ARGS)
+{ combine_single<uint16_t>(DAV1D_CUDA_MC_W_AVG, d, ds, a, b, w, h, wt, nullptr, 0, bitdepth_max); }
+static void mask8(uint8_t *d, ptrdiff_t ds, const int16_t *a, const int16_t *b, int w, int h, const uint8_t *m)
+{ combine_single<uint8_t>(DAV1D_CUDA_MC_MASK, d, ds, a, b, w, h, 0, (uint8_t *)m, 0, 0xff); }
+static void mask16(uint16_t *d, ptrdiff_t ds, const int16_t *a, const int16_t *b, int w, int h, const uint8_t *m HBD_ARGS)
+{ combine_single<uint16_t>(DAV1D_CUDA_MC_MASK, d, ds, a, b, w, h, 0, (uint8_t *)m, 0, bitdepth_max); }
+template <int SS> static void wmask8(uint8_t *d, ptrdiff_t ds, const int16_t *a, const int16_t *b, int w, int h, uint8_t *m, int sign)
+{ combine_single<uint8_t>(DAV1D_CUDA_MC_W_MASK, d, ds, a, b, w, h, sign, m, SS, 0xff); }
+template <int SS> static void wmask16(uint16_t *d, ptrdiff_t ds, const int16_t *a, const int16_t *b, int w, int h, uint8_t *m, int sign HBD_ARGS)
+{ combine_single<uint16_t>(DAV1D_CUDA_MC_W_MASK, d, ds, a, b, w, h, sign, m, SS, bitdepth_max); }
+template <typename pixel> static void blend_p(pixel *d, ptrdiff_t ds, const pixel *t, int w, int h, const uint8_t *m)
+{ blend_single<pixel>(0, d, ds, t, w, h, m); }
+template <typename pixel> static void blend_v_p(pixel *d, ptrdiff_t ds, const pixel *t, int w, int h)
+{ blend_single<pixel>(1, d, ds, t, w, h, nullptr); }
+template <typename pixel> static void blend_h_p(pixel *d, ptrdiff_t ds, const pixel *t, int w, int h)
+{ blend_single<pixel>(2, d, ds, t, w, h, nullptr); }
+static void warp8(uint8_t *d, ptrdiff_t ds, const uint8_t *s, ptrdiff_t ss, const int16_t *abcd, int mx, int my)
+{ warp_single<uint8_t, false>(d, ds, s, ss, abcd, mx, my, 0xff); }
+static void warp16(uint16_t *d, ptrdiff_t ds, const uint16_t *s, ptrdiff_t ss, const int16_t *abcd, int mx, int my HBD_ARGS)
+{ warp_single<uint16_t, false>(d, ds, s, ss, abcd, mx, my, bitdepth_max); }
+static void warpt8(int16_t *t, ptrdiff_t ts, const uint8_t *s, ptrdiff_t ss, const int16_t *abcd, int mx, int my)
+{ warp_single<uint8_t, true>(t, ts * 2, s, ss, abcd, mx, my, 0xff); }
+static void warpt16(int16_t *t, ptrdiff_t ts, const uint16_t *s, ptrdiff_t ss, const int16_t *abcd, int mx, int my HBD_ARGS)
+{ warp_single<uint16_t, true>(t, ts * 2, s, ss, abcd, mx, my, bitdepth_max); }
+template <typename pixel> static void emu_p(intptr_t bw, intptr_t bh, intptr_t iw, intptr_t ih, intptr_t x, intptr_t y,
+                                           pixel *d, ptrdiff_t ds, const pixel *r, ptrdiff_t rs)
+{ emu_edge_single<pixel>(bw, bh, iw, ih, x, y, d, ds, r, rs); }
+
+template <bool HBD, int F> static void fill_filter(Dav1dCudaMCDSPContext *c) {
+    c->mc[F] = HBD ? (void *)put16<F> : (void *)put8<F>;
+    c->mct[F] = HBD ? (void *)prep16<F> : (void *)prep8<F>;
+    c->mc_scaled[F] = HBD ? (void *)puts16<F> : (void *)puts8<F>;
+    c->mct_scaled[F] = HBD ? (void *)preps16<F> : (void *)preps8<F>;
+}
+
+template <bool HBD> static void fill_mc(Dav1dCudaMCDSPContext *c) {
+    Staging &s = staging();
+    {
+        std::lock_guard<std::mutex> lk(s.mu);
+        if (!s.ensure(1 << 20)) return;
+    }
+    fill_filter<HBD, 0>(c); fill_filter<HBD, 1>(c); fill_filter<HBD, 2>(c); fill_filter<HBD, 3>(c);
+    fill_filter<HBD, 4>(c); fill_filter<HBD, 5>(c); fill_filter<HBD, 6>(c); fill_filter<HBD, 7>(c);
+    fill_filter<HBD, 8>(c); fill_filter<HBD, 9>(c);
+    typedef typename std::conditional<HBD, uint16_t, uint8_t>::type pixel;
+    c->avg = HBD ? (void *)avg16 : (void *)avg8;
+    c->w_avg = HBD ? (void *)wavg16 : (void *)wavg8;
+    c->mask = HBD ? (void *)mask16 : (void *)mask8;
+    c->w_mask[0] = HBD ? (void *)wmask16<0> : (void *)wmask8<0>;
+    c->w_mask[1] = HBD ? (void *)wmask16<1> : (void *)wmask8<1>;
+    c->w_mask[2] = HBD ? (void *)wmask16<2> : (void *)wmask8<2>;
+    c->blend = (void *)blend_p<pixel>;
+    c->blend_v = (void *)blend_v_p<pixel>;
+    c->blend_h = (void *)blend_h_p<pixel>;
+    c->warp8x8 = HBD ? (void *)warp16 : (void *)warp8;
+    c->warp8x8t = HBD ? (void *)warpt16 : (void *)warpt8;
+    c->emu_edge = (void *)emu_p<pixel>;
+    // c->resize is left as set by the caller (super-resolution is a post-filter)
+}
+
+}  // namespace d1
+
+using namespace d1;
+
+extern "C" {
+
+void dav1d_cuda_mc_dsp_init_8bpc(Dav1dCudaMCDSPContext *c) { fill_mc<false>(c); }
+void dav1d_cuda_mc_dsp_init_16bpc(Dav1dCudaMCDSPContext *c) { fill_mc<true>(c); }
+
+static int mc_batch_common(Dav1dCudaContext *c, const Dav1dCudaPicture *dst,
+                           const Dav1dCudaPicture *const refs[7], const Dav1dCudaMcDesc *descs,
+                           const uint32_t *tiles, int n_tiles, uint8_t *masks, int16_t *tmp, bool compound)
+{
+    if (!c || !dst || !descs || !tiles) return -22;
+    McArgs a;
+    memset(&a, 0, sizeof(a));
+    a.dst = pic_view(dst);
+    for (int i = 0; i < 7; i++)
+        if (refs[i]) a.refs[i] = pic_view(refs[i]);
+    a.descs = descs;
+    a.tiles = tiles;
+    a.n_tiles = n_tiles;
+    a.masks = masks;
+    a.tmp = tmp;
+    return compound ? mc_compound_launch(a, c->stream) : mc_put_launch(a, c->stream);
+}
+
+int dav1d_cuda_mc_tiles(uint32_t desc_index, int w, int h, uint32_t *out) {
+    int n = 0;
+    for (int ty = 0; ty * MC_T < h; ty++)
+        for (int tx = 0; tx * MC_T < w; tx++)
+            out[n++] = desc_index * 16 + ty * 4 + tx;
+    return n;
+}
+
+int dav1d_cuda_mc_put_batch(Dav1dCudaContext *c, const Dav1dCudaPicture *dst,
+                            const Dav1dCudaPicture *const refs[7], const Dav1dCudaMcDesc *descs,
+                            const uint32_t *tiles, int n_tiles, int16_t *tmp)
+{
+    return mc_batch_common(c, dst, refs, descs, tiles, n_tiles, nullptr, tmp, false);
+}
+
+int dav1d_cuda_mc_compound_batch(Dav1dCudaContext *c, const Dav1dCudaPicture *dst,
+                                 const Dav1dCudaPicture *const refs[7], const Dav1dCudaMcDesc *descs,
+                                 const uint32_t *tiles, int n_tiles, uint8_t *masks)
+{
+    return mc_batch_common(c, dst, refs, descs, tiles, n_tiles, masks, nullptr, true);
+}
+
+}  // extern "C"

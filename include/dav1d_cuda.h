@@ -253,6 +253,29 @@ DAV1D_CUDA_API int dav1d_cuda_itx_batch(Dav1dCudaContext *c, const Dav1dCudaPict
                                         const int32_t class_count[DAV1D_CUDA_N_RECT_TX_SIZES],
                                         int zero_coefs);
 
+/* Motion compensation.  `tiles` (device) lists the 32x32 work tiles:
+ * tiles[i] = desc_index * 16 + (tile_row * 4 + tile_col); the recorder emits
+ * one entry per 32x32 (or smaller, at the block edge) tile of each block
+ * (dav1d_cuda_mc_tiles() does it for one block).
+ *  - put_batch: kinds PUT (-> dst picture) and PREP (-> int16 pool `tmp`).
+ *  - compound_batch: kinds AVG / W_AVG / MASK / W_MASK, the two predictions
+ *    and the combine fused in one kernel (the int16 intermediates never
+ *    reach HBM).  `masks` (device) holds wedge masks (read by MASK) and
+ *    receives the segmentation masks W_MASK emits; a MASK descriptor that
+ *    consumes a mask emitted by a W_MASK descriptor must be submitted in a
+ *    later launch (luma before chroma, recon_tmpl.c:1852-1905). */
+DAV1D_CUDA_API int dav1d_cuda_mc_put_batch(Dav1dCudaContext *c, const Dav1dCudaPicture *dst,
+                                           const Dav1dCudaPicture *const refs[7],
+                                           const Dav1dCudaMcDesc *descs, const uint32_t *tiles,
+                                           int n_tiles, int16_t *tmp);
+DAV1D_CUDA_API int dav1d_cuda_mc_compound_batch(Dav1dCudaContext *c, const Dav1dCudaPicture *dst,
+                                                const Dav1dCudaPicture *const refs[7],
+                                                const Dav1dCudaMcDesc *descs, const uint32_t *tiles,
+                                                int n_tiles, uint8_t *masks);
+/* Host helper: append the tile codes of block `desc_index` (w x h) to `out`
+ * (room for 16 entries); returns the number written. */
+DAV1D_CUDA_API int dav1d_cuda_mc_tiles(uint32_t desc_index, int w, int h, uint32_t *out);
+
 #ifdef __cplusplus
 }
 #endif
