@@ -1,0 +1,490 @@
+// Intra prediction device functions, executed by one warp per (transform)
+// block.  `edge` is the reference's `topleft` pointer convention
+// (src/ipred_prepare.h:66-72): edge[0] corner, edge[1..] top (+top-right),
+// edge[-1..] left going down (+bottom-left).  `dst` may be global or shared.
+//
+// Reference being matched bit for bit: src/ipred_tmpl.c
+//   DC family :86-218   V/H :220-242   Paeth :244-265   smooth* :267-325
+//   edge filter/upsample :327-406   Z1 :408-460  Z2 :462-540  Z3 :542-599
+//   filter-intra :618-655   cfl_ac :657-703   cfl_pred :71-84   pal_pred :717-730
+// and src/ipred_prepare_tmpl.c:77-204 for the on-device edge preparation.
+#pragma once
+#include "common.cuh"
+#include "tables.cuh"
+
+namespace d1 {
+
+enum {
+    M_DC = 0, M_VERT, M_HOR, M_LEFT_DC, M_TOP_DC, M_DC_128, M_Z1, M_Z2, M_Z3,
+    M_SMOOTH, M_SMOOTH_V, M_SMOOTH_H, M_PAETH, M_FILTER
+};
+
+constexpr int IPRED_SCRATCH = 2 * 64 + 2 * 64 + 16;   // pixels of edge scratch for Z modes
+
+DEV int warp_sum(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// dc value for the DC / TOP_DC / LEFT_DC / DC_128 variants (ipred_tmpl.c:86-218)
+template <typename pixel>
+DEV int ipred_dc_value(const int mode, const pixel *edge, const int w, const int h, const int bdmax, const int lane) {
+    if (mode == M_DC_128) return (bdmax + 1) >> 1;
+    int part = 0;
+    if (mode == M_DC || mode == M_TOP_DC)
+        for (int i = lane; i < w; i += 32) part += edge[1 + i];
+    if (mode == M_DC || mode == M_LEFT_DC)
+        for (int i = lane; i < h; i += 32) part += edge[-(1 + i)];
+    const unsigned sum = (unsigned)warp_sum(part);
+    if (mode == M_TOP_DC) return (int)((sum + (w >> 1)) >> (31 - __clz(w)));
+    if (mode == M_LEFT_DC) return (int)((sum + (h >> 1)) >> (31 - __clz(h)));
+    unsigned dc = sum + ((w + h) >> 1);
+    dc >>= __ffs(w + h) - 1;
+    if (w != h) {
+        const bool x4 = w > h * 2 || h > w * 2;
+        if (PxTraits<pixel>::hbd) dc = (dc * (x4 ? 0x6667u : 0xAAABu)) >> 17;
+        else dc = (dc * (x4 ? 0x3334u : 0x5556u)) >> 16;
+    }
+    return (int)dc;
+}
+
+DEV int filter_strength(const int wh, const int angle, const int is_sm) {   // ipred_tmpl.c:327-360
+    if (is_sm) {
+        if (wh <= 8) { if (angle >= 64) return 2; if (angle >= 40) return 1; }
+        else if (wh <= 16) { if (angle >= 48) return 2; if (angle >= 20) return 1; }
+        else if (wh <= 24) { if (angle >= 4) return 3; }
+        else return 3;
+    } else {
+        if (wh <= 8) { if (angle >= 56) return 1; }
+        else if (wh <= 16) { if (angle >= 40) return 1; }
+        else if (wh <= 24) { if (angle >= 32) return 3; if (angle >= 16) return 2; if (angle >= 8) return 1; }
+        else if (wh <= 32) { if (angle >= 32) return 3; if (angle >= 4) return 2; return 1; }
+        else return 3;
+    }
+    return 0;
+}
+DEV int use_upsample(const int wh, const int angle, const int is_sm) { return angle < 40 && wh <= (16 >> is_sm); }
+
+// filter_edge (ipred_tmpl.c:362-385), out[0..sz)
+template <typename pixel>
+DEV void edge_filter(pixel *out, const int sz, const int lim_from, const int lim_to, const pixel *in,
+                     const int from, const int to, const int strength, const int lane)
+{
+    const int k0 = strength == 3 ? 2 : 0;
+    const int k1 = strength == 1 ? 4 : strength == 2 ? 5 : 4;
+    const int k2 = strength == 1 ? 8 : strength == 2 ? 6 : 4;
+    for (int i = lane; i < sz; i += 32) {
+        int v;
+        if (i < imin(sz, lim_from) || i >= imin(lim_to, sz)) {
+            v = in[iclip(i, from, to - 1)];
+        } else {
+            const int s = in[iclip(i - 2, from, to - 1)] * k0 + in[iclip(i - 1, from, to - 1)] * k1 +
+                          in[iclip(i, from, to - 1)] * k2 + in[iclip(i + 1, from, to - 1)] * k1 +
+                          in[iclip(i + 2, from, to - 1)] * k0;
+            v = (s + 8) >> 4;
+        }
+        out[i] = (pixel)v;
+    }
+}
+
+// upsample_edge (ipred_tmpl.c:391-406), out[0 .. 2*hsz-2]
+template <typename pixel>
+DEV void edge_upsample(pixel *out, const int hsz, const pixel *in, const int from, const int to,
+                       const int bdmax, const int lane)
+{
+    for (int i = lane; i < hsz; i += 32) {
+        out[i * 2] = in[iclip(i, from, to - 1)];
+        if (i < hsz - 1) {
+            const int s = -in[iclip(i - 1, from, to - 1)] + 9 * in[iclip(i, from, to - 1)] +
+                          9 * in[iclip(i + 1, from, to - 1)] - in[iclip(i + 2, from, to - 1)];
+            out[i * 2 + 1] = (pixel)clip_px<pixel>((s + 8) >> 4, bdmax);
+        }
+    }
+}
+
+// All 14 predictors. `scratch`: IPRED_SCRATCH pixels of shared memory (Z modes).
+template <typename pixel>
+DEV void ipred_block(const int mode, pixel *dst, const int dstride, const pixel *edge, const int w, const int h,
+                     int angle, const int max_w, const int max_h, const int bdmax, pixel *scratch, const int lane)
+{
+    const int n = w * h;
+    switch (mode) {
+    case M_DC: case M_TOP_DC: case M_LEFT_DC: case M_DC_128: {
+        const int dc = ipred_dc_value<pixel>(mode, edge, w, h, bdmax, lane);
+        for (int i = lane; i < n; i += 32) dst[(i / w) * dstride + (i % w)] = (pixel)dc;
+        break;
+    }
+    case M_VERT:
+        for (int i = lane; i < n; i += 32) dst[(i / w) * dstride + (i % w)] = edge[1 + (i % w)];
+        break;
+    case M_HOR:
+        for (int i = lane; i < n; i += 32) dst[(i / w) * dstride + (i % w)] = edge[-(1 + (i / w))];
+        break;
+    case M_PAETH: {
+        const int tl = edge[0];
+        for (int i = lane; i < n; i += 32) {
+            const int y = i / w, x = i % w;
+            const int left = edge[-(y + 1)], top = edge[1 + x];
+            const int base = left + top - tl;
+            const int ld = iabs(left - base), td = iabs(top - base), tld = iabs(tl - base);
+            dst[y * dstride + x] = (pixel)(ld <= td && ld <= tld ? left : td <= tld ? top : tl);
+        }
+        break;
+    }
+    case M_SMOOTH: {
+        const uint8_t *wh = g_sm_weights + w, *wv = g_sm_weights + h;
+        const int right = edge[w], bottom = edge[-h];
+        for (int i = lane; i < n; i += 32) {
+            const int y = i / w, x = i % w;
+            const int p = wv[y] * edge[1 + x] + (256 - wv[y]) * bottom +
+                          wh[x] * edge[-(1 + y)] + (256 - wh[x]) * right;
+            dst[y * dstride + x] = (pixel)((p + 256) >> 9);
+        }
+        break;
+    }
+    case M_SMOOTH_V: {
+        const uint8_t *wv = g_sm_weights + h;
+        const int bottom = edge[-h];
+        for (int i = lane; i < n; i += 32) {
+            const int y = i / w, x = i % w;
+            dst[y * dstride + x] = (pixel)((wv[y] * edge[1 + x] + (256 - wv[y]) * bottom + 128) >> 8);
+        }
+        break;
+    }
+    case M_SMOOTH_H: {
+        const uint8_t *wh = g_sm_weights + w;
+        const int right = edge[w];
+        for (int i = lane; i < n; i += 32) {
+            const int y = i / w, x = i % w;
+            dst[y * dstride + x] = (pixel)((wh[x] * edge[-(y + 1)] + (256 - wh[x]) * right + 128) >> 8);
+        }
+        break;
+    }
+    case M_Z1: {
+        const int is_sm = (angle >> 9) & 1, ef = angle >> 10;
+        angle &= 511;
+        int dx = g_dr_intra_derivative[angle >> 1];
+        const int ups = ef ? use_upsample(w + h, 90 - angle, is_sm) : 0;
+        const pixel *top;
+        int max_base_x;
+        if (ups) {
+            edge_upsample<pixel>(scratch, w + h, edge + 1, -1, w + imin(w, h), bdmax, lane);
+            top = scratch;
+            max_base_x = 2 * (w + h) - 2;
+            dx <<= 1;
+        } else {
+            const int fs = ef ? filter_strength(w + h, 90 - angle, is_sm) : 0;
+            if (fs) {
+                edge_filter<pixel>(scratch, w + h, 0, w + h, edge + 1, -1, w + imin(w, h), fs, lane);
+                top = scratch;
+                max_base_x = w + h - 1;
+            } else {
+                top = edge + 1;
+                max_base_x = w + imin(w, h) - 1;
+            }
+        }
+        __syncwarp();
+        const int inc = 1 + ups;
+        for (int i = lane; i < n; i += 32) {
+            const int y = i / w, x = i % w;
+            const int xpos = (y + 1) * dx, frac = xpos & 0x3E;
+            const int base = (xpos >> 6) + x * inc;
+            int v;
+            if (base < max_base_x) v = (top[base] * (64 - frac) + top[base + 1] * frac + 32) >> 6;
+            else v = top[max_base_x];
+            dst[y * dstride + x] = (pixel)v;
+        }
+        break;
+    }
+    case M_Z3: {
+        const int is_sm = (angle >> 9) & 1, ef = angle >> 10;
+        angle &= 511;
+        int dy = g_dr_intra_derivative[(270 - angle) >> 1];
+        const int ups = ef ? use_upsample(w + h, angle - 180, is_sm) : 0;
+        const pixel *left;
+        int max_base_y;
+        if (ups) {
+            edge_upsample<pixel>(scratch, w + h, edge - (w + h), imax(w - h, 0), w + h + 1, bdmax, lane);
+            left = scratch + 2 * (w + h) - 2;
+            max_base_y = 2 * (w + h) - 2;
+            dy <<= 1;
+        } else {
+            const int fs = ef ? filter_strength(w + h, angle - 180, is_sm) : 0;
+            if (fs) {
+                edge_filter<pixel>(scratch, w + h, 0, w + h, edge - (w + h), imax(w - h, 0), w + h + 1, fs, lane);
+                left = scratch + w + h - 1;
+                max_base_y = w + h - 1;
+            } else {
+                left = edge - 1;
+                max_base_y = h + imin(w, h) - 1;
+            }
+        }
+        __syncwarp();
+        const int inc = 1 + ups;
+        for (int i = lane; i < n; i += 32) {
+            const int y = i / w, x = i % w;
+            const int ypos = (x + 1) * dy, frac = ypos & 0x3E;
+            const int base = (ypos >> 6) + y * inc;
+            int v;
+            if (base < max_base_y) v = (left[-base] * (64 - frac) + left[-(base + 1)] * frac + 32) >> 6;
+            else v = left[-max_base_y];
+            dst[y * dstride + x] = (pixel)v;
+        }
+        break;
+    }
+    case M_Z2: {
+        const int is_sm = (angle >> 9) & 1, ef = angle >> 10;
+        angle &= 511;
+        int dy = g_dr_intra_derivative[(angle - 90) >> 1];
+        int dx = g_dr_intra_derivative[(180 - angle) >> 1];
+        const int ups_l = ef ? use_upsample(w + h, 180 - angle, is_sm) : 0;
+        const int ups_a = ef ? use_upsample(w + h, angle - 90, is_sm) : 0;
+        pixel *tl = scratch + 128 + 8;
+        if (ups_a) {
+            edge_upsample<pixel>(tl, w + 1, edge, 0, w + 1, bdmax, lane);
+            dx <<= 1;
+        } else {
+            const int fs = ef ? filter_strength(w + h, angle - 90, is_sm) : 0;
+            if (fs) edge_filter<pixel>(tl + 1, w, 0, max_w, edge + 1, -1, w, fs, lane);
+            else for (int i = lane; i < w; i += 32) tl[1 + i] = edge[1 + i];
+        }
+        if (ups_l) {
+            edge_upsample<pixel>(tl - h * 2, h + 1, edge - h, 0, h + 1, bdmax, lane);
+            dy <<= 1;
+        } else {
+            const int fs = ef ? filter_strength(w + h, 180 - angle, is_sm) : 0;
+            if (fs) edge_filter<pixel>(tl - h, h, h - max_h, h, edge - h, 0, h + 1, fs, lane);
+            else for (int i = lane; i < h; i += 32) tl[-h + i] = edge[-h + i];
+        }
+        __syncwarp();
+        if (lane == 0) tl[0] = edge[0];
+        __syncwarp();
+        const int inc_x = 1 + ups_a;
+        const pixel *left = tl - (1 + ups_l);
+        for (int i = lane; i < n; i += 32) {
+            const int y = i / w, x = i % w;
+            const int xpos = ((1 + ups_a) << 6) - dx * (y + 1);
+            const int base_x = (xpos >> 6) + x * inc_x;
+            int v;
+            if (base_x >= 0) {
+                const int fx = xpos & 0x3E;
+                v = tl[base_x] * (64 - fx) + tl[base_x + 1] * fx;
+            } else {
+                const int ypos = (y << (6 + ups_l)) - dy * (x + 1);
+                const int base_y = ypos >> 6, fy = ypos & 0x3E;
+                v = left[-base_y] * (64 - fy) + left[-(base_y + 1)] * fy;
+            }
+            dst[y * dstride + x] = (pixel)((v + 32) >> 6);
+        }
+        break;
+    }
+    default: {   // M_FILTER: 4x2 sub-blocks on anti-diagonals
+        const int8_t *taps = g_filter_intra_taps + (angle & 511) * 64;
+        const int nbx = w >> 2, nby = h >> 1;
+        for (int d = 0; d < nbx + nby - 1; d++) {
+            // sub-blocks with bx + by == d; 8 outputs each
+            const int by_lo = imax(0, d - (nbx - 1)), by_hi = imin(d, nby - 1);
+            const int cnt = (by_hi - by_lo + 1) * 8;
+            for (int i = lane; i < cnt; i += 32) {
+                const int by = by_lo + (i >> 3), bx = d - by, o = i & 7;
+                const int x = bx * 4, y = by * 2;
+                int p[7];
+                // p0 = (x-1, y-1), p1..p4 = (x..x+3, y-1), p5 = (x-1, y), p6 = (x-1, y+1)
+                if (y == 0) {
+                    p[0] = edge[x];           // edge[0] when x == 0, else top[x-1]
+#pragma unroll
+                    for (int k = 0; k < 4; k++) p[1 + k] = edge[1 + x + k];
+                } else {
+                    p[0] = x == 0 ? edge[-y] : dst[(y - 1) * dstride + x - 1];
+#pragma unroll
+                    for (int k = 0; k < 4; k++) p[1 + k] = dst[(y - 1) * dstride + x + k];
+                }
+                if (x == 0) {
+                    p[5] = edge[-(1 + y)];
+                    p[6] = edge[-(2 + y)];
+                } else {
+                    p[5] = dst[y * dstride + x - 1];
+                    p[6] = dst[(y + 1) * dstride + x - 1];
+                }
+                const int8_t *f = taps + o * 8;
+                int acc = 0;
+#pragma unroll
+                for (int k = 0; k < 7; k++) acc += f[k] * p[k];
+                dst[(y + (o >> 2)) * dstride + x + (o & 3)] = (pixel)clip_px<pixel>((acc + 8) >> 4, bdmax);
+            }
+            __syncwarp();
+        }
+        break;
+    }
+    }
+    __syncwarp();
+}
+
+// cfl_pred (ipred_tmpl.c:71-84) with the dc of `dc_mode` (DC / LEFT_DC / TOP_DC / DC_128)
+template <typename pixel>
+DEV void cfl_pred_block(const int dc_mode, pixel *dst, const int dstride, const pixel *edge, const int w, const int h,
+                        const int16_t *ac, const int alpha, const int bdmax, const int lane)
+{
+    const int dc = ipred_dc_value<pixel>(dc_mode, edge, w, h, bdmax, lane);
+    for (int i = lane; i < w * h; i += 32) {
+        const int diff = alpha * ac[i];
+        const int m = (iabs(diff) + 32) >> 6;
+        dst[(i / w) * dstride + (i % w)] = (pixel)clip_px<pixel>(dc + (diff < 0 ? -m : m), bdmax);
+    }
+}
+
+// cfl_ac (ipred_tmpl.c:657-703): ac[w*h] dense from the reconstructed luma
+template <typename pixel>
+DEV void cfl_ac_block(int16_t *ac, const pixel *ypx, const int ystride, const int w_pad, const int h_pad,
+                      const int w, const int h, const int ss_hor, const int ss_ver, const int lane)
+{
+    const int vw = w - 4 * w_pad, vh = h - 4 * h_pad;
+    int part = 0;
+    for (int i = lane; i < w * h; i += 32) {
+        const int y = imin(i / w, vh - 1), x = imin(i % w, vw - 1);
+        const pixel *p = ypx + (y << ss_ver) * ystride + (x << ss_hor);
+        int s = p[0];
+        if (ss_hor) s += p[1];
+        if (ss_ver) {
+            s += p[ystride];
+            if (ss_hor) s += p[ystride + 1];
+        }
+        const int v = s << (1 + !ss_ver + !ss_hor);
+        ac[i] = (int16_t)v;
+        part += v;
+    }
+    const int log2sz = (__ffs(w) - 1) + (__ffs(h) - 1);
+    const int sum = (warp_sum(part) + ((1 << log2sz) >> 1)) >> log2sz;
+    __syncwarp();
+    for (int i = lane; i < w * h; i += 32) ac[i] = (int16_t)(ac[i] - sum);
+    __syncwarp();
+}
+
+// pal_pred (ipred_tmpl.c:717-730): two pixels per index byte
+template <typename pixel>
+DEV void pal_pred_block(pixel *dst, const int dstride, const pixel *pal, const uint8_t *idx, const int w, const int h,
+                        const int tid, const int nthr)
+{
+    const int hw = w >> 1;
+    for (int i = tid; i < hw * h; i += nthr) {
+        const int y = i / hw, x2 = i % hw;
+        const int v = idx[i];
+        dst[y * dstride + 2 * x2] = pal[v & 7];
+        dst[y * dstride + 2 * x2 + 1] = pal[v >> 4];
+    }
+}
+
+// ------------------------------------------------------------------ edge preparation
+// dav1d_prepare_intra_edges (ipred_prepare_tmpl.c:77-204).  x, y, w, h, tw, th
+// in 4-pixel units; `dst` = the block's top-left in the frame; `top_sb_edge`
+// = optional pre-filter row backup (may be null).  Writes edge[-2*th*4 ..
+// 2*tw*4] as needed and returns the DSP mode index; *angle: in = angle_delta,
+// out = absolute angle.
+template <typename pixel>
+DEV int prepare_edges(const int x, const int have_left, const int y, const int have_top, const int w, const int h,
+                      const int edge_flags, const pixel *dst, const int stride, const pixel *top_sb_edge,
+                      int mode, int *angle, const int tw, const int th, const int filter_edge_flag,
+                      pixel *edge, const int bdmax, const int lane)
+{
+    const int bitdepth = PxTraits<pixel>::bitdepth(bdmax);
+    if (mode >= 1 && mode <= 8) {            // VERT .. VERT_LEFT: directional
+        int a;
+        switch (mode) {
+        case 1: a = 90; break;  case 2: a = 180; break; case 3: a = 45; break;  case 4: a = 135; break;
+        case 5: a = 113; break; case 6: a = 157; break; case 7: a = 203; break; default: a = 67; break;
+        }
+        a += 3 * *angle;
+        *angle = a;
+        if (a <= 90) mode = a < 90 && have_top ? M_Z1 : M_VERT;
+        else if (a < 180) mode = M_Z2;
+        else mode = a > 180 && have_left ? M_Z3 : M_HOR;
+    } else if (mode == 0) {                  // DC_PRED
+        mode = have_left ? (have_top ? M_DC : M_LEFT_DC) : (have_top ? M_TOP_DC : M_DC_128);
+    } else if (mode == 12) {                 // PAETH_PRED
+        mode = have_left ? (have_top ? M_PAETH : M_HOR) : (have_top ? M_VERT : M_DC_128);
+    }
+    // needs: bit0 left, bit1 top, bit2 topleft, bit3 topright, bit4 bottomleft
+    int needs;
+    switch (mode) {
+    case M_DC: needs = 3; break;
+    case M_VERT: needs = 2; break;
+    case M_HOR: needs = 1; break;
+    case M_LEFT_DC: needs = 1; break;
+    case M_TOP_DC: needs = 2; break;
+    case M_DC_128: needs = 0; break;
+    case M_Z1: needs = 2 | 8 | 4; break;
+    case M_Z2: needs = 1 | 2 | 4; break;
+    case M_Z3: needs = 1 | 16 | 4; break;
+    case M_SMOOTH: case M_SMOOTH_V: case M_SMOOTH_H: needs = 3; break;
+    default: needs = 1 | 2 | 4; break;       // PAETH, FILTER
+    }
+    const pixel *dst_top = nullptr;
+    if (have_top && ((needs & 2) || (needs & 4) || ((needs & 1) && !have_left)))
+        dst_top = top_sb_edge ? top_sb_edge + x * 4 : dst - stride;
+
+    if (needs & 1) {
+        const int sz = th << 2;
+        pixel *left = edge - sz;
+        if (have_left) {
+            const int px_have = imin(sz, (h - y) << 2);
+            for (int i = lane; i < sz; i += 32)
+                left[sz - 1 - i] = dst[stride * imin(i, px_have - 1) - 1];
+        } else {
+            const pixel v = have_top ? *dst_top : (pixel)(((1 << bitdepth) >> 1) + 1);
+            for (int i = lane; i < sz; i += 32) left[i] = v;
+        }
+        if (needs & 16) {
+            const int have_bl = (!have_left || y + th >= h) ? 0 : (edge_flags & 8);
+            if (have_bl) {
+                const int px_have = imin(sz, (h - y - th) << 2);
+                for (int i = lane; i < sz; i += 32)
+                    left[-(i + 1)] = dst[(sz + imin(i, px_have - 1)) * stride - 1];
+            } else {
+                // replicate left[0] = bottom-most left pixel
+                pixel v;
+                if (have_left) v = dst[stride * (imin(sz, (h - y) << 2) - 1) - 1];
+                else v = have_top ? *dst_top : (pixel)(((1 << bitdepth) >> 1) + 1);
+                for (int i = lane; i < sz; i += 32) left[-(i + 1)] = v;
+            }
+        }
+    }
+    if (needs & 2) {
+        const int sz = tw << 2;
+        pixel *top = edge + 1;
+        if (have_top) {
+            const int px_have = imin(sz, (w - x) << 2);
+            for (int i = lane; i < sz; i += 32) top[i] = dst_top[imin(i, px_have - 1)];
+        } else {
+            const pixel v = have_left ? dst[-1] : (pixel)(((1 << bitdepth) >> 1) - 1);
+            for (int i = lane; i < sz; i += 32) top[i] = v;
+        }
+        if (needs & 8) {
+            const int have_tr = (!have_top || x + tw >= w) ? 0 : (edge_flags & 1);
+            if (have_tr) {
+                const int px_have = imin(sz, (w - x - tw) << 2);
+                for (int i = lane; i < sz; i += 32) top[sz + i] = dst_top[sz + imin(i, px_have - 1)];
+            } else {
+                pixel v;   // top[sz - 1]
+                if (have_top) v = dst_top[imin(sz, (w - x) << 2) - 1];
+                else v = have_left ? dst[-1] : (pixel)(((1 << bitdepth) >> 1) - 1);
+                for (int i = lane; i < sz; i += 32) top[sz + i] = v;
+            }
+        }
+    }
+    __syncwarp();
+    if (needs & 4) {
+        if (lane == 0) {
+            int v;
+            if (have_left) v = have_top ? dst_top[-1] : dst[-1];
+            else v = have_top ? *dst_top : (1 << bitdepth) >> 1;
+            if (mode == M_Z2 && tw + th >= 6 && filter_edge_flag)
+                v = ((edge[-1] + edge[1]) * 5 + v * 6 + 8) >> 4;
+            edge[0] = (pixel)v;
+        }
+    }
+    __syncwarp();
+    return mode;
+}
+
+}  // namespace d1
