@@ -6,5 +6,5 @@ CPU fallback: if the shared library is missing, importing `lib()` raises.
 """
 from .binding import (  # noqa: F401
     lib, LIB_PATH, MCDSPContext, InvTxfmDSPContext, IntraPredDSPContext,
-    ItxDesc, McSrc, McDesc, IntraDesc, Plane, Picture, TX_DIMS, check_error,
+    ItxDesc, McSrc, McDesc, IntraDesc, WarpDesc, ReconBatch, Plane, Picture, TX_DIMS, check_error,
 )

@@ -51,16 +51,6 @@ class McDesc(C.Structure):
                 ("aux_off", C.c_uint32)]
 
 
-class IntraDesc(C.Structure):
-    _fields_ = [("x4", C.c_uint16), ("y4", C.c_uint16), ("tile_x4_start", C.c_uint16),
-                ("tile_y4_start", C.c_uint16), ("tile_x4_end", C.c_uint16),
-                ("tile_y4_end", C.c_uint16), ("plane", C.c_uint8), ("tw4", C.c_uint8),
-                ("th4", C.c_uint8), ("mode", C.c_uint8), ("angle_delta", C.c_int8),
-                ("edge_flags", C.c_uint8), ("flags", C.c_uint16), ("eob", C.c_int16),
-                ("tx", C.c_uint8), ("txtp", C.c_uint8), ("coef_off", C.c_uint32),
-                ("level", C.c_uint32)]
-
-
 class Plane(C.Structure):
     _fields_ = [("data", C.c_void_p), ("stride", C.c_ssize_t), ("w", C.c_int32), ("h", C.c_int32)]
 
@@ -70,7 +60,7 @@ class Picture(C.Structure):
                 ("ss_ver", C.c_int32)]
 
 
-assert C.sizeof(ItxDesc) == 16 and C.sizeof(McDesc) == 40 and C.sizeof(IntraDesc) == 32
+assert C.sizeof(ItxDesc) == 16 and C.sizeof(McDesc) == 40
 
 _lib = None
 
@@ -98,6 +88,7 @@ def lib():
     L.dav1d_cuda_picture_download.argtypes = [C.c_void_p, C.POINTER(Picture), C.c_int, C.c_void_p, C.c_ssize_t]
     L.dav1d_cuda_itx_batch.argtypes = [C.c_void_p, C.POINTER(Picture), C.c_void_p, C.c_void_p,
                                        C.POINTER(C.c_int32), C.c_int]
+    bind_frame_api(L)
     _lib = L
     return L
 
@@ -108,3 +99,57 @@ def check_error():
     if e:
         msg = L.dav1d_cuda_last_error_string().decode()
         raise RuntimeError(f"dav1d_cuda error {e}: {msg}")
+
+
+# ---------------------------------------------------------------- frame-level batch
+class WarpDesc(C.Structure):
+    _fields_ = [("x", C.c_uint16), ("y", C.c_uint16), ("sx", C.c_int32), ("sy", C.c_int32),
+                ("mx", C.c_int32), ("my", C.c_int32), ("abcd", C.c_int16 * 4),
+                ("plane", C.c_uint8), ("ref", C.c_uint8), ("pad", C.c_uint16)]
+
+
+class IntraDesc40(C.Structure):
+    _fields_ = [("x4", C.c_uint16), ("y4", C.c_uint16), ("tile_x4_start", C.c_uint16),
+                ("tile_y4_start", C.c_uint16), ("tile_x4_end", C.c_uint16),
+                ("tile_y4_end", C.c_uint16), ("plane", C.c_uint8), ("tw4", C.c_uint8),
+                ("th4", C.c_uint8), ("mode", C.c_uint8), ("angle_delta", C.c_int8),
+                ("edge_flags", C.c_uint8), ("flags", C.c_uint16), ("eob", C.c_int16),
+                ("tx", C.c_uint8), ("txtp", C.c_uint8), ("coef_off", C.c_uint32),
+                ("aux", C.c_uint32), ("level", C.c_uint32), ("pad", C.c_uint32)]
+
+
+IntraDesc = IntraDesc40
+assert C.sizeof(IntraDesc) == 40 and C.sizeof(WarpDesc) == 32
+
+
+class ReconBatch(C.Structure):
+    _fields_ = [("dst", C.POINTER(Picture)), ("refs", C.POINTER(Picture) * 7),
+                ("bw4", C.c_int32), ("bh4", C.c_int32),
+                ("cf", C.c_void_p), ("masks", C.c_void_p), ("pal", C.c_void_p), ("pal_idx", C.c_void_p),
+                ("mc_put", C.c_void_p), ("mc_put_tiles", C.c_void_p), ("n_mc_put_tiles", C.c_int32),
+                ("mc_comp", C.c_void_p), ("mc_comp_tiles", C.c_void_p), ("n_mc_comp_tiles", C.c_int32 * 2),
+                ("warp", C.c_void_p), ("n_warp", C.c_int32),
+                ("itx", C.c_void_p), ("itx_class_count", C.c_int32 * N_RECT_TX_SIZES),
+                ("intra", C.c_void_p), ("intra_level_start", C.POINTER(C.c_int32)), ("n_levels", C.c_int32)]
+
+
+def bind_frame_api(L):
+    L.dav1d_cuda_intra_schedule.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                            C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int]
+    L.dav1d_cuda_recon_submit.argtypes = [C.c_void_p, C.POINTER(ReconBatch)]
+    L.dav1d_cuda_recon_graph_build.argtypes = [C.c_void_p, C.POINTER(ReconBatch), C.POINTER(C.c_void_p)]
+    L.dav1d_cuda_recon_graph_launch.argtypes = [C.c_void_p, C.c_void_p]
+    L.dav1d_cuda_recon_graph_free.argtypes = [C.c_void_p]
+    L.dav1d_cuda_malloc.restype = C.c_void_p
+    L.dav1d_cuda_malloc.argtypes = [C.c_size_t]
+    L.dav1d_cuda_free.argtypes = [C.c_void_p]
+    L.dav1d_cuda_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+    L.dav1d_cuda_download.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+    L.dav1d_cuda_host_alloc.restype = C.c_void_p
+    L.dav1d_cuda_host_alloc.argtypes = [C.c_size_t]
+    L.dav1d_cuda_host_free.argtypes = [C.c_void_p]
+    L.dav1d_cuda_event_create.restype = C.c_void_p
+    L.dav1d_cuda_event_record.argtypes = [C.c_void_p, C.c_void_p]
+    L.dav1d_cuda_event_elapsed_ms.restype = C.c_float
+    L.dav1d_cuda_event_elapsed_ms.argtypes = [C.c_void_p, C.c_void_p]
+    L.dav1d_cuda_event_destroy.argtypes = [C.c_void_p]

@@ -7,6 +7,9 @@
 
 namespace d1 {
 
+void mc_init_attrs();
+void recon_init_attrs();
+
 static std::atomic<int> g_err{0};
 static char g_err_msg[512] = "";
 static std::mutex g_err_mu;
@@ -97,11 +100,18 @@ int dav1d_cuda_open(Dav1dCudaContext **out, int device, void *stream) {
     c->device = device;
     c->own_stream = false;
     c->stream = (cudaStream_t)stream;
+    if (!stream) {   // no caller stream: give the context its own so that contexts run concurrently
+        D1_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        c->own_stream = true;
+    }
     c->tmp_pool = nullptr;
     c->tmp_pool_bytes = 0;
     cudaDeviceProp prop;
     D1_CHECK(cudaGetDeviceProperties(&prop, device));
     c->num_sms = prop.multiProcessorCount;
+    mc_init_attrs();
+    recon_init_attrs();
+    cudaGetLastError();
     *out = c;
     return 0;
 }

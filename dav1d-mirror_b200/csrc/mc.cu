@@ -11,6 +11,7 @@
 namespace d1 {
 
 constexpr int MC_WARPS = 4;
+void mc_init_attrs();
 
 struct McArgs {
     PicView dst;
@@ -251,7 +252,7 @@ static int launch_compound(const McArgs &a, cudaStream_t st) {
     static bool attr_done = false;
     const size_t smem = MC_WARPS * sizeof(McSmemCompound<pixel>);
     if (!attr_done) {
-        cudaFuncSetAttribute(mc_compound_kernel<pixel>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        mc_init_attrs();
         attr_done = true;
     }
     const int grid = (a.n_tiles + MC_WARPS - 1) / MC_WARPS;
@@ -267,6 +268,30 @@ int mc_put_launch(const McArgs &a, cudaStream_t st) {
 int mc_compound_launch(const McArgs &a, cudaStream_t st) {
     if (a.n_tiles <= 0) return 0;
     return a.dst.bdmax > 0xff ? launch_compound<uint16_t>(a, st) : launch_compound<uint8_t>(a, st);
+}
+
+int mc_put_launch_raw(const PicView &dst, const PicView *refs, const Dav1dCudaMcDesc *descs,
+                      const uint32_t *tiles, int n_tiles, uint8_t *masks, int16_t *tmp, bool compound,
+                      cudaStream_t st)
+{
+    if (n_tiles <= 0 || !descs || !tiles) return 0;
+    McArgs a;
+    memset(&a, 0, sizeof(a));
+    a.dst = dst;
+    for (int i = 0; i < 7; i++) a.refs[i] = refs[i];
+    a.descs = descs;
+    a.tiles = tiles;
+    a.n_tiles = n_tiles;
+    a.masks = masks;
+    a.tmp = tmp;
+    return compound ? mc_compound_launch(a, st) : mc_put_launch(a, st);
+}
+
+void mc_init_attrs() {
+    cudaFuncSetAttribute(mc_compound_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)(MC_WARPS * sizeof(McSmemCompound<uint16_t>)));
+    cudaFuncSetAttribute(mc_compound_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)(MC_WARPS * sizeof(McSmemCompound<uint8_t>)));
 }
 
 // ------------------------------------------------------------ per-call surface

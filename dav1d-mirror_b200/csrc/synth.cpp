@@ -1,0 +1,572 @@
+// Synthetic block-descriptor source (host only, no CUDA): stands in for
+// dav1d's pass 1 (entropy decode + mode/MV parse, src/decode.c:717-1250) when
+// no bitstreams are available.  For one frame it produces, in decode order,
+// exactly the DSP calls src/recon_tmpl.c would make for a random partition /
+// mode / MV / coefficient assignment, as the descriptor arrays of
+// include/dav1d_cuda.h (the recorder's output) plus the decode order the
+// sequential oracle replays.
+//
+// Workload shape follows SURVEY.md 8(d) configs 2-4: random partition tree per
+// 64x64 superblock (NONE/H/V/SPLIT/H4/V4, blocks 8x8..64x64 luma), intra vs
+// inter per block, 13 intra modes + angle deltas, filter-intra, palette, CfL,
+// 10 MC filters, random MVs (+-mv_range px at 1/8 pel, so some windows leave
+// the frame), put / avg / w_avg / wedge mask / segmentation w_mask / warp,
+// largest transform or one split, transform type uniform over the legal types
+// of the size, three eob classes (dc only / low frequency / full).
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+#include <vector>
+#include "../../include/dav1d_cuda.h"
+
+extern "C" {
+
+typedef struct D1SynthParams {
+    int32_t w, h;               // luma size, multiples of 8
+    int32_t ss_hor, ss_ver;     // chroma subsampling (both 1 = 4:2:0, both 0 = 4:4:4, or luma only with no_chroma)
+    int32_t bitdepth_max;
+    int32_t no_chroma;          // 1 = luma plane only
+    uint64_t seed;
+    float p_intra;              // fraction of blocks coded intra
+    float p_residual;           // fraction of blocks carrying a residual
+    float p_tx_split;           // probability of one transform split
+    float p_filter_intra, p_palette, p_cfl;
+    float p_avg, p_w_avg, p_wedge, p_seg, p_warp;   // of inter blocks; remainder = single-reference put
+    int32_t mv_range;           // pixels
+    int32_t n_refs;             // 1..7
+    int32_t edge_filter;        // sequence-level intra_edge_filter
+    int32_t only_tx;            // >= 0: frame tiled with inter blocks of this tx size only (config 2); else -1
+    int32_t only_txtp;          // with only_tx: >= 0 fixes the type
+    int32_t eob_class;          // -1 random, 0 dc-only, 1 low-frequency, 2 full
+} D1SynthParams;
+
+typedef struct D1SynthFrame {
+    Dav1dCudaMcDesc *mc_put;   int32_t n_mc_put;   uint32_t *mc_put_tiles;  int32_t n_mc_put_tiles;
+    Dav1dCudaMcDesc *mc_comp;  int32_t n_mc_comp;  uint32_t *mc_comp_tiles; int32_t n_mc_comp_tiles[2];
+    Dav1dCudaWarpDesc *warp;   int32_t n_warp;
+    Dav1dCudaItxDesc *itx;     int32_t n_itx;      int32_t itx_class_count[19];
+    Dav1dCudaIntraDesc *intra; int32_t n_intra;    // decode order
+    void *cf;                  uint64_t cf_elems;  // int16 (8 bpc) / int32 coefficients
+    uint8_t *masks;            uint64_t masks_bytes;
+    void *pal;                 uint64_t pal_px;
+    uint8_t *pal_idx;          uint64_t pal_idx_bytes;
+    uint32_t *order;           int32_t n_order;    // (class << 28) | index, decode order
+    int32_t bw4, bh4;
+    double algo_bytes;         // algorithmic HBM bytes of the frame (SURVEY 8d accounting)
+    double luma_px;            // luma pixels covered
+    int64_t n_blocks, n_intra_blocks;
+} D1SynthFrame;
+
+}  // extern "C"
+
+namespace {
+
+struct Rng {
+    uint64_t s;
+    explicit Rng(uint64_t seed) : s(seed * 0x9E3779B97F4A7C15ull + 0x1234567ull) { next(); next(); }
+    uint64_t next() { s ^= s >> 12; s ^= s << 25; s ^= s >> 27; return s * 0x2545F4914F6CDD1Dull; }
+    uint32_t u32() { return (uint32_t)(next() >> 32); }
+    int range(int n) { return (int)(((uint64_t)u32() * (uint64_t)n) >> 32); }      // [0, n)
+    int irange(int lo, int hi) { return lo + range(hi - lo + 1); }                 // [lo, hi]
+    float unit() { return (u32() >> 8) * (1.0f / 16777216.0f); }
+    bool chance(float p) { return unit() < p; }
+};
+
+// enum RectTxfmSize -> dims in 4-px units (levels.h:44-78)
+const uint8_t TXW4[19] = { 1, 2, 4, 8, 16, 1, 2, 2, 4, 4, 8, 8, 16, 1, 4, 2, 8, 4, 16 };
+const uint8_t TXH4[19] = { 1, 2, 4, 8, 16, 2, 1, 4, 2, 8, 4, 16, 8, 4, 1, 8, 2, 16, 4 };
+
+int tx_from_dims(int w4, int h4) {
+    for (int t = 0; t < 19; t++)
+        if (TXW4[t] == w4 && TXH4[t] == h4) return t;
+    return -1;
+}
+
+// populated itxfm_add slots per size (itx_tmpl.c:248-268)
+int pick_txtp(Rng &r, int tx) {
+    const int w4 = TXW4[tx], h4 = TXH4[tx], m = std::max(w4, h4);
+    if (m == 16) return 0;
+    if (m == 8) return r.chance(0.5f) ? 0 : 9;
+    if (w4 == 4 && h4 == 4) { static const int t[12] = { 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11 }; return t[r.range(12)]; }
+    if (tx == 0 && r.chance(0.04f)) return 16;   // WHT_WHT
+    return r.range(16);
+}
+
+struct Gen {
+    const D1SynthParams &P;
+    Rng rng;
+    int bw4, bh4, hbd;
+    std::vector<Dav1dCudaMcDesc> put, comp0, comp1;
+    std::vector<Dav1dCudaWarpDesc> warp;
+    std::vector<Dav1dCudaItxDesc> itx;
+    std::vector<Dav1dCudaIntraDesc> intra;
+    std::vector<int32_t> cf32;
+    std::vector<uint8_t> masks, pal_idx;
+    std::vector<uint16_t> pal;
+    struct Ord { uint8_t cls; uint32_t idx; };   // cls 1 = comp wave 0, 5 = comp wave 1 (remapped later)
+    std::vector<Ord> order;
+    std::vector<uint8_t> decoded[3];             // per plane, 4x4 cells
+    int pw4[3], ph4[3];
+    double algo = 0, luma_px = 0;
+    int64_t n_blocks = 0, n_intra_blocks = 0;
+    int Bp, Bc;
+
+    explicit Gen(const D1SynthParams &p) : P(p), rng(p.seed) {
+        bw4 = p.w / 4; bh4 = p.h / 4; hbd = p.bitdepth_max > 0xff;
+        Bp = hbd ? 2 : 1; Bc = hbd ? 4 : 2;
+        for (int pl = 0; pl < 3; pl++) {
+            const int sh = pl ? p.ss_hor : 0, sv = pl ? p.ss_ver : 0;
+            pw4[pl] = (bw4 + sh) >> sh; ph4[pl] = (bh4 + sv) >> sv;
+            decoded[pl].assign((size_t)pw4[pl] * ph4[pl], 0);
+        }
+    }
+    int nplanes() const { return P.no_chroma ? 1 : 3; }
+
+    // ---- coefficients: column-major sw x sh block appended to the stream
+    uint32_t emit_coefs(int tx, int txtp, int16_t *eob_out) {
+        const int w = TXW4[tx] * 4, h = TXH4[tx] * 4, sw = std::min(w, 32), sh = std::min(h, 32);
+        const uint32_t off = (uint32_t)cf32.size();
+        cf32.resize(cf32.size() + (size_t)sw * sh, 0);
+        int32_t *c = cf32.data() + off;
+        const int cls = P.eob_class >= 0 ? P.eob_class : (rng.chance(0.2f) ? 0 : rng.chance(0.6f) ? 1 : 2);
+        // amplitude so that the reconstructed residual spans a good part of the pixel range
+        const double amp = (double)P.bitdepth_max * 8.0 * sqrt((double)(w * h)) / 16.0;
+        const int cmax = hbd ? (P.bitdepth_max > 1023 ? 524287 : 131071) : 32767;   // recon_tmpl.c:594
+        int last = 0;
+        if (cls == 0) {
+            c[0] = rng.irange(-std::min(cmax, (int)amp), std::min(cmax, (int)amp));
+            if (txtp == 16) c[0] = rng.irange(-P.bitdepth_max * 4, P.bitdepth_max * 4);
+        } else {
+            const int lw = cls == 1 ? std::min(sw, 8) : sw, lh = cls == 1 ? std::min(sh, 8) : sh;
+            for (int x = 0; x < lw; x++)
+                for (int y = 0; y < lh; y++) {
+                    if (cls == 1 && rng.chance(0.5f)) continue;
+                    const double decay = 1.0 / (1.0 + 0.75 * (x + y));
+                    int a = (int)(amp * decay);
+                    if (txtp == 16) a = P.bitdepth_max * 2;
+                    a = std::max(1, std::min(a, cmax));
+                    const int v = rng.irange(-a, a);
+                    c[y + x * sh] = v;
+                    if (v) last = y + x * sh;
+                }
+            if (!last) { c[1 % (sw * sh)] = 1; last = 1; }
+        }
+        *eob_out = (int16_t)(cls == 0 ? 0 : std::min(last, sw * sh - 1));
+        algo += (double)sw * sh * Bc;
+        return off;
+    }
+
+    void mark(int pl, int x4, int y4, int w4, int h4) {
+        for (int y = y4; y < std::min(y4 + h4, ph4[pl]); y++)
+            for (int x = x4; x < std::min(x4 + w4, pw4[pl]); x++) decoded[pl][(size_t)y * pw4[pl] + x] = 1;
+    }
+    bool all_decoded(int pl, int x0, int y0, int x1, int y1) const {
+        if (x0 < 0 || y0 < 0 || x1 > pw4[pl] || y1 > ph4[pl] || x0 >= x1 || y0 >= y1) return false;
+        for (int y = y0; y < y1; y++)
+            for (int x = x0; x < x1; x++)
+                if (!decoded[pl][(size_t)y * pw4[pl] + x]) return false;
+        return true;
+    }
+
+    void add_itx(int pl, int x4, int y4, int tx) {
+        Dav1dCudaItxDesc d;
+        memset(&d, 0, sizeof(d));
+        d.plane = (uint8_t)pl; d.x = (uint16_t)(x4 * 4); d.y = (uint16_t)(y4 * 4);
+        d.tx = (uint8_t)tx;
+        d.txtp = (uint8_t)(P.only_txtp >= 0 ? P.only_txtp : pick_txtp(rng, tx));
+        d.coef_off = emit_coefs(tx, d.txtp, &d.eob);
+        algo += 2.0 * Bp * TXW4[tx] * TXH4[tx] * 16;
+        order.push_back({ 3, (uint32_t)itx.size() });
+        itx.push_back(d);
+    }
+
+    // one tx-sized intra-class op
+    void add_intra(int pl, int x4, int y4, int tw4, int th4, int mode, int angle_delta, int flags,
+                   bool residual, uint32_t aux = 0, uint32_t idx_off = 0)
+    {
+        Dav1dCudaIntraDesc d;
+        memset(&d, 0, sizeof(d));
+        d.x4 = (uint16_t)x4; d.y4 = (uint16_t)y4;
+        d.tile_x4_start = 0; d.tile_y4_start = 0;
+        d.tile_x4_end = (uint16_t)pw4[pl]; d.tile_y4_end = (uint16_t)ph4[pl];
+        d.plane = (uint8_t)pl; d.tw4 = (uint8_t)tw4; d.th4 = (uint8_t)th4;
+        d.mode = (uint8_t)mode; d.angle_delta = (int8_t)angle_delta;
+        d.flags = (uint16_t)flags;
+        d.aux = aux;
+        d.eob = -1;
+        if (mode <= 13) {
+            const bool tr = y4 > 0 && all_decoded(pl, x4 + tw4, y4 - 1, std::min(x4 + 2 * tw4, pw4[pl]), y4);
+            const bool bl = x4 > 0 && all_decoded(pl, x4 - 1, y4 + th4, x4, std::min(y4 + 2 * th4, ph4[pl]));
+            d.edge_flags = (uint8_t)((tr ? 1 : 0) | (bl ? 8 : 0));
+        }
+        const int w = tw4 * 4, h = th4 * 4;
+        if (mode == DAV1D_CUDA_INTRA_PAL) {
+            d.coef_off = idx_off;
+            algo += (double)Bp * w * h + 0.5 * w * h;
+        } else {
+            if (mode != DAV1D_CUDA_INTRA_NONE) algo += (double)Bp * (2 * w + 2 * h + 1);
+            if (mode == DAV1D_CUDA_INTRA_CFL) algo += (double)Bp * (w << P.ss_hor) * (h << P.ss_ver);
+            if (mode != DAV1D_CUDA_INTRA_NONE || residual) algo += (double)Bp * w * h;   // final write
+            if (mode == DAV1D_CUDA_INTRA_NONE) algo += (double)Bp * w * h;               // read back pal pred
+            if (residual) {
+                d.tx = (uint8_t)tx_from_dims(tw4, th4);
+                d.txtp = (uint8_t)pick_txtp(rng, d.tx);
+                d.coef_off = emit_coefs(d.tx, d.txtp, &d.eob);
+            }
+        }
+        order.push_back({ 4, (uint32_t)intra.size() });
+        intra.push_back(d);
+        if (mode != DAV1D_CUDA_INTRA_PAL) mark(pl, x4, y4, tw4, th4);
+    }
+
+    static void split_tx(int &tw4, int &th4) {   // halve the longer side (both if square)
+        if (tw4 == th4) { if (tw4 > 1) { tw4 >>= 1; th4 >>= 1; } }
+        else if (tw4 > th4) tw4 >>= 1;
+        else th4 >>= 1;
+    }
+
+    void intra_block(int bx4, int by4, int w4, int h4) {
+        n_intra_blocks++;
+        const bool residual = rng.chance(P.p_residual);
+        const int flags = (P.edge_filter ? 1024 : 0) | (rng.chance(0.25f) ? 512 : 0);
+        int tw4 = std::min(w4, 16), th4 = std::min(h4, 16);
+        if (rng.chance(P.p_tx_split)) split_tx(tw4, th4);
+        const bool pal = w4 <= 16 && h4 <= 16 && rng.chance(P.p_palette);
+        int mode = rng.range(13), delta = 0;
+        if (!pal && w4 <= 8 && h4 <= 8 && rng.chance(P.p_filter_intra)) { mode = DAV1D_CUDA_INTRA_FILTER; delta = rng.range(5); }
+        else if (mode >= 1 && mode <= 8) delta = rng.irange(-3, 3);
+        uint32_t pal_off = 0, idx_off = 0;
+        if (pal) {
+            pal_off = (uint32_t)pal_px_alloc();
+            idx_off = (uint32_t)pal_idx_alloc(w4 * 4 * h4 * 4 / 2);
+            add_intra(0, bx4, by4, w4, h4, DAV1D_CUDA_INTRA_PAL, 0, 0, false, pal_off, idx_off);
+        }
+        for (int y = 0; y < h4; y += th4)
+            for (int x = 0; x < w4; x += tw4) {
+                if (pal) {
+                    if (residual) add_intra(0, bx4 + x, by4 + y, tw4, th4, DAV1D_CUDA_INTRA_NONE, 0, 0, true);
+                    else mark(0, bx4 + x, by4 + y, tw4, th4);
+                } else {
+                    add_intra(0, bx4 + x, by4 + y, tw4, th4, mode, delta, flags, residual);
+                }
+            }
+        if (pal) mark(0, bx4, by4, w4, h4);
+        if (P.no_chroma) return;
+        // ---- chroma
+        const int sh = P.ss_hor, sv = P.ss_ver;
+        const int cx4 = bx4 >> sh, cy4 = by4 >> sv, cw4 = w4 >> sh, ch4 = h4 >> sv;
+        const int uvtw4 = std::min(cw4, 8), uvth4 = std::min(ch4, 8);
+        const bool cfl = !pal && w4 <= 8 && h4 <= 8 && rng.chance(P.p_cfl);
+        const int uvflags = (P.edge_filter ? 1024 : 0) | (rng.chance(0.25f) ? 512 : 0);
+        int uvmode = rng.range(13), uvdelta = 0;
+        if (uvmode >= 1 && uvmode <= 8) uvdelta = rng.irange(-3, 3);
+        uint32_t uvpal_off[2] = { 0, 0 }, uvidx_off = 0;
+        if (pal) {
+            uvpal_off[0] = (uint32_t)pal_px_alloc();
+            uvpal_off[1] = (uint32_t)pal_px_alloc();
+            uvidx_off = (uint32_t)pal_idx_alloc(cw4 * 4 * ch4 * 4 / 2);
+        }
+        int wpad = 0, hpad = 0;
+        if (cfl && rng.chance(0.1f)) { wpad = rng.range(cw4); hpad = rng.range(ch4); }
+        for (int pl = 1; pl <= 2; pl++) {
+            if (pal) add_intra(pl, cx4, cy4, cw4, ch4, DAV1D_CUDA_INTRA_PAL, 0, 0, false, uvpal_off[pl - 1], uvidx_off);
+            int alpha = 0;
+            if (cfl) alpha = (rng.range(16) + 1) * (rng.chance(0.5f) ? -1 : 1);
+            if (cfl && pl == 2 && rng.chance(0.2f)) alpha = 0;    // alpha 0 -> plain DC_PRED (recon_tmpl.c:1479)
+            for (int y = 0; y < ch4; y += uvth4)
+                for (int x = 0; x < cw4; x += uvtw4) {
+                    if (pal) {
+                        if (residual) add_intra(pl, cx4 + x, cy4 + y, uvtw4, uvth4, DAV1D_CUDA_INTRA_NONE, 0, 0, true);
+                    } else if (cfl && alpha) {
+                        add_intra(pl, cx4 + x, cy4 + y, uvtw4, uvth4, DAV1D_CUDA_INTRA_CFL, alpha, 0, residual,
+                                  (uint32_t)(wpad | (hpad << 8)));
+                    } else {
+                        add_intra(pl, cx4 + x, cy4 + y, uvtw4, uvth4, cfl ? 0 : uvmode, cfl ? 0 : uvdelta,
+                                  uvflags, residual);
+                    }
+                }
+            mark(pl, cx4, cy4, cw4, ch4);
+        }
+    }
+
+    size_t pal_px_alloc() {
+        const size_t o = pal.size();
+        for (int i = 0; i < 8; i++) pal.push_back((uint16_t)(rng.u32() & P.bitdepth_max));
+        return o;
+    }
+    size_t pal_idx_alloc(int bytes) {
+        const size_t o = pal_idx.size();
+        for (int i = 0; i < bytes; i++) pal_idx.push_back((uint8_t)(rng.u32() & 0x77));
+        return o;
+    }
+
+    Dav1dCudaMcSrc make_src(int pl, int bx4, int by4, int ref, int mvx, int mvy, int filter) {
+        const int sh = pl ? P.ss_hor : 0, sv = pl ? P.ss_ver : 0;   // recon_tmpl.c:966-977,1003
+        Dav1dCudaMcSrc s;
+        s.ref = (uint8_t)ref; s.filter_2d = (uint8_t)filter;
+        const int mx = mvx & (15 >> !sh), my = mvy & (15 >> !sv);
+        s.mx = (uint8_t)(mx << !sh); s.my = (uint8_t)(my << !sv);
+        s.x = bx4 * (4 >> sh) + (mvx >> (3 + sh));
+        s.y = by4 * (4 >> sv) + (mvy >> (3 + sv));
+        return s;
+    }
+
+    void inter_block(int bx4, int by4, int w4, int h4) {
+        const float u = rng.unit();
+        float acc = P.p_avg;
+        int kind = DAV1D_CUDA_MC_PUT;
+        bool is_warp = false;
+        if (u < acc) kind = DAV1D_CUDA_MC_AVG;
+        else if (u < (acc += P.p_w_avg)) kind = DAV1D_CUDA_MC_W_AVG;
+        else if (u < (acc += P.p_wedge)) kind = DAV1D_CUDA_MC_MASK;
+        else if (u < (acc += P.p_seg)) kind = DAV1D_CUDA_MC_W_MASK;
+        else if (u < (acc += P.p_warp) && w4 >= 4 && h4 >= 4) is_warp = true;
+        const int filter = rng.range(10);
+        const int R = P.mv_range * 8;
+        int ref[2], mvx[2], mvy[2];
+        for (int i = 0; i < 2; i++) {
+            ref[i] = rng.range(P.n_refs);
+            mvx[i] = rng.irange(-R, R); mvy[i] = rng.irange(-R, R);
+            if (rng.chance(0.1f)) mvx[i] &= ~7;    // integer-pel columns / rows now and then
+            if (rng.chance(0.1f)) mvy[i] &= ~7;
+        }
+        const int weight = rng.irange(1, 15), sign = rng.range(2);
+        uint32_t seg_off = 0, wedge_off[3] = { 0, 0, 0 };
+        for (int pl = 0; pl < nplanes(); pl++) {
+            const int sh = pl ? P.ss_hor : 0, sv = pl ? P.ss_ver : 0;
+            const int w = (w4 * 4) >> sh, h = (h4 * 4) >> sv;
+            const int x = (bx4 * 4) >> sh, y = (by4 * 4) >> sv;
+            if (is_warp) {
+                // per-8x8 calls of warp_affine() (recon_tmpl.c:1151-1191) with random shear parameters
+                int16_t abcd[4];
+                for (int k = 0; k < 4; k++) abcd[k] = (int16_t)(rng.irange(0, 0x1fff) - 0xa00);
+                for (int yy = 0; yy < h; yy += 8)
+                    for (int xx = 0; xx < w; xx += 8) {
+                        Dav1dCudaWarpDesc d;
+                        memset(&d, 0, sizeof(d));
+                        d.plane = (uint8_t)pl; d.ref = (uint8_t)ref[0];
+                        d.x = (uint16_t)(x + xx); d.y = (uint16_t)(y + yy);
+                        d.sx = x + xx + ((mvx[0] >> (3 + sh))); d.sy = y + yy + ((mvy[0] >> (3 + sv)));
+                        d.mx = (rng.irange(0, 0x1fff) - 0xa00) & ~0x3f;
+                        d.my = (rng.irange(0, 0x1fff) - 0xa00) & ~0x3f;
+                        memcpy(d.abcd, abcd, sizeof(abcd));
+                        order.push_back({ 2, (uint32_t)warp.size() });
+                        warp.push_back(d);
+                    }
+                algo += 2.0 * Bp * w * h;
+                continue;
+            }
+            Dav1dCudaMcDesc d;
+            memset(&d, 0, sizeof(d));
+            d.x = (uint16_t)x; d.y = (uint16_t)y; d.w = (uint8_t)w; d.h = (uint8_t)h;
+            d.plane = (uint8_t)pl; d.kind = (uint8_t)kind;
+            d.src[0] = make_src(pl, bx4, by4, ref[0], mvx[0], mvy[0], filter);
+            d.src[1] = make_src(pl, bx4, by4, ref[1], mvx[1], mvy[1], filter);
+            bool wave1 = false;
+            if (kind == DAV1D_CUDA_MC_PUT) {
+                algo += 2.0 * Bp * w * h;
+                order.push_back({ 0, (uint32_t)put.size() });
+                put.push_back(d);
+                continue;
+            }
+            algo += 3.0 * Bp * w * h;
+            if (kind == DAV1D_CUDA_MC_W_AVG) d.weight = (uint8_t)weight;
+            if (kind == DAV1D_CUDA_MC_MASK || kind == DAV1D_CUDA_MC_W_MASK) {
+                if (sign) std::swap(d.src[0], d.src[1]);   // tmp[mask_sign], tmp[!mask_sign]
+            }
+            if (kind == DAV1D_CUDA_MC_MASK) {               // wedge: one mask table per plane size
+                wedge_off[pl] = (uint32_t)masks.size();
+                for (int i = 0; i < w * h; i++) masks.push_back((uint8_t)rng.range(65));
+                d.aux_off = wedge_off[pl];
+                algo += (double)w * h;
+            } else if (kind == DAV1D_CUDA_MC_W_MASK) {
+                if (pl == 0) {
+                    const int lay = P.no_chroma ? 0 : (P.ss_hor ? (P.ss_ver ? 2 : 1) : 0);
+                    const int mw = w >> (lay >= 1), mh = h >> (lay == 2);
+                    seg_off = (uint32_t)masks.size();
+                    masks.resize(masks.size() + (size_t)mw * mh, 0);
+                    d.aux_off = seg_off; d.mask_ss = (uint8_t)lay; d.weight = (uint8_t)sign;
+                    algo += (double)mw * mh;
+                } else {
+                    d.kind = DAV1D_CUDA_MC_MASK;            // chroma reuses the luma-derived mask
+                    d.aux_off = seg_off;
+                    wave1 = true;
+                    algo += (double)w * h;
+                }
+            }
+            if (wave1) { order.push_back({ 5, (uint32_t)comp1.size() }); comp1.push_back(d); }
+            else { order.push_back({ 1, (uint32_t)comp0.size() }); comp0.push_back(d); }
+        }
+        // ---- residual
+        if (rng.chance(P.p_residual)) {
+            int tw4 = std::min(w4, 16), th4 = std::min(h4, 16);
+            if (rng.chance(P.p_tx_split)) split_tx(tw4, th4);
+            const int tx = tx_from_dims(tw4, th4);
+            for (int y = 0; y < h4; y += th4)
+                for (int x = 0; x < w4; x += tw4) add_itx(0, bx4 + x, by4 + y, tx);
+            if (!P.no_chroma) {
+                const int cw4 = w4 >> P.ss_hor, ch4 = h4 >> P.ss_ver;
+                const int utw4 = std::min(cw4, 8), uth4 = std::min(ch4, 8);
+                const int utx = tx_from_dims(utw4, uth4);
+                for (int pl = 1; pl <= 2; pl++)
+                    for (int y = 0; y < ch4; y += uth4)
+                        for (int x = 0; x < cw4; x += utw4)
+                            add_itx(pl, (bx4 >> P.ss_hor) + x, (by4 >> P.ss_ver) + y, utx);
+            }
+        }
+        for (int pl = 0; pl < nplanes(); pl++) {
+            const int sh = pl ? P.ss_hor : 0, sv = pl ? P.ss_ver : 0;
+            mark(pl, bx4 >> sh, by4 >> sv, w4 >> sh, h4 >> sv);
+        }
+    }
+
+    void block(int bx4, int by4, int w4, int h4) {
+        n_blocks++;
+        luma_px += 16.0 * w4 * h4;
+        if (rng.chance(P.p_intra)) intra_block(bx4, by4, w4, h4);
+        else inter_block(bx4, by4, w4, h4);
+    }
+
+    // recursive partition of an s4 x s4 (4-px units) square at (bx4, by4), decode (Z) order
+    void partition(int bx4, int by4, int s4) {
+        if (bx4 >= bw4 || by4 >= bh4) return;
+        const bool fits = bx4 + s4 <= bw4 && by4 + s4 <= bh4;
+        int choice;   // 0 NONE 1 H 2 V 3 SPLIT 4 H4 5 V4
+        if (!fits) choice = 3;
+        else if (s4 == 2) choice = 0;
+        else {
+            const int r = rng.range(100);
+            if (s4 == 16) choice = r < 8 ? 0 : r < 16 ? 1 : r < 24 ? 2 : r < 28 ? 4 : r < 32 ? 5 : 3;
+            else if (s4 == 8) choice = r < 25 ? 0 : r < 38 ? 1 : r < 51 ? 2 : r < 56 ? 4 : r < 61 ? 5 : 3;
+            else choice = r < 40 ? 0 : r < 55 ? 1 : r < 70 ? 2 : 3;      // s4 == 4 (16x16)
+        }
+        const int hs = s4 >> 1, q = s4 >> 2;
+        switch (choice) {
+        case 0: block(bx4, by4, s4, s4); break;
+        case 1: block(bx4, by4, s4, hs); block(bx4, by4 + hs, s4, hs); break;
+        case 2: block(bx4, by4, hs, s4); block(bx4 + hs, by4, hs, s4); break;
+        case 4: for (int i = 0; i < 4; i++) block(bx4, by4 + i * q, s4, q); break;
+        case 5: for (int i = 0; i < 4; i++) block(bx4 + i * q, by4, q, s4); break;
+        default:
+            partition(bx4, by4, hs); partition(bx4 + hs, by4, hs);
+            partition(bx4, by4 + hs, hs); partition(bx4 + hs, by4 + hs, hs);
+            break;
+        }
+    }
+
+    void run() {
+        if (P.only_tx >= 0) {   // config 2: plane tiled with one transform size, residual on top of a put
+            const int tw4 = TXW4[P.only_tx], th4 = TXH4[P.only_tx];
+            for (int y = 0; y + th4 <= bh4; y += th4)
+                for (int x = 0; x + tw4 <= bw4; x += tw4) { add_itx(0, x, y, P.only_tx); luma_px += 16.0 * tw4 * th4; }
+            return;
+        }
+        for (int y = 0; y < bh4; y += 16)
+            for (int x = 0; x < bw4; x += 16) partition(x, y, 16);
+    }
+};
+
+int mc_tiles(uint32_t desc_index, int w, int h, uint32_t *out) {   // == dav1d_cuda_mc_tiles()
+    int n = 0;
+    for (int ty = 0; ty * 32 < h; ty++)
+        for (int tx = 0; tx * 32 < w; tx++) out[n++] = desc_index * 16 + ty * 4 + tx;
+    return n;
+}
+
+template <typename T> T *dup(const std::vector<T> &v) {
+    T *p = (T *)malloc(std::max<size_t>(v.size(), 1) * sizeof(T));
+    if (!v.empty()) memcpy(p, v.data(), v.size() * sizeof(T));
+    return p;
+}
+
+}  // namespace
+
+extern "C" {
+
+__attribute__((visibility("default"))) void d1synth_default_params(D1SynthParams *p, int w, int h, int bitdepth_max, uint64_t seed) {
+    memset(p, 0, sizeof(*p));
+    p->w = w; p->h = h; p->ss_hor = 1; p->ss_ver = 1; p->bitdepth_max = bitdepth_max; p->seed = seed;
+    p->p_intra = 0.3f; p->p_residual = 0.6f; p->p_tx_split = 0.5f;
+    p->p_filter_intra = 0.05f; p->p_palette = 0.02f; p->p_cfl = 0.25f;
+    p->p_avg = 0.2f; p->p_w_avg = 0.1f; p->p_wedge = 0.1f; p->p_seg = 0.05f; p->p_warp = 0.05f;
+    p->mv_range = 128; p->n_refs = 2; p->edge_filter = 1; p->only_tx = -1; p->only_txtp = -1; p->eob_class = -1;
+}
+
+__attribute__((visibility("default"))) int d1synth_generate(const D1SynthParams *p, D1SynthFrame *f) {
+    if (!p || !f || (p->w & 7) || (p->h & 7) || p->w <= 0 || p->h <= 0) return -22;
+    Gen g(*p);
+    g.run();
+    memset(f, 0, sizeof(*f));
+    // compound: wave 0 then wave 1
+    std::vector<Dav1dCudaMcDesc> comp(g.comp0);
+    comp.insert(comp.end(), g.comp1.begin(), g.comp1.end());
+    // itx: stable sort by class
+    std::vector<uint32_t> itx_new(g.itx.size());
+    std::vector<Dav1dCudaItxDesc> itx_sorted(g.itx.size());
+    {
+        int32_t start[20] = { 0 };
+        for (auto &d : g.itx) f->itx_class_count[d.tx]++;
+        for (int t = 0; t < 19; t++) start[t + 1] = start[t] + f->itx_class_count[t];
+        for (size_t i = 0; i < g.itx.size(); i++) {
+            const uint32_t n = (uint32_t)start[g.itx[i].tx]++;
+            itx_new[i] = n;
+            itx_sorted[n] = g.itx[i];
+        }
+    }
+    // tiles
+    std::vector<uint32_t> put_tiles, comp_tiles;
+    uint32_t buf[16];
+    for (size_t i = 0; i < g.put.size(); i++) {
+        const int n = mc_tiles((uint32_t)i, g.put[i].w, g.put[i].h, buf);
+        put_tiles.insert(put_tiles.end(), buf, buf + n);
+    }
+    for (size_t i = 0; i < comp.size(); i++) {
+        const int n = mc_tiles((uint32_t)i, comp[i].w, comp[i].h, buf);
+        comp_tiles.insert(comp_tiles.end(), buf, buf + n);
+        f->n_mc_comp_tiles[i < g.comp0.size() ? 0 : 1] += n;
+    }
+    std::vector<uint32_t> order(g.order.size());
+    for (size_t i = 0; i < g.order.size(); i++) {
+        uint32_t cls = g.order[i].cls, idx = g.order[i].idx;
+        if (cls == 5) { cls = 1; idx += (uint32_t)g.comp0.size(); }
+        if (cls == 3) idx = itx_new[idx];
+        order[i] = (cls << 28) | idx;
+    }
+    f->mc_put = dup(g.put); f->n_mc_put = (int32_t)g.put.size();
+    f->mc_put_tiles = dup(put_tiles); f->n_mc_put_tiles = (int32_t)put_tiles.size();
+    f->mc_comp = dup(comp); f->n_mc_comp = (int32_t)comp.size();
+    f->mc_comp_tiles = dup(comp_tiles);
+    f->warp = dup(g.warp); f->n_warp = (int32_t)g.warp.size();
+    f->itx = dup(itx_sorted); f->n_itx = (int32_t)itx_sorted.size();
+    f->intra = dup(g.intra); f->n_intra = (int32_t)g.intra.size();
+    f->cf_elems = g.cf32.size();
+    if (g.hbd) f->cf = dup(g.cf32);
+    else {
+        std::vector<int16_t> c16(g.cf32.begin(), g.cf32.end());
+        f->cf = dup(c16);
+    }
+    f->masks = dup(g.masks); f->masks_bytes = g.masks.size();
+    if (g.hbd) f->pal = dup(g.pal);
+    else {
+        std::vector<uint8_t> p8(g.pal.begin(), g.pal.end());
+        f->pal = dup(p8);
+    }
+    f->pal_px = g.pal.size();
+    f->pal_idx = dup(g.pal_idx); f->pal_idx_bytes = g.pal_idx.size();
+    f->order = dup(order); f->n_order = (int32_t)order.size();
+    f->bw4 = g.bw4; f->bh4 = g.bh4;
+    f->algo_bytes = g.algo; f->luma_px = g.luma_px;
+    f->n_blocks = g.n_blocks; f->n_intra_blocks = g.n_intra_blocks;
+    return 0;
+}
+
+__attribute__((visibility("default"))) void d1synth_free(D1SynthFrame *f) {
+    if (!f) return;
+    free(f->mc_put); free(f->mc_put_tiles); free(f->mc_comp); free(f->mc_comp_tiles); free(f->warp);
+    free(f->itx); free(f->intra); free(f->cf); free(f->masks); free(f->pal); free(f->pal_idx); free(f->order);
+    memset(f, 0, sizeof(*f));
+}
+
+}  // extern "C"

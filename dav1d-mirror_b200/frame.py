@@ -1,0 +1,257 @@
+"""Frame-level host glue over the C ABI: synthetic descriptor source
+(libd1synth.so), level scheduling, upload of descriptor arrays into HBM and
+submission of one frame's reconstruction batch.  Used by tests/ and bench.py;
+all device work goes through libdav1d_cuda.so."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import binding as B
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SYNTH_PATH = os.path.join(HERE, "libd1synth.so")
+
+
+class SynthParams(C.Structure):
+    _fields_ = [("w", C.c_int32), ("h", C.c_int32), ("ss_hor", C.c_int32), ("ss_ver", C.c_int32),
+                ("bitdepth_max", C.c_int32), ("no_chroma", C.c_int32), ("seed", C.c_uint64),
+                ("p_intra", C.c_float), ("p_residual", C.c_float), ("p_tx_split", C.c_float),
+                ("p_filter_intra", C.c_float), ("p_palette", C.c_float), ("p_cfl", C.c_float),
+                ("p_avg", C.c_float), ("p_w_avg", C.c_float), ("p_wedge", C.c_float),
+                ("p_seg", C.c_float), ("p_warp", C.c_float),
+                ("mv_range", C.c_int32), ("n_refs", C.c_int32), ("edge_filter", C.c_int32),
+                ("only_tx", C.c_int32), ("only_txtp", C.c_int32), ("eob_class", C.c_int32)]
+
+
+class SynthFrame(C.Structure):
+    _fields_ = [("mc_put", C.c_void_p), ("n_mc_put", C.c_int32), ("mc_put_tiles", C.c_void_p),
+                ("n_mc_put_tiles", C.c_int32),
+                ("mc_comp", C.c_void_p), ("n_mc_comp", C.c_int32), ("mc_comp_tiles", C.c_void_p),
+                ("n_mc_comp_tiles", C.c_int32 * 2),
+                ("warp", C.c_void_p), ("n_warp", C.c_int32),
+                ("itx", C.c_void_p), ("n_itx", C.c_int32), ("itx_class_count", C.c_int32 * 19),
+                ("intra", C.c_void_p), ("n_intra", C.c_int32),
+                ("cf", C.c_void_p), ("cf_elems", C.c_uint64),
+                ("masks", C.c_void_p), ("masks_bytes", C.c_uint64),
+                ("pal", C.c_void_p), ("pal_px", C.c_uint64),
+                ("pal_idx", C.c_void_p), ("pal_idx_bytes", C.c_uint64),
+                ("order", C.c_void_p), ("n_order", C.c_int32),
+                ("bw4", C.c_int32), ("bh4", C.c_int32),
+                ("algo_bytes", C.c_double), ("luma_px", C.c_double),
+                ("n_blocks", C.c_int64), ("n_intra_blocks", C.c_int64)]
+
+
+_synth = None
+
+
+def synth_lib():
+    global _synth
+    if _synth is None:
+        if not os.path.exists(SYNTH_PATH):
+            raise RuntimeError(f"{SYNTH_PATH} missing: run `make -C dav1d-mirror_b200`")
+        _synth = C.CDLL(SYNTH_PATH)
+        _synth.d1synth_default_params.argtypes = [C.POINTER(SynthParams), C.c_int, C.c_int, C.c_int, C.c_uint64]
+        _synth.d1synth_generate.argtypes = [C.POINTER(SynthParams), C.POINTER(SynthFrame)]
+        _synth.d1synth_free.argtypes = [C.POINTER(SynthFrame)]
+    return _synth
+
+
+def _np_from(ptr, nbytes):
+    if not nbytes:
+        return np.zeros(0, dtype=np.uint8)
+    return np.frombuffer((C.c_char * nbytes).from_address(ptr), dtype=np.uint8).copy()
+
+
+class HostFrame:
+    """One synthetic frame on the host: descriptor arrays (numpy byte buffers in
+    the C ABI's struct layouts), coefficient stream, pools, decode order."""
+
+    def __init__(self, w, h, bitdepth_max, seed, **kw):
+        S = synth_lib()
+        p = SynthParams()
+        S.d1synth_default_params(C.byref(p), w, h, bitdepth_max, seed)
+        for k, v in kw.items():
+            if not hasattr(p, k):
+                raise KeyError(k)
+            setattr(p, k, v)
+        f = SynthFrame()
+        r = S.d1synth_generate(C.byref(p), C.byref(f))
+        if r:
+            raise RuntimeError(f"d1synth_generate failed: {r}")
+        self.params = p
+        self.w, self.h, self.bdmax = w, h, bitdepth_max
+        self.ss_hor, self.ss_ver, self.no_chroma = p.ss_hor, p.ss_ver, p.no_chroma
+        self.hbd = bitdepth_max > 0xff
+        self.bw4, self.bh4 = f.bw4, f.bh4
+        self.mc_put = _np_from(f.mc_put, f.n_mc_put * C.sizeof(B.McDesc))
+        self.mc_put_tiles = _np_from(f.mc_put_tiles, f.n_mc_put_tiles * 4)
+        self.mc_comp = _np_from(f.mc_comp, f.n_mc_comp * C.sizeof(B.McDesc))
+        ntc = f.n_mc_comp_tiles[0] + f.n_mc_comp_tiles[1]
+        self.mc_comp_tiles = _np_from(f.mc_comp_tiles, ntc * 4)
+        self.n_mc_put_tiles = f.n_mc_put_tiles
+        self.n_mc_comp_tiles = (f.n_mc_comp_tiles[0], f.n_mc_comp_tiles[1])
+        self.warp = _np_from(f.warp, f.n_warp * C.sizeof(B.WarpDesc))
+        self.n_warp = f.n_warp
+        self.itx = _np_from(f.itx, f.n_itx * C.sizeof(B.ItxDesc))
+        self.itx_class_count = [f.itx_class_count[i] for i in range(19)]
+        self.intra = _np_from(f.intra, f.n_intra * C.sizeof(B.IntraDesc))   # decode order
+        self.n_intra = f.n_intra
+        self.cf = _np_from(f.cf, f.cf_elems * (4 if self.hbd else 2))
+        self.masks = _np_from(f.masks, f.masks_bytes)
+        self.pal = _np_from(f.pal, f.pal_px * (2 if self.hbd else 1))
+        self.pal_idx = _np_from(f.pal_idx, f.pal_idx_bytes)
+        self.order = _np_from(f.order, f.n_order * 4)
+        self.algo_bytes, self.luma_px = f.algo_bytes, f.luma_px
+        self.n_blocks, self.n_intra_blocks = f.n_blocks, f.n_intra_blocks
+        S.d1synth_free(C.byref(f))
+        self.intra_sorted = None
+        self.level_start = None
+        self.n_levels = 0
+
+    def schedule(self):
+        """Dependency levels of the intra-class descriptors (dav1d_cuda_intra_schedule)."""
+        L = B.lib()
+        n = self.n_intra
+        order = (C.c_int32 * max(n, 1))()
+        max_levels = 1 << 16
+        level_start = (C.c_int32 * (max_levels + 1))()
+        descs = self.intra.copy()
+        nl = L.dav1d_cuda_intra_schedule(descs.ctypes.data, n, self.bw4, self.bh4,
+                                         0 if self.no_chroma else self.ss_hor,
+                                         0 if self.no_chroma else self.ss_ver, order, level_start, max_levels)
+        if nl < 0:
+            raise RuntimeError(f"dav1d_cuda_intra_schedule: {nl}")
+        perm = np.frombuffer(order, dtype=np.int32, count=n).copy() if n else np.zeros(0, np.int32)
+        rec = descs.reshape(n, C.sizeof(B.IntraDesc)) if n else descs.reshape(0, C.sizeof(B.IntraDesc))
+        self.intra_sorted = np.ascontiguousarray(rec[perm]).reshape(-1)
+        self.level_start = np.frombuffer(level_start, dtype=np.int32, count=nl + 1).copy()
+        self.n_levels = nl
+        return nl
+
+    def plane_shape(self, pl):
+        sh = self.ss_hor if pl else 0
+        sv = self.ss_ver if pl else 0
+        return ((self.h + sv) >> sv, (self.w + sh) >> sh)
+
+    def host_bytes(self):
+        """Bytes a decoder would ship host->device for this frame (descriptors + coefficients + pools)."""
+        n = sum(a.nbytes for a in (self.mc_put, self.mc_put_tiles, self.mc_comp, self.mc_comp_tiles, self.warp,
+                                   self.itx, self.cf, self.masks, self.pal, self.pal_idx))
+        return n + (self.intra_sorted.nbytes if self.intra_sorted is not None else self.intra.nbytes)
+
+
+def random_planes(hf, seed):
+    """Reference / initial picture content: uniform random pixels (checkasm's worst case)."""
+    rng = np.random.default_rng(seed)
+    dt = np.uint16 if hf.hbd else np.uint8
+    return [rng.integers(0, hf.bdmax + 1, size=hf.plane_shape(pl), dtype=np.int32).astype(dt)
+            for pl in range(1 if hf.no_chroma else 3)]
+
+
+class DeviceFrame:
+    """Device-resident state for reconstructing `hf` with libdav1d_cuda.so."""
+
+    def __init__(self, ctx, hf, n_refs=2):
+        self.L = B.lib()
+        self.ctx = ctx
+        self.hf = hf
+        L = self.L
+        self.dst = B.Picture()
+        self.refs = [B.Picture() for _ in range(n_refs)]
+        for pic in [self.dst] + self.refs:
+            r = L.dav1d_cuda_picture_alloc(ctx, C.byref(pic), hf.w, hf.h, hf.ss_hor, hf.ss_ver, hf.bdmax)
+            if r:
+                raise RuntimeError("dav1d_cuda_picture_alloc failed")
+        if hf.intra_sorted is None:
+            hf.schedule()
+        self._dev = {}
+        self._host = {}
+        for name in ("mc_put", "mc_put_tiles", "mc_comp", "mc_comp_tiles", "warp", "itx", "intra_sorted", "cf",
+                     "masks", "pal", "pal_idx"):
+            arr = getattr(hf, name)
+            self._host[name] = arr
+            self._dev[name] = L.dav1d_cuda_malloc(max(arr.nbytes, 256))
+            if not self._dev[name]:
+                raise RuntimeError("dav1d_cuda_malloc failed")
+        self._level_start = (C.c_int32 * (hf.n_levels + 1))(*hf.level_start.tolist())
+        b = B.ReconBatch()
+        b.dst = C.pointer(self.dst)
+        for i in range(7):
+            b.refs[i] = C.pointer(self.refs[i]) if i < n_refs else None
+        b.bw4, b.bh4 = hf.bw4, hf.bh4
+        d = self._dev
+        b.cf, b.masks, b.pal, b.pal_idx = d["cf"], d["masks"], d["pal"], d["pal_idx"]
+        b.mc_put, b.mc_put_tiles, b.n_mc_put_tiles = d["mc_put"], d["mc_put_tiles"], hf.n_mc_put_tiles
+        b.mc_comp, b.mc_comp_tiles = d["mc_comp"], d["mc_comp_tiles"]
+        b.n_mc_comp_tiles[0], b.n_mc_comp_tiles[1] = hf.n_mc_comp_tiles
+        b.warp, b.n_warp = d["warp"], hf.n_warp
+        b.itx = d["itx"]
+        for i in range(19):
+            b.itx_class_count[i] = hf.itx_class_count[i]
+        b.intra = d["intra_sorted"]
+        b.intra_level_start = self._level_start
+        b.n_levels = hf.n_levels
+        self.batch = b
+        self.graph = None
+
+    def upload_descriptors(self):
+        for name, arr in self._host.items():
+            if arr.nbytes:
+                self.L.dav1d_cuda_upload(self.ctx, self._dev[name], arr.ctypes.data, arr.nbytes)
+
+    def upload_picture(self, pic, planes):
+        for pl, a in enumerate(planes):
+            self.L.dav1d_cuda_picture_upload(self.ctx, C.byref(pic), pl, a.ctypes.data, a.strides[0])
+
+    def download_picture(self, pic=None):
+        pic = pic or self.dst
+        hf = self.hf
+        out = []
+        for pl in range(1 if hf.no_chroma else 3):
+            a = np.zeros(hf.plane_shape(pl), dtype=np.uint16 if hf.hbd else np.uint8)
+            self.L.dav1d_cuda_picture_download(self.ctx, C.byref(pic), pl, a.ctypes.data, a.strides[0])
+            out.append(a)
+        self.L.dav1d_cuda_synchronize(self.ctx)
+        return out
+
+    def submit(self):
+        r = self.L.dav1d_cuda_recon_submit(self.ctx, C.byref(self.batch))
+        if r:
+            raise RuntimeError(f"dav1d_cuda_recon_submit: {r}")
+
+    def build_graph(self):
+        g = C.c_void_p()
+        n = self.L.dav1d_cuda_recon_graph_build(self.ctx, C.byref(self.batch), C.byref(g))
+        if n < 0:
+            raise RuntimeError(f"dav1d_cuda_recon_graph_build: {n}")
+        self.graph = g
+        self.graph_nodes = n
+        return n
+
+    def launch_graph(self):
+        r = self.L.dav1d_cuda_recon_graph_launch(self.ctx, self.graph)
+        if r:
+            raise RuntimeError(f"dav1d_cuda_recon_graph_launch: {r}")
+
+    def close(self):
+        L = self.L
+        L.dav1d_cuda_synchronize(self.ctx)
+        if self.graph:
+            L.dav1d_cuda_recon_graph_free(self.graph)
+            self.graph = None
+        for p in self._dev.values():
+            L.dav1d_cuda_free(p)
+        self._dev = {}
+        for pic in [self.dst] + self.refs:
+            L.dav1d_cuda_picture_free(self.ctx, C.byref(pic))
+
+
+def open_context(device=0, stream=None):
+    L = B.lib()
+    ctx = C.c_void_p()
+    r = L.dav1d_cuda_open(C.byref(ctx), device, stream)
+    if r:
+        B.check_error()
+        raise RuntimeError(f"dav1d_cuda_open: {r}")
+    return ctx

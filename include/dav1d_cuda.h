@@ -200,31 +200,55 @@ typedef struct Dav1dCudaMcDesc {   /* 40 bytes */
                               PREP: int16 offset into the tmp pool */
 } Dav1dCudaMcDesc;
 
-/* -- intra prediction, one descriptor per transform block in decode order
- * (recon_tmpl.c:1259-1300, 1503-1576), optionally fused with its residual.
- * The fields are the arguments of dav1d_prepare_intra_edges +
- * intra_pred[m]; mode/angle resolution happens on the device. */
-typedef struct Dav1dCudaIntraDesc {  /* 32 bytes */
+/* -- intra-class operations, one descriptor per transform block in decode
+ * order (recon_tmpl.c:1259-1300 luma, :1372-1417 CfL, :1226-1243 palette,
+ * :1503-1576 chroma), optionally fused with the block's residual.  The fields
+ * are the arguments of dav1d_prepare_intra_edges + intra_pred[m] /
+ * cfl_ac + cfl_pred[m] / pal_pred; mode -> DSP index and absolute angle are
+ * resolved on the device exactly like ipred_prepare_tmpl.c:94-117. */
+enum Dav1dCudaIntraKind {
+    /* 0..12: bitstream enum IntraPredMode (DC, VERT, HOR, D45.., SMOOTH*, PAETH) */
+    DAV1D_CUDA_INTRA_FILTER = 13,   /* filter-intra, angle_delta = filter index 0..4 */
+    DAV1D_CUDA_INTRA_CFL    = 14,   /* cfl_ac + DC edges + cfl_pred, angle_delta = alpha */
+    DAV1D_CUDA_INTRA_PAL    = 15,   /* pal_pred: coef_off = byte offset of the packed indices,
+                                       aux = palette offset (in pixels) in the palette pool */
+    DAV1D_CUDA_INTRA_NONE   = 255   /* residual only (e.g. tx blocks of a palette block) */
+};
+
+typedef struct Dav1dCudaIntraDesc {  /* 40 bytes */
     uint16_t x4, y4;       /* position in 4-px units of THIS plane */
     uint16_t tile_x4_start;/* have_left = x4 > tile_x4_start */
     uint16_t tile_y4_start;/* have_top  = y4 > tile_y4_start */
     uint16_t tile_x4_end, tile_y4_end;   /* w, h arguments (tile end, frame end) */
     uint8_t  plane;
-    uint8_t  tw4, th4;     /* transform size in 4-px units */
-    uint8_t  mode;         /* bitstream enum IntraPredMode 0..12, or FILTER_PRED=13 */
-    int8_t   angle_delta;  /* -3..3; FILTER_PRED: filter index 0..4 */
+    uint8_t  tw4, th4;     /* transform (prediction) size in 4-px units */
+    uint8_t  mode;         /* enum IntraPredMode 0..12 or enum Dav1dCudaIntraKind */
+    int8_t   angle_delta;  /* -3..3 | filter index | cfl alpha */
     uint8_t  edge_flags;   /* bit0 top-has-right, bit3 left-has-bottom (EDGE_I444_*) */
     uint16_t flags;        /* bit9 smooth neighbour, bit10 edge filter (ipred_prepare.h:87-93) */
     int16_t  eob;          /* < 0: no residual */
     uint8_t  tx, txtp;     /* residual transform, if any */
-    uint32_t coef_off;
-    uint32_t level;        /* dependency level (filled by the recorder) */
+    uint32_t coef_off;     /* into the cf stream (PAL: into the index pool) */
+    uint32_t aux;          /* CFL: w_pad | h_pad << 8 (4-px units); PAL: palette offset */
+    uint32_t level;        /* dependency level >= 1, filled by dav1d_cuda_intra_schedule() */
+    uint32_t pad;
 } Dav1dCudaIntraDesc;
+
+/* -- warped motion, one descriptor per 8x8 (warp_affine(), recon_tmpl.c:1134-1193) */
+typedef struct Dav1dCudaWarpDesc {   /* 32 bytes */
+    uint16_t x, y;         /* destination of the 8x8 in `plane` */
+    int32_t  sx, sy;       /* integer source position (dx, dy of recon_tmpl.c:1163-1164) */
+    int32_t  mx, my;       /* fractional parts handed to warp8x8 (recon_tmpl.c:1165-1167) */
+    int16_t  abcd[4];
+    uint8_t  plane, ref;
+    uint16_t pad;
+} Dav1dCudaWarpDesc;
 
 typedef struct Dav1dCudaContext Dav1dCudaContext;
 
-/* `stream` is a cudaStream_t (or NULL for the legacy default stream): the
- * caller may pass the stream it already orders its own work on. */
+/* `stream` is a cudaStream_t the caller already orders its work on, or NULL:
+ * the context then creates its own non-blocking stream (one context per
+ * decoder instance / stream of frames; contexts run concurrently). */
 DAV1D_CUDA_API int  dav1d_cuda_open(Dav1dCudaContext **out, int device, void *stream);
 DAV1D_CUDA_API void dav1d_cuda_close(Dav1dCudaContext *c);
 DAV1D_CUDA_API int  dav1d_cuda_synchronize(Dav1dCudaContext *c);
@@ -275,6 +299,77 @@ DAV1D_CUDA_API int dav1d_cuda_mc_compound_batch(Dav1dCudaContext *c, const Dav1d
 /* Host helper: append the tile codes of block `desc_index` (w x h) to `out`
  * (room for 16 entries); returns the number written. */
 DAV1D_CUDA_API int dav1d_cuda_mc_tiles(uint32_t desc_index, int w, int h, uint32_t *out);
+
+DAV1D_CUDA_API int dav1d_cuda_warp_batch(Dav1dCudaContext *c, const Dav1dCudaPicture *dst,
+                                         const Dav1dCudaPicture *const refs[7],
+                                         const Dav1dCudaWarpDesc *descs, int n);
+
+/* Host-side scheduling of intra-class descriptors (the recorder's job).
+ * `descs[0..n)` are in decode order; every pixel they read from the current
+ * frame was produced either by an inter block (level 0: final after the MC and
+ * inter-residual launches) or by an earlier descriptor.  Writes descs[i].level
+ * (>= 1) and returns the number of levels; `order[0..n)` receives the
+ * permutation that sorts the descriptors by level (stable), and
+ * `level_start[0..n_levels]` the first sorted index of each level
+ * (level_start must have room for max_levels + 1 entries).  Returns < 0 if
+ * more than max_levels levels are needed. */
+DAV1D_CUDA_API int dav1d_cuda_intra_schedule(Dav1dCudaIntraDesc *descs, int n, int bw4, int bh4,
+                                             int ss_hor, int ss_ver, int32_t *order,
+                                             int32_t *level_start, int max_levels);
+
+/* One launch per dependency level over level-sorted descriptors (device).
+ * `level_start` is a HOST array of n_levels + 1 sorted offsets.  `pal` /
+ * `pal_idx` are the palette pixel pool and the packed index pool (device). */
+DAV1D_CUDA_API int dav1d_cuda_intra_batch(Dav1dCudaContext *c, const Dav1dCudaPicture *dst,
+                                          int bw4, int bh4, void *cf,
+                                          const Dav1dCudaIntraDesc *descs,
+                                          const int32_t *level_start, int n_levels,
+                                          const void *pal, const uint8_t *pal_idx);
+
+/* A whole frame's reconstruction as device-resident batches:
+ *   phase A  motion compensation (put, fused compound in two waves, warp)
+ *   phase B  inter residuals (itxfm_add per size class)
+ *   phase C  intra-class operations, one launch per dependency level.
+ * Replaces pass 2 (DAV1D_TASK_TYPE_TILE_RECONSTRUCTION, thread_task.c:757-761)
+ * for one frame.  Asynchronous on the context's stream. */
+typedef struct Dav1dCudaReconBatch {
+    const Dav1dCudaPicture *dst;
+    const Dav1dCudaPicture *refs[7];
+    int32_t bw4, bh4;                 /* f->bw, f->bh: frame size in 4-px units */
+    void *cf;                         /* device coefficient stream */
+    uint8_t *masks;                   /* device: wedge masks / emitted seg masks */
+    const void *pal;                  /* device: palette pixels */
+    const uint8_t *pal_idx;           /* device: packed palette indices */
+    const Dav1dCudaMcDesc *mc_put;    const uint32_t *mc_put_tiles;  int32_t n_mc_put_tiles;
+    const Dav1dCudaMcDesc *mc_comp;   const uint32_t *mc_comp_tiles; int32_t n_mc_comp_tiles[2];
+    const Dav1dCudaWarpDesc *warp;    int32_t n_warp;
+    const Dav1dCudaItxDesc *itx;      int32_t itx_class_count[DAV1D_CUDA_N_RECT_TX_SIZES];
+    const Dav1dCudaIntraDesc *intra;  const int32_t *intra_level_start; int32_t n_levels;
+} Dav1dCudaReconBatch;
+
+DAV1D_CUDA_API int dav1d_cuda_recon_submit(Dav1dCudaContext *c, const Dav1dCudaReconBatch *b);
+/* Same, but the launches are captured into a CUDA graph once and replayed:
+ * dav1d_cuda_recon_graph_build() records `b`, dav1d_cuda_recon_graph_launch()
+ * replays it on the context's stream (the device buffers `b` points to may be
+ * rewritten between launches, their addresses and counts may not). */
+typedef struct Dav1dCudaReconGraph Dav1dCudaReconGraph;
+DAV1D_CUDA_API int dav1d_cuda_recon_graph_build(Dav1dCudaContext *c, const Dav1dCudaReconBatch *b,
+                                                Dav1dCudaReconGraph **out);
+DAV1D_CUDA_API int dav1d_cuda_recon_graph_launch(Dav1dCudaContext *c, Dav1dCudaReconGraph *g);
+DAV1D_CUDA_API void dav1d_cuda_recon_graph_free(Dav1dCudaReconGraph *g);
+
+/* Plain device memory for descriptor arrays / coefficient streams. */
+DAV1D_CUDA_API void *dav1d_cuda_malloc(size_t bytes);
+DAV1D_CUDA_API void  dav1d_cuda_free(void *p);
+DAV1D_CUDA_API int   dav1d_cuda_upload(Dav1dCudaContext *c, void *dev, const void *host, size_t bytes);
+DAV1D_CUDA_API int   dav1d_cuda_download(Dav1dCudaContext *c, void *host, const void *dev, size_t bytes);
+DAV1D_CUDA_API void *dav1d_cuda_host_alloc(size_t bytes);   /* pinned */
+DAV1D_CUDA_API void  dav1d_cuda_host_free(void *p);
+/* CUDA-event timing on the context's stream (bench.py times the launching stream). */
+DAV1D_CUDA_API void *dav1d_cuda_event_create(void);
+DAV1D_CUDA_API int   dav1d_cuda_event_record(Dav1dCudaContext *c, void *ev);
+DAV1D_CUDA_API float dav1d_cuda_event_elapsed_ms(void *start, void *stop);   /* syncs on stop */
+DAV1D_CUDA_API void  dav1d_cuda_event_destroy(void *ev);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,55 @@
+"""Run the sequential frame-level oracle (oracle/ref_frame.c inside
+oracle/_ref/libdav1d_ref.so) on a HostFrame. TEST INFRASTRUCTURE ONLY."""
+import ctypes as C
+
+import numpy as np
+
+import _d1pkg
+
+pkg = _d1pkg.load_pkg()
+
+
+class OracleFrame(C.Structure):
+    _fields_ = [("dst", C.c_void_p * 3), ("dst_stride", C.c_ssize_t * 3),
+                ("ref", (C.c_void_p * 3) * 7), ("ref_stride", (C.c_ssize_t * 3) * 7),
+                ("w", C.c_int32), ("h", C.c_int32), ("ss_hor", C.c_int32), ("ss_ver", C.c_int32),
+                ("bitdepth_max", C.c_int32), ("bw4", C.c_int32), ("bh4", C.c_int32),
+                ("cf", C.c_void_p), ("masks", C.c_void_p), ("pal", C.c_void_p), ("pal_idx", C.c_void_p),
+                ("mc_put", C.c_void_p), ("mc_comp", C.c_void_p), ("warp", C.c_void_p), ("itx", C.c_void_p),
+                ("intra", C.c_void_p), ("order", C.c_void_p), ("n_order", C.c_int32)]
+
+
+def make_oracle_frame(hf, dst_planes, ref_planes_list, keep):
+    """dst_planes: list of numpy planes (modified in place); ref_planes_list: list (per ref) of plane lists."""
+    of = OracleFrame()
+    npl = len(dst_planes)
+    for pl in range(3):
+        if pl < npl:
+            of.dst[pl] = dst_planes[pl].ctypes.data
+            of.dst_stride[pl] = dst_planes[pl].strides[0]
+    for r, planes in enumerate(ref_planes_list):
+        for pl in range(npl):
+            of.ref[r][pl] = planes[pl].ctypes.data
+            of.ref_stride[r][pl] = planes[pl].strides[0]
+    of.w, of.h = hf.w, hf.h
+    of.ss_hor, of.ss_ver = hf.ss_hor, hf.ss_ver
+    of.bitdepth_max = hf.bdmax
+    of.bw4, of.bh4 = hf.bw4, hf.bh4
+    masks = hf.masks.copy()       # W_MASK writes into it
+    keep.append(masks)
+    for name, arr in (("cf", hf.cf), ("masks", masks), ("pal", hf.pal), ("pal_idx", hf.pal_idx),
+                      ("mc_put", hf.mc_put), ("mc_comp", hf.mc_comp), ("warp", hf.warp), ("itx", hf.itx),
+                      ("intra", hf.intra), ("order", hf.order)):
+        setattr(of, name, arr.ctypes.data if arr.nbytes else None)
+    of.n_order = hf.order.nbytes // 4
+    return of
+
+
+def run_oracle(ref, hf, dst_planes, ref_planes_list):
+    keep = []
+    of = make_oracle_frame(hf, dst_planes, ref_planes_list, keep)
+    fn = ref.lib.oracle_ref_frame_run
+    fn.argtypes = [C.POINTER(OracleFrame)]
+    fn.restype = None
+    fn(C.byref(of))
+    return dst_planes

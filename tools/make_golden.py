@@ -1,0 +1,25 @@
+#!/usr/bin/env python3
+"""Write tests/golden/frame_md5.json: MD5 of the frames the reference-driven
+oracle (oracle/_ref, i.e. the reference's own C templates) reconstructs for the
+fixed synthetic cases of tests/test_frame.py.  Run in the container that has
+/root/reference (after `make -C oracle ref`)."""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import refdsp  # noqa: E402
+import test_frame as T  # noqa: E402
+
+ref = refdsp.RefDSP()
+out = {}
+for name, (w, h, bd, seed, kw) in T.CASES.items():
+    hf = T.F.HostFrame(w, h, bd, seed, **kw)
+    _, _, planes = T.oracle_planes(ref, hf, seed)
+    out[name] = T.md5_planes(planes)
+    print(name, out[name], "blocks", hf.n_blocks, "intra", hf.n_intra_blocks, "levels", hf.schedule())
+with open(T.GOLDEN, "w") as f:
+    json.dump(out, f, indent=1, sort_keys=True)
