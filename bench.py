@@ -1,0 +1,350 @@
+#!/usr/bin/env python3
+"""Headline benchmark: Mpix/s of mc + itx + ipred reconstruction per B200.
+
+Workload (BASELINE.json configs[3]/[4]): full synthetic 4K 10-bit 4:2:0 frame
+reconstruction - motion compensation (put / fused compound / warp), inter
+residual inverse transforms and level-scheduled intra prediction (+CfL,
+palette, filter-intra) - for `--streams` independent streams per GPU, each
+with its own reference frames in HBM.  A step = one frame of every stream.
+
+  python bench.py --gpus N --steps K --warmup W            (our CUDA path)
+  python bench.py --impl reference ...                     (reference C templates on host cores)
+
+`value`  : luma Mpix/s with descriptors/coefficients/refs resident in HBM.
+`e2e`    : same metric through the C ABI with HOST buffers - every step ships
+           descriptors + coefficients H2D from pinned memory and reads the
+           reconstructed frame back D2H, inside the timed region.
+Timing: CUDA events on the launching streams (fork/join through events), max
+over ranks.  No collectives on the data path (streams are independent).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+L2_MB = 126.0
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--streams", type=int, default=8, help="independent 4K streams per GPU")
+    ap.add_argument("--width", type=int, default=3840)
+    ap.add_argument("--height", type=int, default=2160)
+    ap.add_argument("--bitdepth-max", type=lambda s: int(s, 0), default=0x3ff)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+# ------------------------------------------------------------------ reference arm / cpu baseline
+def cpu_reference_run(args, steps, warmup, frames_per_step=None):
+    """Times the reference's own C templates (oracle/_ref, compiled from /root/reference) replaying
+    the same descriptors sequentially, one frame per host thread."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import _d1pkg
+    _d1pkg.load_pkg()
+    from dav1d_mirror_b200 import frame as F
+    import refdsp
+    import refframe
+    ref = refdsp.RefDSP()
+    cores = os.cpu_count() or 1
+    n = frames_per_step or cores
+    # a bounded sample: n frames (distinct seeds cycle over 4 descriptor sets)
+    hfs = [F.HostFrame(args.width, args.height, args.bitdepth_max, 1000 + i) for i in range(min(n, 4))]
+    keep, ofs = [], (refframe.OracleFrame * n)()
+    refs_by_set = [[F.random_planes(hf, 7 + r) for r in range(2)] for hf in hfs]
+    for i in range(n):
+        hf = hfs[i % len(hfs)]
+        dst = F.random_planes(hf, 99 + i)
+        keep.append(dst)
+        ofs[i] = refframe.make_oracle_frame(hf, dst, refs_by_set[i % len(hfs)], keep)
+    fn = ref.lib.oracle_ref_frames_run_mt
+    fn.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    fn.restype = None
+    for _ in range(warmup):
+        fn(ofs, n, cores)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        fn(ofs, n, cores)
+    dt = time.perf_counter() - t0
+    luma = hfs[0].luma_px
+    mpix = n * steps * luma / dt / 1e6
+    return {"value": mpix, "unit": "Mpix/s", "cores": min(cores, n), "kind": "reference",
+            "sample": f"{n} frames/step x {steps} steps of {args.width}x{args.height} "
+                      f"{'10' if args.bitdepth_max == 0x3ff else '12' if args.bitdepth_max > 0x3ff else '8'}-bit 4:2:0, "
+                      f"reference C templates (gcc -O3, no asm: no nasm in the image), one frame per thread",
+            "seconds": dt, "ms_per_step": dt / steps * 1e3}
+
+
+def main_reference(args):
+    rank, world, local = dist_env()
+    if rank != 0:
+        return
+    r = cpu_reference_run(args, max(1, args.steps), max(0, min(args.warmup, 1)))
+    out = {"metric": "Mpix/s of mc+itx+ipred recon", "impl": "reference", "value": r["value"], "unit": "Mpix/s",
+           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u16" if args.bitdepth_max > 0xff else "u8",
+           "data": "synthetic",
+           "config": workload_config(args, None),
+           "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+           "e2e": {"value": r["value"], "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+def workload_config(args, extra):
+    bits = 10 if args.bitdepth_max == 0x3ff else 12 if args.bitdepth_max > 0x3ff else 8
+    cfg = {"workload": f"full synthetic {args.width}x{args.height} {bits}-bit 4:2:0 reconstruction "
+                       f"(MC put/compound/warp + itx + level-scheduled intra/CfL/palette), "
+                       f"{args.streams} independent streams per GPU (BASELINE configs[3]/[4])",
+           "streams_per_gpu": args.streams, "frame": [args.width, args.height], "bitdepth": bits,
+           "mix": "30% intra blocks, 60% blocks with residual, inter: put 50/avg 20/w_avg 10/wedge 10/seg 5/warp 5",
+           "parallelism": "independent streams, no collective"}
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+# ------------------------------------------------------------------ our arm
+def main_ours(args):
+    rank, world, local = dist_env()
+    import torch
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    import _d1pkg
+    pkg = _d1pkg.load_pkg()
+    from dav1d_mirror_b200 import frame as F
+    L = pkg.lib()
+    if not L.dav1d_cuda_available():
+        raise RuntimeError("no CUDA device: this benchmark has no CPU fallback")
+    S = args.streams
+    # ---- build S streams (contexts) with their own pictures + descriptor sets
+    n_sets = min(S, 4)
+    hfs = [F.HostFrame(args.width, args.height, args.bitdepth_max, 1000 + 17 * rank + i) for i in range(n_sets)]
+    for hf in hfs:
+        hf.schedule()
+    ctxs, dfs = [], []
+    main_ctx = F.open_context(local)
+    for s in range(S):
+        ctx = F.open_context(local)
+        hf = hfs[s % n_sets]
+        df = F.DeviceFrame(ctx, hf, n_refs=2)
+        df.upload_descriptors()
+        for r in range(2):
+            df.upload_picture(df.refs[r], F.random_planes(hf, 7 + r + 10 * s))
+        df.upload_picture(df.dst, F.random_planes(hf, 99 + s))
+        L.dav1d_cuda_synchronize(ctx)
+        if not args.no_graph:
+            df.build_graph()
+        ctxs.append(ctx)
+        dfs.append(df)
+    pkg.check_error()
+    luma_px = hfs[0].luma_px
+    algo_step = sum(dfs[s].hf.algo_bytes for s in range(S))
+    footprint_mb = S * (3 * args.width * args.height * 1.5 * (2 if args.bitdepth_max > 0xff else 1) +
+                        hfs[0].host_bytes()) / 1e6
+
+    ev_start, ev_stop = L.dav1d_cuda_event_create(), L.dav1d_cuda_event_create()
+    ev_done = [L.dav1d_cuda_event_create() for _ in range(S)]
+
+    def run_step(e2e=False):
+        for s in range(S):
+            df = dfs[s]
+            if e2e:
+                df.upload_descriptors_pinned()
+            if args.no_graph:
+                df.submit()
+            else:
+                df.launch_graph()
+            if e2e:
+                df.download_pinned()
+
+    def timed(nsteps, e2e=False):
+        """fork: every stream waits for ev_start; join: main stream waits for every stream's done event."""
+        L.dav1d_cuda_event_record(main_ctx, ev_start)
+        for s in range(S):
+            L.dav1d_cuda_stream_wait_event(ctxs[s], ev_start)
+        for _ in range(nsteps):
+            run_step(e2e)
+        for s in range(S):
+            L.dav1d_cuda_event_record(ctxs[s], ev_done[s])
+            L.dav1d_cuda_stream_wait_event(main_ctx, ev_done[s])
+        L.dav1d_cuda_event_record(main_ctx, ev_stop)
+        return L.dav1d_cuda_event_elapsed_ms(ev_start, ev_stop)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    # ---- warm-up + timed region (device-resident)
+    for _ in range(max(args.warmup, 3)):
+        run_step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = L.dav1d_cuda_launch_count()
+    barrier()
+    ms = timed(args.steps)
+    barrier()
+    launches = L.dav1d_cuda_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms = max_over_ranks(ms)
+    pkg.check_error()
+    value = world * S * args.steps * luma_px / (ms * 1e-3) / 1e6
+
+    # ---- end to end with host buffers (pinned), copies inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        for df in dfs:
+            df.alloc_pinned()
+        for _ in range(2):
+            run_step(e2e=True)
+        barrier()
+        e2e_steps = max(3, min(args.steps, 10))
+        ems = max_over_ranks(timed(e2e_steps, e2e=True))
+        barrier()
+        pkg.check_error()
+        h2d = sum(df.hf.host_bytes() for df in dfs)
+        d2h = sum(df.pinned_out_bytes for df in dfs)
+        e2e = {"value": world * S * e2e_steps * luma_px / (ems * 1e-3) / 1e6, "unit": "Mpix/s",
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
+               "ms_per_step": ems / e2e_steps}
+
+    # ---- per-launch-class timing of stream 0's frame (roofline of the dominant kernel)
+    roof = None
+    if rank == 0:
+        peak, peak_src = peaks()
+        cls_ms = dfs[0].time_classes(reps=5, flush_mb=256)
+        dom = max(cls_ms, key=lambda k: cls_ms[k])
+        alg = dfs[0].hf.algo_class[dom]
+        achieved = alg / (cls_ms[dom] * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes": alg, "ms": cls_ms[dom],
+                "per_class_ms": cls_ms,
+                "per_class_gbs": {k: (dfs[0].hf.algo_class[k] / (v * 1e-3) / 1e9 if v > 0 else None)
+                                  for k, v in cls_ms.items()},
+                "frame_algorithmic_bytes": dfs[0].hf.algo_bytes,
+                "whole_step": {"achieved": world * algo_step * args.steps / (ms * 1e-3) / 1e9 / world,
+                               "frac": algo_step * args.steps / (ms * 1e-3) / 1e9 / peak}}
+
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        # bounded sample: one frame per host thread, a few steps (about 10-30 s of CPU work in total)
+        r = cpu_reference_run(args, steps=3, warmup=1)
+        cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        out = {"metric": "Mpix/s of mc+itx+ipred recon", "value": value, "unit": "Mpix/s", "n_gpus": world,
+               "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+               "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": "u16" if args.bitdepth_max > 0xff else "u8", "data": "synthetic",
+               "config": workload_config(args, {
+                   "l2": f"inputs larger than L2: working set {footprint_mb:.0f} MB per GPU vs {L2_MB:.0f} MB L2"
+                   if footprint_mb > 2 * L2_MB else f"working set {footprint_mb:.0f} MB; L2 NOT exceeded",
+                   "cuda_graph": not args.no_graph,
+                   "levels": [int(df.hf.n_levels) for df in dfs[:n_sets]],
+                   "launches_per_frame": int(launches / max(1, args.steps * S))}),
+               "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
+               "hbm_frac_of_8TBs": algo_step * args.steps / (ms * 1e-3) / 8e12}
+        print(json.dumps(out), flush=True)
+    for df in dfs:
+        df.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        main_reference(a)
+    else:
+        main_ours(a)

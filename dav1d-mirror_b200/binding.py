@@ -134,6 +134,14 @@ class ReconBatch(C.Structure):
 
 
 def bind_frame_api(L):
+    L.dav1d_cuda_mc_put_batch.argtypes = [C.c_void_p, C.POINTER(Picture), C.POINTER(C.POINTER(Picture)),
+                                          C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    L.dav1d_cuda_mc_compound_batch.argtypes = [C.c_void_p, C.POINTER(Picture), C.POINTER(C.POINTER(Picture)),
+                                               C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    L.dav1d_cuda_warp_batch.argtypes = [C.c_void_p, C.POINTER(Picture), C.POINTER(C.POINTER(Picture)),
+                                        C.c_void_p, C.c_int]
+    L.dav1d_cuda_intra_batch.argtypes = [C.c_void_p, C.POINTER(Picture), C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                         C.POINTER(C.c_int32), C.c_int, C.c_void_p, C.c_void_p]
     L.dav1d_cuda_intra_schedule.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                             C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int]
     L.dav1d_cuda_recon_submit.argtypes = [C.c_void_p, C.POINTER(ReconBatch)]
@@ -145,11 +153,13 @@ def bind_frame_api(L):
     L.dav1d_cuda_free.argtypes = [C.c_void_p]
     L.dav1d_cuda_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
     L.dav1d_cuda_download.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+    L.dav1d_cuda_memset.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t]
     L.dav1d_cuda_host_alloc.restype = C.c_void_p
     L.dav1d_cuda_host_alloc.argtypes = [C.c_size_t]
     L.dav1d_cuda_host_free.argtypes = [C.c_void_p]
     L.dav1d_cuda_event_create.restype = C.c_void_p
     L.dav1d_cuda_event_record.argtypes = [C.c_void_p, C.c_void_p]
+    L.dav1d_cuda_stream_wait_event.argtypes = [C.c_void_p, C.c_void_p]
     L.dav1d_cuda_event_elapsed_ms.restype = C.c_float
     L.dav1d_cuda_event_elapsed_ms.argtypes = [C.c_void_p, C.c_void_p]
     L.dav1d_cuda_event_destroy.argtypes = [C.c_void_p]

@@ -358,6 +358,10 @@ int dav1d_cuda_download(Dav1dCudaContext *c, void *host, const void *dev, size_t
     D1_CHECK(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, c->stream));
     return 0;
 }
+int dav1d_cuda_memset(Dav1dCudaContext *c, void *dev, int value, size_t bytes) {
+    D1_CHECK(cudaMemsetAsync(dev, value, bytes, c->stream));
+    return 0;
+}
 void *dav1d_cuda_host_alloc(size_t bytes) {
     void *p = nullptr;
     if (!cuda_ok(cudaMallocHost(&p, bytes ? bytes : 1), "cudaMallocHost")) return nullptr;
@@ -371,6 +375,10 @@ void *dav1d_cuda_event_create(void) {
 }
 int dav1d_cuda_event_record(Dav1dCudaContext *c, void *ev) {
     D1_CHECK(cudaEventRecord((cudaEvent_t)ev, c->stream));
+    return 0;
+}
+int dav1d_cuda_stream_wait_event(Dav1dCudaContext *c, void *ev) {
+    D1_CHECK(cudaStreamWaitEvent(c->stream, (cudaEvent_t)ev, 0));
     return 0;
 }
 float dav1d_cuda_event_elapsed_ms(void *start, void *stop) {

@@ -55,6 +55,7 @@ typedef struct D1SynthFrame {
     uint32_t *order;           int32_t n_order;    // (class << 28) | index, decode order
     int32_t bw4, bh4;
     double algo_bytes;         // algorithmic HBM bytes of the frame (SURVEY 8d accounting)
+    double algo_class[5];      // same, split by launch class: put, compound, warp, itx, intra
     double luma_px;            // luma pixels covered
     int64_t n_blocks, n_intra_blocks;
 } D1SynthFrame;
@@ -110,6 +111,9 @@ struct Gen {
     std::vector<uint8_t> decoded[3];             // per plane, 4x4 cells
     int pw4[3], ph4[3];
     double algo = 0, luma_px = 0;
+    double algo_cls[5] = { 0, 0, 0, 0, 0 };
+    int cur_cls = 0;
+    void add_bytes(int cls, double b) { algo += b; algo_cls[cls] += b; }
     int64_t n_blocks = 0, n_intra_blocks = 0;
     int Bp, Bc;
 
@@ -154,7 +158,7 @@ struct Gen {
             if (!last) { c[1 % (sw * sh)] = 1; last = 1; }
         }
         *eob_out = (int16_t)(cls == 0 ? 0 : std::min(last, sw * sh - 1));
-        algo += (double)sw * sh * Bc;
+        add_bytes(cur_cls, (double)sw * sh * Bc);
         return off;
     }
 
@@ -176,8 +180,9 @@ struct Gen {
         d.plane = (uint8_t)pl; d.x = (uint16_t)(x4 * 4); d.y = (uint16_t)(y4 * 4);
         d.tx = (uint8_t)tx;
         d.txtp = (uint8_t)(P.only_txtp >= 0 ? P.only_txtp : pick_txtp(rng, tx));
+        cur_cls = 3;
         d.coef_off = emit_coefs(tx, d.txtp, &d.eob);
-        algo += 2.0 * Bp * TXW4[tx] * TXH4[tx] * 16;
+        add_bytes(3, 2.0 * Bp * TXW4[tx] * TXH4[tx] * 16);
         order.push_back({ 3, (uint32_t)itx.size() });
         itx.push_back(d);
     }
@@ -202,14 +207,15 @@ struct Gen {
             d.edge_flags = (uint8_t)((tr ? 1 : 0) | (bl ? 8 : 0));
         }
         const int w = tw4 * 4, h = th4 * 4;
+        cur_cls = 4;
         if (mode == DAV1D_CUDA_INTRA_PAL) {
             d.coef_off = idx_off;
-            algo += (double)Bp * w * h + 0.5 * w * h;
+            add_bytes(4, (double)Bp * w * h + 0.5 * w * h);
         } else {
-            if (mode != DAV1D_CUDA_INTRA_NONE) algo += (double)Bp * (2 * w + 2 * h + 1);
-            if (mode == DAV1D_CUDA_INTRA_CFL) algo += (double)Bp * (w << P.ss_hor) * (h << P.ss_ver);
-            if (mode != DAV1D_CUDA_INTRA_NONE || residual) algo += (double)Bp * w * h;   // final write
-            if (mode == DAV1D_CUDA_INTRA_NONE) algo += (double)Bp * w * h;               // read back pal pred
+            if (mode != DAV1D_CUDA_INTRA_NONE) add_bytes(4, (double)Bp * (2 * w + 2 * h + 1));
+            if (mode == DAV1D_CUDA_INTRA_CFL) add_bytes(4, (double)Bp * (w << P.ss_hor) * (h << P.ss_ver));
+            if (mode != DAV1D_CUDA_INTRA_NONE || residual) add_bytes(4, (double)Bp * w * h);   // final write
+            if (mode == DAV1D_CUDA_INTRA_NONE) add_bytes(4, (double)Bp * w * h);               // read back pal pred
             if (residual) {
                 d.tx = (uint8_t)tx_from_dims(tw4, th4);
                 d.txtp = (uint8_t)pick_txtp(rng, d.tx);
@@ -355,7 +361,7 @@ struct Gen {
                         order.push_back({ 2, (uint32_t)warp.size() });
                         warp.push_back(d);
                     }
-                algo += 2.0 * Bp * w * h;
+                add_bytes(2, 2.0 * Bp * w * h);
                 continue;
             }
             Dav1dCudaMcDesc d;
@@ -366,12 +372,12 @@ struct Gen {
             d.src[1] = make_src(pl, bx4, by4, ref[1], mvx[1], mvy[1], filter);
             bool wave1 = false;
             if (kind == DAV1D_CUDA_MC_PUT) {
-                algo += 2.0 * Bp * w * h;
+                add_bytes(0, 2.0 * Bp * w * h);
                 order.push_back({ 0, (uint32_t)put.size() });
                 put.push_back(d);
                 continue;
             }
-            algo += 3.0 * Bp * w * h;
+            add_bytes(1, 3.0 * Bp * w * h);
             if (kind == DAV1D_CUDA_MC_W_AVG) d.weight = (uint8_t)weight;
             if (kind == DAV1D_CUDA_MC_MASK || kind == DAV1D_CUDA_MC_W_MASK) {
                 if (sign) std::swap(d.src[0], d.src[1]);   // tmp[mask_sign], tmp[!mask_sign]
@@ -380,7 +386,7 @@ struct Gen {
                 wedge_off[pl] = (uint32_t)masks.size();
                 for (int i = 0; i < w * h; i++) masks.push_back((uint8_t)rng.range(65));
                 d.aux_off = wedge_off[pl];
-                algo += (double)w * h;
+                add_bytes(1, (double)w * h);
             } else if (kind == DAV1D_CUDA_MC_W_MASK) {
                 if (pl == 0) {
                     const int lay = P.no_chroma ? 0 : (P.ss_hor ? (P.ss_ver ? 2 : 1) : 0);
@@ -388,12 +394,12 @@ struct Gen {
                     seg_off = (uint32_t)masks.size();
                     masks.resize(masks.size() + (size_t)mw * mh, 0);
                     d.aux_off = seg_off; d.mask_ss = (uint8_t)lay; d.weight = (uint8_t)sign;
-                    algo += (double)mw * mh;
+                    add_bytes(1, (double)mw * mh);
                 } else {
                     d.kind = DAV1D_CUDA_MC_MASK;            // chroma reuses the luma-derived mask
                     d.aux_off = seg_off;
                     wave1 = true;
-                    algo += (double)w * h;
+                    add_bytes(1, (double)w * h);
                 }
             }
             if (wave1) { order.push_back({ 5, (uint32_t)comp1.size() }); comp1.push_back(d); }
@@ -558,6 +564,7 @@ __attribute__((visibility("default"))) int d1synth_generate(const D1SynthParams 
     f->order = dup(order); f->n_order = (int32_t)order.size();
     f->bw4 = g.bw4; f->bh4 = g.bh4;
     f->algo_bytes = g.algo; f->luma_px = g.luma_px;
+    for (int i = 0; i < 5; i++) f->algo_class[i] = g.algo_cls[i];
     f->n_blocks = g.n_blocks; f->n_intra_blocks = g.n_intra_blocks;
     return 0;
 }

@@ -38,7 +38,7 @@ class SynthFrame(C.Structure):
                 ("pal_idx", C.c_void_p), ("pal_idx_bytes", C.c_uint64),
                 ("order", C.c_void_p), ("n_order", C.c_int32),
                 ("bw4", C.c_int32), ("bh4", C.c_int32),
-                ("algo_bytes", C.c_double), ("luma_px", C.c_double),
+                ("algo_bytes", C.c_double), ("algo_class", C.c_double * 5), ("luma_px", C.c_double),
                 ("n_blocks", C.c_int64), ("n_intra_blocks", C.c_int64)]
 
 
@@ -103,6 +103,7 @@ class HostFrame:
         self.pal_idx = _np_from(f.pal_idx, f.pal_idx_bytes)
         self.order = _np_from(f.order, f.n_order * 4)
         self.algo_bytes, self.luma_px = f.algo_bytes, f.luma_px
+        self.algo_class = dict(zip(("mc_put", "mc_compound", "warp", "itx", "intra"), list(f.algo_class)))
         self.n_blocks, self.n_intra_blocks = f.n_blocks, f.n_intra_blocks
         S.d1synth_free(C.byref(f))
         self.intra_sorted = None
@@ -215,6 +216,86 @@ class DeviceFrame:
         self.L.dav1d_cuda_synchronize(self.ctx)
         return out
 
+    # ---- end-to-end path: host buffers in pinned memory
+    def alloc_pinned(self):
+        if getattr(self, "_pinned", None):
+            return
+        L = self.L
+        self._pinned = {}
+        for name, arr in self._host.items():
+            if not arr.nbytes:
+                continue
+            p = L.dav1d_cuda_host_alloc(arr.nbytes)
+            C.memmove(p, arr.ctypes.data, arr.nbytes)
+            self._pinned[name] = (p, arr.nbytes)
+        hf = self.hf
+        self._pinned_out = []
+        self.pinned_out_bytes = 0
+        for pl in range(1 if hf.no_chroma else 3):
+            hh, ww = hf.plane_shape(pl)
+            row = ww * (2 if hf.hbd else 1)
+            p = L.dav1d_cuda_host_alloc(row * hh)
+            self._pinned_out.append((p, row))
+            self.pinned_out_bytes += row * hh
+
+    def upload_descriptors_pinned(self):
+        for name, (p, n) in self._pinned.items():
+            self.L.dav1d_cuda_upload(self.ctx, self._dev[name], p, n)
+
+    def download_pinned(self):
+        for pl, (p, row) in enumerate(self._pinned_out):
+            self.L.dav1d_cuda_picture_download(self.ctx, C.byref(self.dst), pl, p, row)
+
+    def pinned_planes(self):
+        """numpy views of the last downloaded frame (after a synchronize)."""
+        hf = self.hf
+        out = []
+        for pl, (p, row) in enumerate(self._pinned_out):
+            hh, ww = hf.plane_shape(pl)
+            a = np.frombuffer((C.c_char * (row * hh)).from_address(p), dtype=np.uint16 if hf.hbd else np.uint8)
+            out.append(a.reshape(hh, ww))
+        return out
+
+    # ---- per-launch-class timing (CUDA events on this context's stream)
+    def time_classes(self, reps=5, flush_mb=256):
+        L, ctx, b = self.L, self.ctx, self.batch
+        refs = (C.POINTER(B.Picture) * 7)(*[b.refs[i] for i in range(7)])
+        flush = L.dav1d_cuda_malloc(flush_mb << 20)
+        e0, e1 = L.dav1d_cuda_event_create(), L.dav1d_cuda_event_create()
+        ntc0, ntc1 = b.n_mc_comp_tiles[0], b.n_mc_comp_tiles[1]
+        cls_count = (C.c_int32 * 19)(*[b.itx_class_count[i] for i in range(19)])
+
+        def run(name):
+            if name == "mc_put":
+                L.dav1d_cuda_mc_put_batch(ctx, b.dst, refs, b.mc_put, b.mc_put_tiles, b.n_mc_put_tiles, None)
+            elif name == "mc_compound":
+                L.dav1d_cuda_mc_compound_batch(ctx, b.dst, refs, b.mc_comp, b.mc_comp_tiles, ntc0, b.masks)
+                if ntc1:
+                    L.dav1d_cuda_mc_compound_batch(ctx, b.dst, refs, b.mc_comp, b.mc_comp_tiles + 4 * ntc0, ntc1,
+                                                   b.masks)
+            elif name == "warp":
+                L.dav1d_cuda_warp_batch(ctx, b.dst, refs, b.warp, b.n_warp)
+            elif name == "itx":
+                L.dav1d_cuda_itx_batch(ctx, b.dst, b.cf, b.itx, cls_count, 0)
+            else:
+                L.dav1d_cuda_intra_batch(ctx, b.dst, b.bw4, b.bh4, b.cf, b.intra, b.intra_level_start, b.n_levels,
+                                         b.pal, b.pal_idx)
+
+        out = {}
+        for name in ("mc_put", "mc_compound", "warp", "itx", "intra"):
+            tot = 0.0
+            for _ in range(reps):
+                L.dav1d_cuda_memset(ctx, flush, 0, flush_mb << 20)     # evict L2
+                L.dav1d_cuda_event_record(ctx, e0)
+                run(name)
+                L.dav1d_cuda_event_record(ctx, e1)
+                tot += L.dav1d_cuda_event_elapsed_ms(e0, e1)
+            out[name] = tot / reps
+        L.dav1d_cuda_event_destroy(e0)
+        L.dav1d_cuda_event_destroy(e1)
+        L.dav1d_cuda_free(flush)
+        return out
+
     def submit(self):
         r = self.L.dav1d_cuda_recon_submit(self.ctx, C.byref(self.batch))
         if r:
@@ -243,6 +324,11 @@ class DeviceFrame:
         for p in self._dev.values():
             L.dav1d_cuda_free(p)
         self._dev = {}
+        for p, _ in getattr(self, "_pinned", {}).values():
+            L.dav1d_cuda_host_free(p)
+        for p, _ in getattr(self, "_pinned_out", []):
+            L.dav1d_cuda_host_free(p)
+        self._pinned, self._pinned_out = {}, []
         for pic in [self.dst] + self.refs:
             L.dav1d_cuda_picture_free(self.ctx, C.byref(pic))
 

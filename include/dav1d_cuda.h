@@ -363,11 +363,13 @@ DAV1D_CUDA_API void *dav1d_cuda_malloc(size_t bytes);
 DAV1D_CUDA_API void  dav1d_cuda_free(void *p);
 DAV1D_CUDA_API int   dav1d_cuda_upload(Dav1dCudaContext *c, void *dev, const void *host, size_t bytes);
 DAV1D_CUDA_API int   dav1d_cuda_download(Dav1dCudaContext *c, void *host, const void *dev, size_t bytes);
+DAV1D_CUDA_API int   dav1d_cuda_memset(Dav1dCudaContext *c, void *dev, int value, size_t bytes);
 DAV1D_CUDA_API void *dav1d_cuda_host_alloc(size_t bytes);   /* pinned */
 DAV1D_CUDA_API void  dav1d_cuda_host_free(void *p);
 /* CUDA-event timing on the context's stream (bench.py times the launching stream). */
 DAV1D_CUDA_API void *dav1d_cuda_event_create(void);
 DAV1D_CUDA_API int   dav1d_cuda_event_record(Dav1dCudaContext *c, void *ev);
+DAV1D_CUDA_API int   dav1d_cuda_stream_wait_event(Dav1dCudaContext *c, void *ev);   /* orders c's stream after ev */
 DAV1D_CUDA_API float dav1d_cuda_event_elapsed_ms(void *start, void *stop);   /* syncs on stop */
 DAV1D_CUDA_API void  dav1d_cuda_event_destroy(void *ev);
 
