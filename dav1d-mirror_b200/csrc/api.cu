@@ -106,6 +106,7 @@ int dav1d_cuda_open(Dav1dCudaContext **out, int device, void *stream) {
     }
     c->tmp_pool = nullptr;
     c->tmp_pool_bytes = 0;
+    c->aux_ready = false;
     cudaDeviceProp prop;
     D1_CHECK(cudaGetDeviceProperties(&prop, device));
     c->num_sms = prop.multiProcessorCount;
@@ -120,6 +121,13 @@ void dav1d_cuda_close(Dav1dCudaContext *c) {
     if (!c) return;
     cudaStreamSynchronize(c->stream);
     if (c->tmp_pool) cudaFree(c->tmp_pool);
+    if (c->aux_ready) {
+        for (int i = 0; i < Dav1dCudaContext::N_AUX; i++) {
+            cudaStreamDestroy(c->aux[i]);
+            cudaEventDestroy(c->ev_join[i]);
+        }
+        cudaEventDestroy(c->ev_fork);
+    }
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
 }

@@ -65,4 +65,10 @@ struct Dav1dCudaContext {
     int num_sms;
     void *tmp_pool;        // int16 scratch for unfused prep/compound
     size_t tmp_pool_bytes;
+    // fork/join inside one frame: independent launch classes run on auxiliary
+    // streams (and become parallel branches when the frame is captured as a graph)
+    static constexpr int N_AUX = 3;
+    cudaStream_t aux[N_AUX];
+    cudaEvent_t ev_fork, ev_join[N_AUX];
+    bool aux_ready;
 };

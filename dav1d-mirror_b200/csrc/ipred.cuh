@@ -11,6 +11,7 @@
 #pragma once
 #include "common.cuh"
 #include "tables.cuh"
+#include "itx.cuh"     // load_px / store_px
 
 namespace d1 {
 
@@ -103,62 +104,84 @@ DEV void edge_upsample(pixel *out, const int hsz, const pixel *in, const int fro
     }
 }
 
+
+// ---- vectorised block fill: each lane produces VW = 8 (w >= 8) or 4 (w == 4)
+// consecutive pixels of a row and writes them with one 64/128-bit store.
+// Blocks are aligned to their own width (AV1 partitioning), so the vector
+// stores are naturally aligned; misaligned callers fall back to scalar stores.
+// f(x, y) -> pixel value
+template <typename pixel, typename F>
+DEV void fill_block(pixel *dst, const int dstride, const int w, const int h, const int lane, F f) {
+    if (w >= 8) {
+        const int segs = w >> 3, sh = 31 - __clz(segs);       // segs = 1, 2, 4, 8
+        const int x0 = (lane & (segs - 1)) << 3;
+        for (int y = lane >> sh; y < h; y += 32 >> sh) {
+            int v[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) v[k] = f(x0 + k, y);
+            store_px<pixel, 8>(dst + y * dstride + x0, v);
+        }
+    } else {
+        for (int y = lane; y < h; y += 32) {
+            int v[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) v[k] = f(k, y);
+            store_px<pixel, 4>(dst + y * dstride, v);
+        }
+    }
+}
+
 // All 14 predictors. `scratch`: IPRED_SCRATCH pixels of shared memory (Z modes).
 template <typename pixel>
 DEV void ipred_block(const int mode, pixel *dst, const int dstride, const pixel *edge, const int w, const int h,
                      int angle, const int max_w, const int max_h, const int bdmax, pixel *scratch, const int lane)
 {
-    const int n = w * h;
     switch (mode) {
     case M_DC: case M_TOP_DC: case M_LEFT_DC: case M_DC_128: {
         const int dc = ipred_dc_value<pixel>(mode, edge, w, h, bdmax, lane);
-        for (int i = lane; i < n; i += 32) dst[(i / w) * dstride + (i % w)] = (pixel)dc;
+        fill_block<pixel>(dst, dstride, w, h, lane, [=](int, int) { return dc; });
         break;
     }
     case M_VERT:
-        for (int i = lane; i < n; i += 32) dst[(i / w) * dstride + (i % w)] = edge[1 + (i % w)];
+        fill_block<pixel>(dst, dstride, w, h, lane, [=](int x, int) { return (int)edge[1 + x]; });
         break;
     case M_HOR:
-        for (int i = lane; i < n; i += 32) dst[(i / w) * dstride + (i % w)] = edge[-(1 + (i / w))];
+        fill_block<pixel>(dst, dstride, w, h, lane, [=](int, int y) { return (int)edge[-(1 + y)]; });
         break;
     case M_PAETH: {
         const int tl = edge[0];
-        for (int i = lane; i < n; i += 32) {
-            const int y = i / w, x = i % w;
+        fill_block<pixel>(dst, dstride, w, h, lane, [=](int x, int y) {
             const int left = edge[-(y + 1)], top = edge[1 + x];
             const int base = left + top - tl;
             const int ld = iabs(left - base), td = iabs(top - base), tld = iabs(tl - base);
-            dst[y * dstride + x] = (pixel)(ld <= td && ld <= tld ? left : td <= tld ? top : tl);
-        }
+            return ld <= td && ld <= tld ? left : td <= tld ? top : tl;
+        });
         break;
     }
     case M_SMOOTH: {
         const uint8_t *wh = g_sm_weights + w, *wv = g_sm_weights + h;
         const int right = edge[w], bottom = edge[-h];
-        for (int i = lane; i < n; i += 32) {
-            const int y = i / w, x = i % w;
+        fill_block<pixel>(dst, dstride, w, h, lane, [=](int x, int y) {
             const int p = wv[y] * edge[1 + x] + (256 - wv[y]) * bottom +
                           wh[x] * edge[-(1 + y)] + (256 - wh[x]) * right;
-            dst[y * dstride + x] = (pixel)((p + 256) >> 9);
-        }
+            return (p + 256) >> 9;
+        });
         break;
     }
     case M_SMOOTH_V: {
         const uint8_t *wv = g_sm_weights + h;
         const int bottom = edge[-h];
-        for (int i = lane; i < n; i += 32) {
-            const int y = i / w, x = i % w;
-            dst[y * dstride + x] = (pixel)((wv[y] * edge[1 + x] + (256 - wv[y]) * bottom + 128) >> 8);
-        }
+        fill_block<pixel>(dst, dstride, w, h, lane, [=](int x, int y) {
+            return (wv[y] * edge[1 + x] + (256 - wv[y]) * bottom + 128) >> 8;
+        });
         break;
     }
     case M_SMOOTH_H: {
         const uint8_t *wh = g_sm_weights + w;
         const int right = edge[w];
-        for (int i = lane; i < n; i += 32) {
-            const int y = i / w, x = i % w;
-            dst[y * dstride + x] = (pixel)((wh[x] * edge[-(y + 1)] + (256 - wh[x]) * right + 128) >> 8);
-        }
+        fill_block<pixel>(dst, dstride, w, h, lane, [=](int x, int y) {
+            return (wh[x] * edge[-(y + 1)] + (256 - wh[x]) * right + 128) >> 8;
+        });
         break;
     }
     case M_Z1: {
@@ -186,15 +209,12 @@ DEV void ipred_block(const int mode, pixel *dst, const int dstride, const pixel 
         }
         __syncwarp();
         const int inc = 1 + ups;
-        for (int i = lane; i < n; i += 32) {
-            const int y = i / w, x = i % w;
+        fill_block<pixel>(dst, dstride, w, h, lane, [=](int x, int y) {
             const int xpos = (y + 1) * dx, frac = xpos & 0x3E;
             const int base = (xpos >> 6) + x * inc;
-            int v;
-            if (base < max_base_x) v = (top[base] * (64 - frac) + top[base + 1] * frac + 32) >> 6;
-            else v = top[max_base_x];
-            dst[y * dstride + x] = (pixel)v;
-        }
+            if (base < max_base_x) return (top[base] * (64 - frac) + top[base + 1] * frac + 32) >> 6;
+            return (int)top[max_base_x];
+        });
         break;
     }
     case M_Z3: {
@@ -222,15 +242,12 @@ DEV void ipred_block(const int mode, pixel *dst, const int dstride, const pixel 
         }
         __syncwarp();
         const int inc = 1 + ups;
-        for (int i = lane; i < n; i += 32) {
-            const int y = i / w, x = i % w;
+        fill_block<pixel>(dst, dstride, w, h, lane, [=](int x, int y) {
             const int ypos = (x + 1) * dy, frac = ypos & 0x3E;
             const int base = (ypos >> 6) + y * inc;
-            int v;
-            if (base < max_base_y) v = (left[-base] * (64 - frac) + left[-(base + 1)] * frac + 32) >> 6;
-            else v = left[-max_base_y];
-            dst[y * dstride + x] = (pixel)v;
-        }
+            if (base < max_base_y) return (left[-base] * (64 - frac) + left[-(base + 1)] * frac + 32) >> 6;
+            return (int)left[-max_base_y];
+        });
         break;
     }
     case M_Z2: {
@@ -262,21 +279,21 @@ DEV void ipred_block(const int mode, pixel *dst, const int dstride, const pixel 
         __syncwarp();
         const int inc_x = 1 + ups_a;
         const pixel *left = tl - (1 + ups_l);
-        for (int i = lane; i < n; i += 32) {
-            const int y = i / w, x = i % w;
+        const pixel *tlc = tl;
+        fill_block<pixel>(dst, dstride, w, h, lane, [=](int x, int y) {
             const int xpos = ((1 + ups_a) << 6) - dx * (y + 1);
             const int base_x = (xpos >> 6) + x * inc_x;
             int v;
             if (base_x >= 0) {
                 const int fx = xpos & 0x3E;
-                v = tl[base_x] * (64 - fx) + tl[base_x + 1] * fx;
+                v = tlc[base_x] * (64 - fx) + tlc[base_x + 1] * fx;
             } else {
                 const int ypos = (y << (6 + ups_l)) - dy * (x + 1);
                 const int base_y = ypos >> 6, fy = ypos & 0x3E;
                 v = left[-base_y] * (64 - fy) + left[-(base_y + 1)] * fy;
             }
-            dst[y * dstride + x] = (pixel)((v + 32) >> 6);
-        }
+            return (v + 32) >> 6;
+        });
         break;
     }
     default: {   // M_FILTER: 4x2 sub-blocks on anti-diagonals
@@ -327,11 +344,12 @@ DEV void cfl_pred_block(const int dc_mode, pixel *dst, const int dstride, const 
                         const int16_t *ac, const int alpha, const int bdmax, const int lane)
 {
     const int dc = ipred_dc_value<pixel>(dc_mode, edge, w, h, bdmax, lane);
-    for (int i = lane; i < w * h; i += 32) {
-        const int diff = alpha * ac[i];
+    fill_block<pixel>(dst, dstride, w, h, lane, [=](int x, int y) {
+        const int diff = alpha * ac[y * w + x];
         const int m = (iabs(diff) + 32) >> 6;
-        dst[(i / w) * dstride + (i % w)] = (pixel)clip_px<pixel>(dc + (diff < 0 ? -m : m), bdmax);
-    }
+        return clip_px<pixel>(dc + (diff < 0 ? -m : m), bdmax);
+    });
+    __syncwarp();
 }
 
 // cfl_ac (ipred_tmpl.c:657-703): ac[w*h] dense from the reconstructed luma
@@ -344,11 +362,11 @@ DEV void cfl_ac_block(int16_t *ac, const pixel *ypx, const int ystride, const in
     for (int i = lane; i < w * h; i += 32) {
         const int y = imin(i / w, vh - 1), x = imin(i % w, vw - 1);
         const pixel *p = ypx + (y << ss_ver) * ystride + (x << ss_hor);
-        int s = p[0];
-        if (ss_hor) s += p[1];
+        int s = __ldcg(p);
+        if (ss_hor) s += __ldcg(p + 1);
         if (ss_ver) {
-            s += p[ystride];
-            if (ss_hor) s += p[ystride + 1];
+            s += __ldcg(p + ystride);
+            if (ss_hor) s += __ldcg(p + ystride + 1);
         }
         const int v = s << (1 + !ss_ver + !ss_hor);
         ac[i] = (int16_t)v;
@@ -429,9 +447,9 @@ DEV int prepare_edges(const int x, const int have_left, const int y, const int h
         if (have_left) {
             const int px_have = imin(sz, (h - y) << 2);
             for (int i = lane; i < sz; i += 32)
-                left[sz - 1 - i] = dst[stride * imin(i, px_have - 1) - 1];
+                left[sz - 1 - i] = __ldcg(dst + stride * imin(i, px_have - 1) - 1);
         } else {
-            const pixel v = have_top ? *dst_top : (pixel)(((1 << bitdepth) >> 1) + 1);
+            const pixel v = have_top ? __ldcg(dst_top) : (pixel)(((1 << bitdepth) >> 1) + 1);
             for (int i = lane; i < sz; i += 32) left[i] = v;
         }
         if (needs & 16) {
@@ -439,12 +457,12 @@ DEV int prepare_edges(const int x, const int have_left, const int y, const int h
             if (have_bl) {
                 const int px_have = imin(sz, (h - y - th) << 2);
                 for (int i = lane; i < sz; i += 32)
-                    left[-(i + 1)] = dst[(sz + imin(i, px_have - 1)) * stride - 1];
+                    left[-(i + 1)] = __ldcg(dst + (sz + imin(i, px_have - 1)) * stride - 1);
             } else {
                 // replicate left[0] = bottom-most left pixel
                 pixel v;
-                if (have_left) v = dst[stride * (imin(sz, (h - y) << 2) - 1) - 1];
-                else v = have_top ? *dst_top : (pixel)(((1 << bitdepth) >> 1) + 1);
+                if (have_left) v = __ldcg(dst + stride * (imin(sz, (h - y) << 2) - 1) - 1);
+                else v = have_top ? __ldcg(dst_top) : (pixel)(((1 << bitdepth) >> 1) + 1);
                 for (int i = lane; i < sz; i += 32) left[-(i + 1)] = v;
             }
         }
@@ -454,20 +472,20 @@ DEV int prepare_edges(const int x, const int have_left, const int y, const int h
         pixel *top = edge + 1;
         if (have_top) {
             const int px_have = imin(sz, (w - x) << 2);
-            for (int i = lane; i < sz; i += 32) top[i] = dst_top[imin(i, px_have - 1)];
+            for (int i = lane; i < sz; i += 32) top[i] = __ldcg(dst_top + imin(i, px_have - 1));
         } else {
-            const pixel v = have_left ? dst[-1] : (pixel)(((1 << bitdepth) >> 1) - 1);
+            const pixel v = have_left ? __ldcg(dst - 1) : (pixel)(((1 << bitdepth) >> 1) - 1);
             for (int i = lane; i < sz; i += 32) top[i] = v;
         }
         if (needs & 8) {
             const int have_tr = (!have_top || x + tw >= w) ? 0 : (edge_flags & 1);
             if (have_tr) {
                 const int px_have = imin(sz, (w - x - tw) << 2);
-                for (int i = lane; i < sz; i += 32) top[sz + i] = dst_top[sz + imin(i, px_have - 1)];
+                for (int i = lane; i < sz; i += 32) top[sz + i] = __ldcg(dst_top + sz + imin(i, px_have - 1));
             } else {
                 pixel v;   // top[sz - 1]
-                if (have_top) v = dst_top[imin(sz, (w - x) << 2) - 1];
-                else v = have_left ? dst[-1] : (pixel)(((1 << bitdepth) >> 1) - 1);
+                if (have_top) v = __ldcg(dst_top + imin(sz, (w - x) << 2) - 1);
+                else v = have_left ? __ldcg(dst - 1) : (pixel)(((1 << bitdepth) >> 1) - 1);
                 for (int i = lane; i < sz; i += 32) top[sz + i] = v;
             }
         }
@@ -476,8 +494,8 @@ DEV int prepare_edges(const int x, const int have_left, const int y, const int h
     if (needs & 4) {
         if (lane == 0) {
             int v;
-            if (have_left) v = have_top ? dst_top[-1] : dst[-1];
-            else v = have_top ? *dst_top : (1 << bitdepth) >> 1;
+            if (have_left) v = have_top ? __ldcg(dst_top - 1) : __ldcg(dst - 1);
+            else v = have_top ? __ldcg(dst_top) : (1 << bitdepth) >> 1;
             if (mode == M_Z2 && tw + th >= 6 && filter_edge_flag)
                 v = ((edge[-1] + edge[1]) * 5 + v * 6 + 8) >> 4;
             edge[0] = (pixel)v;

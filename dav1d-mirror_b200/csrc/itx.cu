@@ -78,6 +78,30 @@ static int launch_itx_tx(int tx, const ItxArgs &a, cudaStream_t st) {
     return -22;
 }
 
+// `streams`/`n_streams`: the size classes touch disjoint pixels, so they are spread
+// round-robin over the given streams (heaviest classes first on their own stream).
+int itx_batch_launch_multi(const PicView &pic, void *cf, const Dav1dCudaItxDesc *descs,
+                           const int32_t *class_count, int zero_coefs, cudaStream_t *streams, int n_streams)
+{
+    int off = 0, k = 0;
+    for (int tx = 0; tx < DAV1D_CUDA_N_RECT_TX_SIZES; tx++) {
+        const int n = class_count[tx];
+        if (n > 0) {
+            ItxArgs a;
+            a.pic = pic;
+            a.cf = cf;
+            a.descs = descs + off;
+            a.n = n;
+            a.zero_coefs = zero_coefs;
+            cudaStream_t st = streams[k++ % n_streams];
+            const int r = pic.bdmax > 0xff ? launch_itx_tx<uint16_t>(tx, a, st) : launch_itx_tx<uint8_t>(tx, a, st);
+            if (r) return r;
+            off += n;
+        }
+    }
+    return 0;
+}
+
 int itx_batch_launch(const PicView &pic, void *cf, const Dav1dCudaItxDesc *descs,
                      const int32_t *class_count, int zero_coefs, cudaStream_t st)
 {

@@ -10,7 +10,53 @@
 #pragma once
 #include "itx_1d.cuh"
 
+#if !defined(__CUDACC__)
+#define __ldcg(p) (*(p))
+#endif
+
 namespace d1 {
+
+#if defined(__CUDACC__)
+// 64/128-bit pixel vectors (L2-coherent loads); scalar fallback when misaligned.
+template <typename pixel, int VW> DEV void load_px(const pixel *p, int *v) {
+    constexpr int BYTES = VW * (int)sizeof(pixel);
+    if (((uintptr_t)p & (BYTES - 1)) == 0) {
+        uint32_t q[BYTES / 4];
+        if (BYTES == 16) { const uint4 t = __ldcg((const uint4 *)p); q[0] = t.x; q[1] = t.y; q[BYTES / 4 - 2] = t.z; q[BYTES / 4 - 1] = t.w; }
+        else if (BYTES == 8) { const uint2 t = __ldcg((const uint2 *)p); q[0] = t.x; q[BYTES / 4 - 1] = t.y; }
+        else q[0] = __ldcg((const uint32_t *)p);
+#pragma unroll
+        for (int k = 0; k < VW; k++)
+            v[k] = sizeof(pixel) == 2 ? (int)((q[k / 2] >> (16 * (k & 1))) & 0xffff) : (int)((q[k / 4] >> (8 * (k & 3))) & 0xff);
+    } else {
+#pragma unroll
+        for (int k = 0; k < VW; k++) v[k] = __ldcg(p + k);
+    }
+}
+template <typename pixel, int VW> DEV void store_px(pixel *p, const int *v) {
+    constexpr int BYTES = VW * (int)sizeof(pixel);
+    if (((uintptr_t)p & (BYTES - 1)) == 0) {
+        if (sizeof(pixel) == 2) {
+            uint32_t q[VW / 2];
+#pragma unroll
+            for (int k = 0; k < VW / 2; k++) q[k] = (uint32_t)(v[2 * k] & 0xffff) | ((uint32_t)v[2 * k + 1] << 16);
+            if (VW == 8) *(uint4 *)p = make_uint4(q[0], q[1], q[VW / 2 - 2], q[VW / 2 - 1]);
+            else *(uint2 *)p = make_uint2(q[0], q[1]);
+        } else {
+            uint32_t q[VW / 4];
+#pragma unroll
+            for (int k = 0; k < VW / 4; k++)
+                q[k] = (uint32_t)(v[4 * k] & 0xff) | ((uint32_t)(v[4 * k + 1] & 0xff) << 8) |
+                       ((uint32_t)(v[4 * k + 2] & 0xff) << 16) | ((uint32_t)v[4 * k + 3] << 24);
+            if (VW == 8) *(uint2 *)p = make_uint2(q[0], q[VW / 4 - 1]);
+            else *(uint32_t *)p = q[0];
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < VW; k++) p[k] = (pixel)v[k];
+    }
+}
+#endif
 
 struct TxDim { uint8_t w, h, shift; };
 
@@ -80,10 +126,24 @@ DEV void itx_block(const bool active, const int gl, int *tile,
         dc = (dc * 181 + 128) >> 8;
         dc = (dc + RND) >> SHIFT;
         dc = (dc * 181 + 128 + 2048) >> 12;
-        for (int i = gl; i < W * H; i += G) {
-            const int y = i / W, x = i % W;
-            pixel *p = dst + y * dstride + x;
-            *p = (pixel)clip_px<pixel>(*p + dc, bdmax);
+        // vectorised read-modify-write, 4 vectors in flight per lane
+        constexpr int VW = W < 8 ? 4 : 8, SEGS = W / VW, NV = SEGS * H;
+        for (int i0 = gl; i0 < NV; i0 += 4 * G) {
+            int v[4][VW];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int i = i0 + u * G;
+                if (i < NV) load_px<pixel, VW>(dst + (i / SEGS) * dstride + (i % SEGS) * VW, v[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int i = i0 + u * G;
+                if (i < NV) {
+#pragma unroll
+                    for (int k = 0; k < VW; k++) v[u][k] = clip_px<pixel>(v[u][k] + dc, bdmax);
+                    store_px<pixel, VW>(dst + (i / SEGS) * dstride + (i % SEGS) * VW, v[u]);
+                }
+            }
         }
     }
     // make sure every lane of the group has read cf[0] before it is cleared
@@ -103,61 +163,100 @@ DEV void itx_block(const bool active, const int gl, int *tile,
 
     const int rk = txtp_row_kind(txtp), ck = txtp_col_kind(txtp);
 
-    // ---- row pass: lane y owns coefficient row y (coeff[y + x*SH], column-major)
-    if (full) {
-        for (int y = gl; y < SH; y += G) {
-            int c[NMAX];
-            int nz = 0;
+    // ---- row pass: lane y owns coefficient row y (coeff[y + x*SH], column-major).
+    // G >= SH, so every row has its own lane.  While loading, each lane records
+    // which of its coefficients are non-zero; OR-reductions inside the group
+    // give the bounding box (nzw x nzh) of the non-zero coefficients, which
+    // selects reduced 1-D transforms (inputs beyond the box are literal zeros).
+    int c[NMAX];
+    unsigned rowmask = 0;
+    if (full && gl < SH) {
 #pragma unroll
-            for (int x = 0; x < SW; x++) {
-                int v = cf[y + x * SH];
-                nz |= v;
-                if (wht) v >>= 2;
-                else if (Geo::RECT2) v = (v * 181 + 128) >> 8;
-                c[x] = v;
-            }
+        for (int x = 0; x < SW; x++) {
+            int v = cf[gl + x * SH];
+            rowmask |= (unsigned)(v != 0) << x;
+            if (wht) v >>= 2;
+            else if (Geo::RECT2) v = (v * 181 + 128) >> 8;
+            c[x] = v;
+        }
 #pragma unroll
-            for (int x = SW; x < NMAX; x++) c[x] = 0;
-            if (zero_coefs) {
+        for (int x = SW; x < NMAX; x++) c[x] = 0;
+        if (zero_coefs) {
 #pragma unroll
-                for (int x = 0; x < SW; x++) cf[y + x * SH] = 0;
-            }
-            int *trow = tile + y * TS;
-            if (nz == 0) {
-                // an all-zero row transforms to zeros (every stage is v*c+rnd>>s and clamp)
+            for (int x = 0; x < SW; x++) cf[gl + x * SH] = 0;
+        }
+    }
+    unsigned colbits = rowmask, rowbits = rowmask ? 1u << gl : 0u;
 #pragma unroll
-                for (int x = 0; x < W; x++) trow[x] = 0;
+    for (int o = G >> 1; o > 0; o >>= 1) {
+        colbits |= __shfl_xor_sync(0xffffffffu, colbits, o);
+        rowbits |= __shfl_xor_sync(0xffffffffu, rowbits, o);
+    }
+    const int nzw = 32 - __clz(colbits), nzh = 32 - __clz(rowbits);    // 0 if the block is all zero
+    const int rows_used = SH <= 8 ? SH : nzh <= 8 ? 8 : (SH <= 16 || nzh <= 16) ? (SH < 16 ? SH : 16) : SH;
+    if (full && gl < rows_used) {
+        int *trow = tile + gl * TS;
+        if (rowmask == 0) {
+            // an all-zero row transforms to zeros (every stage is v*c+rnd>>s and clamp)
+#pragma unroll
+            for (int x = 0; x < W; x++) trow[x] = 0;
+        } else {
+            itx1d_dispatch<W>(c, rk, rowcl, nzw);
+            if (wht) {
+#pragma unroll
+                for (int x = 0; x < W; x++) trow[x] = c[x];
             } else {
-                itx1d_run<W>(c, rk, rowcl);
-                if (wht) {
 #pragma unroll
-                    for (int x = 0; x < W; x++) trow[x] = c[x];
-                } else {
-#pragma unroll
-                    for (int x = 0; x < W; x++) trow[x] = colcl((c[x] + RND) >> SHIFT);
-                }
+                for (int x = 0; x < W; x++) trow[x] = colcl((c[x] + RND) >> SHIFT);
             }
         }
     }
     __syncwarp();
-    // ---- column pass: lane x owns column x
+    // ---- column pass: lane x owns column x; only rows < rows_used of the tile are non-zero
     if (full) {
         for (int x = gl; x < W; x += G) {
-            int c[NMAX];
-#pragma unroll
-            for (int y = 0; y < SH; y++) c[y] = tile[y * TS + x];
-#pragma unroll
-            for (int y = SH; y < NMAX; y++) c[y] = 0;
-            itx1d_run<H>(c, ck, colcl);
             pixel *p = dst + x;
-            if (wht) {
+            // Read-modify-write of the destination column in chunks of CH rows.
+            // The loads of the first chunk are issued BEFORE the 1-D transform and
+            // those of chunk k+1 before the stores of chunk k, so the global-memory
+            // latency overlaps the arithmetic (otherwise every load would have to
+            // wait behind the previous store).  __ldcg: L2-coherent reads (the intra
+            // dataflow kernel consumes pixels written by other SMs in the same launch).
+            constexpr int CH = H < 16 ? H : 16;
+            int dpx[CH];
 #pragma unroll
-                for (int y = 0; y < H; y++)
-                    p[y * dstride] = (pixel)clip_px<pixel>(p[y * dstride] + c[y], bdmax);
+            for (int y = 0; y < CH; y++) dpx[y] = __ldcg(p + y * dstride);
+            if (SH > 16 && rows_used > 16) {
+#pragma unroll
+                for (int y = 0; y < SH; y++) c[y] = tile[y * TS + x];
+            } else if (SH > 8 && rows_used > 8) {
+#pragma unroll
+                for (int y = 0; y < (SH < 16 ? SH : 16); y++) c[y] = tile[y * TS + x];
+#pragma unroll
+                for (int y = 16; y < SH; y++) c[y] = 0;
             } else {
 #pragma unroll
-                for (int y = 0; y < H; y++)
-                    p[y * dstride] = (pixel)clip_px<pixel>(p[y * dstride] + ((c[y] + 8) >> 4), bdmax);
+                for (int y = 0; y < (SH < 8 ? SH : 8); y++) c[y] = tile[y * TS + x];
+#pragma unroll
+                for (int y = 8; y < SH; y++) c[y] = 0;
+            }
+#pragma unroll
+            for (int y = SH; y < NMAX; y++) c[y] = 0;
+            itx1d_dispatch<H>(c, ck, colcl, rows_used);
+#pragma unroll
+            for (int y0 = 0; y0 < H; y0 += CH) {
+                int cur[CH];
+#pragma unroll
+                for (int y = 0; y < CH; y++) cur[y] = dpx[y];
+                if (y0 + CH < H) {
+#pragma unroll
+                    for (int y = 0; y < CH; y++) dpx[y] = __ldcg(p + (y0 + CH + y) * dstride);
+                }
+#pragma unroll
+                for (int y = 0; y < CH; y++) {
+                    const int r = wht ? c[y0 + y] : (c[y0 + y] + 8) >> 4;
+                    p[(y0 + y) * dstride] = (pixel)clip_px<pixel>(cur[y] + r, bdmax);
+                }
             }
         }
     }

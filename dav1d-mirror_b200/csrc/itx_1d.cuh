@@ -679,4 +679,21 @@ template <int N> HD void itx1d_run(int *c, const int kind, const Clamp cl) {
     }
 }
 
+// Same with the knowledge that inputs c[NZ..] are zero: writing them as literal
+// zeros lets the compiler fold the butterflies that only see zeros (exact:
+// every stage maps 0 -> 0).  `nz` = number of leading inputs that may be
+// non-zero; buckets of 8 / 16 / all.
+template <int N, int NZ> HD void itx1d_run_nz(int *c, const int kind, const Clamp cl) {
+    constexpr int NIN = N == 64 ? 32 : N;
+#pragma unroll
+    for (int k = NZ; k < NIN; k++) c[k] = 0;
+    itx1d_run<N>(c, kind, cl);
+}
+template <int N> HD void itx1d_dispatch(int *c, const int kind, const Clamp cl, const int nz) {
+    constexpr int NIN = N == 64 ? 32 : N;
+    if (NIN > 8 && nz <= 8) itx1d_run_nz<N, (NIN > 8 ? 8 : NIN)>(c, kind, cl);
+    else if (NIN > 16 && nz <= 16) itx1d_run_nz<N, (NIN > 16 ? 16 : NIN)>(c, kind, cl);
+    else itx1d_run<N>(c, kind, cl);
+}
+
 }  // namespace d1

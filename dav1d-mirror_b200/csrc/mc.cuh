@@ -21,14 +21,19 @@ namespace d1 {
 
 constexpr int MC_T = 32;                 // tile edge
 constexpr int MC_ROWS = MC_T + 7;        // rows/cols of the staged window
-constexpr int MC_SRC_STRIDE = 40;        // pixels
 constexpr int MC_MID_STRIDE = MC_T;      // int16
+// Staged window row: the 16-byte aligned superset of the (tw+7) needed pixels,
+// i.e. up to 39 + (vector width - 1) pixels: 48 u16 (6 vectors) / 64 u8 (4 vectors).
+template <typename pixel> struct McSrcGeo {
+    static constexpr int VPX = 16 / (int)sizeof(pixel);      // pixels per 16-byte vector
+    static constexpr int STRIDE = sizeof(pixel) == 2 ? 48 : 64;
+};
 
-template <typename pixel> struct McSmem {
-    pixel src[MC_ROWS * MC_SRC_STRIDE];
+template <typename pixel> struct __align__(16) McSmem {
+    pixel src[MC_ROWS * McSrcGeo<pixel>::STRIDE];
     int16_t mid[MC_ROWS * MC_MID_STRIDE];
 };
-template <typename pixel> struct McSmemCompound {
+template <typename pixel> struct __align__(16) McSmemCompound {
     McSmem<pixel> s;
     int16_t ta[MC_T * MC_T];
     int16_t tb[MC_T * MC_T];
@@ -80,7 +85,7 @@ DEV void mc_hpass(const pixel *s_src, const int *fh, const int tw, const int r_l
     const int total = (r_hi - r_lo) * nst;
     for (int s = lane; s < total; s += 32) {
         const int r = r_lo + s / nst, c0 = (s % nst) * SW;
-        const pixel *p = s_src + r * MC_SRC_STRIDE + c0;
+        const pixel *p = s_src + r * McSrcGeo<pixel>::STRIDE + c0;
         int v[SW + 7];
 #pragma unroll
         for (int k = 0; k < SW + 7; k++) v[k] = p[k];
@@ -96,7 +101,7 @@ DEV void mc_hpass(const pixel *s_src, const int *fh, const int tw, const int r_l
 }
 
 // Vertical pass: 8 output rows per lane, column x. SRC is the staged pixel
-// window (column offset 3, stride MC_SRC_STRIDE) or the int16 mid tile.
+// window (column offset 3, stride McSrcGeo::STRIDE) or the int16 mid tile.
 template <typename pixel, bool PREP, typename SRC>
 DEV void mc_vpass(const SRC *src, const int sstride, const int *fv, const int tw, const int th,
                   const int rnd, const int sh, const int bdmax,
@@ -140,48 +145,71 @@ DEV void mc_tile(const PlaneView &ref, const int sx, const int sy, const int tw,
     if (mx) mc_load_taps(fh, filter_2d, false, mx, bw);
     if (my) mc_load_taps(fv, filter_2d, true, my, bh);
 
-    // ---- stage the window: rows/cols -3..+4 only where a filter needs them
+    // ---- stage the window: rows/cols -3..+4 only where a filter needs them.
+    // Fast path (window columns inside the plane): 16-byte cp.async copies of
+    // the aligned superset of each row, global -> shared without a register
+    // round trip; `off` = position of window column 0 inside the staged row.
+    // Row indices are clamped in both paths (top/bottom edge emulation); tiles
+    // that cross the left/right picture edge take the per-pixel clamped path.
+    constexpr int SS = McSrcGeo<pixel>::STRIDE, VPX = McSrcGeo<pixel>::VPX;
     const int c_lo = mx ? 0 : 3, c_hi = mx ? tw + 7 : tw + 3;
     const int r_lo = my ? 0 : 3, r_hi = my ? th + 7 : th + 3;
+    int off = 0;
     {
         const pixel *rp = (const pixel *)ref.data;
         const int64_t rstride = ref.stride / (int64_t)sizeof(pixel);
-        const int ncols = c_hi - c_lo;
-        const int lpr = ncols <= 8 ? 8 : ncols <= 16 ? 16 : 32;     // lanes per row
-        const int rpi = 32 / lpr;                                   // rows per iteration
-        const int lr = lane / lpr, lc = lane % lpr;
-        for (int r = r_lo + lr; r < r_hi; r += rpi) {
-            const int yy = iclip(sy - 3 + r, 0, ref.h - 1);
-            const pixel *row = rp + yy * rstride;
-            for (int c = c_lo + lc; c < c_hi; c += lpr) {
-                const int xx = iclip(sx - 3 + c, 0, ref.w - 1);
-                sm->src[r * MC_SRC_STRIDE + c] = row[xx];
+        if (sx - 3 >= 0 && sx - 3 + c_hi <= ref.w) {
+            const int a0 = (sx - 3) & ~(VPX - 1);
+            off = (sx - 3) - a0;
+            const int v_lo = (off + c_lo) / VPX, nv = (off + c_hi - 1) / VPX - v_lo + 1;
+            const int total = (r_hi - r_lo) * nv;
+            for (int i = lane; i < total; i += 32) {
+                const int r = r_lo + i / nv, v = v_lo + i % nv;
+                const int yy = iclip(sy - 3 + r, 0, ref.h - 1);
+                const pixel *g = rp + yy * rstride + a0 + v * VPX;
+                const unsigned sa = (unsigned)__cvta_generic_to_shared(sm->src + r * SS + v * VPX);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(sa), "l"(g) : "memory");
+            }
+            asm volatile("cp.async.wait_all;" ::: "memory");
+        } else {
+            const int ncols = c_hi - c_lo;
+            const int lpr = ncols <= 8 ? 8 : ncols <= 16 ? 16 : 32;     // lanes per row
+            const int rpi = 32 / lpr;                                   // rows per iteration
+            const int lr = lane / lpr, lc = lane % lpr;
+            for (int r = r_lo + lr; r < r_hi; r += rpi) {
+                const int yy = iclip(sy - 3 + r, 0, ref.h - 1);
+                const pixel *row = rp + yy * rstride;
+                for (int c = c_lo + lc; c < c_hi; c += lpr) {
+                    const int xx = iclip(sx - 3 + c, 0, ref.w - 1);
+                    sm->src[r * SS + c] = row[xx];
+                }
             }
         }
     }
     __syncwarp();
+    const pixel *wsrc = sm->src + off;      // window column c lives at wsrc[r * SS + c]
 
     if (mx && my) {
         const int sh1 = bs - ib, rnd1 = (1 << sh1) >> 1;
-        if (tw >= 8)      mc_hpass<pixel, PREP, 8, false>(sm->src, fh, tw, 0, th + 7, rnd1, sh1, bdmax, sm->mid, nullptr, 0, lane);
-        else if (tw == 4) mc_hpass<pixel, PREP, 4, false>(sm->src, fh, tw, 0, th + 7, rnd1, sh1, bdmax, sm->mid, nullptr, 0, lane);
-        else              mc_hpass<pixel, PREP, 2, false>(sm->src, fh, tw, 0, th + 7, rnd1, sh1, bdmax, sm->mid, nullptr, 0, lane);
+        if (tw >= 8)      mc_hpass<pixel, PREP, 8, false>(wsrc, fh, tw, 0, th + 7, rnd1, sh1, bdmax, sm->mid, nullptr, 0, lane);
+        else if (tw == 4) mc_hpass<pixel, PREP, 4, false>(wsrc, fh, tw, 0, th + 7, rnd1, sh1, bdmax, sm->mid, nullptr, 0, lane);
+        else              mc_hpass<pixel, PREP, 2, false>(wsrc, fh, tw, 0, th + 7, rnd1, sh1, bdmax, sm->mid, nullptr, 0, lane);
         __syncwarp();
         const int sh2 = PREP ? bs : bs + ib, rnd2 = (1 << sh2) >> 1;
         mc_vpass<pixel, PREP, int16_t>(sm->mid, MC_MID_STRIDE, fv, tw, th, rnd2, sh2, bdmax, out, ostride, lane);
     } else if (mx) {
         const int sh = PREP ? bs - ib : bs;
         const int rnd = PREP ? (1 << sh) >> 1 : (1 << (bs - 1)) + ((1 << (bs - ib)) >> 1);
-        if (tw >= 8)      mc_hpass<pixel, PREP, 8, true>(sm->src, fh, tw, 3, th + 3, rnd, sh, bdmax, nullptr, out, ostride, lane);
-        else if (tw == 4) mc_hpass<pixel, PREP, 4, true>(sm->src, fh, tw, 3, th + 3, rnd, sh, bdmax, nullptr, out, ostride, lane);
-        else              mc_hpass<pixel, PREP, 2, true>(sm->src, fh, tw, 3, th + 3, rnd, sh, bdmax, nullptr, out, ostride, lane);
+        if (tw >= 8)      mc_hpass<pixel, PREP, 8, true>(wsrc, fh, tw, 3, th + 3, rnd, sh, bdmax, nullptr, out, ostride, lane);
+        else if (tw == 4) mc_hpass<pixel, PREP, 4, true>(wsrc, fh, tw, 3, th + 3, rnd, sh, bdmax, nullptr, out, ostride, lane);
+        else              mc_hpass<pixel, PREP, 2, true>(wsrc, fh, tw, 3, th + 3, rnd, sh, bdmax, nullptr, out, ostride, lane);
     } else if (my) {
         const int sh = PREP ? bs - ib : bs, rnd = (1 << sh) >> 1;
-        mc_vpass<pixel, PREP, pixel>(sm->src + 3, MC_SRC_STRIDE, fv, tw, th, rnd, sh, bdmax, out, ostride, lane);
+        mc_vpass<pixel, PREP, pixel>(wsrc + 3, SS, fv, tw, th, rnd, sh, bdmax, out, ostride, lane);
     } else {
         for (int i = lane; i < tw * th; i += 32) {
             const int y = i / tw, x = i % tw;
-            const int px = sm->src[(y + 3) * MC_SRC_STRIDE + x + 3];
+            const int px = wsrc[(y + 3) * SS + x + 3];
             if (PREP) out[y * ostride + x] = (typename O::type)((px << ib) - PxTraits<pixel>::prep_bias);
             else out[y * ostride + x] = (typename O::type)px;
         }

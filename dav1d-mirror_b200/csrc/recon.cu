@@ -5,6 +5,7 @@
 //
 // Reference call sites replaced: dav1d_recon_b_intra (src/recon_tmpl.c:1195-1596)
 // and, through the MC / ITX launches, dav1d_recon_b_inter (:1598-2036).
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include <vector>
@@ -18,6 +19,8 @@ namespace d1 {
 // defined in itx.cu / mc.cu
 int itx_batch_launch(const PicView &pic, void *cf, const Dav1dCudaItxDesc *descs,
                      const int32_t *class_count, int zero_coefs, cudaStream_t st);
+int itx_batch_launch_multi(const PicView &pic, void *cf, const Dav1dCudaItxDesc *descs,
+                           const int32_t *class_count, int zero_coefs, cudaStream_t *streams, int n_streams);
 struct McArgs;
 int mc_put_launch_raw(const PicView &dst, const PicView *refs, const Dav1dCudaMcDesc *descs,
                       const uint32_t *tiles, int n_tiles, uint8_t *masks, int16_t *tmp, bool compound,
@@ -43,6 +46,10 @@ struct IntraArgs {
     int n;
     const void *pal;
     const uint8_t *pal_idx;
+    // dataflow variant
+    const int32_t *dep_start;
+    const int32_t *deps;
+    unsigned *sync;
 };
 
 template <typename pixel, int W, int H>
@@ -53,14 +60,9 @@ DEV void intra_residual(int *tile, void *cf, const Dav1dCudaIntraDesc &d, pixel 
     itx_block<pixel, W, H, 32>(true, lane, tile, (coef *)cf + d.coef_off, d.eob, d.txtp, dst, stride, bdmax, false);
 }
 
+// One intra-class operation (prediction [+ residual]) by one warp.
 template <typename pixel>
-__global__ void __launch_bounds__(INTRA_WARPS * 32) intra_level_kernel(const __grid_constant__ IntraArgs a) {
-    extern __shared__ __align__(16) uint8_t intra_smem_raw[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int idx = blockIdx.x * INTRA_WARPS + warp;
-    if (idx >= a.n) return;
-    IntraSmem<pixel> *sm = (IntraSmem<pixel> *)intra_smem_raw + warp;
-    const Dav1dCudaIntraDesc d = a.descs[idx];
+__device__ __noinline__ void intra_op(const IntraArgs &a, const Dav1dCudaIntraDesc &d, IntraSmem<pixel> *sm, const int lane) {
     const int pl = d.plane;
     const int ss_hor = pl ? a.pic.ss_hor : 0, ss_ver = pl ? a.pic.ss_ver : 0;
     const PlaneView &pv = a.pic.p[pl];
@@ -116,12 +118,125 @@ __global__ void __launch_bounds__(INTRA_WARPS * 32) intra_level_kernel(const __g
     }
 }
 
+// Level-synchronous variant: one launch per dependency level.
+template <typename pixel>
+__global__ void __launch_bounds__(INTRA_WARPS * 32, 4) intra_level_kernel(const __grid_constant__ IntraArgs a) {
+    extern __shared__ __align__(16) uint8_t intra_smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int idx = blockIdx.x * INTRA_WARPS + warp;
+    if (idx >= a.n) return;
+    IntraSmem<pixel> *sm = (IntraSmem<pixel> *)intra_smem_raw + warp;
+    const Dav1dCudaIntraDesc d = a.descs[idx];
+    intra_op<pixel>(a, d, sm, lane);
+}
+
+// Multi-frame variant: dependency level l of SEVERAL frames (independent
+// streams) in one launch, so the per-level latency is shared by all of them.
+struct IntraFrameParams {
+    PicView pic;
+    int bw4, bh4;
+    void *cf;
+    const Dav1dCudaIntraDesc *descs;     // level-sorted
+    const void *pal;
+    const uint8_t *pal_idx;
+};
+struct IntraSeg { int frame, first_cta, desc_off, count; };
+struct IntraMultiArgs {
+    const IntraFrameParams *frames;
+    const IntraSeg *segs;
+    int n_segs;
+};
+
+template <typename pixel>
+__global__ void __launch_bounds__(INTRA_WARPS * 32, 4) intra_multi_kernel(const IntraMultiArgs m) {
+    extern __shared__ __align__(16) uint8_t intra_smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    IntraSmem<pixel> *sm = (IntraSmem<pixel> *)intra_smem_raw + warp;
+    int s = 0;
+    while (s + 1 < m.n_segs && (int)blockIdx.x >= m.segs[s + 1].first_cta) s++;
+    const IntraSeg seg = m.segs[s];
+    const int idx = ((int)blockIdx.x - seg.first_cta) * INTRA_WARPS + warp;
+    if (idx >= seg.count) return;
+    const IntraFrameParams &fp = m.frames[seg.frame];
+    IntraArgs a;
+    a.pic = fp.pic; a.bw4 = fp.bw4; a.bh4 = fp.bh4; a.cf = fp.cf;
+    a.descs = fp.descs; a.n = seg.count; a.pal = fp.pal; a.pal_idx = fp.pal_idx;
+    a.dep_start = nullptr; a.deps = nullptr; a.sync = nullptr;
+    const Dav1dCudaIntraDesc d = fp.descs[seg.desc_off + idx];
+    intra_op<pixel>(a, d, sm, lane);
+}
+
+// Dataflow variant: ONE persistent launch for the whole intra phase.  Warps
+// claim operations in level-sorted (= topological) order from a global
+// counter and wait on the completion flags of exactly the operations whose
+// pixels they read (dependency lists built by dav1d_cuda_intra_schedule()).
+// Every dependency has a smaller sorted index, i.e. it was claimed earlier by
+// a warp that is already running, so waiting cannot deadlock.
+// sync[0] = claim counter, sync[1 + i] = completion flag of operation i
+// (zeroed by a memset node before the launch).
+DEV unsigned ld_acquire(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+DEV void st_release(unsigned *p, unsigned v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+
+template <typename pixel>
+__global__ void __launch_bounds__(INTRA_WARPS * 32, 4) intra_flow_kernel(const __grid_constant__ IntraArgs a) {
+    extern __shared__ __align__(16) uint8_t intra_smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    IntraSmem<pixel> *sm = (IntraSmem<pixel> *)intra_smem_raw + warp;
+    unsigned *counter = a.sync, *flags = a.sync + 1;
+    for (;;) {
+        int idx = 0;
+        if (lane == 0) idx = (int)atomicAdd(counter, 1u);
+        idx = __shfl_sync(0xffffffffu, idx, 0);
+        if (idx >= a.n) break;
+        const Dav1dCudaIntraDesc d = a.descs[idx];
+        const int d0 = a.dep_start[idx], d1 = a.dep_start[idx + 1];
+        for (int k = d0 + lane; k < d1; k += 32) {
+            const unsigned *f = flags + a.deps[k];
+            unsigned ns = 32;
+            while (ld_acquire(f) == 0) { __nanosleep(ns); if (ns < 1024) ns <<= 1; }
+        }
+        __syncwarp();
+        intra_op<pixel>(a, d, sm, lane);
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) st_release(flags + idx, 1u);
+    }
+}
+
 template <typename pixel>
 static int launch_intra_level(const IntraArgs &a, cudaStream_t st) {
     const int grid = (a.n + INTRA_WARPS - 1) / INTRA_WARPS;
     intra_level_kernel<pixel><<<grid, INTRA_WARPS * 32, INTRA_WARPS * sizeof(IntraSmem<pixel>), st>>>(a);
     count_launch();
     return cuda_ok(cudaGetLastError(), "intra_level_kernel") ? 0 : -5;
+}
+
+static int g_flow_blocks[2] = { 0, 0 };   // persistent grid size per pixel type (set in recon_init_attrs)
+
+static int intra_flow_launch(const PicView &pic, int bw4, int bh4, void *cf, const Dav1dCudaIntraDesc *descs, int n,
+                             const int32_t *dep_start, const int32_t *deps, unsigned *sync, const void *pal,
+                             const uint8_t *pal_idx, cudaStream_t st)
+{
+    if (n <= 0) return 0;
+    IntraArgs a;
+    a.pic = pic; a.bw4 = bw4; a.bh4 = bh4; a.cf = cf;
+    a.descs = descs; a.n = n; a.pal = pal; a.pal_idx = pal_idx;
+    a.dep_start = dep_start; a.deps = deps; a.sync = sync;
+    if (!cuda_ok(cudaMemsetAsync(sync, 0, (size_t)(n + 1) * sizeof(unsigned), st), "memset(intra sync)")) return -5;
+    const bool hbd = pic.bdmax > 0xff;
+    // experiment knob: D1_FLOW_BLOCKS caps the persistent grid (share of the GPU per stream)
+    static const int cap = getenv("D1_FLOW_BLOCKS") ? atoi(getenv("D1_FLOW_BLOCKS")) : 1 << 30;
+    const int grid = std::min(std::min(g_flow_blocks[hbd], cap), (n + INTRA_WARPS - 1) / INTRA_WARPS);
+    if (hbd) intra_flow_kernel<uint16_t><<<grid, INTRA_WARPS * 32, INTRA_WARPS * sizeof(IntraSmem<uint16_t>), st>>>(a);
+    else intra_flow_kernel<uint8_t><<<grid, INTRA_WARPS * 32, INTRA_WARPS * sizeof(IntraSmem<uint8_t>), st>>>(a);
+    count_launch();
+    return cuda_ok(cudaGetLastError(), "intra_flow_kernel") ? 0 : -5;
 }
 
 static int intra_batch_launch(const PicView &pic, int bw4, int bh4, void *cf, const Dav1dCudaIntraDesc *descs,
@@ -136,6 +251,7 @@ static int intra_batch_launch(const PicView &pic, int bw4, int bh4, void *cf, co
         a.descs = descs + level_start[l];
         a.n = n;
         a.pal = pal; a.pal_idx = pal_idx;
+        a.dep_start = nullptr; a.deps = nullptr; a.sync = nullptr;
         const int r = pic.bdmax > 0xff ? launch_intra_level<uint16_t>(a, st) : launch_intra_level<uint8_t>(a, st);
         if (r) return r;
     }
@@ -184,31 +300,179 @@ static void refs_view(PicView *out, const Dav1dCudaPicture *const refs[7]) {
         if (refs[i]) out[i] = pic_view(refs[i]);
 }
 
-static int recon_submit_on(const Dav1dCudaReconBatch *b, cudaStream_t st) {
+static bool ensure_aux(Dav1dCudaContext *c) {
+    if (c->aux_ready) return true;
+    for (int i = 0; i < Dav1dCudaContext::N_AUX; i++) {
+        if (!cuda_ok(cudaStreamCreateWithFlags(&c->aux[i], cudaStreamNonBlocking), "aux stream")) return false;
+        if (!cuda_ok(cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming), "aux event")) return false;
+    }
+    if (!cuda_ok(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming), "fork event")) return false;
+    c->aux_ready = true;
+    return true;
+}
+
+// fork: aux streams wait for everything submitted to `st` so far
+static bool fork_aux(Dav1dCudaContext *c, cudaStream_t st) {
+    if (!cuda_ok(cudaEventRecord(c->ev_fork, st), "fork record")) return false;
+    for (int i = 0; i < Dav1dCudaContext::N_AUX; i++)
+        if (!cuda_ok(cudaStreamWaitEvent(c->aux[i], c->ev_fork, 0), "fork wait")) return false;
+    return true;
+}
+// join: `st` waits for the aux streams
+static bool join_aux(Dav1dCudaContext *c, cudaStream_t st) {
+    for (int i = 0; i < Dav1dCudaContext::N_AUX; i++) {
+        if (!cuda_ok(cudaEventRecord(c->ev_join[i], c->aux[i]), "join record")) return false;
+        if (!cuda_ok(cudaStreamWaitEvent(st, c->ev_join[i], 0), "join wait")) return false;
+    }
+    return true;
+}
+
+// One frame.  Launch classes that touch disjoint pixels run as parallel
+// branches: {put} | {compound wave 0 -> wave 1} | {warp}, then the 19 transform
+// size classes spread over 4 streams, then the intra phase.
+static int recon_submit_on(Dav1dCudaContext *c, const Dav1dCudaReconBatch *b, cudaStream_t st) {
     const PicView dst = pic_view(b->dst);
     PicView refs[7];
     refs_view(refs, b->refs);
+    if (!ensure_aux(c)) return -5;
     int r;
+    // experiment knob (tools/exp_frame.py): D1_PHASE_MASK selects launch classes
+    // bit0 put, bit1 compound, bit2 warp, bit3 itx, bit4 intra; default all
+    static const int mask = getenv("D1_PHASE_MASK") ? atoi(getenv("D1_PHASE_MASK")) : 31;
     // phase A: prediction from reference frames
-    if ((r = mc_put_launch_raw(dst, refs, b->mc_put, b->mc_put_tiles, b->n_mc_put_tiles, nullptr, nullptr, false, st)))
+    if (!fork_aux(c, st)) return -5;
+    if ((mask & 1) && (r = mc_put_launch_raw(dst, refs, b->mc_put, b->mc_put_tiles, b->n_mc_put_tiles, nullptr,
+                                             nullptr, false, st)))
         return r;
-    if ((r = mc_put_launch_raw(dst, refs, b->mc_comp, b->mc_comp_tiles, b->n_mc_comp_tiles[0], b->masks, nullptr,
-                               true, st)))
+    if ((mask & 2) && (r = mc_put_launch_raw(dst, refs, b->mc_comp, b->mc_comp_tiles, b->n_mc_comp_tiles[0],
+                                             b->masks, nullptr, true, c->aux[0])))
         return r;
-    if ((r = mc_put_launch_raw(dst, refs, b->mc_comp, b->mc_comp_tiles + b->n_mc_comp_tiles[0],
-                               b->n_mc_comp_tiles[1], b->masks, nullptr, true, st)))
+    if ((mask & 2) && (r = mc_put_launch_raw(dst, refs, b->mc_comp, b->mc_comp_tiles + b->n_mc_comp_tiles[0],
+                                             b->n_mc_comp_tiles[1], b->masks, nullptr, true, c->aux[0])))
         return r;
-    if ((r = warp_batch_launch(dst, refs, b->warp, b->n_warp, st))) return r;
+    if ((mask & 4) && (r = warp_batch_launch(dst, refs, b->warp, b->n_warp, c->aux[1]))) return r;
+    if (!join_aux(c, st)) return -5;
     // phase B: inter residuals
-    if (b->itx && (r = itx_batch_launch(dst, b->cf, b->itx, b->itx_class_count, 0, st))) return r;
-    // phase C: intra-class operations, level by level
-    if (b->intra && (r = intra_batch_launch(dst, b->bw4, b->bh4, b->cf, b->intra, b->intra_level_start, b->n_levels,
-                                            b->pal, b->pal_idx, st)))
+    if (b->itx && (mask & 8)) {
+        if (!fork_aux(c, st)) return -5;
+        cudaStream_t ss[1 + Dav1dCudaContext::N_AUX] = { st, c->aux[0], c->aux[1], c->aux[2] };
+        if ((r = itx_batch_launch_multi(dst, b->cf, b->itx, b->itx_class_count, 0, ss, 1 + Dav1dCudaContext::N_AUX)))
+            return r;
+        if (!join_aux(c, st)) return -5;
+    }
+    // phase C: intra-class operations
+    if (!(mask & 16)) return 0;
+    if (b->intra && b->intra_deps && b->intra_sync) {
+        const int n = b->intra_level_start[b->n_levels];
+        if ((r = intra_flow_launch(dst, b->bw4, b->bh4, b->cf, b->intra, n, b->intra_dep_start, b->intra_deps,
+                                   (unsigned *)b->intra_sync, b->pal, b->pal_idx, st)))
+            return r;
+    } else if (b->intra && (r = intra_batch_launch(dst, b->bw4, b->bh4, b->cf, b->intra, b->intra_level_start,
+                                                   b->n_levels, b->pal, b->pal_idx, st)))
         return r;
     return 0;
 }
 
+// Frames of several independent streams in one submission.  Phases A and B are
+// launched per frame (spread over the fork/join streams); phase C runs one
+// launch per dependency level covering that level of every frame.
+// `tab` = device scratch for the per-frame parameter table + segment tables
+// (uploaded here from `tab_host`, which must stay valid until the copy ran).
+struct MultiTables {
+    std::vector<IntraFrameParams> frames;
+    std::vector<IntraSeg> segs;          // all levels, concatenated
+    std::vector<int> level_seg_start;    // per level: first seg; size n_levels + 1
+    std::vector<int> level_ctas;
+};
+
+static void build_multi_tables(const Dav1dCudaReconBatch *const *bs, int n, MultiTables &t) {
+    int max_levels = 0;
+    t.frames.resize(n);
+    for (int f = 0; f < n; f++) {
+        const Dav1dCudaReconBatch *b = bs[f];
+        IntraFrameParams &p = t.frames[f];
+        p.pic = pic_view(b->dst); p.bw4 = b->bw4; p.bh4 = b->bh4; p.cf = b->cf;
+        p.descs = b->intra; p.pal = b->pal; p.pal_idx = b->pal_idx;
+        if (b->intra) max_levels = std::max(max_levels, (int)b->n_levels);
+    }
+    t.level_seg_start.assign(1, 0);
+    for (int l = 0; l < max_levels; l++) {
+        int cta = 0;
+        for (int f = 0; f < n; f++) {
+            const Dav1dCudaReconBatch *b = bs[f];
+            if (!b->intra || l >= b->n_levels) continue;
+            const int cnt = b->intra_level_start[l + 1] - b->intra_level_start[l];
+            if (cnt <= 0) continue;
+            t.segs.push_back({ f, cta, b->intra_level_start[l], cnt });
+            cta += (cnt + INTRA_WARPS - 1) / INTRA_WARPS;
+        }
+        t.level_seg_start.push_back((int)t.segs.size());
+        t.level_ctas.push_back(cta);
+    }
+}
+
+static int recon_submit_multi_on(Dav1dCudaContext *c, const Dav1dCudaReconBatch *const *bs, int n,
+                                 const IntraFrameParams *d_frames, const IntraSeg *d_segs, const MultiTables &t,
+                                 cudaStream_t st)
+{
+    if (!ensure_aux(c)) return -5;
+    int r;
+    static const int mask = getenv("D1_PHASE_MASK") ? atoi(getenv("D1_PHASE_MASK")) : 31;
+    cudaStream_t ss[1 + Dav1dCudaContext::N_AUX] = { st, c->aux[0], c->aux[1], c->aux[2] };
+    constexpr int NS = 1 + Dav1dCudaContext::N_AUX;
+    // phases A + B per frame, frame f on stream f % NS (MC then residual of a frame stay ordered)
+    if (!fork_aux(c, st)) return -5;
+    for (int f = 0; f < n; f++) {
+        const Dav1dCudaReconBatch *b = bs[f];
+        cudaStream_t s = ss[f % NS];
+        const PicView dst = pic_view(b->dst);
+        PicView refs[7];
+        refs_view(refs, b->refs);
+        if ((mask & 1) && (r = mc_put_launch_raw(dst, refs, b->mc_put, b->mc_put_tiles, b->n_mc_put_tiles, nullptr,
+                                                 nullptr, false, s))) return r;
+        if ((mask & 2) && (r = mc_put_launch_raw(dst, refs, b->mc_comp, b->mc_comp_tiles, b->n_mc_comp_tiles[0],
+                                                 b->masks, nullptr, true, s))) return r;
+        if ((mask & 2) && (r = mc_put_launch_raw(dst, refs, b->mc_comp, b->mc_comp_tiles + b->n_mc_comp_tiles[0],
+                                                 b->n_mc_comp_tiles[1], b->masks, nullptr, true, s))) return r;
+        if ((mask & 4) && (r = warp_batch_launch(dst, refs, b->warp, b->n_warp, s))) return r;
+        if ((mask & 8) && b->itx && (r = itx_batch_launch(dst, b->cf, b->itx, b->itx_class_count, 0, s))) return r;
+    }
+    if (!join_aux(c, st)) return -5;
+    if (!(mask & 16)) return 0;
+    // phase C: one launch per level over all frames
+    const bool hbd = bs[0]->dst->bitdepth_max > 0xff;
+    for (size_t l = 0; l + 1 < t.level_seg_start.size(); l++) {
+        const int s0 = t.level_seg_start[l], s1 = t.level_seg_start[l + 1];
+        if (s1 <= s0) continue;
+        IntraMultiArgs m;
+        m.frames = d_frames; m.segs = d_segs + s0; m.n_segs = s1 - s0;
+        const int grid = t.level_ctas[l];
+        if (hbd) intra_multi_kernel<uint16_t><<<grid, INTRA_WARPS * 32, INTRA_WARPS * sizeof(IntraSmem<uint16_t>), st>>>(m);
+        else intra_multi_kernel<uint8_t><<<grid, INTRA_WARPS * 32, INTRA_WARPS * sizeof(IntraSmem<uint8_t>), st>>>(m);
+        count_launch();
+        if (!cuda_ok(cudaGetLastError(), "intra_multi_kernel")) return -5;
+    }
+    return 0;
+}
+
 void recon_init_attrs() {
+    cudaFuncSetAttribute(intra_multi_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)(INTRA_WARPS * sizeof(IntraSmem<uint16_t>)));
+    cudaFuncSetAttribute(intra_multi_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)(INTRA_WARPS * sizeof(IntraSmem<uint8_t>)));
+    cudaFuncSetAttribute(intra_flow_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)(INTRA_WARPS * sizeof(IntraSmem<uint16_t>)));
+    cudaFuncSetAttribute(intra_flow_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)(INTRA_WARPS * sizeof(IntraSmem<uint8_t>)));
+    int dev = 0, sms = 0, occ = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, intra_flow_kernel<uint8_t>, INTRA_WARPS * 32,
+                                                  INTRA_WARPS * sizeof(IntraSmem<uint8_t>));
+    g_flow_blocks[0] = std::max(1, occ) * std::max(1, sms);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, intra_flow_kernel<uint16_t>, INTRA_WARPS * 32,
+                                                  INTRA_WARPS * sizeof(IntraSmem<uint16_t>));
+    g_flow_blocks[1] = std::max(1, occ) * std::max(1, sms);
     cudaFuncSetAttribute(intra_level_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)(INTRA_WARPS * sizeof(IntraSmem<uint16_t>)));
     cudaFuncSetAttribute(intra_level_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -223,6 +487,7 @@ struct Dav1dCudaReconGraph {
     cudaGraph_t graph;
     cudaGraphExec_t exec;
     int n_nodes;
+    void *tables;          // device: multi-frame parameter/segment tables (multi graphs only)
 };
 
 extern "C" {
@@ -242,19 +507,34 @@ int dav1d_cuda_warp_batch(Dav1dCudaContext *c, const Dav1dCudaPicture *dst, cons
 int dav1d_cuda_intra_schedule(Dav1dCudaIntraDesc *descs, int n, int bw4, int bh4, int ss_hor, int ss_ver,
                               int32_t *order, int32_t *level_start, int max_levels)
 {
+    return dav1d_cuda_intra_schedule_deps(descs, n, bw4, bh4, ss_hor, ss_ver, order, level_start, max_levels,
+                                          nullptr, nullptr, 0);
+}
+
+int dav1d_cuda_intra_schedule_deps(Dav1dCudaIntraDesc *descs, int n, int bw4, int bh4, int ss_hor, int ss_ver,
+                                   int32_t *order, int32_t *level_start, int max_levels,
+                                   int32_t *dep_start, int32_t *deps, int max_deps)
+{
     if (!descs || n < 0 || !order || !level_start) return -22;
     const int pw[3] = { bw4, (bw4 + ss_hor) >> ss_hor, (bw4 + ss_hor) >> ss_hor };
     const int ph[3] = { bh4, (bh4 + ss_ver) >> ss_ver, (bh4 + ss_ver) >> ss_ver };
-    std::vector<int32_t> map[3];
-    for (int p = 0; p < 3; p++) map[p].assign((size_t)pw[p] * ph[p], 0);
+    // per 4x4 cell: decode-order index of the operation that produced its final pixels (-1: inter phases)
+    std::vector<int32_t> prod[3];
+    for (int p = 0; p < 3; p++) prod[p].assign((size_t)pw[p] * ph[p], -1);
+    std::vector<int32_t> dlist;              // dependency lists in decode order (CSR)
+    std::vector<int32_t> dstart(n + 1, 0);
+    std::vector<int32_t> cur;
     int n_levels = 0;
     for (int i = 0; i < n; i++) {
         Dav1dCudaIntraDesc &d = descs[i];
         const int p = d.plane, W = pw[p], H = ph[p];
         const int x0 = d.x4, y0 = d.y4, x1 = std::min<int>(x0 + d.tw4, W), y1 = std::min<int>(y0 + d.th4, H);
-        int lv = 0;
+        cur.clear();
         auto dep = [&](int pl, int x, int y) {
-            if (x >= 0 && y >= 0 && x < pw[pl] && y < ph[pl]) lv = std::max(lv, map[pl][(size_t)y * pw[pl] + x]);
+            if (x >= 0 && y >= 0 && x < pw[pl] && y < ph[pl]) {
+                const int32_t q = prod[pl][(size_t)y * pw[pl] + x];
+                if (q >= 0 && (cur.empty() || cur.back() != q)) cur.push_back(q);
+            }
         };
         if (d.mode == DAV1D_CUDA_INTRA_NONE) {
             for (int y = y0; y < y1; y++)
@@ -275,19 +555,52 @@ int dav1d_cuda_intra_schedule(Dav1dCudaIntraDesc *descs, int n, int bw4, int bh4
                     for (int x = x0 << sh; x < ((x0 + d.tw4) << sh); x++) dep(0, x, y);
             }
         }
+        std::sort(cur.begin(), cur.end());
+        cur.erase(std::unique(cur.begin(), cur.end()), cur.end());
+        int lv = 0;
+        for (int32_t q : cur) lv = std::max<int>(lv, (int)descs[q].level);
         lv += 1;
         d.level = (uint32_t)lv;
         n_levels = std::max(n_levels, lv);
+        dlist.insert(dlist.end(), cur.begin(), cur.end());
+        dstart[i + 1] = (int32_t)dlist.size();
         for (int y = y0; y < y1; y++)
-            for (int x = x0; x < x1; x++) map[p][(size_t)y * W + x] = lv;
+            for (int x = x0; x < x1; x++) prod[p][(size_t)y * W + x] = i;
     }
     if (n_levels > max_levels) return -34;
     std::vector<int32_t> cnt(n_levels + 2, 0);
     for (int i = 0; i < n; i++) cnt[descs[i].level]++;          // levels are 1-based
     level_start[0] = 0;
     for (int l = 1; l <= n_levels; l++) level_start[l] = level_start[l - 1] + cnt[l];
-    std::vector<int32_t> pos(level_start, level_start + n_levels + 1);
-    for (int i = 0; i < n; i++) order[pos[descs[i].level - 1]++] = i;
+    // Within a level, group operations that run the same code (residual size, prediction
+    // mode, transform type): the fused kernel is ~1.5 MB of SASS and co-resident warps that
+    // execute different paths thrash the instruction cache (measured 4x on a 4K frame).
+    std::vector<int32_t> inv(n);
+    {
+        std::vector<std::pair<uint64_t, int32_t>> keyed(n);
+        for (int i = 0; i < n; i++) {
+            const Dav1dCudaIntraDesc &d = descs[i];
+            const uint64_t res = d.eob >= 0 ? 1 + d.tx : 0;
+            const uint64_t key = ((uint64_t)d.level << 32) | (res << 16) | ((uint64_t)d.mode << 8) |
+                                 (d.eob >= 0 ? d.txtp : 0);
+            keyed[i] = { key, i };
+        }
+        std::stable_sort(keyed.begin(), keyed.end(),
+                         [](const std::pair<uint64_t, int32_t> &a, const std::pair<uint64_t, int32_t> &b) {
+                             return a.first < b.first;
+                         });
+        for (int s2 = 0; s2 < n; s2++) { order[s2] = keyed[s2].second; inv[keyed[s2].second] = s2; }
+    }
+    if (dep_start && deps) {
+        if ((int)dlist.size() > max_deps) return -28;
+        int k = 0;
+        for (int s = 0; s < n; s++) {          // sorted order, indices translated to sorted space
+            const int i = order[s];
+            dep_start[s] = k;
+            for (int j = dstart[i]; j < dstart[i + 1]; j++) deps[k++] = inv[dlist[j]];
+        }
+        dep_start[n] = k;
+    }
     return n_levels;
 }
 
@@ -301,7 +614,7 @@ int dav1d_cuda_intra_batch(Dav1dCudaContext *c, const Dav1dCudaPicture *dst, int
 
 int dav1d_cuda_recon_submit(Dav1dCudaContext *c, const Dav1dCudaReconBatch *b) {
     if (!c || !b || !b->dst) return -22;
-    return recon_submit_on(b, c->stream);
+    return recon_submit_on(c, b, c->stream);
 }
 
 int dav1d_cuda_recon_graph_build(Dav1dCudaContext *c, const Dav1dCudaReconBatch *b, Dav1dCudaReconGraph **out) {
@@ -310,7 +623,7 @@ int dav1d_cuda_recon_graph_build(Dav1dCudaContext *c, const Dav1dCudaReconBatch 
     cudaStream_t cap;
     D1_CHECK(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
     D1_CHECK(cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal));
-    const int r = recon_submit_on(b, cap);
+    const int r = recon_submit_on(c, b, cap);
     cudaGraph_t graph = nullptr;
     const cudaError_t e = cudaStreamEndCapture(cap, &graph);
     cudaStreamDestroy(cap);
@@ -318,11 +631,50 @@ int dav1d_cuda_recon_graph_build(Dav1dCudaContext *c, const Dav1dCudaReconBatch 
     if (!cuda_ok(e, "cudaStreamEndCapture")) return -5;
     Dav1dCudaReconGraph *g = new Dav1dCudaReconGraph();
     g->graph = graph;
+    g->tables = nullptr;
     size_t nn = 0;
     cudaGraphGetNodes(graph, nullptr, &nn);
     g->n_nodes = (int)nn;
     if (!cuda_ok(cudaGraphInstantiate(&g->exec, graph, 0), "cudaGraphInstantiate")) {
         cudaGraphDestroy(graph);
+        delete g;
+        return -5;
+    }
+    *out = g;
+    return g->n_nodes;
+}
+
+// Multi-frame graph: the frames of `n` independent streams in one graph.
+int dav1d_cuda_recon_graph_build_multi(Dav1dCudaContext *c, const Dav1dCudaReconBatch *const *bs, int n,
+                                       Dav1dCudaReconGraph **out)
+{
+    if (!c || !bs || n < 1 || !out) return -22;
+    *out = nullptr;
+    MultiTables t;
+    build_multi_tables(bs, n, t);
+    const size_t fb = t.frames.size() * sizeof(IntraFrameParams), sb = t.segs.size() * sizeof(IntraSeg);
+    uint8_t *tab = nullptr;
+    D1_CHECK(cudaMalloc(&tab, fb + sb + 64));
+    D1_CHECK(cudaMemcpy(tab, t.frames.data(), fb, cudaMemcpyHostToDevice));
+    if (sb) D1_CHECK(cudaMemcpy(tab + fb, t.segs.data(), sb, cudaMemcpyHostToDevice));
+    cudaStream_t cap;
+    D1_CHECK(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
+    D1_CHECK(cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal));
+    const int r = recon_submit_multi_on(c, bs, n, (const IntraFrameParams *)tab, (const IntraSeg *)(tab + fb), t, cap);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(cap, &graph);
+    cudaStreamDestroy(cap);
+    if (r) { if (graph) cudaGraphDestroy(graph); cudaFree(tab); return r; }
+    if (!cuda_ok(e, "cudaStreamEndCapture")) { cudaFree(tab); return -5; }
+    Dav1dCudaReconGraph *g = new Dav1dCudaReconGraph();
+    g->graph = graph;
+    g->tables = tab;
+    size_t nn = 0;
+    cudaGraphGetNodes(graph, nullptr, &nn);
+    g->n_nodes = (int)nn;
+    if (!cuda_ok(cudaGraphInstantiate(&g->exec, graph, 0), "cudaGraphInstantiate")) {
+        cudaGraphDestroy(graph);
+        cudaFree(tab);
         delete g;
         return -5;
     }
@@ -341,6 +693,7 @@ void dav1d_cuda_recon_graph_free(Dav1dCudaReconGraph *g) {
     if (!g) return;
     cudaGraphExecDestroy(g->exec);
     cudaGraphDestroy(g->graph);
+    if (g->tables) cudaFree(g->tables);
     delete g;
 }
 

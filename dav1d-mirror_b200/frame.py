@@ -118,11 +118,17 @@ class HostFrame:
         max_levels = 1 << 16
         level_start = (C.c_int32 * (max_levels + 1))()
         descs = self.intra.copy()
-        nl = L.dav1d_cuda_intra_schedule(descs.ctypes.data, n, self.bw4, self.bh4,
-                                         0 if self.no_chroma else self.ss_hor,
-                                         0 if self.no_chroma else self.ss_ver, order, level_start, max_levels)
+        max_deps = 96 * max(n, 1)
+        dep_start = np.zeros(n + 1, dtype=np.int32)
+        deps = np.zeros(max_deps, dtype=np.int32)
+        nl = L.dav1d_cuda_intra_schedule_deps(descs.ctypes.data, n, self.bw4, self.bh4,
+                                              0 if self.no_chroma else self.ss_hor,
+                                              0 if self.no_chroma else self.ss_ver, order, level_start, max_levels,
+                                              dep_start.ctypes.data, deps.ctypes.data, max_deps)
         if nl < 0:
-            raise RuntimeError(f"dav1d_cuda_intra_schedule: {nl}")
+            raise RuntimeError(f"dav1d_cuda_intra_schedule_deps: {nl}")
+        self.dep_start = dep_start.view(np.uint8)
+        self.deps = deps[:max(int(dep_start[n]), 1)].copy().view(np.uint8)
         perm = np.frombuffer(order, dtype=np.int32, count=n).copy() if n else np.zeros(0, np.int32)
         rec = descs.reshape(n, C.sizeof(B.IntraDesc)) if n else descs.reshape(0, C.sizeof(B.IntraDesc))
         self.intra_sorted = np.ascontiguousarray(rec[perm]).reshape(-1)
@@ -139,6 +145,8 @@ class HostFrame:
         """Bytes a decoder would ship host->device for this frame (descriptors + coefficients + pools)."""
         n = sum(a.nbytes for a in (self.mc_put, self.mc_put_tiles, self.mc_comp, self.mc_comp_tiles, self.warp,
                                    self.itx, self.cf, self.masks, self.pal, self.pal_idx))
+        if self.intra_sorted is not None:
+            n += self.dep_start.nbytes + self.deps.nbytes
         return n + (self.intra_sorted.nbytes if self.intra_sorted is not None else self.intra.nbytes)
 
 
@@ -153,7 +161,7 @@ def random_planes(hf, seed):
 class DeviceFrame:
     """Device-resident state for reconstructing `hf` with libdav1d_cuda.so."""
 
-    def __init__(self, ctx, hf, n_refs=2):
+    def __init__(self, ctx, hf, n_refs=2, dataflow=True):
         self.L = B.lib()
         self.ctx = ctx
         self.hf = hf
@@ -169,7 +177,7 @@ class DeviceFrame:
         self._dev = {}
         self._host = {}
         for name in ("mc_put", "mc_put_tiles", "mc_comp", "mc_comp_tiles", "warp", "itx", "intra_sorted", "cf",
-                     "masks", "pal", "pal_idx"):
+                     "masks", "pal", "pal_idx", "dep_start", "deps"):
             arr = getattr(hf, name)
             self._host[name] = arr
             self._dev[name] = L.dav1d_cuda_malloc(max(arr.nbytes, 256))
@@ -193,6 +201,9 @@ class DeviceFrame:
         b.intra = d["intra_sorted"]
         b.intra_level_start = self._level_start
         b.n_levels = hf.n_levels
+        self._sync = L.dav1d_cuda_malloc(4 * (hf.n_intra + 1))
+        if dataflow:
+            b.intra_dep_start, b.intra_deps, b.intra_sync = d["dep_start"], d["deps"], self._sync
         self.batch = b
         self.graph = None
 
@@ -323,6 +334,7 @@ class DeviceFrame:
             self.graph = None
         for p in self._dev.values():
             L.dav1d_cuda_free(p)
+        L.dav1d_cuda_free(self._sync)
         self._dev = {}
         for p, _ in getattr(self, "_pinned", {}).values():
             L.dav1d_cuda_host_free(p)
@@ -331,6 +343,32 @@ class DeviceFrame:
         self._pinned, self._pinned_out = {}, []
         for pic in [self.dst] + self.refs:
             L.dav1d_cuda_picture_free(self.ctx, C.byref(pic))
+
+
+class MultiFrame:
+    """Frames of several independent streams submitted as one graph
+    (dav1d_cuda_recon_graph_build_multi): level-synchronous intra launches shared by all."""
+
+    def __init__(self, ctx, dfs):
+        self.L = B.lib()
+        self.ctx = ctx
+        self.dfs = dfs
+        arr = (C.POINTER(B.ReconBatch) * len(dfs))(*[C.pointer(df.batch) for df in dfs])
+        g = C.c_void_p()
+        n = self.L.dav1d_cuda_recon_graph_build_multi(ctx, arr, len(dfs), C.byref(g))
+        if n < 0:
+            raise RuntimeError(f"dav1d_cuda_recon_graph_build_multi: {n}")
+        self.graph, self.graph_nodes = g, n
+
+    def launch(self):
+        r = self.L.dav1d_cuda_recon_graph_launch(self.ctx, self.graph)
+        if r:
+            raise RuntimeError(f"dav1d_cuda_recon_graph_launch: {r}")
+
+    def close(self):
+        if self.graph:
+            self.L.dav1d_cuda_recon_graph_free(self.graph)
+            self.graph = None
 
 
 def open_context(device=0, stream=None):

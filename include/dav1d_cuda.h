@@ -317,6 +317,15 @@ DAV1D_CUDA_API int dav1d_cuda_intra_schedule(Dav1dCudaIntraDesc *descs, int n, i
                                              int ss_hor, int ss_ver, int32_t *order,
                                              int32_t *level_start, int max_levels);
 
+/* Same, and additionally the per-operation dependency lists for the dataflow
+ * kernel: for the operation at sorted index s, deps[dep_start[s] ..
+ * dep_start[s+1]) are the SORTED indices of the operations whose pixels it
+ * reads (always < s).  dep_start needs n + 1 entries, deps max_deps. */
+DAV1D_CUDA_API int dav1d_cuda_intra_schedule_deps(Dav1dCudaIntraDesc *descs, int n, int bw4, int bh4,
+                                                  int ss_hor, int ss_ver, int32_t *order,
+                                                  int32_t *level_start, int max_levels,
+                                                  int32_t *dep_start, int32_t *deps, int max_deps);
+
 /* One launch per dependency level over level-sorted descriptors (device).
  * `level_start` is a HOST array of n_levels + 1 sorted offsets.  `pal` /
  * `pal_idx` are the palette pixel pool and the packed index pool (device). */
@@ -345,6 +354,10 @@ typedef struct Dav1dCudaReconBatch {
     const Dav1dCudaWarpDesc *warp;    int32_t n_warp;
     const Dav1dCudaItxDesc *itx;      int32_t itx_class_count[DAV1D_CUDA_N_RECT_TX_SIZES];
     const Dav1dCudaIntraDesc *intra;  const int32_t *intra_level_start; int32_t n_levels;
+    /* optional (device): dependency lists from dav1d_cuda_intra_schedule_deps() and a scratch of
+     * (n_intra + 1) uint32.  When all three are set phase C is ONE persistent dataflow launch
+     * instead of one launch per level. */
+    const int32_t *intra_dep_start; const int32_t *intra_deps; void *intra_sync;
 } Dav1dCudaReconBatch;
 
 DAV1D_CUDA_API int dav1d_cuda_recon_submit(Dav1dCudaContext *c, const Dav1dCudaReconBatch *b);
@@ -355,6 +368,14 @@ DAV1D_CUDA_API int dav1d_cuda_recon_submit(Dav1dCudaContext *c, const Dav1dCudaR
 typedef struct Dav1dCudaReconGraph Dav1dCudaReconGraph;
 DAV1D_CUDA_API int dav1d_cuda_recon_graph_build(Dav1dCudaContext *c, const Dav1dCudaReconBatch *b,
                                                 Dav1dCudaReconGraph **out);
+/* Frames of `n` independent streams (one batch each, same pixel type) as ONE
+ * graph: MC / residual launches per frame on parallel branches, and ONE
+ * intra launch per dependency level covering that level of every frame, so
+ * the level-to-level latency is shared by all streams (server-side batching
+ * of independent decoder instances). */
+DAV1D_CUDA_API int dav1d_cuda_recon_graph_build_multi(Dav1dCudaContext *c,
+                                                      const Dav1dCudaReconBatch *const *batches, int n,
+                                                      Dav1dCudaReconGraph **out);
 DAV1D_CUDA_API int dav1d_cuda_recon_graph_launch(Dav1dCudaContext *c, Dav1dCudaReconGraph *g);
 DAV1D_CUDA_API void dav1d_cuda_recon_graph_free(Dav1dCudaReconGraph *g);
 
