@@ -131,7 +131,8 @@ class ReconBatch(C.Structure):
                 ("warp", C.c_void_p), ("n_warp", C.c_int32),
                 ("itx", C.c_void_p), ("itx_class_count", C.c_int32 * N_RECT_TX_SIZES),
                 ("intra", C.c_void_p), ("intra_level_start", C.POINTER(C.c_int32)), ("n_levels", C.c_int32),
-                ("intra_dep_start", C.c_void_p), ("intra_deps", C.c_void_p), ("intra_sync", C.c_void_p)]
+                ("intra_dep_start", C.c_void_p), ("intra_deps", C.c_void_p), ("intra_sync", C.c_void_p),
+                ("intra_class_start", C.POINTER(C.c_int32))]
 
 
 def bind_frame_api(L):
@@ -147,7 +148,7 @@ def bind_frame_api(L):
                                             C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int]
     L.dav1d_cuda_intra_schedule_deps.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                                  C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int,
-                                                 C.c_void_p, C.c_void_p, C.c_int]
+                                                 C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     L.dav1d_cuda_recon_submit.argtypes = [C.c_void_p, C.POINTER(ReconBatch)]
     L.dav1d_cuda_recon_graph_build.argtypes = [C.c_void_p, C.POINTER(ReconBatch), C.POINTER(C.c_void_p)]
     L.dav1d_cuda_recon_graph_build_multi.argtypes = [C.c_void_p, C.POINTER(C.POINTER(ReconBatch)), C.c_int,

@@ -441,65 +441,53 @@ DEV int prepare_edges(const int x, const int have_left, const int y, const int h
     if (have_top && ((needs & 2) || (needs & 4) || ((needs & 1) && !have_left)))
         dst_top = top_sb_edge ? top_sb_edge + x * 4 : dst - stride;
 
-    if (needs & 1) {
-        const int sz = th << 2;
-        pixel *left = edge - sz;
-        if (have_left) {
-            const int px_have = imin(sz, (h - y) << 2);
-            for (int i = lane; i < sz; i += 32)
-                left[sz - 1 - i] = __ldcg(dst + stride * imin(i, px_have - 1) - 1);
-        } else {
-            const pixel v = have_top ? __ldcg(dst_top) : (pixel)(((1 << bitdepth) >> 1) + 1);
-            for (int i = lane; i < sz; i += 32) left[i] = v;
-        }
-        if (needs & 16) {
-            const int have_bl = (!have_left || y + th >= h) ? 0 : (edge_flags & 8);
-            if (have_bl) {
-                const int px_have = imin(sz, (h - y - th) << 2);
-                for (int i = lane; i < sz; i += 32)
-                    left[-(i + 1)] = __ldcg(dst + (sz + imin(i, px_have - 1)) * stride - 1);
-            } else {
-                // replicate left[0] = bottom-most left pixel
-                pixel v;
-                if (have_left) v = __ldcg(dst + stride * (imin(sz, (h - y) << 2) - 1) - 1);
-                else v = have_top ? __ldcg(dst_top) : (pixel)(((1 << bitdepth) >> 1) + 1);
-                for (int i = lane; i < sz; i += 32) left[-(i + 1)] = v;
-            }
-        }
+    // Every edge entry is one pixel of the frame (or a constant).  All loads are
+    // issued first - they are independent, so their latencies overlap - and the
+    // shared-memory stores follow; one warp barrier at the end.
+    const int mid = (1 << bitdepth) >> 1;
+    const int szl = th << 2, szt = tw << 2;
+    const int have_l = have_left && (needs & 1), pxl = imin(szl, (h - y) << 2);
+    const int have_bl = (needs & 16) && have_left && y + th < h && (edge_flags & 8);
+    const int pxbl = imin(szl, (h - y - th) << 2);
+    const int pxt = imin(szt, (w - x) << 2);
+    const int have_tr = (needs & 8) && have_top && x + tw < w && (edge_flags & 1);
+    const int pxtr = imin(szt, (w - x - tw) << 2);
+    auto ld = [](const pixel *p, const int dflt) { return p ? (int)__ldcg(p) : dflt; };
+    // fallbacks when a side is unavailable (ipred_prepare_tmpl.c:139-197)
+    const pixel *no_left = have_top ? dst_top : nullptr;                      // else mid + 1
+    const pixel *no_top = have_left ? dst - 1 : nullptr;                      // else mid - 1
+    int vl[2] = { 0, 0 }, vbl[2] = { 0, 0 }, vt[2] = { 0, 0 }, vtr[2] = { 0, 0 }, vc = 0;
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const int i = lane + 32 * k;
+        if ((needs & 1) && i < szl)
+            vl[k] = have_left ? (int)__ldcg(dst + stride * imin(i, pxl - 1) - 1) : ld(no_left, mid + 1);
+        if ((needs & 16) && i < szl)
+            vbl[k] = have_bl ? (int)__ldcg(dst + (szl + imin(i, pxbl - 1)) * stride - 1)
+                   : have_left ? (int)__ldcg(dst + stride * (pxl - 1) - 1) : ld(no_left, mid + 1);
+        if ((needs & 2) && i < szt)
+            vt[k] = have_top ? (int)__ldcg(dst_top + imin(i, pxt - 1)) : ld(no_top, mid - 1);
+        if ((needs & 8) && i < szt)
+            vtr[k] = have_tr ? (int)__ldcg(dst_top + szt + imin(i, pxtr - 1))
+                   : have_top ? (int)__ldcg(dst_top + pxt - 1) : ld(no_top, mid - 1);
     }
-    if (needs & 2) {
-        const int sz = tw << 2;
-        pixel *top = edge + 1;
-        if (have_top) {
-            const int px_have = imin(sz, (w - x) << 2);
-            for (int i = lane; i < sz; i += 32) top[i] = __ldcg(dst_top + imin(i, px_have - 1));
-        } else {
-            const pixel v = have_left ? __ldcg(dst - 1) : (pixel)(((1 << bitdepth) >> 1) - 1);
-            for (int i = lane; i < sz; i += 32) top[i] = v;
-        }
-        if (needs & 8) {
-            const int have_tr = (!have_top || x + tw >= w) ? 0 : (edge_flags & 1);
-            if (have_tr) {
-                const int px_have = imin(sz, (w - x - tw) << 2);
-                for (int i = lane; i < sz; i += 32) top[sz + i] = __ldcg(dst_top + sz + imin(i, px_have - 1));
-            } else {
-                pixel v;   // top[sz - 1]
-                if (have_top) v = __ldcg(dst_top + imin(sz, (w - x) << 2) - 1);
-                else v = have_left ? __ldcg(dst - 1) : (pixel)(((1 << bitdepth) >> 1) - 1);
-                for (int i = lane; i < sz; i += 32) top[sz + i] = v;
-            }
-        }
+    if ((needs & 4) && lane == 0) {
+        if (have_left) vc = have_top ? __ldcg(dst_top - 1) : __ldcg(dst - 1);
+        else vc = have_top ? (int)__ldcg(dst_top) : mid;
     }
-    __syncwarp();
-    if (needs & 4) {
-        if (lane == 0) {
-            int v;
-            if (have_left) v = have_top ? __ldcg(dst_top - 1) : __ldcg(dst - 1);
-            else v = have_top ? __ldcg(dst_top) : (1 << bitdepth) >> 1;
-            if (mode == M_Z2 && tw + th >= 6 && filter_edge_flag)
-                v = ((edge[-1] + edge[1]) * 5 + v * 6 + 8) >> 4;
-            edge[0] = (pixel)v;
-        }
+    (void)have_l;
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const int i = lane + 32 * k;
+        if ((needs & 1) && i < szl) edge[-1 - i] = (pixel)vl[k];             // left[szl-1-i] = edge[-szl + szl-1-i]
+        if ((needs & 16) && i < szl) edge[-szl - 1 - i] = (pixel)vbl[k];
+        if ((needs & 2) && i < szt) edge[1 + i] = (pixel)vt[k];
+        if ((needs & 8) && i < szt) edge[1 + szt + i] = (pixel)vtr[k];
+    }
+    if ((needs & 4) && lane == 0) {
+        // Z2 corner smoothing uses edge[-1] and edge[1]: both live in lane 0's registers
+        if (mode == M_Z2 && tw + th >= 6 && filter_edge_flag) vc = ((vl[0] + vt[0]) * 5 + vc * 6 + 8) >> 4;
+        edge[0] = (pixel)vc;
     }
     __syncwarp();
     return mode;

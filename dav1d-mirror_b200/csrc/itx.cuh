@@ -101,9 +101,127 @@ template <int W, int H> struct ItxGeom {
     static constexpr bool RECT2 = (W * 2 == H) || (H * 2 == W);
 };
 
+// The two passes are NOT inlined and depend only on the transform length (5
+// variants each) instead of on the 19 (W, H) pairs: the fused intra kernel
+// would otherwise carry ~1.5 MB of SASS and thrash the instruction cache.
+//
+// Row pass: lane gl (< SH, G >= SH) owns coefficient row gl (coeff[gl + x*SH],
+// column-major).  While loading, each lane records which coefficients are
+// non-zero; OR-reductions inside the group give the bounding box of the
+// non-zero coefficients, which selects reduced 1-D transforms (inputs beyond
+// the box are literal zeros).  Writes rows [0, rows_used) of the tile and
+// returns rows_used (8, 16 or SH).
+template <typename coef, int W>
+__device__ __noinline__ int itx_row_pass(const bool full, const int gl, const int G, coef *cf, const int SH,
+                                         const bool rect2, const int shift, const int rk, const Clamp rowcl,
+                                         const Clamp colcl, int *tile, const bool zero_coefs)
+{
+    constexpr int SW = W < 32 ? W : 32, TS = W + 1;
+    const bool wht = rk == K_WHT;
+    const int rnd = (1 << shift) >> 1;
+    int c[W];
+    unsigned rowmask = 0;
+    if (full && gl < SH) {
+#pragma unroll
+        for (int x = 0; x < SW; x++) {
+            int v = cf[gl + x * SH];
+            rowmask |= (unsigned)(v != 0) << x;
+            if (wht) v >>= 2;
+            else if (rect2) v = (v * 181 + 128) >> 8;
+            c[x] = v;
+        }
+#pragma unroll
+        for (int x = SW; x < W; x++) c[x] = 0;
+        if (zero_coefs) {
+#pragma unroll
+            for (int x = 0; x < SW; x++) cf[gl + x * SH] = 0;
+        }
+    }
+    unsigned colbits = rowmask, rowbits = rowmask ? 1u << gl : 0u;
+    for (int o = G >> 1; o > 0; o >>= 1) {
+        colbits |= __shfl_xor_sync(0xffffffffu, colbits, o);
+        rowbits |= __shfl_xor_sync(0xffffffffu, rowbits, o);
+    }
+    const int nzw = 32 - __clz(colbits), nzh = 32 - __clz(rowbits);    // 0 if the block is all zero
+    const int rows_used = SH <= 8 ? SH : nzh <= 8 ? 8 : (SH <= 16 || nzh <= 16) ? (SH < 16 ? SH : 16) : SH;
+    if (full && gl < rows_used) {
+        int *trow = tile + gl * TS;
+        if (rowmask == 0) {
+            // an all-zero row transforms to zeros (every stage is v*c+rnd>>s and clamp)
+#pragma unroll
+            for (int x = 0; x < W; x++) trow[x] = 0;
+        } else {
+            itx1d_dispatch<W>(c, rk, rowcl, nzw);
+            if (wht) {
+#pragma unroll
+                for (int x = 0; x < W; x++) trow[x] = c[x];
+            } else {
+#pragma unroll
+                for (int x = 0; x < W; x++) trow[x] = colcl((c[x] + rnd) >> shift);
+            }
+        }
+    }
+    return rows_used;
+}
+
+// Column pass: lane gl owns columns gl, gl+G, ...; only rows < rows_used of the
+// tile are non-zero.  Read-modify-write of the destination column in chunks of
+// CH rows: the loads of the first chunk are issued BEFORE the 1-D transform and
+// those of chunk k+1 before the stores of chunk k, so the global-memory latency
+// overlaps the arithmetic.  __ldcg: L2-coherent reads (the intra dataflow
+// kernel consumes pixels written by other SMs in the same launch).
+template <typename pixel, int H>
+__device__ __noinline__ void itx_col_pass(const bool full, const int gl, const int G, const int *tile, const int TS,
+                                          const int W, const int rows_used, const int ck, const Clamp colcl,
+                                          pixel *dst, const int dstride, const int bdmax)
+{
+    constexpr int SH = H < 32 ? H : 32;
+    const bool wht = ck == K_WHT;
+    if (!full) return;
+    for (int x = gl; x < W; x += G) {
+        pixel *p = dst + x;
+        constexpr int CH = H < 16 ? H : 16;
+        int c[H], dpx[CH];
+#pragma unroll
+        for (int y = 0; y < CH; y++) dpx[y] = __ldcg(p + y * dstride);
+        if (SH > 16 && rows_used > 16) {
+#pragma unroll
+            for (int y = 0; y < SH; y++) c[y] = tile[y * TS + x];
+        } else if (SH > 8 && rows_used > 8) {
+#pragma unroll
+            for (int y = 0; y < (SH < 16 ? SH : 16); y++) c[y] = tile[y * TS + x];
+#pragma unroll
+            for (int y = 16; y < SH; y++) c[y] = 0;
+        } else {
+#pragma unroll
+            for (int y = 0; y < (SH < 8 ? SH : 8); y++) c[y] = tile[y * TS + x];
+#pragma unroll
+            for (int y = 8; y < SH; y++) c[y] = 0;
+        }
+#pragma unroll
+        for (int y = SH; y < H; y++) c[y] = 0;
+        itx1d_dispatch<H>(c, ck, colcl, rows_used);
+#pragma unroll
+        for (int y0 = 0; y0 < H; y0 += CH) {
+            int cur[CH];
+#pragma unroll
+            for (int y = 0; y < CH; y++) cur[y] = dpx[y];
+            if (y0 + CH < H) {
+#pragma unroll
+                for (int y = 0; y < CH; y++) dpx[y] = __ldcg(p + (y0 + CH + y) * dstride);
+            }
+#pragma unroll
+            for (int y = 0; y < CH; y++) {
+                const int r = wht ? c[y0 + y] : (c[y0 + y] + 8) >> 4;
+                p[(y0 + y) * dstride] = (pixel)clip_px<pixel>(cur[y] + r, bdmax);
+            }
+        }
+    }
+}
+
 // `gl` = lane index inside the group, `G` = group size (power of two >= 4),
 // `tile` = this group's shared scratch (ItxGeom::TILE_INTS ints).
-// `dst`/`dstride` (in pixels) may point to global or shared memory.
+// `dst`/`dstride` (in pixels) point to global memory.
 // All lanes of the warp must call this (it contains __syncwarp()); lanes of a
 // group without a block pass active = false.
 template <typename pixel, int W, int H, int G>
@@ -112,12 +230,11 @@ DEV void itx_block(const bool active, const int gl, int *tile,
                    pixel *dst, const int dstride, const int bdmax, const bool zero_coefs)
 {
     typedef ItxGeom<W, H> Geo;
-    constexpr int SW = Geo::SW, SH = Geo::SH, TS = Geo::TSTRIDE, SHIFT = Geo::SHIFT;
+    typedef typename PxTraits<pixel>::coef coef;
+    constexpr int SH = Geo::SH, TS = Geo::TSTRIDE, SHIFT = Geo::SHIFT;
     constexpr int RND = (1 << SHIFT) >> 1;
-    constexpr int NMAX = W > H ? W : H;
 
     const bool dc_only = active && eob == 0 && txtp == 0;    // has_dconly: DCT_DCT only
-    const bool wht = (W == 4 && H == 4) && txtp == 16;
 
     if (dc_only) {
         int dc = 0;
@@ -160,106 +277,12 @@ DEV void itx_block(const bool active, const int gl, int *tile,
     }
     rowcl.hi = ~rowcl.lo;
     colcl.hi = ~colcl.lo;
-
     const int rk = txtp_row_kind(txtp), ck = txtp_col_kind(txtp);
 
-    // ---- row pass: lane y owns coefficient row y (coeff[y + x*SH], column-major).
-    // G >= SH, so every row has its own lane.  While loading, each lane records
-    // which of its coefficients are non-zero; OR-reductions inside the group
-    // give the bounding box (nzw x nzh) of the non-zero coefficients, which
-    // selects reduced 1-D transforms (inputs beyond the box are literal zeros).
-    int c[NMAX];
-    unsigned rowmask = 0;
-    if (full && gl < SH) {
-#pragma unroll
-        for (int x = 0; x < SW; x++) {
-            int v = cf[gl + x * SH];
-            rowmask |= (unsigned)(v != 0) << x;
-            if (wht) v >>= 2;
-            else if (Geo::RECT2) v = (v * 181 + 128) >> 8;
-            c[x] = v;
-        }
-#pragma unroll
-        for (int x = SW; x < NMAX; x++) c[x] = 0;
-        if (zero_coefs) {
-#pragma unroll
-            for (int x = 0; x < SW; x++) cf[gl + x * SH] = 0;
-        }
-    }
-    unsigned colbits = rowmask, rowbits = rowmask ? 1u << gl : 0u;
-#pragma unroll
-    for (int o = G >> 1; o > 0; o >>= 1) {
-        colbits |= __shfl_xor_sync(0xffffffffu, colbits, o);
-        rowbits |= __shfl_xor_sync(0xffffffffu, rowbits, o);
-    }
-    const int nzw = 32 - __clz(colbits), nzh = 32 - __clz(rowbits);    // 0 if the block is all zero
-    const int rows_used = SH <= 8 ? SH : nzh <= 8 ? 8 : (SH <= 16 || nzh <= 16) ? (SH < 16 ? SH : 16) : SH;
-    if (full && gl < rows_used) {
-        int *trow = tile + gl * TS;
-        if (rowmask == 0) {
-            // an all-zero row transforms to zeros (every stage is v*c+rnd>>s and clamp)
-#pragma unroll
-            for (int x = 0; x < W; x++) trow[x] = 0;
-        } else {
-            itx1d_dispatch<W>(c, rk, rowcl, nzw);
-            if (wht) {
-#pragma unroll
-                for (int x = 0; x < W; x++) trow[x] = c[x];
-            } else {
-#pragma unroll
-                for (int x = 0; x < W; x++) trow[x] = colcl((c[x] + RND) >> SHIFT);
-            }
-        }
-    }
+    const int rows_used = itx_row_pass<coef, W>(full, gl, G, cf, SH, Geo::RECT2, SHIFT, rk, rowcl, colcl, tile,
+                                                zero_coefs);
     __syncwarp();
-    // ---- column pass: lane x owns column x; only rows < rows_used of the tile are non-zero
-    if (full) {
-        for (int x = gl; x < W; x += G) {
-            pixel *p = dst + x;
-            // Read-modify-write of the destination column in chunks of CH rows.
-            // The loads of the first chunk are issued BEFORE the 1-D transform and
-            // those of chunk k+1 before the stores of chunk k, so the global-memory
-            // latency overlaps the arithmetic (otherwise every load would have to
-            // wait behind the previous store).  __ldcg: L2-coherent reads (the intra
-            // dataflow kernel consumes pixels written by other SMs in the same launch).
-            constexpr int CH = H < 16 ? H : 16;
-            int dpx[CH];
-#pragma unroll
-            for (int y = 0; y < CH; y++) dpx[y] = __ldcg(p + y * dstride);
-            if (SH > 16 && rows_used > 16) {
-#pragma unroll
-                for (int y = 0; y < SH; y++) c[y] = tile[y * TS + x];
-            } else if (SH > 8 && rows_used > 8) {
-#pragma unroll
-                for (int y = 0; y < (SH < 16 ? SH : 16); y++) c[y] = tile[y * TS + x];
-#pragma unroll
-                for (int y = 16; y < SH; y++) c[y] = 0;
-            } else {
-#pragma unroll
-                for (int y = 0; y < (SH < 8 ? SH : 8); y++) c[y] = tile[y * TS + x];
-#pragma unroll
-                for (int y = 8; y < SH; y++) c[y] = 0;
-            }
-#pragma unroll
-            for (int y = SH; y < NMAX; y++) c[y] = 0;
-            itx1d_dispatch<H>(c, ck, colcl, rows_used);
-#pragma unroll
-            for (int y0 = 0; y0 < H; y0 += CH) {
-                int cur[CH];
-#pragma unroll
-                for (int y = 0; y < CH; y++) cur[y] = dpx[y];
-                if (y0 + CH < H) {
-#pragma unroll
-                    for (int y = 0; y < CH; y++) dpx[y] = __ldcg(p + (y0 + CH + y) * dstride);
-                }
-#pragma unroll
-                for (int y = 0; y < CH; y++) {
-                    const int r = wht ? c[y0 + y] : (c[y0 + y] + 8) >> 4;
-                    p[(y0 + y) * dstride] = (pixel)clip_px<pixel>(cur[y] + r, bdmax);
-                }
-            }
-        }
-    }
+    itx_col_pass<pixel, H>(full, gl, G, tile, TS, W, rows_used, ck, colcl, dst, dstride, bdmax);
     __syncwarp();
 }
 

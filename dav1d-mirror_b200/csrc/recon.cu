@@ -31,9 +31,21 @@ constexpr int EDGE_BUF = 288;
 constexpr int EDGE_C = 144;
 constexpr int INTRA_TILE_INTS = 32 * 65;
 
-template <typename pixel> struct IntraSmem {
-    int tile[INTRA_TILE_INTS];
-    int16_t ac[32 * 32];
+// Size classes of intra-class operations: each class gets its own kernel
+// instantiation (smaller code footprint -> instruction cache, fewer registers
+// and less shared memory for the small sizes that dominate the count).
+//   0 = any size (dataflow / multi-frame variants), 1 = up to 8x8,
+//   2 = up to 16x16, 3 = larger
+template <int CLS> struct IntraCls {
+    static constexpr int TILE_INTS = CLS == 1 ? 8 * 9 : CLS == 2 ? 16 * 17 : INTRA_TILE_INTS;
+    static constexpr int AC_N = CLS == 1 ? 8 * 8 : CLS == 2 ? 16 * 16 : 32 * 32;
+    static constexpr int MIN_BLOCKS = CLS == 1 ? 8 : CLS == 2 ? 6 : 4;
+};
+HD int intra_size_class(const int w, const int h) { return (w <= 8 && h <= 8) ? 1 : (w <= 16 && h <= 16) ? 2 : 3; }
+
+template <typename pixel, int CLS = 0> struct IntraSmem {
+    int tile[IntraCls<CLS>::TILE_INTS];
+    int16_t ac[IntraCls<CLS>::AC_N];
     pixel edge[EDGE_BUF];
     pixel scratch[IPRED_SCRATCH];
 };
@@ -50,6 +62,7 @@ struct IntraArgs {
     const int32_t *dep_start;
     const int32_t *deps;
     unsigned *sync;
+    int opw;               // level kernels: operations per warp
 };
 
 template <typename pixel, int W, int H>
@@ -61,8 +74,9 @@ DEV void intra_residual(int *tile, void *cf, const Dav1dCudaIntraDesc &d, pixel 
 }
 
 // One intra-class operation (prediction [+ residual]) by one warp.
-template <typename pixel>
-__device__ __noinline__ void intra_op(const IntraArgs &a, const Dav1dCudaIntraDesc &d, IntraSmem<pixel> *sm, const int lane) {
+template <typename pixel, int CLS>
+__device__ __noinline__ void intra_op(const IntraArgs &a, const Dav1dCudaIntraDesc &d, IntraSmem<pixel, CLS> *sm,
+                                      const int lane) {
     const int pl = d.plane;
     const int ss_hor = pl ? a.pic.ss_hor : 0, ss_ver = pl ? a.pic.ss_ver : 0;
     const PlaneView &pv = a.pic.p[pl];
@@ -72,6 +86,15 @@ __device__ __noinline__ void intra_op(const IntraArgs &a, const Dav1dCudaIntraDe
     const int bdmax = a.pic.bdmax;
     pixel *edge = sm->edge + EDGE_C;
     const int have_left = d.x4 > d.tile_x4_start, have_top = d.y4 > d.tile_y4_start;
+
+    if (d.eob >= 0) {
+        // pull the block's coefficients towards the SM while the prediction runs
+        typedef typename PxTraits<pixel>::coef coef;
+        const int ncoef = imin(w, 32) * imin(h, 32);
+        const char *cp = (const char *)((const coef *)a.cf + d.coef_off);
+        for (int o = lane * 128; o < ncoef * (int)sizeof(coef); o += 32 * 128)
+            asm volatile("prefetch.global.L2 [%0];" :: "l"(cp + o));
+    }
 
     if (d.mode == DAV1D_CUDA_INTRA_PAL) {
         pal_pred_block<pixel>(dst, stride, (const pixel *)a.pal + d.aux, a.pal_idx + d.coef_off, w, h, lane, 32);
@@ -95,39 +118,47 @@ __device__ __noinline__ void intra_op(const IntraArgs &a, const Dav1dCudaIntraDe
     }
     __syncwarp();
     if (d.eob < 0) return;
+#define D1_TXCASE(T, W, H) \
+    case T: \
+        if constexpr (CLS == 0 || CLS == ((W <= 8 && H <= 8) ? 1 : (W <= 16 && H <= 16) ? 2 : 3)) \
+            intra_residual<pixel, W, H>(sm->tile, a.cf, d, dst, stride, bdmax, lane); \
+        break;
     switch (d.tx) {
-    case 0: intra_residual<pixel, 4, 4>(sm->tile, a.cf, d, dst, stride, bdmax, lane); break;
-    case 1: intra_residual<pixel, 8, 8>(sm->tile, a.cf, d, dst, stride, bdmax, lane); break;
-    case 2: intra_residual<pixel, 16, 16>(sm->tile, a.cf, d, dst, stride, bdmax, lane); break;
-    case 3: intra_residual<pixel, 32, 32>(sm->tile, a.cf, d, dst, stride, bdmax, lane); break;
-    case 4: intra_residual<pixel, 64, 64>(sm->tile, a.cf, d, dst, stride, bdmax, lane); break;
-    case 5: intra_residual<pixel, 4, 8>(sm->tile, a.cf, d, dst, stride, bdmax, lane); break;
-    case 6: intra_residual<pixel, 8, 4>(sm->tile, a.cf, d, dst, stride, bdmax, lane); break;
-    case 7: intra_residual<pixel, 8, 16>(sm->tile, a.cf, d, dst, stride, bdmax, lane); break;
-    case 8: intra_residual<pixel, 16, 8>(sm->tile, a.cf, d, dst, stride, bdmax, lane); break;
-    case 9: intra_residual<pixel, 16, 32>(sm->tile, a.cf, d, dst, stride, bdmax, lane); break;
-    case 10: intra_residual<pixel, 32, 16>(sm->tile, a.cf, d, dst, stride, bdmax, lane); break;
-    case 11: intra_residual<pixel, 32, 64>(sm->tile, a.cf, d, dst, stride, bdmax, lane); break;
-    case 12: intra_residual<pixel, 64, 32>(sm->tile, a.cf, d, dst, stride, bdmax, lane); break;
-    case 13: intra_residual<pixel, 4, 16>(sm->tile, a.cf, d, dst, stride, bdmax, lane); break;
-    case 14: intra_residual<pixel, 16, 4>(sm->tile, a.cf, d, dst, stride, bdmax, lane); break;
-    case 15: intra_residual<pixel, 8, 32>(sm->tile, a.cf, d, dst, stride, bdmax, lane); break;
-    case 16: intra_residual<pixel, 32, 8>(sm->tile, a.cf, d, dst, stride, bdmax, lane); break;
-    case 17: intra_residual<pixel, 16, 64>(sm->tile, a.cf, d, dst, stride, bdmax, lane); break;
-    default: intra_residual<pixel, 64, 16>(sm->tile, a.cf, d, dst, stride, bdmax, lane); break;
+    D1_TXCASE(0, 4, 4)
+    D1_TXCASE(1, 8, 8)
+    D1_TXCASE(2, 16, 16)
+    D1_TXCASE(3, 32, 32)
+    D1_TXCASE(4, 64, 64)
+    D1_TXCASE(5, 4, 8)
+    D1_TXCASE(6, 8, 4)
+    D1_TXCASE(7, 8, 16)
+    D1_TXCASE(8, 16, 8)
+    D1_TXCASE(9, 16, 32)
+    D1_TXCASE(10, 32, 16)
+    D1_TXCASE(11, 32, 64)
+    D1_TXCASE(12, 64, 32)
+    D1_TXCASE(13, 4, 16)
+    D1_TXCASE(14, 16, 4)
+    D1_TXCASE(15, 8, 32)
+    D1_TXCASE(16, 32, 8)
+    D1_TXCASE(17, 16, 64)
+    D1_TXCASE(18, 64, 16)
+    default: break;
     }
+#undef D1_TXCASE
 }
 
 // Level-synchronous variant: one launch per dependency level.
-template <typename pixel>
-__global__ void __launch_bounds__(INTRA_WARPS * 32, 4) intra_level_kernel(const __grid_constant__ IntraArgs a) {
+template <typename pixel, int CLS>
+__global__ void __launch_bounds__(INTRA_WARPS * 32, IntraCls<CLS>::MIN_BLOCKS)
+intra_level_kernel(const __grid_constant__ IntraArgs a) {
     extern __shared__ __align__(16) uint8_t intra_smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int idx = blockIdx.x * INTRA_WARPS + warp;
     if (idx >= a.n) return;
-    IntraSmem<pixel> *sm = (IntraSmem<pixel> *)intra_smem_raw + warp;
+    IntraSmem<pixel, CLS> *sm = (IntraSmem<pixel, CLS> *)intra_smem_raw + warp;
     const Dav1dCudaIntraDesc d = a.descs[idx];
-    intra_op<pixel>(a, d, sm, lane);
+    intra_op<pixel, CLS>(a, d, sm, lane);
 }
 
 // Multi-frame variant: dependency level l of SEVERAL frames (independent
@@ -161,9 +192,9 @@ __global__ void __launch_bounds__(INTRA_WARPS * 32, 4) intra_multi_kernel(const 
     IntraArgs a;
     a.pic = fp.pic; a.bw4 = fp.bw4; a.bh4 = fp.bh4; a.cf = fp.cf;
     a.descs = fp.descs; a.n = seg.count; a.pal = fp.pal; a.pal_idx = fp.pal_idx;
-    a.dep_start = nullptr; a.deps = nullptr; a.sync = nullptr;
+    a.dep_start = nullptr; a.deps = nullptr; a.sync = nullptr; a.opw = 1;
     const Dav1dCudaIntraDesc d = fp.descs[seg.desc_off + idx];
-    intra_op<pixel>(a, d, sm, lane);
+    intra_op<pixel, 0>(a, d, sm, lane);
 }
 
 // Dataflow variant: ONE persistent launch for the whole intra phase.  Warps
@@ -202,19 +233,28 @@ __global__ void __launch_bounds__(INTRA_WARPS * 32, 4) intra_flow_kernel(const _
             while (ld_acquire(f) == 0) { __nanosleep(ns); if (ns < 1024) ns <<= 1; }
         }
         __syncwarp();
-        intra_op<pixel>(a, d, sm, lane);
+        intra_op<pixel, 0>(a, d, sm, lane);
         __threadfence();
         __syncwarp();
         if (lane == 0) st_release(flags + idx, 1u);
     }
 }
 
-template <typename pixel>
-static int launch_intra_level(const IntraArgs &a, cudaStream_t st) {
+template <typename pixel, int CLS>
+static int launch_intra_level_cls(const IntraArgs &a, cudaStream_t st) {
     const int grid = (a.n + INTRA_WARPS - 1) / INTRA_WARPS;
-    intra_level_kernel<pixel><<<grid, INTRA_WARPS * 32, INTRA_WARPS * sizeof(IntraSmem<pixel>), st>>>(a);
+    intra_level_kernel<pixel, CLS><<<grid, INTRA_WARPS * 32, INTRA_WARPS * sizeof(IntraSmem<pixel, CLS>), st>>>(a);
     count_launch();
     return cuda_ok(cudaGetLastError(), "intra_level_kernel") ? 0 : -5;
+}
+template <typename pixel>
+static int launch_intra_level(const IntraArgs &a, cudaStream_t st, const int cls = 0) {
+    switch (cls) {
+    case 1: return launch_intra_level_cls<pixel, 1>(a, st);
+    case 2: return launch_intra_level_cls<pixel, 2>(a, st);
+    case 3: return launch_intra_level_cls<pixel, 3>(a, st);
+    default: return launch_intra_level_cls<pixel, 0>(a, st);
+    }
 }
 
 static int g_flow_blocks[2] = { 0, 0 };   // persistent grid size per pixel type (set in recon_init_attrs)
@@ -227,7 +267,7 @@ static int intra_flow_launch(const PicView &pic, int bw4, int bh4, void *cf, con
     IntraArgs a;
     a.pic = pic; a.bw4 = bw4; a.bh4 = bh4; a.cf = cf;
     a.descs = descs; a.n = n; a.pal = pal; a.pal_idx = pal_idx;
-    a.dep_start = dep_start; a.deps = deps; a.sync = sync;
+    a.dep_start = dep_start; a.deps = deps; a.sync = sync; a.opw = 1;
     if (!cuda_ok(cudaMemsetAsync(sync, 0, (size_t)(n + 1) * sizeof(unsigned), st), "memset(intra sync)")) return -5;
     const bool hbd = pic.bdmax > 0xff;
     // experiment knob: D1_FLOW_BLOCKS caps the persistent grid (share of the GPU per stream)
@@ -237,6 +277,43 @@ static int intra_flow_launch(const PicView &pic, int bw4, int bh4, void *cf, con
     else intra_flow_kernel<uint8_t><<<grid, INTRA_WARPS * 32, INTRA_WARPS * sizeof(IntraSmem<uint8_t>), st>>>(a);
     count_launch();
     return cuda_ok(cudaGetLastError(), "intra_flow_kernel") ? 0 : -5;
+}
+
+static bool ensure_aux(Dav1dCudaContext *c);
+static bool fork_aux(Dav1dCudaContext *c, cudaStream_t st);
+static bool join_aux(Dav1dCudaContext *c, cudaStream_t st);
+
+// Per level the three size classes run as parallel launches (class_start holds
+// 3 * n_levels + 1 offsets into the level- and class-sorted descriptor array).
+static int intra_batch_launch_classes(Dav1dCudaContext *c, const PicView &pic, int bw4, int bh4, void *cf,
+                                      const Dav1dCudaIntraDesc *descs, const int32_t *class_start, int n_levels,
+                                      const void *pal, const uint8_t *pal_idx, cudaStream_t st)
+{
+    if (!ensure_aux(c)) return -5;
+    for (int l = 0; l < n_levels; l++) {
+        int nz = 0;
+        for (int k = 0; k < 3; k++) nz += class_start[3 * l + k + 1] > class_start[3 * l + k];
+        const bool par = nz > 1;
+        if (par && !fork_aux(c, st)) return -5;
+        int used = 0;
+        for (int k = 0; k < 3; k++) {
+            const int n = class_start[3 * l + k + 1] - class_start[3 * l + k];
+            if (n <= 0) continue;
+            IntraArgs a;
+            a.pic = pic; a.bw4 = bw4; a.bh4 = bh4; a.cf = cf;
+            a.descs = descs + class_start[3 * l + k];
+            a.n = n;
+            a.pal = pal; a.pal_idx = pal_idx;
+            a.dep_start = nullptr; a.deps = nullptr; a.sync = nullptr;
+            cudaStream_t s = used == 0 ? st : c->aux[used - 1];
+            used++;
+            const int r = pic.bdmax > 0xff ? launch_intra_level<uint16_t>(a, s, k + 1)
+                                           : launch_intra_level<uint8_t>(a, s, k + 1);
+            if (r) return r;
+        }
+        if (par && !join_aux(c, st)) return -5;
+    }
+    return 0;
 }
 
 static int intra_batch_launch(const PicView &pic, int bw4, int bh4, void *cf, const Dav1dCudaIntraDesc *descs,
@@ -367,6 +444,10 @@ static int recon_submit_on(Dav1dCudaContext *c, const Dav1dCudaReconBatch *b, cu
         if ((r = intra_flow_launch(dst, b->bw4, b->bh4, b->cf, b->intra, n, b->intra_dep_start, b->intra_deps,
                                    (unsigned *)b->intra_sync, b->pal, b->pal_idx, st)))
             return r;
+    } else if (b->intra && b->intra_class_start) {
+        if ((r = intra_batch_launch_classes(c, dst, b->bw4, b->bh4, b->cf, b->intra, b->intra_class_start, b->n_levels,
+                                            b->pal, b->pal_idx, st)))
+            return r;
     } else if (b->intra && (r = intra_batch_launch(dst, b->bw4, b->bh4, b->cf, b->intra, b->intra_level_start,
                                                    b->n_levels, b->pal, b->pal_idx, st)))
         return r;
@@ -473,10 +554,14 @@ void recon_init_attrs() {
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, intra_flow_kernel<uint16_t>, INTRA_WARPS * 32,
                                                   INTRA_WARPS * sizeof(IntraSmem<uint16_t>));
     g_flow_blocks[1] = std::max(1, occ) * std::max(1, sms);
-    cudaFuncSetAttribute(intra_level_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)(INTRA_WARPS * sizeof(IntraSmem<uint16_t>)));
-    cudaFuncSetAttribute(intra_level_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)(INTRA_WARPS * sizeof(IntraSmem<uint8_t>)));
+    cudaFuncSetAttribute(intra_level_kernel<uint16_t, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)(INTRA_WARPS * sizeof(IntraSmem<uint16_t, 0>)));
+    cudaFuncSetAttribute(intra_level_kernel<uint8_t, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)(INTRA_WARPS * sizeof(IntraSmem<uint8_t, 0>)));
+    cudaFuncSetAttribute(intra_level_kernel<uint16_t, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)(INTRA_WARPS * sizeof(IntraSmem<uint16_t, 3>)));
+    cudaFuncSetAttribute(intra_level_kernel<uint8_t, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)(INTRA_WARPS * sizeof(IntraSmem<uint8_t, 3>)));
 }
 
 }  // namespace d1
@@ -508,12 +593,12 @@ int dav1d_cuda_intra_schedule(Dav1dCudaIntraDesc *descs, int n, int bw4, int bh4
                               int32_t *order, int32_t *level_start, int max_levels)
 {
     return dav1d_cuda_intra_schedule_deps(descs, n, bw4, bh4, ss_hor, ss_ver, order, level_start, max_levels,
-                                          nullptr, nullptr, 0);
+                                          nullptr, nullptr, 0, nullptr);
 }
 
 int dav1d_cuda_intra_schedule_deps(Dav1dCudaIntraDesc *descs, int n, int bw4, int bh4, int ss_hor, int ss_ver,
                                    int32_t *order, int32_t *level_start, int max_levels,
-                                   int32_t *dep_start, int32_t *deps, int max_deps)
+                                   int32_t *dep_start, int32_t *deps, int max_deps, int32_t *class_start)
 {
     if (!descs || n < 0 || !order || !level_start) return -22;
     const int pw[3] = { bw4, (bw4 + ss_hor) >> ss_hor, (bw4 + ss_hor) >> ss_hor };
@@ -581,7 +666,8 @@ int dav1d_cuda_intra_schedule_deps(Dav1dCudaIntraDesc *descs, int n, int bw4, in
         for (int i = 0; i < n; i++) {
             const Dav1dCudaIntraDesc &d = descs[i];
             const uint64_t res = d.eob >= 0 ? 1 + d.tx : 0;
-            const uint64_t key = ((uint64_t)d.level << 32) | (res << 16) | ((uint64_t)d.mode << 8) |
+            const uint64_t cls = (uint64_t)intra_size_class(d.tw4 * 4, d.th4 * 4);
+            const uint64_t key = ((uint64_t)d.level << 32) | (cls << 28) | (res << 16) | ((uint64_t)d.mode << 8) |
                                  (d.eob >= 0 ? d.txtp : 0);
             keyed[i] = { key, i };
         }
@@ -590,6 +676,16 @@ int dav1d_cuda_intra_schedule_deps(Dav1dCudaIntraDesc *descs, int n, int bw4, in
                              return a.first < b.first;
                          });
         for (int s2 = 0; s2 < n; s2++) { order[s2] = keyed[s2].second; inv[keyed[s2].second] = s2; }
+        if (class_start) {
+            // offsets of (level, class) runs in the sorted order: 3 * n_levels + 1 entries
+            int k = 0;
+            for (int l = 1; l <= n_levels; l++)
+                for (uint64_t c2 = 1; c2 <= 3; c2++) {
+                    class_start[3 * (l - 1) + (int)c2 - 1] = k;
+                    while (k < n && (keyed[k].first >> 32) == (uint64_t)l && ((keyed[k].first >> 28) & 15) == c2) k++;
+                }
+            class_start[3 * n_levels] = k;
+        }
     }
     if (dep_start && deps) {
         if ((int)dlist.size() > max_deps) return -28;

@@ -121,10 +121,12 @@ class HostFrame:
         max_deps = 96 * max(n, 1)
         dep_start = np.zeros(n + 1, dtype=np.int32)
         deps = np.zeros(max_deps, dtype=np.int32)
+        class_start = np.zeros(3 * max_levels + 1, dtype=np.int32)
         nl = L.dav1d_cuda_intra_schedule_deps(descs.ctypes.data, n, self.bw4, self.bh4,
                                               0 if self.no_chroma else self.ss_hor,
                                               0 if self.no_chroma else self.ss_ver, order, level_start, max_levels,
-                                              dep_start.ctypes.data, deps.ctypes.data, max_deps)
+                                              dep_start.ctypes.data, deps.ctypes.data, max_deps,
+                                              class_start.ctypes.data)
         if nl < 0:
             raise RuntimeError(f"dav1d_cuda_intra_schedule_deps: {nl}")
         self.dep_start = dep_start.view(np.uint8)
@@ -133,6 +135,7 @@ class HostFrame:
         rec = descs.reshape(n, C.sizeof(B.IntraDesc)) if n else descs.reshape(0, C.sizeof(B.IntraDesc))
         self.intra_sorted = np.ascontiguousarray(rec[perm]).reshape(-1)
         self.level_start = np.frombuffer(level_start, dtype=np.int32, count=nl + 1).copy()
+        self.class_start = class_start[:3 * nl + 1].copy()
         self.n_levels = nl
         return nl
 
@@ -161,7 +164,7 @@ def random_planes(hf, seed):
 class DeviceFrame:
     """Device-resident state for reconstructing `hf` with libdav1d_cuda.so."""
 
-    def __init__(self, ctx, hf, n_refs=2, dataflow=True):
+    def __init__(self, ctx, hf, n_refs=2, dataflow=False, classes=False):
         self.L = B.lib()
         self.ctx = ctx
         self.hf = hf
@@ -202,8 +205,11 @@ class DeviceFrame:
         b.intra_level_start = self._level_start
         b.n_levels = hf.n_levels
         self._sync = L.dav1d_cuda_malloc(4 * (hf.n_intra + 1))
+        self._class_start = (C.c_int32 * (3 * hf.n_levels + 1))(*hf.class_start.tolist())
         if dataflow:
             b.intra_dep_start, b.intra_deps, b.intra_sync = d["dep_start"], d["deps"], self._sync
+        elif classes:
+            b.intra_class_start = self._class_start
         self.batch = b
         self.graph = None
 

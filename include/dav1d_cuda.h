@@ -324,7 +324,12 @@ DAV1D_CUDA_API int dav1d_cuda_intra_schedule(Dav1dCudaIntraDesc *descs, int n, i
 DAV1D_CUDA_API int dav1d_cuda_intra_schedule_deps(Dav1dCudaIntraDesc *descs, int n, int bw4, int bh4,
                                                   int ss_hor, int ss_ver, int32_t *order,
                                                   int32_t *level_start, int max_levels,
-                                                  int32_t *dep_start, int32_t *deps, int max_deps);
+                                                  int32_t *dep_start, int32_t *deps, int max_deps,
+                                                  int32_t *class_start);
+/* class_start (optional, 3 * max_levels + 1 entries): within a level the
+ * operations are grouped by size class (<= 8x8, <= 16x16, larger); the
+ * (level, class) run k = 3 * level + class spans sorted indices
+ * [class_start[k], class_start[k + 1]). */
 
 /* One launch per dependency level over level-sorted descriptors (device).
  * `level_start` is a HOST array of n_levels + 1 sorted offsets.  `pal` /
@@ -358,6 +363,9 @@ typedef struct Dav1dCudaReconBatch {
      * (n_intra + 1) uint32.  When all three are set phase C is ONE persistent dataflow launch
      * instead of one launch per level. */
     const int32_t *intra_dep_start; const int32_t *intra_deps; void *intra_sync;
+    /* optional (host): size-class runs from dav1d_cuda_intra_schedule_deps(); when set (and the
+     * dataflow fields are not) every level is launched as up to three size-specialised kernels. */
+    const int32_t *intra_class_start;
 } Dav1dCudaReconBatch;
 
 DAV1D_CUDA_API int dav1d_cuda_recon_submit(Dav1dCudaContext *c, const Dav1dCudaReconBatch *b);

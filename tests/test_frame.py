@@ -95,9 +95,9 @@ def test_schedule_levels_are_consistent():
         m[y4[i]:y4[i] + th4[i], x4[i]:x4[i] + tw4[i]] = level[i]
 
 
-def run_gpu(hf, refs, init, use_graph=False, dataflow=True):
+def run_gpu(hf, refs, init, use_graph=False, dataflow=False, classes=True):
     ctx = F.open_context(0)
-    df = F.DeviceFrame(ctx, hf, n_refs=len(refs), dataflow=dataflow)
+    df = F.DeviceFrame(ctx, hf, n_refs=len(refs), dataflow=dataflow, classes=classes)
     try:
         df.upload_descriptors()
         for r, planes in enumerate(refs):
@@ -122,12 +122,14 @@ def test_frame_parity_small(ref, name):
     w, h, bd, seed, kw = CASES[name]
     hf = F.HostFrame(w, h, bd, seed, **kw)
     refs, init, want = oracle_planes(ref, hf, seed)
-    for dataflow in (True, False):
-        got = run_gpu(hf, refs, init, use_graph=(seed % 2 == 0), dataflow=dataflow)
+    # the three schedulers of the intra phase: size-class level kernels (default), one
+    # kernel per level, persistent dataflow kernel
+    for dataflow, classes in ((False, True), (False, False), (True, False)):
+        got = run_gpu(hf, refs, init, use_graph=(seed % 2 == 0), dataflow=dataflow, classes=classes)
         for pl, (a, b) in enumerate(zip(want, got)):
             bad = np.argwhere(a != b)
-            assert bad.size == 0, (f"{name} dataflow={dataflow}: plane {pl} first mismatch at (y,x)={bad[0]} "
-                                   f"ref={a[tuple(bad[0])]} got={b[tuple(bad[0])]} n={len(bad)}")
+            assert bad.size == 0, (f"{name} dataflow={dataflow} classes={classes}: plane {pl} first mismatch at "
+                                   f"(y,x)={bad[0]} ref={a[tuple(bad[0])]} got={b[tuple(bad[0])]} n={len(bad)}")
 
 
 @pytest.mark.gpu
