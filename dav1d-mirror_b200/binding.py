@@ -132,7 +132,7 @@ class ReconBatch(C.Structure):
                 ("itx", C.c_void_p), ("itx_class_count", C.c_int32 * N_RECT_TX_SIZES),
                 ("intra", C.c_void_p), ("intra_level_start", C.POINTER(C.c_int32)), ("n_levels", C.c_int32),
                 ("intra_dep_start", C.c_void_p), ("intra_deps", C.c_void_p), ("intra_sync", C.c_void_p),
-                ("intra_class_start", C.POINTER(C.c_int32))]
+                ("intra_class_start", C.POINTER(C.c_int32)), ("intra_host", C.c_void_p)]
 
 
 def bind_frame_api(L):

@@ -171,11 +171,10 @@ struct IntraFrameParams {
     const void *pal;
     const uint8_t *pal_idx;
 };
-struct IntraSeg { int frame, first_cta, desc_off, count; };
 struct IntraMultiArgs {
     const IntraFrameParams *frames;
-    const IntraSeg *segs;
-    int n_segs;
+    const uint32_t *items;        // this level's operations: frame << 24 | sorted index inside the frame
+    int n;
 };
 
 template <typename pixel>
@@ -183,17 +182,15 @@ __global__ void __launch_bounds__(INTRA_WARPS * 32, 4) intra_multi_kernel(const 
     extern __shared__ __align__(16) uint8_t intra_smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     IntraSmem<pixel> *sm = (IntraSmem<pixel> *)intra_smem_raw + warp;
-    int s = 0;
-    while (s + 1 < m.n_segs && (int)blockIdx.x >= m.segs[s + 1].first_cta) s++;
-    const IntraSeg seg = m.segs[s];
-    const int idx = ((int)blockIdx.x - seg.first_cta) * INTRA_WARPS + warp;
-    if (idx >= seg.count) return;
-    const IntraFrameParams &fp = m.frames[seg.frame];
+    const int i = blockIdx.x * INTRA_WARPS + warp;
+    if (i >= m.n) return;
+    const uint32_t item = m.items[i];
+    const IntraFrameParams &fp = m.frames[item >> 24];
     IntraArgs a;
     a.pic = fp.pic; a.bw4 = fp.bw4; a.bh4 = fp.bh4; a.cf = fp.cf;
-    a.descs = fp.descs; a.n = seg.count; a.pal = fp.pal; a.pal_idx = fp.pal_idx;
+    a.descs = fp.descs; a.n = m.n; a.pal = fp.pal; a.pal_idx = fp.pal_idx;
     a.dep_start = nullptr; a.deps = nullptr; a.sync = nullptr; a.opw = 1;
-    const Dav1dCudaIntraDesc d = fp.descs[seg.desc_off + idx];
+    const Dav1dCudaIntraDesc d = fp.descs[item & 0xffffff];
     intra_op<pixel, 0>(a, d, sm, lane);
 }
 
@@ -461,12 +458,19 @@ static int recon_submit_on(Dav1dCudaContext *c, const Dav1dCudaReconBatch *b, cu
 // (uploaded here from `tab_host`, which must stay valid until the copy ran).
 struct MultiTables {
     std::vector<IntraFrameParams> frames;
-    std::vector<IntraSeg> segs;          // all levels, concatenated
-    std::vector<int> level_seg_start;    // per level: first seg; size n_levels + 1
-    std::vector<int> level_ctas;
+    std::vector<uint32_t> items;         // all levels, concatenated
+    std::vector<int> level_start;        // per level: first item; size n_levels + 1
 };
 
-static void build_multi_tables(const Dav1dCudaReconBatch *const *bs, int n, MultiTables &t) {
+static uint64_t intra_code_key(const Dav1dCudaIntraDesc &d) {
+    const uint64_t res = d.eob >= 0 ? 1 + d.tx : 0;
+    const uint64_t cls = (uint64_t)intra_size_class(d.tw4 * 4, d.th4 * 4);
+    return (cls << 28) | (res << 16) | ((uint64_t)d.mode << 8) | (d.eob >= 0 ? d.txtp : 0);
+}
+
+// Level l of every frame merged and sorted by code path (needs the host copy of
+// each frame's sorted descriptors, Dav1dCudaReconBatch.intra_host).
+static int build_multi_tables(const Dav1dCudaReconBatch *const *bs, int n, MultiTables &t) {
     int max_levels = 0;
     t.frames.resize(n);
     for (int f = 0; f < n; f++) {
@@ -474,26 +478,33 @@ static void build_multi_tables(const Dav1dCudaReconBatch *const *bs, int n, Mult
         IntraFrameParams &p = t.frames[f];
         p.pic = pic_view(b->dst); p.bw4 = b->bw4; p.bh4 = b->bh4; p.cf = b->cf;
         p.descs = b->intra; p.pal = b->pal; p.pal_idx = b->pal_idx;
-        if (b->intra) max_levels = std::max(max_levels, (int)b->n_levels);
+        if (b->intra && b->n_levels > 0) {
+            if (!b->intra_host) return -22;
+            max_levels = std::max(max_levels, (int)b->n_levels);
+        }
     }
-    t.level_seg_start.assign(1, 0);
+    t.level_start.assign(1, 0);
+    std::vector<std::pair<uint64_t, uint32_t>> lv;
     for (int l = 0; l < max_levels; l++) {
-        int cta = 0;
+        lv.clear();
         for (int f = 0; f < n; f++) {
             const Dav1dCudaReconBatch *b = bs[f];
-            if (!b->intra || l >= b->n_levels) continue;
-            const int cnt = b->intra_level_start[l + 1] - b->intra_level_start[l];
-            if (cnt <= 0) continue;
-            t.segs.push_back({ f, cta, b->intra_level_start[l], cnt });
-            cta += (cnt + INTRA_WARPS - 1) / INTRA_WARPS;
+            if (!b->intra || !b->intra_host || l >= b->n_levels) continue;
+            for (int i = b->intra_level_start[l]; i < b->intra_level_start[l + 1]; i++)
+                lv.push_back({ intra_code_key(b->intra_host[i]), ((uint32_t)f << 24) | (uint32_t)i });
         }
-        t.level_seg_start.push_back((int)t.segs.size());
-        t.level_ctas.push_back(cta);
+        std::stable_sort(lv.begin(), lv.end(),
+                         [](const std::pair<uint64_t, uint32_t> &x, const std::pair<uint64_t, uint32_t> &y) {
+                             return x.first < y.first;
+                         });
+        for (auto &e : lv) t.items.push_back(e.second);
+        t.level_start.push_back((int)t.items.size());
     }
+    return 0;
 }
 
 static int recon_submit_multi_on(Dav1dCudaContext *c, const Dav1dCudaReconBatch *const *bs, int n,
-                                 const IntraFrameParams *d_frames, const IntraSeg *d_segs, const MultiTables &t,
+                                 const IntraFrameParams *d_frames, const uint32_t *d_items, const MultiTables &t,
                                  cudaStream_t st)
 {
     if (!ensure_aux(c)) return -5;
@@ -522,12 +533,12 @@ static int recon_submit_multi_on(Dav1dCudaContext *c, const Dav1dCudaReconBatch 
     if (!(mask & 16)) return 0;
     // phase C: one launch per level over all frames
     const bool hbd = bs[0]->dst->bitdepth_max > 0xff;
-    for (size_t l = 0; l + 1 < t.level_seg_start.size(); l++) {
-        const int s0 = t.level_seg_start[l], s1 = t.level_seg_start[l + 1];
+    for (size_t l = 0; l + 1 < t.level_start.size(); l++) {
+        const int s0 = t.level_start[l], s1 = t.level_start[l + 1];
         if (s1 <= s0) continue;
         IntraMultiArgs m;
-        m.frames = d_frames; m.segs = d_segs + s0; m.n_segs = s1 - s0;
-        const int grid = t.level_ctas[l];
+        m.frames = d_frames; m.items = d_items + s0; m.n = s1 - s0;
+        const int grid = (m.n + INTRA_WARPS - 1) / INTRA_WARPS;
         if (hbd) intra_multi_kernel<uint16_t><<<grid, INTRA_WARPS * 32, INTRA_WARPS * sizeof(IntraSmem<uint16_t>), st>>>(m);
         else intra_multi_kernel<uint8_t><<<grid, INTRA_WARPS * 32, INTRA_WARPS * sizeof(IntraSmem<uint8_t>), st>>>(m);
         count_launch();
@@ -746,17 +757,19 @@ int dav1d_cuda_recon_graph_build_multi(Dav1dCudaContext *c, const Dav1dCudaRecon
 {
     if (!c || !bs || n < 1 || !out) return -22;
     *out = nullptr;
+    if (n > 255) return -22;
     MultiTables t;
-    build_multi_tables(bs, n, t);
-    const size_t fb = t.frames.size() * sizeof(IntraFrameParams), sb = t.segs.size() * sizeof(IntraSeg);
+    if (build_multi_tables(bs, n, t)) return -22;
+    const size_t fb = (t.frames.size() * sizeof(IntraFrameParams) + 255) & ~(size_t)255;
+    const size_t sb = t.items.size() * sizeof(uint32_t);
     uint8_t *tab = nullptr;
     D1_CHECK(cudaMalloc(&tab, fb + sb + 64));
-    D1_CHECK(cudaMemcpy(tab, t.frames.data(), fb, cudaMemcpyHostToDevice));
-    if (sb) D1_CHECK(cudaMemcpy(tab + fb, t.segs.data(), sb, cudaMemcpyHostToDevice));
+    D1_CHECK(cudaMemcpy(tab, t.frames.data(), t.frames.size() * sizeof(IntraFrameParams), cudaMemcpyHostToDevice));
+    if (sb) D1_CHECK(cudaMemcpy(tab + fb, t.items.data(), sb, cudaMemcpyHostToDevice));
     cudaStream_t cap;
     D1_CHECK(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
     D1_CHECK(cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal));
-    const int r = recon_submit_multi_on(c, bs, n, (const IntraFrameParams *)tab, (const IntraSeg *)(tab + fb), t, cap);
+    const int r = recon_submit_multi_on(c, bs, n, (const IntraFrameParams *)tab, (const uint32_t *)(tab + fb), t, cap);
     cudaGraph_t graph = nullptr;
     const cudaError_t e = cudaStreamEndCapture(cap, &graph);
     cudaStreamDestroy(cap);

@@ -206,6 +206,7 @@ class DeviceFrame:
         b.n_levels = hf.n_levels
         self._sync = L.dav1d_cuda_malloc(4 * (hf.n_intra + 1))
         self._class_start = (C.c_int32 * (3 * hf.n_levels + 1))(*hf.class_start.tolist())
+        b.intra_host = hf.intra_sorted.ctypes.data if hf.intra_sorted.nbytes else None
         if dataflow:
             b.intra_dep_start, b.intra_deps, b.intra_sync = d["dep_start"], d["deps"], self._sync
         elif classes:

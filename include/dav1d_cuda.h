@@ -366,6 +366,9 @@ typedef struct Dav1dCudaReconBatch {
     /* optional (host): size-class runs from dav1d_cuda_intra_schedule_deps(); when set (and the
      * dataflow fields are not) every level is launched as up to three size-specialised kernels. */
     const int32_t *intra_class_start;
+    /* optional (host): copy of the sorted `intra` array; needed by
+     * dav1d_cuda_recon_graph_build_multi() to merge the frames' levels by code path. */
+    const Dav1dCudaIntraDesc *intra_host;
 } Dav1dCudaReconBatch;
 
 DAV1D_CUDA_API int dav1d_cuda_recon_submit(Dav1dCudaContext *c, const Dav1dCudaReconBatch *b);
