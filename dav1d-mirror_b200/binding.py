@@ -130,9 +130,12 @@ class ReconBatch(C.Structure):
                 ("mc_comp", C.c_void_p), ("mc_comp_tiles", C.c_void_p), ("n_mc_comp_tiles", C.c_int32 * 2),
                 ("warp", C.c_void_p), ("n_warp", C.c_int32),
                 ("itx", C.c_void_p), ("itx_class_count", C.c_int32 * N_RECT_TX_SIZES),
+                ("itx_tasks", C.c_void_p), ("n_itx_tasks", C.c_int32 * 2),
                 ("intra", C.c_void_p), ("intra_level_start", C.POINTER(C.c_int32)), ("n_levels", C.c_int32),
                 ("intra_dep_start", C.c_void_p), ("intra_deps", C.c_void_p), ("intra_sync", C.c_void_p),
-                ("intra_class_start", C.POINTER(C.c_int32)), ("intra_host", C.c_void_p)]
+                ("intra_class_start", C.POINTER(C.c_int32)), ("intra_host", C.c_void_p),
+                ("intra_itx", C.c_void_p), ("intra_itx_tasks", C.c_void_p),
+                ("intra_itx_task_start", C.POINTER(C.c_int32))]
 
 
 def bind_frame_api(L):
@@ -149,6 +152,12 @@ def bind_frame_api(L):
     L.dav1d_cuda_intra_schedule_deps.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                                  C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int,
                                                  C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    L.dav1d_cuda_itx_tasks.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int32),
+                                       C.POINTER(C.c_int32)]
+    L.dav1d_cuda_intra_residual_tasks.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.c_int, C.c_void_p, C.c_void_p,
+                                                  C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    L.dav1d_cuda_itx_task_batch.argtypes = [C.c_void_p, C.POINTER(Picture), C.c_void_p, C.c_void_p, C.c_void_p,
+                                            C.c_int, C.c_int, C.c_int]
     L.dav1d_cuda_recon_submit.argtypes = [C.c_void_p, C.POINTER(ReconBatch)]
     L.dav1d_cuda_recon_graph_build.argtypes = [C.c_void_p, C.POINTER(ReconBatch), C.POINTER(C.c_void_p)]
     L.dav1d_cuda_recon_graph_build_multi.argtypes = [C.c_void_p, C.POINTER(C.POINTER(ReconBatch)), C.c_int,

@@ -111,8 +111,15 @@ template <int W, int H> struct ItxGeom {
 // non-zero coefficients, which selects reduced 1-D transforms (inputs beyond
 // the box are literal zeros).  Writes rows [0, rows_used) of the tile and
 // returns rows_used (8, 16 or SH).
+// (inlined in the per-size / task kernels of itx.cu, shared out of line in the fused intra
+// kernel of recon.cu, which defines D1_ITX_PASS_NOINLINE)
+#if defined(D1_ITX_PASS_NOINLINE)
+#define D1_ITX_PASS __device__ __noinline__
+#else
+#define D1_ITX_PASS __device__ __forceinline__
+#endif
 template <typename coef, int W>
-__device__ __noinline__ int itx_row_pass(const bool full, const int gl, const int G, coef *cf, const int SH,
+D1_ITX_PASS int itx_row_pass(const bool full, const int gl, const int G, coef *cf, const int SH,
                                          const bool rect2, const int shift, const int rk, const Clamp rowcl,
                                          const Clamp colcl, int *tile, const bool zero_coefs)
 {
@@ -171,7 +178,7 @@ __device__ __noinline__ int itx_row_pass(const bool full, const int gl, const in
 // overlaps the arithmetic.  __ldcg: L2-coherent reads (the intra dataflow
 // kernel consumes pixels written by other SMs in the same launch).
 template <typename pixel, int H>
-__device__ __noinline__ void itx_col_pass(const bool full, const int gl, const int G, const int *tile, const int TS,
+D1_ITX_PASS void itx_col_pass(const bool full, const int gl, const int G, const int *tile, const int TS,
                                           const int W, const int rows_used, const int ck, const Clamp colcl,
                                           pixel *dst, const int dstride, const int bdmax)
 {

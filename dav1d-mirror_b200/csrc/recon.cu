@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <vector>
 #include "ctx.h"
+#define D1_ITX_PASS_NOINLINE
 #include "itx.cuh"
 #include "ipred.cuh"
 #include "mc.cuh"
@@ -21,6 +22,10 @@ int itx_batch_launch(const PicView &pic, void *cf, const Dav1dCudaItxDesc *descs
                      const int32_t *class_count, int zero_coefs, cudaStream_t st);
 int itx_batch_launch_multi(const PicView &pic, void *cf, const Dav1dCudaItxDesc *descs,
                            const int32_t *class_count, int zero_coefs, cudaStream_t *streams, int n_streams);
+int itx_task_launch(const PicView &pic, void *cf, const Dav1dCudaItxDesc *descs, const uint32_t *tasks,
+                    int n_small, int n_big, int zero_coefs, cudaStream_t st_small, cudaStream_t st_big);
+int itx_build_tasks(const Dav1dCudaItxDesc *descs, int n, int index_base, uint32_t *tasks, int *n_small, int *n_big);
+void itx_init_attrs();
 struct McArgs;
 int mc_put_launch_raw(const PicView &dst, const PicView *refs, const Dav1dCudaMcDesc *descs,
                       const uint32_t *tiles, int n_tiles, uint8_t *masks, int16_t *tmp, bool compound,
@@ -35,11 +40,11 @@ constexpr int INTRA_TILE_INTS = 32 * 65;
 // instantiation (smaller code footprint -> instruction cache, fewer registers
 // and less shared memory for the small sizes that dominate the count).
 //   0 = any size (dataflow / multi-frame variants), 1 = up to 8x8,
-//   2 = up to 16x16, 3 = larger
+//   2 = up to 16x16, 3 = larger, 4 = prediction only (residuals run as transform tasks)
 template <int CLS> struct IntraCls {
-    static constexpr int TILE_INTS = CLS == 1 ? 8 * 9 : CLS == 2 ? 16 * 17 : INTRA_TILE_INTS;
+    static constexpr int TILE_INTS = CLS == 4 ? 4 : CLS == 1 ? 8 * 9 : CLS == 2 ? 16 * 17 : INTRA_TILE_INTS;
     static constexpr int AC_N = CLS == 1 ? 8 * 8 : CLS == 2 ? 16 * 16 : 32 * 32;
-    static constexpr int MIN_BLOCKS = CLS == 1 ? 8 : CLS == 2 ? 6 : 4;
+    static constexpr int MIN_BLOCKS = CLS == 1 || CLS == 4 ? 8 : CLS == 2 ? 6 : 4;
 };
 HD int intra_size_class(const int w, const int h) { return (w <= 8 && h <= 8) ? 1 : (w <= 16 && h <= 16) ? 2 : 3; }
 
@@ -87,7 +92,7 @@ __device__ __noinline__ void intra_op(const IntraArgs &a, const Dav1dCudaIntraDe
     pixel *edge = sm->edge + EDGE_C;
     const int have_left = d.x4 > d.tile_x4_start, have_top = d.y4 > d.tile_y4_start;
 
-    if (d.eob >= 0) {
+    if (CLS != 4 && d.eob >= 0) {
         // pull the block's coefficients towards the SM while the prediction runs
         typedef typename PxTraits<pixel>::coef coef;
         const int ncoef = imin(w, 32) * imin(h, 32);
@@ -117,7 +122,7 @@ __device__ __noinline__ void intra_op(const IntraArgs &a, const Dav1dCudaIntraDe
         ipred_block<pixel>(m, dst, stride, edge, w, h, angle | d.flags, max_w, max_h, bdmax, sm->scratch, lane);
     }
     __syncwarp();
-    if (d.eob < 0) return;
+    if (CLS == 4 || d.eob < 0) return;
 #define D1_TXCASE(T, W, H) \
     case T: \
         if constexpr (CLS == 0 || CLS == ((W <= 8 && H <= 8) ? 1 : (W <= 16 && H <= 16) ? 2 : 3)) \
@@ -250,6 +255,7 @@ static int launch_intra_level(const IntraArgs &a, cudaStream_t st, const int cls
     case 1: return launch_intra_level_cls<pixel, 1>(a, st);
     case 2: return launch_intra_level_cls<pixel, 2>(a, st);
     case 3: return launch_intra_level_cls<pixel, 3>(a, st);
+    case 4: return launch_intra_level_cls<pixel, 4>(a, st);
     default: return launch_intra_level_cls<pixel, 0>(a, st);
     }
 }
@@ -309,6 +315,30 @@ static int intra_batch_launch_classes(Dav1dCudaContext *c, const PicView &pic, i
             if (r) return r;
         }
         if (par && !join_aux(c, st)) return -5;
+    }
+    return 0;
+}
+
+// Split variant: per level a prediction-only launch followed by the level's residuals as
+// transform tasks (small sizes, then the rare large ones).
+static int intra_batch_launch_split(const PicView &pic, int bw4, int bh4, void *cf, const Dav1dCudaIntraDesc *descs,
+                                    const int32_t *level_start, int n_levels, const void *pal,
+                                    const uint8_t *pal_idx, const Dav1dCudaItxDesc *itx, const uint32_t *tasks,
+                                    const int32_t *task_start, cudaStream_t st)
+{
+    for (int l = 0; l < n_levels; l++) {
+        const int n = level_start[l + 1] - level_start[l];
+        if (n <= 0) continue;
+        IntraArgs a;
+        a.pic = pic; a.bw4 = bw4; a.bh4 = bh4; a.cf = cf;
+        a.descs = descs + level_start[l];
+        a.n = n;
+        a.pal = pal; a.pal_idx = pal_idx;
+        a.dep_start = nullptr; a.deps = nullptr; a.sync = nullptr; a.opw = 1;
+        int r = pic.bdmax > 0xff ? launch_intra_level<uint16_t>(a, st, 4) : launch_intra_level<uint8_t>(a, st, 4);
+        if (r) return r;
+        const int ns = task_start[2 * l + 1] - task_start[2 * l], nb = task_start[2 * l + 2] - task_start[2 * l + 1];
+        if (ns + nb > 0 && (r = itx_task_launch(pic, cf, itx, tasks + task_start[2 * l], ns, nb, 0, st, st))) return r;
     }
     return 0;
 }
@@ -427,7 +457,13 @@ static int recon_submit_on(Dav1dCudaContext *c, const Dav1dCudaReconBatch *b, cu
     if ((mask & 4) && (r = warp_batch_launch(dst, refs, b->warp, b->n_warp, c->aux[1]))) return r;
     if (!join_aux(c, st)) return -5;
     // phase B: inter residuals
-    if (b->itx && (mask & 8)) {
+    if (b->itx && b->itx_tasks && (mask & 8)) {
+        if (!fork_aux(c, st)) return -5;
+        if ((r = itx_task_launch(dst, b->cf, b->itx, b->itx_tasks, b->n_itx_tasks[0], b->n_itx_tasks[1], 0, st,
+                                 c->aux[0])))
+            return r;
+        if (!join_aux(c, st)) return -5;
+    } else if (b->itx && (mask & 8)) {
         if (!fork_aux(c, st)) return -5;
         cudaStream_t ss[1 + Dav1dCudaContext::N_AUX] = { st, c->aux[0], c->aux[1], c->aux[2] };
         if ((r = itx_batch_launch_multi(dst, b->cf, b->itx, b->itx_class_count, 0, ss, 1 + Dav1dCudaContext::N_AUX)))
@@ -440,6 +476,11 @@ static int recon_submit_on(Dav1dCudaContext *c, const Dav1dCudaReconBatch *b, cu
         const int n = b->intra_level_start[b->n_levels];
         if ((r = intra_flow_launch(dst, b->bw4, b->bh4, b->cf, b->intra, n, b->intra_dep_start, b->intra_deps,
                                    (unsigned *)b->intra_sync, b->pal, b->pal_idx, st)))
+            return r;
+    } else if (b->intra && b->intra_itx && b->intra_itx_tasks && b->intra_itx_task_start) {
+        if ((r = intra_batch_launch_split(dst, b->bw4, b->bh4, b->cf, b->intra, b->intra_level_start, b->n_levels,
+                                          b->pal, b->pal_idx, b->intra_itx, b->intra_itx_tasks,
+                                          b->intra_itx_task_start, st)))
             return r;
     } else if (b->intra && b->intra_class_start) {
         if ((r = intra_batch_launch_classes(c, dst, b->bw4, b->bh4, b->cf, b->intra, b->intra_class_start, b->n_levels,
@@ -548,6 +589,7 @@ static int recon_submit_multi_on(Dav1dCudaContext *c, const Dav1dCudaReconBatch 
 }
 
 void recon_init_attrs() {
+    itx_init_attrs();
     cudaFuncSetAttribute(intra_multi_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)(INTRA_WARPS * sizeof(IntraSmem<uint16_t>)));
     cudaFuncSetAttribute(intra_multi_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -709,6 +751,39 @@ int dav1d_cuda_intra_schedule_deps(Dav1dCudaIntraDesc *descs, int n, int bw4, in
         dep_start[n] = k;
     }
     return n_levels;
+}
+
+int dav1d_cuda_intra_residual_tasks(const Dav1dCudaIntraDesc *sd, const int32_t *level_start, int n_levels,
+                                    Dav1dCudaItxDesc *itx, uint32_t *tasks, int32_t *task_start, int32_t *n_tasks)
+{
+    if (!sd || !level_start || !itx || !tasks || !task_start || !n_tasks) return -22;
+    int n_itx = 0, k = 0;
+    std::vector<Dav1dCudaItxDesc> lv;
+    for (int l = 0; l < n_levels; l++) {
+        lv.clear();
+        for (int i = level_start[l]; i < level_start[l + 1]; i++) {
+            const Dav1dCudaIntraDesc &d = sd[i];
+            if (d.eob < 0 || d.mode == DAV1D_CUDA_INTRA_PAL) continue;
+            Dav1dCudaItxDesc t;
+            memset(&t, 0, sizeof(t));
+            t.coef_off = d.coef_off; t.x = (uint16_t)(d.x4 * 4); t.y = (uint16_t)(d.y4 * 4);
+            t.eob = d.eob; t.plane = d.plane; t.tx = d.tx; t.txtp = d.txtp;
+            lv.push_back(t);
+        }
+        std::stable_sort(lv.begin(), lv.end(), [](const Dav1dCudaItxDesc &x, const Dav1dCudaItxDesc &y) {
+            return x.tx != y.tx ? x.tx < y.tx : x.txtp < y.txtp;
+        });
+        for (auto &t : lv) itx[n_itx++] = t;
+        int ns = 0, nb = 0;
+        const int made = itx_build_tasks(itx + n_itx - (int)lv.size(), (int)lv.size(), n_itx - (int)lv.size(),
+                                         tasks + k, &ns, &nb);
+        task_start[2 * l] = k;
+        task_start[2 * l + 1] = k + ns;
+        k += made;
+    }
+    task_start[2 * n_levels] = k;
+    *n_tasks = k;
+    return n_itx;
 }
 
 int dav1d_cuda_intra_batch(Dav1dCudaContext *c, const Dav1dCudaPicture *dst, int bw4, int bh4, void *cf,

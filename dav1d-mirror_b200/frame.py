@@ -136,6 +136,25 @@ class HostFrame:
         self.intra_sorted = np.ascontiguousarray(rec[perm]).reshape(-1)
         self.level_start = np.frombuffer(level_start, dtype=np.int32, count=nl + 1).copy()
         self.class_start = class_start[:3 * nl + 1].copy()
+        # inter residuals: task codes over the class-sorted itx array
+        n_itx = self.itx.nbytes // C.sizeof(B.ItxDesc)
+        tasks = np.zeros(max(n_itx, 1), dtype=np.uint32)
+        ns, nb = C.c_int32(), C.c_int32()
+        k = L.dav1d_cuda_itx_tasks(self.itx.ctypes.data, n_itx, 0, tasks.ctypes.data, C.byref(ns), C.byref(nb)) \
+            if n_itx else 0
+        self.itx_tasks = tasks[:max(k, 1)].copy().view(np.uint8)
+        self.n_itx_tasks = (ns.value, nb.value)
+        # intra residuals as transform descriptors + tasks per level
+        iitx = np.zeros(max(n, 1) * C.sizeof(B.ItxDesc), dtype=np.uint8)
+        itasks = np.zeros(max(n, 1), dtype=np.uint32)
+        tstart = (C.c_int32 * (2 * nl + 1))()
+        nt = C.c_int32()
+        lstart = (C.c_int32 * (nl + 1))(*self.level_start.tolist())
+        ni = L.dav1d_cuda_intra_residual_tasks(self.intra_sorted.ctypes.data, lstart, nl, iitx.ctypes.data,
+                                               itasks.ctypes.data, tstart, C.byref(nt)) if n else 0
+        self.intra_itx = iitx[:max(ni, 1) * C.sizeof(B.ItxDesc)].copy()
+        self.intra_itx_tasks = itasks[:max(nt.value, 1)].copy().view(np.uint8)
+        self.intra_itx_task_start = np.frombuffer(tstart, dtype=np.int32, count=2 * nl + 1).copy()
         self.n_levels = nl
         return nl
 
@@ -149,7 +168,7 @@ class HostFrame:
         n = sum(a.nbytes for a in (self.mc_put, self.mc_put_tiles, self.mc_comp, self.mc_comp_tiles, self.warp,
                                    self.itx, self.cf, self.masks, self.pal, self.pal_idx))
         if self.intra_sorted is not None:
-            n += self.dep_start.nbytes + self.deps.nbytes
+            n += self.itx_tasks.nbytes + self.intra_itx.nbytes + self.intra_itx_tasks.nbytes
         return n + (self.intra_sorted.nbytes if self.intra_sorted is not None else self.intra.nbytes)
 
 
@@ -164,7 +183,7 @@ def random_planes(hf, seed):
 class DeviceFrame:
     """Device-resident state for reconstructing `hf` with libdav1d_cuda.so."""
 
-    def __init__(self, ctx, hf, n_refs=2, dataflow=False, classes=False):
+    def __init__(self, ctx, hf, n_refs=2, dataflow=False, classes=False, tasks=True):
         self.L = B.lib()
         self.ctx = ctx
         self.hf = hf
@@ -180,7 +199,7 @@ class DeviceFrame:
         self._dev = {}
         self._host = {}
         for name in ("mc_put", "mc_put_tiles", "mc_comp", "mc_comp_tiles", "warp", "itx", "intra_sorted", "cf",
-                     "masks", "pal", "pal_idx", "dep_start", "deps"):
+                     "masks", "pal", "pal_idx", "dep_start", "deps", "itx_tasks", "intra_itx", "intra_itx_tasks"):
             arr = getattr(hf, name)
             self._host[name] = arr
             self._dev[name] = L.dav1d_cuda_malloc(max(arr.nbytes, 256))
@@ -206,11 +225,18 @@ class DeviceFrame:
         b.n_levels = hf.n_levels
         self._sync = L.dav1d_cuda_malloc(4 * (hf.n_intra + 1))
         self._class_start = (C.c_int32 * (3 * hf.n_levels + 1))(*hf.class_start.tolist())
+        self._itx_task_start = (C.c_int32 * (2 * hf.n_levels + 1))(*hf.intra_itx_task_start.tolist())
+        if tasks:
+            b.itx_tasks = d["itx_tasks"]
+            b.n_itx_tasks[0], b.n_itx_tasks[1] = hf.n_itx_tasks
         b.intra_host = hf.intra_sorted.ctypes.data if hf.intra_sorted.nbytes else None
         if dataflow:
             b.intra_dep_start, b.intra_deps, b.intra_sync = d["dep_start"], d["deps"], self._sync
         elif classes:
             b.intra_class_start = self._class_start
+        elif tasks:
+            b.intra_itx, b.intra_itx_tasks = d["intra_itx"], d["intra_itx_tasks"]
+            b.intra_itx_task_start = self._itx_task_start
         self.batch = b
         self.graph = None
 
@@ -275,44 +301,35 @@ class DeviceFrame:
         return out
 
     # ---- per-launch-class timing (CUDA events on this context's stream)
-    def time_classes(self, reps=5, flush_mb=256):
+    def run_class(self, name):
+        """Launch one launch class of this frame (asynchronously on the context's stream)."""
         L, ctx, b = self.L, self.ctx, self.batch
-        refs = (C.POINTER(B.Picture) * 7)(*[b.refs[i] for i in range(7)])
-        flush = L.dav1d_cuda_malloc(flush_mb << 20)
-        e0, e1 = L.dav1d_cuda_event_create(), L.dav1d_cuda_event_create()
+        if not hasattr(self, "_refs_arr"):
+            self._refs_arr = (C.POINTER(B.Picture) * 7)(*[b.refs[i] for i in range(7)])
+            self._cls_count = (C.c_int32 * 19)(*[b.itx_class_count[i] for i in range(19)])
+        refs = self._refs_arr
         ntc0, ntc1 = b.n_mc_comp_tiles[0], b.n_mc_comp_tiles[1]
-        cls_count = (C.c_int32 * 19)(*[b.itx_class_count[i] for i in range(19)])
-
-        def run(name):
-            if name == "mc_put":
-                L.dav1d_cuda_mc_put_batch(ctx, b.dst, refs, b.mc_put, b.mc_put_tiles, b.n_mc_put_tiles, None)
-            elif name == "mc_compound":
-                L.dav1d_cuda_mc_compound_batch(ctx, b.dst, refs, b.mc_comp, b.mc_comp_tiles, ntc0, b.masks)
-                if ntc1:
-                    L.dav1d_cuda_mc_compound_batch(ctx, b.dst, refs, b.mc_comp, b.mc_comp_tiles + 4 * ntc0, ntc1,
-                                                   b.masks)
-            elif name == "warp":
-                L.dav1d_cuda_warp_batch(ctx, b.dst, refs, b.warp, b.n_warp)
-            elif name == "itx":
-                L.dav1d_cuda_itx_batch(ctx, b.dst, b.cf, b.itx, cls_count, 0)
+        if name == "mc_put":
+            L.dav1d_cuda_mc_put_batch(ctx, b.dst, refs, b.mc_put, b.mc_put_tiles, b.n_mc_put_tiles, None)
+        elif name == "mc_compound":
+            L.dav1d_cuda_mc_compound_batch(ctx, b.dst, refs, b.mc_comp, b.mc_comp_tiles, ntc0, b.masks)
+            if ntc1:
+                L.dav1d_cuda_mc_compound_batch(ctx, b.dst, refs, b.mc_comp, b.mc_comp_tiles + 4 * ntc0, ntc1,
+                                               b.masks)
+        elif name == "warp":
+            L.dav1d_cuda_warp_batch(ctx, b.dst, refs, b.warp, b.n_warp)
+        elif name == "itx":
+            if b.itx_tasks:
+                L.dav1d_cuda_itx_task_batch(ctx, b.dst, b.cf, b.itx, b.itx_tasks, b.n_itx_tasks[0],
+                                            b.n_itx_tasks[1], 0)
             else:
-                L.dav1d_cuda_intra_batch(ctx, b.dst, b.bw4, b.bh4, b.cf, b.intra, b.intra_level_start, b.n_levels,
-                                         b.pal, b.pal_idx)
+                L.dav1d_cuda_itx_batch(ctx, b.dst, b.cf, b.itx, self._cls_count, 0)
+        else:
+            L.dav1d_cuda_intra_batch(ctx, b.dst, b.bw4, b.bh4, b.cf, b.intra, b.intra_level_start, b.n_levels,
+                                     b.pal, b.pal_idx)
 
-        out = {}
-        for name in ("mc_put", "mc_compound", "warp", "itx", "intra"):
-            tot = 0.0
-            for _ in range(reps):
-                L.dav1d_cuda_memset(ctx, flush, 0, flush_mb << 20)     # evict L2
-                L.dav1d_cuda_event_record(ctx, e0)
-                run(name)
-                L.dav1d_cuda_event_record(ctx, e1)
-                tot += L.dav1d_cuda_event_elapsed_ms(e0, e1)
-            out[name] = tot / reps
-        L.dav1d_cuda_event_destroy(e0)
-        L.dav1d_cuda_event_destroy(e1)
-        L.dav1d_cuda_free(flush)
-        return out
+    def time_classes(self, reps=5, flush_mb=256):
+        return time_classes([self], reps=reps, flush_mb=flush_mb)
 
     def submit(self):
         r = self.L.dav1d_cuda_recon_submit(self.ctx, C.byref(self.batch))
@@ -350,6 +367,40 @@ class DeviceFrame:
         self._pinned, self._pinned_out = {}, []
         for pic in [self.dst] + self.refs:
             L.dav1d_cuda_picture_free(self.ctx, C.byref(pic))
+
+
+CLASSES = ("mc_put", "mc_compound", "warp", "itx", "intra")
+
+
+def time_classes(dfs, reps=3, flush_mb=0):
+    """Average duration (ms) of every launch class of ONE frame, measured with CUDA events on the
+    launching stream.  With several frames the launches rotate over them, so the data of a frame has
+    left the L2 (working set of all frames >> L2) by the time it is touched again while the code stays
+    warm; with a single frame an explicit L2 flush (memset) is issued between repetitions."""
+    L = B.lib()
+    out = {}
+    flush = L.dav1d_cuda_malloc(flush_mb << 20) if flush_mb else None
+    evs = [(L.dav1d_cuda_event_create(), L.dav1d_cuda_event_create()) for _ in dfs]
+    for name in CLASSES:
+        tot, n = 0.0, 0
+        for rep in range(reps + 1):
+            for df, (e0, e1) in zip(dfs, evs):
+                if flush:
+                    L.dav1d_cuda_memset(df.ctx, flush, 0, flush_mb << 20)
+                L.dav1d_cuda_event_record(df.ctx, e0)
+                df.run_class(name)
+                L.dav1d_cuda_event_record(df.ctx, e1)
+                ms = L.dav1d_cuda_event_elapsed_ms(e0, e1)
+                if rep:                      # first round = warm-up
+                    tot += ms
+                    n += 1
+        out[name] = tot / max(n, 1)
+    for e0, e1 in evs:
+        L.dav1d_cuda_event_destroy(e0)
+        L.dav1d_cuda_event_destroy(e1)
+    if flush:
+        L.dav1d_cuda_free(flush)
+    return out
 
 
 class MultiFrame:

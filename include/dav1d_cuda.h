@@ -277,6 +277,19 @@ DAV1D_CUDA_API int dav1d_cuda_itx_batch(Dav1dCudaContext *c, const Dav1dCudaPict
                                         const int32_t class_count[DAV1D_CUDA_N_RECT_TX_SIZES],
                                         int zero_coefs);
 
+/* All transform sizes in (at most) two launches.  A task = up to 32/G
+ * consecutive descriptors of one size for one warp (G = lanes per block);
+ * dav1d_cuda_itx_tasks() (host) builds the task codes for `n` descriptors that
+ * are grouped by `tx` (any order of the groups): tasks[0 .. *n_small) cover the
+ * sizes up to 16x16, the next *n_big the larger ones; `index_base` is added to
+ * the descriptor indices (position of descs_host[0] inside the device array).
+ * Returns the number of tasks (<= n). */
+DAV1D_CUDA_API int dav1d_cuda_itx_tasks(const Dav1dCudaItxDesc *descs_host, int n, int index_base,
+                                        uint32_t *tasks, int32_t *n_small, int32_t *n_big);
+DAV1D_CUDA_API int dav1d_cuda_itx_task_batch(Dav1dCudaContext *c, const Dav1dCudaPicture *dst, void *cf,
+                                             const Dav1dCudaItxDesc *descs, const uint32_t *tasks,
+                                             int n_small, int n_big, int zero_coefs);
+
 /* Motion compensation.  `tiles` (device) lists the 32x32 work tiles:
  * tiles[i] = desc_index * 16 + (tile_row * 4 + tile_col); the recorder emits
  * one entry per 32x32 (or smaller, at the block edge) tile of each block
@@ -331,6 +344,15 @@ DAV1D_CUDA_API int dav1d_cuda_intra_schedule_deps(Dav1dCudaIntraDesc *descs, int
  * (level, class) run k = 3 * level + class spans sorted indices
  * [class_start[k], class_start[k + 1]). */
 
+/* Host: residuals of level-sorted intra descriptors as transform descriptors grouped by
+ * (level, size): itx[0 .. returned count), task codes per level in `tasks`, and
+ * task_start[2*l], task_start[2*l+1] = first small / first big task of level l
+ * (task_start[2*n_levels] = total).  `itx` and `tasks` need room for n entries. */
+DAV1D_CUDA_API int dav1d_cuda_intra_residual_tasks(const Dav1dCudaIntraDesc *sorted_descs,
+                                                   const int32_t *level_start, int n_levels,
+                                                   Dav1dCudaItxDesc *itx, uint32_t *tasks,
+                                                   int32_t *task_start, int32_t *n_tasks);
+
 /* One launch per dependency level over level-sorted descriptors (device).
  * `level_start` is a HOST array of n_levels + 1 sorted offsets.  `pal` /
  * `pal_idx` are the palette pixel pool and the packed index pool (device). */
@@ -358,6 +380,9 @@ typedef struct Dav1dCudaReconBatch {
     const Dav1dCudaMcDesc *mc_comp;   const uint32_t *mc_comp_tiles; int32_t n_mc_comp_tiles[2];
     const Dav1dCudaWarpDesc *warp;    int32_t n_warp;
     const Dav1dCudaItxDesc *itx;      int32_t itx_class_count[DAV1D_CUDA_N_RECT_TX_SIZES];
+    /* optional (device): task codes from dav1d_cuda_itx_tasks() over `itx`; when set phase B is two
+     * launches (small / large sizes) instead of one per size */
+    const uint32_t *itx_tasks;        int32_t n_itx_tasks[2];
     const Dav1dCudaIntraDesc *intra;  const int32_t *intra_level_start; int32_t n_levels;
     /* optional (device): dependency lists from dav1d_cuda_intra_schedule_deps() and a scratch of
      * (n_intra + 1) uint32.  When all three are set phase C is ONE persistent dataflow launch
@@ -369,6 +394,12 @@ typedef struct Dav1dCudaReconBatch {
     /* optional (host): copy of the sorted `intra` array; needed by
      * dav1d_cuda_recon_graph_build_multi() to merge the frames' levels by code path. */
     const Dav1dCudaIntraDesc *intra_host;
+    /* optional: residuals of the intra-class operations as transform descriptors + tasks per level
+     * (dav1d_cuda_intra_residual_tasks()).  When set, the level kernels only predict and every level
+     * is followed by the task-based transform launches (lane groups, one size per warp). */
+    const Dav1dCudaItxDesc *intra_itx;        /* device */
+    const uint32_t *intra_itx_tasks;          /* device */
+    const int32_t *intra_itx_task_start;      /* host: 2 * n_levels + 1 offsets (small, big per level) */
 } Dav1dCudaReconBatch;
 
 DAV1D_CUDA_API int dav1d_cuda_recon_submit(Dav1dCudaContext *c, const Dav1dCudaReconBatch *b);

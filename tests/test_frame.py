@@ -95,9 +95,9 @@ def test_schedule_levels_are_consistent():
         m[y4[i]:y4[i] + th4[i], x4[i]:x4[i] + tw4[i]] = level[i]
 
 
-def run_gpu(hf, refs, init, use_graph=False, dataflow=False, classes=True):
+def run_gpu(hf, refs, init, use_graph=False, dataflow=False, classes=False, tasks=True):
     ctx = F.open_context(0)
-    df = F.DeviceFrame(ctx, hf, n_refs=len(refs), dataflow=dataflow, classes=classes)
+    df = F.DeviceFrame(ctx, hf, n_refs=len(refs), dataflow=dataflow, classes=classes, tasks=tasks)
     try:
         df.upload_descriptors()
         for r, planes in enumerate(refs):
@@ -122,14 +122,16 @@ def test_frame_parity_small(ref, name):
     w, h, bd, seed, kw = CASES[name]
     hf = F.HostFrame(w, h, bd, seed, **kw)
     refs, init, want = oracle_planes(ref, hf, seed)
-    # the three schedulers of the intra phase: size-class level kernels (default), one
-    # kernel per level, persistent dataflow kernel
-    for dataflow, classes in ((False, True), (False, False), (True, False)):
-        got = run_gpu(hf, refs, init, use_graph=(seed % 2 == 0), dataflow=dataflow, classes=classes)
+    # the executors of the intra phase: prediction-only levels + transform tasks (default), fused
+    # level kernel, size-class level kernels, persistent dataflow kernel
+    for dataflow, classes, tasks in ((False, False, True), (False, False, False), (False, True, False),
+                                     (True, False, False)):
+        got = run_gpu(hf, refs, init, use_graph=(seed % 2 == 0), dataflow=dataflow, classes=classes, tasks=tasks)
         for pl, (a, b) in enumerate(zip(want, got)):
             bad = np.argwhere(a != b)
-            assert bad.size == 0, (f"{name} dataflow={dataflow} classes={classes}: plane {pl} first mismatch at "
-                                   f"(y,x)={bad[0]} ref={a[tuple(bad[0])]} got={b[tuple(bad[0])]} n={len(bad)}")
+            assert bad.size == 0, (f"{name} dataflow={dataflow} classes={classes} tasks={tasks}: plane {pl} first "
+                                   f"mismatch at (y,x)={bad[0]} ref={a[tuple(bad[0])]} got={b[tuple(bad[0])]} "
+                                   f"n={len(bad)}")
 
 
 @pytest.mark.gpu

@@ -26,11 +26,11 @@ main = F.open_context(0)
 e0, e1 = L.dav1d_cuda_event_create(), L.dav1d_cuda_event_create()
 
 
-def build(dataflow, n, classes=True):
+def build(dataflow, n, classes=False, tasks=True):
     ctxs, dfs = [], []
     for s in range(n):
         ctx = F.open_context(0)
-        df = F.DeviceFrame(ctx, hfs[s % len(hfs)], dataflow=dataflow, classes=classes)
+        df = F.DeviceFrame(ctx, hfs[s % len(hfs)], dataflow=dataflow, classes=classes, tasks=tasks)
         df.upload_descriptors()
         for r in range(2):
             df.upload_picture(df.refs[r], F.random_planes(df.hf, 7 + r))
@@ -60,16 +60,18 @@ def timed(ctxs, dfs, steps):
     return ms
 
 
-for dataflow, classes in ((False, True), (False, False), (True, False)):
+for dataflow, classes, tasks in ((False, False, True), (False, False, False)):
     for n in sorted(set([1, 2, S])):
-        ctxs, dfs = build(dataflow, n, classes)
+        ctxs, dfs = build(dataflow, n, classes, tasks)
         timed(ctxs, dfs, 3)
         ms = timed(ctxs, dfs, reps)
         per_frame = ms / (reps * n)
-        print(f"dataflow={int(dataflow)} classes={int(classes)} streams={n}: {per_frame*1e3:8.1f} us/frame  "
+        print(f"dataflow={int(dataflow)} tasks={int(tasks)} streams={n}: {per_frame*1e3:8.1f} us/frame  "
               f"{hfs[0].luma_px / per_frame / 1e3:9.0f} Mpix/s  nodes={dfs[0].graph_nodes}", flush=True)
-        if n == 1 and not dataflow and classes:
+        if n == 1 and tasks:
             print("   classes(ms):", {k: round(v, 4) for k, v in dfs[0].time_classes(reps=5).items()}, flush=True)
+        if n == S and tasks:
+            print("   classes rotating over streams (ms):", {k: round(v, 4) for k, v in F.time_classes(dfs, reps=3).items()}, flush=True)
         for df in dfs:
             df.close()
         for c in ctxs:
@@ -79,7 +81,7 @@ for n in sorted(set([1, S, 2 * S])):
     ctx = F.open_context(0)
     dfs = []
     for s_ in range(n):
-        df = F.DeviceFrame(ctx, hfs[s_ % len(hfs)], dataflow=False)
+        df = F.DeviceFrame(ctx, hfs[s_ % len(hfs)], dataflow=False, tasks=False)
         df.upload_descriptors()
         for r in range(2):
             df.upload_picture(df.refs[r], F.random_planes(df.hf, 7 + r))
