@@ -642,6 +642,22 @@ int dav1d_cuda_warp_batch(Dav1dCudaContext *c, const Dav1dCudaPicture *dst, cons
 // Level assignment, see include/dav1d_cuda.h.  Per plane a map of 4x4 cells
 // holds the level at which the cell's pixels become final (0 = produced by
 // the inter phases).
+// Edges the resolved predictor needs: bit0 left, bit1 top, bit2 topleft, bit3 topright,
+// bit4 bottomleft (host mirror of the table in csrc/ipred.cuh prepare_edges()).
+static int intra_needs(int mode, int angle_delta, int have_left, int have_top) {
+    if (mode >= 1 && mode <= 8) {
+        static const int base[8] = { 90, 180, 45, 135, 113, 157, 203, 67 };
+        const int a = base[mode - 1] + 3 * angle_delta;
+        if (a <= 90) return (a < 90 && have_top) ? (2 | 8 | 4) : 2;             // Z1 : VERT
+        if (a < 180) return 1 | 2 | 4;                                          // Z2
+        return (a > 180 && have_left) ? (1 | 16 | 4) : 1;                       // Z3 : HOR
+    }
+    if (mode == 0) return have_left ? (have_top ? 3 : 1) : (have_top ? 2 : 0);  // DC family
+    if (mode == 12) return have_left ? (have_top ? 7 : 1) : (have_top ? 2 : 0); // PAETH -> HOR / VERT / DC_128
+    if (mode >= 9 && mode <= 11) return 3;                                      // SMOOTH*
+    return 1 | 2 | 4;                                                           // FILTER
+}
+
 int dav1d_cuda_intra_schedule(Dav1dCudaIntraDesc *descs, int n, int bw4, int bh4, int ss_hor, int ss_ver,
                               int32_t *order, int32_t *level_start, int max_levels)
 {
@@ -678,13 +694,23 @@ int dav1d_cuda_intra_schedule_deps(Dav1dCudaIntraDesc *descs, int n, int bw4, in
             for (int y = y0; y < y1; y++)
                 for (int x = x0; x < x1; x++) dep(p, x, y);
         } else if (d.mode != DAV1D_CUDA_INTRA_PAL) {
+            // exactly the pixels dav1d_prepare_intra_edges reads for the resolved mode
+            // (ipred_prepare_tmpl.c:50-74 needs_* table, :94-117 mode resolution)
             const int have_left = x0 > d.tile_x4_start, have_top = y0 > d.tile_y4_start;
-            if (have_top) {
-                const int xe = std::min<int>(x0 + d.tw4 + ((d.edge_flags & 1) ? d.tw4 : 0), d.tile_x4_end);
-                for (int x = x0 - have_left; x < xe; x++) dep(p, x, y0 - 1);
+            const int needs = intra_needs(d.mode == DAV1D_CUDA_INTRA_CFL ? 0 : d.mode, d.angle_delta, have_left,
+                                          have_top);
+            // bit0 left, bit1 top, bit2 topleft, bit3 topright, bit4 bottomleft
+            const bool rd_top = have_top && ((needs & 2) || (needs & 4) || ((needs & 1) && !have_left));
+            if (rd_top) {
+                const bool tr = (needs & 8) && (d.edge_flags & 1);
+                const int xs = ((needs & 4) && have_left) ? x0 - 1 : x0;
+                const int xe = (needs & 2) ? std::min<int>(x0 + d.tw4 + (tr ? d.tw4 : 0), d.tile_x4_end) : x0 + 1;
+                for (int x = xs; x < xe; x++) dep(p, x, y0 - 1);
             }
-            if (have_left) {
-                const int ye = std::min<int>(y0 + d.th4 + ((d.edge_flags & 8) ? d.th4 : 0), d.tile_y4_end);
+            const bool rd_left = have_left && ((needs & 1) || ((needs & 2) && !have_top) || ((needs & 4) && !have_top));
+            if (rd_left) {
+                const bool bl = (needs & 16) && (d.edge_flags & 8);
+                const int ye = (needs & 1) ? std::min<int>(y0 + d.th4 + (bl ? d.th4 : 0), d.tile_y4_end) : y0 + 1;
                 for (int y = y0; y < ye; y++) dep(p, x0 - 1, y);
             }
             if (d.mode == DAV1D_CUDA_INTRA_CFL) {
