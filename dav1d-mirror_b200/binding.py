@@ -128,6 +128,7 @@ class ReconBatch(C.Structure):
                 ("cf", C.c_void_p), ("masks", C.c_void_p), ("pal", C.c_void_p), ("pal_idx", C.c_void_p),
                 ("mc_put", C.c_void_p), ("mc_put_tiles", C.c_void_p), ("n_mc_put_tiles", C.c_int32),
                 ("mc_comp", C.c_void_p), ("mc_comp_tiles", C.c_void_p), ("n_mc_comp_tiles", C.c_int32 * 2),
+                ("n_mc_put_small", C.c_int32), ("n_mc_comp_small", C.c_int32 * 2),
                 ("warp", C.c_void_p), ("n_warp", C.c_int32),
                 ("itx", C.c_void_p), ("itx_class_count", C.c_int32 * N_RECT_TX_SIZES),
                 ("itx_tasks", C.c_void_p), ("n_itx_tasks", C.c_int32 * 2),
@@ -140,9 +141,9 @@ class ReconBatch(C.Structure):
 
 def bind_frame_api(L):
     L.dav1d_cuda_mc_put_batch.argtypes = [C.c_void_p, C.POINTER(Picture), C.POINTER(C.POINTER(Picture)),
-                                          C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+                                          C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     L.dav1d_cuda_mc_compound_batch.argtypes = [C.c_void_p, C.POINTER(Picture), C.POINTER(C.POINTER(Picture)),
-                                               C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+                                               C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     L.dav1d_cuda_warp_batch.argtypes = [C.c_void_p, C.POINTER(Picture), C.POINTER(C.POINTER(Picture)),
                                         C.c_void_p, C.c_int]
     L.dav1d_cuda_intra_batch.argtypes = [C.c_void_p, C.POINTER(Picture), C.c_int, C.c_int, C.c_void_p, C.c_void_p,
@@ -159,6 +160,7 @@ def bind_frame_api(L):
     L.dav1d_cuda_itx_task_batch.argtypes = [C.c_void_p, C.POINTER(Picture), C.c_void_p, C.c_void_p, C.c_void_p,
                                             C.c_int, C.c_int, C.c_int]
     L.dav1d_cuda_recon_submit.argtypes = [C.c_void_p, C.POINTER(ReconBatch)]
+    L.dav1d_cuda_recon_submit_phases.argtypes = [C.c_void_p, C.POINTER(ReconBatch), C.c_int]
     L.dav1d_cuda_recon_graph_build.argtypes = [C.c_void_p, C.POINTER(ReconBatch), C.POINTER(C.c_void_p)]
     L.dav1d_cuda_recon_graph_build_multi.argtypes = [C.c_void_p, C.POINTER(C.POINTER(ReconBatch)), C.c_int,
                                                      C.POINTER(C.c_void_p)]

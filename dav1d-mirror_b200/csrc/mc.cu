@@ -19,6 +19,7 @@ struct McArgs {
     const Dav1dCudaMcDesc *descs;
     const uint32_t *tiles;      // desc_index * 16 + (ty * 4 + tx), 32x32 tiles
     int n_tiles;
+    int n_small;                // leading tiles of at most 8x8 (grouped four per warp)
     uint8_t *masks;             // wedge / segmentation masks (device)
     int16_t *tmp;               // int16 pool for PREP output
 };
@@ -33,14 +34,23 @@ DEV TileGeo tile_geo(const Dav1dCudaMcDesc &d, const int t) {
     return g;
 }
 
-// ---- put / prep: one warp per 32x32 tile
-template <typename pixel>
+// ---- put / prep: one warp per tile of up to 32x32, or (SMALL) four tiles of up to 8x8 per
+// warp, one per group of 8 lanes (the groups may take different filter paths: every barrier
+// inside mc_tile() is restricted to the group's lanes)
+template <bool SMALL> struct McVar {
+    static constexpr int G = SMALL ? 8 : 32, TMAX = SMALL ? 8 : 32, TPW = 32 / G;
+};
+
+template <typename pixel, bool SMALL>
 __global__ void __launch_bounds__(MC_WARPS * 32) mc_put_kernel(const __grid_constant__ McArgs a) {
     extern __shared__ __align__(16) uint8_t mc_smem_raw[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int ti = blockIdx.x * MC_WARPS + warp;
+    typedef McVar<SMALL> V;
+    const int wl = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int grp = wl / V::G, lane = wl % V::G;
+    const unsigned gmask = SMALL ? 0xffu << (8 * grp) : 0xffffffffu;
+    const int ti = (blockIdx.x * MC_WARPS + warp) * V::TPW + grp;
     if (ti >= a.n_tiles) return;
-    McSmem<pixel> *sm = (McSmem<pixel> *)mc_smem_raw + warp;
+    McSmem<pixel, V::TMAX> *sm = (McSmem<pixel, V::TMAX> *)mc_smem_raw + (warp * V::TPW + grp);
     const uint32_t tcode = a.tiles[ti];
     const Dav1dCudaMcDesc d = a.descs[tcode >> 4];
     const TileGeo g = tile_geo(d, tcode & 15);
@@ -48,33 +58,37 @@ __global__ void __launch_bounds__(MC_WARPS * 32) mc_put_kernel(const __grid_cons
     const PlaneView &ref = a.refs[s.ref].p[d.plane];
     if (d.kind == DAV1D_CUDA_MC_PREP) {
         int16_t *out = a.tmp + d.aux_off + g.y0 * d.w + g.x0;
-        mc_tile<pixel, true>(ref, s.x + g.x0, s.y + g.y0, g.tw, g.th, d.w, d.h, s.mx, s.my, s.filter_2d,
-                             a.dst.bdmax, sm, out, d.w, lane);
+        mc_tile<pixel, true, V::TMAX, V::G>(ref, s.x + g.x0, s.y + g.y0, g.tw, g.th, d.w, d.h, s.mx, s.my,
+                                            s.filter_2d, a.dst.bdmax, sm, out, d.w, lane, gmask);
     } else {
         const PlaneView &dp = a.dst.p[d.plane];
         const int dstride = (int)(dp.stride / (int)sizeof(pixel));
         pixel *out = (pixel *)dp.data + (int64_t)(d.y + g.y0) * dstride + d.x + g.x0;
-        mc_tile<pixel, false>(ref, s.x + g.x0, s.y + g.y0, g.tw, g.th, d.w, d.h, s.mx, s.my, s.filter_2d,
-                              a.dst.bdmax, sm, out, dstride, lane);
+        mc_tile<pixel, false, V::TMAX, V::G>(ref, s.x + g.x0, s.y + g.y0, g.tw, g.th, d.w, d.h, s.mx, s.my,
+                                             s.filter_2d, a.dst.bdmax, sm, out, dstride, lane, gmask);
     }
 }
 
 // ---- fused compound: two preps into shared int16 tiles, then the combine
-template <typename pixel>
+template <typename pixel, bool SMALL>
 __global__ void __launch_bounds__(MC_WARPS * 32) mc_compound_kernel(const __grid_constant__ McArgs a) {
     extern __shared__ __align__(16) uint8_t mc_smem_raw[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int ti = blockIdx.x * MC_WARPS + warp;
+    typedef McVar<SMALL> V;
+    const int wl = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int grp = wl / V::G, lane = wl % V::G;
+    const unsigned gmask = SMALL ? 0xffu << (8 * grp) : 0xffffffffu;
+    const int ti = (blockIdx.x * MC_WARPS + warp) * V::TPW + grp;
     if (ti >= a.n_tiles) return;
-    McSmemCompound<pixel> *sm = (McSmemCompound<pixel> *)mc_smem_raw + warp;
+    McSmemCompound<pixel, V::TMAX> *sm = (McSmemCompound<pixel, V::TMAX> *)mc_smem_raw + (warp * V::TPW + grp);
     const uint32_t tcode = a.tiles[ti];
     const Dav1dCudaMcDesc d = a.descs[tcode >> 4];
     const TileGeo g = tile_geo(d, tcode & 15);
     for (int i = 0; i < 2; i++) {
         const Dav1dCudaMcSrc s = d.src[i];
         const PlaneView &ref = a.refs[s.ref].p[d.plane];
-        mc_tile<pixel, true>(ref, s.x + g.x0, s.y + g.y0, g.tw, g.th, d.w, d.h, s.mx, s.my, s.filter_2d,
-                             a.dst.bdmax, &sm->s, i ? sm->tb : sm->ta, MC_T, lane);
+        mc_tile<pixel, true, V::TMAX, V::G>(ref, s.x + g.x0, s.y + g.y0, g.tw, g.th, d.w, d.h, s.mx, s.my,
+                                            s.filter_2d, a.dst.bdmax, &sm->s, i ? sm->tb : sm->ta, V::TMAX, lane,
+                                            gmask);
     }
     const PlaneView &dp = a.dst.p[d.plane];
     const int dstride = (int)(dp.stride / (int)sizeof(pixel));
@@ -89,8 +103,8 @@ __global__ void __launch_bounds__(MC_WARPS * 32) mc_compound_kernel(const __grid
         ms = d.w >> ssh;
         mask = a.masks + d.aux_off + (g.y0 >> ssv) * ms + (g.x0 >> ssh);
     }
-    mc_combine<pixel>(d.kind, sm->ta, sm->tb, MC_T, out, dstride, g.tw, g.th, d.weight, mask, ms, d.mask_ss,
-                      a.dst.bdmax, lane, 32);
+    mc_combine<pixel>(d.kind, sm->ta, sm->tb, V::TMAX, out, dstride, g.tw, g.th, d.weight, mask, ms, d.mask_ss,
+                      a.dst.bdmax, lane, V::G);
 }
 
 // ---- stand-alone ops on one block (per-call surface + unfused batch use)
@@ -240,39 +254,40 @@ static std::vector<uint32_t> tiles_for(int desc_idx, int w, int h) {
     return t;
 }
 
-template <typename pixel>
-static int launch_put(const McArgs &a, cudaStream_t st) {
-    const int grid = (a.n_tiles + MC_WARPS - 1) / MC_WARPS;
-    mc_put_kernel<pixel><<<grid, MC_WARPS * 32, MC_WARPS * sizeof(McSmem<pixel>), st>>>(a);
-    count_launch();
-    return cuda_ok(cudaGetLastError(), "mc_put_kernel") ? 0 : -5;
-}
-template <typename pixel>
-static int launch_compound(const McArgs &a, cudaStream_t st) {
-    static bool attr_done = false;
-    const size_t smem = MC_WARPS * sizeof(McSmemCompound<pixel>);
-    if (!attr_done) {
-        mc_init_attrs();
-        attr_done = true;
+// a.tiles[0 .. a.n_small) are tiles of at most 8x8 (four per warp), the rest one per warp
+template <typename pixel, bool COMPOUND>
+static int launch_mc(McArgs a, cudaStream_t st) {
+    const int n_small = a.n_small, n_big = a.n_tiles - a.n_small;
+    const uint32_t *tiles = a.tiles;
+    if (n_small > 0) {
+        a.tiles = tiles; a.n_tiles = n_small;
+        const int grid = (n_small + MC_WARPS * 4 - 1) / (MC_WARPS * 4);
+        if (COMPOUND) mc_compound_kernel<pixel, true><<<grid, MC_WARPS * 32, MC_WARPS * 4 * sizeof(McSmemCompound<pixel, 8>), st>>>(a);
+        else mc_put_kernel<pixel, true><<<grid, MC_WARPS * 32, MC_WARPS * 4 * sizeof(McSmem<pixel, 8>), st>>>(a);
+        count_launch();
     }
-    const int grid = (a.n_tiles + MC_WARPS - 1) / MC_WARPS;
-    mc_compound_kernel<pixel><<<grid, MC_WARPS * 32, smem, st>>>(a);
-    count_launch();
-    return cuda_ok(cudaGetLastError(), "mc_compound_kernel") ? 0 : -5;
+    if (n_big > 0) {
+        a.tiles = tiles + n_small; a.n_tiles = n_big;
+        const int grid = (n_big + MC_WARPS - 1) / MC_WARPS;
+        if (COMPOUND) mc_compound_kernel<pixel, false><<<grid, MC_WARPS * 32, MC_WARPS * sizeof(McSmemCompound<pixel, 32>), st>>>(a);
+        else mc_put_kernel<pixel, false><<<grid, MC_WARPS * 32, MC_WARPS * sizeof(McSmem<pixel, 32>), st>>>(a);
+        count_launch();
+    }
+    return cuda_ok(cudaGetLastError(), COMPOUND ? "mc_compound_kernel" : "mc_put_kernel") ? 0 : -5;
 }
 
 int mc_put_launch(const McArgs &a, cudaStream_t st) {
     if (a.n_tiles <= 0) return 0;
-    return a.dst.bdmax > 0xff ? launch_put<uint16_t>(a, st) : launch_put<uint8_t>(a, st);
+    return a.dst.bdmax > 0xff ? launch_mc<uint16_t, false>(a, st) : launch_mc<uint8_t, false>(a, st);
 }
 int mc_compound_launch(const McArgs &a, cudaStream_t st) {
     if (a.n_tiles <= 0) return 0;
-    return a.dst.bdmax > 0xff ? launch_compound<uint16_t>(a, st) : launch_compound<uint8_t>(a, st);
+    return a.dst.bdmax > 0xff ? launch_mc<uint16_t, true>(a, st) : launch_mc<uint8_t, true>(a, st);
 }
 
 int mc_put_launch_raw(const PicView &dst, const PicView *refs, const Dav1dCudaMcDesc *descs,
-                      const uint32_t *tiles, int n_tiles, uint8_t *masks, int16_t *tmp, bool compound,
-                      cudaStream_t st)
+                      const uint32_t *tiles, int n_tiles, int n_small, uint8_t *masks, int16_t *tmp,
+                      bool compound, cudaStream_t st)
 {
     if (n_tiles <= 0 || !descs || !tiles) return 0;
     McArgs a;
@@ -282,16 +297,17 @@ int mc_put_launch_raw(const PicView &dst, const PicView *refs, const Dav1dCudaMc
     a.descs = descs;
     a.tiles = tiles;
     a.n_tiles = n_tiles;
+    a.n_small = n_small;
     a.masks = masks;
     a.tmp = tmp;
     return compound ? mc_compound_launch(a, st) : mc_put_launch(a, st);
 }
 
 void mc_init_attrs() {
-    cudaFuncSetAttribute(mc_compound_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)(MC_WARPS * sizeof(McSmemCompound<uint16_t>)));
-    cudaFuncSetAttribute(mc_compound_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)(MC_WARPS * sizeof(McSmemCompound<uint8_t>)));
+    cudaFuncSetAttribute(mc_compound_kernel<uint16_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)(MC_WARPS * sizeof(McSmemCompound<uint16_t, 32>)));
+    cudaFuncSetAttribute(mc_compound_kernel<uint8_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)(MC_WARPS * sizeof(McSmemCompound<uint8_t, 32>)));
 }
 
 // ------------------------------------------------------------ per-call surface
@@ -339,6 +355,7 @@ static void mc_single(const int filter, void *out_host, const ptrdiff_t out_stri
     a.descs = (const Dav1dCudaMcDesc *)st.dev(o_desc);
     a.tiles = (const uint32_t *)st.dev(o_tiles);
     a.n_tiles = (int)tiles.size();
+    a.n_small = (w <= 8 && h <= 8) ? a.n_tiles : 0;
     a.tmp = (int16_t *)st.dev(o_out);
     if (mc_put_launch(a, st.stream())) return;
     if (!st.download(o_out, ostride * h) || !st.sync()) return;
@@ -613,7 +630,8 @@ void dav1d_cuda_mc_dsp_init_16bpc(Dav1dCudaMCDSPContext *c) { fill_mc<true>(c); 
 
 static int mc_batch_common(Dav1dCudaContext *c, const Dav1dCudaPicture *dst,
                            const Dav1dCudaPicture *const refs[7], const Dav1dCudaMcDesc *descs,
-                           const uint32_t *tiles, int n_tiles, uint8_t *masks, int16_t *tmp, bool compound)
+                           const uint32_t *tiles, int n_tiles, int n_small, uint8_t *masks, int16_t *tmp,
+                           bool compound)
 {
     if (!c || !dst || !descs || !tiles) return -22;
     McArgs a;
@@ -624,6 +642,7 @@ static int mc_batch_common(Dav1dCudaContext *c, const Dav1dCudaPicture *dst,
     a.descs = descs;
     a.tiles = tiles;
     a.n_tiles = n_tiles;
+    a.n_small = n_small;
     a.masks = masks;
     a.tmp = tmp;
     return compound ? mc_compound_launch(a, c->stream) : mc_put_launch(a, c->stream);
@@ -639,16 +658,16 @@ int dav1d_cuda_mc_tiles(uint32_t desc_index, int w, int h, uint32_t *out) {
 
 int dav1d_cuda_mc_put_batch(Dav1dCudaContext *c, const Dav1dCudaPicture *dst,
                             const Dav1dCudaPicture *const refs[7], const Dav1dCudaMcDesc *descs,
-                            const uint32_t *tiles, int n_tiles, int16_t *tmp)
+                            const uint32_t *tiles, int n_tiles, int n_small, int16_t *tmp)
 {
-    return mc_batch_common(c, dst, refs, descs, tiles, n_tiles, nullptr, tmp, false);
+    return mc_batch_common(c, dst, refs, descs, tiles, n_tiles, n_small, nullptr, tmp, false);
 }
 
 int dav1d_cuda_mc_compound_batch(Dav1dCudaContext *c, const Dav1dCudaPicture *dst,
                                  const Dav1dCudaPicture *const refs[7], const Dav1dCudaMcDesc *descs,
-                                 const uint32_t *tiles, int n_tiles, uint8_t *masks)
+                                 const uint32_t *tiles, int n_tiles, int n_small, uint8_t *masks)
 {
-    return mc_batch_common(c, dst, refs, descs, tiles, n_tiles, masks, nullptr, true);
+    return mc_batch_common(c, dst, refs, descs, tiles, n_tiles, n_small, masks, nullptr, true);
 }
 
 }  // extern "C"

@@ -24,19 +24,21 @@ constexpr int MC_ROWS = MC_T + 7;        // rows/cols of the staged window
 constexpr int MC_MID_STRIDE = MC_T;      // int16
 // Staged window row: the 16-byte aligned superset of the (tw+7) needed pixels,
 // i.e. up to 39 + (vector width - 1) pixels: 48 u16 (6 vectors) / 64 u8 (4 vectors).
-template <typename pixel> struct McSrcGeo {
+// TMAX = largest tile edge of the kernel variant: 32 (one tile per warp) or 8 (four
+// tiles of at most 8x8 per warp, one per group of 8 lanes): rows of 15 + 7 px -> 24 u16 / 32 u8.
+template <typename pixel, int TMAX = MC_T> struct McSrcGeo {
     static constexpr int VPX = 16 / (int)sizeof(pixel);      // pixels per 16-byte vector
-    static constexpr int STRIDE = sizeof(pixel) == 2 ? 48 : 64;
+    static constexpr int STRIDE = TMAX == 32 ? (sizeof(pixel) == 2 ? 48 : 64) : (sizeof(pixel) == 2 ? 24 : 32);
 };
 
-template <typename pixel> struct __align__(16) McSmem {
-    pixel src[MC_ROWS * McSrcGeo<pixel>::STRIDE];
-    int16_t mid[MC_ROWS * MC_MID_STRIDE];
+template <typename pixel, int TMAX = MC_T> struct __align__(16) McSmem {
+    pixel src[(TMAX + 7) * McSrcGeo<pixel, TMAX>::STRIDE];
+    int16_t mid[(TMAX + 7) * TMAX];
 };
-template <typename pixel> struct __align__(16) McSmemCompound {
-    McSmem<pixel> s;
-    int16_t ta[MC_T * MC_T];
-    int16_t tb[MC_T * MC_T];
+template <typename pixel, int TMAX = MC_T> struct __align__(16) McSmemCompound {
+    McSmem<pixel, TMAX> s;
+    int16_t ta[TMAX * TMAX];
+    int16_t tb[TMAX * TMAX];
 };
 
 // 8 taps for one direction (warp-uniform). `dim` is the full block's width
@@ -76,16 +78,16 @@ template <typename pixel> struct McOut<pixel, true> {
 
 // Horizontal pass over rows [r_lo, r_hi) of the staged window. SW outputs per lane.
 // FIN = false: write int16 mid ((sum + rnd) >> sh); FIN = true: finish to `out`.
-template <typename pixel, bool PREP, int SW, bool FIN>
+template <typename pixel, bool PREP, int SW, bool FIN, int TMAX, int G>
 DEV void mc_hpass(const pixel *s_src, const int *fh, const int tw, const int r_lo, const int r_hi,
                   const int rnd, const int sh, const int bdmax, int16_t *s_mid,
                   typename McOut<pixel, PREP>::type *out, const int ostride, const int lane)
 {
     const int nst = tw / SW;
     const int total = (r_hi - r_lo) * nst;
-    for (int s = lane; s < total; s += 32) {
+    for (int s = lane; s < total; s += G) {
         const int r = r_lo + s / nst, c0 = (s % nst) * SW;
-        const pixel *p = s_src + r * McSrcGeo<pixel>::STRIDE + c0;
+        const pixel *p = s_src + r * McSrcGeo<pixel, TMAX>::STRIDE + c0;
         int v[SW + 7];
 #pragma unroll
         for (int k = 0; k < SW + 7; k++) v[k] = p[k];
@@ -95,21 +97,21 @@ DEV void mc_hpass(const pixel *s_src, const int *fh, const int tw, const int r_l
 #pragma unroll
             for (int k = 0; k < 8; k++) sum += fh[k] * v[o + k];
             if (FIN) out[(r - 3) * ostride + c0 + o] = McOut<pixel, PREP>::fin(sum, rnd, sh, bdmax);
-            else s_mid[r * MC_MID_STRIDE + c0 + o] = (int16_t)((sum + rnd) >> sh);
+            else s_mid[r * TMAX + c0 + o] = (int16_t)((sum + rnd) >> sh);
         }
     }
 }
 
 // Vertical pass: 8 output rows per lane, column x. SRC is the staged pixel
 // window (column offset 3, stride McSrcGeo::STRIDE) or the int16 mid tile.
-template <typename pixel, bool PREP, typename SRC>
+template <typename pixel, bool PREP, typename SRC, int G>
 DEV void mc_vpass(const SRC *src, const int sstride, const int *fv, const int tw, const int th,
                   const int rnd, const int sh, const int bdmax,
                   typename McOut<pixel, PREP>::type *out, const int ostride, const int lane)
 {
     const int nvs = (th + 7) >> 3;
     const int total = tw * nvs;
-    for (int s = lane; s < total; s += 32) {
+    for (int s = lane; s < total; s += G) {
         const int x = s % tw, y0 = (s / tw) * 8;
         const SRC *p = src + y0 * sstride + x;
         int v[15];
@@ -132,11 +134,14 @@ DEV void mc_vpass(const SRC *src, const int sstride, const int *fv, const int tw
 //   sx, sy    integer sample position of the tile's top-left in the reference
 //   tw, th    tile size (<= 32); bw, bh: full block size (filter selection)
 //   out       tile's top-left in the destination (pixels, or int16 for prep)
-template <typename pixel, bool PREP>
+//   lane      lane index inside the group of G lanes that owns this tile (G = 32: the warp;
+//             G = 8: four tiles per warp, `gmask` = the group's lanes for the barriers)
+template <typename pixel, bool PREP, int TMAX = MC_T, int G = 32>
 DEV void mc_tile(const PlaneView &ref, const int sx, const int sy, const int tw, const int th,
                  const int bw, const int bh, const int mx, const int my, const int filter_2d,
-                 const int bdmax, McSmem<pixel> *sm,
-                 typename McOut<pixel, PREP>::type *out, const int ostride, const int lane)
+                 const int bdmax, McSmem<pixel, TMAX> *sm,
+                 typename McOut<pixel, PREP>::type *out, const int ostride, const int lane,
+                 const unsigned gmask = 0xffffffffu)
 {
     typedef McOut<pixel, PREP> O;
     const int ib = PxTraits<pixel>::inter_bits(bdmax);
@@ -151,7 +156,7 @@ DEV void mc_tile(const PlaneView &ref, const int sx, const int sy, const int tw,
     // round trip; `off` = position of window column 0 inside the staged row.
     // Row indices are clamped in both paths (top/bottom edge emulation); tiles
     // that cross the left/right picture edge take the per-pixel clamped path.
-    constexpr int SS = McSrcGeo<pixel>::STRIDE, VPX = McSrcGeo<pixel>::VPX;
+    constexpr int SS = McSrcGeo<pixel, TMAX>::STRIDE, VPX = McSrcGeo<pixel, TMAX>::VPX;
     const int c_lo = mx ? 0 : 3, c_hi = mx ? tw + 7 : tw + 3;
     const int r_lo = my ? 0 : 3, r_hi = my ? th + 7 : th + 3;
     int off = 0;
@@ -163,7 +168,7 @@ DEV void mc_tile(const PlaneView &ref, const int sx, const int sy, const int tw,
             off = (sx - 3) - a0;
             const int v_lo = (off + c_lo) / VPX, nv = (off + c_hi - 1) / VPX - v_lo + 1;
             const int total = (r_hi - r_lo) * nv;
-            for (int i = lane; i < total; i += 32) {
+            for (int i = lane; i < total; i += G) {
                 const int r = r_lo + i / nv, v = v_lo + i % nv;
                 const int yy = iclip(sy - 3 + r, 0, ref.h - 1);
                 const pixel *g = rp + yy * rstride + a0 + v * VPX;
@@ -173,8 +178,8 @@ DEV void mc_tile(const PlaneView &ref, const int sx, const int sy, const int tw,
             asm volatile("cp.async.wait_all;" ::: "memory");
         } else {
             const int ncols = c_hi - c_lo;
-            const int lpr = ncols <= 8 ? 8 : ncols <= 16 ? 16 : 32;     // lanes per row
-            const int rpi = 32 / lpr;                                   // rows per iteration
+            const int lpr = ncols <= 8 || G == 8 ? 8 : ncols <= 16 ? 16 : 32;   // lanes per row
+            const int rpi = G / lpr;                                   // rows per iteration
             const int lr = lane / lpr, lc = lane % lpr;
             for (int r = r_lo + lr; r < r_hi; r += rpi) {
                 const int yy = iclip(sy - 3 + r, 0, ref.h - 1);
@@ -186,35 +191,35 @@ DEV void mc_tile(const PlaneView &ref, const int sx, const int sy, const int tw,
             }
         }
     }
-    __syncwarp();
+    __syncwarp(gmask);
     const pixel *wsrc = sm->src + off;      // window column c lives at wsrc[r * SS + c]
 
     if (mx && my) {
         const int sh1 = bs - ib, rnd1 = (1 << sh1) >> 1;
-        if (tw >= 8)      mc_hpass<pixel, PREP, 8, false>(wsrc, fh, tw, 0, th + 7, rnd1, sh1, bdmax, sm->mid, nullptr, 0, lane);
-        else if (tw == 4) mc_hpass<pixel, PREP, 4, false>(wsrc, fh, tw, 0, th + 7, rnd1, sh1, bdmax, sm->mid, nullptr, 0, lane);
-        else              mc_hpass<pixel, PREP, 2, false>(wsrc, fh, tw, 0, th + 7, rnd1, sh1, bdmax, sm->mid, nullptr, 0, lane);
-        __syncwarp();
+        if (tw >= 8)      mc_hpass<pixel, PREP, 8, false, TMAX, G>(wsrc, fh, tw, 0, th + 7, rnd1, sh1, bdmax, sm->mid, nullptr, 0, lane);
+        else if (tw == 4) mc_hpass<pixel, PREP, 4, false, TMAX, G>(wsrc, fh, tw, 0, th + 7, rnd1, sh1, bdmax, sm->mid, nullptr, 0, lane);
+        else              mc_hpass<pixel, PREP, 2, false, TMAX, G>(wsrc, fh, tw, 0, th + 7, rnd1, sh1, bdmax, sm->mid, nullptr, 0, lane);
+        __syncwarp(gmask);
         const int sh2 = PREP ? bs : bs + ib, rnd2 = (1 << sh2) >> 1;
-        mc_vpass<pixel, PREP, int16_t>(sm->mid, MC_MID_STRIDE, fv, tw, th, rnd2, sh2, bdmax, out, ostride, lane);
+        mc_vpass<pixel, PREP, int16_t, G>(sm->mid, TMAX, fv, tw, th, rnd2, sh2, bdmax, out, ostride, lane);
     } else if (mx) {
         const int sh = PREP ? bs - ib : bs;
         const int rnd = PREP ? (1 << sh) >> 1 : (1 << (bs - 1)) + ((1 << (bs - ib)) >> 1);
-        if (tw >= 8)      mc_hpass<pixel, PREP, 8, true>(wsrc, fh, tw, 3, th + 3, rnd, sh, bdmax, nullptr, out, ostride, lane);
-        else if (tw == 4) mc_hpass<pixel, PREP, 4, true>(wsrc, fh, tw, 3, th + 3, rnd, sh, bdmax, nullptr, out, ostride, lane);
-        else              mc_hpass<pixel, PREP, 2, true>(wsrc, fh, tw, 3, th + 3, rnd, sh, bdmax, nullptr, out, ostride, lane);
+        if (tw >= 8)      mc_hpass<pixel, PREP, 8, true, TMAX, G>(wsrc, fh, tw, 3, th + 3, rnd, sh, bdmax, nullptr, out, ostride, lane);
+        else if (tw == 4) mc_hpass<pixel, PREP, 4, true, TMAX, G>(wsrc, fh, tw, 3, th + 3, rnd, sh, bdmax, nullptr, out, ostride, lane);
+        else              mc_hpass<pixel, PREP, 2, true, TMAX, G>(wsrc, fh, tw, 3, th + 3, rnd, sh, bdmax, nullptr, out, ostride, lane);
     } else if (my) {
         const int sh = PREP ? bs - ib : bs, rnd = (1 << sh) >> 1;
-        mc_vpass<pixel, PREP, pixel>(wsrc + 3, SS, fv, tw, th, rnd, sh, bdmax, out, ostride, lane);
+        mc_vpass<pixel, PREP, pixel, G>(wsrc + 3, SS, fv, tw, th, rnd, sh, bdmax, out, ostride, lane);
     } else {
-        for (int i = lane; i < tw * th; i += 32) {
+        for (int i = lane; i < tw * th; i += G) {
             const int y = i / tw, x = i % tw;
             const int px = wsrc[(y + 3) * SS + x + 3];
             if (PREP) out[y * ostride + x] = (typename O::type)((px << ib) - PxTraits<pixel>::prep_bias);
             else out[y * ostride + x] = (typename O::type)px;
         }
     }
-    __syncwarp();
+    __syncwarp(gmask);
 }
 
 // ------------------------------------------------------------ compound combine

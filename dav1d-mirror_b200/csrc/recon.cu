@@ -28,8 +28,8 @@ int itx_build_tasks(const Dav1dCudaItxDesc *descs, int n, int index_base, uint32
 void itx_init_attrs();
 struct McArgs;
 int mc_put_launch_raw(const PicView &dst, const PicView *refs, const Dav1dCudaMcDesc *descs,
-                      const uint32_t *tiles, int n_tiles, uint8_t *masks, int16_t *tmp, bool compound,
-                      cudaStream_t st);
+                      const uint32_t *tiles, int n_tiles, int n_small, uint8_t *masks, int16_t *tmp,
+                      bool compound, cudaStream_t st);
 
 constexpr int INTRA_WARPS = 4;
 constexpr int EDGE_BUF = 288;
@@ -434,7 +434,8 @@ static bool join_aux(Dav1dCudaContext *c, cudaStream_t st) {
 // One frame.  Launch classes that touch disjoint pixels run as parallel
 // branches: {put} | {compound wave 0 -> wave 1} | {warp}, then the 19 transform
 // size classes spread over 4 streams, then the intra phase.
-static int recon_submit_on(Dav1dCudaContext *c, const Dav1dCudaReconBatch *b, cudaStream_t st) {
+static int recon_submit_on(Dav1dCudaContext *c, const Dav1dCudaReconBatch *b, cudaStream_t st,
+                           const int phase_mask = 31) {
     const PicView dst = pic_view(b->dst);
     PicView refs[7];
     refs_view(refs, b->refs);
@@ -442,17 +443,18 @@ static int recon_submit_on(Dav1dCudaContext *c, const Dav1dCudaReconBatch *b, cu
     int r;
     // experiment knob (tools/exp_frame.py): D1_PHASE_MASK selects launch classes
     // bit0 put, bit1 compound, bit2 warp, bit3 itx, bit4 intra; default all
-    static const int mask = getenv("D1_PHASE_MASK") ? atoi(getenv("D1_PHASE_MASK")) : 31;
+    static const int env_mask = getenv("D1_PHASE_MASK") ? atoi(getenv("D1_PHASE_MASK")) : 31;
+    const int mask = env_mask & phase_mask;
     // phase A: prediction from reference frames
     if (!fork_aux(c, st)) return -5;
-    if ((mask & 1) && (r = mc_put_launch_raw(dst, refs, b->mc_put, b->mc_put_tiles, b->n_mc_put_tiles, nullptr,
+    if ((mask & 1) && (r = mc_put_launch_raw(dst, refs, b->mc_put, b->mc_put_tiles, b->n_mc_put_tiles, b->n_mc_put_small, nullptr,
                                              nullptr, false, st)))
         return r;
     if ((mask & 2) && (r = mc_put_launch_raw(dst, refs, b->mc_comp, b->mc_comp_tiles, b->n_mc_comp_tiles[0],
-                                             b->masks, nullptr, true, c->aux[0])))
+                                             b->n_mc_comp_small[0], b->masks, nullptr, true, c->aux[0])))
         return r;
     if ((mask & 2) && (r = mc_put_launch_raw(dst, refs, b->mc_comp, b->mc_comp_tiles + b->n_mc_comp_tiles[0],
-                                             b->n_mc_comp_tiles[1], b->masks, nullptr, true, c->aux[0])))
+                                             b->n_mc_comp_tiles[1], b->n_mc_comp_small[1], b->masks, nullptr, true, c->aux[0])))
         return r;
     if ((mask & 4) && (r = warp_batch_launch(dst, refs, b->warp, b->n_warp, c->aux[1]))) return r;
     if (!join_aux(c, st)) return -5;
@@ -561,12 +563,12 @@ static int recon_submit_multi_on(Dav1dCudaContext *c, const Dav1dCudaReconBatch 
         const PicView dst = pic_view(b->dst);
         PicView refs[7];
         refs_view(refs, b->refs);
-        if ((mask & 1) && (r = mc_put_launch_raw(dst, refs, b->mc_put, b->mc_put_tiles, b->n_mc_put_tiles, nullptr,
+        if ((mask & 1) && (r = mc_put_launch_raw(dst, refs, b->mc_put, b->mc_put_tiles, b->n_mc_put_tiles, b->n_mc_put_small, nullptr,
                                                  nullptr, false, s))) return r;
         if ((mask & 2) && (r = mc_put_launch_raw(dst, refs, b->mc_comp, b->mc_comp_tiles, b->n_mc_comp_tiles[0],
-                                                 b->masks, nullptr, true, s))) return r;
+                                                 b->n_mc_comp_small[0], b->masks, nullptr, true, s))) return r;
         if ((mask & 2) && (r = mc_put_launch_raw(dst, refs, b->mc_comp, b->mc_comp_tiles + b->n_mc_comp_tiles[0],
-                                                 b->n_mc_comp_tiles[1], b->masks, nullptr, true, s))) return r;
+                                                 b->n_mc_comp_tiles[1], b->n_mc_comp_small[1], b->masks, nullptr, true, s))) return r;
         if ((mask & 4) && (r = warp_batch_launch(dst, refs, b->warp, b->n_warp, s))) return r;
         if ((mask & 8) && b->itx && (r = itx_batch_launch(dst, b->cf, b->itx, b->itx_class_count, 0, s))) return r;
     }
@@ -823,6 +825,11 @@ int dav1d_cuda_intra_batch(Dav1dCudaContext *c, const Dav1dCudaPicture *dst, int
 int dav1d_cuda_recon_submit(Dav1dCudaContext *c, const Dav1dCudaReconBatch *b) {
     if (!c || !b || !b->dst) return -22;
     return recon_submit_on(c, b, c->stream);
+}
+
+int dav1d_cuda_recon_submit_phases(Dav1dCudaContext *c, const Dav1dCudaReconBatch *b, int phase_mask) {
+    if (!c || !b || !b->dst) return -22;
+    return recon_submit_on(c, b, c->stream, phase_mask);
 }
 
 int dav1d_cuda_recon_graph_build(Dav1dCudaContext *c, const Dav1dCudaReconBatch *b, Dav1dCudaReconGraph **out) {

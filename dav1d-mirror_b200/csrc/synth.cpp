@@ -45,6 +45,7 @@ typedef struct D1SynthParams {
 typedef struct D1SynthFrame {
     Dav1dCudaMcDesc *mc_put;   int32_t n_mc_put;   uint32_t *mc_put_tiles;  int32_t n_mc_put_tiles;
     Dav1dCudaMcDesc *mc_comp;  int32_t n_mc_comp;  uint32_t *mc_comp_tiles; int32_t n_mc_comp_tiles[2];
+    int32_t n_mc_put_small;    int32_t n_mc_comp_small[2];   // leading tiles of blocks <= 8x8 per list / wave
     Dav1dCudaWarpDesc *warp;   int32_t n_warp;
     Dav1dCudaItxDesc *itx;     int32_t n_itx;      int32_t itx_class_count[19];
     Dav1dCudaIntraDesc *intra; int32_t n_intra;    // decode order
@@ -521,18 +522,26 @@ __attribute__((visibility("default"))) int d1synth_generate(const D1SynthParams 
             itx_sorted[n] = g.itx[i];
         }
     }
-    // tiles
+    // tiles: per list (put, compound wave 0, compound wave 1) the tiles of blocks of at most
+    // 8x8 samples first (they are processed four per warp), then the others
     std::vector<uint32_t> put_tiles, comp_tiles;
     uint32_t buf[16];
-    for (size_t i = 0; i < g.put.size(); i++) {
-        const int n = mc_tiles((uint32_t)i, g.put[i].w, g.put[i].h, buf);
-        put_tiles.insert(put_tiles.end(), buf, buf + n);
-    }
-    for (size_t i = 0; i < comp.size(); i++) {
-        const int n = mc_tiles((uint32_t)i, comp[i].w, comp[i].h, buf);
-        comp_tiles.insert(comp_tiles.end(), buf, buf + n);
-        f->n_mc_comp_tiles[i < g.comp0.size() ? 0 : 1] += n;
-    }
+    auto emit = [&](const std::vector<Dav1dCudaMcDesc> &v, size_t lo, size_t hi, std::vector<uint32_t> &out,
+                    int32_t *n_small) {
+        const size_t base = out.size();
+        for (int pass = 0; pass < 2; pass++)
+            for (size_t i = lo; i < hi; i++) {
+                const bool small = v[i].w <= 8 && v[i].h <= 8;
+                if (small != (pass == 0)) continue;
+                const int n = mc_tiles((uint32_t)i, v[i].w, v[i].h, buf);
+                out.insert(out.end(), buf, buf + n);
+                if (small) *n_small += n;
+            }
+        return (int32_t)(out.size() - base);
+    };
+    emit(g.put, 0, g.put.size(), put_tiles, &f->n_mc_put_small);
+    f->n_mc_comp_tiles[0] = emit(comp, 0, g.comp0.size(), comp_tiles, &f->n_mc_comp_small[0]);
+    f->n_mc_comp_tiles[1] = emit(comp, g.comp0.size(), comp.size(), comp_tiles, &f->n_mc_comp_small[1]);
     std::vector<uint32_t> order(g.order.size());
     for (size_t i = 0; i < g.order.size(); i++) {
         uint32_t cls = g.order[i].cls, idx = g.order[i].idx;

@@ -29,6 +29,7 @@ class SynthFrame(C.Structure):
                 ("n_mc_put_tiles", C.c_int32),
                 ("mc_comp", C.c_void_p), ("n_mc_comp", C.c_int32), ("mc_comp_tiles", C.c_void_p),
                 ("n_mc_comp_tiles", C.c_int32 * 2),
+                ("n_mc_put_small", C.c_int32), ("n_mc_comp_small", C.c_int32 * 2),
                 ("warp", C.c_void_p), ("n_warp", C.c_int32),
                 ("itx", C.c_void_p), ("n_itx", C.c_int32), ("itx_class_count", C.c_int32 * 19),
                 ("intra", C.c_void_p), ("n_intra", C.c_int32),
@@ -91,6 +92,8 @@ class HostFrame:
         self.mc_comp_tiles = _np_from(f.mc_comp_tiles, ntc * 4)
         self.n_mc_put_tiles = f.n_mc_put_tiles
         self.n_mc_comp_tiles = (f.n_mc_comp_tiles[0], f.n_mc_comp_tiles[1])
+        self.n_mc_put_small = f.n_mc_put_small
+        self.n_mc_comp_small = (f.n_mc_comp_small[0], f.n_mc_comp_small[1])
         self.warp = _np_from(f.warp, f.n_warp * C.sizeof(B.WarpDesc))
         self.n_warp = f.n_warp
         self.itx = _np_from(f.itx, f.n_itx * C.sizeof(B.ItxDesc))
@@ -216,6 +219,8 @@ class DeviceFrame:
         b.mc_put, b.mc_put_tiles, b.n_mc_put_tiles = d["mc_put"], d["mc_put_tiles"], hf.n_mc_put_tiles
         b.mc_comp, b.mc_comp_tiles = d["mc_comp"], d["mc_comp_tiles"]
         b.n_mc_comp_tiles[0], b.n_mc_comp_tiles[1] = hf.n_mc_comp_tiles
+        b.n_mc_put_small = hf.n_mc_put_small
+        b.n_mc_comp_small[0], b.n_mc_comp_small[1] = hf.n_mc_comp_small
         b.warp, b.n_warp = d["warp"], hf.n_warp
         b.itx = d["itx"]
         for i in range(19):
@@ -302,31 +307,11 @@ class DeviceFrame:
 
     # ---- per-launch-class timing (CUDA events on this context's stream)
     def run_class(self, name):
-        """Launch one launch class of this frame (asynchronously on the context's stream)."""
-        L, ctx, b = self.L, self.ctx, self.batch
-        if not hasattr(self, "_refs_arr"):
-            self._refs_arr = (C.POINTER(B.Picture) * 7)(*[b.refs[i] for i in range(7)])
-            self._cls_count = (C.c_int32 * 19)(*[b.itx_class_count[i] for i in range(19)])
-        refs = self._refs_arr
-        ntc0, ntc1 = b.n_mc_comp_tiles[0], b.n_mc_comp_tiles[1]
-        if name == "mc_put":
-            L.dav1d_cuda_mc_put_batch(ctx, b.dst, refs, b.mc_put, b.mc_put_tiles, b.n_mc_put_tiles, None)
-        elif name == "mc_compound":
-            L.dav1d_cuda_mc_compound_batch(ctx, b.dst, refs, b.mc_comp, b.mc_comp_tiles, ntc0, b.masks)
-            if ntc1:
-                L.dav1d_cuda_mc_compound_batch(ctx, b.dst, refs, b.mc_comp, b.mc_comp_tiles + 4 * ntc0, ntc1,
-                                               b.masks)
-        elif name == "warp":
-            L.dav1d_cuda_warp_batch(ctx, b.dst, refs, b.warp, b.n_warp)
-        elif name == "itx":
-            if b.itx_tasks:
-                L.dav1d_cuda_itx_task_batch(ctx, b.dst, b.cf, b.itx, b.itx_tasks, b.n_itx_tasks[0],
-                                            b.n_itx_tasks[1], 0)
-            else:
-                L.dav1d_cuda_itx_batch(ctx, b.dst, b.cf, b.itx, self._cls_count, 0)
-        else:
-            L.dav1d_cuda_intra_batch(ctx, b.dst, b.bw4, b.bh4, b.cf, b.intra, b.intra_level_start, b.n_levels,
-                                     b.pal, b.pal_idx)
+        """Launch one launch class of this frame exactly as the submit does (async on the context's stream)."""
+        bit = {"mc_put": 1, "mc_compound": 2, "warp": 4, "itx": 8, "intra": 16}[name]
+        r = self.L.dav1d_cuda_recon_submit_phases(self.ctx, C.byref(self.batch), bit)
+        if r:
+            raise RuntimeError(f"dav1d_cuda_recon_submit_phases: {r}")
 
     def time_classes(self, reps=5, flush_mb=256):
         return time_classes([self], reps=reps, flush_mb=flush_mb)

@@ -293,7 +293,8 @@ DAV1D_CUDA_API int dav1d_cuda_itx_task_batch(Dav1dCudaContext *c, const Dav1dCud
 /* Motion compensation.  `tiles` (device) lists the 32x32 work tiles:
  * tiles[i] = desc_index * 16 + (tile_row * 4 + tile_col); the recorder emits
  * one entry per 32x32 (or smaller, at the block edge) tile of each block
- * (dav1d_cuda_mc_tiles() does it for one block).
+ * (dav1d_cuda_mc_tiles() does it for one block).  The first `n_small` entries of a tile list
+ * must be the tiles of blocks of at most 8x8 samples: they are processed four per warp.
  *  - put_batch: kinds PUT (-> dst picture) and PREP (-> int16 pool `tmp`).
  *  - compound_batch: kinds AVG / W_AVG / MASK / W_MASK, the two predictions
  *    and the combine fused in one kernel (the int16 intermediates never
@@ -304,11 +305,11 @@ DAV1D_CUDA_API int dav1d_cuda_itx_task_batch(Dav1dCudaContext *c, const Dav1dCud
 DAV1D_CUDA_API int dav1d_cuda_mc_put_batch(Dav1dCudaContext *c, const Dav1dCudaPicture *dst,
                                            const Dav1dCudaPicture *const refs[7],
                                            const Dav1dCudaMcDesc *descs, const uint32_t *tiles,
-                                           int n_tiles, int16_t *tmp);
+                                           int n_tiles, int n_small, int16_t *tmp);
 DAV1D_CUDA_API int dav1d_cuda_mc_compound_batch(Dav1dCudaContext *c, const Dav1dCudaPicture *dst,
                                                 const Dav1dCudaPicture *const refs[7],
                                                 const Dav1dCudaMcDesc *descs, const uint32_t *tiles,
-                                                int n_tiles, uint8_t *masks);
+                                                int n_tiles, int n_small, uint8_t *masks);
 /* Host helper: append the tile codes of block `desc_index` (w x h) to `out`
  * (room for 16 entries); returns the number written. */
 DAV1D_CUDA_API int dav1d_cuda_mc_tiles(uint32_t desc_index, int w, int h, uint32_t *out);
@@ -378,6 +379,8 @@ typedef struct Dav1dCudaReconBatch {
     const uint8_t *pal_idx;           /* device: packed palette indices */
     const Dav1dCudaMcDesc *mc_put;    const uint32_t *mc_put_tiles;  int32_t n_mc_put_tiles;
     const Dav1dCudaMcDesc *mc_comp;   const uint32_t *mc_comp_tiles; int32_t n_mc_comp_tiles[2];
+    /* leading small (<= 8x8) tiles of mc_put_tiles and of each compound wave */
+    int32_t n_mc_put_small;           int32_t n_mc_comp_small[2];
     const Dav1dCudaWarpDesc *warp;    int32_t n_warp;
     const Dav1dCudaItxDesc *itx;      int32_t itx_class_count[DAV1D_CUDA_N_RECT_TX_SIZES];
     /* optional (device): task codes from dav1d_cuda_itx_tasks() over `itx`; when set phase B is two
@@ -403,6 +406,11 @@ typedef struct Dav1dCudaReconBatch {
 } Dav1dCudaReconBatch;
 
 DAV1D_CUDA_API int dav1d_cuda_recon_submit(Dav1dCudaContext *c, const Dav1dCudaReconBatch *b);
+/* Only the launch classes selected by phase_mask (bit0 put, bit1 compound, bit2 warp, bit3 inter
+ * residual, bit4 intra), exactly as dav1d_cuda_recon_submit() would launch them - used to time
+ * one class with CUDA events. */
+DAV1D_CUDA_API int dav1d_cuda_recon_submit_phases(Dav1dCudaContext *c, const Dav1dCudaReconBatch *b,
+                                                  int phase_mask);
 /* Same, but the launches are captured into a CUDA graph once and replayed:
  * dav1d_cuda_recon_graph_build() records `b`, dav1d_cuda_recon_graph_launch()
  * replays it on the context's stream (the device buffers `b` points to may be
