@@ -135,6 +135,7 @@ class ReconBatch(C.Structure):
                 ("intra", C.c_void_p), ("intra_level_start", C.POINTER(C.c_int32)), ("n_levels", C.c_int32),
                 ("intra_dep_start", C.c_void_p), ("intra_deps", C.c_void_p), ("intra_sync", C.c_void_p),
                 ("intra_class_start", C.POINTER(C.c_int32)), ("intra_host", C.c_void_p),
+                ("intra_tasks", C.c_void_p), ("intra_task_start", C.POINTER(C.c_int32)),
                 ("intra_itx", C.c_void_p), ("intra_itx_tasks", C.c_void_p),
                 ("intra_itx_task_start", C.POINTER(C.c_int32))]
 
@@ -155,6 +156,8 @@ def bind_frame_api(L):
                                                  C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     L.dav1d_cuda_itx_tasks.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int32),
                                        C.POINTER(C.c_int32)]
+    L.dav1d_cuda_intra_tasks.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.c_int, C.c_void_p,
+                                         C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     L.dav1d_cuda_intra_residual_tasks.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.c_int, C.c_void_p, C.c_void_p,
                                                   C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     L.dav1d_cuda_itx_task_batch.argtypes = [C.c_void_p, C.POINTER(Picture), C.c_void_p, C.c_void_p, C.c_void_p,

@@ -3,6 +3,7 @@
 // the same kernels on one staged block.  Reference: src/mc_tmpl.c.
 #include <string.h>
 #include <vector>
+#include <algorithm>
 #include <type_traits>
 #include "ctx.h"
 #include "stage.h"
@@ -41,6 +42,10 @@ template <bool SMALL> struct McVar {
     static constexpr int G = SMALL ? 8 : 32, TMAX = SMALL ? 8 : 32, TPW = 32 / G;
 };
 
+// The grid is capped at the number of blocks that are resident at once (launch_mc) and every
+// warp (group) strides over the tile list: warps are independent, so a slow tile (picture edge,
+// large window) delays only its own warp instead of holding a block's slot, and the next
+// tile's descriptor is fetched while the current tile is computed.
 template <typename pixel, bool SMALL>
 __global__ void __launch_bounds__(MC_WARPS * 32) mc_put_kernel(const __grid_constant__ McArgs a) {
     extern __shared__ __align__(16) uint8_t mc_smem_raw[];
@@ -48,24 +53,36 @@ __global__ void __launch_bounds__(MC_WARPS * 32) mc_put_kernel(const __grid_cons
     const int wl = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int grp = wl / V::G, lane = wl % V::G;
     const unsigned gmask = SMALL ? 0xffu << (8 * grp) : 0xffffffffu;
-    const int ti = (blockIdx.x * MC_WARPS + warp) * V::TPW + grp;
+    const int stride = gridDim.x * MC_WARPS * V::TPW;
+    int ti = (blockIdx.x * MC_WARPS + warp) * V::TPW + grp;
     if (ti >= a.n_tiles) return;
     McSmem<pixel, V::TMAX> *sm = (McSmem<pixel, V::TMAX> *)mc_smem_raw + (warp * V::TPW + grp);
-    const uint32_t tcode = a.tiles[ti];
-    const Dav1dCudaMcDesc d = a.descs[tcode >> 4];
-    const TileGeo g = tile_geo(d, tcode & 15);
-    const Dav1dCudaMcSrc s = d.src[0];
-    const PlaneView &ref = a.refs[s.ref].p[d.plane];
-    if (d.kind == DAV1D_CUDA_MC_PREP) {
-        int16_t *out = a.tmp + d.aux_off + g.y0 * d.w + g.x0;
-        mc_tile<pixel, true, V::TMAX, V::G>(ref, s.x + g.x0, s.y + g.y0, g.tw, g.th, d.w, d.h, s.mx, s.my,
-                                            s.filter_2d, a.dst.bdmax, sm, out, d.w, lane, gmask);
-    } else {
-        const PlaneView &dp = a.dst.p[d.plane];
-        const int dstride = (int)(dp.stride / (int)sizeof(pixel));
-        pixel *out = (pixel *)dp.data + (int64_t)(d.y + g.y0) * dstride + d.x + g.x0;
-        mc_tile<pixel, false, V::TMAX, V::G>(ref, s.x + g.x0, s.y + g.y0, g.tw, g.th, d.w, d.h, s.mx, s.my,
-                                             s.filter_2d, a.dst.bdmax, sm, out, dstride, lane, gmask);
+    uint32_t tcode = a.tiles[ti];
+    Dav1dCudaMcDesc d = a.descs[tcode >> 4];
+    for (;;) {
+        const int tn = ti + stride;
+        uint32_t ncode = 0;
+        Dav1dCudaMcDesc nd;
+        if (tn < a.n_tiles) {
+            ncode = a.tiles[tn];
+            nd = a.descs[ncode >> 4];
+        }
+        const TileGeo g = tile_geo(d, tcode & 15);
+        const Dav1dCudaMcSrc s = d.src[0];
+        const PlaneView &ref = a.refs[s.ref].p[d.plane];
+        if (d.kind == DAV1D_CUDA_MC_PREP) {
+            int16_t *out = a.tmp + d.aux_off + g.y0 * d.w + g.x0;
+            mc_tile<pixel, true, V::TMAX, V::G>(ref, s.x + g.x0, s.y + g.y0, g.tw, g.th, d.w, d.h, s.mx, s.my,
+                                                s.filter_2d, a.dst.bdmax, sm, out, d.w, lane, gmask);
+        } else {
+            const PlaneView &dp = a.dst.p[d.plane];
+            const int dstride = (int)(dp.stride / (int)sizeof(pixel));
+            pixel *out = (pixel *)dp.data + (int64_t)(d.y + g.y0) * dstride + d.x + g.x0;
+            mc_tile<pixel, false, V::TMAX, V::G>(ref, s.x + g.x0, s.y + g.y0, g.tw, g.th, d.w, d.h, s.mx, s.my,
+                                                 s.filter_2d, a.dst.bdmax, sm, out, dstride, lane, gmask);
+        }
+        if (tn >= a.n_tiles) break;
+        ti = tn; tcode = ncode; d = nd;
     }
 }
 
@@ -77,34 +94,47 @@ __global__ void __launch_bounds__(MC_WARPS * 32) mc_compound_kernel(const __grid
     const int wl = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int grp = wl / V::G, lane = wl % V::G;
     const unsigned gmask = SMALL ? 0xffu << (8 * grp) : 0xffffffffu;
-    const int ti = (blockIdx.x * MC_WARPS + warp) * V::TPW + grp;
+    const int stride = gridDim.x * MC_WARPS * V::TPW;
+    int ti = (blockIdx.x * MC_WARPS + warp) * V::TPW + grp;
     if (ti >= a.n_tiles) return;
     McSmemCompound<pixel, V::TMAX> *sm = (McSmemCompound<pixel, V::TMAX> *)mc_smem_raw + (warp * V::TPW + grp);
-    const uint32_t tcode = a.tiles[ti];
-    const Dav1dCudaMcDesc d = a.descs[tcode >> 4];
-    const TileGeo g = tile_geo(d, tcode & 15);
-    for (int i = 0; i < 2; i++) {
-        const Dav1dCudaMcSrc s = d.src[i];
-        const PlaneView &ref = a.refs[s.ref].p[d.plane];
-        mc_tile<pixel, true, V::TMAX, V::G>(ref, s.x + g.x0, s.y + g.y0, g.tw, g.th, d.w, d.h, s.mx, s.my,
-                                            s.filter_2d, a.dst.bdmax, &sm->s, i ? sm->tb : sm->ta, V::TMAX, lane,
-                                            gmask);
+    uint32_t tcode = a.tiles[ti];
+    Dav1dCudaMcDesc d = a.descs[tcode >> 4];
+    for (;;) {
+        const int tn = ti + stride;
+        uint32_t ncode = 0;
+        Dav1dCudaMcDesc nd;
+        if (tn < a.n_tiles) {
+            ncode = a.tiles[tn];
+            nd = a.descs[ncode >> 4];
+        }
+        const TileGeo g = tile_geo(d, tcode & 15);
+        for (int i = 0; i < 2; i++) {
+            const Dav1dCudaMcSrc s = d.src[i];
+            const PlaneView &ref = a.refs[s.ref].p[d.plane];
+            mc_tile<pixel, true, V::TMAX, V::G>(ref, s.x + g.x0, s.y + g.y0, g.tw, g.th, d.w, d.h, s.mx, s.my,
+                                                s.filter_2d, a.dst.bdmax, &sm->s, i ? sm->tb : sm->ta, V::TMAX, lane,
+                                                gmask);
+        }
+        const PlaneView &dp = a.dst.p[d.plane];
+        const int dstride = (int)(dp.stride / (int)sizeof(pixel));
+        pixel *out = (pixel *)dp.data + (int64_t)(d.y + g.y0) * dstride + d.x + g.x0;
+        uint8_t *mask = nullptr;
+        int ms = 0;
+        if (d.kind == DAV1D_CUDA_MC_MASK) {
+            ms = d.w;
+            mask = a.masks + d.aux_off + g.y0 * ms + g.x0;
+        } else if (d.kind == DAV1D_CUDA_MC_W_MASK) {
+            const int ssh = d.mask_ss >= 1, ssv = d.mask_ss == 2;
+            ms = d.w >> ssh;
+            mask = a.masks + d.aux_off + (g.y0 >> ssv) * ms + (g.x0 >> ssh);
+        }
+        mc_combine<pixel>(d.kind, sm->ta, sm->tb, V::TMAX, out, dstride, g.tw, g.th, d.weight, mask, ms, d.mask_ss,
+                          a.dst.bdmax, lane, V::G);
+        if (tn >= a.n_tiles) break;
+        __syncwarp(gmask);      // the combine's reads of ta/tb end before the next tile's writes
+        ti = tn; tcode = ncode; d = nd;
     }
-    const PlaneView &dp = a.dst.p[d.plane];
-    const int dstride = (int)(dp.stride / (int)sizeof(pixel));
-    pixel *out = (pixel *)dp.data + (int64_t)(d.y + g.y0) * dstride + d.x + g.x0;
-    uint8_t *mask = nullptr;
-    int ms = 0;
-    if (d.kind == DAV1D_CUDA_MC_MASK) {
-        ms = d.w;
-        mask = a.masks + d.aux_off + g.y0 * ms + g.x0;
-    } else if (d.kind == DAV1D_CUDA_MC_W_MASK) {
-        const int ssh = d.mask_ss >= 1, ssv = d.mask_ss == 2;
-        ms = d.w >> ssh;
-        mask = a.masks + d.aux_off + (g.y0 >> ssv) * ms + (g.x0 >> ssh);
-    }
-    mc_combine<pixel>(d.kind, sm->ta, sm->tb, V::TMAX, out, dstride, g.tw, g.th, d.weight, mask, ms, d.mask_ss,
-                      a.dst.bdmax, lane, V::G);
 }
 
 // ---- stand-alone ops on one block (per-call surface + unfused batch use)
@@ -255,22 +285,50 @@ static std::vector<uint32_t> tiles_for(int desc_idx, int w, int h) {
 }
 
 // a.tiles[0 .. a.n_small) are tiles of at most 8x8 (four per warp), the rest one per warp
+// resident blocks per SM of a kernel variant x number of SMs (cached per variant)
+template <typename K> static int resident_blocks(K kernel, size_t smem, int &cache) {
+    if (cache <= 0) {
+        int dev = 0, sms = 148, per_sm = 1;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, MC_WARPS * 32, smem) != cudaSuccess || per_sm < 1)
+            per_sm = 1;
+        cache = sms * per_sm;
+    }
+    return cache;
+}
+
 template <typename pixel, bool COMPOUND>
 static int launch_mc(McArgs a, cudaStream_t st) {
+    static int cap_small = 0, cap_big = 0;
     const int n_small = a.n_small, n_big = a.n_tiles - a.n_small;
     const uint32_t *tiles = a.tiles;
     if (n_small > 0) {
         a.tiles = tiles; a.n_tiles = n_small;
-        const int grid = (n_small + MC_WARPS * 4 - 1) / (MC_WARPS * 4);
-        if (COMPOUND) mc_compound_kernel<pixel, true><<<grid, MC_WARPS * 32, MC_WARPS * 4 * sizeof(McSmemCompound<pixel, 8>), st>>>(a);
-        else mc_put_kernel<pixel, true><<<grid, MC_WARPS * 32, MC_WARPS * 4 * sizeof(McSmem<pixel, 8>), st>>>(a);
+        int grid = (n_small + MC_WARPS * 4 - 1) / (MC_WARPS * 4);
+        if (COMPOUND) {
+            const size_t smem = MC_WARPS * 4 * sizeof(McSmemCompound<pixel, 8>);
+            grid = std::min(grid, resident_blocks(mc_compound_kernel<pixel, true>, smem, cap_small));
+            mc_compound_kernel<pixel, true><<<grid, MC_WARPS * 32, smem, st>>>(a);
+        } else {
+            const size_t smem = MC_WARPS * 4 * sizeof(McSmem<pixel, 8>);
+            grid = std::min(grid, resident_blocks(mc_put_kernel<pixel, true>, smem, cap_small));
+            mc_put_kernel<pixel, true><<<grid, MC_WARPS * 32, smem, st>>>(a);
+        }
         count_launch();
     }
     if (n_big > 0) {
         a.tiles = tiles + n_small; a.n_tiles = n_big;
-        const int grid = (n_big + MC_WARPS - 1) / MC_WARPS;
-        if (COMPOUND) mc_compound_kernel<pixel, false><<<grid, MC_WARPS * 32, MC_WARPS * sizeof(McSmemCompound<pixel, 32>), st>>>(a);
-        else mc_put_kernel<pixel, false><<<grid, MC_WARPS * 32, MC_WARPS * sizeof(McSmem<pixel, 32>), st>>>(a);
+        int grid = (n_big + MC_WARPS - 1) / MC_WARPS;
+        if (COMPOUND) {
+            const size_t smem = MC_WARPS * sizeof(McSmemCompound<pixel, 32>);
+            grid = std::min(grid, resident_blocks(mc_compound_kernel<pixel, false>, smem, cap_big));
+            mc_compound_kernel<pixel, false><<<grid, MC_WARPS * 32, smem, st>>>(a);
+        } else {
+            const size_t smem = MC_WARPS * sizeof(McSmem<pixel, 32>);
+            grid = std::min(grid, resident_blocks(mc_put_kernel<pixel, false>, smem, cap_big));
+            mc_put_kernel<pixel, false><<<grid, MC_WARPS * 32, smem, st>>>(a);
+        }
         count_launch();
     }
     return cuda_ok(cudaGetLastError(), COMPOUND ? "mc_compound_kernel" : "mc_put_kernel") ? 0 : -5;

@@ -319,6 +319,98 @@ static int intra_batch_launch_classes(Dav1dCudaContext *c, const PicView &pic, i
     return 0;
 }
 
+// Fused task variant (default): per level ONE launch (two when operations larger than 16x16
+// exist).  A task = up to 32/G consecutive level-sorted operations whose residuals have the
+// same transform size: the warp predicts them one after the other (whole warp per block), then
+// runs all their residuals at once in groups of G lanes like itx_task_kernel; an operation
+// without residual is a task of its own (tx code 31).
+struct IntraTaskArgs {
+    IntraArgs a;
+    const uint32_t *tasks;
+    int n_tasks;
+};
+
+template <typename pixel, bool BIG> struct IntraTaskSmem {
+    IntraSmem<pixel, 4> pred;
+    int tiles[BIG ? INTRA_TILE_INTS : 2 * 16 * 17];
+};
+
+template <typename pixel, int W, int H>
+DEV void intra_task_residual(const IntraArgs &a, const int first, const int cnt, int *tiles, const int lane) {
+    typedef ItxGeom<W, H> Geo;
+    typedef typename PxTraits<pixel>::coef coef;
+    constexpr int G = Geo::GMIN;
+    const int grp = lane / G, gl = lane % G;
+    const bool active = grp < cnt;
+    Dav1dCudaIntraDesc d;
+    if (active) d = a.descs[first + grp];
+    else { d.coef_off = 0; d.x4 = d.y4 = 0; d.eob = 0; d.plane = 0; d.txtp = 0; }
+    const PlaneView &pv = a.pic.p[d.plane];
+    const int stride = (int)(pv.stride / (int)sizeof(pixel));
+    pixel *dst = (pixel *)pv.data + (int64_t)d.y4 * 4 * stride + d.x4 * 4;
+    itx_block<pixel, W, H, G>(active, gl, tiles + grp * Geo::TILE_INTS, (coef *)a.cf + d.coef_off, d.eob, d.txtp,
+                              dst, stride, a.pic.bdmax, false);
+}
+
+template <typename pixel, bool BIG>
+__global__ void __launch_bounds__(INTRA_WARPS * 32, BIG ? 4 : 8)
+intra_task_kernel(const __grid_constant__ IntraTaskArgs m) {
+    extern __shared__ __align__(16) uint8_t intra_smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int t = blockIdx.x * INTRA_WARPS + warp;
+    if (t >= m.n_tasks) return;
+    IntraTaskSmem<pixel, BIG> *sm = (IntraTaskSmem<pixel, BIG> *)intra_smem_raw + warp;
+    const uint32_t code = m.tasks[t];
+    const int first = (int)(code >> 8), tx = (code >> 3) & 31, cnt = (int)(code & 7) + 1;
+    for (int k = 0; k < cnt; k++) {
+        const Dav1dCudaIntraDesc d = m.a.descs[first + k];
+        intra_op<pixel, 4>(m.a, d, &sm->pred, lane);
+        __syncwarp();
+    }
+    if (tx == 31) return;
+#define D1_ITASK(T, W, H) \
+    case T: \
+        if constexpr (BIG == (W > 16 || H > 16)) intra_task_residual<pixel, W, H>(m.a, first, cnt, sm->tiles, lane); \
+        break;
+    switch (tx) {
+    D1_ITASK(0, 4, 4) D1_ITASK(1, 8, 8) D1_ITASK(2, 16, 16) D1_ITASK(3, 32, 32) D1_ITASK(4, 64, 64)
+    D1_ITASK(5, 4, 8) D1_ITASK(6, 8, 4) D1_ITASK(7, 8, 16) D1_ITASK(8, 16, 8) D1_ITASK(9, 16, 32)
+    D1_ITASK(10, 32, 16) D1_ITASK(11, 32, 64) D1_ITASK(12, 64, 32) D1_ITASK(13, 4, 16) D1_ITASK(14, 16, 4)
+    D1_ITASK(15, 8, 32) D1_ITASK(16, 32, 8) D1_ITASK(17, 16, 64) D1_ITASK(18, 64, 16)
+    default: break;
+    }
+#undef D1_ITASK
+}
+
+static int intra_task_launch(const PicView &pic, int bw4, int bh4, void *cf, const Dav1dCudaIntraDesc *descs,
+                             const void *pal, const uint8_t *pal_idx, const uint32_t *tasks,
+                             const int32_t *task_start, int n_levels, cudaStream_t st)
+{
+    IntraTaskArgs m;
+    m.a.pic = pic; m.a.bw4 = bw4; m.a.bh4 = bh4; m.a.cf = cf; m.a.descs = descs; m.a.n = 0;
+    m.a.pal = pal; m.a.pal_idx = pal_idx;
+    m.a.dep_start = nullptr; m.a.deps = nullptr; m.a.sync = nullptr; m.a.opw = 1;
+    const bool hbd = pic.bdmax > 0xff;
+    for (int l = 0; l < n_levels; l++) {
+        const int ns = task_start[2 * l + 1] - task_start[2 * l], nb = task_start[2 * l + 2] - task_start[2 * l + 1];
+        if (ns > 0) {
+            m.tasks = tasks + task_start[2 * l]; m.n_tasks = ns;
+            const int grid = (ns + INTRA_WARPS - 1) / INTRA_WARPS;
+            if (hbd) intra_task_kernel<uint16_t, false><<<grid, INTRA_WARPS * 32, INTRA_WARPS * sizeof(IntraTaskSmem<uint16_t, false>), st>>>(m);
+            else intra_task_kernel<uint8_t, false><<<grid, INTRA_WARPS * 32, INTRA_WARPS * sizeof(IntraTaskSmem<uint8_t, false>), st>>>(m);
+            count_launch();
+        }
+        if (nb > 0) {
+            m.tasks = tasks + task_start[2 * l + 1]; m.n_tasks = nb;
+            const int grid = (nb + INTRA_WARPS - 1) / INTRA_WARPS;
+            if (hbd) intra_task_kernel<uint16_t, true><<<grid, INTRA_WARPS * 32, INTRA_WARPS * sizeof(IntraTaskSmem<uint16_t, true>), st>>>(m);
+            else intra_task_kernel<uint8_t, true><<<grid, INTRA_WARPS * 32, INTRA_WARPS * sizeof(IntraTaskSmem<uint8_t, true>), st>>>(m);
+            count_launch();
+        }
+    }
+    return cuda_ok(cudaGetLastError(), "intra_task_kernel") ? 0 : -5;
+}
+
 // Split variant: per level a prediction-only launch followed by the level's residuals as
 // transform tasks (small sizes, then the rare large ones).
 static int intra_batch_launch_split(const PicView &pic, int bw4, int bh4, void *cf, const Dav1dCudaIntraDesc *descs,
@@ -335,10 +427,13 @@ static int intra_batch_launch_split(const PicView &pic, int bw4, int bh4, void *
         a.n = n;
         a.pal = pal; a.pal_idx = pal_idx;
         a.dep_start = nullptr; a.deps = nullptr; a.sync = nullptr; a.opw = 1;
-        int r = pic.bdmax > 0xff ? launch_intra_level<uint16_t>(a, st, 4) : launch_intra_level<uint8_t>(a, st, 4);
+        static const int part = getenv("D1_INTRA_PART") ? atoi(getenv("D1_INTRA_PART")) : 3;   // experiment knob
+        int r = 0;
+        if (part & 1) r = pic.bdmax > 0xff ? launch_intra_level<uint16_t>(a, st, 4) : launch_intra_level<uint8_t>(a, st, 4);
         if (r) return r;
         const int ns = task_start[2 * l + 1] - task_start[2 * l], nb = task_start[2 * l + 2] - task_start[2 * l + 1];
-        if (ns + nb > 0 && (r = itx_task_launch(pic, cf, itx, tasks + task_start[2 * l], ns, nb, 0, st, st))) return r;
+        if ((part & 2) && ns + nb > 0 &&
+            (r = itx_task_launch(pic, cf, itx, tasks + task_start[2 * l], ns, nb, 0, st, st))) return r;
     }
     return 0;
 }
@@ -479,6 +574,10 @@ static int recon_submit_on(Dav1dCudaContext *c, const Dav1dCudaReconBatch *b, cu
         if ((r = intra_flow_launch(dst, b->bw4, b->bh4, b->cf, b->intra, n, b->intra_dep_start, b->intra_deps,
                                    (unsigned *)b->intra_sync, b->pal, b->pal_idx, st)))
             return r;
+    } else if (b->intra && b->intra_tasks && b->intra_task_start) {
+        if ((r = intra_task_launch(dst, b->bw4, b->bh4, b->cf, b->intra, b->pal, b->pal_idx, b->intra_tasks,
+                                   b->intra_task_start, b->n_levels, st)))
+            return r;
     } else if (b->intra && b->intra_itx && b->intra_itx_tasks && b->intra_itx_task_start) {
         if ((r = intra_batch_launch_split(dst, b->bw4, b->bh4, b->cf, b->intra, b->intra_level_start, b->n_levels,
                                           b->pal, b->pal_idx, b->intra_itx, b->intra_itx_tasks,
@@ -592,6 +691,10 @@ static int recon_submit_multi_on(Dav1dCudaContext *c, const Dav1dCudaReconBatch 
 
 void recon_init_attrs() {
     itx_init_attrs();
+    cudaFuncSetAttribute(intra_task_kernel<uint16_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)(INTRA_WARPS * sizeof(IntraTaskSmem<uint16_t, true>)));
+    cudaFuncSetAttribute(intra_task_kernel<uint8_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)(INTRA_WARPS * sizeof(IntraTaskSmem<uint8_t, true>)));
     cudaFuncSetAttribute(intra_multi_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)(INTRA_WARPS * sizeof(IntraSmem<uint16_t>)));
     cudaFuncSetAttribute(intra_multi_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -779,6 +882,41 @@ int dav1d_cuda_intra_schedule_deps(Dav1dCudaIntraDesc *descs, int n, int bw4, in
         dep_start[n] = k;
     }
     return n_levels;
+}
+
+// Task codes for the fused task kernel, see include/dav1d_cuda.h.
+int dav1d_cuda_intra_tasks(const Dav1dCudaIntraDesc *sd, const int32_t *level_start, int n_levels,
+                           uint32_t *tasks, int32_t *task_start, int32_t *n_tasks)
+{
+    if (!sd || !level_start || !tasks || !task_start || !n_tasks) return -22;
+    static const uint8_t w4[19] = { 1, 2, 4, 8, 16, 1, 2, 2, 4, 4, 8, 8, 16, 1, 4, 2, 8, 4, 16 };
+    static const uint8_t h4[19] = { 1, 2, 4, 8, 16, 2, 1, 4, 2, 8, 4, 16, 8, 4, 1, 8, 2, 16, 4 };
+    int k = 0;
+    for (int l = 0; l < n_levels; l++) {
+        task_start[2 * l] = k;
+        for (int pass = 0; pass < 2; pass++) {       // small operations first, then those larger than 16x16
+            if (pass == 1) task_start[2 * l + 1] = k;
+            int i = level_start[l];
+            while (i < level_start[l + 1]) {
+                const Dav1dCudaIntraDesc &d = sd[i];
+                const bool big = d.tw4 > 4 || d.th4 > 4;
+                const bool res = d.eob >= 0 && d.mode != DAV1D_CUDA_INTRA_PAL;
+                int j = i + 1, bpw = 1;
+                if (res) {
+                    const int sw = w4[d.tx] * 4 < 32 ? w4[d.tx] * 4 : 32, sh = h4[d.tx] * 4 < 32 ? h4[d.tx] * 4 : 32;
+                    bpw = 32 / (sh > sw ? sh : sw);
+                    while (j < level_start[l + 1] && j - i < bpw && sd[j].eob >= 0 &&
+                           sd[j].mode != DAV1D_CUDA_INTRA_PAL && sd[j].tx == d.tx) j++;
+                }
+                if (big == (pass == 1))
+                    tasks[k++] = ((uint32_t)i << 8) | ((uint32_t)(res ? d.tx : 31) << 3) | (uint32_t)(j - i - 1);
+                i = j;
+            }
+        }
+    }
+    task_start[2 * n_levels] = k;
+    *n_tasks = k;
+    return k;
 }
 
 int dav1d_cuda_intra_residual_tasks(const Dav1dCudaIntraDesc *sd, const int32_t *level_start, int n_levels,

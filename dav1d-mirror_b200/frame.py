@@ -158,6 +158,15 @@ class HostFrame:
         self.intra_itx = iitx[:max(ni, 1) * C.sizeof(B.ItxDesc)].copy()
         self.intra_itx_tasks = itasks[:max(nt.value, 1)].copy().view(np.uint8)
         self.intra_itx_task_start = np.frombuffer(tstart, dtype=np.int32, count=2 * nl + 1).copy()
+        # fused task codes over the sorted intra array
+        ftasks = np.zeros(max(n, 1), dtype=np.uint32)
+        fstart = (C.c_int32 * (2 * nl + 1))()
+        fn = C.c_int32()
+        if n:
+            L.dav1d_cuda_intra_tasks(self.intra_sorted.ctypes.data, lstart, nl, ftasks.ctypes.data, fstart,
+                                     C.byref(fn))
+        self.intra_tasks = ftasks[:max(fn.value, 1)].copy().view(np.uint8)
+        self.intra_task_start = np.frombuffer(fstart, dtype=np.int32, count=2 * nl + 1).copy()
         self.n_levels = nl
         return nl
 
@@ -202,7 +211,8 @@ class DeviceFrame:
         self._dev = {}
         self._host = {}
         for name in ("mc_put", "mc_put_tiles", "mc_comp", "mc_comp_tiles", "warp", "itx", "intra_sorted", "cf",
-                     "masks", "pal", "pal_idx", "dep_start", "deps", "itx_tasks", "intra_itx", "intra_itx_tasks"):
+                     "masks", "pal", "pal_idx", "dep_start", "deps", "itx_tasks", "intra_itx", "intra_itx_tasks",
+                     "intra_tasks"):
             arr = getattr(hf, name)
             self._host[name] = arr
             self._dev[name] = L.dav1d_cuda_malloc(max(arr.nbytes, 256))
@@ -239,9 +249,13 @@ class DeviceFrame:
             b.intra_dep_start, b.intra_deps, b.intra_sync = d["dep_start"], d["deps"], self._sync
         elif classes:
             b.intra_class_start = self._class_start
-        elif tasks:
+        elif tasks == 1:
             b.intra_itx, b.intra_itx_tasks = d["intra_itx"], d["intra_itx_tasks"]
             b.intra_itx_task_start = self._itx_task_start
+        elif tasks:
+            self._task_start = (C.c_int32 * (2 * hf.n_levels + 1))(*hf.intra_task_start.tolist())
+            b.intra_tasks = d["intra_tasks"]
+            b.intra_task_start = self._task_start
         self.batch = b
         self.graph = None
 

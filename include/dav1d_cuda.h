@@ -345,6 +345,14 @@ DAV1D_CUDA_API int dav1d_cuda_intra_schedule_deps(Dav1dCudaIntraDesc *descs, int
  * (level, class) run k = 3 * level + class spans sorted indices
  * [class_start[k], class_start[k + 1]). */
 
+/* Host: task codes (first_index << 8 | tx << 3 | count - 1, tx = 31: no residual) over the
+ * level-sorted descriptors for the fused task kernel; task_start[2*l] / [2*l+1] = first task of
+ * level l for operations up to 16x16 / larger, task_start[2*n_levels] = total.  `tasks` needs room
+ * for one entry per descriptor.  Returns the number of tasks. */
+DAV1D_CUDA_API int dav1d_cuda_intra_tasks(const Dav1dCudaIntraDesc *sorted_descs, const int32_t *level_start,
+                                          int n_levels, uint32_t *tasks, int32_t *task_start,
+                                          int32_t *n_tasks);
+
 /* Host: residuals of level-sorted intra descriptors as transform descriptors grouped by
  * (level, size): itx[0 .. returned count), task codes per level in `tasks`, and
  * task_start[2*l], task_start[2*l+1] = first small / first big task of level l
@@ -400,6 +408,11 @@ typedef struct Dav1dCudaReconBatch {
     /* optional: residuals of the intra-class operations as transform descriptors + tasks per level
      * (dav1d_cuda_intra_residual_tasks()).  When set, the level kernels only predict and every level
      * is followed by the task-based transform launches (lane groups, one size per warp). */
+    /* optional (preferred): task codes over the level-sorted `intra` array from
+     * dav1d_cuda_intra_tasks(): per level one fused launch in which a warp predicts up to 32/G
+     * same-size operations and then runs their residuals in groups of G lanes. */
+    const uint32_t *intra_tasks;              /* device */
+    const int32_t *intra_task_start;          /* host: 2 * n_levels + 1 offsets (small, big per level) */
     const Dav1dCudaItxDesc *intra_itx;        /* device */
     const uint32_t *intra_itx_tasks;          /* device */
     const int32_t *intra_itx_task_start;      /* host: 2 * n_levels + 1 offsets (small, big per level) */

@@ -123,9 +123,10 @@ def test_frame_parity_small(ref, name):
     hf = F.HostFrame(w, h, bd, seed, **kw)
     refs, init, want = oracle_planes(ref, hf, seed)
     # the executors of the intra phase: prediction-only levels + transform tasks (default), fused
-    # level kernel, size-class level kernels, persistent dataflow kernel
-    for dataflow, classes, tasks in ((False, False, True), (False, False, False), (False, True, False),
-                                     (True, False, False)):
+    # task kernel, fused one-warp-per-block level kernel, size-class level kernels, persistent
+    # dataflow kernel
+    for dataflow, classes, tasks in ((False, False, 1), (False, False, 2), (False, False, 0), (False, True, 0),
+                                     (True, False, 0)):
         got = run_gpu(hf, refs, init, use_graph=(seed % 2 == 0), dataflow=dataflow, classes=classes, tasks=tasks)
         for pl, (a, b) in enumerate(zip(want, got)):
             bad = np.argwhere(a != b)

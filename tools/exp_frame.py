@@ -60,7 +60,7 @@ def timed(ctxs, dfs, steps):
     return ms
 
 
-for dataflow, classes, tasks in ((False, False, True), (False, False, False)):
+for dataflow, classes, tasks in ((False, False, 1), (False, False, 0)):
     for n in sorted(set([1, 2, S])):
         ctxs, dfs = build(dataflow, n, classes, tasks)
         timed(ctxs, dfs, 3)
@@ -68,9 +68,9 @@ for dataflow, classes, tasks in ((False, False, True), (False, False, False)):
         per_frame = ms / (reps * n)
         print(f"dataflow={int(dataflow)} tasks={int(tasks)} streams={n}: {per_frame*1e3:8.1f} us/frame  "
               f"{hfs[0].luma_px / per_frame / 1e3:9.0f} Mpix/s  nodes={dfs[0].graph_nodes}", flush=True)
-        if n == 1 and tasks:
+        if n == 1 and tasks == 1:
             print("   classes(ms):", {k: round(v, 4) for k, v in dfs[0].time_classes(reps=5).items()}, flush=True)
-        if n == S and tasks:
+        if n == S and tasks == 1:
             print("   classes rotating over streams (ms):", {k: round(v, 4) for k, v in F.time_classes(dfs, reps=3).items()}, flush=True)
         for df in dfs:
             df.close()

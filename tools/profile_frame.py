@@ -21,7 +21,7 @@ w, h, bd = kw.pop("w", w), kw.pop("h", h), kw.pop("bd", bd)
 hf = F.HostFrame(w, h, bd, 1000, **kw)
 hf.schedule()
 ctx = F.open_context(0)
-df = F.DeviceFrame(ctx, hf)
+df = F.DeviceFrame(ctx, hf, tasks=int(os.environ.get('D1_TASKS', '1')))
 df.upload_descriptors()
 for r in range(2):
     df.upload_picture(df.refs[r], F.random_planes(hf, 7 + r))
