@@ -41,7 +41,11 @@ template <> struct PxTraits<uint16_t> {
 };
 
 template <typename pixel> HD int clip_px(int v, int bdmax) {
+#ifdef __CUDA_ARCH__
+    return min(max(v, 0), bdmax);
+#else
     return v < 0 ? 0 : v > bdmax ? bdmax : v;
+#endif
 }
 
 }  // namespace d1

@@ -19,7 +19,14 @@ namespace d1 {
 
 struct Clamp {
     int lo, hi;
-    HD int operator()(int v) const { return v < lo ? lo : v > hi ? hi : v; }
+    // lo <= hi always: two min/max instead of the compare + select chain of the ternary form
+    HD int operator()(int v) const {
+#ifdef __CUDA_ARCH__
+        return min(max(v, lo), hi);
+#else
+        return v < lo ? lo : v > hi ? hi : v;
+#endif
+    }
 };
 
 HD int m12(int a, int ca, int b, int cb) { return (a * ca + b * cb + 2048) >> 12; }

@@ -937,7 +937,8 @@ int dav1d_cuda_intra_residual_tasks(const Dav1dCudaIntraDesc *sd, const int32_t 
             lv.push_back(t);
         }
         std::stable_sort(lv.begin(), lv.end(), [](const Dav1dCudaItxDesc &x, const Dav1dCudaItxDesc &y) {
-            return x.tx != y.tx ? x.tx < y.tx : x.txtp < y.txtp;
+            const int kx = x.eob == 0 && x.txtp == 0 ? 0 : 1 + x.txtp, ky = y.eob == 0 && y.txtp == 0 ? 0 : 1 + y.txtp;
+            return x.tx != y.tx ? x.tx < y.tx : kx < ky;
         });
         for (auto &t : lv) itx[n_itx++] = t;
         int ns = 0, nb = 0;

@@ -509,17 +509,23 @@ __attribute__((visibility("default"))) int d1synth_generate(const D1SynthParams 
     // compound: wave 0 then wave 1
     std::vector<Dav1dCudaMcDesc> comp(g.comp0);
     comp.insert(comp.end(), g.comp1.begin(), g.comp1.end());
-    // itx: stable sort by class
+    // itx: stable sort by class and, inside a class, by transform type (dc-only blocks first):
+    // neighbouring warps then run the same 1-D transforms, which keeps the groups of a warp
+    // convergent and the instruction working set of an SM small
     std::vector<uint32_t> itx_new(g.itx.size());
     std::vector<Dav1dCudaItxDesc> itx_sorted(g.itx.size());
     {
-        int32_t start[20] = { 0 };
         for (auto &d : g.itx) f->itx_class_count[d.tx]++;
-        for (int t = 0; t < 19; t++) start[t + 1] = start[t] + f->itx_class_count[t];
-        for (size_t i = 0; i < g.itx.size(); i++) {
-            const uint32_t n = (uint32_t)start[g.itx[i].tx]++;
-            itx_new[i] = n;
-            itx_sorted[n] = g.itx[i];
+        std::vector<uint32_t> idx(g.itx.size());
+        for (size_t i = 0; i < idx.size(); i++) idx[i] = (uint32_t)i;
+        auto key = [&](uint32_t i) {
+            const Dav1dCudaItxDesc &d = g.itx[i];
+            return ((int)d.tx << 8) | (d.eob == 0 && d.txtp == 0 ? 0 : 1 + d.txtp);
+        };
+        std::stable_sort(idx.begin(), idx.end(), [&](uint32_t x, uint32_t y) { return key(x) < key(y); });
+        for (size_t n = 0; n < idx.size(); n++) {
+            itx_new[idx[n]] = (uint32_t)n;
+            itx_sorted[n] = g.itx[idx[n]];
         }
     }
     // tiles: per list (put, compound wave 0, compound wave 1) the tiles of blocks of at most
