@@ -40,6 +40,12 @@ template <> struct PxTraits<uint16_t> {
     HD static int inter_bits(int bdmax) { return bdmax > 1023 ? 2 : 4; }
 };
 
+// programmatic dependent launch, see d1::launch_pdl (ctx.h); no-ops in a plain launch
+#ifdef __CUDACC__
+DEV void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+DEV void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
+
 template <typename pixel> HD int clip_px(int v, int bdmax) {
 #ifdef __CUDA_ARCH__
     return min(max(v, 0), bdmax);

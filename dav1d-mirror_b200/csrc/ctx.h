@@ -6,6 +6,8 @@
 #include <stdint.h>
 #include <stddef.h>
 #include <mutex>
+#include <utility>
+#include <stdlib.h>
 #include "../../include/dav1d_cuda.h"
 
 namespace d1 {
@@ -16,6 +18,34 @@ void count_launch(int n = 1);
 
 #define D1_CHECK(call) do { if (!d1::cuda_ok((call), #call)) return -5; } while (0)
 #define D1_CHECKV(call) do { if (!d1::cuda_ok((call), #call)) return; } while (0)
+
+// Programmatic dependent launch (PDL): a kernel launched with this helper may start while
+// its stream predecessor is still running (which hides the launch gap and the prologue's
+// loads in chains of small launches, e.g. one per wavefront level).  Such a kernel issues
+// griddepcontrol.launch_dependents first and griddepcontrol.wait before it touches anything
+// the predecessor writes (d1::pdl_* in common.cuh); only launch-invariant inputs
+// (descriptors, task lists) are read before the wait.  Measured on B200 inside captured graphs
+// it did NOT pay (4K frame, 93 nodes: 836 -> 866 us alone, 272 -> 287 us/frame with 8 streams),
+// so the attribute is off unless D1_PDL=1; the device-side instructions are no-ops then.
+inline bool pdl_enabled() {
+    static const bool on = getenv("D1_PDL") && atoi(getenv("D1_PDL")) != 0;
+    return on;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem,
+                              cudaStream_t st, Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 // Device views handed to kernels by value.
 struct PlaneView {
@@ -40,6 +70,19 @@ inline PicView pic_view(const Dav1dCudaPicture *pic) {
     v.ss_ver = pic->ss_ver;
     return v;
 }
+
+// Multi-frame transform tasks (itx.cu / recon.cu): per-frame planes, coefficients and the
+// frame's level-sorted residual descriptors.
+struct ItxFrameRef {
+    PicView pic;
+    void *cf;
+    const Dav1dCudaItxDesc *descs;
+};
+struct ItxMultiArgs {
+    const ItxFrameRef *frames;
+    const uint2 *tasks;          // x = task code (see dav1d_cuda_itx_tasks), y = frame
+    int n_tasks;
+};
 
 // Per-call staging: one arena per process, serialised by a mutex.  The
 // reference calls DSP functions concurrently from many threads

@@ -78,128 +78,11 @@ static int launch_itx_tx(int tx, const ItxArgs &a, cudaStream_t st) {
     return -22;
 }
 
-// ---- all transform sizes in one launch -------------------------------------
-// The recorder groups descriptors by size; a "task" is up to 32/G consecutive
-// descriptors of one size handled by one warp (G lanes per block), encoded as
-// first_index << 8 | tx << 3 | (count - 1).  Two instantiations: sizes up to
-// 16x16 (few registers, 2 KB of shared memory per warp) and the larger ones.
-struct ItxTaskArgs {
-    PicView pic;
-    void *cf;
-    const Dav1dCudaItxDesc *descs;
-    const uint32_t *tasks;
-    int n_tasks;
-    int zero_coefs;
-};
-
-constexpr int ITX_TASK_SMEM_SMALL = 2 * 16 * 17 * 4;     // 16x16: two blocks per warp
-constexpr int ITX_TASK_SMEM_BIG = 32 * 65 * 4;           // 64-wide: one block per warp
-
-template <typename pixel, int W, int H>
-DEV void itx_task_body(const ItxTaskArgs &a, const int first, const int cnt, int *smem, const int lane) {
-    typedef ItxGeom<W, H> Geo;
-    typedef typename PxTraits<pixel>::coef coef;
-    constexpr int G = Geo::GMIN;
-    const int grp = lane / G, gl = lane % G;
-    const bool active = grp < cnt;
-    Dav1dCudaItxDesc d;
-    if (active) d = a.descs[first + grp];
-    else { d.coef_off = 0; d.x = d.y = 0; d.eob = 0; d.plane = 0; d.tx = 0; d.txtp = 0; }
-    int *tile = smem + grp * Geo::TILE_INTS;
-    const PlaneView &pv = a.pic.p[d.plane];
-    const int dstride = (int)(pv.stride / (int)sizeof(pixel));
-    pixel *dst = (pixel *)pv.data + (int64_t)d.y * dstride + d.x;
-    itx_block<pixel, W, H, G>(active, gl, tile, (coef *)a.cf + d.coef_off, d.eob, d.txtp, dst, dstride,
-                              a.pic.bdmax, a.zero_coefs != 0);
-}
-
-template <typename pixel, bool BIG>
-__global__ void __launch_bounds__(ITX_WARPS * 32, BIG ? 4 : 8) itx_task_kernel(const __grid_constant__ ItxTaskArgs a) {
-    extern __shared__ int itx_smem[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int t = blockIdx.x * ITX_WARPS + warp;
-    if (t >= a.n_tasks) return;
-    int *smem = itx_smem + warp * ((BIG ? ITX_TASK_SMEM_BIG : ITX_TASK_SMEM_SMALL) / 4);
-    const uint32_t code = a.tasks[t];
-    const int first = (int)(code >> 8), tx = (code >> 3) & 31, cnt = (int)(code & 7) + 1;
-#define D1_TASKCASE(T, W, H) \
-    case T: \
-        if constexpr (BIG == (W > 16 || H > 16)) itx_task_body<pixel, W, H>(a, first, cnt, smem, lane); \
-        break;
-    switch (tx) {
-    D1_TASKCASE(0, 4, 4) D1_TASKCASE(1, 8, 8) D1_TASKCASE(2, 16, 16) D1_TASKCASE(3, 32, 32) D1_TASKCASE(4, 64, 64)
-    D1_TASKCASE(5, 4, 8) D1_TASKCASE(6, 8, 4) D1_TASKCASE(7, 8, 16) D1_TASKCASE(8, 16, 8) D1_TASKCASE(9, 16, 32)
-    D1_TASKCASE(10, 32, 16) D1_TASKCASE(11, 32, 64) D1_TASKCASE(12, 64, 32) D1_TASKCASE(13, 4, 16)
-    D1_TASKCASE(14, 16, 4) D1_TASKCASE(15, 8, 32) D1_TASKCASE(16, 32, 8) D1_TASKCASE(17, 16, 64)
-    D1_TASKCASE(18, 64, 16)
-    default: break;
-    }
-#undef D1_TASKCASE
-}
-
-// blocks of one size a warp takes: 32 / G
-static int itx_bpw(int tx) {
-    const TxDim t = tx_dim(tx);
-    const int sw = t.w < 32 ? t.w : 32, sh = t.h < 32 ? t.h : 32;
-    return 32 / (sh > sw ? sh : sw);
-}
-
-// tasks[0 .. n_small) = sizes up to 16x16, tasks[n_small .. n_small + n_big) = larger
+// (the task kernels - all transform sizes in one launch - live in itx_task.cuh, instantiated per
+// pixel type in itx_task8.cu / itx_task16.cu)
 int itx_task_launch(const PicView &pic, void *cf, const Dav1dCudaItxDesc *descs, const uint32_t *tasks,
-                    int n_small, int n_big, int zero_coefs, cudaStream_t st_small, cudaStream_t st_big)
-{
-    ItxTaskArgs a;
-    a.pic = pic; a.cf = cf; a.descs = descs; a.zero_coefs = zero_coefs;
-    const bool hbd = pic.bdmax > 0xff;
-    if (n_small > 0) {
-        a.tasks = tasks; a.n_tasks = n_small;
-        const int grid = (n_small + ITX_WARPS - 1) / ITX_WARPS;
-        if (hbd) itx_task_kernel<uint16_t, false><<<grid, ITX_WARPS * 32, ITX_WARPS * ITX_TASK_SMEM_SMALL, st_small>>>(a);
-        else itx_task_kernel<uint8_t, false><<<grid, ITX_WARPS * 32, ITX_WARPS * ITX_TASK_SMEM_SMALL, st_small>>>(a);
-        count_launch();
-    }
-    if (n_big > 0) {
-        a.tasks = tasks + n_small; a.n_tasks = n_big;
-        const int grid = (n_big + ITX_WARPS - 1) / ITX_WARPS;
-        if (hbd) itx_task_kernel<uint16_t, true><<<grid, ITX_WARPS * 32, ITX_WARPS * ITX_TASK_SMEM_BIG, st_big>>>(a);
-        else itx_task_kernel<uint8_t, true><<<grid, ITX_WARPS * 32, ITX_WARPS * ITX_TASK_SMEM_BIG, st_big>>>(a);
-        count_launch();
-    }
-    return cuda_ok(cudaGetLastError(), "itx_task_kernel") ? 0 : -5;
-}
-
-// host: task codes for `n` descriptors (host copy) that are grouped by tx; small sizes first
-int itx_build_tasks(const Dav1dCudaItxDesc *descs, int n, int index_base, uint32_t *tasks, int *n_small, int *n_big) {
-    int k = 0;
-    *n_small = *n_big = 0;
-    for (int pass = 0; pass < 2; pass++) {
-        int i = 0;
-        while (i < n) {
-            const int tx = descs[i].tx;
-            int j = i;
-            while (j < n && descs[j].tx == tx) j++;
-            const TxDim t = tx_dim(tx);
-            const bool big = t.w > 16 || t.h > 16;
-            if (big == (pass == 1)) {
-                const int bpw = itx_bpw(tx);
-                for (int f = i; f < j; f += bpw) {
-                    const int cnt = (j - f) < bpw ? (j - f) : bpw;
-                    tasks[k++] = ((uint32_t)(index_base + f) << 8) | ((uint32_t)tx << 3) | (uint32_t)(cnt - 1);
-                    if (big) (*n_big)++; else (*n_small)++;
-                }
-            }
-            i = j;
-        }
-    }
-    return k;
-}
-
-void itx_init_attrs() {
-    cudaFuncSetAttribute(itx_task_kernel<uint16_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         ITX_WARPS * ITX_TASK_SMEM_BIG);
-    cudaFuncSetAttribute(itx_task_kernel<uint8_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         ITX_WARPS * ITX_TASK_SMEM_BIG);
-}
+                    int n_small, int n_big, int zero_coefs, cudaStream_t st_small, cudaStream_t st_big);
+int itx_build_tasks(const Dav1dCudaItxDesc *descs, int n, int index_base, uint32_t *tasks, int *n_small, int *n_big);
 
 // `streams`/`n_streams`: the size classes touch disjoint pixels, so they are spread
 // round-robin over the given streams (heaviest classes first on their own stream).

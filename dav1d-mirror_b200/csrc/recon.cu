@@ -25,6 +25,8 @@ int itx_batch_launch_multi(const PicView &pic, void *cf, const Dav1dCudaItxDesc 
 int itx_task_launch(const PicView &pic, void *cf, const Dav1dCudaItxDesc *descs, const uint32_t *tasks,
                     int n_small, int n_big, int zero_coefs, cudaStream_t st_small, cudaStream_t st_big);
 int itx_build_tasks(const Dav1dCudaItxDesc *descs, int n, int index_base, uint32_t *tasks, int *n_small, int *n_big);
+int itx_multi_task_launch(const ItxFrameRef *frames, const uint2 *tasks, int n_small, int n_big, bool hbd,
+                          cudaStream_t st_small, cudaStream_t st_big);
 void itx_init_attrs();
 struct McArgs;
 int mc_put_launch_raw(const PicView &dst, const PicView *refs, const Dav1dCudaMcDesc *descs,
@@ -160,9 +162,11 @@ intra_level_kernel(const __grid_constant__ IntraArgs a) {
     extern __shared__ __align__(16) uint8_t intra_smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int idx = blockIdx.x * INTRA_WARPS + warp;
+    pdl_launch_dependents();
     if (idx >= a.n) return;
     IntraSmem<pixel, CLS> *sm = (IntraSmem<pixel, CLS> *)intra_smem_raw + warp;
     const Dav1dCudaIntraDesc d = a.descs[idx];
+    pdl_wait();
     intra_op<pixel, CLS>(a, d, sm, lane);
 }
 
@@ -182,11 +186,11 @@ struct IntraMultiArgs {
     int n;
 };
 
-template <typename pixel>
-__global__ void __launch_bounds__(INTRA_WARPS * 32, 4) intra_multi_kernel(const IntraMultiArgs m) {
+template <typename pixel, int CLS>
+__global__ void __launch_bounds__(INTRA_WARPS * 32, IntraCls<CLS>::MIN_BLOCKS) intra_multi_kernel(const IntraMultiArgs m) {
     extern __shared__ __align__(16) uint8_t intra_smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    IntraSmem<pixel> *sm = (IntraSmem<pixel> *)intra_smem_raw + warp;
+    IntraSmem<pixel, CLS> *sm = (IntraSmem<pixel, CLS> *)intra_smem_raw + warp;
     const int i = blockIdx.x * INTRA_WARPS + warp;
     if (i >= m.n) return;
     const uint32_t item = m.items[i];
@@ -196,7 +200,7 @@ __global__ void __launch_bounds__(INTRA_WARPS * 32, 4) intra_multi_kernel(const 
     a.descs = fp.descs; a.n = m.n; a.pal = fp.pal; a.pal_idx = fp.pal_idx;
     a.dep_start = nullptr; a.deps = nullptr; a.sync = nullptr; a.opw = 1;
     const Dav1dCudaIntraDesc d = fp.descs[item & 0xffffff];
-    intra_op<pixel, 0>(a, d, sm, lane);
+    intra_op<pixel, CLS>(a, d, sm, lane);
 }
 
 // Dataflow variant: ONE persistent launch for the whole intra phase.  Warps
@@ -245,7 +249,7 @@ __global__ void __launch_bounds__(INTRA_WARPS * 32, 4) intra_flow_kernel(const _
 template <typename pixel, int CLS>
 static int launch_intra_level_cls(const IntraArgs &a, cudaStream_t st) {
     const int grid = (a.n + INTRA_WARPS - 1) / INTRA_WARPS;
-    intra_level_kernel<pixel, CLS><<<grid, INTRA_WARPS * 32, INTRA_WARPS * sizeof(IntraSmem<pixel, CLS>), st>>>(a);
+    launch_pdl(intra_level_kernel<pixel, CLS>, grid, INTRA_WARPS * 32, INTRA_WARPS * sizeof(IntraSmem<pixel, CLS>), st, a);
     count_launch();
     return cuda_ok(cudaGetLastError(), "intra_level_kernel") ? 0 : -5;
 }
@@ -428,7 +432,15 @@ static int intra_batch_launch_split(const PicView &pic, int bw4, int bh4, void *
         a.pal = pal; a.pal_idx = pal_idx;
         a.dep_start = nullptr; a.deps = nullptr; a.sync = nullptr; a.opw = 1;
         static const int part = getenv("D1_INTRA_PART") ? atoi(getenv("D1_INTRA_PART")) : 3;   // experiment knob
+        // Levels with few operations (the long tail of the wavefront) are latency-bound: one
+        // fused launch (prediction + residual by the same warp) instead of up to three.
+        static const int fuse_below = getenv("D1_INTRA_FUSE_BELOW") ? atoi(getenv("D1_INTRA_FUSE_BELOW")) : 512;
         int r = 0;
+        if (n < fuse_below) {
+            r = pic.bdmax > 0xff ? launch_intra_level<uint16_t>(a, st, 0) : launch_intra_level<uint8_t>(a, st, 0);
+            if (r) return r;
+            continue;
+        }
         if (part & 1) r = pic.bdmax > 0xff ? launch_intra_level<uint16_t>(a, st, 4) : launch_intra_level<uint8_t>(a, st, 4);
         if (r) return r;
         const int ns = task_start[2 * l + 1] - task_start[2 * l], nb = task_start[2 * l + 2] - task_start[2 * l + 1];
@@ -602,6 +614,12 @@ struct MultiTables {
     std::vector<IntraFrameParams> frames;
     std::vector<uint32_t> items;         // all levels, concatenated
     std::vector<int> level_start;        // per level: first item; size n_levels + 1
+    // split execution (frames that carry intra_itx): residual tasks (code, frame) of all
+    // frames per level, small sizes then large ones
+    bool split = false;
+    std::vector<ItxFrameRef> itx_frames;
+    std::vector<uint2> rtasks;
+    std::vector<int> rtask_start;        // 2 * n_levels + 1
 };
 
 static uint64_t intra_code_key(const Dav1dCudaIntraDesc &d) {
@@ -642,11 +660,57 @@ static int build_multi_tables(const Dav1dCudaReconBatch *const *bs, int n, Multi
         for (auto &e : lv) t.items.push_back(e.second);
         t.level_start.push_back((int)t.items.size());
     }
+    // residual tasks: regenerated on the host from each frame's sorted descriptors (the same
+    // deterministic routine that produced the frame's device arrays intra_itx / intra_itx_tasks)
+    t.split = n > 0;
+    for (int f = 0; f < n; f++)
+        if (bs[f]->intra && bs[f]->n_levels > 0 && !bs[f]->intra_itx) t.split = false;
+    if (!t.split) return 0;
+    t.itx_frames.resize(n);
+    struct Key { uint32_t key; uint2 tk; };
+    std::vector<std::vector<Key>> per_level(2 * (size_t)max_levels);
+    for (int f = 0; f < n; f++) {
+        const Dav1dCudaReconBatch *b = bs[f];
+        t.itx_frames[f].pic = pic_view(b->dst);
+        t.itx_frames[f].cf = b->cf;
+        t.itx_frames[f].descs = b->intra_itx;
+        if (!b->intra || b->n_levels <= 0) continue;
+        const int n_ops = b->intra_level_start[b->n_levels];
+        std::vector<Dav1dCudaItxDesc> itx((size_t)std::max(n_ops, 1));
+        std::vector<uint32_t> tasks((size_t)std::max(n_ops, 1));
+        std::vector<int32_t> tstart(2 * (size_t)b->n_levels + 1);
+        int32_t nt = 0;
+        if (dav1d_cuda_intra_residual_tasks(b->intra_host, b->intra_level_start, b->n_levels, itx.data(),
+                                            tasks.data(), tstart.data(), &nt) < 0) return -22;
+        for (int l = 0; l < b->n_levels; l++)
+            for (int half = 0; half < 2; half++)
+                for (int k = tstart[2 * l + half]; k < tstart[2 * l + half + 1]; k++) {
+                    const Dav1dCudaItxDesc &d0 = itx[tasks[k] >> 8];
+                    const uint32_t tp = d0.eob == 0 && d0.txtp == 0 ? 0 : 1 + d0.txtp;
+                    per_level[2 * (size_t)l + half].push_back(
+                        { (((tasks[k] >> 3) & 31) << 8) | tp, make_uint2(tasks[k], (unsigned)f) });
+                }
+    }
+    t.rtask_start.assign(1, 0);
+    for (auto &v : per_level) {
+        std::stable_sort(v.begin(), v.end(), [](const Key &x, const Key &y) { return x.key < y.key; });
+        for (auto &e : v) t.rtasks.push_back(e.tk);
+        t.rtask_start.push_back((int)t.rtasks.size());
+    }
     return 0;
 }
 
+template <typename pixel, int CLS>
+static int launch_intra_multi(const IntraMultiArgs &m, cudaStream_t st) {
+    const int grid = (m.n + INTRA_WARPS - 1) / INTRA_WARPS;
+    intra_multi_kernel<pixel, CLS><<<grid, INTRA_WARPS * 32, INTRA_WARPS * sizeof(IntraSmem<pixel, CLS>), st>>>(m);
+    count_launch();
+    return cuda_ok(cudaGetLastError(), "intra_multi_kernel") ? 0 : -5;
+}
+
 static int recon_submit_multi_on(Dav1dCudaContext *c, const Dav1dCudaReconBatch *const *bs, int n,
-                                 const IntraFrameParams *d_frames, const uint32_t *d_items, const MultiTables &t,
+                                 const IntraFrameParams *d_frames, const uint32_t *d_items,
+                                 const ItxFrameRef *d_itx_frames, const uint2 *d_rtasks, const MultiTables &t,
                                  cudaStream_t st)
 {
     if (!ensure_aux(c)) return -5;
@@ -669,22 +733,29 @@ static int recon_submit_multi_on(Dav1dCudaContext *c, const Dav1dCudaReconBatch 
         if ((mask & 2) && (r = mc_put_launch_raw(dst, refs, b->mc_comp, b->mc_comp_tiles + b->n_mc_comp_tiles[0],
                                                  b->n_mc_comp_tiles[1], b->n_mc_comp_small[1], b->masks, nullptr, true, s))) return r;
         if ((mask & 4) && (r = warp_batch_launch(dst, refs, b->warp, b->n_warp, s))) return r;
-        if ((mask & 8) && b->itx && (r = itx_batch_launch(dst, b->cf, b->itx, b->itx_class_count, 0, s))) return r;
+        if ((mask & 8) && b->itx && b->itx_tasks) {
+            if ((r = itx_task_launch(dst, b->cf, b->itx, b->itx_tasks, b->n_itx_tasks[0], b->n_itx_tasks[1], 0, s, s)))
+                return r;
+        } else if ((mask & 8) && b->itx && (r = itx_batch_launch(dst, b->cf, b->itx, b->itx_class_count, 0, s))) return r;
     }
     if (!join_aux(c, st)) return -5;
     if (!(mask & 16)) return 0;
-    // phase C: one launch per level over all frames
+    // phase C: per level one set of launches over all frames: prediction, then the residual
+    // tasks (small / large sizes); levels with few operations run fused (one launch)
     const bool hbd = bs[0]->dst->bitdepth_max > 0xff;
+    static const int fuse_below = getenv("D1_INTRA_FUSE_BELOW") ? atoi(getenv("D1_INTRA_FUSE_BELOW")) : 512;
     for (size_t l = 0; l + 1 < t.level_start.size(); l++) {
         const int s0 = t.level_start[l], s1 = t.level_start[l + 1];
         if (s1 <= s0) continue;
         IntraMultiArgs m;
         m.frames = d_frames; m.items = d_items + s0; m.n = s1 - s0;
-        const int grid = (m.n + INTRA_WARPS - 1) / INTRA_WARPS;
-        if (hbd) intra_multi_kernel<uint16_t><<<grid, INTRA_WARPS * 32, INTRA_WARPS * sizeof(IntraSmem<uint16_t>), st>>>(m);
-        else intra_multi_kernel<uint8_t><<<grid, INTRA_WARPS * 32, INTRA_WARPS * sizeof(IntraSmem<uint8_t>), st>>>(m);
-        count_launch();
-        if (!cuda_ok(cudaGetLastError(), "intra_multi_kernel")) return -5;
+        if (!t.split || m.n < fuse_below) {
+            if ((r = hbd ? launch_intra_multi<uint16_t, 0>(m, st) : launch_intra_multi<uint8_t, 0>(m, st))) return r;
+            continue;
+        }
+        if ((r = hbd ? launch_intra_multi<uint16_t, 4>(m, st) : launch_intra_multi<uint8_t, 4>(m, st))) return r;
+        const int a0 = t.rtask_start[2 * l], a1 = t.rtask_start[2 * l + 1], a2 = t.rtask_start[2 * l + 2];
+        if (a2 > a0 && (r = itx_multi_task_launch(d_itx_frames, d_rtasks + a0, a1 - a0, a2 - a1, hbd, st, st))) return r;
     }
     return 0;
 }
@@ -695,9 +766,9 @@ void recon_init_attrs() {
                          (int)(INTRA_WARPS * sizeof(IntraTaskSmem<uint16_t, true>)));
     cudaFuncSetAttribute(intra_task_kernel<uint8_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)(INTRA_WARPS * sizeof(IntraTaskSmem<uint8_t, true>)));
-    cudaFuncSetAttribute(intra_multi_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaFuncSetAttribute(intra_multi_kernel<uint16_t, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)(INTRA_WARPS * sizeof(IntraSmem<uint16_t>)));
-    cudaFuncSetAttribute(intra_multi_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaFuncSetAttribute(intra_multi_kernel<uint8_t, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)(INTRA_WARPS * sizeof(IntraSmem<uint8_t>)));
     cudaFuncSetAttribute(intra_flow_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)(INTRA_WARPS * sizeof(IntraSmem<uint16_t>)));
@@ -1008,15 +1079,24 @@ int dav1d_cuda_recon_graph_build_multi(Dav1dCudaContext *c, const Dav1dCudaRecon
     MultiTables t;
     if (build_multi_tables(bs, n, t)) return -22;
     const size_t fb = (t.frames.size() * sizeof(IntraFrameParams) + 255) & ~(size_t)255;
-    const size_t sb = t.items.size() * sizeof(uint32_t);
+    const size_t sb = (t.items.size() * sizeof(uint32_t) + 255) & ~(size_t)255;
+    const size_t ib = (t.itx_frames.size() * sizeof(ItxFrameRef) + 255) & ~(size_t)255;
+    const size_t rb = t.rtasks.size() * sizeof(uint2);
     uint8_t *tab = nullptr;
-    D1_CHECK(cudaMalloc(&tab, fb + sb + 64));
+    D1_CHECK(cudaMalloc(&tab, fb + sb + ib + rb + 64));
     D1_CHECK(cudaMemcpy(tab, t.frames.data(), t.frames.size() * sizeof(IntraFrameParams), cudaMemcpyHostToDevice));
-    if (sb) D1_CHECK(cudaMemcpy(tab + fb, t.items.data(), sb, cudaMemcpyHostToDevice));
+    if (!t.items.empty())
+        D1_CHECK(cudaMemcpy(tab + fb, t.items.data(), t.items.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    if (!t.itx_frames.empty())
+        D1_CHECK(cudaMemcpy(tab + fb + sb, t.itx_frames.data(), t.itx_frames.size() * sizeof(ItxFrameRef),
+                            cudaMemcpyHostToDevice));
+    if (rb) D1_CHECK(cudaMemcpy(tab + fb + sb + ib, t.rtasks.data(), rb, cudaMemcpyHostToDevice));
     cudaStream_t cap;
     D1_CHECK(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
     D1_CHECK(cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal));
-    const int r = recon_submit_multi_on(c, bs, n, (const IntraFrameParams *)tab, (const uint32_t *)(tab + fb), t, cap);
+    const int r = recon_submit_multi_on(c, bs, n, (const IntraFrameParams *)tab, (const uint32_t *)(tab + fb),
+                                        (const ItxFrameRef *)(tab + fb + sb), (const uint2 *)(tab + fb + sb + ib), t,
+                                        cap);
     cudaGraph_t graph = nullptr;
     const cudaError_t e = cudaStreamEndCapture(cap, &graph);
     cudaStreamDestroy(cap);

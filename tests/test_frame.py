@@ -168,12 +168,24 @@ def test_config4_full_4k(ref, bd):
             assert bad.size == 0, f"rep {rep} plane {pl}: {len(bad)} mismatches, first at {bad[0]}"
 
 
+MULTI_SPECS = {
+    # small frames: every level is below the fusing threshold (one fused launch per level)
+    "small": [(256, 192, 0x3ff, 21, {}), (256, 192, 0x3ff, 22, {"p_intra": 0.7}), (256, 192, 0xfff, 23, {}),
+              (256, 192, 0x3ff, 24, {"p_intra": 0.0})],
+    # 1080p frames: the first levels take the split path (prediction launch + residual tasks
+    # merged over the frames), the tail the fused one
+    "1080p": [(1920, 1080, 0x3ff, 31, {"p_intra": 0.6}), (1920, 1080, 0x3ff, 32, {}),
+              (1280, 720, 0x3ff, 33, {"p_intra": 1.0})],
+    "8bit": [(640, 368, 0xff, 41, {"p_intra": 0.8}), (640, 368, 0xff, 42, {})],
+}
+
+
 @pytest.mark.gpu
-def test_multi_frame_batched_graph(ref):
+@pytest.mark.parametrize("case", sorted(MULTI_SPECS))
+def test_multi_frame_batched_graph(ref, case):
     """Several independent streams in one graph (dav1d_cuda_recon_graph_build_multi): every frame
     must match its own sequential oracle."""
-    specs = [(256, 192, 0x3ff, 21, {}), (256, 192, 0x3ff, 22, {"p_intra": 0.7}), (256, 192, 0xfff, 23, {}),
-             (256, 192, 0x3ff, 24, {"p_intra": 0.0})]
+    specs = MULTI_SPECS[case]
     hfs = [F.HostFrame(w, h, bd, seed, **kw) for (w, h, bd, seed, kw) in specs]
     want = [oracle_planes(ref, hf, sp[3]) for hf, sp in zip(hfs, specs)]
     ctx = F.open_context(0)

@@ -77,11 +77,11 @@ for dataflow, classes, tasks in ((False, False, 1), (False, False, 0)):
         for c in ctxs:
             L.dav1d_cuda_close(c)
 # ---- multi-frame batched graph: all S frames in one graph on one context
-for n in sorted(set([1, S, 2 * S])):
+for n, mt in [(1, 1), (S, 0), (S, 1), (2 * S, 1)]:
     ctx = F.open_context(0)
     dfs = []
     for s_ in range(n):
-        df = F.DeviceFrame(ctx, hfs[s_ % len(hfs)], dataflow=False, tasks=False)
+        df = F.DeviceFrame(ctx, hfs[s_ % len(hfs)], dataflow=False, tasks=mt)
         df.upload_descriptors()
         for r in range(2):
             df.upload_picture(df.refs[r], F.random_planes(df.hf, 7 + r))
@@ -97,10 +97,57 @@ for n in sorted(set([1, S, 2 * S])):
     L.dav1d_cuda_event_record(ctx, e1)
     ms = L.dav1d_cuda_event_elapsed_ms(e0, e1)
     per_frame = ms / (reps * n)
-    print(f"multi-frame graph frames={n}: {per_frame*1e3:8.1f} us/frame  {hfs[0].luma_px / per_frame / 1e3:9.0f} Mpix/s"
+    print(f"multi-frame graph tasks={mt} frames={n}: {per_frame*1e3:8.1f} us/frame  {hfs[0].luma_px / per_frame / 1e3:9.0f} Mpix/s"
           f"  nodes={mf.graph_nodes}", flush=True)
     mf.close()
     for df in dfs:
         df.close()
     L.dav1d_cuda_close(ctx)
+pkg.check_error()
+# ---- several multi-frame graphs in flight: G groups of n frames, each group on its own context
+for G, n in [(2, S), (4, S // 2), (2, 2 * S)]:
+    if n < 1:
+        continue
+    ctxs, mfs, alldfs = [], [], []
+    for g in range(G):
+        ctx = F.open_context(0)
+        dfs = []
+        for s_ in range(n):
+            df = F.DeviceFrame(ctx, hfs[(g * n + s_) % len(hfs)], dataflow=False, tasks=1)
+            df.upload_descriptors()
+            for r in range(2):
+                df.upload_picture(df.refs[r], F.random_planes(df.hf, 7 + r))
+            df.upload_picture(df.dst, F.random_planes(df.hf, 99))
+            dfs.append(df)
+        L.dav1d_cuda_synchronize(ctx)
+        ctxs.append(ctx)
+        mfs.append(F.MultiFrame(ctx, dfs))
+        alldfs.append(dfs)
+    for _ in range(3):
+        for mf in mfs:
+            mf.launch()
+    for c in ctxs:
+        L.dav1d_cuda_synchronize(c)
+    dones = [L.dav1d_cuda_event_create() for _ in ctxs]
+    L.dav1d_cuda_event_record(main, e0)
+    for c in ctxs:
+        L.dav1d_cuda_stream_wait_event(c, e0)
+    for _ in range(reps):
+        for mf in mfs:
+            mf.launch()
+    for c, d in zip(ctxs, dones):
+        L.dav1d_cuda_event_record(c, d)
+        L.dav1d_cuda_stream_wait_event(main, d)
+    L.dav1d_cuda_event_record(main, e1)
+    ms = L.dav1d_cuda_event_elapsed_ms(e0, e1)
+    per_frame = ms / (reps * n * G)
+    print(f"multi-frame graphs in flight={G} x frames={n}: {per_frame*1e3:8.1f} us/frame"
+          f"  {hfs[0].luma_px / per_frame / 1e3:9.0f} Mpix/s", flush=True)
+    for mf in mfs:
+        mf.close()
+    for dfs in alldfs:
+        for df in dfs:
+            df.close()
+    for c in ctxs:
+        L.dav1d_cuda_close(c)
 pkg.check_error()
