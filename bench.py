@@ -5,7 +5,8 @@ Workload (BASELINE.json configs[3]/[4]): full synthetic 4K 10-bit 4:2:0 frame
 reconstruction - motion compensation (put / fused compound / warp), inter
 residual inverse transforms and level-scheduled intra prediction (+CfL,
 palette, filter-intra) - for `--streams` independent streams per GPU, each
-with its own reference frames in HBM.  A step = one frame of every stream.
+with its own reference frames in HBM.  A step = one frame of every stream; the frames of
+`--group` streams are submitted together as one CUDA graph.
 
   python bench.py --gpus N --steps K --warmup W            (our CUDA path)
   python bench.py --impl reference ...                     (reference C templates on host cores)
@@ -40,17 +41,22 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--streams", type=int, default=8, help="independent 4K streams per GPU")
+    ap.add_argument("--streams", type=int, default=32, help="independent 4K streams per GPU")
+    ap.add_argument("--group", type=int, default=8,
+                    help="streams whose frames are submitted as one graph (level-synchronous intra launches "
+                         "shared by the group); 0 = one graph per stream")
     ap.add_argument("--width", type=int, default=3840)
     ap.add_argument("--height", type=int, default=2160)
     ap.add_argument("--bitdepth-max", type=lambda s: int(s, 0), default=0x3ff)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--batched", action="store_true",
-                    help="all streams of a GPU in ONE graph (dav1d_cuda_recon_graph_build_multi): intra levels "
-                         "of every stream share a launch")
-    return ap.parse_args()
+    ap.add_argument("--batched", action="store_true", help="all streams of a GPU in ONE graph (--group = --streams)")
+    a = ap.parse_args()
+    if a.batched:
+        a.group = a.streams
+    a.group = min(a.group, a.streams)
+    return a
 
 
 def peaks():
@@ -208,23 +214,31 @@ def main_ours(args):
     hfs = [F.HostFrame(args.width, args.height, args.bitdepth_max, 1000 + my_streams[i]) for i in range(n_sets)]
     for hf in hfs:
         hf.schedule()
-    ctxs, dfs = [], []
+    # Frames are submitted in groups of `--group` streams: one captured graph per group whose
+    # intra phase runs one set of launches per dependency level for the whole group
+    # (dav1d_cuda_recon_graph_build_multi); the groups run concurrently on their own CUDA
+    # streams.  --group 0: one graph per stream (dav1d_cuda_recon_graph_build).
+    G = args.group if args.group > 0 else 1
+    batched = args.group > 0 and not args.no_graph
+    ctxs, dfs, units = [], [], []
     main_ctx = F.open_context(local)
-    shared_ctx = F.open_context(local) if args.batched else None
-    for s in range(S):
-        ctx = shared_ctx if args.batched else F.open_context(local)
-        hf = hfs[s % n_sets]
-        df = F.DeviceFrame(ctx, hf, n_refs=2)
-        df.upload_descriptors()
-        for r in range(2):
-            df.upload_picture(df.refs[r], F.random_planes(hf, 7 + r + 10 * s))
-        df.upload_picture(df.dst, F.random_planes(hf, 99 + s))
-        L.dav1d_cuda_synchronize(ctx)
-        if not args.no_graph and not args.batched:
-            df.build_graph()
+    for g0 in range(0, S, G):
+        ctx = F.open_context(local)
         ctxs.append(ctx)
-        dfs.append(df)
-    multi = F.MultiFrame(shared_ctx, dfs) if args.batched else None
+        gdfs = []
+        for s in range(g0, min(S, g0 + G)):
+            hf = hfs[s % n_sets]
+            df = F.DeviceFrame(ctx, hf, n_refs=2)
+            df.upload_descriptors()
+            for r in range(2):
+                df.upload_picture(df.refs[r], F.random_planes(hf, 7 + r + 10 * s))
+            df.upload_picture(df.dst, F.random_planes(hf, 99 + s))
+            if not args.no_graph and not batched:
+                df.build_graph()
+            gdfs.append(df)
+            dfs.append(df)
+        L.dav1d_cuda_synchronize(ctx)
+        units.append((ctx, F.MultiFrame(ctx, gdfs) if batched else None, gdfs))
     pkg.check_error()
     luma_px = hfs[0].luma_px
     algo_step = sum(dfs[s].hf.algo_bytes for s in range(S))
@@ -232,39 +246,35 @@ def main_ours(args):
                         hfs[0].host_bytes()) / 1e6
 
     ev_start, ev_stop = L.dav1d_cuda_event_create(), L.dav1d_cuda_event_create()
-    ev_done = [L.dav1d_cuda_event_create() for _ in range(S)]
+    ev_done = [L.dav1d_cuda_event_create() for _ in ctxs]
 
     def run_step(e2e=False):
-        if multi is not None:
+        for ctx, multi, gdfs in units:
             if e2e:
-                for df in dfs:
+                for df in gdfs:
                     df.upload_descriptors_pinned()
-            multi.launch()
-            if e2e:
-                for df in dfs:
-                    df.download_pinned()
-            return
-        for s in range(S):
-            df = dfs[s]
-            if e2e:
-                df.upload_descriptors_pinned()
-            if args.no_graph:
-                df.submit()
+            if multi is not None:
+                multi.launch()
             else:
-                df.launch_graph()
+                for df in gdfs:
+                    if args.no_graph:
+                        df.submit()
+                    else:
+                        df.launch_graph()
             if e2e:
-                df.download_pinned()
+                for df in gdfs:
+                    df.download_pinned()
 
     def timed(nsteps, e2e=False):
-        """fork: every stream waits for ev_start; join: main stream waits for every stream's done event."""
+        """fork: every group's stream waits for ev_start; join: main stream waits for every done event."""
         L.dav1d_cuda_event_record(main_ctx, ev_start)
-        for s in range(S):
-            L.dav1d_cuda_stream_wait_event(ctxs[s], ev_start)
+        for c in ctxs:
+            L.dav1d_cuda_stream_wait_event(c, ev_start)
         for _ in range(nsteps):
             run_step(e2e)
-        for s in range(S):
-            L.dav1d_cuda_event_record(ctxs[s], ev_done[s])
-            L.dav1d_cuda_stream_wait_event(main_ctx, ev_done[s])
+        for c, ev in zip(ctxs, ev_done):
+            L.dav1d_cuda_event_record(c, ev)
+            L.dav1d_cuda_stream_wait_event(main_ctx, ev)
         L.dav1d_cuda_event_record(main_ctx, ev_stop)
         return L.dav1d_cuda_event_elapsed_ms(ev_start, ev_stop)
 
@@ -310,7 +320,7 @@ def main_ours(args):
         ems = max_over_ranks(timed(e2e_steps, e2e=True))
         barrier()
         pkg.check_error()
-        h2d = sum(df.hf.host_bytes() for df in dfs)
+        h2d = sum(df.arena_bytes for df in dfs)
         d2h = sum(df.pinned_out_bytes for df in dfs)
         e2e = {"value": world * S * e2e_steps * luma_px / (ems * 1e-3) / 1e6, "unit": "Mpix/s",
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
@@ -349,14 +359,17 @@ def main_ours(args):
                "config": workload_config(args, {
                    "l2": f"inputs larger than L2: working set {footprint_mb:.0f} MB per GPU vs {L2_MB:.0f} MB L2"
                    if footprint_mb > 2 * L2_MB else f"working set {footprint_mb:.0f} MB; L2 NOT exceeded",
-                   "cuda_graph": not args.no_graph, "batched_streams": bool(args.batched),
+                   "cuda_graph": not args.no_graph,
+                   "submission": (f"{len(units)} graphs in flight, each the frames of {G} streams (level-synchronous "
+                                  f"intra launches shared by the group)") if batched else "one graph per stream",
                    "levels": [int(df.hf.n_levels) for df in dfs[:n_sets]],
                    "launches_per_frame": int(launches / max(1, args.steps * S))}),
                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
                "hbm_frac_of_8TBs": algo_step * args.steps / (ms * 1e-3) / 8e12}
         print(json.dumps(out), flush=True)
-    if multi is not None:
-        multi.close()
+    for _, multi, _ in units:
+        if multi is not None:
+            multi.close()
     for df in dfs:
         df.close()
     if world > 1:

@@ -36,7 +36,7 @@ class IntraPredDSPContext(C.Structure):
 class ItxDesc(C.Structure):
     _fields_ = [("coef_off", C.c_uint32), ("x", C.c_uint16), ("y", C.c_uint16),
                 ("eob", C.c_int16), ("plane", C.c_uint8), ("tx", C.c_uint8),
-                ("txtp", C.c_uint8), ("pad", C.c_uint8 * 3)]
+                ("txtp", C.c_uint8), ("cw4", C.c_uint8), ("ch4", C.c_uint8), ("pad", C.c_uint8)]
 
 
 class McSrc(C.Structure):
@@ -115,7 +115,8 @@ class IntraDesc40(C.Structure):
                 ("th4", C.c_uint8), ("mode", C.c_uint8), ("angle_delta", C.c_int8),
                 ("edge_flags", C.c_uint8), ("flags", C.c_uint16), ("eob", C.c_int16),
                 ("tx", C.c_uint8), ("txtp", C.c_uint8), ("coef_off", C.c_uint32),
-                ("aux", C.c_uint32), ("level", C.c_uint32), ("pad", C.c_uint32)]
+                ("aux", C.c_uint32), ("level", C.c_uint32), ("cw4", C.c_uint8), ("ch4", C.c_uint8),
+                ("pad", C.c_uint16)]
 
 
 IntraDesc = IntraDesc40

@@ -30,14 +30,14 @@ __global__ void __launch_bounds__(ITX_WARPS * 32) itx_kernel(const ItxArgs a) {
     const bool active = blk < a.n;
     Dav1dCudaItxDesc d;
     if (active) d = a.descs[blk];
-    else { d.coef_off = 0; d.x = d.y = 0; d.eob = 0; d.plane = 0; d.tx = 0; d.txtp = 0; }
+    else { d.coef_off = 0; d.x = d.y = 0; d.eob = 0; d.plane = 0; d.tx = 0; d.txtp = 0; d.cw4 = d.ch4 = 0; }
     int *tile = itx_smem + (warp * BPW + grp) * Geo::TILE_INTS;
     const PlaneView pv = a.pic.p[d.plane];
     const int dstride = (int)(pv.stride / (int)sizeof(pixel));
     pixel *dst = (pixel *)pv.data + (int64_t)d.y * dstride + d.x;
     coef *cf = (coef *)a.cf + d.coef_off;
     itx_block<pixel, W, H, G>(active, gl, tile, cf, d.eob, d.txtp, dst, dstride,
-                              a.pic.bdmax, a.zero_coefs != 0);
+                              a.pic.bdmax, a.zero_coefs != 0, d.cw4, d.ch4);
 }
 
 template <typename pixel, int W, int H>

@@ -121,17 +121,19 @@ template <int W, int H> struct ItxGeom {
 template <typename coef, int W>
 D1_ITX_PASS int itx_row_pass(const bool full, const int gl, const int G, coef *cf, const int SH,
                                          const bool rect2, const int shift, const int rk, const Clamp rowcl,
-                                         const Clamp colcl, int *tile, const bool zero_coefs)
+                                         const Clamp colcl, int *tile, const bool zero_coefs,
+                                         const int cw, const int ch)
 {
     constexpr int SW = W < 32 ? W : 32, TS = W + 1;
     const bool wht = rk == K_WHT;
     const int rnd = (1 << shift) >> 1;
     int c[W];
     unsigned rowmask = 0;
-    if (full && gl < SH) {
+    // stored coefficients: cw columns x ch rows, stride ch (dense: cw = SW, ch = SH)
+    if (full && gl < ch) {
 #pragma unroll
         for (int x = 0; x < SW; x++) {
-            int v = cf[gl + x * SH];
+            int v = x < cw ? (int)cf[gl + x * ch] : 0;
             rowmask |= (unsigned)(v != 0) << x;
             if (wht) v >>= 2;
             else if (rect2) v = (v * 181 + 128) >> 8;
@@ -141,7 +143,8 @@ D1_ITX_PASS int itx_row_pass(const bool full, const int gl, const int G, coef *c
         for (int x = SW; x < W; x++) c[x] = 0;
         if (zero_coefs) {
 #pragma unroll
-            for (int x = 0; x < SW; x++) cf[gl + x * SH] = 0;
+            for (int x = 0; x < SW; x++)
+                if (x < cw) cf[gl + x * ch] = 0;
         }
     }
     unsigned colbits = rowmask, rowbits = rowmask ? 1u << gl : 0u;
@@ -234,7 +237,8 @@ D1_ITX_PASS void itx_col_pass(const bool full, const int gl, const int G, const 
 template <typename pixel, int W, int H, int G>
 DEV void itx_block(const bool active, const int gl, int *tile,
                    typename PxTraits<pixel>::coef *cf, const int eob, const int txtp,
-                   pixel *dst, const int dstride, const int bdmax, const bool zero_coefs)
+                   pixel *dst, const int dstride, const int bdmax, const bool zero_coefs,
+                   const int cw4 = 0, const int ch4 = 0)
 {
     typedef ItxGeom<W, H> Geo;
     typedef typename PxTraits<pixel>::coef coef;
@@ -287,7 +291,7 @@ DEV void itx_block(const bool active, const int gl, int *tile,
     const int rk = txtp_row_kind(txtp), ck = txtp_col_kind(txtp);
 
     const int rows_used = itx_row_pass<coef, W>(full, gl, G, cf, SH, Geo::RECT2, SHIFT, rk, rowcl, colcl, tile,
-                                                zero_coefs);
+                                                zero_coefs, cw4 ? cw4 * 4 : Geo::SW, ch4 ? ch4 * 4 : SH);
     __syncwarp();
     itx_col_pass<pixel, H>(full, gl, G, tile, TS, W, rows_used, ck, colcl, dst, dstride, bdmax);
     __syncwarp();

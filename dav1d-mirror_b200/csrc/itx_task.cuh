@@ -41,13 +41,13 @@ DEV void itx_task_body(const PicView &pic, void *cf, const Dav1dCudaItxDesc *des
     const bool active = grp < cnt;
     Dav1dCudaItxDesc d;
     if (active) d = descs[first + grp];
-    else { d.coef_off = 0; d.x = d.y = 0; d.eob = 0; d.plane = 0; d.tx = 0; d.txtp = 0; }
+    else { d.coef_off = 0; d.x = d.y = 0; d.eob = 0; d.plane = 0; d.tx = 0; d.txtp = 0; d.cw4 = d.ch4 = 0; }
     int *tile = smem + grp * Geo::TILE_INTS;
     const PlaneView &pv = pic.p[d.plane];
     const int dstride = (int)(pv.stride / (int)sizeof(pixel));
     pixel *dst = (pixel *)pv.data + (int64_t)d.y * dstride + d.x;
     itx_block<pixel, W, H, G>(active, gl, tile, (coef *)cf + d.coef_off, d.eob, d.txtp, dst, dstride,
-                              pic.bdmax, zero_coefs);
+                              pic.bdmax, zero_coefs, d.cw4, d.ch4);
 }
 
 template <typename pixel, bool BIG>

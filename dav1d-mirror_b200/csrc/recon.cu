@@ -77,7 +77,8 @@ DEV void intra_residual(int *tile, void *cf, const Dav1dCudaIntraDesc &d, pixel 
                         const int bdmax, const int lane)
 {
     typedef typename PxTraits<pixel>::coef coef;
-    itx_block<pixel, W, H, 32>(true, lane, tile, (coef *)cf + d.coef_off, d.eob, d.txtp, dst, stride, bdmax, false);
+    itx_block<pixel, W, H, 32>(true, lane, tile, (coef *)cf + d.coef_off, d.eob, d.txtp, dst, stride, bdmax, false,
+                               d.cw4, d.ch4);
 }
 
 // One intra-class operation (prediction [+ residual]) by one warp.
@@ -348,12 +349,12 @@ DEV void intra_task_residual(const IntraArgs &a, const int first, const int cnt,
     const bool active = grp < cnt;
     Dav1dCudaIntraDesc d;
     if (active) d = a.descs[first + grp];
-    else { d.coef_off = 0; d.x4 = d.y4 = 0; d.eob = 0; d.plane = 0; d.txtp = 0; }
+    else { d.coef_off = 0; d.x4 = d.y4 = 0; d.eob = 0; d.plane = 0; d.txtp = 0; d.cw4 = d.ch4 = 0; }
     const PlaneView &pv = a.pic.p[d.plane];
     const int stride = (int)(pv.stride / (int)sizeof(pixel));
     pixel *dst = (pixel *)pv.data + (int64_t)d.y4 * 4 * stride + d.x4 * 4;
     itx_block<pixel, W, H, G>(active, gl, tiles + grp * Geo::TILE_INTS, (coef *)a.cf + d.coef_off, d.eob, d.txtp,
-                              dst, stride, a.pic.bdmax, false);
+                              dst, stride, a.pic.bdmax, false, d.cw4, d.ch4);
 }
 
 template <typename pixel, bool BIG>
@@ -1004,7 +1005,7 @@ int dav1d_cuda_intra_residual_tasks(const Dav1dCudaIntraDesc *sd, const int32_t 
             Dav1dCudaItxDesc t;
             memset(&t, 0, sizeof(t));
             t.coef_off = d.coef_off; t.x = (uint16_t)(d.x4 * 4); t.y = (uint16_t)(d.y4 * 4);
-            t.eob = d.eob; t.plane = d.plane; t.tx = d.tx; t.txtp = d.txtp;
+            t.eob = d.eob; t.plane = d.plane; t.tx = d.tx; t.txtp = d.txtp; t.cw4 = d.cw4; t.ch4 = d.ch4;
             lv.push_back(t);
         }
         std::stable_sort(lv.begin(), lv.end(), [](const Dav1dCudaItxDesc &x, const Dav1dCudaItxDesc &y) {

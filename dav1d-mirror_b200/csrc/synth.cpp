@@ -40,6 +40,7 @@ typedef struct D1SynthParams {
     int32_t only_tx;            // >= 0: frame tiled with inter blocks of this tx size only (config 2); else -1
     int32_t only_txtp;          // with only_tx: >= 0 fixes the type
     int32_t eob_class;          // -1 random, 0 dc-only, 1 low-frequency, 2 full
+    int32_t dense_coefs;        // 1: dense coefficient blocks (reference layout) instead of packed ones
 } D1SynthParams;
 
 typedef struct D1SynthFrame {
@@ -129,12 +130,14 @@ struct Gen {
     }
     int nplanes() const { return P.no_chroma ? 1 : 3; }
 
-    // ---- coefficients: column-major sw x sh block appended to the stream
-    uint32_t emit_coefs(int tx, int txtp, int16_t *eob_out) {
+    // ---- coefficients: the bounding box of the non-zero coefficients (rounded up to 4 x 4)
+    // of the column-major sw x sh block is appended to the stream (packed format of
+    // Dav1dCudaItxDesc: cw4 columns x ch4 rows of four, stride 4 * ch4); P.dense_coefs keeps
+    // the reference's dense sw x sh layout (cw4 = ch4 = 0)
+    uint32_t emit_coefs(int tx, int txtp, int16_t *eob_out, uint8_t *cw4_out, uint8_t *ch4_out) {
         const int w = TXW4[tx] * 4, h = TXH4[tx] * 4, sw = std::min(w, 32), sh = std::min(h, 32);
-        const uint32_t off = (uint32_t)cf32.size();
-        cf32.resize(cf32.size() + (size_t)sw * sh, 0);
-        int32_t *c = cf32.data() + off;
+        int32_t c[32 * 32];
+        memset(c, 0, sizeof(int32_t) * sw * sh);
         const int cls = P.eob_class >= 0 ? P.eob_class : (rng.chance(0.2f) ? 0 : rng.chance(0.6f) ? 1 : 2);
         // amplitude so that the reconstructed residual spans a good part of the pixel range
         const double amp = (double)P.bitdepth_max * 8.0 * sqrt((double)(w * h)) / 16.0;
@@ -159,7 +162,21 @@ struct Gen {
             if (!last) { c[1 % (sw * sh)] = 1; last = 1; }
         }
         *eob_out = (int16_t)(cls == 0 ? 0 : std::min(last, sw * sh - 1));
-        add_bytes(cur_cls, (double)sw * sh * Bc);
+        add_bytes(cur_cls, (double)sw * sh * Bc);      // algorithmic bytes: the dense block
+        const uint32_t off = (uint32_t)cf32.size();
+        if (P.dense_coefs) {
+            *cw4_out = *ch4_out = 0;
+            cf32.insert(cf32.end(), c, c + sw * sh);
+            return off;
+        }
+        int nzw = 1, nzh = 1;
+        for (int x = 0; x < sw; x++)
+            for (int y = 0; y < sh; y++)
+                if (c[y + x * sh]) { nzw = std::max(nzw, x + 1); nzh = std::max(nzh, y + 1); }
+        const int cw = (nzw + 3) & ~3, ch = (nzh + 3) & ~3;
+        *cw4_out = (uint8_t)(cw / 4); *ch4_out = (uint8_t)(ch / 4);
+        for (int x = 0; x < cw; x++)
+            for (int y = 0; y < ch; y++) cf32.push_back(c[y + x * sh]);
         return off;
     }
 
@@ -182,7 +199,7 @@ struct Gen {
         d.tx = (uint8_t)tx;
         d.txtp = (uint8_t)(P.only_txtp >= 0 ? P.only_txtp : pick_txtp(rng, tx));
         cur_cls = 3;
-        d.coef_off = emit_coefs(tx, d.txtp, &d.eob);
+        d.coef_off = emit_coefs(tx, d.txtp, &d.eob, &d.cw4, &d.ch4);
         add_bytes(3, 2.0 * Bp * TXW4[tx] * TXH4[tx] * 16);
         order.push_back({ 3, (uint32_t)itx.size() });
         itx.push_back(d);
@@ -220,7 +237,7 @@ struct Gen {
             if (residual) {
                 d.tx = (uint8_t)tx_from_dims(tw4, th4);
                 d.txtp = (uint8_t)pick_txtp(rng, d.tx);
-                d.coef_off = emit_coefs(d.tx, d.txtp, &d.eob);
+                d.coef_off = emit_coefs(d.tx, d.txtp, &d.eob, &d.cw4, &d.ch4);
             }
         }
         order.push_back({ 4, (uint32_t)intra.size() });
@@ -498,7 +515,7 @@ __attribute__((visibility("default"))) void d1synth_default_params(D1SynthParams
     p->p_intra = 0.3f; p->p_residual = 0.6f; p->p_tx_split = 0.5f;
     p->p_filter_intra = 0.05f; p->p_palette = 0.02f; p->p_cfl = 0.25f;
     p->p_avg = 0.2f; p->p_w_avg = 0.1f; p->p_wedge = 0.1f; p->p_seg = 0.05f; p->p_warp = 0.05f;
-    p->mv_range = 128; p->n_refs = 2; p->edge_filter = 1; p->only_tx = -1; p->only_txtp = -1; p->eob_class = -1;
+    p->mv_range = 128; p->n_refs = 2; p->edge_filter = 1; p->only_tx = -1; p->only_txtp = -1; p->eob_class = -1; p->dense_coefs = 0;
 }
 
 __attribute__((visibility("default"))) int d1synth_generate(const D1SynthParams *p, D1SynthFrame *f) {

@@ -21,7 +21,8 @@ class SynthParams(C.Structure):
                 ("p_avg", C.c_float), ("p_w_avg", C.c_float), ("p_wedge", C.c_float),
                 ("p_seg", C.c_float), ("p_warp", C.c_float),
                 ("mv_range", C.c_int32), ("n_refs", C.c_int32), ("edge_filter", C.c_int32),
-                ("only_tx", C.c_int32), ("only_txtp", C.c_int32), ("eob_class", C.c_int32)]
+                ("only_tx", C.c_int32), ("only_txtp", C.c_int32), ("eob_class", C.c_int32),
+                ("dense_coefs", C.c_int32)]
 
 
 class SynthFrame(C.Structure):
@@ -208,16 +209,34 @@ class DeviceFrame:
                 raise RuntimeError("dav1d_cuda_picture_alloc failed")
         if hf.intra_sorted is None:
             hf.schedule()
+        # one device arena per frame for descriptors, task lists, coefficients and pools (each array
+        # 256-byte aligned): the end-to-end path ships it with ONE host->device copy from a pinned
+        # mirror (every extra copy costs ~10 us of copy-engine time, tools/exp_copy.py)
         self._dev = {}
         self._host = {}
+        names = ["mc_put", "mc_put_tiles", "mc_comp", "mc_comp_tiles", "warp", "itx", "intra_sorted", "cf",
+                 "masks", "pal", "pal_idx", "itx_tasks"]
+        if dataflow:
+            names += ["dep_start", "deps"]
+        elif tasks == 1:
+            names += ["intra_itx", "intra_itx_tasks"]
+        elif tasks:
+            names += ["intra_tasks"]
+        self._off = {}
+        off = 0
+        for name in names:
+            arr = getattr(hf, name)
+            self._host[name] = arr
+            self._off[name] = off
+            off += (max(arr.nbytes, 256) + 255) & ~255
+        self.arena_bytes = off
+        self._arena = L.dav1d_cuda_malloc(off)
+        if not self._arena:
+            raise RuntimeError("dav1d_cuda_malloc failed")
         for name in ("mc_put", "mc_put_tiles", "mc_comp", "mc_comp_tiles", "warp", "itx", "intra_sorted", "cf",
                      "masks", "pal", "pal_idx", "dep_start", "deps", "itx_tasks", "intra_itx", "intra_itx_tasks",
                      "intra_tasks"):
-            arr = getattr(hf, name)
-            self._host[name] = arr
-            self._dev[name] = L.dav1d_cuda_malloc(max(arr.nbytes, 256))
-            if not self._dev[name]:
-                raise RuntimeError("dav1d_cuda_malloc failed")
+            self._dev[name] = self._arena + self._off[name] if name in self._off else None
         self._level_start = (C.c_int32 * (hf.n_levels + 1))(*hf.level_start.tolist())
         b = B.ReconBatch()
         b.dst = C.pointer(self.dst)
@@ -284,39 +303,39 @@ class DeviceFrame:
         if getattr(self, "_pinned", None):
             return
         L = self.L
-        self._pinned = {}
+        # pinned mirror of the descriptor arena
+        self._pinned = L.dav1d_cuda_host_alloc(self.arena_bytes)
         for name, arr in self._host.items():
-            if not arr.nbytes:
-                continue
-            p = L.dav1d_cuda_host_alloc(arr.nbytes)
-            C.memmove(p, arr.ctypes.data, arr.nbytes)
-            self._pinned[name] = (p, arr.nbytes)
+            if arr.nbytes:
+                C.memmove(self._pinned + self._off[name], arr.ctypes.data, arr.nbytes)
+        # pinned host frame with the device picture's layout (plane offsets and strides): the
+        # reconstructed frame comes back with ONE device->host copy
         hf = self.hf
-        self._pinned_out = []
-        self.pinned_out_bytes = 0
-        for pl in range(1 if hf.no_chroma else 3):
-            hh, ww = hf.plane_shape(pl)
-            row = ww * (2 if hf.hbd else 1)
-            p = L.dav1d_cuda_host_alloc(row * hh)
-            self._pinned_out.append((p, row))
-            self.pinned_out_bytes += row * hh
+        npl = 1 if hf.no_chroma else 3
+        bpp = 2 if hf.hbd else 1
+        base = self.dst.p[0].data
+        last = self.dst.p[npl - 1]
+        self.pinned_out_bytes = (last.data - base) + (last.h - 1) * last.stride + last.w * bpp
+        self._pinned_out = L.dav1d_cuda_host_alloc(self.pinned_out_bytes)
 
     def upload_descriptors_pinned(self):
-        for name, (p, n) in self._pinned.items():
-            self.L.dav1d_cuda_upload(self.ctx, self._dev[name], p, n)
+        self.L.dav1d_cuda_upload(self.ctx, self._arena, self._pinned, self.arena_bytes)
 
     def download_pinned(self):
-        for pl, (p, row) in enumerate(self._pinned_out):
-            self.L.dav1d_cuda_picture_download(self.ctx, C.byref(self.dst), pl, p, row)
+        self.L.dav1d_cuda_download(self.ctx, self._pinned_out, self.dst.p[0].data, self.pinned_out_bytes)
 
     def pinned_planes(self):
         """numpy views of the last downloaded frame (after a synchronize)."""
         hf = self.hf
         out = []
-        for pl, (p, row) in enumerate(self._pinned_out):
+        bpp = 2 if hf.hbd else 1
+        base = self.dst.p[0].data
+        for pl in range(1 if hf.no_chroma else 3):
             hh, ww = hf.plane_shape(pl)
-            a = np.frombuffer((C.c_char * (row * hh)).from_address(p), dtype=np.uint16 if hf.hbd else np.uint8)
-            out.append(a.reshape(hh, ww))
+            p = self.dst.p[pl]
+            a = np.frombuffer((C.c_char * (p.stride * hh)).from_address(self._pinned_out + (p.data - base)),
+                              dtype=np.uint16 if hf.hbd else np.uint8)
+            out.append(a.reshape(hh, p.stride // bpp)[:, :ww])
         return out
 
     # ---- per-launch-class timing (CUDA events on this context's stream)
@@ -355,15 +374,15 @@ class DeviceFrame:
         if self.graph:
             L.dav1d_cuda_recon_graph_free(self.graph)
             self.graph = None
-        for p in self._dev.values():
-            L.dav1d_cuda_free(p)
+        if self._arena:
+            L.dav1d_cuda_free(self._arena)
+            self._arena = None
         L.dav1d_cuda_free(self._sync)
         self._dev = {}
-        for p, _ in getattr(self, "_pinned", {}).values():
-            L.dav1d_cuda_host_free(p)
-        for p, _ in getattr(self, "_pinned_out", []):
-            L.dav1d_cuda_host_free(p)
-        self._pinned, self._pinned_out = {}, []
+        if getattr(self, "_pinned", None):
+            L.dav1d_cuda_host_free(self._pinned)
+            L.dav1d_cuda_host_free(self._pinned_out)
+        self._pinned, self._pinned_out = None, None
         for pic in [self.dst] + self.refs:
             L.dav1d_cuda_picture_free(self.ctx, C.byref(pic))
 

@@ -162,7 +162,12 @@ typedef struct Dav1dCudaItxDesc {
     uint8_t  plane;
     uint8_t  tx;           /* enum RectTxfmSize */
     uint8_t  txtp;         /* enum TxfmType (incl. WHT_WHT = 16) */
-    uint8_t  pad[3];
+    uint8_t  cw4, ch4;     /* packed coefficients: only the first 4*cw4 columns x 4*ch4 rows (the
+                            * bounding box of the non-zero coefficients, rounded up to 4) are stored,
+                            * column-major with stride 4*ch4: coef(row y, col x) = cf[coef_off + y +
+                            * x * 4*ch4]; everything outside is zero and is neither stored, shipped
+                            * nor read.  0, 0 = dense min(w,32) x min(h,32) as the reference stores it */
+    uint8_t  pad;
 } Dav1dCudaItxDesc;
 
 /* -- motion compensation (mc()/obmc() call sites: recon_tmpl.c:957-1069).
@@ -231,7 +236,8 @@ typedef struct Dav1dCudaIntraDesc {  /* 40 bytes */
     uint32_t coef_off;     /* into the cf stream (PAL: into the index pool) */
     uint32_t aux;          /* CFL: w_pad | h_pad << 8 (4-px units); PAL: palette offset */
     uint32_t level;        /* dependency level >= 1, filled by dav1d_cuda_intra_schedule() */
-    uint32_t pad;
+    uint8_t  cw4, ch4;     /* packed residual coefficients, see Dav1dCudaItxDesc (0, 0 = dense) */
+    uint16_t pad;
 } Dav1dCudaIntraDesc;
 
 /* -- warped motion, one descriptor per 8x8 (warp_affine(), recon_tmpl.c:1134-1193) */

@@ -98,12 +98,22 @@ static const pixel *mc_src(const OracleFrame *f, Scratch *s, const Dav1dCudaMcSr
 }
 
 static void run_itx(const OracleFrame *f, Scratch *s, const Dav1dInvTxfmDSPContext *itx, pixel *dst,
-                    ptrdiff_t stride, int tx, int txtp, int eob, uint32_t coef_off)
+                    ptrdiff_t stride, int tx, int txtp, int eob, uint32_t coef_off, int cw4, int ch4)
 {
     BD_DECL
     const int w = tx_w4[tx] * 4, h = tx_h4[tx] * 4;
-    const int n = imin(w, 32) * imin(h, 32);
-    memcpy(s->cf, (const coef *) f->cf + coef_off, n * sizeof(coef));   /* the call zeroes its input */
+    const int sw = imin(w, 32), sh = imin(h, 32);
+    const coef *src = (const coef *) f->cf + coef_off;
+    if (!cw4 || !ch4) {
+        memcpy(s->cf, src, sw * sh * sizeof(coef));   /* the call zeroes its input */
+    } else {
+        /* packed descriptor format (include/dav1d_cuda.h): 4*cw4 columns x 4*ch4 rows,
+         * column-major with stride 4*ch4 -> the dense sw x sh block the reference takes */
+        const int cw = cw4 * 4, ch = ch4 * 4;
+        memset(s->cf, 0, sw * sh * sizeof(coef));
+        for (int x = 0; x < cw; x++)
+            memcpy(s->cf + x * sh, src + x * ch, ch * sizeof(coef));
+    }
     itx->itxfm_add[tx][txtp](dst, stride, s->cf, eob BD_ARG);
 }
 
@@ -175,7 +185,7 @@ void bitfn(run_frame)(const OracleFrame *const f) {
             const Dav1dCudaItxDesc *const d = &f->itx[idx];
             const ptrdiff_t dstride = f->dst_stride[d->plane];
             pixel *const dst = (pixel *) f->dst[d->plane] + PXSTRIDE(dstride) * d->y + d->x;
-            run_itx(f, s, &itx, dst, dstride, d->tx, d->txtp, d->eob, d->coef_off);
+            run_itx(f, s, &itx, dst, dstride, d->tx, d->txtp, d->eob, d->coef_off, d->cw4, d->ch4);
         } else {
             const Dav1dCudaIntraDesc *const d = &f->intra[idx];
             const int pl = d->plane;
@@ -210,7 +220,7 @@ void bitfn(run_frame)(const OracleFrame *const f) {
                 ip.intra_pred[m](dst, dstride, edge, w, h, angle | d->flags, max_w, max_h BD_ARG);
             }
             if (d->eob >= 0 && d->mode != DAV1D_CUDA_INTRA_PAL)
-                run_itx(f, s, &itx, dst, dstride, d->tx, d->txtp, d->eob, d->coef_off);
+                run_itx(f, s, &itx, dst, dstride, d->tx, d->txtp, d->eob, d->coef_off, d->cw4, d->ch4);
         }
     }
     free(s);
