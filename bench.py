@@ -326,23 +326,60 @@ def main_ours(args):
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
                "ms_per_step": ems / e2e_steps}
 
-    # ---- per-launch-class timing of stream 0's frame (roofline of the dominant kernel)
+    # ---- per-launch-class timing (roofline of the dominant class), measured live with CUDA events
+    # in the regime of the timed region: for every class a graph per group that holds only that
+    # class's launches (dav1d_cuda_recon_graph_build_multi_phases), all groups in flight at once.
+    # Reported per FRAME: class time of one step / frames per step.  `solo_ms` = the same classes
+    # of ONE frame alone on the GPU (latency, not throughput).
     roof = None
     if rank == 0:
         peak, peak_src = peaks()
-        # rotate over all resident streams: data cold (working set >> L2), code warm
-        cls_ms = F.time_classes(dfs, reps=3, flush_mb=0 if footprint_mb > 2 * L2_MB else 256)
+        cls_bits = {"mc_put": 1, "mc_compound": 2, "warp": 4, "itx": 8, "intra": 16}
+        cls_ms = {}
+        if batched:
+            for name, bit in cls_bits.items():
+                cg = [F.MultiFrame(ctx, gdfs, phase_mask=bit) for ctx, _, gdfs in units]
+
+                def step_cls():
+                    for g in cg:
+                        g.launch()
+                for _ in range(2):
+                    step_cls()
+                torch.cuda.synchronize()
+                L.dav1d_cuda_event_record(main_ctx, ev_start)
+                for c in ctxs:
+                    L.dav1d_cuda_stream_wait_event(c, ev_start)
+                reps = 3
+                for _ in range(reps):
+                    step_cls()
+                for c, ev in zip(ctxs, ev_done):
+                    L.dav1d_cuda_event_record(c, ev)
+                    L.dav1d_cuda_stream_wait_event(main_ctx, ev)
+                L.dav1d_cuda_event_record(main_ctx, ev_stop)
+                cls_ms[name] = L.dav1d_cuda_event_elapsed_ms(ev_start, ev_stop) / (reps * S)
+                for g in cg:
+                    g.close()
+        solo_ms = F.time_classes(dfs[:min(S, 8)], reps=2, flush_mb=0 if footprint_mb > 2 * L2_MB else 256)
+        if not cls_ms:
+            cls_ms = solo_ms
         dom = max(cls_ms, key=lambda k: cls_ms[k])
-        alg = dfs[0].hf.algo_class[dom]
+        alg = sum(df.hf.algo_class[dom] for df in dfs) / S
         achieved = alg / (cls_ms[dom] * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
+        if os.path.exists(tp):
+            with open(tp) as f:
+                traffic = json.load(f).get(dom, {}).get("dram_bytes_per_frame")
         roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes": alg, "ms": cls_ms[dom],
+                "per": "frame (launch class of one frame; class time of a step / frames per step)",
                 "per_class_ms": cls_ms,
-                "per_class_gbs": {k: (dfs[0].hf.algo_class[k] / (v * 1e-3) / 1e9 if v > 0 else None)
+                "per_class_gbs": {k: (sum(df.hf.algo_class[k] for df in dfs) / S / (v * 1e-3) / 1e9 if v > 0 else None)
                                   for k, v in cls_ms.items()},
+                "solo_frame_class_ms": solo_ms,
                 "frame_algorithmic_bytes": dfs[0].hf.algo_bytes,
-                "whole_step": {"achieved": world * algo_step * args.steps / (ms * 1e-3) / 1e9 / world,
+                "whole_step": {"achieved": algo_step * args.steps / (ms * 1e-3) / 1e9,
                                "frac": algo_step * args.steps / (ms * 1e-3) / 1e9 / peak}}
 
     cpu = None

@@ -166,6 +166,8 @@ def bind_frame_api(L):
     L.dav1d_cuda_recon_submit.argtypes = [C.c_void_p, C.POINTER(ReconBatch)]
     L.dav1d_cuda_recon_submit_phases.argtypes = [C.c_void_p, C.POINTER(ReconBatch), C.c_int]
     L.dav1d_cuda_recon_graph_build.argtypes = [C.c_void_p, C.POINTER(ReconBatch), C.POINTER(C.c_void_p)]
+    L.dav1d_cuda_recon_graph_build_multi_phases.argtypes = [C.c_void_p, C.POINTER(C.POINTER(ReconBatch)), C.c_int,
+                                                            C.c_int, C.POINTER(C.c_void_p)]
     L.dav1d_cuda_recon_graph_build_multi.argtypes = [C.c_void_p, C.POINTER(C.POINTER(ReconBatch)), C.c_int,
                                                      C.POINTER(C.c_void_p)]
     L.dav1d_cuda_recon_graph_launch.argtypes = [C.c_void_p, C.c_void_p]

@@ -712,11 +712,12 @@ static int launch_intra_multi(const IntraMultiArgs &m, cudaStream_t st) {
 static int recon_submit_multi_on(Dav1dCudaContext *c, const Dav1dCudaReconBatch *const *bs, int n,
                                  const IntraFrameParams *d_frames, const uint32_t *d_items,
                                  const ItxFrameRef *d_itx_frames, const uint2 *d_rtasks, const MultiTables &t,
-                                 cudaStream_t st)
+                                 cudaStream_t st, const int phase_mask)
 {
     if (!ensure_aux(c)) return -5;
     int r;
-    static const int mask = getenv("D1_PHASE_MASK") ? atoi(getenv("D1_PHASE_MASK")) : 31;
+    static const int env_mask = getenv("D1_PHASE_MASK") ? atoi(getenv("D1_PHASE_MASK")) : 31;
+    const int mask = env_mask & phase_mask;
     cudaStream_t ss[1 + Dav1dCudaContext::N_AUX] = { st, c->aux[0], c->aux[1], c->aux[2] };
     constexpr int NS = 1 + Dav1dCudaContext::N_AUX;
     // phases A + B per frame, frame f on stream f % NS (MC then residual of a frame stay ordered)
@@ -1074,6 +1075,12 @@ int dav1d_cuda_recon_graph_build(Dav1dCudaContext *c, const Dav1dCudaReconBatch 
 int dav1d_cuda_recon_graph_build_multi(Dav1dCudaContext *c, const Dav1dCudaReconBatch *const *bs, int n,
                                        Dav1dCudaReconGraph **out)
 {
+    return dav1d_cuda_recon_graph_build_multi_phases(c, bs, n, 31, out);
+}
+
+int dav1d_cuda_recon_graph_build_multi_phases(Dav1dCudaContext *c, const Dav1dCudaReconBatch *const *bs, int n,
+                                              int phase_mask, Dav1dCudaReconGraph **out)
+{
     if (!c || !bs || n < 1 || !out) return -22;
     *out = nullptr;
     if (n > 255) return -22;
@@ -1097,7 +1104,7 @@ int dav1d_cuda_recon_graph_build_multi(Dav1dCudaContext *c, const Dav1dCudaRecon
     D1_CHECK(cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal));
     const int r = recon_submit_multi_on(c, bs, n, (const IntraFrameParams *)tab, (const uint32_t *)(tab + fb),
                                         (const ItxFrameRef *)(tab + fb + sb), (const uint2 *)(tab + fb + sb + ib), t,
-                                        cap);
+                                        cap, phase_mask);
     cudaGraph_t graph = nullptr;
     const cudaError_t e = cudaStreamEndCapture(cap, &graph);
     cudaStreamDestroy(cap);

@@ -425,13 +425,13 @@ class MultiFrame:
     """Frames of several independent streams submitted as one graph
     (dav1d_cuda_recon_graph_build_multi): level-synchronous intra launches shared by all."""
 
-    def __init__(self, ctx, dfs):
+    def __init__(self, ctx, dfs, phase_mask=31):
         self.L = B.lib()
         self.ctx = ctx
         self.dfs = dfs
         arr = (C.POINTER(B.ReconBatch) * len(dfs))(*[C.pointer(df.batch) for df in dfs])
         g = C.c_void_p()
-        n = self.L.dav1d_cuda_recon_graph_build_multi(ctx, arr, len(dfs), C.byref(g))
+        n = self.L.dav1d_cuda_recon_graph_build_multi_phases(ctx, arr, len(dfs), phase_mask, C.byref(g))
         if n < 0:
             raise RuntimeError(f"dav1d_cuda_recon_graph_build_multi: {n}")
         self.graph, self.graph_nodes = g, n

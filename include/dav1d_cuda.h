@@ -438,13 +438,21 @@ typedef struct Dav1dCudaReconGraph Dav1dCudaReconGraph;
 DAV1D_CUDA_API int dav1d_cuda_recon_graph_build(Dav1dCudaContext *c, const Dav1dCudaReconBatch *b,
                                                 Dav1dCudaReconGraph **out);
 /* Frames of `n` independent streams (one batch each, same pixel type) as ONE
- * graph: MC / residual launches per frame on parallel branches, and ONE
- * intra launch per dependency level covering that level of every frame, so
- * the level-to-level latency is shared by all streams (server-side batching
- * of independent decoder instances). */
+ * graph: MC / residual launches per frame on parallel branches, and per
+ * dependency level ONE set of intra launches covering that level of every
+ * frame (prediction, then the residual tasks of all frames merged and ordered
+ * by transform size and type; levels with few operations: one fused launch),
+ * so the level-to-level latency is shared by all streams (server-side
+ * batching of independent decoder instances).  Frames that carry intra_itx /
+ * intra_itx_tasks take the split path, others the fused one. */
 DAV1D_CUDA_API int dav1d_cuda_recon_graph_build_multi(Dav1dCudaContext *c,
                                                       const Dav1dCudaReconBatch *const *batches, int n,
                                                       Dav1dCudaReconGraph **out);
+/* Same with a subset of the launch classes (bits as in dav1d_cuda_recon_submit_phases):
+ * used by bench.py to time one class in the batched regime. */
+DAV1D_CUDA_API int dav1d_cuda_recon_graph_build_multi_phases(Dav1dCudaContext *c,
+                                                             const Dav1dCudaReconBatch *const *batches, int n,
+                                                             int phase_mask, Dav1dCudaReconGraph **out);
 DAV1D_CUDA_API int dav1d_cuda_recon_graph_launch(Dav1dCudaContext *c, Dav1dCudaReconGraph *g);
 DAV1D_CUDA_API void dav1d_cuda_recon_graph_free(Dav1dCudaReconGraph *g);
 
