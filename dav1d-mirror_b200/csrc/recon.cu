@@ -173,14 +173,9 @@ intra_level_kernel(const __grid_constant__ IntraArgs a) {
 
 // Multi-frame variant: dependency level l of SEVERAL frames (independent
 // streams) in one launch, so the per-level latency is shared by all of them.
-struct IntraFrameParams {
-    PicView pic;
-    int bw4, bh4;
-    void *cf;
-    const Dav1dCudaIntraDesc *descs;     // level-sorted
-    const void *pal;
-    const uint8_t *pal_idx;
-};
+// per-frame arguments in a device table: the kernel hands intra_op() a reference INTO the
+// table (a per-thread copy would live in local memory: intra_op is not inlined)
+typedef IntraArgs IntraFrameParams;
 struct IntraMultiArgs {
     const IntraFrameParams *frames;
     const uint32_t *items;        // this level's operations: frame << 24 | sorted index inside the frame
@@ -195,12 +190,8 @@ __global__ void __launch_bounds__(INTRA_WARPS * 32, IntraCls<CLS>::MIN_BLOCKS) i
     const int i = blockIdx.x * INTRA_WARPS + warp;
     if (i >= m.n) return;
     const uint32_t item = m.items[i];
-    const IntraFrameParams &fp = m.frames[item >> 24];
-    IntraArgs a;
-    a.pic = fp.pic; a.bw4 = fp.bw4; a.bh4 = fp.bh4; a.cf = fp.cf;
-    a.descs = fp.descs; a.n = m.n; a.pal = fp.pal; a.pal_idx = fp.pal_idx;
-    a.dep_start = nullptr; a.deps = nullptr; a.sync = nullptr; a.opw = 1;
-    const Dav1dCudaIntraDesc d = fp.descs[item & 0xffffff];
+    const IntraFrameParams &a = m.frames[item >> 24];
+    const Dav1dCudaIntraDesc d = a.descs[item & 0xffffff];
     intra_op<pixel, CLS>(a, d, sm, lane);
 }
 
@@ -638,7 +629,8 @@ static int build_multi_tables(const Dav1dCudaReconBatch *const *bs, int n, Multi
         const Dav1dCudaReconBatch *b = bs[f];
         IntraFrameParams &p = t.frames[f];
         p.pic = pic_view(b->dst); p.bw4 = b->bw4; p.bh4 = b->bh4; p.cf = b->cf;
-        p.descs = b->intra; p.pal = b->pal; p.pal_idx = b->pal_idx;
+        p.descs = b->intra; p.n = 0; p.pal = b->pal; p.pal_idx = b->pal_idx;
+        p.dep_start = nullptr; p.deps = nullptr; p.sync = nullptr; p.opw = 1;
         if (b->intra && b->n_levels > 0) {
             if (!b->intra_host) return -22;
             max_levels = std::max(max_levels, (int)b->n_levels);
