@@ -196,6 +196,8 @@ def main_ours(args):
     import torch
     import torch.distributed as dist
     if world > 1:
+        # NCCL's version / debug lines go to stderr: stdout carries only the JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     import _d1pkg

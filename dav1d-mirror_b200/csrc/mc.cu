@@ -47,7 +47,7 @@ template <bool SMALL> struct McVar {
 // large window) delays only its own warp instead of holding a block's slot, and the next
 // tile's descriptor is fetched while the current tile is computed.
 template <typename pixel, bool SMALL>
-__global__ void __launch_bounds__(MC_WARPS * 32) mc_put_kernel(const __grid_constant__ McArgs a) {
+__global__ void __launch_bounds__(MC_WARPS * 32, 8) mc_put_kernel(const __grid_constant__ McArgs a) {
     extern __shared__ __align__(16) uint8_t mc_smem_raw[];
     typedef McVar<SMALL> V;
     const int wl = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(MC_WARPS * 32) mc_put_kernel(const __grid_cons
 
 // ---- fused compound: two preps into shared int16 tiles, then the combine
 template <typename pixel, bool SMALL>
-__global__ void __launch_bounds__(MC_WARPS * 32) mc_compound_kernel(const __grid_constant__ McArgs a) {
+__global__ void __launch_bounds__(MC_WARPS * 32, SMALL ? 6 : 5) mc_compound_kernel(const __grid_constant__ McArgs a) {
     extern __shared__ __align__(16) uint8_t mc_smem_raw[];
     typedef McVar<SMALL> V;
     const int wl = threadIdx.x & 31, warp = threadIdx.x >> 5;
