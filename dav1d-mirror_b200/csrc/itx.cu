@@ -79,7 +79,7 @@ static int launch_itx_tx(int tx, const ItxArgs &a, cudaStream_t st) {
 }
 
 // (the task kernels - all transform sizes in one launch - live in itx_task.cuh, instantiated per
-// pixel type in itx_task8.cu / itx_task16.cu)
+// pixel type and size group in itx_task_{s,b}{8,16}.cu, host side in itx_task.cu)
 int itx_task_launch(const PicView &pic, void *cf, const Dav1dCudaItxDesc *descs, const uint32_t *tasks,
                     int n_small, int n_big, int zero_coefs, cudaStream_t st_small, cudaStream_t st_big);
 int itx_build_tasks(const Dav1dCudaItxDesc *descs, int n, int index_base, uint32_t *tasks, int *n_small, int *n_big);

@@ -1,11 +1,17 @@
-// 10/12-bit instantiation of the transform task kernels (itx_task.cuh) + the host-side
-// task builder and the launch entry points shared by both pixel types.
+// Host side of the transform task kernels (itx_task.cuh): launch entry points shared by both
+// pixel types and the task builder.
 #include <string.h>
 #include "itx_task.cuh"
 namespace d1 {
 
-int itx_task_launch_16bpc(const ItxTaskArgs &a, int n_small, int n_big, cudaStream_t st_small, cudaStream_t st_big) {
-    return itx_task_launch_px<uint16_t>(a, n_small, n_big, st_small, st_big);
+static int itx_task_launch_both(ItxTaskArgs a, int n_small, int n_big, bool hbd, cudaStream_t st_small,
+                                cudaStream_t st_big)
+{
+    int r = hbd ? itx_task_small_16bpc(a, n_small, st_small) : itx_task_small_8bpc(a, n_small, st_small);
+    if (r) return r;
+    if (a.tasks) a.tasks += n_small;
+    if (a.mtasks) a.mtasks += n_small;
+    return hbd ? itx_task_big_16bpc(a, n_big, st_big) : itx_task_big_8bpc(a, n_big, st_big);
 }
 
 // tasks[0 .. n_small) = sizes up to 16x16, tasks[n_small .. n_small + n_big) = larger
@@ -15,8 +21,7 @@ int itx_task_launch(const PicView &pic, void *cf, const Dav1dCudaItxDesc *descs,
     ItxTaskArgs a;
     a.pic = pic; a.cf = cf; a.descs = descs; a.tasks = tasks; a.frames = nullptr; a.mtasks = nullptr;
     a.n_tasks = 0; a.zero_coefs = zero_coefs;
-    return pic.bdmax > 0xff ? itx_task_launch_16bpc(a, n_small, n_big, st_small, st_big)
-                            : itx_task_launch_8bpc(a, n_small, n_big, st_small, st_big);
+    return itx_task_launch_both(a, n_small, n_big, pic.bdmax > 0xff, st_small, st_big);
 }
 
 // one dependency level of several frames: tasks = (code, frame)
@@ -26,8 +31,7 @@ int itx_multi_task_launch(const ItxFrameRef *frames, const uint2 *tasks, int n_s
     ItxTaskArgs a;
     memset(&a, 0, sizeof(a));
     a.frames = frames; a.mtasks = tasks;
-    return hbd ? itx_task_launch_16bpc(a, n_small, n_big, st_small, st_big)
-               : itx_task_launch_8bpc(a, n_small, n_big, st_small, st_big);
+    return itx_task_launch_both(a, n_small, n_big, hbd, st_small, st_big);
 }
 
 // blocks of one size a warp takes: 32 / G

@@ -8,8 +8,9 @@
 // descriptors in the launch parameters) and the merged dependency level of several frames
 // (task = (code, frame), per-frame parameters from a device table).
 //
-// Included by itx_task8.cu / itx_task16.cu, one pixel type each, so that the two halves of
-// this (large: every 1-D transform inlined per block shape) code build in parallel.
+// Included by itx_task_{s,b}{8,16}.cu - one translation unit per pixel type and size group, so
+// that the pieces of this large code build in parallel and can choose between inlined (small
+// sizes: fewer registers) and shared out-of-line row / column passes (D1_ITX_PASS_NOINLINE).
 #pragma once
 #include "ctx.h"
 #include "itx.cuh"
@@ -88,33 +89,28 @@ __global__ void __launch_bounds__(ITX_TASK_WARPS * 32, BIG ? 4 : 8) itx_task_ker
 #undef D1_TASKCASE
 }
 
-// tasks[0 .. n_small) = sizes up to 16x16, the following n_big = larger ones
-template <typename pixel>
-int itx_task_launch_px(ItxTaskArgs a, int n_small, int n_big, cudaStream_t st_small, cudaStream_t st_big) {
+// one launch: n tasks of the small (<= 16x16) or the large sizes
+template <typename pixel, bool BIG>
+int itx_task_launch_one(ItxTaskArgs a, int n, cudaStream_t st) {
     static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(itx_task_kernel<pixel, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (!attr && BIG) {
+        cudaFuncSetAttribute(itx_task_kernel<pixel, BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              ITX_TASK_WARPS * ITX_TASK_SMEM_BIG);
         attr = true;
     }
-    if (n_small > 0) {
-        a.n_tasks = n_small;
-        const int grid = (n_small + ITX_TASK_WARPS - 1) / ITX_TASK_WARPS;
-        launch_pdl(itx_task_kernel<pixel, false>, grid, ITX_TASK_WARPS * 32, ITX_TASK_WARPS * ITX_TASK_SMEM_SMALL, st_small, a);
-        count_launch();
-    }
-    if (n_big > 0) {
-        if (a.tasks) a.tasks += n_small;
-        if (a.mtasks) a.mtasks += n_small;
-        a.n_tasks = n_big;
-        const int grid = (n_big + ITX_TASK_WARPS - 1) / ITX_TASK_WARPS;
-        launch_pdl(itx_task_kernel<pixel, true>, grid, ITX_TASK_WARPS * 32, ITX_TASK_WARPS * ITX_TASK_SMEM_BIG, st_big, a);
-        count_launch();
-    }
+    if (n <= 0) return 0;
+    a.n_tasks = n;
+    const int grid = (n + ITX_TASK_WARPS - 1) / ITX_TASK_WARPS;
+    launch_pdl(itx_task_kernel<pixel, BIG>, grid, ITX_TASK_WARPS * 32,
+               ITX_TASK_WARPS * (BIG ? ITX_TASK_SMEM_BIG : ITX_TASK_SMEM_SMALL), st, a);
+    count_launch();
     return cuda_ok(cudaGetLastError(), "itx_task_kernel") ? 0 : -5;
 }
 
-int itx_task_launch_8bpc(const ItxTaskArgs &a, int n_small, int n_big, cudaStream_t st_small, cudaStream_t st_big);
-int itx_task_launch_16bpc(const ItxTaskArgs &a, int n_small, int n_big, cudaStream_t st_small, cudaStream_t st_big);
+// one translation unit per (pixel type, size group): itx_task_{s,b}{8,16}.cu
+int itx_task_small_8bpc(const ItxTaskArgs &a, int n, cudaStream_t st);
+int itx_task_big_8bpc(const ItxTaskArgs &a, int n, cudaStream_t st);
+int itx_task_small_16bpc(const ItxTaskArgs &a, int n, cudaStream_t st);
+int itx_task_big_16bpc(const ItxTaskArgs &a, int n, cudaStream_t st);
 
 }  // namespace d1

@@ -1,0 +1,10 @@
+// transform task kernel, sizes above 16x16, 10/12-bit pixels (itx_task.cuh)
+#ifdef D1_ITX_BIG_NOINLINE
+#define D1_ITX_PASS_NOINLINE
+#endif
+#include "itx_task.cuh"
+namespace d1 {
+int itx_task_big_16bpc(const ItxTaskArgs &a, int n, cudaStream_t st) {
+    return itx_task_launch_one<uint16_t, true>(a, n, st);
+}
+}  // namespace d1
