@@ -26,6 +26,11 @@ CASES = {
     "420_10b_intra_heavy": (384, 256, 0x3ff, 6, {"p_intra": 0.8, "p_palette": 0.1, "p_cfl": 0.6,
                                                  "p_filter_intra": 0.2}),
     "420_8b_inter_only": (384, 320, 0xff, 7, {"p_intra": 0.0, "mv_range": 300}),
+    # ragged picture sizes (not multiples of the 64x64 superblock / of 8 in chroma)
+    "420_10b_ragged": (328, 200, 0x3ff, 8, {}),
+    "420_8b_ragged": (200, 120, 0xff, 10, {"p_intra": 0.6}),
+    # dense coefficient blocks (the reference's layout, cw4 = ch4 = 0) through the batched path
+    "420_10b_dense_coefs": (256, 192, 0x3ff, 12, {"dense_coefs": 1}),
 }
 
 
@@ -208,3 +213,72 @@ def test_multi_frame_batched_graph(ref, case):
     for df in dfs:
         df.close()
     pkg.lib().dav1d_cuda_close(ctx)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["420_10b_small", "420_8b_ragged"])
+def test_end_to_end_pinned_path(ref, name):
+    """The end-to-end path of bench.py: descriptors + coefficients from ONE pinned arena (one H2D
+    copy), group graph, the reconstructed picture back with ONE D2H copy - bit-exact vs the oracle,
+    twice in a row (the arena is re-shipped every step)."""
+    w, h, bd, seed, kw = CASES[name]
+    hf = F.HostFrame(w, h, bd, seed, **kw)
+    refs, init, want = oracle_planes(ref, hf, seed)
+    ctx = F.open_context(0)
+    df = F.DeviceFrame(ctx, hf, n_refs=len(refs))
+    try:
+        for r, planes in enumerate(refs):
+            df.upload_picture(df.refs[r], planes)
+        df.alloc_pinned()
+        mf = F.MultiFrame(ctx, [df])
+        for _ in range(2):
+            df.upload_picture(df.dst, init)
+            df.upload_descriptors_pinned()
+            mf.launch()
+            df.download_pinned()
+            pkg.lib().dav1d_cuda_synchronize(ctx)
+            for pl, (a, b) in enumerate(zip(want, df.pinned_planes())):
+                assert np.array_equal(a, b), f"plane {pl}"
+        pkg.check_error()
+        mf.close()
+    finally:
+        df.close()
+        pkg.lib().dav1d_cuda_close(ctx)
+
+
+@pytest.mark.gpu
+def test_empty_batch_is_a_no_op(ref):
+    """A frame without any descriptor (and a group that contains one): nothing is launched, the
+    destination picture is untouched, no error is raised."""
+    hf = F.HostFrame(128, 128, 0x3ff, 77, p_intra=0.0)
+    init = F.random_planes(hf, 5)
+    ctx = F.open_context(0)
+    df = F.DeviceFrame(ctx, hf)
+    try:
+        df.upload_picture(df.dst, init)
+        b = df.batch
+        b.n_mc_put_tiles = 0
+        b.n_mc_put_small = 0
+        b.n_mc_comp_tiles[0] = b.n_mc_comp_tiles[1] = 0
+        b.n_mc_comp_small[0] = b.n_mc_comp_small[1] = 0
+        b.n_warp = 0
+        b.n_itx_tasks[0] = b.n_itx_tasks[1] = 0
+        for i in range(19):
+            b.itx_class_count[i] = 0
+        b.n_levels = 0
+        l0 = pkg.lib().dav1d_cuda_launch_count()
+        df.submit()
+        got = df.download_picture()
+        assert pkg.lib().dav1d_cuda_launch_count() == l0
+        for a, g in zip(init, got):
+            assert np.array_equal(a, g)
+        mf = F.MultiFrame(ctx, [df])
+        mf.launch()
+        got = df.download_picture()
+        for a, g in zip(init, got):
+            assert np.array_equal(a, g)
+        pkg.check_error()
+        mf.close()
+    finally:
+        df.close()
+        pkg.lib().dav1d_cuda_close(ctx)
