@@ -245,6 +245,11 @@ struct Gen {
         if (mode != DAV1D_CUDA_INTRA_PAL) mark(pl, x4, y4, tw4, th4);
     }
 
+    // transform shapes are at most 4:1 (4:2:2 chroma of a 1:2 block would be 1:8)
+    static void fit_tx(int &tw4, int &th4) {
+        while (tw4 > 4 * th4) tw4 >>= 1;
+        while (th4 > 4 * tw4) th4 >>= 1;
+    }
     static void split_tx(int &tw4, int &th4) {   // halve the longer side (both if square)
         if (tw4 == th4) { if (tw4 > 1) { tw4 >>= 1; th4 >>= 1; } }
         else if (tw4 > th4) tw4 >>= 1;
@@ -281,7 +286,8 @@ struct Gen {
         // ---- chroma
         const int sh = P.ss_hor, sv = P.ss_ver;
         const int cx4 = bx4 >> sh, cy4 = by4 >> sv, cw4 = w4 >> sh, ch4 = h4 >> sv;
-        const int uvtw4 = std::min(cw4, 8), uvth4 = std::min(ch4, 8);
+        int uvtw4 = std::min(cw4, 8), uvth4 = std::min(ch4, 8);
+        fit_tx(uvtw4, uvth4);
         const bool cfl = !pal && w4 <= 8 && h4 <= 8 && rng.chance(P.p_cfl);
         const int uvflags = (P.edge_filter ? 1024 : 0) | (rng.chance(0.25f) ? 512 : 0);
         int uvmode = rng.range(13), uvdelta = 0;
@@ -432,7 +438,8 @@ struct Gen {
                 for (int x = 0; x < w4; x += tw4) add_itx(0, bx4 + x, by4 + y, tx);
             if (!P.no_chroma) {
                 const int cw4 = w4 >> P.ss_hor, ch4 = h4 >> P.ss_ver;
-                const int utw4 = std::min(cw4, 8), uth4 = std::min(ch4, 8);
+                int utw4 = std::min(cw4, 8), uth4 = std::min(ch4, 8);
+                fit_tx(utw4, uth4);
                 const int utx = tx_from_dims(utw4, uth4);
                 for (int pl = 1; pl <= 2; pl++)
                     for (int y = 0; y < ch4; y += uth4)

@@ -26,6 +26,9 @@ CASES = {
     "420_10b_intra_heavy": (384, 256, 0x3ff, 6, {"p_intra": 0.8, "p_palette": 0.1, "p_cfl": 0.6,
                                                  "p_filter_intra": 0.2}),
     "420_8b_inter_only": (384, 320, 0xff, 7, {"p_intra": 0.0, "mv_range": 300}),
+    "422_10b_intra_heavy": (256, 192, 0x3ff, 9, {"ss_hor": 1, "ss_ver": 0, "p_intra": 0.8, "p_cfl": 0.6,
+                                                 "p_palette": 0.1}),
+    "422_8b_small": (192, 128, 0xff, 13, {"ss_hor": 1, "ss_ver": 0}),
     # ragged picture sizes (not multiples of the 64x64 superblock / of 8 in chroma)
     "420_10b_ragged": (328, 200, 0x3ff, 8, {}),
     "420_8b_ragged": (200, 120, 0xff, 10, {"p_intra": 0.6}),
