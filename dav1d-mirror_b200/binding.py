@@ -47,7 +47,7 @@ class McSrc(C.Structure):
 class McDesc(C.Structure):
     _fields_ = [("x", C.c_uint16), ("y", C.c_uint16), ("w", C.c_uint8), ("h", C.c_uint8),
                 ("plane", C.c_uint8), ("kind", C.c_uint8), ("src", McSrc * 2),
-                ("weight", C.c_uint8), ("mask_ss", C.c_uint8), ("pad", C.c_uint16),
+                ("weight", C.c_uint8), ("mask_ss", C.c_uint8), ("aux16", C.c_uint16),
                 ("aux_off", C.c_uint32)]
 
 
@@ -130,6 +130,7 @@ class ReconBatch(C.Structure):
                 ("mc_put", C.c_void_p), ("mc_put_tiles", C.c_void_p), ("n_mc_put_tiles", C.c_int32),
                 ("mc_comp", C.c_void_p), ("mc_comp_tiles", C.c_void_p), ("n_mc_comp_tiles", C.c_int32 * 2),
                 ("n_mc_put_small", C.c_int32), ("n_mc_comp_small", C.c_int32 * 2),
+                ("mc_obmc", C.c_void_p), ("mc_obmc_tiles", C.c_void_p), ("n_mc_obmc_tiles", C.c_int32 * 2),
                 ("warp", C.c_void_p), ("n_warp", C.c_int32),
                 ("itx", C.c_void_p), ("itx_class_count", C.c_int32 * N_RECT_TX_SIZES),
                 ("itx_tasks", C.c_void_p), ("n_itx_tasks", C.c_int32 * 2),

@@ -137,6 +137,47 @@ __global__ void __launch_bounds__(MC_WARPS * 32, SMALL ? 6 : 5) mc_compound_kern
     }
 }
 
+// ---- OBMC (obmc(), recon_tmpl.c:1071-1131): the neighbour's prediction of a tile into a shared
+// pixel tile ("lap"), then blend_h (top neighbour: rows < 3/4 of the blend height, mask
+// obmc_masks[bh + y]) or blend_v (left neighbour: columns < 3/4 of the width, obmc_masks[w + x])
+// onto the block's own prediction (mc_tmpl.c:655-681).
+template <typename pixel> struct __align__(16) McSmemObmc {
+    McSmem<pixel, 32> s;
+    pixel lap[32 * 32];
+};
+
+template <typename pixel>
+__global__ void __launch_bounds__(MC_WARPS * 32) mc_obmc_kernel(const __grid_constant__ McArgs a) {
+    extern __shared__ __align__(16) uint8_t mc_smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ti = blockIdx.x * MC_WARPS + warp;
+    if (ti >= a.n_tiles) return;
+    McSmemObmc<pixel> *sm = (McSmemObmc<pixel> *)mc_smem_raw + warp;
+    const uint32_t tcode = a.tiles[ti];
+    const Dav1dCudaMcDesc d = a.descs[tcode >> 4];
+    const TileGeo g = tile_geo(d, tcode & 15);
+    const Dav1dCudaMcSrc s = d.src[0];
+    const PlaneView &ref = a.refs[s.ref].p[d.plane];
+    mc_tile<pixel, false, 32, 32>(ref, s.x + g.x0, s.y + g.y0, g.tw, g.th, d.w, d.h, s.mx, s.my, s.filter_2d,
+                                  a.dst.bdmax, &sm->s, sm->lap, 32, lane);
+    const PlaneView &dp = a.dst.p[d.plane];
+    const int dstride = (int)(dp.stride / (int)sizeof(pixel));
+    pixel *dst = (pixel *)dp.data + (int64_t)(d.y + g.y0) * dstride + d.x + g.x0;
+    const bool horz = d.kind == DAV1D_CUDA_MC_OBMC_H;
+    const int bh = horz ? d.aux16 : d.h;
+    // region of the whole block that is blended, clipped to this tile
+    const int lim_x = horz ? d.w : (d.w * 3) >> 2, lim_y = horz ? (bh * 3) >> 2 : d.h;
+    const int nx = imin(g.tw, lim_x - g.x0), ny = imin(g.th, lim_y - g.y0);
+    if (nx <= 0 || ny <= 0) return;
+    for (int i = lane; i < ny * 32; i += 32) {
+        const int y = i >> 5, x = i & 31;
+        if (x >= nx) continue;
+        const int m = horz ? g_obmc_masks[bh + g.y0 + y] : g_obmc_masks[d.w + g.x0 + x];
+        const int p = dst[y * dstride + x], q = sm->lap[y * 32 + x];
+        dst[y * dstride + x] = (pixel)((p * (64 - m) + q * m + 32) >> 6);
+    }
+}
+
 // ---- stand-alone ops on one block (per-call surface + unfused batch use)
 struct BlockOp {
     int kind;                 // combine: Dav1dCudaMcKind; blend: 0/1/2
@@ -332,6 +373,22 @@ static int launch_mc(McArgs a, cudaStream_t st) {
         count_launch();
     }
     return cuda_ok(cudaGetLastError(), COMPOUND ? "mc_compound_kernel" : "mc_put_kernel") ? 0 : -5;
+}
+
+int mc_obmc_launch_raw(const PicView &dst, const PicView *refs, const Dav1dCudaMcDesc *descs,
+                       const uint32_t *tiles, int n_tiles, cudaStream_t st)
+{
+    if (n_tiles <= 0 || !descs || !tiles) return 0;
+    McArgs a;
+    memset(&a, 0, sizeof(a));
+    a.dst = dst;
+    for (int i = 0; i < 7; i++) a.refs[i] = refs[i];
+    a.descs = descs; a.tiles = tiles; a.n_tiles = n_tiles;
+    const int grid = (n_tiles + MC_WARPS - 1) / MC_WARPS;
+    if (dst.bdmax > 0xff) mc_obmc_kernel<uint16_t><<<grid, MC_WARPS * 32, MC_WARPS * sizeof(McSmemObmc<uint16_t>), st>>>(a);
+    else mc_obmc_kernel<uint8_t><<<grid, MC_WARPS * 32, MC_WARPS * sizeof(McSmemObmc<uint8_t>), st>>>(a);
+    count_launch();
+    return cuda_ok(cudaGetLastError(), "mc_obmc_kernel") ? 0 : -5;
 }
 
 int mc_put_launch(const McArgs &a, cudaStream_t st) {

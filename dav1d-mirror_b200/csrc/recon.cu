@@ -25,6 +25,8 @@ int itx_batch_launch_multi(const PicView &pic, void *cf, const Dav1dCudaItxDesc 
 int itx_task_launch(const PicView &pic, void *cf, const Dav1dCudaItxDesc *descs, const uint32_t *tasks,
                     int n_small, int n_big, int zero_coefs, cudaStream_t st_small, cudaStream_t st_big);
 int itx_build_tasks(const Dav1dCudaItxDesc *descs, int n, int index_base, uint32_t *tasks, int *n_small, int *n_big);
+int mc_obmc_launch_raw(const PicView &dst, const PicView *refs, const Dav1dCudaMcDesc *descs,
+                       const uint32_t *tiles, int n_tiles, cudaStream_t st);
 int itx_multi_task_launch(const ItxFrameRef *frames, const uint2 *tasks, int n_small, int n_big, bool hbd,
                           cudaStream_t st_small, cudaStream_t st_big);
 void itx_init_attrs();
@@ -557,6 +559,12 @@ static int recon_submit_on(Dav1dCudaContext *c, const Dav1dCudaReconBatch *b, cu
         return r;
     if ((mask & 4) && (r = warp_batch_launch(dst, refs, b->warp, b->n_warp, c->aux[1]))) return r;
     if (!join_aux(c, st)) return -5;
+    // OBMC blends onto the finished predictions: top neighbours, then left neighbours
+    if ((mask & 1) && b->mc_obmc) {
+        if ((r = mc_obmc_launch_raw(dst, refs, b->mc_obmc, b->mc_obmc_tiles, b->n_mc_obmc_tiles[0], st))) return r;
+        if ((r = mc_obmc_launch_raw(dst, refs, b->mc_obmc, b->mc_obmc_tiles + b->n_mc_obmc_tiles[0],
+                                    b->n_mc_obmc_tiles[1], st))) return r;
+    }
     // phase B: inter residuals
     if (b->itx && b->itx_tasks && (mask & 8)) {
         if (!fork_aux(c, st)) return -5;
@@ -727,6 +735,11 @@ static int recon_submit_multi_on(Dav1dCudaContext *c, const Dav1dCudaReconBatch 
         if ((mask & 2) && (r = mc_put_launch_raw(dst, refs, b->mc_comp, b->mc_comp_tiles + b->n_mc_comp_tiles[0],
                                                  b->n_mc_comp_tiles[1], b->n_mc_comp_small[1], b->masks, nullptr, true, s))) return r;
         if ((mask & 4) && (r = warp_batch_launch(dst, refs, b->warp, b->n_warp, s))) return r;
+        if ((mask & 1) && b->mc_obmc) {
+            if ((r = mc_obmc_launch_raw(dst, refs, b->mc_obmc, b->mc_obmc_tiles, b->n_mc_obmc_tiles[0], s))) return r;
+            if ((r = mc_obmc_launch_raw(dst, refs, b->mc_obmc, b->mc_obmc_tiles + b->n_mc_obmc_tiles[0],
+                                        b->n_mc_obmc_tiles[1], s))) return r;
+        }
         if ((mask & 8) && b->itx && b->itx_tasks) {
             if ((r = itx_task_launch(dst, b->cf, b->itx, b->itx_tasks, b->n_itx_tasks[0], b->n_itx_tasks[1], 0, s, s)))
                 return r;

@@ -41,6 +41,7 @@ typedef struct D1SynthParams {
     int32_t only_txtp;          // with only_tx: >= 0 fixes the type
     int32_t eob_class;          // -1 random, 0 dc-only, 1 low-frequency, 2 full
     int32_t dense_coefs;        // 1: dense coefficient blocks (reference layout) instead of packed ones
+    float p_obmc;               // single-reference blocks (>= 8x8) that get OBMC blends
 } D1SynthParams;
 
 typedef struct D1SynthFrame {
@@ -60,6 +61,7 @@ typedef struct D1SynthFrame {
     double algo_class[5];      // same, split by launch class: put, compound, warp, itx, intra
     double luma_px;            // luma pixels covered
     int64_t n_blocks, n_intra_blocks;
+    Dav1dCudaMcDesc *mc_obmc;  int32_t n_mc_obmc;  uint32_t *mc_obmc_tiles; int32_t n_mc_obmc_tiles[2];
 } D1SynthFrame;
 
 }  // extern "C"
@@ -101,7 +103,7 @@ struct Gen {
     const D1SynthParams &P;
     Rng rng;
     int bw4, bh4, hbd;
-    std::vector<Dav1dCudaMcDesc> put, comp0, comp1;
+    std::vector<Dav1dCudaMcDesc> put, comp0, comp1, obmc_h, obmc_v;
     std::vector<Dav1dCudaWarpDesc> warp;
     std::vector<Dav1dCudaItxDesc> itx;
     std::vector<Dav1dCudaIntraDesc> intra;
@@ -343,6 +345,53 @@ struct Gen {
         return s;
     }
 
+    // obmc() (recon_tmpl.c:1071-1131) with random neighbours: per top / left neighbour (width or
+    // height step4 in {2,4,8,16}, inter with probability 0.7, at most min(log2(dim), 4) of them) a
+    // prediction with the neighbour's motion vector + blend_h / blend_v
+    void add_obmc(int pl, int bx4, int by4, int w4, int h4) {
+        const int sh = pl ? P.ss_hor : 0, sv = pl ? P.ss_ver : 0;
+        const int h_mul = 4 >> sh, v_mul = 4 >> sv;
+        const int R = P.mv_range * 8;
+        auto ilog2 = [](int v) { int l = 0; while (v > 1) { v >>= 1; l++; } return l; };
+        auto neighbour = [&](int x4, int y4, int ow4, int mh4, int kind, int blend_h) {
+            Dav1dCudaMcDesc d;
+            memset(&d, 0, sizeof(d));
+            d.plane = (uint8_t)pl; d.kind = (uint8_t)kind;
+            d.x = (uint16_t)(((bx4 * 4) >> sh) + (x4 - bx4) * h_mul);
+            d.y = (uint16_t)(((by4 * 4) >> sv) + (y4 - by4) * v_mul);
+            d.w = (uint8_t)(ow4 * h_mul); d.h = (uint8_t)(mh4 * v_mul);
+            d.aux16 = (uint16_t)blend_h;
+            d.src[0] = make_src(pl, x4, y4, rng.range(P.n_refs), rng.irange(-R, R), rng.irange(-R, R), rng.range(10));
+            add_bytes(0, 4.0 * Bp * d.w * d.h);     // reference read + blend read-modify-write
+            if (kind == DAV1D_CUDA_MC_OBMC_H) { order.push_back({ 6, (uint32_t)obmc_h.size() }); obmc_h.push_back(d); }
+            else { order.push_back({ 7, (uint32_t)obmc_v.size() }); obmc_v.push_back(d); }
+        };
+        if (by4 > 0 && (!pl || w4 * h_mul + h4 * v_mul >= 16)) {
+            for (int i = 0, x = 0; x < w4 && i < std::min(ilog2(w4), 4);) {
+                int step4 = 2 << rng.range(4);
+                while (x > 0 && x % step4) step4 >>= 1;      // neighbours are aligned to their own size
+                if (rng.chance(0.7f)) {
+                    const int ow4 = std::min(step4, w4), oh4 = std::min(h4, 16) >> 1;
+                    neighbour(bx4 + x, by4, ow4, (oh4 * 3 + 3) >> 2, DAV1D_CUDA_MC_OBMC_H, v_mul * oh4);
+                    i++;
+                }
+                x += step4;
+            }
+        }
+        if (bx4 > 0) {
+            for (int i = 0, y = 0; y < h4 && i < std::min(ilog2(h4), 4);) {
+                int step4 = 2 << rng.range(4);
+                while (y > 0 && y % step4) step4 >>= 1;
+                if (rng.chance(0.7f)) {
+                    const int ow4 = std::min(w4, 16) >> 1, oh4 = std::min(step4, h4);
+                    neighbour(bx4, by4 + y, ow4, oh4, DAV1D_CUDA_MC_OBMC_V, 0);
+                    i++;
+                }
+                y += step4;
+            }
+        }
+    }
+
     void inter_block(int bx4, int by4, int w4, int h4) {
         const float u = rng.unit();
         float acc = P.p_avg;
@@ -363,6 +412,9 @@ struct Gen {
             if (rng.chance(0.1f)) mvy[i] &= ~7;
         }
         const int weight = rng.irange(1, 15), sign = rng.range(2);
+        // OBMC: single-reference, translational blocks of at least 8x8 on even 4x4 coordinates
+        const bool do_obmc = P.p_obmc > 0.f && kind == DAV1D_CUDA_MC_PUT && !is_warp && w4 >= 2 && h4 >= 2 &&
+                             !(bx4 & 1) && !(by4 & 1) && rng.chance(P.p_obmc);
         uint32_t seg_off = 0, wedge_off[3] = { 0, 0, 0 };
         for (int pl = 0; pl < nplanes(); pl++) {
             const int sh = pl ? P.ss_hor : 0, sv = pl ? P.ss_ver : 0;
@@ -399,6 +451,7 @@ struct Gen {
                 add_bytes(0, 2.0 * Bp * w * h);
                 order.push_back({ 0, (uint32_t)put.size() });
                 put.push_back(d);
+                if (do_obmc) add_obmc(pl, bx4, by4, w4, h4);
                 continue;
             }
             add_bytes(1, 3.0 * Bp * w * h);
@@ -522,7 +575,7 @@ __attribute__((visibility("default"))) void d1synth_default_params(D1SynthParams
     p->p_intra = 0.3f; p->p_residual = 0.6f; p->p_tx_split = 0.5f;
     p->p_filter_intra = 0.05f; p->p_palette = 0.02f; p->p_cfl = 0.25f;
     p->p_avg = 0.2f; p->p_w_avg = 0.1f; p->p_wedge = 0.1f; p->p_seg = 0.05f; p->p_warp = 0.05f;
-    p->mv_range = 128; p->n_refs = 2; p->edge_filter = 1; p->only_tx = -1; p->only_txtp = -1; p->eob_class = -1; p->dense_coefs = 0;
+    p->mv_range = 128; p->n_refs = 2; p->edge_filter = 1; p->only_tx = -1; p->only_txtp = -1; p->eob_class = -1; p->dense_coefs = 0; p->p_obmc = 0.f;
 }
 
 __attribute__((visibility("default"))) int d1synth_generate(const D1SynthParams *p, D1SynthFrame *f) {
@@ -572,10 +625,26 @@ __attribute__((visibility("default"))) int d1synth_generate(const D1SynthParams 
     emit(g.put, 0, g.put.size(), put_tiles, &f->n_mc_put_small);
     f->n_mc_comp_tiles[0] = emit(comp, 0, g.comp0.size(), comp_tiles, &f->n_mc_comp_small[0]);
     f->n_mc_comp_tiles[1] = emit(comp, g.comp0.size(), comp.size(), comp_tiles, &f->n_mc_comp_small[1]);
+    // OBMC: blend_h wave, then blend_v wave (one descriptor array, tiles per wave)
+    std::vector<Dav1dCudaMcDesc> obmc(g.obmc_h);
+    obmc.insert(obmc.end(), g.obmc_v.begin(), g.obmc_v.end());
+    std::vector<uint32_t> obmc_tiles;
+    for (int wave = 0; wave < 2; wave++) {
+        const size_t lo = wave ? g.obmc_h.size() : 0, hi = wave ? obmc.size() : g.obmc_h.size();
+        const size_t base = obmc_tiles.size();
+        for (size_t i = lo; i < hi; i++) {
+            const int n = mc_tiles((uint32_t)i, obmc[i].w, obmc[i].h, buf);
+            obmc_tiles.insert(obmc_tiles.end(), buf, buf + n);
+        }
+        f->n_mc_obmc_tiles[wave] = (int32_t)(obmc_tiles.size() - base);
+    }
+    f->mc_obmc = dup(obmc); f->n_mc_obmc = (int32_t)obmc.size();
+    f->mc_obmc_tiles = dup(obmc_tiles);
     std::vector<uint32_t> order(g.order.size());
     for (size_t i = 0; i < g.order.size(); i++) {
         uint32_t cls = g.order[i].cls, idx = g.order[i].idx;
         if (cls == 5) { cls = 1; idx += (uint32_t)g.comp0.size(); }
+        if (cls == 7) { cls = 6; idx += (uint32_t)g.obmc_h.size(); }
         if (cls == 3) idx = itx_new[idx];
         order[i] = (cls << 28) | idx;
     }
@@ -611,6 +680,7 @@ __attribute__((visibility("default"))) int d1synth_generate(const D1SynthParams 
 __attribute__((visibility("default"))) void d1synth_free(D1SynthFrame *f) {
     if (!f) return;
     free(f->mc_put); free(f->mc_put_tiles); free(f->mc_comp); free(f->mc_comp_tiles); free(f->warp);
+    free(f->mc_obmc); free(f->mc_obmc_tiles);
     free(f->itx); free(f->intra); free(f->cf); free(f->masks); free(f->pal); free(f->pal_idx); free(f->order);
     memset(f, 0, sizeof(*f));
 }

@@ -22,7 +22,7 @@ class SynthParams(C.Structure):
                 ("p_seg", C.c_float), ("p_warp", C.c_float),
                 ("mv_range", C.c_int32), ("n_refs", C.c_int32), ("edge_filter", C.c_int32),
                 ("only_tx", C.c_int32), ("only_txtp", C.c_int32), ("eob_class", C.c_int32),
-                ("dense_coefs", C.c_int32)]
+                ("dense_coefs", C.c_int32), ("p_obmc", C.c_float)]
 
 
 class SynthFrame(C.Structure):
@@ -41,7 +41,9 @@ class SynthFrame(C.Structure):
                 ("order", C.c_void_p), ("n_order", C.c_int32),
                 ("bw4", C.c_int32), ("bh4", C.c_int32),
                 ("algo_bytes", C.c_double), ("algo_class", C.c_double * 5), ("luma_px", C.c_double),
-                ("n_blocks", C.c_int64), ("n_intra_blocks", C.c_int64)]
+                ("n_blocks", C.c_int64), ("n_intra_blocks", C.c_int64),
+                ("mc_obmc", C.c_void_p), ("n_mc_obmc", C.c_int32), ("mc_obmc_tiles", C.c_void_p),
+                ("n_mc_obmc_tiles", C.c_int32 * 2)]
 
 
 _synth = None
@@ -95,6 +97,9 @@ class HostFrame:
         self.n_mc_comp_tiles = (f.n_mc_comp_tiles[0], f.n_mc_comp_tiles[1])
         self.n_mc_put_small = f.n_mc_put_small
         self.n_mc_comp_small = (f.n_mc_comp_small[0], f.n_mc_comp_small[1])
+        self.mc_obmc = _np_from(f.mc_obmc, f.n_mc_obmc * C.sizeof(B.McDesc))
+        self.n_mc_obmc_tiles = (f.n_mc_obmc_tiles[0], f.n_mc_obmc_tiles[1])
+        self.mc_obmc_tiles = _np_from(f.mc_obmc_tiles, (f.n_mc_obmc_tiles[0] + f.n_mc_obmc_tiles[1]) * 4)
         self.warp = _np_from(f.warp, f.n_warp * C.sizeof(B.WarpDesc))
         self.n_warp = f.n_warp
         self.itx = _np_from(f.itx, f.n_itx * C.sizeof(B.ItxDesc))
@@ -179,6 +184,7 @@ class HostFrame:
     def host_bytes(self):
         """Bytes a decoder would ship host->device for this frame (descriptors + coefficients + pools)."""
         n = sum(a.nbytes for a in (self.mc_put, self.mc_put_tiles, self.mc_comp, self.mc_comp_tiles, self.warp,
+                                   self.mc_obmc, self.mc_obmc_tiles,
                                    self.itx, self.cf, self.masks, self.pal, self.pal_idx))
         if self.intra_sorted is not None:
             n += self.itx_tasks.nbytes + self.intra_itx.nbytes + self.intra_itx_tasks.nbytes
@@ -216,6 +222,8 @@ class DeviceFrame:
         self._host = {}
         names = ["mc_put", "mc_put_tiles", "mc_comp", "mc_comp_tiles", "warp", "itx", "intra_sorted", "cf",
                  "masks", "pal", "pal_idx", "itx_tasks"]
+        if hf.mc_obmc.nbytes:
+            names += ["mc_obmc", "mc_obmc_tiles"]
         if dataflow:
             names += ["dep_start", "deps"]
         elif tasks == 1:
@@ -235,7 +243,7 @@ class DeviceFrame:
             raise RuntimeError("dav1d_cuda_malloc failed")
         for name in ("mc_put", "mc_put_tiles", "mc_comp", "mc_comp_tiles", "warp", "itx", "intra_sorted", "cf",
                      "masks", "pal", "pal_idx", "dep_start", "deps", "itx_tasks", "intra_itx", "intra_itx_tasks",
-                     "intra_tasks"):
+                     "intra_tasks", "mc_obmc", "mc_obmc_tiles"):
             self._dev[name] = self._arena + self._off[name] if name in self._off else None
         self._level_start = (C.c_int32 * (hf.n_levels + 1))(*hf.level_start.tolist())
         b = B.ReconBatch()
@@ -251,6 +259,9 @@ class DeviceFrame:
         b.n_mc_put_small = hf.n_mc_put_small
         b.n_mc_comp_small[0], b.n_mc_comp_small[1] = hf.n_mc_comp_small
         b.warp, b.n_warp = d["warp"], hf.n_warp
+        if hf.mc_obmc.nbytes:
+            b.mc_obmc, b.mc_obmc_tiles = d["mc_obmc"], d["mc_obmc_tiles"]
+            b.n_mc_obmc_tiles[0], b.n_mc_obmc_tiles[1] = hf.n_mc_obmc_tiles
         b.itx = d["itx"]
         for i in range(19):
             b.itx_class_count[i] = hf.itx_class_count[i]

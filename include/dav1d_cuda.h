@@ -181,7 +181,12 @@ enum Dav1dCudaMcKind {
     DAV1D_CUDA_MC_W_AVG  = 2,  /* 2x mct + w_avg   (:1847-1851)             */
     DAV1D_CUDA_MC_MASK   = 3,  /* 2x mct + mask    (:1859-1868, wedge/chroma seg) */
     DAV1D_CUDA_MC_W_MASK = 4,  /* 2x mct + w_mask  (:1852-1858) writes seg mask */
-    DAV1D_CUDA_MC_PREP   = 5   /* dsp->mc.mct[filter] into the int16 tmp pool */
+    DAV1D_CUDA_MC_PREP   = 5,  /* dsp->mc.mct[filter] into the int16 tmp pool */
+    /* overlapped block motion compensation, obmc() (recon_tmpl.c:1071-1131): the prediction of a
+     * neighbour's motion vector over the block's edge region into a scratch tile + blend onto the
+     * block's own prediction.  w, h = the size handed to mc() (it selects the 4-tap sets). */
+    DAV1D_CUDA_MC_OBMC_H = 6,  /* top neighbour:  mc + blend_h(dst, lap, w, aux16)  (:1093-1103) */
+    DAV1D_CUDA_MC_OBMC_V = 7   /* left neighbour: mc + blend_v(dst, lap, w, h)      (:1117-1127) */
 };
 
 typedef struct Dav1dCudaMcSrc {
@@ -199,7 +204,7 @@ typedef struct Dav1dCudaMcDesc {   /* 40 bytes */
     Dav1dCudaMcSrc src[2]; /* src[1] unused for PUT/PREP */
     uint8_t  weight;       /* W_AVG: jnt weight 1..15; W_MASK: sign */
     uint8_t  mask_ss;      /* W_MASK: 0=444 1=422 2=420 layout of the emitted mask */
-    uint16_t pad;
+    uint16_t aux16;        /* OBMC_H: the height blend_h gets (v_mul * oh4 >= h) */
     uint32_t aux_off;      /* MASK: byte offset of the w*h mask in `masks`;
                               W_MASK: byte offset the emitted mask is written to in `masks`;
                               PREP: int16 offset into the tmp pool */
@@ -395,6 +400,10 @@ typedef struct Dav1dCudaReconBatch {
     const Dav1dCudaMcDesc *mc_comp;   const uint32_t *mc_comp_tiles; int32_t n_mc_comp_tiles[2];
     /* leading small (<= 8x8) tiles of mc_put_tiles and of each compound wave */
     int32_t n_mc_put_small;           int32_t n_mc_comp_small[2];
+    /* optional: OBMC blends, run after the prediction launches and before the residuals in two
+     * waves - [0] all OBMC_H tiles, [1] all OBMC_V tiles (the two regions of a block overlap in
+     * its top-left corner and the reference blends top neighbours first) */
+    const Dav1dCudaMcDesc *mc_obmc;   const uint32_t *mc_obmc_tiles; int32_t n_mc_obmc_tiles[2];
     const Dav1dCudaWarpDesc *warp;    int32_t n_warp;
     const Dav1dCudaItxDesc *itx;      int32_t itx_class_count[DAV1D_CUDA_N_RECT_TX_SIZES];
     /* optional (device): task codes from dav1d_cuda_itx_tasks() over `itx`; when set phase B is two
@@ -411,14 +420,15 @@ typedef struct Dav1dCudaReconBatch {
     /* optional (host): copy of the sorted `intra` array; needed by
      * dav1d_cuda_recon_graph_build_multi() to merge the frames' levels by code path. */
     const Dav1dCudaIntraDesc *intra_host;
-    /* optional: residuals of the intra-class operations as transform descriptors + tasks per level
-     * (dav1d_cuda_intra_residual_tasks()).  When set, the level kernels only predict and every level
-     * is followed by the task-based transform launches (lane groups, one size per warp). */
-    /* optional (preferred): task codes over the level-sorted `intra` array from
+    /* optional (experimental executor): task codes over the level-sorted `intra` array from
      * dav1d_cuda_intra_tasks(): per level one fused launch in which a warp predicts up to 32/G
      * same-size operations and then runs their residuals in groups of G lanes. */
     const uint32_t *intra_tasks;              /* device */
     const int32_t *intra_task_start;          /* host: 2 * n_levels + 1 offsets (small, big per level) */
+    /* optional (preferred): residuals of the intra-class operations as transform descriptors +
+     * tasks per level (dav1d_cuda_intra_residual_tasks()).  When set, the level kernels only
+     * predict and every level is followed by the task-based transform launches (lane groups, one
+     * size per warp); levels with few operations run as one fused launch. */
     const Dav1dCudaItxDesc *intra_itx;        /* device */
     const uint32_t *intra_itx_tasks;          /* device */
     const int32_t *intra_itx_task_start;      /* host: 2 * n_levels + 1 offsets (small, big per level) */

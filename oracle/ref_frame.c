@@ -49,8 +49,9 @@ typedef struct OracleFrame {
     const Dav1dCudaWarpDesc *warp;
     const Dav1dCudaItxDesc *itx;
     const Dav1dCudaIntraDesc *intra;
-    const uint32_t *order;        /* (class << 28) | index; class: 0 put 1 comp 2 warp 3 itx 4 intra */
+    const uint32_t *order;        /* (class << 28) | index; class: 0 put 1 comp 2 warp 3 itx 4 intra 6 obmc */
     int32_t n_order;
+    const Dav1dCudaMcDesc *mc_obmc;
 } OracleFrame;
 
 #if BITDEPTH == 8
@@ -163,6 +164,19 @@ void bitfn(run_frame)(const OracleFrame *const f) {
                                       f->masks + d->aux_off, d->weight BD_ARG);
                 break;
             }
+        } else if (cls == 6) {
+            /* obmc(), recon_tmpl.c:1071-1131: neighbour's prediction into the lap buffer + blend */
+            const Dav1dCudaMcDesc *const d = &f->mc_obmc[idx];
+            const int pl = d->plane;
+            const ptrdiff_t dstride = f->dst_stride[pl];
+            pixel *const dst = (pixel *) f->dst[pl] + PXSTRIDE(dstride) * d->y + d->x;
+            pixel *const lap = (pixel *) s->tmp[0];
+            ptrdiff_t rs;
+            const pixel *src = mc_src(f, s, &d->src[0], pl, d->w, d->h, &rs, &mc);
+            mc.mc[d->src[0].filter_2d](lap, d->w * sizeof(pixel), src, rs, d->w, d->h,
+                                       d->src[0].mx, d->src[0].my BD_ARG);
+            if (d->kind == DAV1D_CUDA_MC_OBMC_H) mc.blend_h(dst, dstride, lap, d->w, d->aux16);
+            else mc.blend_v(dst, dstride, lap, d->w, d->h);
         } else if (cls == 2) {
             const Dav1dCudaWarpDesc *const d = &f->warp[idx];
             const int pl = d->plane;

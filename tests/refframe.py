@@ -16,7 +16,8 @@ class OracleFrame(C.Structure):
                 ("bitdepth_max", C.c_int32), ("bw4", C.c_int32), ("bh4", C.c_int32),
                 ("cf", C.c_void_p), ("masks", C.c_void_p), ("pal", C.c_void_p), ("pal_idx", C.c_void_p),
                 ("mc_put", C.c_void_p), ("mc_comp", C.c_void_p), ("warp", C.c_void_p), ("itx", C.c_void_p),
-                ("intra", C.c_void_p), ("order", C.c_void_p), ("n_order", C.c_int32)]
+                ("intra", C.c_void_p), ("order", C.c_void_p), ("n_order", C.c_int32),
+                ("mc_obmc", C.c_void_p)]
 
 
 def make_oracle_frame(hf, dst_planes, ref_planes_list, keep):
@@ -39,7 +40,7 @@ def make_oracle_frame(hf, dst_planes, ref_planes_list, keep):
     keep.append(masks)
     for name, arr in (("cf", hf.cf), ("masks", masks), ("pal", hf.pal), ("pal_idx", hf.pal_idx),
                       ("mc_put", hf.mc_put), ("mc_comp", hf.mc_comp), ("warp", hf.warp), ("itx", hf.itx),
-                      ("intra", hf.intra), ("order", hf.order)):
+                      ("intra", hf.intra), ("order", hf.order), ("mc_obmc", hf.mc_obmc)):
         setattr(of, name, arr.ctypes.data if arr.nbytes else None)
     of.n_order = hf.order.nbytes // 4
     return of

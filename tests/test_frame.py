@@ -29,6 +29,10 @@ CASES = {
     "422_10b_intra_heavy": (256, 192, 0x3ff, 9, {"ss_hor": 1, "ss_ver": 0, "p_intra": 0.8, "p_cfl": 0.6,
                                                  "p_palette": 0.1}),
     "422_8b_small": (192, 128, 0xff, 13, {"ss_hor": 1, "ss_ver": 0}),
+    # OBMC: neighbour predictions blended onto single-reference blocks (obmc(), recon_tmpl.c:1071-1131)
+    "420_10b_obmc": (320, 256, 0x3ff, 14, {"p_obmc": 0.6, "p_intra": 0.1, "p_avg": 0.05, "p_w_avg": 0.05,
+                                           "p_wedge": 0.02, "p_seg": 0.02}),
+    "444_8b_obmc": (256, 192, 0xff, 15, {"p_obmc": 0.5, "ss_hor": 0, "ss_ver": 0}),
     # ragged picture sizes (not multiples of the 64x64 superblock / of 8 in chroma)
     "420_10b_ragged": (328, 200, 0x3ff, 8, {}),
     "420_8b_ragged": (200, 120, 0xff, 10, {"p_intra": 0.6}),
@@ -184,7 +188,7 @@ MULTI_SPECS = {
     # merged over the frames), the tail the fused one
     "1080p": [(1920, 1080, 0x3ff, 31, {"p_intra": 0.6}), (1920, 1080, 0x3ff, 32, {}),
               (1280, 720, 0x3ff, 33, {"p_intra": 1.0})],
-    "8bit": [(640, 368, 0xff, 41, {"p_intra": 0.8}), (640, 368, 0xff, 42, {})],
+    "8bit": [(640, 368, 0xff, 41, {"p_intra": 0.8}), (640, 368, 0xff, 42, {"p_obmc": 0.5})],
 }
 
 
