@@ -117,6 +117,22 @@ __device__ __noinline__ void intra_op(const IntraArgs &a, const Dav1dCudaIntraDe
         const int m = prepare_edges<pixel>(d.x4, have_left, d.y4, have_top, d.tile_x4_end, d.tile_y4_end, 0, dst,
                                            stride, nullptr, 0, &angle, d.tw4, d.th4, 0, edge, bdmax, lane);
         cfl_pred_block<pixel>(m, dst, stride, edge, w, h, sm->ac, d.angle_delta, bdmax, lane);
+    } else if (d.mode == DAV1D_CUDA_INTRA_II) {
+        // inter-intra: predict the whole block into scratch (the ac buffer holds w*h pixels of the
+        // operation's size class), then mc.blend onto the inter prediction (mc_tmpl.c:642-653)
+        int angle = 0;
+        const int m = prepare_edges<pixel>(d.x4, have_left, d.y4, have_top, d.tile_x4_end, d.tile_y4_end, 0, dst,
+                                           stride, nullptr, d.angle_delta, &angle, d.tw4, d.th4, 0, edge, bdmax, lane);
+        pixel *tmp = (pixel *)sm->ac;
+        ipred_block<pixel>(m, tmp, w, edge, w, h, 0, 0, 0, bdmax, sm->scratch, lane);
+        __syncwarp();
+        const uint8_t *mask = a.pal_idx + d.coef_off;
+        const int lw = 31 - __clz(w);
+        for (int i = lane; i < w * h; i += 32) {
+            const int y = i >> lw, x = i & (w - 1);
+            const int mk = mask[i], p = dst[y * stride + x], q = tmp[i];
+            dst[y * stride + x] = (pixel)((p * (64 - mk) + q * mk + 32) >> 6);
+        }
     } else if (d.mode != DAV1D_CUDA_INTRA_NONE) {
         int angle = d.angle_delta;
         const int m = prepare_edges<pixel>(d.x4, have_left, d.y4, have_top, d.tile_x4_end, d.tile_y4_end,
@@ -880,8 +896,9 @@ int dav1d_cuda_intra_schedule_deps(Dav1dCudaIntraDesc *descs, int n, int bw4, in
             // exactly the pixels dav1d_prepare_intra_edges reads for the resolved mode
             // (ipred_prepare_tmpl.c:50-74 needs_* table, :94-117 mode resolution)
             const int have_left = x0 > d.tile_x4_start, have_top = y0 > d.tile_y4_start;
-            const int needs = intra_needs(d.mode == DAV1D_CUDA_INTRA_CFL ? 0 : d.mode, d.angle_delta, have_left,
-                                          have_top);
+            const int needs = d.mode == DAV1D_CUDA_INTRA_II ? intra_needs(d.angle_delta, 0, have_left, have_top)
+                              : intra_needs(d.mode == DAV1D_CUDA_INTRA_CFL ? 0 : d.mode, d.angle_delta, have_left,
+                                            have_top);
             // bit0 left, bit1 top, bit2 topleft, bit3 topright, bit4 bottomleft
             const bool rd_top = have_top && ((needs & 2) || (needs & 4) || ((needs & 1) && !have_left));
             if (rd_top) {

@@ -42,6 +42,7 @@ typedef struct D1SynthParams {
     int32_t eob_class;          // -1 random, 0 dc-only, 1 low-frequency, 2 full
     int32_t dense_coefs;        // 1: dense coefficient blocks (reference layout) instead of packed ones
     float p_obmc;               // single-reference blocks (>= 8x8) that get OBMC blends
+    float p_ii;                 // single-reference blocks (8x8..32x32) with inter-intra prediction
 } D1SynthParams;
 
 typedef struct D1SynthFrame {
@@ -231,6 +232,9 @@ struct Gen {
         if (mode == DAV1D_CUDA_INTRA_PAL) {
             d.coef_off = idx_off;
             add_bytes(4, (double)Bp * w * h + 0.5 * w * h);
+        } else if (mode == DAV1D_CUDA_INTRA_II) {
+            d.coef_off = idx_off;                                   // blend mask in the byte pool
+            add_bytes(4, (double)Bp * (2 * w + 2 * h + 1) + 2.0 * Bp * w * h + (double)w * h);
         } else {
             if (mode != DAV1D_CUDA_INTRA_NONE) add_bytes(4, (double)Bp * (2 * w + 2 * h + 1));
             if (mode == DAV1D_CUDA_INTRA_CFL) add_bytes(4, (double)Bp * (w << P.ss_hor) * (h << P.ss_ver));
@@ -415,6 +419,9 @@ struct Gen {
         // OBMC: single-reference, translational blocks of at least 8x8 on even 4x4 coordinates
         const bool do_obmc = P.p_obmc > 0.f && kind == DAV1D_CUDA_MC_PUT && !is_warp && w4 >= 2 && h4 >= 2 &&
                              !(bx4 & 1) && !(by4 & 1) && rng.chance(P.p_obmc);
+        // inter-intra: single-reference translational blocks of 8x8..32x32 without OBMC
+        const bool do_ii = P.p_ii > 0.f && kind == DAV1D_CUDA_MC_PUT && !is_warp && !do_obmc && w4 >= 2 && h4 >= 2 &&
+                           w4 <= 8 && h4 <= 8 && rng.chance(P.p_ii);
         uint32_t seg_off = 0, wedge_off[3] = { 0, 0, 0 };
         for (int pl = 0; pl < nplanes(); pl++) {
             const int sh = pl ? P.ss_hor : 0, sv = pl ? P.ss_ver : 0;
@@ -482,8 +489,39 @@ struct Gen {
             if (wave1) { order.push_back({ 5, (uint32_t)comp1.size() }); comp1.push_back(d); }
             else { order.push_back({ 1, (uint32_t)comp0.size() }); comp0.push_back(d); }
         }
+        if (do_ii) {
+            // intra prediction of the whole block blended onto the inter prediction; the block then
+            // belongs to the wavefront: its residuals follow as residual-only intra-class operations
+            static const int ii_modes[4] = { 0, 1, 2, 9 };          // DC, VERT, HOR, SMOOTH
+            const int m = ii_modes[rng.range(4)];
+            for (int pl = 0; pl < nplanes(); pl++) {
+                const int sh = pl ? P.ss_hor : 0, sv = pl ? P.ss_ver : 0;
+                const int cw4 = w4 >> sh, ch4 = h4 >> sv;
+                const size_t off = pal_idx.size();
+                for (int i = 0; i < cw4 * 4 * ch4 * 4; i++) pal_idx.push_back((uint8_t)rng.range(65));
+                add_intra(pl, bx4 >> sh, by4 >> sv, cw4, ch4, DAV1D_CUDA_INTRA_II, m, 0, false, 0, (uint32_t)off);
+            }
+        }
         // ---- residual
-        if (rng.chance(P.p_residual)) {
+        if (do_ii) {
+            if (rng.chance(P.p_residual)) {
+                int tw4 = std::min(w4, 16), th4 = std::min(h4, 16);
+                if (rng.chance(P.p_tx_split)) split_tx(tw4, th4);
+                for (int y = 0; y < h4; y += th4)
+                    for (int x = 0; x < w4; x += tw4)
+                        add_intra(0, bx4 + x, by4 + y, tw4, th4, DAV1D_CUDA_INTRA_NONE, 0, 0, true);
+                if (!P.no_chroma) {
+                    const int cw4 = w4 >> P.ss_hor, ch4 = h4 >> P.ss_ver;
+                    int utw4 = std::min(cw4, 8), uth4 = std::min(ch4, 8);
+                    fit_tx(utw4, uth4);
+                    for (int pl = 1; pl <= 2; pl++)
+                        for (int y = 0; y < ch4; y += uth4)
+                            for (int x = 0; x < cw4; x += utw4)
+                                add_intra(pl, (bx4 >> P.ss_hor) + x, (by4 >> P.ss_ver) + y, utw4, uth4,
+                                          DAV1D_CUDA_INTRA_NONE, 0, 0, true);
+                }
+            }
+        } else if (rng.chance(P.p_residual)) {
             int tw4 = std::min(w4, 16), th4 = std::min(h4, 16);
             if (rng.chance(P.p_tx_split)) split_tx(tw4, th4);
             const int tx = tx_from_dims(tw4, th4);
@@ -575,7 +613,7 @@ __attribute__((visibility("default"))) void d1synth_default_params(D1SynthParams
     p->p_intra = 0.3f; p->p_residual = 0.6f; p->p_tx_split = 0.5f;
     p->p_filter_intra = 0.05f; p->p_palette = 0.02f; p->p_cfl = 0.25f;
     p->p_avg = 0.2f; p->p_w_avg = 0.1f; p->p_wedge = 0.1f; p->p_seg = 0.05f; p->p_warp = 0.05f;
-    p->mv_range = 128; p->n_refs = 2; p->edge_filter = 1; p->only_tx = -1; p->only_txtp = -1; p->eob_class = -1; p->dense_coefs = 0; p->p_obmc = 0.f;
+    p->mv_range = 128; p->n_refs = 2; p->edge_filter = 1; p->only_tx = -1; p->only_txtp = -1; p->eob_class = -1; p->dense_coefs = 0; p->p_obmc = 0.f; p->p_ii = 0.f;
 }
 
 __attribute__((visibility("default"))) int d1synth_generate(const D1SynthParams *p, D1SynthFrame *f) {

@@ -222,7 +222,13 @@ enum Dav1dCudaIntraKind {
     DAV1D_CUDA_INTRA_CFL    = 14,   /* cfl_ac + DC edges + cfl_pred, angle_delta = alpha */
     DAV1D_CUDA_INTRA_PAL    = 15,   /* pal_pred: coef_off = byte offset of the packed indices,
                                        aux = palette offset (in pixels) in the palette pool */
-    DAV1D_CUDA_INTRA_NONE   = 255   /* residual only (e.g. tx blocks of a palette block) */
+    DAV1D_CUDA_INTRA_II     = 16,   /* inter-intra (recon_tmpl.c:1658-1681, 1779-1817): intra prediction of
+                                       the whole block (angle_delta = IntraPredMode DC/VERT/HOR/SMOOTH,
+                                       edge_flags 0, no edge filter) into scratch + mc.blend onto the inter
+                                       prediction; coef_off = byte offset of the w*h blend mask in the
+                                       `pal_idx` byte pool.  The block's residuals follow as
+                                       DAV1D_CUDA_INTRA_NONE operations */
+    DAV1D_CUDA_INTRA_NONE   = 255   /* residual only (e.g. tx blocks of a palette or inter-intra block) */
 };
 
 typedef struct Dav1dCudaIntraDesc {  /* 40 bytes */

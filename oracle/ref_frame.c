@@ -222,6 +222,16 @@ void bitfn(run_frame)(const OracleFrame *const f) {
                                                       d->tile_y4_end, 0, dst, dstride, NULL, DC_PRED, &angle,
                                                       d->tw4, d->th4, 0, edge BD_ARG);
                 ip.cfl_pred[m](dst, dstride, edge, w, h, s->ac, d->angle_delta BD_ARG);
+            } else if (d->mode == DAV1D_CUDA_INTRA_II) {
+                /* inter-intra, recon_tmpl.c:1658-1681 */
+                int angle = 0;
+                pixel *const tmp = (pixel *) s->tmp[0];
+                const enum IntraPredMode m =
+                    bytefn(dav1d_prepare_intra_edges)(d->x4, have_left, d->y4, have_top, d->tile_x4_end,
+                                                      d->tile_y4_end, 0, dst, dstride, NULL, d->angle_delta,
+                                                      &angle, d->tw4, d->th4, 0, edge BD_ARG);
+                ip.intra_pred[m](tmp, w * sizeof(pixel), edge, w, h, 0, 0, 0 BD_ARG);
+                mc.blend(dst, dstride, tmp, w, h, f->pal_idx + d->coef_off);
             } else if (d->mode != DAV1D_CUDA_INTRA_NONE) {
                 int angle = d->angle_delta;
                 const enum IntraPredMode m =

@@ -33,6 +33,10 @@ CASES = {
     "420_10b_obmc": (320, 256, 0x3ff, 14, {"p_obmc": 0.6, "p_intra": 0.1, "p_avg": 0.05, "p_w_avg": 0.05,
                                            "p_wedge": 0.02, "p_seg": 0.02}),
     "444_8b_obmc": (256, 192, 0xff, 15, {"p_obmc": 0.5, "ss_hor": 0, "ss_ver": 0}),
+    # inter-intra: whole-block intra prediction blended onto an inter prediction, residuals in the wavefront
+    "420_10b_interintra": (320, 256, 0x3ff, 16, {"p_ii": 0.5, "p_intra": 0.2, "p_obmc": 0.2}),
+    "444_8b_interintra": (256, 192, 0xff, 17, {"p_ii": 0.6, "ss_hor": 0, "ss_ver": 0}),
+    "422_12b_interintra": (256, 192, 0xfff, 18, {"p_ii": 0.6, "ss_hor": 1, "ss_ver": 0, "p_intra": 0.3}),
     # ragged picture sizes (not multiples of the 64x64 superblock / of 8 in chroma)
     "420_10b_ragged": (328, 200, 0x3ff, 8, {}),
     "420_8b_ragged": (200, 120, 0xff, 10, {"p_intra": 0.6}),
@@ -188,7 +192,7 @@ MULTI_SPECS = {
     # merged over the frames), the tail the fused one
     "1080p": [(1920, 1080, 0x3ff, 31, {"p_intra": 0.6}), (1920, 1080, 0x3ff, 32, {}),
               (1280, 720, 0x3ff, 33, {"p_intra": 1.0})],
-    "8bit": [(640, 368, 0xff, 41, {"p_intra": 0.8}), (640, 368, 0xff, 42, {"p_obmc": 0.5})],
+    "8bit": [(640, 368, 0xff, 41, {"p_intra": 0.8}), (640, 368, 0xff, 42, {"p_obmc": 0.5, "p_ii": 0.3})],
 }
 
 
