@@ -117,6 +117,43 @@ __device__ __noinline__ void intra_op(const IntraArgs &a, const Dav1dCudaIntraDe
         const int m = prepare_edges<pixel>(d.x4, have_left, d.y4, have_top, d.tile_x4_end, d.tile_y4_end, 0, dst,
                                            stride, nullptr, 0, &angle, d.tw4, d.th4, 0, edge, bdmax, lane);
         cfl_pred_block<pixel>(m, dst, stride, edge, w, h, sm->ac, d.angle_delta, bdmax, lane);
+    } else if (d.mode == DAV1D_CUDA_INTRA_IBC) {
+        // intrabc: put_bilin (mc_tmpl.c:395-450) from the current picture; coordinates clamped to
+        // the 4*bw4 x 4*bh4 area (= emu_edge, recon_tmpl.c:974-995)
+        const int sx = (int16_t)(d.aux & 0xffff), sy = (int16_t)(d.aux >> 16);
+        const int mx = d.angle_delta, my = d.flags;
+        const int pw = (4 * a.bw4) >> ss_hor, ph = (4 * a.bh4) >> ss_ver;
+        const int ib = PxTraits<pixel>::inter_bits(bdmax);
+        const pixel *base = (const pixel *)pv.data;
+        const int lw = 31 - __clz(w);
+        for (int i = lane; i < w * h; i += 32) {
+            const int y = i >> lw, x = i & (w - 1);
+            const int x0 = iclip(sx + x, 0, pw - 1), x1 = iclip(sx + x + 1, 0, pw - 1);
+            const int y0 = iclip(sy + y, 0, ph - 1), y1 = iclip(sy + y + 1, 0, ph - 1);
+            const int p00 = __ldcg(base + (int64_t)y0 * stride + x0);
+            int out;
+            if (mx && my) {
+                const int p01 = __ldcg(base + (int64_t)y0 * stride + x1);
+                const int p10 = __ldcg(base + (int64_t)y1 * stride + x0);
+                const int p11 = __ldcg(base + (int64_t)y1 * stride + x1);
+                const int sh1 = 4 - ib, r1 = (1 << sh1) >> 1;
+                const int m0 = (16 * p00 + mx * (p01 - p00) + r1) >> sh1;
+                const int m1 = (16 * p10 + mx * (p11 - p10) + r1) >> sh1;
+                const int sh2 = 4 + ib;
+                out = clip_px<pixel>((16 * m0 + my * (m1 - m0) + ((1 << sh2) >> 1)) >> sh2, bdmax);
+            } else if (mx) {
+                const int p01 = __ldcg(base + (int64_t)y0 * stride + x1);
+                const int sh1 = 4 - ib;
+                const int px = (16 * p00 + mx * (p01 - p00) + ((1 << sh1) >> 1)) >> sh1;
+                out = clip_px<pixel>((px + ((1 << ib) >> 1)) >> ib, bdmax);
+            } else if (my) {
+                const int p10 = __ldcg(base + (int64_t)y1 * stride + x0);
+                out = clip_px<pixel>((16 * p00 + my * (p10 - p00) + 8) >> 4, bdmax);
+            } else {
+                out = p00;
+            }
+            dst[y * stride + x] = (pixel)out;
+        }
     } else if (d.mode == DAV1D_CUDA_INTRA_II) {
         // inter-intra: predict the whole block into scratch (the ac buffer holds w*h pixels of the
         // operation's size class), then mc.blend onto the inter prediction (mc_tmpl.c:642-653)
@@ -892,6 +929,16 @@ int dav1d_cuda_intra_schedule_deps(Dav1dCudaIntraDesc *descs, int n, int bw4, in
         if (d.mode == DAV1D_CUDA_INTRA_NONE) {
             for (int y = y0; y < y1; y++)
                 for (int x = x0; x < x1; x++) dep(p, x, y);
+        } else if (d.mode == DAV1D_CUDA_INTRA_IBC) {
+            // every operation that produced a pixel of the (clamped) source area
+            const int sx = (int16_t)(d.aux & 0xffff), sy = (int16_t)(d.aux >> 16);
+            const int px_w = 4 * W, px_h = 4 * H;
+            const int xa = std::max(0, std::min(sx, px_w - 1)) >> 2;
+            const int xb = std::max(0, std::min(sx + 4 * d.tw4 + (d.angle_delta ? 1 : 0) - 1, px_w - 1)) >> 2;
+            const int ya = std::max(0, std::min(sy, px_h - 1)) >> 2;
+            const int yb = std::max(0, std::min(sy + 4 * d.th4 + (d.flags ? 1 : 0) - 1, px_h - 1)) >> 2;
+            for (int y = ya; y <= yb; y++)
+                for (int x = xa; x <= xb; x++) dep(p, x, y);
         } else if (d.mode != DAV1D_CUDA_INTRA_PAL) {
             // exactly the pixels dav1d_prepare_intra_edges reads for the resolved mode
             // (ipred_prepare_tmpl.c:50-74 needs_* table, :94-117 mode resolution)

@@ -43,6 +43,7 @@ typedef struct D1SynthParams {
     int32_t dense_coefs;        // 1: dense coefficient blocks (reference layout) instead of packed ones
     float p_obmc;               // single-reference blocks (>= 8x8) that get OBMC blends
     float p_ii;                 // single-reference blocks (8x8..32x32) with inter-intra prediction
+    float p_ibc;                // intra-coded blocks predicted by intrabc (copy from the current picture)
 } D1SynthParams;
 
 typedef struct D1SynthFrame {
@@ -232,6 +233,8 @@ struct Gen {
         if (mode == DAV1D_CUDA_INTRA_PAL) {
             d.coef_off = idx_off;
             add_bytes(4, (double)Bp * w * h + 0.5 * w * h);
+        } else if (mode == DAV1D_CUDA_INTRA_IBC) {
+            add_bytes(4, 2.0 * Bp * w * h);
         } else if (mode == DAV1D_CUDA_INTRA_II) {
             d.coef_off = idx_off;                                   // blend mask in the byte pool
             add_bytes(4, (double)Bp * (2 * w + 2 * h + 1) + 2.0 * Bp * w * h + (double)w * h);
@@ -262,7 +265,47 @@ struct Gen {
         else th4 >>= 1;
     }
 
+    // intrabc block (recon_tmpl.c:1624-1637): prediction = bilinear mc() from the already decoded
+    // part of the CURRENT picture (any position in the superblock rows above; now and then past the
+    // right edge, which the reference pads with emu_edge), residuals as residual-only operations
+    bool ibc_block(int bx4, int by4, int w4, int h4) {
+        const int sb_top = (by4 & ~15) * 4, wpx = w4 * 4, hpx = h4 * 4;
+        if (w4 < 2 || h4 < 2 || w4 > 16 || h4 > 16 || sb_top < hpx + 2) return false;
+        const int W = bw4 * 4;
+        const int sxl = rng.chance(0.1f) ? W - wpx + 2 * rng.range(4) : 2 * rng.range((W - wpx) / 2 + 1);
+        const int syl = 2 * rng.range((sb_top - hpx - 2) / 2 + 1);
+        const bool half = rng.chance(0.5f);          // odd luma vector components: half-pel chroma
+        n_intra_blocks++;
+        for (int pl = 0; pl < nplanes(); pl++) {
+            const int sh = pl ? P.ss_hor : 0, sv = pl ? P.ss_ver : 0;
+            const int lx = sxl + (half ? 1 : 0), ly = syl + (half ? 1 : 0);
+            const int sx = lx >> sh, sy = ly >> sv;
+            const int mx = (sh && (lx & 1)) ? 8 : 0, my = (sv && (ly & 1)) ? 8 : 0;
+            add_intra(pl, bx4 >> sh, by4 >> sv, w4 >> sh, h4 >> sv, DAV1D_CUDA_INTRA_IBC, mx, my, false,
+                      (uint32_t)(sx & 0xffff) | ((uint32_t)(sy & 0xffff) << 16));
+        }
+        if (rng.chance(P.p_residual)) {
+            int tw4 = std::min(w4, 16), th4 = std::min(h4, 16);
+            if (rng.chance(P.p_tx_split)) split_tx(tw4, th4);
+            for (int y = 0; y < h4; y += th4)
+                for (int x = 0; x < w4; x += tw4)
+                    add_intra(0, bx4 + x, by4 + y, tw4, th4, DAV1D_CUDA_INTRA_NONE, 0, 0, true);
+            if (!P.no_chroma) {
+                const int cw4 = w4 >> P.ss_hor, ch4 = h4 >> P.ss_ver;
+                int utw4 = std::min(cw4, 8), uth4 = std::min(ch4, 8);
+                fit_tx(utw4, uth4);
+                for (int pl = 1; pl <= 2; pl++)
+                    for (int y = 0; y < ch4; y += uth4)
+                        for (int x = 0; x < cw4; x += utw4)
+                            add_intra(pl, (bx4 >> P.ss_hor) + x, (by4 >> P.ss_ver) + y, utw4, uth4,
+                                      DAV1D_CUDA_INTRA_NONE, 0, 0, true);
+            }
+        }
+        return true;
+    }
+
     void intra_block(int bx4, int by4, int w4, int h4) {
+        if (P.p_ibc > 0.f && rng.chance(P.p_ibc) && ibc_block(bx4, by4, w4, h4)) return;
         n_intra_blocks++;
         const bool residual = rng.chance(P.p_residual);
         const int flags = (P.edge_filter ? 1024 : 0) | (rng.chance(0.25f) ? 512 : 0);
@@ -613,7 +656,7 @@ __attribute__((visibility("default"))) void d1synth_default_params(D1SynthParams
     p->p_intra = 0.3f; p->p_residual = 0.6f; p->p_tx_split = 0.5f;
     p->p_filter_intra = 0.05f; p->p_palette = 0.02f; p->p_cfl = 0.25f;
     p->p_avg = 0.2f; p->p_w_avg = 0.1f; p->p_wedge = 0.1f; p->p_seg = 0.05f; p->p_warp = 0.05f;
-    p->mv_range = 128; p->n_refs = 2; p->edge_filter = 1; p->only_tx = -1; p->only_txtp = -1; p->eob_class = -1; p->dense_coefs = 0; p->p_obmc = 0.f; p->p_ii = 0.f;
+    p->mv_range = 128; p->n_refs = 2; p->edge_filter = 1; p->only_tx = -1; p->only_txtp = -1; p->eob_class = -1; p->dense_coefs = 0; p->p_obmc = 0.f; p->p_ii = 0.f; p->p_ibc = 0.f;
 }
 
 __attribute__((visibility("default"))) int d1synth_generate(const D1SynthParams *p, D1SynthFrame *f) {

@@ -22,7 +22,7 @@ class SynthParams(C.Structure):
                 ("p_seg", C.c_float), ("p_warp", C.c_float),
                 ("mv_range", C.c_int32), ("n_refs", C.c_int32), ("edge_filter", C.c_int32),
                 ("only_tx", C.c_int32), ("only_txtp", C.c_int32), ("eob_class", C.c_int32),
-                ("dense_coefs", C.c_int32), ("p_obmc", C.c_float), ("p_ii", C.c_float)]
+                ("dense_coefs", C.c_int32), ("p_obmc", C.c_float), ("p_ii", C.c_float), ("p_ibc", C.c_float)]
 
 
 class SynthFrame(C.Structure):

@@ -228,6 +228,12 @@ enum Dav1dCudaIntraKind {
                                        prediction; coef_off = byte offset of the w*h blend mask in the
                                        `pal_idx` byte pool.  The block's residuals follow as
                                        DAV1D_CUDA_INTRA_NONE operations */
+    DAV1D_CUDA_INTRA_IBC    = 17,   /* intrabc (recon_tmpl.c:1624-1637): bilinear mc() from the CURRENT picture,
+                                       aux = source x | y << 16 (int16 each, pixels of this plane),
+                                       angle_delta = mx, flags = my (0 or 8); reads are clamped to the
+                                       4*bw4 x 4*bh4 area like emu_edge does (:974-995).  Scheduled after the
+                                       operations that produced the source area; residuals follow as
+                                       DAV1D_CUDA_INTRA_NONE operations */
     DAV1D_CUDA_INTRA_NONE   = 255   /* residual only (e.g. tx blocks of a palette or inter-intra block) */
 };
 

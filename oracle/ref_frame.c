@@ -222,6 +222,22 @@ void bitfn(run_frame)(const OracleFrame *const f) {
                                                       d->tile_y4_end, 0, dst, dstride, NULL, DC_PRED, &angle,
                                                       d->tw4, d->th4, 0, edge BD_ARG);
                 ip.cfl_pred[m](dst, dstride, edge, w, h, s->ac, d->angle_delta BD_ARG);
+            } else if (d->mode == DAV1D_CUDA_INTRA_IBC) {
+                /* intrabc: mc() with FILTER_2D_BILINEAR from the current picture, recon_tmpl.c:1624-1637 */
+                const int dx = (int16_t) (d->aux & 0xffff), dy = (int16_t) (d->aux >> 16);
+                const int mx = d->angle_delta, my = d->flags;
+                const int pw = (4 * f->bw4) >> ss_hor, ph = (4 * f->bh4) >> ss_ver;
+                const pixel *ref = (const pixel *) f->dst[pl];
+                ptrdiff_t rs = dstride;
+                if (dx < !!mx * 3 || dy < !!my * 3 || dx + w + !!mx * 4 > pw || dy + h + !!my * 4 > ph) {
+                    mc.emu_edge(w + !!mx * 7, h + !!my * 7, pw, ph, dx - !!mx * 3, dy - !!my * 3,
+                                s->emu, 192 * sizeof(pixel), ref, rs);
+                    ref = &s->emu[192 * !!my * 3 + !!mx * 3];
+                    rs = 192 * sizeof(pixel);
+                } else {
+                    ref += PXSTRIDE(rs) * dy + dx;
+                }
+                mc.mc[FILTER_2D_BILINEAR](dst, dstride, ref, rs, w, h, mx, my BD_ARG);
             } else if (d->mode == DAV1D_CUDA_INTRA_II) {
                 /* inter-intra, recon_tmpl.c:1658-1681 */
                 int angle = 0;

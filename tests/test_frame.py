@@ -37,6 +37,10 @@ CASES = {
     "420_10b_interintra": (320, 256, 0x3ff, 16, {"p_ii": 0.5, "p_intra": 0.2, "p_obmc": 0.2}),
     "444_8b_interintra": (256, 192, 0xff, 17, {"p_ii": 0.6, "ss_hor": 0, "ss_ver": 0}),
     "422_12b_interintra": (256, 192, 0xfff, 18, {"p_ii": 0.6, "ss_hor": 1, "ss_ver": 0, "p_intra": 0.3}),
+    # intrabc: blocks copied (bilinear, half-pel in subsampled chroma) from the decoded part of the current picture
+    "420_10b_intrabc": (384, 320, 0x3ff, 19, {"p_ibc": 0.5, "p_intra": 0.7}),
+    "444_8b_intrabc": (256, 256, 0xff, 20, {"p_ibc": 0.6, "p_intra": 1.0, "ss_hor": 0, "ss_ver": 0}),
+    "422_12b_intrabc": (256, 256, 0xfff, 21, {"p_ibc": 0.5, "p_intra": 0.8, "ss_hor": 1, "ss_ver": 0}),
     # ragged picture sizes (not multiples of the 64x64 superblock / of 8 in chroma)
     "420_10b_ragged": (328, 200, 0x3ff, 8, {}),
     "420_8b_ragged": (200, 120, 0xff, 10, {"p_intra": 0.6}),
@@ -192,7 +196,7 @@ MULTI_SPECS = {
     # merged over the frames), the tail the fused one
     "1080p": [(1920, 1080, 0x3ff, 31, {"p_intra": 0.6}), (1920, 1080, 0x3ff, 32, {}),
               (1280, 720, 0x3ff, 33, {"p_intra": 1.0})],
-    "8bit": [(640, 368, 0xff, 41, {"p_intra": 0.8}), (640, 368, 0xff, 42, {"p_obmc": 0.5, "p_ii": 0.3})],
+    "8bit": [(640, 368, 0xff, 41, {"p_intra": 0.8, "p_ibc": 0.3}), (640, 368, 0xff, 42, {"p_obmc": 0.5, "p_ii": 0.3})],
 }
 
 
