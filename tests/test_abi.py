@@ -45,3 +45,30 @@ def test_no_device_means_loud_failure_not_fallback():
     assert all(p is None for p in mc.mc) and mc.avg is None
     assert L.dav1d_cuda_last_error() != 0
     L.dav1d_cuda_clear_error()
+
+
+def test_ctypes_mirror_matches_the_header(tmp_path):
+    """sizeof / offsetof of the batch structs as the C compiler lays them out == the ctypes mirror."""
+    import subprocess
+    from dav1d_mirror_b200 import binding as B
+    src = tmp_path / "sz.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <stddef.h>
+#include "dav1d_cuda.h"
+int main(void) {
+    printf("%zu %zu %zu %zu %zu %zu ", sizeof(Dav1dCudaItxDesc), sizeof(Dav1dCudaMcDesc), sizeof(Dav1dCudaIntraDesc),
+           sizeof(Dav1dCudaWarpDesc), sizeof(Dav1dCudaPicture), sizeof(Dav1dCudaReconBatch));
+    printf("%zu %zu %zu %zu %zu\n", offsetof(Dav1dCudaReconBatch, mc_obmc), offsetof(Dav1dCudaReconBatch, itx_tasks),
+           offsetof(Dav1dCudaReconBatch, intra_host), offsetof(Dav1dCudaReconBatch, intra_itx_task_start),
+           offsetof(Dav1dCudaIntraDesc, cw4));
+    return 0;
+}
+''')
+    exe = tmp_path / "sz"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    want = [C.sizeof(B.ItxDesc), C.sizeof(B.McDesc), C.sizeof(B.IntraDesc), C.sizeof(B.WarpDesc),
+            C.sizeof(B.Picture), C.sizeof(B.ReconBatch), B.ReconBatch.mc_obmc.offset, B.ReconBatch.itx_tasks.offset,
+            B.ReconBatch.intra_host.offset, B.ReconBatch.intra_itx_task_start.offset, B.IntraDesc.cw4.offset]
+    assert got == want, (got, want)
