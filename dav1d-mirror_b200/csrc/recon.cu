@@ -100,7 +100,7 @@ __device__ __noinline__ void intra_op(const IntraArgs &a, const Dav1dCudaIntraDe
     if (CLS != 4 && d.eob >= 0) {
         // pull the block's coefficients towards the SM while the prediction runs
         typedef typename PxTraits<pixel>::coef coef;
-        const int ncoef = imin(w, 32) * imin(h, 32);
+        const int ncoef = d.cw4 ? 16 * d.cw4 * d.ch4 : imin(w, 32) * imin(h, 32);   // packed box or dense block
         const char *cp = (const char *)((const coef *)a.cf + d.coef_off);
         for (int o = lane * 128; o < ncoef * (int)sizeof(coef); o += 32 * 128)
             asm volatile("prefetch.global.L2 [%0];" :: "l"(cp + o));
