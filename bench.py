@@ -77,12 +77,13 @@ class ClockSampler:
         self.index = index
         self.proc = None
         self.lines = []
+        self.marks = []
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -90,29 +91,43 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
+
+    def mark(self):
+        """host time stamp: samples between the first and the last mark are 'during the timed region'"""
+        self.marks.append(time.time())
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.1)
         self.proc.terminate()
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for n, v in zip(names, f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
+
+        def digest(lines):
+            sm, mx, reasons = [], [], set()
+            for ln in lines:
+                f = [x.strip() for x in ln.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for n, v in zip(names, f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            return sm, mx, reasons
+        lo, hi = (self.marks[0], self.marks[-1]) if len(self.marks) >= 2 else (0.0, float("inf"))
+        inside = [ln for t, ln in self.lines if lo <= t <= hi + 0.02]
+        window = "timed region"
+        sm, mx, reasons = digest(inside)
+        if not sm:       # region shorter than the sampling period: use the warm-up + timed window
+            sm, mx, reasons = digest([ln for _, ln in self.lines])
+            window = "warm-up + timed region"
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 def dist_env():
@@ -294,16 +309,19 @@ def main_ours(args):
         return ms
 
     # ---- warm-up + timed region (device-resident)
-    for _ in range(max(args.warmup, 3)):
-        run_step()
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+        time.sleep(0.3)          # nvidia-smi needs a moment before its first sample
+    for _ in range(max(args.warmup, 3)):
+        run_step()
+    barrier()
     launches0 = L.dav1d_cuda_launch_count()
     barrier()
+    sampler.mark()
     ms = timed(args.steps)
     barrier()
+    sampler.mark()
     launches = L.dav1d_cuda_launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
     ms = max_over_ranks(ms)
