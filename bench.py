@@ -210,11 +210,21 @@ def main_ours(args):
     rank, world, local = dist_env()
     import torch
     import torch.distributed as dist
-    if world > 1:
-        # NCCL's version / debug lines go to stderr: stdout carries only the JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
+    if world > 1:
+        # stdout carries only the JSON line: NCCL prints its version banner to fd 1 when the
+        # communicator is created (first collective), so fd 1 points at stderr until that is done
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     import _d1pkg
     pkg = _d1pkg.load_pkg()
     from dav1d_mirror_b200 import frame as F
