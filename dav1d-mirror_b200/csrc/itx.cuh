@@ -122,22 +122,34 @@ template <typename coef, int W>
 D1_ITX_PASS int itx_row_pass(const bool full, const int gl, const int G, coef *cf, const int SH,
                                          const bool rect2, const int shift, const int rk, const Clamp rowcl,
                                          const Clamp colcl, int *tile, const bool zero_coefs,
-                                         const int cw, const int ch)
+                                         const int cw, const int ch, const bool box)
 {
     constexpr int SW = W < 32 ? W : 32, TS = W + 1;
-    const bool wht = rk == K_WHT;
+    const bool wht = W == 4 && rk == K_WHT;      // WHT exists for 4x4 only
     const int rnd = (1 << shift) >> 1;
     int c[W];
     unsigned rowmask = 0;
     // stored coefficients: cw columns x ch rows, stride ch (dense: cw = SW, ch = SH)
     if (full && gl < ch) {
+        if (box) {
+            // packed descriptor: the non-zero box is given, no need to look at the values
 #pragma unroll
-        for (int x = 0; x < SW; x++) {
-            int v = x < cw ? (int)cf[gl + x * ch] : 0;
-            rowmask |= (unsigned)(v != 0) << x;
-            if (wht) v >>= 2;
-            else if (rect2) v = (v * 181 + 128) >> 8;
-            c[x] = v;
+            for (int x = 0; x < SW; x++) {
+                int v = x < cw ? (int)cf[gl + x * ch] : 0;
+                if (wht) v >>= 2;
+                else if (rect2) v = (v * 181 + 128) >> 8;
+                c[x] = v;
+            }
+            rowmask = cw >= 32 ? ~0u : (1u << cw) - 1u;
+        } else {
+#pragma unroll
+            for (int x = 0; x < SW; x++) {
+                int v = x < cw ? (int)cf[gl + x * ch] : 0;
+                rowmask |= (unsigned)(v != 0) << x;
+                if (wht) v >>= 2;
+                else if (rect2) v = (v * 181 + 128) >> 8;
+                c[x] = v;
+            }
         }
 #pragma unroll
         for (int x = SW; x < W; x++) c[x] = 0;
@@ -186,7 +198,7 @@ D1_ITX_PASS void itx_col_pass(const bool full, const int gl, const int G, const 
                                           pixel *dst, const int dstride, const int bdmax)
 {
     constexpr int SH = H < 32 ? H : 32;
-    const bool wht = ck == K_WHT;
+    const bool wht = H == 4 && ck == K_WHT;      // WHT exists for 4x4 only
     if (!full) return;
     for (int x = gl; x < W; x += G) {
         pixel *p = dst + x;
@@ -291,7 +303,7 @@ DEV void itx_block(const bool active, const int gl, int *tile,
     const int rk = txtp_row_kind(txtp), ck = txtp_col_kind(txtp);
 
     const int rows_used = itx_row_pass<coef, W>(full, gl, G, cf, SH, Geo::RECT2, SHIFT, rk, rowcl, colcl, tile,
-                                                zero_coefs, cw4 ? cw4 * 4 : Geo::SW, ch4 ? ch4 * 4 : SH);
+                                                zero_coefs, cw4 ? cw4 * 4 : Geo::SW, ch4 ? ch4 * 4 : SH, cw4 != 0);
     __syncwarp();
     itx_col_pass<pixel, H>(full, gl, G, tile, TS, W, rows_used, ck, colcl, dst, dstride, bdmax);
     __syncwarp();
