@@ -348,7 +348,7 @@ struct Gen {
             uvidx_off = (uint32_t)pal_idx_alloc(cw4 * 4 * ch4 * 4 / 2);
         }
         int wpad = 0, hpad = 0;
-        if (cfl && rng.chance(0.1f)) { wpad = rng.range(cw4); hpad = rng.range(ch4); }
+        if (cfl && rng.chance(0.1f)) { wpad = rng.range(uvtw4); hpad = rng.range(uvth4); }   // per CfL operation (tx block)
         for (int pl = 1; pl <= 2; pl++) {
             if (pal) add_intra(pl, cx4, cy4, cw4, ch4, DAV1D_CUDA_INTRA_PAL, 0, 0, false, uvpal_off[pl - 1], uvidx_off);
             int alpha = 0;
@@ -463,8 +463,12 @@ struct Gen {
         const bool do_obmc = P.p_obmc > 0.f && kind == DAV1D_CUDA_MC_PUT && !is_warp && w4 >= 2 && h4 >= 2 &&
                              !(bx4 & 1) && !(by4 & 1) && rng.chance(P.p_obmc);
         // inter-intra: single-reference translational blocks of 8x8..32x32 without OBMC
+        // (chroma prediction blocks must keep an aspect ratio of at most 4: an 8x32 block in 4:2:2 would
+        // need a 4x32 predictor, which the reference does not have - recon_tmpl.c:1780-1782)
+        const int ii_cw4 = std::max(1, w4 >> P.ss_hor), ii_ch4 = std::max(1, h4 >> P.ss_ver);
         const bool do_ii = P.p_ii > 0.f && kind == DAV1D_CUDA_MC_PUT && !is_warp && !do_obmc && w4 >= 2 && h4 >= 2 &&
-                           w4 <= 8 && h4 <= 8 && rng.chance(P.p_ii);
+                           w4 <= 8 && h4 <= 8 && (P.no_chroma || (ii_cw4 <= 4 * ii_ch4 && ii_ch4 <= 4 * ii_cw4)) &&
+                           rng.chance(P.p_ii);
         uint32_t seg_off = 0, wedge_off[3] = { 0, 0, 0 };
         for (int pl = 0; pl < nplanes(); pl++) {
             const int sh = pl ? P.ss_hor : 0, sv = pl ? P.ss_ver : 0;
