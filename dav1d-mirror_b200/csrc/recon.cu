@@ -233,7 +233,7 @@ intra_level_kernel(const __grid_constant__ IntraArgs a) {
 typedef IntraArgs IntraFrameParams;
 struct IntraMultiArgs {
     const IntraFrameParams *frames;
-    const uint32_t *items;        // this level's operations: frame << 24 | sorted index inside the frame
+    const Dav1dCudaIntraDesc *items;   // this level's operations: descriptor copies, `pad` = frame index
     int n;
 };
 
@@ -244,9 +244,10 @@ __global__ void __launch_bounds__(INTRA_WARPS * 32, IntraCls<CLS>::MIN_BLOCKS) i
     IntraSmem<pixel, CLS> *sm = (IntraSmem<pixel, CLS> *)intra_smem_raw + warp;
     const int i = blockIdx.x * INTRA_WARPS + warp;
     if (i >= m.n) return;
-    const uint32_t item = m.items[i];
-    const IntraFrameParams &a = m.frames[item >> 24];
-    const Dav1dCudaIntraDesc d = a.descs[item & 0xffffff];
+    // the merged level carries descriptor COPIES (consecutive warps read consecutive descriptors,
+    // one dependent load less than an index into the frame's own array)
+    const Dav1dCudaIntraDesc d = m.items[i];
+    const IntraFrameParams &a = m.frames[d.pad];
     intra_op<pixel, CLS>(a, d, sm, lane);
 }
 
@@ -665,7 +666,7 @@ static int recon_submit_on(Dav1dCudaContext *c, const Dav1dCudaReconBatch *b, cu
 // (uploaded here from `tab_host`, which must stay valid until the copy ran).
 struct MultiTables {
     std::vector<IntraFrameParams> frames;
-    std::vector<uint32_t> items;         // all levels, concatenated
+    std::vector<Dav1dCudaIntraDesc> items;   // all levels, concatenated: descriptor copies, pad = frame
     std::vector<int> level_start;        // per level: first item; size n_levels + 1
     // split execution (frames that carry intra_itx): residual tasks (code, frame) of all
     // frames per level, small sizes then large ones
@@ -711,7 +712,11 @@ static int build_multi_tables(const Dav1dCudaReconBatch *const *bs, int n, Multi
                          [](const std::pair<uint64_t, uint32_t> &x, const std::pair<uint64_t, uint32_t> &y) {
                              return x.first < y.first;
                          });
-        for (auto &e : lv) t.items.push_back(e.second);
+        for (auto &e : lv) {
+            Dav1dCudaIntraDesc d = bs[e.second >> 24]->intra_host[e.second & 0xffffff];
+            d.pad = (uint16_t)(e.second >> 24);
+            t.items.push_back(d);
+        }
         t.level_start.push_back((int)t.items.size());
     }
     // residual tasks: regenerated on the host from each frame's sorted descriptors (the same
@@ -763,7 +768,7 @@ static int launch_intra_multi(const IntraMultiArgs &m, cudaStream_t st) {
 }
 
 static int recon_submit_multi_on(Dav1dCudaContext *c, const Dav1dCudaReconBatch *const *bs, int n,
-                                 const IntraFrameParams *d_frames, const uint32_t *d_items,
+                                 const IntraFrameParams *d_frames, const Dav1dCudaIntraDesc *d_items,
                                  const ItxFrameRef *d_itx_frames, const uint2 *d_rtasks, const MultiTables &t,
                                  cudaStream_t st, const int phase_mask)
 {
@@ -1156,14 +1161,15 @@ int dav1d_cuda_recon_graph_build_multi_phases(Dav1dCudaContext *c, const Dav1dCu
     MultiTables t;
     if (build_multi_tables(bs, n, t)) return -22;
     const size_t fb = (t.frames.size() * sizeof(IntraFrameParams) + 255) & ~(size_t)255;
-    const size_t sb = (t.items.size() * sizeof(uint32_t) + 255) & ~(size_t)255;
+    const size_t sb = (t.items.size() * sizeof(Dav1dCudaIntraDesc) + 255) & ~(size_t)255;
     const size_t ib = (t.itx_frames.size() * sizeof(ItxFrameRef) + 255) & ~(size_t)255;
     const size_t rb = t.rtasks.size() * sizeof(uint2);
     uint8_t *tab = nullptr;
     D1_CHECK(cudaMalloc(&tab, fb + sb + ib + rb + 64));
     D1_CHECK(cudaMemcpy(tab, t.frames.data(), t.frames.size() * sizeof(IntraFrameParams), cudaMemcpyHostToDevice));
     if (!t.items.empty())
-        D1_CHECK(cudaMemcpy(tab + fb, t.items.data(), t.items.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        D1_CHECK(cudaMemcpy(tab + fb, t.items.data(), t.items.size() * sizeof(Dav1dCudaIntraDesc),
+                            cudaMemcpyHostToDevice));
     if (!t.itx_frames.empty())
         D1_CHECK(cudaMemcpy(tab + fb + sb, t.itx_frames.data(), t.itx_frames.size() * sizeof(ItxFrameRef),
                             cudaMemcpyHostToDevice));
@@ -1171,7 +1177,7 @@ int dav1d_cuda_recon_graph_build_multi_phases(Dav1dCudaContext *c, const Dav1dCu
     cudaStream_t cap;
     D1_CHECK(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
     D1_CHECK(cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal));
-    const int r = recon_submit_multi_on(c, bs, n, (const IntraFrameParams *)tab, (const uint32_t *)(tab + fb),
+    const int r = recon_submit_multi_on(c, bs, n, (const IntraFrameParams *)tab, (const Dav1dCudaIntraDesc *)(tab + fb),
                                         (const ItxFrameRef *)(tab + fb + sb), (const uint2 *)(tab + fb + sb + ib), t,
                                         cap, phase_mask);
     cudaGraph_t graph = nullptr;
