@@ -24,13 +24,14 @@ int itx_task_launch(const PicView &pic, void *cf, const Dav1dCudaItxDesc *descs,
     return itx_task_launch_both(a, n_small, n_big, pic.bdmax > 0xff, st_small, st_big);
 }
 
-// one dependency level of several frames: tasks = (code, frame)
-int itx_multi_task_launch(const ItxFrameRef *frames, const uint2 *tasks, int n_small, int n_big, bool hbd,
-                          cudaStream_t st_small, cudaStream_t st_big)
+// one dependency level of several frames: tasks = (code, frame), code indexes `descs` = the
+// residual descriptors of all frames concatenated
+int itx_multi_task_launch(const ItxFrameRef *frames, const Dav1dCudaItxDesc *descs, const uint2 *tasks, int n_small,
+                          int n_big, bool hbd, cudaStream_t st_small, cudaStream_t st_big)
 {
     ItxTaskArgs a;
     memset(&a, 0, sizeof(a));
-    a.frames = frames; a.mtasks = tasks;
+    a.frames = frames; a.mtasks = tasks; a.descs = descs;
     return itx_task_launch_both(a, n_small, n_big, hbd, st_small, st_big);
 }
 

@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(ITX_TASK_WARPS * 32, BIG ? 4 : 8) itx_task_ker
     if (a.frames) {
         const uint2 tk = a.mtasks[t];
         const ItxFrameRef *fr = a.frames + tk.y;
-        code = tk.x; pic = &fr->pic; cf = fr->cf; descs = fr->descs;
+        code = tk.x; pic = &fr->pic; cf = fr->cf;      // descs: the frames' descriptors concatenated (a.descs)
     } else {
         code = a.tasks[t];
     }

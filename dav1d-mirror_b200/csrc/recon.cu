@@ -27,8 +27,8 @@ int itx_task_launch(const PicView &pic, void *cf, const Dav1dCudaItxDesc *descs,
 int itx_build_tasks(const Dav1dCudaItxDesc *descs, int n, int index_base, uint32_t *tasks, int *n_small, int *n_big);
 int mc_obmc_launch_raw(const PicView &dst, const PicView *refs, const Dav1dCudaMcDesc *descs,
                        const uint32_t *tiles, int n_tiles, cudaStream_t st);
-int itx_multi_task_launch(const ItxFrameRef *frames, const uint2 *tasks, int n_small, int n_big, bool hbd,
-                          cudaStream_t st_small, cudaStream_t st_big);
+int itx_multi_task_launch(const ItxFrameRef *frames, const Dav1dCudaItxDesc *descs, const uint2 *tasks, int n_small,
+                          int n_big, bool hbd, cudaStream_t st_small, cudaStream_t st_big);
 void itx_init_attrs();
 struct McArgs;
 int mc_put_launch_raw(const PicView &dst, const PicView *refs, const Dav1dCudaMcDesc *descs,
@@ -672,7 +672,8 @@ struct MultiTables {
     // frames per level, small sizes then large ones
     bool split = false;
     std::vector<ItxFrameRef> itx_frames;
-    std::vector<uint2> rtasks;
+    std::vector<Dav1dCudaItxDesc> ritx;  // residual descriptors of all frames, concatenated (copies)
+    std::vector<uint2> rtasks;           // code (first index into ritx) , frame
     std::vector<int> rtask_start;        // 2 * n_levels + 1
 };
 
@@ -739,15 +740,20 @@ static int build_multi_tables(const Dav1dCudaReconBatch *const *bs, int n, Multi
         std::vector<uint32_t> tasks((size_t)std::max(n_ops, 1));
         std::vector<int32_t> tstart(2 * (size_t)b->n_levels + 1);
         int32_t nt = 0;
-        if (dav1d_cuda_intra_residual_tasks(b->intra_host, b->intra_level_start, b->n_levels, itx.data(),
-                                            tasks.data(), tstart.data(), &nt) < 0) return -22;
+        const int n_itx = dav1d_cuda_intra_residual_tasks(b->intra_host, b->intra_level_start, b->n_levels, itx.data(),
+                                                          tasks.data(), tstart.data(), &nt);
+        if (n_itx < 0) return -22;
+        const uint32_t off = (uint32_t)t.ritx.size();
+        if (off + (uint32_t)n_itx >= (1u << 24)) return -22;        // task codes hold 24-bit indices
+        t.ritx.insert(t.ritx.end(), itx.begin(), itx.begin() + n_itx);
         for (int l = 0; l < b->n_levels; l++)
             for (int half = 0; half < 2; half++)
                 for (int k = tstart[2 * l + half]; k < tstart[2 * l + half + 1]; k++) {
                     const Dav1dCudaItxDesc &d0 = itx[tasks[k] >> 8];
                     const uint32_t tp = d0.eob == 0 && d0.txtp == 0 ? 0 : 1 + d0.txtp;
+                    const uint32_t code = (((tasks[k] >> 8) + off) << 8) | (tasks[k] & 0xff);
                     per_level[2 * (size_t)l + half].push_back(
-                        { (((tasks[k] >> 3) & 31) << 8) | tp, make_uint2(tasks[k], (unsigned)f) });
+                        { (((tasks[k] >> 3) & 31) << 8) | tp, make_uint2(code, (unsigned)f) });
                 }
     }
     t.rtask_start.assign(1, 0);
@@ -769,7 +775,8 @@ static int launch_intra_multi(const IntraMultiArgs &m, cudaStream_t st) {
 
 static int recon_submit_multi_on(Dav1dCudaContext *c, const Dav1dCudaReconBatch *const *bs, int n,
                                  const IntraFrameParams *d_frames, const Dav1dCudaIntraDesc *d_items,
-                                 const ItxFrameRef *d_itx_frames, const uint2 *d_rtasks, const MultiTables &t,
+                                 const ItxFrameRef *d_itx_frames, const Dav1dCudaItxDesc *d_ritx, const uint2 *d_rtasks,
+                                 const MultiTables &t,
                                  cudaStream_t st, const int phase_mask)
 {
     if (!ensure_aux(c)) return -5;
@@ -820,7 +827,7 @@ static int recon_submit_multi_on(Dav1dCudaContext *c, const Dav1dCudaReconBatch 
         }
         if ((r = hbd ? launch_intra_multi<uint16_t, 4>(m, st) : launch_intra_multi<uint8_t, 4>(m, st))) return r;
         const int a0 = t.rtask_start[2 * l], a1 = t.rtask_start[2 * l + 1], a2 = t.rtask_start[2 * l + 2];
-        if (a2 > a0 && (r = itx_multi_task_launch(d_itx_frames, d_rtasks + a0, a1 - a0, a2 - a1, hbd, st, st))) return r;
+        if (a2 > a0 && (r = itx_multi_task_launch(d_itx_frames, d_ritx, d_rtasks + a0, a1 - a0, a2 - a1, hbd, st, st))) return r;
     }
     return 0;
 }
@@ -1163,9 +1170,10 @@ int dav1d_cuda_recon_graph_build_multi_phases(Dav1dCudaContext *c, const Dav1dCu
     const size_t fb = (t.frames.size() * sizeof(IntraFrameParams) + 255) & ~(size_t)255;
     const size_t sb = (t.items.size() * sizeof(Dav1dCudaIntraDesc) + 255) & ~(size_t)255;
     const size_t ib = (t.itx_frames.size() * sizeof(ItxFrameRef) + 255) & ~(size_t)255;
-    const size_t rb = t.rtasks.size() * sizeof(uint2);
+    const size_t rb = (t.rtasks.size() * sizeof(uint2) + 255) & ~(size_t)255;
+    const size_t xb = t.ritx.size() * sizeof(Dav1dCudaItxDesc);
     uint8_t *tab = nullptr;
-    D1_CHECK(cudaMalloc(&tab, fb + sb + ib + rb + 64));
+    D1_CHECK(cudaMalloc(&tab, fb + sb + ib + rb + xb + 64));
     D1_CHECK(cudaMemcpy(tab, t.frames.data(), t.frames.size() * sizeof(IntraFrameParams), cudaMemcpyHostToDevice));
     if (!t.items.empty())
         D1_CHECK(cudaMemcpy(tab + fb, t.items.data(), t.items.size() * sizeof(Dav1dCudaIntraDesc),
@@ -1173,13 +1181,16 @@ int dav1d_cuda_recon_graph_build_multi_phases(Dav1dCudaContext *c, const Dav1dCu
     if (!t.itx_frames.empty())
         D1_CHECK(cudaMemcpy(tab + fb + sb, t.itx_frames.data(), t.itx_frames.size() * sizeof(ItxFrameRef),
                             cudaMemcpyHostToDevice));
-    if (rb) D1_CHECK(cudaMemcpy(tab + fb + sb + ib, t.rtasks.data(), rb, cudaMemcpyHostToDevice));
+    if (!t.rtasks.empty())
+        D1_CHECK(cudaMemcpy(tab + fb + sb + ib, t.rtasks.data(), t.rtasks.size() * sizeof(uint2), cudaMemcpyHostToDevice));
+    if (xb) D1_CHECK(cudaMemcpy(tab + fb + sb + ib + rb, t.ritx.data(), xb, cudaMemcpyHostToDevice));
     cudaStream_t cap;
     D1_CHECK(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
     D1_CHECK(cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal));
     const int r = recon_submit_multi_on(c, bs, n, (const IntraFrameParams *)tab, (const Dav1dCudaIntraDesc *)(tab + fb),
-                                        (const ItxFrameRef *)(tab + fb + sb), (const uint2 *)(tab + fb + sb + ib), t,
-                                        cap, phase_mask);
+                                        (const ItxFrameRef *)(tab + fb + sb),
+                                        (const Dav1dCudaItxDesc *)(tab + fb + sb + ib + rb),
+                                        (const uint2 *)(tab + fb + sb + ib), t, cap, phase_mask);
     cudaGraph_t graph = nullptr;
     const cudaError_t e = cudaStreamEndCapture(cap, &graph);
     cudaStreamDestroy(cap);
