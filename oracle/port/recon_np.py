@@ -7,12 +7,12 @@ tests/test_port.py; where the two exist side by side the compiled reference is t
 the parity tests use, this file documents the arithmetic in executable form and is the
 checker of last resort where /root/reference cannot be compiled.
 
-Covered: put / prep 8-tap + bilinear (all four (mx, my) paths), avg, w_avg, mask, blend,
-blend_v, blend_h; intra DC family, V, H, Paeth, smooth / smooth_v / smooth_h; itxfm_add for
-the 4/8/16-point DCT and identity transforms (9 block sizes, 4 type combinations).
-NOT covered (the compiled reference is the only checker): w_mask, warp, scaled MC, ADST / flipADST /
-WHT / 32- and 64-point transforms, directional + filter-intra + CfL + palette prediction,
-edge preparation.
+Covered: put / prep 8-tap + bilinear (all four (mx, my) paths), avg, w_avg, mask, w_mask
+(444 / 422 / 420), blend, blend_v, blend_h, warp8x8 / warp8x8t; intra DC family, V, H, Paeth,
+smooth / smooth_v / smooth_h, cfl_ac (three layouts), cfl_pred, pal_pred; itxfm_add for the
+4/8/16-point DCT and identity transforms (9 block sizes, 4 type combinations).
+NOT covered (the compiled reference is the only checker): scaled MC, emu_edge, ADST / flipADST /
+WHT / 32- and 64-point transforms, directional + filter-intra prediction, edge preparation.
 """
 import os
 import re
@@ -34,6 +34,7 @@ def _table(name, dtype, shape):
 SUBPEL = _table("SUBPEL_FILTERS", np.int64, (6, 15, 8))
 SM_WEIGHTS = _table("SM_WEIGHTS", np.int64, (128,))
 OBMC_MASKS = _table("OBMC_MASKS", np.int64, (64,))
+WARP_FILTER = _table("WARP_FILTER", np.int64, (193, 8))
 
 
 def inter_bits(bdmax):           # get_intermediate_bits(), include/common/bitdepth.h:60-76
@@ -144,6 +145,42 @@ def blend_h(dst, tmp):                       # blend_h_c, mc_tmpl.c:668-681: fir
     return out
 
 
+def w_mask(t1, t2, sign, ss_hor, ss_ver, bdmax):
+    """w_mask_c (mc_tmpl.c:683-728): blend with a mask derived from |t1 - t2|; returns (pixels, mask at the
+    chroma resolution of the layout: 444 m, 422 (m + n + 1 - sign) >> 1, 420 (sum of four + 2 - sign) >> 2)."""
+    ib = inter_bits(bdmax)
+    bitdepth = {0xff: 8, 0x3ff: 10, 0xfff: 12}[bdmax]
+    a, b = t1.astype(np.int64), t2.astype(np.int64)
+    mask_sh = bitdepth + ib - 4
+    m = np.minimum(38 + ((np.abs(a - b) + (1 << (mask_sh - 5))) >> mask_sh), 64)
+    px = np.clip((a * m + b * (64 - m) + (32 << ib) + 64 * prep_bias(bdmax)) >> (ib + 6), 0, bdmax)
+    if not ss_hor:
+        return px, m
+    pair = m[:, 0::2] + m[:, 1::2]
+    if not ss_ver:
+        return px, (pair + 1 - sign) >> 1
+    return px, (pair[0::2] + pair[1::2] + 2 - sign) >> 2
+
+
+def warp8x8(src, abcd, mx, my, bdmax, prep=False):
+    """warp_affine_8x8_c / warp_affine_8x8t_c (mc_tmpl.c:758-825).  src: int array with the block's
+    top-left at [3, 3] (15 x 15 window).  Per-pixel filters from dav1d_mc_warp_filter[64 + ((t + 512) >> 10)]."""
+    s = src.astype(np.int64)
+    ib = inter_bits(bdmax)
+    mid = np.zeros((15, 8), np.int64)
+    for y in range(15):
+        for x in range(8):
+            f = WARP_FILTER[64 + ((mx + y * abcd[1] + x * abcd[0] + 512) >> 10)]
+            mid[y, x] = (int((f * s[y, x:x + 8]).sum()) + ((1 << (7 - ib)) >> 1)) >> (7 - ib)
+    out = np.zeros((8, 8), np.int64)
+    sh = 7 if prep else 7 + ib
+    for y in range(8):
+        for x in range(8):
+            f = WARP_FILTER[64 + ((my + y * abcd[3] + x * abcd[2] + 512) >> 10)]
+            out[y, x] = (int((f * mid[y:y + 8, x]).sum()) + ((1 << sh) >> 1)) >> sh
+    return out - prep_bias(bdmax) if prep else np.clip(out, 0, bdmax)
+
+
 # ------------------------------------------------------------------ intra prediction
 def _dc_gen(s, w, h, hbd):
     """dc_gen (ipred_tmpl.c:140-166): (sum + (w + h) / 2) / (w + h) with the reference's
@@ -192,6 +229,36 @@ def ipred(mode, top, left, topleft, w, h, bdmax):
     if mode == 11:                               # smooth_h, :311-327
         return (wh[None, :] * left[:, None] + (256 - wh[None, :]) * right + 128) >> 8
     raise ValueError(mode)
+
+
+def cfl_ac(luma, w_pad, h_pad, cw, ch, ss_hor, ss_ver):
+    """cfl_ac_c (ipred_tmpl.c:657-703): subsampled luma * 8 over the un-padded area, edge replication into
+    the padded part, minus the rounded mean.  luma: co-located luma block ((ch << ss_ver) x (cw << ss_hor))."""
+    y = luma.astype(np.int64)
+    if ss_hor:
+        y = y[:, 0::2] + y[:, 1::2]
+    if ss_ver:
+        y = y[0::2] + y[1::2]
+    ac = y[:ch, :cw] << (1 + (not ss_ver) + (not ss_hor))
+    vw, vh = cw - 4 * w_pad, ch - 4 * h_pad
+    ac[:, vw:] = ac[:, vw - 1:vw]
+    ac[vh:] = ac[vh - 1:vh]
+    log2sz = int(np.log2(cw)) + int(np.log2(ch))
+    return ac - ((int(ac.sum()) + ((1 << log2sz) >> 1)) >> log2sz)
+
+
+def cfl_pred(dc, ac, alpha, bdmax):
+    """cfl_pred (ipred_tmpl.c:71-84): dc + sign(alpha * ac) * ((|alpha * ac| + 32) >> 6)."""
+    diff = alpha * ac.astype(np.int64)
+    return np.clip(dc + np.sign(diff) * ((np.abs(diff) + 32) >> 6), 0, bdmax)
+
+
+def pal_pred(pal, idx, w, h):
+    """pal_pred_c (ipred_tmpl.c:717-730): two 3-bit indices per byte, low nibble first."""
+    i = idx[:w * h // 2].astype(np.int64)
+    out = np.empty(w * h, np.int64)
+    out[0::2], out[1::2] = pal[i & 7], pal[i >> 4]
+    return out.reshape(h, w)
 
 
 # ------------------------------------------------------------------ inverse transforms (subset)
