@@ -827,7 +827,14 @@ static int recon_submit_multi_on(Dav1dCudaContext *c, const Dav1dCudaReconBatch 
         }
         if ((r = hbd ? launch_intra_multi<uint16_t, 4>(m, st) : launch_intra_multi<uint8_t, 4>(m, st))) return r;
         const int a0 = t.rtask_start[2 * l], a1 = t.rtask_start[2 * l + 1], a2 = t.rtask_start[2 * l + 2];
-        if (a2 > a0 && (r = itx_multi_task_launch(d_itx_frames, d_ritx, d_rtasks + a0, a1 - a0, a2 - a1, hbd, st, st))) return r;
+        if (a2 > a0) {
+            // the level's small and large transform tasks touch disjoint blocks: parallel branches
+            const bool par = a1 > a0 && a2 > a1;
+            if (par && !fork_aux(c, st)) return -5;
+            if ((r = itx_multi_task_launch(d_itx_frames, d_ritx, d_rtasks + a0, a1 - a0, a2 - a1, hbd, st,
+                                           par ? c->aux[0] : st))) return r;
+            if (par && !join_aux(c, st)) return -5;
+        }
     }
     return 0;
 }
