@@ -139,7 +139,8 @@ class ReconBatch(C.Structure):
                 ("intra_class_start", C.POINTER(C.c_int32)), ("intra_host", C.c_void_p),
                 ("intra_tasks", C.c_void_p), ("intra_task_start", C.POINTER(C.c_int32)),
                 ("intra_itx", C.c_void_p), ("intra_itx_tasks", C.c_void_p),
-                ("intra_itx_task_start", C.POINTER(C.c_int32))]
+                ("intra_itx_task_start", C.POINTER(C.c_int32)),
+                ("intra_dep_start_host", C.c_void_p), ("intra_deps_host", C.c_void_p)]
 
 
 def bind_frame_api(L):

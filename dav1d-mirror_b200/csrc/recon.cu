@@ -294,6 +294,50 @@ __global__ void __launch_bounds__(INTRA_WARPS * 32, 4) intra_flow_kernel(const _
     }
 }
 
+// Dataflow launch for the TAIL of a group's wavefront (multi-frame graphs): the operations of the
+// last levels of all frames in level order, dependencies as indices into that array.  A wait is
+// bounded (about a second): a scheduling bug must not hang the GPU; it raises flags[-1 + 0] = sync[0]'s
+// top bit instead, which the host never expects to see.
+struct IntraFlowMultiArgs {
+    const IntraFrameParams *frames;
+    const Dav1dCudaIntraDesc *items;     // descriptor copies, pad = frame
+    const int32_t *dep_start, *deps;
+    unsigned *sync;                      // [0] claim counter, [1 + i] completion flag of operation i
+    int n;
+};
+
+template <typename pixel>
+__global__ void __launch_bounds__(INTRA_WARPS * 32, 4) intra_flow_multi_kernel(const __grid_constant__ IntraFlowMultiArgs m) {
+    extern __shared__ __align__(16) uint8_t intra_smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    IntraSmem<pixel> *sm = (IntraSmem<pixel> *)intra_smem_raw + warp;
+    unsigned *counter = m.sync, *flags = m.sync + 1;
+    for (;;) {
+        int idx = 0;
+        if (lane == 0) idx = (int)(atomicAdd(counter, 1u) & 0x7fffffffu);
+        idx = __shfl_sync(0xffffffffu, idx, 0);
+        if (idx >= m.n) break;
+        const Dav1dCudaIntraDesc d = m.items[idx];
+        const IntraFrameParams &a = m.frames[d.pad];
+        const int d0 = m.dep_start[idx], d1 = m.dep_start[idx + 1];
+        for (int k = d0 + lane; k < d1; k += 32) {
+            const unsigned *f = flags + m.deps[k];
+            unsigned ns = 32, waited = 0;
+            while (ld_acquire(f) == 0) {
+                __nanosleep(ns);
+                waited += ns;
+                if (ns < 1024) ns <<= 1;
+                if (waited > (1u << 30)) { atomicOr(counter, 0x80000000u); break; }
+            }
+        }
+        __syncwarp();
+        intra_op<pixel, 0>(a, d, sm, lane);
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) st_release(flags + idx, 1u);
+    }
+}
+
 template <typename pixel, int CLS>
 static int launch_intra_level_cls(const IntraArgs &a, cudaStream_t st) {
     const int grid = (a.n + INTRA_WARPS - 1) / INTRA_WARPS;
@@ -674,6 +718,10 @@ struct MultiTables {
     std::vector<ItxFrameRef> itx_frames;
     std::vector<Dav1dCudaItxDesc> ritx;  // residual descriptors of all frames, concatenated (copies)
     std::vector<uint2> rtasks;           // code (first index into ritx) , frame
+    // tail of the wavefront as one dataflow launch: levels [tail_level, n_levels) = items
+    // [level_start[tail_level], end) with dependency lists relative to that range
+    int tail_level = -1;
+    std::vector<int32_t> tail_dep_start, tail_deps;
     std::vector<int> rtask_start;        // 2 * n_levels + 1
 };
 
@@ -700,6 +748,7 @@ static int build_multi_tables(const Dav1dCudaReconBatch *const *bs, int n, Multi
         }
     }
     t.level_start.assign(1, 0);
+    std::vector<int32_t> item_src;           // per item: sorted index inside its frame
     std::vector<std::pair<uint64_t, uint32_t>> lv;
     for (int l = 0; l < max_levels; l++) {
         lv.clear();
@@ -717,8 +766,42 @@ static int build_multi_tables(const Dav1dCudaReconBatch *const *bs, int n, Multi
             Dav1dCudaIntraDesc d = bs[e.second >> 24]->intra_host[e.second & 0xffffff];
             d.pad = (uint16_t)(e.second >> 24);
             t.items.push_back(d);
+            item_src.push_back((int32_t)(e.second & 0xffffff));
         }
         t.level_start.push_back((int)t.items.size());
+    }
+    // ---- tail: the last levels, each below the fusing threshold, when every frame brings its
+    // dependency lists (experiment knob D1_INTRA_TAIL=0 keeps one fused launch per level)
+    {
+        static const int fuse_below = getenv("D1_INTRA_FUSE_BELOW") ? atoi(getenv("D1_INTRA_FUSE_BELOW")) : 512;
+        static const bool tail_on = !getenv("D1_INTRA_TAIL") || atoi(getenv("D1_INTRA_TAIL")) != 0;
+        bool have = tail_on && max_levels > 0;
+        for (int f = 0; f < n; f++)
+            if (bs[f]->intra && bs[f]->n_levels > 0 && (!bs[f]->intra_dep_start_host || !bs[f]->intra_deps_host)) have = false;
+        int tl = max_levels;
+        while (have && tl > 0 && t.level_start[tl] - t.level_start[tl - 1] < fuse_below) tl--;
+        if (have && max_levels - tl >= 3) {            // worth it from three launches on
+            const int t0 = t.level_start[tl], t1 = (int)t.items.size();
+            // (frame, sorted index inside the frame) -> index inside the tail
+            std::vector<std::vector<int32_t>> pos(n);
+            for (int f = 0; f < n; f++)
+                if (bs[f]->intra && bs[f]->n_levels > 0) pos[f].assign(bs[f]->intra_level_start[bs[f]->n_levels], -1);
+            for (int j = t0; j < t1; j++) pos[t.items[j].pad][item_src[j]] = j - t0;
+            t.tail_dep_start.assign(1, 0);
+            for (int j = t0; j < t1; j++) {
+                const int f = t.items[j].pad;
+                const int32_t i = item_src[j];
+                const int32_t *ds = bs[f]->intra_dep_start_host, *dd = bs[f]->intra_deps_host;
+                for (int k = ds[i]; k < ds[i + 1]; k++) {
+                    const int32_t q = pos[f][dd[k]];
+                    if (q < 0) continue;               // produced by an earlier launch of this graph
+                    if (q >= j - t0) return -22;       // would wait for a later operation: scheduler bug
+                    t.tail_deps.push_back(q);
+                }
+                t.tail_dep_start.push_back((int32_t)t.tail_deps.size());
+            }
+            t.tail_level = tl;
+        }
     }
     // residual tasks: regenerated on the host from each frame's sorted descriptors (the same
     // deterministic routine that produced the frame's device arrays intra_itx / intra_itx_tasks)
@@ -762,6 +845,27 @@ static int build_multi_tables(const Dav1dCudaReconBatch *const *bs, int n, Multi
         for (auto &e : v) t.rtasks.push_back(e.tk);
         t.rtask_start.push_back((int)t.rtasks.size());
     }
+    // TIMING-ONLY experiment knob (results are WRONG: dependencies are ignored): D1_INTRA_FLAT=1 runs
+    // all intra-class operations of the group as ONE level = the throughput floor of the kernels
+    // without the wavefront's launch chain (tools/exp_frame.py)
+    static const bool flat = getenv("D1_INTRA_FLAT") && atoi(getenv("D1_INTRA_FLAT")) != 0;
+    if (flat && max_levels > 1) {
+        std::stable_sort(t.items.begin(), t.items.end(), [](const Dav1dCudaIntraDesc &x, const Dav1dCudaIntraDesc &y) {
+            return intra_code_key(x) < intra_code_key(y);
+        });
+        t.level_start = { 0, (int)t.items.size() };
+        t.tail_level = -1;
+        std::vector<Key> all[2];
+        for (size_t i = 0; i < per_level.size(); i++)
+            all[i & 1].insert(all[i & 1].end(), per_level[i].begin(), per_level[i].end());
+        t.rtasks.clear();
+        t.rtask_start.assign(1, 0);
+        for (auto &v : all) {
+            std::stable_sort(v.begin(), v.end(), [](const Key &x, const Key &y) { return x.key < y.key; });
+            for (auto &e : v) t.rtasks.push_back(e.tk);
+            t.rtask_start.push_back((int)t.rtasks.size());
+        }
+    }
     return 0;
 }
 
@@ -776,6 +880,7 @@ static int launch_intra_multi(const IntraMultiArgs &m, cudaStream_t st) {
 static int recon_submit_multi_on(Dav1dCudaContext *c, const Dav1dCudaReconBatch *const *bs, int n,
                                  const IntraFrameParams *d_frames, const Dav1dCudaIntraDesc *d_items,
                                  const ItxFrameRef *d_itx_frames, const Dav1dCudaItxDesc *d_ritx, const uint2 *d_rtasks,
+                                 const int32_t *d_tail_dep_start, const int32_t *d_tail_deps, unsigned *d_tail_sync,
                                  const MultiTables &t,
                                  cudaStream_t st, const int phase_mask)
 {
@@ -816,7 +921,8 @@ static int recon_submit_multi_on(Dav1dCudaContext *c, const Dav1dCudaReconBatch 
     // tasks (small / large sizes); levels with few operations run fused (one launch)
     const bool hbd = bs[0]->dst->bitdepth_max > 0xff;
     static const int fuse_below = getenv("D1_INTRA_FUSE_BELOW") ? atoi(getenv("D1_INTRA_FUSE_BELOW")) : 512;
-    for (size_t l = 0; l + 1 < t.level_start.size(); l++) {
+    const size_t n_level_launches = t.tail_level >= 0 ? (size_t)t.tail_level : t.level_start.size() - 1;
+    for (size_t l = 0; l < n_level_launches; l++) {
         const int s0 = t.level_start[l], s1 = t.level_start[l + 1];
         if (s1 <= s0) continue;
         IntraMultiArgs m;
@@ -836,6 +942,21 @@ static int recon_submit_multi_on(Dav1dCudaContext *c, const Dav1dCudaReconBatch 
             if (par && !join_aux(c, st)) return -5;
         }
     }
+    if (t.tail_level >= 0) {
+        // the tail of the wavefront: one dataflow launch for all remaining levels of the group
+        IntraFlowMultiArgs fm;
+        fm.frames = d_frames;
+        fm.items = d_items + t.level_start[t.tail_level];
+        fm.n = (int)t.items.size() - t.level_start[t.tail_level];
+        fm.dep_start = d_tail_dep_start; fm.deps = d_tail_deps; fm.sync = d_tail_sync;
+        if (!cuda_ok(cudaMemsetAsync(d_tail_sync, 0, (size_t)(fm.n + 1) * sizeof(unsigned), st), "memset(tail sync)"))
+            return -5;
+        const int grid = std::min(g_flow_blocks[hbd], (fm.n + INTRA_WARPS - 1) / INTRA_WARPS);
+        if (hbd) intra_flow_multi_kernel<uint16_t><<<grid, INTRA_WARPS * 32, INTRA_WARPS * sizeof(IntraSmem<uint16_t>), st>>>(fm);
+        else intra_flow_multi_kernel<uint8_t><<<grid, INTRA_WARPS * 32, INTRA_WARPS * sizeof(IntraSmem<uint8_t>), st>>>(fm);
+        count_launch();
+        if (!cuda_ok(cudaGetLastError(), "intra_flow_multi_kernel")) return -5;
+    }
     return 0;
 }
 
@@ -848,6 +969,10 @@ void recon_init_attrs() {
     cudaFuncSetAttribute(intra_multi_kernel<uint16_t, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)(INTRA_WARPS * sizeof(IntraSmem<uint16_t>)));
     cudaFuncSetAttribute(intra_multi_kernel<uint8_t, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)(INTRA_WARPS * sizeof(IntraSmem<uint8_t>)));
+    cudaFuncSetAttribute(intra_flow_multi_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)(INTRA_WARPS * sizeof(IntraSmem<uint16_t>)));
+    cudaFuncSetAttribute(intra_flow_multi_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)(INTRA_WARPS * sizeof(IntraSmem<uint8_t>)));
     cudaFuncSetAttribute(intra_flow_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)(INTRA_WARPS * sizeof(IntraSmem<uint16_t>)));
@@ -1178,9 +1303,19 @@ int dav1d_cuda_recon_graph_build_multi_phases(Dav1dCudaContext *c, const Dav1dCu
     const size_t sb = (t.items.size() * sizeof(Dav1dCudaIntraDesc) + 255) & ~(size_t)255;
     const size_t ib = (t.itx_frames.size() * sizeof(ItxFrameRef) + 255) & ~(size_t)255;
     const size_t rb = (t.rtasks.size() * sizeof(uint2) + 255) & ~(size_t)255;
-    const size_t xb = t.ritx.size() * sizeof(Dav1dCudaItxDesc);
+    const size_t xb = (t.ritx.size() * sizeof(Dav1dCudaItxDesc) + 255) & ~(size_t)255;
+    const size_t n_tail = t.tail_level >= 0 ? t.items.size() - (size_t)t.level_start[t.tail_level] : 0;
+    const size_t tsb = (t.tail_dep_start.size() * sizeof(int32_t) + 255) & ~(size_t)255;
+    const size_t tdb = (t.tail_deps.size() * sizeof(int32_t) + 255) & ~(size_t)255;
+    const size_t tyb = ((n_tail + 1) * sizeof(unsigned) + 255) & ~(size_t)255;
     uint8_t *tab = nullptr;
-    D1_CHECK(cudaMalloc(&tab, fb + sb + ib + rb + xb + 64));
+    D1_CHECK(cudaMalloc(&tab, fb + sb + ib + rb + xb + tsb + tdb + tyb + 64));
+    if (!t.tail_dep_start.empty())
+        D1_CHECK(cudaMemcpy(tab + fb + sb + ib + rb + xb, t.tail_dep_start.data(),
+                            t.tail_dep_start.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    if (!t.tail_deps.empty())
+        D1_CHECK(cudaMemcpy(tab + fb + sb + ib + rb + xb + tsb, t.tail_deps.data(),
+                            t.tail_deps.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
     D1_CHECK(cudaMemcpy(tab, t.frames.data(), t.frames.size() * sizeof(IntraFrameParams), cudaMemcpyHostToDevice));
     if (!t.items.empty())
         D1_CHECK(cudaMemcpy(tab + fb, t.items.data(), t.items.size() * sizeof(Dav1dCudaIntraDesc),
@@ -1190,14 +1325,19 @@ int dav1d_cuda_recon_graph_build_multi_phases(Dav1dCudaContext *c, const Dav1dCu
                             cudaMemcpyHostToDevice));
     if (!t.rtasks.empty())
         D1_CHECK(cudaMemcpy(tab + fb + sb + ib, t.rtasks.data(), t.rtasks.size() * sizeof(uint2), cudaMemcpyHostToDevice));
-    if (xb) D1_CHECK(cudaMemcpy(tab + fb + sb + ib + rb, t.ritx.data(), xb, cudaMemcpyHostToDevice));
+    if (!t.ritx.empty())
+        D1_CHECK(cudaMemcpy(tab + fb + sb + ib + rb, t.ritx.data(), t.ritx.size() * sizeof(Dav1dCudaItxDesc),
+                            cudaMemcpyHostToDevice));
     cudaStream_t cap;
     D1_CHECK(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
     D1_CHECK(cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal));
     const int r = recon_submit_multi_on(c, bs, n, (const IntraFrameParams *)tab, (const Dav1dCudaIntraDesc *)(tab + fb),
                                         (const ItxFrameRef *)(tab + fb + sb),
                                         (const Dav1dCudaItxDesc *)(tab + fb + sb + ib + rb),
-                                        (const uint2 *)(tab + fb + sb + ib), t, cap, phase_mask);
+                                        (const uint2 *)(tab + fb + sb + ib),
+                                        (const int32_t *)(tab + fb + sb + ib + rb + xb),
+                                        (const int32_t *)(tab + fb + sb + ib + rb + xb + tsb),
+                                        (unsigned *)(tab + fb + sb + ib + rb + xb + tsb + tdb), t, cap, phase_mask);
     cudaGraph_t graph = nullptr;
     const cudaError_t e = cudaStreamEndCapture(cap, &graph);
     cudaStreamDestroy(cap);

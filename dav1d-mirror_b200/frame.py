@@ -275,6 +275,9 @@ class DeviceFrame:
             b.itx_tasks = d["itx_tasks"]
             b.n_itx_tasks[0], b.n_itx_tasks[1] = hf.n_itx_tasks
         b.intra_host = hf.intra_sorted.ctypes.data if hf.intra_sorted.nbytes else None
+        if hf.intra_sorted.nbytes and hf.dep_start.nbytes:
+            b.intra_dep_start_host = hf.dep_start.ctypes.data
+            b.intra_deps_host = hf.deps.ctypes.data if hf.deps.nbytes else hf.dep_start.ctypes.data
         if dataflow:
             b.intra_dep_start, b.intra_deps, b.intra_sync = d["dep_start"], d["deps"], self._sync
         elif classes:

@@ -444,6 +444,12 @@ typedef struct Dav1dCudaReconBatch {
     const Dav1dCudaItxDesc *intra_itx;        /* device */
     const uint32_t *intra_itx_tasks;          /* device */
     const int32_t *intra_itx_task_start;      /* host: 2 * n_levels + 1 offsets (small, big per level) */
+    /* optional (host): the dependency lists of dav1d_cuda_intra_schedule_deps() (dep_start: n_intra + 1,
+     * deps: indices into the sorted `intra` array).  With them dav1d_cuda_recon_graph_build_multi() runs
+     * the TAIL of the wavefront - the last levels, each with few operations - as ONE dataflow launch for
+     * the whole group (completion flags per operation) instead of one launch per level. */
+    const int32_t *intra_dep_start_host;
+    const int32_t *intra_deps_host;
 } Dav1dCudaReconBatch;
 
 DAV1D_CUDA_API int dav1d_cuda_recon_submit(Dav1dCudaContext *c, const Dav1dCudaReconBatch *b);
