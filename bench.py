@@ -211,6 +211,19 @@ def main_ours(args):
     import torch
     import torch.distributed as dist
     torch.cuda.set_device(local)
+    # host threads and the pinned staging buffers of a rank live on the CPUs next to its GPU
+    # (NUMA placement matters once several GPUs copy at the same time)
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = [64 * i + b for i, wd in enumerate(words) for b in range(64) if (int(wd) >> b) & 1 and 64 * i + b < ncpu]
+        if cpus and len(cpus) < ncpu:
+            os.sched_setaffinity(0, cpus)
+    except Exception:
+        pass
     if world > 1:
         # stdout carries only the JSON line: NCCL prints its version banner to fd 1 when the
         # communicator is created (first collective), so fd 1 points at stderr until that is done
