@@ -115,7 +115,7 @@ class IntraDesc40(C.Structure):
                 ("th4", C.c_uint8), ("mode", C.c_uint8), ("angle_delta", C.c_int8),
                 ("edge_flags", C.c_uint8), ("flags", C.c_uint16), ("eob", C.c_int16),
                 ("tx", C.c_uint8), ("txtp", C.c_uint8), ("coef_off", C.c_uint32),
-                ("aux", C.c_uint32), ("level", C.c_uint32), ("cw4", C.c_uint8), ("ch4", C.c_uint8),
+                ("aux", C.c_uint32), ("blk", C.c_uint32), ("cw4", C.c_uint8), ("ch4", C.c_uint8),
                 ("pad", C.c_uint16)]
 
 
@@ -134,13 +134,12 @@ class ReconBatch(C.Structure):
                 ("warp", C.c_void_p), ("n_warp", C.c_int32),
                 ("itx", C.c_void_p), ("itx_class_count", C.c_int32 * N_RECT_TX_SIZES),
                 ("itx_tasks", C.c_void_p), ("n_itx_tasks", C.c_int32 * 2),
-                ("intra", C.c_void_p), ("intra_level_start", C.POINTER(C.c_int32)), ("n_levels", C.c_int32),
-                ("intra_dep_start", C.c_void_p), ("intra_deps", C.c_void_p), ("intra_sync", C.c_void_p),
-                ("intra_class_start", C.POINTER(C.c_int32)), ("intra_host", C.c_void_p),
-                ("intra_tasks", C.c_void_p), ("intra_task_start", C.POINTER(C.c_int32)),
-                ("intra_itx", C.c_void_p), ("intra_itx_tasks", C.c_void_p),
-                ("intra_itx_task_start", C.POINTER(C.c_int32)),
-                ("intra_dep_start_host", C.c_void_p), ("intra_deps_host", C.c_void_p)]
+                ("intra", C.c_void_p), ("n_intra", C.c_int32),
+                ("intra_units", C.c_void_p), ("n_intra_units", C.c_int32),
+                ("intra_cellmap", C.c_void_p)]
+
+
+MAX_GROUP = 16
 
 
 def bind_frame_api(L):
@@ -150,23 +149,17 @@ def bind_frame_api(L):
                                                C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     L.dav1d_cuda_warp_batch.argtypes = [C.c_void_p, C.POINTER(Picture), C.POINTER(C.POINTER(Picture)),
                                         C.c_void_p, C.c_int]
-    L.dav1d_cuda_intra_batch.argtypes = [C.c_void_p, C.POINTER(Picture), C.c_int, C.c_int, C.c_void_p, C.c_void_p,
-                                         C.POINTER(C.c_int32), C.c_int, C.c_void_p, C.c_void_p]
-    L.dav1d_cuda_intra_schedule.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
-                                            C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int]
-    L.dav1d_cuda_intra_schedule_deps.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
-                                                 C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int,
-                                                 C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    L.dav1d_cuda_intra_cellmap_bytes.restype = C.c_size_t
+    L.dav1d_cuda_intra_cellmap_bytes.argtypes = [C.c_int] * 4
+    L.dav1d_cuda_intra_units.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
     L.dav1d_cuda_itx_tasks.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int32),
                                        C.POINTER(C.c_int32)]
-    L.dav1d_cuda_intra_tasks.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.c_int, C.c_void_p,
-                                         C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
-    L.dav1d_cuda_intra_residual_tasks.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.c_int, C.c_void_p, C.c_void_p,
-                                                  C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     L.dav1d_cuda_itx_task_batch.argtypes = [C.c_void_p, C.POINTER(Picture), C.c_void_p, C.c_void_p, C.c_void_p,
                                             C.c_int, C.c_int, C.c_int]
     L.dav1d_cuda_recon_submit.argtypes = [C.c_void_p, C.POINTER(ReconBatch)]
     L.dav1d_cuda_recon_submit_phases.argtypes = [C.c_void_p, C.POINTER(ReconBatch), C.c_int]
+    L.dav1d_cuda_recon_group_submit.argtypes = [C.c_void_p, C.POINTER(C.POINTER(ReconBatch)), C.c_int]
+    L.dav1d_cuda_recon_group_submit_phases.argtypes = [C.c_void_p, C.POINTER(C.POINTER(ReconBatch)), C.c_int, C.c_int]
     L.dav1d_cuda_recon_graph_build.argtypes = [C.c_void_p, C.POINTER(ReconBatch), C.POINTER(C.c_void_p)]
     L.dav1d_cuda_recon_graph_build_multi_phases.argtypes = [C.c_void_p, C.POINTER(C.POINTER(ReconBatch)), C.c_int,
                                                             C.c_int, C.POINTER(C.c_void_p)]

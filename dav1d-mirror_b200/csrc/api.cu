@@ -95,21 +95,36 @@ int dav1d_cuda_open(Dav1dCudaContext **out, int device, void *stream) {
         set_error(-22, "dav1d_cuda_open", "no such device");
         return -22;
     }
+    // One GPU per process: the per-call staging arena, the occupancy figures of the persistent
+    // kernels and the kernel attributes are process-wide and belong to the first device used.
+    static std::atomic<int> g_device{-1};
+    int expect = -1;
+    if (!g_device.compare_exchange_strong(expect, device) && expect != device) {
+        set_error(-22, "dav1d_cuda_open", "this process already uses another device (one GPU per process)");
+        return -22;
+    }
     D1_CHECK(cudaSetDevice(device));
     Dav1dCudaContext *c = new Dav1dCudaContext();
+    memset(c, 0, sizeof(*c));
     c->device = device;
-    c->own_stream = false;
     c->stream = (cudaStream_t)stream;
+    bool ok = true;
     if (!stream) {   // no caller stream: give the context its own so that contexts run concurrently
-        D1_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-        c->own_stream = true;
+        ok = cuda_ok(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "cudaStreamCreate");
+        c->own_stream = ok;
     }
-    c->tmp_pool = nullptr;
-    c->tmp_pool_bytes = 0;
-    c->aux_ready = false;
-    cudaDeviceProp prop;
-    D1_CHECK(cudaGetDeviceProperties(&prop, device));
-    c->num_sms = prop.multiProcessorCount;
+    int sms = 0;
+    ok = ok && cuda_ok(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device), "cudaDeviceGetAttribute");
+    c->num_sms = sms;
+    ok = ok && cuda_ok(cudaMalloc(&c->claim, (Dav1dCudaContext::N_CLAIM + 1) * sizeof(unsigned)), "cudaMalloc(claim)");
+    ok = ok && cuda_ok(cudaMemset(c->claim, 0, (Dav1dCudaContext::N_CLAIM + 1) * sizeof(unsigned)), "cudaMemset(claim)");
+    if (!ok) {
+        if (c->claim) cudaFree(c->claim);
+        if (c->own_stream) cudaStreamDestroy(c->stream);
+        delete c;
+        return -5;
+    }
+    c->status = c->claim + Dav1dCudaContext::N_CLAIM;
     mc_init_attrs();
     recon_init_attrs();
     cudaGetLastError();
@@ -129,12 +144,24 @@ void dav1d_cuda_close(Dav1dCudaContext *c) {
         cudaEventDestroy(c->ev_fork);
     }
     if (c->own_stream) cudaStreamDestroy(c->stream);
+    if (c->claim) cudaFree(c->claim);
     delete c;
 }
 
 int dav1d_cuda_synchronize(Dav1dCudaContext *c) {
+    if (!c) return -22;
+    D1_CHECK(cudaSetDevice(c->device));
     D1_CHECK(cudaStreamSynchronize(c->stream));
     D1_CHECK(cudaGetLastError());
+    // status word of the intra executor: a dependency that never became final
+    unsigned st = 0;
+    D1_CHECK(cudaMemcpy(&st, c->status, sizeof(st), cudaMemcpyDeviceToHost));
+    if (st) {
+        cudaMemset(c->status, 0, sizeof(st));
+        set_error(-5, "intra executor", "a dependency wait timed out: the frame is incomplete "
+                                        "(descriptor order / unit table inconsistent, or a stalled GPU)");
+        return -5;
+    }
     return 0;
 }
 
@@ -142,8 +169,8 @@ int dav1d_cuda_synchronize(Dav1dCudaContext *c) {
 int dav1d_cuda_picture_alloc(Dav1dCudaContext *c, Dav1dCudaPicture *pic,
                              int w, int h, int ss_hor, int ss_ver, int bitdepth_max)
 {
-    (void)c;
-    if (!pic || w <= 0 || h <= 0) return -22;
+    if (!c || !pic || w <= 0 || h <= 0) return -22;
+    D1_CHECK(cudaSetDevice(c->device));
     memset(pic, 0, sizeof(*pic));
     const int hbd = bitdepth_max > 0xff;
     const int aligned_w = (w + 127) & ~127;

@@ -78,11 +78,6 @@ struct ItxFrameRef {
     void *cf;
     const Dav1dCudaItxDesc *descs;
 };
-struct ItxMultiArgs {
-    const ItxFrameRef *frames;
-    const uint2 *tasks;          // x = task code (see dav1d_cuda_itx_tasks), y = frame
-    int n_tasks;
-};
 
 // Per-call staging: one arena per process, serialised by a mutex.  The
 // reference calls DSP functions concurrently from many threads
@@ -114,4 +109,10 @@ struct Dav1dCudaContext {
     cudaStream_t aux[N_AUX];
     cudaEvent_t ev_fork, ev_join[N_AUX];
     bool aux_ready;
+    // intra executor: claim counters (one per submission in flight, used round robin) and the
+    // status word the kernels raise (bit0: a dependency wait timed out); device memory
+    static constexpr int N_CLAIM = 8;
+    unsigned *claim;
+    unsigned *status;
+    unsigned claim_next;
 };

@@ -43,7 +43,8 @@ class SynthFrame(C.Structure):
                 ("algo_bytes", C.c_double), ("algo_class", C.c_double * 5), ("luma_px", C.c_double),
                 ("n_blocks", C.c_int64), ("n_intra_blocks", C.c_int64),
                 ("mc_obmc", C.c_void_p), ("n_mc_obmc", C.c_int32), ("mc_obmc_tiles", C.c_void_p),
-                ("n_mc_obmc_tiles", C.c_int32 * 2)]
+                ("n_mc_obmc_tiles", C.c_int32 * 2),
+                ("intra_units", C.c_void_p), ("n_intra_units", C.c_int32)]
 
 
 _synth = None
@@ -114,38 +115,13 @@ class HostFrame:
         self.algo_bytes, self.luma_px = f.algo_bytes, f.luma_px
         self.algo_class = dict(zip(("mc_put", "mc_compound", "warp", "itx", "intra"), list(f.algo_class)))
         self.n_blocks, self.n_intra_blocks = f.n_blocks, f.n_intra_blocks
+        # intra-class operations stay in decode order; the recorder names the units (coding
+        # blocks) as (first, count) pairs in the order they are to be claimed
+        self.n_intra_units = f.n_intra_units
+        self.intra_units = _np_from(f.intra_units, f.n_intra_units * 8)
         S.d1synth_free(C.byref(f))
-        self.intra_sorted = None
-        self.level_start = None
-        self.n_levels = 0
-
-    def schedule(self):
-        """Dependency levels of the intra-class descriptors (dav1d_cuda_intra_schedule)."""
+        # inter residuals: task codes over the (size, type)-sorted itx array (linear pass)
         L = B.lib()
-        n = self.n_intra
-        order = (C.c_int32 * max(n, 1))()
-        max_levels = 1 << 16
-        level_start = (C.c_int32 * (max_levels + 1))()
-        descs = self.intra.copy()
-        max_deps = 96 * max(n, 1)
-        dep_start = np.zeros(n + 1, dtype=np.int32)
-        deps = np.zeros(max_deps, dtype=np.int32)
-        class_start = np.zeros(3 * max_levels + 1, dtype=np.int32)
-        nl = L.dav1d_cuda_intra_schedule_deps(descs.ctypes.data, n, self.bw4, self.bh4,
-                                              0 if self.no_chroma else self.ss_hor,
-                                              0 if self.no_chroma else self.ss_ver, order, level_start, max_levels,
-                                              dep_start.ctypes.data, deps.ctypes.data, max_deps,
-                                              class_start.ctypes.data)
-        if nl < 0:
-            raise RuntimeError(f"dav1d_cuda_intra_schedule_deps: {nl}")
-        self.dep_start = dep_start.view(np.uint8)
-        self.deps = deps[:max(int(dep_start[n]), 1)].copy().view(np.uint8)
-        perm = np.frombuffer(order, dtype=np.int32, count=n).copy() if n else np.zeros(0, np.int32)
-        rec = descs.reshape(n, C.sizeof(B.IntraDesc)) if n else descs.reshape(0, C.sizeof(B.IntraDesc))
-        self.intra_sorted = np.ascontiguousarray(rec[perm]).reshape(-1)
-        self.level_start = np.frombuffer(level_start, dtype=np.int32, count=nl + 1).copy()
-        self.class_start = class_start[:3 * nl + 1].copy()
-        # inter residuals: task codes over the class-sorted itx array
         n_itx = self.itx.nbytes // C.sizeof(B.ItxDesc)
         tasks = np.zeros(max(n_itx, 1), dtype=np.uint32)
         ns, nb = C.c_int32(), C.c_int32()
@@ -153,28 +129,6 @@ class HostFrame:
             if n_itx else 0
         self.itx_tasks = tasks[:max(k, 1)].copy().view(np.uint8)
         self.n_itx_tasks = (ns.value, nb.value)
-        # intra residuals as transform descriptors + tasks per level
-        iitx = np.zeros(max(n, 1) * C.sizeof(B.ItxDesc), dtype=np.uint8)
-        itasks = np.zeros(max(n, 1), dtype=np.uint32)
-        tstart = (C.c_int32 * (2 * nl + 1))()
-        nt = C.c_int32()
-        lstart = (C.c_int32 * (nl + 1))(*self.level_start.tolist())
-        ni = L.dav1d_cuda_intra_residual_tasks(self.intra_sorted.ctypes.data, lstart, nl, iitx.ctypes.data,
-                                               itasks.ctypes.data, tstart, C.byref(nt)) if n else 0
-        self.intra_itx = iitx[:max(ni, 1) * C.sizeof(B.ItxDesc)].copy()
-        self.intra_itx_tasks = itasks[:max(nt.value, 1)].copy().view(np.uint8)
-        self.intra_itx_task_start = np.frombuffer(tstart, dtype=np.int32, count=2 * nl + 1).copy()
-        # fused task codes over the sorted intra array
-        ftasks = np.zeros(max(n, 1), dtype=np.uint32)
-        fstart = (C.c_int32 * (2 * nl + 1))()
-        fn = C.c_int32()
-        if n:
-            L.dav1d_cuda_intra_tasks(self.intra_sorted.ctypes.data, lstart, nl, ftasks.ctypes.data, fstart,
-                                     C.byref(fn))
-        self.intra_tasks = ftasks[:max(fn.value, 1)].copy().view(np.uint8)
-        self.intra_task_start = np.frombuffer(fstart, dtype=np.int32, count=2 * nl + 1).copy()
-        self.n_levels = nl
-        return nl
 
     def plane_shape(self, pl):
         sh = self.ss_hor if pl else 0
@@ -182,13 +136,10 @@ class HostFrame:
         return ((self.h + sv) >> sv, (self.w + sh) >> sh)
 
     def host_bytes(self):
-        """Bytes a decoder would ship host->device for this frame (descriptors + coefficients + pools)."""
-        n = sum(a.nbytes for a in (self.mc_put, self.mc_put_tiles, self.mc_comp, self.mc_comp_tiles, self.warp,
-                                   self.mc_obmc, self.mc_obmc_tiles,
-                                   self.itx, self.cf, self.masks, self.pal, self.pal_idx))
-        if self.intra_sorted is not None:
-            n += self.itx_tasks.nbytes + self.intra_itx.nbytes + self.intra_itx_tasks.nbytes
-        return n + (self.intra_sorted.nbytes if self.intra_sorted is not None else self.intra.nbytes)
+        """Bytes a decoder ships host->device for this frame (descriptors + coefficients + pools)."""
+        return sum(a.nbytes for a in (self.mc_put, self.mc_put_tiles, self.mc_comp, self.mc_comp_tiles, self.warp,
+                                      self.mc_obmc, self.mc_obmc_tiles, self.itx, self.itx_tasks, self.cf, self.masks,
+                                      self.pal, self.pal_idx, self.intra, self.intra_units))
 
 
 def random_planes(hf, seed):
@@ -200,12 +151,16 @@ def random_planes(hf, seed):
 
 
 class DeviceFrame:
-    """Device-resident state for reconstructing `hf` with libdav1d_cuda.so."""
+    """Device-resident state of one stream: destination + reference pictures, the cell map of the
+    intra executor and ONE descriptor arena that receives, frame after frame, the descriptor set
+    of the frame to reconstruct (`hf`, or - use(k) - one of several sets of the same geometry)."""
 
-    def __init__(self, ctx, hf, n_refs=2, dataflow=False, classes=False, tasks=True):
+    def __init__(self, ctx, hf, n_refs=2, tasks=True, units=True, more_sets=()):
+        """tasks: explicit transform task codes (else the implicit per-size runs); units: the
+        recorder's unit table (one unit per coding block) and block hints - else superblock units
+        cut by dav1d_cuda_intra_units() and no hints, i.e. every dependency goes through the cell map."""
         self.L = B.lib()
         self.ctx = ctx
-        self.hf = hf
         L = self.L
         self.dst = B.Picture()
         self.refs = [B.Picture() for _ in range(n_refs)]
@@ -213,45 +168,61 @@ class DeviceFrame:
             r = L.dav1d_cuda_picture_alloc(ctx, C.byref(pic), hf.w, hf.h, hf.ss_hor, hf.ss_ver, hf.bdmax)
             if r:
                 raise RuntimeError("dav1d_cuda_picture_alloc failed")
-        if hf.intra_sorted is None:
-            hf.schedule()
-        # one device arena per frame for descriptors, task lists, coefficients and pools (each array
-        # 256-byte aligned): the end-to-end path ships it with ONE host->device copy from a pinned
+        ssh = 0 if hf.no_chroma else hf.ss_hor
+        ssv = 0 if hf.no_chroma else hf.ss_ver
+        self._cellmap_bytes = L.dav1d_cuda_intra_cellmap_bytes(hf.bw4, hf.bh4, ssh, ssv)
+        self._cellmap = L.dav1d_cuda_malloc(self._cellmap_bytes)
+        L.dav1d_cuda_memset(ctx, self._cellmap, 0, self._cellmap_bytes)       # once; frames leave it at zero
+        # one device arena for descriptors, task lists, coefficients and pools (each array 256-byte
+        # aligned): the end-to-end path ships a frame's set with ONE host->device copy from a pinned
         # mirror (every extra copy costs ~10 us of copy-engine time, tools/exp_copy.py)
-        self._dev = {}
-        self._host = {}
-        names = ["mc_put", "mc_put_tiles", "mc_comp", "mc_comp_tiles", "warp", "itx", "intra_sorted", "cf",
-                 "masks", "pal", "pal_idx", "itx_tasks"]
-        if hf.mc_obmc.nbytes:
-            names += ["mc_obmc", "mc_obmc_tiles"]
-        if dataflow:
-            names += ["dep_start", "deps"]
-        elif tasks == 1:
-            names += ["intra_itx", "intra_itx_tasks"]
-        elif tasks:
-            names += ["intra_tasks"]
-        self._off = {}
-        off = 0
-        for name in names:
-            arr = getattr(hf, name)
-            self._host[name] = arr
-            self._off[name] = off
-            off += (max(arr.nbytes, 256) + 255) & ~255
-        self.arena_bytes = off
-        self._arena = L.dav1d_cuda_malloc(off)
+        self._sets = []
+        for h in [hf] + list(more_sets):
+            assert (h.w, h.h, h.bdmax, h.ss_hor, h.ss_ver) == (hf.w, hf.h, hf.bdmax, hf.ss_hor, hf.ss_ver)
+            self._sets.append(self._layout(h, units))
+        self._arena_cap = max(st["bytes"] for st in self._sets)
+        self._arena = L.dav1d_cuda_malloc(self._arena_cap)
         if not self._arena:
             raise RuntimeError("dav1d_cuda_malloc failed")
-        for name in ("mc_put", "mc_put_tiles", "mc_comp", "mc_comp_tiles", "warp", "itx", "intra_sorted", "cf",
-                     "masks", "pal", "pal_idx", "dep_start", "deps", "itx_tasks", "intra_itx", "intra_itx_tasks",
-                     "intra_tasks", "mc_obmc", "mc_obmc_tiles"):
-            self._dev[name] = self._arena + self._off[name] if name in self._off else None
-        self._level_start = (C.c_int32 * (hf.n_levels + 1))(*hf.level_start.tolist())
+        for st in self._sets:
+            st["batch"] = self._make_batch(st, n_refs, tasks)
+        self.graph = None
+        self._pinned = None
+        self.use(0)
+
+    def _layout(self, hf, units):
+        L = self.L
+        names = ["mc_put", "mc_put_tiles", "mc_comp", "mc_comp_tiles", "warp", "itx", "intra", "intra_units",
+                 "cf", "masks", "pal", "pal_idx", "itx_tasks"]
+        alt = {}
+        n_units = hf.n_intra_units
+        if not units and hf.n_intra:
+            intra = hf.intra.copy().reshape(hf.n_intra, C.sizeof(B.IntraDesc))
+            intra[:, 32:36] = 0                                  # no block hints
+            us = np.zeros(2 * hf.n_intra, dtype=np.uint32)
+            n_units = L.dav1d_cuda_intra_units(intra.ctypes.data, hf.n_intra, 0 if hf.no_chroma else hf.ss_hor,
+                                               0 if hf.no_chroma else hf.ss_ver, 4, 0 if hf.params.p_ibc > 0 else 2,
+                                               us.ctypes.data, hf.n_intra)
+            assert n_units > 0
+            alt = {"intra": intra.reshape(-1), "intra_units": us[:2 * n_units].copy().view(np.uint8)}
+        if hf.mc_obmc.nbytes:
+            names += ["mc_obmc", "mc_obmc_tiles"]
+        host, offs, off = {}, {}, 0
+        for name in names:
+            arr = alt.get(name, getattr(hf, name))
+            host[name] = arr
+            offs[name] = off
+            off += (max(arr.nbytes, 256) + 255) & ~255
+        return {"hf": hf, "host": host, "off": offs, "bytes": off, "n_units": n_units, "pinned": None}
+
+    def _make_batch(self, st, n_refs, tasks):
+        hf = st["hf"]
+        d = {name: self._arena + o for name, o in st["off"].items()}
         b = B.ReconBatch()
         b.dst = C.pointer(self.dst)
         for i in range(7):
             b.refs[i] = C.pointer(self.refs[i]) if i < n_refs else None
         b.bw4, b.bh4 = hf.bw4, hf.bh4
-        d = self._dev
         b.cf, b.masks, b.pal, b.pal_idx = d["cf"], d["masks"], d["pal"], d["pal_idx"]
         b.mc_put, b.mc_put_tiles, b.n_mc_put_tiles = d["mc_put"], d["mc_put_tiles"], hf.n_mc_put_tiles
         b.mc_comp, b.mc_comp_tiles = d["mc_comp"], d["mc_comp_tiles"]
@@ -265,37 +236,32 @@ class DeviceFrame:
         b.itx = d["itx"]
         for i in range(19):
             b.itx_class_count[i] = hf.itx_class_count[i]
-        b.intra = d["intra_sorted"]
-        b.intra_level_start = self._level_start
-        b.n_levels = hf.n_levels
-        self._sync = L.dav1d_cuda_malloc(4 * (hf.n_intra + 1))
-        self._class_start = (C.c_int32 * (3 * hf.n_levels + 1))(*hf.class_start.tolist())
-        self._itx_task_start = (C.c_int32 * (2 * hf.n_levels + 1))(*hf.intra_itx_task_start.tolist())
         if tasks:
             b.itx_tasks = d["itx_tasks"]
             b.n_itx_tasks[0], b.n_itx_tasks[1] = hf.n_itx_tasks
-        b.intra_host = hf.intra_sorted.ctypes.data if hf.intra_sorted.nbytes else None
-        if hf.intra_sorted.nbytes and hf.dep_start.nbytes:
-            b.intra_dep_start_host = hf.dep_start.ctypes.data
-            b.intra_deps_host = hf.deps.ctypes.data if hf.deps.nbytes else hf.dep_start.ctypes.data
-        if dataflow:
-            b.intra_dep_start, b.intra_deps, b.intra_sync = d["dep_start"], d["deps"], self._sync
-        elif classes:
-            b.intra_class_start = self._class_start
-        elif tasks == 1:
-            b.intra_itx, b.intra_itx_tasks = d["intra_itx"], d["intra_itx_tasks"]
-            b.intra_itx_task_start = self._itx_task_start
-        elif tasks:
-            self._task_start = (C.c_int32 * (2 * hf.n_levels + 1))(*hf.intra_task_start.tolist())
-            b.intra_tasks = d["intra_tasks"]
-            b.intra_task_start = self._task_start
-        self.batch = b
-        self.graph = None
+        b.intra, b.n_intra = d["intra"], hf.n_intra
+        b.intra_units, b.n_intra_units = d["intra_units"], st["n_units"]
+        b.intra_cellmap = self._cellmap
+        return b
+
+    def use(self, k):
+        """Make descriptor set k the frame to reconstruct next (its arrays still have to be shipped)."""
+        st = self._sets[k % len(self._sets)]
+        self._cur = st
+        self.hf, self._host, self._off = st["hf"], st["host"], st["off"]
+        self._dev = {name: self._arena + o for name, o in st["off"].items()}
+        self.arena_bytes, self.batch = st["bytes"], st["batch"]
 
     def upload_descriptors(self):
         for name, arr in self._host.items():
             if arr.nbytes:
                 self.L.dav1d_cuda_upload(self.ctx, self._dev[name], arr.ctypes.data, arr.nbytes)
+
+    def cellmap_is_clear(self):
+        buf = np.ones(self._cellmap_bytes, dtype=np.uint8)
+        self.L.dav1d_cuda_download(self.ctx, buf.ctypes.data, self._cellmap, self._cellmap_bytes)
+        self.L.dav1d_cuda_synchronize(self.ctx)
+        return not buf.any()
 
     def upload_picture(self, pic, planes):
         for pl, a in enumerate(planes):
@@ -314,14 +280,16 @@ class DeviceFrame:
 
     # ---- end-to-end path: host buffers in pinned memory
     def alloc_pinned(self):
-        if getattr(self, "_pinned", None):
+        if self._pinned:
             return
         L = self.L
-        # pinned mirror of the descriptor arena
-        self._pinned = L.dav1d_cuda_host_alloc(self.arena_bytes)
-        for name, arr in self._host.items():
-            if arr.nbytes:
-                C.memmove(self._pinned + self._off[name], arr.ctypes.data, arr.nbytes)
+        # pinned mirrors of the descriptor sets
+        for st in self._sets:
+            st["pinned"] = L.dav1d_cuda_host_alloc(st["bytes"])
+            for name, arr in st["host"].items():
+                if arr.nbytes:
+                    C.memmove(st["pinned"] + st["off"][name], arr.ctypes.data, arr.nbytes)
+        self._pinned = True
         # pinned host frame with the device picture's layout (plane offsets and strides): the
         # reconstructed frame comes back with ONE device->host copy
         hf = self.hf
@@ -333,7 +301,7 @@ class DeviceFrame:
         self._pinned_out = L.dav1d_cuda_host_alloc(self.pinned_out_bytes)
 
     def upload_descriptors_pinned(self):
-        self.L.dav1d_cuda_upload(self.ctx, self._arena, self._pinned, self.arena_bytes)
+        self.L.dav1d_cuda_upload(self.ctx, self._arena, self._cur["pinned"], self.arena_bytes)
 
     def download_pinned(self):
         self.L.dav1d_cuda_download(self.ctx, self._pinned_out, self.dst.p[0].data, self.pinned_out_bytes)
@@ -391,10 +359,11 @@ class DeviceFrame:
         if self._arena:
             L.dav1d_cuda_free(self._arena)
             self._arena = None
-        L.dav1d_cuda_free(self._sync)
+        L.dav1d_cuda_free(self._cellmap)
         self._dev = {}
-        if getattr(self, "_pinned", None):
-            L.dav1d_cuda_host_free(self._pinned)
+        if self._pinned:
+            for st in self._sets:
+                L.dav1d_cuda_host_free(st["pinned"])
             L.dav1d_cuda_host_free(self._pinned_out)
         self._pinned, self._pinned_out = None, None
         for pic in [self.dst] + self.refs:
@@ -436,24 +405,31 @@ def time_classes(dfs, reps=3, flush_mb=0):
 
 
 class MultiFrame:
-    """Frames of several independent streams submitted as one graph
-    (dav1d_cuda_recon_graph_build_multi): level-synchronous intra launches shared by all."""
+    """Frames of several independent streams submitted together (dav1d_cuda_recon_group_submit):
+    one intra executor launch for the whole group.  graph=True captures the launches once
+    (dav1d_cuda_recon_graph_build_multi) and replays them."""
 
-    def __init__(self, ctx, dfs, phase_mask=31):
+    def __init__(self, ctx, dfs, phase_mask=31, graph=False):
         self.L = B.lib()
         self.ctx = ctx
         self.dfs = dfs
-        arr = (C.POINTER(B.ReconBatch) * len(dfs))(*[C.pointer(df.batch) for df in dfs])
-        g = C.c_void_p()
-        n = self.L.dav1d_cuda_recon_graph_build_multi_phases(ctx, arr, len(dfs), phase_mask, C.byref(g))
-        if n < 0:
-            raise RuntimeError(f"dav1d_cuda_recon_graph_build_multi: {n}")
-        self.graph, self.graph_nodes = g, n
+        self.phase_mask = phase_mask
+        self.arr = (C.POINTER(B.ReconBatch) * len(dfs))(*[C.pointer(df.batch) for df in dfs])
+        self.graph = None
+        if graph:
+            g = C.c_void_p()
+            n = self.L.dav1d_cuda_recon_graph_build_multi_phases(ctx, self.arr, len(dfs), phase_mask, C.byref(g))
+            if n < 0:
+                raise RuntimeError(f"dav1d_cuda_recon_graph_build_multi: {n}")
+            self.graph, self.graph_nodes = g, n
 
     def launch(self):
-        r = self.L.dav1d_cuda_recon_graph_launch(self.ctx, self.graph)
+        if self.graph:
+            r = self.L.dav1d_cuda_recon_graph_launch(self.ctx, self.graph)
+        else:
+            r = self.L.dav1d_cuda_recon_group_submit_phases(self.ctx, self.arr, len(self.dfs), self.phase_mask)
         if r:
-            raise RuntimeError(f"dav1d_cuda_recon_graph_launch: {r}")
+            raise RuntimeError(f"group submission failed: {r}")
 
     def close(self):
         if self.graph:

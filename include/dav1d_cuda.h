@@ -210,7 +210,7 @@ typedef struct Dav1dCudaMcDesc {   /* 40 bytes */
                               PREP: int16 offset into the tmp pool */
 } Dav1dCudaMcDesc;
 
-/* -- intra-class operations, one descriptor per transform block in decode
+/* -- intra-class operations, one descriptor per transform block in DECODE
  * order (recon_tmpl.c:1259-1300 luma, :1372-1417 CfL, :1226-1243 palette,
  * :1503-1576 chroma), optionally fused with the block's residual.  The fields
  * are the arguments of dav1d_prepare_intra_edges + intra_pred[m] /
@@ -237,6 +237,9 @@ enum Dav1dCudaIntraKind {
     DAV1D_CUDA_INTRA_NONE   = 255   /* residual only (e.g. tx blocks of a palette or inter-intra block) */
 };
 
+#define DAV1D_CUDA_INTRA_BLK(dx4, dy4, lw, lh) \
+    ((uint32_t)(dx4) | (uint32_t)(dy4) << 4 | (uint32_t)(lw) << 8 | (uint32_t)(lh) << 12 | 1u << 16)
+
 typedef struct Dav1dCudaIntraDesc {  /* 40 bytes */
     uint16_t x4, y4;       /* position in 4-px units of THIS plane */
     uint16_t tile_x4_start;/* have_left = x4 > tile_x4_start */
@@ -252,7 +255,11 @@ typedef struct Dav1dCudaIntraDesc {  /* 40 bytes */
     uint8_t  tx, txtp;     /* residual transform, if any */
     uint32_t coef_off;     /* into the cf stream (PAL: into the index pool) */
     uint32_t aux;          /* CFL: w_pad | h_pad << 8 (4-px units); PAL: palette offset */
-    uint32_t level;        /* dependency level >= 1, filled by dav1d_cuda_intra_schedule() */
+    uint32_t blk;          /* optional hint, 0 = none: DAV1D_CUDA_INTRA_BLK(dx4, dy4, log2 bw4, log2 bh4) - the
+                            * operation lies dx4, dy4 cells right of / below the origin of a bw4 x bh4 cell rectangle
+                            * of this plane (its coding block) whose operations ALL belong to the operation's unit:
+                            * neighbour pixels inside the rectangle are then known to be final without a look at the
+                            * cell map (they were written by the same warp) */
     uint8_t  cw4, ch4;     /* packed residual coefficients, see Dav1dCudaItxDesc (0, 0 = dense) */
     uint16_t pad;
 } Dav1dCudaIntraDesc;
@@ -274,6 +281,9 @@ typedef struct Dav1dCudaContext Dav1dCudaContext;
  * decoder instance / stream of frames; contexts run concurrently). */
 DAV1D_CUDA_API int  dav1d_cuda_open(Dav1dCudaContext **out, int device, void *stream);
 DAV1D_CUDA_API void dav1d_cuda_close(Dav1dCudaContext *c);
+/* Waits for the context's stream; also reads the context's device status word: a dependency wait
+ * of the intra executor that timed out (the frame is then incomplete) is reported as -EIO (-5)
+ * through the return value and dav1d_cuda_last_error(). */
 DAV1D_CUDA_API int  dav1d_cuda_synchronize(Dav1dCudaContext *c);
 
 /* HBM picture allocation with the reference's geometry (src/picture.c:46-84:
@@ -341,63 +351,28 @@ DAV1D_CUDA_API int dav1d_cuda_warp_batch(Dav1dCudaContext *c, const Dav1dCudaPic
                                          const Dav1dCudaPicture *const refs[7],
                                          const Dav1dCudaWarpDesc *descs, int n);
 
-/* Host-side scheduling of intra-class descriptors (the recorder's job).
- * `descs[0..n)` are in decode order; every pixel they read from the current
- * frame was produced either by an inter block (level 0: final after the MC and
- * inter-residual launches) or by an earlier descriptor.  Writes descs[i].level
- * (>= 1) and returns the number of levels; `order[0..n)` receives the
- * permutation that sorts the descriptors by level (stable), and
- * `level_start[0..n_levels]` the first sorted index of each level
- * (level_start must have room for max_levels + 1 entries).  Returns < 0 if
- * more than max_levels levels are needed. */
-DAV1D_CUDA_API int dav1d_cuda_intra_schedule(Dav1dCudaIntraDesc *descs, int n, int bw4, int bh4,
-                                             int ss_hor, int ss_ver, int32_t *order,
-                                             int32_t *level_start, int max_levels);
-
-/* Same, and additionally the per-operation dependency lists for the dataflow
- * kernel: for the operation at sorted index s, deps[dep_start[s] ..
- * dep_start[s+1]) are the SORTED indices of the operations whose pixels it
- * reads (always < s).  dep_start needs n + 1 entries, deps max_deps. */
-DAV1D_CUDA_API int dav1d_cuda_intra_schedule_deps(Dav1dCudaIntraDesc *descs, int n, int bw4, int bh4,
-                                                  int ss_hor, int ss_ver, int32_t *order,
-                                                  int32_t *level_start, int max_levels,
-                                                  int32_t *dep_start, int32_t *deps, int max_deps,
-                                                  int32_t *class_start);
-/* class_start (optional, 3 * max_levels + 1 entries): within a level the
- * operations are grouped by size class (<= 8x8, <= 16x16, larger); the
- * (level, class) run k = 3 * level + class spans sorted indices
- * [class_start[k], class_start[k + 1]). */
-
-/* Host: task codes (first_index << 8 | tx << 3 | count - 1, tx = 31: no residual) over the
- * level-sorted descriptors for the fused task kernel; task_start[2*l] / [2*l+1] = first task of
- * level l for operations up to 16x16 / larger, task_start[2*n_levels] = total.  `tasks` needs room
- * for one entry per descriptor.  Returns the number of tasks. */
-DAV1D_CUDA_API int dav1d_cuda_intra_tasks(const Dav1dCudaIntraDesc *sorted_descs, const int32_t *level_start,
-                                          int n_levels, uint32_t *tasks, int32_t *task_start,
-                                          int32_t *n_tasks);
-
-/* Host: residuals of level-sorted intra descriptors as transform descriptors grouped by
- * (level, size): itx[0 .. returned count), task codes per level in `tasks`, and
- * task_start[2*l], task_start[2*l+1] = first small / first big task of level l
- * (task_start[2*n_levels] = total).  `itx` and `tasks` need room for n entries. */
-DAV1D_CUDA_API int dav1d_cuda_intra_residual_tasks(const Dav1dCudaIntraDesc *sorted_descs,
-                                                   const int32_t *level_start, int n_levels,
-                                                   Dav1dCudaItxDesc *itx, uint32_t *tasks,
-                                                   int32_t *task_start, int32_t *n_tasks);
-
-/* One launch per dependency level over level-sorted descriptors (device).
- * `level_start` is a HOST array of n_levels + 1 sorted offsets.  `pal` /
- * `pal_idx` are the palette pixel pool and the packed index pool (device). */
-DAV1D_CUDA_API int dav1d_cuda_intra_batch(Dav1dCudaContext *c, const Dav1dCudaPicture *dst,
-                                          int bw4, int bh4, void *cf,
-                                          const Dav1dCudaIntraDesc *descs,
-                                          const int32_t *level_start, int n_levels,
-                                          const void *pal, const uint8_t *pal_idx);
+/* Intra-class operations are executed in ONE persistent launch per group of frames
+ * (csrc/recon2.cu): the recorder hands over the descriptors in decode order and the offsets of
+ * the "units" (superblocks) they belong to; warps claim units in decode order, run a unit's
+ * operations one after the other and, before an operation reads pixels outside its own unit,
+ * wait on a per-4x4-cell completion map in device memory.  Nothing is scheduled on the host.
+ *
+ * Cell map: dav1d_cuda_intra_cellmap_bytes() bytes of device memory per stream, zeroed ONCE by
+ * the caller (every frame leaves it at zero again). */
+DAV1D_CUDA_API size_t dav1d_cuda_intra_cellmap_bytes(int bw4, int bh4, int ss_hor, int ss_ver);
+/* Host helper for recorders that do not track the units themselves: cuts `descs[0..n)` (decode
+ * order) wherever the luma superblock changes (unit_log2 = 4: 64x64, 5: 128x128) and writes the
+ * units as (first, count) pairs to units[0 .. 2 * returned count).  wave_gradient > 0 orders the
+ * units as a wavefront (stable sort by superblock column + wave_gradient * superblock row, bw4 =
+ * frame width in 4-px units); 2 is right for frames without intrabc, 0 keeps decode order.
+ * < 0: max_units too small. */
+DAV1D_CUDA_API int dav1d_cuda_intra_units(const Dav1dCudaIntraDesc *descs, int n, int ss_hor, int ss_ver,
+                                          int unit_log2, int wave_gradient, uint32_t *units, int max_units);
 
 /* A whole frame's reconstruction as device-resident batches:
  *   phase A  motion compensation (put, fused compound in two waves, warp)
  *   phase B  inter residuals (itxfm_add per size class)
- *   phase C  intra-class operations, one launch per dependency level.
+ *   phase C  intra-class operations: cell-map set-up + one persistent executor launch.
  * Replaces pass 2 (DAV1D_TASK_TYPE_TILE_RECONSTRUCTION, thread_task.c:757-761)
  * for one frame.  Asynchronous on the context's stream. */
 typedef struct Dav1dCudaReconBatch {
@@ -421,63 +396,47 @@ typedef struct Dav1dCudaReconBatch {
     /* optional (device): task codes from dav1d_cuda_itx_tasks() over `itx`; when set phase B is two
      * launches (small / large sizes) instead of one per size */
     const uint32_t *itx_tasks;        int32_t n_itx_tasks[2];
-    const Dav1dCudaIntraDesc *intra;  const int32_t *intra_level_start; int32_t n_levels;
-    /* optional (device): dependency lists from dav1d_cuda_intra_schedule_deps() and a scratch of
-     * (n_intra + 1) uint32.  When all three are set phase C is ONE persistent dataflow launch
-     * instead of one launch per level. */
-    const int32_t *intra_dep_start; const int32_t *intra_deps; void *intra_sync;
-    /* optional (host): size-class runs from dav1d_cuda_intra_schedule_deps(); when set (and the
-     * dataflow fields are not) every level is launched as up to three size-specialised kernels. */
-    const int32_t *intra_class_start;
-    /* optional (host): copy of the sorted `intra` array; needed by
-     * dav1d_cuda_recon_graph_build_multi() to merge the frames' levels by code path. */
-    const Dav1dCudaIntraDesc *intra_host;
-    /* optional (experimental executor): task codes over the level-sorted `intra` array from
-     * dav1d_cuda_intra_tasks(): per level one fused launch in which a warp predicts up to 32/G
-     * same-size operations and then runs their residuals in groups of G lanes. */
-    const uint32_t *intra_tasks;              /* device */
-    const int32_t *intra_task_start;          /* host: 2 * n_levels + 1 offsets (small, big per level) */
-    /* optional (preferred): residuals of the intra-class operations as transform descriptors +
-     * tasks per level (dav1d_cuda_intra_residual_tasks()).  When set, the level kernels only
-     * predict and every level is followed by the task-based transform launches (lane groups, one
-     * size per warp); levels with few operations run as one fused launch. */
-    const Dav1dCudaItxDesc *intra_itx;        /* device */
-    const uint32_t *intra_itx_tasks;          /* device */
-    const int32_t *intra_itx_task_start;      /* host: 2 * n_levels + 1 offsets (small, big per level) */
-    /* optional (host): the dependency lists of dav1d_cuda_intra_schedule_deps() (dep_start: n_intra + 1,
-     * deps: indices into the sorted `intra` array).  With them dav1d_cuda_recon_graph_build_multi() runs
-     * the TAIL of the wavefront - the last levels, each with few operations - as ONE dataflow launch for
-     * the whole group (completion flags per operation) instead of one launch per level. */
-    const int32_t *intra_dep_start_host;
-    const int32_t *intra_deps_host;
+    /* intra-class operations in decode order (device) and the units they are executed in:
+     * intra_units (device) holds n_intra_units pairs (first operation, count).  A unit is a run of
+     * operations one warp executes in order - normally the operations of one coding block.  Units
+     * are claimed in ARRAY order: the operations of a unit may only read pixels of their own unit
+     * or of units that precede it in the array.  Decode order always qualifies; a wavefront order
+     * (superblock column + 2 * superblock row, dav1d_cuda_intra_units()) keeps the units in flight
+     * independent of each other.  Smaller units expose more parallelism, larger ones skip more
+     * look-ups of the cell map (Dav1dCudaIntraDesc.blk).
+     * intra_cellmap: see dav1d_cuda_intra_cellmap_bytes(). */
+    const Dav1dCudaIntraDesc *intra;  int32_t n_intra;
+    const uint32_t *intra_units;      int32_t n_intra_units;
+    uint8_t *intra_cellmap;
 } Dav1dCudaReconBatch;
 
+enum { DAV1D_CUDA_MAX_GROUP = 16 };   /* frames per group submission */
+
 DAV1D_CUDA_API int dav1d_cuda_recon_submit(Dav1dCudaContext *c, const Dav1dCudaReconBatch *b);
-/* Only the launch classes selected by phase_mask (bit0 put, bit1 compound, bit2 warp, bit3 inter
- * residual, bit4 intra), exactly as dav1d_cuda_recon_submit() would launch them - used to time
- * one class with CUDA events. */
+/* Only the launch classes selected by phase_mask (bit0 put + OBMC, bit1 compound, bit2 warp, bit3
+ * inter residual, bit4 intra), exactly as dav1d_cuda_recon_submit() would launch them - used to
+ * time one class with CUDA events. */
 DAV1D_CUDA_API int dav1d_cuda_recon_submit_phases(Dav1dCudaContext *c, const Dav1dCudaReconBatch *b,
                                                   int phase_mask);
-/* Same, but the launches are captured into a CUDA graph once and replayed:
- * dav1d_cuda_recon_graph_build() records `b`, dav1d_cuda_recon_graph_launch()
- * replays it on the context's stream (the device buffers `b` points to may be
- * rewritten between launches, their addresses and counts may not). */
+/* Frames of `n` (<= DAV1D_CUDA_MAX_GROUP) independent streams, same pixel type, in one submission:
+ * MC / residual launches per frame on parallel branches and ONE intra executor launch for the
+ * whole group (server-side batching of independent decoder instances).  No frame of the group may
+ * use another member's destination as a reference (-EINVAL).  Nothing is prepared on the host:
+ * the call only launches; a fresh set of descriptors costs the same as a repeated one. */
+DAV1D_CUDA_API int dav1d_cuda_recon_group_submit(Dav1dCudaContext *c,
+                                                 const Dav1dCudaReconBatch *const *batches, int n);
+DAV1D_CUDA_API int dav1d_cuda_recon_group_submit_phases(Dav1dCudaContext *c,
+                                                        const Dav1dCudaReconBatch *const *batches, int n,
+                                                        int phase_mask);
+/* The same launches captured into a CUDA graph once and replayed: _graph_build*() record,
+ * dav1d_cuda_recon_graph_launch() replays on the context's stream (the device buffers the batches
+ * point to may be rewritten between launches, their addresses and counts may not). */
 typedef struct Dav1dCudaReconGraph Dav1dCudaReconGraph;
 DAV1D_CUDA_API int dav1d_cuda_recon_graph_build(Dav1dCudaContext *c, const Dav1dCudaReconBatch *b,
                                                 Dav1dCudaReconGraph **out);
-/* Frames of `n` independent streams (one batch each, same pixel type) as ONE
- * graph: MC / residual launches per frame on parallel branches, and per
- * dependency level ONE set of intra launches covering that level of every
- * frame (prediction, then the residual tasks of all frames merged and ordered
- * by transform size and type; levels with few operations: one fused launch),
- * so the level-to-level latency is shared by all streams (server-side
- * batching of independent decoder instances).  Frames that carry intra_itx /
- * intra_itx_tasks take the split path, others the fused one. */
 DAV1D_CUDA_API int dav1d_cuda_recon_graph_build_multi(Dav1dCudaContext *c,
                                                       const Dav1dCudaReconBatch *const *batches, int n,
                                                       Dav1dCudaReconGraph **out);
-/* Same with a subset of the launch classes (bits as in dav1d_cuda_recon_submit_phases):
- * used by bench.py to time one class in the batched regime. */
 DAV1D_CUDA_API int dav1d_cuda_recon_graph_build_multi_phases(Dav1dCudaContext *c,
                                                              const Dav1dCudaReconBatch *const *batches, int n,
                                                              int phase_mask, Dav1dCudaReconGraph **out);

@@ -1,5 +1,5 @@
 """Frame-level parity: the batched CUDA reconstruction (MC -> inter residual ->
-level-scheduled intra) against the sequential oracle that replays the same
+intra executor) against the sequential oracle that replays the same
 descriptors in decode order through the reference's C DSP tables."""
 import ctypes as C
 import hashlib
@@ -75,49 +75,50 @@ def test_generator_and_oracle_match_golden(ref):
         assert md5_planes(out) == gold[name], name
 
 
-def test_schedule_levels_are_consistent():
-    """CPU: every intra-class descriptor is scheduled after the ones whose pixels it reads."""
+def test_units_cover_the_operations_in_decode_order():
+    """CPU: the recorder's unit table (one unit per coding block) partitions the intra-class
+    operations, the block hint of every operation names a rectangle that holds it and only
+    operations of its own unit, and dav1d_cuda_intra_units() (the helper for recorders that do
+    not track units) cuts the array into superblock runs."""
     hf = F.HostFrame(256, 192, 0x3ff, 11, p_intra=0.7, p_palette=0.1, p_cfl=0.5)
-    nl = hf.schedule()
-    assert nl >= 1
     n = hf.n_intra
-    rec = np.frombuffer(hf.intra_sorted, dtype=np.uint8).reshape(n, 40)
-    lv = rec[:, 32:36].copy().view(np.uint32).reshape(-1)
-    assert (np.diff(lv.astype(np.int64)) >= 0).all()
-    ls = hf.level_start
-    assert ls[0] == 0 and ls[-1] == n
-    for l in range(nl):
-        assert (lv[ls[l]:ls[l + 1]] == l + 1).all()
-    # dependency lists: every dependency precedes its consumer (sorted index and level)
-    dep_start = hf.dep_start.view(np.int32)
-    deps = hf.deps.view(np.int32)
-    assert dep_start[0] == 0 and len(dep_start) == n + 1
-    for s_ in range(n):
-        for k in range(dep_start[s_], dep_start[s_ + 1]):
-            assert deps[k] < s_ and lv[deps[k]] < lv[s_]
-    # a directional / smooth / paeth block right of an intra block it reads must come later: spot-check
-    # with the conservative superset rule on modes that need left AND top (smooth = 9..11)
+    up = hf.intra_units.view(np.uint32).reshape(-1, 2).astype(int)
+    assert len(up) == hf.n_intra_units and (up[:, 1] > 0).all()
+    # the units partition the operations (claim order = wavefront order, so sort by first)
+    srt = up[np.argsort(up[:, 0])]
+    assert srt[0, 0] == 0 and (srt[:-1, 0] + srt[:-1, 1] == srt[1:, 0]).all() and srt[-1, 0] + srt[-1, 1] == n
+    rec = np.frombuffer(hf.intra, dtype=np.uint8).reshape(n, 40)
     x4 = rec[:, 0:2].copy().view(np.uint16).reshape(-1).astype(int)
     y4 = rec[:, 2:4].copy().view(np.uint16).reshape(-1).astype(int)
-    plane, tw4, th4, mode = rec[:, 12].astype(int), rec[:, 13].astype(int), rec[:, 14].astype(int), rec[:, 15].astype(int)
-    pos = {}
+    plane, tw4, th4 = rec[:, 12].astype(int), rec[:, 13].astype(int), rec[:, 14].astype(int)
+    blk = rec[:, 32:36].copy().view(np.uint32).reshape(-1).astype(int)
+    unit_of = np.zeros(n, dtype=int)
+    for u, (first, cnt) in enumerate(up):
+        unit_of[first:first + cnt] = u
+    owner = {}
     for i in range(n):
-        if mode[i] == 15:
-            continue
-        for yy in range(y4[i], y4[i] + th4[i]):
-            for xx in range(x4[i], x4[i] + tw4[i]):
-                pos[(plane[i], xx, yy)] = i
-    for i in range(n):
-        if 9 <= mode[i] <= 11:
-            for key in ((plane[i], x4[i] - 1, y4[i]), (plane[i], x4[i], y4[i] - 1)):
-                j = pos.get(key)
-                if j is not None and j != i:
-                    assert lv[j] < lv[i], (i, j)
+        assert blk[i] >> 16 == 1
+        ox, oy = x4[i] - (blk[i] & 15), y4[i] - ((blk[i] >> 4) & 15)
+        bw, bh = 1 << ((blk[i] >> 8) & 15), 1 << ((blk[i] >> 12) & 15)
+        assert ox >= 0 and oy >= 0 and x4[i] + tw4[i] <= ox + max(bw, tw4[i]) and y4[i] + th4[i] <= oy + max(bh, th4[i])
+        for yy in range(oy, oy + bh):
+            for xx in range(ox, ox + bw):
+                assert owner.setdefault((plane[i], xx, yy), unit_of[i]) == unit_of[i], i
+    # wave order: a unit's superblock wave never decreases along the array
+    sbw = [(x4[f] << (1 if plane[f] else 0) >> 4) + 2 * (y4[f] << (1 if plane[f] else 0) >> 4) for f in up[:, 0]]
+    assert (np.diff(sbw) >= 0).all()
+    for grad in (0, 2):
+        out = np.zeros(2 * n, dtype=np.uint32)
+        nu = pkg.lib().dav1d_cuda_intra_units(hf.intra.ctypes.data, n, 1, 1, 4, grad, out.ctypes.data, n)
+        o = out[:2 * nu].reshape(-1, 2).astype(int)
+        assert 0 < nu <= (256 // 64) * (192 // 64) and o[:, 1].sum() == n
+        if grad == 0:
+            assert o[0, 0] == 0 and (o[:-1, 0] + o[:-1, 1] == o[1:, 0]).all()
 
 
-def run_gpu(hf, refs, init, use_graph=False, dataflow=False, classes=False, tasks=True):
+def run_gpu(hf, refs, init, use_graph=False, tasks=True, units=True):
     ctx = F.open_context(0)
-    df = F.DeviceFrame(ctx, hf, n_refs=len(refs), dataflow=dataflow, classes=classes, tasks=tasks)
+    df = F.DeviceFrame(ctx, hf, n_refs=len(refs), tasks=tasks, units=units)
     try:
         df.upload_descriptors()
         for r, planes in enumerate(refs):
@@ -130,6 +131,7 @@ def run_gpu(hf, refs, init, use_graph=False, dataflow=False, classes=False, task
             df.submit()
         out = df.download_picture()
         pkg.check_error()
+        assert df.cellmap_is_clear(), "the cell map must be back at zero after a frame"
     finally:
         df.close()
         pkg.lib().dav1d_cuda_close(ctx)
@@ -142,15 +144,13 @@ def test_frame_parity_small(ref, name):
     w, h, bd, seed, kw = CASES[name]
     hf = F.HostFrame(w, h, bd, seed, **kw)
     refs, init, want = oracle_planes(ref, hf, seed)
-    # the executors of the intra phase: prediction-only levels + transform tasks (default), fused
-    # task kernel, fused one-warp-per-block level kernel, size-class level kernels, persistent
-    # dataflow kernel
-    for dataflow, classes, tasks in ((False, False, 1), (False, False, 2), (False, False, 0), (False, True, 0),
-                                     (True, False, 0)):
-        got = run_gpu(hf, refs, init, use_graph=(seed % 2 == 0), dataflow=dataflow, classes=classes, tasks=tasks)
+    # explicit transform tasks + block units with hints (the benchmark's configuration); implicit
+    # per-size transform runs; superblock units without hints (every dependency through the cell map)
+    for tasks, units in ((True, True), (False, True), (True, False)):
+        got = run_gpu(hf, refs, init, use_graph=(seed % 2 == 0), tasks=tasks, units=units)
         for pl, (a, b) in enumerate(zip(want, got)):
             bad = np.argwhere(a != b)
-            assert bad.size == 0, (f"{name} dataflow={dataflow} classes={classes} tasks={tasks}: plane {pl} first "
+            assert bad.size == 0, (f"{name} tasks={tasks} units={units}: plane {pl} first "
                                    f"mismatch at (y,x)={bad[0]} ref={a[tuple(bad[0])]} got={b[tuple(bad[0])]} "
                                    f"n={len(bad)}")
 
@@ -181,19 +181,16 @@ def test_config4_full_4k(ref, bd):
     """BASELINE config 4 (+ the 12-bit spot check of config 5): full synthetic 4K reconstruction."""
     hf = F.HostFrame(3840, 2160, bd, 400 + bd)
     refs, init, want = oracle_planes(ref, hf, 400)
-    for rep in range(3):      # the dataflow kernel's schedule is timing dependent: repeat
-        got = run_gpu(hf, refs, init, use_graph=True)
+    for rep in range(3):      # the executor's schedule is timing dependent: repeat
+        got = run_gpu(hf, refs, init, use_graph=(rep == 1))
         for pl, (a, b) in enumerate(zip(want, got)):
             bad = np.argwhere(a != b)
             assert bad.size == 0, f"rep {rep} plane {pl}: {len(bad)} mismatches, first at {bad[0]}"
 
 
 MULTI_SPECS = {
-    # small frames: every level is below the fusing threshold (one fused launch per level)
     "small": [(256, 192, 0x3ff, 21, {}), (256, 192, 0x3ff, 22, {"p_intra": 0.7}), (256, 192, 0xfff, 23, {}),
               (256, 192, 0x3ff, 24, {"p_intra": 0.0})],
-    # 1080p frames: the first levels take the split path (prediction launch + residual tasks
-    # merged over the frames), the tail the fused one
     "1080p": [(1920, 1080, 0x3ff, 31, {"p_intra": 0.6}), (1920, 1080, 0x3ff, 32, {}),
               (1280, 720, 0x3ff, 33, {"p_intra": 1.0})],
     "8bit": [(640, 368, 0xff, 41, {"p_intra": 0.8, "p_ibc": 0.3}), (640, 368, 0xff, 42, {"p_obmc": 0.5, "p_ii": 0.3})],
@@ -202,29 +199,32 @@ MULTI_SPECS = {
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("case", sorted(MULTI_SPECS))
-def test_multi_frame_batched_graph(ref, case):
-    """Several independent streams in one graph (dav1d_cuda_recon_graph_build_multi): every frame
-    must match its own sequential oracle."""
+def test_multi_frame_group(ref, case):
+    """Several independent streams in one submission (dav1d_cuda_recon_group_submit, then the same
+    launches replayed from a captured graph): every frame must match its own sequential oracle."""
     specs = MULTI_SPECS[case]
     hfs = [F.HostFrame(w, h, bd, seed, **kw) for (w, h, bd, seed, kw) in specs]
     want = [oracle_planes(ref, hf, sp[3]) for hf, sp in zip(hfs, specs)]
     ctx = F.open_context(0)
     dfs = []
     for hf, (refs, init, _) in zip(hfs, want):
-        df = F.DeviceFrame(ctx, hf, dataflow=False)
+        df = F.DeviceFrame(ctx, hf)
         df.upload_descriptors()
         for r, planes in enumerate(refs):
             df.upload_picture(df.refs[r], planes)
         df.upload_picture(df.dst, init)
         dfs.append(df)
-    mf = F.MultiFrame(ctx, dfs)
-    mf.launch()
-    for i, (df, (_, _, exp)) in enumerate(zip(dfs, want)):
-        got = df.download_picture()
-        for pl, (a, b) in enumerate(zip(exp, got)):
-            assert np.array_equal(a, b), f"frame {i} plane {pl}"
-    pkg.check_error()
-    mf.close()
+    for graph in (False, True):
+        for df, (_, init, _) in zip(dfs, want):
+            df.upload_picture(df.dst, init)
+        mf = F.MultiFrame(ctx, dfs, graph=graph)
+        mf.launch()
+        for i, (df, (_, _, exp)) in enumerate(zip(dfs, want)):
+            got = df.download_picture()
+            for pl, (a, b) in enumerate(zip(exp, got)):
+                assert np.array_equal(a, b), f"graph={graph} frame {i} plane {pl}"
+        pkg.check_error()
+        mf.close()
     for df in dfs:
         df.close()
     pkg.lib().dav1d_cuda_close(ctx)
@@ -280,7 +280,7 @@ def test_empty_batch_is_a_no_op(ref):
         b.n_itx_tasks[0] = b.n_itx_tasks[1] = 0
         for i in range(19):
             b.itx_class_count[i] = 0
-        b.n_levels = 0
+        b.n_intra = 0
         l0 = pkg.lib().dav1d_cuda_launch_count()
         df.submit()
         got = df.download_picture()

@@ -19,7 +19,6 @@ for a in sys.argv[2:]:
     kw[k] = float(v) if "." in v else int(v, 0)
 w, h, bd = kw.pop("w", w), kw.pop("h", h), kw.pop("bd", bd)
 hf = F.HostFrame(w, h, bd, 1000, **kw)
-hf.schedule()
 ctx = F.open_context(0)
 df = F.DeviceFrame(ctx, hf, tasks=int(os.environ.get('D1_TASKS', '1')))
 df.upload_descriptors()
@@ -30,5 +29,5 @@ for _ in range(reps):
     df.submit()
 pkg.lib().dav1d_cuda_synchronize(ctx)
 pkg.check_error()
-print("ok levels", hf.n_levels, "launches", pkg.lib().dav1d_cuda_launch_count())
+print("ok units", hf.n_intra_units, "launches", pkg.lib().dav1d_cuda_launch_count())
 df.close()

@@ -50,7 +50,7 @@ def run_one(seed):
         df.upload_picture(df.refs[k], planes)
     df.upload_picture(df.dst, init)
     if seed & 1:
-        mf = F.MultiFrame(ctx, [df])
+        mf = F.MultiFrame(ctx, [df], graph=bool(seed & 2))
         mf.launch()
     else:
         mf = None
@@ -63,7 +63,7 @@ def run_one(seed):
         mf.close()
     df.close()
     L.dav1d_cuda_close(ctx)
-    return ok, f"{seed} {w}x{h} {hex(bd)} {kw} levels {hf.n_levels}"
+    return ok, f"{seed} {w}x{h} {hex(bd)} {kw} units {hf.n_intra_units}"
 
 
 if __name__ == "__main__":
