@@ -115,7 +115,7 @@ class IntraDesc40(C.Structure):
                 ("th4", C.c_uint8), ("mode", C.c_uint8), ("angle_delta", C.c_int8),
                 ("edge_flags", C.c_uint8), ("flags", C.c_uint16), ("eob", C.c_int16),
                 ("tx", C.c_uint8), ("txtp", C.c_uint8), ("coef_off", C.c_uint32),
-                ("aux", C.c_uint32), ("blk", C.c_uint32), ("cw4", C.c_uint8), ("ch4", C.c_uint8),
+                ("aux", C.c_uint32), ("reserved", C.c_uint32), ("cw4", C.c_uint8), ("ch4", C.c_uint8),
                 ("pad", C.c_uint16)]
 
 
@@ -135,11 +135,13 @@ class ReconBatch(C.Structure):
                 ("itx", C.c_void_p), ("itx_class_count", C.c_int32 * N_RECT_TX_SIZES),
                 ("itx_tasks", C.c_void_p), ("n_itx_tasks", C.c_int32 * 2),
                 ("intra", C.c_void_p), ("n_intra", C.c_int32),
-                ("intra_units", C.c_void_p), ("n_intra_units", C.c_int32),
-                ("intra_cellmap", C.c_void_p)]
+                ("intra_cellmap", C.c_void_p),
+                ("intra_itx", C.c_void_p), ("intra_itx_class_count", C.c_int32 * N_RECT_TX_SIZES),
+                ("intra_itx_tasks", C.c_void_p), ("n_intra_itx_tasks", C.c_int32 * 2),
+                ("intra_res", C.POINTER(Picture))]
 
 
-MAX_GROUP = 16
+MAX_GROUP = 64
 
 
 def bind_frame_api(L):
@@ -151,7 +153,6 @@ def bind_frame_api(L):
                                         C.c_void_p, C.c_int]
     L.dav1d_cuda_intra_cellmap_bytes.restype = C.c_size_t
     L.dav1d_cuda_intra_cellmap_bytes.argtypes = [C.c_int] * 4
-    L.dav1d_cuda_intra_units.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
     L.dav1d_cuda_itx_tasks.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int32),
                                        C.POINTER(C.c_int32)]
     L.dav1d_cuda_itx_task_batch.argtypes = [C.c_void_p, C.POINTER(Picture), C.c_void_p, C.c_void_p, C.c_void_p,

@@ -116,15 +116,14 @@ int dav1d_cuda_open(Dav1dCudaContext **out, int device, void *stream) {
     int sms = 0;
     ok = ok && cuda_ok(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device), "cudaDeviceGetAttribute");
     c->num_sms = sms;
-    ok = ok && cuda_ok(cudaMalloc(&c->claim, (Dav1dCudaContext::N_CLAIM + 1) * sizeof(unsigned)), "cudaMalloc(claim)");
-    ok = ok && cuda_ok(cudaMemset(c->claim, 0, (Dav1dCudaContext::N_CLAIM + 1) * sizeof(unsigned)), "cudaMemset(claim)");
+    ok = ok && cuda_ok(cudaMalloc(&c->status, 64), "cudaMalloc(status)");
+    ok = ok && cuda_ok(cudaMemset(c->status, 0, 64), "cudaMemset(status)");
     if (!ok) {
-        if (c->claim) cudaFree(c->claim);
+        if (c->status) cudaFree(c->status);
         if (c->own_stream) cudaStreamDestroy(c->stream);
         delete c;
         return -5;
     }
-    c->status = c->claim + Dav1dCudaContext::N_CLAIM;
     mc_init_attrs();
     recon_init_attrs();
     cudaGetLastError();
@@ -144,7 +143,8 @@ void dav1d_cuda_close(Dav1dCudaContext *c) {
         cudaEventDestroy(c->ev_fork);
     }
     if (c->own_stream) cudaStreamDestroy(c->stream);
-    if (c->claim) cudaFree(c->claim);
+    if (c->status) cudaFree(c->status);
+    if (c->rounds_ws) cudaFree(c->rounds_ws);
     delete c;
 }
 
@@ -158,8 +158,8 @@ int dav1d_cuda_synchronize(Dav1dCudaContext *c) {
     D1_CHECK(cudaMemcpy(&st, c->status, sizeof(st), cudaMemcpyDeviceToHost));
     if (st) {
         cudaMemset(c->status, 0, sizeof(st));
-        set_error(-5, "intra executor", "a dependency wait timed out: the frame is incomplete "
-                                        "(descriptor order / unit table inconsistent, or a stalled GPU)");
+        set_error(-5, "intra executor", "intra-class operations wait for each other: the frame is incomplete "
+                                        "(inconsistent descriptors)");
         return -5;
     }
     return 0;

@@ -75,6 +75,7 @@ inline PicView pic_view(const Dav1dCudaPicture *pic) {
 // frame's level-sorted residual descriptors.
 struct ItxFrameRef {
     PicView pic;
+    PicView res;          // int16 residual planes (intra residual pre-pass)
     void *cf;
     const Dav1dCudaItxDesc *descs;
 };
@@ -109,10 +110,9 @@ struct Dav1dCudaContext {
     cudaStream_t aux[N_AUX];
     cudaEvent_t ev_fork, ev_join[N_AUX];
     bool aux_ready;
-    // intra executor: claim counters (one per submission in flight, used round robin) and the
-    // status word the kernels raise (bit0: a dependency wait timed out); device memory
-    static constexpr int N_CLAIM = 8;
-    unsigned *claim;
+    // intra executor: the status word the kernel raises (bit0: operations that wait for each
+    // other) and the workspace of its rounds (pending / ready lists, counters); device memory
     unsigned *status;
-    unsigned claim_next;
+    void *rounds_ws;
+    size_t rounds_ws_bytes;
 };

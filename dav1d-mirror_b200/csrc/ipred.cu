@@ -19,37 +19,46 @@ struct IpredArgs {
     const int16_t *ac; int alpha; // cfl_pred
 };
 
-template <typename pixel> __global__ void ipred_kernel(const IpredArgs a) {
+// one block by one warp: the same set-up + pixel loop the batched executor runs (recon2.cu)
+template <typename pixel, bool CFL> __global__ void ipred_kernel(const IpredArgs a) {
     __shared__ pixel s_edge[EDGE_BUF];
     __shared__ pixel s_scratch[IPRED_SCRATCH];
+    __shared__ pixel s_tile[32 * 32];
     const int lane = threadIdx.x;
+    const Grp g = grp_warp(lane);
     const pixel *ge = (const pixel *)a.edge;
     for (int i = -2 * a.h + lane; i <= 2 * a.w; i += 32) s_edge[EDGE_C + i] = ge[i];
     __syncwarp();
-    ipred_block<pixel>(a.mode, (pixel *)a.dst, a.dstride, s_edge + EDGE_C, a.w, a.h, a.angle, a.max_w, a.max_h,
-                       a.bdmax, s_scratch, lane);
-}
-
-template <typename pixel> __global__ void cfl_pred_kernel(const IpredArgs a) {
-    __shared__ pixel s_edge[EDGE_BUF];
-    const int lane = threadIdx.x;
-    const pixel *ge = (const pixel *)a.edge;
-    for (int i = -2 * a.h + lane; i <= 2 * a.w; i += 32) s_edge[EDGE_C + i] = ge[i];
-    __syncwarp();
-    cfl_pred_block<pixel>(a.mode, (pixel *)a.dst, a.dstride, s_edge + EDGE_C, a.w, a.h, a.ac, a.alpha, a.bdmax, lane);
+    PixParams<pixel> P;
+    if (CFL) P = cfl_setup<pixel>(g, a.mode, s_edge + EDGE_C, a.w, a.h, a.ac, a.alpha, a.bdmax);
+    else P = ipred_setup<pixel>(g, a.mode, a.angle, a.w, a.h, a.max_w, a.max_h, s_edge + EDGE_C, s_scratch, s_tile, a.bdmax);
+    pixel *dst = (pixel *)a.dst;
+    const int lw = 31 - __clz(a.w);
+    for (int i = lane; i < a.w * a.h; i += 32) {
+        const int y = i >> lw, x = i & (a.w - 1);
+        dst[y * a.dstride + x] = (pixel)ipred_pixel<pixel>(P, x, y, i, a.bdmax);
+    }
 }
 
 struct CflAcArgs { int16_t *ac; const void *y; int ystride, w_pad, h_pad, w, h, ss_hor, ss_ver; };
 template <typename pixel> __global__ void cfl_ac_kernel(const CflAcArgs a) {
-    cfl_ac_block<pixel>(a.ac, (const pixel *)a.y, a.ystride, a.w_pad, a.h_pad, a.w, a.h, a.ss_hor, a.ss_ver, threadIdx.x);
+    cfl_ac_block<pixel>(grp_warp(threadIdx.x), a.ac, (const pixel *)a.y, a.ystride, a.w_pad, a.h_pad, a.w, a.h,
+                        a.ss_hor, a.ss_ver);
 }
 
+// pal_pred (ipred_tmpl.c:717-730): two pixels per index byte
 struct PalArgs { void *dst; int dstride; const void *pal; const uint8_t *idx; int w, h; };
 template <typename pixel> __global__ void pal_pred_kernel(const PalArgs a) {
     __shared__ pixel s_pal[8];
     if (threadIdx.x < 8) s_pal[threadIdx.x] = ((const pixel *)a.pal)[threadIdx.x];
     __syncthreads();
-    pal_pred_block<pixel>((pixel *)a.dst, a.dstride, s_pal, a.idx, a.w, a.h, threadIdx.x, blockDim.x);
+    pixel *dst = (pixel *)a.dst;
+    const int lw = 31 - __clz(a.w);
+    for (int i = threadIdx.x; i < a.w * a.h; i += blockDim.x) {
+        const int y = i >> lw, x = i & (a.w - 1);
+        const int v = a.idx[i >> 1];
+        dst[y * a.dstride + x] = s_pal[(x & 1) ? v >> 4 : v & 7];
+    }
 }
 
 struct PrepArgs {
@@ -63,9 +72,9 @@ template <typename pixel> __global__ void prepare_edges_kernel(const PrepArgs a)
     __shared__ pixel s_edge[EDGE_BUF];
     const int lane = threadIdx.x;
     int angle = a.angle;
-    const int m = prepare_edges<pixel>(a.x, a.have_left, a.y, a.have_top, a.w, a.h, a.edge_flags,
+    const int m = prepare_edges<pixel>(grp_warp(lane), a.x, a.have_left, a.y, a.have_top, a.w, a.h, a.edge_flags,
                                        (const pixel *)a.dst, a.stride, (const pixel *)a.top_sb_edge, a.mode,
-                                       &angle, a.tw, a.th, a.filter_edge, s_edge + EDGE_C, a.bdmax, lane);
+                                       &angle, a.tw, a.th, a.filter_edge, s_edge + EDGE_C, a.bdmax);
     // copy out only what the reference defines for this mode is not knowable by the
     // caller; the per-call wrapper merges by the same `needs` rules on the host.
     pixel *out = (pixel *)a.edge_out;
@@ -97,8 +106,8 @@ static void ipred_single(const int mode, pixel *dst, const ptrdiff_t stride, con
     a.dst = st.dev(o_out); a.dstride = (int)(ostride / sizeof(pixel));
     a.edge = (const pixel *)st.dev(o_edge) + elo;
     a.ac = (const int16_t *)st.dev(o_ac); a.alpha = alpha;
-    if (cfl) cfl_pred_kernel<pixel><<<1, 32, 0, st.stream()>>>(a);
-    else ipred_kernel<pixel><<<1, 32, 0, st.stream()>>>(a);
+    if (cfl) ipred_kernel<pixel, true><<<1, 32, 0, st.stream()>>>(a);
+    else ipred_kernel<pixel, false><<<1, 32, 0, st.stream()>>>(a);
     count_launch();
     if (!cuda_ok(cudaGetLastError(), "ipred_kernel")) return;
     if (!st.download(o_out, ostride * h) || !st.sync()) return;

@@ -3,6 +3,7 @@
 // frame or for the merged frames of a group, and the Dav1dInvTxfmDSPContext overrides built on
 // the same kernel.  Reference: src/itx_tmpl.c:40-284 (driver + init), src/itx_1d.c.
 #include <string.h>
+#include <mutex>
 #include <vector>
 #include "ctx.h"
 #include "itx2.cuh"
@@ -11,7 +12,7 @@ namespace d1 {
 
 constexpr int ITX2_WARPS = 4;
 constexpr int ITX2_INTS_SMALL = 2 * 16 * 17;   // per warp: sizes up to 16x16 (two 16x16 per warp)
-constexpr int ITX2_INTS_BIG = 32 * 65;         // per warp: one block of up to 64x64
+constexpr int ITX2_INTS_BIG = 64 * 65;         // per warp: one block of up to 64x64
 
 // Three ways to name the work of a launch:
 //   tasks  : task codes (first_index << 8 | tx << 3 | count - 1) over `descs` of one frame
@@ -21,6 +22,8 @@ constexpr int ITX2_INTS_BIG = 32 * 65;         // per warp: one block of up to 6
 //            descriptor of size t (tasks are derived: consecutive runs of 32 / G blocks)
 struct Itx2Args {
     PicView pic;
+    PicView res;                 // to_res: int16 planes that receive the residual instead of dst += residual
+    int to_res;
     void *cf;
     const Dav1dCudaItxDesc *descs;
     const uint32_t *tasks;
@@ -39,20 +42,20 @@ HD int itx2_group(const int tx) {              // lanes per block
 }
 
 template <typename pixel, bool BIG>
-__global__ void __launch_bounds__(ITX2_WARPS * 32, BIG ? 4 : 8) itx2_task_kernel(const __grid_constant__ Itx2Args a) {
+__global__ void __launch_bounds__(ITX2_WARPS * 32, BIG ? 3 : 8) itx2_task_kernel(const __grid_constant__ Itx2Args a) {
     extern __shared__ int itx2_smem[];
     typedef typename PxTraits<pixel>::coef coef;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int t = blockIdx.x * ITX2_WARPS + warp;
     if (t >= a.n_tasks) return;
     int *smem = itx2_smem + warp * (BIG ? ITX2_INTS_BIG : ITX2_INTS_SMALL);
-    const PicView *pic = &a.pic;
+    const PicView *pic = &a.pic, *rpic = &a.res;
     void *cf = a.cf;
     int first, tx, cnt;
     if (a.mtasks) {
         const uint2 tk = a.mtasks[t];
         const ItxFrameRef *fr = a.frames + tk.y;
-        pic = &fr->pic; cf = fr->cf;
+        pic = &fr->pic; cf = fr->cf; rpic = &fr->res;
         first = (int)(tk.x >> 8); tx = (tk.x >> 3) & 31; cnt = (int)(tk.x & 7) + 1;
     } else if (a.tasks) {
         const uint32_t code = a.tasks[t];
@@ -73,8 +76,15 @@ __global__ void __launch_bounds__(ITX2_WARPS * 32, BIG ? 4 : 8) itx2_task_kernel
     const PlaneView &pv = pic->p[d.plane];
     const int dstride = (int)(pv.stride / (int)sizeof(pixel));
     pixel *dst = (pixel *)pv.data + (int64_t)d.y * dstride + d.x;
+    int16_t *res = nullptr;
+    int rstride = 0;
+    if (a.to_res) {
+        const PlaneView &rv = rpic->p[d.plane];
+        rstride = (int)(rv.stride / 2);
+        res = (int16_t *)rv.data + (int64_t)d.y * rstride + d.x;
+    }
     itx2_block<pixel, BIG ? 64 : 16>(active, gl, G, smem + grp * itx2_tile_ints(tx), (coef *)cf + d.coef_off, tx,
-                                     d.txtp, d.eob, d.cw4, d.ch4, dst, dstride, dst, dstride, pic->bdmax,
+                                     d.txtp, d.eob, d.cw4, d.ch4, dst, dstride, res, rstride, pic->bdmax,
                                      a.zero_coefs != 0);
 }
 
@@ -84,6 +94,12 @@ static int itx2_launch_one(Itx2Args a, int n, cudaStream_t st) {
     a.n_tasks = n;
     const int grid = (n + ITX2_WARPS - 1) / ITX2_WARPS;
     const size_t smem = (size_t)ITX2_WARPS * (BIG ? ITX2_INTS_BIG : ITX2_INTS_SMALL) * sizeof(int);
+    if (BIG) {      // more than the default 48 KB (the per-call surface launches without a context)
+        static std::once_flag once;
+        std::call_once(once, [&] {
+            cudaFuncSetAttribute(itx2_task_kernel<pixel, BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        });
+    }
     itx2_task_kernel<pixel, BIG><<<grid, ITX2_WARPS * 32, smem, st>>>(a);
     count_launch();
     return cuda_ok(cudaGetLastError(), "itx2_task_kernel") ? 0 : -5;
@@ -97,31 +113,28 @@ static int itx2_launch_both(Itx2Args a, int n_small, int n_big, bool hbd, cudaSt
     return hbd ? itx2_launch_one<uint16_t, true>(a, n_big, st_big) : itx2_launch_one<uint8_t, true>(a, n_big, st_big);
 }
 
-void itx_init_attrs() {
-    cudaFuncSetAttribute(itx2_task_kernel<uint8_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         ITX2_WARPS * ITX2_INTS_BIG * (int)sizeof(int));
-    cudaFuncSetAttribute(itx2_task_kernel<uint16_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         ITX2_WARPS * ITX2_INTS_BIG * (int)sizeof(int));
-}
+void itx_init_attrs() {}
 
 // tasks[0 .. n_small) = sizes up to 16x16, tasks[n_small .. n_small + n_big) = larger
-int itx_task_launch(const PicView &pic, void *cf, const Dav1dCudaItxDesc *descs, const uint32_t *tasks,
-                    int n_small, int n_big, int zero_coefs, cudaStream_t st_small, cudaStream_t st_big)
+int itx_task_launch(const PicView &pic, const PicView *res, void *cf, const Dav1dCudaItxDesc *descs,
+                    const uint32_t *tasks, int n_small, int n_big, int zero_coefs, cudaStream_t st_small,
+                    cudaStream_t st_big)
 {
     Itx2Args a;
     memset(&a, 0, sizeof(a));
     a.pic = pic; a.cf = cf; a.descs = descs; a.tasks = tasks; a.zero_coefs = zero_coefs;
+    if (res) { a.res = *res; a.to_res = 1; }
     return itx2_launch_both(a, n_small, n_big, pic.bdmax > 0xff, st_small, st_big);
 }
 
 // the frames of a group: tasks = (code, frame), code indexes `descs` = the descriptors of all
 // frames concatenated
 int itx_multi_task_launch(const ItxFrameRef *frames, const Dav1dCudaItxDesc *descs, const uint2 *tasks, int n_small,
-                          int n_big, bool hbd, cudaStream_t st_small, cudaStream_t st_big)
+                          int n_big, bool hbd, bool to_res, cudaStream_t st_small, cudaStream_t st_big)
 {
     Itx2Args a;
     memset(&a, 0, sizeof(a));
-    a.frames = frames; a.mtasks = tasks; a.descs = descs;
+    a.frames = frames; a.mtasks = tasks; a.descs = descs; a.to_res = to_res;
     return itx2_launch_both(a, n_small, n_big, hbd, st_small, st_big);
 }
 
@@ -129,7 +142,7 @@ static bool tx_is_big(int tx) { const TxDim t = tx_dim(tx); return t.w > 16 || t
 
 // descriptors grouped by tx (class_count[t] of size t, increasing t): one launch for the sizes up
 // to 16x16, one for the larger ones; the tasks are implicit
-int itx_batch_launch(const PicView &pic, void *cf, const Dav1dCudaItxDesc *descs,
+int itx_batch_launch(const PicView &pic, const PicView *res, void *cf, const Dav1dCudaItxDesc *descs,
                      const int32_t *class_count, int zero_coefs, cudaStream_t st)
 {
     const bool hbd = pic.bdmax > 0xff;
@@ -137,6 +150,7 @@ int itx_batch_launch(const PicView &pic, void *cf, const Dav1dCudaItxDesc *descs
         Itx2Args a;
         memset(&a, 0, sizeof(a));
         a.pic = pic; a.cf = cf; a.descs = descs; a.zero_coefs = zero_coefs;
+        if (res) { a.res = *res; a.to_res = 1; }
         int off = 0, nt = 0;
         for (int tx = 0; tx < DAV1D_CUDA_N_RECT_TX_SIZES; tx++) {
             const int n = class_count[tx] > 0 ? class_count[tx] : 0;
@@ -241,7 +255,7 @@ static void itx_single(const int tx, const int txtp, pixel *dst, const ptrdiff_t
     pv.bdmax = bdmax;
     int32_t cls[DAV1D_CUDA_N_RECT_TX_SIZES] = { 0 };
     cls[tx] = 1;
-    if (itx_batch_launch(pv, s.dev + cf_off, (const Dav1dCudaItxDesc *)(s.dev + desc_off), cls, 0, s.stream))
+    if (itx_batch_launch(pv, nullptr, s.dev + cf_off, (const Dav1dCudaItxDesc *)(s.dev + desc_off), cls, 0, s.stream))
         return;
     D1_CHECKV(cudaMemcpyAsync(s.host + px_off, s.dev + px_off, tile_stride * h, cudaMemcpyDeviceToHost, s.stream));
     D1_CHECKV(cudaStreamSynchronize(s.stream));
@@ -351,7 +365,7 @@ int dav1d_cuda_itx_task_batch(Dav1dCudaContext *c, const Dav1dCudaPicture *dst, 
                               int zero_coefs)
 {
     if (!c || !dst || !descs || !tasks) return -22;
-    return itx_task_launch(pic_view(dst), cf, descs, tasks, n_small, n_big, zero_coefs, c->stream, c->stream);
+    return itx_task_launch(pic_view(dst), nullptr, cf, descs, tasks, n_small, n_big, zero_coefs, c->stream, c->stream);
 }
 
 int dav1d_cuda_itx_batch(Dav1dCudaContext *c, const Dav1dCudaPicture *dst, void *cf,
@@ -359,7 +373,7 @@ int dav1d_cuda_itx_batch(Dav1dCudaContext *c, const Dav1dCudaPicture *dst, void 
                          const int32_t class_count[DAV1D_CUDA_N_RECT_TX_SIZES], int zero_coefs)
 {
     if (!c || !dst || !descs || !class_count) return -22;
-    return itx_batch_launch(pic_view(dst), cf, descs, class_count, zero_coefs, c->stream);
+    return itx_batch_launch(pic_view(dst), nullptr, cf, descs, class_count, zero_coefs, c->stream);
 }
 
 }  // extern "C"

@@ -14,7 +14,7 @@
 // min(w,32) x min(h,32)); inputs beyond the box are literal zeros, which selects the reduced
 // 8- / 16-input variants of the long DCTs (exact: every stage maps 0 -> 0).
 //
-// Everything below the kernels is __host__ __device__: tests/host/itx2_check.cpp runs the same
+// Everything here is __host__ __device__: tests/host/itx2_check.cpp runs the same
 // code lane by lane on the CPU against the reference's itxfm_add for all 156 slots.
 #pragma once
 #include "itx_geom.cuh"
@@ -27,37 +27,12 @@ namespace d1 {
 #define D1_ITX2_FN inline
 #endif
 
-// Output stage shared by all 1-D functions.
-//   row mode  (dst == nullptr): q[k * ostride] = cl2((c[k] + rnd) >> sh)
-//   final mode: dst[k * dstride] = clip_px(pred[k * pstride] + ((c[k] + rnd) >> sh))
-// `pred` is a generic pointer: the destination picture itself (inter residuals: read-modify-write)
-// or a shared-memory prediction tile (intra executor).  Reversed strides give FLIPADST.
-template <typename pixel, int N>
-HD void itx2_out(const int *c, int *q, const int ostride, const pixel *pred, const int pstride, pixel *dst,
-                 const int dstride, const int rnd, const int sh, const Clamp cl2, const int bdmax)
-{
-    if (dst) {
-        constexpr int CH = N < 16 ? N : 16;      // loads of a chunk in flight together
-#pragma unroll
-        for (int k0 = 0; k0 < N; k0 += CH) {
-            int pv[CH];
-#pragma unroll
-            for (int k = 0; k < CH; k++) pv[k] = pred[(k0 + k) * pstride];
-#pragma unroll
-            for (int k = 0; k < CH; k++)
-                dst[(k0 + k) * dstride] = (pixel)clip_px<pixel>(pv[k] + ((c[k0 + k] + rnd) >> sh), bdmax);
-        }
-    } else {
-#pragma unroll
-        for (int k = 0; k < N; k++) q[k * ostride] = cl2((c[k] + rnd) >> sh);
-    }
-}
-
-// One N-point transform of kind KIND (K_DCT / K_ADST / K_WHT) whose inputs beyond NZ are zero.
-template <typename pixel, int N, int KIND, int NZ>
-D1_ITX2_FN void itx2_vec(const int *p, const int istride, int *q, const int ostride, const pixel *pred,
-                         const int pstride, pixel *dst, const int dstride, const Clamp cl, const int rnd,
-                         const int sh, const Clamp cl2, const int bdmax)
+// One N-point transform of kind KIND (K_DCT / K_ADST / K_WHT) whose inputs beyond NZ are zero:
+// c[k] = p[k * istride], transform, q[k * ostride] = cl2((c[k] + rnd) >> sh).  Works in place
+// (q == p) and, with a reversed output (negative ostride), gives FLIPADST.
+template <int N, int KIND, int NZ>
+D1_ITX2_FN void itx2_vec(const int *p, const int istride, int *q, const int ostride, const Clamp cl, const int rnd,
+                         const int sh, const Clamp cl2)
 {
     int c[N];
 #pragma unroll
@@ -77,15 +52,14 @@ D1_ITX2_FN void itx2_vec(const int *p, const int istride, int *q, const int ostr
     } else {
         iwht4<1>(c);
     }
-    itx2_out<pixel, N>(c, q, ostride, pred, pstride, dst, dstride, rnd, sh, cl2, bdmax);
+#pragma unroll
+    for (int k = 0; k < N; k++) q[k * ostride] = cl2((c[k] + rnd) >> sh);
 }
 
 // identity: element-wise, run-time length (itx_1d.c:983-1017):
 //   4: v + (v*1697 + 2048 >> 12)   8: 2v   16: 2v + (v*1697 + 1024 >> 11)   32: 4v
-template <typename pixel>
 HD void itx2_identity(const int n, const int nz, const int *p, const int istride, int *q, const int ostride,
-                      const pixel *pred, const int pstride, pixel *dst, const int dstride, const int rnd,
-                      const int sh, const Clamp cl2, const int bdmax)
+                      const int rnd, const int sh, const Clamp cl2)
 {
     const int m = n == 4 ? 1 : n == 32 ? 4 : 2;
     const int fm = (n == 4 || n == 16) ? 1697 : 0, fr = n == 4 ? 2048 : 1024, fs = n == 4 ? 12 : 11;
@@ -93,9 +67,7 @@ HD void itx2_identity(const int n, const int nz, const int *p, const int istride
     for (int k = 0; k < n; k++) {
         int v = k < nz ? p[k * istride] : 0;
         v = v * m + ((v * fm + fr) >> fs);
-        const int r = (v + rnd) >> sh;
-        if (dst) dst[k * dstride] = (pixel)clip_px<pixel>(pred[k * pstride] + r, bdmax);
-        else q[k * ostride] = cl2(r);
+        q[k * ostride] = cl2((v + rnd) >> sh);
     }
 }
 
@@ -112,18 +84,14 @@ HD int itx2_nzb(const int n, const int kind, const int nz) {
 // One vector: n-point transform `kind` (enum Itx1d; FLIPADST = ADST with the output order reversed).
 // MAXN: longest transform the calling kernel can meet (prunes the long DCTs, and with them their
 // registers, from the kernel that only runs sizes up to 16x16).
-template <typename pixel, int MAXN = 64>
+template <int MAXN = 64>
 HD void itx2_run(const int n, const int kind, const int nz, const int *p, const int istride, int *q, int ostride,
-                 const pixel *pred, int pstride, pixel *dst, int dstride, const Clamp cl, const int rnd,
-                 const int sh, const Clamp cl2, const int bdmax)
+                 const Clamp cl, const int rnd, const int sh, const Clamp cl2)
 {
-    if (kind == K_FLIPADST) {
-        if (dst) { pred += (n - 1) * pstride; dst += (n - 1) * dstride; pstride = -pstride; dstride = -dstride; }
-        else { q += (n - 1) * ostride; ostride = -ostride; }
-    }
-#define D1_V(N, K, NZ) itx2_vec<pixel, N, K, NZ>(p, istride, q, ostride, pred, pstride, dst, dstride, cl, rnd, sh, cl2, bdmax)
+    if (kind == K_FLIPADST) { q += (n - 1) * ostride; ostride = -ostride; }
+#define D1_V(N, K, NZ) itx2_vec<N, K, NZ>(p, istride, q, ostride, cl, rnd, sh, cl2)
     if (kind == K_IDENTITY) {
-        itx2_identity<pixel>(n, nz, p, istride, q, ostride, pred, pstride, dst, dstride, rnd, sh, cl2, bdmax);
+        itx2_identity(n, nz, p, istride, q, ostride, rnd, sh, cl2);
     } else if (kind == K_DCT) {
         const int b = itx2_nzb(n, K_DCT, nz);
         switch (n) {
@@ -186,7 +154,7 @@ HD Itx2Blk itx2_setup(const int tx, const int txtp, const int eob, const int cw4
 
 HD int itx2_tile_ints(const int tx) {          // shared-memory ints one block of size tx needs
     const TxDim t = tx_dim(tx);
-    return (t.h < 32 ? t.h : 32) * (t.w + 1);
+    return t.h * (t.w + 1);
 }
 
 // ---- the phases of one block; lane gl of a group of G lanes (G >= max(sw, sh), power of two).
@@ -195,26 +163,36 @@ HD int itx2_tile_ints(const int tx) {          // shared-memory ints one block o
 
 // dc-only (itx_tmpl.c:53-65): every pixel gets the same offset
 template <typename pixel>
-HD void itx2_phase_dc(const Itx2Blk &b, const int gl, const int G, const typename PxTraits<pixel>::coef *cf,
-                      const pixel *pred, const int pstride, pixel *dst, const int dstride, const int bdmax)
-{
+HD int itx2_dc_value(const Itx2Blk &b, const typename PxTraits<pixel>::coef *cf) {
     int dc = cf[0];
     if (b.rect2) dc = (dc * 181 + 128) >> 8;
     dc = (dc * 181 + 128) >> 8;
     dc = (dc + ((1 << b.shift) >> 1)) >> b.shift;
-    dc = (dc * 181 + 128 + 2048) >> 12;
+    return (dc * 181 + 128 + 2048) >> 12;
+}
+
+// Last phase: residual r(x, y) = dc (dc-only blocks) or the column pass's output in the tile ->
+//   res == nullptr: dst = clip_px(dst + r)          (inter residuals: read-modify-write)
+//   res != nullptr: res = saturate_int16(r)         (intra residuals, added by the intra executor
+//                   to the prediction: clip_px(pred + r) is the same for the saturated r)
+// Four pixels per lane and step, four steps' loads in flight.
+template <typename pixel>
+HD void itx2_phase_out(const Itx2Blk &b, const int gl, const int G, const int *tile, const int dc, pixel *dst,
+                       const int dstride, int16_t *res, const int rstride, const int bdmax)
+{
     const int ls = b.lw - 2, nv = b.h << ls;          // 4-pixel segments per row: w / 4
-    // four segments per lane and step: their loads are in flight together
     for (int i0 = gl; i0 < nv; i0 += 4 * G) {
         int v[4][4];
 #pragma unroll
         for (int u = 0; u < 4; u++) {
             const int i = i0 + u * G;
-            if (i < nv) {
+            if (i < nv && !res) {
                 const int y = i >> ls, x = (i - (y << ls)) * 4;
-                const pixel *pp = pred + y * pstride + x;
-#pragma unroll
-                for (int k = 0; k < 4; k++) v[u][k] = pp[k];
+#if defined(__CUDA_ARCH__)
+                load_px<pixel, 4>(dst + y * dstride + x, v[u]);
+#else
+                for (int k = 0; k < 4; k++) v[u][k] = dst[y * dstride + x + k];
+#endif
             }
         }
 #pragma unroll
@@ -222,14 +200,22 @@ HD void itx2_phase_dc(const Itx2Blk &b, const int gl, const int G, const typenam
             const int i = i0 + u * G;
             if (i < nv) {
                 const int y = i >> ls, x = (i - (y << ls)) * 4;
-                pixel *dp = dst + y * dstride + x;
+                int r[4];
 #pragma unroll
-                for (int k = 0; k < 4; k++) v[u][k] = clip_px<pixel>(v[u][k] + dc, bdmax);
+                for (int k = 0; k < 4; k++) r[k] = b.dc_only ? dc : tile[y * b.ts + x + k];
+                if (res) {
+                    int16_t *rp = res + y * rstride + x;
+#pragma unroll
+                    for (int k = 0; k < 4; k++) rp[k] = (int16_t)(r[k] < -32768 ? -32768 : r[k] > 32767 ? 32767 : r[k]);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; k++) v[u][k] = clip_px<pixel>(v[u][k] + r[k], bdmax);
 #if defined(__CUDA_ARCH__)
-                store_px<pixel, 4>(dp, v[u]);
+                    store_px<pixel, 4>(dst + y * dstride + x, v[u]);
 #else
-                for (int k = 0; k < 4; k++) dp[k] = (pixel)v[u][k];
+                    for (int k = 0; k < 4; k++) dst[y * dstride + x + k] = (pixel)v[u][k];
 #endif
+                }
             }
         }
     }
@@ -268,44 +254,47 @@ HD void itx2_phase_stage(const Itx2Blk &b, const int gl, const int G, typename P
         for (int x = gl; x < b.w; x += G) tile[y * b.ts + x] = 0;
 }
 
-template <typename pixel, int MAXN = 64>
-HD void itx2_phase_rows(const Itx2Blk &b, const int gl, int *tile, const int bdmax) {
+template <int MAXN = 64>
+HD void itx2_phase_rows(const Itx2Blk &b, const int gl, int *tile) {
     if (gl >= b.ch) return;
     int *row = tile + gl * b.ts;
     const int rnd = b.wht ? 0 : (1 << b.shift) >> 1, sh = b.wht ? 0 : b.shift;
     Clamp c2 = b.colcl;
     if (b.wht) { c2.lo = (int)0x80000000; c2.hi = 0x7fffffff; }
-    itx2_run<pixel, MAXN>(b.w, b.rk, b.cw, row, 1, row, 1, nullptr, 0, nullptr, 0, b.rowcl, rnd, sh, c2, bdmax);
+    itx2_run<MAXN>(b.w, b.rk, b.cw, row, 1, row, 1, b.rowcl, rnd, sh, c2);
 }
 
-template <typename pixel, int MAXN = 64>
-HD void itx2_phase_cols(const Itx2Blk &b, const int gl, const int G, int *tile, const pixel *pred,
-                        const int pstride, pixel *dst, const int dstride, const int bdmax)
-{
+// column pass in place: column x of the tile (rows < cin in, rows < h out), (t + 8) >> 4 (WHT: t)
+template <int MAXN = 64>
+HD void itx2_phase_cols(const Itx2Blk &b, const int gl, const int G, int *tile) {
     const int rnd = b.wht ? 0 : 8, sh = b.wht ? 0 : 4;
+    Clamp c2;
+    c2.lo = (int)0x80000000; c2.hi = 0x7fffffff;
     for (int x = gl; x < b.w; x += G)
-        itx2_run<pixel, MAXN>(b.h, b.ck, b.ch, tile + x, b.ts, nullptr, 0, pred + x, pstride, dst + x, dstride, b.colcl,
-                        rnd, sh, b.colcl, bdmax);
+        itx2_run<MAXN>(b.h, b.ck, b.ch, tile + x, b.ts, tile + x, b.ts, b.colcl, rnd, sh, c2);
 }
 
 #if defined(__CUDACC__)
 // One block by the group of G lanes that contains this lane (all lanes of the warp call this;
-// lanes of a group without a block pass active = false).
+// lanes of a group without a block pass active = false).  res: see itx2_phase_out.
 template <typename pixel, int MAXN = 64>
 DEV void itx2_block(const bool active, const int gl, const int G, int *tile, typename PxTraits<pixel>::coef *cf,
-                    const int tx, const int txtp, const int eob, const int cw4, const int ch4, const pixel *pred,
-                    const int pstride, pixel *dst, const int dstride, const int bdmax, const bool zero_coefs)
+                    const int tx, const int txtp, const int eob, const int cw4, const int ch4, pixel *dst,
+                    const int dstride, int16_t *res, const int rstride, const int bdmax, const bool zero_coefs)
 {
     const Itx2Blk b = itx2_setup<pixel>(tx, txtp, eob, cw4, ch4, bdmax);
-    if (active && b.dc_only) itx2_phase_dc<pixel>(b, gl, G, cf, pred, pstride, dst, dstride, bdmax);
-    __syncwarp();
+    int dc = 0;
+    if (active && b.dc_only) dc = itx2_dc_value<pixel>(b, cf);
+    __syncwarp();                                   // every lane has read cf[0] before it is cleared
     if (active && b.dc_only && gl == 0 && zero_coefs) cf[0] = 0;
     const bool full = active && !b.dc_only;
     if (full) itx2_phase_stage<pixel>(b, gl, G, cf, tile, zero_coefs);
     __syncwarp();
-    if (full) itx2_phase_rows<pixel, MAXN>(b, gl, tile, bdmax);
+    if (full) itx2_phase_rows<MAXN>(b, gl, tile);
     __syncwarp();
-    if (full) itx2_phase_cols<pixel, MAXN>(b, gl, G, tile, pred, pstride, dst, dstride, bdmax);
+    if (full) itx2_phase_cols<MAXN>(b, gl, G, tile);
+    __syncwarp();
+    if (active) itx2_phase_out<pixel>(b, gl, G, tile, dc, dst, dstride, res, rstride, bdmax);
     __syncwarp();
 }
 #endif

@@ -8,20 +8,25 @@
 // (recon_tmpl.c:1259-1347), so the intra-class operations of a frame form a dependency DAG.  The
 // reference resolves it by decoding superblocks in order (and, across threads, by superblock-row
 // progress counters: src/decode.c:2001-2090, src/thread_task.c:409-430).  Here ONE persistent
-// launch per group of frames does the same at a finer grain:
-//   * the recorder hands over the operations in DECODE order plus the offsets of the "units"
-//     (superblocks) they belong to - nothing is scheduled, sorted or levelled on the host;
-//   * a warp claims units in decode order from a counter (units of the group's frames
-//     interleaved) and executes the unit's operations one after the other;
-//   * a byte per 4x4 cell and plane counts the operations that still have to write the cell
-//     (set up by a small marking launch, back at zero when the frame is done: the map needs no
-//     clearing between frames).  Before an operation reads pixels OUTSIDE its own unit it waits
-//     until their cells are at zero; every cell it waits for belongs to a unit that precedes it
-//     in decode order, i.e. one that was claimed earlier by a warp that is running: no deadlock.
-//   * prediction and residual of an operation are fused: the predictor writes a shared-memory
-//     tile, the column pass of the inverse transform adds it and stores the final pixels once.
-// A wait is bounded; a stalled dependency sets the context's status word, the remaining
-// operations are abandoned, and dav1d_cuda_synchronize() reports the failure.
+// cooperative launch per group of frames runs the DAG level by level, and finds the levels itself:
+//   * the recorder hands over the operations in decode order - nothing is scheduled, sorted or
+//     levelled on the host;
+//   * a byte per 4x4 cell and plane counts the operations that still have to write the cell (set
+//     up by a small marking launch, back at zero when the frame is done: the map needs no clearing
+//     between frames);
+//   * round r: (1) every pending operation is looked at by one THREAD: it is ready when the cells
+//     of the pixels it reads are at zero (dav1d_prepare_intra_edges' own rules); ready operations
+//     go to the round's list with a key (predictor class, size class), the others stay pending;
+//     (2) the list is sorted by key (counting sort); (3) warps execute it - four small
+//     operations per warp, one per octet of lanes, neighbouring warps on the same predictor - and
+//     count the cells down.  Grid barriers separate the steps.  The operations of a round are
+//     independent of each other by construction, so nothing ever waits: round r executes exactly
+//     dependency level r.
+//   * the residuals do not depend on neighbours: a transform pre-pass (itx2.cu, next to the motion
+//     compensation) leaves them in an int16 plane and the executor adds them to its predictions.
+// A frame whose descriptors are inconsistent (operations that wait for each other) ends with
+// pending operations and no ready one: the executor raises the context's status word and stops;
+// dav1d_cuda_synchronize() reports it.
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
@@ -34,10 +39,11 @@
 namespace d1 {
 
 // defined in itx2.cu / mc.cu
-int itx_batch_launch(const PicView &pic, void *cf, const Dav1dCudaItxDesc *descs,
+int itx_batch_launch(const PicView &pic, const PicView *res, void *cf, const Dav1dCudaItxDesc *descs,
                      const int32_t *class_count, int zero_coefs, cudaStream_t st);
-int itx_task_launch(const PicView &pic, void *cf, const Dav1dCudaItxDesc *descs, const uint32_t *tasks,
-                    int n_small, int n_big, int zero_coefs, cudaStream_t st_small, cudaStream_t st_big);
+int itx_task_launch(const PicView &pic, const PicView *res, void *cf, const Dav1dCudaItxDesc *descs,
+                    const uint32_t *tasks, int n_small, int n_big, int zero_coefs, cudaStream_t st_small,
+                    cudaStream_t st_big);
 int mc_obmc_launch_raw(const PicView &dst, const PicView *refs, const Dav1dCudaMcDesc *descs,
                        const uint32_t *tiles, int n_tiles, cudaStream_t st);
 void itx_init_attrs();
@@ -45,39 +51,26 @@ int mc_put_launch_raw(const PicView &dst, const PicView *refs, const Dav1dCudaMc
                       const uint32_t *tiles, int n_tiles, int n_small, uint8_t *masks, int16_t *tmp,
                       bool compound, cudaStream_t st);
 
-constexpr int I2_WARPS = 4;
 constexpr int EDGE_BUF = 288;
 constexpr int EDGE_C = 144;
 constexpr int I2_MAXF = DAV1D_CUDA_MAX_GROUP;
-// bytes of the tile region: one 64-wide transform tile (32 x 65 ints), or - operations up to
-// 32x32 - a 32 x 33 int transform tile, then the prediction tile, then the CfL ac / scratch tile
-constexpr int I2_TILE_INTS = 32 * 65;
-constexpr int I2_PRED_OFF = 32 * 33 * 4;                 // 4224
-constexpr int I2_AC_OFF = I2_PRED_OFF + 32 * 32 * 2;     // 6272 (+ 2048 = 8320)
-
-template <typename pixel> struct __align__(16) Intra2Smem {
-    int tile[I2_TILE_INTS];
-    pixel edge[EDGE_BUF];
-    pixel scratch[IPRED_SCRATCH];
-};
 
 // one frame of the group
 struct Intra2Frame {
     PicView pic;
+    PicView res;                         // int16 residual planes written by the transform pre-pass
     int bw4, bh4;
     void *cf;
     const Dav1dCudaIntraDesc *descs;     // decode order
     const void *pal;
     const uint8_t *pal_idx;
-    const uint2 *units;                  // (first operation, count) in claim order
-    int n_units, n_ops;
+    int n_ops;
     uint8_t *map;                        // cell map: plane 0, 1, 2 one after the other
 };
 struct Intra2Args {
     Intra2Frame f[I2_MAXF];
-    int nf, max_units;
-    unsigned *claim;                     // claim counter of this launch (zeroed before)
-    unsigned *status;                    // context status word: bit0 = a dependency wait timed out
+    int nf;
+    unsigned *status;                    // context status word: bit0 = operations that wait for each other
 };
 
 HD int map_w(const Intra2Frame &f, const int pl) { return pl ? (f.bw4 + f.pic.ss_hor) >> f.pic.ss_hor : f.bw4; }
@@ -104,253 +97,353 @@ HD int intra_needs(const int mode, const int angle_delta, const int have_left, c
     return 1 | 2 | 4;                                                           // FILTER
 }
 
-DEV unsigned ld_acquire_u8(const uint8_t *p) {
+DEV unsigned ld_acquire_u32(const unsigned *p) {
     unsigned v;
-    asm volatile("ld.acquire.gpu.global.u8 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-DEV unsigned ld_relaxed_u32(const unsigned *p) {
-    unsigned v;
-    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
 
-// Wait until the cell (cx, cy) of plane pl is final.  Returns false when the wait was abandoned.
-DEV bool wait_cell(const Intra2Frame &f, const int pl, const int cx, const int cy, unsigned *status) {
-    const uint8_t *p = f.map + map_off(f, pl) + cy * map_w(f, pl) + cx;
-    unsigned ns = 32, waited = 0;
-    while (ld_acquire_u8(p) != 0) {
-        if (ld_relaxed_u32(status) & 1u) return false;
-        __nanosleep(ns);
-        waited += ns;
-        if (ns < 1024) ns <<= 1;
-        if (waited > (1u << 28)) { atomicOr(status, 1u); return false; }      // ~0.27 s
+// Grid barrier of the cooperative launch: a monotonic arrival counter (zeroed before the launch).
+DEV void grid_barrier(unsigned *bar, unsigned &target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        target += gridDim.x;
+        __threadfence();
+        atomicAdd(bar, 1u);
+        while (ld_acquire_u32(bar) < target) __nanosleep(32);
+        __threadfence();
     }
+    __syncthreads();
+}
+
+// ---- step 1 of a round: is operation d ready?  One thread, L2 loads of the map bytes.
+DEV bool cells_are(const uint8_t *m, const int W, const int x0, const int x1, const int y0, const int y1, const int want) {
+    for (int y = y0; y < y1; y++)
+        for (int x = x0; x < x1; x++)
+            if (__ldcg(m + y * W + x) != want) return false;
     return true;
 }
 
-// The cells whose pixels operation d reads and that lie outside d's own unit must be final.
-// Exactly the pixels dav1d_prepare_intra_edges reads for the resolved mode (plus the source area
-// of an intrabc block); cells of the operation's own unit were written by this warp.
-DEV bool intra2_wait(const Intra2Frame &f, const Dav1dCudaIntraDesc &d, const int lane, unsigned *status) {
+DEV bool op_ready(const Intra2Frame &f, const Dav1dCudaIntraDesc &d, int *cls_out) {
     const int mode = d.mode;
-    if (mode == DAV1D_CUDA_INTRA_NONE || mode == DAV1D_CUDA_INTRA_PAL) return true;
     const int pl = d.plane;
     const int sh = pl ? f.pic.ss_hor : 0, sv = pl ? f.pic.ss_ver : 0;
     const int W = map_w(f, pl), H = map_h(f, pl);
+    const uint8_t *m = f.map + map_off(f, pl);
     const int x0 = d.x4, y0 = d.y4;
-    // cells known to be written by this warp: the operation's coding block (descriptor hint)
-    int rx0 = x0, ry0 = y0, rx1 = x0, ry1 = y0;          // empty
-    if (d.blk >> 16) {
-        rx0 = x0 - (int)(d.blk & 15); ry0 = y0 - (int)((d.blk >> 4) & 15);
-        rx1 = rx0 + (1 << ((d.blk >> 8) & 15)); ry1 = ry0 + (1 << ((d.blk >> 12) & 15));
+    if (mode == DAV1D_CUDA_INTRA_PAL) { *cls_out = 15; return true; }
+    if (mode == DAV1D_CUDA_INTRA_NONE) {
+        // residual on top of an earlier operation's pixels (palette, inter-intra, intrabc): that one is done
+        *cls_out = 18;
+        return cells_are(m, W, x0, imin(x0 + d.tw4, W), y0, imin(y0 + d.th4, H), 1);
     }
-    bool ok = true;
     if (mode == DAV1D_CUDA_INTRA_IBC) {
+        *cls_out = 16;
         const int sx = (int16_t)(d.aux & 0xffff), sy = (int16_t)(d.aux >> 16);
         const int pw = 4 * W, ph = 4 * H;
         const int xa = iclip(sx, 0, pw - 1) >> 2, xb = iclip(sx + 4 * d.tw4 + (d.angle_delta ? 1 : 0) - 1, 0, pw - 1) >> 2;
         const int ya = iclip(sy, 0, ph - 1) >> 2, yb = iclip(sy + 4 * d.th4 + (d.flags ? 1 : 0) - 1, 0, ph - 1) >> 2;
-        const int nx = xb - xa + 1, n = nx * (yb - ya + 1);
-        for (int j = lane; j < n; j += 32) {
-            const int cy = ya + j / nx, cx = xa + j % nx;
-            if (cx >= rx0 && cx < rx1 && cy >= ry0 && cy < ry1) continue;
-            ok &= wait_cell(f, pl, cx, cy, status);
-        }
-    } else {
-        const int have_left = x0 > d.tile_x4_start, have_top = y0 > d.tile_y4_start;
-        const int needs = mode == DAV1D_CUDA_INTRA_II ? intra_needs(d.angle_delta, 0, have_left, have_top)
-                        : intra_needs(mode == DAV1D_CUDA_INTRA_CFL ? 0 : mode, d.angle_delta, have_left, have_top);
-        // top row: [xs, xe) at y0 - 1
-        int xs = 0, xe = 0;
-        if (have_top && ((needs & 2) || (needs & 4) || ((needs & 1) && !have_left))) {
-            const bool tr = (needs & 8) && (d.edge_flags & 1);
-            xs = ((needs & 4) && have_left) ? x0 - 1 : x0;
-            xe = (needs & 2) ? imin(x0 + d.tw4 + (tr ? d.tw4 : 0), d.tile_x4_end) : x0 + 1;
-            xe = imin(xe, W);
-        }
-        // left column: [y0, ye) at x0 - 1
-        int ye = y0;
-        if (have_left && ((needs & 1) || ((needs & 2) && !have_top) || ((needs & 4) && !have_top))) {
-            const bool bl = (needs & 16) && (d.edge_flags & 8);
-            ye = (needs & 1) ? imin(y0 + d.th4 + (bl ? d.th4 : 0), d.tile_y4_end) : y0 + 1;
-            ye = imin(ye, H);
-        }
-        const int nt = xe - xs, n = nt + (ye - y0);
-        for (int j = lane; j < n; j += 32) {
-            const int cx = j < nt ? xs + j : x0 - 1, cy = j < nt ? y0 - 1 : y0 + (j - nt);
-            if (cx >= rx0 && cx < rx1 && cy >= ry0 && cy < ry1) continue;
-            ok &= wait_cell(f, pl, cx, cy, status);
-        }
-        // CfL reads the co-located luma: the same block, i.e. the same unit (without any hint:
-        // check the cells)
-        if (mode == DAV1D_CUDA_INTRA_CFL && !(d.blk >> 16)) {
-            const int lw4 = d.tw4 << sh, lh4 = d.th4 << sv;
-            for (int j = lane; j < lw4 * lh4; j += 32) {
-                const int cx = (x0 << sh) + j % lw4, cy = (y0 << sv) + j / lw4;
-                if (cx < f.bw4 && cy < f.bh4) ok &= wait_cell(f, 0, cx, cy, status);
-            }
-        }
+        return cells_are(m, W, xa, xb + 1, ya, yb + 1, 0);
     }
-    return __all_sync(0xffffffffu, ok);
+    const int have_left = x0 > d.tile_x4_start, have_top = y0 > d.tile_y4_start;
+    int ang = mode == DAV1D_CUDA_INTRA_II ? 0 : d.angle_delta;
+    const int rm = ipred_resolve_mode(mode == DAV1D_CUDA_INTRA_II ? d.angle_delta : mode == DAV1D_CUDA_INTRA_CFL ? 0 : mode,
+                                      &ang, have_left, have_top);
+    *cls_out = mode == DAV1D_CUDA_INTRA_II ? 17 : mode == DAV1D_CUDA_INTRA_CFL ? 14 : rm;
+    const int needs = ipred_mode_needs(rm);
+    // exactly the pixels dav1d_prepare_intra_edges reads (ipred_prepare_tmpl.c:119-200)
+    if (have_top && ((needs & 2) || (needs & 4) || ((needs & 1) && !have_left))) {
+        const bool tr = (needs & 8) && (d.edge_flags & 1);
+        const int xs = ((needs & 4) && have_left) ? x0 - 1 : x0;
+        int xe = (needs & 2) ? imin(x0 + d.tw4 + (tr ? d.tw4 : 0), d.tile_x4_end) : x0 + 1;
+        xe = imin(xe, W);
+        if (!cells_are(m, W, xs, xe, y0 - 1, y0, 0)) return false;
+    }
+    if (have_left && ((needs & 1) || ((needs & 2) && !have_top) || ((needs & 4) && !have_top))) {
+        const bool bl = (needs & 16) && (d.edge_flags & 8);
+        int ye = (needs & 1) ? imin(y0 + d.th4 + (bl ? d.th4 : 0), d.tile_y4_end) : y0 + 1;
+        ye = imin(ye, H);
+        if (!cells_are(m, W, x0 - 1, x0, y0, ye, 0)) return false;
+    }
+    if (mode == DAV1D_CUDA_INTRA_CFL)      // the co-located luma
+        return cells_are(f.map, f.bw4, x0 << sh, imin((x0 + d.tw4) << sh, f.bw4), y0 << sv,
+                         imin((y0 + d.th4) << sv, f.bh4), 0);
+    return true;
 }
 
-// The operation's pixels are stored: one count less on each of its cells.
-DEV void intra2_publish(const Intra2Frame &f, const Dav1dCudaIntraDesc &d, const int lane) {
-    __syncwarp();
-    __threadfence();
-    const int pl = d.plane, W = map_w(f, pl), H = map_h(f, pl);
-    uint8_t *m = f.map + map_off(f, pl);
-    const int ltw = 31 - __clz((int)d.tw4);              // tw4 is a power of two
-    const int n = d.th4 << ltw;
-    for (int j = lane; j < n; j += 32) {
-        const int cx = d.x4 + (j & (d.tw4 - 1)), cy = d.y4 + (j >> ltw);
-        if (cx < W && cy < H) {
-            uint8_t *p = m + cy * W + cx;
-            *(volatile uint8_t *)p = (uint8_t)(*(volatile uint8_t *)p - 1);
-        }
-    }
-}
-
-// One intra-class operation (prediction [+ residual]) by one warp.
+// ---- step 3: one operation by a group of lanes (a warp, or an octet for operations of up to 64
+// pixels): edge preparation, then ONE loop over the block's pixels (a pixel per lane and step)
+// that evaluates the predictor, adds the residual of the transform pre-pass and stores the final
+// pixel; then the operation's cells are counted down.
 template <typename pixel>
-__device__ __noinline__ void intra2_op(const Intra2Frame &a, const Dav1dCudaIntraDesc &d, Intra2Smem<pixel> *sm,
-                                       const int lane) {
-    typedef typename PxTraits<pixel>::coef coef;
+__device__ __noinline__ void intra_exec(const Grp g, const Intra2Frame &a, const Dav1dCudaIntraDesc &d,
+                                        pixel *edge_buf, pixel *scratch, int16_t *tile) {
     const int pl = d.plane;
     const int ss_hor = pl ? a.pic.ss_hor : 0, ss_ver = pl ? a.pic.ss_ver : 0;
     const PlaneView &pv = a.pic.p[pl];
     const int stride = (int)(pv.stride / (int)sizeof(pixel));
     pixel *dst = (pixel *)pv.data + (int64_t)d.y4 * 4 * stride + d.x4 * 4;
     const int w = d.tw4 * 4, h = d.th4 * 4;
+    const int lw = 31 - __clz(w);
     const int bdmax = a.pic.bdmax;
-    pixel *edge = sm->edge + EDGE_C;
+    pixel *edge = edge_buf + EDGE_C;
     const int have_left = d.x4 > d.tile_x4_start, have_top = d.y4 > d.tile_y4_start;
     const int mode = d.mode;
     const bool has_res = d.eob >= 0 && mode != DAV1D_CUDA_INTRA_PAL;
-    pixel *ptile = (pixel *)((char *)sm->tile + I2_PRED_OFF);
-    int16_t *ac = (int16_t *)((char *)sm->tile + I2_AC_OFF);
-    // with a residual to follow, predictions of up to 32x32 go to the shared tile
-    const bool to_tile = has_res && w <= 32 && h <= 32 &&
-                         (mode <= DAV1D_CUDA_INTRA_FILTER || mode == DAV1D_CUDA_INTRA_CFL);
-    pixel *pout = to_tile ? ptile : dst;
-    const int pstride = to_tile ? w : stride;
-
+    const int16_t *res = nullptr;
+    int rstride = 0;
     if (has_res) {
-        // pull the block's coefficients towards the SM while the prediction runs
-        const int ncoef = d.cw4 ? 16 * d.cw4 * d.ch4 : imin(w, 32) * imin(h, 32);
-        const char *cp = (const char *)((const coef *)a.cf + d.coef_off);
-        for (int o = lane * 128; o < ncoef * (int)sizeof(coef); o += 32 * 128)
-            asm volatile("prefetch.global.L2 [%0];" :: "l"(cp + o));
+        const PlaneView &rv = a.res.p[pl];
+        rstride = (int)(rv.stride / 2);
+        res = (const int16_t *)rv.data + (int64_t)d.y4 * 4 * rstride + d.x4 * 4;
     }
-
+    // what the pixel loop does: 0 predictor, 1 palette, 2 intrabc, 3 keep the current pixel
+    int kind = 3;
+    PixParams<pixel> P;
+    P.pm = PM_CONST; P.p0 = P.p1 = P.p2 = P.p3 = 0; P.edge = P.e0 = P.e1 = edge; P.tile = tile; P.w = w; P.h = h;
+    const uint8_t *bmask = nullptr;                // inter-intra blend mask
     if (mode == DAV1D_CUDA_INTRA_PAL) {
-        pal_pred_block<pixel>(dst, stride, (const pixel *)a.pal + d.aux, a.pal_idx + d.coef_off, w, h, lane, 32);
+        kind = 1;
+    } else if (mode == DAV1D_CUDA_INTRA_IBC) {
+        kind = 2;
     } else if (mode == DAV1D_CUDA_INTRA_CFL) {
         const PlaneView &lv = a.pic.p[0];
         const int lstride = (int)(lv.stride / (int)sizeof(pixel));
         const pixel *luma = (const pixel *)lv.data + (int64_t)((d.y4 * 4) << ss_ver) * lstride + ((d.x4 * 4) << ss_hor);
-        cfl_ac_block<pixel>(ac, luma, lstride, d.aux & 0xff, (d.aux >> 8) & 0xff, w, h, ss_hor, ss_ver, lane);
+        cfl_ac_block<pixel>(g, tile, luma, lstride, d.aux & 0xff, (d.aux >> 8) & 0xff, w, h, ss_hor, ss_ver);
         int angle = 0;
-        const int m = prepare_edges<pixel>(d.x4, have_left, d.y4, have_top, d.tile_x4_end, d.tile_y4_end, 0, dst,
-                                           stride, nullptr, 0, &angle, d.tw4, d.th4, 0, edge, bdmax, lane);
-        cfl_pred_block<pixel>(m, pout, pstride, edge, w, h, ac, d.angle_delta, bdmax, lane);
-    } else if (mode == DAV1D_CUDA_INTRA_IBC) {
-        // intrabc: put_bilin (mc_tmpl.c:395-450) from the current picture; coordinates clamped to
-        // the 4*bw4 x 4*bh4 area (= emu_edge, recon_tmpl.c:974-995)
-        const int sx = (int16_t)(d.aux & 0xffff), sy = (int16_t)(d.aux >> 16);
-        const int mx = d.angle_delta, my = d.flags;
-        const int pw = (4 * a.bw4) >> ss_hor, ph = (4 * a.bh4) >> ss_ver;
-        const int ib = PxTraits<pixel>::inter_bits(bdmax);
-        const pixel *base = (const pixel *)pv.data;
-        const int lw = 31 - __clz(w);
-        for (int i = lane; i < w * h; i += 32) {
-            const int y = i >> lw, x = i & (w - 1);
-            const int xa = iclip(sx + x, 0, pw - 1), xb = iclip(sx + x + 1, 0, pw - 1);
-            const int ya = iclip(sy + y, 0, ph - 1), yb = iclip(sy + y + 1, 0, ph - 1);
-            const int p00 = __ldcg(base + (int64_t)ya * stride + xa);
-            int out;
-            if (mx && my) {
-                const int p01 = __ldcg(base + (int64_t)ya * stride + xb);
-                const int p10 = __ldcg(base + (int64_t)yb * stride + xa);
-                const int p11 = __ldcg(base + (int64_t)yb * stride + xb);
-                const int sh1 = 4 - ib, r1 = (1 << sh1) >> 1;
-                const int m0 = (16 * p00 + mx * (p01 - p00) + r1) >> sh1;
-                const int m1 = (16 * p10 + mx * (p11 - p10) + r1) >> sh1;
-                const int sh2 = 4 + ib;
-                out = clip_px<pixel>((16 * m0 + my * (m1 - m0) + ((1 << sh2) >> 1)) >> sh2, bdmax);
-            } else if (mx) {
-                const int p01 = __ldcg(base + (int64_t)ya * stride + xb);
-                const int sh1 = 4 - ib;
-                const int px = (16 * p00 + mx * (p01 - p00) + ((1 << sh1) >> 1)) >> sh1;
-                out = clip_px<pixel>((px + ((1 << ib) >> 1)) >> ib, bdmax);
-            } else if (my) {
-                const int p10 = __ldcg(base + (int64_t)yb * stride + xa);
-                out = clip_px<pixel>((16 * p00 + my * (p10 - p00) + 8) >> 4, bdmax);
-            } else {
-                out = p00;
-            }
-            dst[y * stride + x] = (pixel)out;
-        }
-    } else if (mode == DAV1D_CUDA_INTRA_II) {
-        // inter-intra: predict the whole block (<= 32x32) into scratch, then mc.blend onto the
-        // inter prediction (mc_tmpl.c:642-653)
-        int angle = 0;
-        const int m = prepare_edges<pixel>(d.x4, have_left, d.y4, have_top, d.tile_x4_end, d.tile_y4_end, 0, dst,
-                                           stride, nullptr, d.angle_delta, &angle, d.tw4, d.th4, 0, edge, bdmax, lane);
-        pixel *tmp = (pixel *)ac;
-        ipred_block<pixel>(m, tmp, w, edge, w, h, 0, 0, 0, bdmax, sm->scratch, lane);
-        __syncwarp();
-        const uint8_t *mask = a.pal_idx + d.coef_off;
-        const int lw = 31 - __clz(w);
-        for (int i = lane; i < w * h; i += 32) {
-            const int y = i >> lw, x = i & (w - 1);
-            const int mk = mask[i], p = dst[y * stride + x], q = tmp[i];
-            dst[y * stride + x] = (pixel)((p * (64 - mk) + q * mk + 32) >> 6);
-        }
+        const int m = prepare_edges<pixel>(g, d.x4, have_left, d.y4, have_top, d.tile_x4_end, d.tile_y4_end, 0, dst,
+                                           stride, nullptr, 0, &angle, d.tw4, d.th4, 0, edge, bdmax);
+        P = cfl_setup<pixel>(g, m, edge, w, h, tile, d.angle_delta, bdmax);
+        kind = 0;
     } else if (mode != DAV1D_CUDA_INTRA_NONE) {
-        int angle = d.angle_delta;
-        const int m = prepare_edges<pixel>(d.x4, have_left, d.y4, have_top, d.tile_x4_end, d.tile_y4_end,
-                                           d.edge_flags, dst, stride, nullptr, mode, &angle, d.tw4, d.th4,
-                                           (d.flags >> 10) & 1, edge, bdmax, lane);
+        // inter-intra (recon_tmpl.c:1658-1681): the whole-block intra prediction (edge_flags 0, no
+        // edge filter) is blended onto the inter prediction that is in dst
+        const bool ii = mode == DAV1D_CUDA_INTRA_II;
+        int angle = ii ? 0 : d.angle_delta;
+        const int m = prepare_edges<pixel>(g, d.x4, have_left, d.y4, have_top, d.tile_x4_end, d.tile_y4_end,
+                                           ii ? 0 : d.edge_flags, dst, stride, nullptr, ii ? d.angle_delta : mode,
+                                           &angle, d.tw4, d.th4, ii ? 0 : (d.flags >> 10) & 1, edge, bdmax);
+        if (ii) { bmask = a.pal_idx + d.coef_off; angle = 0; }
+        else angle |= d.flags;
         const int max_w = ((4 * a.bw4 + ss_hor) >> ss_hor) - 4 * d.x4;
         const int max_h = ((4 * a.bh4 + ss_ver) >> ss_ver) - 4 * d.y4;
-        ipred_block<pixel>(m, pout, pstride, edge, w, h, angle | d.flags, max_w, max_h, bdmax, sm->scratch, lane);
+        P = ipred_setup<pixel>(g, m, angle, w, h, max_w, max_h, edge, scratch, (pixel *)tile, bdmax);
+        kind = 0;
     }
-    __syncwarp();
-    if (!has_res) return;
-    itx2_block<pixel, 64>(true, lane, 32, sm->tile, (coef *)a.cf + d.coef_off, d.tx, d.txtp, d.eob, d.cw4, d.ch4,
-                          to_tile ? ptile : dst, to_tile ? w : stride, dst, stride, bdmax, false);
+    grp_sync(g);
+
+    const pixel *base = (const pixel *)pv.data;
+    const int ib = PxTraits<pixel>::inter_bits(bdmax);
+    const int n = w * h;
+#pragma unroll 1
+    for (int i = g.gl; i < n; i += g.G) {
+        const int y = i >> lw, x = i & (w - 1);
+        int v;
+        if (kind == 0) {
+            v = ipred_pixel<pixel>(P, x, y, i, bdmax);
+        } else if (kind == 1) {
+            // pal_pred (ipred_tmpl.c:717-730): two pixels per index byte
+            const int idx = (a.pal_idx + d.coef_off)[i >> 1];
+            v = ((const pixel *)a.pal + d.aux)[(x & 1) ? idx >> 4 : idx & 7];
+        } else if (kind == 2) {
+            // intrabc: put_bilin (mc_tmpl.c:395-450) from the current picture; coordinates clamped
+            // to the 4*bw4 x 4*bh4 area (= emu_edge, recon_tmpl.c:974-995)
+            const int sx = (int16_t)(d.aux & 0xffff), sy = (int16_t)(d.aux >> 16);
+            const int mx = d.angle_delta, my = d.flags;
+            const int pw = (4 * a.bw4) >> ss_hor, ph = (4 * a.bh4) >> ss_ver;
+            const int xa = iclip(sx + x, 0, pw - 1), xb = iclip(sx + x + 1, 0, pw - 1);
+            const int ya = iclip(sy + y, 0, ph - 1), yb = iclip(sy + y + 1, 0, ph - 1);
+            const int q00 = __ldcg(base + (int64_t)ya * stride + xa), q01 = __ldcg(base + (int64_t)ya * stride + xb);
+            const int q10 = __ldcg(base + (int64_t)yb * stride + xa), q11 = __ldcg(base + (int64_t)yb * stride + xb);
+            if (mx && my) {
+                const int sh1 = 4 - ib, r1 = (1 << sh1) >> 1;
+                const int m0 = (16 * q00 + mx * (q01 - q00) + r1) >> sh1;
+                const int m1 = (16 * q10 + mx * (q11 - q10) + r1) >> sh1;
+                const int sh2 = 4 + ib;
+                v = clip_px<pixel>((16 * m0 + my * (m1 - m0) + ((1 << sh2) >> 1)) >> sh2, bdmax);
+            } else if (mx) {
+                const int sh1 = 4 - ib;
+                const int px = (16 * q00 + mx * (q01 - q00) + ((1 << sh1) >> 1)) >> sh1;
+                v = clip_px<pixel>((px + ((1 << ib) >> 1)) >> ib, bdmax);
+            } else if (my) {
+                v = clip_px<pixel>((16 * q00 + my * (q10 - q00) + 8) >> 4, bdmax);
+            } else {
+                v = q00;
+            }
+        } else {
+            v = __ldcg(dst + y * stride + x);      // residual on top of what an earlier round left there
+        }
+        if (bmask) {
+            // mc.blend of the intra prediction onto the inter prediction (mc_tmpl.c:642-653)
+            const int mk = bmask[i], p = __ldcg(dst + y * stride + x);
+            v = (p * (64 - mk) + v * mk + 32) >> 6;
+        }
+        if (res) v = clip_px<pixel>(v + res[y * rstride + x], bdmax);
+        dst[y * stride + x] = (pixel)v;
+    }
+    // the operation's pixels are stored: one count less on each of its cells (the grid barrier at
+    // the end of the round makes pixels and counts visible together)
+    {
+        const int W = map_w(a, pl), H = map_h(a, pl);
+        uint8_t *m = a.map + map_off(a, pl);
+        const int ltw = 31 - __clz((int)d.tw4);
+        const int nc = d.th4 << ltw;
+        for (int j = g.gl; j < nc; j += g.G) {
+            const int cx = d.x4 + (j & (d.tw4 - 1)), cy = d.y4 + (j >> ltw);
+            if (cx < W && cy < H) {
+                uint8_t *p = m + cy * W + cx;
+                *(volatile uint8_t *)p = (uint8_t)(__ldcg(p) - 1);
+            }
+        }
+    }
+    grp_sync(g);
 }
 
-// The persistent executor: see the header of this file.
+// per-warp shared memory of step 3: four octets (or one warp: slot 0) of edge + Z-mode scratch,
+// and the CfL ac / filter-intra tile (1024 values for a warp-wide operation, 256 per octet)
+template <typename pixel> struct __align__(16) ExecSmem {
+    pixel edge[4][EDGE_BUF];
+    pixel scratch[4][IPRED_SCRATCH];
+    int16_t tile[32 * 32];
+};
+
+constexpr int R_WARPS = 8;
+constexpr int R_BINS = 64;              // sort key: (small ? 0 : 32) + predictor class
+// counters of a round (two sets, used alternately)
+struct RoundCtr {
+    unsigned n_next, n_ready;
+    unsigned hist[R_BINS];
+    unsigned cursor[R_BINS];
+};
+struct RoundsArgs {
+    Intra2Args g;
+    int op_base[I2_MAXF + 1];           // first global operation number of every frame
+    unsigned *pend[2];                  // pending operation ids (frame << 24 | index)
+    unsigned *ready;                    // ready operations of the round, unsorted
+    uint8_t *ready_key;
+    unsigned *sorted;                   // ... sorted by key
+    unsigned *bar;                      // grid barrier counter (zeroed before the launch)
+    RoundCtr *ctr;                      // [2] (zeroed before the launch)
+};
+
 template <typename pixel>
-__global__ void __launch_bounds__(I2_WARPS * 32, 4) intra2_kernel(const __grid_constant__ Intra2Args a) {
-    extern __shared__ __align__(16) uint8_t intra2_smem_raw[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    Intra2Smem<pixel> *sm = (Intra2Smem<pixel> *)intra2_smem_raw + warp;
-    const unsigned total = (unsigned)a.max_units * (unsigned)a.nf;
-    for (;;) {
-        unsigned k = 0;
-        if (lane == 0) k = atomicAdd(a.claim, 1u);
-        k = __shfl_sync(0xffffffffu, k, 0);
-        if (k >= total) break;
-        // claim k -> frame k % nf, unit k / nf: the frames of the group advance together
-        const Intra2Frame &f = a.f[k % (unsigned)a.nf];
-        const int u = (int)(k / (unsigned)a.nf);
-        if (u >= f.n_units) continue;
-        const uint2 un = f.units[u];
-        const int i0 = (int)un.x, i1 = (int)(un.x + un.y);
-        if (i0 >= i1) continue;
-        Dav1dCudaIntraDesc d = f.descs[i0];
-        for (int i = i0; i < i1; i++) {
-            Dav1dCudaIntraDesc dn;
-            if (i + 1 < i1) dn = f.descs[i + 1];             // next descriptor in flight during this operation
-            if (!intra2_wait(f, d, lane, a.status)) return;  // abandoned: the host reports it
-            intra2_op<pixel>(f, d, sm, lane);
-            intra2_publish(f, d, lane);
-            d = dn;
+__global__ void __launch_bounds__(R_WARPS * 32, 3) intra_rounds_kernel(const __grid_constant__ RoundsArgs a) {
+    extern __shared__ __align__(16) uint8_t rounds_smem_raw[];
+    __shared__ unsigned s_hist[R_BINS], s_base[R_BINS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned gtid = blockIdx.x * blockDim.x + tid, gthreads = gridDim.x * blockDim.x;
+    ExecSmem<pixel> *sm = (ExecSmem<pixel> *)rounds_smem_raw + warp;
+    unsigned target = 0;
+    unsigned n_pend = (unsigned)a.op_base[a.g.nf];
+    for (int round = 0; n_pend > 0; round++) {
+        RoundCtr *ctr = a.ctr + (round & 1), *nxt = a.ctr + ((round & 1) ^ 1);
+        const unsigned *pend = a.pend[round & 1];
+        unsigned *pend_next = a.pend[(round & 1) ^ 1];
+        // ---- step 1: every pending operation is looked at by one thread
+        if (tid < R_BINS) s_hist[tid] = 0;
+        __syncthreads();
+        for (unsigned k0 = blockIdx.x * blockDim.x; k0 < n_pend; k0 += gthreads) {
+            const unsigned k = k0 + tid;
+            bool ready = false, live = k < n_pend;
+            unsigned id = 0;
+            int key = 0;
+            if (live) {
+                if (round == 0) {
+                    int fi = 0;
+                    while (fi + 1 < a.g.nf && (unsigned)a.op_base[fi + 1] <= k) fi++;
+                    id = ((unsigned)fi << 24) | (k - (unsigned)a.op_base[fi]);
+                } else {
+                    id = __ldcg(pend + k);
+                }
+                const Intra2Frame &f = a.g.f[id >> 24];
+                const Dav1dCudaIntraDesc d = f.descs[id & 0xffffffu];
+                int cls = 0;
+                ready = op_ready(f, d, &cls);
+                key = (d.tw4 * d.th4 <= 4 ? 0 : 32) + cls;
+            }
+            // warp-aggregated appends
+            const unsigned mr = __ballot_sync(0xffffffffu, ready), mp = __ballot_sync(0xffffffffu, live && !ready);
+            unsigned br = 0, bp = 0;
+            if (lane == 0) {
+                if (mr) br = atomicAdd(&ctr->n_ready, __popc(mr));
+                if (mp) bp = atomicAdd(&ctr->n_next, __popc(mp));
+            }
+            br = __shfl_sync(0xffffffffu, br, 0);
+            bp = __shfl_sync(0xffffffffu, bp, 0);
+            const unsigned lt = (1u << lane) - 1u;
+            if (ready) {
+                const unsigned pos = br + __popc(mr & lt);
+                a.ready[pos] = id;
+                a.ready_key[pos] = (uint8_t)key;
+                atomicAdd(&s_hist[key], 1u);
+            } else if (live) {
+                pend_next[bp + __popc(mp & lt)] = id;
+            }
         }
+        __syncthreads();
+        if (tid < R_BINS && s_hist[tid]) atomicAdd(&ctr->hist[tid], s_hist[tid]);
+        grid_barrier(a.bar, target);
+        const unsigned n_ready = ld_acquire_u32(&ctr->n_ready), n_next = ld_acquire_u32(&ctr->n_next);
+        if (n_ready == 0) {
+            // pending operations, none ready: they wait for each other - inconsistent descriptors
+            if (gtid == 0) atomicOr(a.g.status, 1u);
+            return;
+        }
+        // ---- step 2: counting sort of the ready list by key.  Start of every bin (all blocks
+        // compute the same prefix), then every block scatters a contiguous chunk of the list.
+        if (tid == 0) {
+            unsigned acc = 0;
+            for (int b = 0; b < R_BINS; b++) { s_base[b] = acc; acc += ld_acquire_u32(&ctr->hist[b]); }
+        }
+        if (tid < R_BINS) s_hist[tid] = 0;
+        __syncthreads();
+        const unsigned n_small = s_base[32];
+        {
+            const unsigned chunk = (n_ready + gridDim.x - 1) / gridDim.x;
+            const unsigned c0 = blockIdx.x * chunk, c1 = min(n_ready, c0 + chunk);
+            for (unsigned k = c0 + tid; k < c1; k += blockDim.x) atomicAdd(&s_hist[__ldcg(a.ready_key + k)], 1u);
+            __syncthreads();
+            if (tid < R_BINS) {
+                const unsigned c = s_hist[tid];
+                s_hist[tid] = s_base[tid] + (c ? atomicAdd(&ctr->cursor[tid], c) : 0u);   // this block's range of the bin
+            }
+            __syncthreads();
+            for (unsigned k = c0 + tid; k < c1; k += blockDim.x) {
+                const unsigned pos = atomicAdd(&s_hist[__ldcg(a.ready_key + k)], 1u);
+                a.sorted[pos] = __ldcg(a.ready + k);
+            }
+        }
+        // the other counter set is free (last read before the previous round's final barrier)
+        if (gtid < sizeof(RoundCtr) / 4) ((unsigned *)nxt)[gtid] = 0;
+        grid_barrier(a.bar, target);
+        // ---- step 3: execute.  Items: four small operations per warp (one per octet), then the
+        // others one per warp
+        {
+            const unsigned items_small = (n_small + 3) / 4, items = items_small + (n_ready - n_small);
+            const unsigned gw = blockIdx.x * R_WARPS + warp, nw = gridDim.x * R_WARPS;
+            for (unsigned it = gw; it < items; it += nw) {
+                if (it < items_small) {
+                    const unsigned k = it * 4 + (lane >> 3);
+                    if (k < n_small) {
+                        const unsigned id = __ldcg(a.sorted + k);
+                        const Intra2Frame &f = a.g.f[id >> 24];
+                        const Dav1dCudaIntraDesc d = f.descs[id & 0xffffffu];
+                        const int o = lane >> 3;
+                        intra_exec<pixel>(grp_octet(lane), f, d, sm->edge[o], sm->scratch[o], sm->tile + 256 * o);
+                    }
+                } else {
+                    const unsigned id = __ldcg(a.sorted + n_small + (it - items_small));
+                    const Intra2Frame &f = a.g.f[id >> 24];
+                    const Dav1dCudaIntraDesc d = f.descs[id & 0xffffffu];
+                    intra_exec<pixel>(grp_warp(lane), f, d, sm->edge[0], sm->scratch[0], sm->tile);
+                }
+                __syncwarp();
+            }
+        }
+        grid_barrier(a.bar, target);
+        n_pend = n_next;
+        if (round > (1 << 20)) { if (gtid == 0) atomicOr(a.g.status, 1u); return; }
     }
 }
 
@@ -370,23 +463,22 @@ __global__ void intra2_mark_kernel(const __grid_constant__ Intra2Args a) {
     }
 }
 
-static int g_i2_blocks[2] = { 0, 0 };   // resident blocks of the executor per pixel type
+static int g_rounds_blocks[2] = { 0, 0 };   // co-resident blocks of the executor per pixel type
+template <typename pixel> static size_t rounds_smem_bytes() { return R_WARPS * sizeof(ExecSmem<pixel>); }
 
 void recon_init_attrs() {
     itx_init_attrs();
-    cudaFuncSetAttribute(intra2_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)(I2_WARPS * sizeof(Intra2Smem<uint8_t>)));
-    cudaFuncSetAttribute(intra2_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)(I2_WARPS * sizeof(Intra2Smem<uint16_t>)));
+    cudaFuncSetAttribute(intra_rounds_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)rounds_smem_bytes<uint8_t>());
+    cudaFuncSetAttribute(intra_rounds_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)rounds_smem_bytes<uint16_t>());
     int dev = 0, sms = 0, occ = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, intra2_kernel<uint8_t>, I2_WARPS * 32,
-                                                  I2_WARPS * sizeof(Intra2Smem<uint8_t>));
-    g_i2_blocks[0] = std::max(1, occ) * std::max(1, sms);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, intra2_kernel<uint16_t>, I2_WARPS * 32,
-                                                  I2_WARPS * sizeof(Intra2Smem<uint16_t>));
-    g_i2_blocks[1] = std::max(1, occ) * std::max(1, sms);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, intra_rounds_kernel<uint8_t>, R_WARPS * 32, rounds_smem_bytes<uint8_t>());
+    g_rounds_blocks[0] = std::max(1, occ) * std::max(1, sms);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, intra_rounds_kernel<uint16_t>, R_WARPS * 32, rounds_smem_bytes<uint16_t>());
+    g_rounds_blocks[1] = std::max(1, occ) * std::max(1, sms);
 }
 
 // ---- warp batch: one warp per 8x8
@@ -457,6 +549,30 @@ static bool join_aux(Dav1dCudaContext *c, cudaStream_t st) {
     return true;
 }
 
+// workspace of the executor's rounds: barrier + counters, then pending x 2, ready, sorted (ids) and
+// the ready keys.  One per context, grown on demand outside any stream capture; submissions of a
+// context are ordered on its stream.
+static size_t rounds_ws_hdr() { return 256 + ((2 * sizeof(RoundCtr) + 255) & ~(size_t)255); }
+static size_t rounds_ws_need(size_t total) {
+    return rounds_ws_hdr() + 4 * ((total * 4 + 255) & ~(size_t)255) + ((total + 255) & ~(size_t)255);
+}
+static int ensure_rounds_ws(Dav1dCudaContext *c, const Dav1dCudaReconBatch *const *bs, int n) {
+    size_t total = 0;
+    for (int f = 0; f < n; f++)
+        if (bs[f] && bs[f]->n_intra > 0) total += (size_t)bs[f]->n_intra;
+    const size_t need = rounds_ws_need(total);
+    if (need <= c->rounds_ws_bytes) return 0;
+    if (c->rounds_ws) {
+        D1_CHECK(cudaStreamSynchronize(c->stream));
+        cudaFree(c->rounds_ws);
+        c->rounds_ws = nullptr; c->rounds_ws_bytes = 0;
+    }
+    const size_t want = need + need / 4;
+    D1_CHECK(cudaMalloc(&c->rounds_ws, want));
+    c->rounds_ws_bytes = want;
+    return 0;
+}
+
 static int check_group(const Dav1dCudaReconBatch *const *bs, int n) {
     if (!bs || n < 1 || n > I2_MAXF) return -22;
     for (int f = 0; f < n; f++) {
@@ -467,8 +583,9 @@ static int check_group(const Dav1dCudaReconBatch *const *bs, int n) {
         for (int g = 0; g < n; g++)
             for (int r = 0; r < 7; r++)
                 if (g != f && bs[g] && bs[g]->refs[r] && bs[g]->refs[r]->p[0].data == b->dst->p[0].data) return -22;
-        if (b->n_intra > 0 && (!b->intra || !b->intra_units || b->n_intra_units < 1 || !b->intra_cellmap))
-            return -22;
+        if (b->n_intra > 0 && (!b->intra || !b->intra_cellmap)) return -22;
+        if (b->n_intra >= (1 << 24)) return -22;
+        if (b->n_intra > 0 && b->intra_itx && !b->intra_res) return -22;
     }
     return 0;
 }
@@ -496,20 +613,16 @@ static int group_submit_on(Dav1dCudaContext *c, const Dav1dCudaReconBatch *const
             const Dav1dCudaReconBatch *b = bs[f];
             Intra2Frame &p = ia.f[f];
             p.pic = pic_view(b->dst); p.bw4 = b->bw4; p.bh4 = b->bh4; p.cf = b->cf;
+            if (b->intra_res) p.res = pic_view(b->intra_res);
             p.descs = b->intra; p.pal = b->pal; p.pal_idx = b->pal_idx;
-            p.units = (const uint2 *)b->intra_units;
-            p.n_units = b->n_intra > 0 ? b->n_intra_units : 0;
             p.n_ops = b->n_intra > 0 ? b->n_intra : 0;
             p.map = b->intra_cellmap;
-            ia.max_units = std::max(ia.max_units, p.n_units);
             n_ops = std::max(n_ops, p.n_ops);
         }
-        ia.claim = c->claim + (c->claim_next++ % Dav1dCudaContext::N_CLAIM);
         ia.status = c->status;
     }
     if (!fork_aux(c, st)) return -5;
     if ((mask & 16) && n_ops > 0) {
-        D1_CHECK(cudaMemsetAsync(ia.claim, 0, sizeof(unsigned), ss[NS - 1]));
         intra2_mark_kernel<<<dim3((unsigned)std::min((n_ops + 255) / 256, 64), (unsigned)n), 256, 0, ss[NS - 1]>>>(ia);
         count_launch();
     }
@@ -533,19 +646,48 @@ static int group_submit_on(Dav1dCudaContext *c, const Dav1dCudaReconBatch *const
                                         b->n_mc_obmc_tiles[1], s))) return r;
         }
         if ((mask & 8) && b->itx && b->itx_tasks) {
-            if ((r = itx_task_launch(dst, b->cf, b->itx, b->itx_tasks, b->n_itx_tasks[0], b->n_itx_tasks[1], 0, s, s)))
+            if ((r = itx_task_launch(dst, nullptr, b->cf, b->itx, b->itx_tasks, b->n_itx_tasks[0], b->n_itx_tasks[1], 0, s, s)))
                 return r;
-        } else if ((mask & 8) && b->itx && (r = itx_batch_launch(dst, b->cf, b->itx, b->itx_class_count, 0, s))) return r;
+        } else if ((mask & 8) && b->itx && (r = itx_batch_launch(dst, nullptr, b->cf, b->itx, b->itx_class_count, 0, s))) return r;
+        // intra residual pre-pass -> int16 residual planes (independent of everything above)
+        if ((mask & 16) && b->n_intra > 0 && b->intra_itx && b->intra_res) {
+            const PicView rv = pic_view(b->intra_res);
+            cudaStream_t s2 = ss[(f + 2) % NS];
+            if (b->intra_itx_tasks) {
+                if ((r = itx_task_launch(dst, &rv, b->cf, b->intra_itx, b->intra_itx_tasks, b->n_intra_itx_tasks[0],
+                                         b->n_intra_itx_tasks[1], 0, s2, s2))) return r;
+            } else if ((r = itx_batch_launch(dst, &rv, b->cf, b->intra_itx, b->intra_itx_class_count, 0, s2))) return r;
+        }
     }
     if (!join_aux(c, st)) return -5;
     if (!(mask & 16) || n_ops <= 0) return 0;
-    const size_t smem = I2_WARPS * (hbd ? sizeof(Intra2Smem<uint16_t>) : sizeof(Intra2Smem<uint8_t>));
-    const long long claims = (long long)ia.max_units * n;
-    const int grid = (int)std::min<long long>(g_i2_blocks[hbd], (claims + I2_WARPS - 1) / I2_WARPS);
-    if (hbd) intra2_kernel<uint16_t><<<grid, I2_WARPS * 32, smem, st>>>(ia);
-    else intra2_kernel<uint8_t><<<grid, I2_WARPS * 32, smem, st>>>(ia);
+    // the executor: one cooperative launch (its blocks wait for each other at the grid barriers)
+    RoundsArgs ra;
+    memset(&ra, 0, sizeof(ra));
+    ra.g = ia;
+    size_t total = 0;
+    for (int f = 0; f < n; f++) { ra.op_base[f] = (int)total; total += (size_t)ia.f[f].n_ops; }
+    ra.op_base[n] = (int)total;
+    if (total >= ((size_t)1 << 31)) return -22;
+    const size_t hdr = rounds_ws_hdr();
+    if (rounds_ws_need(total) > c->rounds_ws_bytes) return -12;      // ensure_rounds_ws() comes first
+    uint8_t *ws = (uint8_t *)c->rounds_ws;
+    ra.bar = (unsigned *)ws;
+    ra.ctr = (RoundCtr *)(ws + 256);
+    const size_t lb = (total * 4 + 255) & ~(size_t)255;
+    ra.pend[0] = (unsigned *)(ws + hdr);
+    ra.pend[1] = (unsigned *)(ws + hdr + lb);
+    ra.ready = (unsigned *)(ws + hdr + 2 * lb);
+    ra.sorted = (unsigned *)(ws + hdr + 3 * lb);
+    ra.ready_key = ws + hdr + 4 * lb;
+    D1_CHECK(cudaMemsetAsync(ws, 0, hdr, st));
+    const size_t smem = hbd ? rounds_smem_bytes<uint16_t>() : rounds_smem_bytes<uint8_t>();
+    const int grid = (int)std::min<size_t>((size_t)g_rounds_blocks[hbd], (total + R_WARPS * 32 - 1) / (R_WARPS * 32));
+    void *kargs[] = { (void *)&ra };
+    const void *fn = hbd ? (const void *)intra_rounds_kernel<uint16_t> : (const void *)intra_rounds_kernel<uint8_t>;
+    D1_CHECK(cudaLaunchCooperativeKernel(fn, dim3((unsigned)grid), dim3(R_WARPS * 32), kargs, smem, st));
     count_launch();
-    return cuda_ok(cudaGetLastError(), "intra2_kernel") ? 0 : -5;
+    return 0;
 }
 
 }  // namespace d1
@@ -575,46 +717,25 @@ size_t dav1d_cuda_intra_cellmap_bytes(int bw4, int bh4, int ss_hor, int ss_ver) 
     return (((size_t)bw4 * bh4 + 2 * cw * ch) + 255) & ~(size_t)255;
 }
 
-// Host helper for recorders that do not track units themselves: the operations (decode order) are
-// cut wherever the luma superblock (unit_log2 = 4: 64x64) changes; optionally wavefront order.
-int dav1d_cuda_intra_units(const Dav1dCudaIntraDesc *descs, int n, int ss_hor, int ss_ver, int unit_log2,
-                           int wave_gradient, uint32_t *units, int max_units)
-{
-    if (!descs || !units || n < 0 || unit_log2 < 1 || wave_gradient < 0) return -22;
-    struct U { uint32_t first, count; int wave; };
-    std::vector<U> us;
-    int last_x = -1, last_y = -1;
-    for (int i = 0; i < n; i++) {
-        const Dav1dCudaIntraDesc &d = descs[i];
-        const int ux = (d.plane ? d.x4 << ss_hor : d.x4) >> unit_log2, uy = (d.plane ? d.y4 << ss_ver : d.y4) >> unit_log2;
-        if (us.empty() || ux != last_x || uy != last_y) {
-            us.push_back({ (uint32_t)i, 0u, ux + wave_gradient * uy });
-            last_x = ux; last_y = uy;
-        }
-        us.back().count++;
-    }
-    if ((int)us.size() > max_units) return -34;
-    if (wave_gradient > 0)
-        std::stable_sort(us.begin(), us.end(), [](const U &a, const U &b) { return a.wave < b.wave; });
-    for (size_t k = 0; k < us.size(); k++) { units[2 * k] = us[k].first; units[2 * k + 1] = us[k].count; }
-    return (int)us.size();
-}
-
 int dav1d_cuda_recon_submit(Dav1dCudaContext *c, const Dav1dCudaReconBatch *b) {
     if (!c || !b) return -22;
     D1_CHECK(cudaSetDevice(c->device));
+    if (ensure_rounds_ws(c, &b, 1)) return -12;
     return group_submit_on(c, &b, 1, c->stream, 31);
 }
 
 int dav1d_cuda_recon_submit_phases(Dav1dCudaContext *c, const Dav1dCudaReconBatch *b, int phase_mask) {
     if (!c || !b) return -22;
     D1_CHECK(cudaSetDevice(c->device));
+    if (ensure_rounds_ws(c, &b, 1)) return -12;
     return group_submit_on(c, &b, 1, c->stream, phase_mask & 31);
 }
 
 int dav1d_cuda_recon_group_submit(Dav1dCudaContext *c, const Dav1dCudaReconBatch *const *bs, int n) {
     if (!c) return -22;
     D1_CHECK(cudaSetDevice(c->device));
+    if (!bs || n < 1 || n > I2_MAXF) return -22;
+    if (ensure_rounds_ws(c, bs, n)) return -12;
     return group_submit_on(c, bs, n, c->stream, 31);
 }
 
@@ -623,6 +744,8 @@ int dav1d_cuda_recon_group_submit_phases(Dav1dCudaContext *c, const Dav1dCudaRec
 {
     if (!c) return -22;
     D1_CHECK(cudaSetDevice(c->device));
+    if (!bs || n < 1 || n > I2_MAXF) return -22;
+    if (ensure_rounds_ws(c, bs, n)) return -12;
     return group_submit_on(c, bs, n, c->stream, phase_mask & 31);
 }
 
@@ -636,6 +759,7 @@ int dav1d_cuda_recon_graph_build_multi_phases(Dav1dCudaContext *c, const Dav1dCu
     D1_CHECK(cudaSetDevice(c->device));
     if (check_group(bs, n)) return -22;
     if (!ensure_aux(c)) return -5;
+    if (ensure_rounds_ws(c, bs, n)) return -12;      // no allocation inside the capture
     cudaStream_t cap;
     D1_CHECK(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
     if (!cuda_ok(cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal), "cudaStreamBeginCapture")) {

@@ -64,7 +64,7 @@ typedef struct D1SynthFrame {
     double luma_px;            // luma pixels covered
     int64_t n_blocks, n_intra_blocks;
     Dav1dCudaMcDesc *mc_obmc;  int32_t n_mc_obmc;  uint32_t *mc_obmc_tiles; int32_t n_mc_obmc_tiles[2];
-    uint32_t *intra_units; int32_t n_intra_units;       // (first operation, count) per coding block that has any, claim order
+    Dav1dCudaItxDesc *intra_itx; int32_t n_intra_itx; int32_t intra_itx_class_count[19];   // the intra residuals as transforms
 } D1SynthFrame;
 
 }  // extern "C"
@@ -110,8 +110,6 @@ struct Gen {
     std::vector<Dav1dCudaWarpDesc> warp;
     std::vector<Dav1dCudaItxDesc> itx;
     std::vector<Dav1dCudaIntraDesc> intra;
-    struct Unit { uint32_t first, count; int wave; };
-    std::vector<Unit> units;                     // one per coding block with intra-class operations
     std::vector<int32_t> cf32;
     std::vector<uint8_t> masks, pal_idx;
     std::vector<uint16_t> pal;
@@ -226,15 +224,6 @@ struct Gen {
         d.flags = (uint16_t)flags;
         d.aux = aux;
         d.eob = -1;
-        {   // where the operation sits inside its coding block (this plane's 4-px units)
-            const int sh = pl ? P.ss_hor : 0, sv = pl ? P.ss_ver : 0;
-            const int ox = cur_bx4 >> sh, oy = cur_by4 >> sv;
-            const int bw = std::max(1, cur_bw4 >> sh), bh = std::max(1, cur_bh4 >> sv);
-            int lw = 0, lh = 0;
-            while ((1 << lw) < bw) lw++;
-            while ((1 << lh) < bh) lh++;
-            d.blk = DAV1D_CUDA_INTRA_BLK(x4 - ox, y4 - oy, lw, lh);
-        }
         if (mode <= 13) {
             const bool tr = y4 > 0 && all_decoded(pl, x4 + tw4, y4 - 1, std::min(x4 + 2 * tw4, pw4[pl]), y4);
             const bool bl = x4 > 0 && all_decoded(pl, x4 - 1, y4 + th4, x4, std::min(y4 + 2 * th4, ph4[pl]));
@@ -603,19 +592,11 @@ struct Gen {
         }
     }
 
-    int cur_bx4 = 0, cur_by4 = 0, cur_bw4 = 1, cur_bh4 = 1;   // the coding block being emitted (luma 4-px units)
     void block(int bx4, int by4, int w4, int h4) {
-        cur_bx4 = bx4; cur_by4 = by4; cur_bw4 = w4; cur_bh4 = h4;
         n_blocks++;
         luma_px += 16.0 * w4 * h4;
-        const size_t first = intra.size();
         if (rng.chance(P.p_intra)) intra_block(bx4, by4, w4, h4);
         else inter_block(bx4, by4, w4, h4);
-        // one unit of the intra executor per coding block that emitted intra-class operations;
-        // wave = superblock column + 2 * superblock row: a superblock only reads pixels of its left,
-        // top-left, top and top-right neighbours, all of them in earlier waves
-        if (intra.size() > first)
-            units.push_back({ (uint32_t)first, (uint32_t)(intra.size() - first), (bx4 >> 4) + 2 * (by4 >> 4) });
     }
 
     // recursive partition of an s4 x s4 (4-px units) square at (bx4, by4), decode (Z) order
@@ -710,6 +691,25 @@ __attribute__((visibility("default"))) int d1synth_generate(const D1SynthParams 
             itx_sorted[n] = g.itx[idx[n]];
         }
     }
+    // the residuals of the intra-class operations as transform descriptors, ordered like `itx`
+    {
+        std::vector<Dav1dCudaItxDesc> v;
+        for (auto &d : g.intra) {
+            if (d.eob < 0 || d.mode == DAV1D_CUDA_INTRA_PAL) continue;
+            Dav1dCudaItxDesc t;
+            memset(&t, 0, sizeof(t));
+            t.coef_off = d.coef_off; t.x = (uint16_t)(d.x4 * 4); t.y = (uint16_t)(d.y4 * 4);
+            t.eob = d.eob; t.plane = d.plane; t.tx = d.tx; t.txtp = d.txtp; t.cw4 = d.cw4; t.ch4 = d.ch4;
+            v.push_back(t);
+            f->intra_itx_class_count[d.tx]++;
+        }
+        std::stable_sort(v.begin(), v.end(), [](const Dav1dCudaItxDesc &x, const Dav1dCudaItxDesc &y) {
+            const int kx = ((int)x.tx << 8) | (x.eob == 0 && x.txtp == 0 ? 0 : 1 + x.txtp);
+            const int ky = ((int)y.tx << 8) | (y.eob == 0 && y.txtp == 0 ? 0 : 1 + y.txtp);
+            return kx < ky;
+        });
+        f->intra_itx = dup(v); f->n_intra_itx = (int32_t)v.size();
+    }
     // tiles: per list (put, compound wave 0, compound wave 1) the tiles of blocks of at most
     // 8x8 samples first (they are processed four per warp), then the others
     std::vector<uint32_t> put_tiles, comp_tiles;
@@ -760,16 +760,6 @@ __attribute__((visibility("default"))) int d1synth_generate(const D1SynthParams 
     f->warp = dup(g.warp); f->n_warp = (int32_t)g.warp.size();
     f->itx = dup(itx_sorted); f->n_itx = (int32_t)itx_sorted.size();
     f->intra = dup(g.intra); f->n_intra = (int32_t)g.intra.size();
-    // Claim order of the units: decode order is always valid; wavefront order (stable sort by wave)
-    // keeps the units a group of warps holds at any time independent of each other.  Intrabc
-    // sources of this generator may lie anywhere in the superblock rows above, which only decode
-    // order respects.
-    if (p->p_ibc <= 0.f)
-        std::stable_sort(g.units.begin(), g.units.end(), [](const Gen::Unit &a, const Gen::Unit &b) { return a.wave < b.wave; });
-    std::vector<uint32_t> upairs;
-    for (auto &u : g.units) { upairs.push_back(u.first); upairs.push_back(u.count); }
-    f->n_intra_units = (int32_t)g.units.size();
-    f->intra_units = dup(upairs);
     f->cf_elems = g.cf32.size();
     if (g.hbd) f->cf = dup(g.cf32);
     else {
@@ -796,7 +786,7 @@ __attribute__((visibility("default"))) void d1synth_free(D1SynthFrame *f) {
     if (!f) return;
     free(f->mc_put); free(f->mc_put_tiles); free(f->mc_comp); free(f->mc_comp_tiles); free(f->warp);
     free(f->mc_obmc); free(f->mc_obmc_tiles);
-    free(f->intra_units);
+    free(f->intra_itx);
     free(f->itx); free(f->intra); free(f->cf); free(f->masks); free(f->pal); free(f->pal_idx); free(f->order);
     memset(f, 0, sizeof(*f));
 }

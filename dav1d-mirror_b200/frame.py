@@ -44,7 +44,7 @@ class SynthFrame(C.Structure):
                 ("n_blocks", C.c_int64), ("n_intra_blocks", C.c_int64),
                 ("mc_obmc", C.c_void_p), ("n_mc_obmc", C.c_int32), ("mc_obmc_tiles", C.c_void_p),
                 ("n_mc_obmc_tiles", C.c_int32 * 2),
-                ("intra_units", C.c_void_p), ("n_intra_units", C.c_int32)]
+                ("intra_itx", C.c_void_p), ("n_intra_itx", C.c_int32), ("intra_itx_class_count", C.c_int32 * 19)]
 
 
 _synth = None
@@ -115,10 +115,10 @@ class HostFrame:
         self.algo_bytes, self.luma_px = f.algo_bytes, f.luma_px
         self.algo_class = dict(zip(("mc_put", "mc_compound", "warp", "itx", "intra"), list(f.algo_class)))
         self.n_blocks, self.n_intra_blocks = f.n_blocks, f.n_intra_blocks
-        # intra-class operations stay in decode order; the recorder names the units (coding
-        # blocks) as (first, count) pairs in the order they are to be claimed
-        self.n_intra_units = f.n_intra_units
-        self.intra_units = _np_from(f.intra_units, f.n_intra_units * 8)
+        # intra-class operations stay in decode order; their residuals are listed a second time as
+        # transform descriptors ordered like `itx`
+        self.intra_itx = _np_from(f.intra_itx, f.n_intra_itx * C.sizeof(B.ItxDesc))
+        self.intra_itx_class_count = [f.intra_itx_class_count[i] for i in range(19)]
         S.d1synth_free(C.byref(f))
         # inter residuals: task codes over the (size, type)-sorted itx array (linear pass)
         L = B.lib()
@@ -129,6 +129,12 @@ class HostFrame:
             if n_itx else 0
         self.itx_tasks = tasks[:max(k, 1)].copy().view(np.uint8)
         self.n_itx_tasks = (ns.value, nb.value)
+        n_iitx = self.intra_itx.nbytes // C.sizeof(B.ItxDesc)
+        tasks = np.zeros(max(n_iitx, 1), dtype=np.uint32)
+        k = L.dav1d_cuda_itx_tasks(self.intra_itx.ctypes.data, n_iitx, 0, tasks.ctypes.data, C.byref(ns), C.byref(nb)) \
+            if n_iitx else 0
+        self.intra_itx_tasks = tasks[:max(k, 1)].copy().view(np.uint8)
+        self.n_intra_itx_tasks = (ns.value, nb.value) if n_iitx else (0, 0)
 
     def plane_shape(self, pl):
         sh = self.ss_hor if pl else 0
@@ -139,7 +145,8 @@ class HostFrame:
         """Bytes a decoder ships host->device for this frame (descriptors + coefficients + pools)."""
         return sum(a.nbytes for a in (self.mc_put, self.mc_put_tiles, self.mc_comp, self.mc_comp_tiles, self.warp,
                                       self.mc_obmc, self.mc_obmc_tiles, self.itx, self.itx_tasks, self.cf, self.masks,
-                                      self.pal, self.pal_idx, self.intra, self.intra_units))
+                                      self.pal, self.pal_idx, self.intra, self.intra_itx,
+                                      self.intra_itx_tasks))
 
 
 def random_planes(hf, seed):
@@ -155,10 +162,8 @@ class DeviceFrame:
     intra executor and ONE descriptor arena that receives, frame after frame, the descriptor set
     of the frame to reconstruct (`hf`, or - use(k) - one of several sets of the same geometry)."""
 
-    def __init__(self, ctx, hf, n_refs=2, tasks=True, units=True, more_sets=()):
-        """tasks: explicit transform task codes (else the implicit per-size runs); units: the
-        recorder's unit table (one unit per coding block) and block hints - else superblock units
-        cut by dav1d_cuda_intra_units() and no hints, i.e. every dependency goes through the cell map."""
+    def __init__(self, ctx, hf, n_refs=2, tasks=True, more_sets=()):
+        """tasks: explicit transform task codes (else the implicit per-size runs)."""
         self.L = B.lib()
         self.ctx = ctx
         L = self.L
@@ -170,6 +175,10 @@ class DeviceFrame:
                 raise RuntimeError("dav1d_cuda_picture_alloc failed")
         ssh = 0 if hf.no_chroma else hf.ss_hor
         ssv = 0 if hf.no_chroma else hf.ss_ver
+        # int16 residual planes of the intra pre-pass: a picture of the same geometry with 16-bit samples
+        self.res = B.Picture()
+        if L.dav1d_cuda_picture_alloc(ctx, C.byref(self.res), hf.w, hf.h, hf.ss_hor, hf.ss_ver, 0xffff):
+            raise RuntimeError("dav1d_cuda_picture_alloc failed")
         self._cellmap_bytes = L.dav1d_cuda_intra_cellmap_bytes(hf.bw4, hf.bh4, ssh, ssv)
         self._cellmap = L.dav1d_cuda_malloc(self._cellmap_bytes)
         L.dav1d_cuda_memset(ctx, self._cellmap, 0, self._cellmap_bytes)       # once; frames leave it at zero
@@ -179,7 +188,7 @@ class DeviceFrame:
         self._sets = []
         for h in [hf] + list(more_sets):
             assert (h.w, h.h, h.bdmax, h.ss_hor, h.ss_ver) == (hf.w, hf.h, hf.bdmax, hf.ss_hor, hf.ss_ver)
-            self._sets.append(self._layout(h, units))
+            self._sets.append(self._layout(h))
         self._arena_cap = max(st["bytes"] for st in self._sets)
         self._arena = L.dav1d_cuda_malloc(self._arena_cap)
         if not self._arena:
@@ -190,21 +199,10 @@ class DeviceFrame:
         self._pinned = None
         self.use(0)
 
-    def _layout(self, hf, units):
-        L = self.L
-        names = ["mc_put", "mc_put_tiles", "mc_comp", "mc_comp_tiles", "warp", "itx", "intra", "intra_units",
-                 "cf", "masks", "pal", "pal_idx", "itx_tasks"]
+    def _layout(self, hf):
+        names = ["mc_put", "mc_put_tiles", "mc_comp", "mc_comp_tiles", "warp", "itx", "intra",
+                 "cf", "masks", "pal", "pal_idx", "itx_tasks", "intra_itx", "intra_itx_tasks"]
         alt = {}
-        n_units = hf.n_intra_units
-        if not units and hf.n_intra:
-            intra = hf.intra.copy().reshape(hf.n_intra, C.sizeof(B.IntraDesc))
-            intra[:, 32:36] = 0                                  # no block hints
-            us = np.zeros(2 * hf.n_intra, dtype=np.uint32)
-            n_units = L.dav1d_cuda_intra_units(intra.ctypes.data, hf.n_intra, 0 if hf.no_chroma else hf.ss_hor,
-                                               0 if hf.no_chroma else hf.ss_ver, 4, 0 if hf.params.p_ibc > 0 else 2,
-                                               us.ctypes.data, hf.n_intra)
-            assert n_units > 0
-            alt = {"intra": intra.reshape(-1), "intra_units": us[:2 * n_units].copy().view(np.uint8)}
         if hf.mc_obmc.nbytes:
             names += ["mc_obmc", "mc_obmc_tiles"]
         host, offs, off = {}, {}, 0
@@ -213,7 +211,7 @@ class DeviceFrame:
             host[name] = arr
             offs[name] = off
             off += (max(arr.nbytes, 256) + 255) & ~255
-        return {"hf": hf, "host": host, "off": offs, "bytes": off, "n_units": n_units, "pinned": None}
+        return {"hf": hf, "host": host, "off": offs, "bytes": off, "pinned": None}
 
     def _make_batch(self, st, n_refs, tasks):
         hf = st["hf"]
@@ -240,8 +238,14 @@ class DeviceFrame:
             b.itx_tasks = d["itx_tasks"]
             b.n_itx_tasks[0], b.n_itx_tasks[1] = hf.n_itx_tasks
         b.intra, b.n_intra = d["intra"], hf.n_intra
-        b.intra_units, b.n_intra_units = d["intra_units"], st["n_units"]
         b.intra_cellmap = self._cellmap
+        b.intra_itx = d["intra_itx"]
+        for i in range(19):
+            b.intra_itx_class_count[i] = hf.intra_itx_class_count[i]
+        if tasks:
+            b.intra_itx_tasks = d["intra_itx_tasks"]
+            b.n_intra_itx_tasks[0], b.n_intra_itx_tasks[1] = hf.n_intra_itx_tasks
+        b.intra_res = C.pointer(self.res)
         return b
 
     def use(self, k):
@@ -366,7 +370,7 @@ class DeviceFrame:
                 L.dav1d_cuda_host_free(st["pinned"])
             L.dav1d_cuda_host_free(self._pinned_out)
         self._pinned, self._pinned_out = None, None
-        for pic in [self.dst] + self.refs:
+        for pic in [self.dst, self.res] + self.refs:
             L.dav1d_cuda_picture_free(self.ctx, C.byref(pic))
 
 

@@ -237,9 +237,6 @@ enum Dav1dCudaIntraKind {
     DAV1D_CUDA_INTRA_NONE   = 255   /* residual only (e.g. tx blocks of a palette or inter-intra block) */
 };
 
-#define DAV1D_CUDA_INTRA_BLK(dx4, dy4, lw, lh) \
-    ((uint32_t)(dx4) | (uint32_t)(dy4) << 4 | (uint32_t)(lw) << 8 | (uint32_t)(lh) << 12 | 1u << 16)
-
 typedef struct Dav1dCudaIntraDesc {  /* 40 bytes */
     uint16_t x4, y4;       /* position in 4-px units of THIS plane */
     uint16_t tile_x4_start;/* have_left = x4 > tile_x4_start */
@@ -255,11 +252,7 @@ typedef struct Dav1dCudaIntraDesc {  /* 40 bytes */
     uint8_t  tx, txtp;     /* residual transform, if any */
     uint32_t coef_off;     /* into the cf stream (PAL: into the index pool) */
     uint32_t aux;          /* CFL: w_pad | h_pad << 8 (4-px units); PAL: palette offset */
-    uint32_t blk;          /* optional hint, 0 = none: DAV1D_CUDA_INTRA_BLK(dx4, dy4, log2 bw4, log2 bh4) - the
-                            * operation lies dx4, dy4 cells right of / below the origin of a bw4 x bh4 cell rectangle
-                            * of this plane (its coding block) whose operations ALL belong to the operation's unit:
-                            * neighbour pixels inside the rectangle are then known to be final without a look at the
-                            * cell map (they were written by the same warp) */
+    uint32_t reserved;     /* 0 */
     uint8_t  cw4, ch4;     /* packed residual coefficients, see Dav1dCudaItxDesc (0, 0 = dense) */
     uint16_t pad;
 } Dav1dCudaIntraDesc;
@@ -281,9 +274,9 @@ typedef struct Dav1dCudaContext Dav1dCudaContext;
  * decoder instance / stream of frames; contexts run concurrently). */
 DAV1D_CUDA_API int  dav1d_cuda_open(Dav1dCudaContext **out, int device, void *stream);
 DAV1D_CUDA_API void dav1d_cuda_close(Dav1dCudaContext *c);
-/* Waits for the context's stream; also reads the context's device status word: a dependency wait
- * of the intra executor that timed out (the frame is then incomplete) is reported as -EIO (-5)
- * through the return value and dav1d_cuda_last_error(). */
+/* Waits for the context's stream; also reads the context's device status word: intra-class
+ * operations that wait for each other (inconsistent descriptors; the frame is then incomplete) are
+ * reported as -EIO (-5) through the return value and dav1d_cuda_last_error(). */
 DAV1D_CUDA_API int  dav1d_cuda_synchronize(Dav1dCudaContext *c);
 
 /* HBM picture allocation with the reference's geometry (src/picture.c:46-84:
@@ -351,28 +344,20 @@ DAV1D_CUDA_API int dav1d_cuda_warp_batch(Dav1dCudaContext *c, const Dav1dCudaPic
                                          const Dav1dCudaPicture *const refs[7],
                                          const Dav1dCudaWarpDesc *descs, int n);
 
-/* Intra-class operations are executed in ONE persistent launch per group of frames
- * (csrc/recon2.cu): the recorder hands over the descriptors in decode order and the offsets of
- * the "units" (superblocks) they belong to; warps claim units in decode order, run a unit's
- * operations one after the other and, before an operation reads pixels outside its own unit,
- * wait on a per-4x4-cell completion map in device memory.  Nothing is scheduled on the host.
+/* Intra-class operations are executed by ONE persistent launch per group of frames
+ * (csrc/recon2.cu): the recorder hands the descriptors over in decode order and that is all - the
+ * kernel finds the dependency levels itself, round by round, from a per-4x4-cell map in device
+ * memory that counts the operations which still have to write the cell.  Nothing is scheduled on
+ * the host.
  *
  * Cell map: dav1d_cuda_intra_cellmap_bytes() bytes of device memory per stream, zeroed ONCE by
  * the caller (every frame leaves it at zero again). */
 DAV1D_CUDA_API size_t dav1d_cuda_intra_cellmap_bytes(int bw4, int bh4, int ss_hor, int ss_ver);
-/* Host helper for recorders that do not track the units themselves: cuts `descs[0..n)` (decode
- * order) wherever the luma superblock changes (unit_log2 = 4: 64x64, 5: 128x128) and writes the
- * units as (first, count) pairs to units[0 .. 2 * returned count).  wave_gradient > 0 orders the
- * units as a wavefront (stable sort by superblock column + wave_gradient * superblock row, bw4 =
- * frame width in 4-px units); 2 is right for frames without intrabc, 0 keeps decode order.
- * < 0: max_units too small. */
-DAV1D_CUDA_API int dav1d_cuda_intra_units(const Dav1dCudaIntraDesc *descs, int n, int ss_hor, int ss_ver,
-                                          int unit_log2, int wave_gradient, uint32_t *units, int max_units);
 
 /* A whole frame's reconstruction as device-resident batches:
  *   phase A  motion compensation (put, fused compound in two waves, warp)
  *   phase B  inter residuals (itxfm_add per size class)
- *   phase C  intra-class operations: cell-map set-up + one persistent executor launch.
+ *   phase C  intra-class operations: residual pre-pass, cell-map set-up, one persistent executor launch.
  * Replaces pass 2 (DAV1D_TASK_TYPE_TILE_RECONSTRUCTION, thread_task.c:757-761)
  * for one frame.  Asynchronous on the context's stream. */
 typedef struct Dav1dCudaReconBatch {
@@ -396,21 +381,23 @@ typedef struct Dav1dCudaReconBatch {
     /* optional (device): task codes from dav1d_cuda_itx_tasks() over `itx`; when set phase B is two
      * launches (small / large sizes) instead of one per size */
     const uint32_t *itx_tasks;        int32_t n_itx_tasks[2];
-    /* intra-class operations in decode order (device) and the units they are executed in:
-     * intra_units (device) holds n_intra_units pairs (first operation, count).  A unit is a run of
-     * operations one warp executes in order - normally the operations of one coding block.  Units
-     * are claimed in ARRAY order: the operations of a unit may only read pixels of their own unit
-     * or of units that precede it in the array.  Decode order always qualifies; a wavefront order
-     * (superblock column + 2 * superblock row, dav1d_cuda_intra_units()) keeps the units in flight
-     * independent of each other.  Smaller units expose more parallelism, larger ones skip more
-     * look-ups of the cell map (Dav1dCudaIntraDesc.blk).
-     * intra_cellmap: see dav1d_cuda_intra_cellmap_bytes(). */
+    /* intra-class operations in decode order (device); intra_cellmap: see
+     * dav1d_cuda_intra_cellmap_bytes() */
     const Dav1dCudaIntraDesc *intra;  int32_t n_intra;
-    const uint32_t *intra_units;      int32_t n_intra_units;
     uint8_t *intra_cellmap;
+    /* The residuals of the intra-class operations (eob >= 0) do not depend on any neighbour: the
+     * recorder lists them a second time as plain transform descriptors, grouped by size exactly
+     * like `itx` (same coef_off / eob / cw4 / ch4 as in the Dav1dCudaIntraDesc), and a pre-pass that
+     * runs next to the motion compensation writes their inverse transforms into the int16
+     * residual planes `intra_res` (a picture of the frame's geometry allocated with
+     * bitdepth_max = 0xffff); the executor adds them to its predictions.  intra_itx_tasks optional
+     * like itx_tasks. */
+    const Dav1dCudaItxDesc *intra_itx; int32_t intra_itx_class_count[DAV1D_CUDA_N_RECT_TX_SIZES];
+    const uint32_t *intra_itx_tasks;   int32_t n_intra_itx_tasks[2];
+    const Dav1dCudaPicture *intra_res;
 } Dav1dCudaReconBatch;
 
-enum { DAV1D_CUDA_MAX_GROUP = 16 };   /* frames per group submission */
+enum { DAV1D_CUDA_MAX_GROUP = 64 };   /* frames per group submission */
 
 DAV1D_CUDA_API int dav1d_cuda_recon_submit(Dav1dCudaContext *c, const Dav1dCudaReconBatch *b);
 /* Only the launch classes selected by phase_mask (bit0 put + OBMC, bit1 compound, bit2 warp, bit3

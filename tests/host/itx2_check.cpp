@@ -18,29 +18,31 @@ static uint32_t rnd() { s ^= s << 13; s ^= s >> 7; s ^= s << 17; return (uint32_
 
 template <typename pixel>
 static void run_itx2(pixel *dst, int dstride, typename d1::PxTraits<pixel>::coef *cf, int tx, int txtp, int eob,
-                     int cw4, int ch4, int bdmax, bool pred_tile)
+                     int cw4, int ch4, int bdmax, bool via_res)
 {
     using namespace d1;
     const Itx2Blk b = itx2_setup<pixel>(tx, txtp, eob, cw4, ch4, bdmax);
     int G = b.sw > b.sh ? b.sw : b.sh;
-    if (rnd() & 1) G = 32;                       // the intra executor runs one block per warp
+    if (rnd() & 1) G = 32;
     static int tile[64 * 65];
     for (int i = 0; i < 64 * 65; i++) tile[i] = (int)rnd();   // stale shared memory
-    // prediction either read from the destination itself or from a separate tile
-    static pixel ptile[64 * 64];
-    const pixel *pred = dst; int pstride = dstride;
-    if (pred_tile) {
-        for (int y = 0; y < b.h; y++) for (int x = 0; x < b.w; x++) ptile[y * b.w + x] = dst[y * dstride + x];
-        for (int y = 0; y < b.h; y++) for (int x = 0; x < b.w; x++) dst[y * dstride + x] = (pixel)rnd();
-        pred = ptile; pstride = b.w;
+    // via_res: the residual goes to an int16 plane first and is added to the prediction afterwards
+    // (what the intra pre-pass + executor do); else read-modify-write of dst (inter residuals)
+    static int16_t resp[64 * 64];
+    for (int i = 0; i < 64 * 64; i++) resp[i] = (int16_t)rnd();
+    int16_t *res = via_res ? resp : nullptr;
+    int dc = 0;
+    if (b.dc_only) dc = itx2_dc_value<pixel>(b, cf);
+    else {
+        for (int gl = 0; gl < G; gl++) itx2_phase_stage<pixel>(b, gl, G, cf, tile, false);
+        for (int gl = 0; gl < G; gl++) itx2_phase_rows<64>(b, gl, tile);
+        for (int gl = 0; gl < G; gl++) itx2_phase_cols<64>(b, gl, G, tile);
     }
-    if (b.dc_only) {
-        for (int gl = 0; gl < G; gl++) itx2_phase_dc<pixel>(b, gl, G, cf, pred, pstride, dst, dstride, bdmax);
-        return;
-    }
-    for (int gl = 0; gl < G; gl++) itx2_phase_stage<pixel>(b, gl, G, cf, tile, false);
-    for (int gl = 0; gl < G; gl++) itx2_phase_rows<pixel>(b, gl, tile, bdmax);
-    for (int gl = 0; gl < G; gl++) itx2_phase_cols<pixel>(b, gl, G, tile, pred, pstride, dst, dstride, bdmax);
+    for (int gl = 0; gl < G; gl++) itx2_phase_out<pixel>(b, gl, G, tile, dc, dst, dstride, res, b.w, bdmax);
+    if (via_res)
+        for (int y = 0; y < b.h; y++)
+            for (int x = 0; x < b.w; x++)
+                dst[y * dstride + x] = (pixel)clip_px<pixel>(dst[y * dstride + x] + resp[y * b.w + x], bdmax);
 }
 
 template <typename pixel>
@@ -91,8 +93,7 @@ static int check_slot(void *fn, int tx, int txtp, int bdmax, int iters) {
         }
         for (int y = 0; y < 64; y++)
             for (int x = 0; x < stride; x++) {
-                // outside the block: itx2 with a prediction tile overwrote nothing there either
-                if (a[y * stride + x] != b[y * stride + x]) {
+                                if (a[y * stride + x] != b[y * stride + x]) {
                     printf("tx %d txtp %d bdmax %x it %d box %dx%d dense %d: mismatch at (%d,%d) ref %d got %d\n", tx, txtp,
                            bdmax, it, bw, bh, (int)use_dense, x, y, (int)a[y * stride + x], (int)b[y * stride + x]);
                     return 1;

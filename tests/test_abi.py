@@ -60,7 +60,7 @@ int main(void) {
     printf("%zu %zu %zu %zu %zu %zu ", sizeof(Dav1dCudaItxDesc), sizeof(Dav1dCudaMcDesc), sizeof(Dav1dCudaIntraDesc),
            sizeof(Dav1dCudaWarpDesc), sizeof(Dav1dCudaPicture), sizeof(Dav1dCudaReconBatch));
     printf("%zu %zu %zu %zu %zu\n", offsetof(Dav1dCudaReconBatch, mc_obmc), offsetof(Dav1dCudaReconBatch, itx_tasks),
-           offsetof(Dav1dCudaReconBatch, intra_units), offsetof(Dav1dCudaReconBatch, intra_cellmap),
+           offsetof(Dav1dCudaReconBatch, intra_itx), offsetof(Dav1dCudaReconBatch, intra_cellmap),
            offsetof(Dav1dCudaIntraDesc, cw4));
     return 0;
 }
@@ -70,5 +70,5 @@ int main(void) {
     got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
     want = [C.sizeof(B.ItxDesc), C.sizeof(B.McDesc), C.sizeof(B.IntraDesc), C.sizeof(B.WarpDesc),
             C.sizeof(B.Picture), C.sizeof(B.ReconBatch), B.ReconBatch.mc_obmc.offset, B.ReconBatch.itx_tasks.offset,
-            B.ReconBatch.intra_units.offset, B.ReconBatch.intra_cellmap.offset, B.IntraDesc.cw4.offset]
+            B.ReconBatch.intra_itx.offset, B.ReconBatch.intra_cellmap.offset, B.IntraDesc.cw4.offset]
     assert got == want, (got, want)

@@ -75,50 +75,9 @@ def test_generator_and_oracle_match_golden(ref):
         assert md5_planes(out) == gold[name], name
 
 
-def test_units_cover_the_operations_in_decode_order():
-    """CPU: the recorder's unit table (one unit per coding block) partitions the intra-class
-    operations, the block hint of every operation names a rectangle that holds it and only
-    operations of its own unit, and dav1d_cuda_intra_units() (the helper for recorders that do
-    not track units) cuts the array into superblock runs."""
-    hf = F.HostFrame(256, 192, 0x3ff, 11, p_intra=0.7, p_palette=0.1, p_cfl=0.5)
-    n = hf.n_intra
-    up = hf.intra_units.view(np.uint32).reshape(-1, 2).astype(int)
-    assert len(up) == hf.n_intra_units and (up[:, 1] > 0).all()
-    # the units partition the operations (claim order = wavefront order, so sort by first)
-    srt = up[np.argsort(up[:, 0])]
-    assert srt[0, 0] == 0 and (srt[:-1, 0] + srt[:-1, 1] == srt[1:, 0]).all() and srt[-1, 0] + srt[-1, 1] == n
-    rec = np.frombuffer(hf.intra, dtype=np.uint8).reshape(n, 40)
-    x4 = rec[:, 0:2].copy().view(np.uint16).reshape(-1).astype(int)
-    y4 = rec[:, 2:4].copy().view(np.uint16).reshape(-1).astype(int)
-    plane, tw4, th4 = rec[:, 12].astype(int), rec[:, 13].astype(int), rec[:, 14].astype(int)
-    blk = rec[:, 32:36].copy().view(np.uint32).reshape(-1).astype(int)
-    unit_of = np.zeros(n, dtype=int)
-    for u, (first, cnt) in enumerate(up):
-        unit_of[first:first + cnt] = u
-    owner = {}
-    for i in range(n):
-        assert blk[i] >> 16 == 1
-        ox, oy = x4[i] - (blk[i] & 15), y4[i] - ((blk[i] >> 4) & 15)
-        bw, bh = 1 << ((blk[i] >> 8) & 15), 1 << ((blk[i] >> 12) & 15)
-        assert ox >= 0 and oy >= 0 and x4[i] + tw4[i] <= ox + max(bw, tw4[i]) and y4[i] + th4[i] <= oy + max(bh, th4[i])
-        for yy in range(oy, oy + bh):
-            for xx in range(ox, ox + bw):
-                assert owner.setdefault((plane[i], xx, yy), unit_of[i]) == unit_of[i], i
-    # wave order: a unit's superblock wave never decreases along the array
-    sbw = [(x4[f] << (1 if plane[f] else 0) >> 4) + 2 * (y4[f] << (1 if plane[f] else 0) >> 4) for f in up[:, 0]]
-    assert (np.diff(sbw) >= 0).all()
-    for grad in (0, 2):
-        out = np.zeros(2 * n, dtype=np.uint32)
-        nu = pkg.lib().dav1d_cuda_intra_units(hf.intra.ctypes.data, n, 1, 1, 4, grad, out.ctypes.data, n)
-        o = out[:2 * nu].reshape(-1, 2).astype(int)
-        assert 0 < nu <= (256 // 64) * (192 // 64) and o[:, 1].sum() == n
-        if grad == 0:
-            assert o[0, 0] == 0 and (o[:-1, 0] + o[:-1, 1] == o[1:, 0]).all()
-
-
-def run_gpu(hf, refs, init, use_graph=False, tasks=True, units=True):
+def run_gpu(hf, refs, init, use_graph=False, tasks=True):
     ctx = F.open_context(0)
-    df = F.DeviceFrame(ctx, hf, n_refs=len(refs), tasks=tasks, units=units)
+    df = F.DeviceFrame(ctx, hf, n_refs=len(refs), tasks=tasks)
     try:
         df.upload_descriptors()
         for r, planes in enumerate(refs):
@@ -144,13 +103,12 @@ def test_frame_parity_small(ref, name):
     w, h, bd, seed, kw = CASES[name]
     hf = F.HostFrame(w, h, bd, seed, **kw)
     refs, init, want = oracle_planes(ref, hf, seed)
-    # explicit transform tasks + block units with hints (the benchmark's configuration); implicit
-    # per-size transform runs; superblock units without hints (every dependency through the cell map)
-    for tasks, units in ((True, True), (False, True), (True, False)):
-        got = run_gpu(hf, refs, init, use_graph=(seed % 2 == 0), tasks=tasks, units=units)
+    # explicit transform tasks (the benchmark's configuration); implicit per-size transform runs
+    for tasks in (True, False):
+        got = run_gpu(hf, refs, init, use_graph=(seed % 2 == 0), tasks=tasks)
         for pl, (a, b) in enumerate(zip(want, got)):
             bad = np.argwhere(a != b)
-            assert bad.size == 0, (f"{name} tasks={tasks} units={units}: plane {pl} first "
+            assert bad.size == 0, (f"{name} tasks={tasks}: plane {pl} first "
                                    f"mismatch at (y,x)={bad[0]} ref={a[tuple(bad[0])]} got={b[tuple(bad[0])]} "
                                    f"n={len(bad)}")
 

@@ -20,6 +20,6 @@ for name, (w, h, bd, seed, kw) in T.CASES.items():
     hf = T.F.HostFrame(w, h, bd, seed, **kw)
     _, _, planes = T.oracle_planes(ref, hf, seed)
     out[name] = T.md5_planes(planes)
-    print(name, out[name], "blocks", hf.n_blocks, "intra", hf.n_intra_blocks, "units", hf.n_intra_units)
+    print(name, out[name], "blocks", hf.n_blocks, "intra", hf.n_intra_blocks, "intra ops", hf.n_intra)
 with open(T.GOLDEN, "w") as f:
     json.dump(out, f, indent=1, sort_keys=True)

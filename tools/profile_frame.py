@@ -29,5 +29,5 @@ for _ in range(reps):
     df.submit()
 pkg.lib().dav1d_cuda_synchronize(ctx)
 pkg.check_error()
-print("ok units", hf.n_intra_units, "launches", pkg.lib().dav1d_cuda_launch_count())
+print("ok intra ops", hf.n_intra, "launches", pkg.lib().dav1d_cuda_launch_count())
 df.close()

@@ -63,7 +63,7 @@ def run_one(seed):
         mf.close()
     df.close()
     L.dav1d_cuda_close(ctx)
-    return ok, f"{seed} {w}x{h} {hex(bd)} {kw} units {hf.n_intra_units}"
+    return ok, f"{seed} {w}x{h} {hex(bd)} {kw} intra ops {hf.n_intra}"
 
 
 if __name__ == "__main__":
