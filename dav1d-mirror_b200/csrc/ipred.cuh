@@ -170,11 +170,12 @@ template <typename pixel> struct PixParams {
 };
 
 // (mode m, angle with the flag bits 9 / 10 of src/ipred_prepare.h:87-93) -> parameters.  scratch:
-// IPRED_SCRATCH pixels for the Z modes; tile: w*h pixels for filter-intra (w, h <= 32).
+// IPRED_SCRATCH pixels for the Z modes (blocks of up to 16 + 4: 80 pixels with z2_centre = 40);
+// tile: w*h pixels for filter-intra (w, h <= 32).
 template <typename pixel>
 DEV PixParams<pixel> ipred_setup(const Grp &g, const int m, const int angle_in, const int w, const int h,
                                  const int max_w, const int max_h, const pixel *edge, pixel *scratch, pixel *tile,
-                                 const int bdmax)
+                                 const int bdmax, const int z2_centre = 128 + 8)
 {
     PixParams<pixel> P;
     P.pm = PM_CONST; P.p0 = P.p1 = P.p2 = P.p3 = 0;
@@ -238,7 +239,7 @@ DEV PixParams<pixel> ipred_setup(const Grp &g, const int m, const int angle_in, 
         int dx = g_dr_intra_derivative[(180 - ang) >> 1];
         const int ups_l = ef ? use_upsample(w + h, 180 - ang, is_sm) : 0;
         const int ups_a = ef ? use_upsample(w + h, ang - 90, is_sm) : 0;
-        pixel *tl = scratch + 128 + 8;
+        pixel *tl = scratch + z2_centre;     // 2h entries below, 2w + 1 above
         if (ups_a) {
             edge_upsample<pixel>(g, tl, w + 1, edge, 0, w + 1, bdmax);
             dx <<= 1;
@@ -430,31 +431,44 @@ DEV int prepare_edges(const Grp &g, const int x, const int have_left, const int 
     const int pxtr = imin(szt, (w - x - tw) << 2);
     // fallbacks when a side is unavailable (ipred_prepare_tmpl.c:139-197): the first pixel of the
     // other side, or mid +- 1
-    // entries: [0, nl) left + bottom-left going down, [nl, nl + nt) top + top-right
+    // the corner first: its load overlaps the others
+    int vc = mid;
+    if ((needs & 4) && g.gl == 0) {
+        if (have_left) vc = have_top ? __ldcg(dst_top - 1) : __ldcg(dst - 1);
+        else vc = have_top ? (int)__ldcg(dst_top) : mid;
+    }
+    // entries: [0, nl) left + bottom-left going down, [nl, nl + nt) top + top-right; four entries
+    // per lane and step, loaded before any of them is stored (independent loads in flight together)
     const int nl = (needs & 16) ? 2 * szl : (needs & 1) ? szl : 0;
     const int nt = (needs & 8) ? 2 * szt : (needs & 2) ? szt : 0;
-    for (int e = g.gl; e < nl + nt; e += g.G) {
-        int v;
-        if (e < nl) {
-            if (!have_left) v = have_top ? (int)__ldcg(dst_top) : mid + 1;
-            else if (e < szl) v = __ldcg(dst + stride * imin(e, pxl - 1) - 1);
-            else if (have_bl) v = __ldcg(dst + (szl + imin(e - szl, pxbl - 1)) * stride - 1);
-            else v = __ldcg(dst + stride * (pxl - 1) - 1);
-            edge[-1 - e] = (pixel)v;
-        } else {
-            const int i = e - nl;
-            if (!have_top) v = have_left ? (int)__ldcg(dst - 1) : mid - 1;
-            else if (i < szt) v = __ldcg(dst_top + imin(i, pxt - 1));
-            else if (have_tr) v = __ldcg(dst_top + szt + imin(i - szt, pxtr - 1));
-            else v = __ldcg(dst_top + pxt - 1);
-            edge[1 + i] = (pixel)v;
+    for (int e0 = g.gl; e0 < nl + nt; e0 += 4 * g.G) {
+        int v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int e = e0 + u * g.G;
+            v[u] = 0;
+            if (e < nl) {
+                if (!have_left) v[u] = have_top ? (int)__ldcg(dst_top) : mid + 1;
+                else if (e < szl) v[u] = __ldcg(dst + stride * imin(e, pxl - 1) - 1);
+                else if (have_bl) v[u] = __ldcg(dst + (szl + imin(e - szl, pxbl - 1)) * stride - 1);
+                else v[u] = __ldcg(dst + stride * (pxl - 1) - 1);
+            } else if (e < nl + nt) {
+                const int i = e - nl;
+                if (!have_top) v[u] = have_left ? (int)__ldcg(dst - 1) : mid - 1;
+                else if (i < szt) v[u] = __ldcg(dst_top + imin(i, pxt - 1));
+                else if (have_tr) v[u] = __ldcg(dst_top + szt + imin(i - szt, pxtr - 1));
+                else v[u] = __ldcg(dst_top + pxt - 1);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int e = e0 + u * g.G;
+            if (e < nl) edge[-1 - e] = (pixel)v[u];
+            else if (e < nl + nt) edge[1 + (e - nl)] = (pixel)v[u];
         }
     }
     grp_sync(g);
     if ((needs & 4) && g.gl == 0) {
-        int vc;
-        if (have_left) vc = have_top ? __ldcg(dst_top - 1) : __ldcg(dst - 1);
-        else vc = have_top ? (int)__ldcg(dst_top) : mid;
         // Z2 corner smoothing (ipred_prepare_tmpl.c:198-200)
         if (mode == M_Z2 && tw + th >= 6 && filter_edge_flag) vc = ((edge[-1] + edge[1]) * 5 + vc * 6 + 8) >> 4;
         edge[0] = (pixel)vc;

@@ -27,6 +27,7 @@
 // A frame whose descriptors are inconsistent (operations that wait for each other) ends with
 // pending operations and no ready one: the executor raises the context's status word and stops;
 // dav1d_cuda_synchronize() reports it.
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
@@ -110,32 +111,38 @@ DEV void grid_barrier(unsigned *bar, unsigned &target) {
         target += gridDim.x;
         __threadfence();
         atomicAdd(bar, 1u);
-        while (ld_acquire_u32(bar) < target) __nanosleep(32);
+        while (ld_acquire_u32(bar) < target) __nanosleep(64);
         __threadfence();
     }
     __syncthreads();
 }
 
 // ---- step 1 of a round: is operation d ready?  One thread, L2 loads of the map bytes.
-DEV bool cells_are(const uint8_t *m, const int W, const int x0, const int x1, const int y0, const int y1, const int want) {
+// all cells of [x0, x1) x [y0, y1) at most `thr`?  else *blocker = map offset of one that is not
+DEV bool cells_le(const uint8_t *map, const unsigned mo, const int W, const int x0, const int x1, const int y0,
+                  const int y1, const unsigned thr, unsigned *blocker) {
     for (int y = y0; y < y1; y++)
-        for (int x = x0; x < x1; x++)
-            if (__ldcg(m + y * W + x) != want) return false;
+        for (int x = x0; x < x1; x++) {
+            const unsigned off = mo + (unsigned)(y * W + x);
+            if (__ldcg(map + off) > thr) { *blocker = off | (thr << 31); return false; }
+        }
     return true;
 }
 
-DEV bool op_ready(const Intra2Frame &f, const Dav1dCudaIntraDesc &d, int *cls_out) {
+// On false *blocker names one cell the operation waits for (bit 31: the cell may stay at 1 - the
+// operation's own count): while that cell is above its threshold there is no need to look again.
+DEV bool op_ready(const Intra2Frame &f, const Dav1dCudaIntraDesc &d, int *cls_out, unsigned *blocker) {
     const int mode = d.mode;
     const int pl = d.plane;
     const int sh = pl ? f.pic.ss_hor : 0, sv = pl ? f.pic.ss_ver : 0;
     const int W = map_w(f, pl), H = map_h(f, pl);
-    const uint8_t *m = f.map + map_off(f, pl);
+    const unsigned mo = (unsigned)map_off(f, pl);
     const int x0 = d.x4, y0 = d.y4;
     if (mode == DAV1D_CUDA_INTRA_PAL) { *cls_out = 15; return true; }
     if (mode == DAV1D_CUDA_INTRA_NONE) {
         // residual on top of an earlier operation's pixels (palette, inter-intra, intrabc): that one is done
         *cls_out = 18;
-        return cells_are(m, W, x0, imin(x0 + d.tw4, W), y0, imin(y0 + d.th4, H), 1);
+        return cells_le(f.map, mo, W, x0, imin(x0 + d.tw4, W), y0, imin(y0 + d.th4, H), 1, blocker);
     }
     if (mode == DAV1D_CUDA_INTRA_IBC) {
         *cls_out = 16;
@@ -143,7 +150,7 @@ DEV bool op_ready(const Intra2Frame &f, const Dav1dCudaIntraDesc &d, int *cls_ou
         const int pw = 4 * W, ph = 4 * H;
         const int xa = iclip(sx, 0, pw - 1) >> 2, xb = iclip(sx + 4 * d.tw4 + (d.angle_delta ? 1 : 0) - 1, 0, pw - 1) >> 2;
         const int ya = iclip(sy, 0, ph - 1) >> 2, yb = iclip(sy + 4 * d.th4 + (d.flags ? 1 : 0) - 1, 0, ph - 1) >> 2;
-        return cells_are(m, W, xa, xb + 1, ya, yb + 1, 0);
+        return cells_le(f.map, mo, W, xa, xb + 1, ya, yb + 1, 0, blocker);
     }
     const int have_left = x0 > d.tile_x4_start, have_top = y0 > d.tile_y4_start;
     int ang = mode == DAV1D_CUDA_INTRA_II ? 0 : d.angle_delta;
@@ -157,17 +164,17 @@ DEV bool op_ready(const Intra2Frame &f, const Dav1dCudaIntraDesc &d, int *cls_ou
         const int xs = ((needs & 4) && have_left) ? x0 - 1 : x0;
         int xe = (needs & 2) ? imin(x0 + d.tw4 + (tr ? d.tw4 : 0), d.tile_x4_end) : x0 + 1;
         xe = imin(xe, W);
-        if (!cells_are(m, W, xs, xe, y0 - 1, y0, 0)) return false;
+        if (!cells_le(f.map, mo, W, xs, xe, y0 - 1, y0, 0, blocker)) return false;
     }
     if (have_left && ((needs & 1) || ((needs & 2) && !have_top) || ((needs & 4) && !have_top))) {
         const bool bl = (needs & 16) && (d.edge_flags & 8);
         int ye = (needs & 1) ? imin(y0 + d.th4 + (bl ? d.th4 : 0), d.tile_y4_end) : y0 + 1;
         ye = imin(ye, H);
-        if (!cells_are(m, W, x0 - 1, x0, y0, ye, 0)) return false;
+        if (!cells_le(f.map, mo, W, x0 - 1, x0, y0, ye, 0, blocker)) return false;
     }
     if (mode == DAV1D_CUDA_INTRA_CFL)      // the co-located luma
-        return cells_are(f.map, f.bw4, x0 << sh, imin((x0 + d.tw4) << sh, f.bw4), y0 << sv,
-                         imin((y0 + d.th4) << sv, f.bh4), 0);
+        return cells_le(f.map, 0u, f.bw4, x0 << sh, imin((x0 + d.tw4) << sh, f.bw4), y0 << sv,
+                        imin((y0 + d.th4) << sv, f.bh4), 0, blocker);
     return true;
 }
 
@@ -175,9 +182,12 @@ DEV bool op_ready(const Intra2Frame &f, const Dav1dCudaIntraDesc &d, int *cls_ou
 // pixels): edge preparation, then ONE loop over the block's pixels (a pixel per lane and step)
 // that evaluates the predictor, adds the residual of the transform pre-pass and stores the final
 // pixel; then the operation's cells are counted down.
+// part / n_parts: the pixel loop of a large operation is shared by several warps (each prepares the
+// edge for itself and takes every n_parts-th chunk of 256 pixels; part 0 counts the cells down).
 template <typename pixel>
 __device__ __noinline__ void intra_exec(const Grp g, const Intra2Frame &a, const Dav1dCudaIntraDesc &d,
-                                        pixel *edge_buf, pixel *scratch, int16_t *tile) {
+                                        pixel *edge, pixel *scratch, const int z2_centre, int16_t *tile,
+                                        const int part, const int n_parts) {
     const int pl = d.plane;
     const int ss_hor = pl ? a.pic.ss_hor : 0, ss_ver = pl ? a.pic.ss_ver : 0;
     const PlaneView &pv = a.pic.p[pl];
@@ -186,7 +196,6 @@ __device__ __noinline__ void intra_exec(const Grp g, const Intra2Frame &a, const
     const int w = d.tw4 * 4, h = d.th4 * 4;
     const int lw = 31 - __clz(w);
     const int bdmax = a.pic.bdmax;
-    pixel *edge = edge_buf + EDGE_C;
     const int have_left = d.x4 > d.tile_x4_start, have_top = d.y4 > d.tile_y4_start;
     const int mode = d.mode;
     const bool has_res = d.eob >= 0 && mode != DAV1D_CUDA_INTRA_PAL;
@@ -196,6 +205,15 @@ __device__ __noinline__ void intra_exec(const Grp g, const Intra2Frame &a, const
         const PlaneView &rv = a.res.p[pl];
         rstride = (int)(rv.stride / 2);
         res = (const int16_t *)rv.data + (int64_t)d.y4 * 4 * rstride + d.x4 * 4;
+    }
+    // first residual / current pixel of this lane: loaded now, used after the edge preparation
+    const int n = w * h;
+    int i = (part << 8) + g.gl;
+    int r_nx = 0, c_nx = 0;
+    const bool rd_dst = mode == DAV1D_CUDA_INTRA_NONE || mode == DAV1D_CUDA_INTRA_II;
+    if (i < n) {
+        if (res) r_nx = res[(i >> lw) * rstride + (i & (w - 1))];
+        if (rd_dst) c_nx = __ldcg(dst + (i >> lw) * stride + (i & (w - 1)));
     }
     // what the pixel loop does: 0 predictor, 1 palette, 2 intrabc, 3 keep the current pixel
     int kind = 3;
@@ -228,17 +246,25 @@ __device__ __noinline__ void intra_exec(const Grp g, const Intra2Frame &a, const
         else angle |= d.flags;
         const int max_w = ((4 * a.bw4 + ss_hor) >> ss_hor) - 4 * d.x4;
         const int max_h = ((4 * a.bh4 + ss_ver) >> ss_ver) - 4 * d.y4;
-        P = ipred_setup<pixel>(g, m, angle, w, h, max_w, max_h, edge, scratch, (pixel *)tile, bdmax);
+        P = ipred_setup<pixel>(g, m, angle, w, h, max_w, max_h, edge, scratch, (pixel *)tile, bdmax, z2_centre);
         kind = 0;
     }
     grp_sync(g);
 
     const pixel *base = (const pixel *)pv.data;
     const int ib = PxTraits<pixel>::inter_bits(bdmax);
-    const int n = w * h;
+    // residual / current pixel of the next step are loaded before this step's pixel is computed
+    const int step = n_parts > 1 ? (n_parts << 8) - 256 + g.G : g.G;   // the next chunk of this part after 256 pixels
 #pragma unroll 1
-    for (int i = g.gl; i < n; i += g.G) {
+    while (i < n) {
         const int y = i >> lw, x = i & (w - 1);
+        const int r_cur = r_nx, c_cur = c_nx;
+        // a part's chunks: [part * 256, part * 256 + 256), then n_parts * 256 further on
+        const int inx = (n_parts > 1 && ((i + g.G) & 255) < g.G) ? i + step : i + g.G;
+        if (inx < n) {
+            if (res) r_nx = res[(inx >> lw) * rstride + (inx & (w - 1))];
+            if (rd_dst) c_nx = __ldcg(dst + (inx >> lw) * stride + (inx & (w - 1)));
+        }
         int v;
         if (kind == 0) {
             v = ipred_pixel<pixel>(P, x, y, i, bdmax);
@@ -272,19 +298,20 @@ __device__ __noinline__ void intra_exec(const Grp g, const Intra2Frame &a, const
                 v = q00;
             }
         } else {
-            v = __ldcg(dst + y * stride + x);      // residual on top of what an earlier round left there
+            v = c_cur;                              // residual on top of what an earlier round left there
         }
         if (bmask) {
             // mc.blend of the intra prediction onto the inter prediction (mc_tmpl.c:642-653)
-            const int mk = bmask[i], p = __ldcg(dst + y * stride + x);
-            v = (p * (64 - mk) + v * mk + 32) >> 6;
+            const int mk = bmask[i];
+            v = (c_cur * (64 - mk) + v * mk + 32) >> 6;
         }
-        if (res) v = clip_px<pixel>(v + res[y * rstride + x], bdmax);
+        if (res) v = clip_px<pixel>(v + r_cur, bdmax);
         dst[y * stride + x] = (pixel)v;
+        i = inx;
     }
     // the operation's pixels are stored: one count less on each of its cells (the grid barrier at
     // the end of the round makes pixels and counts visible together)
-    {
+    if (part == 0) {
         const int W = map_w(a, pl), H = map_h(a, pl);
         uint8_t *m = a.map + map_off(a, pl);
         const int ltw = 31 - __clz((int)d.tw4);
@@ -292,43 +319,73 @@ __device__ __noinline__ void intra_exec(const Grp g, const Intra2Frame &a, const
         for (int j = g.gl; j < nc; j += g.G) {
             const int cx = d.x4 + (j & (d.tw4 - 1)), cy = d.y4 + (j >> ltw);
             if (cx < W && cy < H) {
-                uint8_t *p = m + cy * W + cx;
-                *(volatile uint8_t *)p = (uint8_t)(__ldcg(p) - 1);
+                // minus one on the cell's byte: a reduction on the containing word (fire and forget)
+                const size_t off = (size_t)(m - a.map) + (size_t)cy * W + cx;
+                atomicAdd((unsigned *)(a.map + (off & ~(size_t)3)), 0u - (1u << (8 * (off & 3))));
             }
         }
     }
     grp_sync(g);
 }
 
-// per-warp shared memory of step 3: four octets (or one warp: slot 0) of edge + Z-mode scratch,
-// and the CfL ac / filter-intra tile (1024 values for a warp-wide operation, 256 per octet)
+// per-warp shared memory of step 3: edge + Z-mode scratch of four octets (operations of up to 64
+// pixels: w, h <= 16, w + h <= 20, i.e. 2 * 16 + 1 + 2 * 16 edge pixels: 80 + 80 pixels per octet) or
+// of one warp-wide operation (EDGE_BUF + IPRED_SCRATCH pixels) in the same bytes, and the CfL ac /
+// filter-intra tile (1024 values for a warp-wide operation, 256 per octet)
+constexpr int OCT_PX = 80, OCT_CENTRE = 36, OCT_Z2 = 40;
 template <typename pixel> struct __align__(16) ExecSmem {
-    pixel edge[4][EDGE_BUF];
-    pixel scratch[4][IPRED_SCRATCH];
+    pixel es[4 * 2 * OCT_PX > EDGE_BUF + IPRED_SCRATCH ? 4 * 2 * OCT_PX : EDGE_BUF + IPRED_SCRATCH];
     int16_t tile[32 * 32];
 };
+// 256-pixel parts of an operation's pixel loop (tile-based predictors - CfL, filter-intra - stay whole)
+DEV int op_parts(const Dav1dCudaIntraDesc &d) {
+    const int px = d.tw4 * d.th4 * 16;
+    if (px <= 256 || d.mode == DAV1D_CUDA_INTRA_CFL || d.mode == DAV1D_CUDA_INTRA_FILTER) return 1;
+    return px >> 8;
+}
 
 constexpr int R_WARPS = 8;
-constexpr int R_BINS = 64;              // sort key: (small ? 0 : 32) + predictor class
+// operation id: part (4 bits) | frame (6 bits) | index inside the frame (20 bits)
+constexpr int OP_FRAME_SHIFT = 20, OP_PART_SHIFT = 28;
+DEV int op_frame(const unsigned id) { return (int)((id >> OP_FRAME_SHIFT) & 63u); }
+DEV int op_index(const unsigned id) { return (int)(id & ((1u << OP_FRAME_SHIFT) - 1u)); }
+constexpr unsigned R_NOCELL = 0x7fffffffu;
+constexpr int R_BINS = 128;             // sort key: size class * 32 + predictor class
+// size classes: 0 = up to 16 pixels, 1 = up to 64 (both: one operation per octet, four per warp),
+// 2 = up to 256, 3 = larger (one operation or 256-pixel part per warp)
+DEV int size_class(const Dav1dCudaIntraDesc &d) {
+    const int c4 = d.tw4 * d.th4;
+    return c4 <= 1 ? 0 : c4 <= 4 ? 1 : c4 <= 16 ? 2 : 3;
+}
 // counters of a round (two sets, used alternately)
 struct RoundCtr {
-    unsigned n_next, n_ready;
+    unsigned n_next, n_ready;          // operations that stay pending / are ready
     unsigned hist[R_BINS];
     unsigned cursor[R_BINS];
 };
 struct RoundsArgs {
     Intra2Args g;
     int op_base[I2_MAXF + 1];           // first global operation number of every frame
-    unsigned *pend[2];                  // pending operation ids (frame << 24 | index)
+    unsigned *pend[2];                  // pending operation ids
+    unsigned *pend_blk[2];              // ... and one cell each of them waits for (R_NOCELL: unknown)
     unsigned *ready;                    // ready operations of the round, unsorted
     uint8_t *ready_key;
     unsigned *sorted;                   // ... sorted by key
     unsigned *bar;                      // grid barrier counter (zeroed before the launch)
     RoundCtr *ctr;                      // [2] (zeroed before the launch)
+#ifdef D1_EXPERIMENT
+    unsigned long long *trace;          // per round: 4 time stamps (ns), pending, ready entries
+#endif
 };
+#ifdef D1_EXPERIMENT
+DEV unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define D1_TRACE(slot, val) do { if (gtid == 0 && a.trace && round < 256) a.trace[round * 6 + (slot)] = (val); } while (0)
+#else
+#define D1_TRACE(slot, val) do { } while (0)
+#endif
 
 template <typename pixel>
-__global__ void __launch_bounds__(R_WARPS * 32, 3) intra_rounds_kernel(const __grid_constant__ RoundsArgs a) {
+__global__ void __launch_bounds__(R_WARPS * 32, 4) intra_rounds_kernel(const __grid_constant__ RoundsArgs a) {
     extern __shared__ __align__(16) uint8_t rounds_smem_raw[];
     __shared__ unsigned s_hist[R_BINS], s_base[R_BINS];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -338,53 +395,71 @@ __global__ void __launch_bounds__(R_WARPS * 32, 3) intra_rounds_kernel(const __g
     unsigned n_pend = (unsigned)a.op_base[a.g.nf];
     for (int round = 0; n_pend > 0; round++) {
         RoundCtr *ctr = a.ctr + (round & 1), *nxt = a.ctr + ((round & 1) ^ 1);
-        const unsigned *pend = a.pend[round & 1];
-        unsigned *pend_next = a.pend[(round & 1) ^ 1];
+        const unsigned *pend = a.pend[round & 1], *pblk = a.pend_blk[round & 1];
+        unsigned *pend_next = a.pend[(round & 1) ^ 1], *pblk_next = a.pend_blk[(round & 1) ^ 1];
         // ---- step 1: every pending operation is looked at by one thread
+        D1_TRACE(0, gtimer()); D1_TRACE(4, n_pend);
         if (tid < R_BINS) s_hist[tid] = 0;
         __syncthreads();
         for (unsigned k0 = blockIdx.x * blockDim.x; k0 < n_pend; k0 += gthreads) {
             const unsigned k = k0 + tid;
             bool ready = false, live = k < n_pend;
-            unsigned id = 0;
-            int key = 0;
+            unsigned id = 0, blk = R_NOCELL;
+            int key = 0, parts = 0;
             if (live) {
                 if (round == 0) {
                     int fi = 0;
                     while (fi + 1 < a.g.nf && (unsigned)a.op_base[fi + 1] <= k) fi++;
-                    id = ((unsigned)fi << 24) | (k - (unsigned)a.op_base[fi]);
+                    id = ((unsigned)fi << OP_FRAME_SHIFT) | (k - (unsigned)a.op_base[fi]);
                 } else {
                     id = __ldcg(pend + k);
+                    blk = __ldcg(pblk + k);
                 }
-                const Intra2Frame &f = a.g.f[id >> 24];
-                const Dav1dCudaIntraDesc d = f.descs[id & 0xffffffu];
-                int cls = 0;
-                ready = op_ready(f, d, &cls);
-                key = (d.tw4 * d.th4 <= 4 ? 0 : 32) + cls;
+                const Intra2Frame &f = a.g.f[op_frame(id)];
+                // the cell this operation was seen waiting for: still above its threshold?
+                const bool still = blk != R_NOCELL && __ldcg(f.map + (blk & 0x7fffffffu)) > (blk >> 31);
+                if (!still) {
+                    const Dav1dCudaIntraDesc d = f.descs[op_index(id)];
+                    int cls = 0;
+                    ready = op_ready(f, d, &cls, &blk);
+                    key = size_class(d) * 32 + cls;
+                    if (ready) parts = op_parts(d);
+                }
             }
-            // warp-aggregated appends
-            const unsigned mr = __ballot_sync(0xffffffffu, ready), mp = __ballot_sync(0xffffffffu, live && !ready);
+            // warp-aggregated appends: a ready operation adds one entry per part to the round's list
+            const unsigned mp = __ballot_sync(0xffffffffu, live && !ready);
+            int incl = parts;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            const int tot = __shfl_sync(0xffffffffu, incl, 31);
             unsigned br = 0, bp = 0;
             if (lane == 0) {
-                if (mr) br = atomicAdd(&ctr->n_ready, __popc(mr));
+                if (tot) br = atomicAdd(&ctr->n_ready, (unsigned)tot);
                 if (mp) bp = atomicAdd(&ctr->n_next, __popc(mp));
             }
             br = __shfl_sync(0xffffffffu, br, 0);
             bp = __shfl_sync(0xffffffffu, bp, 0);
-            const unsigned lt = (1u << lane) - 1u;
             if (ready) {
-                const unsigned pos = br + __popc(mr & lt);
-                a.ready[pos] = id;
-                a.ready_key[pos] = (uint8_t)key;
-                atomicAdd(&s_hist[key], 1u);
+                const unsigned pos = br + (unsigned)(incl - parts);
+                for (int q = 0; q < parts; q++) {
+                    a.ready[pos + q] = id | ((unsigned)q << OP_PART_SHIFT);
+                    a.ready_key[pos + q] = (uint8_t)key;
+                }
+                atomicAdd(&s_hist[key], (unsigned)parts);
             } else if (live) {
-                pend_next[bp + __popc(mp & lt)] = id;
+                const unsigned pos = bp + __popc(mp & ((1u << lane) - 1u));
+                pend_next[pos] = id;
+                pblk_next[pos] = blk;
             }
         }
         __syncthreads();
         if (tid < R_BINS && s_hist[tid]) atomicAdd(&ctr->hist[tid], s_hist[tid]);
         grid_barrier(a.bar, target);
         const unsigned n_ready = ld_acquire_u32(&ctr->n_ready), n_next = ld_acquire_u32(&ctr->n_next);
+        D1_TRACE(1, gtimer()); D1_TRACE(5, n_ready);
         if (n_ready == 0) {
             // pending operations, none ready: they wait for each other - inconsistent descriptors
             if (gtid == 0) atomicOr(a.g.status, 1u);
@@ -392,13 +467,30 @@ __global__ void __launch_bounds__(R_WARPS * 32, 3) intra_rounds_kernel(const __g
         }
         // ---- step 2: counting sort of the ready list by key.  Start of every bin (all blocks
         // compute the same prefix), then every block scatters a contiguous chunk of the list.
-        if (tid == 0) {
-            unsigned acc = 0;
-            for (int b = 0; b < R_BINS; b++) { s_base[b] = acc; acc += ld_acquire_u32(&ctr->hist[b]); }
+        if (tid < R_BINS) {                    // warps 0..3: exclusive prefix over the bins
+            const unsigned h = ld_acquire_u32(&ctr->hist[tid]);
+            unsigned incl = h;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            s_base[tid] = incl - h;
+            if (lane == 31) s_hist[warp] = incl;      // total of this warp's 32 bins
         }
+        __syncthreads();
+        if (tid < R_BINS) {
+            unsigned add = 0;
+            for (int q = 0; q < warp; q++) add += s_hist[q];
+            s_base[tid] += add;
+        }
+        __syncthreads();
+        const unsigned n_tot_check = s_base[R_BINS - 1];
+        (void)n_tot_check;
         if (tid < R_BINS) s_hist[tid] = 0;
         __syncthreads();
-        const unsigned n_small = s_base[32];
+        // list layout: [octet-mode entries | warp-mode entries]
+        const unsigned n_oct = s_base[64];
         {
             const unsigned chunk = (n_ready + gridDim.x - 1) / gridDim.x;
             const unsigned c0 = blockIdx.x * chunk, c1 = min(n_ready, c0 + chunk);
@@ -417,31 +509,35 @@ __global__ void __launch_bounds__(R_WARPS * 32, 3) intra_rounds_kernel(const __g
         // the other counter set is free (last read before the previous round's final barrier)
         if (gtid < sizeof(RoundCtr) / 4) ((unsigned *)nxt)[gtid] = 0;
         grid_barrier(a.bar, target);
+        D1_TRACE(2, gtimer());
         // ---- step 3: execute.  Items: four small operations per warp (one per octet), then the
         // others one per warp
         {
-            const unsigned items_small = (n_small + 3) / 4, items = items_small + (n_ready - n_small);
+            const unsigned items_oct = (n_oct + 3) / 4, items = items_oct + (n_ready - n_oct);
             const unsigned gw = blockIdx.x * R_WARPS + warp, nw = gridDim.x * R_WARPS;
+            const int o = lane >> 3;
             for (unsigned it = gw; it < items; it += nw) {
-                if (it < items_small) {
-                    const unsigned k = it * 4 + (lane >> 3);
-                    if (k < n_small) {
+                if (it < items_oct) {
+                    const unsigned k = it * 4 + o;
+                    if (k < n_oct) {
                         const unsigned id = __ldcg(a.sorted + k);
-                        const Intra2Frame &f = a.g.f[id >> 24];
-                        const Dav1dCudaIntraDesc d = f.descs[id & 0xffffffu];
-                        const int o = lane >> 3;
-                        intra_exec<pixel>(grp_octet(lane), f, d, sm->edge[o], sm->scratch[o], sm->tile + 256 * o);
+                        const Intra2Frame &f = a.g.f[op_frame(id)];
+                        const Dav1dCudaIntraDesc d = f.descs[op_index(id)];
+                        pixel *es = sm->es + o * 2 * OCT_PX;
+                        intra_exec<pixel>(grp_octet(lane), f, d, es + OCT_CENTRE, es + OCT_PX, OCT_Z2, sm->tile + 256 * o, 0, 1);
                     }
                 } else {
-                    const unsigned id = __ldcg(a.sorted + n_small + (it - items_small));
-                    const Intra2Frame &f = a.g.f[id >> 24];
-                    const Dav1dCudaIntraDesc d = f.descs[id & 0xffffffu];
-                    intra_exec<pixel>(grp_warp(lane), f, d, sm->edge[0], sm->scratch[0], sm->tile);
+                    const unsigned id = __ldcg(a.sorted + n_oct + (it - items_oct));
+                    const Intra2Frame &f = a.g.f[op_frame(id)];
+                    const Dav1dCudaIntraDesc d = f.descs[op_index(id)];
+                    intra_exec<pixel>(grp_warp(lane), f, d, sm->es + EDGE_C, sm->es + EDGE_BUF, 128 + 8, sm->tile,
+                                      (int)(id >> OP_PART_SHIFT), op_parts(d));
                 }
                 __syncwarp();
             }
         }
         grid_barrier(a.bar, target);
+        D1_TRACE(3, gtimer());
         n_pend = n_next;
         if (round > (1 << 20)) { if (gtid == 0) atomicOr(a.g.status, 1u); return; }
     }
@@ -553,14 +649,27 @@ static bool join_aux(Dav1dCudaContext *c, cudaStream_t st) {
 // the ready keys.  One per context, grown on demand outside any stream capture; submissions of a
 // context are ordered on its stream.
 static size_t rounds_ws_hdr() { return 256 + ((2 * sizeof(RoundCtr) + 255) & ~(size_t)255); }
-static size_t rounds_ws_need(size_t total) {
-    return rounds_ws_hdr() + 4 * ((total * 4 + 255) & ~(size_t)255) + ((total + 255) & ~(size_t)255);
+#ifdef D1_EXPERIMENT
+static unsigned long long *d1_last_trace = nullptr;
+#endif
+static size_t al256(size_t v) { return (v + 255) & ~(size_t)255; }
+// total = operations of the group (pending lists); cap = entries a round's list can hold: an
+// operation per entry, large ones one entry per 256 pixels
+static size_t rounds_ws_need(size_t total, size_t cap) {
+    return rounds_ws_hdr() + 4 * al256(total * 4) + 2 * al256(cap * 4) + al256(cap);
+}
+static void rounds_counts(const Dav1dCudaReconBatch *const *bs, int n, size_t *total, size_t *cap) {
+    *total = 0; *cap = 0;
+    for (int f = 0; f < n; f++) {
+        if (!bs[f] || bs[f]->n_intra <= 0) continue;
+        *total += (size_t)bs[f]->n_intra;
+        *cap += (size_t)bs[f]->n_intra + 3 * ((size_t)bs[f]->bw4 * bs[f]->bh4 * 16 / 256 + 1);
+    }
 }
 static int ensure_rounds_ws(Dav1dCudaContext *c, const Dav1dCudaReconBatch *const *bs, int n) {
-    size_t total = 0;
-    for (int f = 0; f < n; f++)
-        if (bs[f] && bs[f]->n_intra > 0) total += (size_t)bs[f]->n_intra;
-    const size_t need = rounds_ws_need(total);
+    size_t total, cap;
+    rounds_counts(bs, n, &total, &cap);
+    const size_t need = rounds_ws_need(total, cap);
     if (need <= c->rounds_ws_bytes) return 0;
     if (c->rounds_ws) {
         D1_CHECK(cudaStreamSynchronize(c->stream));
@@ -584,7 +693,7 @@ static int check_group(const Dav1dCudaReconBatch *const *bs, int n) {
             for (int r = 0; r < 7; r++)
                 if (g != f && bs[g] && bs[g]->refs[r] && bs[g]->refs[r]->p[0].data == b->dst->p[0].data) return -22;
         if (b->n_intra > 0 && (!b->intra || !b->intra_cellmap)) return -22;
-        if (b->n_intra >= (1 << 24)) return -22;
+        if (b->n_intra >= (1 << 20)) return -22;
         if (b->n_intra > 0 && b->intra_itx && !b->intra_res) return -22;
     }
     return 0;
@@ -670,19 +779,34 @@ static int group_submit_on(Dav1dCudaContext *c, const Dav1dCudaReconBatch *const
     ra.op_base[n] = (int)total;
     if (total >= ((size_t)1 << 31)) return -22;
     const size_t hdr = rounds_ws_hdr();
-    if (rounds_ws_need(total) > c->rounds_ws_bytes) return -12;      // ensure_rounds_ws() comes first
+    size_t total2, cap;
+    rounds_counts(bs, n, &total2, &cap);
+    if (rounds_ws_need(total, cap) > c->rounds_ws_bytes) return -12;      // ensure_rounds_ws() comes first
     uint8_t *ws = (uint8_t *)c->rounds_ws;
     ra.bar = (unsigned *)ws;
     ra.ctr = (RoundCtr *)(ws + 256);
-    const size_t lb = (total * 4 + 255) & ~(size_t)255;
+    const size_t lb = al256(total * 4), cb = al256(cap * 4);
     ra.pend[0] = (unsigned *)(ws + hdr);
     ra.pend[1] = (unsigned *)(ws + hdr + lb);
-    ra.ready = (unsigned *)(ws + hdr + 2 * lb);
-    ra.sorted = (unsigned *)(ws + hdr + 3 * lb);
-    ra.ready_key = ws + hdr + 4 * lb;
+    ra.pend_blk[0] = (unsigned *)(ws + hdr + 2 * lb);
+    ra.pend_blk[1] = (unsigned *)(ws + hdr + 3 * lb);
+    ra.ready = (unsigned *)(ws + hdr + 4 * lb);
+    ra.sorted = (unsigned *)(ws + hdr + 4 * lb + cb);
+    ra.ready_key = ws + hdr + 4 * lb + 2 * cb;
     D1_CHECK(cudaMemsetAsync(ws, 0, hdr, st));
+#ifdef D1_EXPERIMENT
+    static unsigned long long *g_trace = nullptr;
+    if (!g_trace) cudaMalloc(&g_trace, 256 * 6 * 8);
+    cudaMemsetAsync(g_trace, 0, 256 * 6 * 8, st);
+    ra.trace = g_trace;
+    d1_last_trace = g_trace;
+#endif
     const size_t smem = hbd ? rounds_smem_bytes<uint16_t>() : rounds_smem_bytes<uint8_t>();
-    const int grid = (int)std::min<size_t>((size_t)g_rounds_blocks[hbd], (total + R_WARPS * 32 - 1) / (R_WARPS * 32));
+    int resident = g_rounds_blocks[hbd];
+#ifdef D1_EXPERIMENT
+    if (getenv("D1_ROUNDS_BPSM")) resident = std::min(resident, atoi(getenv("D1_ROUNDS_BPSM")) * c->num_sms);
+#endif
+    const int grid = (int)std::min<size_t>((size_t)resident, (total + R_WARPS * 32 - 1) / (R_WARPS * 32));
     void *kargs[] = { (void *)&ra };
     const void *fn = hbd ? (const void *)intra_rounds_kernel<uint16_t> : (const void *)intra_rounds_kernel<uint8_t>;
     D1_CHECK(cudaLaunchCooperativeKernel(fn, dim3((unsigned)grid), dim3(R_WARPS * 32), kargs, smem, st));
@@ -716,6 +840,16 @@ size_t dav1d_cuda_intra_cellmap_bytes(int bw4, int bh4, int ss_hor, int ss_ver) 
     const size_t cw = (size_t)((bw4 + ss_hor) >> ss_hor), ch = (size_t)((bh4 + ss_ver) >> ss_ver);
     return (((size_t)bw4 * bh4 + 2 * cw * ch) + 255) & ~(size_t)255;
 }
+
+#ifdef D1_EXPERIMENT
+// experiment builds only (make EXTRA=-DD1_EXPERIMENT): per-round time stamps of the last executor launch
+__attribute__((visibility("default"))) int dav1d_cuda_debug_rounds_trace(unsigned long long *host, int rounds) {
+    if (!d1_last_trace) return -1;
+    cudaDeviceSynchronize();
+    cudaMemcpy(host, d1_last_trace, (size_t)rounds * 6 * 8, cudaMemcpyDeviceToHost);
+    return 0;
+}
+#endif
 
 int dav1d_cuda_recon_submit(Dav1dCudaContext *c, const Dav1dCudaReconBatch *b) {
     if (!c || !b) return -22;
