@@ -118,14 +118,27 @@ DEV void grid_barrier(unsigned *bar, unsigned &target) {
 }
 
 // ---- step 1 of a round: is operation d ready?  One thread, L2 loads of the map bytes.
-// all cells of [x0, x1) x [y0, y1) at most `thr`?  else *blocker = map offset of one that is not
+// all cells of [x0, x1) x [y0, y1) at most `thr`?  else *blocker = map offset of one that is not.
+// Eight loads are in flight at a time (a thread that checks the 48 neighbour cells of a 64x64
+// block one after the other would hold its whole block up at the end of the step).
 DEV bool cells_le(const uint8_t *map, const unsigned mo, const int W, const int x0, const int x1, const int y0,
                   const int y1, const unsigned thr, unsigned *blocker) {
-    for (int y = y0; y < y1; y++)
-        for (int x = x0; x < x1; x++) {
-            const unsigned off = mo + (unsigned)(y * W + x);
-            if (__ldcg(map + off) > thr) { *blocker = off | (thr << 31); return false; }
+    const int nx = x1 - x0, n = nx * (y1 - y0);
+    if (n <= 0) return true;
+    for (int j0 = 0; j0 < n; j0 += 8) {
+        unsigned v[8], off[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const int j = imin(j0 + u, n - 1);
+            const int y = y1 - y0 == 1 ? y0 : nx == 1 ? y0 + j : y0 + j / nx;
+            const int x = y1 - y0 == 1 ? x0 + j : nx == 1 ? x0 : x0 + j % nx;
+            off[u] = mo + (unsigned)(y * W + x);
+            v[u] = __ldcg(map + off[u]);
         }
+#pragma unroll
+        for (int u = 0; u < 8; u++)
+            if (v[u] > thr) { *blocker = off[u] | (thr << 31); return false; }
+    }
     return true;
 }
 
@@ -182,6 +195,12 @@ DEV bool op_ready(const Intra2Frame &f, const Dav1dCudaIntraDesc &d, int *cls_ou
 // pixels): edge preparation, then ONE loop over the block's pixels (a pixel per lane and step)
 // that evaluates the predictor, adds the residual of the transform pre-pass and stores the final
 // pixel; then the operation's cells are counted down.
+#ifdef D1_EXPERIMENT
+__device__ int g_skip;
+#define D1_SKIP(bit) (g_skip & (bit))
+#else
+#define D1_SKIP(bit) 0
+#endif
 // part / n_parts: the pixel loop of a large operation is shared by several warps (each prepares the
 // edge for itself and takes every n_parts-th chunk of 256 pixels; part 0 counts the cells down).
 template <typename pixel>
@@ -207,20 +226,26 @@ __device__ __noinline__ void intra_exec(const Grp g, const Intra2Frame &a, const
         res = (const int16_t *)rv.data + (int64_t)d.y4 * 4 * rstride + d.x4 * 4;
     }
     // first residual / current pixel of this lane: loaded now, used after the edge preparation
+    // Four pixels of a row per lane and step.  Residuals / current pixels of a step are loaded one
+    // step ahead (the first ones right here, so that they overlap the edge preparation).
     const int n = w * h;
-    int i = (part << 8) + g.gl;
-    int r_nx = 0, c_nx = 0;
+    const int i0 = (part << 8) + 4 * g.gl;
     const bool rd_dst = mode == DAV1D_CUDA_INTRA_NONE || mode == DAV1D_CUDA_INTRA_II;
-    if (i < n) {
-        if (res) r_nx = res[(i >> lw) * rstride + (i & (w - 1))];
-        if (rd_dst) c_nx = __ldcg(dst + (i >> lw) * stride + (i & (w - 1)));
+    uint2 r_first = make_uint2(0u, 0u);
+    int c_first[4] = { 0, 0, 0, 0 };
+    if (i0 < n) {
+        if (res) r_first = *(const uint2 *)(res + (i0 >> lw) * rstride + (i0 & (w - 1)));
+        if (rd_dst) load_px<pixel, 4>(dst + (i0 >> lw) * stride + (i0 & (w - 1)), c_first);
     }
     // what the pixel loop does: 0 predictor, 1 palette, 2 intrabc, 3 keep the current pixel
     int kind = 3;
     PixParams<pixel> P;
     P.pm = PM_CONST; P.p0 = P.p1 = P.p2 = P.p3 = 0; P.edge = P.e0 = P.e1 = edge; P.tile = tile; P.w = w; P.h = h;
     const uint8_t *bmask = nullptr;                // inter-intra blend mask
-    if (mode == DAV1D_CUDA_INTRA_PAL) {
+    if (D1_SKIP(8)) return;
+    if (D1_SKIP(1)) {
+        kind = 0;
+    } else if (mode == DAV1D_CUDA_INTRA_PAL) {
         kind = 1;
     } else if (mode == DAV1D_CUDA_INTRA_IBC) {
         kind = 2;
@@ -251,33 +276,62 @@ __device__ __noinline__ void intra_exec(const Grp g, const Intra2Frame &a, const
     }
     grp_sync(g);
 
-    const pixel *base = (const pixel *)pv.data;
-    const int ib = PxTraits<pixel>::inter_bits(bdmax);
-    // residual / current pixel of the next step are loaded before this step's pixel is computed
-    const int step = n_parts > 1 ? (n_parts << 8) - 256 + g.G : g.G;   // the next chunk of this part after 256 pixels
+    // ---- the pixel loop, one instance per predictor (the warps of a round are sorted by predictor
+    // class, so neighbouring warps run the same instance)
+    const int step = n_parts > 1 ? (n_parts << 8) - 256 + 4 * g.G : 4 * g.G;   // the next chunk of this part after 256 pixels
+    auto run = [&](auto pix) {
+        int i = i0;
+        uint2 r_nx = r_first;
+        int c_nx[4] = { c_first[0], c_first[1], c_first[2], c_first[3] };
 #pragma unroll 1
-    while (i < n) {
-        const int y = i >> lw, x = i & (w - 1);
-        const int r_cur = r_nx, c_cur = c_nx;
-        // a part's chunks: [part * 256, part * 256 + 256), then n_parts * 256 further on
-        const int inx = (n_parts > 1 && ((i + g.G) & 255) < g.G) ? i + step : i + g.G;
-        if (inx < n) {
-            if (res) r_nx = res[(inx >> lw) * rstride + (inx & (w - 1))];
-            if (rd_dst) c_nx = __ldcg(dst + (inx >> lw) * stride + (inx & (w - 1)));
+        while (i < n) {
+            const int y = i >> lw, x = i & (w - 1);
+            const uint2 r_cur = r_nx;
+            int c_cur[4] = { c_nx[0], c_nx[1], c_nx[2], c_nx[3] };
+            const int inx = (n_parts > 1 && ((i + 4 * g.G) & 255) < 4 * g.G) ? i + step : i + 4 * g.G;
+            if (inx < n) {
+                if (res) r_nx = *(const uint2 *)(res + (inx >> lw) * rstride + (inx & (w - 1)));
+                if (rd_dst) load_px<pixel, 4>(dst + (inx >> lw) * stride + (inx & (w - 1)), c_nx);
+            }
+            int v[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                v[k] = pix(x + k, y, i + k, c_cur[k]);
+                if (bmask) v[k] = (c_cur[k] * (64 - bmask[i + k]) + v[k] * bmask[i + k] + 32) >> 6;    // mc.blend (mc_tmpl.c:642-653)
+            }
+            if (res) {
+                v[0] = clip_px<pixel>(v[0] + (int)(int16_t)(r_cur.x & 0xffff), bdmax);
+                v[1] = clip_px<pixel>(v[1] + ((int)r_cur.x >> 16), bdmax);
+                v[2] = clip_px<pixel>(v[2] + (int)(int16_t)(r_cur.y & 0xffff), bdmax);
+                v[3] = clip_px<pixel>(v[3] + ((int)r_cur.y >> 16), bdmax);
+            }
+            store_px<pixel, 4>(dst + y * stride + x, v);
+            i = inx;
         }
-        int v;
-        if (kind == 0) {
-            v = ipred_pixel<pixel>(P, x, y, i, bdmax);
-        } else if (kind == 1) {
-            // pal_pred (ipred_tmpl.c:717-730): two pixels per index byte
-            const int idx = (a.pal_idx + d.coef_off)[i >> 1];
-            v = ((const pixel *)a.pal + d.aux)[(x & 1) ? idx >> 4 : idx & 7];
-        } else if (kind == 2) {
-            // intrabc: put_bilin (mc_tmpl.c:395-450) from the current picture; coordinates clamped
-            // to the 4*bw4 x 4*bh4 area (= emu_edge, recon_tmpl.c:974-995)
-            const int sx = (int16_t)(d.aux & 0xffff), sy = (int16_t)(d.aux >> 16);
-            const int mx = d.angle_delta, my = d.flags;
-            const int pw = (4 * a.bw4) >> ss_hor, ph = (4 * a.bh4) >> ss_ver;
+    };
+    if (D1_SKIP(2)) {
+    } else if (kind == 0) {
+        const pixel *e = P.edge;
+        switch (P.pm) {
+        case PM_CONST: run([&](int, int, int, int) { return P.p0; }); break;
+        case PM_V: run([&](int x, int, int, int) { return (int)e[1 + x]; }); break;
+        case PM_H: run([&](int, int y, int, int) { return (int)e[-(1 + y)]; }); break;
+        default: run([&](int x, int y, int i, int) { return ipred_pixel<pixel>(P, x, y, i, bdmax); }); break;
+        }
+    } else if (kind == 1) {
+        // pal_pred (ipred_tmpl.c:717-730): two pixels per index byte
+        const uint8_t *idx = a.pal_idx + d.coef_off;
+        const pixel *pal = (const pixel *)a.pal + d.aux;
+        run([&](int x, int, int i, int) { const int q = idx[i >> 1]; return (int)pal[(x & 1) ? q >> 4 : q & 7]; });
+    } else if (kind == 2) {
+        // intrabc: put_bilin (mc_tmpl.c:395-450) from the current picture; coordinates clamped to
+        // the 4*bw4 x 4*bh4 area (= emu_edge, recon_tmpl.c:974-995)
+        const pixel *base = (const pixel *)pv.data;
+        const int ib = PxTraits<pixel>::inter_bits(bdmax);
+        const int sx = (int16_t)(d.aux & 0xffff), sy = (int16_t)(d.aux >> 16);
+        const int mx = d.angle_delta, my = d.flags;
+        const int pw = (4 * a.bw4) >> ss_hor, ph = (4 * a.bh4) >> ss_ver;
+        run([&](int x, int y, int, int) {
             const int xa = iclip(sx + x, 0, pw - 1), xb = iclip(sx + x + 1, 0, pw - 1);
             const int ya = iclip(sy + y, 0, ph - 1), yb = iclip(sy + y + 1, 0, ph - 1);
             const int q00 = __ldcg(base + (int64_t)ya * stride + xa), q01 = __ldcg(base + (int64_t)ya * stride + xb);
@@ -287,31 +341,22 @@ __device__ __noinline__ void intra_exec(const Grp g, const Intra2Frame &a, const
                 const int m0 = (16 * q00 + mx * (q01 - q00) + r1) >> sh1;
                 const int m1 = (16 * q10 + mx * (q11 - q10) + r1) >> sh1;
                 const int sh2 = 4 + ib;
-                v = clip_px<pixel>((16 * m0 + my * (m1 - m0) + ((1 << sh2) >> 1)) >> sh2, bdmax);
+                return clip_px<pixel>((16 * m0 + my * (m1 - m0) + ((1 << sh2) >> 1)) >> sh2, bdmax);
             } else if (mx) {
                 const int sh1 = 4 - ib;
                 const int px = (16 * q00 + mx * (q01 - q00) + ((1 << sh1) >> 1)) >> sh1;
-                v = clip_px<pixel>((px + ((1 << ib) >> 1)) >> ib, bdmax);
+                return clip_px<pixel>((px + ((1 << ib) >> 1)) >> ib, bdmax);
             } else if (my) {
-                v = clip_px<pixel>((16 * q00 + my * (q10 - q00) + 8) >> 4, bdmax);
-            } else {
-                v = q00;
+                return clip_px<pixel>((16 * q00 + my * (q10 - q00) + 8) >> 4, bdmax);
             }
-        } else {
-            v = c_cur;                              // residual on top of what an earlier round left there
-        }
-        if (bmask) {
-            // mc.blend of the intra prediction onto the inter prediction (mc_tmpl.c:642-653)
-            const int mk = bmask[i];
-            v = (c_cur * (64 - mk) + v * mk + 32) >> 6;
-        }
-        if (res) v = clip_px<pixel>(v + r_cur, bdmax);
-        dst[y * stride + x] = (pixel)v;
-        i = inx;
+            return q00;
+        });
+    } else {
+        run([&](int, int, int, int c) { return c; });      // residual on top of what an earlier round left there
     }
     // the operation's pixels are stored: one count less on each of its cells (the grid barrier at
     // the end of the round makes pixels and counts visible together)
-    if (part == 0) {
+    if (part == 0 && !D1_SKIP(4)) {
         const int W = map_w(a, pl), H = map_h(a, pl);
         uint8_t *m = a.map + map_off(a, pl);
         const int ltw = 31 - __clz((int)d.tw4);
@@ -375,6 +420,7 @@ struct RoundsArgs {
     RoundCtr *ctr;                      // [2] (zeroed before the launch)
 #ifdef D1_EXPERIMENT
     unsigned long long *trace;          // per round: 4 time stamps (ns), pending, ready entries
+    int skip;                           // timing experiments (wrong results): 1 edges + set-up, 2 pixel loop, 4 count-down, 8 whole exec
 #endif
 };
 #ifdef D1_EXPERIMENT
@@ -393,6 +439,9 @@ __global__ void __launch_bounds__(R_WARPS * 32, 4) intra_rounds_kernel(const __g
     ExecSmem<pixel> *sm = (ExecSmem<pixel> *)rounds_smem_raw + warp;
     unsigned target = 0;
     unsigned n_pend = (unsigned)a.op_base[a.g.nf];
+#ifdef D1_EXPERIMENT
+    if (gtid == 0) g_skip = a.skip;
+#endif
     for (int round = 0; n_pend > 0; round++) {
         RoundCtr *ctr = a.ctr + (round & 1), *nxt = a.ctr + ((round & 1) ^ 1);
         const unsigned *pend = a.pend[round & 1], *pblk = a.pend_blk[round & 1];
@@ -799,6 +848,7 @@ static int group_submit_on(Dav1dCudaContext *c, const Dav1dCudaReconBatch *const
     if (!g_trace) cudaMalloc(&g_trace, 256 * 6 * 8);
     cudaMemsetAsync(g_trace, 0, 256 * 6 * 8, st);
     ra.trace = g_trace;
+    ra.skip = getenv("D1_SKIP") ? atoi(getenv("D1_SKIP")) : 0;
     d1_last_trace = g_trace;
 #endif
     const size_t smem = hbd ? rounds_smem_bytes<uint16_t>() : rounds_smem_bytes<uint8_t>();
