@@ -3,18 +3,20 @@
 
 Workload (BASELINE.json configs[3]/[4]): full synthetic 4K 10-bit 4:2:0 frame
 reconstruction - motion compensation (put / fused compound / warp), inter
-residual inverse transforms and level-scheduled intra prediction (+CfL,
-palette, filter-intra) - for `--streams` independent streams per GPU, each
-with its own reference frames in HBM.  A step = one frame of every stream; the frames of
-`--group` streams are submitted together as one CUDA graph.
+residual inverse transforms and intra prediction (+CfL, palette,
+filter-intra) - for `--streams` independent streams per GPU, each with its
+own reference frames in HBM.  A step = one frame of every stream; the frames of
+`--group` streams are submitted together (dav1d_cuda_recon_group_submit).
 
   python bench.py --gpus N --steps K --warmup W            (our CUDA path)
   python bench.py --impl reference ...                     (reference C templates on host cores)
 
 `value`  : luma Mpix/s with descriptors/coefficients/refs resident in HBM.
-`e2e`    : same metric through the C ABI with HOST buffers - every step ships
-           descriptors + coefficients H2D from pinned memory and reads the
-           reconstructed frame back D2H, inside the timed region.
+`e2e`    : same metric through the C ABI with HOST buffers - every step takes
+           the NEXT frame of every stream (a different descriptor set than the
+           step before), ships descriptors + coefficients H2D from pinned
+           memory, submits and reads the reconstructed frame back D2H, all
+           inside the timed region.  The library does no host-side scheduling.
 Timing: CUDA events on the launching streams (fork/join through events), max
 over ranks.  No collectives on the data path (streams are independent).
 """
@@ -41,21 +43,20 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--streams", type=int, default=32, help="independent 4K streams per GPU")
-    ap.add_argument("--group", type=int, default=8,
-                    help="streams whose frames are submitted as one graph (level-synchronous intra launches "
-                         "shared by the group); 0 = one graph per stream")
+    ap.add_argument("--streams", type=int, default=64, help="independent 4K streams per GPU")
+    ap.add_argument("--group", type=int, default=32,
+                    help="streams whose frames are submitted together (dav1d_cuda_recon_group_submit: one intra "
+                         "executor launch per group)")
     ap.add_argument("--width", type=int, default=3840)
     ap.add_argument("--height", type=int, default=2160)
     ap.add_argument("--bitdepth-max", type=lambda s: int(s, 0), default=0x3ff)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--batched", action="store_true", help="all streams of a GPU in ONE graph (--group = --streams)")
+    ap.add_argument("--no-verify", action="store_true")
+    ap.add_argument("--graph", action="store_true", help="replay the group submission from a captured CUDA graph "
+                                                         "(device-resident arm only; e2e always submits directly)")
     a = ap.parse_args()
-    if a.batched:
-        a.group = a.streams
-    a.group = min(a.group, a.streams)
+    a.group = max(1, min(a.group, a.streams, 64))
     return a
 
 
@@ -174,35 +175,38 @@ def cpu_reference_run(args, steps, warmup, frames_per_step=None):
             "sample": f"{n} frames/step x {steps} steps of {args.width}x{args.height} "
                       f"{'10' if args.bitdepth_max == 0x3ff else '12' if args.bitdepth_max > 0x3ff else '8'}-bit 4:2:0, "
                       f"reference C templates (gcc -O3, no asm: no nasm in the image), one frame per thread",
-            "seconds": dt, "ms_per_step": dt / steps * 1e3}
+            "seconds": dt, "ms_per_step": dt / steps * 1e3, "frames_per_step": n}
 
 
 def main_reference(args):
     rank, world, local = dist_env()
     if rank != 0:
         return
-    r = cpu_reference_run(args, max(1, args.steps), max(0, min(args.warmup, 1)))
+    # bounded: a step = one frame per host thread; the requested steps / warm-up are capped so that
+    # the run ends within a few minutes, and the line reports what was actually run
+    steps, warmup = max(1, min(args.steps, 8)), max(0, min(args.warmup, 1))
+    r = cpu_reference_run(args, steps, warmup)
     out = {"metric": "Mpix/s of mc+itx+ipred recon", "impl": "reference", "value": r["value"], "unit": "Mpix/s",
-           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
+           "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": r["ms_per_step"],
+           "requested": {"steps": args.steps, "warmup": args.warmup},
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u16" if args.bitdepth_max > 0xff else "u8",
            "data": "synthetic",
-           "config": workload_config(args, None),
+           "config": workload_config(args),
+           "config_extra": {"frames_per_step": r["frames_per_step"], "host_threads": r["cores"]},
            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
            "e2e": {"value": r["value"], "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)
 
 
-def workload_config(args, extra):
+def workload_config(args):
+    """The same dictionary for both arms (what is measured); arm-specific details go to config_extra."""
     bits = 10 if args.bitdepth_max == 0x3ff else 12 if args.bitdepth_max > 0x3ff else 8
-    cfg = {"workload": f"full synthetic {args.width}x{args.height} {bits}-bit 4:2:0 reconstruction "
-                       f"(MC put/compound/warp + itx + level-scheduled intra/CfL/palette), "
-                       f"{args.streams} independent streams per GPU (BASELINE configs[3]/[4])",
-           "streams_per_gpu": args.streams, "frame": [args.width, args.height], "bitdepth": bits,
-           "mix": "30% intra blocks, 60% blocks with residual, inter: put 50/avg 20/w_avg 10/wedge 10/seg 5/warp 5",
-           "parallelism": "independent streams, no collective"}
-    if extra:
-        cfg.update(extra)
-    return cfg
+    return {"workload": f"full synthetic {args.width}x{args.height} {bits}-bit 4:2:0 reconstruction "
+                        f"(MC put/compound/warp + itx + intra/CfL/palette), independent streams, one frame per "
+                        f"stream and step (BASELINE configs[3]/[4])",
+            "frame": [args.width, args.height], "bitdepth": bits,
+            "mix": "30% intra blocks, 60% blocks with residual, inter: put 50/avg 20/w_avg 10/wedge 10/seg 5/warp 5",
+            "parallelism": "independent streams, no collective"}
 
 
 # ------------------------------------------------------------------ our arm
@@ -249,17 +253,15 @@ def main_ours(args):
     # weak scaling: world * S independent streams, stream i -> rank i mod world (replicas only)
     my_streams = D.streams_of_rank(world * S, world, rank)
     assert len(my_streams) == S
-    # ---- build S streams (contexts) with their own pictures + descriptor sets
-    n_sets = min(S, 4)
-    hfs = [F.HostFrame(args.width, args.height, args.bitdepth_max, 1000 + my_streams[i]) for i in range(n_sets)]
-    for hf in hfs:
-        hf.schedule()
-    # Frames are submitted in groups of `--group` streams: one captured graph per group whose
-    # intra phase runs one set of launches per dependency level for the whole group
-    # (dav1d_cuda_recon_graph_build_multi); the groups run concurrently on their own CUDA
-    # streams.  --group 0: one graph per stream (dav1d_cuda_recon_graph_build).
-    G = args.group if args.group > 0 else 1
-    batched = args.group > 0 and not args.no_graph
+    # ---- S streams with their own pictures.  Every stream cycles through N_SETS different frames
+    # (descriptor sets): a step reconstructs the NEXT frame of every stream, never the same one
+    # twice in a row.  The last stream of a rank is 12-bit (BASELINE config 5's spot check; 10- and
+    # 12-bit frames share the pixel type and may share a group).
+    N_SETS = 4
+    bd12 = 0xfff if args.bitdepth_max == 0x3ff else args.bitdepth_max
+    sets = {bd: [F.HostFrame(args.width, args.height, bd, 1000 + 17 * rank + i) for i in range(N_SETS)]
+            for bd in {args.bitdepth_max, bd12}}
+    G = args.group
     ctxs, dfs, units = [], [], []
     plane_cache = {}
     main_ctx = F.open_context(local)
@@ -268,49 +270,50 @@ def main_ours(args):
         ctxs.append(ctx)
         gdfs = []
         for s in range(g0, min(S, g0 + G)):
-            hf = hfs[s % n_sets]
-            df = F.DeviceFrame(ctx, hf, n_refs=2)
+            bd = bd12 if s == S - 1 else args.bitdepth_max
+            hfs = sets[bd][s % N_SETS:] + sets[bd][:s % N_SETS]        # the stream's frame sequence
+            df = F.DeviceFrame(ctx, hfs[0], n_refs=2, more_sets=hfs[1:])
             df.upload_descriptors()
-            # picture CONTENT is generated once per descriptor set and pixel role (host-side setup time);
-            # every stream still owns its own reference / destination pictures in HBM
-            key = s % n_sets
-            if key not in plane_cache:
-                plane_cache[key] = [F.random_planes(hf, 7 + r + 10 * key) for r in range(2)] + \
-                                   [F.random_planes(hf, 99 + key)]
+            # picture CONTENT is generated once per bit depth and role (host-side set-up time); every
+            # stream owns its own reference / destination pictures in HBM
+            if bd not in plane_cache:
+                plane_cache[bd] = [F.random_planes(hfs[0], 7 + r) for r in range(2)] + [F.random_planes(hfs[0], 99)]
             for r in range(2):
-                df.upload_picture(df.refs[r], plane_cache[key][r])
-            df.upload_picture(df.dst, plane_cache[key][2])
-            if not args.no_graph and not batched:
-                df.build_graph()
+                df.upload_picture(df.refs[r], plane_cache[bd][r])
+            df.upload_picture(df.dst, plane_cache[bd][2])
             gdfs.append(df)
             dfs.append(df)
         L.dav1d_cuda_synchronize(ctx)
-        units.append((ctx, F.MultiFrame(ctx, gdfs) if batched else None, gdfs))
+        units.append([ctx, None, gdfs])
     pkg.check_error()
-    luma_px = hfs[0].luma_px
-    algo_step = sum(dfs[s].hf.algo_bytes for s in range(S))
-    footprint_mb = S * (3 * args.width * args.height * 1.5 * (2 if args.bitdepth_max > 0xff else 1) +
-                        hfs[0].host_bytes()) / 1e6
+    luma_px = dfs[0].hf.luma_px
+    footprint_mb = S * (4 * args.width * args.height * 1.5 * 2 + max(h.host_bytes() for h in sets[args.bitdepth_max])) / 1e6
 
     ev_start, ev_stop = L.dav1d_cuda_event_create(), L.dav1d_cuda_event_create()
     ev_done = [L.dav1d_cuda_event_create() for _ in ctxs]
+    step_no = [0]
+    host_s = [0.0]
 
-    def run_step(e2e=False):
-        for ctx, multi, gdfs in units:
+    def run_step(e2e=False, resident_rotate=True):
+        """One frame of every stream.  Device-resident arm: the descriptor sets of the step were
+        shipped before the timed region (all N_SETS sets of a stream cannot be resident in ONE arena,
+        so this arm replays set 0); e2e arm: every stream takes its NEXT frame - the descriptor set
+        goes host -> device from pinned memory, the group is submitted, the picture comes back."""
+        t0 = time.perf_counter()
+        k = step_no[0]
+        step_no[0] += 1
+        for u in units:
+            ctx, multi, gdfs = u
             if e2e:
                 for df in gdfs:
+                    df.use(k)
                     df.upload_descriptors_pinned()
-            if multi is not None:
-                multi.launch()
-            else:
-                for df in gdfs:
-                    if args.no_graph:
-                        df.submit()
-                    else:
-                        df.launch_graph()
+                u[1] = multi = F.MultiFrame(ctx, gdfs)          # batch pointers of the sets in use: host structs only
+            multi.launch()
             if e2e:
                 for df in gdfs:
                     df.download_pinned()
+        host_s[0] += time.perf_counter() - t0
 
     def timed(nsteps, e2e=False):
         """fork: every group's stream waits for ev_start; join: main stream waits for every done event."""
@@ -338,97 +341,140 @@ def main_ours(args):
             return float(t.item())
         return ms
 
-    # ---- warm-up + timed region (device-resident)
+    # ---- device-resident arm: descriptors, coefficients and references are in HBM when the timed
+    # region starts; a step = one group submission per group (a handful of launches: nothing is
+    # scheduled, merged or captured on the host)
+    for u in units:
+        u[1] = F.MultiFrame(u[0], u[2], graph=args.graph)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
         time.sleep(0.3)          # nvidia-smi needs a moment before its first sample
-    for _ in range(max(args.warmup, 3)):
+    warmup = max(args.warmup, 3)
+    for _ in range(warmup):
         run_step()
     barrier()
     launches0 = L.dav1d_cuda_launch_count()
     barrier()
     sampler.mark()
+    host_s[0] = 0.0
     ms = timed(args.steps)
     barrier()
     sampler.mark()
     launches = L.dav1d_cuda_launch_count() - launches0
+    host_resident_ms = host_s[0] * 1e3 / (args.steps * S)
     clocks = sampler.stop() if rank == 0 else None
     ms = max_over_ranks(ms)
+    for c in ctxs:
+        if L.dav1d_cuda_synchronize(c):
+            pkg.check_error()
     pkg.check_error()
     value = world * S * args.steps * luma_px / (ms * 1e-3) / 1e6
+    algo_step = sum(df.hf.algo_bytes for df in dfs)
 
-    # ---- end to end with host buffers (pinned), copies inside the timed region
+    # ---- verification of the timed configuration (outside the timed region): one 10-bit and the
+    # 12-bit stream of this rank against the oracle (the reference's C templates), bit for bit
+    verified = None
+    if rank == 0 and not args.no_verify:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import refdsp
+        import refframe
+        ref = refdsp.RefDSP()
+        verified = []
+        for s_idx in sorted({0, S - 1}):
+            df = dfs[s_idx]
+            bd = df.hf.bdmax
+            refs = plane_cache[bd][:2]
+            df.upload_picture(df.dst, plane_cache[bd][2])
+            want = refframe.run_oracle(ref, df.hf, [p.copy() for p in plane_cache[bd][2]], refs)
+            mf1 = F.MultiFrame(df.ctx, [df])
+            mf1.launch()
+            got = df.download_picture()
+            ok = all(np.array_equal(a, b) for a, b in zip(want, got))
+            verified.append({"stream": s_idx, "bitdepth_max": bd, "bit_exact_vs_oracle": bool(ok)})
+            if not ok:
+                raise RuntimeError(f"stream {s_idx}: output differs from the oracle")
+        pkg.check_error()
+
+    # ---- end to end with host buffers (pinned): every step takes the NEXT frame of every stream
+    # (a different descriptor set than the step before), ships it H2D, submits, reads the picture back
     e2e = None
     if not args.no_e2e:
+        shared_pinned = {}
         for df in dfs:
-            df.alloc_pinned()
+            df.alloc_pinned(share=shared_pinned)
         for _ in range(2):
             run_step(e2e=True)
         barrier()
         e2e_steps = max(3, min(args.steps, 10))
+        host_s[0] = 0.0
         ems = max_over_ranks(timed(e2e_steps, e2e=True))
         barrier()
         pkg.check_error()
-        h2d = sum(df.arena_bytes for df in dfs)
+        h2d = sum(sum(st["bytes"] for st in df._sets) / len(df._sets) for df in dfs)
         d2h = sum(df.pinned_out_bytes for df in dfs)
         e2e = {"value": world * S * e2e_steps * luma_px / (ems * 1e-3) / 1e6, "unit": "Mpix/s",
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
-               "ms_per_step": ems / e2e_steps}
+               "ms_per_step": ems / e2e_steps,
+               "fresh_frames": f"every stream cycles through {N_SETS} different descriptor sets, one per step",
+               "includes": ["descriptor + coefficient upload", "group submission (launches only: the library does no "
+                            "host-side scheduling, table merging or graph capture)", "picture download"],
+               "host_ms_per_frame": host_s[0] * 1e3 / (e2e_steps * S), "host_threads": 1}
+        for u in units:
+            for df in u[2]:
+                df.use(0)
+                df.upload_descriptors_pinned()      # the arena holds the last e2e frame: back to set 0
+            L.dav1d_cuda_synchronize(u[0])
+            u[1] = F.MultiFrame(u[0], u[2])
 
     # ---- per-launch-class timing (roofline of the dominant class), measured live with CUDA events
-    # in the regime of the timed region: for every class a graph per group that holds only that
-    # class's launches (dav1d_cuda_recon_graph_build_multi_phases), all groups in flight at once.
-    # Reported per FRAME: class time of one step / frames per step.  `solo_ms` = the same classes
-    # of ONE frame alone on the GPU (latency, not throughput).
+    # in the regime of the timed region: for every class a submission per group that holds only that
+    # class's launches (dav1d_cuda_recon_group_submit_phases), all groups in flight at once.
+    # Reported per FRAME: class time of one step / frames per step.
     roof = None
     if rank == 0:
         peak, peak_src = peaks()
         cls_bits = {"mc_put": 1, "mc_compound": 2, "warp": 4, "itx": 8, "intra": 16}
         cls_ms = {}
-        if batched:
-            for name, bit in cls_bits.items():
-                cg = [F.MultiFrame(ctx, gdfs, phase_mask=bit) for ctx, _, gdfs in units]
+        for name, bit in cls_bits.items():
+            cg = [F.MultiFrame(ctx, gdfs, phase_mask=bit) for ctx, _, gdfs in units]
 
-                def step_cls():
-                    for g in cg:
-                        g.launch()
-                for _ in range(2):
-                    step_cls()
-                torch.cuda.synchronize()
-                L.dav1d_cuda_event_record(main_ctx, ev_start)
-                for c in ctxs:
-                    L.dav1d_cuda_stream_wait_event(c, ev_start)
-                reps = 3
-                for _ in range(reps):
-                    step_cls()
-                for c, ev in zip(ctxs, ev_done):
-                    L.dav1d_cuda_event_record(c, ev)
-                    L.dav1d_cuda_stream_wait_event(main_ctx, ev)
-                L.dav1d_cuda_event_record(main_ctx, ev_stop)
-                cls_ms[name] = L.dav1d_cuda_event_elapsed_ms(ev_start, ev_stop) / (reps * S)
+            def step_cls():
                 for g in cg:
-                    g.close()
-        solo_ms = F.time_classes(dfs[:min(S, 8)], reps=2, flush_mb=0 if footprint_mb > 2 * L2_MB else 256)
-        if not cls_ms:
-            cls_ms = solo_ms
+                    g.launch()
+            for _ in range(2):
+                step_cls()
+            torch.cuda.synchronize()
+            L.dav1d_cuda_event_record(main_ctx, ev_start)
+            for c in ctxs:
+                L.dav1d_cuda_stream_wait_event(c, ev_start)
+            reps = 3
+            for _ in range(reps):
+                step_cls()
+            for c, ev in zip(ctxs, ev_done):
+                L.dav1d_cuda_event_record(c, ev)
+                L.dav1d_cuda_stream_wait_event(main_ctx, ev)
+            L.dav1d_cuda_event_record(main_ctx, ev_stop)
+            cls_ms[name] = L.dav1d_cuda_event_elapsed_ms(ev_start, ev_stop) / (reps * S)
         dom = max(cls_ms, key=lambda k: cls_ms[k])
         alg = sum(df.hf.algo_class[dom] for df in dfs) / S
         achieved = alg / (cls_ms[dom] * 1e-3) / 1e9
         traffic = None
-        tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
+        tp = os.path.join(ROOT, "profiles", "r2_traffic.json")
         if os.path.exists(tp):
             with open(tp) as f:
                 traffic = json.load(f).get(dom, {}).get("dram_bytes_per_frame")
         roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "traffic_source": "profiles/r2_traffic.json (ncu dram__bytes of this class at the benched shape)"
+                if traffic else None,
                 "algorithmic_bytes": alg, "ms": cls_ms[dom],
                 "per": "frame (launch class of one frame; class time of a step / frames per step)",
                 "per_class_ms": cls_ms,
                 "per_class_gbs": {k: (sum(df.hf.algo_class[k] for df in dfs) / S / (v * 1e-3) / 1e9 if v > 0 else None)
                                   for k, v in cls_ms.items()},
-                "solo_frame_class_ms": solo_ms,
                 "frame_algorithmic_bytes": dfs[0].hf.algo_bytes,
+                "frame_algorithmic_bytes_packed_coefs": dfs[0].hf.algo_bytes - dfs[0].hf.dense_coef_bytes + dfs[0].hf.cf.nbytes,
                 "whole_step": {"achieved": algo_step * args.steps / (ms * 1e-3) / 1e9,
                                "frac": algo_step * args.steps / (ms * 1e-3) / 1e9 / peak}}
 
@@ -440,23 +486,28 @@ def main_ours(args):
 
     if rank == 0:
         out = {"metric": "Mpix/s of mc+itx+ipred recon", "value": value, "unit": "Mpix/s", "n_gpus": world,
-               "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+               "steps": args.steps, "warmup": warmup, "ms_per_step": ms / args.steps,
                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                "dtype": "u16" if args.bitdepth_max > 0xff else "u8", "data": "synthetic",
-               "config": workload_config(args, {
+               "config": workload_config(args),
+               "config_extra": {
+                   "streams_per_gpu": S, "frames_per_group_submission": G,
                    "l2": f"inputs larger than L2: working set {footprint_mb:.0f} MB per GPU vs {L2_MB:.0f} MB L2"
                    if footprint_mb > 2 * L2_MB else f"working set {footprint_mb:.0f} MB; L2 NOT exceeded",
-                   "cuda_graph": not args.no_graph,
-                   "submission": (f"{len(units)} graphs in flight, each the frames of {G} streams (level-synchronous "
-                                  f"intra launches shared by the group)") if batched else "one graph per stream",
-                   "levels": [int(df.hf.n_levels) for df in dfs[:n_sets]],
-                   "launches_per_frame": int(launches / max(1, args.steps * S))}),
+                   "cuda_graph": bool(args.graph),
+                   "submission": f"{len(units)} group submissions per step, each the frames of {G} streams "
+                                 f"(dav1d_cuda_recon_group_submit: nothing scheduled on the host)",
+                   "twelve_bit_stream": "the last stream of every rank is 12-bit",
+                   "intra_ops_per_frame": int(dfs[0].hf.n_intra),
+                   "launches_per_frame": launches / max(1, args.steps * S),
+                   "host_ms_per_frame_resident": host_resident_ms},
                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
+               "verified": verified,
                "hbm_frac_of_8TBs": algo_step * args.steps / (ms * 1e-3) / 8e12}
         print(json.dumps(out), flush=True)
-    for _, multi, _ in units:
-        if multi is not None:
-            multi.close()
+    for u in units:
+        if u[1] is not None:
+            u[1].close()
     for df in dfs:
         df.close()
     if world > 1:

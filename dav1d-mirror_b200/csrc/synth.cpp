@@ -65,6 +65,7 @@ typedef struct D1SynthFrame {
     int64_t n_blocks, n_intra_blocks;
     Dav1dCudaMcDesc *mc_obmc;  int32_t n_mc_obmc;  uint32_t *mc_obmc_tiles; int32_t n_mc_obmc_tiles[2];
     Dav1dCudaItxDesc *intra_itx; int32_t n_intra_itx; int32_t intra_itx_class_count[19];   // the intra residuals as transforms
+    double dense_coef_bytes;   // part of algo_bytes that counts DENSE coefficient blocks; the packed stream is cf_elems
 } D1SynthFrame;
 
 }  // extern "C"
@@ -117,7 +118,7 @@ struct Gen {
     std::vector<Ord> order;
     std::vector<uint8_t> decoded[3];             // per plane, 4x4 cells
     int pw4[3], ph4[3];
-    double algo = 0, luma_px = 0;
+    double algo = 0, luma_px = 0, dense_coef_bytes = 0;
     double algo_cls[5] = { 0, 0, 0, 0, 0 };
     int cur_cls = 0;
     void add_bytes(int cls, double b) { algo += b; algo_cls[cls] += b; }
@@ -168,6 +169,7 @@ struct Gen {
         }
         *eob_out = (int16_t)(cls == 0 ? 0 : std::min(last, sw * sh - 1));
         add_bytes(cur_cls, (double)sw * sh * Bc);      // algorithmic bytes: the dense block
+        dense_coef_bytes += (double)sw * sh * Bc;
         const uint32_t off = (uint32_t)cf32.size();
         if (P.dense_coefs) {
             *cw4_out = *ch4_out = 0;
@@ -776,7 +778,7 @@ __attribute__((visibility("default"))) int d1synth_generate(const D1SynthParams 
     f->pal_idx = dup(g.pal_idx); f->pal_idx_bytes = g.pal_idx.size();
     f->order = dup(order); f->n_order = (int32_t)order.size();
     f->bw4 = g.bw4; f->bh4 = g.bh4;
-    f->algo_bytes = g.algo; f->luma_px = g.luma_px;
+    f->algo_bytes = g.algo; f->luma_px = g.luma_px; f->dense_coef_bytes = g.dense_coef_bytes;
     for (int i = 0; i < 5; i++) f->algo_class[i] = g.algo_cls[i];
     f->n_blocks = g.n_blocks; f->n_intra_blocks = g.n_intra_blocks;
     return 0;

@@ -44,7 +44,8 @@ class SynthFrame(C.Structure):
                 ("n_blocks", C.c_int64), ("n_intra_blocks", C.c_int64),
                 ("mc_obmc", C.c_void_p), ("n_mc_obmc", C.c_int32), ("mc_obmc_tiles", C.c_void_p),
                 ("n_mc_obmc_tiles", C.c_int32 * 2),
-                ("intra_itx", C.c_void_p), ("n_intra_itx", C.c_int32), ("intra_itx_class_count", C.c_int32 * 19)]
+                ("intra_itx", C.c_void_p), ("n_intra_itx", C.c_int32), ("intra_itx_class_count", C.c_int32 * 19),
+                ("dense_coef_bytes", C.c_double)]
 
 
 _synth = None
@@ -115,6 +116,7 @@ class HostFrame:
         self.algo_bytes, self.luma_px = f.algo_bytes, f.luma_px
         self.algo_class = dict(zip(("mc_put", "mc_compound", "warp", "itx", "intra"), list(f.algo_class)))
         self.n_blocks, self.n_intra_blocks = f.n_blocks, f.n_intra_blocks
+        self.dense_coef_bytes = f.dense_coef_bytes
         # intra-class operations stay in decode order; their residuals are listed a second time as
         # transform descriptors ordered like `itx`
         self.intra_itx = _np_from(f.intra_itx, f.n_intra_itx * C.sizeof(B.ItxDesc))
@@ -283,16 +285,26 @@ class DeviceFrame:
         return out
 
     # ---- end-to-end path: host buffers in pinned memory
-    def alloc_pinned(self):
+    def alloc_pinned(self, share=None):
+        """share: a dict that keeps ONE pinned mirror per descriptor set for all the streams that
+        decode it (the bench's streams cycle through the same few sets); such mirrors are not freed
+        by close()."""
         if self._pinned:
             return
         L = self.L
         # pinned mirrors of the descriptor sets
+        self._own_pinned = share is None
         for st in self._sets:
+            key = id(st["hf"])
+            if share is not None and key in share:
+                st["pinned"] = share[key]
+                continue
             st["pinned"] = L.dav1d_cuda_host_alloc(st["bytes"])
             for name, arr in st["host"].items():
                 if arr.nbytes:
                     C.memmove(st["pinned"] + st["off"][name], arr.ctypes.data, arr.nbytes)
+            if share is not None:
+                share[key] = st["pinned"]
         self._pinned = True
         # pinned host frame with the device picture's layout (plane offsets and strides): the
         # reconstructed frame comes back with ONE device->host copy
@@ -366,8 +378,9 @@ class DeviceFrame:
         L.dav1d_cuda_free(self._cellmap)
         self._dev = {}
         if self._pinned:
-            for st in self._sets:
-                L.dav1d_cuda_host_free(st["pinned"])
+            if self._own_pinned:
+                for st in self._sets:
+                    L.dav1d_cuda_host_free(st["pinned"])
             L.dav1d_cuda_host_free(self._pinned_out)
         self._pinned, self._pinned_out = None, None
         for pic in [self.dst, self.res] + self.refs:
