@@ -44,9 +44,12 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--streams", type=int, default=64, help="independent 4K streams per GPU")
-    ap.add_argument("--group", type=int, default=32,
+    ap.add_argument("--group", type=int, default=64,
                     help="streams whose frames are submitted together (dav1d_cuda_recon_group_submit: one intra "
-                         "executor launch per group)")
+                         "executor launch per group) in the device-resident arm")
+    ap.add_argument("--e2e-group", type=int, default=16,
+                    help="same for the end-to-end arm: smaller groups on their own CUDA streams, so that the "
+                         "copies of one group overlap the kernels of the others")
     ap.add_argument("--width", type=int, default=3840)
     ap.add_argument("--height", type=int, default=2160)
     ap.add_argument("--bitdepth-max", type=lambda s: int(s, 0), default=0x3ff)
@@ -57,6 +60,7 @@ def parse_args():
                                                          "(device-resident arm only; e2e always submits directly)")
     a = ap.parse_args()
     a.group = max(1, min(a.group, a.streams, 64))
+    a.e2e_group = max(1, min(a.e2e_group, a.streams, 64))
     return a
 
 
@@ -396,37 +400,6 @@ def main_ours(args):
                 raise RuntimeError(f"stream {s_idx}: output differs from the oracle")
         pkg.check_error()
 
-    # ---- end to end with host buffers (pinned): every step takes the NEXT frame of every stream
-    # (a different descriptor set than the step before), ships it H2D, submits, reads the picture back
-    e2e = None
-    if not args.no_e2e:
-        shared_pinned = {}
-        for df in dfs:
-            df.alloc_pinned(share=shared_pinned)
-        for _ in range(2):
-            run_step(e2e=True)
-        barrier()
-        e2e_steps = max(3, min(args.steps, 10))
-        host_s[0] = 0.0
-        ems = max_over_ranks(timed(e2e_steps, e2e=True))
-        barrier()
-        pkg.check_error()
-        h2d = sum(sum(st["bytes"] for st in df._sets) / len(df._sets) for df in dfs)
-        d2h = sum(df.pinned_out_bytes for df in dfs)
-        e2e = {"value": world * S * e2e_steps * luma_px / (ems * 1e-3) / 1e6, "unit": "Mpix/s",
-               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
-               "ms_per_step": ems / e2e_steps,
-               "fresh_frames": f"every stream cycles through {N_SETS} different descriptor sets, one per step",
-               "includes": ["descriptor + coefficient upload", "group submission (launches only: the library does no "
-                            "host-side scheduling, table merging or graph capture)", "picture download"],
-               "host_ms_per_frame": host_s[0] * 1e3 / (e2e_steps * S), "host_threads": 1}
-        for u in units:
-            for df in u[2]:
-                df.use(0)
-                df.upload_descriptors_pinned()      # the arena holds the last e2e frame: back to set 0
-            L.dav1d_cuda_synchronize(u[0])
-            u[1] = F.MultiFrame(u[0], u[2])
-
     # ---- per-launch-class timing (roofline of the dominant class), measured live with CUDA events
     # in the regime of the timed region: for every class a submission per group that holds only that
     # class's launches (dav1d_cuda_recon_group_submit_phases), all groups in flight at once.
@@ -477,6 +450,53 @@ def main_ours(args):
                 "frame_algorithmic_bytes_packed_coefs": dfs[0].hf.algo_bytes - dfs[0].hf.dense_coef_bytes + dfs[0].hf.cf.nbytes,
                 "whole_step": {"achieved": algo_step * args.steps / (ms * 1e-3) / 1e9,
                                "frac": algo_step * args.steps / (ms * 1e-3) / 1e9 / peak}}
+
+    # ---- end to end with host buffers (pinned): every step takes the NEXT frame of every stream
+    # (a different descriptor set than the step before), ships it H2D, submits, reads the picture back
+    e2e = None
+    if not args.no_e2e:
+        shared_pinned = {}
+        for df in dfs:
+            df.alloc_pinned(share=shared_pinned)
+        # regroup: --e2e-group streams per submission, every group on its own context / CUDA stream
+        for u in units:
+            if u[1] is not None:
+                u[1].close()
+        GE = args.e2e_group
+        e2e_ctxs = [F.open_context(local) for _ in range(0, S, GE)]
+        units[:] = []
+        for gi, g0 in enumerate(range(0, S, GE)):
+            gdfs = dfs[g0:g0 + GE]
+            for df in gdfs:
+                df.ctx = e2e_ctxs[gi]
+            units.append([e2e_ctxs[gi], None, gdfs])
+        ctxs[:] = e2e_ctxs
+        while len(ev_done) < len(ctxs):
+            ev_done.append(L.dav1d_cuda_event_create())
+        for _ in range(2):
+            run_step(e2e=True)
+        barrier()
+        e2e_steps = max(3, min(args.steps, 10))
+        host_s[0] = 0.0
+        ems = max_over_ranks(timed(e2e_steps, e2e=True))
+        barrier()
+        pkg.check_error()
+        h2d = sum(sum(st["bytes"] for st in df._sets) / len(df._sets) for df in dfs)
+        d2h = sum(df.pinned_out_bytes for df in dfs)
+        e2e = {"value": world * S * e2e_steps * luma_px / (ems * 1e-3) / 1e6, "unit": "Mpix/s",
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
+               "ms_per_step": ems / e2e_steps,
+               "fresh_frames": f"every stream cycles through {N_SETS} different descriptor sets, one per step",
+               "includes": ["descriptor + coefficient upload", "group submission (launches only: the library does no "
+                            "host-side scheduling, table merging or graph capture)", "picture download"],
+               "host_ms_per_frame": host_s[0] * 1e3 / (e2e_steps * S), "host_threads": 1,
+               "frames_per_group_submission": GE, "groups_in_flight": len(units)}
+        for u in units:
+            for df in u[2]:
+                df.use(0)
+                df.upload_descriptors_pinned()      # the arena holds the last e2e frame: back to set 0
+            L.dav1d_cuda_synchronize(u[0])
+            u[1] = F.MultiFrame(u[0], u[2])
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
