@@ -95,7 +95,7 @@ DEV int use_upsample(const int wh, const int angle, const int is_sm) { return an
 
 // filter_edge (ipred_tmpl.c:362-385), out[0..sz)
 template <typename pixel>
-DEV void edge_filter(const Grp &g, pixel *out, const int sz, const int lim_from, const int lim_to, const pixel *in,
+__device__ __noinline__ void edge_filter(const Grp &g, pixel *out, const int sz, const int lim_from, const int lim_to, const pixel *in,
                      const int from, const int to, const int strength)
 {
     const int k0 = strength == 3 ? 2 : 0;
@@ -117,7 +117,7 @@ DEV void edge_filter(const Grp &g, pixel *out, const int sz, const int lim_from,
 
 // upsample_edge (ipred_tmpl.c:391-406), out[0 .. 2*hsz-2]
 template <typename pixel>
-DEV void edge_upsample(const Grp &g, pixel *out, const int hsz, const pixel *in, const int from, const int to,
+__device__ __noinline__ void edge_upsample(const Grp &g, pixel *out, const int hsz, const pixel *in, const int from, const int to,
                        const int bdmax)
 {
     for (int i = g.gl; i < hsz; i += g.G) {
@@ -157,7 +157,7 @@ DEV int ipred_dc_value(const Grp &g, const int mode, const pixel *edge, const in
 // and the CfL cases
 enum PixMode {
     PM_CONST, PM_V, PM_H, PM_PAETH, PM_SMOOTH, PM_SMOOTH_V, PM_SMOOTH_H, PM_Z1, PM_Z2, PM_Z3,
-    PM_TILE, PM_CFL
+    PM_TILE, PM_CFL, PM_PAL
 };
 
 template <typename pixel> struct PixParams {
@@ -172,9 +172,10 @@ template <typename pixel> struct PixParams {
 // (mode m, angle with the flag bits 9 / 10 of src/ipred_prepare.h:87-93) -> parameters.  scratch:
 // IPRED_SCRATCH pixels for the Z modes (blocks of up to 16 + 4: 80 pixels with z2_centre = 40);
 // tile: w*h pixels for filter-intra (w, h <= 32).
-template <typename pixel>
+// tile_t: sample type of the filter-intra tile (pixel for the per-call kernel, uint16_t for the executor)
+template <typename pixel, typename tile_t = pixel>
 DEV PixParams<pixel> ipred_setup(const Grp &g, const int m, const int angle_in, const int w, const int h,
-                                 const int max_w, const int max_h, const pixel *edge, pixel *scratch, pixel *tile,
+                                 const int max_w, const int max_h, const pixel *edge, pixel *scratch, tile_t *tile,
                                  const int bdmax, const int z2_centre = 128 + 8)
 {
     PixParams<pixel> P;
@@ -291,7 +292,7 @@ DEV PixParams<pixel> ipred_setup(const Grp &g, const int m, const int angle_in, 
                 int acc = 0;
 #pragma unroll
                 for (int k = 0; k < 7; k++) acc += f[k] * p[k];
-                tile[(y + (o >> 2)) * w + x + (o & 3)] = (pixel)clip_px<pixel>((acc + 8) >> 4, bdmax);
+                tile[(y + (o >> 2)) * w + x + (o & 3)] = (tile_t)clip_px<pixel>((acc + 8) >> 4, bdmax);
             }
             grp_sync(g);
         }
@@ -367,6 +368,10 @@ DEV int ipred_pixel(const PixParams<pixel> &P, const int x, const int y, const i
         return (v + 32) >> 6;
     }
     case PM_TILE: return ((const pixel *)P.tile)[i];
+    case PM_PAL: {                              // pal_pred (ipred_tmpl.c:717-730): tile = packed indices, e0 = palette
+        const int q = ((const uint8_t *)P.tile)[i >> 1];
+        return P.e0[(x & 1) ? q >> 4 : q & 7];
+    }
     default: {                                  // PM_CFL
         const int diff = P.p1 * ((const int16_t *)P.tile)[i];
         const int mg = (iabs(diff) + 32) >> 6;

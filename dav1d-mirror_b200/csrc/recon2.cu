@@ -7,26 +7,30 @@
 // Intra executor.  Intra prediction of a transform block reads final pixels of its neighbours
 // (recon_tmpl.c:1259-1347), so the intra-class operations of a frame form a dependency DAG.  The
 // reference resolves it by decoding superblocks in order (and, across threads, by superblock-row
-// progress counters: src/decode.c:2001-2090, src/thread_task.c:409-430).  Here ONE persistent
-// cooperative launch per group of frames runs the DAG level by level, and finds the levels itself:
-//   * the recorder hands over the operations in decode order - nothing is scheduled, sorted or
-//     levelled on the host;
-//   * a byte per 4x4 cell and plane counts the operations that still have to write the cell (set
-//     up by a small marking launch, back at zero when the frame is done: the map needs no clearing
-//     between frames);
-//   * round r: (1) every pending operation is looked at by one THREAD: it is ready when the cells
-//     of the pixels it reads are at zero (dav1d_prepare_intra_edges' own rules); ready operations
-//     go to the round's list with a key (predictor class, size class), the others stay pending;
-//     (2) the list is sorted by key (counting sort); (3) warps execute it - four small
-//     operations per warp, one per octet of lanes, neighbouring warps on the same predictor - and
-//     count the cells down.  Grid barriers separate the steps.  The operations of a round are
-//     independent of each other by construction, so nothing ever waits: round r executes exactly
-//     dependency level r.
+// progress counters: src/decode.c:2001-2090, src/thread_task.c:409-430).  Here the recorder hands
+// over the operations in decode order and nothing is scheduled, sorted or levelled on the host.
+// Per group of frames, all on the device and without a host round trip:
+//   1. mark      a byte per 4x4 cell and plane counts the operations that will write the cell;
+//   2. levels    one THREAD per operation, claimed in decode order: the operation's dependency
+//                level is one more than the highest level among the writers of the cells it reads
+//                (dav1d_prepare_intra_edges' own rules decide which cells those are).  Writers
+//                publish their level in a second per-cell map, readers poll it: the levels spread
+//                through the frame as a dataflow wave, no barrier anywhere;
+//   3. sort      counting sort of the operations by (level, predictor class, size class);
+//   4. execute   ONE persistent launch: warps claim chunks of the sorted list with a ticket -
+//                four small operations per warp (one per octet of lanes) or one large one - wait
+//                until the count of every cell they read is at zero, predict, add the residual of
+//                the transform pre-pass, store, and count their own cells down.  Claims follow the
+//                level order, so whatever an operation waits for has been claimed before it by a
+//                running warp: the launch cannot dead-lock whatever its residency, and because a
+//                level's operations are independent the waits only show up in the thin tail of
+//                the wavefront, where they cost one operation's latency per level instead of a
+//                kernel launch or a grid barrier.
 //   * the residuals do not depend on neighbours: a transform pre-pass (itx2.cu, next to the motion
 //     compensation) leaves them in an int16 plane and the executor adds them to its predictions.
-// A frame whose descriptors are inconsistent (operations that wait for each other) ends with
-// pending operations and no ready one: the executor raises the context's status word and stops;
-// dav1d_cuda_synchronize() reports it.
+// A frame whose descriptors are inconsistent (operations that wait for each other or for a later
+// one) runs into the bounded waits of steps 2 / 4: the context's status word is raised and
+// dav1d_cuda_synchronize() reports -EIO; the launch always terminates.
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -66,36 +70,39 @@ struct Intra2Frame {
     const void *pal;
     const uint8_t *pal_idx;
     int n_ops;
-    uint8_t *map;                        // cell map: plane 0, 1, 2 one after the other
+    unsigned op_base;                    // number of the frame's first operation inside the group
+    // cell maps (one allocation handed over by the caller): cnt = operations that still have to
+    // write the cell, lvl = level + 1 of the cell's writer (bit 15: a residual-only operation will
+    // write the cell once more).  Plane pl: mh[pl] rows of ms[pl] cells starting at cell mo[pl].
+    uint8_t *cnt;
+    uint16_t *lvl;
+    int mw[3], mh[3], ms[3];
+    unsigned mo[3];
+    unsigned map_words;                  // size of the whole allocation in 32-bit words
 };
 struct Intra2Args {
     Intra2Frame f[I2_MAXF];
     int nf;
-    unsigned *status;                    // context status word: bit0 = operations that wait for each other
+    unsigned *status;                    // context status word, see ST_*
 };
+// status bits raised by the executor
+constexpr unsigned ST_STUCK = 1u;        // operations that wait for each other (inconsistent descriptors)
+constexpr unsigned ST_DEPTH = 2u;        // more dependency levels than the sort supports
+constexpr unsigned ST_CELLS = 4u;        // a cell with more than two writers
 
-HD int map_w(const Intra2Frame &f, const int pl) { return pl ? (f.bw4 + f.pic.ss_hor) >> f.pic.ss_hor : f.bw4; }
-HD int map_h(const Intra2Frame &f, const int pl) { return pl ? (f.bh4 + f.pic.ss_ver) >> f.pic.ss_ver : f.bh4; }
-HD int map_off(const Intra2Frame &f, const int pl) {
-    const int s0 = f.bw4 * f.bh4, s1 = map_w(f, 1) * map_h(f, 1);
-    return pl == 0 ? 0 : pl == 1 ? s0 : s0 + s1;
-}
-
-// Edges the resolved predictor needs: bit0 left, bit1 top, bit2 topleft, bit3 topright,
-// bit4 bottomleft (mirror of the table in ipred.cuh prepare_edges(); ipred_prepare_tmpl.c:50-74,94-117)
-HD int intra_needs(const int mode, const int angle_delta, const int have_left, const int have_top) {
-    if (mode >= 1 && mode <= 8) {
-        const int base = mode == 1 ? 90 : mode == 2 ? 180 : mode == 3 ? 45 : mode == 4 ? 135 : mode == 5 ? 113
-                       : mode == 6 ? 157 : mode == 7 ? 203 : 67;
-        const int a = base + 3 * angle_delta;
-        if (a <= 90) return (a < 90 && have_top) ? (2 | 8 | 4) : 2;             // Z1 : VERT
-        if (a < 180) return 1 | 2 | 4;                                          // Z2
-        return (a > 180 && have_left) ? (1 | 16 | 4) : 1;                       // Z3 : HOR
+struct MapGeo { int mw[3], mh[3], ms[3]; unsigned mo[3]; unsigned cells; };
+static inline MapGeo map_geo(const int bw4, const int bh4, const int ss_hor, const int ss_ver) {
+    MapGeo g;
+    unsigned off = 0;
+    for (int pl = 0; pl < 3; pl++) {
+        g.mw[pl] = pl ? (bw4 + ss_hor) >> ss_hor : bw4;
+        g.mh[pl] = pl ? (bh4 + ss_ver) >> ss_ver : bh4;
+        g.ms[pl] = (g.mw[pl] + 3) & ~3;                  // rows start on a word
+        g.mo[pl] = off;
+        off += (unsigned)(g.ms[pl] * g.mh[pl]);
     }
-    if (mode == 0) return have_left ? (have_top ? 3 : 1) : (have_top ? 2 : 0);  // DC family
-    if (mode == 12) return have_left ? (have_top ? 7 : 1) : (have_top ? 2 : 0); // PAETH -> HOR / VERT / DC_128
-    if (mode >= 9 && mode <= 11) return 3;                                      // SMOOTH*
-    return 1 | 2 | 4;                                                           // FILTER
+    g.cells = (off + 15u) & ~15u;
+    return g;
 }
 
 DEV unsigned ld_acquire_u32(const unsigned *p) {
@@ -103,59 +110,36 @@ DEV unsigned ld_acquire_u32(const unsigned *p) {
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-
-// Grid barrier of the cooperative launch: a monotonic arrival counter (zeroed before the launch).
-DEV void grid_barrier(unsigned *bar, unsigned &target) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        target += gridDim.x;
-        __threadfence();
-        atomicAdd(bar, 1u);
-        while (ld_acquire_u32(bar) < target) __nanosleep(64);
-        __threadfence();
-    }
-    __syncthreads();
+DEV unsigned ld_acquire_u8(const uint8_t *p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u8 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+DEV unsigned ld_relaxed_u16(const uint16_t *p) {
+    unsigned short v;
+    asm volatile("ld.relaxed.gpu.global.u16 %0, [%1];" : "=h"(v) : "l"(p) : "memory");
+    return v;
+}
+DEV void st_relaxed_u16(uint16_t *p, const unsigned v) {
+    asm volatile("st.relaxed.gpu.global.u16 [%0], %1;" :: "l"(p), "h"((unsigned short)v) : "memory");
 }
 
-// ---- step 1 of a round: is operation d ready?  One thread, L2 loads of the map bytes.
-// all cells of [x0, x1) x [y0, y1) at most `thr`?  else *blocker = map offset of one that is not.
-// Eight loads are in flight at a time (a thread that checks the 48 neighbour cells of a 64x64
-// block one after the other would hold its whole block up at the end of the step).
-DEV bool cells_le(const uint8_t *map, const unsigned mo, const int W, const int x0, const int x1, const int y0,
-                  const int y1, const unsigned thr, unsigned *blocker) {
-    const int nx = x1 - x0, n = nx * (y1 - y0);
-    if (n <= 0) return true;
-    for (int j0 = 0; j0 < n; j0 += 8) {
-        unsigned v[8], off[8];
-#pragma unroll
-        for (int u = 0; u < 8; u++) {
-            const int j = imin(j0 + u, n - 1);
-            const int y = y1 - y0 == 1 ? y0 : nx == 1 ? y0 + j : y0 + j / nx;
-            const int x = y1 - y0 == 1 ? x0 + j : nx == 1 ? x0 : x0 + j % nx;
-            off[u] = mo + (unsigned)(y * W + x);
-            v[u] = __ldcg(map + off[u]);
-        }
-#pragma unroll
-        for (int u = 0; u < 8; u++)
-            if (v[u] > thr) { *blocker = off[u] | (thr << 31); return false; }
-    }
-    return true;
-}
-
-// On false *blocker names one cell the operation waits for (bit 31: the cell may stay at 1 - the
-// operation's own count): while that cell is above its threshold there is no need to look again.
-DEV bool op_ready(const Intra2Frame &f, const Dav1dCudaIntraDesc &d, int *cls_out, unsigned *blocker) {
+// The cells an operation reads, as up to three rectangles of the cell maps: fn(plane, x0, x1, y0,
+// y1, own) - own: the operation's own cells (a residual on top of an earlier operation's pixels:
+// that one has to be done, the count stays at 1).  Exactly the pixels dav1d_prepare_intra_edges
+// reads (ipred_prepare_tmpl.c:119-200), the co-located luma of CfL (recon_tmpl.c:1372-1417) and
+// the source area of intrabc (:1624-1637).  *cls_out: predictor class 0..18 of the operation.
+template <typename F>
+DEV void op_deps(const Intra2Frame &f, const Dav1dCudaIntraDesc &d, int *cls_out, F &&fn) {
     const int mode = d.mode;
     const int pl = d.plane;
-    const int sh = pl ? f.pic.ss_hor : 0, sv = pl ? f.pic.ss_ver : 0;
-    const int W = map_w(f, pl), H = map_h(f, pl);
-    const unsigned mo = (unsigned)map_off(f, pl);
+    const int W = f.mw[pl], H = f.mh[pl];
     const int x0 = d.x4, y0 = d.y4;
-    if (mode == DAV1D_CUDA_INTRA_PAL) { *cls_out = 15; return true; }
+    if (mode == DAV1D_CUDA_INTRA_PAL) { *cls_out = 15; return; }
     if (mode == DAV1D_CUDA_INTRA_NONE) {
-        // residual on top of an earlier operation's pixels (palette, inter-intra, intrabc): that one is done
         *cls_out = 18;
-        return cells_le(f.map, mo, W, x0, imin(x0 + d.tw4, W), y0, imin(y0 + d.th4, H), 1, blocker);
+        fn(pl, x0, imin(x0 + d.tw4, W), y0, imin(y0 + d.th4, H), true);
+        return;
     }
     if (mode == DAV1D_CUDA_INTRA_IBC) {
         *cls_out = 16;
@@ -163,7 +147,8 @@ DEV bool op_ready(const Intra2Frame &f, const Dav1dCudaIntraDesc &d, int *cls_ou
         const int pw = 4 * W, ph = 4 * H;
         const int xa = iclip(sx, 0, pw - 1) >> 2, xb = iclip(sx + 4 * d.tw4 + (d.angle_delta ? 1 : 0) - 1, 0, pw - 1) >> 2;
         const int ya = iclip(sy, 0, ph - 1) >> 2, yb = iclip(sy + 4 * d.th4 + (d.flags ? 1 : 0) - 1, 0, ph - 1) >> 2;
-        return cells_le(f.map, mo, W, xa, xb + 1, ya, yb + 1, 0, blocker);
+        fn(pl, xa, xb + 1, ya, yb + 1, false);
+        return;
     }
     const int have_left = x0 > d.tile_x4_start, have_top = y0 > d.tile_y4_start;
     int ang = mode == DAV1D_CUDA_INTRA_II ? 0 : d.angle_delta;
@@ -171,42 +156,95 @@ DEV bool op_ready(const Intra2Frame &f, const Dav1dCudaIntraDesc &d, int *cls_ou
                                       &ang, have_left, have_top);
     *cls_out = mode == DAV1D_CUDA_INTRA_II ? 17 : mode == DAV1D_CUDA_INTRA_CFL ? 14 : rm;
     const int needs = ipred_mode_needs(rm);
-    // exactly the pixels dav1d_prepare_intra_edges reads (ipred_prepare_tmpl.c:119-200)
     if (have_top && ((needs & 2) || (needs & 4) || ((needs & 1) && !have_left))) {
         const bool tr = (needs & 8) && (d.edge_flags & 1);
         const int xs = ((needs & 4) && have_left) ? x0 - 1 : x0;
         int xe = (needs & 2) ? imin(x0 + d.tw4 + (tr ? d.tw4 : 0), d.tile_x4_end) : x0 + 1;
         xe = imin(xe, W);
-        if (!cells_le(f.map, mo, W, xs, xe, y0 - 1, y0, 0, blocker)) return false;
+        fn(pl, xs, xe, y0 - 1, y0, false);
     }
     if (have_left && ((needs & 1) || ((needs & 2) && !have_top) || ((needs & 4) && !have_top))) {
         const bool bl = (needs & 16) && (d.edge_flags & 8);
         int ye = (needs & 1) ? imin(y0 + d.th4 + (bl ? d.th4 : 0), d.tile_y4_end) : y0 + 1;
         ye = imin(ye, H);
-        if (!cells_le(f.map, mo, W, x0 - 1, x0, y0, ye, 0, blocker)) return false;
+        fn(pl, x0 - 1, x0, y0, ye, false);
     }
-    if (mode == DAV1D_CUDA_INTRA_CFL)      // the co-located luma
-        return cells_le(f.map, 0u, f.bw4, x0 << sh, imin((x0 + d.tw4) << sh, f.bw4), y0 << sv,
-                        imin((y0 + d.th4) << sv, f.bh4), 0, blocker);
-    return true;
+    if (mode == DAV1D_CUDA_INTRA_CFL) {    // the co-located luma
+        const int sh = f.pic.ss_hor, sv = f.pic.ss_ver;
+        fn(0, x0 << sh, imin((x0 + d.tw4) << sh, f.bw4), y0 << sv, imin((y0 + d.th4) << sv, f.bh4), false);
+    }
 }
 
-// ---- step 3: one operation by a group of lanes (a warp, or an octet for operations of up to 64
-// pixels): edge preparation, then ONE loop over the block's pixels (a pixel per lane and step)
-// that evaluates the predictor, adds the residual of the transform pre-pass and stores the final
-// pixel; then the operation's cells are counted down.
-#ifdef D1_EXPERIMENT
-__device__ int g_skip;
-#define D1_SKIP(bit) (g_skip & (bit))
-#else
-#define D1_SKIP(bit) 0
-#endif
-// part / n_parts: the pixel loop of a large operation is shared by several warps (each prepares the
-// edge for itself and takes every n_parts-th chunk of 256 pixels; part 0 counts the cells down).
+// ---- one operation by a group of lanes (a warp, or an octet for operations of up to 64 pixels).
+// Two compact stages per strip of up to 1024 pixels: (A) the predictor, one pixel per lane and
+// step, into a 16-bit tile in shared memory - a single loop with the predictor switch inside, so
+// the code every warp of an SM runs stays small; (B) eight pixels of a row per lane and step:
+// tile (or current picture) + inter-intra blend + residual of the transform pre-pass -> picture.
+template <int N> struct IntC { static constexpr int value = N; };
+constexpr int EX_MAX_POLLS = 1 << 15;
+// wait until the counts of the cells the operation reads are down (group-parallel polling)
+DEV bool exec_wait(const Grp g, const Intra2Frame &f, const Dav1dCudaIntraDesc &d) {
+    int cls, polls = 0;
+    bool ok = true;
+    op_deps(f, d, &cls, [&](const int pl, const int x0, const int x1, const int y0, const int y1, const bool own) {
+        const int nx = x1 - x0, n = nx * (y1 - y0);
+        const unsigned thr = own ? 1u : 0u;
+        const uint8_t *m = f.cnt + f.mo[pl];
+        const int S = f.ms[pl];
+        for (int j = g.gl; j < n; j += g.G) {
+            const int y = y1 - y0 == 1 ? y0 : nx == 1 ? y0 + j : y0 + j / nx;
+            const int x = y1 - y0 == 1 ? x0 + j : nx == 1 ? x0 : x0 + j % nx;
+            const uint8_t *p = m + (size_t)y * S + x;
+            // back off: many warps poll in the thin tail of the wavefront, the few that work need the issue slots
+            unsigned ns = 32;
+            while (ld_acquire_u8(p) > thr) {
+                if (++polls > EX_MAX_POLLS) { ok = false; break; }
+                __nanosleep(ns);
+                ns = min(ns * 2u, 2048u);
+            }
+        }
+    });
+    return __all_sync(g.mask, ok);
+}
+
+// The operation's pixels are stored: one count less on each of its cells.  Every lane makes its own
+// stores visible (fence), the group meets, then the counts go down: whoever sees a count at zero
+// sees the pixels.
+DEV void exec_done(const Grp g, const Intra2Frame &a, const Dav1dCudaIntraDesc &d) {
+    const int pl = d.plane;
+    __threadfence();
+    grp_sync(g);
+    {
+        const int W = a.mw[pl], H = a.mh[pl], S = a.ms[pl];
+        const int ltw = 31 - __clz((int)d.tw4);
+        if (d.tw4 >= 4 && !(d.x4 & 3)) {
+            // rows of whole words (tx blocks are aligned to their size, rows of the map to a word)
+            const int wpr = d.tw4 >> 2, nwd = d.th4 * wpr;
+            for (int j = g.gl; j < nwd; j += g.G) {
+                const int cy = d.y4 + j / wpr, cx = d.x4 + 4 * (j % wpr);
+                if (cy < H && cx < W) {
+                    const int nb = imin(4, W - cx);
+                    atomicAdd((unsigned *)(a.cnt + a.mo[pl] + (size_t)cy * S + cx), 0u - (0x01010101u >> (8 * (4 - nb))));
+                }
+            }
+        } else {
+            const int nc = d.th4 << ltw;
+            for (int j = g.gl; j < nc; j += g.G) {
+                const int cx = d.x4 + (j & (d.tw4 - 1)), cy = d.y4 + (j >> ltw);
+                if (cx < W && cy < H) {
+                    const size_t off = (size_t)a.mo[pl] + (size_t)cy * S + cx;
+                    atomicAdd((unsigned *)(a.cnt + (off & ~(size_t)3)), 0u - (1u << (8 * (off & 3))));
+                }
+            }
+        }
+    }
+    grp_sync(g);
+}
+
 template <typename pixel>
-__device__ __noinline__ void intra_exec(const Grp g, const Intra2Frame &a, const Dav1dCudaIntraDesc &d,
-                                        pixel *edge, pixel *scratch, const int z2_centre, int16_t *tile,
-                                        const int part, const int n_parts) {
+__device__ __noinline__ bool intra_exec(const Grp g, const Intra2Frame &a, const Dav1dCudaIntraDesc &d,
+                                        pixel *edge, pixel *scratch, const int z2_centre, uint16_t *tile)
+{
     const int pl = d.plane;
     const int ss_hor = pl ? a.pic.ss_hor : 0, ss_ver = pl ? a.pic.ss_ver : 0;
     const PlaneView &pv = a.pic.p[pl];
@@ -215,162 +253,158 @@ __device__ __noinline__ void intra_exec(const Grp g, const Intra2Frame &a, const
     const int w = d.tw4 * 4, h = d.th4 * 4;
     const int lw = 31 - __clz(w);
     const int bdmax = a.pic.bdmax;
-    const int have_left = d.x4 > d.tile_x4_start, have_top = d.y4 > d.tile_y4_start;
     const int mode = d.mode;
     const bool has_res = d.eob >= 0 && mode != DAV1D_CUDA_INTRA_PAL;
+    const int rps = imin(h, 1024 >> lw);           // rows of a strip
     const int16_t *res = nullptr;
     int rstride = 0;
+    // the lane's first residuals: loaded now, used after the wait and the prediction
+    uint4 r0 = make_uint4(0u, 0u, 0u, 0u);
     if (has_res) {
         const PlaneView &rv = a.res.p[pl];
         rstride = (int)(rv.stride / 2);
         res = (const int16_t *)rv.data + (int64_t)d.y4 * 4 * rstride + d.x4 * 4;
+        const int i = g.gl * (w >= 8 ? 8 : 4);
+        if (i < w * rps) {
+            const int16_t *rp = res + (i >> lw) * rstride + (i & (w - 1));
+            if (w >= 8) r0 = __ldcg((const uint4 *)rp);
+            else { const uint2 t = __ldcg((const uint2 *)rp); r0.x = t.x; r0.y = t.y; }
+        }
     }
-    // first residual / current pixel of this lane: loaded now, used after the edge preparation
-    // Four pixels of a row per lane and step.  Residuals / current pixels of a step are loaded one
-    // step ahead (the first ones right here, so that they overlap the edge preparation).
-    const int n = w * h;
-    const int i0 = (part << 8) + 4 * g.gl;
-    const bool rd_dst = mode == DAV1D_CUDA_INTRA_NONE || mode == DAV1D_CUDA_INTRA_II;
-    uint2 r_first = make_uint2(0u, 0u);
-    int c_first[4] = { 0, 0, 0, 0 };
-    if (i0 < n) {
-        if (res) r_first = *(const uint2 *)(res + (i0 >> lw) * rstride + (i0 & (w - 1)));
-        if (rd_dst) load_px<pixel, 4>(dst + (i0 >> lw) * stride + (i0 & (w - 1)), c_first);
-    }
-    // what the pixel loop does: 0 predictor, 1 palette, 2 intrabc, 3 keep the current pixel
-    int kind = 3;
-    PixParams<pixel> P;
-    P.pm = PM_CONST; P.p0 = P.p1 = P.p2 = P.p3 = 0; P.edge = P.e0 = P.e1 = edge; P.tile = tile; P.w = w; P.h = h;
-    const uint8_t *bmask = nullptr;                // inter-intra blend mask
-    if (D1_SKIP(8)) return;
-    if (D1_SKIP(1)) {
-        kind = 0;
-    } else if (mode == DAV1D_CUDA_INTRA_PAL) {
-        kind = 1;
-    } else if (mode == DAV1D_CUDA_INTRA_IBC) {
-        kind = 2;
-    } else if (mode == DAV1D_CUDA_INTRA_CFL) {
-        const PlaneView &lv = a.pic.p[0];
-        const int lstride = (int)(lv.stride / (int)sizeof(pixel));
-        const pixel *luma = (const pixel *)lv.data + (int64_t)((d.y4 * 4) << ss_ver) * lstride + ((d.x4 * 4) << ss_hor);
-        cfl_ac_block<pixel>(g, tile, luma, lstride, d.aux & 0xff, (d.aux >> 8) & 0xff, w, h, ss_hor, ss_ver);
-        int angle = 0;
-        const int m = prepare_edges<pixel>(g, d.x4, have_left, d.y4, have_top, d.tile_x4_end, d.tile_y4_end, 0, dst,
-                                           stride, nullptr, 0, &angle, d.tw4, d.th4, 0, edge, bdmax);
-        P = cfl_setup<pixel>(g, m, edge, w, h, tile, d.angle_delta, bdmax);
-        kind = 0;
-    } else if (mode != DAV1D_CUDA_INTRA_NONE) {
-        // inter-intra (recon_tmpl.c:1658-1681): the whole-block intra prediction (edge_flags 0, no
-        // edge filter) is blended onto the inter prediction that is in dst
-        const bool ii = mode == DAV1D_CUDA_INTRA_II;
-        int angle = ii ? 0 : d.angle_delta;
-        const int m = prepare_edges<pixel>(g, d.x4, have_left, d.y4, have_top, d.tile_x4_end, d.tile_y4_end,
-                                           ii ? 0 : d.edge_flags, dst, stride, nullptr, ii ? d.angle_delta : mode,
-                                           &angle, d.tw4, d.th4, ii ? 0 : (d.flags >> 10) & 1, edge, bdmax);
-        if (ii) { bmask = a.pal_idx + d.coef_off; angle = 0; }
-        else angle |= d.flags;
-        const int max_w = ((4 * a.bw4 + ss_hor) >> ss_hor) - 4 * d.x4;
-        const int max_h = ((4 * a.bh4 + ss_ver) >> ss_ver) - 4 * d.y4;
-        P = ipred_setup<pixel>(g, m, angle, w, h, max_w, max_h, edge, scratch, (pixel *)tile, bdmax, z2_centre);
-        kind = 0;
-    }
-    grp_sync(g);
-
-    // ---- the pixel loop, one instance per predictor (the warps of a round are sorted by predictor
-    // class, so neighbouring warps run the same instance)
-    const int step = n_parts > 1 ? (n_parts << 8) - 256 + 4 * g.G : 4 * g.G;   // the next chunk of this part after 256 pixels
-    auto run = [&](auto pix) {
-        int i = i0;
-        uint2 r_nx = r_first;
-        int c_nx[4] = { c_first[0], c_first[1], c_first[2], c_first[3] };
+    const bool ok = exec_wait(g, a, d);
+    if (ok) {
+        const int have_left = d.x4 > d.tile_x4_start, have_top = d.y4 > d.tile_y4_start;
+        // stage A: 0 predictor (P), 1 intrabc, 2 nothing (the tile is filled / the current picture is the source)
+        int kind = 0;
+        PixParams<pixel> P;
+        P.pm = PM_CONST; P.p0 = P.p1 = P.p2 = P.p3 = 0; P.edge = P.e0 = P.e1 = edge; P.tile = tile; P.w = w; P.h = h;
+        const uint8_t *bmask = nullptr;                // inter-intra blend mask
+        if (mode == DAV1D_CUDA_INTRA_PAL) {
+            P.pm = PM_PAL; P.tile = a.pal_idx + d.coef_off; P.e0 = (const pixel *)a.pal + d.aux;
+        } else if (mode == DAV1D_CUDA_INTRA_IBC) {
+            kind = 1;
+        } else if (mode == DAV1D_CUDA_INTRA_NONE) {
+            kind = 2;
+        } else if (mode == DAV1D_CUDA_INTRA_CFL) {
+            const PlaneView &lv = a.pic.p[0];
+            const int lstride = (int)(lv.stride / (int)sizeof(pixel));
+            const pixel *luma = (const pixel *)lv.data + (int64_t)((d.y4 * 4) << ss_ver) * lstride + ((d.x4 * 4) << ss_hor);
+            cfl_ac_block<pixel>(g, (int16_t *)tile, luma, lstride, d.aux & 0xff, (d.aux >> 8) & 0xff, w, h, ss_hor, ss_ver);
+            int angle = 0;
+            const int m = prepare_edges<pixel>(g, d.x4, have_left, d.y4, have_top, d.tile_x4_end, d.tile_y4_end, 0, dst,
+                                               stride, nullptr, 0, &angle, d.tw4, d.th4, 0, edge, bdmax);
+            P = cfl_setup<pixel>(g, m, edge, w, h, (const int16_t *)tile, d.angle_delta, bdmax);
+        } else {
+            // inter-intra (recon_tmpl.c:1658-1681): the whole-block intra prediction (edge_flags 0, no
+            // edge filter) is blended onto the inter prediction that is in dst
+            const bool ii = mode == DAV1D_CUDA_INTRA_II;
+            int angle = ii ? 0 : d.angle_delta;
+            const int m = prepare_edges<pixel>(g, d.x4, have_left, d.y4, have_top, d.tile_x4_end, d.tile_y4_end,
+                                               ii ? 0 : d.edge_flags, dst, stride, nullptr, ii ? d.angle_delta : mode,
+                                               &angle, d.tw4, d.th4, ii ? 0 : (d.flags >> 10) & 1, edge, bdmax);
+            if (ii) { bmask = a.pal_idx + d.coef_off; angle = 0; }
+            else angle |= d.flags;
+            const int max_w = ((4 * a.bw4 + ss_hor) >> ss_hor) - 4 * d.x4;
+            const int max_h = ((4 * a.bh4 + ss_ver) >> ss_ver) - 4 * d.y4;
+            P = ipred_setup<pixel, uint16_t>(g, m, angle, w, h, max_w, max_h, edge, scratch, tile, bdmax, z2_centre);
+            if (P.pm == PM_TILE) kind = 2;             // filter-intra: the set-up left the prediction in the tile
+        }
+        grp_sync(g);
+        const bool from_dst = mode == DAV1D_CUDA_INTRA_NONE;
+        for (int y0 = 0; y0 < h; y0 += rps) {
+            const int n = rps << lw;
+            if (kind == 0) {
 #pragma unroll 1
-        while (i < n) {
-            const int y = i >> lw, x = i & (w - 1);
-            const uint2 r_cur = r_nx;
-            int c_cur[4] = { c_nx[0], c_nx[1], c_nx[2], c_nx[3] };
-            const int inx = (n_parts > 1 && ((i + 4 * g.G) & 255) < 4 * g.G) ? i + step : i + 4 * g.G;
-            if (inx < n) {
-                if (res) r_nx = *(const uint2 *)(res + (inx >> lw) * rstride + (inx & (w - 1)));
-                if (rd_dst) load_px<pixel, 4>(dst + (inx >> lw) * stride + (inx & (w - 1)), c_nx);
+                for (int i = g.gl; i < n; i += g.G) {
+                    const int y = y0 + (i >> lw), x = i & (w - 1);
+                    tile[i] = (uint16_t)ipred_pixel<pixel>(P, x, y, (y << lw) + x, bdmax);
+                }
+            } else if (kind == 1) {
+                // intrabc: put_bilin (mc_tmpl.c:395-450) from the current picture; coordinates clamped to
+                // the 4*bw4 x 4*bh4 area (= emu_edge, recon_tmpl.c:974-995)
+                const pixel *base = (const pixel *)pv.data;
+                const int ib = PxTraits<pixel>::inter_bits(bdmax);
+                const int sx = (int16_t)(d.aux & 0xffff), sy = (int16_t)(d.aux >> 16);
+                const int mx = d.angle_delta, my = d.flags;
+                const int pw = (4 * a.bw4) >> ss_hor, ph = (4 * a.bh4) >> ss_ver;
+#pragma unroll 1
+                for (int i = g.gl; i < n; i += g.G) {
+                    const int y = y0 + (i >> lw), x = i & (w - 1);
+                    const int xa = iclip(sx + x, 0, pw - 1), xb = iclip(sx + x + 1, 0, pw - 1);
+                    const int ya = iclip(sy + y, 0, ph - 1), yb = iclip(sy + y + 1, 0, ph - 1);
+                    const int q00 = __ldcg(base + (int64_t)ya * stride + xa), q01 = __ldcg(base + (int64_t)ya * stride + xb);
+                    const int q10 = __ldcg(base + (int64_t)yb * stride + xa), q11 = __ldcg(base + (int64_t)yb * stride + xb);
+                    int v = q00;
+                    if (mx && my) {
+                        const int sh1 = 4 - ib, r1 = (1 << sh1) >> 1;
+                        const int m0 = (16 * q00 + mx * (q01 - q00) + r1) >> sh1;
+                        const int m1 = (16 * q10 + mx * (q11 - q10) + r1) >> sh1;
+                        const int sh2 = 4 + ib;
+                        v = clip_px<pixel>((16 * m0 + my * (m1 - m0) + ((1 << sh2) >> 1)) >> sh2, bdmax);
+                    } else if (mx) {
+                        const int sh1 = 4 - ib;
+                        const int px = (16 * q00 + mx * (q01 - q00) + ((1 << sh1) >> 1)) >> sh1;
+                        v = clip_px<pixel>((px + ((1 << ib) >> 1)) >> ib, bdmax);
+                    } else if (my) {
+                        v = clip_px<pixel>((16 * q00 + my * (q10 - q00) + 8) >> 4, bdmax);
+                    }
+                    tile[i] = (uint16_t)v;
+                }
             }
-            int v[4];
+            grp_sync(g);
+            auto stage_b = [&](auto pwc) {
+                constexpr int PW = decltype(pwc)::value;
+#pragma unroll 1
+                for (int i = g.gl * PW; i < n; i += g.G * PW) {
+                    const int y = y0 + (i >> lw), x = i & (w - 1);
+                    pixel *p = dst + y * stride + x;
+                    int v[PW];
+                    if (from_dst) {
+                        load_px<pixel, PW>(p, v);
+                    } else if (PW == 8) {
+                        const uint4 t = *(const uint4 *)(tile + i);
+                        v[0] = t.x & 0xffff; v[1] = t.x >> 16; v[2] = t.y & 0xffff; v[3] = t.y >> 16;
+                        v[PW - 4] = t.z & 0xffff; v[PW - 3] = t.z >> 16; v[PW - 2] = t.w & 0xffff; v[PW - 1] = t.w >> 16;
+                    } else {
+                        const uint2 t = *(const uint2 *)(tile + i);
+                        v[0] = t.x & 0xffff; v[1] = t.x >> 16; v[2] = t.y & 0xffff; v[3] = t.y >> 16;
+                    }
+                    if (bmask) {
+                        // mc.blend (mc_tmpl.c:642-653) of the intra prediction onto the inter prediction
+                        int c[PW];
+                        load_px<pixel, PW>(p, c);
+                        const uint8_t *mk = bmask + (y << lw) + x;
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                v[k] = pix(x + k, y, i + k, c_cur[k]);
-                if (bmask) v[k] = (c_cur[k] * (64 - bmask[i + k]) + v[k] * bmask[i + k] + 32) >> 6;    // mc.blend (mc_tmpl.c:642-653)
-            }
-            if (res) {
-                v[0] = clip_px<pixel>(v[0] + (int)(int16_t)(r_cur.x & 0xffff), bdmax);
-                v[1] = clip_px<pixel>(v[1] + ((int)r_cur.x >> 16), bdmax);
-                v[2] = clip_px<pixel>(v[2] + (int)(int16_t)(r_cur.y & 0xffff), bdmax);
-                v[3] = clip_px<pixel>(v[3] + ((int)r_cur.y >> 16), bdmax);
-            }
-            store_px<pixel, 4>(dst + y * stride + x, v);
-            i = inx;
-        }
-    };
-    if (D1_SKIP(2)) {
-    } else if (kind == 0) {
-        const pixel *e = P.edge;
-        switch (P.pm) {
-        case PM_CONST: run([&](int, int, int, int) { return P.p0; }); break;
-        case PM_V: run([&](int x, int, int, int) { return (int)e[1 + x]; }); break;
-        case PM_H: run([&](int, int y, int, int) { return (int)e[-(1 + y)]; }); break;
-        default: run([&](int x, int y, int i, int) { return ipred_pixel<pixel>(P, x, y, i, bdmax); }); break;
-        }
-    } else if (kind == 1) {
-        // pal_pred (ipred_tmpl.c:717-730): two pixels per index byte
-        const uint8_t *idx = a.pal_idx + d.coef_off;
-        const pixel *pal = (const pixel *)a.pal + d.aux;
-        run([&](int x, int, int i, int) { const int q = idx[i >> 1]; return (int)pal[(x & 1) ? q >> 4 : q & 7]; });
-    } else if (kind == 2) {
-        // intrabc: put_bilin (mc_tmpl.c:395-450) from the current picture; coordinates clamped to
-        // the 4*bw4 x 4*bh4 area (= emu_edge, recon_tmpl.c:974-995)
-        const pixel *base = (const pixel *)pv.data;
-        const int ib = PxTraits<pixel>::inter_bits(bdmax);
-        const int sx = (int16_t)(d.aux & 0xffff), sy = (int16_t)(d.aux >> 16);
-        const int mx = d.angle_delta, my = d.flags;
-        const int pw = (4 * a.bw4) >> ss_hor, ph = (4 * a.bh4) >> ss_ver;
-        run([&](int x, int y, int, int) {
-            const int xa = iclip(sx + x, 0, pw - 1), xb = iclip(sx + x + 1, 0, pw - 1);
-            const int ya = iclip(sy + y, 0, ph - 1), yb = iclip(sy + y + 1, 0, ph - 1);
-            const int q00 = __ldcg(base + (int64_t)ya * stride + xa), q01 = __ldcg(base + (int64_t)ya * stride + xb);
-            const int q10 = __ldcg(base + (int64_t)yb * stride + xa), q11 = __ldcg(base + (int64_t)yb * stride + xb);
-            if (mx && my) {
-                const int sh1 = 4 - ib, r1 = (1 << sh1) >> 1;
-                const int m0 = (16 * q00 + mx * (q01 - q00) + r1) >> sh1;
-                const int m1 = (16 * q10 + mx * (q11 - q10) + r1) >> sh1;
-                const int sh2 = 4 + ib;
-                return clip_px<pixel>((16 * m0 + my * (m1 - m0) + ((1 << sh2) >> 1)) >> sh2, bdmax);
-            } else if (mx) {
-                const int sh1 = 4 - ib;
-                const int px = (16 * q00 + mx * (q01 - q00) + ((1 << sh1) >> 1)) >> sh1;
-                return clip_px<pixel>((px + ((1 << ib) >> 1)) >> ib, bdmax);
-            } else if (my) {
-                return clip_px<pixel>((16 * q00 + my * (q10 - q00) + 8) >> 4, bdmax);
-            }
-            return q00;
-        });
-    } else {
-        run([&](int, int, int, int c) { return c; });      // residual on top of what an earlier round left there
-    }
-    // the operation's pixels are stored: one count less on each of its cells (the grid barrier at
-    // the end of the round makes pixels and counts visible together)
-    if (part == 0 && !D1_SKIP(4)) {
-        const int W = map_w(a, pl), H = map_h(a, pl);
-        uint8_t *m = a.map + map_off(a, pl);
-        const int ltw = 31 - __clz((int)d.tw4);
-        const int nc = d.th4 << ltw;
-        for (int j = g.gl; j < nc; j += g.G) {
-            const int cx = d.x4 + (j & (d.tw4 - 1)), cy = d.y4 + (j >> ltw);
-            if (cx < W && cy < H) {
-                // minus one on the cell's byte: a reduction on the containing word (fire and forget)
-                const size_t off = (size_t)(m - a.map) + (size_t)cy * W + cx;
-                atomicAdd((unsigned *)(a.map + (off & ~(size_t)3)), 0u - (1u << (8 * (off & 3))));
-            }
+                        for (int k = 0; k < PW; k++) v[k] = (c[k] * (64 - mk[k]) + v[k] * mk[k] + 32) >> 6;
+                    }
+                    if (has_res) {
+                        uint4 r = r0;
+                        if (y0 || i != g.gl * PW) {
+                            const int16_t *rp = res + y * rstride + x;
+                            if (PW == 8) r = __ldcg((const uint4 *)rp);
+                            else { const uint2 t = __ldcg((const uint2 *)rp); r.x = t.x; r.y = t.y; }
+                        }
+                        v[0] = clip_px<pixel>(v[0] + (int)(int16_t)(r.x & 0xffff), bdmax);
+                        v[1] = clip_px<pixel>(v[1] + ((int)r.x >> 16), bdmax);
+                        v[2] = clip_px<pixel>(v[2] + (int)(int16_t)(r.y & 0xffff), bdmax);
+                        v[3] = clip_px<pixel>(v[3] + ((int)r.y >> 16), bdmax);
+                        if (PW == 8) {
+                            v[PW - 4] = clip_px<pixel>(v[PW - 4] + (int)(int16_t)(r.z & 0xffff), bdmax);
+                            v[PW - 3] = clip_px<pixel>(v[PW - 3] + ((int)r.z >> 16), bdmax);
+                            v[PW - 2] = clip_px<pixel>(v[PW - 2] + (int)(int16_t)(r.w & 0xffff), bdmax);
+                            v[PW - 1] = clip_px<pixel>(v[PW - 1] + ((int)r.w >> 16), bdmax);
+                        }
+                    }
+                    store_px<pixel, PW>(p, v);
+                }
+            };
+            if (w >= 8) stage_b(IntC<8>());
+            else stage_b(IntC<4>());
+            grp_sync(g);
         }
     }
-    grp_sync(g);
+    exec_done(g, a, d);
+    return ok;
 }
 
 // per-warp shared memory of step 3: edge + Z-mode scratch of four octets (operations of up to 64
@@ -380,250 +414,295 @@ __device__ __noinline__ void intra_exec(const Grp g, const Intra2Frame &a, const
 constexpr int OCT_PX = 80, OCT_CENTRE = 36, OCT_Z2 = 40;
 template <typename pixel> struct __align__(16) ExecSmem {
     pixel es[4 * 2 * OCT_PX > EDGE_BUF + IPRED_SCRATCH ? 4 * 2 * OCT_PX : EDGE_BUF + IPRED_SCRATCH];
-    int16_t tile[32 * 32];
+    uint16_t tile[32 * 32];
 };
-// 256-pixel parts of an operation's pixel loop (tile-based predictors - CfL, filter-intra - stay whole)
-DEV int op_parts(const Dav1dCudaIntraDesc &d) {
-    const int px = d.tw4 * d.th4 * 16;
-    if (px <= 256 || d.mode == DAV1D_CUDA_INTRA_CFL || d.mode == DAV1D_CUDA_INTRA_FILTER) return 1;
-    return px >> 8;
-}
-
 constexpr int R_WARPS = 8;
-// operation id: part (4 bits) | frame (6 bits) | index inside the frame (20 bits)
-constexpr int OP_FRAME_SHIFT = 20, OP_PART_SHIFT = 28;
+// operation id: frame (6 bits) | index inside the frame (20 bits); EMPTY = no operation in the slot
+constexpr int OP_FRAME_SHIFT = 20;
+constexpr unsigned OP_EMPTY = 0xffffffffu;
 DEV int op_frame(const unsigned id) { return (int)((id >> OP_FRAME_SHIFT) & 63u); }
 DEV int op_index(const unsigned id) { return (int)(id & ((1u << OP_FRAME_SHIFT) - 1u)); }
-constexpr unsigned R_NOCELL = 0x7fffffffu;
-constexpr int R_BINS = 128;             // sort key: size class * 32 + predictor class
-// size classes: 0 = up to 16 pixels, 1 = up to 64 (both: one operation per octet, four per warp),
-// 2 = up to 256, 3 = larger (one operation or 256-pixel part per warp)
-DEV int size_class(const Dav1dCudaIntraDesc &d) {
+// Sort key: level * 32 + bin.  Bins 0..15: operations of up to 64 pixels (one per octet of lanes,
+// four per warp), bins 16..31: larger ones (one per warp); inside each half the predictor group, so
+// that the octets of a warp and the warps of an SM mostly run the same code.
+constexpr int N_BINS = 32;
+constexpr int MAX_LEVELS = 16384;
+constexpr int HIST_SMEM_LEVELS = 64;     // levels whose bins a block counts in shared memory
+DEV int op_bin(const Dav1dCudaIntraDesc &d, const int cls) {
     const int c4 = d.tw4 * d.th4;
-    return c4 <= 1 ? 0 : c4 <= 4 ? 1 : c4 <= 16 ? 2 : 3;
-}
-// counters of a round (two sets, used alternately)
-struct RoundCtr {
-    unsigned n_next, n_ready;          // operations that stay pending / are ready
-    unsigned hist[R_BINS];
-    unsigned cursor[R_BINS];
-};
-struct RoundsArgs {
-    Intra2Args g;
-    int op_base[I2_MAXF + 1];           // first global operation number of every frame
-    unsigned *pend[2];                  // pending operation ids
-    unsigned *pend_blk[2];              // ... and one cell each of them waits for (R_NOCELL: unknown)
-    unsigned *ready;                    // ready operations of the round, unsorted
-    uint8_t *ready_key;
-    unsigned *sorted;                   // ... sorted by key
-    unsigned *bar;                      // grid barrier counter (zeroed before the launch)
-    RoundCtr *ctr;                      // [2] (zeroed before the launch)
-#ifdef D1_EXPERIMENT
-    unsigned long long *trace;          // per round: 4 time stamps (ns), pending, ready entries
-    int skip;                           // timing experiments (wrong results): 1 edges + set-up, 2 pixel loop, 4 count-down, 8 whole exec
-#endif
-};
-#ifdef D1_EXPERIMENT
-DEV unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
-#define D1_TRACE(slot, val) do { if (gtid == 0 && a.trace && round < 256) a.trace[round * 6 + (slot)] = (val); } while (0)
-#else
-#define D1_TRACE(slot, val) do { } while (0)
-#endif
-
-template <typename pixel>
-__global__ void __launch_bounds__(R_WARPS * 32, 4) intra_rounds_kernel(const __grid_constant__ RoundsArgs a) {
-    extern __shared__ __align__(16) uint8_t rounds_smem_raw[];
-    __shared__ unsigned s_hist[R_BINS], s_base[R_BINS];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const unsigned gtid = blockIdx.x * blockDim.x + tid, gthreads = gridDim.x * blockDim.x;
-    ExecSmem<pixel> *sm = (ExecSmem<pixel> *)rounds_smem_raw + warp;
-    unsigned target = 0;
-    unsigned n_pend = (unsigned)a.op_base[a.g.nf];
-#ifdef D1_EXPERIMENT
-    if (gtid == 0) g_skip = a.skip;
-#endif
-    for (int round = 0; n_pend > 0; round++) {
-        RoundCtr *ctr = a.ctr + (round & 1), *nxt = a.ctr + ((round & 1) ^ 1);
-        const unsigned *pend = a.pend[round & 1], *pblk = a.pend_blk[round & 1];
-        unsigned *pend_next = a.pend[(round & 1) ^ 1], *pblk_next = a.pend_blk[(round & 1) ^ 1];
-        // ---- step 1: every pending operation is looked at by one thread
-        D1_TRACE(0, gtimer()); D1_TRACE(4, n_pend);
-        if (tid < R_BINS) s_hist[tid] = 0;
-        __syncthreads();
-        for (unsigned k0 = blockIdx.x * blockDim.x; k0 < n_pend; k0 += gthreads) {
-            const unsigned k = k0 + tid;
-            bool ready = false, live = k < n_pend;
-            unsigned id = 0, blk = R_NOCELL;
-            int key = 0, parts = 0;
-            if (live) {
-                if (round == 0) {
-                    int fi = 0;
-                    while (fi + 1 < a.g.nf && (unsigned)a.op_base[fi + 1] <= k) fi++;
-                    id = ((unsigned)fi << OP_FRAME_SHIFT) | (k - (unsigned)a.op_base[fi]);
-                } else {
-                    id = __ldcg(pend + k);
-                    blk = __ldcg(pblk + k);
-                }
-                const Intra2Frame &f = a.g.f[op_frame(id)];
-                // the cell this operation was seen waiting for: still above its threshold?
-                const bool still = blk != R_NOCELL && __ldcg(f.map + (blk & 0x7fffffffu)) > (blk >> 31);
-                if (!still) {
-                    const Dav1dCudaIntraDesc d = f.descs[op_index(id)];
-                    int cls = 0;
-                    ready = op_ready(f, d, &cls, &blk);
-                    key = size_class(d) * 32 + cls;
-                    if (ready) parts = op_parts(d);
-                }
-            }
-            // warp-aggregated appends: a ready operation adds one entry per part to the round's list
-            const unsigned mp = __ballot_sync(0xffffffffu, live && !ready);
-            int incl = parts;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += t;
-            }
-            const int tot = __shfl_sync(0xffffffffu, incl, 31);
-            unsigned br = 0, bp = 0;
-            if (lane == 0) {
-                if (tot) br = atomicAdd(&ctr->n_ready, (unsigned)tot);
-                if (mp) bp = atomicAdd(&ctr->n_next, __popc(mp));
-            }
-            br = __shfl_sync(0xffffffffu, br, 0);
-            bp = __shfl_sync(0xffffffffu, bp, 0);
-            if (ready) {
-                const unsigned pos = br + (unsigned)(incl - parts);
-                for (int q = 0; q < parts; q++) {
-                    a.ready[pos + q] = id | ((unsigned)q << OP_PART_SHIFT);
-                    a.ready_key[pos + q] = (uint8_t)key;
-                }
-                atomicAdd(&s_hist[key], (unsigned)parts);
-            } else if (live) {
-                const unsigned pos = bp + __popc(mp & ((1u << lane) - 1u));
-                pend_next[pos] = id;
-                pblk_next[pos] = blk;
-            }
-        }
-        __syncthreads();
-        if (tid < R_BINS && s_hist[tid]) atomicAdd(&ctr->hist[tid], s_hist[tid]);
-        grid_barrier(a.bar, target);
-        const unsigned n_ready = ld_acquire_u32(&ctr->n_ready), n_next = ld_acquire_u32(&ctr->n_next);
-        D1_TRACE(1, gtimer()); D1_TRACE(5, n_ready);
-        if (n_ready == 0) {
-            // pending operations, none ready: they wait for each other - inconsistent descriptors
-            if (gtid == 0) atomicOr(a.g.status, 1u);
-            return;
-        }
-        // ---- step 2: counting sort of the ready list by key.  Start of every bin (all blocks
-        // compute the same prefix), then every block scatters a contiguous chunk of the list.
-        if (tid < R_BINS) {                    // warps 0..3: exclusive prefix over the bins
-            const unsigned h = ld_acquire_u32(&ctr->hist[tid]);
-            unsigned incl = h;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += t;
-            }
-            s_base[tid] = incl - h;
-            if (lane == 31) s_hist[warp] = incl;      // total of this warp's 32 bins
-        }
-        __syncthreads();
-        if (tid < R_BINS) {
-            unsigned add = 0;
-            for (int q = 0; q < warp; q++) add += s_hist[q];
-            s_base[tid] += add;
-        }
-        __syncthreads();
-        const unsigned n_tot_check = s_base[R_BINS - 1];
-        (void)n_tot_check;
-        if (tid < R_BINS) s_hist[tid] = 0;
-        __syncthreads();
-        // list layout: [octet-mode entries | warp-mode entries]
-        const unsigned n_oct = s_base[64];
-        {
-            const unsigned chunk = (n_ready + gridDim.x - 1) / gridDim.x;
-            const unsigned c0 = blockIdx.x * chunk, c1 = min(n_ready, c0 + chunk);
-            for (unsigned k = c0 + tid; k < c1; k += blockDim.x) atomicAdd(&s_hist[__ldcg(a.ready_key + k)], 1u);
-            __syncthreads();
-            if (tid < R_BINS) {
-                const unsigned c = s_hist[tid];
-                s_hist[tid] = s_base[tid] + (c ? atomicAdd(&ctr->cursor[tid], c) : 0u);   // this block's range of the bin
-            }
-            __syncthreads();
-            for (unsigned k = c0 + tid; k < c1; k += blockDim.x) {
-                const unsigned pos = atomicAdd(&s_hist[__ldcg(a.ready_key + k)], 1u);
-                a.sorted[pos] = __ldcg(a.ready + k);
-            }
-        }
-        // the other counter set is free (last read before the previous round's final barrier)
-        if (gtid < sizeof(RoundCtr) / 4) ((unsigned *)nxt)[gtid] = 0;
-        grid_barrier(a.bar, target);
-        D1_TRACE(2, gtimer());
-        // ---- step 3: execute.  Items: four small operations per warp (one per octet), then the
-        // others one per warp
-        {
-            const unsigned items_oct = (n_oct + 3) / 4, items = items_oct + (n_ready - n_oct);
-            const unsigned gw = blockIdx.x * R_WARPS + warp, nw = gridDim.x * R_WARPS;
-            const int o = lane >> 3;
-            for (unsigned it = gw; it < items; it += nw) {
-                if (it < items_oct) {
-                    const unsigned k = it * 4 + o;
-                    if (k < n_oct) {
-                        const unsigned id = __ldcg(a.sorted + k);
-                        const Intra2Frame &f = a.g.f[op_frame(id)];
-                        const Dav1dCudaIntraDesc d = f.descs[op_index(id)];
-                        pixel *es = sm->es + o * 2 * OCT_PX;
-                        intra_exec<pixel>(grp_octet(lane), f, d, es + OCT_CENTRE, es + OCT_PX, OCT_Z2, sm->tile + 256 * o, 0, 1);
-                    }
-                } else {
-                    const unsigned id = __ldcg(a.sorted + n_oct + (it - items_oct));
-                    const Intra2Frame &f = a.g.f[op_frame(id)];
-                    const Dav1dCudaIntraDesc d = f.descs[op_index(id)];
-                    intra_exec<pixel>(grp_warp(lane), f, d, sm->es + EDGE_C, sm->es + EDGE_BUF, 128 + 8, sm->tile,
-                                      (int)(id >> OP_PART_SHIFT), op_parts(d));
-                }
-                __syncwarp();
-            }
-        }
-        grid_barrier(a.bar, target);
-        D1_TRACE(3, gtimer());
-        n_pend = n_next;
-        if (round > (1 << 20)) { if (gtid == 0) atomicOr(a.g.status, 1u); return; }
+    // cls: 0..13 DSP-table predictor, 14 CfL, 15 palette, 16 intrabc, 17 inter-intra, 18 residual only
+    int grp;
+    switch (cls) {
+    case M_DC: case M_LEFT_DC: case M_TOP_DC: case M_DC_128: grp = 0; break;
+    case M_VERT: case M_HOR: grp = 1; break;
+    case M_PAETH: case M_SMOOTH: case M_SMOOTH_V: case M_SMOOTH_H: grp = 2; break;
+    case M_Z1: case M_Z3: grp = 3; break;
+    case M_Z2: grp = 4; break;
+    case M_FILTER: case 14: grp = 5; break;
+    case 17: grp = 7; break;
+    default: grp = 6; break;
     }
+    return (c4 <= 4 ? 0 : 16) + (c4 <= 1 || (c4 > 4 && c4 <= 16) ? 0 : 8) + grp;
 }
+DEV bool bin_is_big(const int bin) { return bin >= 16; }
 
-// cell map set-up: every operation adds one to each of its cells (four cells per word)
-__global__ void intra2_mark_kernel(const __grid_constant__ Intra2Args a) {
-    const int fi = blockIdx.y;
-    const Intra2Frame &f = a.f[fi];
+// control block of a group's executor (device memory, cleared before the mark launch)
+struct ExecCtl {
+    unsigned ticket;                    // next chunk of four slots to claim
+    unsigned n_chunks;                  // written by the scan
+    unsigned max_level;
+    unsigned pad;
+    unsigned lvl_ticket[I2_MAXF];       // per frame: next block of operations of the level pass
+};
+struct SchedArgs {
+    Intra2Args g;
+    ExecCtl *ctl;
+    unsigned *key;                      // per operation of the group: level * 32 + bin
+    unsigned *bins;                     // MAX_LEVELS * N_BINS counters -> slot offsets -> cursors
+    unsigned *slots;                    // the sorted list: operation ids, OP_EMPTY padding
+    unsigned n_slots_cap;
+};
+
+// ---- 1. mark: every operation adds one to each of its cells (launched after the maps are cleared)
+__global__ void intra_clear_kernel(const __grid_constant__ Intra2Args a) {
+    const Intra2Frame &f = a.f[blockIdx.y];
+    if (f.n_ops <= 0) return;
+    uint4 *p = (uint4 *)f.cnt;
+    const unsigned n = f.map_words >> 2;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        p[i] = make_uint4(0u, 0u, 0u, 0u);
+}
+__global__ void intra_mark_kernel(const __grid_constant__ Intra2Args a) {
+    const Intra2Frame &f = a.f[blockIdx.y];
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < f.n_ops; i += gridDim.x * blockDim.x) {
         const Dav1dCudaIntraDesc &d = f.descs[i];
-        const int pl = d.plane, W = map_w(f, pl), H = map_h(f, pl);
-        uint8_t *m = f.map + map_off(f, pl);
-        for (int y = d.y4; y < imin(d.y4 + d.th4, H); y++)
-            for (int x = d.x4; x < imin(d.x4 + d.tw4, W); x++) {
-                const size_t off = (size_t)(m - f.map) + (size_t)y * W + x;
-                atomicAdd((unsigned *)(f.map + (off & ~(size_t)3)), 1u << (8 * (off & 3)));
-            }
+        const int pl = d.plane, W = f.mw[pl], H = f.mh[pl], S = f.ms[pl];
+        const int x4 = d.x4, tw4 = d.tw4, y1 = imin(d.y4 + d.th4, H);
+        if (tw4 >= 4 && !(x4 & 3)) {
+            for (int y = d.y4; y < y1; y++)
+                for (int x = x4; x < imin(x4 + tw4, W); x += 4) {
+                    const int nb = imin(4, W - x);
+                    atomicAdd((unsigned *)(f.cnt + f.mo[pl] + (size_t)y * S + x), 0x01010101u >> (8 * (4 - nb)));
+                }
+        } else {
+            for (int y = d.y4; y < y1; y++)
+                for (int x = x4; x < imin(x4 + tw4, W); x++) {
+                    const size_t off = (size_t)f.mo[pl] + (size_t)y * S + x;
+                    atomicAdd((unsigned *)(f.cnt + (off & ~(size_t)3)), 1u << (8 * (off & 3)));
+                }
+        }
     }
 }
 
-static int g_rounds_blocks[2] = { 0, 0 };   // co-resident blocks of the executor per pixel type
-template <typename pixel> static size_t rounds_smem_bytes() { return R_WARPS * sizeof(ExecSmem<pixel>); }
+// ---- 2. levels.  One thread per operation; blocks take the operations of their frame in decode
+// order (ticket), so the writers a thread polls for belong to a block that is already running.
+constexpr int LV_THREADS = 256;
+constexpr unsigned LV_FLAG = 0x8000u;
+constexpr int LV_MAX_POLLS = 1 << 15;
+__global__ void __launch_bounds__(LV_THREADS) intra_levels_kernel(const __grid_constant__ SchedArgs a) {
+    __shared__ unsigned s_chunk;
+    const Intra2Frame &f = a.g.f[blockIdx.x];
+    if (threadIdx.x == 0) s_chunk = atomicAdd(&a.ctl->lvl_ticket[blockIdx.x], 1u);
+    __syncthreads();
+    // consecutive operations (neighbours in the frame, often dependent) go to different warps
+    const int t = (int)threadIdx.x;
+    const int i = (int)s_chunk * LV_THREADS + (t & 31) * (LV_THREADS / 32) + (t >> 5);
+    if (i >= f.n_ops) return;
+    const Dav1dCudaIntraDesc d = f.descs[i];
+    int cls = 0, polls = 0;
+    unsigned level = 0, bad = 0;
+    op_deps(f, d, &cls, [&](const int pl, const int x0, const int x1, const int y0, const int y1, const bool own) {
+        const unsigned base = f.mo[pl];
+        const int S = f.ms[pl];
+        const int nx = x1 - x0, n = nx * (y1 - y0);
+        // four cells at a time: their loads are in flight together
+        for (int j0 = 0; j0 < n; j0 += 4) {
+            unsigned c[4], cn[4], v[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int j = imin(j0 + u, n - 1);
+                const int y = y1 - y0 == 1 ? y0 : nx == 1 ? y0 + j : y0 + j / nx;
+                const int x = y1 - y0 == 1 ? x0 + j : nx == 1 ? x0 : x0 + j % nx;
+                c[u] = base + (unsigned)(y * S + x);
+                cn[u] = __ldcg(f.cnt + c[u]);
+                v[u] = ld_relaxed_u16(f.lvl + c[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                if (cn[u] == 0 || (own && cn[u] == 1)) continue;     // nobody (else) writes the cell in this phase
+                if (cn[u] > 2) bad |= ST_CELLS;
+                unsigned ns = 32;
+                while (v[u] == 0 || (!own && (v[u] & LV_FLAG))) {
+                    if (++polls > LV_MAX_POLLS) { bad |= ST_STUCK; v[u] = 1; break; }
+                    __nanosleep(ns);
+                    ns = min(ns * 2u, 1024u);
+                    v[u] = ld_relaxed_u16(f.lvl + c[u]);
+                }
+                level = max(level, v[u] & (LV_FLAG - 1u));
+            }
+        }
+    });
+    if (level >= (unsigned)MAX_LEVELS) { bad |= ST_DEPTH; level = MAX_LEVELS - 1; }
+    // publish: level + 1 in the operation's cells; flagged where a residual-only operation follows
+    {
+        const int pl = d.plane, W = f.mw[pl], H = f.mh[pl], S = f.ms[pl];
+        const bool primary = d.mode != DAV1D_CUDA_INTRA_NONE;
+        for (int y = d.y4; y < imin(d.y4 + d.th4, H); y++)
+            for (int x = d.x4; x < imin(d.x4 + d.tw4, W); x++) {
+                const unsigned c = f.mo[pl] + (unsigned)(y * S + x);
+                const bool more = primary && __ldcg(f.cnt + c) > 1;
+                st_relaxed_u16(f.lvl + c, (level + 1u) | (more ? LV_FLAG : 0u));
+            }
+    }
+    a.key[f.op_base + (unsigned)i] = level * N_BINS + (unsigned)op_bin(d, cls);
+    if (level > __ldcg(&a.ctl->max_level)) atomicMax(&a.ctl->max_level, level);
+    if (bad) atomicOr(a.g.status, bad);
+}
+
+// ---- 3. sort.  COUNT: histogram of the keys; scan: counters -> first slot of every bin; !COUNT:
+// every operation takes its slot.  Blocks aggregate the bins of the first levels in shared memory.
+template <bool COUNT>
+__global__ void __launch_bounds__(256) intra_sort_kernel(const __grid_constant__ SchedArgs a) {
+    __shared__ unsigned s_cnt[HIST_SMEM_LEVELS * N_BINS];
+    const Intra2Frame &f = a.g.f[blockIdx.y];
+    const int i0 = (int)blockIdx.x * 1024;
+    if (i0 >= f.n_ops) return;
+    for (int q = threadIdx.x; q < HIST_SMEM_LEVELS * N_BINS; q += blockDim.x) s_cnt[q] = 0;
+    __syncthreads();
+    unsigned key[4], rank[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+        const int i = i0 + u * 256 + (int)threadIdx.x;
+        key[u] = OP_EMPTY;
+        rank[u] = 0;
+        if (i < f.n_ops) {
+            key[u] = __ldcg(a.key + f.op_base + (unsigned)i);
+            const unsigned step = COUNT ? 1u : (bin_is_big((int)(key[u] & (N_BINS - 1))) ? 4u : 1u);
+            if (key[u] < HIST_SMEM_LEVELS * N_BINS) rank[u] = atomicAdd(&s_cnt[key[u]], step);
+            else if (COUNT) atomicAdd(a.bins + key[u], 1u);
+            else rank[u] = atomicAdd(a.bins + key[u], step);
+        }
+    }
+    __syncthreads();
+    // the block's share of every bin it met: counted (COUNT) or reserved (-> s_cnt = first slot)
+    for (int q = threadIdx.x; q < HIST_SMEM_LEVELS * N_BINS; q += blockDim.x) {
+        const unsigned c = s_cnt[q];
+        if (c) s_cnt[q] = atomicAdd(a.bins + q, c);
+    }
+    if (COUNT) return;
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+        if (key[u] == OP_EMPTY) continue;
+        const unsigned pos = rank[u] + (key[u] < HIST_SMEM_LEVELS * N_BINS ? s_cnt[key[u]] : 0u);
+        const unsigned id = ((unsigned)blockIdx.y << OP_FRAME_SHIFT) | (unsigned)(i0 + u * 256 + (int)threadIdx.x);
+        if (bin_is_big((int)(key[u] & (N_BINS - 1)))) {
+            if (pos + 4 <= a.n_slots_cap) *(uint4 *)(a.slots + pos) = make_uint4(id, OP_EMPTY, OP_EMPTY, OP_EMPTY);
+        } else if (pos < a.n_slots_cap) {
+            a.slots[pos] = id;
+        }
+    }
+}
+// Slots of a level: its small operations (padded to a multiple of four: a chunk never spans two
+// levels or mixes the two kinds), then four slots per large operation (the first one is used).
+__global__ void __launch_bounds__(1024) intra_scan_kernel(const __grid_constant__ SchedArgs a) {
+    __shared__ unsigned s_warp[32];
+    __shared__ unsigned s_carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n_lev = (int)min(a.ctl->max_level + 1u, (unsigned)MAX_LEVELS);
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (int l0 = 0; l0 < n_lev; l0 += 1024) {
+        const int l = l0 + tid;
+        unsigned ns = 0, nb = 0;
+        if (l < n_lev) {
+            const uint4 *p = (const uint4 *)(a.bins + (size_t)l * N_BINS);
+#pragma unroll
+            for (int q = 0; q < 4; q++) { const uint4 v = p[q]; ns += v.x + v.y + v.z + v.w; }
+#pragma unroll
+            for (int q = 4; q < 8; q++) { const uint4 v = p[q]; nb += v.x + v.y + v.z + v.w; }
+        }
+        const unsigned mine = ((ns + 3u) & ~3u) + 4u * nb;
+        unsigned incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        unsigned before = s_carry;
+        for (int q = 0; q < warp; q++) before += s_warp[q];
+        unsigned run = before + incl - mine;          // first slot of level l
+        if (l < n_lev) {
+            unsigned *b = a.bins + (size_t)l * N_BINS;
+            const unsigned small_end = run + ((ns + 3u) & ~3u);
+            for (int q = 0; q < 16; q++) { const unsigned c = b[q]; b[q] = run; run += c; }
+            for (; run < small_end; run++)
+                if (run < a.n_slots_cap) a.slots[run] = OP_EMPTY;
+            for (int q = 16; q < 32; q++) { const unsigned c = b[q]; b[q] = run; run += 4u * c; }
+        }
+        __syncthreads();
+        if (tid == 1023) s_carry = before + incl;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        a.ctl->n_chunks = min(s_carry, a.n_slots_cap) >> 2;
+        a.ctl->ticket = 0;
+    }
+}
+
+// ---- 4. execute
+template <typename pixel>
+__global__ void __launch_bounds__(R_WARPS * 32, 4) intra_exec_kernel(const __grid_constant__ SchedArgs a) {
+    extern __shared__ __align__(16) uint8_t exec_smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    ExecSmem<pixel> *sm = (ExecSmem<pixel> *)exec_smem_raw + warp;
+    const unsigned n_chunks = __ldcg(&a.ctl->n_chunks);
+    const int o = lane >> 3;
+    // a warp claims one chunk (four slots) at a time, the next claim is in flight while it works
+    unsigned nxt = 0;
+    if (lane == 0) nxt = atomicAdd(&a.ctl->ticket, 1u);
+    for (;;) {
+        const unsigned c = __shfl_sync(0xffffffffu, nxt, 0);
+        if (c >= n_chunks) break;
+        const unsigned id = __ldcg(a.slots + 4 * c + o);
+        const unsigned id0 = __shfl_sync(0xffffffffu, id, 0);
+        if (lane == 0) nxt = atomicAdd(&a.ctl->ticket, 1u);
+        if (id0 == OP_EMPTY) continue;
+        const Intra2Frame &f0 = a.g.f[op_frame(id0)];
+        const Dav1dCudaIntraDesc d0 = f0.descs[op_index(id0)];
+        bool ok = true;
+        if (d0.tw4 * d0.th4 > 4) {
+            // one large operation for the whole warp
+            ok = intra_exec<pixel>(grp_warp(lane), f0, d0, sm->es + EDGE_C, sm->es + EDGE_BUF, 128 + 8, sm->tile);
+        } else if (id != OP_EMPTY) {
+            const Intra2Frame &f = a.g.f[op_frame(id)];
+            const Dav1dCudaIntraDesc d = f.descs[op_index(id)];
+            pixel *es = sm->es + o * 2 * OCT_PX;
+            ok = intra_exec<pixel>(grp_octet(lane), f, d, es + OCT_CENTRE, es + OCT_PX, OCT_Z2, sm->tile + 256 * o);
+        }
+        if (!ok && (lane & 7) == 0) atomicOr(a.g.status, ST_STUCK);
+        __syncwarp();
+    }
+}
+
+static int g_exec_blocks[2] = { 0, 0 };   // resident blocks of the executor per pixel type
+template <typename pixel> static size_t exec_smem_bytes() { return R_WARPS * sizeof(ExecSmem<pixel>); }
 
 void recon_init_attrs() {
     itx_init_attrs();
-    cudaFuncSetAttribute(intra_rounds_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)rounds_smem_bytes<uint8_t>());
-    cudaFuncSetAttribute(intra_rounds_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)rounds_smem_bytes<uint16_t>());
+    cudaFuncSetAttribute(intra_exec_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)exec_smem_bytes<uint8_t>());
+    cudaFuncSetAttribute(intra_exec_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)exec_smem_bytes<uint16_t>());
     int dev = 0, sms = 0, occ = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, intra_rounds_kernel<uint8_t>, R_WARPS * 32, rounds_smem_bytes<uint8_t>());
-    g_rounds_blocks[0] = std::max(1, occ) * std::max(1, sms);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, intra_rounds_kernel<uint16_t>, R_WARPS * 32, rounds_smem_bytes<uint16_t>());
-    g_rounds_blocks[1] = std::max(1, occ) * std::max(1, sms);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, intra_exec_kernel<uint8_t>, R_WARPS * 32, exec_smem_bytes<uint8_t>());
+    g_exec_blocks[0] = std::max(1, occ) * std::max(1, sms);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, intra_exec_kernel<uint16_t>, R_WARPS * 32, exec_smem_bytes<uint16_t>());
+    g_exec_blocks[1] = std::max(1, occ) * std::max(1, sms);
 }
 
 // ---- warp batch: one warp per 8x8
@@ -694,31 +773,21 @@ static bool join_aux(Dav1dCudaContext *c, cudaStream_t st) {
     return true;
 }
 
-// workspace of the executor's rounds: barrier + counters, then pending x 2, ready, sorted (ids) and
-// the ready keys.  One per context, grown on demand outside any stream capture; submissions of a
-// context are ordered on its stream.
-static size_t rounds_ws_hdr() { return 256 + ((2 * sizeof(RoundCtr) + 255) & ~(size_t)255); }
-#ifdef D1_EXPERIMENT
-static unsigned long long *d1_last_trace = nullptr;
-#endif
+// Workspace of a group's scheduling passes: control block, the sort's bins, one key per operation
+// and the sorted slot list.  One per context, grown on demand outside any stream capture;
+// submissions of a context are ordered on its stream.
 static size_t al256(size_t v) { return (v + 255) & ~(size_t)255; }
-// total = operations of the group (pending lists); cap = entries a round's list can hold: an
-// operation per entry, large ones one entry per 256 pixels
-static size_t rounds_ws_need(size_t total, size_t cap) {
-    return rounds_ws_hdr() + 4 * al256(total * 4) + 2 * al256(cap * 4) + al256(cap);
-}
-static void rounds_counts(const Dav1dCudaReconBatch *const *bs, int n, size_t *total, size_t *cap) {
-    *total = 0; *cap = 0;
-    for (int f = 0; f < n; f++) {
-        if (!bs[f] || bs[f]->n_intra <= 0) continue;
-        *total += (size_t)bs[f]->n_intra;
-        *cap += (size_t)bs[f]->n_intra + 3 * ((size_t)bs[f]->bw4 * bs[f]->bh4 * 16 / 256 + 1);
-    }
+static size_t ws_hdr_bytes() { return al256(sizeof(ExecCtl)) + al256((size_t)MAX_LEVELS * N_BINS * 4); }
+static size_t ws_slots_cap(size_t total) { return 4 * total + 4 * (size_t)MAX_LEVELS; }
+static size_t ws_need(size_t total) { return ws_hdr_bytes() + al256(total * 4) + al256(ws_slots_cap(total) * 4); }
+static size_t group_ops(const Dav1dCudaReconBatch *const *bs, int n) {
+    size_t total = 0;
+    for (int f = 0; f < n; f++)
+        if (bs[f] && bs[f]->n_intra > 0) total += (size_t)bs[f]->n_intra;
+    return total;
 }
 static int ensure_rounds_ws(Dav1dCudaContext *c, const Dav1dCudaReconBatch *const *bs, int n) {
-    size_t total, cap;
-    rounds_counts(bs, n, &total, &cap);
-    const size_t need = rounds_ws_need(total, cap);
+    const size_t need = ws_need(group_ops(bs, n));
     if (need <= c->rounds_ws_bytes) return 0;
     if (c->rounds_ws) {
         D1_CHECK(cudaStreamSynchronize(c->stream));
@@ -761,10 +830,13 @@ static int group_submit_on(Dav1dCudaContext *c, const Dav1dCudaReconBatch *const
     cudaStream_t ss[1 + Dav1dCudaContext::N_AUX] = { st, c->aux[0], c->aux[1], c->aux[2] };
     constexpr int NS = 1 + Dav1dCudaContext::N_AUX;
     const bool hbd = bs[0]->dst->bitdepth_max > 0xff;
-    // intra: cell map set-up first, on its own branch (it touches nothing the other phases use)
-    Intra2Args ia;
-    memset(&ia, 0, sizeof(ia));
+    // intra: the scheduling passes (cell maps, levels, sort) touch nothing the other phases use and
+    // run on their own branch next to them
+    SchedArgs sa;
+    memset(&sa, 0, sizeof(sa));
+    Intra2Args &ia = sa.g;
     int n_ops = 0;
+    size_t total = 0;
     if (mask & 16) {
         ia.nf = n;
         for (int f = 0; f < n; f++) {
@@ -774,15 +846,37 @@ static int group_submit_on(Dav1dCudaContext *c, const Dav1dCudaReconBatch *const
             if (b->intra_res) p.res = pic_view(b->intra_res);
             p.descs = b->intra; p.pal = b->pal; p.pal_idx = b->pal_idx;
             p.n_ops = b->n_intra > 0 ? b->n_intra : 0;
-            p.map = b->intra_cellmap;
+            p.op_base = (unsigned)total;
+            total += (size_t)p.n_ops;
+            const MapGeo mg = map_geo(b->bw4, b->bh4, b->dst->ss_hor, b->dst->ss_ver);
+            for (int pl = 0; pl < 3; pl++) { p.mw[pl] = mg.mw[pl]; p.mh[pl] = mg.mh[pl]; p.ms[pl] = mg.ms[pl]; p.mo[pl] = mg.mo[pl]; }
+            p.cnt = b->intra_cellmap;
+            p.lvl = (uint16_t *)(b->intra_cellmap + mg.cells);
+            p.map_words = mg.cells * 3u / 4u;
             n_ops = std::max(n_ops, p.n_ops);
         }
         ia.status = c->status;
+        if (total >= ((size_t)1 << 31)) return -22;
+        if (ws_need(total) > c->rounds_ws_bytes) return -12;      // ensure_rounds_ws() comes first
+        uint8_t *ws = (uint8_t *)c->rounds_ws;
+        sa.ctl = (ExecCtl *)ws;
+        sa.bins = (unsigned *)(ws + al256(sizeof(ExecCtl)));
+        sa.key = (unsigned *)(ws + ws_hdr_bytes());
+        sa.slots = (unsigned *)(ws + ws_hdr_bytes() + al256(total * 4));
+        sa.n_slots_cap = (unsigned)std::min<size_t>(ws_slots_cap(total), 0xfffffff0u);
     }
     if (!fork_aux(c, st)) return -5;
     if ((mask & 16) && n_ops > 0) {
-        intra2_mark_kernel<<<dim3((unsigned)std::min((n_ops + 255) / 256, 64), (unsigned)n), 256, 0, ss[NS - 1]>>>(ia);
-        count_launch();
+        cudaStream_t si = ss[NS - 1];
+        D1_CHECK(cudaMemsetAsync(c->rounds_ws, 0, ws_hdr_bytes(), si));
+        intra_clear_kernel<<<dim3(64u, (unsigned)n), 256, 0, si>>>(ia);
+        intra_mark_kernel<<<dim3((unsigned)std::min((n_ops + 255) / 256, 64), (unsigned)n), 256, 0, si>>>(ia);
+        intra_levels_kernel<<<dim3((unsigned)n, (unsigned)((n_ops + LV_THREADS - 1) / LV_THREADS)), LV_THREADS, 0, si>>>(sa);   // frames interleaved
+        intra_sort_kernel<true><<<dim3((unsigned)((n_ops + 1023) / 1024), (unsigned)n), 256, 0, si>>>(sa);
+        intra_scan_kernel<<<1, 1024, 0, si>>>(sa);
+        intra_sort_kernel<false><<<dim3((unsigned)((n_ops + 1023) / 1024), (unsigned)n), 256, 0, si>>>(sa);
+        count_launch(6);
+        if (!cuda_ok(cudaGetLastError(), "intra scheduling passes")) return -5;
     }
     for (int f = 0; f < n; f++) {
         const Dav1dCudaReconBatch *b = bs[f];
@@ -819,49 +913,14 @@ static int group_submit_on(Dav1dCudaContext *c, const Dav1dCudaReconBatch *const
     }
     if (!join_aux(c, st)) return -5;
     if (!(mask & 16) || n_ops <= 0) return 0;
-    // the executor: one cooperative launch (its blocks wait for each other at the grid barriers)
-    RoundsArgs ra;
-    memset(&ra, 0, sizeof(ra));
-    ra.g = ia;
-    size_t total = 0;
-    for (int f = 0; f < n; f++) { ra.op_base[f] = (int)total; total += (size_t)ia.f[f].n_ops; }
-    ra.op_base[n] = (int)total;
-    if (total >= ((size_t)1 << 31)) return -22;
-    const size_t hdr = rounds_ws_hdr();
-    size_t total2, cap;
-    rounds_counts(bs, n, &total2, &cap);
-    if (rounds_ws_need(total, cap) > c->rounds_ws_bytes) return -12;      // ensure_rounds_ws() comes first
-    uint8_t *ws = (uint8_t *)c->rounds_ws;
-    ra.bar = (unsigned *)ws;
-    ra.ctr = (RoundCtr *)(ws + 256);
-    const size_t lb = al256(total * 4), cb = al256(cap * 4);
-    ra.pend[0] = (unsigned *)(ws + hdr);
-    ra.pend[1] = (unsigned *)(ws + hdr + lb);
-    ra.pend_blk[0] = (unsigned *)(ws + hdr + 2 * lb);
-    ra.pend_blk[1] = (unsigned *)(ws + hdr + 3 * lb);
-    ra.ready = (unsigned *)(ws + hdr + 4 * lb);
-    ra.sorted = (unsigned *)(ws + hdr + 4 * lb + cb);
-    ra.ready_key = ws + hdr + 4 * lb + 2 * cb;
-    D1_CHECK(cudaMemsetAsync(ws, 0, hdr, st));
-#ifdef D1_EXPERIMENT
-    static unsigned long long *g_trace = nullptr;
-    if (!g_trace) cudaMalloc(&g_trace, 256 * 6 * 8);
-    cudaMemsetAsync(g_trace, 0, 256 * 6 * 8, st);
-    ra.trace = g_trace;
-    ra.skip = getenv("D1_SKIP") ? atoi(getenv("D1_SKIP")) : 0;
-    d1_last_trace = g_trace;
-#endif
-    const size_t smem = hbd ? rounds_smem_bytes<uint16_t>() : rounds_smem_bytes<uint8_t>();
-    int resident = g_rounds_blocks[hbd];
-#ifdef D1_EXPERIMENT
-    if (getenv("D1_ROUNDS_BPSM")) resident = std::min(resident, atoi(getenv("D1_ROUNDS_BPSM")) * c->num_sms);
-#endif
-    const int grid = (int)std::min<size_t>((size_t)resident, (total + R_WARPS * 32 - 1) / (R_WARPS * 32));
-    void *kargs[] = { (void *)&ra };
-    const void *fn = hbd ? (const void *)intra_rounds_kernel<uint16_t> : (const void *)intra_rounds_kernel<uint8_t>;
-    D1_CHECK(cudaLaunchCooperativeKernel(fn, dim3((unsigned)grid), dim3(R_WARPS * 32), kargs, smem, st));
+    // the executor: one persistent launch, as many blocks as the device holds at once (any number
+    // would do: chunks are claimed by ticket)
+    const size_t smem = hbd ? exec_smem_bytes<uint16_t>() : exec_smem_bytes<uint8_t>();
+    const int grid = (int)std::min<size_t>((size_t)g_exec_blocks[hbd], (total + R_WARPS * 4 - 1) / (R_WARPS * 4));
+    if (hbd) intra_exec_kernel<uint16_t><<<grid, R_WARPS * 32, smem, st>>>(sa);
+    else intra_exec_kernel<uint8_t><<<grid, R_WARPS * 32, smem, st>>>(sa);
     count_launch();
-    return 0;
+    return cuda_ok(cudaGetLastError(), "intra_exec_kernel") ? 0 : -5;
 }
 
 }  // namespace d1
@@ -887,19 +946,10 @@ int dav1d_cuda_warp_batch(Dav1dCudaContext *c, const Dav1dCudaPicture *dst, cons
 }
 
 size_t dav1d_cuda_intra_cellmap_bytes(int bw4, int bh4, int ss_hor, int ss_ver) {
-    const size_t cw = (size_t)((bw4 + ss_hor) >> ss_hor), ch = (size_t)((bh4 + ss_ver) >> ss_ver);
-    return (((size_t)bw4 * bh4 + 2 * cw * ch) + 255) & ~(size_t)255;
+    // a count byte and a 16-bit level per 4x4 cell of the three planes
+    return ((size_t)map_geo(bw4, bh4, ss_hor, ss_ver).cells * 3 + 255) & ~(size_t)255;
 }
 
-#ifdef D1_EXPERIMENT
-// experiment builds only (make EXTRA=-DD1_EXPERIMENT): per-round time stamps of the last executor launch
-__attribute__((visibility("default"))) int dav1d_cuda_debug_rounds_trace(unsigned long long *host, int rounds) {
-    if (!d1_last_trace) return -1;
-    cudaDeviceSynchronize();
-    cudaMemcpy(host, d1_last_trace, (size_t)rounds * 6 * 8, cudaMemcpyDeviceToHost);
-    return 0;
-}
-#endif
 
 int dav1d_cuda_recon_submit(Dav1dCudaContext *c, const Dav1dCudaReconBatch *b) {
     if (!c || !b) return -22;

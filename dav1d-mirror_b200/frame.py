@@ -182,8 +182,7 @@ class DeviceFrame:
         if L.dav1d_cuda_picture_alloc(ctx, C.byref(self.res), hf.w, hf.h, hf.ss_hor, hf.ss_ver, 0xffff):
             raise RuntimeError("dav1d_cuda_picture_alloc failed")
         self._cellmap_bytes = L.dav1d_cuda_intra_cellmap_bytes(hf.bw4, hf.bh4, ssh, ssv)
-        self._cellmap = L.dav1d_cuda_malloc(self._cellmap_bytes)
-        L.dav1d_cuda_memset(ctx, self._cellmap, 0, self._cellmap_bytes)       # once; frames leave it at zero
+        self._cellmap = L.dav1d_cuda_malloc(self._cellmap_bytes)              # cleared by every submission
         # one device arena for descriptors, task lists, coefficients and pools (each array 256-byte
         # aligned): the end-to-end path ships a frame's set with ONE host->device copy from a pinned
         # mirror (every extra copy costs ~10 us of copy-engine time, tools/exp_copy.py)
@@ -264,8 +263,16 @@ class DeviceFrame:
                 self.L.dav1d_cuda_upload(self.ctx, self._dev[name], arr.ctypes.data, arr.nbytes)
 
     def cellmap_is_clear(self):
-        buf = np.ones(self._cellmap_bytes, dtype=np.uint8)
-        self.L.dav1d_cuda_download(self.ctx, buf.ctypes.data, self._cellmap, self._cellmap_bytes)
+        """The count part of the cell map (one byte per 4x4 cell of the three planes, rows padded to
+        a word; the 16-bit level map follows it) is back at zero once a frame is complete."""
+        hf = self.hf
+        cells = 0
+        for pl in range(3):
+            w4 = (hf.bw4 + self.dst.ss_hor) >> self.dst.ss_hor if pl else hf.bw4
+            h4 = (hf.bh4 + self.dst.ss_ver) >> self.dst.ss_ver if pl else hf.bh4
+            cells += ((w4 + 3) & ~3) * h4
+        buf = np.ones(cells, dtype=np.uint8)
+        self.L.dav1d_cuda_download(self.ctx, buf.ctypes.data, self._cellmap, cells)
         self.L.dav1d_cuda_synchronize(self.ctx)
         return not buf.any()
 
