@@ -138,7 +138,7 @@ class ReconBatch(C.Structure):
                 ("intra_cellmap", C.c_void_p),
                 ("intra_itx", C.c_void_p), ("intra_itx_class_count", C.c_int32 * N_RECT_TX_SIZES),
                 ("intra_itx_tasks", C.c_void_p), ("n_intra_itx_tasks", C.c_int32 * 2),
-                ("intra_res", C.POINTER(Picture))]
+                ("intra_res", C.POINTER(Picture)), ("intra_levels_recorded", C.c_int32)]
 
 
 MAX_GROUP = 64
@@ -153,6 +153,8 @@ def bind_frame_api(L):
                                         C.c_void_p, C.c_int]
     L.dav1d_cuda_intra_cellmap_bytes.restype = C.c_size_t
     L.dav1d_cuda_intra_cellmap_bytes.argtypes = [C.c_int] * 4
+    L.dav1d_cuda_intra_levels.argtypes = [C.c_void_p] + [C.c_int] * 5
+    L.dav1d_cuda_intra_levels.restype = C.c_int
     L.dav1d_cuda_itx_tasks.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int32),
                                        C.POINTER(C.c_int32)]
     L.dav1d_cuda_itx_task_batch.argtypes = [C.c_void_p, C.POINTER(Picture), C.c_void_p, C.c_void_p, C.c_void_p,

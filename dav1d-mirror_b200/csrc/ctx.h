@@ -106,7 +106,7 @@ struct Dav1dCudaContext {
     size_t tmp_pool_bytes;
     // fork/join inside one frame: independent launch classes run on auxiliary
     // streams (and become parallel branches when the frame is captured as a graph)
-    static constexpr int N_AUX = 3;
+    static constexpr int N_AUX = 15;
     cudaStream_t aux[N_AUX];
     cudaEvent_t ev_fork, ev_join[N_AUX];
     bool aux_ready;

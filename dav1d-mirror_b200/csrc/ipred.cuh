@@ -36,6 +36,7 @@ struct Grp {
 };
 DEV Grp grp_warp(const int lane) { return Grp{ lane, 32, 0xffffffffu }; }
 DEV Grp grp_octet(const int lane) { return Grp{ lane & 7, 8, 0xffu << (lane & 24) }; }
+DEV Grp grp_quad(const int lane) { return Grp{ lane & 3, 4, 0xfu << (lane & 28) }; }
 DEV void grp_sync(const Grp &g) { __syncwarp(g.mask); }
 DEV int grp_sum(const Grp &g, int v) {
     for (int o = g.G >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(g.mask, v, o);
@@ -76,7 +77,7 @@ HD int ipred_mode_needs(const int m) {
     }
 }
 
-DEV int filter_strength(const int wh, const int angle, const int is_sm) {   // ipred_tmpl.c:327-360
+static __device__ __noinline__ int filter_strength(const int wh, const int angle, const int is_sm) {   // ipred_tmpl.c:327-360
     if (is_sm) {
         if (wh <= 8) { if (angle >= 64) return 2; if (angle >= 40) return 1; }
         else if (wh <= 16) { if (angle >= 48) return 2; if (angle >= 20) return 1; }
@@ -132,7 +133,7 @@ __device__ __noinline__ void edge_upsample(const Grp &g, pixel *out, const int h
 
 // dc value for the DC / TOP_DC / LEFT_DC / DC_128 variants (ipred_tmpl.c:86-218)
 template <typename pixel>
-DEV int ipred_dc_value(const Grp &g, const int mode, const pixel *edge, const int w, const int h, const int bdmax) {
+__device__ __noinline__ int ipred_dc_value(const Grp &g, const int mode, const pixel *edge, const int w, const int h, const int bdmax) {
     if (mode == M_DC_128) return (bdmax + 1) >> 1;
     int part = 0;
     if (mode == M_DC || mode == M_TOP_DC)
@@ -377,6 +378,122 @@ DEV int ipred_pixel(const PixParams<pixel> &P, const int x, const int y, const i
         const int mg = (iabs(diff) + 32) >> 6;
         return clip_px<pixel>(P.p0 + (diff < 0 ? -mg : mg), bdmax);
     }
+    }
+}
+
+// PW pixels of row y starting at x (index i = y * w + x): the predictor switch once per segment, a
+// straight-line body per pixel.  tile_t: sample type of a PM_TILE tile.
+template <typename pixel, int PW, typename tile_t>
+DEV void ipred_seg(const PixParams<pixel> &P, const int x, const int y, const int i, const int bdmax, int *v) {
+    const pixel *edge = P.edge;
+    switch (P.pm) {
+    case PM_CONST:
+#pragma unroll
+        for (int k = 0; k < PW; k++) v[k] = P.p0;
+        break;
+    case PM_V:
+#pragma unroll
+        for (int k = 0; k < PW; k++) v[k] = edge[1 + x + k];
+        break;
+    case PM_H: {
+        const int l = edge[-(1 + y)];
+#pragma unroll
+        for (int k = 0; k < PW; k++) v[k] = l;
+        break;
+    }
+    case PM_PAETH: {
+        const int left = edge[-(y + 1)], tl = P.p0;
+#pragma unroll
+        for (int k = 0; k < PW; k++) {
+            const int top = edge[1 + x + k];
+            const int bs = left + top - tl;
+            const int ld = iabs(left - bs), td = iabs(top - bs), tld = iabs(tl - bs);
+            v[k] = ld <= td && ld <= tld ? left : td <= tld ? top : tl;
+        }
+        break;
+    }
+    case PM_SMOOTH: {
+        const int wv = g_sm_weights[P.h + y], left = edge[-(1 + y)];
+        const int vert = (256 - wv) * P.p1 + 256;
+#pragma unroll
+        for (int k = 0; k < PW; k++) {
+            const int wh = g_sm_weights[P.w + x + k];
+            v[k] = (wv * edge[1 + x + k] + vert + wh * left + (256 - wh) * P.p0) >> 9;
+        }
+        break;
+    }
+    case PM_SMOOTH_V: {
+        const int wv = g_sm_weights[P.h + y];
+#pragma unroll
+        for (int k = 0; k < PW; k++) v[k] = (wv * edge[1 + x + k] + (256 - wv) * P.p1 + 128) >> 8;
+        break;
+    }
+    case PM_SMOOTH_H: {
+        const int left = edge[-(y + 1)];
+#pragma unroll
+        for (int k = 0; k < PW; k++) {
+            const int wh = g_sm_weights[P.w + x + k];
+            v[k] = (wh * left + (256 - wh) * P.p0 + 128) >> 8;
+        }
+        break;
+    }
+    case PM_Z1: {
+        const int xpos = (y + 1) * P.p0, frac = xpos & 0x3E;
+        const int b0 = (xpos >> 6) + x * P.p2;
+#pragma unroll
+        for (int k = 0; k < PW; k++) {
+            const int bx = b0 + k * P.p2;
+            v[k] = bx < P.p1 ? (P.e0[bx] * (64 - frac) + P.e0[bx + 1] * frac + 32) >> 6 : (int)P.e0[P.p1];
+        }
+        break;
+    }
+    case PM_Z3: {
+#pragma unroll
+        for (int k = 0; k < PW; k++) {
+            const int ypos = (x + k + 1) * P.p0, frac = ypos & 0x3E;
+            const int by = (ypos >> 6) + y * P.p2;
+            v[k] = by < P.p1 ? (P.e0[-by] * (64 - frac) + P.e0[-(by + 1)] * frac + 32) >> 6 : (int)P.e0[-P.p1];
+        }
+        break;
+    }
+    case PM_Z2: {
+        const int xpos = ((1 + P.p2) << 6) - P.p0 * (y + 1), fx = xpos & 0x3E;
+#pragma unroll
+        for (int k = 0; k < PW; k++) {
+            const int base_x = (xpos >> 6) + (x + k) * (1 + P.p2);
+            int t;
+            if (base_x >= 0) {
+                t = P.e0[base_x] * (64 - fx) + P.e0[base_x + 1] * fx;
+            } else {
+                const int ypos = (y << (6 + P.p3)) - P.p1 * (x + k + 1);
+                const int base_y = ypos >> 6, fy = ypos & 0x3E;
+                t = P.e1[-base_y] * (64 - fy) + P.e1[-(base_y + 1)] * fy;
+            }
+            v[k] = (t + 32) >> 6;
+        }
+        break;
+    }
+    case PM_TILE:
+#pragma unroll
+        for (int k = 0; k < PW; k++) v[k] = ((const tile_t *)P.tile)[i + k];
+        break;
+    case PM_PAL: {                              // pal_pred (ipred_tmpl.c:717-730): tile = packed indices, e0 = palette
+#pragma unroll
+        for (int k = 0; k < PW; k += 2) {
+            const int q = ((const uint8_t *)P.tile)[(i + k) >> 1];
+            v[k] = P.e0[q & 7];
+            v[k + 1] = P.e0[q >> 4];
+        }
+        break;
+    }
+    default:                                    // PM_CFL
+#pragma unroll
+        for (int k = 0; k < PW; k++) {
+            const int diff = P.p1 * ((const int16_t *)P.tile)[i + k];
+            const int mg = (iabs(diff) + 32) >> 6;
+            v[k] = clip_px<pixel>(P.p0 + (diff < 0 ? -mg : mg), bdmax);
+        }
+        break;
     }
 }
 

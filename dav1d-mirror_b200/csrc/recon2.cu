@@ -36,10 +36,13 @@
 #include <string.h>
 #include <algorithm>
 #include <vector>
+#include <cooperative_groups.h>
 #include "ctx.h"
 #include "itx2.cuh"
 #include "ipred.cuh"
 #include "mc.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace d1 {
 
@@ -79,6 +82,7 @@ struct Intra2Frame {
     int mw[3], mh[3], ms[3];
     unsigned mo[3];
     unsigned map_words;                  // size of the whole allocation in 32-bit words
+    int recorded_levels;                 // the descriptors carry their dependency level (reserved = level + 1)
 };
 struct Intra2Args {
     Intra2Frame f[I2_MAXF];
@@ -124,13 +128,21 @@ DEV void st_relaxed_u16(uint16_t *p, const unsigned v) {
     asm volatile("st.relaxed.gpu.global.u16 [%0], %1;" :: "l"(p), "h"((unsigned short)v) : "memory");
 }
 
+// cell j of the rectangle [x0, x0 + nx) x [y0, y0 + ny): rows, columns and power-of-two widths
+// without a division (the general case is the source area of an intrabc block)
+DEV void rect_cell(const int j, const int x0, const int nx, const int y0, const int ny, int *x, int *y) {
+    if (ny == 1) { *x = x0 + j; *y = y0; }
+    else if ((nx & (nx - 1)) == 0) { const int sh = 31 - __clz(nx); *x = x0 + (j & (nx - 1)); *y = y0 + (j >> sh); }
+    else { *x = x0 + j % nx; *y = y0 + j / nx; }
+}
+
 // The cells an operation reads, as up to three rectangles of the cell maps: fn(plane, x0, x1, y0,
 // y1, own) - own: the operation's own cells (a residual on top of an earlier operation's pixels:
 // that one has to be done, the count stays at 1).  Exactly the pixels dav1d_prepare_intra_edges
 // reads (ipred_prepare_tmpl.c:119-200), the co-located luma of CfL (recon_tmpl.c:1372-1417) and
 // the source area of intrabc (:1624-1637).  *cls_out: predictor class 0..18 of the operation.
 template <typename F>
-DEV void op_deps(const Intra2Frame &f, const Dav1dCudaIntraDesc &d, int *cls_out, F &&fn) {
+HD void op_deps(const Intra2Frame &f, const Dav1dCudaIntraDesc &d, int *cls_out, F &&fn) {
     const int mode = d.mode;
     const int pl = d.plane;
     const int W = f.mw[pl], H = f.mh[pl];
@@ -192,8 +204,8 @@ DEV bool exec_wait(const Grp g, const Intra2Frame &f, const Dav1dCudaIntraDesc &
         const uint8_t *m = f.cnt + f.mo[pl];
         const int S = f.ms[pl];
         for (int j = g.gl; j < n; j += g.G) {
-            const int y = y1 - y0 == 1 ? y0 : nx == 1 ? y0 + j : y0 + j / nx;
-            const int x = y1 - y0 == 1 ? x0 + j : nx == 1 ? x0 : x0 + j % nx;
+            int x, y;
+            rect_cell(j, x0, nx, y0, y1 - y0, &x, &y);
             const uint8_t *p = m + (size_t)y * S + x;
             // back off: many warps poll in the thin tail of the wavefront, the few that work need the issue slots
             unsigned ns = 32;
@@ -219,9 +231,9 @@ DEV void exec_done(const Grp g, const Intra2Frame &a, const Dav1dCudaIntraDesc &
         const int ltw = 31 - __clz((int)d.tw4);
         if (d.tw4 >= 4 && !(d.x4 & 3)) {
             // rows of whole words (tx blocks are aligned to their size, rows of the map to a word)
-            const int wpr = d.tw4 >> 2, nwd = d.th4 * wpr;
+            const int lwpr = ltw - 2, nwd = d.th4 << lwpr;
             for (int j = g.gl; j < nwd; j += g.G) {
-                const int cy = d.y4 + j / wpr, cx = d.x4 + 4 * (j % wpr);
+                const int cy = d.y4 + (j >> lwpr), cx = d.x4 + 4 * (j & ((1 << lwpr) - 1));
                 if (cy < H && cx < W) {
                     const int nb = imin(4, W - cx);
                     atomicAdd((unsigned *)(a.cnt + a.mo[pl] + (size_t)cy * S + cx), 0u - (0x01010101u >> (8 * (4 - nb))));
@@ -242,9 +254,17 @@ DEV void exec_done(const Grp g, const Intra2Frame &a, const Dav1dCudaIntraDesc &
 }
 
 template <typename pixel>
-__device__ __noinline__ bool intra_exec(const Grp g, const Intra2Frame &a, const Dav1dCudaIntraDesc &d,
+__device__ __noinline__ bool intra_exec(const Grp g, const Intra2Frame &a, const Dav1dCudaIntraDesc *dp,
                                         pixel *edge, pixel *scratch, const int z2_centre, uint16_t *tile)
 {
+    // the descriptor in registers: five 64-bit loads, every lane of the group the same address
+    Dav1dCudaIntraDesc d;
+    {
+        const uint2 *q = (const uint2 *)dp;
+        uint2 *o = (uint2 *)&d;
+#pragma unroll
+        for (int k = 0; k < 5; k++) o[k] = __ldg(q + k);
+    }
     const int pl = d.plane;
     const int ss_hor = pl ? a.pic.ss_hor : 0, ss_ver = pl ? a.pic.ss_ver : 0;
     const PlaneView &pv = a.pic.p[pl];
@@ -264,11 +284,11 @@ __device__ __noinline__ bool intra_exec(const Grp g, const Intra2Frame &a, const
         const PlaneView &rv = a.res.p[pl];
         rstride = (int)(rv.stride / 2);
         res = (const int16_t *)rv.data + (int64_t)d.y4 * 4 * rstride + d.x4 * 4;
-        const int i = g.gl * (w >= 8 ? 8 : 4);
+        const int i = g.gl * 4;
         if (i < w * rps) {
             const int16_t *rp = res + (i >> lw) * rstride + (i & (w - 1));
-            if (w >= 8) r0 = __ldcg((const uint4 *)rp);
-            else { const uint2 t = __ldcg((const uint2 *)rp); r0.x = t.x; r0.y = t.y; }
+            const uint2 t = __ldcg((const uint2 *)rp);
+            r0.x = t.x; r0.y = t.y;
         }
     }
     const bool ok = exec_wait(g, a, d);
@@ -285,41 +305,37 @@ __device__ __noinline__ bool intra_exec(const Grp g, const Intra2Frame &a, const
             kind = 1;
         } else if (mode == DAV1D_CUDA_INTRA_NONE) {
             kind = 2;
-        } else if (mode == DAV1D_CUDA_INTRA_CFL) {
-            const PlaneView &lv = a.pic.p[0];
-            const int lstride = (int)(lv.stride / (int)sizeof(pixel));
-            const pixel *luma = (const pixel *)lv.data + (int64_t)((d.y4 * 4) << ss_ver) * lstride + ((d.x4 * 4) << ss_hor);
-            cfl_ac_block<pixel>(g, (int16_t *)tile, luma, lstride, d.aux & 0xff, (d.aux >> 8) & 0xff, w, h, ss_hor, ss_ver);
-            int angle = 0;
-            const int m = prepare_edges<pixel>(g, d.x4, have_left, d.y4, have_top, d.tile_x4_end, d.tile_y4_end, 0, dst,
-                                               stride, nullptr, 0, &angle, d.tw4, d.th4, 0, edge, bdmax);
-            P = cfl_setup<pixel>(g, m, edge, w, h, (const int16_t *)tile, d.angle_delta, bdmax);
         } else {
-            // inter-intra (recon_tmpl.c:1658-1681): the whole-block intra prediction (edge_flags 0, no
-            // edge filter) is blended onto the inter prediction that is in dst
-            const bool ii = mode == DAV1D_CUDA_INTRA_II;
-            int angle = ii ? 0 : d.angle_delta;
+            // CfL (recon_tmpl.c:1372-1417): ac from the co-located luma, DC edges; inter-intra
+            // (:1658-1681): the whole-block intra prediction (edge_flags 0, no edge filter) is blended
+            // onto the inter prediction that is in dst
+            const bool cfl = mode == DAV1D_CUDA_INTRA_CFL, ii = mode == DAV1D_CUDA_INTRA_II;
+            if (cfl) {
+                const PlaneView &lv = a.pic.p[0];
+                const int lstride = (int)(lv.stride / (int)sizeof(pixel));
+                const pixel *luma = (const pixel *)lv.data + (int64_t)((d.y4 * 4) << ss_ver) * lstride + ((d.x4 * 4) << ss_hor);
+                cfl_ac_block<pixel>(g, (int16_t *)tile, luma, lstride, d.aux & 0xff, (d.aux >> 8) & 0xff, w, h, ss_hor, ss_ver);
+            }
+            int angle = (cfl || ii) ? 0 : d.angle_delta;
             const int m = prepare_edges<pixel>(g, d.x4, have_left, d.y4, have_top, d.tile_x4_end, d.tile_y4_end,
-                                               ii ? 0 : d.edge_flags, dst, stride, nullptr, ii ? d.angle_delta : mode,
-                                               &angle, d.tw4, d.th4, ii ? 0 : (d.flags >> 10) & 1, edge, bdmax);
-            if (ii) { bmask = a.pal_idx + d.coef_off; angle = 0; }
-            else angle |= d.flags;
-            const int max_w = ((4 * a.bw4 + ss_hor) >> ss_hor) - 4 * d.x4;
-            const int max_h = ((4 * a.bh4 + ss_ver) >> ss_ver) - 4 * d.y4;
-            P = ipred_setup<pixel, uint16_t>(g, m, angle, w, h, max_w, max_h, edge, scratch, tile, bdmax, z2_centre);
-            if (P.pm == PM_TILE) kind = 2;             // filter-intra: the set-up left the prediction in the tile
+                                               (cfl || ii) ? 0 : d.edge_flags, dst, stride, nullptr,
+                                               cfl ? 0 : ii ? d.angle_delta : mode, &angle, d.tw4, d.th4,
+                                               (cfl || ii) ? 0 : (d.flags >> 10) & 1, edge, bdmax);
+            if (cfl) {
+                P = cfl_setup<pixel>(g, m, edge, w, h, (const int16_t *)tile, d.angle_delta, bdmax);
+            } else {
+                if (ii) { bmask = a.pal_idx + d.coef_off; angle = 0; }
+                else angle |= d.flags;
+                const int max_w = ((4 * a.bw4 + ss_hor) >> ss_hor) - 4 * d.x4;
+                const int max_h = ((4 * a.bh4 + ss_ver) >> ss_ver) - 4 * d.y4;
+                P = ipred_setup<pixel, uint16_t>(g, m, angle, w, h, max_w, max_h, edge, scratch, tile, bdmax, z2_centre);
+            }
         }
         grp_sync(g);
         const bool from_dst = mode == DAV1D_CUDA_INTRA_NONE;
         for (int y0 = 0; y0 < h; y0 += rps) {
             const int n = rps << lw;
-            if (kind == 0) {
-#pragma unroll 1
-                for (int i = g.gl; i < n; i += g.G) {
-                    const int y = y0 + (i >> lw), x = i & (w - 1);
-                    tile[i] = (uint16_t)ipred_pixel<pixel>(P, x, y, (y << lw) + x, bdmax);
-                }
-            } else if (kind == 1) {
+            if (kind == 1) {
                 // intrabc: put_bilin (mc_tmpl.c:395-450) from the current picture; coordinates clamped to
                 // the 4*bw4 x 4*bh4 area (= emu_edge, recon_tmpl.c:974-995)
                 const pixel *base = (const pixel *)pv.data;
@@ -350,8 +366,9 @@ __device__ __noinline__ bool intra_exec(const Grp g, const Intra2Frame &a, const
                     }
                     tile[i] = (uint16_t)v;
                 }
+                P.pm = PM_TILE; P.tile = tile;
+                grp_sync(g);
             }
-            grp_sync(g);
             auto stage_b = [&](auto pwc) {
                 constexpr int PW = decltype(pwc)::value;
 #pragma unroll 1
@@ -359,16 +376,8 @@ __device__ __noinline__ bool intra_exec(const Grp g, const Intra2Frame &a, const
                     const int y = y0 + (i >> lw), x = i & (w - 1);
                     pixel *p = dst + y * stride + x;
                     int v[PW];
-                    if (from_dst) {
-                        load_px<pixel, PW>(p, v);
-                    } else if (PW == 8) {
-                        const uint4 t = *(const uint4 *)(tile + i);
-                        v[0] = t.x & 0xffff; v[1] = t.x >> 16; v[2] = t.y & 0xffff; v[3] = t.y >> 16;
-                        v[PW - 4] = t.z & 0xffff; v[PW - 3] = t.z >> 16; v[PW - 2] = t.w & 0xffff; v[PW - 1] = t.w >> 16;
-                    } else {
-                        const uint2 t = *(const uint2 *)(tile + i);
-                        v[0] = t.x & 0xffff; v[1] = t.x >> 16; v[2] = t.y & 0xffff; v[3] = t.y >> 16;
-                    }
+                    if (from_dst) load_px<pixel, PW>(p, v);
+                    else ipred_seg<pixel, PW, uint16_t>(P, x, y, kind == 1 ? i : (y << lw) + x, bdmax, v);
                     if (bmask) {
                         // mc.blend (mc_tmpl.c:642-653) of the intra prediction onto the inter prediction
                         int c[PW];
@@ -398,8 +407,7 @@ __device__ __noinline__ bool intra_exec(const Grp g, const Intra2Frame &a, const
                     store_px<pixel, PW>(p, v);
                 }
             };
-            if (w >= 8) stage_b(IntC<8>());
-            else stage_b(IntC<4>());
+            stage_b(IntC<4>());
             grp_sync(g);
         }
     }
@@ -407,13 +415,26 @@ __device__ __noinline__ bool intra_exec(const Grp g, const Intra2Frame &a, const
     return ok;
 }
 
-// per-warp shared memory of step 3: edge + Z-mode scratch of four octets (operations of up to 64
-// pixels: w, h <= 16, w + h <= 20, i.e. 2 * 16 + 1 + 2 * 16 edge pixels: 80 + 80 pixels per octet) or
-// of one warp-wide operation (EDGE_BUF + IPRED_SCRATCH pixels) in the same bytes, and the CfL ac /
-// filter-intra tile (1024 values for a warp-wide operation, 256 per octet)
-constexpr int OCT_PX = 80, OCT_CENTRE = 36, OCT_Z2 = 40;
+// Per-warp shared memory of the executor.  A warp works on one chunk at a time, split into groups
+// of G lanes, one operation per group (the operations of a chunk share their size class):
+//   G = 1   4x4                 edge[-8..8], 24 pixels of Z-mode scratch, tile of 16
+//   G = 4   up to 64 pixels     edge[-32..32] in 72 pixels, 56 of scratch, tile of 64
+//   G = 8   up to 256 pixels    edge[-64..64] in 136 pixels, 80 of scratch, tile of 256
+//   G = 16  up to 512 pixels    as G = 8, tile of 512
+//   G = 32  anything            EDGE_BUF + IPRED_SCRATCH pixels, tile of 1024
+// The per-lane regions of G = 1 are an odd number of words apart (no bank conflicts when the 32
+// lanes walk their own edges in step).
+struct GrpSmem { int es_stride, centre, scr, z2c, tile_stride; };
+template <typename pixel> DEV GrpSmem grp_smem(const int G) {
+    if (G == 1) return GrpSmem{ sizeof(pixel) == 2 ? 50 : 52, 8, 26, 8, 20 };
+    if (G == 4) return GrpSmem{ 128, 36, 72, 24, 64 };
+    if (G == 8) return GrpSmem{ 216, 68, 136, 40, 256 };
+    if (G == 16) return GrpSmem{ 216, 68, 136, 40, 512 };
+    return GrpSmem{ 0, EDGE_C, EDGE_BUF, 128 + 8, 0 };
+}
+constexpr int ES_PX = 32 * 52;
 template <typename pixel> struct __align__(16) ExecSmem {
-    pixel es[4 * 2 * OCT_PX > EDGE_BUF + IPRED_SCRATCH ? 4 * 2 * OCT_PX : EDGE_BUF + IPRED_SCRATCH];
+    pixel es[ES_PX];
     uint16_t tile[32 * 32];
 };
 constexpr int R_WARPS = 8;
@@ -422,29 +443,28 @@ constexpr int OP_FRAME_SHIFT = 20;
 constexpr unsigned OP_EMPTY = 0xffffffffu;
 DEV int op_frame(const unsigned id) { return (int)((id >> OP_FRAME_SHIFT) & 63u); }
 DEV int op_index(const unsigned id) { return (int)(id & ((1u << OP_FRAME_SHIFT) - 1u)); }
-// Sort key: level * 32 + bin.  Bins 0..15: operations of up to 64 pixels (one per octet of lanes,
-// four per warp), bins 16..31: larger ones (one per warp); inside each half the predictor group, so
-// that the octets of a warp and the warps of an SM mostly run the same code.
-constexpr int N_BINS = 32;
-constexpr int MAX_LEVELS = 16384;
-constexpr int HIST_SMEM_LEVELS = 64;     // levels whose bins a block counts in shared memory
+// Sort key: level * 256 + bin, bin = size class * 32 + predictor class.  Size classes: 0 4x4, 1 up
+// to 64 pixels, 2 up to 256, 3 up to 512, 4 larger; predictor class: the DSP-table predictor 0..13,
+// CfL, palette, intrabc, inter-intra, residual only - so the groups of a warp and the warps of an SM
+// mostly run the same code path.
+// Slots: the sorted list is cut into chunks of 32 slots, one chunk per warp and claim; an operation
+// of size class s takes 1, 4, 8, 16 or 32 slots (the first one holds its id), i.e. as many slots as
+// it gets lanes; the regions of a level are padded to whole chunks.  Levels with few operations
+// (the thin tail of the wavefront, where latency is all that counts) give every operation a warp.
+constexpr int N_BINS = 256;
+constexpr int MAX_LEVELS = 8192;
+constexpr int HIST_SMEM_LEVELS = 16;     // levels whose bins a block counts in shared memory
+constexpr unsigned THIN_LEVEL_OPS = 512;
 DEV int op_bin(const Dav1dCudaIntraDesc &d, const int cls) {
     const int c4 = d.tw4 * d.th4;
     // cls: 0..13 DSP-table predictor, 14 CfL, 15 palette, 16 intrabc, 17 inter-intra, 18 residual only
-    int grp;
-    switch (cls) {
-    case M_DC: case M_LEFT_DC: case M_TOP_DC: case M_DC_128: grp = 0; break;
-    case M_VERT: case M_HOR: grp = 1; break;
-    case M_PAETH: case M_SMOOTH: case M_SMOOTH_V: case M_SMOOTH_H: grp = 2; break;
-    case M_Z1: case M_Z3: grp = 3; break;
-    case M_Z2: grp = 4; break;
-    case M_FILTER: case 14: grp = 5; break;
-    case 17: grp = 7; break;
-    default: grp = 6; break;
-    }
-    return (c4 <= 4 ? 0 : 16) + (c4 <= 1 || (c4 > 4 && c4 <= 16) ? 0 : 8) + grp;
+    return (c4 <= 1 ? 0 : c4 <= 4 ? 32 : c4 <= 16 ? 64 : c4 <= 32 ? 96 : 128) + cls;
 }
-DEV bool bin_is_big(const int bin) { return bin >= 16; }
+// slots (= lanes) an operation of this bin takes
+DEV unsigned bin_slots(const unsigned bin, const bool thin) {
+    const unsigned sc = bin >> 5;
+    return thin || sc >= 4 ? 32u : sc == 0 ? 1u : 2u << sc;
+}
 
 // control block of a group's executor (device memory, cleared before the mark launch)
 struct ExecCtl {
@@ -452,13 +472,13 @@ struct ExecCtl {
     unsigned n_chunks;                  // written by the scan
     unsigned max_level;
     unsigned pad;
-    unsigned lvl_ticket[I2_MAXF];       // per frame: next block of operations of the level pass
 };
 struct SchedArgs {
     Intra2Args g;
     ExecCtl *ctl;
     unsigned *key;                      // per operation of the group: level * 32 + bin
     unsigned *bins;                     // MAX_LEVELS * N_BINS counters -> slot offsets -> cursors
+    uint8_t *thin;                      // per level: every operation gets a whole warp
     unsigned *slots;                    // the sorted list: operation ids, OP_EMPTY padding
     unsigned n_slots_cap;
 };
@@ -494,68 +514,138 @@ __global__ void intra_mark_kernel(const __grid_constant__ Intra2Args a) {
     }
 }
 
-// ---- 2. levels.  One thread per operation; blocks take the operations of their frame in decode
-// order (ticket), so the writers a thread polls for belong to a block that is already running.
-constexpr int LV_THREADS = 256;
+// ---- 2. levels.  A cluster of LV_CL blocks per frame, every thread owns the operations t, t + T,
+// t + 2T, ... (T threads per frame).  Rounds: a thread looks at each of its unresolved operations;
+// one whose cells all carry the level of their writer (or have no writer) takes its own level and
+// publishes it; a cluster barrier ends the round.  Nobody spins: a round is a sweep over what is
+// left, and the sweeps of all frames run side by side.
+constexpr int LV_THREADS = 1024, LV_CL = 4;
 constexpr unsigned LV_FLAG = 0x8000u;
-constexpr int LV_MAX_POLLS = 1 << 15;
-__global__ void __launch_bounds__(LV_THREADS) intra_levels_kernel(const __grid_constant__ SchedArgs a) {
-    __shared__ unsigned s_chunk;
-    const Intra2Frame &f = a.g.f[blockIdx.x];
-    if (threadIdx.x == 0) s_chunk = atomicAdd(&a.ctl->lvl_ticket[blockIdx.x], 1u);
-    __syncthreads();
-    // consecutive operations (neighbours in the frame, often dependent) go to different warps
-    const int t = (int)threadIdx.x;
-    const int i = (int)s_chunk * LV_THREADS + (t & 31) * (LV_THREADS / 32) + (t >> 5);
-    if (i >= f.n_ops) return;
-    const Dav1dCudaIntraDesc d = f.descs[i];
-    int cls = 0, polls = 0;
-    unsigned level = 0, bad = 0;
-    op_deps(f, d, &cls, [&](const int pl, const int x0, const int x1, const int y0, const int y1, const bool own) {
-        const unsigned base = f.mo[pl];
-        const int S = f.ms[pl];
-        const int nx = x1 - x0, n = nx * (y1 - y0);
-        // four cells at a time: their loads are in flight together
-        for (int j0 = 0; j0 < n; j0 += 4) {
-            unsigned c[4], cn[4], v[4];
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const int j = imin(j0 + u, n - 1);
-                const int y = y1 - y0 == 1 ? y0 : nx == 1 ? y0 + j : y0 + j / nx;
-                const int x = y1 - y0 == 1 ? x0 + j : nx == 1 ? x0 : x0 + j % nx;
-                c[u] = base + (unsigned)(y * S + x);
-                cn[u] = __ldcg(f.cnt + c[u]);
-                v[u] = ld_relaxed_u16(f.lvl + c[u]);
-            }
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                if (cn[u] == 0 || (own && cn[u] == 1)) continue;     // nobody (else) writes the cell in this phase
-                if (cn[u] > 2) bad |= ST_CELLS;
-                unsigned ns = 32;
-                while (v[u] == 0 || (!own && (v[u] & LV_FLAG))) {
-                    if (++polls > LV_MAX_POLLS) { bad |= ST_STUCK; v[u] = 1; break; }
-                    __nanosleep(ns);
-                    ns = min(ns * 2u, 1024u);
-                    v[u] = ld_relaxed_u16(f.lvl + c[u]);
+__global__ void __cluster_dims__(LV_CL, 1, 1) __launch_bounds__(LV_THREADS, 1)
+intra_levels_kernel(const __grid_constant__ SchedArgs a) {
+    __shared__ unsigned s_flags[2];
+    cg::cluster_group cluster = cg::this_cluster();
+    const Intra2Frame &f = a.g.f[blockIdx.y];
+    if (f.recorded_levels) return;       // (the whole cluster)
+    constexpr int T = LV_THREADS * LV_CL;
+    const int t = (int)(blockIdx.x * LV_THREADS + threadIdx.x);
+    unsigned max_level = 0, bad = 0;
+    int round = 0;
+    // 64 operations per thread at a time (decode order is a topological order: a later part of the
+    // frame never feeds an earlier one)
+    for (int base = 0; base < f.n_ops; base += 64 * T) {
+        unsigned long long todo = 0;
+        for (int k = 0; k < 64; k++)
+            if (base + k * T + t < f.n_ops) todo |= 1ull << k;
+        bool first = true;
+        for (;; round++) {
+            bool progress = false;
+            // an unresolved operation remembers one cell it was seen waiting for (in its key slot):
+            // only when that cell carries its level is the operation looked at again
+            unsigned long long cand = todo;
+            if (!first) {
+                for (unsigned long long m = todo; m; m &= m - 1) {
+                    const int k = __ffsll((long long)m) - 1;
+                    const unsigned kb = __ldcg(a.key + f.op_base + (unsigned)(base + k * T + t));
+                    const unsigned v = __ldcg(f.lvl + (kb & 0x3fffffffu));
+                    if (v == 0 || (!(kb & 0x40000000u) && (v & LV_FLAG))) cand &= ~(1ull << k);
                 }
-                level = max(level, v[u] & (LV_FLAG - 1u));
+            }
+            first = false;
+            for (unsigned long long m = cand; m; m &= m - 1) {
+                const int k = __ffsll((long long)m) - 1;
+                const int i = base + k * T + t;
+                const Dav1dCudaIntraDesc d = f.descs[i];
+                int cls = 0;
+                unsigned level = 0, blocker = 0;
+                bool ready = true;
+                op_deps(f, d, &cls, [&](const int pl, const int x0, const int x1, const int y0, const int y1, const bool own) {
+                    if (!ready) return;
+                    const unsigned cb = f.mo[pl];
+                    const int S = f.ms[pl];
+                    const int nx = x1 - x0, n = nx * (y1 - y0);
+                    // four cells at a time: their loads are in flight together
+                    for (int j0 = 0; j0 < n && ready; j0 += 4) {
+                        unsigned cc[4], cn[4], v[4];
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            int x, y;
+                            rect_cell(imin(j0 + u, n - 1), x0, nx, y0, y1 - y0, &x, &y);
+                            const unsigned c = cb + (unsigned)(y * S + x);
+                            cc[u] = c;
+                            cn[u] = __ldcg(f.cnt + c);
+                            v[u] = __ldcg(f.lvl + c);
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            if (cn[u] == 0 || (own && cn[u] == 1)) continue;     // nobody (else) writes the cell in this phase
+                            if (cn[u] > 2) bad |= ST_CELLS;
+                            if (v[u] == 0 || (!own && (v[u] & LV_FLAG))) { ready = false; blocker = cc[u] | (own ? 0x40000000u : 0u); }
+                            level = max(level, v[u] & (LV_FLAG - 1u));
+                        }
+                    }
+                });
+                if (!ready) { a.key[f.op_base + (unsigned)i] = blocker; continue; }
+                if (level >= (unsigned)MAX_LEVELS) { bad |= ST_DEPTH; level = MAX_LEVELS - 1; }
+                // publish: level + 1 in the operation's cells; flagged where a residual-only operation follows
+                const int pl = d.plane, W = f.mw[pl], H = f.mh[pl], S = f.ms[pl];
+                const bool primary = d.mode != DAV1D_CUDA_INTRA_NONE;
+                for (int y = d.y4; y < imin(d.y4 + d.th4, H); y++)
+                    for (int x = d.x4; x < imin(d.x4 + d.tw4, W); x++) {
+                        const unsigned c = f.mo[pl] + (unsigned)(y * S + x);
+                        const bool more = primary && __ldcg(f.cnt + c) > 1;
+                        f.lvl[c] = (uint16_t)((level + 1u) | (more ? LV_FLAG : 0u));
+                    }
+                a.key[f.op_base + (unsigned)i] = level * N_BINS + (unsigned)op_bin(d, cls);
+                max_level = max(max_level, level);
+                todo &= ~(1ull << k);
+                progress = true;
+            }
+            // end of the round: does anybody in the cluster have work left, did anybody get on?
+            const int any_p = __syncthreads_or(progress), any_t = __syncthreads_or(todo != 0);
+            if (threadIdx.x == 0) s_flags[round & 1] = (any_p ? 1u : 0u) | (any_t ? 2u : 0u);
+            __threadfence();
+            cluster.sync();
+            unsigned all = 0;
+            for (int r = 0; r < LV_CL; r++) all |= *cluster.map_shared_rank(&s_flags[round & 1], r);
+            if (!(all & 2u)) { round++; break; }
+            if (!(all & 1u)) {              // operations left, none resolved: they wait for each other
+                bad |= ST_STUCK;
+                // their keys still have to be valid: level 0
+                for (unsigned long long m = todo; m; m &= m - 1) {
+                    const int i = base + (__ffsll((long long)m) - 1) * T + t;
+                    const Dav1dCudaIntraDesc d = f.descs[i];
+                    int cls = 0;
+                    op_deps(f, d, &cls, [&](int, int, int, int, int, bool) {});
+                    a.key[f.op_base + (unsigned)i] = (unsigned)op_bin(d, cls);
+                }
+                round++;
+                break;
             }
         }
-    });
-    if (level >= (unsigned)MAX_LEVELS) { bad |= ST_DEPTH; level = MAX_LEVELS - 1; }
-    // publish: level + 1 in the operation's cells; flagged where a residual-only operation follows
-    {
-        const int pl = d.plane, W = f.mw[pl], H = f.mh[pl], S = f.ms[pl];
-        const bool primary = d.mode != DAV1D_CUDA_INTRA_NONE;
-        for (int y = d.y4; y < imin(d.y4 + d.th4, H); y++)
-            for (int x = d.x4; x < imin(d.x4 + d.tw4, W); x++) {
-                const unsigned c = f.mo[pl] + (unsigned)(y * S + x);
-                const bool more = primary && __ldcg(f.cnt + c) > 1;
-                st_relaxed_u16(f.lvl + c, (level + 1u) | (more ? LV_FLAG : 0u));
-            }
     }
-    a.key[f.op_base + (unsigned)i] = level * N_BINS + (unsigned)op_bin(d, cls);
-    if (level > __ldcg(&a.ctl->max_level)) atomicMax(&a.ctl->max_level, level);
+    if (max_level > __ldcg(&a.ctl->max_level)) atomicMax(&a.ctl->max_level, max_level);
+    if (bad) atomicOr(a.g.status, bad);
+    cluster.sync();      // no block leaves while its flags may still be read
+}
+
+// ---- 2'. frames whose recorder assigned the levels (dav1d_cuda_intra_levels(), a linear pass in
+// decode order on the host): only the sort keys are left to do
+__global__ void __launch_bounds__(256) intra_keys_kernel(const __grid_constant__ SchedArgs a) {
+    const Intra2Frame &f = a.g.f[blockIdx.y];
+    if (!f.recorded_levels) return;
+    unsigned max_level = 0, bad = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < f.n_ops; i += gridDim.x * blockDim.x) {
+        const Dav1dCudaIntraDesc d = f.descs[i];
+        int cls = 0;
+        op_deps(f, d, &cls, [&](int, int, int, int, int, bool) {});
+        unsigned level = (d.reserved & 0xffffu) - 1u;
+        if ((d.reserved & 0xffffu) == 0) { bad |= ST_STUCK; level = 0; }       // not a recorded level
+        if (level >= (unsigned)MAX_LEVELS) { bad |= ST_DEPTH; level = MAX_LEVELS - 1; }
+        a.key[f.op_base + (unsigned)i] = level * N_BINS + (unsigned)op_bin(d, cls);
+        max_level = max(max_level, level);
+    }
+    if (max_level > __ldcg(&a.ctl->max_level)) atomicMax(&a.ctl->max_level, max_level);
     if (bad) atomicOr(a.g.status, bad);
 }
 
@@ -577,7 +667,7 @@ __global__ void __launch_bounds__(256) intra_sort_kernel(const __grid_constant__
         rank[u] = 0;
         if (i < f.n_ops) {
             key[u] = __ldcg(a.key + f.op_base + (unsigned)i);
-            const unsigned step = COUNT ? 1u : (bin_is_big((int)(key[u] & (N_BINS - 1))) ? 4u : 1u);
+            const unsigned step = COUNT ? 1u : bin_slots(key[u] & (N_BINS - 1), __ldcg(a.thin + key[u] / N_BINS) != 0);
             if (key[u] < HIST_SMEM_LEVELS * N_BINS) rank[u] = atomicAdd(&s_cnt[key[u]], step);
             else if (COUNT) atomicAdd(a.bins + key[u], 1u);
             else rank[u] = atomicAdd(a.bins + key[u], step);
@@ -596,15 +686,17 @@ __global__ void __launch_bounds__(256) intra_sort_kernel(const __grid_constant__
         if (key[u] == OP_EMPTY) continue;
         const unsigned pos = rank[u] + (key[u] < HIST_SMEM_LEVELS * N_BINS ? s_cnt[key[u]] : 0u);
         const unsigned id = ((unsigned)blockIdx.y << OP_FRAME_SHIFT) | (unsigned)(i0 + u * 256 + (int)threadIdx.x);
-        if (bin_is_big((int)(key[u] & (N_BINS - 1)))) {
-            if (pos + 4 <= a.n_slots_cap) *(uint4 *)(a.slots + pos) = make_uint4(id, OP_EMPTY, OP_EMPTY, OP_EMPTY);
-        } else if (pos < a.n_slots_cap) {
+        const unsigned ns = bin_slots(key[u] & (N_BINS - 1), __ldcg(a.thin + key[u] / N_BINS) != 0);
+        if (pos + ns > a.n_slots_cap) continue;
+        if (ns == 1) {
             a.slots[pos] = id;
+        } else {
+            *(uint4 *)(a.slots + pos) = make_uint4(id, OP_EMPTY, OP_EMPTY, OP_EMPTY);
+            for (unsigned q = 4; q < ns; q += 4) *(uint4 *)(a.slots + pos + q) = make_uint4(OP_EMPTY, OP_EMPTY, OP_EMPTY, OP_EMPTY);
         }
     }
 }
-// Slots of a level: its small operations (padded to a multiple of four: a chunk never spans two
-// levels or mixes the two kinds), then four slots per large operation (the first one is used).
+// Slots of a level: one region per size class, each padded to whole chunks with empty slots.
 __global__ void __launch_bounds__(1024) intra_scan_kernel(const __grid_constant__ SchedArgs a) {
     __shared__ unsigned s_warp[32];
     __shared__ unsigned s_carry;
@@ -614,15 +706,18 @@ __global__ void __launch_bounds__(1024) intra_scan_kernel(const __grid_constant_
     __syncthreads();
     for (int l0 = 0; l0 < n_lev; l0 += 1024) {
         const int l = l0 + tid;
-        unsigned ns = 0, nb = 0;
+        unsigned nc[5] = { 0, 0, 0, 0, 0 };
         if (l < n_lev) {
             const uint4 *p = (const uint4 *)(a.bins + (size_t)l * N_BINS);
 #pragma unroll
-            for (int q = 0; q < 4; q++) { const uint4 v = p[q]; ns += v.x + v.y + v.z + v.w; }
-#pragma unroll
-            for (int q = 4; q < 8; q++) { const uint4 v = p[q]; nb += v.x + v.y + v.z + v.w; }
+            for (int sc = 0; sc < 5; sc++)
+#pragma unroll 4
+                for (int q = 0; q < 8; q++) { const uint4 v = p[sc * 8 + q]; nc[sc] += v.x + v.y + v.z + v.w; }
         }
-        const unsigned mine = ((ns + 3u) & ~3u) + 4u * nb;
+        const bool thin = nc[0] + nc[1] + nc[2] + nc[3] + nc[4] < THIN_LEVEL_OPS;
+        unsigned mine = 0;
+#pragma unroll
+        for (int sc = 0; sc < 5; sc++) mine += (bin_slots(sc * 32, thin) * nc[sc] + 31u) & ~31u;
         unsigned incl = mine;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -635,19 +730,21 @@ __global__ void __launch_bounds__(1024) intra_scan_kernel(const __grid_constant_
         for (int q = 0; q < warp; q++) before += s_warp[q];
         unsigned run = before + incl - mine;          // first slot of level l
         if (l < n_lev) {
+            a.thin[l] = thin ? 1 : 0;
             unsigned *b = a.bins + (size_t)l * N_BINS;
-            const unsigned small_end = run + ((ns + 3u) & ~3u);
-            for (int q = 0; q < 16; q++) { const unsigned c = b[q]; b[q] = run; run += c; }
-            for (; run < small_end; run++)
-                if (run < a.n_slots_cap) a.slots[run] = OP_EMPTY;
-            for (int q = 16; q < 32; q++) { const unsigned c = b[q]; b[q] = run; run += 4u * c; }
+            for (int sc = 0; sc < 5; sc++) {
+                const unsigned per = bin_slots(sc * 32, thin), end = run + ((per * nc[sc] + 31u) & ~31u);
+                for (int q = sc * 32; q < sc * 32 + 32; q++) { const unsigned c = b[q]; b[q] = run; run += per * c; }
+                for (; run < end; run++)
+                    if (run < a.n_slots_cap) a.slots[run] = OP_EMPTY;
+            }
         }
         __syncthreads();
         if (tid == 1023) s_carry = before + incl;
         __syncthreads();
     }
     if (tid == 0) {
-        a.ctl->n_chunks = min(s_carry, a.n_slots_cap) >> 2;
+        a.ctl->n_chunks = min(s_carry, a.n_slots_cap) >> 5;
         a.ctl->ticket = 0;
     }
 }
@@ -659,30 +756,29 @@ __global__ void __launch_bounds__(R_WARPS * 32, 4) intra_exec_kernel(const __gri
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     ExecSmem<pixel> *sm = (ExecSmem<pixel> *)exec_smem_raw + warp;
     const unsigned n_chunks = __ldcg(&a.ctl->n_chunks);
-    const int o = lane >> 3;
-    // a warp claims one chunk (four slots) at a time, the next claim is in flight while it works
+    // a warp claims one chunk (32 slots) at a time, the next claim is in flight while it works
     unsigned nxt = 0;
     if (lane == 0) nxt = atomicAdd(&a.ctl->ticket, 1u);
     for (;;) {
         const unsigned c = __shfl_sync(0xffffffffu, nxt, 0);
         if (c >= n_chunks) break;
-        const unsigned id = __ldcg(a.slots + 4 * c + o);
-        const unsigned id0 = __shfl_sync(0xffffffffu, id, 0);
+        const unsigned sl = __ldcg(a.slots + 32 * c + lane);
         if (lane == 0) nxt = atomicAdd(&a.ctl->ticket, 1u);
-        if (id0 == OP_EMPTY) continue;
-        const Intra2Frame &f0 = a.g.f[op_frame(id0)];
-        const Dav1dCudaIntraDesc d0 = f0.descs[op_index(id0)];
+        // lanes per operation = spacing of the used slots (a lone operation gets the whole warp)
+        if (!__ballot_sync(0xffffffffu, sl != OP_EMPTY)) continue;
+        const unsigned at = __reduce_or_sync(0xffffffffu, sl != OP_EMPTY ? (unsigned)lane : 0u);
+        const int G = at ? (int)(at & (0u - at)) : 32;
+        const int gi = lane / G;
+        const unsigned id = __shfl_sync(0xffffffffu, sl, gi * G);
         bool ok = true;
-        if (d0.tw4 * d0.th4 > 4) {
-            // one large operation for the whole warp
-            ok = intra_exec<pixel>(grp_warp(lane), f0, d0, sm->es + EDGE_C, sm->es + EDGE_BUF, 128 + 8, sm->tile);
-        } else if (id != OP_EMPTY) {
+        if (id != OP_EMPTY) {
+            const Grp g = Grp{ lane & (G - 1), G, G == 32 ? 0xffffffffu : ((1u << G) - 1u) << (lane & ~(G - 1)) };
+            const GrpSmem gs = grp_smem<pixel>(G);
             const Intra2Frame &f = a.g.f[op_frame(id)];
-            const Dav1dCudaIntraDesc d = f.descs[op_index(id)];
-            pixel *es = sm->es + o * 2 * OCT_PX;
-            ok = intra_exec<pixel>(grp_octet(lane), f, d, es + OCT_CENTRE, es + OCT_PX, OCT_Z2, sm->tile + 256 * o);
+            pixel *es = sm->es + gi * gs.es_stride;
+            ok = intra_exec<pixel>(g, f, f.descs + op_index(id), es + gs.centre, es + gs.scr, gs.z2c, sm->tile + gi * gs.tile_stride);
         }
-        if (!ok && (lane & 7) == 0) atomicOr(a.g.status, ST_STUCK);
+        if (!ok) atomicOr(a.g.status, ST_STUCK);
         __syncwarp();
     }
 }
@@ -696,6 +792,8 @@ void recon_init_attrs() {
                          (int)exec_smem_bytes<uint8_t>());
     cudaFuncSetAttribute(intra_exec_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)exec_smem_bytes<uint16_t>());
+    cudaFuncSetAttribute(intra_exec_kernel<uint8_t>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(intra_exec_kernel<uint16_t>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     int dev = 0, sms = 0, occ = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -777,8 +875,8 @@ static bool join_aux(Dav1dCudaContext *c, cudaStream_t st) {
 // and the sorted slot list.  One per context, grown on demand outside any stream capture;
 // submissions of a context are ordered on its stream.
 static size_t al256(size_t v) { return (v + 255) & ~(size_t)255; }
-static size_t ws_hdr_bytes() { return al256(sizeof(ExecCtl)) + al256((size_t)MAX_LEVELS * N_BINS * 4); }
-static size_t ws_slots_cap(size_t total) { return 4 * total + 4 * (size_t)MAX_LEVELS; }
+static size_t ws_hdr_bytes() { return al256(sizeof(ExecCtl)) + al256((size_t)MAX_LEVELS * N_BINS * 4) + al256(MAX_LEVELS); }
+static size_t ws_slots_cap(size_t total) { return 32 * total + 160 * (size_t)MAX_LEVELS; }
 static size_t ws_need(size_t total) { return ws_hdr_bytes() + al256(total * 4) + al256(ws_slots_cap(total) * 4); }
 static size_t group_ops(const Dav1dCudaReconBatch *const *bs, int n) {
     size_t total = 0;
@@ -827,15 +925,17 @@ static int group_submit_on(Dav1dCudaContext *c, const Dav1dCudaReconBatch *const
     int r;
     if ((r = check_group(bs, n))) return r;
     if (!ensure_aux(c)) return -5;
-    cudaStream_t ss[1 + Dav1dCudaContext::N_AUX] = { st, c->aux[0], c->aux[1], c->aux[2] };
     constexpr int NS = 1 + Dav1dCudaContext::N_AUX;
+    cudaStream_t ss[NS];
+    ss[0] = st;
+    for (int i = 0; i < Dav1dCudaContext::N_AUX; i++) ss[1 + i] = c->aux[i];
     const bool hbd = bs[0]->dst->bitdepth_max > 0xff;
     // intra: the scheduling passes (cell maps, levels, sort) touch nothing the other phases use and
     // run on their own branch next to them
     SchedArgs sa;
     memset(&sa, 0, sizeof(sa));
     Intra2Args &ia = sa.g;
-    int n_ops = 0;
+    int n_ops = 0, n_rec = 0;
     size_t total = 0;
     if (mask & 16) {
         ia.nf = n;
@@ -846,6 +946,8 @@ static int group_submit_on(Dav1dCudaContext *c, const Dav1dCudaReconBatch *const
             if (b->intra_res) p.res = pic_view(b->intra_res);
             p.descs = b->intra; p.pal = b->pal; p.pal_idx = b->pal_idx;
             p.n_ops = b->n_intra > 0 ? b->n_intra : 0;
+            p.recorded_levels = b->intra_levels_recorded;
+            n_rec += b->intra_levels_recorded ? 1 : 0;
             p.op_base = (unsigned)total;
             total += (size_t)p.n_ops;
             const MapGeo mg = map_geo(b->bw4, b->bh4, b->dst->ss_hor, b->dst->ss_ver);
@@ -861,6 +963,7 @@ static int group_submit_on(Dav1dCudaContext *c, const Dav1dCudaReconBatch *const
         uint8_t *ws = (uint8_t *)c->rounds_ws;
         sa.ctl = (ExecCtl *)ws;
         sa.bins = (unsigned *)(ws + al256(sizeof(ExecCtl)));
+        sa.thin = ws + al256(sizeof(ExecCtl)) + al256((size_t)MAX_LEVELS * N_BINS * 4);
         sa.key = (unsigned *)(ws + ws_hdr_bytes());
         sa.slots = (unsigned *)(ws + ws_hdr_bytes() + al256(total * 4));
         sa.n_slots_cap = (unsigned)std::min<size_t>(ws_slots_cap(total), 0xfffffff0u);
@@ -871,11 +974,13 @@ static int group_submit_on(Dav1dCudaContext *c, const Dav1dCudaReconBatch *const
         D1_CHECK(cudaMemsetAsync(c->rounds_ws, 0, ws_hdr_bytes(), si));
         intra_clear_kernel<<<dim3(64u, (unsigned)n), 256, 0, si>>>(ia);
         intra_mark_kernel<<<dim3((unsigned)std::min((n_ops + 255) / 256, 64), (unsigned)n), 256, 0, si>>>(ia);
-        intra_levels_kernel<<<dim3((unsigned)n, (unsigned)((n_ops + LV_THREADS - 1) / LV_THREADS)), LV_THREADS, 0, si>>>(sa);   // frames interleaved
+        int n_sched = 5;
+        if (n_rec < n) { intra_levels_kernel<<<dim3((unsigned)LV_CL, (unsigned)n), LV_THREADS, 0, si>>>(sa); n_sched++; }   // a cluster per frame
+        if (n_rec > 0) { intra_keys_kernel<<<dim3((unsigned)std::min((n_ops + 255) / 256, 64), (unsigned)n), 256, 0, si>>>(sa); n_sched++; }
         intra_sort_kernel<true><<<dim3((unsigned)((n_ops + 1023) / 1024), (unsigned)n), 256, 0, si>>>(sa);
         intra_scan_kernel<<<1, 1024, 0, si>>>(sa);
         intra_sort_kernel<false><<<dim3((unsigned)((n_ops + 1023) / 1024), (unsigned)n), 256, 0, si>>>(sa);
-        count_launch(6);
+        count_launch(n_sched);
         if (!cuda_ok(cudaGetLastError(), "intra scheduling passes")) return -5;
     }
     for (int f = 0; f < n; f++) {
@@ -904,7 +1009,7 @@ static int group_submit_on(Dav1dCudaContext *c, const Dav1dCudaReconBatch *const
         // intra residual pre-pass -> int16 residual planes (independent of everything above)
         if ((mask & 16) && b->n_intra > 0 && b->intra_itx && b->intra_res) {
             const PicView rv = pic_view(b->intra_res);
-            cudaStream_t s2 = ss[(f + 2) % NS];
+            cudaStream_t s2 = ss[(f + NS / 2) % NS];
             if (b->intra_itx_tasks) {
                 if ((r = itx_task_launch(dst, &rv, b->cf, b->intra_itx, b->intra_itx_tasks, b->n_intra_itx_tasks[0],
                                          b->n_intra_itx_tasks[1], 0, s2, s2))) return r;
@@ -950,6 +1055,42 @@ size_t dav1d_cuda_intra_cellmap_bytes(int bw4, int bh4, int ss_hor, int ss_ver) 
     return ((size_t)map_geo(bw4, bh4, ss_hor, ss_ver).cells * 3 + 255) & ~(size_t)255;
 }
 
+
+// Recorder-side dependency levels: ONE pass over the descriptors in decode order (linear in the
+// number of operations), the per-cell level map of the frame kept in host memory.  level + 1 goes to
+// the descriptors' `reserved` field.  Returns the number of levels, or a negative errno.
+int dav1d_cuda_intra_levels(Dav1dCudaIntraDesc *descs, int n, int bw4, int bh4, int ss_hor, int ss_ver) {
+    if (!descs || n < 0 || bw4 <= 0 || bh4 <= 0) return -22;
+    Intra2Frame f;
+    memset(&f, 0, sizeof(f));
+    f.bw4 = bw4; f.bh4 = bh4; f.pic.ss_hor = ss_hor; f.pic.ss_ver = ss_ver;
+    const MapGeo mg = map_geo(bw4, bh4, ss_hor, ss_ver);
+    for (int pl = 0; pl < 3; pl++) { f.mw[pl] = mg.mw[pl]; f.mh[pl] = mg.mh[pl]; f.ms[pl] = mg.ms[pl]; f.mo[pl] = mg.mo[pl]; }
+    static thread_local std::vector<uint16_t> map;
+    map.assign(mg.cells, 0);
+    unsigned n_levels = 0;
+    for (int i = 0; i < n; i++) {
+        Dav1dCudaIntraDesc &d = descs[i];
+        if (d.plane > 2 || d.x4 >= f.mw[d.plane] || d.y4 >= f.mh[d.plane]) return -22;
+        int cls = 0;
+        unsigned level = 0;
+        op_deps(f, d, &cls, [&](const int pl, const int x0, const int x1, const int y0, const int y1, bool) {
+            for (int y = y0; y < y1; y++) {
+                const uint16_t *row = map.data() + f.mo[pl] + (size_t)y * f.ms[pl];
+                for (int x = x0; x < x1; x++) level = std::max<unsigned>(level, row[x]);
+            }
+        });
+        if (level >= 0xfffeu) return -34;
+        d.reserved = (d.reserved & 0xffff0000u) | (level + 1u);
+        n_levels = std::max(n_levels, level + 1u);
+        const int pl = d.plane;
+        for (int y = d.y4; y < imin(d.y4 + d.th4, f.mh[pl]); y++) {
+            uint16_t *row = map.data() + f.mo[pl] + (size_t)y * f.ms[pl];
+            for (int x = d.x4; x < imin(d.x4 + d.tw4, f.mw[pl]); x++) row[x] = (uint16_t)(level + 1u);
+        }
+    }
+    return (int)n_levels;
+}
 
 int dav1d_cuda_recon_submit(Dav1dCudaContext *c, const Dav1dCudaReconBatch *b) {
     if (!c || !b) return -22;

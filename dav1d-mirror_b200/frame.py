@@ -137,6 +137,22 @@ class HostFrame:
             if n_iitx else 0
         self.intra_itx_tasks = tasks[:max(k, 1)].copy().view(np.uint8)
         self.n_intra_itx_tasks = (ns.value, nb.value) if n_iitx else (0, 0)
+        self.n_levels = None
+
+    def record_levels(self, into=None):
+        """The recorder's linear pass over the intra-class descriptors (decode order): dependency
+        level + 1 into `reserved`.  into: address of another copy of the descriptor array (a pinned
+        mirror) to annotate instead of self.intra."""
+        if not self.n_intra:
+            return 0
+        ssh = 0 if self.no_chroma else self.ss_hor
+        ssv = 0 if self.no_chroma else self.ss_ver
+        r = B.lib().dav1d_cuda_intra_levels(into or self.intra.ctypes.data, self.n_intra, self.bw4, self.bh4, ssh, ssv)
+        if r < 0:
+            raise RuntimeError(f"dav1d_cuda_intra_levels: {r}")
+        if not into:
+            self.n_levels = r
+        return r
 
     def plane_shape(self, pl):
         sh = self.ss_hor if pl else 0
@@ -247,6 +263,7 @@ class DeviceFrame:
             b.intra_itx_tasks = d["intra_itx_tasks"]
             b.n_intra_itx_tasks[0], b.n_intra_itx_tasks[1] = hf.n_intra_itx_tasks
         b.intra_res = C.pointer(self.res)
+        b.intra_levels_recorded = 1 if hf.n_levels else 0
         return b
 
     def use(self, k):

@@ -252,7 +252,7 @@ typedef struct Dav1dCudaIntraDesc {  /* 40 bytes */
     uint8_t  tx, txtp;     /* residual transform, if any */
     uint32_t coef_off;     /* into the cf stream (PAL: into the index pool) */
     uint32_t aux;          /* CFL: w_pad | h_pad << 8 (4-px units); PAL: palette offset */
-    uint32_t reserved;     /* 0 */
+    uint32_t reserved;     /* 0, or level + 1 in the low 16 bits: dav1d_cuda_intra_levels() */
     uint8_t  cw4, ch4;     /* packed residual coefficients, see Dav1dCudaItxDesc (0, 0 = dense) */
     uint16_t pad;
 } Dav1dCudaIntraDesc;
@@ -353,6 +353,15 @@ DAV1D_CUDA_API int dav1d_cuda_warp_batch(Dav1dCudaContext *c, const Dav1dCudaPic
  * Cell map: dav1d_cuda_intra_cellmap_bytes() bytes of device memory per stream, zeroed ONCE by
  * the caller (every frame leaves it at zero again). */
 DAV1D_CUDA_API size_t dav1d_cuda_intra_cellmap_bytes(int bw4, int bh4, int ss_hor, int ss_ver);
+/* Optional recorder-side pass (host, linear in n, no device work): the dependency level of every
+ * intra-class operation - one more than the highest level among the operations that wrote a pixel
+ * it reads (0: nothing it reads is written in this phase) - from ONE walk over the descriptors in
+ * decode order, exactly the order the recorder emits them in.  level + 1 is stored in the low 16
+ * bits of `reserved`; set Dav1dCudaReconBatch.intra_levels_recorded.  The device only uses the
+ * levels to ORDER its work (operations still wait for the pixels they read), so a wrong level costs
+ * time or raises the status word, never a wrong pixel.  Returns the number of levels or -errno. */
+DAV1D_CUDA_API int dav1d_cuda_intra_levels(Dav1dCudaIntraDesc *descs, int n, int bw4, int bh4,
+                                           int ss_hor, int ss_ver);
 
 /* A whole frame's reconstruction as device-resident batches:
  *   phase A  motion compensation (put, fused compound in two waves, warp)
@@ -395,6 +404,9 @@ typedef struct Dav1dCudaReconBatch {
     const Dav1dCudaItxDesc *intra_itx; int32_t intra_itx_class_count[DAV1D_CUDA_N_RECT_TX_SIZES];
     const uint32_t *intra_itx_tasks;   int32_t n_intra_itx_tasks[2];
     const Dav1dCudaPicture *intra_res;
+    /* non-zero: the recorder ran dav1d_cuda_intra_levels() over `intra` (the descriptors carry their
+     * dependency level); zero: the device works the levels out itself (a cluster of blocks per frame) */
+    int32_t intra_levels_recorded;
 } Dav1dCudaReconBatch;
 
 enum { DAV1D_CUDA_MAX_GROUP = 64 };   /* frames per group submission */

@@ -103,8 +103,12 @@ def test_frame_parity_small(ref, name):
     w, h, bd, seed, kw = CASES[name]
     hf = F.HostFrame(w, h, bd, seed, **kw)
     refs, init, want = oracle_planes(ref, hf, seed)
-    # explicit transform tasks (the benchmark's configuration); implicit per-size transform runs
+    # explicit transform tasks (the benchmark's configuration); implicit per-size transform runs.
+    # First with the dependency levels worked out on the device, then with the recorder's pass
+    # (dav1d_cuda_intra_levels) over the same descriptors.
     for tasks in (True, False):
+        if not tasks:
+            hf.record_levels()
         got = run_gpu(hf, refs, init, use_graph=(seed % 2 == 0), tasks=tasks)
         for pl, (a, b) in enumerate(zip(want, got)):
             bad = np.argwhere(a != b)

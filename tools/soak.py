@@ -40,6 +40,8 @@ def run_one(seed):
     if r.integers(8) == 0:
         kw["no_chroma"] = 1
     hf = F.HostFrame(w, h, bd, seed, **kw)
+    if seed & 4:
+        hf.record_levels()       # the recorder's level pass instead of the device's
     refs = [F.random_planes(hf, seed * 10 + k) for k in range(2)]
     init = F.random_planes(hf, seed * 10 + 5)
     want = refframe.run_oracle(ref, hf, [p.copy() for p in init], refs)

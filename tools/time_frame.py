@@ -17,8 +17,13 @@ L = pkg.lib()
 groups = int(sys.argv[1]) if len(sys.argv) > 1 else 4
 per_group = int(sys.argv[2]) if len(sys.argv) > 2 else 8
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 5
+only = sys.argv[4].split(",") if len(sys.argv) > 4 and sys.argv[4] != "all" else None
+record = len(sys.argv) > 5 and sys.argv[5] == "record"      # the recorder's level pass instead of the device's
 w, h, bd = 3840, 2160, 0x3ff
 hfs = [F.HostFrame(w, h, bd, 1000 + i) for i in range(4)]
+if record:
+    for hf in hfs:
+        hf.record_levels()
 planes = {k: [F.random_planes(hfs[k], 7 + r + 10 * k) for r in range(3)] for k in range(4)}
 main = F.open_context(0)
 units = []
@@ -40,6 +45,8 @@ evs = [L.dav1d_cuda_event_create() for _ in units]
 S = groups * per_group
 for name, mask in (("all", 31), ("mc_put", 1), ("mc_compound", 2), ("warp", 4), ("itx", 8), ("intra", 16),
                    ("all_graph", 31)):
+    if only and name not in only:
+        continue
     mfs = [F.MultiFrame(ctx, dfs, phase_mask=mask, graph=name.endswith("graph")) for ctx, dfs in units]
     for _ in range(2):
         for m in mfs:
