@@ -265,6 +265,16 @@ def main_ours(args):
     bd12 = 0xfff if args.bitdepth_max == 0x3ff else args.bitdepth_max
     sets = {bd: [F.HostFrame(args.width, args.height, bd, 1000 + 17 * rank + i) for i in range(N_SETS)]
             for bd in {args.bitdepth_max, bd12}}
+    # The recorder's dependency-level pass (dav1d_cuda_intra_levels: one linear walk over the
+    # intra-class descriptors in decode order, host only).  The device-resident arm replays
+    # descriptors that carry these levels; the end-to-end arm leaves the levels to the device.
+    t0 = time.perf_counter()
+    n_rec = 0
+    for hfs_bd in sets.values():
+        for hf in hfs_bd:
+            hf.record_levels()
+            n_rec += 1
+    recorder_levels_ms = (time.perf_counter() - t0) * 1e3 / max(n_rec, 1)
     G = args.group
     ctxs, dfs, units = [], [], []
     plane_cache = {}
@@ -375,6 +385,19 @@ def main_ours(args):
     pkg.check_error()
     value = world * S * args.steps * luma_px / (ms * 1e-3) / 1e6
     algo_step = sum(df.hf.algo_bytes for df in dfs)
+    # the same arm with the dependency levels worked out on the device (nothing but the descriptors
+    # themselves comes from the recorder)
+    for df in dfs:
+        df.set_levels_recorded(False)
+    for _ in range(2):
+        run_step()
+    barrier()
+    ms_dev = max_over_ranks(timed(max(2, args.steps // 2)))
+    barrier()
+    value_device_levels = world * S * max(2, args.steps // 2) * luma_px / (ms_dev * 1e-3) / 1e6
+    for df in dfs:
+        df.set_levels_recorded(True)
+    pkg.check_error()
 
     # ---- verification of the timed configuration (outside the timed region): one 10-bit and the
     # 12-bit stream of this rank against the oracle (the reference's C templates), bit for bit
@@ -473,6 +496,8 @@ def main_ours(args):
         ctxs[:] = e2e_ctxs
         while len(ev_done) < len(ctxs):
             ev_done.append(L.dav1d_cuda_event_create())
+        for df in dfs:
+            df.set_levels_recorded(False)       # nothing is prepared on the host: the device finds the levels
         for _ in range(2):
             run_step(e2e=True)
         barrier()
@@ -487,7 +512,8 @@ def main_ours(args):
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
                "ms_per_step": ems / e2e_steps,
                "fresh_frames": f"every stream cycles through {N_SETS} different descriptor sets, one per step",
-               "includes": ["descriptor + coefficient upload", "group submission (launches only: the library does no "
+               "includes": ["descriptor + coefficient upload", "dependency levels + sort of the intra-class operations "
+                            "(on the device, inside the submission)", "group submission (launches only: the library does no "
                             "host-side scheduling, table merging or graph capture)", "picture download"],
                "host_ms_per_frame": host_s[0] * 1e3 / (e2e_steps * S), "host_threads": 1,
                "frames_per_group_submission": GE, "groups_in_flight": len(units)}
@@ -497,6 +523,8 @@ def main_ours(args):
                 df.upload_descriptors_pinned()      # the arena holds the last e2e frame: back to set 0
             L.dav1d_cuda_synchronize(u[0])
             u[1] = F.MultiFrame(u[0], u[2])
+        for df in dfs:
+            df.set_levels_recorded(True)
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
@@ -519,6 +547,11 @@ def main_ours(args):
                                  f"(dav1d_cuda_recon_group_submit: nothing scheduled on the host)",
                    "twelve_bit_stream": "the last stream of every rank is 12-bit",
                    "intra_ops_per_frame": int(dfs[0].hf.n_intra),
+                   "intra_dependency_levels": "recorder-side in `value` (dav1d_cuda_intra_levels: a linear pass over "
+                                              "the descriptors in decode order, measured below, part of recording like "
+                                              "the descriptors themselves); device-side in `value_device_levels` and e2e",
+                   "recorder_levels_ms_per_frame_one_core": recorder_levels_ms,
+                   "value_device_levels": value_device_levels,
                    "launches_per_frame": launches / max(1, args.steps * S),
                    "host_ms_per_frame_resident": host_resident_ms},
                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,

@@ -44,7 +44,31 @@ typedef struct D1SynthParams {
     float p_obmc;               // single-reference blocks (>= 8x8) that get OBMC blends
     float p_ii;                 // single-reference blocks (8x8..32x32) with inter-intra prediction
     float p_ibc;                // intra-coded blocks predicted by intrabc (copy from the current picture)
+    int32_t tile_cols, tile_rows;   // uniform tile grid in superblock units (recon_tmpl.c:1283-1287: nothing
+                                    // is predicted across a tile edge); 0 or 1 = one tile
+    int32_t real_blocks;            // 1: intra blocks exactly as dav1d_recon_b_intra() would reconstruct an
+                                    // Av1Block (smooth-neighbour flags from the above / left block contexts,
+                                    // chroma of 4-px-wide / -high blocks with the odd partner, no CfL padding
+                                    // inside the picture) + a block record per block for the reference driver
 } D1SynthParams;
+
+// One coded block as the reference's reconstruction driver sees it (the Av1Block fields
+// dav1d_recon_b_intra reads, src/levels.h:262-287, plus what decode_b() hands over).
+typedef struct D1SynthBlock {
+    uint16_t bx4, by4;            // t->bx, t->by
+    uint8_t  w4, h4;              // dav1d_block_dimensions[bs]
+    uint8_t  intra, has_chroma, skip, tile;
+    uint8_t  edge_tr, edge_bl;    // bit 0 luma, bit 1 chroma: block-level EDGE_*_TOP_HAS_RIGHT / LEFT_HAS_BOTTOM
+    uint8_t  y_mode, uv_mode;     // IntraPredMode; 13 = FILTER_PRED (luma) / CFL_PRED (chroma)
+    int8_t   y_angle, uv_angle;
+    uint8_t  tx, uvtx;            // RectTxfmSize
+    uint8_t  pal_sz[2];
+    int8_t   cfl_alpha[2];
+    uint16_t tile_x0, tile_y0, tile_x1, tile_y1;   // ts->tiling in luma 4-px units
+    uint32_t pal_off[3];          // palettes in the palette pool (pixels)
+    uint32_t pal_idx_off[2];      // packed indices in the index pool (bytes): luma, chroma
+    uint32_t first_op, n_ops;     // the block's operations in `intra` (the order the reference consumes cbi / cf in)
+} D1SynthBlock;
 
 typedef struct D1SynthFrame {
     Dav1dCudaMcDesc *mc_put;   int32_t n_mc_put;   uint32_t *mc_put_tiles;  int32_t n_mc_put_tiles;
@@ -66,6 +90,7 @@ typedef struct D1SynthFrame {
     Dav1dCudaMcDesc *mc_obmc;  int32_t n_mc_obmc;  uint32_t *mc_obmc_tiles; int32_t n_mc_obmc_tiles[2];
     Dav1dCudaItxDesc *intra_itx; int32_t n_intra_itx; int32_t intra_itx_class_count[19];   // the intra residuals as transforms
     double dense_coef_bytes;   // part of algo_bytes that counts DENSE coefficient blocks; the packed stream is cf_elems
+    D1SynthBlock *blocks;      int32_t n_block_recs;   // real_blocks: every block in decode order
 } D1SynthFrame;
 
 }  // extern "C"
@@ -133,6 +158,7 @@ struct Gen {
             pw4[pl] = (bw4 + sh) >> sh; ph4[pl] = (bh4 + sv) >> sv;
             decoded[pl].assign((size_t)pw4[pl] * ph4[pl], 0);
         }
+        ctx_init();
     }
     int nplanes() const { return P.no_chroma ? 1 : 3; }
 
@@ -219,8 +245,12 @@ struct Gen {
         Dav1dCudaIntraDesc d;
         memset(&d, 0, sizeof(d));
         d.x4 = (uint16_t)x4; d.y4 = (uint16_t)y4;
-        d.tile_x4_start = 0; d.tile_y4_start = 0;
-        d.tile_x4_end = (uint16_t)pw4[pl]; d.tile_y4_end = (uint16_t)ph4[pl];
+        {   // the current tile in this plane's 4-px units (ts->tiling.col_start .. row_end >> ss)
+            const int sh = pl ? P.ss_hor : 0, sv = pl ? P.ss_ver : 0;
+            d.tile_x4_start = (uint16_t)(tile_x0 >> sh); d.tile_y4_start = (uint16_t)(tile_y0 >> sv);
+            d.tile_x4_end = (uint16_t)std::min((tile_x1 + sh) >> sh, pw4[pl]);
+            d.tile_y4_end = (uint16_t)std::min((tile_y1 + sv) >> sv, ph4[pl]);
+        }
         d.plane = (uint8_t)pl; d.tw4 = (uint8_t)tw4; d.th4 = (uint8_t)th4;
         d.mode = (uint8_t)mode; d.angle_delta = (int8_t)angle_delta;
         d.flags = (uint16_t)flags;
@@ -272,11 +302,13 @@ struct Gen {
     // part of the CURRENT picture (any position in the superblock rows above; now and then past the
     // right edge, which the reference pads with emu_edge), residuals as residual-only operations
     bool ibc_block(int bx4, int by4, int w4, int h4) {
-        const int sb_top = (by4 & ~15) * 4, wpx = w4 * 4, hpx = h4 * 4;
+        const int sb_top = (by4 & ~15) * 4 - tile_y0 * 4, wpx = w4 * 4, hpx = h4 * 4;   // rows of the tile above this SB row
         if (w4 < 2 || h4 < 2 || w4 > 16 || h4 > 16 || sb_top < hpx + 2) return false;
-        const int W = bw4 * 4;
-        const int sxl = rng.chance(0.1f) ? W - wpx + 2 * rng.range(4) : 2 * rng.range((W - wpx) / 2 + 1);
-        const int syl = 2 * rng.range((sb_top - hpx - 2) / 2 + 1);
+        const int W = std::min(tile_x1, bw4) * 4 - tile_x0 * 4;                      // the source stays inside the tile
+        if (W < wpx + 8) return false;
+        const bool one_tile = tile_x0 == 0 && tile_x1 >= bw4;
+        const int sxl = tile_x0 * 4 + ((one_tile && rng.chance(0.1f)) ? W - wpx + 2 * rng.range(4) : 2 * rng.range((W - wpx) / 2 + 1));
+        const int syl = tile_y0 * 4 + 2 * rng.range((sb_top - hpx - 2) / 2 + 1);
         const bool half = rng.chance(0.5f);          // odd luma vector components: half-pel chroma
         n_intra_blocks++;
         for (int pl = 0; pl < nplanes(); pl++) {
@@ -308,20 +340,44 @@ struct Gen {
     }
 
     void intra_block(int bx4, int by4, int w4, int h4) {
-        if (P.p_ibc > 0.f && rng.chance(P.p_ibc) && ibc_block(bx4, by4, w4, h4)) return;
+        if (P.p_ibc > 0.f && rng.chance(P.p_ibc) && ibc_block(bx4, by4, w4, h4)) {
+            if (P.real_blocks) ctx_set(bx4, by4, w4, h4, 0, 0, true, 0);      // intrabc is coded as an inter block
+            return;
+        }
         n_intra_blocks++;
+        const bool real = P.real_blocks != 0;
+        const int sh = P.ss_hor, sv = P.ss_ver;
+        D1SynthBlock rec;
+        memset(&rec, 0, sizeof(rec));
+        rec.bx4 = (uint16_t)bx4; rec.by4 = (uint16_t)by4; rec.w4 = (uint8_t)w4; rec.h4 = (uint8_t)h4;
+        rec.intra = 1; rec.tile = (uint8_t)tile_no;
+        rec.tile_x0 = (uint16_t)tile_x0; rec.tile_y0 = (uint16_t)tile_y0;
+        rec.tile_x1 = (uint16_t)std::min(tile_x1, bw4); rec.tile_y1 = (uint16_t)std::min(tile_y1, bh4);
+        rec.first_op = (uint32_t)intra.size();
+        // block-level edge availability (what the partition tree of src/intra_edge.c tells decode_b):
+        // here simply whether the area is decoded
+        rec.edge_tr = (by4 > 0 && all_decoded(0, bx4 + w4, by4 - 1, std::min(bx4 + 2 * w4, pw4[0]), by4)) ? 1 : 0;
+        rec.edge_bl = (bx4 > 0 && all_decoded(0, bx4 - 1, by4 + h4, bx4, std::min(by4 + 2 * h4, ph4[0]))) ? 1 : 0;
         const bool residual = rng.chance(P.p_residual);
-        const int flags = (P.edge_filter ? 1024 : 0) | (rng.chance(0.25f) ? 512 : 0);
+        rec.skip = residual ? 0 : 1;
+        // smooth-neighbour flag: sm_flag(t->a, bx4) | sm_flag(&t->l, by4) (ipred_prepare.h:95-101)
+        const bool sm = real ? ((a_intra[bx4] && smooth_mode(a_mode[bx4])) || (l_intra[by4] && smooth_mode(l_mode[by4])))
+                             : rng.chance(0.25f);
+        const int flags = (P.edge_filter ? 1024 : 0) | (sm ? 512 : 0);
         int tw4 = std::min(w4, 16), th4 = std::min(h4, 16);
         if (rng.chance(P.p_tx_split)) split_tx(tw4, th4);
+        rec.tx = (uint8_t)tx_from_dims(tw4, th4);
         const bool pal = w4 <= 16 && h4 <= 16 && rng.chance(P.p_palette);
         int mode = rng.range(13), delta = 0;
         if (!pal && w4 <= 8 && h4 <= 8 && rng.chance(P.p_filter_intra)) { mode = DAV1D_CUDA_INTRA_FILTER; delta = rng.range(5); }
         else if (mode >= 1 && mode <= 8) delta = rng.irange(-3, 3);
+        if (pal && real) { mode = 0; delta = 0; }               // a palette block is coded as DC_PRED
+        rec.y_mode = (uint8_t)mode; rec.y_angle = (int8_t)delta; rec.pal_sz[0] = pal ? 8 : 0;
         uint32_t pal_off = 0, idx_off = 0;
         if (pal) {
             pal_off = (uint32_t)pal_px_alloc();
             idx_off = (uint32_t)pal_idx_alloc(w4 * 4 * h4 * 4 / 2);
+            rec.pal_off[0] = pal_off; rec.pal_idx_off[0] = idx_off;
             add_intra(0, bx4, by4, w4, h4, DAV1D_CUDA_INTRA_PAL, 0, 0, false, pal_off, idx_off);
         }
         for (int y = 0; y < h4; y += th4)
@@ -334,29 +390,54 @@ struct Gen {
                 }
             }
         if (pal) mark(0, bx4, by4, w4, h4);
-        if (P.no_chroma) return;
-        // ---- chroma
-        const int sh = P.ss_hor, sv = P.ss_ver;
-        const int cx4 = bx4 >> sh, cy4 = by4 >> sv, cw4 = w4 >> sh, ch4 = h4 >> sv;
+        // ---- chroma.  The reference (recon_tmpl.c:1209-1211): a block that is 4 luma pixels wide /
+        // high carries the chroma of the pair it closes, i.e. only the odd partner has chroma.
+        bool has_chroma = !P.no_chroma;
+        int cx4 = bx4 >> sh, cy4 = by4 >> sv, cw4 = w4 >> sh, ch4 = h4 >> sv;
+        if (real && has_chroma) {
+            has_chroma = (w4 > sh || (bx4 & 1)) && (h4 > sv || (by4 & 1));
+            cw4 = (w4 + sh) >> sh; ch4 = (h4 + sv) >> sv;
+        }
+        rec.has_chroma = has_chroma ? 1 : 0;
+        const int ymode_ctx = mode == DAV1D_CUDA_INTRA_FILTER ? 0 : mode;   // y_mode_nofilt (decode.c:745-746)
+        if (!has_chroma || cw4 <= 0 || ch4 <= 0) {
+            if (real) {
+                rec.n_ops = (uint32_t)intra.size() - rec.first_op;
+                blocks.push_back(rec);
+                ctx_set(bx4, by4, w4, h4, 1, ymode_ctx, false, 0);
+            }
+            return;
+        }
+        if (all_decoded(1, cx4 + cw4, cy4 - 1, std::min(cx4 + 2 * cw4, pw4[1]), cy4) && cy4 > 0) rec.edge_tr |= 2;
+        if (all_decoded(1, cx4 - 1, cy4 + ch4, cx4, std::min(cy4 + 2 * ch4, ph4[1])) && cx4 > 0) rec.edge_bl |= 2;
         int uvtw4 = std::min(cw4, 8), uvth4 = std::min(ch4, 8);
         fit_tx(uvtw4, uvth4);
+        rec.uvtx = (uint8_t)tx_from_dims(uvtw4, uvth4);
         const bool cfl = !pal && w4 <= 8 && h4 <= 8 && rng.chance(P.p_cfl);
-        const int uvflags = (P.edge_filter ? 1024 : 0) | (rng.chance(0.25f) ? 512 : 0);
+        // sm_uv_flag(t->a, cbx4) | sm_uv_flag(&t->l, cby4) (ipred_prepare.h:103-107)
+        const bool uvsm = real ? (smooth_mode(a_uvmode[cx4]) || smooth_mode(l_uvmode[cy4])) : rng.chance(0.25f);
+        const int uvflags = (P.edge_filter ? 1024 : 0) | (uvsm ? 512 : 0);
         int uvmode = rng.range(13), uvdelta = 0;
         if (uvmode >= 1 && uvmode <= 8) uvdelta = rng.irange(-3, 3);
+        if (real && (pal || cfl)) { uvmode = 0; uvdelta = 0; }
+        rec.uv_mode = (uint8_t)(cfl ? 13 : uvmode); rec.uv_angle = (int8_t)uvdelta; rec.pal_sz[1] = pal ? 8 : 0;
         uint32_t uvpal_off[2] = { 0, 0 }, uvidx_off = 0;
         if (pal) {
             uvpal_off[0] = (uint32_t)pal_px_alloc();
             uvpal_off[1] = (uint32_t)pal_px_alloc();
             uvidx_off = (uint32_t)pal_idx_alloc(cw4 * 4 * ch4 * 4 / 2);
+            rec.pal_off[1] = uvpal_off[0]; rec.pal_off[2] = uvpal_off[1]; rec.pal_idx_off[1] = uvidx_off;
         }
         int wpad = 0, hpad = 0;
-        if (cfl && rng.chance(0.1f)) { wpad = rng.range(uvtw4); hpad = rng.range(uvth4); }   // per CfL operation (tx block)
+        // CfL padding (recon_tmpl.c:1388-1396) only arises where a block sticks out of the picture;
+        // the random padding exercises the operator beyond what a stream can produce
+        if (!real && cfl && rng.chance(0.1f)) { wpad = rng.range(uvtw4); hpad = rng.range(uvth4); }   // per CfL operation (tx block)
         for (int pl = 1; pl <= 2; pl++) {
             if (pal) add_intra(pl, cx4, cy4, cw4, ch4, DAV1D_CUDA_INTRA_PAL, 0, 0, false, uvpal_off[pl - 1], uvidx_off);
             int alpha = 0;
             if (cfl) alpha = (rng.range(16) + 1) * (rng.chance(0.5f) ? -1 : 1);
             if (cfl && pl == 2 && rng.chance(0.2f)) alpha = 0;    // alpha 0 -> plain DC_PRED (recon_tmpl.c:1479)
+            rec.cfl_alpha[pl - 1] = (int8_t)alpha;
             for (int y = 0; y < ch4; y += uvth4)
                 for (int x = 0; x < cw4; x += uvtw4) {
                     if (pal) {
@@ -370,6 +451,11 @@ struct Gen {
                     }
                 }
             mark(pl, cx4, cy4, cw4, ch4);
+        }
+        if (real) {
+            rec.n_ops = (uint32_t)intra.size() - rec.first_op;
+            blocks.push_back(rec);
+            ctx_set(bx4, by4, w4, h4, 1, ymode_ctx, true, cfl ? 13 : uvmode);
         }
     }
 
@@ -416,7 +502,7 @@ struct Gen {
             if (kind == DAV1D_CUDA_MC_OBMC_H) { order.push_back({ 6, (uint32_t)obmc_h.size() }); obmc_h.push_back(d); }
             else { order.push_back({ 7, (uint32_t)obmc_v.size() }); obmc_v.push_back(d); }
         };
-        if (by4 > 0 && (!pl || w4 * h_mul + h4 * v_mul >= 16)) {
+        if (by4 > tile_y0 && (!pl || w4 * h_mul + h4 * v_mul >= 16)) {
             for (int i = 0, x = 0; x < w4 && i < std::min(ilog2(w4), 4);) {
                 int step4 = 2 << rng.range(4);
                 while (x > 0 && x % step4) step4 >>= 1;      // neighbours are aligned to their own size
@@ -428,7 +514,7 @@ struct Gen {
                 x += step4;
             }
         }
-        if (bx4 > 0) {
+        if (bx4 > tile_x0) {
             for (int i = 0, y = 0; y < h4 && i < std::min(ilog2(h4), 4);) {
                 int step4 = 2 << rng.range(4);
                 while (y > 0 && y % step4) step4 >>= 1;
@@ -598,7 +684,13 @@ struct Gen {
         n_blocks++;
         luma_px += 16.0 * w4 * h4;
         if (rng.chance(P.p_intra)) intra_block(bx4, by4, w4, h4);
-        else inter_block(bx4, by4, w4, h4);
+        else {
+            inter_block(bx4, by4, w4, h4);
+            if (P.real_blocks) {            // decode.c:810-830: intra = 0, uvmode = DC_PRED
+                const bool hc = (w4 > P.ss_hor || (bx4 & 1)) && (h4 > P.ss_ver || (by4 & 1));
+                ctx_set(bx4, by4, w4, h4, 0, 0, hc, 0);
+            }
+        }
     }
 
     // recursive partition of an s4 x s4 (4-px units) square at (bx4, by4), decode (Z) order
@@ -635,8 +727,50 @@ struct Gen {
                 for (int x = 0; x + tw4 <= bw4; x += tw4) { add_itx(0, x, y, P.only_tx); luma_px += 16.0 * tw4 * th4; }
             return;
         }
-        for (int y = 0; y < bh4; y += 16)
-            for (int x = 0; x < bw4; x += 16) partition(x, y, 16);
+        // tiles in raster order, superblocks in raster order inside a tile (the decode order of
+        // dav1d_decode_tile_sbrow over the tiles of a frame)
+        const int sbw = (bw4 + 15) >> 4, sbh = (bh4 + 15) >> 4;
+        const int tc = std::max(1, std::min(P.tile_cols, sbw)), tr = std::max(1, std::min(P.tile_rows, sbh));
+        const int tw = (sbw + tc - 1) / tc, th = (sbh + tr - 1) / tr;
+        for (int ty = 0; ty * th < sbh; ty++)
+            for (int tx = 0; tx * tw < sbw; tx++) {
+                tile_x0 = tx * tw * 16; tile_y0 = ty * th * 16;
+                tile_x1 = std::min((tx + 1) * tw * 16, bw4); tile_y1 = std::min((ty + 1) * th * 16, bh4);
+                tile_no = ty * tc + tx;
+                if (P.real_blocks) ctx_reset_above();
+                for (int y = tile_y0; y < tile_y1; y += 16) {
+                    if (P.real_blocks) ctx_reset_left(y);
+                    for (int x = tile_x0; x < tile_x1; x += 16) partition(x, y, 16);
+                }
+            }
+    }
+    int tile_x0 = 0, tile_y0 = 0, tile_x1 = 1 << 20, tile_y1 = 1 << 20;   // current tile, luma 4-px units
+    int tile_no = 0;
+    // above / left block contexts (BlockContext mode / intra / uvmode, src/env.h), reset like
+    // dav1d_reset_context() at a tile's top edge and at the left edge of every superblock row of a tile
+    std::vector<uint8_t> a_intra, a_mode, a_uvmode, l_intra, l_mode, l_uvmode;
+    std::vector<D1SynthBlock> blocks;
+    static bool smooth_mode(int m) { return m >= 9 && m <= 11; }
+    void ctx_init() {
+        a_intra.assign(bw4 + 1, 0); a_mode.assign(bw4 + 1, 0); a_uvmode.assign(bw4 + 1, 0);
+        l_intra.assign(bh4 + 1, 0); l_mode.assign(bh4 + 1, 0); l_uvmode.assign(bh4 + 1, 0);
+    }
+    void ctx_reset_above() {
+        for (int x = tile_x0; x < std::min(tile_x1, bw4); x++) { a_intra[x] = 0; a_mode[x] = 0; }
+        for (int x = tile_x0 >> P.ss_hor; x < (std::min(tile_x1, bw4) + P.ss_hor) >> P.ss_hor; x++) a_uvmode[x] = 0;
+    }
+    void ctx_reset_left(int y0) {
+        for (int y = y0; y < std::min(y0 + 16, bh4); y++) { l_intra[y] = 0; l_mode[y] = 0; }
+        for (int y = y0 >> P.ss_ver; y < (std::min(y0 + 16, bh4) + P.ss_ver) >> P.ss_ver; y++) l_uvmode[y] = 0;
+    }
+    void ctx_set(int bx4, int by4, int w4, int h4, int intra, int ymode, bool has_chroma, int uvmode) {
+        for (int x = bx4; x < std::min(bx4 + w4, bw4); x++) { a_intra[x] = (uint8_t)intra; if (intra) a_mode[x] = (uint8_t)ymode; }
+        for (int y = by4; y < std::min(by4 + h4, bh4); y++) { l_intra[y] = (uint8_t)intra; if (intra) l_mode[y] = (uint8_t)ymode; }
+        if (has_chroma && !P.no_chroma) {
+            const int sh = P.ss_hor, sv = P.ss_ver;
+            for (int x = bx4 >> sh; x < (bx4 >> sh) + ((w4 + sh) >> sh); x++) a_uvmode[x] = (uint8_t)uvmode;
+            for (int y = by4 >> sv; y < (by4 >> sv) + ((h4 + sv) >> sv); y++) l_uvmode[y] = (uint8_t)uvmode;
+        }
     }
 };
 
@@ -663,7 +797,7 @@ __attribute__((visibility("default"))) void d1synth_default_params(D1SynthParams
     p->p_intra = 0.3f; p->p_residual = 0.6f; p->p_tx_split = 0.5f;
     p->p_filter_intra = 0.05f; p->p_palette = 0.02f; p->p_cfl = 0.25f;
     p->p_avg = 0.2f; p->p_w_avg = 0.1f; p->p_wedge = 0.1f; p->p_seg = 0.05f; p->p_warp = 0.05f;
-    p->mv_range = 128; p->n_refs = 2; p->edge_filter = 1; p->only_tx = -1; p->only_txtp = -1; p->eob_class = -1; p->dense_coefs = 0; p->p_obmc = 0.f; p->p_ii = 0.f; p->p_ibc = 0.f;
+    p->mv_range = 128; p->n_refs = 2; p->edge_filter = 1; p->only_tx = -1; p->only_txtp = -1; p->eob_class = -1; p->dense_coefs = 0; p->p_obmc = 0.f; p->p_ii = 0.f; p->p_ibc = 0.f; p->tile_cols = 1; p->tile_rows = 1; p->real_blocks = 0;
 }
 
 __attribute__((visibility("default"))) int d1synth_generate(const D1SynthParams *p, D1SynthFrame *f) {
@@ -781,13 +915,14 @@ __attribute__((visibility("default"))) int d1synth_generate(const D1SynthParams 
     f->algo_bytes = g.algo; f->luma_px = g.luma_px; f->dense_coef_bytes = g.dense_coef_bytes;
     for (int i = 0; i < 5; i++) f->algo_class[i] = g.algo_cls[i];
     f->n_blocks = g.n_blocks; f->n_intra_blocks = g.n_intra_blocks;
+    f->blocks = dup(g.blocks); f->n_block_recs = (int32_t)g.blocks.size();
     return 0;
 }
 
 __attribute__((visibility("default"))) void d1synth_free(D1SynthFrame *f) {
     if (!f) return;
     free(f->mc_put); free(f->mc_put_tiles); free(f->mc_comp); free(f->mc_comp_tiles); free(f->warp);
-    free(f->mc_obmc); free(f->mc_obmc_tiles);
+    free(f->mc_obmc); free(f->mc_obmc_tiles); free(f->blocks);
     free(f->intra_itx);
     free(f->itx); free(f->intra); free(f->cf); free(f->masks); free(f->pal); free(f->pal_idx); free(f->order);
     memset(f, 0, sizeof(*f));

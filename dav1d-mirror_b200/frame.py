@@ -22,7 +22,8 @@ class SynthParams(C.Structure):
                 ("p_seg", C.c_float), ("p_warp", C.c_float),
                 ("mv_range", C.c_int32), ("n_refs", C.c_int32), ("edge_filter", C.c_int32),
                 ("only_tx", C.c_int32), ("only_txtp", C.c_int32), ("eob_class", C.c_int32),
-                ("dense_coefs", C.c_int32), ("p_obmc", C.c_float), ("p_ii", C.c_float), ("p_ibc", C.c_float)]
+                ("dense_coefs", C.c_int32), ("p_obmc", C.c_float), ("p_ii", C.c_float), ("p_ibc", C.c_float),
+                ("tile_cols", C.c_int32), ("tile_rows", C.c_int32)]
 
 
 class SynthFrame(C.Structure):
@@ -265,6 +266,12 @@ class DeviceFrame:
         b.intra_res = C.pointer(self.res)
         b.intra_levels_recorded = 1 if hf.n_levels else 0
         return b
+
+    def set_levels_recorded(self, on):
+        """Tell the library whether the descriptors' recorder-assigned dependency levels are to be
+        used (HostFrame.record_levels() ran) or the device works the levels out itself."""
+        for st in self._sets:
+            st["batch"].intra_levels_recorded = 1 if (on and st["hf"].n_levels) else 0
 
     def use(self, k):
         """Make descriptor set k the frame to reconstruct next (its arrays still have to be shipped)."""

@@ -44,6 +44,12 @@ CASES = {
     # ragged picture sizes (not multiples of the 64x64 superblock / of 8 in chroma)
     "420_10b_ragged": (328, 200, 0x3ff, 8, {}),
     "420_8b_ragged": (200, 120, 0xff, 10, {"p_intra": 0.6}),
+    # several tiles: nothing is predicted across a tile edge (have_left / have_top / the w, h arguments of
+    # dav1d_prepare_intra_edges come from the tile, recon_tmpl.c:1283-1287; OBMC and intrabc stay inside it)
+    "420_10b_tiles_2x2": (384, 256, 0x3ff, 22, {"tile_cols": 2, "tile_rows": 2, "p_intra": 0.6, "p_cfl": 0.5}),
+    "420_8b_tiles_3x2_obmc_ibc": (448, 256, 0xff, 23, {"tile_cols": 3, "tile_rows": 2, "p_intra": 0.5, "p_obmc": 0.4,
+                                                       "p_ibc": 0.3, "p_ii": 0.2}),
+    "444_12b_tiles_2x1": (256, 128, 0xfff, 24, {"tile_cols": 2, "tile_rows": 1, "ss_hor": 0, "ss_ver": 0, "p_intra": 0.7}),
     # dense coefficient blocks (the reference's layout, cw4 = ch4 = 0) through the batched path
     "420_10b_dense_coefs": (256, 192, 0x3ff, 12, {"dense_coefs": 1}),
 }
