@@ -706,6 +706,9 @@ struct Gen {
             else if (s4 == 8) choice = r < 25 ? 0 : r < 38 ? 1 : r < 51 ? 2 : r < 56 ? 4 : r < 61 ? 5 : 3;
             else choice = r < 40 ? 0 : r < 55 ? 1 : r < 70 ? 2 : 3;      // s4 == 4 (16x16)
         }
+        // 4:2:2 has no block whose chroma would be 1:4 or narrower: no vertical two- / four-way split
+        // (the 0 entries of dav1d_max_txfm_size_for_bs, tables.c:171-195)
+        if (P.real_blocks && P.ss_hor && !P.ss_ver && !P.no_chroma) choice = choice == 2 ? 1 : choice == 5 ? 4 : choice;
         const int hs = s4 >> 1, q = s4 >> 2;
         switch (choice) {
         case 0: block(bx4, by4, s4, s4); break;

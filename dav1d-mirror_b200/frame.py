@@ -23,7 +23,7 @@ class SynthParams(C.Structure):
                 ("mv_range", C.c_int32), ("n_refs", C.c_int32), ("edge_filter", C.c_int32),
                 ("only_tx", C.c_int32), ("only_txtp", C.c_int32), ("eob_class", C.c_int32),
                 ("dense_coefs", C.c_int32), ("p_obmc", C.c_float), ("p_ii", C.c_float), ("p_ibc", C.c_float),
-                ("tile_cols", C.c_int32), ("tile_rows", C.c_int32)]
+                ("tile_cols", C.c_int32), ("tile_rows", C.c_int32), ("real_blocks", C.c_int32)]
 
 
 class SynthFrame(C.Structure):
@@ -46,7 +46,7 @@ class SynthFrame(C.Structure):
                 ("mc_obmc", C.c_void_p), ("n_mc_obmc", C.c_int32), ("mc_obmc_tiles", C.c_void_p),
                 ("n_mc_obmc_tiles", C.c_int32 * 2),
                 ("intra_itx", C.c_void_p), ("n_intra_itx", C.c_int32), ("intra_itx_class_count", C.c_int32 * 19),
-                ("dense_coef_bytes", C.c_double)]
+                ("dense_coef_bytes", C.c_double), ("blocks", C.c_void_p), ("n_block_recs", C.c_int32)]
 
 
 _synth = None
@@ -118,6 +118,9 @@ class HostFrame:
         self.algo_class = dict(zip(("mc_put", "mc_compound", "warp", "itx", "intra"), list(f.algo_class)))
         self.n_blocks, self.n_intra_blocks = f.n_blocks, f.n_intra_blocks
         self.dense_coef_bytes = f.dense_coef_bytes
+        # real_blocks: one record per coded block (the Av1Block fields the reference's driver reads), 60 bytes each
+        self.n_block_recs = f.n_block_recs
+        self.blocks = _np_from(f.blocks, f.n_block_recs * 60)
         # intra-class operations stay in decode order; their residuals are listed a second time as
         # transform descriptors ordered like `itx`
         self.intra_itx = _np_from(f.intra_itx, f.n_intra_itx * C.sizeof(B.ItxDesc))

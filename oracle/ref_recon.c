@@ -1,0 +1,253 @@
+/*
+ * oracle/ref_recon.c - TEST INFRASTRUCTURE ONLY (never linked into the product).
+ *
+ * Frame-level checker that runs the reference's OWN reconstruction driver:
+ * dav1d_recon_b_intra_{8,16}bpc (src/recon_tmpl.c:1195-1596, compiled where it
+ * lies under /root/reference by oracle/Makefile) is called block by block, in
+ * decode order, on a frame context laid out the way pass 2 of frame threading
+ * finds it (src/internal.h:276-293: cbi, cf, pal, pal_idx handed over by pass 1;
+ * src/decode.c:741-772 for the block-context updates after each block;
+ * src/decode.c:2677 for the per-superblock-row edge backup).
+ *
+ * The blocks come from the synthetic generator's block records (D1SynthBlock,
+ * dav1d-mirror_b200/csrc/synth.cpp with real_blocks = 1): the Av1Block fields
+ * the driver reads.  Nothing here decides a DSP call: which predictor, which
+ * edge flags per transform block, CfL / palette order, tile edges, the
+ * superblock-row edge backup - all of that is the reference's code.  Only the
+ * coefficient / index streams are re-packed into the layout pass 1 leaves them
+ * in.  Compiled twice (BITDEPTH 8 / 16); this file is this repo's own code.
+ */
+#include "config.h"
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "common/attributes.h"
+#include "common/bitdepth.h"
+#include "common/intops.h"
+#include "src/internal.h"
+#include "src/levels.h"
+#include "src/intra_edge.h"
+#include "src/tables.h"
+#include "src/recon.h"
+#include "src/mc.h"
+#include "src/itx.h"
+#include "src/ipred.h"
+
+#include "dav1d_cuda.h"
+
+#define EXPORT __attribute__((visibility("default")))
+
+/* == D1SynthBlock of dav1d-mirror_b200/csrc/synth.cpp */
+typedef struct D1SynthBlock {
+    uint16_t bx4, by4;
+    uint8_t  w4, h4;
+    uint8_t  intra, has_chroma, skip, tile;
+    uint8_t  edge_tr, edge_bl;
+    uint8_t  y_mode, uv_mode;
+    int8_t   y_angle, uv_angle;
+    uint8_t  tx, uvtx;
+    uint8_t  pal_sz[2];
+    int8_t   cfl_alpha[2];
+    uint16_t tile_x0, tile_y0, tile_x1, tile_y1;
+    uint32_t pal_off[3];
+    uint32_t pal_idx_off[2];
+    uint32_t first_op, n_ops;
+} D1SynthBlock;
+
+typedef struct OracleReconFrame {
+    void *dst[3];
+    ptrdiff_t dst_stride[3];
+    int32_t w, h, ss_hor, ss_ver, bitdepth_max, no_chroma, intra_edge_filter;
+    const D1SynthBlock *blocks;
+    int32_t n_blocks;
+    const Dav1dCudaIntraDesc *ops;     /* the blocks' operations: eob / txtp / coefficient offsets per transform block */
+    const void *cf;                    /* generator coefficient stream (packed or dense blocks) */
+    const void *pal;                   /* palette pool */
+    const uint8_t *pal_idx;            /* packed index pool */
+} OracleReconFrame;
+
+#if BITDEPTH == 8
+#define SUFFIX(name) name##_8bpc
+#else
+#define SUFFIX(name) name##_16bpc
+#endif
+
+static int bs_from_dims(const int w4, const int h4) {
+    for (int bs = 0; bs < N_BS_SIZES; bs++)
+        if (dav1d_block_dimensions[bs][0] == w4 && dav1d_block_dimensions[bs][1] == h4) return bs;
+    return -1;
+}
+
+/* one transform block of the generator's stream -> the dense min(w,32) x min(h,32) block pass 1 stores */
+static void dense_coefs(coef *out, const OracleReconFrame *fr, const Dav1dCudaIntraDesc *d) {
+    const TxfmInfo *const t = &dav1d_txfm_dimensions[d->tx];
+    const int sw = imin(t->w * 4, 32), sh = imin(t->h * 4, 32);
+    const coef *src = (const coef *)fr->cf + d->coef_off;
+    memset(out, 0, sizeof(coef) * sw * sh);
+    if (!d->cw4 || !d->ch4) {
+        memcpy(out, src, sizeof(coef) * sw * sh);
+    } else {
+        const int cw = d->cw4 * 4, ch = d->ch4 * 4;
+        for (int x = 0; x < cw; x++)
+            for (int y = 0; y < ch; y++) out[y + x * sh] = src[y + x * ch];
+    }
+}
+
+/* Reconstructs every intra block of the frame through dav1d_recon_b_intra.  Returns 0, or a
+ * negative value when the records hold something this harness does not drive (inter blocks). */
+EXPORT int SUFFIX(oracle_recon_intra_frame)(const OracleReconFrame *const fr) {
+    int ret = 0;
+    Dav1dDSPContext dsp;
+    memset(&dsp, 0, sizeof(dsp));
+    SUFFIX(dav1d_mc_dsp_init)(&dsp.mc);
+    SUFFIX(dav1d_itx_dsp_init)(&dsp.itx, fr->bitdepth_max > 1023 ? 12 : fr->bitdepth_max > 255 ? 10 : 8);
+    SUFFIX(dav1d_intra_pred_dsp_init)(&dsp.ipred);
+
+    Dav1dSequenceHeader seq;
+    Dav1dFrameHeader hdr;
+    memset(&seq, 0, sizeof(seq));
+    memset(&hdr, 0, sizeof(hdr));
+    seq.intra_edge_filter = fr->intra_edge_filter;
+    seq.hbd = fr->bitdepth_max > 1023 ? 2 : fr->bitdepth_max > 255 ? 1 : 0;
+    hdr.frame_type = DAV1D_FRAME_TYPE_KEY;
+
+    Dav1dFrameContext *const f = calloc(1, sizeof(*f));
+    Dav1dTileState *const ts = calloc(1, sizeof(*ts));
+    Dav1dTaskContext *t = NULL;
+    if (posix_memalign((void **)&t, 64, sizeof(*t))) { free(f); free(ts); return -12; }
+    memset(t, 0, sizeof(*t));
+    f->seq_hdr = &seq;
+    f->frame_hdr = &hdr;
+    f->dsp = &dsp;
+    f->bitdepth_max = fr->bitdepth_max;
+    f->cur.data[0] = fr->dst[0]; f->cur.data[1] = fr->dst[1]; f->cur.data[2] = fr->dst[2];
+    f->cur.stride[0] = fr->dst_stride[0]; f->cur.stride[1] = fr->dst_stride[1];
+    f->cur.p.w = fr->w; f->cur.p.h = fr->h;
+    f->cur.p.bpc = fr->bitdepth_max > 1023 ? 12 : fr->bitdepth_max > 255 ? 10 : 8;
+    f->cur.p.layout = fr->no_chroma ? DAV1D_PIXEL_LAYOUT_I400 :
+                      fr->ss_ver ? DAV1D_PIXEL_LAYOUT_I420 : fr->ss_hor ? DAV1D_PIXEL_LAYOUT_I422 : DAV1D_PIXEL_LAYOUT_I444;
+    const int ss_hor = !fr->no_chroma && fr->ss_hor, ss_ver = !fr->no_chroma && fr->ss_ver;
+    /* decode.c:3557-3570 */
+    f->bw = ((fr->w + 7) >> 3) << 1;
+    f->bh = ((fr->h + 7) >> 3) << 1;
+    f->sb128w = (f->bw + 31) >> 5;
+    f->sb128h = (f->bh + 31) >> 5;
+    f->sb_shift = 4;
+    f->sb_step = 16;
+    f->sbh = (f->bh + f->sb_step - 1) >> f->sb_shift;
+    f->b4_stride = (f->bw + 31) & ~31;
+    /* the superblock-row edge backups (decode.c:3045-3060) */
+    const size_t edge_px = (size_t)f->sb128w * 128 * (f->sbh + 1);
+    pixel *const edge_buf = calloc(3 * edge_px, sizeof(pixel));
+    f->ipred_edge[0] = edge_buf; f->ipred_edge[1] = edge_buf + edge_px; f->ipred_edge[2] = edge_buf + 2 * edge_px;
+    /* palettes per 8x8 (internal.h:285) */
+    const size_t n_pal = (size_t)(f->b4_stride >> 1) * (size_t)((f->bh + 33) >> 1);
+    f->frame_thread.pal = calloc(n_pal, sizeof(*f->frame_thread.pal));
+    BlockContext *const a = calloc((size_t)f->sb128w + 1, sizeof(*a));
+    f->a = a;
+
+    t->f = f;
+    t->ts = ts;
+    t->frame_thread.pass = 2;
+
+    /* per-block streams: pass 1 leaves cbi / cf / pal_idx as consecutive runs; a block's share is
+     * built right before the call */
+    int16_t cbi[3 * 256 + 8];
+    coef *const cfbuf = aligned_alloc(64, sizeof(coef) * 64 * 1024);
+    uint8_t *const idxbuf = aligned_alloc(64, 8192);
+    if (!edge_buf || !f->frame_thread.pal || !a || !cfbuf || !idxbuf) { ret = -12; goto done; }
+
+    int cur_tile = -1, cur_sbrow = -1;
+    for (int i = 0; i < fr->n_blocks; i++) {
+        const D1SynthBlock *const s = &fr->blocks[i];
+        if (!s->intra) { ret = -38; goto done; }
+        const int sbrow = s->by4 >> f->sb_shift;
+        if (s->tile != cur_tile || sbrow != cur_sbrow) {
+            if (cur_tile >= 0) {            /* decode.c:2677: end of a tile's superblock row */
+                t->by = cur_sbrow << f->sb_shift;
+                SUFFIX(dav1d_backup_ipred_edge)(t);
+            }
+            if (s->tile != cur_tile) {      /* decode.c:2593-2600, dav1d_reset_context: above context of the tile */
+                for (int x = s->tile_x0 >> 5; x <= (s->tile_x1 - 1) >> 5; x++) memset(&a[x], 0, sizeof(a[x]));
+            }
+            memset(&t->l, 0, sizeof(t->l)); /* decode.c:2560-2565: left context at the start of a superblock row */
+            ts->tiling.col_start = s->tile_x0; ts->tiling.col_end = s->tile_x1;
+            ts->tiling.row_start = s->tile_y0; ts->tiling.row_end = s->tile_y1;
+            cur_tile = s->tile; cur_sbrow = sbrow;
+        }
+        const int bs = bs_from_dims(s->w4, s->h4);
+        if (bs < 0) { ret = -22; goto done; }
+        Av1Block b;
+        memset(&b, 0, sizeof(b));
+        b.bs = bs; b.intra = 1; b.skip = s->skip; b.uvtx = s->uvtx;
+        b.y_mode = s->y_mode; b.uv_mode = s->uv_mode; b.tx = s->tx;
+        b.pal_sz[0] = s->pal_sz[0]; b.pal_sz[1] = s->pal_sz[1];
+        b.y_angle = s->y_angle; b.uv_angle = s->uv_angle;
+        b.cfl_alpha[0] = s->cfl_alpha[0]; b.cfl_alpha[1] = s->cfl_alpha[1];
+        t->bx = s->bx4; t->by = s->by4;
+        t->a = &a[s->bx4 >> 5];
+
+        /* the block's cbi / cf run: one entry per transform block with a residual field, in the
+         * order the block's operations were recorded (luma raster, then U raster, then V raster) */
+        int n_cbi = 0;
+        coef *cfp = cfbuf;
+        for (unsigned k = 0; k < s->n_ops; k++) {
+            const Dav1dCudaIntraDesc *const d = &fr->ops[s->first_op + k];
+            if (d->mode == DAV1D_CUDA_INTRA_PAL) continue;         /* whole-block palette prediction: no coefficients */
+            if (s->skip) continue;
+            const TxfmInfo *const td = &dav1d_txfm_dimensions[d->tx];
+            cbi[n_cbi++] = (int16_t)((d->eob << 5) + d->txtp);
+            if (d->eob >= 0) dense_coefs(cfp, fr, d);
+            cfp += imin(td->w, 8) * imin(td->h, 8) * 16;
+        }
+        ts->frame_thread[0].cbi = cbi;
+        ts->frame_thread[0].cf = cfbuf;
+        /* palette colours and indices where pass 1 puts them (recon_tmpl.c:1238-1241, 1430-1434) */
+        if (s->pal_sz[0] || s->pal_sz[1]) {
+            pixel (*const pal)[8] = f->frame_thread.pal[((s->by4 >> 1) + (s->bx4 & 1)) * (f->b4_stride >> 1) +
+                                                         ((s->bx4 >> 1) + (s->by4 & 1))];
+            for (int pl = 0; pl < 3; pl++)
+                if (s->pal_sz[pl ? 1 : 0])
+                    memcpy(pal[pl], (const pixel *)fr->pal + s->pal_off[pl], 8 * sizeof(pixel));
+            uint8_t *ip = idxbuf;
+            if (s->pal_sz[0]) {
+                memcpy(ip, fr->pal_idx + s->pal_idx_off[0], s->w4 * s->h4 * 8);
+                ip += s->w4 * s->h4 * 8;
+            }
+            if (s->pal_sz[1] && s->has_chroma) {
+                const int cbw4 = (s->w4 + ss_hor) >> ss_hor, cbh4 = (s->h4 + ss_ver) >> ss_ver;
+                memcpy(ip, fr->pal_idx + s->pal_idx_off[1], cbw4 * cbh4 * 8);
+            }
+            ts->frame_thread[0].pal_idx = idxbuf;
+        }
+        /* block-level edge flags as decode_b() gets them from the partition tree (intra_edge.h) */
+        const int ef = ((s->edge_tr & 1) ? EDGE_I444_TOP_HAS_RIGHT : 0) | ((s->edge_bl & 1) ? EDGE_I444_LEFT_HAS_BOTTOM : 0) |
+                       ((s->edge_tr & 2) ? (EDGE_I420_TOP_HAS_RIGHT | EDGE_I422_TOP_HAS_RIGHT) : 0) |
+                       ((s->edge_bl & 2) ? (EDGE_I420_LEFT_HAS_BOTTOM | EDGE_I422_LEFT_HAS_BOTTOM) : 0);
+        SUFFIX(dav1d_recon_b_intra)(t, bs, ef, &b);
+
+        /* decode.c:744-772: the block's modes into the above / left contexts */
+        const int bx4 = s->bx4 & 31, by4 = s->by4 & 31;
+        const int y_mode_nofilt = s->y_mode == FILTER_PRED ? DC_PRED : s->y_mode;
+        for (int x = 0; x < s->w4; x++) { t->a->mode[bx4 + x] = y_mode_nofilt; t->a->intra[bx4 + x] = 1; }
+        for (int y = 0; y < s->h4; y++) { t->l.mode[by4 + y] = y_mode_nofilt; t->l.intra[by4 + y] = 1; }
+        if (s->has_chroma) {
+            const int cbx4 = bx4 >> ss_hor, cby4 = by4 >> ss_ver;
+            const int cbw4 = (s->w4 + ss_hor) >> ss_hor, cbh4 = (s->h4 + ss_ver) >> ss_ver;
+            for (int x = 0; x < cbw4; x++) t->a->uvmode[cbx4 + x] = s->uv_mode;
+            for (int y = 0; y < cbh4; y++) t->l.uvmode[cby4 + y] = s->uv_mode;
+        }
+    }
+done:
+    free(idxbuf); free(cfbuf); free(a); free(f->frame_thread.pal); free(edge_buf);
+    free(t); free(ts); free(f);
+    return ret;
+}
+
+#if BITDEPTH == 8
+/* recon_tmpl.c also holds the inter and post-filter drivers; what they call outside the files this
+ * checker compiles is never reached from dav1d_recon_b_intra */
+#define STUB(name) void name(void) { abort(); }
+#include "ref_recon_stubs.h"
+#endif

@@ -54,3 +54,35 @@ def run_oracle(ref, hf, dst_planes, ref_planes_list):
     fn.restype = None
     fn(C.byref(of))
     return dst_planes
+
+
+class OracleReconFrame(C.Structure):
+    """oracle/ref_recon.c: input of the checker that runs the reference's own dav1d_recon_b_intra."""
+    _fields_ = [("dst", C.c_void_p * 3), ("dst_stride", C.c_ssize_t * 3),
+                ("w", C.c_int32), ("h", C.c_int32), ("ss_hor", C.c_int32), ("ss_ver", C.c_int32),
+                ("bitdepth_max", C.c_int32), ("no_chroma", C.c_int32), ("intra_edge_filter", C.c_int32),
+                ("blocks", C.c_void_p), ("n_blocks", C.c_int32),
+                ("ops", C.c_void_p), ("cf", C.c_void_p), ("pal", C.c_void_p), ("pal_idx", C.c_void_p)]
+
+
+def run_reference_driver(ref, hf, dst_planes):
+    """All-intra frame generated with real_blocks=1 through dav1d_recon_b_intra_{8,16}bpc, block by
+    block in decode order (modifies dst_planes in place)."""
+    assert hf.n_block_recs > 0, "generate the frame with real_blocks=1"
+    of = OracleReconFrame()
+    for pl, a in enumerate(dst_planes):
+        of.dst[pl] = a.ctypes.data
+        of.dst_stride[pl] = a.strides[0]
+    of.w, of.h, of.ss_hor, of.ss_ver = hf.w, hf.h, hf.ss_hor, hf.ss_ver
+    of.bitdepth_max, of.no_chroma = hf.bdmax, hf.no_chroma
+    of.intra_edge_filter = hf.params.edge_filter
+    of.blocks, of.n_blocks = hf.blocks.ctypes.data, hf.n_block_recs
+    for name, arr in (("ops", hf.intra), ("cf", hf.cf), ("pal", hf.pal), ("pal_idx", hf.pal_idx)):
+        setattr(of, name, arr.ctypes.data if arr.nbytes else None)
+    fn = getattr(ref.lib, "oracle_recon_intra_frame_16bpc" if hf.hbd else "oracle_recon_intra_frame_8bpc")
+    fn.argtypes = [C.POINTER(OracleReconFrame)]
+    fn.restype = C.c_int
+    r = fn(C.byref(of))
+    if r:
+        raise RuntimeError(f"oracle_recon_intra_frame: {r}")
+    return dst_planes

@@ -1,0 +1,98 @@
+"""Frame parity against the reference's OWN reconstruction driver.
+
+oracle/ref_recon.c calls dav1d_recon_b_intra_{8,16}bpc (src/recon_tmpl.c:1195-1596, compiled where it
+lies under /root/reference) block by block on Av1Block-style records of synthetic all-intra frames
+(generator option real_blocks: block contexts, chroma ownership of 4-pixel blocks, tile resets as
+src/decode.c does them).  Everything the driver decides - predictor and angle, edge flags per
+transform block, CfL / palette order, smooth-neighbour flags from the above / left contexts, tile
+edges, the superblock-row edge backup - is the reference's code; the descriptors the CUDA path
+consumes are recorded independently by the generator.
+
+ * CPU: the descriptor-driven oracle (oracle/ref_frame.c, the bench's CPU arm) reproduces the
+   reference driver bit for bit - i.e. the descriptors mean what recon_tmpl.c means;
+ * GPU: libdav1d_cuda.so reconstructs the same frames bit for bit."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+import _d1pkg
+import refframe
+
+pkg = _d1pkg.load_pkg()
+from dav1d_mirror_b200 import frame as F  # noqa: E402
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_driver_md5.json")
+
+CASES = {
+    # name: (w, h, bdmax, seed, kwargs) - all blocks intra, Av1Block semantics
+    "luma_8b": (256, 256, 0xff, 5, {"no_chroma": 1}),
+    "420_10b_cfl_pal_filter": (384, 256, 0x3ff, 6, {"p_palette": 0.1, "p_cfl": 0.6, "p_filter_intra": 0.2}),
+    "444_8b_cfl_pal": (256, 192, 0xff, 7, {"ss_hor": 0, "ss_ver": 0, "p_cfl": 0.4, "p_palette": 0.1}),
+    "422_12b_cfl_filter": (256, 192, 0xfff, 8, {"ss_hor": 1, "ss_ver": 0, "p_cfl": 0.5, "p_filter_intra": 0.1}),
+    "420_10b_tiles_2x2": (384, 256, 0x3ff, 9, {"tile_cols": 2, "tile_rows": 2, "p_cfl": 0.5}),
+    "420_8b_ragged": (328, 200, 0xff, 10, {"p_cfl": 0.5, "p_palette": 0.1}),
+    "420_12b_no_edge_filter_split": (320, 192, 0xfff, 11, {"edge_filter": 0, "p_tx_split": 1.0, "p_residual": 1.0}),
+    "444_10b_tiles_3x2_no_residual": (448, 256, 0x3ff, 12, {"ss_hor": 0, "ss_ver": 0, "tile_cols": 3, "tile_rows": 2,
+                                                            "p_residual": 0.0, "p_palette": 0.15}),
+}
+
+
+def make(name):
+    w, h, bd, seed, kw = CASES[name]
+    hf = F.HostFrame(w, h, bd, seed, p_intra=1.0, real_blocks=1, **kw)
+    init = F.random_planes(hf, seed * 10 + 5)
+    return hf, init
+
+
+def md5_planes(planes):
+    m = hashlib.md5()
+    for p in planes:
+        m.update(np.ascontiguousarray(p).tobytes())
+    return m.hexdigest()
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_descriptors_mean_what_the_reference_driver_means(ref, name):
+    hf, init = make(name)
+    want = refframe.run_reference_driver(ref, hf, [p.copy() for p in init])
+    got = refframe.run_oracle(ref, hf, [p.copy() for p in init], [])
+    for pl, (a, b) in enumerate(zip(want, got)):
+        bad = np.argwhere(a != b)
+        assert bad.size == 0, f"{name}: plane {pl}: {len(bad)} pixels differ, first at (y,x)={bad[0]}"
+    with open(GOLDEN) as f:
+        assert md5_planes(want) == json.load(f)[name], name      # drift of generator / reference build
+
+
+def test_random_all_intra_frames_against_the_reference_driver(ref):
+    rng = np.random.default_rng(20261019)
+    for k in range(12):
+        lay = [(1, 1), (1, 0), (0, 0)][rng.integers(3)]
+        kw = dict(ss_hor=lay[0], ss_ver=lay[1], p_cfl=float(rng.choice([0, 0.5])), p_palette=float(rng.choice([0, 0.15])),
+                  p_filter_intra=float(rng.choice([0, 0.2])), tile_cols=int(rng.integers(1, 4)),
+                  tile_rows=int(rng.integers(1, 3)), p_tx_split=float(rng.choice([0, 0.5, 1.0])),
+                  p_residual=float(rng.choice([0.3, 0.6, 1.0])), edge_filter=int(rng.integers(2)))
+        w, h = int(rng.integers(8, 60)) * 8, int(rng.integers(8, 40)) * 8
+        bd = [0xff, 0x3ff, 0xfff][rng.integers(3)]
+        hf = F.HostFrame(w, h, bd, 500 + k, p_intra=1.0, real_blocks=1, **kw)
+        init = F.random_planes(hf, 9000 + k)
+        want = refframe.run_reference_driver(ref, hf, [p.copy() for p in init])
+        got = refframe.run_oracle(ref, hf, [p.copy() for p in init], [])
+        assert all(np.array_equal(a, b) for a, b in zip(want, got)), (k, w, h, hex(bd), kw)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", list(CASES))
+def test_cuda_frame_equals_the_reference_driver(ref, name):
+    import test_frame
+    hf, init = make(name)
+    want = refframe.run_reference_driver(ref, hf, [p.copy() for p in init])
+    for record in (False, True):
+        if record:
+            hf.record_levels()
+        got = test_frame.run_gpu(hf, [], init, use_graph=False)
+        for pl, (a, b) in enumerate(zip(want, got)):
+            bad = np.argwhere(a != b)
+            assert bad.size == 0, f"{name} (recorded levels: {record}): plane {pl}: {len(bad)} pixels differ, first {bad[0]}"

@@ -23,3 +23,15 @@ for name, (w, h, bd, seed, kw) in T.CASES.items():
     print(name, out[name], "blocks", hf.n_blocks, "intra", hf.n_intra_blocks, "intra ops", hf.n_intra)
 with open(T.GOLDEN, "w") as f:
     json.dump(out, f, indent=1, sort_keys=True)
+
+# frames reconstructed by the reference's own driver (dav1d_recon_b_intra, oracle/ref_recon.c)
+import refframe  # noqa: E402
+import test_reference_driver as R  # noqa: E402
+
+out = {}
+for name in R.CASES:
+    hf, init = R.make(name)
+    out[name] = R.md5_planes(refframe.run_reference_driver(ref, hf, [p.copy() for p in init]))
+    print(name, out[name], "blocks", hf.n_block_recs, "intra ops", hf.n_intra)
+with open(R.GOLDEN, "w") as f:
+    json.dump(out, f, indent=1, sort_keys=True)
