@@ -12,6 +12,7 @@ namespace d1 {
 
 constexpr int ITX2_WARPS = 4;
 constexpr int ITX2_INTS_SMALL = 2 * 16 * 17;   // per warp: sizes up to 16x16 (two 16x16 per warp)
+constexpr int ITX2_INTS_MID = 32 * 33;         // per warp: one block of up to 32x32
 constexpr int ITX2_INTS_BIG = 64 * 65;         // per warp: one block of up to 64x64
 
 // Three ways to name the work of a launch:
@@ -41,14 +42,24 @@ HD int itx2_group(const int tx) {              // lanes per block
     return sh > sw ? sh : sw;
 }
 
-template <typename pixel, bool BIG>
-__global__ void __launch_bounds__(ITX2_WARPS * 32, BIG ? 3 : 8) itx2_task_kernel(const __grid_constant__ Itx2Args a) {
+// CLS: 0 sizes up to 16x16 (several blocks per warp), 1 larger sizes without a 64-point side, 2 the
+// sizes with a 64-point side.  The task list of the larger sizes is handed to both CLS 1 and CLS 2;
+// each takes its own tasks (the 64-point class needs four times the shared memory and twice the
+// registers of the 32-point one, and would halve its occupancy).
+template <int CLS> struct Itx2Cls {
+    static constexpr int MAXN = CLS == 0 ? 16 : CLS == 1 ? 32 : 64;
+    static constexpr int INTS = CLS == 0 ? ITX2_INTS_SMALL : CLS == 1 ? ITX2_INTS_MID : ITX2_INTS_BIG;
+    static constexpr int MIN_BLOCKS = CLS == 0 ? 8 : CLS == 1 ? 5 : 3;
+};
+template <typename pixel, int CLS>
+__global__ void __launch_bounds__(ITX2_WARPS * 32, Itx2Cls<CLS>::MIN_BLOCKS) itx2_task_kernel(const __grid_constant__ Itx2Args a) {
+    constexpr bool BIG = CLS > 0;
     extern __shared__ int itx2_smem[];
     typedef typename PxTraits<pixel>::coef coef;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int t = blockIdx.x * ITX2_WARPS + warp;
     if (t >= a.n_tasks) return;
-    int *smem = itx2_smem + warp * (BIG ? ITX2_INTS_BIG : ITX2_INTS_SMALL);
+    int *smem = itx2_smem + warp * Itx2Cls<CLS>::INTS;
     const PicView *pic = &a.pic, *rpic = &a.res;
     void *cf = a.cf;
     int first, tx, cnt;
@@ -67,6 +78,10 @@ __global__ void __launch_bounds__(ITX2_WARPS * 32, BIG ? 3 : 8) itx2_task_kernel
         first = a.cls_desc[tx] + (t - a.cls_task[tx]) * bpw;
         cnt = imin(bpw, a.cls_desc[tx + 1] - first);
     }
+    if (CLS > 0) {
+        const TxDim td = tx_dim(tx);
+        if ((td.w == 64 || td.h == 64) != (CLS == 2)) return;      // the other large class takes it
+    }
     const int G = itx2_group(tx);
     const int grp = lane / G, gl = lane % G;
     const bool active = grp < cnt;
@@ -83,26 +98,32 @@ __global__ void __launch_bounds__(ITX2_WARPS * 32, BIG ? 3 : 8) itx2_task_kernel
         rstride = (int)(rv.stride / 2);
         res = (int16_t *)rv.data + (int64_t)d.y * rstride + d.x;
     }
-    itx2_block<pixel, BIG ? 64 : 16>(active, gl, G, smem + grp * itx2_tile_ints(tx), (coef *)cf + d.coef_off, tx,
+    itx2_block<pixel, Itx2Cls<CLS>::MAXN>(active, gl, G, smem + grp * itx2_tile_ints(tx), (coef *)cf + d.coef_off, tx,
                                      d.txtp, d.eob, d.cw4, d.ch4, dst, dstride, res, rstride, pic->bdmax,
                                      a.zero_coefs != 0);
 }
 
+template <typename pixel, int CLS>
+static int itx2_launch_cls(Itx2Args a, int n, cudaStream_t st) {
+    a.n_tasks = n;
+    const int grid = (n + ITX2_WARPS - 1) / ITX2_WARPS;
+    const size_t smem = (size_t)ITX2_WARPS * Itx2Cls<CLS>::INTS * sizeof(int);
+    if (CLS == 2) {      // more than the default 48 KB (the per-call surface launches without a context)
+        static std::once_flag once;
+        std::call_once(once, [&] {
+            cudaFuncSetAttribute(itx2_task_kernel<pixel, CLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        });
+    }
+    itx2_task_kernel<pixel, CLS><<<grid, ITX2_WARPS * 32, smem, st>>>(a);
+    count_launch();
+    return cuda_ok(cudaGetLastError(), "itx2_task_kernel") ? 0 : -5;
+}
 template <typename pixel, bool BIG>
 static int itx2_launch_one(Itx2Args a, int n, cudaStream_t st) {
     if (n <= 0) return 0;
-    a.n_tasks = n;
-    const int grid = (n + ITX2_WARPS - 1) / ITX2_WARPS;
-    const size_t smem = (size_t)ITX2_WARPS * (BIG ? ITX2_INTS_BIG : ITX2_INTS_SMALL) * sizeof(int);
-    if (BIG) {      // more than the default 48 KB (the per-call surface launches without a context)
-        static std::once_flag once;
-        std::call_once(once, [&] {
-            cudaFuncSetAttribute(itx2_task_kernel<pixel, BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        });
-    }
-    itx2_task_kernel<pixel, BIG><<<grid, ITX2_WARPS * 32, smem, st>>>(a);
-    count_launch();
-    return cuda_ok(cudaGetLastError(), "itx2_task_kernel") ? 0 : -5;
+    if (!BIG) return itx2_launch_cls<pixel, 0>(a, n, st);
+    const int r = itx2_launch_cls<pixel, 1>(a, n, st);
+    return r ? r : itx2_launch_cls<pixel, 2>(a, n, st);
 }
 
 static int itx2_launch_both(Itx2Args a, int n_small, int n_big, bool hbd, cudaStream_t st_small, cudaStream_t st_big) {
