@@ -265,3 +265,36 @@ def test_empty_batch_is_a_no_op(ref):
     finally:
         df.close()
         pkg.lib().dav1d_cuda_close(ctx)
+
+
+@pytest.mark.gpu
+def test_inconsistent_descriptors_are_reported_not_hidden():
+    """Two intra-class operations that both claim to be the (first) writer of the same cells: whatever
+    reads those cells can never learn their level.  The launch must terminate, dav1d_cuda_synchronize()
+    must return an error (-EIO) and the sticky error must be set - never a silently wrong frame."""
+    import ctypes as C
+    L = pkg.lib()
+    hf = F.HostFrame(256, 192, 0x3ff, 31, p_intra=1.0)
+    d = hf.intra.reshape(-1, 40)
+    # duplicate a regular prediction in the middle of the frame (decode order kept for everything else)
+    k = next(i for i in range(len(d) // 3, len(d)) if d[i, 15] <= 12 and d[i, 0] > 8 and d[i, 2] > 8)
+    hf.intra = np.concatenate([d[:k + 1], d[k:k + 1], d[k + 1:]]).reshape(-1).copy()
+    hf.n_intra += 1
+    hf.intra_itx = hf.intra_itx[:0]            # keep it simple: no residual pre-pass lists
+    hf.intra_itx_class_count = [0] * 19
+    hf.intra_itx_tasks = hf.intra_itx_tasks[:4] * 0
+    hf.n_intra_itx_tasks = (0, 0)
+    ctx = F.open_context(0)
+    df = F.DeviceFrame(ctx, hf, n_refs=0)
+    try:
+        df.upload_descriptors()
+        df.upload_picture(df.dst, F.random_planes(hf, 1))
+        df.submit()
+        r = L.dav1d_cuda_synchronize(ctx)
+        assert r != 0 and L.dav1d_cuda_last_error() != 0
+        L.dav1d_cuda_clear_error()
+        assert L.dav1d_cuda_synchronize(ctx) == 0      # the status word was consumed; the context is usable again
+    finally:
+        df.close()
+        L.dav1d_cuda_close(ctx)
+        L.dav1d_cuda_clear_error()
