@@ -255,7 +255,8 @@ DEV void exec_done(const Grp g, const Intra2Frame &a, const Dav1dCudaIntraDesc &
 
 template <typename pixel>
 __device__ __noinline__ bool intra_exec(const Grp g, const Intra2Frame &a, const Dav1dCudaIntraDesc *dp,
-                                        pixel *edge, pixel *scratch, const int z2_centre, uint16_t *tile)
+                                        pixel *edge, pixel *scratch, const int z2_centre, uint16_t *tile,
+                                        const bool settled)
 {
     // the descriptor in registers: five 64-bit loads, every lane of the group the same address
     Dav1dCudaIntraDesc d;
@@ -291,7 +292,8 @@ __device__ __noinline__ bool intra_exec(const Grp g, const Intra2Frame &a, const
             r0.x = t.x; r0.y = t.y;
         }
     }
-    const bool ok = exec_wait(g, a, d);
+    // settled: every lower level is complete - nothing this operation reads can still change
+    const bool ok = settled || exec_wait(g, a, d);
     if (ok) {
         const int have_left = d.x4 > d.tile_x4_start, have_top = d.y4 > d.tile_y4_start;
         // stage A: 0 predictor (P), 1 intrabc, 2 nothing (the tile is filled / the current picture is the source)
@@ -471,7 +473,7 @@ struct ExecCtl {
     unsigned ticket;                    // next chunk of four slots to claim
     unsigned n_chunks;                  // written by the scan
     unsigned max_level;
-    unsigned pad;
+    int levels_done;                    // all chunks of the levels up to this one are complete (-1: none yet)
 };
 struct SchedArgs {
     Intra2Args g;
@@ -479,6 +481,8 @@ struct SchedArgs {
     unsigned *key;                      // per operation of the group: level * 32 + bin
     unsigned *bins;                     // MAX_LEVELS * N_BINS counters -> slot offsets -> cursors
     uint8_t *thin;                      // per level: every operation gets a whole warp
+    unsigned *lvl_end;                  // per level: one past its last chunk
+    unsigned *lvl_left;                 // per level: chunks that are not complete yet
     unsigned *slots;                    // the sorted list: operation ids, OP_EMPTY padding
     unsigned n_slots_cap;
 };
@@ -731,6 +735,8 @@ __global__ void __launch_bounds__(1024) intra_scan_kernel(const __grid_constant_
         unsigned run = before + incl - mine;          // first slot of level l
         if (l < n_lev) {
             a.thin[l] = thin ? 1 : 0;
+            a.lvl_end[l] = (run + mine) >> 5;
+            a.lvl_left[l] = mine >> 5;
             unsigned *b = a.bins + (size_t)l * N_BINS;
             for (int sc = 0; sc < 5; sc++) {
                 const unsigned per = bin_slots(sc * 32, thin), end = run + ((per * nc[sc] + 31u) & ~31u);
@@ -746,12 +752,13 @@ __global__ void __launch_bounds__(1024) intra_scan_kernel(const __grid_constant_
     if (tid == 0) {
         a.ctl->n_chunks = min(s_carry, a.n_slots_cap) >> 5;
         a.ctl->ticket = 0;
+        a.ctl->levels_done = -1;
     }
 }
 
 // ---- 4. execute
 template <typename pixel>
-__global__ void __launch_bounds__(R_WARPS * 32, 4) intra_exec_kernel(const __grid_constant__ SchedArgs a) {
+__global__ void __launch_bounds__(R_WARPS * 32, 3) intra_exec_kernel(const __grid_constant__ SchedArgs a) {
     extern __shared__ __align__(16) uint8_t exec_smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     ExecSmem<pixel> *sm = (ExecSmem<pixel> *)exec_smem_raw + warp;
@@ -759,27 +766,45 @@ __global__ void __launch_bounds__(R_WARPS * 32, 4) intra_exec_kernel(const __gri
     // a warp claims one chunk (32 slots) at a time, the next claim is in flight while it works
     unsigned nxt = 0;
     if (lane == 0) nxt = atomicAdd(&a.ctl->ticket, 1u);
+    const int n_lev = (int)min(__ldcg(&a.ctl->max_level) + 1u, (unsigned)MAX_LEVELS);
+    int level = 0, known_done = -1;
+    unsigned level_end = __ldcg(a.lvl_end);
     for (;;) {
         const unsigned c = __shfl_sync(0xffffffffu, nxt, 0);
         if (c >= n_chunks) break;
         const unsigned sl = __ldcg(a.slots + 32 * c + lane);
         if (lane == 0) nxt = atomicAdd(&a.ctl->ticket, 1u);
-        // lanes per operation = spacing of the used slots (a lone operation gets the whole warp)
-        if (!__ballot_sync(0xffffffffu, sl != OP_EMPTY)) continue;
-        const unsigned at = __reduce_or_sync(0xffffffffu, sl != OP_EMPTY ? (unsigned)lane : 0u);
-        const int G = at ? (int)(at & (0u - at)) : 32;
-        const int gi = lane / G;
-        const unsigned id = __shfl_sync(0xffffffffu, sl, gi * G);
+        // the chunk's level (claims only move forward); are all lower levels complete?  Then nothing
+        // the chunk's operations read can still change and they need not look at the cell counts.
+        while (c >= level_end && level + 1 < n_lev) level_end = __ldcg(a.lvl_end + ++level);
+        if (known_done < level - 1) known_done = (int)ld_acquire_u32((const unsigned *)&a.ctl->levels_done);
+        const bool settled = known_done >= level - 1;
         bool ok = true;
-        if (id != OP_EMPTY) {
-            const Grp g = Grp{ lane & (G - 1), G, G == 32 ? 0xffffffffu : ((1u << G) - 1u) << (lane & ~(G - 1)) };
-            const GrpSmem gs = grp_smem<pixel>(G);
-            const Intra2Frame &f = a.g.f[op_frame(id)];
-            pixel *es = sm->es + gi * gs.es_stride;
-            ok = intra_exec<pixel>(g, f, f.descs + op_index(id), es + gs.centre, es + gs.scr, gs.z2c, sm->tile + gi * gs.tile_stride);
+        if (__ballot_sync(0xffffffffu, sl != OP_EMPTY)) {
+            // lanes per operation = spacing of the used slots (a lone operation gets the whole warp)
+            const unsigned at = __reduce_or_sync(0xffffffffu, sl != OP_EMPTY ? (unsigned)lane : 0u);
+            const int G = at ? (int)(at & (0u - at)) : 32;
+            const int gi = lane / G;
+            const unsigned id = __shfl_sync(0xffffffffu, sl, gi * G);
+            if (id != OP_EMPTY) {
+                const Grp g = Grp{ lane & (G - 1), G, G == 32 ? 0xffffffffu : ((1u << G) - 1u) << (lane & ~(G - 1)) };
+                const GrpSmem gs = grp_smem<pixel>(G);
+                const Intra2Frame &f = a.g.f[op_frame(id)];
+                pixel *es = sm->es + gi * gs.es_stride;
+                ok = intra_exec<pixel>(g, f, f.descs + op_index(id), es + gs.centre, es + gs.scr, gs.z2c,
+                                       sm->tile + gi * gs.tile_stride, settled);
+            }
         }
         if (!ok) atomicOr(a.g.status, ST_STUCK);
         __syncwarp();
+        // the chunk is complete (every lane fenced its stores before its cells were counted down):
+        // one chunk less in its level; whoever completes a level moves levels_done forward
+        if (lane == 0 && atomicSub(a.lvl_left + level, 1u) == 1u) {
+            __threadfence();
+            int d = (int)ld_acquire_u32((const unsigned *)&a.ctl->levels_done);
+            while (d + 1 < n_lev && ld_acquire_u32(a.lvl_left + d + 1) == 0u) d++;
+            atomicMax(&a.ctl->levels_done, d);
+        }
     }
 }
 
@@ -875,7 +900,7 @@ static bool join_aux(Dav1dCudaContext *c, cudaStream_t st) {
 // and the sorted slot list.  One per context, grown on demand outside any stream capture;
 // submissions of a context are ordered on its stream.
 static size_t al256(size_t v) { return (v + 255) & ~(size_t)255; }
-static size_t ws_hdr_bytes() { return al256(sizeof(ExecCtl)) + al256((size_t)MAX_LEVELS * N_BINS * 4) + al256(MAX_LEVELS); }
+static size_t ws_hdr_bytes() { return al256(sizeof(ExecCtl)) + al256((size_t)MAX_LEVELS * N_BINS * 4) + al256(MAX_LEVELS) + 2 * al256((size_t)MAX_LEVELS * 4); }
 static size_t ws_slots_cap(size_t total) { return 32 * total + 160 * (size_t)MAX_LEVELS; }
 static size_t ws_need(size_t total) { return ws_hdr_bytes() + al256(total * 4) + al256(ws_slots_cap(total) * 4); }
 static size_t group_ops(const Dav1dCudaReconBatch *const *bs, int n) {
@@ -964,6 +989,8 @@ static int group_submit_on(Dav1dCudaContext *c, const Dav1dCudaReconBatch *const
         sa.ctl = (ExecCtl *)ws;
         sa.bins = (unsigned *)(ws + al256(sizeof(ExecCtl)));
         sa.thin = ws + al256(sizeof(ExecCtl)) + al256((size_t)MAX_LEVELS * N_BINS * 4);
+        sa.lvl_end = (unsigned *)(sa.thin + al256(MAX_LEVELS));
+        sa.lvl_left = sa.lvl_end + al256((size_t)MAX_LEVELS * 4) / 4;
         sa.key = (unsigned *)(ws + ws_hdr_bytes());
         sa.slots = (unsigned *)(ws + ws_hdr_bytes() + al256(total * 4));
         sa.n_slots_cap = (unsigned)std::min<size_t>(ws_slots_cap(total), 0xfffffff0u);
