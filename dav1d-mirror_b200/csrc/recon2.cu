@@ -778,6 +778,12 @@ __global__ void __launch_bounds__(R_WARPS * 32, 3) intra_exec_kernel(const __gri
         // the chunk's operations read can still change and they need not look at the cell counts.
         while (c >= level_end && level + 1 < n_lev) level_end = __ldcg(a.lvl_end + ++level);
         if (known_done < level - 1) known_done = (int)ld_acquire_u32((const unsigned *)&a.ctl->levels_done);
+        // far ahead of the wavefront (the thin tail: more warps than work): sleep on the one progress word
+        // instead of polling cells; the cell counts are only looked at within one level of the front
+        for (int naps = 0; known_done < level - 2 && naps < (1 << 15); naps++) {
+            __nanosleep(1500);
+            known_done = (int)ld_acquire_u32((const unsigned *)&a.ctl->levels_done);
+        }
         const bool settled = known_done >= level - 1;
         bool ok = true;
         if (__ballot_sync(0xffffffffu, sl != OP_EMPTY)) {
