@@ -13,7 +13,7 @@ KERNELS = ["mc_put_kernelItLb0", "mc_put_kernelItLb1", "mc_compound_kernelItLb0"
            "itx2_task_kernelItLi0", "itx2_task_kernelItLi1", "itx2_task_kernelItLi2",
            "intra_exec_kernelIt", "intra_levels_kernel", "intra_sort_kernelILb0", "intra_scan_kernel",
            "intra_mark_kernel"]
-SHOW = re.compile(r"\b(LDGSTS|LDGDEPBAR|DEPBAR|IDP|ATOMG|ATOMS|RED|MEMBAR|NANOSLEEP|UCGABAR|CGABAR|UBLKCP|UTMALDG|SYNCS|"
+SHOW = re.compile(r"\b(LDGSTS|LDGDEPBAR|DEPBAR|IDP|ATOMG|ATOMS|RED|MEMBAR|NANOSLEEP|UCGABAR_ARV|UCGABAR_WAIT|CGAERRBAR|CCTL|UBLKCP|UTMALDG|SYNCS|"
                   r"LD\.E\.[A-Z0-9.]*STRONG|REDUX|MATCH|VOTE|SHFL|PRMT|SHF)\b")
 ins = re.compile(r"^\s+/\*([0-9a-f]+)\*/\s+(.*?);")
 for obj in sorted(os.listdir(BUILD)):
