@@ -51,6 +51,19 @@ class McDesc(C.Structure):
                 ("aux_off", C.c_uint32)]
 
 
+class Dav1dPictureMirror(C.Structure):
+    """== Dav1dPicture (include/dav1d/picture.h:53-105): what the allocator callbacks fill."""
+    _fields_ = [("seq_hdr", C.c_void_p), ("frame_hdr", C.c_void_p), ("data", C.c_void_p * 3),
+                ("stride", C.c_ssize_t * 2), ("w", C.c_int32), ("h", C.c_int32), ("layout", C.c_int32),
+                ("bpc", C.c_int32), ("opaque", C.c_uint64 * 24), ("allocator_data", C.c_void_p)]
+
+
+class PicAllocator(C.Structure):
+    _fields_ = [("cookie", C.c_void_p),
+                ("alloc_picture_callback", C.CFUNCTYPE(C.c_int, C.POINTER(Dav1dPictureMirror), C.c_void_p)),
+                ("release_picture_callback", C.CFUNCTYPE(None, C.POINTER(Dav1dPictureMirror), C.c_void_p))]
+
+
 class Plane(C.Structure):
     _fields_ = [("data", C.c_void_p), ("stride", C.c_ssize_t), ("w", C.c_int32), ("h", C.c_int32)]
 
@@ -151,6 +164,11 @@ def bind_frame_api(L):
                                                C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     L.dav1d_cuda_warp_batch.argtypes = [C.c_void_p, C.POINTER(Picture), C.POINTER(C.POINTER(Picture)),
                                         C.c_void_p, C.c_int]
+    L.dav1d_cuda_pic_allocator_init.argtypes = [C.c_void_p, C.POINTER(PicAllocator)]
+    L.dav1d_cuda_picture_of.argtypes = [C.POINTER(Dav1dPictureMirror)]
+    L.dav1d_cuda_picture_of.restype = C.POINTER(Picture)
+    L.dav1d_cuda_picture_to_host.argtypes = [C.c_void_p, C.POINTER(Dav1dPictureMirror)]
+    L.dav1d_cuda_picture_to_device.argtypes = [C.c_void_p, C.POINTER(Dav1dPictureMirror)]
     L.dav1d_cuda_intra_cellmap_bytes.restype = C.c_size_t
     L.dav1d_cuda_intra_cellmap_bytes.argtypes = [C.c_int] * 4
     L.dav1d_cuda_intra_levels.argtypes = [C.c_void_p] + [C.c_int] * 5

@@ -200,6 +200,89 @@ int dav1d_cuda_picture_alloc(Dav1dCudaContext *c, Dav1dCudaPicture *pic,
     return 0;
 }
 
+// ---- Dav1dPicAllocator seam: pictures with a twin in HBM and one in pinned host memory
+namespace {
+struct TwinPicture {
+    uint32_t magic;
+    Dav1dCudaContext *ctx;
+    Dav1dCudaPicture dev;
+    uint8_t *host;           // pinned; data[] of the Dav1dPicture point into it
+    size_t bytes;            // of either copy (planes + padding)
+};
+constexpr uint32_t TWIN_MAGIC = 0x44315450u;     // "D1TP"
+
+int twin_alloc(Dav1dCudaDav1dPicture *p, void *cookie) {
+    Dav1dCudaContext *c = (Dav1dCudaContext *)cookie;
+    if (!p || !c || p->p.w <= 0 || p->p.h <= 0 || (p->p.bpc != 8 && p->p.bpc != 10 && p->p.bpc != 12)) return -22;
+    const int layout = p->p.layout;                    // I400 0, I420 1, I422 2, I444 3
+    const int has_chroma = layout != 0;
+    const int ss_ver = layout == 1, ss_hor = layout != 3;
+    TwinPicture *t = new TwinPicture();
+    t->magic = TWIN_MAGIC; t->ctx = c;
+    // the device copy: same rules as src/picture.c:46-84 (dav1d_cuda_picture_alloc)
+    const int r = dav1d_cuda_picture_alloc(c, &t->dev, p->p.w, p->p.h, ss_hor, ss_ver, (1 << p->p.bpc) - 1);
+    if (r) { delete t; return -12; }
+    const int aligned_h = (p->p.h + 127) & ~127;
+    const ptrdiff_t y_stride = t->dev.p[0].stride, uv_stride = has_chroma ? t->dev.p[1].stride : 0;
+    const size_t y_sz = (size_t)y_stride * aligned_h, uv_sz = (size_t)t->dev.p[1].stride * (aligned_h >> ss_ver);
+    t->bytes = y_sz + 2 * uv_sz;
+    if (!cuda_ok(cudaMallocHost((void **)&t->host, t->bytes + 64), "cudaMallocHost(picture)")) {
+        dav1d_cuda_picture_free(c, &t->dev);
+        delete t;
+        return -12;
+    }
+    memset(t->host, 0, t->bytes + 64);
+    p->stride[0] = y_stride;
+    p->stride[1] = uv_stride;
+    p->data[0] = t->host;                               // cudaMallocHost memory is page-aligned (>= DAV1D_PICTURE_ALIGNMENT)
+    p->data[1] = has_chroma ? t->host + y_sz : nullptr;
+    p->data[2] = has_chroma ? t->host + y_sz + uv_sz : nullptr;
+    p->allocator_data = t;
+    return 0;
+}
+void twin_release(Dav1dCudaDav1dPicture *p, void *) {
+    TwinPicture *t = p ? (TwinPicture *)p->allocator_data : nullptr;
+    if (!t || t->magic != TWIN_MAGIC) return;
+    cudaSetDevice(t->ctx->device);
+    cudaStreamSynchronize(t->ctx->stream);              // a copy or a batch may still use the picture
+    dav1d_cuda_picture_free(t->ctx, &t->dev);
+    cudaFreeHost(t->host);
+    t->magic = 0;
+    delete t;
+    p->allocator_data = nullptr;
+}
+TwinPicture *twin_of(const Dav1dCudaDav1dPicture *p) {
+    TwinPicture *t = p ? (TwinPicture *)p->allocator_data : nullptr;
+    return t && t->magic == TWIN_MAGIC ? t : nullptr;
+}
+}  // namespace
+
+int dav1d_cuda_pic_allocator_init(Dav1dCudaContext *c, Dav1dCudaPicAllocator *a) {
+    if (!c || !a) return -22;
+    a->cookie = c;
+    a->alloc_picture_callback = twin_alloc;
+    a->release_picture_callback = twin_release;
+    return 0;
+}
+const Dav1dCudaPicture *dav1d_cuda_picture_of(const Dav1dCudaDav1dPicture *pic) {
+    TwinPicture *t = twin_of(pic);
+    return t ? &t->dev : nullptr;
+}
+int dav1d_cuda_picture_to_host(Dav1dCudaContext *c, const Dav1dCudaDav1dPicture *pic) {
+    TwinPicture *t = twin_of(pic);
+    if (!c || !t) return -22;
+    D1_CHECK(cudaSetDevice(c->device));
+    D1_CHECK(cudaMemcpyAsync(t->host, t->dev.p[0].data, t->bytes, cudaMemcpyDeviceToHost, c->stream));
+    return 0;
+}
+int dav1d_cuda_picture_to_device(Dav1dCudaContext *c, const Dav1dCudaDav1dPicture *pic) {
+    TwinPicture *t = twin_of(pic);
+    if (!c || !t) return -22;
+    D1_CHECK(cudaSetDevice(c->device));
+    D1_CHECK(cudaMemcpyAsync(t->dev.p[0].data, t->host, t->bytes, cudaMemcpyHostToDevice, c->stream));
+    return 0;
+}
+
 void dav1d_cuda_picture_free(Dav1dCudaContext *c, Dav1dCudaPicture *pic) {
     (void)c;
     if (pic && pic->p[0].data) cudaFree(pic->p[0].data);

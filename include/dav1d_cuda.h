@@ -290,6 +290,35 @@ DAV1D_CUDA_API int  dav1d_cuda_picture_upload(Dav1dCudaContext *c, const Dav1dCu
 DAV1D_CUDA_API int  dav1d_cuda_picture_download(Dav1dCudaContext *c, const Dav1dCudaPicture *pic, int plane,
                                                 void *host, ptrdiff_t host_stride);
 
+/* ---- Dav1dPicAllocator seam (include/dav1d/picture.h:107-146, src/picture.c:46-88).
+ * dav1d asks its allocator for every frame (dav1d_thread_picture_alloc -> picture_alloc_with_edges ->
+ * allocator.alloc_picture_callback).  dav1d_cuda_pic_allocator_init() fills a Dav1dPicAllocator whose
+ * pictures live TWICE with the geometry of the default allocator: in HBM (the Dav1dCudaPicture the
+ * batches reconstruct into and predict from) and in pinned host memory (what `data[]` points to, so
+ * that dav1d_get_picture() consumers and the CPU post-filters keep working).  The two are moved with
+ * ONE copy (same strides, one allocation each):
+ *   dav1d_cuda_picture_to_host()    after reconstruction, before the CPU reads the frame;
+ *   dav1d_cuda_picture_to_device()  after the CPU changed it (post-filters), before it serves as a reference.
+ * Dav1dSettings.allocator = *(Dav1dPicAllocator *) &a;  the structs below are layout-identical mirrors. */
+typedef struct Dav1dCudaDav1dPicture {        /* == Dav1dPicture, include/dav1d/picture.h:53-105 (272 bytes) */
+    void *seq_hdr, *frame_hdr;
+    void *data[3];
+    ptrdiff_t stride[2];
+    struct { int32_t w, h, layout /* enum Dav1dPixelLayout: I400 0, I420 1, I422 2, I444 3 */, bpc; } p;
+    uint64_t opaque[24];                      /* m, metadata, reference bookkeeping: not touched */
+    void *allocator_data;
+} Dav1dCudaDav1dPicture;
+typedef struct Dav1dCudaPicAllocator {        /* == Dav1dPicAllocator */
+    void *cookie;
+    int (*alloc_picture_callback)(Dav1dCudaDav1dPicture *pic, void *cookie);
+    void (*release_picture_callback)(Dav1dCudaDav1dPicture *pic, void *cookie);
+} Dav1dCudaPicAllocator;
+DAV1D_CUDA_API int dav1d_cuda_pic_allocator_init(Dav1dCudaContext *c, Dav1dCudaPicAllocator *a);
+/* The HBM twin of a picture this allocator handed out (NULL for any other picture). */
+DAV1D_CUDA_API const Dav1dCudaPicture *dav1d_cuda_picture_of(const Dav1dCudaDav1dPicture *pic);
+DAV1D_CUDA_API int dav1d_cuda_picture_to_host(Dav1dCudaContext *c, const Dav1dCudaDav1dPicture *pic);
+DAV1D_CUDA_API int dav1d_cuda_picture_to_device(Dav1dCudaContext *c, const Dav1dCudaDav1dPicture *pic);
+
 /* Operator-class launches.  All pointers inside the argument list that are
  * documented as "device" must be device pointers; the calls are asynchronous
  * on the context's stream. */

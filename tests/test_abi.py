@@ -72,3 +72,45 @@ int main(void) {
             C.sizeof(B.Picture), C.sizeof(B.ReconBatch), B.ReconBatch.mc_obmc.offset, B.ReconBatch.itx_tasks.offset,
             B.ReconBatch.intra_itx.offset, B.ReconBatch.intra_cellmap.offset, B.IntraDesc.cw4.offset]
     assert got == want, (got, want)
+
+
+def test_picture_mirror_matches_the_reference_header(tmp_path):
+    """Dav1dCudaDav1dPicture / Dav1dCudaPicAllocator are layout-identical to the reference's Dav1dPicture /
+    Dav1dPicAllocator (include/dav1d/picture.h:53-146): compiled against both headers where the reference
+    tree exists (this container); the GPU box checks the sizes recorded here."""
+    import subprocess
+    from dav1d_mirror_b200 import binding as B
+    assert C.sizeof(B.Dav1dPictureMirror) == 272 and B.Dav1dPictureMirror.allocator_data.offset == 264
+    assert B.Dav1dPictureMirror.data.offset == 16 and B.Dav1dPictureMirror.stride.offset == 40
+    assert B.Dav1dPictureMirror.w.offset == 56 and C.sizeof(B.PicAllocator) == 24
+    ref = "/root/reference/include"
+    if not os.path.isdir(ref):
+        return
+    src = tmp_path / "pic.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <stddef.h>
+#include "dav1d/picture.h"
+#include "dav1d_cuda.h"
+#define SAME(a, b) if ((a) != (b)) { printf("%s != %s\n", #a, #b); bad = 1; }
+int main(void) {
+    int bad = 0;
+    SAME(sizeof(Dav1dPicture), sizeof(Dav1dCudaDav1dPicture))
+    SAME(offsetof(Dav1dPicture, data), offsetof(Dav1dCudaDav1dPicture, data))
+    SAME(offsetof(Dav1dPicture, stride), offsetof(Dav1dCudaDav1dPicture, stride))
+    SAME(offsetof(Dav1dPicture, p.w), offsetof(Dav1dCudaDav1dPicture, p.w))
+    SAME(offsetof(Dav1dPicture, p.layout), offsetof(Dav1dCudaDav1dPicture, p.layout))
+    SAME(offsetof(Dav1dPicture, p.bpc), offsetof(Dav1dCudaDav1dPicture, p.bpc))
+    SAME(offsetof(Dav1dPicture, allocator_data), offsetof(Dav1dCudaDav1dPicture, allocator_data))
+    SAME(sizeof(Dav1dPicAllocator), sizeof(Dav1dCudaPicAllocator))
+    SAME(offsetof(Dav1dPicAllocator, alloc_picture_callback), offsetof(Dav1dCudaPicAllocator, alloc_picture_callback))
+    SAME(offsetof(Dav1dPicAllocator, release_picture_callback), offsetof(Dav1dCudaPicAllocator, release_picture_callback))
+    SAME(DAV1D_PIXEL_LAYOUT_I400, 0) SAME(DAV1D_PIXEL_LAYOUT_I420, 1) SAME(DAV1D_PIXEL_LAYOUT_I422, 2) SAME(DAV1D_PIXEL_LAYOUT_I444, 3)
+    puts(bad ? "MISMATCH" : "OK");
+    return bad;
+}
+''')
+    exe = tmp_path / "pic"
+    subprocess.check_call(["gcc", "-I", ref, "-I", os.path.join(ROOT, "oracle", "ref_cfg"),
+                           "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    assert subprocess.check_output([str(exe)]).decode().strip() == "OK"
