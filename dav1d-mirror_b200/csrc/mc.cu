@@ -57,6 +57,7 @@ __global__ void __launch_bounds__(MC_WARPS * 32, 8) mc_put_kernel(const __grid_c
     int ti = (blockIdx.x * MC_WARPS + warp) * V::TPW + grp;
     if (ti >= a.n_tiles) return;
     McSmem<pixel, V::TMAX> *sm = (McSmem<pixel, V::TMAX> *)mc_smem_raw + (warp * V::TPW + grp);
+    mc_smem_init(sm, lane, gmask);
     uint32_t tcode = a.tiles[ti];
     Dav1dCudaMcDesc d = a.descs[tcode >> 4];
     for (;;) {
@@ -98,6 +99,7 @@ __global__ void __launch_bounds__(MC_WARPS * 32, SMALL ? 6 : 5) mc_compound_kern
     int ti = (blockIdx.x * MC_WARPS + warp) * V::TPW + grp;
     if (ti >= a.n_tiles) return;
     McSmemCompound<pixel, V::TMAX> *sm = (McSmemCompound<pixel, V::TMAX> *)mc_smem_raw + (warp * V::TPW + grp);
+    mc_smem_init(&sm->s, lane, gmask);
     uint32_t tcode = a.tiles[ti];
     Dav1dCudaMcDesc d = a.descs[tcode >> 4];
     for (;;) {
@@ -153,6 +155,7 @@ __global__ void __launch_bounds__(MC_WARPS * 32) mc_obmc_kernel(const __grid_con
     const int ti = blockIdx.x * MC_WARPS + warp;
     if (ti >= a.n_tiles) return;
     McSmemObmc<pixel> *sm = (McSmemObmc<pixel> *)mc_smem_raw + warp;
+    mc_smem_init(&sm->s, lane, 0xffffffffu);
     const uint32_t tcode = a.tiles[ti];
     const Dav1dCudaMcDesc d = a.descs[tcode >> 4];
     const TileGeo g = tile_geo(d, tcode & 15);
