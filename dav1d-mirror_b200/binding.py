@@ -64,6 +64,25 @@ class PicAllocator(C.Structure):
                 ("release_picture_callback", C.CFUNCTYPE(None, C.POINTER(Dav1dPictureMirror), C.c_void_p))]
 
 
+class BlockIntra(C.Structure):
+    _fields_ = [("bx4", C.c_uint16), ("by4", C.c_uint16), ("bw4", C.c_uint8), ("bh4", C.c_uint8),
+                ("y_mode", C.c_uint8), ("uv_mode", C.c_uint8), ("y_angle", C.c_int8), ("uv_angle", C.c_int8),
+                ("tx", C.c_uint8), ("uvtx", C.c_uint8), ("pal_sz", C.c_uint8 * 2), ("cfl_alpha", C.c_int8 * 2),
+                ("skip", C.c_uint8), ("edge_flags", C.c_uint8), ("sm_flags", C.c_uint8), ("pad", C.c_uint8),
+                ("pal_off", C.c_uint32 * 3), ("pal_idx_off", C.c_uint32 * 2)]
+
+
+class TxCoef(C.Structure):
+    _fields_ = [("coef_off", C.c_uint32), ("eob", C.c_int16), ("txtp", C.c_uint8), ("cw4", C.c_uint8),
+                ("ch4", C.c_uint8), ("pad", C.c_uint8 * 3)]
+
+
+class Recorder(C.Structure):
+    _fields_ = [("bw4", C.c_int32), ("bh4", C.c_int32), ("layout", C.c_int32), ("intra_edge_filter", C.c_int32),
+                ("tile_col_start", C.c_int32), ("tile_col_end", C.c_int32), ("tile_row_start", C.c_int32),
+                ("tile_row_end", C.c_int32), ("intra", C.c_void_p), ("n_intra", C.c_int32), ("cap_intra", C.c_int32)]
+
+
 class Plane(C.Structure):
     _fields_ = [("data", C.c_void_p), ("stride", C.c_ssize_t), ("w", C.c_int32), ("h", C.c_int32)]
 
@@ -169,6 +188,7 @@ def bind_frame_api(L):
     L.dav1d_cuda_picture_of.restype = C.POINTER(Picture)
     L.dav1d_cuda_picture_to_host.argtypes = [C.c_void_p, C.POINTER(Dav1dPictureMirror)]
     L.dav1d_cuda_picture_to_device.argtypes = [C.c_void_p, C.POINTER(Dav1dPictureMirror)]
+    L.dav1d_cuda_record_b_intra.argtypes = [C.POINTER(Recorder), C.POINTER(BlockIntra), C.c_void_p, C.c_int]
     L.dav1d_cuda_intra_cellmap_bytes.restype = C.c_size_t
     L.dav1d_cuda_intra_cellmap_bytes.argtypes = [C.c_int] * 4
     L.dav1d_cuda_intra_levels.argtypes = [C.c_void_p] + [C.c_int] * 5

@@ -68,6 +68,8 @@ typedef struct D1SynthBlock {
     uint32_t pal_off[3];          // palettes in the palette pool (pixels)
     uint32_t pal_idx_off[2];      // packed indices in the index pool (bytes): luma, chroma
     uint32_t first_op, n_ops;     // the block's operations in `intra` (the order the reference consumes cbi / cf in)
+    uint8_t  sm_flags, pad[3];    // bit 0 / 1: smooth neighbour of the luma / chroma block (what sm_flag / sm_uv_flag
+                                  // return for the contexts above; the reference driver derives it itself)
 } D1SynthBlock;
 
 typedef struct D1SynthFrame {
@@ -364,6 +366,7 @@ struct Gen {
         const bool sm = real ? ((a_intra[bx4] && smooth_mode(a_mode[bx4])) || (l_intra[by4] && smooth_mode(l_mode[by4])))
                              : rng.chance(0.25f);
         const int flags = (P.edge_filter ? 1024 : 0) | (sm ? 512 : 0);
+        rec.sm_flags = sm ? 1 : 0;
         int tw4 = std::min(w4, 16), th4 = std::min(h4, 16);
         if (rng.chance(P.p_tx_split)) split_tx(tw4, th4);
         rec.tx = (uint8_t)tx_from_dims(tw4, th4);
@@ -417,6 +420,7 @@ struct Gen {
         // sm_uv_flag(t->a, cbx4) | sm_uv_flag(&t->l, cby4) (ipred_prepare.h:103-107)
         const bool uvsm = real ? (smooth_mode(a_uvmode[cx4]) || smooth_mode(l_uvmode[cy4])) : rng.chance(0.25f);
         const int uvflags = (P.edge_filter ? 1024 : 0) | (uvsm ? 512 : 0);
+        rec.sm_flags |= uvsm ? 2 : 0;
         int uvmode = rng.range(13), uvdelta = 0;
         if (uvmode >= 1 && uvmode <= 8) uvdelta = rng.irange(-3, 3);
         if (real && (pal || cfl)) { uvmode = 0; uvdelta = 0; }

@@ -118,9 +118,9 @@ class HostFrame:
         self.algo_class = dict(zip(("mc_put", "mc_compound", "warp", "itx", "intra"), list(f.algo_class)))
         self.n_blocks, self.n_intra_blocks = f.n_blocks, f.n_intra_blocks
         self.dense_coef_bytes = f.dense_coef_bytes
-        # real_blocks: one record per coded block (the Av1Block fields the reference's driver reads), 60 bytes each
+        # real_blocks: one record per coded block (the Av1Block fields the reference's driver reads), 64 bytes each
         self.n_block_recs = f.n_block_recs
-        self.blocks = _np_from(f.blocks, f.n_block_recs * 60)
+        self.blocks = _np_from(f.blocks, f.n_block_recs * 64)
         # intra-class operations stay in decode order; their residuals are listed a second time as
         # transform descriptors ordered like `itx`
         self.intra_itx = _np_from(f.intra_itx, f.n_intra_itx * C.sizeof(B.ItxDesc))

@@ -267,6 +267,49 @@ typedef struct Dav1dCudaWarpDesc {   /* 32 bytes */
     uint16_t pad;
 } Dav1dCudaWarpDesc;
 
+/* ---- the recorder: recon_tmpl.c's drivers as descriptor emitters (host, no device work).
+ * dav1d_cuda_record_b_intra() is dav1d_recon_b_intra() (src/recon_tmpl.c:1195-1596) with every DSP call
+ * replaced by one appended Dav1dCudaIntraDesc: same loops over the 64x64 units and transform blocks of
+ * the block, same refinement of the block-level edge flags per transform block (:1270-1274,:1466-1476),
+ * same order of palette / CfL / prediction / residual, the tile from `ts->tiling`.  The block is given
+ * as the Av1Block fields that function reads (src/levels.h:262-287) plus what decode_b() hands over. */
+typedef struct Dav1dCudaBlockIntra {
+    uint16_t bx4, by4;            /* t->bx, t->by (4-px units) */
+    uint8_t  bw4, bh4;            /* dav1d_block_dimensions[bs] */
+    uint8_t  y_mode, uv_mode;     /* enum IntraPredMode; FILTER_PRED (luma) / CFL_PRED (chroma) = 13 */
+    int8_t   y_angle, uv_angle;   /* b->y_angle (filter index for FILTER_PRED), b->uv_angle */
+    uint8_t  tx, uvtx;            /* b->tx, b->uvtx: enum RectTxfmSize */
+    uint8_t  pal_sz[2];           /* b->pal_sz */
+    int8_t   cfl_alpha[2];        /* b->cfl_alpha */
+    uint8_t  skip;                /* b->skip */
+    uint8_t  edge_flags;          /* enum EdgeFlags as passed by decode_b() (src/intra_edge.h:27-32) */
+    uint8_t  sm_flags;            /* bit 0: sm_flag(t->a, bx4) | sm_flag(&t->l, by4) != 0; bit 1: the same for
+                                     sm_uv_flag (src/ipred_prepare.h:95-107) */
+    uint8_t  pad;
+    uint32_t pal_off[3];          /* the block's palettes in the palette pool (pixels): Y, U, V */
+    uint32_t pal_idx_off[2];      /* its packed indices in the index pool (bytes): luma, chroma */
+} Dav1dCudaBlockIntra;
+/* One entry per transform block in the order dav1d_recon_b_intra consumes `cbi` / `cf` (luma raster,
+ * then U raster, then V raster; none for a skip block): eob / txtp = the cbi entry, coef_off (+ cw4, ch4
+ * for a packed box, else 0) = where the block's coefficients are in the cf stream. */
+typedef struct Dav1dCudaTxCoef {
+    uint32_t coef_off;
+    int16_t  eob;
+    uint8_t  txtp, cw4, ch4, pad[3];
+} Dav1dCudaTxCoef;
+typedef struct Dav1dCudaRecorder {
+    int32_t bw4, bh4;             /* f->bw, f->bh */
+    int32_t layout;               /* enum Dav1dPixelLayout: I400 0, I420 1, I422 2, I444 3 */
+    int32_t intra_edge_filter;    /* f->seq_hdr->intra_edge_filter */
+    int32_t tile_col_start, tile_col_end, tile_row_start, tile_row_end;   /* ts->tiling (luma 4-px units) */
+    Dav1dCudaIntraDesc *intra;    /* output array (decode order) */
+    int32_t n_intra, cap_intra;
+} Dav1dCudaRecorder;
+/* Appends the block's operations; returns how many, or a negative errno (-ENOSPC: `intra` is full,
+ * -EINVAL: fields that no stream produces, n_tx != the block's transform blocks). */
+DAV1D_CUDA_API int dav1d_cuda_record_b_intra(Dav1dCudaRecorder *r, const Dav1dCudaBlockIntra *b,
+                                             const Dav1dCudaTxCoef *tx, int n_tx);
+
 typedef struct Dav1dCudaContext Dav1dCudaContext;
 
 /* `stream` is a cudaStream_t the caller already orders its work on, or NULL:

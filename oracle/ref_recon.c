@@ -53,6 +53,7 @@ typedef struct D1SynthBlock {
     uint32_t pal_off[3];
     uint32_t pal_idx_off[2];
     uint32_t first_op, n_ops;
+    uint8_t  sm_flags, pad[3];
 } D1SynthBlock;
 
 typedef struct OracleReconFrame {

@@ -1,0 +1,111 @@
+"""The product's recorder - dav1d_cuda_record_b_intra(), the transcription of dav1d_recon_b_intra()
+(src/recon_tmpl.c:1195-1596) into descriptor emission - run over the Av1Block-style records of synthetic
+all-intra frames: the descriptors it emits are, field for field, the ones the generator recorded
+independently, and those reproduce the reference driver's pixels bit for bit
+(tests/test_reference_driver.py).  CPU only."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import _d1pkg
+
+pkg = _d1pkg.load_pkg()
+from dav1d_mirror_b200 import binding as B  # noqa: E402
+from dav1d_mirror_b200 import frame as F  # noqa: E402
+import test_reference_driver as R  # noqa: E402
+
+BLK = np.dtype([("bx4", "u2"), ("by4", "u2"), ("w4", "u1"), ("h4", "u1"), ("intra", "u1"), ("has_chroma", "u1"),
+                ("skip", "u1"), ("tile", "u1"), ("edge_tr", "u1"), ("edge_bl", "u1"), ("y_mode", "u1"), ("uv_mode", "u1"),
+                ("y_angle", "i1"), ("uv_angle", "i1"), ("tx", "u1"), ("uvtx", "u1"), ("pal_sz", "u1", 2),
+                ("cfl_alpha", "i1", 2), ("tile_rect", "u2", 4), ("pad0", "u2"), ("pal_off", "u4", 3),
+                ("pal_idx_off", "u4", 2), ("first_op", "u4"), ("n_ops", "u4"), ("sm_flags", "u1"), ("pad", "u1", 3)])
+OP = np.dtype([("x4", "u2"), ("y4", "u2"), ("tile_x4_start", "u2"), ("tile_y4_start", "u2"), ("tile_x4_end", "u2"),
+               ("tile_y4_end", "u2"), ("plane", "u1"), ("tw4", "u1"), ("th4", "u1"), ("mode", "u1"),
+               ("angle_delta", "i1"), ("edge_flags", "u1"), ("flags", "u2"), ("eob", "i2"), ("tx", "u1"), ("txtp", "u1"),
+               ("coef_off", "u4"), ("aux", "u4"), ("reserved", "u4"), ("cw4", "u1"), ("ch4", "u1"), ("pad", "u2")])
+
+
+def record_frame(hf):
+    assert BLK.itemsize == 64 and OP.itemsize == 40
+    L = pkg.lib()
+    blocks = np.frombuffer(hf.blocks.tobytes(), dtype=BLK)
+    ops = np.frombuffer(hf.intra.tobytes(), dtype=OP)
+    out = np.zeros(len(ops) + 16, dtype=OP)
+    r = B.Recorder()
+    r.bw4, r.bh4 = hf.bw4, hf.bh4
+    r.layout = 0 if hf.no_chroma else 1 if hf.ss_ver else 2 if hf.ss_hor else 3
+    r.intra_edge_filter = hf.params.edge_filter
+    r.intra, r.n_intra, r.cap_intra = out.ctypes.data, 0, len(out)
+    for s in blocks:
+        r.tile_col_start, r.tile_row_start, r.tile_col_end, r.tile_row_end = (int(v) for v in s["tile_rect"])
+        b = B.BlockIntra()
+        b.bx4, b.by4, b.bw4, b.bh4 = int(s["bx4"]), int(s["by4"]), int(s["w4"]), int(s["h4"])
+        b.y_mode, b.uv_mode, b.y_angle, b.uv_angle = int(s["y_mode"]), int(s["uv_mode"]), int(s["y_angle"]), int(s["uv_angle"])
+        b.tx, b.uvtx, b.skip, b.sm_flags = int(s["tx"]), int(s["uvtx"]), int(s["skip"]), int(s["sm_flags"])
+        for k in range(2):
+            b.pal_sz[k], b.cfl_alpha[k], b.pal_idx_off[k] = int(s["pal_sz"][k]), int(s["cfl_alpha"][k]), int(s["pal_idx_off"][k])
+        for k in range(3):
+            b.pal_off[k] = int(s["pal_off"][k])
+        # block-level EdgeFlags (src/intra_edge.h:27-32): bit 0 of the record = luma, bit 1 = the chroma layout
+        b.edge_flags = ((1 if s["edge_tr"] & 1 else 0) | (8 if s["edge_bl"] & 1 else 0) |
+                        (6 if s["edge_tr"] & 2 else 0) | (48 if s["edge_bl"] & 2 else 0))
+        mine = ops[s["first_op"]:s["first_op"] + s["n_ops"]]
+        # the block's cbi / cf entries in consumption order: every transform block of a non-skip block
+        txs = [(int(o["coef_off"]), int(o["eob"]), int(o["txtp"]), int(o["cw4"]), int(o["ch4"]))
+               for o in mine if o["mode"] != 15 and not s["skip"]]
+        arr = (B.TxCoef * max(len(txs), 1))()
+        for k, (co, eob, txtp, cw4, ch4) in enumerate(txs):
+            arr[k].coef_off, arr[k].eob, arr[k].txtp, arr[k].cw4, arr[k].ch4 = co, eob, txtp, cw4, ch4
+        n = L.dav1d_cuda_record_b_intra(C.byref(r), C.byref(b), arr, len(txs))
+        assert n == s["n_ops"], (n, int(s["n_ops"]), s)
+    return ops, out[:r.n_intra]
+
+
+@pytest.mark.parametrize("name", list(R.CASES))
+def test_recorder_emits_the_generators_descriptors(name):
+    hf, _ = R.make(name)
+    want, got = record_frame(hf)
+    assert len(want) == len(got)
+    # The top-right / bottom-left bits only reach the predictor through have_top / have_left
+    # (ipred_prepare_tmpl.c:139-170); without the neighbour they carry no meaning (the reference sets
+    # bottom-left for every transform block above the last row, the generator only where pixels exist).
+    want, got = want.copy(), got.copy()
+    for a in (want, got):
+        a["edge_flags"] &= np.where(a["y4"] > a["tile_y4_start"], 0xff, 0xfe).astype(np.uint8)
+        a["edge_flags"] &= np.where(a["x4"] > a["tile_x4_start"], 0xff, 0xf7).astype(np.uint8)
+    for f in OP.names:
+        if f in ("reserved", "pad"):
+            continue
+        bad = np.nonzero(want[f] != got[f])[0]
+        assert bad.size == 0, f"{name}: field {f} differs at operation {bad[0]}: {want[bad[0]]} vs {got[bad[0]]}"
+
+
+def test_recorder_rejects_what_it_cannot_record():
+    L = pkg.lib()
+    out = np.zeros(4, dtype=OP)
+    r = B.Recorder()
+    r.bw4 = r.bh4 = 16
+    r.layout, r.tile_col_end, r.tile_row_end = 1, 16, 16
+    r.intra, r.cap_intra = out.ctypes.data, 1
+    b = B.BlockIntra()
+    b.bw4 = b.bh4 = 4
+    b.tx, b.uvtx, b.skip = 2, 1, 1               # 16x16 luma transform, 8x8 chroma: three operations
+    assert L.dav1d_cuda_record_b_intra(C.byref(r), C.byref(b), None, 0) == -28 and r.n_intra == 0   # -ENOSPC, nothing kept
+    r.cap_intra = 4
+    assert L.dav1d_cuda_record_b_intra(C.byref(r), C.byref(b), None, 0) == 3
+    b.skip = 0
+    assert L.dav1d_cuda_record_b_intra(C.byref(r), C.byref(b), None, 0) == -22                      # cbi entries missing
+
+
+@pytest.mark.parametrize("name", ["420_10b_cfl_pal_filter", "422_12b_cfl_filter", "420_10b_tiles_2x2", "444_8b_cfl_pal"])
+def test_recorded_descriptors_reproduce_the_reference_driver(ref, name):
+    """End to end on the CPU: Av1Block records -> product recorder -> descriptors -> sequential replay through the
+    reference DSP tables == dav1d_recon_b_intra on the same records."""
+    import refframe
+    hf, init = R.make(name)
+    want = refframe.run_reference_driver(ref, hf, [p.copy() for p in init])
+    _, got_ops = record_frame(hf)
+    hf.intra = np.frombuffer(got_ops.tobytes(), dtype=np.uint8).copy()
+    got = refframe.run_oracle(ref, hf, [p.copy() for p in init], [])
+    assert all(np.array_equal(a, b) for a, b in zip(want, got))
