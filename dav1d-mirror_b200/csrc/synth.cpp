@@ -70,7 +70,19 @@ typedef struct D1SynthBlock {
     uint32_t first_op, n_ops;     // the block's operations in `intra` (the order the reference consumes cbi / cf in)
     uint8_t  sm_flags, pad[3];    // bit 0 / 1: smooth neighbour of the luma / chroma block (what sm_flag / sm_uv_flag
                                   // return for the contexts above; the reference driver derives it itself)
+    // inter blocks (intra = 0): what dav1d_recon_b_inter reads
+    int16_t  mvx[2], mvy[2];      // b->mv[i] (1/8 luma pixel)
+    uint8_t  ref[2];              // b->ref[i]
+    uint8_t  comp_kind;           // enum Dav1dCudaMcKind: PUT / AVG / W_AVG / W_MASK (segmentation mask)
+    uint8_t  filter2d, mask_sign, max_ytx, tx_split, jnt_weight;   // tx_split: b->tx_split0 (one level), b->max_ytx
+    uint32_t first_tx, n_tx;      // the block's cbi / cf entries in `tx_recs` (consumption order)
 } D1SynthBlock;
+// One cbi / cf entry of an inter block: (eob << 5) | txtp and where the coefficients are
+typedef struct D1SynthTx {
+    uint32_t coef_off;
+    int16_t  eob;
+    uint8_t  txtp, cw4, ch4, tx, plane, pad;
+} D1SynthTx;
 
 typedef struct D1SynthFrame {
     Dav1dCudaMcDesc *mc_put;   int32_t n_mc_put;   uint32_t *mc_put_tiles;  int32_t n_mc_put_tiles;
@@ -93,6 +105,7 @@ typedef struct D1SynthFrame {
     Dav1dCudaItxDesc *intra_itx; int32_t n_intra_itx; int32_t intra_itx_class_count[19];   // the intra residuals as transforms
     double dense_coef_bytes;   // part of algo_bytes that counts DENSE coefficient blocks; the packed stream is cf_elems
     D1SynthBlock *blocks;      int32_t n_block_recs;   // real_blocks: every block in decode order
+    D1SynthTx *tx_recs;        int32_t n_tx_recs;      // real_blocks: cbi / cf entries of the inter blocks
 } D1SynthFrame;
 
 }  // extern "C"
@@ -238,6 +251,13 @@ struct Gen {
         add_bytes(3, 2.0 * Bp * TXW4[tx] * TXH4[tx] * 16);
         order.push_back({ 3, (uint32_t)itx.size() });
         itx.push_back(d);
+        if (P.real_blocks) {
+            D1SynthTx t;
+            memset(&t, 0, sizeof(t));
+            t.coef_off = d.coef_off; t.eob = d.eob; t.txtp = d.txtp; t.cw4 = d.cw4; t.ch4 = d.ch4;
+            t.tx = (uint8_t)tx; t.plane = (uint8_t)pl;
+            tx_recs.push_back(t);
+        }
     }
 
     // one tx-sized intra-class op
@@ -551,7 +571,26 @@ struct Gen {
             if (rng.chance(0.1f)) mvx[i] &= ~7;    // integer-pel columns / rows now and then
             if (rng.chance(0.1f)) mvy[i] &= ~7;
         }
-        const int weight = rng.irange(1, 15), sign = rng.range(2);
+        int weight = rng.irange(1, 15);
+        const int sign = rng.range(2);
+        if (P.real_blocks) weight = jnt_weight_of(ref[0], ref[1]);    // COMP_INTER_WEIGHTED_AVG takes it from the frame
+        D1SynthBlock rec_inter;
+        memset(&rec_inter, 0, sizeof(rec_inter));
+        rec_inter.bx4 = (uint16_t)bx4; rec_inter.by4 = (uint16_t)by4; rec_inter.w4 = (uint8_t)w4; rec_inter.h4 = (uint8_t)h4;
+        rec_inter.intra = 0; rec_inter.has_chroma = P.no_chroma ? 0 : 1; rec_inter.skip = 1; rec_inter.tile = (uint8_t)tile_no;
+        rec_inter.tile_x0 = (uint16_t)tile_x0; rec_inter.tile_y0 = (uint16_t)tile_y0;
+        rec_inter.tile_x1 = (uint16_t)std::min(tile_x1, bw4); rec_inter.tile_y1 = (uint16_t)std::min(tile_y1, bh4);
+        for (int i = 0; i < 2; i++) { rec_inter.mvx[i] = (int16_t)mvx[i]; rec_inter.mvy[i] = (int16_t)mvy[i]; rec_inter.ref[i] = (uint8_t)ref[i]; }
+        rec_inter.comp_kind = (uint8_t)(is_warp ? 255 : kind); rec_inter.filter2d = (uint8_t)filter;
+        rec_inter.mask_sign = (uint8_t)sign; rec_inter.jnt_weight = (uint8_t)weight;
+        rec_inter.first_tx = (uint32_t)tx_recs.size();
+        {   // the largest transforms of the block (b->max_ytx, b->uvtx) also when it carries no residual
+            int a = std::min(w4, 16), b2 = std::min(h4, 16);
+            rec_inter.max_ytx = (uint8_t)tx_from_dims(a, b2);
+            int ua = std::min(std::max(1, w4 >> P.ss_hor), 8), ub = std::min(std::max(1, h4 >> P.ss_ver), 8);
+            fit_tx(ua, ub);
+            rec_inter.uvtx = (uint8_t)tx_from_dims(ua, ub);
+        }
         // OBMC: single-reference, translational blocks of at least 8x8 on even 4x4 coordinates
         const bool do_obmc = P.p_obmc > 0.f && kind == DAV1D_CUDA_MC_PUT && !is_warp && w4 >= 2 && h4 >= 2 &&
                              !(bx4 & 1) && !(by4 & 1) && rng.chance(P.p_obmc);
@@ -663,7 +702,9 @@ struct Gen {
             }
         } else if (rng.chance(P.p_residual)) {
             int tw4 = std::min(w4, 16), th4 = std::min(h4, 16);
-            if (rng.chance(P.p_tx_split)) split_tx(tw4, th4);
+            rec_inter.max_ytx = (uint8_t)tx_from_dims(tw4, th4);
+            rec_inter.skip = 0;
+            if (rng.chance(P.p_tx_split)) { split_tx(tw4, th4); rec_inter.tx_split = tw4 * th4 < std::min(w4, 16) * std::min(h4, 16); }
             const int tx = tx_from_dims(tw4, th4);
             for (int y = 0; y < h4; y += th4)
                 for (int x = 0; x < w4; x += tw4) add_itx(0, bx4 + x, by4 + y, tx);
@@ -672,11 +713,16 @@ struct Gen {
                 int utw4 = std::min(cw4, 8), uth4 = std::min(ch4, 8);
                 fit_tx(utw4, uth4);
                 const int utx = tx_from_dims(utw4, uth4);
+                rec_inter.uvtx = (uint8_t)utx;
                 for (int pl = 1; pl <= 2; pl++)
                     for (int y = 0; y < ch4; y += uth4)
                         for (int x = 0; x < cw4; x += utw4)
                             add_itx(pl, (bx4 >> P.ss_hor) + x, (by4 >> P.ss_ver) + y, utx);
             }
+        }
+        if (P.real_blocks) {
+            rec_inter.n_tx = (uint32_t)tx_recs.size() - rec_inter.first_tx;
+            blocks.push_back(rec_inter);
         }
         for (int pl = 0; pl < nplanes(); pl++) {
             const int sh = pl ? P.ss_hor : 0, sv = pl ? P.ss_ver : 0;
@@ -713,6 +759,9 @@ struct Gen {
         // 4:2:2 has no block whose chroma would be 1:4 or narrower: no vertical two- / four-way split
         // (the 0 entries of dav1d_max_txfm_size_for_bs, tables.c:171-195)
         if (P.real_blocks && P.ss_hor && !P.ss_ver && !P.no_chroma) choice = choice == 2 ? 1 : choice == 5 ? 4 : choice;
+        // frames with inter blocks: no 4-pixel-wide / -high blocks (their chroma is predicted with the
+        // neighbours' motion vectors from the refmvs rows, recon_tmpl.c:1683-1751, which the records do not carry)
+        if (P.real_blocks && P.p_intra < 1.f) choice = choice == 4 ? 1 : choice == 5 ? (P.ss_hor && !P.ss_ver && !P.no_chroma ? 1 : 2) : choice;
         const int hs = s4 >> 1, q = s4 >> 2;
         switch (choice) {
         case 0: block(bx4, by4, s4, s4); break;
@@ -757,6 +806,9 @@ struct Gen {
     // dav1d_reset_context() at a tile's top edge and at the left edge of every superblock row of a tile
     std::vector<uint8_t> a_intra, a_mode, a_uvmode, l_intra, l_mode, l_uvmode;
     std::vector<D1SynthBlock> blocks;
+    std::vector<D1SynthTx> tx_recs;
+    // f->jnt_weights[ref0][ref1] of the synthetic frame header (real_blocks)
+    static int jnt_weight_of(int r0, int r1) { return 1 + (r0 * 7 + r1 * 3 + 4) % 15; }
     static bool smooth_mode(int m) { return m >= 9 && m <= 11; }
     void ctx_init() {
         a_intra.assign(bw4 + 1, 0); a_mode.assign(bw4 + 1, 0); a_uvmode.assign(bw4 + 1, 0);
@@ -923,13 +975,14 @@ __attribute__((visibility("default"))) int d1synth_generate(const D1SynthParams 
     for (int i = 0; i < 5; i++) f->algo_class[i] = g.algo_cls[i];
     f->n_blocks = g.n_blocks; f->n_intra_blocks = g.n_intra_blocks;
     f->blocks = dup(g.blocks); f->n_block_recs = (int32_t)g.blocks.size();
+    f->tx_recs = dup(g.tx_recs); f->n_tx_recs = (int32_t)g.tx_recs.size();
     return 0;
 }
 
 __attribute__((visibility("default"))) void d1synth_free(D1SynthFrame *f) {
     if (!f) return;
     free(f->mc_put); free(f->mc_put_tiles); free(f->mc_comp); free(f->mc_comp_tiles); free(f->warp);
-    free(f->mc_obmc); free(f->mc_obmc_tiles); free(f->blocks);
+    free(f->mc_obmc); free(f->mc_obmc_tiles); free(f->blocks); free(f->tx_recs);
     free(f->intra_itx);
     free(f->itx); free(f->intra); free(f->cf); free(f->masks); free(f->pal); free(f->pal_idx); free(f->order);
     memset(f, 0, sizeof(*f));

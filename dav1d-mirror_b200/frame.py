@@ -46,7 +46,8 @@ class SynthFrame(C.Structure):
                 ("mc_obmc", C.c_void_p), ("n_mc_obmc", C.c_int32), ("mc_obmc_tiles", C.c_void_p),
                 ("n_mc_obmc_tiles", C.c_int32 * 2),
                 ("intra_itx", C.c_void_p), ("n_intra_itx", C.c_int32), ("intra_itx_class_count", C.c_int32 * 19),
-                ("dense_coef_bytes", C.c_double), ("blocks", C.c_void_p), ("n_block_recs", C.c_int32)]
+                ("dense_coef_bytes", C.c_double), ("blocks", C.c_void_p), ("n_block_recs", C.c_int32),
+                ("tx_recs", C.c_void_p), ("n_tx_recs", C.c_int32)]
 
 
 _synth = None
@@ -118,9 +119,10 @@ class HostFrame:
         self.algo_class = dict(zip(("mc_put", "mc_compound", "warp", "itx", "intra"), list(f.algo_class)))
         self.n_blocks, self.n_intra_blocks = f.n_blocks, f.n_intra_blocks
         self.dense_coef_bytes = f.dense_coef_bytes
-        # real_blocks: one record per coded block (the Av1Block fields the reference's driver reads), 64 bytes each
+        # real_blocks: one record per coded block (the Av1Block fields the reference's driver reads), 88 bytes each
         self.n_block_recs = f.n_block_recs
-        self.blocks = _np_from(f.blocks, f.n_block_recs * 64)
+        self.blocks = _np_from(f.blocks, f.n_block_recs * 88)
+        self.tx_recs = _np_from(f.tx_recs, f.n_tx_recs * 12)          # cbi / cf entries of the inter blocks
         # intra-class operations stay in decode order; their residuals are listed a second time as
         # transform descriptors ordered like `itx`
         self.intra_itx = _np_from(f.intra_itx, f.n_intra_itx * C.sizeof(B.ItxDesc))

@@ -54,7 +54,17 @@ typedef struct D1SynthBlock {
     uint32_t pal_idx_off[2];
     uint32_t first_op, n_ops;
     uint8_t  sm_flags, pad[3];
+    int16_t  mvx[2], mvy[2];
+    uint8_t  ref[2];
+    uint8_t  comp_kind;
+    uint8_t  filter2d, mask_sign, max_ytx, tx_split, jnt_weight;
+    uint32_t first_tx, n_tx;
 } D1SynthBlock;
+typedef struct D1SynthTx {
+    uint32_t coef_off;
+    int16_t  eob;
+    uint8_t  txtp, cw4, ch4, tx, plane, pad;
+} D1SynthTx;
 
 typedef struct OracleReconFrame {
     void *dst[3];
@@ -66,6 +76,10 @@ typedef struct OracleReconFrame {
     const void *cf;                    /* generator coefficient stream (packed or dense blocks) */
     const void *pal;                   /* palette pool */
     const uint8_t *pal_idx;            /* packed index pool */
+    const void *ref[7][3];             /* reference pictures (inter blocks), same geometry as dst */
+    ptrdiff_t ref_stride[7][2];
+    int32_t n_refs;
+    const D1SynthTx *tx_recs;          /* cbi / cf entries of the inter blocks */
 } OracleReconFrame;
 
 #if BITDEPTH == 8
@@ -81,23 +95,29 @@ static int bs_from_dims(const int w4, const int h4) {
 }
 
 /* one transform block of the generator's stream -> the dense min(w,32) x min(h,32) block pass 1 stores */
-static void dense_coefs(coef *out, const OracleReconFrame *fr, const Dav1dCudaIntraDesc *d) {
-    const TxfmInfo *const t = &dav1d_txfm_dimensions[d->tx];
+static void dense_coefs2(coef *out, const OracleReconFrame *fr, const int tx, const uint32_t coef_off,
+                         const int cw4, const int ch4)
+{
+    const TxfmInfo *const t = &dav1d_txfm_dimensions[tx];
     const int sw = imin(t->w * 4, 32), sh = imin(t->h * 4, 32);
-    const coef *src = (const coef *)fr->cf + d->coef_off;
+    const coef *src = (const coef *)fr->cf + coef_off;
     memset(out, 0, sizeof(coef) * sw * sh);
-    if (!d->cw4 || !d->ch4) {
+    if (!cw4 || !ch4) {
         memcpy(out, src, sizeof(coef) * sw * sh);
     } else {
-        const int cw = d->cw4 * 4, ch = d->ch4 * 4;
+        const int cw = cw4 * 4, ch = ch4 * 4;
         for (int x = 0; x < cw; x++)
             for (int y = 0; y < ch; y++) out[y + x * sh] = src[y + x * ch];
     }
 }
+static void dense_coefs(coef *out, const OracleReconFrame *fr, const Dav1dCudaIntraDesc *d) {
+    dense_coefs2(out, fr, d->tx, d->coef_off, d->cw4, d->ch4);
+}
 
-/* Reconstructs every intra block of the frame through dav1d_recon_b_intra.  Returns 0, or a
- * negative value when the records hold something this harness does not drive (inter blocks). */
-EXPORT int SUFFIX(oracle_recon_intra_frame)(const OracleReconFrame *const fr) {
+/* Reconstructs every block of the frame through dav1d_recon_b_intra / dav1d_recon_b_inter.  Returns 0, or
+ * a negative value when the records hold something this harness does not drive (warped, OBMC, inter-intra,
+ * wedge and intrabc blocks: they need refmvs rows / mask tables the records do not carry). */
+EXPORT int SUFFIX(oracle_recon_frame)(const OracleReconFrame *const fr) {
     int ret = 0;
     Dav1dDSPContext dsp;
     memset(&dsp, 0, sizeof(dsp));
@@ -111,7 +131,7 @@ EXPORT int SUFFIX(oracle_recon_intra_frame)(const OracleReconFrame *const fr) {
     memset(&hdr, 0, sizeof(hdr));
     seq.intra_edge_filter = fr->intra_edge_filter;
     seq.hbd = fr->bitdepth_max > 1023 ? 2 : fr->bitdepth_max > 255 ? 1 : 0;
-    hdr.frame_type = DAV1D_FRAME_TYPE_KEY;
+    hdr.frame_type = fr->n_refs > 0 ? DAV1D_FRAME_TYPE_INTER : DAV1D_FRAME_TYPE_KEY;
 
     Dav1dFrameContext *const f = calloc(1, sizeof(*f));
     Dav1dTileState *const ts = calloc(1, sizeof(*ts));
@@ -147,6 +167,16 @@ EXPORT int SUFFIX(oracle_recon_intra_frame)(const OracleReconFrame *const fr) {
     f->frame_thread.pal = calloc(n_pal, sizeof(*f->frame_thread.pal));
     BlockContext *const a = calloc((size_t)f->sb128w + 1, sizeof(*a));
     f->a = a;
+    /* reference pictures: same size as the current one (no scaling: f->svc stays zero) and the weights of
+     * COMP_INTER_WEIGHTED_AVG, a table of the frame (the generator draws the same table) */
+    for (int i = 0; i < fr->n_refs && i < 7; i++) {
+        Dav1dPicture *const rp = &f->refp[i].p;
+        rp->data[0] = (void *)fr->ref[i][0]; rp->data[1] = (void *)fr->ref[i][1]; rp->data[2] = (void *)fr->ref[i][2];
+        rp->stride[0] = fr->ref_stride[i][0]; rp->stride[1] = fr->ref_stride[i][1];
+        rp->p = f->cur.p;
+    }
+    for (int i = 0; i < 7; i++)
+        for (int j = 0; j < 7; j++) f->jnt_weights[i][j] = 1 + (i * 7 + j * 3 + 4) % 15;
 
     t->f = f;
     t->ts = ts;
@@ -162,7 +192,7 @@ EXPORT int SUFFIX(oracle_recon_intra_frame)(const OracleReconFrame *const fr) {
     int cur_tile = -1, cur_sbrow = -1;
     for (int i = 0; i < fr->n_blocks; i++) {
         const D1SynthBlock *const s = &fr->blocks[i];
-        if (!s->intra) { ret = -38; goto done; }
+        if (!s->intra && (s->comp_kind > DAV1D_CUDA_MC_W_MASK || s->comp_kind == DAV1D_CUDA_MC_MASK)) { ret = -38; goto done; }
         const int sbrow = s->by4 >> f->sb_shift;
         if (s->tile != cur_tile || sbrow != cur_sbrow) {
             if (cur_tile >= 0) {            /* decode.c:2677: end of a tile's superblock row */
@@ -179,6 +209,46 @@ EXPORT int SUFFIX(oracle_recon_intra_frame)(const OracleReconFrame *const fr) {
         }
         const int bs = bs_from_dims(s->w4, s->h4);
         if (bs < 0) { ret = -22; goto done; }
+        if (!s->intra) {
+            /* ---- inter block: dav1d_recon_b_inter (recon_tmpl.c:1598-2036) */
+            Av1Block b;
+            memset(&b, 0, sizeof(b));
+            b.bs = bs; b.intra = 0; b.skip = s->skip; b.uvtx = s->uvtx;
+            b.comp_type = s->comp_kind == DAV1D_CUDA_MC_PUT ? COMP_INTER_NONE :
+                          s->comp_kind == DAV1D_CUDA_MC_AVG ? COMP_INTER_AVG :
+                          s->comp_kind == DAV1D_CUDA_MC_W_AVG ? COMP_INTER_WEIGHTED_AVG : COMP_INTER_SEG;
+            b.inter_mode = 0; b.motion_mode = MM_TRANSLATION; b.interintra_type = 0;
+            for (int k = 0; k < 2; k++) { b.mv[k].x = s->mvx[k]; b.mv[k].y = s->mvy[k]; b.ref[k] = (int8_t)s->ref[k]; }
+            b.filter2d = s->filter2d; b.mask_sign = s->mask_sign;
+            b.max_ytx = s->max_ytx; b.tx_split0 = s->tx_split ? 1 : 0; b.tx_split1 = 0;
+            if (f->jnt_weights[b.ref[0]][b.ref[1]] != s->jnt_weight && s->comp_kind == DAV1D_CUDA_MC_W_AVG) { ret = -22; goto done; }
+            t->bx = s->bx4; t->by = s->by4;
+            t->a = &a[s->bx4 >> 5];
+            int n_cbi = 0;
+            coef *cfp = cfbuf;
+            for (unsigned k = 0; k < s->n_tx; k++) {
+                const D1SynthTx *const x = &fr->tx_recs[s->first_tx + k];
+                const TxfmInfo *const td = &dav1d_txfm_dimensions[x->tx];
+                cbi[n_cbi++] = (int16_t)((x->eob << 5) + x->txtp);
+                if (x->eob >= 0) dense_coefs2(cfp, fr, x->tx, x->coef_off, x->cw4, x->ch4);
+                /* luma: recon_tmpl.c:776-778; chroma: :1951 */
+                cfp += x->plane ? td->w * td->h * 16 : imin(td->w, 8) * imin(td->h, 8) * 16;
+            }
+            ts->frame_thread[0].cbi = cbi;
+            ts->frame_thread[0].cf = cfbuf;
+            if (SUFFIX(dav1d_recon_b_inter)(t, bs, &b)) { ret = -5; goto done; }
+            /* decode.c:808-830: filters, intra = 0, uvmode = DC_PRED into the contexts */
+            const int bx4 = s->bx4 & 31, by4 = s->by4 & 31;
+            const uint8_t *const filter = dav1d_filter_dir[b.filter2d];
+            for (int x = 0; x < s->w4; x++) { t->a->filter[0][bx4 + x] = filter[0]; t->a->filter[1][bx4 + x] = filter[1]; t->a->intra[bx4 + x] = 0; }
+            for (int y = 0; y < s->h4; y++) { t->l.filter[0][by4 + y] = filter[0]; t->l.filter[1][by4 + y] = filter[1]; t->l.intra[by4 + y] = 0; }
+            if (s->has_chroma) {
+                const int cbx4 = bx4 >> ss_hor, cby4 = by4 >> ss_ver;
+                for (int x = 0; x < (s->w4 + ss_hor) >> ss_hor; x++) t->a->uvmode[cbx4 + x] = DC_PRED;
+                for (int y = 0; y < (s->h4 + ss_ver) >> ss_ver; y++) t->l.uvmode[cby4 + y] = DC_PRED;
+            }
+            continue;
+        }
         Av1Block b;
         memset(&b, 0, sizeof(b));
         b.bs = bs; b.intra = 1; b.skip = s->skip; b.uvtx = s->uvtx;

@@ -62,12 +62,14 @@ class OracleReconFrame(C.Structure):
                 ("w", C.c_int32), ("h", C.c_int32), ("ss_hor", C.c_int32), ("ss_ver", C.c_int32),
                 ("bitdepth_max", C.c_int32), ("no_chroma", C.c_int32), ("intra_edge_filter", C.c_int32),
                 ("blocks", C.c_void_p), ("n_blocks", C.c_int32),
-                ("ops", C.c_void_p), ("cf", C.c_void_p), ("pal", C.c_void_p), ("pal_idx", C.c_void_p)]
+                ("ops", C.c_void_p), ("cf", C.c_void_p), ("pal", C.c_void_p), ("pal_idx", C.c_void_p),
+                ("ref", (C.c_void_p * 3) * 7), ("ref_stride", (C.c_ssize_t * 2) * 7), ("n_refs", C.c_int32),
+                ("tx_recs", C.c_void_p)]
 
 
-def run_reference_driver(ref, hf, dst_planes):
-    """All-intra frame generated with real_blocks=1 through dav1d_recon_b_intra_{8,16}bpc, block by
-    block in decode order (modifies dst_planes in place)."""
+def run_reference_driver(ref, hf, dst_planes, ref_planes_list=()):
+    """Frame generated with real_blocks=1 through dav1d_recon_b_intra / dav1d_recon_b_inter_{8,16}bpc, block
+    by block in decode order (modifies dst_planes in place)."""
     assert hf.n_block_recs > 0, "generate the frame with real_blocks=1"
     of = OracleReconFrame()
     for pl, a in enumerate(dst_planes):
@@ -79,10 +81,17 @@ def run_reference_driver(ref, hf, dst_planes):
     of.blocks, of.n_blocks = hf.blocks.ctypes.data, hf.n_block_recs
     for name, arr in (("ops", hf.intra), ("cf", hf.cf), ("pal", hf.pal), ("pal_idx", hf.pal_idx)):
         setattr(of, name, arr.ctypes.data if arr.nbytes else None)
-    fn = getattr(ref.lib, "oracle_recon_intra_frame_16bpc" if hf.hbd else "oracle_recon_intra_frame_8bpc")
+    for r, planes in enumerate(ref_planes_list):
+        for pl, a in enumerate(planes):
+            of.ref[r][pl] = a.ctypes.data
+        of.ref_stride[r][0] = planes[0].strides[0]
+        of.ref_stride[r][1] = planes[1].strides[0] if len(planes) > 1 else 0
+    of.n_refs = len(ref_planes_list)
+    of.tx_recs = hf.tx_recs.ctypes.data if hf.tx_recs.nbytes else None
+    fn = getattr(ref.lib, "oracle_recon_frame_16bpc" if hf.hbd else "oracle_recon_frame_8bpc")
     fn.argtypes = [C.POINTER(OracleReconFrame)]
     fn.restype = C.c_int
     r = fn(C.byref(of))
     if r:
-        raise RuntimeError(f"oracle_recon_intra_frame: {r}")
+        raise RuntimeError(f"oracle_recon_frame: {r}")
     return dst_planes

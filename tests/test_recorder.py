@@ -19,7 +19,10 @@ BLK = np.dtype([("bx4", "u2"), ("by4", "u2"), ("w4", "u1"), ("h4", "u1"), ("intr
                 ("skip", "u1"), ("tile", "u1"), ("edge_tr", "u1"), ("edge_bl", "u1"), ("y_mode", "u1"), ("uv_mode", "u1"),
                 ("y_angle", "i1"), ("uv_angle", "i1"), ("tx", "u1"), ("uvtx", "u1"), ("pal_sz", "u1", 2),
                 ("cfl_alpha", "i1", 2), ("tile_rect", "u2", 4), ("pad0", "u2"), ("pal_off", "u4", 3),
-                ("pal_idx_off", "u4", 2), ("first_op", "u4"), ("n_ops", "u4"), ("sm_flags", "u1"), ("pad", "u1", 3)])
+                ("pal_idx_off", "u4", 2), ("first_op", "u4"), ("n_ops", "u4"), ("sm_flags", "u1"), ("pad", "u1", 3),
+                ("mvx", "i2", 2), ("mvy", "i2", 2), ("ref", "u1", 2), ("comp_kind", "u1"), ("filter2d", "u1"),
+                ("mask_sign", "u1"), ("max_ytx", "u1"), ("tx_split", "u1"), ("jnt_weight", "u1"), ("first_tx", "u4"),
+                ("n_tx", "u4")])
 OP = np.dtype([("x4", "u2"), ("y4", "u2"), ("tile_x4_start", "u2"), ("tile_y4_start", "u2"), ("tile_x4_end", "u2"),
                ("tile_y4_end", "u2"), ("plane", "u1"), ("tw4", "u1"), ("th4", "u1"), ("mode", "u1"),
                ("angle_delta", "i1"), ("edge_flags", "u1"), ("flags", "u2"), ("eob", "i2"), ("tx", "u1"), ("txtp", "u1"),
@@ -27,7 +30,7 @@ OP = np.dtype([("x4", "u2"), ("y4", "u2"), ("tile_x4_start", "u2"), ("tile_y4_st
 
 
 def record_frame(hf):
-    assert BLK.itemsize == 64 and OP.itemsize == 40
+    assert BLK.itemsize == 88 and OP.itemsize == 40
     L = pkg.lib()
     blocks = np.frombuffer(hf.blocks.tobytes(), dtype=BLK)
     ops = np.frombuffer(hf.intra.tobytes(), dtype=OP)
@@ -62,7 +65,7 @@ def record_frame(hf):
     return ops, out[:r.n_intra]
 
 
-@pytest.mark.parametrize("name", list(R.CASES))
+@pytest.mark.parametrize("name", [n for n in R.CASES if not n.startswith("inter_")])
 def test_recorder_emits_the_generators_descriptors(name):
     hf, _ = R.make(name)
     want, got = record_frame(hf)

@@ -1,12 +1,17 @@
-"""Frame parity against the reference's OWN reconstruction driver.
+"""Frame parity against the reference's OWN reconstruction drivers.
 
-oracle/ref_recon.c calls dav1d_recon_b_intra_{8,16}bpc (src/recon_tmpl.c:1195-1596, compiled where it
-lies under /root/reference) block by block on Av1Block-style records of synthetic all-intra frames
-(generator option real_blocks: block contexts, chroma ownership of 4-pixel blocks, tile resets as
-src/decode.c does them).  Everything the driver decides - predictor and angle, edge flags per
-transform block, CfL / palette order, smooth-neighbour flags from the above / left contexts, tile
-edges, the superblock-row edge backup - is the reference's code; the descriptors the CUDA path
-consumes are recorded independently by the generator.
+oracle/ref_recon.c calls dav1d_recon_b_intra_{8,16}bpc (src/recon_tmpl.c:1195-1596) and
+dav1d_recon_b_inter_{8,16}bpc (:1598-2036), compiled where they lie under /root/reference, block by block
+on Av1Block-style records of synthetic frames (generator option real_blocks: block contexts, chroma
+ownership of 4-pixel blocks, tile resets as src/decode.c does them).  Everything the drivers decide -
+predictor and angle, edge flags per transform block, CfL / palette order, smooth-neighbour flags from the
+above / left contexts, tile edges, the superblock-row edge backup; for inter blocks the source position
+and sub-pel phase per plane, the emu_edge decision, the compound combine and its mask hand-over to
+chroma, the transform tree and the cbi / cf consumption order - is the reference's code; the descriptors
+the CUDA path consumes are recorded independently by the generator.  Inter coverage: single-reference
+and compound (avg, distance-weighted avg, segmentation mask) blocks with residuals; warped, OBMC,
+inter-intra, wedge and intrabc blocks need refmvs rows / mask tables the records do not carry and stay
+on the descriptor-replay oracle (tests/test_frame.py).
 
  * CPU: the descriptor-driven oracle (oracle/ref_frame.c, the bench's CPU arm) reproduces the
    reference driver bit for bit - i.e. the descriptors mean what recon_tmpl.c means;
@@ -37,14 +42,32 @@ CASES = {
     "420_12b_no_edge_filter_split": (320, 192, 0xfff, 11, {"edge_filter": 0, "p_tx_split": 1.0, "p_residual": 1.0}),
     "444_10b_tiles_3x2_no_residual": (448, 256, 0x3ff, 12, {"ss_hor": 0, "ss_ver": 0, "tile_cols": 3, "tile_rows": 2,
                                                             "p_residual": 0.0, "p_palette": 0.15}),
+    # frames with inter blocks (dav1d_recon_b_inter): put / avg / w_avg / segmentation-mask compound + residual trees
+    "inter_420_8b_put_only": (256, 192, 0xff, 31, {"p_intra": 0.0, "p_avg": 0, "p_w_avg": 0, "p_seg": 0}),
+    "inter_420_10b_mixed": (320, 256, 0x3ff, 32, {"p_intra": 0.3, "p_avg": 0.2, "p_w_avg": 0.15, "p_seg": 0.15, "p_cfl": 0.4}),
+    "inter_444_12b": (256, 192, 0xfff, 33, {"ss_hor": 0, "ss_ver": 0, "p_intra": 0.2, "p_avg": 0.2, "p_w_avg": 0.2, "p_seg": 0.2}),
+    "inter_422_10b": (256, 192, 0x3ff, 34, {"ss_hor": 1, "ss_ver": 0, "p_intra": 0.3, "p_avg": 0.2, "p_w_avg": 0.1, "p_seg": 0.2}),
+    "inter_420_8b_long_vectors_ragged": (200, 136, 0xff, 35, {"p_intra": 0.1, "mv_range": 300, "p_avg": 0.2, "p_w_avg": 0.1,
+                                                            "p_seg": 0.1}),
+    "inter_420_10b_tiles_2x2": (384, 256, 0x3ff, 36, {"tile_cols": 2, "tile_rows": 2, "p_intra": 0.4, "p_avg": 0.2, "p_seg": 0.1}),
+    "inter_luma_8b": (256, 256, 0xff, 37, {"no_chroma": 1, "p_intra": 0.3, "p_avg": 0.3, "p_seg": 0.2}),
 }
 
 
 def make(name):
     w, h, bd, seed, kw = CASES[name]
-    hf = F.HostFrame(w, h, bd, seed, p_intra=1.0, real_blocks=1, **kw)
+    kw = dict(kw)
+    kw.setdefault("p_intra", 1.0)
+    kw.setdefault("p_wedge", 0.0)
+    kw.setdefault("p_warp", 0.0)
+    hf = F.HostFrame(w, h, bd, seed, real_blocks=1, **kw)
     init = F.random_planes(hf, seed * 10 + 5)
     return hf, init
+
+
+def refs_of(hf, name):
+    seed = CASES[name][3]
+    return [F.random_planes(hf, seed * 10 + k) for k in range(2)] if hf.params.p_intra < 1.0 else []
 
 
 def md5_planes(planes):
@@ -57,8 +80,9 @@ def md5_planes(planes):
 @pytest.mark.parametrize("name", list(CASES))
 def test_descriptors_mean_what_the_reference_driver_means(ref, name):
     hf, init = make(name)
-    want = refframe.run_reference_driver(ref, hf, [p.copy() for p in init])
-    got = refframe.run_oracle(ref, hf, [p.copy() for p in init], [])
+    refs = refs_of(hf, name)
+    want = refframe.run_reference_driver(ref, hf, [p.copy() for p in init], refs)
+    got = refframe.run_oracle(ref, hf, [p.copy() for p in init], refs)
     for pl, (a, b) in enumerate(zip(want, got)):
         bad = np.argwhere(a != b)
         assert bad.size == 0, f"{name}: plane {pl}: {len(bad)} pixels differ, first at (y,x)={bad[0]}"
@@ -66,20 +90,24 @@ def test_descriptors_mean_what_the_reference_driver_means(ref, name):
         assert md5_planes(want) == json.load(f)[name], name      # drift of generator / reference build
 
 
-def test_random_all_intra_frames_against_the_reference_driver(ref):
+def test_random_frames_against_the_reference_drivers(ref):
     rng = np.random.default_rng(20261019)
-    for k in range(12):
+    for k in range(16):
         lay = [(1, 1), (1, 0), (0, 0)][rng.integers(3)]
         kw = dict(ss_hor=lay[0], ss_ver=lay[1], p_cfl=float(rng.choice([0, 0.5])), p_palette=float(rng.choice([0, 0.15])),
+                  p_intra=float(rng.choice([1.0, 0.5, 0.2, 0.0])), p_wedge=0.0, p_warp=0.0,
+                  p_avg=float(rng.choice([0, 0.2])), p_w_avg=float(rng.choice([0, 0.2])), p_seg=float(rng.choice([0, 0.2])),
+                  mv_range=int(rng.choice([16, 128, 400])),
                   p_filter_intra=float(rng.choice([0, 0.2])), tile_cols=int(rng.integers(1, 4)),
                   tile_rows=int(rng.integers(1, 3)), p_tx_split=float(rng.choice([0, 0.5, 1.0])),
                   p_residual=float(rng.choice([0.3, 0.6, 1.0])), edge_filter=int(rng.integers(2)))
         w, h = int(rng.integers(8, 60)) * 8, int(rng.integers(8, 40)) * 8
         bd = [0xff, 0x3ff, 0xfff][rng.integers(3)]
-        hf = F.HostFrame(w, h, bd, 500 + k, p_intra=1.0, real_blocks=1, **kw)
+        hf = F.HostFrame(w, h, bd, 500 + k, real_blocks=1, **kw)
         init = F.random_planes(hf, 9000 + k)
-        want = refframe.run_reference_driver(ref, hf, [p.copy() for p in init])
-        got = refframe.run_oracle(ref, hf, [p.copy() for p in init], [])
+        refs = [F.random_planes(hf, 9100 + 2 * k + j) for j in range(2)]
+        want = refframe.run_reference_driver(ref, hf, [p.copy() for p in init], refs)
+        got = refframe.run_oracle(ref, hf, [p.copy() for p in init], refs)
         assert all(np.array_equal(a, b) for a, b in zip(want, got)), (k, w, h, hex(bd), kw)
 
 
@@ -88,11 +116,12 @@ def test_random_all_intra_frames_against_the_reference_driver(ref):
 def test_cuda_frame_equals_the_reference_driver(ref, name):
     import test_frame
     hf, init = make(name)
-    want = refframe.run_reference_driver(ref, hf, [p.copy() for p in init])
+    refs = refs_of(hf, name)
+    want = refframe.run_reference_driver(ref, hf, [p.copy() for p in init], refs)
     for record in (False, True):
         if record:
             hf.record_levels()
-        got = test_frame.run_gpu(hf, [], init, use_graph=False)
+        got = test_frame.run_gpu(hf, refs, init, use_graph=False)
         for pl, (a, b) in enumerate(zip(want, got)):
             bad = np.argwhere(a != b)
             assert bad.size == 0, f"{name} (recorded levels: {record}): plane {pl}: {len(bad)} pixels differ, first {bad[0]}"

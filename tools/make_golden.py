@@ -31,7 +31,7 @@ import test_reference_driver as R  # noqa: E402
 out = {}
 for name in R.CASES:
     hf, init = R.make(name)
-    out[name] = R.md5_planes(refframe.run_reference_driver(ref, hf, [p.copy() for p in init]))
+    out[name] = R.md5_planes(refframe.run_reference_driver(ref, hf, [p.copy() for p in init], R.refs_of(hf, name)))
     print(name, out[name], "blocks", hf.n_block_recs, "intra ops", hf.n_intra)
 with open(R.GOLDEN, "w") as f:
     json.dump(out, f, indent=1, sort_keys=True)
