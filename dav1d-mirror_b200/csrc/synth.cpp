@@ -513,7 +513,8 @@ struct Gen {
         const int h_mul = 4 >> sh, v_mul = 4 >> sv;
         const int R = P.mv_range * 8;
         auto ilog2 = [](int v) { int l = 0; while (v > 1) { v >>= 1; l++; } return l; };
-        auto neighbour = [&](int x4, int y4, int ow4, int mh4, int kind, int blend_h) {
+        struct NbMv { int ref, mvx, mvy, filter; };
+        auto neighbour = [&](int x4, int y4, int ow4, int mh4, int kind, int blend_h, const NbMv *nb = nullptr) {
             Dav1dCudaMcDesc d;
             memset(&d, 0, sizeof(d));
             d.plane = (uint8_t)pl; d.kind = (uint8_t)kind;
@@ -521,11 +522,44 @@ struct Gen {
             d.y = (uint16_t)(((by4 * 4) >> sv) + (y4 - by4) * v_mul);
             d.w = (uint8_t)(ow4 * h_mul); d.h = (uint8_t)(mh4 * v_mul);
             d.aux16 = (uint16_t)blend_h;
-            d.src[0] = make_src(pl, x4, y4, rng.range(P.n_refs), rng.irange(-R, R), rng.irange(-R, R), rng.range(10));
+            if (nb) d.src[0] = make_src(pl, x4, y4, nb->ref, nb->mvx, nb->mvy, nb->filter);
+            else d.src[0] = make_src(pl, x4, y4, rng.range(P.n_refs), rng.irange(-R, R), rng.irange(-R, R), rng.range(10));
             add_bytes(0, 4.0 * Bp * d.w * d.h);     // reference read + blend read-modify-write
             if (kind == DAV1D_CUDA_MC_OBMC_H) { order.push_back({ 6, (uint32_t)obmc_h.size() }); obmc_h.push_back(d); }
             else { order.push_back({ 7, (uint32_t)obmc_v.size() }); obmc_v.push_back(d); }
         };
+        if (P.real_blocks) {
+            // obmc() (recon_tmpl.c:1071-1131) over the ACTUAL neighbours: the blocks whose bottom row /
+            // right column lies along this block's top / left edge (what the refmvs rows hold), looked at
+            // at the odd 4x4 position of every step; inter neighbours only
+            if (by4 > tile_y0 && (!pl || w4 * h_mul + h4 * v_mul >= 16)) {
+                for (int i = 0, x = 0; x < w4 && i < std::min(ilog2(w4), 4);) {
+                    const Nb &a = nb_above[bx4 + x + 1];
+                    const int step4 = std::min(std::max((int)a.w4, 2), 16);
+                    if (a.inter) {
+                        const int ow4 = std::min(step4, w4), oh4 = std::min(h4, 16) >> 1;
+                        const NbMv m = { a.ref, a.mvx, a.mvy, a.filter };
+                        neighbour(bx4 + x, by4, ow4, (oh4 * 3 + 3) >> 2, DAV1D_CUDA_MC_OBMC_H, v_mul * oh4, &m);
+                        i++;
+                    }
+                    x += step4;
+                }
+            }
+            if (bx4 > tile_x0) {
+                for (int i = 0, y = 0; y < h4 && i < std::min(ilog2(h4), 4);) {
+                    const Nb &l = nb_left[by4 + y + 1];
+                    const int step4 = std::min(std::max((int)l.h4, 2), 16);
+                    if (l.inter) {
+                        const int ow4 = std::min(w4, 16) >> 1, oh4 = std::min(step4, h4);
+                        const NbMv m = { l.ref, l.mvx, l.mvy, l.filter };
+                        neighbour(bx4, by4 + y, ow4, oh4, DAV1D_CUDA_MC_OBMC_V, 0, &m);
+                        i++;
+                    }
+                    y += step4;
+                }
+            }
+            return;
+        }
         if (by4 > tile_y0 && (!pl || w4 * h_mul + h4 * v_mul >= 16)) {
             for (int i = 0, x = 0; x < w4 && i < std::min(ilog2(w4), 4);) {
                 int step4 = 2 << rng.range(4);
@@ -722,7 +756,9 @@ struct Gen {
         }
         if (P.real_blocks) {
             rec_inter.n_tx = (uint32_t)tx_recs.size() - rec_inter.first_tx;
+            rec_inter.pad[0] = do_obmc ? 1 : 0;                 // b->motion_mode == MM_OBMC
             blocks.push_back(rec_inter);
+            nb_set(bx4, by4, w4, h4, 1, ref[0], mvx[0], mvy[0], filter);
         }
         for (int pl = 0; pl < nplanes(); pl++) {
             const int sh = pl ? P.ss_hor : 0, sv = pl ? P.ss_ver : 0;
@@ -733,8 +769,10 @@ struct Gen {
     void block(int bx4, int by4, int w4, int h4) {
         n_blocks++;
         luma_px += 16.0 * w4 * h4;
-        if (rng.chance(P.p_intra)) intra_block(bx4, by4, w4, h4);
-        else {
+        if (rng.chance(P.p_intra)) {
+            intra_block(bx4, by4, w4, h4);
+            if (P.real_blocks) nb_set(bx4, by4, w4, h4, 0, 0, 0, 0, 0);
+        } else {
             inter_block(bx4, by4, w4, h4);
             if (P.real_blocks) {            // decode.c:810-830: intra = 0, uvmode = DC_PRED
                 const bool hc = (w4 > P.ss_hor || (bx4 & 1)) && (h4 > P.ss_ver || (by4 & 1));
@@ -807,12 +845,21 @@ struct Gen {
     std::vector<uint8_t> a_intra, a_mode, a_uvmode, l_intra, l_mode, l_uvmode;
     std::vector<D1SynthBlock> blocks;
     std::vector<D1SynthTx> tx_recs;
+    // what the refmvs rows and the filter contexts tell obmc() about the block above a column / left of a row
+    struct Nb { uint8_t inter, ref, filter, w4, h4; int16_t mvx, mvy; };
+    std::vector<Nb> nb_above, nb_left;
+    void nb_set(int bx4, int by4, int w4, int h4, int inter, int ref, int mvx, int mvy, int filter) {
+        const Nb n = { (uint8_t)inter, (uint8_t)ref, (uint8_t)filter, (uint8_t)w4, (uint8_t)h4, (int16_t)mvx, (int16_t)mvy };
+        for (int x = bx4; x < std::min(bx4 + w4, bw4); x++) nb_above[x] = n;
+        for (int y = by4; y < std::min(by4 + h4, bh4); y++) nb_left[y] = n;
+    }
     // f->jnt_weights[ref0][ref1] of the synthetic frame header (real_blocks)
     static int jnt_weight_of(int r0, int r1) { return 1 + (r0 * 7 + r1 * 3 + 4) % 15; }
     static bool smooth_mode(int m) { return m >= 9 && m <= 11; }
     void ctx_init() {
         a_intra.assign(bw4 + 1, 0); a_mode.assign(bw4 + 1, 0); a_uvmode.assign(bw4 + 1, 0);
         l_intra.assign(bh4 + 1, 0); l_mode.assign(bh4 + 1, 0); l_uvmode.assign(bh4 + 1, 0);
+        nb_above.assign(bw4 + 2, Nb{ 0, 0, 0, 1, 1, 0, 0 }); nb_left.assign(bh4 + 2, Nb{ 0, 0, 0, 1, 1, 0, 0 });
     }
     void ctx_reset_above() {
         for (int x = tile_x0; x < std::min(tile_x1, bw4); x++) { a_intra[x] = 0; a_mode[x] = 0; }

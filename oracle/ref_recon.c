@@ -115,8 +115,8 @@ static void dense_coefs(coef *out, const OracleReconFrame *fr, const Dav1dCudaIn
 }
 
 /* Reconstructs every block of the frame through dav1d_recon_b_intra / dav1d_recon_b_inter.  Returns 0, or
- * a negative value when the records hold something this harness does not drive (warped, OBMC, inter-intra,
- * wedge and intrabc blocks: they need refmvs rows / mask tables the records do not carry). */
+ * a negative value when the records hold something this harness does not drive (warped, inter-intra,
+ * wedge and intrabc blocks: they need warp parameters / mask tables the records do not carry). */
 EXPORT int SUFFIX(oracle_recon_frame)(const OracleReconFrame *const fr) {
     int ret = 0;
     Dav1dDSPContext dsp;
@@ -181,13 +181,18 @@ EXPORT int SUFFIX(oracle_recon_frame)(const OracleReconFrame *const fr) {
     t->f = f;
     t->ts = ts;
     t->frame_thread.pass = 2;
+    /* the refmvs rows obmc() reads its neighbours from (recon_tmpl.c:1078): one block array for the whole
+     * frame, 5 rows of margin above; every block writes its area after reconstruction the way
+     * decode.c:756-767 / 815-826 do through splat_mv (bottom row and right column are what is read) */
+    const int rstride = f->b4_stride + 32;
+    refmvs_block *const rmv = calloc((size_t)(f->bh + 64 + 5) * rstride, sizeof(*rmv));
 
     /* per-block streams: pass 1 leaves cbi / cf / pal_idx as consecutive runs; a block's share is
      * built right before the call */
     int16_t cbi[3 * 256 + 8];
     coef *const cfbuf = aligned_alloc(64, sizeof(coef) * 64 * 1024);
     uint8_t *const idxbuf = aligned_alloc(64, 8192);
-    if (!edge_buf || !f->frame_thread.pal || !a || !cfbuf || !idxbuf) { ret = -12; goto done; }
+    if (!edge_buf || !f->frame_thread.pal || !a || !cfbuf || !idxbuf || !rmv) { ret = -12; goto done; }
 
     int cur_tile = -1, cur_sbrow = -1;
     for (int i = 0; i < fr->n_blocks; i++) {
@@ -217,7 +222,9 @@ EXPORT int SUFFIX(oracle_recon_frame)(const OracleReconFrame *const fr) {
             b.comp_type = s->comp_kind == DAV1D_CUDA_MC_PUT ? COMP_INTER_NONE :
                           s->comp_kind == DAV1D_CUDA_MC_AVG ? COMP_INTER_AVG :
                           s->comp_kind == DAV1D_CUDA_MC_W_AVG ? COMP_INTER_WEIGHTED_AVG : COMP_INTER_SEG;
-            b.inter_mode = 0; b.motion_mode = MM_TRANSLATION; b.interintra_type = 0;
+            b.inter_mode = 0; b.motion_mode = s->pad[0] ? MM_OBMC : MM_TRANSLATION; b.interintra_type = 0;
+            for (int r = 0; r < 32 + 5; r++)
+                t->rt.r[r] = rmv + (size_t)((s->by4 & ~31) + r) * rstride;      /* row (by & ~31) - 5 + r, margin 5 */
             for (int k = 0; k < 2; k++) { b.mv[k].x = s->mvx[k]; b.mv[k].y = s->mvy[k]; b.ref[k] = (int8_t)s->ref[k]; }
             b.filter2d = s->filter2d; b.mask_sign = s->mask_sign;
             b.max_ytx = s->max_ytx; b.tx_split0 = s->tx_split ? 1 : 0; b.tx_split1 = 0;
@@ -237,6 +244,15 @@ EXPORT int SUFFIX(oracle_recon_frame)(const OracleReconFrame *const fr) {
             ts->frame_thread[0].cbi = cbi;
             ts->frame_thread[0].cf = cfbuf;
             if (SUFFIX(dav1d_recon_b_inter)(t, bs, &b)) { ret = -5; goto done; }
+            /* decode.c:815-826 (splat_oneref_mv / splat_tworef_mv) */
+            for (int y = 0; y < s->h4 && s->by4 + y < f->bh + 32; y++)
+                for (int x = 0; x < s->w4 && s->bx4 + x < f->b4_stride + 32; x++) {
+                    refmvs_block *const rb = &rmv[(size_t)(s->by4 + y + 5) * rstride + s->bx4 + x];
+                    rb->mv.mv[0] = b.mv[0]; rb->mv.mv[1] = b.mv[1];
+                    rb->ref.ref[0] = b.ref[0] + 1;
+                    rb->ref.ref[1] = b.comp_type == COMP_INTER_NONE ? -1 : b.ref[1] + 1;
+                    rb->bs = bs; rb->mf = 0;
+                }
             /* decode.c:808-830: filters, intra = 0, uvmode = DC_PRED into the contexts */
             const int bx4 = s->bx4 & 31, by4 = s->by4 & 31;
             const uint8_t *const filter = dav1d_filter_dir[b.filter2d];
@@ -298,6 +314,13 @@ EXPORT int SUFFIX(oracle_recon_frame)(const OracleReconFrame *const fr) {
                        ((s->edge_bl & 2) ? (EDGE_I420_LEFT_HAS_BOTTOM | EDGE_I422_LEFT_HAS_BOTTOM) : 0);
         SUFFIX(dav1d_recon_b_intra)(t, bs, ef, &b);
 
+        /* decode.c:756-767 (splat_intraref): ref 0 = intra */
+        for (int y = 0; y < s->h4 && s->by4 + y < f->bh + 32; y++)
+            for (int x = 0; x < s->w4 && s->bx4 + x < f->b4_stride + 32; x++) {
+                refmvs_block *const rb = &rmv[(size_t)(s->by4 + y + 5) * rstride + s->bx4 + x];
+                memset(rb, 0, sizeof(*rb));
+                rb->ref.ref[1] = -1; rb->bs = bs;
+            }
         /* decode.c:744-772: the block's modes into the above / left contexts */
         const int bx4 = s->bx4 & 31, by4 = s->by4 & 31;
         const int y_mode_nofilt = s->y_mode == FILTER_PRED ? DC_PRED : s->y_mode;
@@ -311,7 +334,7 @@ EXPORT int SUFFIX(oracle_recon_frame)(const OracleReconFrame *const fr) {
         }
     }
 done:
-    free(idxbuf); free(cfbuf); free(a); free(f->frame_thread.pal); free(edge_buf);
+    free(rmv); free(idxbuf); free(cfbuf); free(a); free(f->frame_thread.pal); free(edge_buf);
     free(t); free(ts); free(f);
     return ret;
 }

@@ -9,9 +9,10 @@ above / left contexts, tile edges, the superblock-row edge backup; for inter blo
 and sub-pel phase per plane, the emu_edge decision, the compound combine and its mask hand-over to
 chroma, the transform tree and the cbi / cf consumption order - is the reference's code; the descriptors
 the CUDA path consumes are recorded independently by the generator.  Inter coverage: single-reference
-and compound (avg, distance-weighted avg, segmentation mask) blocks with residuals; warped, OBMC,
-inter-intra, wedge and intrabc blocks need refmvs rows / mask tables the records do not carry and stay
-on the descriptor-replay oracle (tests/test_frame.py).
+and compound (avg, distance-weighted avg, segmentation mask) blocks with residuals, and OBMC (obmc(),
+recon_tmpl.c:1071-1132, over refmvs rows the harness fills the way decode.c does after every block);
+warped, inter-intra, wedge and intrabc blocks need warp parameters / mask tables the records do not
+carry and stay on the descriptor-replay oracle (tests/test_frame.py).
 
  * CPU: the descriptor-driven oracle (oracle/ref_frame.c, the bench's CPU arm) reproduces the
    reference driver bit for bit - i.e. the descriptors mean what recon_tmpl.c means;
@@ -51,6 +52,14 @@ CASES = {
                                                             "p_seg": 0.1}),
     "inter_420_10b_tiles_2x2": (384, 256, 0x3ff, 36, {"tile_cols": 2, "tile_rows": 2, "p_intra": 0.4, "p_avg": 0.2, "p_seg": 0.1}),
     "inter_luma_8b": (256, 256, 0xff, 37, {"no_chroma": 1, "p_intra": 0.3, "p_avg": 0.3, "p_seg": 0.2}),
+    # overlapped block motion compensation: obmc() reads the ACTUAL above / left neighbours from the refmvs rows
+    "obmc_420_8b": (256, 192, 0xff, 41, {"p_intra": 0.2, "p_avg": 0, "p_w_avg": 0, "p_seg": 0, "p_obmc": 0.8}),
+    "obmc_420_10b_mixed": (320, 256, 0x3ff, 42, {"p_intra": 0.3, "p_avg": 0.2, "p_w_avg": 0.15, "p_seg": 0.15, "p_cfl": 0.4,
+                                                 "p_obmc": 0.5}),
+    "obmc_444_12b": (256, 192, 0xfff, 43, {"ss_hor": 0, "ss_ver": 0, "p_intra": 0.2, "p_avg": 0.2, "p_obmc": 0.6}),
+    "obmc_422_10b": (256, 192, 0x3ff, 44, {"ss_hor": 1, "ss_ver": 0, "p_intra": 0.3, "p_avg": 0.2, "p_obmc": 0.6}),
+    "obmc_420_8b_long_vectors_ragged": (200, 136, 0xff, 45, {"p_intra": 0.1, "mv_range": 300, "p_avg": 0.2, "p_obmc": 0.6}),
+    "obmc_420_10b_tiles_2x2": (384, 256, 0x3ff, 46, {"tile_cols": 2, "tile_rows": 2, "p_intra": 0.4, "p_avg": 0.2, "p_obmc": 0.7}),
 }
 
 
@@ -97,7 +106,7 @@ def test_random_frames_against_the_reference_drivers(ref):
         kw = dict(ss_hor=lay[0], ss_ver=lay[1], p_cfl=float(rng.choice([0, 0.5])), p_palette=float(rng.choice([0, 0.15])),
                   p_intra=float(rng.choice([1.0, 0.5, 0.2, 0.0])), p_wedge=0.0, p_warp=0.0,
                   p_avg=float(rng.choice([0, 0.2])), p_w_avg=float(rng.choice([0, 0.2])), p_seg=float(rng.choice([0, 0.2])),
-                  mv_range=int(rng.choice([16, 128, 400])),
+                  p_obmc=float(rng.choice([0, 0.5])), mv_range=int(rng.choice([16, 128, 400])),
                   p_filter_intra=float(rng.choice([0, 0.2])), tile_cols=int(rng.integers(1, 4)),
                   tile_rows=int(rng.integers(1, 3)), p_tx_split=float(rng.choice([0, 0.5, 1.0])),
                   p_residual=float(rng.choice([0.3, 0.6, 1.0])), edge_filter=int(rng.integers(2)))
