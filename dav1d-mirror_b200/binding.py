@@ -155,6 +155,17 @@ IntraDesc = IntraDesc40
 assert C.sizeof(IntraDesc) == 40 and C.sizeof(WarpDesc) == 32
 
 
+class McScaledSrc(C.Structure):
+    _fields_ = [("pos_x", C.c_int32), ("pos_y", C.c_int32), ("step_x", C.c_int32), ("step_y", C.c_int32),
+                ("ref", C.c_uint8), ("filter_2d", C.c_uint8), ("pad", C.c_uint16)]
+
+
+class McScaledDesc(C.Structure):
+    _fields_ = [("x", C.c_uint16), ("y", C.c_uint16), ("w", C.c_uint8), ("h", C.c_uint8), ("plane", C.c_uint8),
+                ("kind", C.c_uint8), ("src", McScaledSrc * 2), ("weight", C.c_uint8), ("mask_ss", C.c_uint8),
+                ("aux16", C.c_uint16), ("aux_off", C.c_uint32)]
+
+
 class ReconBatch(C.Structure):
     _fields_ = [("dst", C.POINTER(Picture)), ("refs", C.POINTER(Picture) * 7),
                 ("bw4", C.c_int32), ("bh4", C.c_int32),
@@ -170,7 +181,8 @@ class ReconBatch(C.Structure):
                 ("intra_cellmap", C.c_void_p),
                 ("intra_itx", C.c_void_p), ("intra_itx_class_count", C.c_int32 * N_RECT_TX_SIZES),
                 ("intra_itx_tasks", C.c_void_p), ("n_intra_itx_tasks", C.c_int32 * 2),
-                ("intra_res", C.POINTER(Picture)), ("intra_levels_recorded", C.c_int32)]
+                ("intra_res", C.POINTER(Picture)), ("intra_levels_recorded", C.c_int32),
+                ("mc_scaled", C.c_void_p), ("n_mc_scaled", C.c_int32 * 4)]
 
 
 MAX_GROUP = 64

@@ -242,6 +242,82 @@ struct ScaledArgs {
 
 constexpr int SC_MAX_ROWS = 72;
 
+// One tile (at most 32x32, top-left (x0, y0) of a w x h block) of a scaled prediction, by one warp.
+// (sx, sy): integer position of the block's top-left in `ref`, read with clamping; mx, my: the
+// 1/1024 remainder; dx, dy: steps.  `mid` holds SC_MAX_ROWS * MC_T int16.  out: the tile's first
+// element, stride ostride.
+template <typename pixel, bool PREP, typename out_t>
+DEV void mc_scaled_tile(const PlaneView &ref, const int sx, const int sy, const int w, const int h, const int mx,
+                        const int my, const int dx, const int dy, const int filter_2d, const int bdmax, const int x0,
+                        const int y0, const int tw, const int th, int16_t *mid, out_t *out, const int ostride,
+                        const int lane)
+{
+    const bool bilin = filter_2d == 9;
+    const int ib = PxTraits<pixel>::inter_bits(bdmax);
+    const int th_t = (0x15A80 >> (2 * filter_2d)) & 3, tv_t = filter_2d % 3;
+    const int hset = w > 4 ? th_t : 3 + (th_t & 1);
+    const int vset = h > 4 ? tv_t : 3 + (tv_t & 1);
+    const pixel *rp = (const pixel *)ref.data;
+    const int64_t rs = ref.stride / (int64_t)sizeof(pixel);
+
+    // rows of `mid` this tile needs, relative to the block's first mid row
+    const int ypos0 = my + y0 * dy;
+    const int row_first = ypos0 >> 10;
+    const int row_last = ((my + (y0 + th - 1) * dy) >> 10) + (bilin ? 1 : 7);
+    const int nrows = row_last - row_first + 1;
+    const int roff = bilin ? 0 : -3;      // mid row r <-> source row sy + roff + r
+    for (int i = lane; i < nrows * tw; i += 32) {
+        const int r = i / tw, x = i % tw;
+        const int pos = mx + (x0 + x) * dx;
+        const int ioff = pos >> 10, fx = (pos & 0x3ff) >> 6;
+        const int yy = iclip(sy + roff + row_first + r, 0, ref.h - 1);
+        const pixel *row = rp + yy * rs;
+        int v;
+        if (bilin) {
+            const int p0 = row[iclip(sx + ioff, 0, ref.w - 1)];
+            const int p1 = row[iclip(sx + ioff + 1, 0, ref.w - 1)];
+            const int sh = 4 - ib;
+            v = (16 * p0 + fx * (p1 - p0) + ((1 << sh) >> 1)) >> sh;
+        } else if (fx) {
+            const int8_t *f = g_subpel_filters + (hset * 15 + fx - 1) * 8;
+            int sum = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) sum += f[k] * row[iclip(sx + ioff + k - 3, 0, ref.w - 1)];
+            const int sh = 6 - ib;
+            v = (sum + ((1 << sh) >> 1)) >> sh;
+        } else {
+            v = row[iclip(sx + ioff, 0, ref.w - 1)] << ib;
+        }
+        mid[r * MC_T + x] = (int16_t)v;
+    }
+    __syncwarp();
+    for (int i = lane; i < tw * th; i += 32) {
+        const int y = i / tw, x = i % tw;
+        const int ypos = my + (y0 + y) * dy;
+        const int r = (ypos >> 10) - row_first, fy = (ypos & 0x3ff) >> 6;
+        const int16_t *m = mid + r * MC_T + x;
+        int res;
+        if (bilin) {
+            const int s = 16 * m[0] + fy * (m[MC_T] - m[0]);
+            if (PREP) res = ((s + 8) >> 4) - PxTraits<pixel>::prep_bias;
+            else res = clip_px<pixel>((s + ((1 << (4 + ib)) >> 1)) >> (4 + ib), bdmax);
+        } else if (fy) {
+            const int8_t *f = g_subpel_filters + (vset * 15 + fy - 1) * 8;
+            int sum = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) sum += f[k] * m[k * MC_T];
+            if (PREP) res = ((sum + 32) >> 6) - PxTraits<pixel>::prep_bias;
+            else res = clip_px<pixel>((sum + ((1 << (6 + ib)) >> 1)) >> (6 + ib), bdmax);
+        } else {
+            const int c = m[3 * MC_T];
+            if (PREP) res = c - PxTraits<pixel>::prep_bias;
+            else res = clip_px<pixel>((c + ((1 << ib) >> 1)) >> ib, bdmax);
+        }
+        out[y * ostride + x] = (out_t)res;
+    }
+    __syncwarp();                           // `mid` may be rewritten by the caller's next tile
+}
+
 template <typename pixel, bool PREP>
 __global__ void __launch_bounds__(MC_WARPS * 32) mc_scaled_kernel(const ScaledArgs a) {
     __shared__ int16_t mid_all[MC_WARPS][SC_MAX_ROWS * MC_T];
@@ -250,73 +326,108 @@ __global__ void __launch_bounds__(MC_WARPS * 32) mc_scaled_kernel(const ScaledAr
     const int tiles_x = (a.w + MC_T - 1) / MC_T, tiles_y = (a.h + MC_T - 1) / MC_T;
     const int t = blockIdx.x * MC_WARPS + warp;
     if (t >= tiles_x * tiles_y) return;
-    int16_t *mid = mid_all[warp];
     const int x0 = (t % tiles_x) * MC_T, y0 = (t / tiles_x) * MC_T;
     const int tw = imin(MC_T, a.w - x0), th = imin(MC_T, a.h - y0);
-    const bool bilin = a.filter_2d == 9;
-    const int ib = PxTraits<pixel>::inter_bits(a.bdmax);
-    const int th_t = (0x15A80 >> (2 * a.filter_2d)) & 3, tv_t = a.filter_2d % 3;
-    const int hset = a.w > 4 ? th_t : 3 + (th_t & 1);
-    const int vset = a.h > 4 ? tv_t : 3 + (tv_t & 1);
-    const pixel *rp = (const pixel *)a.ref.data;
-    const int64_t rs = a.ref.stride / (int64_t)sizeof(pixel);
+    mc_scaled_tile<pixel, PREP, out_t>(a.ref, a.sx, a.sy, a.w, a.h, a.mx, a.my, a.dx, a.dy, a.filter_2d, a.bdmax, x0, y0,
+                                       tw, th, mid_all[warp], (out_t *)a.out + y0 * a.ostride + x0, a.ostride, lane);
+}
 
-    // rows of `mid` this tile needs, relative to the block's first mid row
-    const int ypos0 = a.my + y0 * a.dy;
-    const int row_first = ypos0 >> 10;
-    const int row_last = ((a.my + (y0 + th - 1) * a.dy) >> 10) + (bilin ? 1 : 7);
-    const int nrows = row_last - row_first + 1;
-    const int roff = bilin ? 0 : -3;      // mid row r <-> source row sy + roff + r
-    for (int i = lane; i < nrows * tw; i += 32) {
-        const int r = i / tw, x = i % tw;
-        const int pos = a.mx + (x0 + x) * a.dx;
-        const int ioff = pos >> 10, fx = (pos & 0x3ff) >> 6;
-        const int yy = iclip(a.sy + roff + row_first + r, 0, a.ref.h - 1);
-        const pixel *row = rp + yy * rs;
-        int v;
-        if (bilin) {
-            const int p0 = row[iclip(a.sx + ioff, 0, a.ref.w - 1)];
-            const int p1 = row[iclip(a.sx + ioff + 1, 0, a.ref.w - 1)];
-            const int sh = 4 - ib;
-            v = (16 * p0 + fx * (p1 - p0) + ((1 << sh) >> 1)) >> sh;
-        } else if (fx) {
-            const int8_t *f = g_subpel_filters + (hset * 15 + fx - 1) * 8;
-            int sum = 0;
-#pragma unroll
-            for (int k = 0; k < 8; k++) sum += f[k] * row[iclip(a.sx + ioff + k - 3, 0, a.ref.w - 1)];
-            const int sh = 6 - ib;
-            v = (sum + ((1 << sh) >> 1)) >> sh;
-        } else {
-            v = row[iclip(a.sx + ioff, 0, a.ref.w - 1)] << ib;
+// ---- batched form (Dav1dCudaMcScaledDesc): one warp per descriptor, tile after tile; one or two
+// scaled predictions into shared tiles, then the same combine / blend code as the same-size path
+struct ScaledBatchArgs {
+    PicView dst;
+    PicView refs[7];
+    const Dav1dCudaMcScaledDesc *descs;
+    int n;
+    uint8_t *masks;
+};
+
+template <typename pixel> struct __align__(16) ScaledSmem {
+    int16_t mid[SC_MAX_ROWS * MC_T];
+    int16_t ta[MC_T * MC_T], tb[MC_T * MC_T];
+};
+
+template <typename pixel>
+__global__ void __launch_bounds__(MC_WARPS * 32) mc_scaled_batch_kernel(const __grid_constant__ ScaledBatchArgs a) {
+    __shared__ ScaledSmem<pixel> sm_all[MC_WARPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int di = blockIdx.x * MC_WARPS + warp;
+    if (di >= a.n) return;
+    ScaledSmem<pixel> *sm = &sm_all[warp];
+    const Dav1dCudaMcScaledDesc d = a.descs[di];
+    const PlaneView &dp = a.dst.p[d.plane];
+    const int dstride = (int)(dp.stride / (int)sizeof(pixel));
+    const bool obmc = d.kind == DAV1D_CUDA_MC_OBMC_H || d.kind == DAV1D_CUDA_MC_OBMC_V;
+    const bool single = d.kind == DAV1D_CUDA_MC_PUT || obmc;
+    for (int y0 = 0; y0 < d.h; y0 += MC_T) {
+        for (int x0 = 0; x0 < d.w; x0 += MC_T) {
+            const int tw = imin(MC_T, d.w - x0), th = imin(MC_T, d.h - y0);
+            pixel *out = (pixel *)dp.data + (int64_t)(d.y + y0) * dstride + d.x + x0;
+            if (single) {
+                const Dav1dCudaMcScaledSrc s = d.src[0];
+                const PlaneView &ref = a.refs[s.ref].p[d.plane];
+                pixel *lap = (pixel *)sm->ta;
+                if (obmc)
+                    mc_scaled_tile<pixel, false, pixel>(ref, s.pos_x >> 10, s.pos_y >> 10, d.w, d.h, s.pos_x & 0x3ff,
+                                                        s.pos_y & 0x3ff, s.step_x, s.step_y, s.filter_2d, a.dst.bdmax, x0,
+                                                        y0, tw, th, sm->mid, lap, MC_T, lane);
+                else
+                    mc_scaled_tile<pixel, false, pixel>(ref, s.pos_x >> 10, s.pos_y >> 10, d.w, d.h, s.pos_x & 0x3ff,
+                                                        s.pos_y & 0x3ff, s.step_x, s.step_y, s.filter_2d, a.dst.bdmax, x0,
+                                                        y0, tw, th, sm->mid, out, dstride, lane);
+                if (obmc) {
+                    const bool horz = d.kind == DAV1D_CUDA_MC_OBMC_H;
+                    const int bh = horz ? d.aux16 : d.h;
+                    const int lim_x = horz ? d.w : (d.w * 3) >> 2, lim_y = horz ? (bh * 3) >> 2 : d.h;
+                    const int nx = imin(tw, lim_x - x0), ny = imin(th, lim_y - y0);
+                    for (int i = lane; i < ny * 32; i += 32) {
+                        const int y = i >> 5, x = i & 31;
+                        if (x >= nx) continue;
+                        const int m = horz ? g_obmc_masks[bh + y0 + y] : g_obmc_masks[d.w + x0 + x];
+                        const int p = out[y * dstride + x], q = lap[y * MC_T + x];
+                        out[y * dstride + x] = (pixel)((p * (64 - m) + q * m + 32) >> 6);
+                    }
+                    __syncwarp();
+                }
+                continue;
+            }
+            for (int i = 0; i < 2; i++) {
+                const Dav1dCudaMcScaledSrc s = d.src[i];
+                const PlaneView &ref = a.refs[s.ref].p[d.plane];
+                mc_scaled_tile<pixel, true, int16_t>(ref, s.pos_x >> 10, s.pos_y >> 10, d.w, d.h, s.pos_x & 0x3ff,
+                                                     s.pos_y & 0x3ff, s.step_x, s.step_y, s.filter_2d, a.dst.bdmax, x0, y0,
+                                                     tw, th, sm->mid, i ? sm->tb : sm->ta, MC_T, lane);
+            }
+            uint8_t *mask = nullptr;
+            int ms = 0;
+            if (d.kind == DAV1D_CUDA_MC_MASK) {
+                ms = d.w;
+                mask = a.masks + d.aux_off + y0 * ms + x0;
+            } else if (d.kind == DAV1D_CUDA_MC_W_MASK) {
+                const int ssh = d.mask_ss >= 1, ssv = d.mask_ss == 2;
+                ms = d.w >> ssh;
+                mask = a.masks + d.aux_off + (y0 >> ssv) * ms + (x0 >> ssh);
+            }
+            mc_combine<pixel>(d.kind, sm->ta, sm->tb, MC_T, out, dstride, tw, th, d.weight, mask, ms, d.mask_ss,
+                              a.dst.bdmax, lane, 32);
+            __syncwarp();
         }
-        mid[r * MC_T + x] = (int16_t)v;
     }
-    __syncwarp();
-    out_t *out = (out_t *)a.out + y0 * a.ostride + x0;
-    for (int i = lane; i < tw * th; i += 32) {
-        const int y = i / tw, x = i % tw;
-        const int ypos = a.my + (y0 + y) * a.dy;
-        const int r = (ypos >> 10) - row_first, fy = (ypos & 0x3ff) >> 6;
-        const int16_t *m = mid + r * MC_T + x;
-        int res;
-        if (bilin) {
-            const int s = 16 * m[0] + fy * (m[MC_T] - m[0]);
-            if (PREP) res = ((s + 8) >> 4) - PxTraits<pixel>::prep_bias;
-            else res = clip_px<pixel>((s + ((1 << (4 + ib)) >> 1)) >> (4 + ib), a.bdmax);
-        } else if (fy) {
-            const int8_t *f = g_subpel_filters + (vset * 15 + fy - 1) * 8;
-            int sum = 0;
-#pragma unroll
-            for (int k = 0; k < 8; k++) sum += f[k] * m[k * MC_T];
-            if (PREP) res = ((sum + 32) >> 6) - PxTraits<pixel>::prep_bias;
-            else res = clip_px<pixel>((sum + ((1 << (6 + ib)) >> 1)) >> (6 + ib), a.bdmax);
-        } else {
-            const int c = m[3 * MC_T];
-            if (PREP) res = c - PxTraits<pixel>::prep_bias;
-            else res = clip_px<pixel>((c + ((1 << ib) >> 1)) >> ib, a.bdmax);
-        }
-        out[y * a.ostride + x] = (out_t)res;
-    }
+}
+
+int mc_scaled_launch_raw(const PicView &dst, const PicView *refs, const Dav1dCudaMcScaledDesc *descs, const int n,
+                         uint8_t *masks, cudaStream_t s)
+{
+    if (n <= 0) return 0;
+    ScaledBatchArgs a;
+    a.dst = dst;
+    for (int i = 0; i < 7; i++) a.refs[i] = refs[i];
+    a.descs = descs; a.n = n; a.masks = masks;
+    const int grid = (n + MC_WARPS - 1) / MC_WARPS;
+    if (dst.bdmax > 0xff) mc_scaled_batch_kernel<uint16_t><<<grid, MC_WARPS * 32, 0, s>>>(a);
+    else mc_scaled_batch_kernel<uint8_t><<<grid, MC_WARPS * 32, 0, s>>>(a);
+    count_launch();
+    return cuda_ok(cudaGetLastError(), "mc_scaled_batch_kernel") ? 0 : -5;
 }
 
 // ------------------------------------------------------------------ launchers

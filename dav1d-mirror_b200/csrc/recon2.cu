@@ -55,6 +55,8 @@ int itx_task_launch(const PicView &pic, const PicView *res, void *cf, const Dav1
 int mc_obmc_launch_raw(const PicView &dst, const PicView *refs, const Dav1dCudaMcDesc *descs,
                        const uint32_t *tiles, int n_tiles, cudaStream_t st);
 void itx_init_attrs();
+int mc_scaled_launch_raw(const PicView &dst, const PicView *refs, const Dav1dCudaMcScaledDesc *descs, int n,
+                         uint8_t *masks, cudaStream_t s);
 int mc_put_launch_raw(const PicView &dst, const PicView *refs, const Dav1dCudaMcDesc *descs,
                       const uint32_t *tiles, int n_tiles, int n_small, uint8_t *masks, int16_t *tmp,
                       bool compound, cudaStream_t st);
@@ -942,6 +944,8 @@ static int check_group(const Dav1dCudaReconBatch *const *bs, int n) {
         if (b->n_intra > 0 && (!b->intra || !b->intra_cellmap)) return -22;
         if (b->n_intra >= (1 << 20)) return -22;
         if (b->n_intra > 0 && b->intra_itx && !b->intra_res) return -22;
+        for (int k = 0; k < 4; k++)
+            if (b->n_mc_scaled[k] < 0 || (b->n_mc_scaled[k] > 0 && !b->mc_scaled)) return -22;
     }
     return 0;
 }
@@ -1029,12 +1033,19 @@ static int group_submit_on(Dav1dCudaContext *c, const Dav1dCudaReconBatch *const
         if ((mask & 2) && (r = mc_put_launch_raw(dst, refs, b->mc_comp, b->mc_comp_tiles + b->n_mc_comp_tiles[0],
                                                  b->n_mc_comp_tiles[1], b->n_mc_comp_small[1], b->masks, nullptr, true, s))) return r;
         if ((mask & 4) && (r = warp_batch_launch(dst, refs, b->warp, b->n_warp, s))) return r;
-        if ((mask & 1) && b->mc_obmc) {
-            // OBMC blends onto the finished predictions: top neighbours, then left neighbours
-            if ((r = mc_obmc_launch_raw(dst, refs, b->mc_obmc, b->mc_obmc_tiles, b->n_mc_obmc_tiles[0], s))) return r;
-            if ((r = mc_obmc_launch_raw(dst, refs, b->mc_obmc, b->mc_obmc_tiles + b->n_mc_obmc_tiles[0],
-                                        b->n_mc_obmc_tiles[1], s))) return r;
-        }
+        // predictions from references of another size: the two compound waves, then (below) the OBMC waves
+        const Dav1dCudaMcScaledDesc *sc = (mask & 3) ? b->mc_scaled : nullptr;
+        const int *nsc = b->n_mc_scaled;
+        if (sc && (r = mc_scaled_launch_raw(dst, refs, sc, nsc[0], b->masks, s))) return r;
+        if (sc && (r = mc_scaled_launch_raw(dst, refs, sc + nsc[0], nsc[1], b->masks, s))) return r;
+        // OBMC blends onto the finished predictions: top neighbours, then left neighbours
+        if ((mask & 1) && b->mc_obmc &&
+            (r = mc_obmc_launch_raw(dst, refs, b->mc_obmc, b->mc_obmc_tiles, b->n_mc_obmc_tiles[0], s))) return r;
+        if (sc && (r = mc_scaled_launch_raw(dst, refs, sc + nsc[0] + nsc[1], nsc[2], b->masks, s))) return r;
+        if ((mask & 1) && b->mc_obmc &&
+            (r = mc_obmc_launch_raw(dst, refs, b->mc_obmc, b->mc_obmc_tiles + b->n_mc_obmc_tiles[0],
+                                    b->n_mc_obmc_tiles[1], s))) return r;
+        if (sc && (r = mc_scaled_launch_raw(dst, refs, sc + nsc[0] + nsc[1] + nsc[2], nsc[3], b->masks, s))) return r;
         if ((mask & 8) && b->itx && b->itx_tasks) {
             if ((r = itx_task_launch(dst, nullptr, b->cf, b->itx, b->itx_tasks, b->n_itx_tasks[0], b->n_itx_tasks[1], 0, s, s)))
                 return r;

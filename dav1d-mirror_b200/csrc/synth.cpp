@@ -50,6 +50,8 @@ typedef struct D1SynthParams {
                                     // Av1Block (smooth-neighbour flags from the above / left block contexts,
                                     // chroma of 4-px-wide / -high blocks with the odd partner, no CfL padding
                                     // inside the picture) + a block record per block for the reference driver
+    int32_t ref_w[7], ref_h[7];     // luma size of reference i when it differs from the frame's (0 = same size):
+                                    // predictions from it go through the scaled branch of mc() (recon_tmpl.c:1010-1065)
 } D1SynthParams;
 
 // One coded block as the reference's reconstruction driver sees it (the Av1Block fields
@@ -106,6 +108,7 @@ typedef struct D1SynthFrame {
     double dense_coef_bytes;   // part of algo_bytes that counts DENSE coefficient blocks; the packed stream is cf_elems
     D1SynthBlock *blocks;      int32_t n_block_recs;   // real_blocks: every block in decode order
     D1SynthTx *tx_recs;        int32_t n_tx_recs;      // real_blocks: cbi / cf entries of the inter blocks
+    Dav1dCudaMcScaledDesc *mc_scaled; int32_t n_mc_scaled[4];   // sections: wave 0, wave 1, OBMC_H, OBMC_V
 } D1SynthFrame;
 
 }  // extern "C"
@@ -505,6 +508,46 @@ struct Gen {
         return s;
     }
 
+    // ---- references of another size (f->svc[ref][0/1], decode.c:3517-3524)
+    std::vector<Dav1dCudaMcScaledDesc> sc[4];
+    bool ref_scaled(int r) const {
+        return (P.ref_w[r] && P.ref_w[r] != P.w) || (P.ref_h[r] && P.ref_h[r] != P.h);
+    }
+    static int scale_fac(int ref_sz, int cur_sz) { return ((ref_sz << 14) + (cur_sz >> 1)) / cur_sz; }
+    // the unscaled source -> what the scaled branch computes for it (recon_tmpl.c:1013-1021): orig_pos in
+    // 1/16 sample = (integer position << 4) + phase
+    Dav1dCudaMcScaledSrc scaled_src(const Dav1dCudaMcSrc &u) const {
+        Dav1dCudaMcScaledSrc o;
+        memset(&o, 0, sizeof(o));
+        o.ref = u.ref; o.filter_2d = u.filter_2d;
+        const int orig[2] = { u.x * 16 + u.mx, u.y * 16 + u.my };
+        int32_t *pos[2] = { &o.pos_x, &o.pos_y }, *step[2] = { &o.step_x, &o.step_y };
+        for (int k = 0; k < 2; k++) {
+            if (!ref_scaled(u.ref)) { *pos[k] = orig[k] * 64; *step[k] = 1024; continue; }
+            const int ref_sz = k ? (P.ref_h[u.ref] ? P.ref_h[u.ref] : P.h) : (P.ref_w[u.ref] ? P.ref_w[u.ref] : P.w);
+            const int scale = scale_fac(ref_sz, k ? P.h : P.w);
+            const int64_t tmp = (int64_t)orig[k] * scale + (int64_t)(scale - 0x4000) * 8;
+            const int mag = (int)(((tmp < 0 ? -tmp : tmp) + 128) >> 8);
+            *pos[k] = (tmp < 0 ? -mag : mag) + 32;
+            *step[k] = (scale + 8) >> 4;
+        }
+        return o;
+    }
+    // a prediction goes to the scaled list when a reference it reads has another size
+    bool route_scaled(const Dav1dCudaMcDesc &d, int section) {
+        const bool two = d.kind != DAV1D_CUDA_MC_PUT && d.kind != DAV1D_CUDA_MC_OBMC_H && d.kind != DAV1D_CUDA_MC_OBMC_V;
+        if (!ref_scaled(d.src[0].ref) && !(two && ref_scaled(d.src[1].ref))) return false;
+        Dav1dCudaMcScaledDesc o;
+        memset(&o, 0, sizeof(o));
+        o.x = d.x; o.y = d.y; o.w = d.w; o.h = d.h; o.plane = d.plane; o.kind = d.kind;
+        o.src[0] = scaled_src(d.src[0]);
+        if (two) o.src[1] = scaled_src(d.src[1]);
+        o.weight = d.weight; o.mask_ss = d.mask_ss; o.aux16 = d.aux16; o.aux_off = d.aux_off;
+        order.push_back({ (uint8_t)(8 + section), (uint32_t)sc[section].size() });
+        sc[section].push_back(o);
+        return true;
+    }
+
     // obmc() (recon_tmpl.c:1071-1131) with random neighbours: per top / left neighbour (width or
     // height step4 in {2,4,8,16}, inter with probability 0.7, at most min(log2(dim), 4) of them) a
     // prediction with the neighbour's motion vector + blend_h / blend_v
@@ -525,6 +568,7 @@ struct Gen {
             if (nb) d.src[0] = make_src(pl, x4, y4, nb->ref, nb->mvx, nb->mvy, nb->filter);
             else d.src[0] = make_src(pl, x4, y4, rng.range(P.n_refs), rng.irange(-R, R), rng.irange(-R, R), rng.range(10));
             add_bytes(0, 4.0 * Bp * d.w * d.h);     // reference read + blend read-modify-write
+            if (route_scaled(d, kind == DAV1D_CUDA_MC_OBMC_H ? 2 : 3)) return;
             if (kind == DAV1D_CUDA_MC_OBMC_H) { order.push_back({ 6, (uint32_t)obmc_h.size() }); obmc_h.push_back(d); }
             else { order.push_back({ 7, (uint32_t)obmc_v.size() }); obmc_v.push_back(d); }
         };
@@ -596,6 +640,8 @@ struct Gen {
         else if (u < (acc += P.p_wedge)) kind = DAV1D_CUDA_MC_MASK;
         else if (u < (acc += P.p_seg)) kind = DAV1D_CUDA_MC_W_MASK;
         else if (u < (acc += P.p_warp) && w4 >= 4 && h4 >= 4) is_warp = true;
+        bool any_scaled = false;
+        for (int i = 0; i < 7; i++) any_scaled |= ref_scaled(i);
         const int filter = rng.range(10);
         const int R = P.mv_range * 8;
         int ref[2], mvx[2], mvy[2];
@@ -605,6 +651,7 @@ struct Gen {
             if (rng.chance(0.1f)) mvx[i] &= ~7;    // integer-pel columns / rows now and then
             if (rng.chance(0.1f)) mvy[i] &= ~7;
         }
+        if (is_warp && any_scaled && ref_scaled(ref[0])) is_warp = false;   // allow_warp needs a same-size reference (decode.c:1828)
         int weight = rng.irange(1, 15);
         const int sign = rng.range(2);
         if (P.real_blocks) weight = jnt_weight_of(ref[0], ref[1]);    // COMP_INTER_WEIGHTED_AVG takes it from the frame
@@ -669,8 +716,10 @@ struct Gen {
             bool wave1 = false;
             if (kind == DAV1D_CUDA_MC_PUT) {
                 add_bytes(0, 2.0 * Bp * w * h);
-                order.push_back({ 0, (uint32_t)put.size() });
-                put.push_back(d);
+                if (!route_scaled(d, 0)) {
+                    order.push_back({ 0, (uint32_t)put.size() });
+                    put.push_back(d);
+                }
                 if (do_obmc) add_obmc(pl, bx4, by4, w4, h4);
                 continue;
             }
@@ -699,6 +748,7 @@ struct Gen {
                     add_bytes(1, (double)w * h);
                 }
             }
+            if (route_scaled(d, wave1 ? 1 : 0)) continue;
             if (wave1) { order.push_back({ 5, (uint32_t)comp1.size() }); comp1.push_back(d); }
             else { order.push_back({ 1, (uint32_t)comp0.size() }); comp0.push_back(d); }
         }
@@ -904,6 +954,7 @@ __attribute__((visibility("default"))) void d1synth_default_params(D1SynthParams
     p->p_filter_intra = 0.05f; p->p_palette = 0.02f; p->p_cfl = 0.25f;
     p->p_avg = 0.2f; p->p_w_avg = 0.1f; p->p_wedge = 0.1f; p->p_seg = 0.05f; p->p_warp = 0.05f;
     p->mv_range = 128; p->n_refs = 2; p->edge_filter = 1; p->only_tx = -1; p->only_txtp = -1; p->eob_class = -1; p->dense_coefs = 0; p->p_obmc = 0.f; p->p_ii = 0.f; p->p_ibc = 0.f; p->tile_cols = 1; p->tile_rows = 1; p->real_blocks = 0;
+    for (int i = 0; i < 7; i++) p->ref_w[i] = p->ref_h[i] = 0;
 }
 
 __attribute__((visibility("default"))) int d1synth_generate(const D1SynthParams *p, D1SynthFrame *f) {
@@ -992,6 +1043,7 @@ __attribute__((visibility("default"))) int d1synth_generate(const D1SynthParams 
         uint32_t cls = g.order[i].cls, idx = g.order[i].idx;
         if (cls == 5) { cls = 1; idx += (uint32_t)g.comp0.size(); }
         if (cls == 7) { cls = 6; idx += (uint32_t)g.obmc_h.size(); }
+        if (cls >= 8) { for (uint32_t k = 8; k < cls; k++) idx += (uint32_t)g.sc[k - 8].size(); cls = 8; }
         if (cls == 3) idx = itx_new[idx];
         order[i] = (cls << 28) | idx;
     }
@@ -1023,13 +1075,19 @@ __attribute__((visibility("default"))) int d1synth_generate(const D1SynthParams 
     f->n_blocks = g.n_blocks; f->n_intra_blocks = g.n_intra_blocks;
     f->blocks = dup(g.blocks); f->n_block_recs = (int32_t)g.blocks.size();
     f->tx_recs = dup(g.tx_recs); f->n_tx_recs = (int32_t)g.tx_recs.size();
+    std::vector<Dav1dCudaMcScaledDesc> scaled;
+    for (int k = 0; k < 4; k++) {
+        scaled.insert(scaled.end(), g.sc[k].begin(), g.sc[k].end());
+        f->n_mc_scaled[k] = (int32_t)g.sc[k].size();
+    }
+    f->mc_scaled = dup(scaled);
     return 0;
 }
 
 __attribute__((visibility("default"))) void d1synth_free(D1SynthFrame *f) {
     if (!f) return;
     free(f->mc_put); free(f->mc_put_tiles); free(f->mc_comp); free(f->mc_comp_tiles); free(f->warp);
-    free(f->mc_obmc); free(f->mc_obmc_tiles); free(f->blocks); free(f->tx_recs);
+    free(f->mc_obmc); free(f->mc_obmc_tiles); free(f->blocks); free(f->tx_recs); free(f->mc_scaled);
     free(f->intra_itx);
     free(f->itx); free(f->intra); free(f->cf); free(f->masks); free(f->pal); free(f->pal_idx); free(f->order);
     memset(f, 0, sizeof(*f));

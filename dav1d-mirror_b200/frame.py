@@ -23,7 +23,8 @@ class SynthParams(C.Structure):
                 ("mv_range", C.c_int32), ("n_refs", C.c_int32), ("edge_filter", C.c_int32),
                 ("only_tx", C.c_int32), ("only_txtp", C.c_int32), ("eob_class", C.c_int32),
                 ("dense_coefs", C.c_int32), ("p_obmc", C.c_float), ("p_ii", C.c_float), ("p_ibc", C.c_float),
-                ("tile_cols", C.c_int32), ("tile_rows", C.c_int32), ("real_blocks", C.c_int32)]
+                ("tile_cols", C.c_int32), ("tile_rows", C.c_int32), ("real_blocks", C.c_int32),
+                ("ref_w", C.c_int32 * 7), ("ref_h", C.c_int32 * 7)]
 
 
 class SynthFrame(C.Structure):
@@ -47,7 +48,8 @@ class SynthFrame(C.Structure):
                 ("n_mc_obmc_tiles", C.c_int32 * 2),
                 ("intra_itx", C.c_void_p), ("n_intra_itx", C.c_int32), ("intra_itx_class_count", C.c_int32 * 19),
                 ("dense_coef_bytes", C.c_double), ("blocks", C.c_void_p), ("n_block_recs", C.c_int32),
-                ("tx_recs", C.c_void_p), ("n_tx_recs", C.c_int32)]
+                ("tx_recs", C.c_void_p), ("n_tx_recs", C.c_int32),
+                ("mc_scaled", C.c_void_p), ("n_mc_scaled", C.c_int32 * 4)]
 
 
 _synth = None
@@ -82,6 +84,10 @@ class HostFrame:
         for k, v in kw.items():
             if not hasattr(p, k):
                 raise KeyError(k)
+            if k in ("ref_w", "ref_h"):          # luma size per reference, 0 = the frame's
+                for i, x in enumerate(v):
+                    getattr(p, k)[i] = x
+                continue
             setattr(p, k, v)
         f = SynthFrame()
         r = S.d1synth_generate(C.byref(p), C.byref(f))
@@ -104,6 +110,8 @@ class HostFrame:
         self.mc_obmc = _np_from(f.mc_obmc, f.n_mc_obmc * C.sizeof(B.McDesc))
         self.n_mc_obmc_tiles = (f.n_mc_obmc_tiles[0], f.n_mc_obmc_tiles[1])
         self.mc_obmc_tiles = _np_from(f.mc_obmc_tiles, (f.n_mc_obmc_tiles[0] + f.n_mc_obmc_tiles[1]) * 4)
+        self.n_mc_scaled = tuple(f.n_mc_scaled[i] for i in range(4))
+        self.mc_scaled = _np_from(f.mc_scaled, sum(self.n_mc_scaled) * C.sizeof(B.McScaledDesc))
         self.warp = _np_from(f.warp, f.n_warp * C.sizeof(B.WarpDesc))
         self.n_warp = f.n_warp
         self.itx = _np_from(f.itx, f.n_itx * C.sizeof(B.ItxDesc))
@@ -160,24 +168,29 @@ class HostFrame:
             self.n_levels = r
         return r
 
-    def plane_shape(self, pl):
+    def plane_shape(self, pl, ref=None):
+        """ref: index of a reference picture (its size may differ from the frame's: params.ref_w / ref_h)."""
         sh = self.ss_hor if pl else 0
         sv = self.ss_ver if pl else 0
-        return ((self.h + sv) >> sv, (self.w + sh) >> sh)
+        w, h = self.ref_size(ref) if ref is not None else (self.w, self.h)
+        return ((h + sv) >> sv, (w + sh) >> sh)
+
+    def ref_size(self, r):
+        return (self.params.ref_w[r] or self.w, self.params.ref_h[r] or self.h)
 
     def host_bytes(self):
         """Bytes a decoder ships host->device for this frame (descriptors + coefficients + pools)."""
         return sum(a.nbytes for a in (self.mc_put, self.mc_put_tiles, self.mc_comp, self.mc_comp_tiles, self.warp,
-                                      self.mc_obmc, self.mc_obmc_tiles, self.itx, self.itx_tasks, self.cf, self.masks,
+                                      self.mc_obmc, self.mc_obmc_tiles, self.mc_scaled, self.itx, self.itx_tasks, self.cf, self.masks,
                                       self.pal, self.pal_idx, self.intra, self.intra_itx,
                                       self.intra_itx_tasks))
 
 
-def random_planes(hf, seed):
+def random_planes(hf, seed, ref=None):
     """Reference / initial picture content: uniform random pixels (checkasm's worst case)."""
     rng = np.random.default_rng(seed)
     dt = np.uint16 if hf.hbd else np.uint8
-    return [rng.integers(0, hf.bdmax + 1, size=hf.plane_shape(pl), dtype=np.int32).astype(dt)
+    return [rng.integers(0, hf.bdmax + 1, size=hf.plane_shape(pl, ref), dtype=np.int32).astype(dt)
             for pl in range(1 if hf.no_chroma else 3)]
 
 
@@ -193,8 +206,9 @@ class DeviceFrame:
         L = self.L
         self.dst = B.Picture()
         self.refs = [B.Picture() for _ in range(n_refs)]
-        for pic in [self.dst] + self.refs:
-            r = L.dav1d_cuda_picture_alloc(ctx, C.byref(pic), hf.w, hf.h, hf.ss_hor, hf.ss_ver, hf.bdmax)
+        for k, pic in enumerate([self.dst] + self.refs):
+            pw, ph = hf.ref_size(k - 1) if k else (hf.w, hf.h)
+            r = L.dav1d_cuda_picture_alloc(ctx, C.byref(pic), pw, ph, hf.ss_hor, hf.ss_ver, hf.bdmax)
             if r:
                 raise RuntimeError("dav1d_cuda_picture_alloc failed")
         ssh = 0 if hf.no_chroma else hf.ss_hor
@@ -228,6 +242,8 @@ class DeviceFrame:
         alt = {}
         if hf.mc_obmc.nbytes:
             names += ["mc_obmc", "mc_obmc_tiles"]
+        if hf.mc_scaled.nbytes:
+            names += ["mc_scaled"]
         host, offs, off = {}, {}, 0
         for name in names:
             arr = alt.get(name, getattr(hf, name))
@@ -254,6 +270,10 @@ class DeviceFrame:
         if hf.mc_obmc.nbytes:
             b.mc_obmc, b.mc_obmc_tiles = d["mc_obmc"], d["mc_obmc_tiles"]
             b.n_mc_obmc_tiles[0], b.n_mc_obmc_tiles[1] = hf.n_mc_obmc_tiles
+        if hf.mc_scaled.nbytes:
+            b.mc_scaled = d["mc_scaled"]
+            for i in range(4):
+                b.n_mc_scaled[i] = hf.n_mc_scaled[i]
         b.itx = d["itx"]
         for i in range(19):
             b.itx_class_count[i] = hf.itx_class_count[i]

@@ -210,6 +210,34 @@ typedef struct Dav1dCudaMcDesc {   /* 40 bytes */
                               PREP: int16 offset into the tmp pool */
 } Dav1dCudaMcDesc;
 
+/* -- motion compensation from a reference of ANOTHER size (the scaled branch of mc(),
+ * recon_tmpl.c:1010-1065; dsp->mc.mc_scaled / mct_scaled, src/mc.h:45-69).  The recorder runs the
+ * scale_mv arithmetic (:1015-1021) and hands over the 1/1024-sample position of the block's
+ * top-left in the reference plane: left = pos_x >> 10 (may be negative or beyond the plane - the
+ * kernel clamps, which is what emu_edge :1036-1044 amounts to), mx = pos_x & 0x3ff, and the
+ * steps f->svc[ref][0/1].step.  A compound block whose other reference has the frame's own size
+ * describes that source with step 1024 and pos = (integer position << 10) + (phase << 6): the
+ * scaled filters then compute exactly what mc / mct compute. */
+typedef struct Dav1dCudaMcScaledSrc {   /* 20 bytes */
+    int32_t  pos_x, pos_y;
+    int32_t  step_x, step_y;
+    uint8_t  ref;          /* index into Dav1dCudaReconBatch.refs[] */
+    uint8_t  filter_2d;    /* enum Filter2d */
+    uint16_t pad;
+} Dav1dCudaMcScaledSrc;
+
+typedef struct Dav1dCudaMcScaledDesc {  /* 56 bytes; fields as in Dav1dCudaMcDesc */
+    uint16_t x, y;
+    uint8_t  w, h;
+    uint8_t  plane;
+    uint8_t  kind;         /* PUT, AVG, W_AVG, MASK, W_MASK, OBMC_H, OBMC_V */
+    Dav1dCudaMcScaledSrc src[2];
+    uint8_t  weight;
+    uint8_t  mask_ss;
+    uint16_t aux16;
+    uint32_t aux_off;
+} Dav1dCudaMcScaledDesc;
+
 /* -- intra-class operations, one descriptor per transform block in DECODE
  * order (recon_tmpl.c:1259-1300 luma, :1372-1417 CfL, :1226-1243 palette,
  * :1503-1576 chroma), optionally fused with the block's residual.  The fields
@@ -479,6 +507,13 @@ typedef struct Dav1dCudaReconBatch {
     /* non-zero: the recorder ran dav1d_cuda_intra_levels() over `intra` (the descriptors carry their
      * dependency level); zero: the device works the levels out itself (a cluster of blocks per frame) */
     int32_t intra_levels_recorded;
+    /* optional: predictions from references of another size, four consecutive sections of
+     * `mc_scaled`: [0] PUT / AVG / W_AVG / wedge MASK / W_MASK, [1] MASK descriptors that read a
+     * mask section [0] emitted (chroma of a segmentation-mask block), [2] OBMC_H, [3] OBMC_V.
+     * [0] and [1] run after the same-size predictions, [2] right after the same-size OBMC_H wave
+     * and [3] after the same-size OBMC_V wave (a block's top blends come before its left blends
+     * whatever the size of the neighbours' references). */
+    const Dav1dCudaMcScaledDesc *mc_scaled; int32_t n_mc_scaled[4];
 } Dav1dCudaReconBatch;
 
 enum { DAV1D_CUDA_MAX_GROUP = 64 };   /* frames per group submission */

@@ -49,9 +49,11 @@ typedef struct OracleFrame {
     const Dav1dCudaWarpDesc *warp;
     const Dav1dCudaItxDesc *itx;
     const Dav1dCudaIntraDesc *intra;
-    const uint32_t *order;        /* (class << 28) | index; class: 0 put 1 comp 2 warp 3 itx 4 intra 6 obmc */
+    const uint32_t *order;        /* (class << 28) | index; class: 0 put 1 comp 2 warp 3 itx 4 intra 6 obmc 8 scaled */
     int32_t n_order;
     const Dav1dCudaMcDesc *mc_obmc;
+    const Dav1dCudaMcScaledDesc *mc_scaled;   /* class 8: index into the four sections stored back to back */
+    int32_t ref_w[7], ref_h[7];               /* luma size of the references (0 = the frame's) */
 } OracleFrame;
 
 #if BITDEPTH == 8
@@ -96,6 +98,35 @@ static const pixel *mc_src(const OracleFrame *f, Scratch *s, const Dav1dCudaMcSr
     }
     *stride = ref_stride;
     return ref + PXSTRIDE(ref_stride) * dy + dx;
+}
+
+/* the scaled branch of mc() (recon_tmpl.c:1022-1064) from the position the recorder worked out:
+ * emu_edge decision, then mc_scaled (dst8) or mct_scaled (dst16) */
+static void mc_scaled_src(const OracleFrame *f, Scratch *s, const Dav1dCudaMcScaledSrc *src, int pl, int bw, int bh,
+                          pixel *dst8, ptrdiff_t dst_stride, int16_t *dst16, const Dav1dMCDSPContext *mc)
+{
+    BD_DECL
+    const int sh = pl ? f->ss_hor : 0, sv = pl ? f->ss_ver : 0;
+    const int w = ((f->ref_w[src->ref] ? f->ref_w[src->ref] : f->w) + sh) >> sh;
+    const int h = ((f->ref_h[src->ref] ? f->ref_h[src->ref] : f->h) + sv) >> sv;
+    const int pos_x = src->pos_x, pos_y = src->pos_y;
+    const int left = pos_x >> 10, top = pos_y >> 10;
+    const int right = ((pos_x + (bw - 1) * src->step_x) >> 10) + 1;
+    const int bottom = ((pos_y + (bh - 1) * src->step_y) >> 10) + 1;
+    const pixel *ref = f->ref[src->ref][pl];
+    ptrdiff_t ref_stride = f->ref_stride[src->ref][pl];
+    if (left < 3 || top < 3 || right + 4 > w || bottom + 4 > h) {
+        mc->emu_edge(right - left + 7, bottom - top + 7, w, h, left - 3, top - 3,
+                     s->emu, 320 * sizeof(pixel), ref, ref_stride);
+        ref = &s->emu[320 * 3 + 3];
+        ref_stride = 320 * sizeof(pixel);
+    } else {
+        ref += PXSTRIDE(ref_stride) * top + left;
+    }
+    if (dst8) mc->mc_scaled[src->filter_2d](dst8, dst_stride, ref, ref_stride, bw, bh, pos_x & 0x3ff, pos_y & 0x3ff,
+                                            src->step_x, src->step_y BD_ARG);
+    else mc->mct_scaled[src->filter_2d](dst16, ref, ref_stride, bw, bh, pos_x & 0x3ff, pos_y & 0x3ff,
+                                        src->step_x, src->step_y BD_ARG);
 }
 
 static void run_itx(const OracleFrame *f, Scratch *s, const Dav1dInvTxfmDSPContext *itx, pixel *dst,
@@ -163,6 +194,36 @@ void bitfn(run_frame)(const OracleFrame *const f) {
                 mc.w_mask[d->mask_ss](dst, dstride, s->tmp[0], s->tmp[1], d->w, d->h,
                                       f->masks + d->aux_off, d->weight BD_ARG);
                 break;
+            }
+        } else if (cls == 8) {
+            const Dav1dCudaMcScaledDesc *const d = &f->mc_scaled[idx];
+            const int pl = d->plane;
+            const ptrdiff_t dstride = f->dst_stride[pl];
+            pixel *const dst = (pixel *) f->dst[pl] + PXSTRIDE(dstride) * d->y + d->x;
+            if (d->kind == DAV1D_CUDA_MC_PUT) {
+                mc_scaled_src(f, s, &d->src[0], pl, d->w, d->h, dst, dstride, NULL, &mc);
+            } else if (d->kind == DAV1D_CUDA_MC_OBMC_H || d->kind == DAV1D_CUDA_MC_OBMC_V) {
+                pixel *const lap = (pixel *) s->tmp[0];
+                mc_scaled_src(f, s, &d->src[0], pl, d->w, d->h, lap, d->w * sizeof(pixel), NULL, &mc);
+                if (d->kind == DAV1D_CUDA_MC_OBMC_H) mc.blend_h(dst, dstride, lap, d->w, d->aux16);
+                else mc.blend_v(dst, dstride, lap, d->w, d->h);
+            } else {
+                for (int k = 0; k < 2; k++) mc_scaled_src(f, s, &d->src[k], pl, d->w, d->h, NULL, 0, s->tmp[k], &mc);
+                switch (d->kind) {
+                case DAV1D_CUDA_MC_AVG:
+                    mc.avg(dst, dstride, s->tmp[0], s->tmp[1], d->w, d->h BD_ARG);
+                    break;
+                case DAV1D_CUDA_MC_W_AVG:
+                    mc.w_avg(dst, dstride, s->tmp[0], s->tmp[1], d->w, d->h, d->weight BD_ARG);
+                    break;
+                case DAV1D_CUDA_MC_MASK:
+                    mc.mask(dst, dstride, s->tmp[0], s->tmp[1], d->w, d->h, f->masks + d->aux_off BD_ARG);
+                    break;
+                default:
+                    mc.w_mask[d->mask_ss](dst, dstride, s->tmp[0], s->tmp[1], d->w, d->h,
+                                          f->masks + d->aux_off, d->weight BD_ARG);
+                    break;
+                }
             }
         } else if (cls == 6) {
             /* obmc(), recon_tmpl.c:1071-1131: neighbour's prediction into the lap buffer + blend */

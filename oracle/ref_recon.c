@@ -80,6 +80,7 @@ typedef struct OracleReconFrame {
     ptrdiff_t ref_stride[7][2];
     int32_t n_refs;
     const D1SynthTx *tx_recs;          /* cbi / cf entries of the inter blocks */
+    int32_t ref_w[7], ref_h[7];        /* luma size of the references (0 = the frame's): scaled prediction */
 } OracleReconFrame;
 
 #if BITDEPTH == 8
@@ -167,13 +168,24 @@ EXPORT int SUFFIX(oracle_recon_frame)(const OracleReconFrame *const fr) {
     f->frame_thread.pal = calloc(n_pal, sizeof(*f->frame_thread.pal));
     BlockContext *const a = calloc((size_t)f->sb128w + 1, sizeof(*a));
     f->a = a;
-    /* reference pictures: same size as the current one (no scaling: f->svc stays zero) and the weights of
+    /* reference pictures (f->svc stays zero for those of the frame's size) and the weights of
      * COMP_INTER_WEIGHTED_AVG, a table of the frame (the generator draws the same table) */
     for (int i = 0; i < fr->n_refs && i < 7; i++) {
         Dav1dPicture *const rp = &f->refp[i].p;
         rp->data[0] = (void *)fr->ref[i][0]; rp->data[1] = (void *)fr->ref[i][1]; rp->data[2] = (void *)fr->ref[i][2];
         rp->stride[0] = fr->ref_stride[i][0]; rp->stride[1] = fr->ref_stride[i][1];
         rp->p = f->cur.p;
+        /* a reference of another size: decode.c:3511-3527 */
+        if (fr->ref_w[i]) rp->p.w = fr->ref_w[i];
+        if (fr->ref_h[i]) rp->p.h = fr->ref_h[i];
+        if (rp->p.w != f->cur.p.w || rp->p.h != f->cur.p.h) {
+#define scale_fac(ref_sz, this_sz) ((((ref_sz) << 14) + ((this_sz) >> 1)) / (this_sz))
+            f->svc[i][0].scale = scale_fac(rp->p.w, f->cur.p.w);
+            f->svc[i][1].scale = scale_fac(rp->p.h, f->cur.p.h);
+            f->svc[i][0].step = (f->svc[i][0].scale + 8) >> 4;
+            f->svc[i][1].step = (f->svc[i][1].scale + 8) >> 4;
+#undef scale_fac
+        }
     }
     for (int i = 0; i < 7; i++)
         for (int j = 0; j < 7; j++) f->jnt_weights[i][j] = 1 + (i * 7 + j * 3 + 4) % 15;

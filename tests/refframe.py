@@ -17,7 +17,7 @@ class OracleFrame(C.Structure):
                 ("cf", C.c_void_p), ("masks", C.c_void_p), ("pal", C.c_void_p), ("pal_idx", C.c_void_p),
                 ("mc_put", C.c_void_p), ("mc_comp", C.c_void_p), ("warp", C.c_void_p), ("itx", C.c_void_p),
                 ("intra", C.c_void_p), ("order", C.c_void_p), ("n_order", C.c_int32),
-                ("mc_obmc", C.c_void_p)]
+                ("mc_obmc", C.c_void_p), ("mc_scaled", C.c_void_p), ("ref_w", C.c_int32 * 7), ("ref_h", C.c_int32 * 7)]
 
 
 def make_oracle_frame(hf, dst_planes, ref_planes_list, keep):
@@ -40,9 +40,11 @@ def make_oracle_frame(hf, dst_planes, ref_planes_list, keep):
     keep.append(masks)
     for name, arr in (("cf", hf.cf), ("masks", masks), ("pal", hf.pal), ("pal_idx", hf.pal_idx),
                       ("mc_put", hf.mc_put), ("mc_comp", hf.mc_comp), ("warp", hf.warp), ("itx", hf.itx),
-                      ("intra", hf.intra), ("order", hf.order), ("mc_obmc", hf.mc_obmc)):
+                      ("intra", hf.intra), ("order", hf.order), ("mc_obmc", hf.mc_obmc), ("mc_scaled", hf.mc_scaled)):
         setattr(of, name, arr.ctypes.data if arr.nbytes else None)
     of.n_order = hf.order.nbytes // 4
+    for r in range(7):
+        of.ref_w[r], of.ref_h[r] = hf.params.ref_w[r], hf.params.ref_h[r]
     return of
 
 
@@ -64,7 +66,7 @@ class OracleReconFrame(C.Structure):
                 ("blocks", C.c_void_p), ("n_blocks", C.c_int32),
                 ("ops", C.c_void_p), ("cf", C.c_void_p), ("pal", C.c_void_p), ("pal_idx", C.c_void_p),
                 ("ref", (C.c_void_p * 3) * 7), ("ref_stride", (C.c_ssize_t * 2) * 7), ("n_refs", C.c_int32),
-                ("tx_recs", C.c_void_p)]
+                ("tx_recs", C.c_void_p), ("ref_w", C.c_int32 * 7), ("ref_h", C.c_int32 * 7)]
 
 
 def run_reference_driver(ref, hf, dst_planes, ref_planes_list=()):
@@ -87,6 +89,8 @@ def run_reference_driver(ref, hf, dst_planes, ref_planes_list=()):
         of.ref_stride[r][0] = planes[0].strides[0]
         of.ref_stride[r][1] = planes[1].strides[0] if len(planes) > 1 else 0
     of.n_refs = len(ref_planes_list)
+    for r in range(7):
+        of.ref_w[r], of.ref_h[r] = hf.params.ref_w[r], hf.params.ref_h[r]
     of.tx_recs = hf.tx_recs.ctypes.data if hf.tx_recs.nbytes else None
     fn = getattr(ref.lib, "oracle_recon_frame_16bpc" if hf.hbd else "oracle_recon_frame_8bpc")
     fn.argtypes = [C.POINTER(OracleReconFrame)]

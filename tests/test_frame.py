@@ -52,12 +52,22 @@ CASES = {
     "444_12b_tiles_2x1": (256, 128, 0xfff, 24, {"tile_cols": 2, "tile_rows": 1, "ss_hor": 0, "ss_ver": 0, "p_intra": 0.7}),
     # dense coefficient blocks (the reference's layout, cw4 = ch4 = 0) through the batched path
     "420_10b_dense_coefs": (256, 192, 0x3ff, 12, {"dense_coefs": 1}),
+    # references of another size: the scaled branch of mc() (recon_tmpl.c:1010-1065) as Dav1dCudaMcScaledDesc -
+    # reference 0 half the frame's size and reference 1 the frame's own (compounds mix both kinds), both
+    # references larger (2x / 1.25x1.5), odd ratios with long vectors that leave the reference
+    "420_10b_scaled_half_and_same": (320, 256, 0x3ff, 25, {"ref_w": [160, 0], "ref_h": [128, 0], "p_obmc": 0.3,
+                                                           "p_intra": 0.15}),
+    "444_8b_scaled_up": (256, 192, 0xff, 26, {"ref_w": [512, 320], "ref_h": [384, 288], "ss_hor": 0, "ss_ver": 0,
+                                              "p_intra": 0.1, "p_obmc": 0.3, "p_avg": 0.2, "p_seg": 0.15}),
+    "422_12b_scaled_odd_long_vectors": (264, 200, 0xfff, 27, {"ref_w": [200, 376], "ref_h": [120, 312], "ss_hor": 1,
+                                                              "ss_ver": 0, "mv_range": 400, "p_intra": 0.1,
+                                                              "p_wedge": 0.2, "p_seg": 0.2}),
 }
 
 
 def oracle_planes(ref, hf, seed):
     import refframe
-    refs = [F.random_planes(hf, seed * 100 + r) for r in range(2)]
+    refs = [F.random_planes(hf, seed * 100 + r, ref=r) for r in range(2)]
     init = F.random_planes(hf, seed * 100 + 50)
     out = refframe.run_oracle(ref, hf, [p.copy() for p in init], refs)
     return refs, init, out

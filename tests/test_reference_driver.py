@@ -60,6 +60,13 @@ CASES = {
     "obmc_422_10b": (256, 192, 0x3ff, 44, {"ss_hor": 1, "ss_ver": 0, "p_intra": 0.3, "p_avg": 0.2, "p_obmc": 0.6}),
     "obmc_420_8b_long_vectors_ragged": (200, 136, 0xff, 45, {"p_intra": 0.1, "mv_range": 300, "p_avg": 0.2, "p_obmc": 0.6}),
     "obmc_420_10b_tiles_2x2": (384, 256, 0x3ff, 46, {"tile_cols": 2, "tile_rows": 2, "p_intra": 0.4, "p_avg": 0.2, "p_obmc": 0.7}),
+    # references of another size: the scaled branch of mc() with f->svc as decode.c:3517-3524 sets it
+    "scaled_420_10b_half_and_same": (320, 256, 0x3ff, 51, {"ref_w": [160, 0], "ref_h": [128, 0], "p_intra": 0.2, "p_avg": 0.2,
+                                                           "p_w_avg": 0.1, "p_seg": 0.15, "p_obmc": 0.3}),
+    "scaled_444_8b_up": (256, 192, 0xff, 52, {"ref_w": [512, 320], "ref_h": [384, 288], "ss_hor": 0, "ss_ver": 0,
+                                              "p_intra": 0.1, "p_avg": 0.2, "p_seg": 0.15, "p_obmc": 0.3}),
+    "scaled_422_12b_odd_long_vectors": (264, 200, 0xfff, 53, {"ref_w": [200, 376], "ref_h": [120, 312], "ss_hor": 1, "ss_ver": 0,
+                                                              "mv_range": 400, "p_intra": 0.1, "p_avg": 0.2, "p_seg": 0.2}),
 }
 
 
@@ -76,7 +83,7 @@ def make(name):
 
 def refs_of(hf, name):
     seed = CASES[name][3]
-    return [F.random_planes(hf, seed * 10 + k) for k in range(2)] if hf.params.p_intra < 1.0 else []
+    return [F.random_planes(hf, seed * 10 + k, ref=k) for k in range(2)] if hf.params.p_intra < 1.0 else []
 
 
 def md5_planes(planes):
