@@ -83,6 +83,30 @@ class Recorder(C.Structure):
                 ("tile_row_end", C.c_int32), ("intra", C.c_void_p), ("n_intra", C.c_int32), ("cap_intra", C.c_int32)]
 
 
+class NbMv(C.Structure):
+    _fields_ = [("mvx", C.c_int16), ("mvy", C.c_int16), ("ref", C.c_int8), ("bw4", C.c_uint8), ("bh4", C.c_uint8),
+                ("filter2d", C.c_uint8)]
+
+
+class BlockInter(C.Structure):
+    _fields_ = [("bx4", C.c_uint16), ("by4", C.c_uint16), ("bw4", C.c_uint8), ("bh4", C.c_uint8),
+                ("comp_type", C.c_uint8), ("motion_mode", C.c_uint8), ("mvx", C.c_int16 * 2), ("mvy", C.c_int16 * 2),
+                ("ref", C.c_int8 * 2), ("filter2d", C.c_uint8), ("mask_sign", C.c_uint8), ("skip", C.c_uint8),
+                ("max_ytx", C.c_uint8), ("uvtx", C.c_uint8), ("interintra_type", C.c_uint8), ("tx_split", C.c_uint16 * 2)]
+
+
+class InterRecorder(C.Structure):
+    _fields_ = [("bw4", C.c_int32), ("bh4", C.c_int32), ("w", C.c_int32), ("h", C.c_int32), ("layout", C.c_int32),
+                ("tile_col_start", C.c_int32), ("tile_row_start", C.c_int32),
+                ("ref_w", C.c_int32 * 7), ("ref_h", C.c_int32 * 7), ("jnt_weights", (C.c_uint8 * 7) * 7),
+                ("pad", C.c_uint8 * 7), ("above", C.c_void_p), ("left", C.c_void_p),
+                ("put", C.c_void_p), ("n_put", C.c_int32), ("cap_put", C.c_int32),
+                ("comp", C.c_void_p * 2), ("n_comp", C.c_int32 * 2), ("cap_comp", C.c_int32 * 2),
+                ("obmc", C.c_void_p * 2), ("n_obmc", C.c_int32 * 2), ("cap_obmc", C.c_int32 * 2),
+                ("scaled", C.c_void_p * 4), ("n_scaled", C.c_int32 * 4), ("cap_scaled", C.c_int32 * 4),
+                ("itx", C.c_void_p), ("n_itx", C.c_int32), ("cap_itx", C.c_int32), ("masks_bytes", C.c_uint32)]
+
+
 class Plane(C.Structure):
     _fields_ = [("data", C.c_void_p), ("stride", C.c_ssize_t), ("w", C.c_int32), ("h", C.c_int32)]
 
@@ -201,6 +225,8 @@ def bind_frame_api(L):
     L.dav1d_cuda_picture_to_host.argtypes = [C.c_void_p, C.POINTER(Dav1dPictureMirror)]
     L.dav1d_cuda_picture_to_device.argtypes = [C.c_void_p, C.POINTER(Dav1dPictureMirror)]
     L.dav1d_cuda_record_b_intra.argtypes = [C.POINTER(Recorder), C.POINTER(BlockIntra), C.c_void_p, C.c_int]
+    L.dav1d_cuda_record_b_inter.argtypes = [C.POINTER(InterRecorder), C.POINTER(BlockInter), C.c_void_p, C.c_int]
+    L.dav1d_cuda_record_nb_intra.argtypes = [C.POINTER(InterRecorder)] + [C.c_int] * 4
     L.dav1d_cuda_intra_cellmap_bytes.restype = C.c_size_t
     L.dav1d_cuda_intra_cellmap_bytes.argtypes = [C.c_int] * 4
     L.dav1d_cuda_intra_levels.argtypes = [C.c_void_p] + [C.c_int] * 5

@@ -136,3 +136,271 @@ extern "C" int dav1d_cuda_record_b_intra(Dav1dCudaRecorder *r, const Dav1dCudaBl
     if (R.err) { r->n_intra = n0; return R.err; }
     return r->n_intra - n0;
 }
+
+// ---------------------------------------------------------------- inter blocks
+namespace {
+
+struct RecInter {
+    Dav1dCudaInterRecorder *r;
+    const Dav1dCudaTxCoef *tx;
+    int n_tx, next_tx, err, n_emitted;
+    int ss_hor, ss_ver;
+
+    template <typename T> T *slot(T *arr, int32_t &n, const int32_t cap) {
+        if (err) return nullptr;
+        if (!arr || n >= cap) { err = -28; return nullptr; }
+        n_emitted++;
+        return &arr[n++];
+    }
+
+    bool ref_scaled(const int ref) const {
+        return (r->ref_w[ref] && r->ref_w[ref] != r->w) || (r->ref_h[ref] && r->ref_h[ref] != r->h);
+    }
+
+    // mc() up to the point where it picks the source: position and phase of the block's top-left in the
+    // reference plane (recon_tmpl.c:969-977, same-size branch)
+    Dav1dCudaMcSrc src_of(const int pl, const int bx, const int by, const int ref, const int mvx, const int mvy,
+                          const int filter_2d) const
+    {
+        const int sh = pl ? ss_hor : 0, sv = pl ? ss_ver : 0;
+        Dav1dCudaMcSrc s;
+        memset(&s, 0, sizeof(s));
+        s.ref = (uint8_t)ref; s.filter_2d = (uint8_t)filter_2d;
+        s.mx = (uint8_t)((mvx & (15 >> !sh)) << !sh);
+        s.my = (uint8_t)((mvy & (15 >> !sv)) << !sv);
+        s.x = bx * (4 >> sh) + (mvx >> (3 + sh));
+        s.y = by * (4 >> sv) + (mvy >> (3 + sv));
+        return s;
+    }
+    // the scaled branch (:1013-1021): orig_pos in 1/16 sample -> scale_mv -> 1/1024 position and step; a
+    // reference of the frame's own size inside a scaled compound is the same position at step 1024
+    Dav1dCudaMcScaledSrc scaled_of(const Dav1dCudaMcSrc &u) const {
+        Dav1dCudaMcScaledSrc o;
+        memset(&o, 0, sizeof(o));
+        o.ref = u.ref; o.filter_2d = u.filter_2d;
+        const int orig[2] = { u.x * 16 + u.mx, u.y * 16 + u.my };
+        int32_t *const pos[2] = { &o.pos_x, &o.pos_y }, *const step[2] = { &o.step_x, &o.step_y };
+        for (int k = 0; k < 2; k++) {
+            if (!ref_scaled(u.ref)) { *pos[k] = orig[k] * 64; *step[k] = 1024; continue; }
+            const int ref_sz = k ? (r->ref_h[u.ref] ? r->ref_h[u.ref] : r->h) : (r->ref_w[u.ref] ? r->ref_w[u.ref] : r->w);
+            const int cur_sz = k ? r->h : r->w;
+            const int scale = ((ref_sz << 14) + (cur_sz >> 1)) / cur_sz;           // decode.c:3517
+            const long long tmp = (long long)orig[k] * scale + (long long)(scale - 0x4000) * 8;
+            const int mag = (int)(((tmp < 0 ? -tmp : tmp) + 128) >> 8);
+            *pos[k] = (tmp < 0 ? -mag : mag) + 32;
+            *step[k] = (scale + 8) >> 4;
+        }
+        return o;
+    }
+
+    // one prediction: to the same-size list `arr` or, when a reference it reads has another size, to the
+    // scaled section `sec`
+    void emit_mc(const Dav1dCudaMcDesc &d, Dav1dCudaMcDesc *arr, int32_t &n, const int32_t cap, const int sec) {
+        const bool two = d.kind != DAV1D_CUDA_MC_PUT && d.kind != DAV1D_CUDA_MC_OBMC_H && d.kind != DAV1D_CUDA_MC_OBMC_V;
+        if (!ref_scaled(d.src[0].ref) && !(two && ref_scaled(d.src[1].ref))) {
+            if (Dav1dCudaMcDesc *o = slot(arr, n, cap)) *o = d;
+            return;
+        }
+        Dav1dCudaMcScaledDesc *o = slot(r->scaled[sec], r->n_scaled[sec], r->cap_scaled[sec]);
+        if (!o) return;
+        memset(o, 0, sizeof(*o));
+        o->x = d.x; o->y = d.y; o->w = d.w; o->h = d.h; o->plane = d.plane; o->kind = d.kind;
+        o->src[0] = scaled_of(d.src[0]);
+        if (two) o->src[1] = scaled_of(d.src[1]);
+        o->weight = d.weight; o->mask_ss = d.mask_ss; o->aux16 = d.aux16; o->aux_off = d.aux_off;
+    }
+
+    // obmc() (:1071-1132)
+    void obmc(const Dav1dCudaBlockInter *b, const int pl, const int w4, const int h4) {
+        const int sh = pl ? ss_hor : 0, sv = pl ? ss_ver : 0;
+        const int h_mul = 4 >> sh, v_mul = 4 >> sv;
+        const int bx = b->bx4, by = b->by4;
+        auto ilog2 = [](int v) { int l = 0; while (v > 1) { v >>= 1; l++; } return l; };
+        auto lap = [&](const Dav1dCudaNbMv &nb, const int x4, const int y4, const int ow4, const int oh4, const int kind,
+                       const int blend_h) {
+            Dav1dCudaMcDesc d;
+            memset(&d, 0, sizeof(d));
+            d.plane = (uint8_t)pl; d.kind = (uint8_t)kind;
+            d.x = (uint16_t)(((bx * 4) >> sh) + (x4 - bx) * h_mul);
+            d.y = (uint16_t)(((by * 4) >> sv) + (y4 - by) * v_mul);
+            d.w = (uint8_t)(ow4 * h_mul); d.h = (uint8_t)(oh4 * v_mul);
+            d.aux16 = (uint16_t)blend_h;
+            d.src[0] = src_of(pl, x4, y4, nb.ref, nb.mvx, nb.mvy, nb.filter2d);
+            const int k = kind == DAV1D_CUDA_MC_OBMC_V;
+            emit_mc(d, r->obmc[k], r->n_obmc[k], r->cap_obmc[k], 2 + k);
+        };
+        if (by > r->tile_row_start && (!pl || b->bw4 * h_mul + b->bh4 * v_mul >= 16)) {
+            for (int i = 0, x = 0; x < w4 && i < imin(ilog2(b->bw4), 4);) {
+                const Dav1dCudaNbMv &a = r->above[bx + x + 1];             // only odd blocks are considered (:1088)
+                const int step4 = imin(imax(a.bw4, 2), 16);
+                if (a.ref >= 0) {
+                    const int ow4 = imin(step4, b->bw4), oh4 = imin(b->bh4, 16) >> 1;
+                    lap(a, bx + x, by, ow4, (oh4 * 3 + 3) >> 2, DAV1D_CUDA_MC_OBMC_H, v_mul * oh4);
+                    i++;
+                }
+                x += step4;
+            }
+        }
+        if (bx > r->tile_col_start) {
+            for (int i = 0, y = 0; y < h4 && i < imin(ilog2(b->bh4), 4);) {
+                const Dav1dCudaNbMv &l = r->left[by + y + 1];
+                const int step4 = imin(imax(l.bh4, 2), 16);
+                if (l.ref >= 0) {
+                    const int ow4 = imin(b->bw4, 16) >> 1, oh4 = imin(step4, b->bh4);
+                    lap(l, bx, by + y, ow4, oh4, DAV1D_CUDA_MC_OBMC_V, 0);
+                    i++;
+                }
+                y += step4;
+            }
+        }
+    }
+
+    // a transform block: consumes one cbi / cf entry, emits itxfm_add when it carries coefficients
+    void emit_tx(const int pl, const int x_px, const int y_px, const int txsz) {
+        if (err) return;
+        if (next_tx >= n_tx) { err = -22; return; }
+        const Dav1dCudaTxCoef &t = tx[next_tx++];
+        if (t.eob < 0) return;
+        Dav1dCudaItxDesc *o = slot(r->itx, r->n_itx, r->cap_itx);
+        if (!o) return;
+        memset(o, 0, sizeof(*o));
+        o->coef_off = t.coef_off; o->x = (uint16_t)x_px; o->y = (uint16_t)y_px; o->eob = t.eob;
+        o->plane = (uint8_t)pl; o->tx = (uint8_t)txsz; o->txtp = t.txtp; o->cw4 = t.cw4; o->ch4 = t.ch4;
+    }
+
+    // read_coef_tree() (:726-823) in pass 2: the split decisions and the frame-edge rules
+    void coef_tree(const int bx, const int by, const int txsz, const int depth, const uint16_t *tx_split, const int x_off,
+                   const int y_off)
+    {
+        static const uint8_t sub_of[19] = { 0, 0, 1, 2, 3, 0, 0, 1, 1, 2, 2, 3, 3, 5, 6, 7, 8, 9, 10 };
+        const TxDim td = tx_dim(txsz);
+        const int txw = td.w >> 2, txh = td.h >> 2;
+        if (depth < 2 && tx_split[depth] && (tx_split[depth] & (1 << (y_off * 4 + x_off)))) {
+            const int sub = sub_of[txsz];
+            const TxDim sd = tx_dim(sub);
+            const int txsw = sd.w >> 2, txsh = sd.h >> 2;
+            coef_tree(bx, by, sub, depth + 1, tx_split, x_off * 2, y_off * 2);
+            if (txw >= txh && bx + txsw < r->bw4) coef_tree(bx + txsw, by, sub, depth + 1, tx_split, x_off * 2 + 1, y_off * 2);
+            if (txh >= txw && by + txsh < r->bh4) {
+                coef_tree(bx, by + txsh, sub, depth + 1, tx_split, x_off * 2, y_off * 2 + 1);
+                if (txw >= txh && bx + txsw < r->bw4)
+                    coef_tree(bx + txsw, by + txsh, sub, depth + 1, tx_split, x_off * 2 + 1, y_off * 2 + 1);
+            }
+        } else {
+            emit_tx(0, bx * 4, by * 4, txsz);
+        }
+    }
+};
+
+void nb_splat(Dav1dCudaInterRecorder *r, const int bx, const int by, const int bw4, const int bh4, const Dav1dCudaNbMv &n) {
+    for (int x = bx; x < imin(bx + bw4, r->bw4); x++) r->above[x] = n;
+    for (int y = by; y < imin(by + bh4, r->bh4); y++) r->left[y] = n;
+}
+
+}  // namespace
+
+extern "C" int dav1d_cuda_record_nb_intra(Dav1dCudaInterRecorder *r, int bx4, int by4, int bw4, int bh4) {
+    if (!r || !r->above || !r->left || bx4 < 0 || by4 < 0 || bx4 >= r->bw4 || by4 >= r->bh4) return -22;
+    Dav1dCudaNbMv n;
+    memset(&n, 0, sizeof(n));
+    n.ref = -1; n.bw4 = (uint8_t)bw4; n.bh4 = (uint8_t)bh4;
+    nb_splat(r, bx4, by4, bw4, bh4, n);
+    return 0;
+}
+
+extern "C" int dav1d_cuda_record_b_inter(Dav1dCudaInterRecorder *r, const Dav1dCudaBlockInter *b,
+                                         const Dav1dCudaTxCoef *tx, int n_tx)
+{
+    if (!r || !b || !r->above || !r->left || (n_tx > 0 && !tx) || r->layout < 0 || r->layout > 3 ||
+        b->max_ytx >= DAV1D_CUDA_N_RECT_TX_SIZES || b->uvtx >= DAV1D_CUDA_N_RECT_TX_SIZES ||
+        b->bx4 >= r->bw4 || b->by4 >= r->bh4 || b->comp_type > 4) return -22;
+    const bool comp = b->comp_type != 0;
+    for (int i = 0; i < (comp ? 2 : 1); i++)
+        if (b->ref[i] < 0 || b->ref[i] > 6) return -22;
+    const int has_uv = r->layout != 0;
+    const int ss_ver = r->layout == 1, ss_hor = has_uv && r->layout != 3;
+    const int bx = b->bx4, by = b->by4, bw4 = b->bw4, bh4 = b->bh4;
+    const bool has_chroma = has_uv && (bw4 > ss_hor || (bx & 1)) && (bh4 > ss_ver || (by & 1));
+    // not transcribed: warped motion, inter-intra, wedge masks, the 4-MV chroma of sub-8x8 blocks
+    if (b->motion_mode > 1 || b->interintra_type || b->comp_type == 4) return -38;
+    if (has_chroma && (bw4 == ss_hor || bh4 == ss_ver)) return -38;
+    if (b->motion_mode == 1 && (comp || (bx & 1) || (by & 1))) return -22;     // obmc(): assert(!(t->bx & 1) && !(t->by & 1))
+
+    RecInter R;
+    R.r = r; R.tx = tx; R.n_tx = n_tx; R.next_tx = 0; R.err = 0; R.n_emitted = 0;
+    R.ss_hor = ss_hor; R.ss_ver = ss_ver;
+    const Dav1dCudaInterRecorder saved = *r;                                   // counters to roll back to
+    const int w4 = imin(bw4, r->bw4 - bx), h4 = imin(bh4, r->bh4 - by);
+    const int lay = !has_uv ? 0 : ss_hor ? (ss_ver ? 2 : 1) : 0;               // w_mask[chr_layout_idx]: 444 0, 422 1, 420 2
+    uint32_t seg_off = 0;
+
+    for (int pl = 0; pl < (has_chroma ? 3 : 1); pl++) {
+        const int sh = pl ? ss_hor : 0, sv = pl ? ss_ver : 0;
+        Dav1dCudaMcDesc d;
+        memset(&d, 0, sizeof(d));
+        d.plane = (uint8_t)pl;
+        d.x = (uint16_t)((bx * 4) >> sh); d.y = (uint16_t)((by * 4) >> sv);
+        d.w = (uint8_t)((bw4 * 4) >> sh); d.h = (uint8_t)((bh4 * 4) >> sv);
+        d.src[0] = R.src_of(pl, bx, by, b->ref[0], b->mvx[0], b->mvy[0], b->filter2d);
+        if (!comp) {                                                           // :1638-1657, 1764-1778
+            d.kind = DAV1D_CUDA_MC_PUT;
+            R.emit_mc(d, r->put, r->n_put, r->cap_put, 0);
+            if (b->motion_mode == 1) R.obmc(b, pl, w4, h4);
+            continue;
+        }
+        d.src[1] = R.src_of(pl, bx, by, b->ref[1], b->mvx[1], b->mvy[1], b->filter2d);
+        int wave = 0;
+        switch (b->comp_type) {                                                // :1842-1868, 1890-1906
+        case 2: d.kind = DAV1D_CUDA_MC_AVG; break;
+        case 1:
+            d.kind = DAV1D_CUDA_MC_W_AVG;
+            d.weight = r->jnt_weights[b->ref[0]][b->ref[1]];
+            break;
+        default:                                                               // COMP_INTER_SEG
+            if (b->mask_sign) { const Dav1dCudaMcSrc t = d.src[0]; d.src[0] = d.src[1]; d.src[1] = t; }   // tmp[mask_sign], tmp[!mask_sign]
+            if (pl == 0) {
+                d.kind = DAV1D_CUDA_MC_W_MASK;
+                seg_off = r->masks_bytes;
+                r->masks_bytes += (uint32_t)((d.w >> (lay >= 1)) * (d.h >> (lay == 2)));
+                d.mask_ss = (uint8_t)lay; d.weight = b->mask_sign;
+            } else {
+                d.kind = DAV1D_CUDA_MC_MASK;                                   // the mask the luma call emitted
+                wave = 1;
+            }
+            d.aux_off = seg_off;
+            break;
+        }
+        R.emit_mc(d, r->comp[wave], r->n_comp[wave], r->cap_comp[wave], wave);
+    }
+
+    if (!b->skip) {                                                            // :1951-2033
+        const TxDim yd = tx_dim(b->max_ytx), ud = tx_dim(b->uvtx);
+        const int ytw = yd.w >> 2, yth = yd.h >> 2, utw = ud.w >> 2, uth = ud.h >> 2;
+        const int cw4 = (w4 + ss_hor) >> ss_hor, ch4 = (h4 + ss_ver) >> ss_ver;
+        for (int init_y = 0; init_y < bh4; init_y += 16)
+            for (int init_x = 0; init_x < bw4; init_x += 16) {
+                int y_off = !!init_y;
+                for (int y = init_y; y < imin(h4, init_y + 16); y += yth, y_off++) {
+                    int x_off = !!init_x;
+                    for (int x = init_x; x < imin(w4, init_x + 16); x += ytw, x_off++)
+                        R.coef_tree(bx + x, by + y, b->max_ytx, 0, b->tx_split, x_off, y_off);
+                }
+                if (has_chroma)
+                    for (int pl = 1; pl <= 2; pl++)
+                        for (int y = init_y >> ss_ver; y < imin(ch4, (init_y + 16) >> ss_ver); y += uth)
+                            for (int x = init_x >> ss_hor; x < imin(cw4, (init_x + 16) >> ss_hor); x += utw)
+                                R.emit_tx(pl, ((bx >> ss_hor) + x) * 4, ((by >> ss_ver) + y) * 4, b->uvtx);
+            }
+    }
+    if (!R.err && R.next_tx != n_tx) R.err = -22;
+    if (R.err) {
+        Dav1dCudaNbMv *const above = r->above, *const left = r->left;
+        *r = saved; r->above = above; r->left = left;
+        return R.err;
+    }
+    // decode.c:815-826 + :808-814: what later blocks' obmc() reads of this one
+    Dav1dCudaNbMv n;
+    n.mvx = b->mvx[0]; n.mvy = b->mvy[0]; n.ref = b->ref[0]; n.bw4 = (uint8_t)bw4; n.bh4 = (uint8_t)bh4; n.filter2d = b->filter2d;
+    nb_splat(r, bx, by, bw4, bh4, n);
+    return R.n_emitted;
+}

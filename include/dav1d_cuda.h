@@ -338,6 +338,57 @@ typedef struct Dav1dCudaRecorder {
 DAV1D_CUDA_API int dav1d_cuda_record_b_intra(Dav1dCudaRecorder *r, const Dav1dCudaBlockIntra *b,
                                              const Dav1dCudaTxCoef *tx, int n_tx);
 
+/* ---- inter half of the recorder: dav1d_recon_b_inter (recon_tmpl.c:1598-2036) with mc() (:957-1069, both
+ * branches), obmc() (:1071-1132) and read_coef_tree() (:726-823) as descriptor emission.  Covers
+ * translational single-reference blocks (optionally with OBMC) and the AVG / WEIGHTED_AVG / SEG compounds,
+ * from references of any size, with their residual transform trees.  Warped / global-motion blocks,
+ * inter-intra, wedge compounds and the 4-MV chroma of sub-8x8 blocks (:1685-1751) are NOT transcribed yet:
+ * the call returns -ENOSYS for them and records nothing. */
+typedef struct Dav1dCudaNbMv {          /* what obmc() reads of a neighbour (refmvs rows + filter contexts) */
+    int16_t mvx, mvy;                   /* r->mv.mv[0] */
+    int8_t  ref;                        /* r->ref.ref[0] - 1: reference index, -1 = intra */
+    uint8_t bw4, bh4;                   /* dav1d_block_dimensions[r->bs] */
+    uint8_t filter2d;                   /* dav1d_filter_2d[ctx->filter[1]][ctx->filter[0]] */
+} Dav1dCudaNbMv;
+typedef struct Dav1dCudaBlockInter {    /* the Av1Block fields dav1d_recon_b_inter reads (src/levels.h:262-287) */
+    uint16_t bx4, by4;                  /* t->bx, t->by */
+    uint8_t  bw4, bh4;                  /* dav1d_block_dimensions[bs] */
+    uint8_t  comp_type;                 /* enum CompInterType: NONE 0, WEIGHTED_AVG 1, AVG 2, SEG 3, WEDGE 4 */
+    uint8_t  motion_mode;               /* enum MotionMode: TRANSLATION 0, OBMC 1, WARP 2 */
+    int16_t  mvx[2], mvy[2];            /* b->mv[i].x / .y */
+    int8_t   ref[2];
+    uint8_t  filter2d, mask_sign, skip;
+    uint8_t  max_ytx, uvtx;             /* enum RectTxfmSize */
+    uint8_t  interintra_type;           /* non-zero: -ENOSYS */
+    uint16_t tx_split[2];               /* b->tx_split0, b->tx_split1 */
+} Dav1dCudaBlockInter;
+typedef struct Dav1dCudaInterRecorder {
+    int32_t bw4, bh4;                   /* f->bw, f->bh */
+    int32_t w, h;                       /* f->cur.p.w, f->cur.p.h */
+    int32_t layout;                     /* enum Dav1dPixelLayout */
+    int32_t tile_col_start, tile_row_start;   /* ts->tiling (luma 4-px units) */
+    int32_t ref_w[7], ref_h[7];         /* f->refp[i].p.p.w / .h (0 = the frame's size) */
+    uint8_t jnt_weights[7][7];          /* f->jnt_weights */
+    uint8_t pad[7];
+    Dav1dCudaNbMv *above, *left;        /* bw4 + 1 / bh4 + 1 entries, zero-initialised by the caller once per
+                                           frame; updated by the recorder after every block */
+    /* outputs, each appended in decode order: the arrays the Dav1dCudaReconBatch takes (tiles from
+     * dav1d_cuda_mc_tiles(), transform tasks from dav1d_cuda_itx_tasks() after sorting `itx` by size) */
+    Dav1dCudaMcDesc *put;      int32_t n_put, cap_put;
+    Dav1dCudaMcDesc *comp[2];  int32_t n_comp[2], cap_comp[2];     /* wave 0, wave 1 (chroma of SEG blocks) */
+    Dav1dCudaMcDesc *obmc[2];  int32_t n_obmc[2], cap_obmc[2];     /* OBMC_H, OBMC_V */
+    Dav1dCudaMcScaledDesc *scaled[4]; int32_t n_scaled[4], cap_scaled[4];
+    Dav1dCudaItxDesc *itx;     int32_t n_itx, cap_itx;
+    uint32_t masks_bytes;               /* running size of the mask pool (segmentation masks are allotted here) */
+} Dav1dCudaInterRecorder;
+/* Appends the block's descriptors; returns how many, or a negative errno (-ENOSPC: an array is full, -EINVAL,
+ * -ENOSYS: see above).  On error nothing of the block is kept.  `tx`: the block's cbi / cf entries in
+ * consumption order (luma tree, then U, then V per 64x64 unit), none when b->skip. */
+DAV1D_CUDA_API int dav1d_cuda_record_b_inter(Dav1dCudaInterRecorder *r, const Dav1dCudaBlockInter *b,
+                                             const Dav1dCudaTxCoef *tx, int n_tx);
+/* An intra block in an inter frame: what obmc() of later blocks sees of it (decode.c:756-767). */
+DAV1D_CUDA_API int dav1d_cuda_record_nb_intra(Dav1dCudaInterRecorder *r, int bx4, int by4, int bw4, int bh4);
+
 typedef struct Dav1dCudaContext Dav1dCudaContext;
 
 /* `stream` is a cudaStream_t the caller already orders its work on, or NULL:

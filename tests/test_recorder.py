@@ -112,3 +112,126 @@ def test_recorded_descriptors_reproduce_the_reference_driver(ref, name):
     hf.intra = np.frombuffer(got_ops.tobytes(), dtype=np.uint8).copy()
     got = refframe.run_oracle(ref, hf, [p.copy() for p in init], [])
     assert all(np.array_equal(a, b) for a, b in zip(want, got))
+
+
+# ---------------------------------------------------------------- inter half
+MC = np.dtype([("x", "u2"), ("y", "u2"), ("w", "u1"), ("h", "u1"), ("plane", "u1"), ("kind", "u1"),
+               ("src", [("x", "i4"), ("y", "i4"), ("ref", "u1"), ("filter_2d", "u1"), ("mx", "u1"), ("my", "u1")], 2),
+               ("weight", "u1"), ("mask_ss", "u1"), ("aux16", "u2"), ("aux_off", "u4")])
+MCS = np.dtype([("x", "u2"), ("y", "u2"), ("w", "u1"), ("h", "u1"), ("plane", "u1"), ("kind", "u1"),
+                ("src", [("pos_x", "i4"), ("pos_y", "i4"), ("step_x", "i4"), ("step_y", "i4"), ("ref", "u1"),
+                         ("filter_2d", "u1"), ("pad", "u2")], 2),
+                ("weight", "u1"), ("mask_ss", "u1"), ("aux16", "u2"), ("aux_off", "u4")])
+ITX = np.dtype([("coef_off", "u4"), ("x", "u2"), ("y", "u2"), ("eob", "i2"), ("plane", "u1"), ("tx", "u1"), ("txtp", "u1"),
+                ("cw4", "u1"), ("ch4", "u1"), ("pad", "u1")])
+TXR = np.dtype([("coef_off", "u4"), ("eob", "i2"), ("txtp", "u1"), ("cw4", "u1"), ("ch4", "u1"), ("tx", "u1"),
+                ("plane", "u1"), ("pad", "u1")])
+# generator's compound kind (enum Dav1dCudaMcKind) -> enum CompInterType
+COMP_TYPE = {0: 0, 1: 2, 2: 1, 4: 3}
+
+
+def record_inter_frame(hf):
+    assert MC.itemsize == 40 and MCS.itemsize == 56 and ITX.itemsize == 16 and TXR.itemsize == 12
+    L = pkg.lib()
+    blocks = np.frombuffer(hf.blocks.tobytes(), dtype=BLK)
+    txr = np.frombuffer(hf.tx_recs.tobytes(), dtype=TXR)
+    r = B.InterRecorder()
+    r.bw4, r.bh4, r.w, r.h = hf.bw4, hf.bh4, hf.w, hf.h
+    r.layout = 0 if hf.no_chroma else 1 if hf.ss_ver else 2 if hf.ss_hor else 3
+    for i in range(7):
+        r.ref_w[i], r.ref_h[i] = hf.params.ref_w[i], hf.params.ref_h[i]
+        for j in range(7):
+            r.jnt_weights[i][j] = 1 + (i * 7 + j * 3 + 4) % 15         # the frame's table (generator + reference harness)
+    above = np.zeros(hf.bw4 + 1, dtype=np.uint64)
+    left = np.zeros(hf.bh4 + 1, dtype=np.uint64)
+    above.view(np.int8)[4::8] = -1
+    left.view(np.int8)[4::8] = -1
+    r.above, r.left = above.ctypes.data, left.ctypes.data
+    cap = 1 << 15
+    out = {"put": np.zeros(cap, dtype=MC), "comp0": np.zeros(cap, dtype=MC), "comp1": np.zeros(cap, dtype=MC),
+           "obmc0": np.zeros(cap, dtype=MC), "obmc1": np.zeros(cap, dtype=MC), "itx": np.zeros(cap, dtype=ITX)}
+    sc = [np.zeros(cap, dtype=MCS) for _ in range(4)]
+    r.put, r.cap_put = out["put"].ctypes.data, cap
+    for k in range(2):
+        r.comp[k], r.cap_comp[k] = out[f"comp{k}"].ctypes.data, cap
+        r.obmc[k], r.cap_obmc[k] = out[f"obmc{k}"].ctypes.data, cap
+    for k in range(4):
+        r.scaled[k], r.cap_scaled[k] = sc[k].ctypes.data, cap
+    r.itx, r.cap_itx = out["itx"].ctypes.data, cap
+    for s in blocks:
+        r.tile_col_start, r.tile_row_start = int(s["tile_rect"][0]), int(s["tile_rect"][1])
+        if s["intra"]:
+            assert L.dav1d_cuda_record_nb_intra(C.byref(r), int(s["bx4"]), int(s["by4"]), int(s["w4"]), int(s["h4"])) == 0
+            continue
+        b = B.BlockInter()
+        b.bx4, b.by4, b.bw4, b.bh4 = int(s["bx4"]), int(s["by4"]), int(s["w4"]), int(s["h4"])
+        b.comp_type, b.motion_mode = COMP_TYPE[int(s["comp_kind"])], int(s["pad"][0])
+        for k in range(2):
+            b.mvx[k], b.mvy[k], b.ref[k] = int(s["mvx"][k]), int(s["mvy"][k]), int(s["ref"][k])
+        b.filter2d, b.mask_sign, b.skip = int(s["filter2d"]), int(s["mask_sign"]), int(s["skip"])
+        b.max_ytx, b.uvtx = int(s["max_ytx"]), int(s["uvtx"])
+        b.tx_split[0] = 1 if s["tx_split"] else 0
+        mine = txr[s["first_tx"]:s["first_tx"] + s["n_tx"]]
+        arr = (B.TxCoef * max(len(mine), 1))()
+        for k, t in enumerate(mine):
+            arr[k].coef_off, arr[k].eob, arr[k].txtp, arr[k].cw4, arr[k].ch4 = (int(t["coef_off"]), int(t["eob"]),
+                                                                                 int(t["txtp"]), int(t["cw4"]), int(t["ch4"]))
+        n = L.dav1d_cuda_record_b_inter(C.byref(r), C.byref(b), arr, len(mine))
+        assert n >= 0, (n, s)
+    got = {"put": out["put"][:r.n_put],
+           "comp": np.concatenate([out["comp0"][:r.n_comp[0]], out["comp1"][:r.n_comp[1]]]),
+           "obmc": np.concatenate([out["obmc0"][:r.n_obmc[0]], out["obmc1"][:r.n_obmc[1]]]),
+           "scaled": np.concatenate([sc[k][:r.n_scaled[k]] for k in range(4)]),
+           "itx": out["itx"][:r.n_itx]}
+    return got, [r.n_scaled[k] for k in range(4)], r.masks_bytes
+
+
+@pytest.mark.parametrize("name", [n for n in R.CASES if n.startswith(("inter_", "obmc_", "scaled_"))])
+def test_inter_recorder_emits_the_generators_descriptors(name):
+    """dav1d_cuda_record_b_inter over the Av1Block-style records == the descriptor arrays the generator wrote
+    for the same blocks (which reproduce dav1d_recon_b_inter's pixels bit for bit, tests/test_reference_driver.py)."""
+    hf, _ = R.make(name)
+    got, n_scaled, masks_bytes = record_inter_frame(hf)
+    want = {"put": np.frombuffer(hf.mc_put.tobytes(), dtype=MC), "comp": np.frombuffer(hf.mc_comp.tobytes(), dtype=MC),
+            "obmc": np.frombuffer(hf.mc_obmc.tobytes(), dtype=MC), "scaled": np.frombuffer(hf.mc_scaled.tobytes(), dtype=MCS),
+            "itx": np.frombuffer(hf.itx.tobytes(), dtype=ITX)}
+    assert tuple(n_scaled) == tuple(hf.n_mc_scaled)
+    assert masks_bytes == hf.masks.nbytes
+    for key in ("put", "comp", "obmc", "scaled"):
+        w, g = want[key].copy(), got[key].copy()
+        assert len(w) == len(g), (key, len(w), len(g))
+        # the second source of a single-reference prediction is never read
+        single = np.isin(w["kind"], (0, 6, 7))
+        for a in (w, g):
+            a["src"][single, 1] = 0
+        assert w.tobytes() == g.tobytes(), (name, key, next(i for i in range(len(w)) if w[i] != g[i]))
+    # the generator hands `itx` over sorted by size class; same multiset
+    w, g = np.sort(want["itx"], order=list(ITX.names)), np.sort(got["itx"], order=list(ITX.names))
+    assert w.tobytes() == g.tobytes(), name
+
+
+def test_inter_recorder_refuses_what_it_does_not_transcribe():
+    L = pkg.lib()
+    r = B.InterRecorder()
+    r.bw4 = r.bh4 = 16
+    r.w = r.h = 64
+    r.layout = 1
+    nb = np.zeros(17, dtype=np.uint64)
+    r.above = r.left = nb.ctypes.data
+    put = np.zeros(8, dtype=MC)
+    r.put, r.cap_put = put.ctypes.data, 2
+    b = B.BlockInter()
+    b.bw4 = b.bh4 = 4
+    b.skip = 1
+    b.motion_mode = 2                                                  # MM_WARP
+    assert L.dav1d_cuda_record_b_inter(C.byref(r), C.byref(b), None, 0) == -38
+    b.motion_mode, b.interintra_type = 0, 1
+    assert L.dav1d_cuda_record_b_inter(C.byref(r), C.byref(b), None, 0) == -38
+    b.interintra_type, b.comp_type = 0, 4                              # COMP_INTER_WEDGE
+    assert L.dav1d_cuda_record_b_inter(C.byref(r), C.byref(b), None, 0) == -38
+    b.comp_type = 0
+    assert L.dav1d_cuda_record_b_inter(C.byref(r), C.byref(b), None, 0) == -28 and r.n_put == 0   # three planes, room for two
+    r.cap_put = 8
+    assert L.dav1d_cuda_record_b_inter(C.byref(r), C.byref(b), None, 0) == 3 and r.n_put == 3
+    b.skip = 0
+    assert L.dav1d_cuda_record_b_inter(C.byref(r), C.byref(b), None, 0) == -22 and r.n_put == 3  # cbi entries missing
