@@ -53,6 +53,9 @@ def parse_args():
     ap.add_argument("--width", type=int, default=3840)
     ap.add_argument("--height", type=int, default=2160)
     ap.add_argument("--bitdepth-max", type=lambda s: int(s, 0), default=0x3ff)
+    ap.add_argument("--coefs", default="int16", choices=["int16", "native"],
+                    help="coefficient stream of high-bit-depth frames: int16 + escape list (cf_int16) or the "
+                         "reference's int32 layout")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-verify", action="store_true")
@@ -214,6 +217,45 @@ def workload_config(args):
 
 
 # ------------------------------------------------------------------ our arm
+def pcie_probe(device, h2d_bytes, d2h_bytes, step_ms):
+    """Both copy directions at once, pinned host memory, bytes in the proportion of one e2e step of this rank
+    (scaled down to at most 512 MB per direction): the time a step's transfers take on this box when nothing
+    else happens."""
+    import torch
+    try:
+        scale = min(1.0, 512e6 / max(h2d_bytes, d2h_bytes, 1))
+        nh, nd = max(int(h2d_bytes * scale), 1 << 20), max(int(d2h_bytes * scale), 1 << 20)
+        dev = torch.device("cuda", device)
+        hs, hd = torch.empty(nh, dtype=torch.uint8, pin_memory=True), torch.empty(nd, dtype=torch.uint8, pin_memory=True)
+        ds, dd = torch.empty(nh, dtype=torch.uint8, device=dev), torch.empty(nd, dtype=torch.uint8, device=dev)
+        s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        best = None
+        for it in range(4):
+            torch.cuda.synchronize(dev)
+            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            e0.record(torch.cuda.current_stream(dev))
+            s1.wait_event(e0)
+            s2.wait_event(e0)
+            with torch.cuda.stream(s1):
+                ds.copy_(hs, non_blocking=True)
+                e1.record(s1)
+            with torch.cuda.stream(s2):
+                hd.copy_(dd, non_blocking=True)
+                e2.record(s2)
+            torch.cuda.synchronize(dev)
+            ms = max(e0.elapsed_time(e1), e0.elapsed_time(e2))
+            if it and (best is None or ms < best[0]):
+                best = (ms, e0.elapsed_time(e1), e0.elapsed_time(e2))
+        ms, ms_h2d, ms_d2h = best
+        floor_ms = ms / scale
+        return {"h2d_gbs": nh / ms_h2d / 1e6, "d2h_gbs": nd / ms_d2h / 1e6, "both_directions": True,
+                "step_transfer_floor_ms": floor_ms, "frac_of_floor": floor_ms / step_ms,
+                "note": "frac_of_floor = time plain pinned copies of one step's bytes take on this box (both "
+                        "directions concurrently) / the measured e2e step"}
+    except Exception as e:       # noqa: BLE001 - the probe must never cost the bench line
+        return {"error": repr(e)}
+
+
 def main_ours(args):
     rank, world, local = dist_env()
     import torch
@@ -268,6 +310,11 @@ def main_ours(args):
     # The recorder's dependency-level pass (dav1d_cuda_intra_levels: one linear walk over the
     # intra-class descriptors in decode order, host only).  The device-resident arm replays
     # descriptors that carry these levels; the end-to-end arm leaves the levels to the device.
+    if args.coefs == "int16":          # the compact stream: int16 storage + escape list (cf_int16), high bit depth only
+        for hfs_bd in sets.values():
+            for hf in hfs_bd:
+                if hf.hbd:
+                    hf.pack_coefs()
     t0 = time.perf_counter()
     n_rec = 0
     for hfs_bd in sets.values():
@@ -472,7 +519,8 @@ def main_ours(args):
                 "per_class_gbs": {k: (sum(df.hf.algo_class[k] for df in dfs) / S / (v * 1e-3) / 1e9 if v > 0 else None)
                                   for k, v in cls_ms.items()},
                 "frame_algorithmic_bytes": dfs[0].hf.algo_bytes,
-                "frame_algorithmic_bytes_packed_coefs": dfs[0].hf.algo_bytes - dfs[0].hf.dense_coef_bytes + dfs[0].hf.cf.nbytes,
+                "frame_algorithmic_bytes_packed_coefs": dfs[0].hf.algo_bytes - dfs[0].hf.dense_coef_bytes +
+                (dfs[0].hf.cf.nbytes if dfs[0].hf.cf16 is None else dfs[0].hf.cf16.nbytes),
                 "whole_step": {"achieved": algo_step * args.steps / (ms * 1e-3) / 1e9,
                                "frac": algo_step * args.steps / (ms * 1e-3) / 1e9 / peak}}
 
@@ -522,6 +570,9 @@ def main_ours(args):
                "host_note": "host_ms is the wall time of the submitting thread (it blocks when the launch queue is "
                             "full); host_cpu_ms is its CPU time",
                "frames_per_group_submission": GE, "groups_in_flight": len(units)}
+        # the bound of this arm: what the PCIe link of THIS box moves when both directions are busy with plain
+        # pinned copies in the step's byte proportion (measured, torch streams; not part of any timed region)
+        e2e["pcie"] = pcie_probe(local, int(h2d), int(d2h), ems / e2e_steps)
         for u in units:
             for df in u[2]:
                 df.use(0)
@@ -551,6 +602,8 @@ def main_ours(args):
                    "submission": f"{len(units)} group submissions per step, each the frames of {G} streams "
                                  f"(dav1d_cuda_recon_group_submit: nothing scheduled on the host)",
                    "twelve_bit_stream": "the last stream of every rank is 12-bit",
+                   "coefficient_stream": ("int16 storage + escape list (Dav1dCudaReconBatch.cf_int16; the CPU arm reads "
+                                          "the int32 stream the reference keeps)" if args.coefs == "int16" else "int32"),
                    "intra_ops_per_frame": int(dfs[0].hf.n_intra),
                    "intra_dependency_levels": "recorder-side in `value` (dav1d_cuda_intra_levels: a linear pass over "
                                               "the descriptors in decode order, measured below, part of recording like "

@@ -206,7 +206,8 @@ class ReconBatch(C.Structure):
                 ("intra_itx", C.c_void_p), ("intra_itx_class_count", C.c_int32 * N_RECT_TX_SIZES),
                 ("intra_itx_tasks", C.c_void_p), ("n_intra_itx_tasks", C.c_int32 * 2),
                 ("intra_res", C.POINTER(Picture)), ("intra_levels_recorded", C.c_int32),
-                ("mc_scaled", C.c_void_p), ("n_mc_scaled", C.c_int32 * 4)]
+                ("mc_scaled", C.c_void_p), ("n_mc_scaled", C.c_int32 * 4),
+                ("cf_int16", C.c_int32), ("cf_esc", C.c_void_p), ("n_cf_esc", C.c_int32)]
 
 
 MAX_GROUP = 64
@@ -225,6 +226,7 @@ def bind_frame_api(L):
     L.dav1d_cuda_picture_to_host.argtypes = [C.c_void_p, C.POINTER(Dav1dPictureMirror)]
     L.dav1d_cuda_picture_to_device.argtypes = [C.c_void_p, C.POINTER(Dav1dPictureMirror)]
     L.dav1d_cuda_record_b_intra.argtypes = [C.POINTER(Recorder), C.POINTER(BlockIntra), C.c_void_p, C.c_int]
+    L.dav1d_cuda_pack_coefs.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_int]
     L.dav1d_cuda_record_b_inter.argtypes = [C.POINTER(InterRecorder), C.POINTER(BlockInter), C.c_void_p, C.c_int]
     L.dav1d_cuda_record_nb_intra.argtypes = [C.POINTER(InterRecorder)] + [C.c_int] * 4
     L.dav1d_cuda_intra_cellmap_bytes.restype = C.c_size_t

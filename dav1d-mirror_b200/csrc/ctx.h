@@ -73,6 +73,13 @@ inline PicView pic_view(const Dav1dCudaPicture *pic) {
 
 // Multi-frame transform tasks (itx.cu / recon.cu): per-frame planes, coefficients and the
 // frame's level-sorted residual descriptors.
+// storage of a frame's coefficient stream (Dav1dCudaReconBatch.cf_int16 / cf_esc)
+struct CoefFmt {
+    int s16;
+    const Dav1dCudaCoefEsc *esc;
+    int n_esc;
+};
+
 struct ItxFrameRef {
     PicView pic;
     PicView res;          // int16 residual planes (intra residual pre-pass)

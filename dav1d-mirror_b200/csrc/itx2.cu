@@ -26,6 +26,9 @@ struct Itx2Args {
     PicView res;                 // to_res: int16 planes that receive the residual instead of dst += residual
     int to_res;
     void *cf;
+    int cf16;                    // high bit depth: compact int16 stream + escape list (Dav1dCudaReconBatch.cf_int16)
+    const Dav1dCudaCoefEsc *esc;
+    int n_esc;
     const Dav1dCudaItxDesc *descs;
     const uint32_t *tasks;
     const ItxFrameRef *frames;
@@ -98,9 +101,19 @@ __global__ void __launch_bounds__(ITX2_WARPS * 32, Itx2Cls<CLS>::MIN_BLOCKS) itx
         rstride = (int)(rv.stride / 2);
         res = (int16_t *)rv.data + (int64_t)d.y * rstride + d.x;
     }
-    itx2_block<pixel, Itx2Cls<CLS>::MAXN>(active, gl, G, smem + grp * itx2_tile_ints(tx), (coef *)cf + d.coef_off, tx,
-                                     d.txtp, d.eob, d.cw4, d.ch4, dst, dstride, res, rstride, pic->bdmax,
-                                     a.zero_coefs != 0);
+    if constexpr (sizeof(coef) == 4) {
+        // the frames of a multi-frame task list carry native coefficients
+        Itx2Coef c;
+        c.s16 = a.mtasks ? 0 : a.cf16; c.esc = a.esc; c.n_esc = a.n_esc; c.off = d.coef_off;
+        c.p = c.s16 ? (void *)((int16_t *)cf + d.coef_off) : (void *)((int32_t *)cf + d.coef_off);
+        itx2_block<pixel, Itx2Cls<CLS>::MAXN, Itx2Coef>(active, gl, G, smem + grp * itx2_tile_ints(tx), c, tx, d.txtp, d.eob,
+                                                        d.cw4, d.ch4, dst, dstride, res, rstride, pic->bdmax,
+                                                        a.zero_coefs != 0);
+    } else {
+        itx2_block<pixel, Itx2Cls<CLS>::MAXN>(active, gl, G, smem + grp * itx2_tile_ints(tx), (coef *)cf + d.coef_off, tx,
+                                              d.txtp, d.eob, d.cw4, d.ch4, dst, dstride, res, rstride, pic->bdmax,
+                                              a.zero_coefs != 0);
+    }
 }
 
 template <typename pixel, int CLS>
@@ -139,11 +152,12 @@ void itx_init_attrs() {}
 // tasks[0 .. n_small) = sizes up to 16x16, tasks[n_small .. n_small + n_big) = larger
 int itx_task_launch(const PicView &pic, const PicView *res, void *cf, const Dav1dCudaItxDesc *descs,
                     const uint32_t *tasks, int n_small, int n_big, int zero_coefs, cudaStream_t st_small,
-                    cudaStream_t st_big)
+                    cudaStream_t st_big, const CoefFmt *fmt)
 {
     Itx2Args a;
     memset(&a, 0, sizeof(a));
     a.pic = pic; a.cf = cf; a.descs = descs; a.tasks = tasks; a.zero_coefs = zero_coefs;
+    if (fmt) { a.cf16 = fmt->s16; a.esc = fmt->esc; a.n_esc = fmt->n_esc; }
     if (res) { a.res = *res; a.to_res = 1; }
     return itx2_launch_both(a, n_small, n_big, pic.bdmax > 0xff, st_small, st_big);
 }
@@ -164,13 +178,14 @@ static bool tx_is_big(int tx) { const TxDim t = tx_dim(tx); return t.w > 16 || t
 // descriptors grouped by tx (class_count[t] of size t, increasing t): one launch for the sizes up
 // to 16x16, one for the larger ones; the tasks are implicit
 int itx_batch_launch(const PicView &pic, const PicView *res, void *cf, const Dav1dCudaItxDesc *descs,
-                     const int32_t *class_count, int zero_coefs, cudaStream_t st)
+                     const int32_t *class_count, int zero_coefs, cudaStream_t st, const CoefFmt *fmt)
 {
     const bool hbd = pic.bdmax > 0xff;
     for (int pass = 0; pass < 2; pass++) {
         Itx2Args a;
         memset(&a, 0, sizeof(a));
         a.pic = pic; a.cf = cf; a.descs = descs; a.zero_coefs = zero_coefs;
+        if (fmt) { a.cf16 = fmt->s16; a.esc = fmt->esc; a.n_esc = fmt->n_esc; }
         if (res) { a.res = *res; a.to_res = 1; }
         int off = 0, nt = 0;
         for (int tx = 0; tx < DAV1D_CUDA_N_RECT_TX_SIZES; tx++) {
@@ -276,7 +291,7 @@ static void itx_single(const int tx, const int txtp, pixel *dst, const ptrdiff_t
     pv.bdmax = bdmax;
     int32_t cls[DAV1D_CUDA_N_RECT_TX_SIZES] = { 0 };
     cls[tx] = 1;
-    if (itx_batch_launch(pv, nullptr, s.dev + cf_off, (const Dav1dCudaItxDesc *)(s.dev + desc_off), cls, 0, s.stream))
+    if (itx_batch_launch(pv, nullptr, s.dev + cf_off, (const Dav1dCudaItxDesc *)(s.dev + desc_off), cls, 0, s.stream, nullptr))
         return;
     D1_CHECKV(cudaMemcpyAsync(s.host + px_off, s.dev + px_off, tile_stride * h, cudaMemcpyDeviceToHost, s.stream));
     D1_CHECKV(cudaStreamSynchronize(s.stream));
@@ -386,7 +401,7 @@ int dav1d_cuda_itx_task_batch(Dav1dCudaContext *c, const Dav1dCudaPicture *dst, 
                               int zero_coefs)
 {
     if (!c || !dst || !descs || !tasks) return -22;
-    return itx_task_launch(pic_view(dst), nullptr, cf, descs, tasks, n_small, n_big, zero_coefs, c->stream, c->stream);
+    return itx_task_launch(pic_view(dst), nullptr, cf, descs, tasks, n_small, n_big, zero_coefs, c->stream, c->stream, nullptr);
 }
 
 int dav1d_cuda_itx_batch(Dav1dCudaContext *c, const Dav1dCudaPicture *dst, void *cf,
@@ -394,7 +409,7 @@ int dav1d_cuda_itx_batch(Dav1dCudaContext *c, const Dav1dCudaPicture *dst, void 
                          const int32_t class_count[DAV1D_CUDA_N_RECT_TX_SIZES], int zero_coefs)
 {
     if (!c || !dst || !descs || !class_count) return -22;
-    return itx_batch_launch(pic_view(dst), nullptr, cf, descs, class_count, zero_coefs, c->stream);
+    return itx_batch_launch(pic_view(dst), nullptr, cf, descs, class_count, zero_coefs, c->stream, nullptr);
 }
 
 }  // extern "C"

@@ -161,10 +161,44 @@ HD int itx2_tile_ints(const int tx) {          // shared-memory ints one block o
 // Between two phases the group synchronises (itx2_block below; the host check runs each phase
 // for all lanes in turn).
 
+// ---- where a block's coefficients come from: a plain pointer into the stream (int16 at 8 bit, int32 at
+// high bit depth: what the reference stores), or - Dav1dCudaReconBatch.cf_int16 - the compact high-bit-depth
+// stream: int16 storage, the value -32768 standing for "look the coefficient up in the escape list"
+struct Itx2Coef {
+    void *p;                            // the block's first coefficient
+    const Dav1dCudaCoefEsc *esc;        // escapes of the frame, sorted by stream offset
+    int n_esc;
+    uint32_t off;                       // stream offset of the block (key into `esc`)
+    int s16;                            // 0: int32 storage
+};
+HD int cf_get(const int16_t *p, const int i) { return p[i]; }
+HD int cf_get(const int32_t *p, const int i) { return p[i]; }
+HD void cf_zero(int16_t *p, const int i) { p[i] = 0; }
+HD void cf_zero(int32_t *p, const int i) { p[i] = 0; }
+HD int cf_escape(const Itx2Coef &c, const int i) {
+    const uint32_t key = c.off + (uint32_t)i;
+    int lo = 0, hi = c.n_esc - 1;
+    while (lo <= hi) {
+        const int mid = (lo + hi) >> 1;
+        const uint32_t o = c.esc[mid].off;
+        if (o == key) return c.esc[mid].value;
+        if (o < key) lo = mid + 1; else hi = mid - 1;
+    }
+    return -32768;                      // not listed: the value itself
+}
+HD int cf_get(const Itx2Coef &c, const int i) {
+    if (!c.s16) return ((const int32_t *)c.p)[i];
+    const int v = ((const int16_t *)c.p)[i];
+    return v == -32768 ? cf_escape(c, i) : v;
+}
+HD void cf_zero(const Itx2Coef &c, const int i) {
+    if (c.s16) ((int16_t *)c.p)[i] = 0; else ((int32_t *)c.p)[i] = 0;
+}
+
 // dc-only (itx_tmpl.c:53-65): every pixel gets the same offset
-template <typename pixel>
-HD int itx2_dc_value(const Itx2Blk &b, const typename PxTraits<pixel>::coef *cf) {
-    int dc = cf[0];
+template <typename pixel, typename CF = const typename PxTraits<pixel>::coef *>
+HD int itx2_dc_value(const Itx2Blk &b, const CF cf) {
+    int dc = cf_get(cf, 0);
     if (b.rect2) dc = (dc * 181 + 128) >> 8;
     dc = (dc * 181 + 128) >> 8;
     dc = (dc + ((1 << b.shift) >> 1)) >> b.shift;
@@ -222,8 +256,8 @@ HD void itx2_phase_out(const Itx2Blk &b, const int gl, const int G, const int *t
 }
 
 // coefficient box -> tile (row-major, stride ts), zeros where the passes read beyond the box
-template <typename pixel>
-HD void itx2_phase_stage(const Itx2Blk &b, const int gl, const int G, typename PxTraits<pixel>::coef *cf,
+template <typename pixel, typename CF = typename PxTraits<pixel>::coef *>
+HD void itx2_phase_stage(const Itx2Blk &b, const int gl, const int G, const CF cf,
                          int *tile, const bool zero_coefs)
 {
     // G >= ch: a lane owns one row of the box and walks along the columns (consecutive lanes read
@@ -234,12 +268,12 @@ HD void itx2_phase_stage(const Itx2Blk &b, const int gl, const int G, typename P
             int v[8];
 #pragma unroll
             for (int k = 0; k < 8; k++)
-                if (k < 4 || x0 + k < b.cw) v[k] = cf[gl + (x0 + k) * b.ch];
+                if (k < 4 || x0 + k < b.cw) v[k] = cf_get(cf, gl + (x0 + k) * b.ch);
 #pragma unroll
             for (int k = 0; k < 8; k++) {
                 if (k < 4 || x0 + k < b.cw) {
                     int t = v[k];
-                    if (zero_coefs) cf[gl + (x0 + k) * b.ch] = 0;
+                    if (zero_coefs) cf_zero(cf, gl + (x0 + k) * b.ch);
                     if (b.wht) t >>= 2;
                     else if (b.rect2) t = (t * 181 + 128) >> 8;
                     tile[gl * b.ts + x0 + k] = t;
@@ -277,18 +311,18 @@ HD void itx2_phase_cols(const Itx2Blk &b, const int gl, const int G, int *tile) 
 #if defined(__CUDACC__)
 // One block by the group of G lanes that contains this lane (all lanes of the warp call this;
 // lanes of a group without a block pass active = false).  res: see itx2_phase_out.
-template <typename pixel, int MAXN = 64>
-DEV void itx2_block(const bool active, const int gl, const int G, int *tile, typename PxTraits<pixel>::coef *cf,
+template <typename pixel, int MAXN = 64, typename CF = typename PxTraits<pixel>::coef *>
+DEV void itx2_block(const bool active, const int gl, const int G, int *tile, const CF cf,
                     const int tx, const int txtp, const int eob, const int cw4, const int ch4, pixel *dst,
                     const int dstride, int16_t *res, const int rstride, const int bdmax, const bool zero_coefs)
 {
     const Itx2Blk b = itx2_setup<pixel>(tx, txtp, eob, cw4, ch4, bdmax);
     int dc = 0;
-    if (active && b.dc_only) dc = itx2_dc_value<pixel>(b, cf);
+    if (active && b.dc_only) dc = itx2_dc_value<pixel, CF>(b, cf);
     __syncwarp();                                   // every lane has read cf[0] before it is cleared
-    if (active && b.dc_only && gl == 0 && zero_coefs) cf[0] = 0;
+    if (active && b.dc_only && gl == 0 && zero_coefs) cf_zero(cf, 0);
     const bool full = active && !b.dc_only;
-    if (full) itx2_phase_stage<pixel>(b, gl, G, cf, tile, zero_coefs);
+    if (full) itx2_phase_stage<pixel, CF>(b, gl, G, cf, tile, zero_coefs);
     __syncwarp();
     if (full) itx2_phase_rows<MAXN>(b, gl, tile);
     __syncwarp();

@@ -48,10 +48,10 @@ namespace d1 {
 
 // defined in itx2.cu / mc.cu
 int itx_batch_launch(const PicView &pic, const PicView *res, void *cf, const Dav1dCudaItxDesc *descs,
-                     const int32_t *class_count, int zero_coefs, cudaStream_t st);
+                     const int32_t *class_count, int zero_coefs, cudaStream_t st, const CoefFmt *fmt = nullptr);
 int itx_task_launch(const PicView &pic, const PicView *res, void *cf, const Dav1dCudaItxDesc *descs,
                     const uint32_t *tasks, int n_small, int n_big, int zero_coefs, cudaStream_t st_small,
-                    cudaStream_t st_big);
+                    cudaStream_t st_big, const CoefFmt *fmt = nullptr);
 int mc_obmc_launch_raw(const PicView &dst, const PicView *refs, const Dav1dCudaMcDesc *descs,
                        const uint32_t *tiles, int n_tiles, cudaStream_t st);
 void itx_init_attrs();
@@ -946,6 +946,7 @@ static int check_group(const Dav1dCudaReconBatch *const *bs, int n) {
         if (b->n_intra > 0 && b->intra_itx && !b->intra_res) return -22;
         for (int k = 0; k < 4; k++)
             if (b->n_mc_scaled[k] < 0 || (b->n_mc_scaled[k] > 0 && !b->mc_scaled)) return -22;
+        if (b->n_cf_esc < 0 || (b->n_cf_esc > 0 && !b->cf_esc)) return -22;
     }
     return 0;
 }
@@ -1046,18 +1047,20 @@ static int group_submit_on(Dav1dCudaContext *c, const Dav1dCudaReconBatch *const
             (r = mc_obmc_launch_raw(dst, refs, b->mc_obmc, b->mc_obmc_tiles + b->n_mc_obmc_tiles[0],
                                     b->n_mc_obmc_tiles[1], s))) return r;
         if (sc && (r = mc_scaled_launch_raw(dst, refs, sc + nsc[0] + nsc[1] + nsc[2], nsc[3], b->masks, s))) return r;
+        const CoefFmt fmt = { hbd && b->cf_int16, b->cf_esc, b->n_cf_esc };
         if ((mask & 8) && b->itx && b->itx_tasks) {
-            if ((r = itx_task_launch(dst, nullptr, b->cf, b->itx, b->itx_tasks, b->n_itx_tasks[0], b->n_itx_tasks[1], 0, s, s)))
-                return r;
-        } else if ((mask & 8) && b->itx && (r = itx_batch_launch(dst, nullptr, b->cf, b->itx, b->itx_class_count, 0, s))) return r;
+            if ((r = itx_task_launch(dst, nullptr, b->cf, b->itx, b->itx_tasks, b->n_itx_tasks[0], b->n_itx_tasks[1], 0, s, s,
+                                     &fmt))) return r;
+        } else if ((mask & 8) && b->itx && (r = itx_batch_launch(dst, nullptr, b->cf, b->itx, b->itx_class_count, 0, s, &fmt)))
+            return r;
         // intra residual pre-pass -> int16 residual planes (independent of everything above)
         if ((mask & 16) && b->n_intra > 0 && b->intra_itx && b->intra_res) {
             const PicView rv = pic_view(b->intra_res);
             cudaStream_t s2 = ss[(f + NS / 2) % NS];
             if (b->intra_itx_tasks) {
                 if ((r = itx_task_launch(dst, &rv, b->cf, b->intra_itx, b->intra_itx_tasks, b->n_intra_itx_tasks[0],
-                                         b->n_intra_itx_tasks[1], 0, s2, s2))) return r;
-            } else if ((r = itx_batch_launch(dst, &rv, b->cf, b->intra_itx, b->intra_itx_class_count, 0, s2))) return r;
+                                         b->n_intra_itx_tasks[1], 0, s2, s2, &fmt))) return r;
+            } else if ((r = itx_batch_launch(dst, &rv, b->cf, b->intra_itx, b->intra_itx_class_count, 0, s2, &fmt))) return r;
         }
     }
     if (!join_aux(c, st)) return -5;

@@ -404,3 +404,18 @@ extern "C" int dav1d_cuda_record_b_inter(Dav1dCudaInterRecorder *r, const Dav1dC
     nb_splat(r, bx, by, bw4, bh4, n);
     return R.n_emitted;
 }
+
+// ---------------------------------------------------------------- compact coefficient stream
+extern "C" int dav1d_cuda_pack_coefs(const int32_t *cf32, size_t n, int16_t *out16, Dav1dCudaCoefEsc *esc, int cap_esc) {
+    if ((n && (!cf32 || !out16)) || cap_esc < 0 || (cap_esc && !esc) || n > 0xffffffffu) return -22;
+    int ne = 0;
+    for (size_t i = 0; i < n; i++) {
+        const int32_t v = cf32[i];
+        if (v > -32768 && v <= 32767) { out16[i] = (int16_t)v; continue; }
+        if (ne >= cap_esc) return -28;
+        out16[i] = -32768;
+        esc[ne].off = (uint32_t)i; esc[ne].value = v;
+        ne++;
+    }
+    return ne;
+}

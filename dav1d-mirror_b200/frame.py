@@ -152,6 +152,7 @@ class HostFrame:
         self.intra_itx_tasks = tasks[:max(k, 1)].copy().view(np.uint8)
         self.n_intra_itx_tasks = (ns.value, nb.value) if n_iitx else (0, 0)
         self.n_levels = None
+        self.cf16 = None                  # pack_coefs()
 
     def record_levels(self, into=None):
         """The recorder's linear pass over the intra-class descriptors (decode order): dependency
@@ -168,6 +169,22 @@ class HostFrame:
             self.n_levels = r
         return r
 
+    def pack_coefs(self):
+        """High bit depth: the compact coefficient stream (Dav1dCudaReconBatch.cf_int16) - int16 storage plus an
+        escape list for what does not fit.  self.cf stays the int32 stream (what the oracle reads); the device
+        arena takes cf16 / cf_esc instead."""
+        assert self.hbd
+        n = self.cf.nbytes // 4
+        self.cf16 = np.zeros(max(n, 1), dtype=np.int16)
+        esc = np.zeros((max(n, 1), 2), dtype=np.int32)
+        k = B.lib().dav1d_cuda_pack_coefs(self.cf.ctypes.data, n, self.cf16.ctypes.data, esc.ctypes.data, len(esc))
+        if k < 0:
+            raise RuntimeError(f"dav1d_cuda_pack_coefs: {k}")
+        self.cf16 = self.cf16.view(np.uint8)
+        self.n_cf_esc = k
+        self.cf_esc = esc[:max(k, 1)].copy().view(np.uint8).reshape(-1)
+        return k
+
     def plane_shape(self, pl, ref=None):
         """ref: index of a reference picture (its size may differ from the frame's: params.ref_w / ref_h)."""
         sh = self.ss_hor if pl else 0
@@ -180,8 +197,9 @@ class HostFrame:
 
     def host_bytes(self):
         """Bytes a decoder ships host->device for this frame (descriptors + coefficients + pools)."""
+        cf = self.cf if self.cf16 is None else np.concatenate([self.cf16, self.cf_esc[:self.n_cf_esc * 8]])
         return sum(a.nbytes for a in (self.mc_put, self.mc_put_tiles, self.mc_comp, self.mc_comp_tiles, self.warp,
-                                      self.mc_obmc, self.mc_obmc_tiles, self.mc_scaled, self.itx, self.itx_tasks, self.cf, self.masks,
+                                      self.mc_obmc, self.mc_obmc_tiles, self.mc_scaled, self.itx, self.itx_tasks, cf, self.masks,
                                       self.pal, self.pal_idx, self.intra, self.intra_itx,
                                       self.intra_itx_tasks))
 
@@ -244,6 +262,10 @@ class DeviceFrame:
             names += ["mc_obmc", "mc_obmc_tiles"]
         if hf.mc_scaled.nbytes:
             names += ["mc_scaled"]
+        if hf.cf16 is not None:
+            alt["cf"] = hf.cf16
+            alt["cf_esc"] = hf.cf_esc
+            names += ["cf_esc"]
         host, offs, off = {}, {}, 0
         for name in names:
             arr = alt.get(name, getattr(hf, name))
@@ -270,6 +292,8 @@ class DeviceFrame:
         if hf.mc_obmc.nbytes:
             b.mc_obmc, b.mc_obmc_tiles = d["mc_obmc"], d["mc_obmc_tiles"]
             b.n_mc_obmc_tiles[0], b.n_mc_obmc_tiles[1] = hf.n_mc_obmc_tiles
+        if hf.cf16 is not None:
+            b.cf_int16, b.cf_esc, b.n_cf_esc = 1, d["cf_esc"], hf.n_cf_esc
         if hf.mc_scaled.nbytes:
             b.mc_scaled = d["mc_scaled"]
             for i in range(4):

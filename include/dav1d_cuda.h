@@ -514,6 +514,13 @@ DAV1D_CUDA_API size_t dav1d_cuda_intra_cellmap_bytes(int bw4, int bh4, int ss_ho
 DAV1D_CUDA_API int dav1d_cuda_intra_levels(Dav1dCudaIntraDesc *descs, int n, int bw4, int bh4,
                                            int ss_hor, int ss_ver);
 
+/* Compact coefficient stream of a high-bit-depth frame (see Dav1dCudaReconBatch.cf_int16). */
+typedef struct Dav1dCudaCoefEsc { uint32_t off; int32_t value; } Dav1dCudaCoefEsc;
+/* Host: out16[i] = cf32[i] where it fits int16 (and is not -32768), else -32768 plus an entry of `esc`
+ * (capacity cap_esc, offsets ascending).  Returns the number of escapes, or -ENOSPC. */
+DAV1D_CUDA_API int dav1d_cuda_pack_coefs(const int32_t *cf32, size_t n, int16_t *out16,
+                                         Dav1dCudaCoefEsc *esc, int cap_esc);
+
 /* A whole frame's reconstruction as device-resident batches:
  *   phase A  motion compensation (put, fused compound in two waves, warp)
  *   phase B  inter residuals (itxfm_add per size class)
@@ -565,6 +572,13 @@ typedef struct Dav1dCudaReconBatch {
      * and [3] after the same-size OBMC_V wave (a block's top blends come before its left blends
      * whatever the size of the neighbours' references). */
     const Dav1dCudaMcScaledDesc *mc_scaled; int32_t n_mc_scaled[4];
+    /* high bit depth only: non-zero = `cf` is the compact stream - int16 storage (coef_off counts int16
+     * elements), half the upload and half the HBM read of the int32 layout the reference keeps
+     * (src/internal.h:288).  The value -32768 marks a coefficient that does not fit (10/12-bit streams
+     * reach 2^(bitdepth+7) - 1 in magnitude, cf_max, recon_tmpl.c:594): its value is in `cf_esc` (device),
+     * sorted by stream offset; dav1d_cuda_pack_coefs() produces both from an int32 stream. */
+    int32_t cf_int16;
+    const Dav1dCudaCoefEsc *cf_esc;   int32_t n_cf_esc;
 } Dav1dCudaReconBatch;
 
 enum { DAV1D_CUDA_MAX_GROUP = 64 };   /* frames per group submission */

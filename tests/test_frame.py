@@ -133,6 +133,56 @@ def test_frame_parity_small(ref, name):
                                    f"n={len(bad)}")
 
 
+def big_coefs(hf, seed):
+    """Some coefficients beyond int16 (legal at 10 / 12 bit: |c| <= cf_max = 2^(bitdepth+7) - 1, recon_tmpl.c:594),
+    the sentinel value itself and the int16 limits."""
+    rng = np.random.default_rng(seed)
+    cf = hf.cf.view(np.int32)
+    nz = np.flatnonzero(cf)
+    pick = rng.choice(nz, size=min(200, len(nz)), replace=False)
+    cf_max = (128 << (12 if hf.bdmax > 0x3ff else 10)) - 1
+    vals = rng.integers(32768, cf_max + 1, size=len(pick)) * rng.choice([-1, 1], size=len(pick))
+    vals[:6] = [-32768, 32767, -32767, 32768, -32769, cf_max]
+    cf[pick] = vals
+    return len(pick)
+
+
+def test_pack_coefs_round_trip():
+    hf = F.HostFrame(256, 192, 0x3ff, 77)
+    n_big = big_coefs(hf, 1)
+    k = hf.pack_coefs()
+    cf = hf.cf.view(np.int32)
+    c16 = hf.cf16.view(np.int16)[:len(cf)]
+    esc = hf.cf_esc.view(np.int32).reshape(-1, 2)[:k]
+    assert 0 < k <= n_big and np.all(np.diff(esc[:, 0]) > 0)
+    back = c16.astype(np.int32)
+    assert np.all(back[esc[:, 0]] == -32768)
+    back[esc[:, 0]] = esc[:, 1]
+    assert np.array_equal(back, cf)
+    small = np.zeros(4, dtype=np.int32)
+    small[:] = [1, 70000, -70000, 3]
+    out = np.zeros(4, dtype=np.int16)
+    e = np.zeros((1, 2), dtype=np.int32)
+    assert pkg.lib().dav1d_cuda_pack_coefs(small.ctypes.data, 4, out.ctypes.data, e.ctypes.data, 1) == -28   # -ENOSPC
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["420_10b_small", "420_12b_small", "422_10b_intra_heavy", "420_10b_dense_coefs"])
+def test_compact_coefficient_stream(ref, name):
+    """High bit depth with the int16 coefficient stream + escape list (Dav1dCudaReconBatch.cf_int16): same
+    pixels as the reference computes from the int32 stream, including coefficients that do not fit int16."""
+    w, h, bd, seed, kw = CASES[name]
+    hf = F.HostFrame(w, h, bd, seed, **kw)
+    big_coefs(hf, seed)
+    refs, init, want = oracle_planes(ref, hf, seed)
+    assert hf.pack_coefs() > 0
+    for tasks in (True, False):
+        got = run_gpu(hf, refs, init, tasks=tasks)
+        for pl, (a, b) in enumerate(zip(want, got)):
+            bad = np.argwhere(a != b)
+            assert bad.size == 0, f"{name} tasks={tasks}: plane {pl}: {len(bad)} pixels differ, first {bad[0]}"
+
+
 @pytest.mark.gpu
 def test_config2_itx_1080p_8bit(ref):
     """BASELINE config 2: batched itxfm_add over all 19 sizes x valid types, 8-bit, 1080p-worth."""
