@@ -104,7 +104,8 @@ __global__ void __launch_bounds__(ITX2_WARPS * 32, Itx2Cls<CLS>::MIN_BLOCKS) itx
     if constexpr (sizeof(coef) == 4) {
         // the frames of a multi-frame task list carry native coefficients
         Itx2Coef c;
-        c.s16 = a.mtasks ? 0 : a.cf16; c.esc = a.esc; c.n_esc = a.n_esc; c.off = d.coef_off;
+        static_assert(sizeof(Itx2Esc) == sizeof(Dav1dCudaCoefEsc), "escape entry layout");
+        c.s16 = a.mtasks ? 0 : a.cf16; c.esc = (const Itx2Esc *)a.esc; c.n_esc = a.n_esc; c.off = d.coef_off;
         c.p = c.s16 ? (void *)((int16_t *)cf + d.coef_off) : (void *)((int32_t *)cf + d.coef_off);
         itx2_block<pixel, Itx2Cls<CLS>::MAXN, Itx2Coef>(active, gl, G, smem + grp * itx2_tile_ints(tx), c, tx, d.txtp, d.eob,
                                                         d.cw4, d.ch4, dst, dstride, res, rstride, pic->bdmax,

@@ -164,9 +164,10 @@ HD int itx2_tile_ints(const int tx) {          // shared-memory ints one block o
 // ---- where a block's coefficients come from: a plain pointer into the stream (int16 at 8 bit, int32 at
 // high bit depth: what the reference stores), or - Dav1dCudaReconBatch.cf_int16 - the compact high-bit-depth
 // stream: int16 storage, the value -32768 standing for "look the coefficient up in the escape list"
+struct Itx2Esc { uint32_t off; int32_t value; };     // == Dav1dCudaCoefEsc (this header is also compiled host-only)
 struct Itx2Coef {
     void *p;                            // the block's first coefficient
-    const Dav1dCudaCoefEsc *esc;        // escapes of the frame, sorted by stream offset
+    const Itx2Esc *esc;                 // escapes of the frame, sorted by stream offset
     int n_esc;
     uint32_t off;                       // stream offset of the block (key into `esc`)
     int s16;                            // 0: int32 storage
