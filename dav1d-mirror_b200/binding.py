@@ -190,6 +190,12 @@ class McScaledDesc(C.Structure):
                 ("aux16", C.c_uint16), ("aux_off", C.c_uint32)]
 
 
+class LfFrame(C.Structure):
+    _fields_ = [("w4", C.c_int32), ("h4", C.c_int32), ("b4_stride", C.c_int32), ("sb128w", C.c_int32),
+                ("filter_uv", C.c_int32), ("masks", C.c_void_p), ("level", C.c_void_p),
+                ("lut_e", C.c_uint8 * 64), ("lut_i", C.c_uint8 * 64)]
+
+
 class ReconBatch(C.Structure):
     _fields_ = [("dst", C.POINTER(Picture)), ("refs", C.POINTER(Picture) * 7),
                 ("bw4", C.c_int32), ("bh4", C.c_int32),
@@ -226,6 +232,7 @@ def bind_frame_api(L):
     L.dav1d_cuda_picture_to_host.argtypes = [C.c_void_p, C.POINTER(Dav1dPictureMirror)]
     L.dav1d_cuda_picture_to_device.argtypes = [C.c_void_p, C.POINTER(Dav1dPictureMirror)]
     L.dav1d_cuda_record_b_intra.argtypes = [C.POINTER(Recorder), C.POINTER(BlockIntra), C.c_void_p, C.c_int]
+    L.dav1d_cuda_loopfilter_frame.argtypes = [C.c_void_p, C.POINTER(Picture), C.POINTER(LfFrame)]
     L.dav1d_cuda_pack_coefs.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_int]
     L.dav1d_cuda_record_b_inter.argtypes = [C.POINTER(InterRecorder), C.POINTER(BlockInter), C.c_void_p, C.c_int]
     L.dav1d_cuda_record_nb_intra.argtypes = [C.POINTER(InterRecorder)] + [C.c_int] * 4

@@ -441,6 +441,29 @@ DAV1D_CUDA_API const Dav1dCudaPicture *dav1d_cuda_picture_of(const Dav1dCudaDav1
 DAV1D_CUDA_API int dav1d_cuda_picture_to_host(Dav1dCudaContext *c, const Dav1dCudaDav1dPicture *pic);
 DAV1D_CUDA_API int dav1d_cuda_picture_to_device(Dav1dCudaContext *c, const Dav1dCudaDav1dPicture *pic);
 
+/* ---- In-loop post-filters, first stage: the deblocking loop filter of a whole frame, in place in HBM.
+ * Replaces dav1d_loopfilter_sbrow_cols / _rows over all superblock rows (src/lf_apply_tmpl.c:306-466,
+ * called from dav1d_filter_sbrow_deblock_cols / _rows, recon_tmpl.c:2038-2071) and the loop_filter_sb
+ * functions they call (src/loopfilter_tmpl.c).  The inputs are dav1d's own structures, copied to the device
+ * as they are when the filter starts:
+ *   masks = f->lf.mask: Av1Filter[f->sb128w * f->sb128h] (src/lf_mask.h:52-58, 1348 bytes each), after the
+ *           tile-edge fix-ups of lf_apply_tmpl.c:323-387 where the frame has several tiles;
+ *   level = f->lf.level: uint8_t[4] per 4x4 block, row stride f->b4_stride (lf_mask.c:307-312);
+ *   lut_e / lut_i = f->lf.lim_lut.e / .i (dav1d_calc_eih).
+ * Two passes (all column edges, then all row edges) of independent edges; asynchronous on the context's
+ * stream.  CDEF, super-resolution and loop restoration are not built: the filtered frame goes to the host
+ * for them (dav1d_cuda_picture_to_host). */
+typedef struct Dav1dCudaLfFrame {
+    int32_t w4, h4;                     /* f->w4, f->h4 */
+    int32_t b4_stride, sb128w;          /* f->b4_stride, f->sb128w */
+    int32_t filter_uv;                  /* frame_hdr->loopfilter.level_u || level_v */
+    const void *masks;                  /* device */
+    const uint8_t *level;               /* device */
+    uint8_t lut_e[64], lut_i[64];
+} Dav1dCudaLfFrame;
+DAV1D_CUDA_API int dav1d_cuda_loopfilter_frame(Dav1dCudaContext *c, const Dav1dCudaPicture *pic,
+                                               const Dav1dCudaLfFrame *lf);
+
 /* Operator-class launches.  All pointers inside the argument list that are
  * documented as "device" must be device pointers; the calls are asynchronous
  * on the context's stream. */

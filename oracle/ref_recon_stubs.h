@@ -3,11 +3,5 @@
  * dav1d_recon_b_intra / dav1d_backup_ipred_edge, so these are never reached. */
 STUB(dav1d_cdef_brow_8bpc)
 STUB(dav1d_cdef_brow_16bpc)
-STUB(dav1d_copy_lpf_8bpc)
-STUB(dav1d_copy_lpf_16bpc)
-STUB(dav1d_loopfilter_sbrow_cols_8bpc)
-STUB(dav1d_loopfilter_sbrow_cols_16bpc)
-STUB(dav1d_loopfilter_sbrow_rows_8bpc)
-STUB(dav1d_loopfilter_sbrow_rows_16bpc)
 STUB(dav1d_lr_sbrow_8bpc)
 STUB(dav1d_lr_sbrow_16bpc)

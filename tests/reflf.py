@@ -1,0 +1,68 @@
+"""Run the reference's own loop-filter path (oracle/ref_lf.c inside oracle/_ref/libdav1d_ref.so) on the block
+records of a HostFrame.  TEST INFRASTRUCTURE ONLY."""
+import ctypes as C
+
+import numpy as np
+
+
+class OracleLfFrame(C.Structure):
+    _fields_ = [("dst", C.c_void_p * 3), ("dst_stride", C.c_ssize_t * 3),
+                ("w", C.c_int32), ("h", C.c_int32), ("ss_hor", C.c_int32), ("ss_ver", C.c_int32),
+                ("bitdepth_max", C.c_int32), ("no_chroma", C.c_int32),
+                ("blocks", C.c_void_p), ("n_blocks", C.c_int32), ("seed", C.c_uint64),
+                ("sharpness", C.c_int32), ("p_zero_level", C.c_int32), ("run", C.c_int32),
+                ("masks", C.c_void_p), ("level", C.c_void_p), ("lut", C.c_void_p),
+                ("b4_stride", C.c_int32), ("sb128w", C.c_int32), ("sb128h", C.c_int32), ("w4", C.c_int32),
+                ("h4", C.c_int32), ("sizeof_av1filter", C.c_int32)]
+
+
+def blocky_planes(hf, seed):
+    """A picture the loop filter has work on: flat 4x4 / 8x8 / 16x16 patches with steps of all sizes between
+    them plus low noise, so that every branch (filter mask on / off, hev, flat8in, flat8out) is taken."""
+    rng = np.random.default_rng(seed)
+    dt = np.uint16 if hf.hbd else np.uint8
+    sh = {0xff: 0, 0x3ff: 2, 0xfff: 4}[hf.bdmax]
+    out = []
+    for pl in range(1 if hf.no_chroma else 3):
+        ph, pw = hf.plane_shape(pl)
+        acc = np.zeros((ph, pw), dtype=np.int64)
+        for cell, amp in ((16, 40), (8, 10), (4, 3)):
+            gh, gw = (ph + cell - 1) // cell, (pw + cell - 1) // cell
+            g = rng.integers(-amp, amp + 1, size=(gh, gw))
+            acc += np.kron(g, np.ones((cell, cell), dtype=np.int64))[:ph, :pw]
+        acc += rng.integers(-1, 2, size=(ph, pw)) * (rng.random((ph, pw)) < 0.3)
+        base = rng.integers(60, 190)
+        out.append(np.clip((acc + base) << sh, 0, hf.bdmax).astype(dt))
+    return out
+
+
+def run_reference_lf(ref, hf, planes, seed, sharpness=0, p_zero_level=100, run=True):
+    """Builds masks / levels / limit table through the reference's lf_mask.c and (run) filters `planes` in place
+    through lf_apply_tmpl.c.  Returns (planes, state) with state = what the device path is given."""
+    assert hf.n_block_recs > 0, "generate the frame with real_blocks=1"
+    of = OracleLfFrame()
+    for pl, a in enumerate(planes):
+        of.dst[pl] = a.ctypes.data
+        of.dst_stride[pl] = a.strides[0]
+    of.w, of.h, of.ss_hor, of.ss_ver = hf.w, hf.h, hf.ss_hor, hf.ss_ver
+    of.bitdepth_max, of.no_chroma = hf.bdmax, hf.no_chroma
+    of.blocks, of.n_blocks = hf.blocks.ctypes.data, hf.n_block_recs
+    of.seed, of.sharpness, of.p_zero_level, of.run = seed, sharpness, p_zero_level, 1 if run else 0
+    sfx = "16bpc" if hf.hbd else "8bpc"
+    geo = getattr(ref.lib, "oracle_lf_geometry_" + sfx)
+    geo.argtypes = [C.POINTER(OracleLfFrame)]
+    geo.restype = None
+    geo(C.byref(of))
+    masks = np.zeros(of.sb128w * of.sb128h * of.sizeof_av1filter, dtype=np.uint8)
+    level = np.zeros(of.b4_stride * 32 * of.sb128h * 4, dtype=np.uint8)
+    lut = np.zeros(144, dtype=np.uint8)
+    of.masks, of.level, of.lut = masks.ctypes.data, level.ctypes.data, lut.ctypes.data
+    fn = getattr(ref.lib, "oracle_lf_frame_" + sfx)
+    fn.argtypes = [C.POINTER(OracleLfFrame)]
+    fn.restype = C.c_int
+    r = fn(C.byref(of))
+    if r:
+        raise RuntimeError(f"oracle_lf_frame: {r}")
+    state = {"masks": masks, "level": level, "lut": lut, "b4_stride": of.b4_stride, "sb128w": of.sb128w,
+             "sb128h": of.sb128h, "w4": of.w4, "h4": of.h4, "sizeof_av1filter": of.sizeof_av1filter}
+    return planes, state

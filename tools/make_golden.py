@@ -35,3 +35,16 @@ for name in R.CASES:
     print(name, out[name], "blocks", hf.n_block_recs, "intra ops", hf.n_intra)
 with open(R.GOLDEN, "w") as f:
     json.dump(out, f, indent=1, sort_keys=True)
+
+# the reference's loop filter over the block records (tests/test_loopfilter.py)
+import reflf  # noqa: E402
+import test_loopfilter as LF  # noqa: E402
+
+out = {}
+for name in LF.CASES:
+    hf, src, seed, sharp = LF.make(name)
+    planes, _ = reflf.run_reference_lf(ref, hf, [p.copy() for p in src], seed, sharpness=sharp)
+    out[name] = LF.md5_planes(planes)
+    print(name, out[name])
+with open(LF.GOLDEN, "w") as f:
+    json.dump(out, f, indent=1, sort_keys=True)
