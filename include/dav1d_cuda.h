@@ -451,7 +451,7 @@ DAV1D_CUDA_API int dav1d_cuda_picture_to_device(Dav1dCudaContext *c, const Dav1d
  *   level = f->lf.level: uint8_t[4] per 4x4 block, row stride f->b4_stride (lf_mask.c:307-312);
  *   lut_e / lut_i = f->lf.lim_lut.e / .i (dav1d_calc_eih).
  * Two passes (all column edges, then all row edges) of independent edges; asynchronous on the context's
- * stream.  CDEF, super-resolution and loop restoration are not built: the filtered frame goes to the host
+ * stream.  Super-resolution and loop restoration are not built: after CDEF (below) the frame goes to the host
  * for them (dav1d_cuda_picture_to_host). */
 typedef struct Dav1dCudaLfFrame {
     int32_t w4, h4;                     /* f->w4, f->h4 */
@@ -463,6 +463,24 @@ typedef struct Dav1dCudaLfFrame {
 } Dav1dCudaLfFrame;
 DAV1D_CUDA_API int dav1d_cuda_loopfilter_frame(Dav1dCudaContext *c, const Dav1dCudaPicture *pic,
                                                const Dav1dCudaLfFrame *lf);
+
+/* Second stage: CDEF of a whole frame, OUT OF PLACE (dst != src; src = the deblocked picture).  Replaces
+ * dav1d_filter_sbrow_cdef over all superblock rows (recon_tmpl.c:2073-2100 -> dav1d_cdef_brow,
+ * src/cdef_apply_tmpl.c:98-309 -> dsp->cdef.dir / .fb[], src/cdef_tmpl.c).  The reference filters in place and
+ * keeps backups so that every tap reads pre-CDEF pixels; a second picture gives the same without backups.
+ *   masks = f->lf.mask (device): Av1Filter.cdef_idx (strength index per 64x64, -1 = unset) and
+ *           Av1Filter.noskip_mask (blocks with coefficients, decode.c:1990-1999);
+ *   y_strength / uv_strength / damping = frame_hdr->cdef.
+ * Blocks the reference leaves alone are copied.  Asynchronous on the context's stream. */
+typedef struct Dav1dCudaCdefFrame {
+    int32_t bw, bh;                     /* f->bw, f->bh: frame size in 4-px units, rounded up to 8 pixels */
+    int32_t sb128w;                     /* f->sb128w */
+    int32_t damping;                    /* frame_hdr->cdef.damping, 3..6 */
+    uint8_t y_strength[8], uv_strength[8];
+    const void *masks;                  /* device */
+} Dav1dCudaCdefFrame;
+DAV1D_CUDA_API int dav1d_cuda_cdef_frame(Dav1dCudaContext *c, const Dav1dCudaPicture *dst,
+                                         const Dav1dCudaPicture *src, const Dav1dCudaCdefFrame *p);
 
 /* Operator-class launches.  All pointers inside the argument list that are
  * documented as "device" must be device pointers; the calls are asynchronous

@@ -66,3 +66,41 @@ def run_reference_lf(ref, hf, planes, seed, sharpness=0, p_zero_level=100, run=T
     state = {"masks": masks, "level": level, "lut": lut, "b4_stride": of.b4_stride, "sb128w": of.sb128w,
              "sb128h": of.sb128h, "w4": of.w4, "h4": of.h4, "sizeof_av1filter": of.sizeof_av1filter}
     return planes, state
+
+
+class OracleCdefFrame(C.Structure):
+    _fields_ = [("dst", C.c_void_p * 3), ("dst_stride", C.c_ssize_t * 3),
+                ("w", C.c_int32), ("h", C.c_int32), ("ss_hor", C.c_int32), ("ss_ver", C.c_int32),
+                ("bitdepth_max", C.c_int32), ("no_chroma", C.c_int32),
+                ("blocks", C.c_void_p), ("n_blocks", C.c_int32), ("seed", C.c_uint64),
+                ("damping", C.c_int32), ("y_strength", C.c_uint8 * 8), ("uv_strength", C.c_uint8 * 8),
+                ("p_unset", C.c_int32), ("run", C.c_int32), ("masks", C.c_void_p),
+                ("sb128w", C.c_int32), ("sb128h", C.c_int32), ("bw", C.c_int32), ("bh", C.c_int32)]
+
+
+def run_reference_cdef(ref, hf, planes, seed, damping, y_strength, uv_strength, p_unset=100, run=True):
+    """CDEF of `planes` in place through dav1d_filter_sbrow_cdef / dav1d_cdef_brow; returns (planes, state) with
+    state = the Av1Filter array (cdef_idx, noskip_mask) and the frame parameters the device path is given."""
+    assert hf.n_block_recs > 0 and hf.w % 8 == 0 and hf.h % 8 == 0
+    of = OracleCdefFrame()
+    for pl, a in enumerate(planes):
+        of.dst[pl] = a.ctypes.data
+        of.dst_stride[pl] = a.strides[0]
+    of.w, of.h, of.ss_hor, of.ss_ver = hf.w, hf.h, hf.ss_hor, hf.ss_ver
+    of.bitdepth_max, of.no_chroma = hf.bdmax, hf.no_chroma
+    of.blocks, of.n_blocks = hf.blocks.ctypes.data, hf.n_block_recs
+    of.seed, of.damping, of.p_unset, of.run = seed, damping, p_unset, 1 if run else 0
+    for k in range(8):
+        of.y_strength[k], of.uv_strength[k] = y_strength[k], uv_strength[k]
+    sb128w, sb128h = (hf.w + 127) // 128, (hf.h + 127) // 128
+    masks = np.zeros(sb128w * sb128h * 1348, dtype=np.uint8)
+    of.masks = masks.ctypes.data
+    fn = getattr(ref.lib, "oracle_cdef_frame_" + ("16bpc" if hf.hbd else "8bpc"))
+    fn.argtypes = [C.POINTER(OracleCdefFrame)]
+    fn.restype = C.c_int
+    r = fn(C.byref(of))
+    if r:
+        raise RuntimeError(f"oracle_cdef_frame: {r}")
+    assert (of.sb128w, of.sb128h) == (sb128w, sb128h)
+    return planes, {"masks": masks, "sb128w": sb128w, "bw": of.bw, "bh": of.bh, "damping": damping,
+                    "y_strength": list(y_strength), "uv_strength": list(uv_strength)}

@@ -48,3 +48,15 @@ for name in LF.CASES:
     print(name, out[name])
 with open(LF.GOLDEN, "w") as f:
     json.dump(out, f, indent=1, sort_keys=True)
+
+# the reference's CDEF (tests/test_cdef.py)
+import test_cdef as CD  # noqa: E402
+
+out = {}
+for name in CD.CASES:
+    hf, src, seed, damping, ys, us = CD.make(name)
+    planes, _ = reflf.run_reference_cdef(ref, hf, [p.copy() for p in src], seed, damping, ys, us)
+    out[name] = CD.md5_planes(planes)
+    print(name, out[name])
+with open(CD.GOLDEN, "w") as f:
+    json.dump(out, f, indent=1, sort_keys=True)

@@ -1,0 +1,63 @@
+#!/usr/bin/env python3
+"""Device deblocking of 4K 10-bit 4:2:0 frames: time per frame with CUDA events, `n` frames in flight on one
+context.  Masks / levels come from the reference's lf_mask.c over the generator's block records (oracle)."""
+import ctypes as C
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import _d1pkg  # noqa: E402
+
+pkg = _d1pkg.load_pkg()
+from dav1d_mirror_b200 import binding as B  # noqa: E402
+from dav1d_mirror_b200 import frame as F  # noqa: E402
+import refdsp  # noqa: E402
+import reflf  # noqa: E402
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 16
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
+w, h, bd = 3840, 2160, 0x3ff
+L = pkg.lib()
+ref = refdsp.RefDSP()
+hf = F.HostFrame(w, h, bd, 1000, real_blocks=1, p_wedge=0.0, p_warp=0.0)
+src = reflf.blocky_planes(hf, 5)
+_, st = reflf.run_reference_lf(ref, hf, [p.copy() for p in src], 7, run=False)
+ctx = F.open_context(0)
+pics = []
+for k in range(n):
+    pic = B.Picture()
+    assert L.dav1d_cuda_picture_alloc(ctx, C.byref(pic), w, h, 1, 1, bd) == 0
+    for pl, a in enumerate(src):
+        L.dav1d_cuda_picture_upload(ctx, C.byref(pic), pl, a.ctypes.data, a.strides[0])
+    pics.append(pic)
+d_masks = L.dav1d_cuda_malloc(st["masks"].nbytes)
+d_level = L.dav1d_cuda_malloc(st["level"].nbytes)
+L.dav1d_cuda_upload(ctx, d_masks, st["masks"].ctypes.data, st["masks"].nbytes)
+L.dav1d_cuda_upload(ctx, d_level, st["level"].ctypes.data, st["level"].nbytes)
+lf = B.LfFrame()
+lf.w4, lf.h4, lf.b4_stride, lf.sb128w, lf.filter_uv = st["w4"], st["h4"], st["b4_stride"], st["sb128w"], 1
+lf.masks, lf.level = d_masks, d_level
+C.memmove(lf.lut_e, st["lut"].ctypes.data, 64)
+C.memmove(lf.lut_i, st["lut"].ctypes.data + 64, 64)
+e0, e1 = L.dav1d_cuda_event_create(), L.dav1d_cuda_event_create()
+for _ in range(2):
+    for pic in pics:
+        L.dav1d_cuda_loopfilter_frame(ctx, C.byref(pic), C.byref(lf))
+L.dav1d_cuda_synchronize(ctx)
+L.dav1d_cuda_event_record(ctx, e0)
+for _ in range(reps):
+    for pic in pics:
+        L.dav1d_cuda_loopfilter_frame(ctx, C.byref(pic), C.byref(lf))
+L.dav1d_cuda_event_record(ctx, e1)
+L.dav1d_cuda_synchronize(ctx)
+ms = L.dav1d_cuda_event_elapsed_ms(e0, e1)
+per = ms / (reps * n) * 1e3
+samples = w * h * 1.5
+alg = samples * 2 * 2 * 2          # two passes, each reads and writes the picture once (an upper bound: the
+                                   # second pass of a fused design would not re-read) - 2 bytes per sample
+print(f"deblock 4K 10-bit 4:2:0: {per:.1f} us/frame, {w * h / per / 1e3:.1f} Gpix/s, "
+      f"{alg / per / 1e3:.0f} GB/s of 2-pass picture traffic ({alg / 1e6:.1f} MB/frame); "
+      f"masks {st['masks'].nbytes / 1e6:.2f} MB + levels {st['level'].nbytes / 1e6:.2f} MB per frame")
+pkg.check_error()
