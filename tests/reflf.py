@@ -104,3 +104,65 @@ def run_reference_cdef(ref, hf, planes, seed, damping, y_strength, uv_strength, 
     assert (of.sb128w, of.sb128h) == (sb128w, sb128h)
     return planes, {"masks": masks, "sb128w": sb128w, "bw": of.bw, "bh": of.bh, "damping": damping,
                     "y_strength": list(y_strength), "uv_strength": list(uv_strength)}
+
+
+class OraclePfFrame(C.Structure):
+    _fields_ = [("dst", C.c_void_p * 3), ("dst_stride", C.c_ssize_t * 3),
+                ("w", C.c_int32), ("h", C.c_int32), ("ss_hor", C.c_int32), ("ss_ver", C.c_int32),
+                ("bitdepth_max", C.c_int32), ("no_chroma", C.c_int32),
+                ("blocks", C.c_void_p), ("n_blocks", C.c_int32), ("seed", C.c_uint64),
+                ("do_deblock", C.c_int32), ("do_cdef", C.c_int32), ("do_lr", C.c_int32), ("run", C.c_int32),
+                ("sharpness", C.c_int32), ("p_zero_level", C.c_int32), ("damping", C.c_int32), ("p_unset", C.c_int32),
+                ("y_strength", C.c_uint8 * 8), ("uv_strength", C.c_uint8 * 8),
+                ("unit_size_log2", C.c_int32 * 2), ("restore_planes", C.c_int32), ("p_lr_none", C.c_int32),
+                ("masks", C.c_void_p), ("level", C.c_void_p), ("lut", C.c_void_p), ("lr_mask", C.c_void_p),
+                ("b4_stride", C.c_int32), ("sb128w", C.c_int32), ("sb128h", C.c_int32), ("w4", C.c_int32),
+                ("h4", C.c_int32), ("bw", C.c_int32), ("bh", C.c_int32), ("sizeof_av1filter", C.c_int32),
+                ("sizeof_av1restoration", C.c_int32)]
+
+
+def run_reference_chain(ref, hf, planes, seed, deblock=True, cdef=True, lr=True, sharpness=0, p_zero_level=100,
+                        damping=4, y_strength=(0,) * 8, uv_strength=(0,) * 8, p_unset=100, unit_size_log2=(6, 6),
+                        restore_planes=7, p_lr_none=150, run=True):
+    """The reference's own post-filter chain (dav1d_filter_sbrow per superblock row) on `planes`, in place, with the
+    stages switched by deblock / cdef / lr.  Returns (planes, state): masks, levels, limit table, restoration units
+    and the frame parameters the device calls take."""
+    assert hf.n_block_recs > 0 and hf.w % 8 == 0 and hf.h % 8 == 0
+    of = OraclePfFrame()
+    for pl, a in enumerate(planes):
+        of.dst[pl] = a.ctypes.data
+        of.dst_stride[pl] = a.strides[0]
+    of.w, of.h, of.ss_hor, of.ss_ver = hf.w, hf.h, hf.ss_hor, hf.ss_ver
+    of.bitdepth_max, of.no_chroma = hf.bdmax, hf.no_chroma
+    of.blocks, of.n_blocks, of.seed = hf.blocks.ctypes.data, hf.n_block_recs, seed
+    of.do_deblock, of.do_cdef, of.do_lr, of.run = int(deblock), int(cdef), int(lr), int(run)
+    of.sharpness, of.p_zero_level, of.damping, of.p_unset = sharpness, p_zero_level, damping, p_unset
+    for k in range(8):
+        of.y_strength[k] = y_strength[k]
+        of.uv_strength[k] = 0 if hf.no_chroma else uv_strength[k]
+    of.unit_size_log2[0], of.unit_size_log2[1] = unit_size_log2
+    of.restore_planes, of.p_lr_none = restore_planes, p_lr_none
+    sfx = "16bpc" if hf.hbd else "8bpc"
+    geo = getattr(ref.lib, "oracle_pf_geometry_" + sfx)
+    geo.argtypes = [C.POINTER(OraclePfFrame)]
+    geo.restype = None
+    geo(C.byref(of))
+    n128 = of.sb128w * of.sb128h
+    masks = np.zeros(n128 * of.sizeof_av1filter, dtype=np.uint8)
+    level = np.zeros(of.b4_stride * 32 * of.sb128h * 4, dtype=np.uint8)
+    lut = np.zeros(144, dtype=np.uint8)
+    lr_mask = np.zeros(n128 * of.sizeof_av1restoration, dtype=np.uint8)
+    of.masks, of.level, of.lut, of.lr_mask = masks.ctypes.data, level.ctypes.data, lut.ctypes.data, lr_mask.ctypes.data
+    fn = getattr(ref.lib, "oracle_pf_frame_" + sfx)
+    fn.argtypes = [C.POINTER(OraclePfFrame)]
+    fn.restype = C.c_int
+    r = fn(C.byref(of))
+    if r:
+        raise RuntimeError(f"oracle_pf_frame: {r}")
+    state = {"masks": masks, "level": level, "lut": lut, "lr_mask": lr_mask, "b4_stride": of.b4_stride,
+             "sb128w": of.sb128w, "sb128h": of.sb128h, "w4": of.w4, "h4": of.h4, "bw": of.bw, "bh": of.bh,
+             "damping": damping, "y_strength": list(y_strength),
+             "uv_strength": [0] * 8 if hf.no_chroma else list(uv_strength),
+             "unit_size_log2": tuple(unit_size_log2), "restore_planes": restore_planes & (1 if hf.no_chroma else 7),
+             "sizeof_av1restoration": of.sizeof_av1restoration}
+    return planes, state
