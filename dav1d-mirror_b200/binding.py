@@ -201,6 +201,11 @@ class CdefFrame(C.Structure):
                 ("y_strength", C.c_uint8 * 8), ("uv_strength", C.c_uint8 * 8), ("masks", C.c_void_p)]
 
 
+class LrFrame(C.Structure):
+    _fields_ = [("w", C.c_int32), ("h", C.c_int32), ("sb128w", C.c_int32), ("sb128", C.c_int32),
+                ("unit_size_log2", C.c_int32 * 2), ("restore_planes", C.c_int32), ("lr_mask", C.c_void_p)]
+
+
 class ReconBatch(C.Structure):
     _fields_ = [("dst", C.POINTER(Picture)), ("refs", C.POINTER(Picture) * 7),
                 ("bw4", C.c_int32), ("bh4", C.c_int32),
@@ -239,6 +244,8 @@ def bind_frame_api(L):
     L.dav1d_cuda_record_b_intra.argtypes = [C.POINTER(Recorder), C.POINTER(BlockIntra), C.c_void_p, C.c_int]
     L.dav1d_cuda_loopfilter_frame.argtypes = [C.c_void_p, C.POINTER(Picture), C.POINTER(LfFrame)]
     L.dav1d_cuda_cdef_frame.argtypes = [C.c_void_p, C.POINTER(Picture), C.POINTER(Picture), C.POINTER(CdefFrame)]
+    L.dav1d_cuda_lr_frame.argtypes = [C.c_void_p, C.POINTER(Picture), C.POINTER(Picture), C.POINTER(Picture),
+                                      C.POINTER(LrFrame)]
     L.dav1d_cuda_pack_coefs.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_int]
     L.dav1d_cuda_record_b_inter.argtypes = [C.POINTER(InterRecorder), C.POINTER(BlockInter), C.c_void_p, C.c_int]
     L.dav1d_cuda_record_nb_intra.argtypes = [C.POINTER(InterRecorder)] + [C.c_int] * 4

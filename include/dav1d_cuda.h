@@ -482,6 +482,25 @@ typedef struct Dav1dCudaCdefFrame {
 DAV1D_CUDA_API int dav1d_cuda_cdef_frame(Dav1dCudaContext *c, const Dav1dCudaPicture *dst,
                                          const Dav1dCudaPicture *src, const Dav1dCudaCdefFrame *p);
 
+/* Third stage: loop restoration (Wiener / self-guided) of a whole frame, OUT OF PLACE.  Replaces dav1d_lr_sbrow
+ * over all superblock rows (src/lr_apply_tmpl.c:165-202 -> lr_sbrow / lr_stripe -> dsp->lr.wiener[] / .sgr[],
+ * src/looprestoration_tmpl.c).  src = the CDEF output; deblocked = the picture before CDEF (the two lines above
+ * and below every 64-row stripe are read from it - what dav1d_copy_lpf saves into f->lf.lr_lpf_line,
+ * lf_apply_tmpl.c:108-175); pass src twice when the frame has no CDEF.
+ *   lr_mask = f->lf.lr_mask (device): Av1Restoration[f->sr_sb128w * f->sb128h] (src/lf_mask.h:40-46,61-63,
+ *             108 bytes each); unit_size_log2 = frame_hdr->restoration.unit_size; restore_planes = f->lf.restore_planes.
+ * 64x64 superblocks only (sb128 != 0: -ENOSYS); no super-resolution (sr_cur == cur). */
+typedef struct Dav1dCudaLrFrame {
+    int32_t w, h;                       /* f->sr_cur.p.p.w / .h */
+    int32_t sb128w;                     /* f->sr_sb128w */
+    int32_t sb128;                      /* seq_hdr->sb128 */
+    int32_t unit_size_log2[2];          /* luma, chroma */
+    int32_t restore_planes;             /* bit 0 Y, 1 U, 2 V */
+    const void *lr_mask;                /* device */
+} Dav1dCudaLrFrame;
+DAV1D_CUDA_API int dav1d_cuda_lr_frame(Dav1dCudaContext *c, const Dav1dCudaPicture *dst, const Dav1dCudaPicture *src,
+                                       const Dav1dCudaPicture *deblocked, const Dav1dCudaLrFrame *p);
+
 /* Operator-class launches.  All pointers inside the argument list that are
  * documented as "device" must be device pointers; the calls are asynchronous
  * on the context's stream. */

@@ -60,3 +60,15 @@ for name in CD.CASES:
     print(name, out[name])
 with open(CD.GOLDEN, "w") as f:
     json.dump(out, f, indent=1, sort_keys=True)
+
+# the reference's post-filter chain (tests/test_postfilter_chain.py)
+import test_postfilter_chain as PF  # noqa: E402
+
+out = {}
+for name in PF.CASES:
+    hf, src, seed, par = PF.make(name)
+    planes, _ = reflf.run_reference_chain(ref, hf, [p.copy() for p in src], seed, **par)
+    out[name] = PF.md5_planes(planes)
+    print(name, out[name])
+with open(PF.GOLDEN, "w") as f:
+    json.dump(out, f, indent=1, sort_keys=True)
