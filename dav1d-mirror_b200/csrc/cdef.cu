@@ -46,9 +46,8 @@ DEV int constrain(const int diff, const int threshold, const int shift) {
 DEV int umin_i(const int a, const int b) { return (unsigned)a < (unsigned)b ? a : b; }
 
 // the (w + 4) x (h + 4) neighbourhood of a block into the warp's tile (padding(), cdef_tmpl.c:57-102)
-template <typename pixel>
-DEV void cdef_load_tile(int16_t *tile, const PlaneView &pv, const int x0, const int y0, const int w, const int h,
-                        const int edges, const int lane)
+template <typename pixel, int w, int h>
+DEV void cdef_load_tile(int16_t *tile, const PlaneView &pv, const int x0, const int y0, const int edges, const int lane)
 {
     const pixel *src = (const pixel *)pv.data;
     const int64_t stride = pv.stride / (int64_t)sizeof(pixel);
@@ -61,8 +60,8 @@ DEV void cdef_load_tile(int16_t *tile, const PlaneView &pv, const int x0, const 
 }
 
 // cdef_filter_block_c (cdef_tmpl.c:104-210) over the tile; pri / sec: strengths (either may be 0, not both)
-template <typename pixel>
-DEV void cdef_filter(const int16_t *tile, const PlaneView &pv, const int x0, const int y0, const int w, const int h,
+template <typename pixel, int w, int h>
+DEV void cdef_filter(const int16_t *tile, const PlaneView &pv, const int x0, const int y0,
                      const int pri, const int sec, const int dir, const int damping, const int bdmax, const int lane)
 {
     pixel *dst = (pixel *)pv.data;
@@ -108,9 +107,8 @@ DEV void cdef_filter(const int16_t *tile, const PlaneView &pv, const int x0, con
     }
 }
 
-template <typename pixel>
-DEV void cdef_copy(const PlaneView &s, const PlaneView &d, const int x0, const int y0, const int w, const int h,
-                   const int lane)
+template <typename pixel, int w, int h>
+DEV void cdef_copy(const PlaneView &s, const PlaneView &d, const int x0, const int y0, const int lane)
 {
     const int64_t ss = s.stride / (int64_t)sizeof(pixel), ds = d.stride / (int64_t)sizeof(pixel);
     for (int i = lane; i < w * h; i += 32) {
@@ -119,10 +117,10 @@ DEV void cdef_copy(const PlaneView &s, const PlaneView &d, const int x0, const i
     }
 }
 
-template <typename pixel>
+template <typename pixel, int cw, int ch>
 __global__ void __launch_bounds__(CDEF_WARPS * 32) cdef_kernel(const __grid_constant__ CdefArgs a) {
     __shared__ int16_t tiles[CDEF_WARPS][TS * TS];
-    __shared__ int partial[CDEF_WARPS][8][16];
+    __shared__ int partial[CDEF_WARPS][8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int w8 = a.bw >> 1, h8 = a.bh >> 1;
     const int blk = blockIdx.x * CDEF_WARPS + warp;
@@ -130,7 +128,6 @@ __global__ void __launch_bounds__(CDEF_WARPS * 32) cdef_kernel(const __grid_cons
     const int bx = (blk % w8) * 2, by = (blk / w8) * 2;                     // 4-px units, as in dav1d_cdef_brow
     int16_t *tile = tiles[warp];
     const int bdm8 = PxTraits<pixel>::bitdepth(a.bdmax) - 8;
-    const int cw = 8 >> a.ss_hor, ch = 8 >> a.ss_ver;
     const int cx0 = (bx * 4) >> a.ss_hor, cy0 = (by * 4) >> a.ss_ver;
 
     // strength index of the 64x64 area and the block's skip bit (cdef_apply_tmpl.c:147-183)
@@ -141,8 +138,8 @@ __global__ void __launch_bounds__(CDEF_WARPS * 32) cdef_kernel(const __grid_cons
     const int y_lvl = cdef_idx >= 0 ? a.y_strength[cdef_idx] : 0, uv_lvl = cdef_idx >= 0 && a.n_planes > 1 ? a.uv_strength[cdef_idx] : 0;
     const bool run = cdef_idx >= 0 && (y_lvl || uv_lvl) && (noskip & (3u << (bx & 30)));
     if (!run) {
-        cdef_copy<pixel>(a.src[0], a.dst[0], bx * 4, by * 4, 8, 8, lane);
-        for (int pl = 1; pl < a.n_planes; pl++) cdef_copy<pixel>(a.src[pl], a.dst[pl], cx0, cy0, cw, ch, lane);
+        cdef_copy<pixel, 8, 8>(a.src[0], a.dst[0], bx * 4, by * 4, lane);
+        for (int pl = 1; pl < a.n_planes; pl++) cdef_copy<pixel, cw, ch>(a.src[pl], a.dst[pl], cx0, cy0, lane);
         return;
     }
     const int edges = (bx > 0 ? 1 : 0) | (bx + 2 < a.bw ? 2 : 0) | (by > 0 ? 4 : 0) | (by + 2 < a.bh ? 8 : 0);
@@ -152,38 +149,39 @@ __global__ void __launch_bounds__(CDEF_WARPS * 32) cdef_kernel(const __grid_cons
     y_sec <<= bdm8; uv_sec <<= bdm8;
     const int damping = a.damping + bdm8;
 
-    cdef_load_tile<pixel>(tile, a.src[0], bx * 4, by * 4, 8, 8, edges, lane);
+    cdef_load_tile<pixel, 8, 8>(tile, a.src[0], bx * 4, by * 4, edges, lane);
     int dir = 0;
     unsigned var = 0;
     if (y_pri || uv_pri) {
         // cdef_find_dir_c (cdef_tmpl.c:233-296): per direction the sums along its lines; the cost of a
         // direction is the sum over its lines of sum^2 * 840 / (pixels on the line)
-        int (*ps)[16] = partial[warp];
-        for (int i = lane; i < 8 * 16; i += 32) ps[i >> 4][i & 15] = 0;
+        // 90 lines in all (15 + 11 + 8 + 11 + 15 + 11 + 8 + 11): a lane sums the pixels of a line, squares,
+        // weighs; the costs of a direction's lines meet in shared memory
+        unsigned *costs = (unsigned *)partial[warp];
+        if (lane < 8) costs[lane] = 0;
         __syncwarp();
-        for (int i = lane; i < 64; i += 32) {
-            const int y = i >> 3, x = i & 7;
-            const int px = (tile[(y + 2) * TS + x + 2] >> bdm8) - 128;
-            atomicAdd(&ps[0][y + x], px);
-            atomicAdd(&ps[1][y + (x >> 1)], px);
-            atomicAdd(&ps[2][y], px);
-            atomicAdd(&ps[3][3 + y - (x >> 1)], px);
-            atomicAdd(&ps[4][7 + y - x], px);
-            atomicAdd(&ps[5][3 - (y >> 1) + x], px);
-            atomicAdd(&ps[6][x], px);
-            atomicAdd(&ps[7][(y >> 1) + x], px);
-        }
-        __syncwarp();
-        unsigned cost = 0;
-        if (lane < 8) {
-            const int d = lane;
-            const int n_lines = (d == 2 || d == 6) ? 8 : (d & 1) ? 11 : 15;
-            for (int l = 0; l < n_lines; l++) {
-                const int len = (d == 2 || d == 6) ? 8 : (d & 1) ? (l < 3 ? 2 * l + 2 : l > 7 ? 2 * (10 - l) + 2 : 8)
-                                                                  : imin(l, 14 - l) + 1;
-                cost += (unsigned)(ps[d][l] * ps[d][l]) * (unsigned)(840 / len);
+        for (int g = lane; g < 90; g += 32) {
+            const int d = g < 15 ? 0 : g < 26 ? 1 : g < 34 ? 2 : g < 45 ? 3 : g < 60 ? 4 : g < 71 ? 5 : g < 79 ? 6 : 7;
+            const int l = g - (d == 0 ? 0 : d == 1 ? 15 : d == 2 ? 26 : d == 3 ? 34 : d == 4 ? 45 : d == 5 ? 60 : d == 6 ? 71 : 79);
+            // pixel t of the line: x = ax * t + bx * (t >> 1) + cx, y likewise (the eight line equations of
+            // cdef_find_dir_c with t along x for d = 0..4 and along y for d = 5..7)
+            const int ax = d < 5, ay = d == 0 ? -1 : d == 4 || d >= 5;
+            const int bx = d == 5 ? 1 : d == 7 ? -1 : 0, by = d == 1 ? -1 : d == 3 ? 1 : 0;
+            const int cx = d < 5 ? 0 : d == 5 ? l - 3 : l;
+            const int cy = d >= 5 ? 0 : d == 3 ? l - 3 : d == 4 ? l - 7 : l;
+            int sum = 0, len = 0;
+#pragma unroll
+            for (int t = 0; t < 8; t++) {
+                const int x = ax * t + bx * (t >> 1) + cx, y = ay * t + by * (t >> 1) + cy;
+                if ((unsigned)x < 8u && (unsigned)y < 8u) {
+                    sum += (tile[(y + 2) * TS + x + 2] >> bdm8) - 128;
+                    len++;
+                }
             }
+            atomicAdd(&costs[d], (unsigned)(sum * sum) * (unsigned)(840 / len));
         }
+        __syncwarp();
+        const unsigned cost = lane < 8 ? costs[lane] : 0;
         unsigned best_cost = __shfl_sync(0xffffffffu, cost, 0);
         for (int n = 1; n < 8; n++) {
             const unsigned c = __shfl_sync(0xffffffffu, cost, n);
@@ -203,16 +201,16 @@ __global__ void __launch_bounds__(CDEF_WARPS * 32) cdef_kernel(const __grid_cons
     } else if (y_sec) {
         sec = y_sec;
     }
-    if (pri || sec) cdef_filter<pixel>(tile, a.dst[0], bx * 4, by * 4, 8, 8, pri, sec, ydir, damping, a.bdmax, lane);
-    else cdef_copy<pixel>(a.src[0], a.dst[0], bx * 4, by * 4, 8, 8, lane);
+    if (pri || sec) cdef_filter<pixel, 8, 8>(tile, a.dst[0], bx * 4, by * 4, pri, sec, ydir, damping, a.bdmax, lane);
+    else cdef_copy<pixel, 8, 8>(a.src[0], a.dst[0], bx * 4, by * 4, lane);
     // chroma (:248-285)
     if (a.n_planes > 1) {
         const int uvdir = uv_pri ? (a.ss_hor && !a.ss_ver ? (0x66654207u >> (4 * dir)) & 7 : dir) : 0;   // uv_dirs[4:2:2] = {7,0,2,4,5,6,6,6}
         for (int pl = 1; pl <= 2; pl++) {
-            if (!uv_lvl) { cdef_copy<pixel>(a.src[pl], a.dst[pl], cx0, cy0, cw, ch, lane); continue; }
+            if (!uv_lvl) { cdef_copy<pixel, cw, ch>(a.src[pl], a.dst[pl], cx0, cy0, lane); continue; }
             __syncwarp();
-            cdef_load_tile<pixel>(tile, a.src[pl], cx0, cy0, cw, ch, edges, lane);
-            cdef_filter<pixel>(tile, a.dst[pl], cx0, cy0, cw, ch, uv_pri, uv_sec, uvdir, damping - 1, a.bdmax, lane);
+            cdef_load_tile<pixel, cw, ch>(tile, a.src[pl], cx0, cy0, edges, lane);
+            cdef_filter<pixel, cw, ch>(tile, a.dst[pl], cx0, cy0, uv_pri, uv_sec, uvdir, damping - 1, a.bdmax, lane);
         }
     }
 }
@@ -239,8 +237,13 @@ extern "C" int dav1d_cuda_cdef_frame(Dav1dCudaContext *c, const Dav1dCudaPicture
     a.masks = (const uint8_t *)p->masks;
     const int n = (p->bw >> 1) * (p->bh >> 1);
     const int grid = (n + CDEF_WARPS - 1) / CDEF_WARPS;
-    if (s.bdmax > 0xff) cdef_kernel<uint16_t><<<grid, CDEF_WARPS * 32, 0, c->stream>>>(a);
-    else cdef_kernel<uint8_t><<<grid, CDEF_WARPS * 32, 0, c->stream>>>(a);
+    const int lay = a.n_planes == 1 ? 0 : s.ss_hor ? (s.ss_ver ? 2 : 1) : 0;      // chroma block: 8x8, 4x8, 4x4
+    const bool hbd = s.bdmax > 0xff;
+#define LAUNCH_CDEF(pixel, cw, ch) cdef_kernel<pixel, cw, ch><<<grid, CDEF_WARPS * 32, 0, c->stream>>>(a)
+    if (lay == 0) { if (hbd) LAUNCH_CDEF(uint16_t, 8, 8); else LAUNCH_CDEF(uint8_t, 8, 8); }
+    else if (lay == 1) { if (hbd) LAUNCH_CDEF(uint16_t, 4, 8); else LAUNCH_CDEF(uint8_t, 4, 8); }
+    else { if (hbd) LAUNCH_CDEF(uint16_t, 4, 4); else LAUNCH_CDEF(uint8_t, 4, 4); }
+#undef LAUNCH_CDEF
     count_launch();
     return cuda_ok(cudaGetLastError(), "cdef_kernel") ? 0 : -5;
 }

@@ -102,17 +102,19 @@ DEV void lf_line(pixel *const dst, const int64_t s, const int wd, int E, int I, 
 }
 
 // DIR 0: column edges (filter_*[0], taps along x); DIR 1: row edges (filter_*[1], taps along y).
-// blockIdx.y = plane (luma launch: 0; chroma launch: 1, 2).
+// blockIdx.z = plane (luma launch: 0; chroma launch: 1, 2).
 template <typename pixel, int DIR>
 __global__ void __launch_bounds__(256) lf_pass_kernel(const __grid_constant__ LfArgs a, const int first_plane) {
-    const int pl = first_plane + blockIdx.y;
+    // DIR 0: a thread per (edge column x4, pixel row); DIR 1: a thread per (pixel column, edge row y4) - no
+    // divisions, consecutive lanes on consecutive edges / pixels of one row
+    const int pl = first_plane + blockIdx.z;
     const int sh = pl ? a.ss_hor : 0, sv = pl ? a.ss_ver : 0;
     const int pw4 = (a.w4 + sh) >> sh, ph4 = (a.h4 + sv) >> sv;
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (int64_t)pw4 * ph4 * 4) return;
+    const int gx = blockIdx.x * blockDim.x + threadIdx.x, gy = blockIdx.y;
     int x4, y4, line;
-    if (DIR == 0) { x4 = (int)(t % pw4); line = (int)((t / pw4) & 3); y4 = (int)(t / pw4) >> 2; }
-    else { line = (int)(t & 3); x4 = (int)((t >> 2) % pw4); y4 = (int)((t >> 2) / pw4); }
+    if (DIR == 0) { x4 = gx; y4 = gy >> 2; line = gy & 3; }
+    else { x4 = gx >> 2; line = gx & 3; y4 = gy; }
+    if (x4 >= pw4 || y4 >= ph4) return;
     if ((DIR == 0 ? x4 : y4) == 0) return;                      // no edge at the frame's left / top border
     // the 128x128 area and the position inside it, in this plane's 4-px units
     const int lx = 5 - sh, ly = 5 - sv;
@@ -163,16 +165,17 @@ extern "C" int dav1d_cuda_loopfilter_frame(Dav1dCudaContext *c, const Dav1dCudaP
     const bool chroma = lf->filter_uv && pic->p[1].data && pic->p[2].data;
     const bool hbd = v.bdmax > 0xff;
     const int cw4 = (lf->w4 + v.ss_hor) >> v.ss_hor, ch4 = (lf->h4 + v.ss_ver) >> v.ss_ver;
-    const unsigned gy = (unsigned)(((int64_t)lf->w4 * lf->h4 * 4 + 255) / 256), gc = (unsigned)(((int64_t)cw4 * ch4 * 4 + 255) / 256);
     for (int dir = 0; dir < 2; dir++) {
         for (int ch = 0; ch < (chroma ? 2 : 1); ch++) {
-            const dim3 grid(ch ? gc : gy, ch ? 2 : 1);
+            const int pw4 = ch ? cw4 : lf->w4, ph4 = ch ? ch4 : lf->h4;
+            const dim3 grid(dir ? (unsigned)((pw4 * 4 + 127) / 128) : (unsigned)((pw4 + 127) / 128),
+                            dir ? (unsigned)ph4 : (unsigned)(ph4 * 4), ch ? 2 : 1);
             if (hbd) {
-                if (dir) lf_pass_kernel<uint16_t, 1><<<grid, 256, 0, c->stream>>>(a, ch);
-                else lf_pass_kernel<uint16_t, 0><<<grid, 256, 0, c->stream>>>(a, ch);
+                if (dir) lf_pass_kernel<uint16_t, 1><<<grid, 128, 0, c->stream>>>(a, ch);
+                else lf_pass_kernel<uint16_t, 0><<<grid, 128, 0, c->stream>>>(a, ch);
             } else {
-                if (dir) lf_pass_kernel<uint8_t, 1><<<grid, 256, 0, c->stream>>>(a, ch);
-                else lf_pass_kernel<uint8_t, 0><<<grid, 256, 0, c->stream>>>(a, ch);
+                if (dir) lf_pass_kernel<uint8_t, 1><<<grid, 128, 0, c->stream>>>(a, ch);
+                else lf_pass_kernel<uint8_t, 0><<<grid, 128, 0, c->stream>>>(a, ch);
             }
             count_launch();
         }

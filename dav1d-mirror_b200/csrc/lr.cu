@@ -46,16 +46,23 @@ DEV unsigned sgr_x_by_x(const unsigned z) {
 
 // A and B of selfguided_filter() (:363-381) at the positions the filter reads: box sums of radius 1 (n = 9) or
 // 2 (n = 25) around (i, j), i in [-1, tw], j in [-1, th] (n = 25: every second row from -1)
-DEV void sgr_ab(const uint16_t *tile, int *A, int *B, const int tw, const int th, const int n, const unsigned s,
-                const int bdm8, const int tid, const int nthr)
+template <int n>
+DEV void sgr_ab(const uint16_t *tile, int *A, int *B, const int tw, const int th, const unsigned s,
+                const int bdm8, const int tid, const int nthr, const uint8_t *x_by_x)
 {
-    const int r = n == 25 ? 2 : 1, step = n == 25 ? 2 : 1;
-    const unsigned one_by_x = n == 25 ? 164 : 455;
-    const int rows = (th + 2 + step - 1) / step;
-    for (int k = tid; k < rows * (tw + 2); k += nthr) {
-        const int j = (k / (tw + 2)) * step - 1, i = k % (tw + 2) - 1;
+    constexpr int r = n == 25 ? 2 : 1, step = n == 25 ? 2 : 1;
+    constexpr unsigned one_by_x = n == 25 ? 164 : 455;
+    const int rows = (th + 2 + step - 1) / step, cols = tw + 2;
+    // (row, column) of k = tid + m * nthr without a division per step
+    const int dq = nthr / cols, dr = nthr % cols;
+    int jr = tid / cols, i0 = tid % cols;
+    for (; jr < rows; jr += dq, i0 += dr) {
+        if (i0 >= cols) { i0 -= cols; jr++; if (jr >= rows) break; }
+        const int j = jr * step - 1, i = i0 - 1;
         int sum = 0, sumsq = 0;
+#pragma unroll
         for (int dy = -r; dy <= r; dy++)
+#pragma unroll
             for (int dx = -r; dx <= r; dx++) {
                 const int v = tile[(j + 3 + dy) * LR_TS + i + 3 + dx];
                 sum += v; sumsq += v * v;
@@ -64,7 +71,7 @@ DEV void sgr_ab(const uint16_t *tile, int *A, int *B, const int tw, const int th
         const int b = (sum + ((1 << bdm8) >> 1)) >> bdm8;
         const unsigned p = (unsigned)imax(a * n - b * b, 0);
         const unsigned z = (p * s + (1u << 19)) >> 20;
-        const unsigned x = sgr_x_by_x(z > 255 ? 255 : z);
+        const unsigned x = x_by_x[z > 255 ? 255 : z];
         A[(j + 1) * LR_AS + i + 1] = (int)((x * (unsigned)sum * one_by_x + (1u << 11)) >> 12);
         B[(j + 1) * LR_AS + i + 1] = (int)x;
     }
@@ -94,6 +101,7 @@ template <typename pixel>
 __global__ void __launch_bounds__(256) lr_kernel(const __grid_constant__ LrArgs a) {
     __shared__ uint16_t tile[(LR_MAXH + 6) * LR_TS];
     __shared__ int AB[2][(LR_MAXH + 2) * LR_AS];       // A / B of the self-guided filter; `hor` of the Wiener filter
+    __shared__ uint8_t x_by_x[256];
     const int pl = blockIdx.z, tid = threadIdx.x;
     const int ssh = pl ? a.ss_hor : 0, ssv = pl ? a.ss_ver : 0;
     const int pw = (a.w + ssh) >> ssh, ph = (a.h + ssv) >> ssv;
@@ -119,8 +127,7 @@ __global__ void __launch_bounds__(256) lr_kernel(const __grid_constant__ LrArgs 
         if (aligned && aligned + half > ph) aligned -= unit;
         aligned <<= ssv;
         const int sb_idx = (aligned >> 7) * a.sb128w, unit_idx = ((aligned >> 6) & 1) << 1;
-        int n_full = 0;
-        while ((n_full + 1) * unit + half <= pw) n_full++;
+        const int n_full = pw >= half ? (pw - half) >> a.unit_log2[!!pl] : 0;     // units before the last, which takes up to 1.5 units
         const int xu = imin(x0 / unit, n_full) * unit;
         const int shift_hor = 7 - ssh;
         u = a.lr_mask + (size_t)(sb_idx + (xu >> shift_hor)) * AV1RESTORATION_BYTES +
@@ -136,8 +143,10 @@ __global__ void __launch_bounds__(256) lr_kernel(const __grid_constant__ LrArgs 
     }
     // padding() (looprestoration_tmpl.c:41-125): rows -3 .. th + 2, columns -3 .. tw + 2
     const bool have_top = y0 > 0, have_bottom = y1 < ph;
-    for (int k = tid; k < (th + 6) * (tw + 6); k += 256) {
-        const int r = k / (tw + 6) - 3, c = k % (tw + 6) - 3;
+    const int tcols = tw + 6, tdq = 256 / tcols, tdr = 256 % tcols;
+    for (int rr = tid / tcols, cc = tid % tcols; rr < th + 6; rr += tdq, cc += tdr) {
+        if (cc >= tcols) { cc -= tcols; rr++; if (rr >= th + 6) break; }
+        const int r = rr - 3, c = cc - 3;
         const int xx = iclip(x0 + c, 0, pw - 1);
         int v;
         if (r < 0) v = have_top ? pre[(int64_t)(y0 - 2 + (r == -1)) * pstride + xx] : src[(int64_t)y0 * sstride + xx];
@@ -147,6 +156,7 @@ __global__ void __launch_bounds__(256) lr_kernel(const __grid_constant__ LrArgs 
     }
     __syncthreads();
     const int bitdepth = PxTraits<pixel>::bitdepth(a.bdmax);
+    if (type > 2) x_by_x[tid] = (uint8_t)sgr_x_by_x(tid);      // visible after the barrier before sgr_ab
     if (type == 2) {
         // DAV1D_RESTORATION_WIENER (enum Dav1dRestorationType: NONE 0, SWITCHABLE 1, WIENER 2, SGRPROJ 3) (lr_stripe :54-72 + wiener_c :131-189)
         int fh[7], fv[7];
@@ -159,7 +169,7 @@ __global__ void __launch_bounds__(256) lr_kernel(const __grid_constant__ LrArgs 
         const int rbh = 3 + (bitdepth == 12) * 2, clip_limit = 1 << (bitdepth + 1 + 7 - rbh);
         uint16_t *hor = (uint16_t *)AB;                // (th + 6) x tw, stride LR_TW
         for (int k = tid; k < (th + 6) * tw; k += 256) {
-            const int j = k / tw, i = k % tw;
+            const int j = tw == LR_TW ? k >> 5 : k / tw, i = tw == LR_TW ? k & 31 : k % tw;
             int sum = 1 << (bitdepth + 6);
 #pragma unroll
             for (int t = 0; t < 7; t++) sum += tile[j * LR_TS + i + t] * fh[t];
@@ -168,7 +178,7 @@ __global__ void __launch_bounds__(256) lr_kernel(const __grid_constant__ LrArgs 
         __syncthreads();
         const int rbv = 11 - (bitdepth == 12) * 2, round_offset = 1 << (bitdepth + rbv - 1);
         for (int k = tid; k < th * tw; k += 256) {
-            const int j = k / tw, i = k % tw;
+            const int j = tw == LR_TW ? k >> 5 : k / tw, i = tw == LR_TW ? k & 31 : k % tw;
             int sum = -round_offset;
 #pragma unroll
             for (int t = 0; t < 7; t++) sum += hor[(j + t) * LR_TW + i] * fv[t];
@@ -189,13 +199,14 @@ __global__ void __launch_bounds__(256) lr_kernel(const __grid_constant__ LrArgs 
         if (!sp) continue;
         const int n = pass ? 9 : 25, wt = pass ? w1 : w0;
         __syncthreads();
-        sgr_ab(tile, AB[0], AB[1], tw, th, n, sp, bdm8, tid, 256);
+        if (pass) sgr_ab<9>(tile, AB[0], AB[1], tw, th, sp, bdm8, tid, 256, x_by_x);
+        else sgr_ab<25>(tile, AB[0], AB[1], tw, th, sp, bdm8, tid, 256, x_by_x);
         __syncthreads();
 #pragma unroll
         for (int q = 0; q < 8; q++) {
             const int k = tid + q * 256;
             if (k < tw * th) {
-                const int j = k / tw, i = k % tw;
+                const int j = tw == LR_TW ? k >> 5 : k / tw, i = tw == LR_TW ? k & 31 : k % tw;
                 acc[q] += wt * sgr_px(AB[0], AB[1], i, j, n, tile[(j + 3) * LR_TS + i + 3]);
             }
         }
@@ -204,7 +215,7 @@ __global__ void __launch_bounds__(256) lr_kernel(const __grid_constant__ LrArgs 
     for (int q = 0; q < 8; q++) {
         const int k = tid + q * 256;
         if (k < tw * th) {
-            const int j = k / tw, i = k % tw;
+            const int j = tw == LR_TW ? k >> 5 : k / tw, i = tw == LR_TW ? k & 31 : k % tw;
             const int px = tile[(j + 3) * LR_TS + i + 3];
             dst[(int64_t)(y0 + j) * dstride + x0 + i] = (pixel)clip_px<pixel>(px + ((acc[q] + (1 << 10)) >> 11), a.bdmax);
         }

@@ -90,4 +90,33 @@ ns = cst["masks"].reshape(-1, 1348)[:, 1284:1348]
 print(f"cdef    4K 10-bit 4:2:0: {per:.1f} us/frame, {w * h / per / 1e3:.1f} Gpix/s, {alg / per / 1e3:.0f} GB/s of "
       f"read-once / write-once picture traffic ({alg / 1e6:.1f} MB/frame); "
       f"{np.unpackbits(ns).mean() * 100:.0f}% of the 8x8 blocks carry coefficients (the others are copied)")
+
+# loop restoration, out of place: CDEF output (`out`) + deblocked picture (pics[0]) -> pics[1]; 64x64 luma units,
+# 32x32 chroma units, every unit restored (half Wiener, half self-guided)
+_, pst = reflf.run_reference_chain(ref, hf, [p.copy() for p in src], 11, deblock=False, cdef=False, lr=True,
+                                   unit_size_log2=(6, 5), p_lr_none=0, run=False)
+d_lr = L.dav1d_cuda_malloc(pst["lr_mask"].nbytes)
+L.dav1d_cuda_upload(ctx, d_lr, pst["lr_mask"].ctypes.data, pst["lr_mask"].nbytes)
+q = B.LrFrame()
+q.w, q.h, q.sb128w, q.sb128 = w, h, pst["sb128w"], 0
+q.unit_size_log2[0], q.unit_size_log2[1] = 6, 5
+q.restore_planes, q.lr_mask = 7, d_lr
+dsts = pics[1:]
+if not dsts:
+    dsts = [B.Picture()]
+    assert L.dav1d_cuda_picture_alloc(ctx, C.byref(dsts[0]), w, h, 1, 1, bd) == 0
+for d in dsts[:2]:
+    L.dav1d_cuda_lr_frame(ctx, C.byref(d), C.byref(out), C.byref(pics[0]), C.byref(q))
+L.dav1d_cuda_synchronize(ctx)
+L.dav1d_cuda_event_record(ctx, e0)
+for _ in range(reps):
+    for d in dsts:
+        L.dav1d_cuda_lr_frame(ctx, C.byref(d), C.byref(out), C.byref(pics[0]), C.byref(q))
+L.dav1d_cuda_event_record(ctx, e1)
+L.dav1d_cuda_synchronize(ctx)
+ms = L.dav1d_cuda_event_elapsed_ms(e0, e1)
+per = ms / (reps * len(dsts)) * 1e3
+alg = samples * 2 * 2
+print(f"lr      4K 10-bit 4:2:0: {per:.1f} us/frame, {w * h / per / 1e3:.1f} Gpix/s, {alg / per / 1e3:.0f} GB/s of "
+      f"read-once / write-once picture traffic ({alg / 1e6:.1f} MB/frame); all units restored, Wiener and self-guided mixed")
 pkg.check_error()
