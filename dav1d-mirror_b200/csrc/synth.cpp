@@ -52,7 +52,18 @@ typedef struct D1SynthParams {
                                     // inside the picture) + a block record per block for the reference driver
     int32_t ref_w[7], ref_h[7];     // luma size of reference i when it differs from the frame's (0 = same size):
                                     // predictions from it go through the scaled branch of mc() (recon_tmpl.c:1010-1065)
+    uint64_t mask_tab;              // real_blocks: address of a D1SynthMaskTab with the decoder's wedge / inter-intra mask
+                                    // tables (the tests fill it from the reference's dav1d_masks); 0 = wedge and
+                                    // inter-intra blocks are not generated in real-block mode
 } D1SynthParams;
+
+// Wedge and inter-intra masks per chroma layout (0 = 4:4:4 / luma, 1 = 4:2:2, 2 = 4:2:0) and block size
+// (w4, h4 in {2, 4, 8}: index log2 - 1): byte offsets into `base` (wedge.h WEDGE_MASK / II_MASK).
+typedef struct D1SynthMaskTab {
+    const uint8_t *base;
+    uint32_t wedge[3][3][3][2][16];     // [layout][w][h][sign][wedge_idx]
+    uint32_t ii[3][3][3][4];            // [layout][w][h][II_DC / VERT / HOR / SMOOTH]
+} D1SynthMaskTab;
 
 // One coded block as the reference's reconstruction driver sees it (the Av1Block fields
 // dav1d_recon_b_intra reads, src/levels.h:262-287, plus what decode_b() hands over).
@@ -640,6 +651,11 @@ struct Gen {
         else if (u < (acc += P.p_wedge)) kind = DAV1D_CUDA_MC_MASK;
         else if (u < (acc += P.p_seg)) kind = DAV1D_CUDA_MC_W_MASK;
         else if (u < (acc += P.p_warp) && w4 >= 4 && h4 >= 4) is_warp = true;
+        const D1SynthMaskTab *const MT = (const D1SynthMaskTab *)(uintptr_t)P.mask_tab;
+        auto l2 = [](int v) { return v == 2 ? 0 : v == 4 ? 1 : 2; };
+        const bool mask_block = w4 >= 2 && h4 >= 2 && w4 <= 8 && h4 <= 8;        // BS_8x8 .. BS_32x32
+        if (P.real_blocks && kind == DAV1D_CUDA_MC_MASK && !(MT && mask_block)) kind = DAV1D_CUDA_MC_AVG;
+        const int wedge_idx = (P.real_blocks && MT) ? rng.range(16) : 0;      // no draw otherwise: older frames keep their streams
         bool any_scaled = false;
         for (int i = 0; i < 7; i++) any_scaled |= ref_scaled(i);
         const int filter = rng.range(10);
@@ -681,7 +697,7 @@ struct Gen {
         const int ii_cw4 = std::max(1, w4 >> P.ss_hor), ii_ch4 = std::max(1, h4 >> P.ss_ver);
         const bool do_ii = P.p_ii > 0.f && kind == DAV1D_CUDA_MC_PUT && !is_warp && !do_obmc && w4 >= 2 && h4 >= 2 &&
                            w4 <= 8 && h4 <= 8 && (P.no_chroma || (ii_cw4 <= 4 * ii_ch4 && ii_ch4 <= 4 * ii_cw4)) &&
-                           rng.chance(P.p_ii);
+                           (!P.real_blocks || MT) && rng.chance(P.p_ii);
         uint32_t seg_off = 0, wedge_off[3] = { 0, 0, 0 };
         for (int pl = 0; pl < nplanes(); pl++) {
             const int sh = pl ? P.ss_hor : 0, sv = pl ? P.ss_ver : 0;
@@ -730,6 +746,12 @@ struct Gen {
             }
             if (kind == DAV1D_CUDA_MC_MASK) {               // wedge: one mask table per plane size
                 wedge_off[pl] = (uint32_t)masks.size();
+                if (P.real_blocks) {
+                    // recon_tmpl.c:1861-1866: luma WEDGE_MASK(0, bs, 0, idx), chroma WEDGE_MASK(layout, bs, sign, idx)
+                    const int lay = pl ? (P.ss_hor ? (P.ss_ver ? 2 : 1) : 0) : 0;
+                    const uint8_t *m = MT->base + MT->wedge[lay][l2(w4)][l2(h4)][pl ? sign : 0][wedge_idx];
+                    masks.insert(masks.end(), m, m + w * h);
+                } else
                 for (int i = 0; i < w * h; i++) masks.push_back((uint8_t)rng.range(65));
                 d.aux_off = wedge_off[pl];
                 add_bytes(1, (double)w * h);
@@ -756,23 +778,44 @@ struct Gen {
             // intra prediction of the whole block blended onto the inter prediction; the block then
             // belongs to the wavefront: its residuals follow as residual-only intra-class operations
             static const int ii_modes[4] = { 0, 1, 2, 9 };          // DC, VERT, HOR, SMOOTH
-            const int m = ii_modes[rng.range(4)];
+            const int ii_mode = rng.range(4), ii_wedge = P.real_blocks ? rng.chance(0.4f) : 0;
+            const int m = ii_modes[ii_mode];
+            rec_inter.pad[1] = (uint8_t)wedge_idx;
+            rec_inter.pad[2] = (uint8_t)((ii_wedge ? 2 : 1) | (ii_mode << 2));   // b->interintra_type | b->interintra_mode << 2
             for (int pl = 0; pl < nplanes(); pl++) {
                 const int sh = pl ? P.ss_hor : 0, sv = pl ? P.ss_ver : 0;
                 const int cw4 = w4 >> sh, ch4 = h4 >> sv;
                 const size_t off = pal_idx.size();
+                if (P.real_blocks) {
+                    // II_MASK(layout of the plane, bs, b) (wedge.h:88-93): the smooth / wedge blend mask of the block size
+                    const int lay = pl ? (P.ss_hor ? (P.ss_ver ? 2 : 1) : 0) : 0;
+                    const uint8_t *mk = MT->base + (ii_wedge ? MT->wedge[lay][l2(w4)][l2(h4)][0][wedge_idx]
+                                                             : MT->ii[lay][l2(w4)][l2(h4)][ii_mode]);
+                    pal_idx.insert(pal_idx.end(), mk, mk + cw4 * 4 * ch4 * 4);
+                } else
                 for (int i = 0; i < cw4 * 4 * ch4 * 4; i++) pal_idx.push_back((uint8_t)rng.range(65));
                 add_intra(pl, bx4 >> sh, by4 >> sv, cw4, ch4, DAV1D_CUDA_INTRA_II, m, 0, false, 0, (uint32_t)off);
             }
         }
         // ---- residual
+        auto rec_tx_of_last_op = [&]() {                  // the cbi / cf entry of the residual-only operation just added
+            if (!P.real_blocks) return;
+            const Dav1dCudaIntraDesc &o = intra.back();
+            D1SynthTx t;
+            memset(&t, 0, sizeof(t));
+            t.coef_off = o.coef_off; t.eob = o.eob; t.txtp = o.txtp; t.cw4 = o.cw4; t.ch4 = o.ch4; t.tx = o.tx; t.plane = o.plane;
+            tx_recs.push_back(t);
+        };
         if (do_ii) {
             if (rng.chance(P.p_residual)) {
                 int tw4 = std::min(w4, 16), th4 = std::min(h4, 16);
-                if (rng.chance(P.p_tx_split)) split_tx(tw4, th4);
+                rec_inter.skip = 0;
+                if (rng.chance(P.p_tx_split)) { split_tx(tw4, th4); rec_inter.tx_split = tw4 * th4 < std::min(w4, 16) * std::min(h4, 16); }
                 for (int y = 0; y < h4; y += th4)
-                    for (int x = 0; x < w4; x += tw4)
+                    for (int x = 0; x < w4; x += tw4) {
                         add_intra(0, bx4 + x, by4 + y, tw4, th4, DAV1D_CUDA_INTRA_NONE, 0, 0, true);
+                        rec_tx_of_last_op();
+                    }
                 if (!P.no_chroma) {
                     const int cw4 = w4 >> P.ss_hor, ch4 = h4 >> P.ss_ver;
                     int utw4 = std::min(cw4, 8), uth4 = std::min(ch4, 8);
@@ -780,8 +823,11 @@ struct Gen {
                     for (int pl = 1; pl <= 2; pl++)
                         for (int y = 0; y < ch4; y += uth4)
                             for (int x = 0; x < cw4; x += utw4)
+                            {
                                 add_intra(pl, (bx4 >> P.ss_hor) + x, (by4 >> P.ss_ver) + y, utw4, uth4,
                                           DAV1D_CUDA_INTRA_NONE, 0, 0, true);
+                                rec_tx_of_last_op();
+                            }
                 }
             }
         } else if (rng.chance(P.p_residual)) {
@@ -807,6 +853,7 @@ struct Gen {
         if (P.real_blocks) {
             rec_inter.n_tx = (uint32_t)tx_recs.size() - rec_inter.first_tx;
             rec_inter.pad[0] = do_obmc ? 1 : 0;                 // b->motion_mode == MM_OBMC
+            if (kind == DAV1D_CUDA_MC_MASK) rec_inter.pad[1] = (uint8_t)wedge_idx;   // b->wedge_idx
             blocks.push_back(rec_inter);
             nb_set(bx4, by4, w4, h4, 1, ref[0], mvx[0], mvy[0], filter);
         }
@@ -955,6 +1002,7 @@ __attribute__((visibility("default"))) void d1synth_default_params(D1SynthParams
     p->p_avg = 0.2f; p->p_w_avg = 0.1f; p->p_wedge = 0.1f; p->p_seg = 0.05f; p->p_warp = 0.05f;
     p->mv_range = 128; p->n_refs = 2; p->edge_filter = 1; p->only_tx = -1; p->only_txtp = -1; p->eob_class = -1; p->dense_coefs = 0; p->p_obmc = 0.f; p->p_ii = 0.f; p->p_ibc = 0.f; p->tile_cols = 1; p->tile_rows = 1; p->real_blocks = 0;
     for (int i = 0; i < 7; i++) p->ref_w[i] = p->ref_h[i] = 0;
+    p->mask_tab = 0;
 }
 
 __attribute__((visibility("default"))) int d1synth_generate(const D1SynthParams *p, D1SynthFrame *f) {

@@ -24,7 +24,14 @@ class SynthParams(C.Structure):
                 ("only_tx", C.c_int32), ("only_txtp", C.c_int32), ("eob_class", C.c_int32),
                 ("dense_coefs", C.c_int32), ("p_obmc", C.c_float), ("p_ii", C.c_float), ("p_ibc", C.c_float),
                 ("tile_cols", C.c_int32), ("tile_rows", C.c_int32), ("real_blocks", C.c_int32),
-                ("ref_w", C.c_int32 * 7), ("ref_h", C.c_int32 * 7)]
+                ("ref_w", C.c_int32 * 7), ("ref_h", C.c_int32 * 7), ("mask_tab", C.c_uint64)]
+
+
+class SynthMaskTab(C.Structure):
+    """D1SynthMaskTab of csrc/synth.cpp: the decoder's wedge / inter-intra mask tables for real-block frames
+    (filled by the tests from the reference's tables; offsets into `base`)."""
+    _fields_ = [("base", C.c_void_p), ("wedge", ((((C.c_uint32 * 16) * 2) * 3) * 3) * 3),
+                ("ii", (((C.c_uint32 * 4) * 3) * 3) * 3)]
 
 
 class SynthFrame(C.Structure):
@@ -84,6 +91,9 @@ class HostFrame:
         for k, v in kw.items():
             if not hasattr(p, k):
                 raise KeyError(k)
+            if k == "mask_tab":                  # a SynthMaskTab (kept alive by the caller)
+                p.mask_tab = C.addressof(v)
+                continue
             if k in ("ref_w", "ref_h"):          # luma size per reference, 0 = the frame's
                 for i, x in enumerate(v):
                     getattr(p, k)[i] = x

@@ -33,6 +33,7 @@
 #include "src/mc.h"
 #include "src/itx.h"
 #include "src/ipred.h"
+#include "src/wedge.h"
 
 #include "dav1d_cuda.h"
 
@@ -120,6 +121,7 @@ static void dense_coefs(coef *out, const OracleReconFrame *fr, const Dav1dCudaIn
  * wedge and intrabc blocks: they need warp parameters / mask tables the records do not carry). */
 EXPORT int SUFFIX(oracle_recon_frame)(const OracleReconFrame *const fr) {
     int ret = 0;
+    dav1d_init_ii_wedge_masks();                   /* src/wedge.c: what dav1d_init_once does (lib.c) */
     Dav1dDSPContext dsp;
     memset(&dsp, 0, sizeof(dsp));
     SUFFIX(dav1d_mc_dsp_init)(&dsp.mc);
@@ -209,7 +211,7 @@ EXPORT int SUFFIX(oracle_recon_frame)(const OracleReconFrame *const fr) {
     int cur_tile = -1, cur_sbrow = -1;
     for (int i = 0; i < fr->n_blocks; i++) {
         const D1SynthBlock *const s = &fr->blocks[i];
-        if (!s->intra && (s->comp_kind > DAV1D_CUDA_MC_W_MASK || s->comp_kind == DAV1D_CUDA_MC_MASK)) { ret = -38; goto done; }
+        if (!s->intra && s->comp_kind > DAV1D_CUDA_MC_W_MASK) { ret = -38; goto done; }   /* warped blocks */
         const int sbrow = s->by4 >> f->sb_shift;
         if (s->tile != cur_tile || sbrow != cur_sbrow) {
             if (cur_tile >= 0) {            /* decode.c:2677: end of a tile's superblock row */
@@ -233,8 +235,11 @@ EXPORT int SUFFIX(oracle_recon_frame)(const OracleReconFrame *const fr) {
             b.bs = bs; b.intra = 0; b.skip = s->skip; b.uvtx = s->uvtx;
             b.comp_type = s->comp_kind == DAV1D_CUDA_MC_PUT ? COMP_INTER_NONE :
                           s->comp_kind == DAV1D_CUDA_MC_AVG ? COMP_INTER_AVG :
-                          s->comp_kind == DAV1D_CUDA_MC_W_AVG ? COMP_INTER_WEIGHTED_AVG : COMP_INTER_SEG;
-            b.inter_mode = 0; b.motion_mode = s->pad[0] ? MM_OBMC : MM_TRANSLATION; b.interintra_type = 0;
+                          s->comp_kind == DAV1D_CUDA_MC_W_AVG ? COMP_INTER_WEIGHTED_AVG :
+                          s->comp_kind == DAV1D_CUDA_MC_MASK ? COMP_INTER_WEDGE : COMP_INTER_SEG;
+            b.wedge_idx = s->pad[1];
+            b.inter_mode = 0; b.motion_mode = s->pad[0] ? MM_OBMC : MM_TRANSLATION;
+            b.interintra_type = s->pad[2] & 3; b.interintra_mode = s->pad[2] >> 2;     /* INTER_INTRA_BLEND / _WEDGE + II_*_PRED */
             for (int r = 0; r < 32 + 5; r++)
                 t->rt.r[r] = rmv + (size_t)((s->by4 & ~31) + r) * rstride;      /* row (by & ~31) - 5 + r, margin 5 */
             for (int k = 0; k < 2; k++) { b.mv[k].x = s->mvx[k]; b.mv[k].y = s->mvy[k]; b.ref[k] = (int8_t)s->ref[k]; }
@@ -352,6 +357,25 @@ done:
 }
 
 #if BITDEPTH == 8
+/* The decoder's wedge / inter-intra masks (src/wedge.c tables through the WEDGE_MASK / II_MASK macros of
+ * src/wedge.h:88-97) for the generator's real-block frames.  lay: 0 = 4:4:4 / luma, 1 = 4:2:2, 2 = 4:2:0. */
+static void masks_once(void) {
+    static int done;
+    if (!done) { dav1d_init_ii_wedge_masks(); done = 1; }
+}
+EXPORT const uint8_t *oracle_wedge_mask(const int lay, const int w4, const int h4, const int sign, const int idx) {
+    const int bs = bs_from_dims(w4, h4);
+    if (bs < BS_32x32 || bs > BS_8x8 || lay < 0 || lay > 2 || idx < 0 || idx > 15) return NULL;
+    masks_once();
+    return WEDGE_MASK(lay, bs, sign & 1, idx);
+}
+EXPORT const uint8_t *oracle_ii_mask(const int lay, const int w4, const int h4, const int mode) {
+    const int bs = bs_from_dims(w4, h4);
+    if (bs < BS_32x32 || bs > BS_8x8 || lay < 0 || lay > 2 || mode < 0 || mode > 3) return NULL;
+    masks_once();
+    return (const uint8_t *) &dav1d_masks + (size_t) dav1d_masks.offsets[lay][bs - BS_32x32].ii[mode] * 8;
+}
+
 /* recon_tmpl.c also holds the inter and post-filter drivers; what they call outside the files this
  * checker compiles is never reached from dav1d_recon_b_intra */
 #define STUB(name) void name(void) { abort(); }

@@ -99,3 +99,41 @@ def run_reference_driver(ref, hf, dst_planes, ref_planes_list=()):
     if r:
         raise RuntimeError(f"oracle_recon_frame: {r}")
     return dst_planes
+
+
+_mask_tab = None
+
+
+def reference_mask_tab(ref):
+    """The decoder's wedge / inter-intra mask tables (reference: dav1d_masks, src/wedge.c) as the generator's
+    D1SynthMaskTab - for real-block frames with wedge compounds or inter-intra blocks (HostFrame(mask_tab=...))."""
+    global _mask_tab
+    if _mask_tab is not None:
+        return _mask_tab[0]
+    from dav1d_mirror_b200 import frame as F
+    L = ref.lib
+    L.oracle_wedge_mask.restype = C.c_void_p
+    L.oracle_wedge_mask.argtypes = [C.c_int] * 5
+    L.oracle_ii_mask.restype = C.c_void_p
+    L.oracle_ii_mask.argtypes = [C.c_int] * 4
+    tab = F.SynthMaskTab()
+    blob = bytearray()
+    for lay in range(3):
+        for wi, w4 in enumerate((2, 4, 8)):
+            for hi, h4 in enumerate((2, 4, 8)):
+                n = (w4 * 4 >> (lay >= 1)) * (h4 * 4 >> (lay == 2))
+                for sign in range(2):
+                    for idx in range(16):
+                        p = L.oracle_wedge_mask(lay, w4, h4, sign, idx)
+                        assert p
+                        tab.wedge[lay][wi][hi][sign][idx] = len(blob)
+                        blob += C.string_at(p, n)
+                for mode in range(4):
+                    p = L.oracle_ii_mask(lay, w4, h4, mode)
+                    assert p
+                    tab.ii[lay][wi][hi][mode] = len(blob)
+                    blob += C.string_at(p, n)
+    buf = np.frombuffer(bytes(blob), dtype=np.uint8).copy()
+    tab.base = buf.ctypes.data
+    _mask_tab = (tab, buf)
+    return tab

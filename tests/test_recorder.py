@@ -65,7 +65,7 @@ def record_frame(hf):
     return ops, out[:r.n_intra]
 
 
-@pytest.mark.parametrize("name", [n for n in R.CASES if not n.startswith(("inter_", "obmc_", "scaled_"))])
+@pytest.mark.parametrize("name", [n for n in R.CASES if not n.startswith(("inter_", "obmc_", "scaled_", "wedge_", "ii_"))])
 def test_recorder_emits_the_generators_descriptors(name):
     hf, _ = R.make(name)
     want, got = record_frame(hf)

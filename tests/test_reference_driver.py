@@ -9,10 +9,11 @@ above / left contexts, tile edges, the superblock-row edge backup; for inter blo
 and sub-pel phase per plane, the emu_edge decision, the compound combine and its mask hand-over to
 chroma, the transform tree and the cbi / cf consumption order - is the reference's code; the descriptors
 the CUDA path consumes are recorded independently by the generator.  Inter coverage: single-reference
-and compound (avg, distance-weighted avg, segmentation mask) blocks with residuals, and OBMC (obmc(),
-recon_tmpl.c:1071-1132, over refmvs rows the harness fills the way decode.c does after every block);
-warped, inter-intra, wedge and intrabc blocks need warp parameters / mask tables the records do not
-carry and stay on the descriptor-replay oracle (tests/test_frame.py).
+and compound (avg, distance-weighted avg, segmentation mask, wedge) blocks with residuals, OBMC (obmc(),
+recon_tmpl.c:1071-1132, over refmvs rows the harness fills the way decode.c does after every block),
+inter-intra blocks (smooth and wedge blends; the generator copies the masks out of the reference's own
+tables) and references of another size; warped and intrabc blocks stay on the descriptor-replay oracle
+(tests/test_frame.py).
 
  * CPU: the descriptor-driven oracle (oracle/ref_frame.c, the bench's CPU arm) reproduces the
    reference driver bit for bit - i.e. the descriptors mean what recon_tmpl.c means;
@@ -60,6 +61,15 @@ CASES = {
     "obmc_422_10b": (256, 192, 0x3ff, 44, {"ss_hor": 1, "ss_ver": 0, "p_intra": 0.3, "p_avg": 0.2, "p_obmc": 0.6}),
     "obmc_420_8b_long_vectors_ragged": (200, 136, 0xff, 45, {"p_intra": 0.1, "mv_range": 300, "p_avg": 0.2, "p_obmc": 0.6}),
     "obmc_420_10b_tiles_2x2": (384, 256, 0x3ff, 46, {"tile_cols": 2, "tile_rows": 2, "p_intra": 0.4, "p_avg": 0.2, "p_obmc": 0.7}),
+    # wedge compounds and inter-intra blocks (smooth and wedge blends) with the reference's own mask tables
+    # (src/wedge.c through WEDGE_MASK / II_MASK); "masks": the generator is handed those tables
+    "wedge_420_8b": (256, 192, 0xff, 101, {"masks": 1, "p_intra": 0.2, "p_avg": 0.1, "p_seg": 0.1, "p_wedge": 0.5}),
+    "ii_420_10b": (320, 256, 0x3ff, 102, {"masks": 1, "p_intra": 0.3, "p_avg": 0.1, "p_ii": 0.7, "p_cfl": 0.4}),
+    "wedge_ii_444_12b": (256, 192, 0xfff, 103, {"masks": 1, "ss_hor": 0, "ss_ver": 0, "p_intra": 0.2, "p_wedge": 0.3, "p_ii": 0.5}),
+    "wedge_ii_422_10b": (256, 192, 0x3ff, 104, {"masks": 1, "ss_hor": 1, "ss_ver": 0, "p_intra": 0.3, "p_wedge": 0.3, "p_ii": 0.5}),
+    "wedge_ii_obmc_420_8b_long_vectors_ragged": (200, 136, 0xff, 105, {"masks": 1, "p_intra": 0.1, "mv_range": 300, "p_wedge": 0.3,
+                                                                       "p_ii": 0.4, "p_obmc": 0.3}),
+    "wedge_ii_luma_8b": (256, 256, 0xff, 107, {"masks": 1, "no_chroma": 1, "p_intra": 0.3, "p_wedge": 0.3, "p_ii": 0.5}),
     # references of another size: the scaled branch of mc() with f->svc as decode.c:3517-3524 sets it
     "scaled_420_10b_half_and_same": (320, 256, 0x3ff, 51, {"ref_w": [160, 0], "ref_h": [128, 0], "p_intra": 0.2, "p_avg": 0.2,
                                                            "p_w_avg": 0.1, "p_seg": 0.15, "p_obmc": 0.3}),
@@ -76,6 +86,9 @@ def make(name):
     kw.setdefault("p_intra", 1.0)
     kw.setdefault("p_wedge", 0.0)
     kw.setdefault("p_warp", 0.0)
+    if kw.pop("masks", 0):
+        import refdsp
+        kw["mask_tab"] = refframe.reference_mask_tab(refdsp.RefDSP())
     hf = F.HostFrame(w, h, bd, seed, real_blocks=1, **kw)
     init = F.random_planes(hf, seed * 10 + 5)
     return hf, init
@@ -113,13 +126,14 @@ def test_random_frames_against_the_reference_drivers(ref):
         kw = dict(ss_hor=lay[0], ss_ver=lay[1], p_cfl=float(rng.choice([0, 0.5])), p_palette=float(rng.choice([0, 0.15])),
                   p_intra=float(rng.choice([1.0, 0.5, 0.2, 0.0])), p_wedge=0.0, p_warp=0.0,
                   p_avg=float(rng.choice([0, 0.2])), p_w_avg=float(rng.choice([0, 0.2])), p_seg=float(rng.choice([0, 0.2])),
-                  p_obmc=float(rng.choice([0, 0.5])), mv_range=int(rng.choice([16, 128, 400])),
+                  p_obmc=float(rng.choice([0, 0.5])), p_ii=float(rng.choice([0, 0.4])), mv_range=int(rng.choice([16, 128, 400])),
                   p_filter_intra=float(rng.choice([0, 0.2])), tile_cols=int(rng.integers(1, 4)),
                   tile_rows=int(rng.integers(1, 3)), p_tx_split=float(rng.choice([0, 0.5, 1.0])),
                   p_residual=float(rng.choice([0.3, 0.6, 1.0])), edge_filter=int(rng.integers(2)))
         w, h = int(rng.integers(8, 60)) * 8, int(rng.integers(8, 40)) * 8
         bd = [0xff, 0x3ff, 0xfff][rng.integers(3)]
-        hf = F.HostFrame(w, h, bd, 500 + k, real_blocks=1, **kw)
+        kw["p_wedge"] = float(rng.choice([0, 0.3]))
+        hf = F.HostFrame(w, h, bd, 500 + k, real_blocks=1, mask_tab=refframe.reference_mask_tab(ref), **kw)
         init = F.random_planes(hf, 9000 + k)
         refs = [F.random_planes(hf, 9100 + 2 * k + j) for j in range(2)]
         want = refframe.run_reference_driver(ref, hf, [p.copy() for p in init], refs)
