@@ -42,8 +42,8 @@ struct Rec {
         d.flags = (uint16_t)flags; d.edge_flags = (uint8_t)edge_flags;
         d.aux = aux;
         d.eob = -1;
-        if (mode == DAV1D_CUDA_INTRA_PAL) {
-            d.coef_off = idx_off;
+        if (mode == DAV1D_CUDA_INTRA_PAL || mode == DAV1D_CUDA_INTRA_II) {
+            d.coef_off = idx_off;                       // packed palette indices / inter-intra blend mask in the byte pool
         } else if (res) {
             if (next_tx >= n_tx) { err = -22; return; }
             const Dav1dCudaTxCoef &t = tx[next_tx++];
@@ -321,8 +321,13 @@ extern "C" int dav1d_cuda_record_b_inter(Dav1dCudaInterRecorder *r, const Dav1dC
     const int ss_ver = r->layout == 1, ss_hor = has_uv && r->layout != 3;
     const int bx = b->bx4, by = b->by4, bw4 = b->bw4, bh4 = b->bh4;
     const bool has_chroma = has_uv && (bw4 > ss_hor || (bx & 1)) && (bh4 > ss_ver || (by & 1));
-    // not transcribed: warped motion, inter-intra, wedge masks, the 4-MV chroma of sub-8x8 blocks
-    if (b->motion_mode > 1 || b->interintra_type || b->comp_type == 4) return -38;
+    // not transcribed: warped motion, the 4-MV chroma of sub-8x8 blocks
+    if (b->motion_mode > 1) return -38;
+    const bool ii = b->interintra_type != 0, wedge = b->comp_type == 4;
+    if (b->interintra_type > 2 || b->interintra_mode > 3 || (ii && (comp || b->motion_mode))) return -22;
+    if ((ii || wedge) && (bw4 < 2 || bh4 < 2 || bw4 > 8 || bh4 > 8)) return -22;          // BS_8x8 .. BS_32x32 (wedge.h:37)
+    if (ii && (!r->intra || !r->intra->intra)) return -22;
+    if (wedge && (!r->masks || !b->wedge_mask[0] || (has_chroma && (!b->wedge_mask[1] || !b->wedge_mask[2])))) return -22;
     if (has_chroma && (bw4 == ss_hor || bh4 == ss_ver)) return -38;
     if (b->motion_mode == 1 && (comp || (bx & 1) || (by & 1))) return -22;     // obmc(): assert(!(t->bx & 1) && !(t->by & 1))
 
@@ -330,6 +335,7 @@ extern "C" int dav1d_cuda_record_b_inter(Dav1dCudaInterRecorder *r, const Dav1dC
     R.r = r; R.tx = tx; R.n_tx = n_tx; R.next_tx = 0; R.err = 0; R.n_emitted = 0;
     R.ss_hor = ss_hor; R.ss_ver = ss_ver;
     const Dav1dCudaInterRecorder saved = *r;                                   // counters to roll back to
+    const int saved_n_intra = r->intra ? r->intra->n_intra : 0;
     const int w4 = imin(bw4, r->bw4 - bx), h4 = imin(bh4, r->bh4 - by);
     const int lay = !has_uv ? 0 : ss_hor ? (ss_ver ? 2 : 1) : 0;               // w_mask[chr_layout_idx]: 444 0, 422 1, 420 2
     uint32_t seg_off = 0;
@@ -352,6 +358,16 @@ extern "C" int dav1d_cuda_record_b_inter(Dav1dCudaInterRecorder *r, const Dav1dC
         int wave = 0;
         switch (b->comp_type) {                                                // :1842-1868, 1890-1906
         case 2: d.kind = DAV1D_CUDA_MC_AVG; break;
+        case 4: {                                                              // COMP_INTER_WEDGE: the plane's mask into the pool
+            if (b->mask_sign) { const Dav1dCudaMcSrc t = d.src[0]; d.src[0] = d.src[1]; d.src[1] = t; }
+            d.kind = DAV1D_CUDA_MC_MASK;
+            const uint32_t n = (uint32_t)d.w * d.h;
+            if (r->masks_bytes + n > r->cap_masks) { R.err = -28; break; }
+            memcpy(r->masks + r->masks_bytes, b->wedge_mask[pl], n);
+            d.aux_off = r->masks_bytes;
+            r->masks_bytes += n;
+            break;
+        }
         case 1:
             d.kind = DAV1D_CUDA_MC_W_AVG;
             d.weight = r->jnt_weights[b->ref[0]][b->ref[1]];
@@ -373,7 +389,46 @@ extern "C" int dav1d_cuda_record_b_inter(Dav1dCudaInterRecorder *r, const Dav1dC
         R.emit_mc(d, r->comp[wave], r->n_comp[wave], r->cap_comp[wave], wave);
     }
 
-    if (!b->skip) {                                                            // :1951-2033
+    // inter-intra (:1658-1681, 1779-1817): per plane the intra prediction of the whole block (no edge flags, no
+    // edge filter) blended onto the inter prediction - an intra-class operation, in decode order with the
+    // frame's other intra-class operations; the block's residuals follow as residual-only operations
+    Rec RI;
+    RI.r = r->intra; RI.b = nullptr; RI.tx = tx; RI.n_tx = n_tx; RI.next_tx = 0; RI.err = 0;
+    RI.ss_hor = ss_hor; RI.ss_ver = ss_ver;
+    if (ii && !R.err) {
+        static const uint8_t ii_pred[4] = { 0, 1, 2, 9 };                      // DC_PRED, VERT_PRED, HOR_PRED, SMOOTH_PRED
+        for (int pl = 0; pl < (has_chroma ? 3 : 1); pl++) {
+            const int sh = pl ? ss_hor : 0, sv = pl ? ss_ver : 0;
+            RI.emit(pl, bx >> sh, by >> sv, bw4 >> sh, bh4 >> sv, DAV1D_CUDA_INTRA_II, ii_pred[b->interintra_mode], 0, 0, false,
+                    0, 0, b->ii_mask_off[pl]);
+        }
+        if (!b->skip) {                                                        // the transform tree (one split level) as operations
+            const TxDim yd = tx_dim(b->max_ytx), ud = tx_dim(b->uvtx);
+            int ytx = b->max_ytx, ytw = yd.w >> 2, yth = yd.h >> 2;
+            if (b->tx_split[0] & 1) {
+                static const uint8_t sub_of[19] = { 0, 0, 1, 2, 3, 0, 0, 1, 1, 2, 2, 3, 3, 5, 6, 7, 8, 9, 10 };
+                ytx = sub_of[ytx];
+                const TxDim sd = tx_dim(ytx);
+                ytw = sd.w >> 2; yth = sd.h >> 2;
+            }
+            if (b->tx_split[0] & ~1 || b->tx_split[1]) RI.err = -38;          // deeper / partial splits of an inter-intra block
+            const int w4c = imin(bw4, r->bw4 - bx), h4c = imin(bh4, r->bh4 - by);
+            for (int y = 0; y < h4c; y += yth)
+                for (int x = 0; x < w4c; x += ytw) RI.emit(0, bx + x, by + y, ytw, yth, DAV1D_CUDA_INTRA_NONE, 0, 0, 0, true, ytx, 0, 0);
+            if (has_chroma) {
+                const int utw = ud.w >> 2, uth = ud.h >> 2;
+                const int cw4 = (w4c + ss_hor) >> ss_hor, ch4 = (h4c + ss_ver) >> ss_ver;
+                for (int pl = 1; pl <= 2; pl++)
+                    for (int y = 0; y < ch4; y += uth)
+                        for (int x = 0; x < cw4; x += utw)
+                            RI.emit(pl, (bx >> ss_hor) + x, (by >> ss_ver) + y, utw, uth, DAV1D_CUDA_INTRA_NONE, 0, 0, 0, true, b->uvtx, 0, 0);
+            }
+        }
+        R.next_tx = RI.next_tx;
+        if (RI.err) R.err = RI.err;
+        R.n_emitted += r->intra->n_intra - saved_n_intra;
+    }
+    if (!b->skip && !ii) {                                                     // :1951-2033
         const TxDim yd = tx_dim(b->max_ytx), ud = tx_dim(b->uvtx);
         const int ytw = yd.w >> 2, yth = yd.h >> 2, utw = ud.w >> 2, uth = ud.h >> 2;
         const int cw4 = (w4 + ss_hor) >> ss_hor, ch4 = (h4 + ss_ver) >> ss_ver;
@@ -394,8 +449,8 @@ extern "C" int dav1d_cuda_record_b_inter(Dav1dCudaInterRecorder *r, const Dav1dC
     }
     if (!R.err && R.next_tx != n_tx) R.err = -22;
     if (R.err) {
-        Dav1dCudaNbMv *const above = r->above, *const left = r->left;
-        *r = saved; r->above = above; r->left = left;
+        *r = saved;
+        if (r->intra) r->intra->n_intra = saved_n_intra;
         return R.err;
     }
     // decode.c:815-826 + :808-814: what later blocks' obmc() reads of this one

@@ -341,9 +341,10 @@ DAV1D_CUDA_API int dav1d_cuda_record_b_intra(Dav1dCudaRecorder *r, const Dav1dCu
 /* ---- inter half of the recorder: dav1d_recon_b_inter (recon_tmpl.c:1598-2036) with mc() (:957-1069, both
  * branches), obmc() (:1071-1132) and read_coef_tree() (:726-823) as descriptor emission.  Covers
  * translational single-reference blocks (optionally with OBMC) and the AVG / WEIGHTED_AVG / SEG compounds,
- * from references of any size, with their residual transform trees.  Warped / global-motion blocks,
- * inter-intra, wedge compounds and the 4-MV chroma of sub-8x8 blocks (:1685-1751) are NOT transcribed yet:
- * the call returns -ENOSYS for them and records nothing. */
+ * the WEDGE compound, inter-intra blocks (the intra prediction + blend and the block's residuals become
+ * intra-class operations appended through `intra`), from references of any size, with their residual
+ * transform trees.  Warped / global-motion blocks and the 4-MV chroma of sub-8x8 blocks (:1685-1751) are NOT
+ * transcribed yet: the call returns -ENOSYS for them and records nothing. */
 typedef struct Dav1dCudaNbMv {          /* what obmc() reads of a neighbour (refmvs rows + filter contexts) */
     int16_t mvx, mvy;                   /* r->mv.mv[0] */
     int8_t  ref;                        /* r->ref.ref[0] - 1: reference index, -1 = intra */
@@ -359,8 +360,18 @@ typedef struct Dav1dCudaBlockInter {    /* the Av1Block fields dav1d_recon_b_int
     int8_t   ref[2];
     uint8_t  filter2d, mask_sign, skip;
     uint8_t  max_ytx, uvtx;             /* enum RectTxfmSize */
-    uint8_t  interintra_type;           /* non-zero: -ENOSYS */
+    uint8_t  interintra_type;           /* enum InterIntraType: NONE 0, BLEND 1, WEDGE 2 */
     uint16_t tx_split[2];               /* b->tx_split0, b->tx_split1 */
+    uint8_t  interintra_mode;           /* enum InterIntraPredMode: II_DC 0, VERT 1, HOR 2, SMOOTH 3 */
+    uint8_t  pad[3];
+    /* COMP_INTER_WEDGE: the block's masks per plane as the driver picks them - luma WEDGE_MASK(0, bs, 0,
+     * wedge_idx), chroma WEDGE_MASK(chr_layout_idx, bs, mask_sign, wedge_idx) (recon_tmpl.c:1861-1866; host
+     * pointers, w * h bytes of the plane block each): copied into the recorder's mask pool. */
+    const uint8_t *wedge_mask[3];
+    /* inter-intra: where the caller put II_MASK(layout of the plane, bs, b) of each plane (wedge.h:88-93,
+     * w * h bytes) in the byte pool that also holds the palette indices (Dav1dCudaReconBatch.pal_idx) */
+    uint32_t ii_mask_off[3];
+    uint32_t pad2;
 } Dav1dCudaBlockInter;
 typedef struct Dav1dCudaInterRecorder {
     int32_t bw4, bh4;                   /* f->bw, f->bh */
@@ -380,6 +391,12 @@ typedef struct Dav1dCudaInterRecorder {
     Dav1dCudaMcScaledDesc *scaled[4]; int32_t n_scaled[4], cap_scaled[4];
     Dav1dCudaItxDesc *itx;     int32_t n_itx, cap_itx;
     uint32_t masks_bytes;               /* running size of the mask pool (segmentation masks are allotted here) */
+    uint32_t cap_masks;                 /* capacity of `masks` */
+    uint8_t *masks;                     /* host mirror of the mask pool: wedge masks are copied into it (the
+                                           segmentation masks' space is only reserved: the device writes them) */
+    Dav1dCudaRecorder *intra;           /* the frame's intra recorder: inter-intra blocks append their intra-class
+                                           operations to its array, in decode order with the intra blocks'
+                                           (its tile_* fields must describe the current tile) */
 } Dav1dCudaInterRecorder;
 /* Appends the block's descriptors; returns how many, or a negative errno (-ENOSPC: an array is full, -EINVAL,
  * -ENOSYS: see above).  On error nothing of the block is kept.  `tx`: the block's cbi / cf entries in

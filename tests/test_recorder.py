@@ -29,6 +29,31 @@ OP = np.dtype([("x4", "u2"), ("y4", "u2"), ("tile_x4_start", "u2"), ("tile_y4_st
                ("coef_off", "u4"), ("aux", "u4"), ("reserved", "u4"), ("cw4", "u1"), ("ch4", "u1"), ("pad", "u2")])
 
 
+def record_intra_block(L, r, s, ops):
+    """One intra block record through dav1d_cuda_record_b_intra into the recorder `r`."""
+    r.tile_col_start, r.tile_row_start, r.tile_col_end, r.tile_row_end = (int(v) for v in s["tile_rect"])
+    b = B.BlockIntra()
+    b.bx4, b.by4, b.bw4, b.bh4 = int(s["bx4"]), int(s["by4"]), int(s["w4"]), int(s["h4"])
+    b.y_mode, b.uv_mode, b.y_angle, b.uv_angle = int(s["y_mode"]), int(s["uv_mode"]), int(s["y_angle"]), int(s["uv_angle"])
+    b.tx, b.uvtx, b.skip, b.sm_flags = int(s["tx"]), int(s["uvtx"]), int(s["skip"]), int(s["sm_flags"])
+    for k in range(2):
+        b.pal_sz[k], b.cfl_alpha[k], b.pal_idx_off[k] = int(s["pal_sz"][k]), int(s["cfl_alpha"][k]), int(s["pal_idx_off"][k])
+    for k in range(3):
+        b.pal_off[k] = int(s["pal_off"][k])
+    # block-level EdgeFlags (src/intra_edge.h:27-32): bit 0 of the record = luma, bit 1 = the chroma layout
+    b.edge_flags = ((1 if s["edge_tr"] & 1 else 0) | (8 if s["edge_bl"] & 1 else 0) |
+                    (6 if s["edge_tr"] & 2 else 0) | (48 if s["edge_bl"] & 2 else 0))
+    mine = ops[s["first_op"]:s["first_op"] + s["n_ops"]]
+    # the block's cbi / cf entries in consumption order: every transform block of a non-skip block
+    txs = [(int(o["coef_off"]), int(o["eob"]), int(o["txtp"]), int(o["cw4"]), int(o["ch4"]))
+           for o in mine if o["mode"] != 15 and not s["skip"]]
+    arr = (B.TxCoef * max(len(txs), 1))()
+    for k, (co, eob, txtp, cw4, ch4) in enumerate(txs):
+        arr[k].coef_off, arr[k].eob, arr[k].txtp, arr[k].cw4, arr[k].ch4 = co, eob, txtp, cw4, ch4
+    n = L.dav1d_cuda_record_b_intra(C.byref(r), C.byref(b), arr, len(txs))
+    assert n == s["n_ops"], (n, int(s["n_ops"]), s)
+
+
 def record_frame(hf):
     assert BLK.itemsize == 88 and OP.itemsize == 40
     L = pkg.lib()
@@ -41,27 +66,7 @@ def record_frame(hf):
     r.intra_edge_filter = hf.params.edge_filter
     r.intra, r.n_intra, r.cap_intra = out.ctypes.data, 0, len(out)
     for s in blocks:
-        r.tile_col_start, r.tile_row_start, r.tile_col_end, r.tile_row_end = (int(v) for v in s["tile_rect"])
-        b = B.BlockIntra()
-        b.bx4, b.by4, b.bw4, b.bh4 = int(s["bx4"]), int(s["by4"]), int(s["w4"]), int(s["h4"])
-        b.y_mode, b.uv_mode, b.y_angle, b.uv_angle = int(s["y_mode"]), int(s["uv_mode"]), int(s["y_angle"]), int(s["uv_angle"])
-        b.tx, b.uvtx, b.skip, b.sm_flags = int(s["tx"]), int(s["uvtx"]), int(s["skip"]), int(s["sm_flags"])
-        for k in range(2):
-            b.pal_sz[k], b.cfl_alpha[k], b.pal_idx_off[k] = int(s["pal_sz"][k]), int(s["cfl_alpha"][k]), int(s["pal_idx_off"][k])
-        for k in range(3):
-            b.pal_off[k] = int(s["pal_off"][k])
-        # block-level EdgeFlags (src/intra_edge.h:27-32): bit 0 of the record = luma, bit 1 = the chroma layout
-        b.edge_flags = ((1 if s["edge_tr"] & 1 else 0) | (8 if s["edge_bl"] & 1 else 0) |
-                        (6 if s["edge_tr"] & 2 else 0) | (48 if s["edge_bl"] & 2 else 0))
-        mine = ops[s["first_op"]:s["first_op"] + s["n_ops"]]
-        # the block's cbi / cf entries in consumption order: every transform block of a non-skip block
-        txs = [(int(o["coef_off"]), int(o["eob"]), int(o["txtp"]), int(o["cw4"]), int(o["ch4"]))
-               for o in mine if o["mode"] != 15 and not s["skip"]]
-        arr = (B.TxCoef * max(len(txs), 1))()
-        for k, (co, eob, txtp, cw4, ch4) in enumerate(txs):
-            arr[k].coef_off, arr[k].eob, arr[k].txtp, arr[k].cw4, arr[k].ch4 = co, eob, txtp, cw4, ch4
-        n = L.dav1d_cuda_record_b_intra(C.byref(r), C.byref(b), arr, len(txs))
-        assert n == s["n_ops"], (n, int(s["n_ops"]), s)
+        record_intra_block(L, r, s, ops)
     return ops, out[:r.n_intra]
 
 
@@ -130,11 +135,29 @@ TXR = np.dtype([("coef_off", "u4"), ("eob", "i2"), ("txtp", "u1"), ("cw4", "u1")
 COMP_TYPE = {0: 0, 1: 2, 2: 1, 4: 3}
 
 
-def record_inter_frame(hf):
+# generator's compound kind 3 (DAV1D_CUDA_MC_MASK on a real-block frame) = COMP_INTER_WEDGE
+COMP_TYPE[3] = 4
+
+
+def record_inter_frame(hf, mask_tab=None):
+    """Every block record of a mixed frame through the product recorder: intra blocks through
+    dav1d_cuda_record_b_intra (when the frame has inter-intra blocks, whose intra-class operations interleave
+    with theirs in decode order), inter blocks through dav1d_cuda_record_b_inter.  `mask_tab`: the reference's
+    wedge / inter-intra tables (refframe.reference_mask_tab) the caller of the recorder picks the masks from."""
     assert MC.itemsize == 40 and MCS.itemsize == 56 and ITX.itemsize == 16 and TXR.itemsize == 12
     L = pkg.lib()
     blocks = np.frombuffer(hf.blocks.tobytes(), dtype=BLK)
     txr = np.frombuffer(hf.tx_recs.tobytes(), dtype=TXR)
+    ops = np.frombuffer(hf.intra.tobytes(), dtype=OP)
+    ops_out = np.zeros(len(ops) + 16, dtype=OP)
+    ri = B.Recorder()
+    ri.bw4, ri.bh4 = hf.bw4, hf.bh4
+    ri.layout = 0 if hf.no_chroma else 1 if hf.ss_ver else 2 if hf.ss_hor else 3
+    ri.intra_edge_filter = hf.params.edge_filter
+    ri.intra, ri.n_intra, ri.cap_intra = ops_out.ctypes.data, 0, len(ops_out)
+    masks = np.zeros(max(hf.masks.nbytes, 1) + 64, dtype=np.uint8)
+    lay_c = 0 if (hf.no_chroma or not hf.ss_hor) else 2 if hf.ss_ver else 1
+    l2 = {2: 0, 4: 1, 8: 2}
     r = B.InterRecorder()
     r.bw4, r.bh4, r.w, r.h = hf.bw4, hf.bh4, hf.w, hf.h
     r.layout = 0 if hf.no_chroma else 1 if hf.ss_ver else 2 if hf.ss_hor else 3
@@ -158,11 +181,15 @@ def record_inter_frame(hf):
     for k in range(4):
         r.scaled[k], r.cap_scaled[k] = sc[k].ctypes.data, cap
     r.itx, r.cap_itx = out["itx"].ctypes.data, cap
+    r.masks, r.cap_masks = masks.ctypes.data, len(masks)
+    r.intra = C.pointer(ri)
     for s in blocks:
         r.tile_col_start, r.tile_row_start = int(s["tile_rect"][0]), int(s["tile_rect"][1])
         if s["intra"]:
             assert L.dav1d_cuda_record_nb_intra(C.byref(r), int(s["bx4"]), int(s["by4"]), int(s["w4"]), int(s["h4"])) == 0
+            record_intra_block(L, ri, s, ops)
             continue
+        ri.tile_col_start, ri.tile_row_start, ri.tile_col_end, ri.tile_row_end = (int(v) for v in s["tile_rect"])
         b = B.BlockInter()
         b.bx4, b.by4, b.bw4, b.bh4 = int(s["bx4"]), int(s["by4"]), int(s["w4"]), int(s["h4"])
         b.comp_type, b.motion_mode = COMP_TYPE[int(s["comp_kind"])], int(s["pad"][0])
@@ -171,6 +198,16 @@ def record_inter_frame(hf):
         b.filter2d, b.mask_sign, b.skip = int(s["filter2d"]), int(s["mask_sign"]), int(s["skip"])
         b.max_ytx, b.uvtx = int(s["max_ytx"]), int(s["uvtx"])
         b.tx_split[0] = 1 if s["tx_split"] else 0
+        wi, hi, wedge_idx = l2.get(int(s["w4"])), l2.get(int(s["h4"])), int(s["pad"][1])
+        if b.comp_type == 4:                                           # the driver's WEDGE_MASK picks (recon_tmpl.c:1861-1866)
+            b.wedge_mask[0] = mask_tab.base + mask_tab.wedge[0][wi][hi][0][wedge_idx]
+            b.wedge_mask[1] = b.wedge_mask[2] = mask_tab.base + mask_tab.wedge[lay_c][wi][hi][b.mask_sign][wedge_idx]
+        if s["pad"][2]:                                                # inter-intra: II_MASK of each plane is in the byte pool
+            b.interintra_type, b.interintra_mode = int(s["pad"][2]) & 3, int(s["pad"][2]) >> 2
+            for pl in range(1 if hf.no_chroma else 3):                 # where the generator's operations say it put them
+                o = ops[ri.n_intra + pl]
+                assert o["mode"] == 16 and o["plane"] == pl, o
+                b.ii_mask_off[pl] = int(o["coef_off"])
         mine = txr[s["first_tx"]:s["first_tx"] + s["n_tx"]]
         arr = (B.TxCoef * max(len(mine), 1))()
         for k, t in enumerate(mine):
@@ -182,16 +219,56 @@ def record_inter_frame(hf):
            "comp": np.concatenate([out["comp0"][:r.n_comp[0]], out["comp1"][:r.n_comp[1]]]),
            "obmc": np.concatenate([out["obmc0"][:r.n_obmc[0]], out["obmc1"][:r.n_obmc[1]]]),
            "scaled": np.concatenate([sc[k][:r.n_scaled[k]] for k in range(4)]),
-           "itx": out["itx"][:r.n_itx]}
+           "itx": out["itx"][:r.n_itx], "intra": ops_out[:ri.n_intra], "masks": masks[:r.masks_bytes]}
     return got, [r.n_scaled[k] for k in range(4)], r.masks_bytes
 
 
-@pytest.mark.parametrize("name", [n for n in R.CASES if n.startswith(("inter_", "obmc_", "scaled_"))])
+def _is_seg_chroma(hf, d):
+    """A MASK-kind chroma descriptor that reads the luma-derived segmentation mask (second wave) rather than a
+    wedge table: its aux_off is the one of a W_MASK luma descriptor."""
+    seg = getattr(hf, "_seg_offs", None)
+    if seg is None:
+        comp = np.frombuffer(hf.mc_comp.tobytes(), dtype=MC)
+        seg = hf._seg_offs = set(int(c["aux_off"]) for c in comp if c["kind"] == 4)
+    return int(d["aux_off"]) in seg
+
+
+def _normalise_edge_bits(a):
+    # top-right / bottom-left only reach the predictor through have_top / have_left (see above)
+    a = a.copy()
+    a["edge_flags"] &= np.where(a["y4"] > a["tile_y4_start"], 0xff, 0xfe).astype(np.uint8)
+    a["edge_flags"] &= np.where(a["x4"] > a["tile_x4_start"], 0xff, 0xf7).astype(np.uint8)
+    return a
+
+
+@pytest.mark.parametrize("name", [n for n in R.CASES if n.startswith(("inter_", "obmc_", "scaled_", "wedge_", "ii_"))])
 def test_inter_recorder_emits_the_generators_descriptors(name):
     """dav1d_cuda_record_b_inter over the Av1Block-style records == the descriptor arrays the generator wrote
-    for the same blocks (which reproduce dav1d_recon_b_inter's pixels bit for bit, tests/test_reference_driver.py)."""
+    for the same blocks (which reproduce dav1d_recon_b_inter's pixels bit for bit, tests/test_reference_driver.py).
+    On the wedge_ / ii_ frames that includes the mask pool (the reference's own wedge tables) and the intra-class
+    operations of the inter-intra blocks, interleaved in decode order with the intra blocks'."""
     hf, _ = R.make(name)
-    got, n_scaled, masks_bytes = record_inter_frame(hf)
+    mask_tab = None
+    if name.startswith(("wedge_", "ii_")):
+        import refdsp
+        import refframe
+        mask_tab = refframe.reference_mask_tab(refdsp.RefDSP())
+    got, n_scaled, masks_bytes = record_inter_frame(hf, mask_tab)
+    want_ops = _normalise_edge_bits(np.frombuffer(hf.intra.tobytes(), dtype=OP))
+    got_ops = _normalise_edge_bits(got["intra"])
+    assert len(want_ops) == len(got_ops), (len(want_ops), len(got_ops))
+    for f in OP.names:
+        if f in ("reserved", "pad"):
+            continue
+        bad = np.nonzero(want_ops[f] != got_ops[f])[0]
+        assert bad.size == 0, f"{name}: field {f} differs at operation {bad[0]}: {want_ops[bad[0]]} vs {got_ops[bad[0]]}"
+    if mask_tab is not None:
+        # segmentation masks are only allotted (the device writes them); wedge masks are the bytes themselves
+        wedge = np.zeros(masks_bytes, dtype=bool)
+        for d in np.frombuffer(hf.mc_comp.tobytes(), dtype=MC):
+            if d["kind"] == 3 and d["plane"] == 0 or (d["kind"] == 3 and not _is_seg_chroma(hf, d)):
+                wedge[d["aux_off"]:d["aux_off"] + int(d["w"]) * int(d["h"])] = True
+        assert np.array_equal(got["masks"][wedge], np.asarray(hf.masks)[:masks_bytes][wedge])
     want = {"put": np.frombuffer(hf.mc_put.tobytes(), dtype=MC), "comp": np.frombuffer(hf.mc_comp.tobytes(), dtype=MC),
             "obmc": np.frombuffer(hf.mc_obmc.tobytes(), dtype=MC), "scaled": np.frombuffer(hf.mc_scaled.tobytes(), dtype=MCS),
             "itx": np.frombuffer(hf.itx.tobytes(), dtype=ITX)}
@@ -226,9 +303,12 @@ def test_inter_recorder_refuses_what_it_does_not_transcribe():
     b.motion_mode = 2                                                  # MM_WARP
     assert L.dav1d_cuda_record_b_inter(C.byref(r), C.byref(b), None, 0) == -38
     b.motion_mode, b.interintra_type = 0, 1
-    assert L.dav1d_cuda_record_b_inter(C.byref(r), C.byref(b), None, 0) == -38
+    assert L.dav1d_cuda_record_b_inter(C.byref(r), C.byref(b), None, 0) == -22    # inter-intra without an intra recorder
     b.interintra_type, b.comp_type = 0, 4                              # COMP_INTER_WEDGE
-    assert L.dav1d_cuda_record_b_inter(C.byref(r), C.byref(b), None, 0) == -38
+    assert L.dav1d_cuda_record_b_inter(C.byref(r), C.byref(b), None, 0) == -22    # ... without the block's masks
+    b.bw4 = 16
+    assert L.dav1d_cuda_record_b_inter(C.byref(r), C.byref(b), None, 0) == -22    # no wedge masks beyond 32x32
+    b.bw4 = 4
     b.comp_type = 0
     assert L.dav1d_cuda_record_b_inter(C.byref(r), C.byref(b), None, 0) == -28 and r.n_put == 0   # three planes, room for two
     r.cap_put = 8
