@@ -56,6 +56,8 @@ def parse_args():
     ap.add_argument("--coefs", default="int16", choices=["int16", "native"],
                     help="coefficient stream of high-bit-depth frames: int16 + escape list (cf_int16) or the "
                          "reference's int32 layout")
+    ap.add_argument("--mc-staging", default="tma_put", choices=["tma", "tma_put", "cp_async"],
+                    help="how the 32x32-tile MC kernels stage the reference windows (dav1d_cuda_set_mc_tma)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-verify", action="store_true")
@@ -294,6 +296,7 @@ def main_ours(args):
     L = pkg.lib()
     if not L.dav1d_cuda_available():
         raise RuntimeError("no CUDA device: this benchmark has no CPU fallback")
+    L.dav1d_cuda_set_mc_tma({"cp_async": 0, "tma_put": 1, "tma": 2}[args.mc_staging])
     from dav1d_mirror_b200 import dist as D
     S = args.streams
     # weak scaling: world * S independent streams, stream i -> rank i mod world (replicas only)
@@ -599,6 +602,10 @@ def main_ours(args):
                    "l2": f"inputs larger than L2: working set {footprint_mb:.0f} MB per GPU vs {L2_MB:.0f} MB L2"
                    if footprint_mb > 2 * L2_MB else f"working set {footprint_mb:.0f} MB; L2 NOT exceeded",
                    "cuda_graph": bool(args.graph),
+                   "mc_window_staging": {"tma": "cp.async.bulk.tensor.2d (TMA, two window buffers per warp) in the 32x32-tile kernels",
+                                         "tma_put": "cp.async.bulk.tensor.2d (TMA, two window buffers per warp) for single-reference "
+                                                    "32x32 tiles; cp.async per lane for compound (measured faster) and 8x8 tiles",
+                                         "cp_async": "cp.async per lane"}[args.mc_staging],
                    "submission": f"{len(units)} group submissions per step, each the frames of {G} streams "
                                  f"(dav1d_cuda_recon_group_submit: nothing scheduled on the host)",
                    "twelve_bit_stream": "the last stream of every rank is 12-bit",

@@ -116,7 +116,7 @@ class Plane(C.Structure):
 
 class Picture(C.Structure):
     _fields_ = [("p", Plane * 3), ("bitdepth_max", C.c_int32), ("ss_hor", C.c_int32),
-                ("ss_ver", C.c_int32)]
+                ("ss_ver", C.c_int32), ("tma", C.c_void_p)]
 
 
 assert C.sizeof(ItxDesc) == 16 and C.sizeof(McDesc) == 40
@@ -143,6 +143,9 @@ def lib():
     L.dav1d_cuda_synchronize.argtypes = [C.c_void_p]
     L.dav1d_cuda_picture_alloc.argtypes = [C.c_void_p, C.POINTER(Picture)] + [C.c_int] * 5
     L.dav1d_cuda_picture_free.argtypes = [C.c_void_p, C.POINTER(Picture)]
+    L.dav1d_cuda_set_mc_tma.argtypes = [C.c_int]
+    L.dav1d_cuda_set_mc_tma.restype = None
+    L.dav1d_cuda_get_mc_tma.restype = C.c_int
     L.dav1d_cuda_picture_upload.argtypes = [C.c_void_p, C.POINTER(Picture), C.c_int, C.c_void_p, C.c_ssize_t]
     L.dav1d_cuda_picture_download.argtypes = [C.c_void_p, C.POINTER(Picture), C.c_int, C.c_void_p, C.c_ssize_t]
     L.dav1d_cuda_itx_batch.argtypes = [C.c_void_p, C.POINTER(Picture), C.c_void_p, C.c_void_p,

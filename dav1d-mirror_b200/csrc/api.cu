@@ -3,11 +3,14 @@
 #include <stdio.h>
 #include <string.h>
 #include <atomic>
+#include <cuda.h>            // CUtensorMap and its enums (types only: no libcuda symbol is linked)
 #include "ctx.h"
 
 namespace d1 {
 
 void mc_init_attrs();
+void mc_set_tma(int mode);
+int mc_get_tma();
 void recon_init_attrs();
 
 static std::atomic<int> g_err{0};
@@ -165,6 +168,55 @@ int dav1d_cuda_synchronize(Dav1dCudaContext *c) {
     return 0;
 }
 
+// Tensor maps of a picture's planes for the TMA staging of the MC kernels (csrc/mc.cuh): per plane
+// MC_TMA_CLASSES maps whose boxes are one staged window row wide (48 16-bit / 64 8-bit pixels) and
+// 15 / 23 / 39 rows high.  cuTensorMapEncodeTiled comes through the runtime's entry-point query: the
+// library does not link libcuda.
+namespace {
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            p = nullptr;
+        }
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+constexpr int TMA_CLASSES = 3;
+const int tma_rows[TMA_CLASSES] = { 15, 23, 39 };
+// false: the picture goes without maps (cp.async staging) - not an error
+bool picture_tensor_maps(Dav1dCudaPicture *pic, void *dev_maps) {
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) return false;
+    const int hbd = pic->bitdepth_max > 0xff;
+    CUtensorMap maps[3 * TMA_CLASSES];
+    memset(maps, 0, sizeof(maps));
+    for (int pl = 0; pl < 3; pl++) {
+        const Dav1dCudaPlane &p = pic->p[pl];
+        if (!p.data || p.w <= 0 || p.h <= 0) continue;
+        if (p.stride <= 0 || (p.stride & 15) || ((uintptr_t)p.data & 15)) return false;
+        for (int k = 0; k < TMA_CLASSES; k++) {
+            const cuuint64_t dims[2] = { (cuuint64_t)(p.stride >> hbd), (cuuint64_t)p.h };
+            const cuuint64_t strides[1] = { (cuuint64_t)p.stride };
+            const cuuint32_t box[2] = { hbd ? 48u : 64u, (cuuint32_t)tma_rows[k] };
+            const cuuint32_t estr[2] = { 1, 1 };
+            if (enc(&maps[pl * TMA_CLASSES + k], hbd ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 2,
+                    p.data, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                    CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                return false;
+        }
+    }
+    return cudaMemcpy(dev_maps, maps, sizeof(maps), cudaMemcpyHostToDevice) == cudaSuccess;
+}
+}  // namespace
+
 // Geometry of the reference's default allocator, src/picture.c:46-84.
 int dav1d_cuda_picture_alloc(Dav1dCudaContext *c, Dav1dCudaPicture *pic,
                              int w, int h, int ss_hor, int ss_ver, int bitdepth_max)
@@ -182,8 +234,10 @@ int dav1d_cuda_picture_alloc(Dav1dCudaContext *c, Dav1dCudaPicture *pic,
     const size_t y_sz = (size_t)y_stride * aligned_h;
     const size_t uv_sz = (size_t)uv_stride * (aligned_h >> ss_ver);
     uint8_t *buf = nullptr;
-    D1_CHECK(cudaMalloc(&buf, y_sz + 2 * uv_sz + 64));
-    D1_CHECK(cudaMemset(buf, 0, y_sz + 2 * uv_sz + 64));
+    // the planes, 64 bytes of slack as the reference has them, then the planes' tensor maps
+    const size_t maps_off = (y_sz + 2 * uv_sz + 64 + 127) & ~(size_t)127;
+    D1_CHECK(cudaMalloc(&buf, maps_off + 3 * TMA_CLASSES * sizeof(CUtensorMap)));
+    D1_CHECK(cudaMemset(buf, 0, maps_off + 3 * TMA_CLASSES * sizeof(CUtensorMap)));
     pic->p[0].data = buf;
     pic->p[0].stride = y_stride;
     pic->p[0].w = w;
@@ -197,8 +251,12 @@ int dav1d_cuda_picture_alloc(Dav1dCudaContext *c, Dav1dCudaPicture *pic,
     pic->bitdepth_max = bitdepth_max;
     pic->ss_hor = ss_hor;
     pic->ss_ver = ss_ver;
+    if (picture_tensor_maps(pic, buf + maps_off)) pic->tma = buf + maps_off;
     return 0;
 }
+
+void dav1d_cuda_set_mc_tma(int mode) { mc_set_tma(mode); }
+int dav1d_cuda_get_mc_tma(void) { return mc_get_tma(); }
 
 // ---- Dav1dPicAllocator seam: pictures with a twin in HBM and one in pinned host memory
 namespace {

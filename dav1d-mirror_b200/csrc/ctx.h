@@ -56,6 +56,7 @@ struct PlaneView {
 struct PicView {
     PlaneView p[3];
     int bdmax, ss_hor, ss_ver;
+    const void *tma;  // Dav1dCudaPicture.tma: the planes' tensor maps in device memory, or null
 };
 inline PicView pic_view(const Dav1dCudaPicture *pic) {
     PicView v;
@@ -68,6 +69,7 @@ inline PicView pic_view(const Dav1dCudaPicture *pic) {
     v.bdmax = pic->bitdepth_max;
     v.ss_hor = pic->ss_hor;
     v.ss_ver = pic->ss_ver;
+    v.tma = pic->tma;
     return v;
 }
 

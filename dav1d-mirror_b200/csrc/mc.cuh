@@ -37,32 +37,46 @@ template <typename pixel, int TMAX = MC_T> struct McSrcGeo {
 template <typename pixel, int TMAX = MC_T> struct __align__(16) McSmem {
     pixel src[(TMAX + 7) * McSrcGeo<pixel, TMAX>::STRIDE];
     int16_t mid[(TMAX + 7) * McSrcGeo<pixel, TMAX>::MID];
-    unsigned long long bar;      // mbarrier the bulk copies of the window complete on (mc_smem_init)
-    unsigned phase, pad;         // its current phase parity
 };
 
-// ---- TMA (bulk async copy) staging helpers: one cp.async.bulk per window row, completion on an
-// mbarrier in the tile's shared memory (expect_tx = bytes of the whole window)
+// ---- TMA staging (32x32-tile kernels, pictures from dav1d_cuda_picture_alloc): the whole window of a tile
+// is ONE cp.async.bulk.tensor.2d request against the reference plane's tensor map (box = STRIDE pixels x
+// 15 / 23 / 39 rows, chosen by the tile height), completing on an mbarrier in the warp's shared memory.
+// Two window buffers per warp: the request of the NEXT window is in flight while the current one is
+// filtered.  Windows that touch the picture border keep the clamped cp.async / per-pixel path (TMA fills
+// out-of-bounds elements with zeros, edge emulation replicates).
 DEV unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-#ifndef D1_MC_TMA
-#define D1_MC_TMA 0
-#endif
-template <typename pixel, int TMAX>
-DEV void mc_smem_init(McSmem<pixel, TMAX> *sm, const int lane, const unsigned gmask) {
-    if (!D1_MC_TMA) return;
+constexpr int MC_TMA_CLASSES = 3;        // tensor maps per plane: box rows 15, 23, 39
+DEV int mc_tma_class(const int th) { return th <= 8 ? 0 : th <= 16 ? 1 : 2; }
+DEV int mc_tma_rows(const int cls) { return cls == 0 ? 15 : cls == 1 ? 23 : 39; }
+template <typename pixel> struct __align__(128) McSmemTma {
+    pixel src[2][(MC_T + 8) * McSrcGeo<pixel, MC_T>::STRIDE];      // 3840 / 2560 bytes each: 128-byte multiples
+    int16_t mid[(MC_T + 7) * McSrcGeo<pixel, MC_T>::MID + 4];
+    unsigned long long bar[2];
+};
+template <typename pixel> struct __align__(128) McSmemTmaCompound {
+    McSmemTma<pixel> s;
+    int16_t ta[MC_T * MC_T];
+    int16_t tb[MC_T * MC_T];
+};
+template <typename pixel>
+DEV void mc_tma_init(McSmemTma<pixel> *sm, const int lane) {
     if (lane == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&sm->bar)) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&sm->bar[0])) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&sm->bar[1])) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        sm->phase = 0;
     }
-    __syncwarp(gmask);
+    __syncwarp();
 }
-DEV void mbar_expect_tx(const unsigned bar, const unsigned bytes) {
+// one lane: expect the box's bytes, then the tensor request (x, y = element coordinates of the window's
+// top-left in the plane)
+DEV void mc_tma_issue(const unsigned dst, const void *tmap, const int x, const int y, const unsigned bytes,
+                      const unsigned bar)
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // earlier generic accesses to the buffer are done
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
-}
-DEV void bulk_g2s(const unsigned dst, const void *src, const unsigned bytes, const unsigned bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 :: "r"(dst), "l"(tmap), "r"(x), "r"(y), "r"(bar) : "memory");
 }
 DEV void mbar_wait(const unsigned bar, const unsigned parity) {
     asm volatile(
@@ -294,32 +308,20 @@ DEV void mc_vpass_dp(const SRC *src, const int sstride, const uint2 t, const int
     }
 }
 
-// One tile of put (PREP = false) / prep (PREP = true).
+// One tile of put (PREP = false) / prep (PREP = true), in two steps: mc_stage() brings the reference
+// window into shared memory, mc_filter() runs the separable filter over it.
 //   ref       reference plane (clamped reads)
 //   sx, sy    integer sample position of the tile's top-left in the reference
 //   tw, th    tile size (<= 32); bw, bh: full block size (filter selection)
 //   out       tile's top-left in the destination (pixels, or int16 for prep)
 //   lane      lane index inside the group of G lanes that owns this tile (G = 32: the warp;
 //             G = 8: four tiles per warp, `gmask` = the group's lanes for the barriers)
-template <typename pixel, bool PREP, int TMAX = MC_T, int G = 32>
-DEV void mc_tile(const PlaneView &ref, const int sx, const int sy, const int tw, const int th,
-                 const int bw, const int bh, const int mx, const int my, const int filter_2d,
-                 const int bdmax, McSmem<pixel, TMAX> *sm,
-                 typename McOut<pixel, PREP>::type *out, const int ostride, const int lane,
-                 const unsigned gmask = 0xffffffffu)
+// mc_stage returns `off`: window column c of row r lives at ssrc[r * STRIDE + off + c].
+template <typename pixel, int TMAX = MC_T, int G = 32>
+DEV int mc_stage(const PlaneView &ref, const int sx, const int sy, const int tw, const int th,
+                 const int mx, const int my, pixel *ssrc, const int lane, const unsigned gmask = 0xffffffffu)
 {
-    typedef McOut<pixel, PREP> O;
-    const int ib = PxTraits<pixel>::inter_bits(bdmax);
-    const int bs = filter_2d == 9 ? 4 : 6;
-    uint2 ph = make_uint2(0, 0), pv = make_uint2(0, 0);
-    if (mx) ph = mc_load_taps(filter_2d, false, mx, bw);
-    if (my) pv = mc_load_taps(filter_2d, true, my, bh);
-
     // ---- stage the window: rows/cols -3..+4 only where a filter needs them.
-    // (D1_MC_TMA=1 builds the TMA variant of the fast path: one cp.async.bulk per window row with
-    // mbarrier completion - bit-exact, but measured slower than the cp.async one on B200: 30 vs 22 us
-    // per 4K frame for put, 57 vs 41 for compound; 39 bulk requests of ~100 bytes per tile are a poor
-    // fit for the copy engine.  Default 0.)
     // Fast path (window columns inside the plane): 16-byte cp.async copies of
     // the aligned superset of each row, global -> shared without a register
     // round trip; `off` = position of window column 0 inside the staged row.
@@ -337,29 +339,11 @@ DEV void mc_tile(const PlaneView &ref, const int sx, const int sy, const int tw,
             const int a0 = (sx - 3) & ~(VPX - 1);
             off = (sx - 3) - a0;
             const int v_lo = (off + c_lo) / VPX, nv = (off + c_hi - 1) / VPX - v_lo + 1;
-#if D1_MC_TMA
-            // TMA: one bulk copy per window row (a lane per row), all of them completing on the
-            // tile's mbarrier; rows beyond the top / bottom picture edge repeat the edge row
-            const unsigned bar = smem_u32(&sm->bar), row_bytes = (unsigned)nv * 16u;
-            const unsigned parity = sm->phase;
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier reads of the window are done
-            if (lane == 0) mbar_expect_tx(bar, row_bytes * (unsigned)(r_hi - r_lo));
-            __syncwarp(gmask);
-            const pixel *gcol = rp + a0 + v_lo * VPX;
-            const unsigned scol = smem_u32(sm->src + v_lo * VPX);
-            for (int r = r_lo + lane; r < r_hi; r += G) {
-                const int yy = iclip(sy - 3 + r, 0, ref.h - 1);
-                bulk_g2s(scol + r * (SS * (int)sizeof(pixel)), gcol + yy * rstride, row_bytes, bar);
-            }
-            mbar_wait(bar, parity);
-            __syncwarp(gmask);
-            if (lane == 0) sm->phase = parity ^ 1u;
-#else
             constexpr int LPR = TMAX == 32 ? 8 : 4;           // lanes per row >= vectors per row
             const int lr = lane / LPR, v = v_lo + lane % LPR;
             if (lane % LPR < nv) {
                 const pixel *gcol = rp + a0 + v * VPX;
-                const unsigned scol = (unsigned)__cvta_generic_to_shared(sm->src + v * VPX);
+                const unsigned scol = (unsigned)__cvta_generic_to_shared(ssrc + v * VPX);
                 for (int r = r_lo + lr; r < r_hi; r += G / LPR) {
                     const int yy = iclip(sy - 3 + r, 0, ref.h - 1);
                     const pixel *g = gcol + yy * rstride;
@@ -368,7 +352,6 @@ DEV void mc_tile(const PlaneView &ref, const int sx, const int sy, const int tw,
                 }
             }
             asm volatile("cp.async.wait_all;" ::: "memory");
-#endif
         } else {
             // per-pixel clamped reads; a lane owns at most two columns and fetches four rows
             // per step so that eight loads are in flight (a load -> shared store -> load chain
@@ -393,14 +376,30 @@ DEV void mc_tile(const PlaneView &ref, const int sx, const int sy, const int tw,
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
                     const int rr = r + u * rpi;
-                    if (rr < r_hi && h1) sm->src[rr * SS + c1] = v1[u];
-                    if (rr < r_hi && h2) sm->src[rr * SS + c2] = v2[u];
+                    if (rr < r_hi && h1) ssrc[rr * SS + c1] = v1[u];
+                    if (rr < r_hi && h2) ssrc[rr * SS + c2] = v2[u];
                 }
             }
         }
     }
     __syncwarp(gmask);
-    const pixel *wsrc = sm->src + off;      // window column c lives at wsrc[r * SS + c]
+    return off;
+}
+
+template <typename pixel, bool PREP, int TMAX = MC_T, int G = 32>
+DEV void mc_filter(const pixel *ssrc, const int off, int16_t *smid, const int tw, const int th,
+                   const int bw, const int bh, const int mx, const int my, const int filter_2d,
+                   const int bdmax, typename McOut<pixel, PREP>::type *out, const int ostride, const int lane,
+                   const unsigned gmask = 0xffffffffu)
+{
+    typedef McOut<pixel, PREP> O;
+    const int ib = PxTraits<pixel>::inter_bits(bdmax);
+    const int bs = filter_2d == 9 ? 4 : 6;
+    uint2 ph = make_uint2(0, 0), pv = make_uint2(0, 0);
+    if (mx) ph = mc_load_taps(filter_2d, false, mx, bw);
+    if (my) pv = mc_load_taps(filter_2d, true, my, bh);
+    constexpr int SS = McSrcGeo<pixel, TMAX>::STRIDE, MS = McSrcGeo<pixel, TMAX>::MID;
+    const pixel *wsrc = ssrc + off;      // window column c lives at wsrc[r * SS + c]
     // paired / vector stores need an even column, an even stride and an aligned base
     const bool vec_ok = (((uintptr_t)out & 7) | (ostride & 3)) == 0;
     const bool pair_ok = (((uintptr_t)out & 3) | (ostride & 1)) == 0 && tw * ((th + 7) >> 3) >= 2 * G;
@@ -409,24 +408,24 @@ DEV void mc_tile(const PlaneView &ref, const int sx, const int sy, const int tw,
         const int sh1 = bs - ib, rnd1 = (1 << sh1) >> 1;
         if (sizeof(pixel) == 2 && tw >= 8) {
             if constexpr (sizeof(pixel) == 2)
-                mc_hpass_dp<pixel, PREP, false, TMAX, G>(sm->src, off, ph, tw, 0, th + 7, rnd1, sh1, bdmax, sm->mid, nullptr, 0, false, lane);
+                mc_hpass_dp<pixel, PREP, false, TMAX, G>(ssrc, off, ph, tw, 0, th + 7, rnd1, sh1, bdmax, smid, nullptr, 0, false, lane);
         } else {
             int fh[8];
             mc_unpack_taps(ph, fh);
-            if (tw >= 8)      mc_hpass<pixel, PREP, 8, false, TMAX, G>(wsrc, fh, tw, 0, th + 7, rnd1, sh1, bdmax, sm->mid, nullptr, 0, lane);
-            else if (tw == 4) mc_hpass<pixel, PREP, 4, false, TMAX, G>(wsrc, fh, tw, 0, th + 7, rnd1, sh1, bdmax, sm->mid, nullptr, 0, lane);
-            else              mc_hpass<pixel, PREP, 2, false, TMAX, G>(wsrc, fh, tw, 0, th + 7, rnd1, sh1, bdmax, sm->mid, nullptr, 0, lane);
+            if (tw >= 8)      mc_hpass<pixel, PREP, 8, false, TMAX, G>(wsrc, fh, tw, 0, th + 7, rnd1, sh1, bdmax, smid, nullptr, 0, lane);
+            else if (tw == 4) mc_hpass<pixel, PREP, 4, false, TMAX, G>(wsrc, fh, tw, 0, th + 7, rnd1, sh1, bdmax, smid, nullptr, 0, lane);
+            else              mc_hpass<pixel, PREP, 2, false, TMAX, G>(wsrc, fh, tw, 0, th + 7, rnd1, sh1, bdmax, smid, nullptr, 0, lane);
         }
         __syncwarp(gmask);
         const int sh2 = PREP ? bs : bs + ib, rnd2 = (1 << sh2) >> 1;
-        if (pair_ok) mc_vpass_dp<pixel, PREP, int16_t, 2, G>(sm->mid, MS, pv, tw, th, rnd2, sh2, bdmax, out, ostride, lane);
-        else         mc_vpass_dp<pixel, PREP, int16_t, 1, G>(sm->mid, MS, pv, tw, th, rnd2, sh2, bdmax, out, ostride, lane);
+        if (pair_ok) mc_vpass_dp<pixel, PREP, int16_t, 2, G>(smid, MS, pv, tw, th, rnd2, sh2, bdmax, out, ostride, lane);
+        else         mc_vpass_dp<pixel, PREP, int16_t, 1, G>(smid, MS, pv, tw, th, rnd2, sh2, bdmax, out, ostride, lane);
     } else if (mx) {
         const int sh = PREP ? bs - ib : bs;
         const int rnd = PREP ? (1 << sh) >> 1 : (1 << (bs - 1)) + ((1 << (bs - ib)) >> 1);
         if (sizeof(pixel) == 2 && tw >= 8) {
             if constexpr (sizeof(pixel) == 2)
-                mc_hpass_dp<pixel, PREP, true, TMAX, G>(sm->src, off, ph, tw, 3, th + 3, rnd, sh, bdmax, nullptr, out, ostride, vec_ok, lane);
+                mc_hpass_dp<pixel, PREP, true, TMAX, G>(ssrc, off, ph, tw, 3, th + 3, rnd, sh, bdmax, nullptr, out, ostride, vec_ok, lane);
         } else {
             int fh[8];
             mc_unpack_taps(ph, fh);
@@ -447,6 +446,19 @@ DEV void mc_tile(const PlaneView &ref, const int sx, const int sy, const int tw,
         }
     }
     __syncwarp(gmask);
+}
+
+
+template <typename pixel, bool PREP, int TMAX = MC_T, int G = 32>
+DEV void mc_tile(const PlaneView &ref, const int sx, const int sy, const int tw, const int th,
+                 const int bw, const int bh, const int mx, const int my, const int filter_2d,
+                 const int bdmax, McSmem<pixel, TMAX> *sm,
+                 typename McOut<pixel, PREP>::type *out, const int ostride, const int lane,
+                 const unsigned gmask = 0xffffffffu)
+{
+    const int off = mc_stage<pixel, TMAX, G>(ref, sx, sy, tw, th, mx, my, sm->src, lane, gmask);
+    mc_filter<pixel, PREP, TMAX, G>(sm->src, off, sm->mid, tw, th, bw, bh, mx, my, filter_2d, bdmax, out, ostride,
+                                    lane, gmask);
 }
 
 // ------------------------------------------------------------ compound combine

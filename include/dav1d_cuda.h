@@ -148,6 +148,10 @@ typedef struct Dav1dCudaPicture {
     Dav1dCudaPlane p[3];
     int32_t bitdepth_max;  /* 0xff, 0x3ff or 0xfff */
     int32_t ss_hor, ss_ver;/* chroma subsampling (4:2:0 = 1,1) */
+    const void *tma;       /* set by dav1d_cuda_picture_alloc: the planes' TMA tensor maps (device memory,
+                            * part of the picture's allocation) - a picture that carries them is staged with
+                            * cp.async.bulk.tensor when it is a reference of the batched MC kernels.
+                            * NULL (pictures described by hand over other memory): cp.async staging */
 } Dav1dCudaPicture;
 
 /* -- inverse transform + add (itxfm_add call sites: recon_tmpl.c:816,1347,1567,2017)
@@ -424,6 +428,14 @@ DAV1D_CUDA_API int  dav1d_cuda_synchronize(Dav1dCudaContext *c);
 DAV1D_CUDA_API int  dav1d_cuda_picture_alloc(Dav1dCudaContext *c, Dav1dCudaPicture *pic,
                                              int w, int h, int ss_hor, int ss_ver, int bitdepth_max);
 DAV1D_CUDA_API void dav1d_cuda_picture_free(Dav1dCudaContext *c, Dav1dCudaPicture *pic);
+/* Staging of the reference windows in the batched 32x32-tile MC kernels (process-wide switch, for
+ * measurements and tests).  With TMA a window is ONE cp.async.bulk.tensor.2d request against the reference's
+ * tensor maps, completing on an mbarrier, into one of two window buffers per warp: the next window is in
+ * flight while the current one is filtered.  mode 0: per-lane cp.async copies everywhere; 1 (default): TMA
+ * for single-reference predictions; 2: TMA for compound predictions too (measured slower than cp.async on
+ * B200: DESIGN.md section 8).  Same pixels in every mode. */
+DAV1D_CUDA_API void dav1d_cuda_set_mc_tma(int mode);
+DAV1D_CUDA_API int  dav1d_cuda_get_mc_tma(void);
 DAV1D_CUDA_API int  dav1d_cuda_picture_upload(Dav1dCudaContext *c, const Dav1dCudaPicture *pic, int plane,
                                               const void *host, ptrdiff_t host_stride);
 DAV1D_CUDA_API int  dav1d_cuda_picture_download(Dav1dCudaContext *c, const Dav1dCudaPicture *pic, int plane,

@@ -13,6 +13,7 @@ import _d1pkg
 
 pkg = _d1pkg.load_pkg()
 from dav1d_mirror_b200 import frame as F  # noqa: E402
+from dav1d_mirror_b200 import binding as B  # noqa: E402
 
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "frame_md5.json")
 
@@ -131,6 +132,47 @@ def test_frame_parity_small(ref, name):
             assert bad.size == 0, (f"{name} tasks={tasks}: plane {pl} first "
                                    f"mismatch at (y,x)={bad[0]} ref={a[tuple(bad[0])]} got={b[tuple(bad[0])]} "
                                    f"n={len(bad)}")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("w,h,bd,seed,kw", [
+    (704, 480, 0x3ff, 901, {"p_intra": 0.1, "mv_range": 48}),
+    (704, 480, 0xff, 902, {"p_intra": 0.1, "mv_range": 48}),
+    (640, 360, 0xfff, 903, {"p_intra": 0.0, "ss_hor": 0, "ss_ver": 0, "p_avg": 0.3, "p_w_avg": 0.2, "p_seg": 0.2}),
+    (328, 200, 0x3ff, 904, {"p_intra": 0.0, "ss_hor": 1, "ss_ver": 0, "mv_range": 400}),
+    (256, 192, 0xff, 905, {"p_intra": 0.0, "no_chroma": 1, "p_obmc": 0.3}),
+])
+def test_mc_window_staging_tma_and_cp_async(ref, w, h, bd, seed, kw):
+    """The 32x32-tile MC kernels stage the reference windows with cp.async.bulk.tensor (pictures from
+    dav1d_cuda_picture_alloc carry tensor maps; windows at the picture border keep the clamped path) - mode 2:
+    all of them, 1 (default): the single-reference ones - or, switched off, with per-lane cp.async: the
+    reference's pixels in every mode, on frames whose windows are mostly interior
+    (short vectors), mostly at the border (long vectors on a small frame) and on odd plane sizes."""
+    L = pkg.lib()
+    hf = F.HostFrame(w, h, bd, seed, **kw)
+    refs, init, want = oracle_planes(ref, hf, seed)
+    assert L.dav1d_cuda_get_mc_tma() == 1
+    try:
+        for on in (2, 1, 0):
+            L.dav1d_cuda_set_mc_tma(on)
+            got = run_gpu(hf, refs, init)
+            for pl, (a, b) in enumerate(zip(want, got)):
+                bad = np.argwhere(a != b)
+                assert bad.size == 0, (f"tma={on} plane {pl}: first mismatch at (y,x)={bad[0]} n={len(bad)}")
+    finally:
+        L.dav1d_cuda_set_mc_tma(1)
+
+
+@pytest.mark.gpu
+def test_allocated_pictures_carry_tensor_maps():
+    L = pkg.lib()
+    ctx = F.open_context(0)
+    pic = B.Picture()
+    assert L.dav1d_cuda_picture_alloc(ctx, C.byref(pic), 320, 200, 1, 1, 0x3ff) == 0
+    assert pic.tma and pic.tma % 128 == 0
+    L.dav1d_cuda_picture_free(ctx, C.byref(pic))
+    assert not pic.tma
+    L.dav1d_cuda_close(ctx)
 
 
 def big_coefs(hf, seed):

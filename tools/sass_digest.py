@@ -9,7 +9,7 @@ import subprocess
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BUILD = os.path.join(ROOT, "dav1d-mirror_b200", "build")
-KERNELS = ["mc_put_kernelItLb0", "mc_put_kernelItLb1", "mc_compound_kernelItLb0", "warp_batch_kernelIt",
+KERNELS = ["mc_put_tma_kernelIt", "mc_compound_tma_kernelIt", "mc_put_kernelItLb0", "mc_put_kernelItLb1", "mc_compound_kernelItLb0", "warp_batch_kernelIt",
            "itx2_task_kernelItLi0", "itx2_task_kernelItLi1", "itx2_task_kernelItLi2",
            "intra_exec_kernelIt", "intra_levels_kernel", "intra_sort_kernelILb0", "intra_scan_kernel",
            "intra_mark_kernel"]
@@ -44,6 +44,7 @@ for obj in sorted(os.listdir(BUILD)):
         print(f"== {name}   ({obj})")
         print(f"   {len(lines)} instructions = {len(lines) * 16 / 1024:.1f} KB")
         print("   " + "  ".join(f"{k}:{v}" for k, v in hist.most_common(22)))
-        for l in list(shown.values())[:28]:
+        first = [l for l in shown.values() if re.search(r"UTMALDG|SYNCS|UBLKCP", l)]
+        for l in (first + [l for l in shown.values() if l not in first])[:28]:
             print("      " + l)
         print()
