@@ -93,8 +93,9 @@ class BlockInter(C.Structure):
                 ("comp_type", C.c_uint8), ("motion_mode", C.c_uint8), ("mvx", C.c_int16 * 2), ("mvy", C.c_int16 * 2),
                 ("ref", C.c_int8 * 2), ("filter2d", C.c_uint8), ("mask_sign", C.c_uint8), ("skip", C.c_uint8),
                 ("max_ytx", C.c_uint8), ("uvtx", C.c_uint8), ("interintra_type", C.c_uint8), ("tx_split", C.c_uint16 * 2),
-                ("interintra_mode", C.c_uint8), ("pad", C.c_uint8 * 3), ("wedge_mask", C.c_void_p * 3),
-                ("ii_mask_off", C.c_uint32 * 3), ("pad2", C.c_uint32)]
+                ("interintra_mode", C.c_uint8), ("warp", C.c_uint8), ("pad", C.c_uint8 * 2), ("wedge_mask", C.c_void_p * 3),
+                ("ii_mask_off", C.c_uint32 * 3), ("pad2", C.c_uint32),
+                ("warp_matrix", C.c_int32 * 6), ("warp_abcd", C.c_int16 * 4)]
 
 
 class InterRecorder(C.Structure):
@@ -107,7 +108,8 @@ class InterRecorder(C.Structure):
                 ("obmc", C.c_void_p * 2), ("n_obmc", C.c_int32 * 2), ("cap_obmc", C.c_int32 * 2),
                 ("scaled", C.c_void_p * 4), ("n_scaled", C.c_int32 * 4), ("cap_scaled", C.c_int32 * 4),
                 ("itx", C.c_void_p), ("n_itx", C.c_int32), ("cap_itx", C.c_int32), ("masks_bytes", C.c_uint32),
-                ("cap_masks", C.c_uint32), ("masks", C.c_void_p), ("intra", C.POINTER(Recorder))]
+                ("cap_masks", C.c_uint32), ("masks", C.c_void_p), ("intra", C.POINTER(Recorder)),
+                ("warp", C.c_void_p), ("n_warp", C.c_int32), ("cap_warp", C.c_int32)]
 
 
 class Plane(C.Structure):

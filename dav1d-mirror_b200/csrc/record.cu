@@ -321,8 +321,10 @@ extern "C" int dav1d_cuda_record_b_inter(Dav1dCudaInterRecorder *r, const Dav1dC
     const int ss_ver = r->layout == 1, ss_hor = has_uv && r->layout != 3;
     const int bx = b->bx4, by = b->by4, bw4 = b->bw4, bh4 = b->bh4;
     const bool has_chroma = has_uv && (bw4 > ss_hor || (bx & 1)) && (bh4 > ss_ver || (by & 1));
-    // not transcribed: warped motion, the 4-MV chroma of sub-8x8 blocks
-    if (b->motion_mode > 1) return -38;
+    // not transcribed: the 4-MV chroma of sub-8x8 blocks
+    if (b->motion_mode > 2 || b->warp > 1) return -22;
+    const bool warp = b->warp != 0;
+    if (warp && (comp || b->motion_mode == 1 || !r->warp)) return -22;
     const bool ii = b->interintra_type != 0, wedge = b->comp_type == 4;
     if (b->interintra_type > 2 || b->interintra_mode > 3 || (ii && (comp || b->motion_mode))) return -22;
     if ((ii || wedge) && (bw4 < 2 || bh4 < 2 || bw4 > 8 || bh4 > 8)) return -22;          // BS_8x8 .. BS_32x32 (wedge.h:37)
@@ -348,6 +350,31 @@ extern "C" int dav1d_cuda_record_b_inter(Dav1dCudaInterRecorder *r, const Dav1dC
         d.x = (uint16_t)((bx * 4) >> sh); d.y = (uint16_t)((by * 4) >> sv);
         d.w = (uint8_t)((bw4 * 4) >> sh); d.h = (uint8_t)((bh4 * 4) >> sv);
         d.src[0] = R.src_of(pl, bx, by, b->ref[0], b->mvx[0], b->mvy[0], b->filter2d);
+        if (!comp && warp && imin(pl ? (bw4 + ss_hor) >> ss_hor : bw4, pl ? (bh4 + ss_ver) >> ss_ver : bh4) > 1) {
+            // warp_affine() (:1134-1193): one warp8x8 per 8x8 of the plane block, positions and fractions from the model
+            if ((d.w | d.h) & 7) { R.err = -22; break; }
+            const int32_t *const mat = b->warp_matrix;
+            for (int y = 0; y < d.h && !R.err; y += 8) {
+                const int src_y = by * 4 + ((y + 4) << sv);
+                const int64_t mat3_y = (int64_t)mat[3] * src_y + mat[0];
+                const int64_t mat5_y = (int64_t)mat[5] * src_y + mat[1];
+                for (int x = 0; x < d.w; x += 8) {
+                    const int src_x = bx * 4 + ((x + 4) << sh);
+                    const int64_t wx = ((int64_t)mat[2] * src_x + mat3_y) >> sh;
+                    const int64_t wy = ((int64_t)mat[4] * src_x + mat5_y) >> sv;
+                    Dav1dCudaWarpDesc *o = R.slot(r->warp, r->n_warp, r->cap_warp);
+                    if (!o) break;
+                    memset(o, 0, sizeof(*o));
+                    o->plane = (uint8_t)pl; o->ref = (uint8_t)b->ref[0];
+                    o->x = (uint16_t)(d.x + x); o->y = (uint16_t)(d.y + y);
+                    o->sx = (int)(wx >> 16) - 4; o->sy = (int)(wy >> 16) - 4;
+                    o->mx = (((int)wx & 0xffff) - b->warp_abcd[0] * 4 - b->warp_abcd[1] * 7) & ~0x3f;
+                    o->my = (((int)wy & 0xffff) - b->warp_abcd[2] * 4 - b->warp_abcd[3] * 4) & ~0x3f;
+                    memcpy(o->abcd, b->warp_abcd, sizeof(o->abcd));
+                }
+            }
+            continue;
+        }
         if (!comp) {                                                           // :1638-1657, 1764-1778
             d.kind = DAV1D_CUDA_MC_PUT;
             R.emit_mc(d, r->put, r->n_put, r->cap_put, 0);

@@ -55,7 +55,15 @@ typedef struct D1SynthParams {
     uint64_t mask_tab;              // real_blocks: address of a D1SynthMaskTab with the decoder's wedge / inter-intra mask
                                     // tables (the tests fill it from the reference's dav1d_masks); 0 = wedge and
                                     // inter-intra blocks are not generated in real-block mode
+    uint64_t warp_tab;              // real_blocks: address of n_warp_tab D1SynthWarp entries - valid local-warp models
+    int32_t n_warp_tab;             // (matrix + the shear parameters the decoder derives from it: the tests make them
+                                    // with the reference's dav1d_get_shear_params); 0 = no warped blocks in real-block mode
 } D1SynthParams;
+// Dav1dWarpedMotionParams as recon_b_inter hands it to warp_affine (t->warpmv of an MM_WARP block)
+typedef struct D1SynthWarp {
+    int32_t matrix[6];
+    int16_t abcd[4];                // alpha, beta, gamma, delta
+} D1SynthWarp;
 
 // Wedge and inter-intra masks per chroma layout (0 = 4:4:4 / luma, 1 = 4:2:2, 2 = 4:2:0) and block size
 // (w4, h4 in {2, 4, 8}: index log2 - 1): byte offsets into `base` (wedge.h WEDGE_MASK / II_MASK).
@@ -89,6 +97,7 @@ typedef struct D1SynthBlock {
     uint8_t  comp_kind;           // enum Dav1dCudaMcKind: PUT / AVG / W_AVG / W_MASK (segmentation mask)
     uint8_t  filter2d, mask_sign, max_ytx, tx_split, jnt_weight;   // tx_split: b->tx_split0 (one level), b->max_ytx
     uint32_t first_tx, n_tx;      // the block's cbi / cf entries in `tx_recs` (consumption order)
+    D1SynthWarp warp;             // comp_kind == 255 (b->motion_mode == MM_WARP): t->warpmv
 } D1SynthBlock;
 // One cbi / cf entry of an inter block: (eob << 5) | txtp and where the coefficients are
 typedef struct D1SynthTx {
@@ -668,6 +677,17 @@ struct Gen {
             if (rng.chance(0.1f)) mvy[i] &= ~7;
         }
         if (is_warp && any_scaled && ref_scaled(ref[0])) is_warp = false;   // allow_warp needs a same-size reference (decode.c:1828)
+        const D1SynthWarp *const WT = (const D1SynthWarp *)(uintptr_t)P.warp_tab;
+        if (is_warp && P.real_blocks && !(WT && P.n_warp_tab > 0)) is_warp = false;
+        D1SynthWarp wm;
+        memset(&wm, 0, sizeof(wm));
+        if (is_warp && P.real_blocks) {
+            // one of the caller's models, translated so that the block lands where its vector points
+            wm = WT[rng.range(P.n_warp_tab)];
+            const int cx = bx4 * 4 + w4 * 2, cy = by4 * 4 + h4 * 2;
+            wm.matrix[0] = mvx[0] * 8192 - (int32_t)(((int64_t)(wm.matrix[2] - 0x10000) * cx + (int64_t)wm.matrix[3] * cy));
+            wm.matrix[1] = mvy[0] * 8192 - (int32_t)(((int64_t)wm.matrix[4] * cx + (int64_t)(wm.matrix[5] - 0x10000) * cy));
+        }
         int weight = rng.irange(1, 15);
         const int sign = rng.range(2);
         if (P.real_blocks) weight = jnt_weight_of(ref[0], ref[1]);    // COMP_INTER_WEIGHTED_AVG takes it from the frame
@@ -703,6 +723,31 @@ struct Gen {
             const int sh = pl ? P.ss_hor : 0, sv = pl ? P.ss_ver : 0;
             const int w = (w4 * 4) >> sh, h = (h4 * 4) >> sv;
             const int x = (bx4 * 4) >> sh, y = (by4 * 4) >> sv;
+            if (is_warp && P.real_blocks) {
+                // warp_affine() (recon_tmpl.c:1134-1193) over the block's 8x8 units of this plane
+                for (int yy = 0; yy < h; yy += 8) {
+                    const int src_y = by4 * 4 + ((yy + 4) << sv);
+                    const int64_t mat3_y = (int64_t)wm.matrix[3] * src_y + wm.matrix[0];
+                    const int64_t mat5_y = (int64_t)wm.matrix[5] * src_y + wm.matrix[1];
+                    for (int xx = 0; xx < w; xx += 8) {
+                        const int src_x = bx4 * 4 + ((xx + 4) << sh);
+                        const int64_t wx = ((int64_t)wm.matrix[2] * src_x + mat3_y) >> sh;
+                        const int64_t wy = ((int64_t)wm.matrix[4] * src_x + mat5_y) >> sv;
+                        Dav1dCudaWarpDesc d;
+                        memset(&d, 0, sizeof(d));
+                        d.plane = (uint8_t)pl; d.ref = (uint8_t)ref[0];
+                        d.x = (uint16_t)(x + xx); d.y = (uint16_t)(y + yy);
+                        d.sx = (int)(wx >> 16) - 4; d.sy = (int)(wy >> 16) - 4;
+                        d.mx = (((int)wx & 0xffff) - wm.abcd[0] * 4 - wm.abcd[1] * 7) & ~0x3f;
+                        d.my = (((int)wy & 0xffff) - wm.abcd[2] * 4 - wm.abcd[3] * 4) & ~0x3f;
+                        memcpy(d.abcd, wm.abcd, sizeof(d.abcd));
+                        order.push_back({ 2, (uint32_t)warp.size() });
+                        warp.push_back(d);
+                    }
+                }
+                add_bytes(2, 2.0 * Bp * w * h);
+                continue;
+            }
             if (is_warp) {
                 // per-8x8 calls of warp_affine() (recon_tmpl.c:1151-1191) with random shear parameters
                 int16_t abcd[4];
@@ -854,6 +899,7 @@ struct Gen {
             rec_inter.n_tx = (uint32_t)tx_recs.size() - rec_inter.first_tx;
             rec_inter.pad[0] = do_obmc ? 1 : 0;                 // b->motion_mode == MM_OBMC
             if (kind == DAV1D_CUDA_MC_MASK) rec_inter.pad[1] = (uint8_t)wedge_idx;   // b->wedge_idx
+            rec_inter.warp = wm;
             blocks.push_back(rec_inter);
             nb_set(bx4, by4, w4, h4, 1, ref[0], mvx[0], mvy[0], filter);
         }
@@ -1002,7 +1048,7 @@ __attribute__((visibility("default"))) void d1synth_default_params(D1SynthParams
     p->p_avg = 0.2f; p->p_w_avg = 0.1f; p->p_wedge = 0.1f; p->p_seg = 0.05f; p->p_warp = 0.05f;
     p->mv_range = 128; p->n_refs = 2; p->edge_filter = 1; p->only_tx = -1; p->only_txtp = -1; p->eob_class = -1; p->dense_coefs = 0; p->p_obmc = 0.f; p->p_ii = 0.f; p->p_ibc = 0.f; p->tile_cols = 1; p->tile_rows = 1; p->real_blocks = 0;
     for (int i = 0; i < 7; i++) p->ref_w[i] = p->ref_h[i] = 0;
-    p->mask_tab = 0;
+    p->mask_tab = 0; p->warp_tab = 0; p->n_warp_tab = 0;
 }
 
 __attribute__((visibility("default"))) int d1synth_generate(const D1SynthParams *p, D1SynthFrame *f) {

@@ -24,7 +24,16 @@ class SynthParams(C.Structure):
                 ("only_tx", C.c_int32), ("only_txtp", C.c_int32), ("eob_class", C.c_int32),
                 ("dense_coefs", C.c_int32), ("p_obmc", C.c_float), ("p_ii", C.c_float), ("p_ibc", C.c_float),
                 ("tile_cols", C.c_int32), ("tile_rows", C.c_int32), ("real_blocks", C.c_int32),
-                ("ref_w", C.c_int32 * 7), ("ref_h", C.c_int32 * 7), ("mask_tab", C.c_uint64)]
+                ("ref_w", C.c_int32 * 7), ("ref_h", C.c_int32 * 7), ("mask_tab", C.c_uint64),
+                ("warp_tab", C.c_uint64), ("n_warp_tab", C.c_int32)]
+
+
+BLOCK_REC_BYTES = 120          # sizeof(D1SynthBlock)
+
+
+class SynthWarp(C.Structure):
+    """D1SynthWarp of csrc/synth.cpp: a local-warp model (Dav1dWarpedMotionParams: matrix + shear parameters)."""
+    _fields_ = [("matrix", C.c_int32 * 6), ("abcd", C.c_int16 * 4)]
 
 
 class SynthMaskTab(C.Structure):
@@ -94,6 +103,9 @@ class HostFrame:
             if k == "mask_tab":                  # a SynthMaskTab (kept alive by the caller)
                 p.mask_tab = C.addressof(v)
                 continue
+            if k == "warp_tab":                  # a ctypes array of SynthWarp (kept alive by the caller)
+                p.warp_tab, p.n_warp_tab = C.addressof(v), len(v)
+                continue
             if k in ("ref_w", "ref_h"):          # luma size per reference, 0 = the frame's
                 for i, x in enumerate(v):
                     getattr(p, k)[i] = x
@@ -139,7 +151,7 @@ class HostFrame:
         self.dense_coef_bytes = f.dense_coef_bytes
         # real_blocks: one record per coded block (the Av1Block fields the reference's driver reads), 88 bytes each
         self.n_block_recs = f.n_block_recs
-        self.blocks = _np_from(f.blocks, f.n_block_recs * 88)
+        self.blocks = _np_from(f.blocks, f.n_block_recs * BLOCK_REC_BYTES)
         self.tx_recs = _np_from(f.tx_recs, f.n_tx_recs * 12)          # cbi / cf entries of the inter blocks
         # intra-class operations stay in decode order; their residuals are listed a second time as
         # transform descriptors ordered like `itx`

@@ -347,8 +347,9 @@ DAV1D_CUDA_API int dav1d_cuda_record_b_intra(Dav1dCudaRecorder *r, const Dav1dCu
  * translational single-reference blocks (optionally with OBMC) and the AVG / WEIGHTED_AVG / SEG compounds,
  * the WEDGE compound, inter-intra blocks (the intra prediction + blend and the block's residuals become
  * intra-class operations appended through `intra`), from references of any size, with their residual
- * transform trees.  Warped / global-motion blocks and the 4-MV chroma of sub-8x8 blocks (:1685-1751) are NOT
- * transcribed yet: the call returns -ENOSYS for them and records nothing. */
+ * transform trees, and warped blocks (local warp and global motion: warp_affine(), :1134-1193, as one
+ * Dav1dCudaWarpDesc per 8x8).  The 4-MV chroma of sub-8x8 blocks (:1685-1751) is NOT transcribed yet: the call
+ * returns -ENOSYS for such a block and records nothing. */
 typedef struct Dav1dCudaNbMv {          /* what obmc() reads of a neighbour (refmvs rows + filter contexts) */
     int16_t mvx, mvy;                   /* r->mv.mv[0] */
     int8_t  ref;                        /* r->ref.ref[0] - 1: reference index, -1 = intra */
@@ -367,7 +368,10 @@ typedef struct Dav1dCudaBlockInter {    /* the Av1Block fields dav1d_recon_b_int
     uint8_t  interintra_type;           /* enum InterIntraType: NONE 0, BLEND 1, WEDGE 2 */
     uint16_t tx_split[2];               /* b->tx_split0, b->tx_split1 */
     uint8_t  interintra_mode;           /* enum InterIntraPredMode: II_DC 0, VERT 1, HOR 2, SMOOTH 3 */
-    uint8_t  pad[3];
+    uint8_t  warp;                      /* 1: the block takes recon_b_inter's warp_affine branch (recon_tmpl.c:1641-1649:
+                                           inter_mode == GLOBALMV && f->gmv_warp_allowed[ref], or motion_mode == MM_WARP &&
+                                           t->warpmv.type > TRANSLATION) with the model in warp_matrix / warp_abcd */
+    uint8_t  pad[2];
     /* COMP_INTER_WEDGE: the block's masks per plane as the driver picks them - luma WEDGE_MASK(0, bs, 0,
      * wedge_idx), chroma WEDGE_MASK(chr_layout_idx, bs, mask_sign, wedge_idx) (recon_tmpl.c:1861-1866; host
      * pointers, w * h bytes of the plane block each): copied into the recorder's mask pool. */
@@ -376,6 +380,10 @@ typedef struct Dav1dCudaBlockInter {    /* the Av1Block fields dav1d_recon_b_int
      * w * h bytes) in the byte pool that also holds the palette indices (Dav1dCudaReconBatch.pal_idx) */
     uint32_t ii_mask_off[3];
     uint32_t pad2;
+    /* warp: the Dav1dWarpedMotionParams handed to warp_affine - t->warpmv or f->frame_hdr->gmv[ref]:
+     * matrix[6] and the shear parameters u.abcd (alpha, beta, gamma, delta) */
+    int32_t  warp_matrix[6];
+    int16_t  warp_abcd[4];
 } Dav1dCudaBlockInter;
 typedef struct Dav1dCudaInterRecorder {
     int32_t bw4, bh4;                   /* f->bw, f->bh */
@@ -401,6 +409,7 @@ typedef struct Dav1dCudaInterRecorder {
     Dav1dCudaRecorder *intra;           /* the frame's intra recorder: inter-intra blocks append their intra-class
                                            operations to its array, in decode order with the intra blocks'
                                            (its tile_* fields must describe the current tile) */
+    Dav1dCudaWarpDesc *warp;   int32_t n_warp, cap_warp;   /* warped blocks: one descriptor per 8x8 and plane */
 } Dav1dCudaInterRecorder;
 /* Appends the block's descriptors; returns how many, or a negative errno (-ENOSPC: an array is full, -EINVAL,
  * -ENOSYS: see above).  On error nothing of the block is kept.  `tx`: the block's cbi / cf entries in

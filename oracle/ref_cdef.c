@@ -29,7 +29,7 @@ typedef struct D1SynthBlock {          /* == dav1d-mirror_b200/csrc/synth.cpp */
     uint16_t bx4, by4;
     uint8_t  w4, h4;
     uint8_t  intra, has_chroma, skip, tile;
-    uint8_t  other[78];
+    uint8_t  other[78 + 32];
 } D1SynthBlock;
 
 typedef struct OracleCdefFrame {
@@ -61,7 +61,7 @@ static uint64_t next_u64(uint64_t *s) {
 }
 
 EXPORT int SUFFIX(oracle_cdef_frame)(OracleCdefFrame *const fr) {
-    _Static_assert(sizeof(D1SynthBlock) == 88, "block record");
+    _Static_assert(sizeof(D1SynthBlock) == 120, "block record");
     Dav1dDSPContext dsp;
     memset(&dsp, 0, sizeof(dsp));
     SUFFIX(dav1d_cdef_dsp_init)(&dsp.cdef);

@@ -51,6 +51,7 @@ typedef struct D1SynthBlock {
     uint8_t  comp_kind;
     uint8_t  filter2d, mask_sign, max_ytx, tx_split, jnt_weight;
     uint32_t first_tx, n_tx;
+    struct { int32_t matrix[6]; int16_t abcd[4]; } warp;
 } D1SynthBlock;
 
 typedef struct OracleLfFrame {

@@ -40,7 +40,7 @@ typedef struct D1SynthBlock {          /* == dav1d-mirror_b200/csrc/synth.cpp */
     uint8_t  tx, uvtx;
     uint8_t  other1[57];
     uint8_t  filter2d, mask_sign, max_ytx, tx_split, jnt_weight;
-    uint8_t  other2[8];
+    uint8_t  other2[8 + 32];
 } D1SynthBlock;
 
 typedef struct OraclePfFrame {
@@ -94,7 +94,7 @@ EXPORT void SUFFIX(oracle_pf_geometry)(OraclePfFrame *const fr) {
 }
 
 EXPORT int SUFFIX(oracle_pf_frame)(OraclePfFrame *const fr) {
-    _Static_assert(sizeof(D1SynthBlock) == 88, "block record");
+    _Static_assert(sizeof(D1SynthBlock) == 120, "block record");
     SUFFIX(oracle_pf_geometry)(fr);
     Dav1dDSPContext dsp;
     memset(&dsp, 0, sizeof(dsp));

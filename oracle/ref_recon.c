@@ -60,6 +60,7 @@ typedef struct D1SynthBlock {
     uint8_t  comp_kind;
     uint8_t  filter2d, mask_sign, max_ytx, tx_split, jnt_weight;
     uint32_t first_tx, n_tx;
+    struct { int32_t matrix[6]; int16_t abcd[4]; } warp;    /* comp_kind == 255: t->warpmv of an MM_WARP block */
 } D1SynthBlock;
 typedef struct D1SynthTx {
     uint32_t coef_off;
@@ -117,8 +118,8 @@ static void dense_coefs(coef *out, const OracleReconFrame *fr, const Dav1dCudaIn
 }
 
 /* Reconstructs every block of the frame through dav1d_recon_b_intra / dav1d_recon_b_inter.  Returns 0, or
- * a negative value when the records hold something this harness does not drive (warped, inter-intra,
- * wedge and intrabc blocks: they need warp parameters / mask tables the records do not carry). */
+ * a negative value when the records hold something this harness does not drive (intrabc blocks, global
+ * motion). */
 EXPORT int SUFFIX(oracle_recon_frame)(const OracleReconFrame *const fr) {
     int ret = 0;
     dav1d_init_ii_wedge_masks();                   /* src/wedge.c: what dav1d_init_once does (lib.c) */
@@ -211,7 +212,7 @@ EXPORT int SUFFIX(oracle_recon_frame)(const OracleReconFrame *const fr) {
     int cur_tile = -1, cur_sbrow = -1;
     for (int i = 0; i < fr->n_blocks; i++) {
         const D1SynthBlock *const s = &fr->blocks[i];
-        if (!s->intra && s->comp_kind > DAV1D_CUDA_MC_W_MASK) { ret = -38; goto done; }   /* warped blocks */
+        if (!s->intra && s->comp_kind > DAV1D_CUDA_MC_W_MASK && s->comp_kind != 255) { ret = -38; goto done; }
         const int sbrow = s->by4 >> f->sb_shift;
         if (s->tile != cur_tile || sbrow != cur_sbrow) {
             if (cur_tile >= 0) {            /* decode.c:2677: end of a tile's superblock row */
@@ -233,12 +234,19 @@ EXPORT int SUFFIX(oracle_recon_frame)(const OracleReconFrame *const fr) {
             Av1Block b;
             memset(&b, 0, sizeof(b));
             b.bs = bs; b.intra = 0; b.skip = s->skip; b.uvtx = s->uvtx;
-            b.comp_type = s->comp_kind == DAV1D_CUDA_MC_PUT ? COMP_INTER_NONE :
+            b.comp_type = s->comp_kind == DAV1D_CUDA_MC_PUT || s->comp_kind == 255 ? COMP_INTER_NONE :
                           s->comp_kind == DAV1D_CUDA_MC_AVG ? COMP_INTER_AVG :
                           s->comp_kind == DAV1D_CUDA_MC_W_AVG ? COMP_INTER_WEIGHTED_AVG :
                           s->comp_kind == DAV1D_CUDA_MC_MASK ? COMP_INTER_WEDGE : COMP_INTER_SEG;
             b.wedge_idx = s->pad[1];
             b.inter_mode = 0; b.motion_mode = s->pad[0] ? MM_OBMC : MM_TRANSLATION;
+            if (s->comp_kind == 255) {      /* local warp: what decode_b() leaves in t->warpmv (decode.c:1828-1860) */
+                b.motion_mode = MM_WARP;
+                memset(&t->warpmv, 0, sizeof(t->warpmv));
+                t->warpmv.type = DAV1D_WM_TYPE_AFFINE;
+                for (int k = 0; k < 6; k++) t->warpmv.matrix[k] = s->warp.matrix[k];
+                for (int k = 0; k < 4; k++) t->warpmv.u.abcd[k] = s->warp.abcd[k];
+            }
             b.interintra_type = s->pad[2] & 3; b.interintra_mode = s->pad[2] >> 2;     /* INTER_INTRA_BLEND / _WEDGE + II_*_PRED */
             for (int r = 0; r < 32 + 5; r++)
                 t->rt.r[r] = rmv + (size_t)((s->by4 & ~31) + r) * rstride;      /* row (by & ~31) - 5 + r, margin 5 */

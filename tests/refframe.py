@@ -101,6 +101,43 @@ def run_reference_driver(ref, hf, dst_planes, ref_planes_list=()):
     return dst_planes
 
 
+_warp_tab = None
+
+
+def reference_warp_tab(ref, n=48, seed=7):
+    """Valid local-warp models for real-block frames (HostFrame(warp_tab=...)): random affine matrices near the
+    identity whose shear parameters are the reference's own (dav1d_get_shear_params, src/warpmv.c:83-106; models
+    it rejects are dropped).  The generator fills in the translation per block."""
+    global _warp_tab
+    if _warp_tab is not None:
+        return _warp_tab
+    from dav1d_mirror_b200 import frame as F
+
+    class WMP(C.Structure):          # Dav1dWarpedMotionParams (include/dav1d/headers.h:85-98)
+        _fields_ = [("type", C.c_int), ("matrix", C.c_int32 * 6), ("abcd", C.c_int16 * 4)]
+    fn = ref.lib.dav1d_get_shear_params
+    fn.argtypes = [C.POINTER(WMP)]
+    fn.restype = C.c_int
+    rng = np.random.default_rng(seed)
+    out = []
+    while len(out) < n:
+        w = WMP()
+        w.type = 3                   # DAV1D_WM_TYPE_AFFINE
+        span = 1 << int(rng.integers(6, 13))
+        m = rng.integers(-span, span + 1, size=4)
+        w.matrix[2], w.matrix[3], w.matrix[4], w.matrix[5] = 0x10000 + int(m[0]), int(m[1]), int(m[2]), 0x10000 + int(m[3])
+        if fn(C.byref(w)):
+            continue
+        e = F.SynthWarp()
+        for k in range(6):
+            e.matrix[k] = w.matrix[k]
+        for k in range(4):
+            e.abcd[k] = w.abcd[k]
+        out.append(e)
+    _warp_tab = (F.SynthWarp * n)(*out)
+    return _warp_tab
+
+
 _mask_tab = None
 
 

@@ -22,7 +22,7 @@ BLK = np.dtype([("bx4", "u2"), ("by4", "u2"), ("w4", "u1"), ("h4", "u1"), ("intr
                 ("pal_idx_off", "u4", 2), ("first_op", "u4"), ("n_ops", "u4"), ("sm_flags", "u1"), ("pad", "u1", 3),
                 ("mvx", "i2", 2), ("mvy", "i2", 2), ("ref", "u1", 2), ("comp_kind", "u1"), ("filter2d", "u1"),
                 ("mask_sign", "u1"), ("max_ytx", "u1"), ("tx_split", "u1"), ("jnt_weight", "u1"), ("first_tx", "u4"),
-                ("n_tx", "u4")])
+                ("n_tx", "u4"), ("warp_matrix", "i4", 6), ("warp_abcd", "i2", 4)])
 OP = np.dtype([("x4", "u2"), ("y4", "u2"), ("tile_x4_start", "u2"), ("tile_y4_start", "u2"), ("tile_x4_end", "u2"),
                ("tile_y4_end", "u2"), ("plane", "u1"), ("tw4", "u1"), ("th4", "u1"), ("mode", "u1"),
                ("angle_delta", "i1"), ("edge_flags", "u1"), ("flags", "u2"), ("eob", "i2"), ("tx", "u1"), ("txtp", "u1"),
@@ -55,7 +55,7 @@ def record_intra_block(L, r, s, ops):
 
 
 def record_frame(hf):
-    assert BLK.itemsize == 88 and OP.itemsize == 40
+    assert BLK.itemsize == 120 and OP.itemsize == 40
     L = pkg.lib()
     blocks = np.frombuffer(hf.blocks.tobytes(), dtype=BLK)
     ops = np.frombuffer(hf.intra.tobytes(), dtype=OP)
@@ -70,7 +70,7 @@ def record_frame(hf):
     return ops, out[:r.n_intra]
 
 
-@pytest.mark.parametrize("name", [n for n in R.CASES if not n.startswith(("inter_", "obmc_", "scaled_", "wedge_", "ii_"))])
+@pytest.mark.parametrize("name", [n for n in R.CASES if not n.startswith(("inter_", "obmc_", "scaled_", "wedge_", "ii_", "warp_"))])
 def test_recorder_emits_the_generators_descriptors(name):
     hf, _ = R.make(name)
     want, got = record_frame(hf)
@@ -131,8 +131,10 @@ ITX = np.dtype([("coef_off", "u4"), ("x", "u2"), ("y", "u2"), ("eob", "i2"), ("p
                 ("cw4", "u1"), ("ch4", "u1"), ("pad", "u1")])
 TXR = np.dtype([("coef_off", "u4"), ("eob", "i2"), ("txtp", "u1"), ("cw4", "u1"), ("ch4", "u1"), ("tx", "u1"),
                 ("plane", "u1"), ("pad", "u1")])
-# generator's compound kind (enum Dav1dCudaMcKind) -> enum CompInterType
-COMP_TYPE = {0: 0, 1: 2, 2: 1, 4: 3}
+WARP = np.dtype([("x", "u2"), ("y", "u2"), ("sx", "i4"), ("sy", "i4"), ("mx", "i4"), ("my", "i4"), ("abcd", "i2", 4),
+                 ("plane", "u1"), ("ref", "u1"), ("pad", "u2")])
+# generator's compound kind (enum Dav1dCudaMcKind; 255 = a warped single-reference block) -> enum CompInterType
+COMP_TYPE = {0: 0, 1: 2, 2: 1, 4: 3, 255: 0}
 
 
 # generator's compound kind 3 (DAV1D_CUDA_MC_MASK on a real-block frame) = COMP_INTER_WEDGE
@@ -144,7 +146,7 @@ def record_inter_frame(hf, mask_tab=None):
     dav1d_cuda_record_b_intra (when the frame has inter-intra blocks, whose intra-class operations interleave
     with theirs in decode order), inter blocks through dav1d_cuda_record_b_inter.  `mask_tab`: the reference's
     wedge / inter-intra tables (refframe.reference_mask_tab) the caller of the recorder picks the masks from."""
-    assert MC.itemsize == 40 and MCS.itemsize == 56 and ITX.itemsize == 16 and TXR.itemsize == 12
+    assert MC.itemsize == 40 and MCS.itemsize == 56 and ITX.itemsize == 16 and TXR.itemsize == 12 and WARP.itemsize == 32
     L = pkg.lib()
     blocks = np.frombuffer(hf.blocks.tobytes(), dtype=BLK)
     txr = np.frombuffer(hf.tx_recs.tobytes(), dtype=TXR)
@@ -183,6 +185,8 @@ def record_inter_frame(hf, mask_tab=None):
     r.itx, r.cap_itx = out["itx"].ctypes.data, cap
     r.masks, r.cap_masks = masks.ctypes.data, len(masks)
     r.intra = C.pointer(ri)
+    warps = np.zeros(cap, dtype=WARP)
+    r.warp, r.cap_warp = warps.ctypes.data, cap
     for s in blocks:
         r.tile_col_start, r.tile_row_start = int(s["tile_rect"][0]), int(s["tile_rect"][1])
         if s["intra"]:
@@ -193,6 +197,12 @@ def record_inter_frame(hf, mask_tab=None):
         b = B.BlockInter()
         b.bx4, b.by4, b.bw4, b.bh4 = int(s["bx4"]), int(s["by4"]), int(s["w4"]), int(s["h4"])
         b.comp_type, b.motion_mode = COMP_TYPE[int(s["comp_kind"])], int(s["pad"][0])
+        if s["comp_kind"] == 255:                                      # MM_WARP with a valid model in t->warpmv
+            b.motion_mode, b.warp = 2, 1
+            for k in range(6):
+                b.warp_matrix[k] = int(s["warp_matrix"][k])
+            for k in range(4):
+                b.warp_abcd[k] = int(s["warp_abcd"][k])
         for k in range(2):
             b.mvx[k], b.mvy[k], b.ref[k] = int(s["mvx"][k]), int(s["mvy"][k]), int(s["ref"][k])
         b.filter2d, b.mask_sign, b.skip = int(s["filter2d"]), int(s["mask_sign"]), int(s["skip"])
@@ -219,7 +229,8 @@ def record_inter_frame(hf, mask_tab=None):
            "comp": np.concatenate([out["comp0"][:r.n_comp[0]], out["comp1"][:r.n_comp[1]]]),
            "obmc": np.concatenate([out["obmc0"][:r.n_obmc[0]], out["obmc1"][:r.n_obmc[1]]]),
            "scaled": np.concatenate([sc[k][:r.n_scaled[k]] for k in range(4)]),
-           "itx": out["itx"][:r.n_itx], "intra": ops_out[:ri.n_intra], "masks": masks[:r.masks_bytes]}
+           "itx": out["itx"][:r.n_itx], "intra": ops_out[:ri.n_intra], "masks": masks[:r.masks_bytes],
+           "warp": warps[:r.n_warp]}
     return got, [r.n_scaled[k] for k in range(4)], r.masks_bytes
 
 
@@ -241,7 +252,7 @@ def _normalise_edge_bits(a):
     return a
 
 
-@pytest.mark.parametrize("name", [n for n in R.CASES if n.startswith(("inter_", "obmc_", "scaled_", "wedge_", "ii_"))])
+@pytest.mark.parametrize("name", [n for n in R.CASES if n.startswith(("inter_", "obmc_", "scaled_", "wedge_", "ii_", "warp_"))])
 def test_inter_recorder_emits_the_generators_descriptors(name):
     """dav1d_cuda_record_b_inter over the Av1Block-style records == the descriptor arrays the generator wrote
     for the same blocks (which reproduce dav1d_recon_b_inter's pixels bit for bit, tests/test_reference_driver.py).
@@ -274,6 +285,7 @@ def test_inter_recorder_emits_the_generators_descriptors(name):
             "itx": np.frombuffer(hf.itx.tobytes(), dtype=ITX)}
     assert tuple(n_scaled) == tuple(hf.n_mc_scaled)
     assert masks_bytes == hf.masks.nbytes
+    assert got["warp"].tobytes() == np.frombuffer(hf.warp.tobytes(), dtype=WARP).tobytes(), name   # decode order
     for key in ("put", "comp", "obmc", "scaled"):
         w, g = want[key].copy(), got[key].copy()
         assert len(w) == len(g), (key, len(w), len(g))
@@ -300,9 +312,9 @@ def test_inter_recorder_refuses_what_it_does_not_transcribe():
     b = B.BlockInter()
     b.bw4 = b.bh4 = 4
     b.skip = 1
-    b.motion_mode = 2                                                  # MM_WARP
-    assert L.dav1d_cuda_record_b_inter(C.byref(r), C.byref(b), None, 0) == -38
-    b.motion_mode, b.interintra_type = 0, 1
+    b.motion_mode, b.warp = 2, 1                                       # MM_WARP without a warp array
+    assert L.dav1d_cuda_record_b_inter(C.byref(r), C.byref(b), None, 0) == -22
+    b.motion_mode, b.warp, b.interintra_type = 0, 0, 1
     assert L.dav1d_cuda_record_b_inter(C.byref(r), C.byref(b), None, 0) == -22    # inter-intra without an intra recorder
     b.interintra_type, b.comp_type = 0, 4                              # COMP_INTER_WEDGE
     assert L.dav1d_cuda_record_b_inter(C.byref(r), C.byref(b), None, 0) == -22    # ... without the block's masks

@@ -70,6 +70,14 @@ CASES = {
     "wedge_ii_obmc_420_8b_long_vectors_ragged": (200, 136, 0xff, 105, {"masks": 1, "p_intra": 0.1, "mv_range": 300, "p_wedge": 0.3,
                                                                        "p_ii": 0.4, "p_obmc": 0.3}),
     "wedge_ii_luma_8b": (256, 256, 0xff, 107, {"masks": 1, "no_chroma": 1, "p_intra": 0.3, "p_wedge": 0.3, "p_ii": 0.5}),
+    # locally warped blocks (MM_WARP): warp_affine() with models whose shear parameters come from the reference's
+    # dav1d_get_shear_params; "warps": the generator is handed those models
+    "warp_420_10b": (320, 256, 0x3ff, 111, {"warps": 1, "p_intra": 0.2, "p_avg": 0.1, "p_warp": 0.6}),
+    "warp_444_8b": (256, 192, 0xff, 112, {"warps": 1, "ss_hor": 0, "ss_ver": 0, "p_intra": 0.1, "p_warp": 0.5, "p_obmc": 0.3}),
+    "warp_422_12b_long_vectors_ragged": (264, 200, 0xfff, 113, {"warps": 1, "ss_hor": 1, "ss_ver": 0, "p_intra": 0.1,
+                                                               "mv_range": 300, "p_warp": 0.6}),
+    "warp_luma_10b_tiles_2x2": (384, 256, 0x3ff, 114, {"warps": 1, "no_chroma": 1, "tile_cols": 2, "tile_rows": 2,
+                                                      "p_intra": 0.3, "p_warp": 0.5}),
     # references of another size: the scaled branch of mc() with f->svc as decode.c:3517-3524 sets it
     "scaled_420_10b_half_and_same": (320, 256, 0x3ff, 51, {"ref_w": [160, 0], "ref_h": [128, 0], "p_intra": 0.2, "p_avg": 0.2,
                                                            "p_w_avg": 0.1, "p_seg": 0.15, "p_obmc": 0.3}),
@@ -89,6 +97,9 @@ def make(name):
     if kw.pop("masks", 0):
         import refdsp
         kw["mask_tab"] = refframe.reference_mask_tab(refdsp.RefDSP())
+    if kw.pop("warps", 0):
+        import refdsp
+        kw["warp_tab"] = refframe.reference_warp_tab(refdsp.RefDSP())
     hf = F.HostFrame(w, h, bd, seed, real_blocks=1, **kw)
     init = F.random_planes(hf, seed * 10 + 5)
     return hf, init
@@ -133,7 +144,9 @@ def test_random_frames_against_the_reference_drivers(ref):
         w, h = int(rng.integers(8, 60)) * 8, int(rng.integers(8, 40)) * 8
         bd = [0xff, 0x3ff, 0xfff][rng.integers(3)]
         kw["p_wedge"] = float(rng.choice([0, 0.3]))
-        hf = F.HostFrame(w, h, bd, 500 + k, real_blocks=1, mask_tab=refframe.reference_mask_tab(ref), **kw)
+        kw["p_warp"] = float(rng.choice([0, 0.3]))
+        hf = F.HostFrame(w, h, bd, 500 + k, real_blocks=1, mask_tab=refframe.reference_mask_tab(ref),
+                         warp_tab=refframe.reference_warp_tab(ref), **kw)
         init = F.random_planes(hf, 9000 + k)
         refs = [F.random_planes(hf, 9100 + 2 * k + j) for j in range(2)]
         want = refframe.run_reference_driver(ref, hf, [p.copy() for p in init], refs)
