@@ -145,6 +145,8 @@ def lib():
     L.dav1d_cuda_synchronize.argtypes = [C.c_void_p]
     L.dav1d_cuda_picture_alloc.argtypes = [C.c_void_p, C.POINTER(Picture)] + [C.c_int] * 5
     L.dav1d_cuda_picture_free.argtypes = [C.c_void_p, C.POINTER(Picture)]
+    L.dav1d_cuda_resize_frame.argtypes = [C.c_void_p, C.POINTER(Picture), C.POINTER(Picture), C.POINTER(C.c_int32),
+                                          C.POINTER(C.c_int32)]
     L.dav1d_cuda_set_mc_tma.argtypes = [C.c_int]
     L.dav1d_cuda_set_mc_tma.restype = None
     L.dav1d_cuda_get_mc_tma.restype = C.c_int

@@ -941,6 +941,85 @@ static void emu_edge_single(const intptr_t bw, const intptr_t bh, const intptr_t
     st.get2d(o_out, ostride, dst, dst_stride, (size_t)bw * sizeof(pixel), (int)bh);
 }
 
+// resize_fn (src/mc.h:110-114, mc_tmpl.c:877-903): horizontal 8-tap upscaling of super-resolution.  The
+// reference walks a row with a running position (mx += dx; src_x += mx >> 14; mx &= 0x3fff); with
+// T = mx0 + x * dx that is filter (T & 0x3fff) >> 8 at source column -1 + (T >> 14): a thread per output pixel.
+struct ResizeArgs {
+    const void *src; int64_t sstride;      // pixels
+    void *dst; int64_t dstride;
+    int dst_w, h, src_w, dx, mx0, bdmax;
+};
+template <typename pixel> __global__ void __launch_bounds__(256) mc_resize_kernel(const ResizeArgs a) {
+    const int x = blockIdx.x * 256 + threadIdx.x;
+    if (x >= a.dst_w) return;
+    const int64_t T = (int64_t)a.mx0 + (int64_t)x * a.dx;       // mx0 = get_upscale_x0() & 0x3fff (decode.c:3582)
+    const int mx = (int)(T & 0x3fff);
+    const int src_x = -1 + (int)(T >> 14);
+    const int8_t *const F = g_resize_filter + (mx >> 8) * 8;
+    int xs[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) xs[k] = iclip(src_x - 3 + k, 0, a.src_w - 1);
+    for (int y = blockIdx.y; y < a.h; y += gridDim.y) {
+        const pixel *s = (const pixel *)a.src + y * a.sstride;
+        int sum = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) sum += F[k] * (int)s[xs[k]];
+        ((pixel *)a.dst)[y * a.dstride + x] = (pixel)clip_px<pixel>((-sum + 64) >> 7, a.bdmax);
+    }
+}
+static int resize_launch(const ResizeArgs &a, const bool hbd, cudaStream_t st) {
+    if (a.dst_w <= 0 || a.h <= 0) return 0;
+    const dim3 grid((unsigned)((a.dst_w + 255) / 256), (unsigned)std::min(a.h, 4096));
+    if (hbd) mc_resize_kernel<uint16_t><<<grid, 256, 0, st>>>(a);
+    else mc_resize_kernel<uint8_t><<<grid, 256, 0, st>>>(a);
+    count_launch();
+    return cuda_ok(cudaGetLastError(), "mc_resize_kernel") ? 0 : -5;
+}
+// super-resolution of a whole picture (dav1d_filter_sbrow_resize over every superblock row,
+// recon_tmpl.c:2104-2137: rows are independent, so the frame is one launch per plane)
+int mc_resize_frame(const PicView &dst, const PicView &src, const int step[2], const int start[2], cudaStream_t st) {
+    for (int pl = 0; pl < 3; pl++) {
+        if (!dst.p[pl].data || !src.p[pl].data) continue;
+        const int px = dst.bdmax > 0xff ? 2 : 1;
+        ResizeArgs a;
+        a.src = src.p[pl].data; a.sstride = src.p[pl].stride / px;
+        a.dst = dst.p[pl].data; a.dstride = dst.p[pl].stride / px;
+        a.dst_w = dst.p[pl].w; a.h = std::min(dst.p[pl].h, src.p[pl].h); a.src_w = src.p[pl].w;
+        a.dx = step[!!pl]; a.mx0 = start[!!pl]; a.bdmax = dst.bdmax;
+        const int r = resize_launch(a, px == 2, st);
+        if (r) return r;
+    }
+    return 0;
+}
+template <typename pixel>
+static void resize_single(pixel *dst, const ptrdiff_t dst_stride, const pixel *src, const ptrdiff_t src_stride,
+                          const int dst_w, const int h, const int src_w, const int dx, const int mx0, const int bdmax)
+{
+    if (dst_w <= 0 || h <= 0 || src_w <= 0) return;
+    const size_t sstride = ((size_t)src_w * sizeof(pixel) + 63) & ~(size_t)63;
+    const size_t ostride = ((size_t)dst_w * sizeof(pixel) + 63) & ~(size_t)63;
+    Staging &sg = staging();
+    std::lock_guard<std::mutex> lk(sg.mu);
+    Stage st(sg);
+    const size_t o_src = st.reserve(sstride * h);
+    const size_t o_out = st.reserve(ostride * h);
+    if (!st.commit()) return;
+    st.put2d(o_src, sstride, src, src_stride, (size_t)src_w * sizeof(pixel), h);
+    if (!st.upload()) return;
+    ResizeArgs a;
+    a.src = st.dev(o_src); a.sstride = (int64_t)(sstride / sizeof(pixel));
+    a.dst = st.dev(o_out); a.dstride = (int64_t)(ostride / sizeof(pixel));
+    a.dst_w = dst_w; a.h = h; a.src_w = src_w; a.dx = dx; a.mx0 = mx0; a.bdmax = bdmax;
+    if (resize_launch(a, sizeof(pixel) == 2, st.stream())) return;
+    if (!st.download(o_out, ostride * h) || !st.sync()) return;
+    st.get2d(o_out, ostride, dst, dst_stride, (size_t)dst_w * sizeof(pixel), h);
+}
+static void resize8(uint8_t *d, ptrdiff_t ds, const uint8_t *s, ptrdiff_t ss, int dst_w, int h, int src_w, int dx, int mx0)
+{ resize_single<uint8_t>(d, ds, s, ss, dst_w, h, src_w, dx, mx0, 0xff); }
+static void resize16(uint16_t *d, ptrdiff_t ds, const uint16_t *s, ptrdiff_t ss, int dst_w, int h, int src_w, int dx, int mx0,
+                     int bitdepth_max)
+{ resize_single<uint16_t>(d, ds, s, ss, dst_w, h, src_w, dx, mx0, bitdepth_max); }
+
 // ---- typed entry points filled into the table
 #define HBD_ARGS , int bitdepth_max
 template <int F> static void put8(uint8_t *d, ptrdiff_t ds, const uint8_t *s, ptrdiff_t ss, int w, int h, int mx, int my)
@@ -1023,7 +1102,7 @@ template <bool HBD> static void fill_mc(Dav1dCudaMCDSPContext *c) {
     c->warp8x8 = HBD ? (void *)warp16 : (void *)warp8;
     c->warp8x8t = HBD ? (void *)warpt16 : (void *)warpt8;
     c->emu_edge = (void *)emu_p<pixel>;
-    // c->resize is left as set by the caller (super-resolution is a post-filter)
+    c->resize = HBD ? (void *)resize16 : (void *)resize8;
 }
 
 }  // namespace d1
@@ -1034,6 +1113,17 @@ extern "C" {
 
 void dav1d_cuda_mc_dsp_init_8bpc(Dav1dCudaMCDSPContext *c) { fill_mc<false>(c); }
 void dav1d_cuda_mc_dsp_init_16bpc(Dav1dCudaMCDSPContext *c) { fill_mc<true>(c); }
+
+int dav1d_cuda_resize_frame(Dav1dCudaContext *c, const Dav1dCudaPicture *dst, const Dav1dCudaPicture *src,
+                            const int32_t resize_step[2], const int32_t resize_start[2])
+{
+    if (!c || !dst || !src || !resize_step || !resize_start) return -22;
+    if (dst->bitdepth_max != src->bitdepth_max || dst->ss_hor != src->ss_hor || dst->ss_ver != src->ss_ver ||
+        dst->p[0].h != src->p[0].h || dst->p[0].data == src->p[0].data) return -22;
+    D1_CHECK(cudaSetDevice(c->device));
+    const int step[2] = { resize_step[0], resize_step[1] }, start[2] = { resize_start[0], resize_start[1] };
+    return mc_resize_frame(pic_view(dst), pic_view(src), step, start, c->stream);
+}
 
 static int mc_batch_common(Dav1dCudaContext *c, const Dav1dCudaPicture *dst,
                            const Dav1dCudaPicture *const refs[7], const Dav1dCudaMcDesc *descs,

@@ -86,7 +86,7 @@ typedef struct Dav1dCudaMCDSPContext {        /* == Dav1dMCDSPContext */
     void *warp8x8;                            /* warp8x8_fn     */
     void *warp8x8t;                           /* warp8x8t_fn    */
     void *emu_edge;                           /* emu_edge_fn    */
-    void *resize;                             /* resize_fn - NOT overridden (super-res is a post-filter) */
+    void *resize;                             /* resize_fn      */
 } Dav1dCudaMCDSPContext;
 
 typedef struct Dav1dCudaInvTxfmDSPContext {   /* == Dav1dInvTxfmDSPContext */
@@ -592,6 +592,13 @@ DAV1D_CUDA_API int dav1d_cuda_mc_tiles(uint32_t desc_index, int w, int h, uint32
 DAV1D_CUDA_API int dav1d_cuda_warp_batch(Dav1dCudaContext *c, const Dav1dCudaPicture *dst,
                                          const Dav1dCudaPicture *const refs[7],
                                          const Dav1dCudaWarpDesc *descs, int n);
+
+/* Super-resolution of a frame on the device: dav1d_filter_sbrow_resize (recon_tmpl.c:2104-2137) over every
+ * superblock row - mc.resize from `src` (the CDEF output, f->cur geometry) into `dst` (f->sr_cur geometry: the
+ * upscaled width, same height), with f->resize_step[] / f->resize_start[] (luma, chroma; decode.c:3576-3583).
+ * Out of place; rows are independent, so the frame is one launch per plane on the context's stream. */
+DAV1D_CUDA_API int dav1d_cuda_resize_frame(Dav1dCudaContext *c, const Dav1dCudaPicture *dst, const Dav1dCudaPicture *src,
+                                           const int32_t resize_step[2], const int32_t resize_start[2]);
 
 /* Intra-class operations are executed by ONE persistent launch per group of frames
  * (csrc/recon2.cu): the recorder hands the descriptors over in decode order and that is all - the

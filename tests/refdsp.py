@@ -34,6 +34,7 @@ def sig_blend(hbd): return [P, SZ, P, I, I, P]
 def sig_blend_dir(hbd): return [P, SZ, P, I, I]
 def sig_warp(hbd): return [P, SZ, P, SZ, P, I, I] + ([I] if hbd else [])
 def sig_emu_edge(hbd): return [C.c_ssize_t] * 6 + [P, SZ, P, SZ]
+def sig_resize(hbd): return [P, SZ, P, SZ, I, I, I, I, I] + ([I] if hbd else [])
 def sig_itx(hbd): return [P, SZ, P, I] + ([I] if hbd else [])
 def sig_ipred(hbd): return [P, SZ, P, I, I, I, I, I] + ([I] if hbd else [])
 def sig_cfl_ac(hbd): return [P, P, SZ, I, I, I, I]
@@ -62,6 +63,7 @@ class DSPTables:
         self.warp8x8 = f(mc.warp8x8, sig_warp)
         self.warp8x8t = f(mc.warp8x8t, sig_warp)
         self.emu_edge = f(mc.emu_edge, sig_emu_edge)
+        self.resize = f(mc.resize, sig_resize)
         self.itxfm_add = [[f(itx.itxfm_add[t][k], sig_itx) for k in range(17)] for t in range(19)]
         self.intra_pred = [f(ipred.intra_pred[i], sig_ipred) for i in range(14)]
         self.cfl_ac = [f(ipred.cfl_ac[i], sig_cfl_ac) for i in range(3)]

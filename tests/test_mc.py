@@ -306,3 +306,91 @@ def test_emu_edge(ref, cuda, hbd):
             h <<= 1
         w <<= 1
     _d1pkg.load_pkg().check_error()
+
+
+def _c_div(a, b):
+    q = abs(a) // abs(b)
+    return q if (a < 0) == (b < 0) else -q
+
+
+def _resize_params(src_w, dst_w):
+    """f->resize_step / f->resize_start as decode.c:3365-3369,3576-3583 compute them."""
+    dx = ((src_w << 14) + (dst_w >> 1)) // dst_w
+    err = dst_w * dx - (src_w << 14)
+    x0 = _c_div(-((dst_w - src_w) << 13) + (dst_w >> 1), dst_w) + 128 - _c_div(err, 2)
+    return dx, x0 & 0x3fff
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("hbd", [False, True])
+def test_resize(ref, cuda, hbd):
+    """mc.resize (mc_tmpl.c:877-903), the sweep of checkasm's check_resize (mc.c:723-771): random source widths
+    16..512, denominators 9..16 (dst_w = w_den * src_w >> 3), 64 rows; plus downscale-free 1:1 and odd strides."""
+    rng = np.random.default_rng(90 + hbd)
+    R, G = ref.bpc[hbd], cuda.bpc[hbd]
+    for it in range(40):
+        bdmax = (0x3ff if rng.integers(2) else 0xfff) if hbd else 0xff
+        w_den = 9 + int(rng.integers(8))
+        src_w = 16 + int(rng.integers(512 - 16 + 1))
+        if it == 0:
+            w_den, src_w = 8, 64                      # 1:1
+        dst_w = w_den * src_w >> 3
+        dx, mx0 = _resize_params(src_w, dst_w)
+        h = 64 if it % 3 else 1 + int(rng.integers(70))
+        sstride = 512 + 8 * int(rng.integers(3))
+        src = rng.integers(0, bdmax + 1, size=(h, sstride)).astype(pdt(hbd))
+        outs = []
+        for T in (R, G):
+            d = np.full((h, 1040), 0x55, dtype=pdt(hbd))
+            args = [d.ctypes.data, 1040 * d.itemsize, src.ctypes.data, sstride * src.itemsize, dst_w, h, src_w, dx, mx0]
+            T.resize(*(args + ([bdmax] if hbd else [])))
+            outs.append(d)
+        assert np.array_equal(outs[0], outs[1]), f"resize src_w={src_w} dst_w={dst_w} dx={dx} mx0={mx0} h={h}"
+    _d1pkg.load_pkg().check_error()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("w,h,ss_hor,ss_ver,bd,den", [(320, 200, 1, 1, 0x3ff, 12), (264, 136, 1, 0, 0xfff, 9),
+                                                     (200, 96, 0, 0, 0xff, 16), (512, 64, 1, 1, 0xff, 11)])
+def test_resize_frame(ref, w, h, ss_hor, ss_ver, bd, den):
+    """dav1d_cuda_resize_frame == mc.resize of the reference over every row of every plane with
+    f->resize_step[] / f->resize_start[] (what dav1d_filter_sbrow_resize, recon_tmpl.c:2104-2137, does one
+    superblock row at a time): a frame of width w upscaled to (w * den + 4) / 8."""
+    import ctypes as C
+    pkg = _d1pkg.load_pkg()
+    from dav1d_mirror_b200 import binding as B
+    from dav1d_mirror_b200 import frame as F
+    L = pkg.lib()
+    hbd = bd > 0xff
+    rng = np.random.default_rng(w * 7 + den)
+    out_w = (w * den + 4) >> 3
+    ctx = F.open_context(0)
+    src, dst = B.Picture(), B.Picture()
+    assert L.dav1d_cuda_picture_alloc(ctx, C.byref(src), w, h, ss_hor, ss_ver, bd) == 0
+    assert L.dav1d_cuda_picture_alloc(ctx, C.byref(dst), out_w, h, ss_hor, ss_ver, bd) == 0
+    in_cw, out_cw = (w + ss_hor) >> ss_hor, (out_w + ss_hor) >> ss_hor
+    step, start = zip(_resize_params(w, out_w), _resize_params(in_cw, out_cw))
+    R = ref.bpc[hbd]
+    want, planes = [], []
+    for pl in range(3):
+        pw, ph = (w, h) if pl == 0 else (in_cw, (h + ss_ver) >> ss_ver)
+        ow = out_w if pl == 0 else out_cw
+        p = rng.integers(0, bd + 1, size=(ph, pw)).astype(pdt(hbd))
+        planes.append(p)
+        assert L.dav1d_cuda_picture_upload(ctx, C.byref(src), pl, p.ctypes.data, p.strides[0]) == 0
+        d = np.zeros((ph, ow), dtype=pdt(hbd))
+        args = [d.ctypes.data, d.strides[0], p.ctypes.data, p.strides[0], ow, ph, pw, step[pl > 0], start[pl > 0]]
+        R.resize(*(args + ([bd] if hbd else [])))
+        want.append(d)
+    st, sa = (C.c_int32 * 2)(*step), (C.c_int32 * 2)(*start)
+    assert L.dav1d_cuda_resize_frame(ctx, C.byref(dst), C.byref(src), st, sa) == 0
+    for pl in range(3):
+        got = np.zeros_like(want[pl])
+        assert L.dav1d_cuda_picture_download(ctx, C.byref(dst), pl, got.ctypes.data, got.strides[0]) == 0
+        L.dav1d_cuda_synchronize(ctx)
+        assert np.array_equal(got, want[pl]), f"plane {pl}"
+    assert L.dav1d_cuda_resize_frame(ctx, C.byref(src), C.byref(src), st, sa) == -22      # in place
+    L.dav1d_cuda_picture_free(ctx, C.byref(src))
+    L.dav1d_cuda_picture_free(ctx, C.byref(dst))
+    L.dav1d_cuda_close(ctx)
+    pkg.check_error()
