@@ -109,7 +109,8 @@ class InterRecorder(C.Structure):
                 ("scaled", C.c_void_p * 4), ("n_scaled", C.c_int32 * 4), ("cap_scaled", C.c_int32 * 4),
                 ("itx", C.c_void_p), ("n_itx", C.c_int32), ("cap_itx", C.c_int32), ("masks_bytes", C.c_uint32),
                 ("cap_masks", C.c_uint32), ("masks", C.c_void_p), ("intra", C.POINTER(Recorder)),
-                ("warp", C.c_void_p), ("n_warp", C.c_int32), ("cap_warp", C.c_int32)]
+                ("warp", C.c_void_p), ("n_warp", C.c_int32), ("cap_warp", C.c_int32),
+                ("intrabc", C.c_int32), ("pad3", C.c_int32)]
 
 
 class Plane(C.Structure):

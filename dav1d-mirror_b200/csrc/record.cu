@@ -326,6 +326,10 @@ extern "C" int dav1d_cuda_record_b_inter(Dav1dCudaInterRecorder *r, const Dav1dC
     const bool warp = b->warp != 0;
     if (warp && (comp || b->motion_mode == 1 || !r->warp)) return -22;
     const bool ii = b->interintra_type != 0, wedge = b->comp_type == 4;
+    // key / intra-only frames: the block is an intrabc block (:1624-1637) - integer-pel vector into the picture
+    // being decoded, bilinear filter, no compound / OBMC / warp / inter-intra (decode.c:1262-1330)
+    const bool ibc = r->intrabc != 0;
+    if (ibc && (comp || ii || warp || b->motion_mode || ((b->mvx[0] | b->mvy[0]) & 7) || !r->intra || !r->intra->intra)) return -22;
     if (b->interintra_type > 2 || b->interintra_mode > 3 || (ii && (comp || b->motion_mode))) return -22;
     if ((ii || wedge) && (bw4 < 2 || bh4 < 2 || bw4 > 8 || bh4 > 8)) return -22;          // BS_8x8 .. BS_32x32 (wedge.h:37)
     if (ii && (!r->intra || !r->intra->intra)) return -22;
@@ -342,7 +346,7 @@ extern "C" int dav1d_cuda_record_b_inter(Dav1dCudaInterRecorder *r, const Dav1dC
     const int lay = !has_uv ? 0 : ss_hor ? (ss_ver ? 2 : 1) : 0;               // w_mask[chr_layout_idx]: 444 0, 422 1, 420 2
     uint32_t seg_off = 0;
 
-    for (int pl = 0; pl < (has_chroma ? 3 : 1); pl++) {
+    for (int pl = 0; pl < (has_chroma && !ibc ? 3 : ibc ? 0 : 1); pl++) {
         const int sh = pl ? ss_hor : 0, sv = pl ? ss_ver : 0;
         Dav1dCudaMcDesc d;
         memset(&d, 0, sizeof(d));
@@ -422,9 +426,21 @@ extern "C" int dav1d_cuda_record_b_inter(Dav1dCudaInterRecorder *r, const Dav1dC
     Rec RI;
     RI.r = r->intra; RI.b = nullptr; RI.tx = tx; RI.n_tx = n_tx; RI.next_tx = 0; RI.err = 0;
     RI.ss_hor = ss_hor; RI.ss_ver = ss_ver;
-    if (ii && !R.err) {
-        static const uint8_t ii_pred[4] = { 0, 1, 2, 9 };                      // DC_PRED, VERT_PRED, HOR_PRED, SMOOTH_PRED
+    if (ibc) {
+        // mc() with &f->sr_cur (:957-1008): position bx * h_mul + (mv >> (3 + ss)), fraction mv & (15 >> !ss) - 0, or
+        // half a chroma pixel for an odd luma vector - as ONE intra-class operation per plane: it reads pixels
+        // earlier operations of this frame write, so it belongs to the wavefront
         for (int pl = 0; pl < (has_chroma ? 3 : 1); pl++) {
+            const int sh = pl ? ss_hor : 0, sv = pl ? ss_ver : 0;
+            const int sx = ((bx & ~sh) * 4 >> sh) + (b->mvx[0] >> (3 + sh)), sy = ((by & ~sv) * 4 >> sv) + (b->mvy[0] >> (3 + sv));
+            const int mx = b->mvx[0] & (15 >> !sh), my = b->mvy[0] & (15 >> !sv);
+            RI.emit(pl, bx >> sh, by >> sv, bw4 >> sh, bh4 >> sv, DAV1D_CUDA_INTRA_IBC, mx, my, 0, false, 0,
+                    (uint32_t)(sx & 0xffff) | ((uint32_t)(sy & 0xffff) << 16), 0);
+        }
+    }
+    if ((ii || ibc) && !R.err) {
+        static const uint8_t ii_pred[4] = { 0, 1, 2, 9 };                      // DC_PRED, VERT_PRED, HOR_PRED, SMOOTH_PRED
+        for (int pl = 0; pl < (!ii ? 0 : has_chroma ? 3 : 1); pl++) {
             const int sh = pl ? ss_hor : 0, sv = pl ? ss_ver : 0;
             RI.emit(pl, bx >> sh, by >> sv, bw4 >> sh, bh4 >> sv, DAV1D_CUDA_INTRA_II, ii_pred[b->interintra_mode], 0, 0, false,
                     0, 0, b->ii_mask_off[pl]);
@@ -438,7 +454,7 @@ extern "C" int dav1d_cuda_record_b_inter(Dav1dCudaInterRecorder *r, const Dav1dC
                 const TxDim sd = tx_dim(ytx);
                 ytw = sd.w >> 2; yth = sd.h >> 2;
             }
-            if (b->tx_split[0] & ~1 || b->tx_split[1]) RI.err = -38;          // deeper / partial splits of an inter-intra block
+            if (b->tx_split[0] & ~1 || b->tx_split[1]) RI.err = -38;          // deeper / partial splits of such a block
             const int w4c = imin(bw4, r->bw4 - bx), h4c = imin(bh4, r->bh4 - by);
             for (int y = 0; y < h4c; y += yth)
                 for (int x = 0; x < w4c; x += ytw) RI.emit(0, bx + x, by + y, ytw, yth, DAV1D_CUDA_INTRA_NONE, 0, 0, 0, true, ytx, 0, 0);
@@ -455,7 +471,7 @@ extern "C" int dav1d_cuda_record_b_inter(Dav1dCudaInterRecorder *r, const Dav1dC
         if (RI.err) R.err = RI.err;
         R.n_emitted += r->intra->n_intra - saved_n_intra;
     }
-    if (!b->skip && !ii) {                                                     // :1951-2033
+    if (!b->skip && !ii && !ibc) {                                             // :1951-2033
         const TxDim yd = tx_dim(b->max_ytx), ud = tx_dim(b->uvtx);
         const int ytw = yd.w >> 2, yth = yd.h >> 2, utw = ud.w >> 2, uth = ud.h >> 2;
         const int cw4 = (w4 + ss_hor) >> ss_hor, ch4 = (h4 + ss_ver) >> ss_ver;

@@ -356,6 +356,33 @@ struct Gen {
         const int syl = tile_y0 * 4 + 2 * rng.range((sb_top - hpx - 2) / 2 + 1);
         const bool half = rng.chance(0.5f);          // odd luma vector components: half-pel chroma
         n_intra_blocks++;
+        // real-block mode: the block record dav1d_recon_b_inter reads for an intrabc block of a key / intra-only
+        // frame (b->intra == 0, integer-pel b->mv[0], FILTER_2D_BILINEAR; decode.c:1262-1330)
+        D1SynthBlock rec;
+        memset(&rec, 0, sizeof(rec));
+        rec.bx4 = (uint16_t)bx4; rec.by4 = (uint16_t)by4; rec.w4 = (uint8_t)w4; rec.h4 = (uint8_t)h4;
+        rec.intra = 0; rec.has_chroma = P.no_chroma ? 0 : 1; rec.skip = 1; rec.tile = (uint8_t)tile_no;
+        rec.tile_x0 = (uint16_t)tile_x0; rec.tile_y0 = (uint16_t)tile_y0;
+        rec.tile_x1 = (uint16_t)std::min(tile_x1, bw4); rec.tile_y1 = (uint16_t)std::min(tile_y1, bh4);
+        rec.comp_kind = 254; rec.filter2d = 9;
+        rec.mvx[0] = (int16_t)((sxl + (half ? 1 : 0) - bx4 * 4) * 8);
+        rec.mvy[0] = (int16_t)((syl + (half ? 1 : 0) - by4 * 4) * 8);
+        rec.first_tx = (uint32_t)tx_recs.size();
+        {
+            int a = std::min(w4, 16), b2 = std::min(h4, 16);
+            rec.max_ytx = (uint8_t)tx_from_dims(a, b2);
+            int ua = std::min(std::max(1, w4 >> P.ss_hor), 8), ub = std::min(std::max(1, h4 >> P.ss_ver), 8);
+            fit_tx(ua, ub);
+            rec.uvtx = (uint8_t)tx_from_dims(ua, ub);
+        }
+        auto rec_tx = [&]() {                             // the cbi / cf entry of the residual-only operation just added
+            if (!P.real_blocks) return;
+            const Dav1dCudaIntraDesc &o = intra.back();
+            D1SynthTx t;
+            memset(&t, 0, sizeof(t));
+            t.coef_off = o.coef_off; t.eob = o.eob; t.txtp = o.txtp; t.cw4 = o.cw4; t.ch4 = o.ch4; t.tx = o.tx; t.plane = o.plane;
+            tx_recs.push_back(t);
+        };
         for (int pl = 0; pl < nplanes(); pl++) {
             const int sh = pl ? P.ss_hor : 0, sv = pl ? P.ss_ver : 0;
             const int lx = sxl + (half ? 1 : 0), ly = syl + (half ? 1 : 0);
@@ -366,20 +393,29 @@ struct Gen {
         }
         if (rng.chance(P.p_residual)) {
             int tw4 = std::min(w4, 16), th4 = std::min(h4, 16);
-            if (rng.chance(P.p_tx_split)) split_tx(tw4, th4);
+            rec.skip = 0;
+            if (rng.chance(P.p_tx_split)) { split_tx(tw4, th4); rec.tx_split = tw4 * th4 < std::min(w4, 16) * std::min(h4, 16); }
             for (int y = 0; y < h4; y += th4)
-                for (int x = 0; x < w4; x += tw4)
+                for (int x = 0; x < w4; x += tw4) {
                     add_intra(0, bx4 + x, by4 + y, tw4, th4, DAV1D_CUDA_INTRA_NONE, 0, 0, true);
+                    rec_tx();
+                }
             if (!P.no_chroma) {
                 const int cw4 = w4 >> P.ss_hor, ch4 = h4 >> P.ss_ver;
                 int utw4 = std::min(cw4, 8), uth4 = std::min(ch4, 8);
                 fit_tx(utw4, uth4);
                 for (int pl = 1; pl <= 2; pl++)
                     for (int y = 0; y < ch4; y += uth4)
-                        for (int x = 0; x < cw4; x += utw4)
+                        for (int x = 0; x < cw4; x += utw4) {
                             add_intra(pl, (bx4 >> P.ss_hor) + x, (by4 >> P.ss_ver) + y, utw4, uth4,
                                       DAV1D_CUDA_INTRA_NONE, 0, 0, true);
+                            rec_tx();
+                        }
             }
+        }
+        if (P.real_blocks) {
+            rec.n_tx = (uint32_t)tx_recs.size() - rec.first_tx;
+            blocks.push_back(rec);
         }
         return true;
     }

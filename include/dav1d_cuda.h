@@ -347,8 +347,8 @@ DAV1D_CUDA_API int dav1d_cuda_record_b_intra(Dav1dCudaRecorder *r, const Dav1dCu
  * translational single-reference blocks (optionally with OBMC) and the AVG / WEIGHTED_AVG / SEG compounds,
  * the WEDGE compound, inter-intra blocks (the intra prediction + blend and the block's residuals become
  * intra-class operations appended through `intra`), from references of any size, with their residual
- * transform trees, and warped blocks (local warp and global motion: warp_affine(), :1134-1193, as one
- * Dav1dCudaWarpDesc per 8x8).  The 4-MV chroma of sub-8x8 blocks (:1685-1751) is NOT transcribed yet: the call
+ * transform trees, warped blocks (local warp and global motion: warp_affine(), :1134-1193, as one
+ * Dav1dCudaWarpDesc per 8x8) and the intrabc blocks of key / intra-only frames.  The 4-MV chroma of sub-8x8 blocks (:1685-1751) is NOT transcribed yet: the call
  * returns -ENOSYS for such a block and records nothing. */
 typedef struct Dav1dCudaNbMv {          /* what obmc() reads of a neighbour (refmvs rows + filter contexts) */
     int16_t mvx, mvy;                   /* r->mv.mv[0] */
@@ -410,6 +410,10 @@ typedef struct Dav1dCudaInterRecorder {
                                            operations to its array, in decode order with the intra blocks'
                                            (its tile_* fields must describe the current tile) */
     Dav1dCudaWarpDesc *warp;   int32_t n_warp, cap_warp;   /* warped blocks: one descriptor per 8x8 and plane */
+    int32_t intrabc;                    /* IS_KEY_OR_INTRA(f->frame_hdr): every block handed to record_b_inter is an
+                                           intrabc block (recon_tmpl.c:1624-1637) - its prediction (bilinear mc() from the
+                                           picture being decoded) and residuals become intra-class operations through `intra` */
+    int32_t pad3;
 } Dav1dCudaInterRecorder;
 /* Appends the block's descriptors; returns how many, or a negative errno (-ENOSPC: an array is full, -EINVAL,
  * -ENOSYS: see above).  On error nothing of the block is kept.  `tx`: the block's cbi / cf entries in

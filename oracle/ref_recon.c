@@ -118,8 +118,7 @@ static void dense_coefs(coef *out, const OracleReconFrame *fr, const Dav1dCudaIn
 }
 
 /* Reconstructs every block of the frame through dav1d_recon_b_intra / dav1d_recon_b_inter.  Returns 0, or
- * a negative value when the records hold something this harness does not drive (intrabc blocks, global
- * motion). */
+ * a negative value when the records hold something this harness does not drive (global motion). */
 EXPORT int SUFFIX(oracle_recon_frame)(const OracleReconFrame *const fr) {
     int ret = 0;
     dav1d_init_ii_wedge_masks();                   /* src/wedge.c: what dav1d_init_once does (lib.c) */
@@ -193,6 +192,8 @@ EXPORT int SUFFIX(oracle_recon_frame)(const OracleReconFrame *const fr) {
     for (int i = 0; i < 7; i++)
         for (int j = 0; j < 7; j++) f->jnt_weights[i][j] = 1 + (i * 7 + j * 3 + 4) % 15;
 
+    /* intrabc predicts from the picture being decoded: mc() is handed &f->sr_cur (recon_tmpl.c:1624-1637) */
+    f->sr_cur.p = f->cur;
     t->f = f;
     t->ts = ts;
     t->frame_thread.pass = 2;
@@ -212,7 +213,8 @@ EXPORT int SUFFIX(oracle_recon_frame)(const OracleReconFrame *const fr) {
     int cur_tile = -1, cur_sbrow = -1;
     for (int i = 0; i < fr->n_blocks; i++) {
         const D1SynthBlock *const s = &fr->blocks[i];
-        if (!s->intra && s->comp_kind > DAV1D_CUDA_MC_W_MASK && s->comp_kind != 255) { ret = -38; goto done; }
+        if (!s->intra && s->comp_kind > DAV1D_CUDA_MC_W_MASK && s->comp_kind < 254) { ret = -38; goto done; }
+        if (!s->intra && s->comp_kind == 254 && (hdr.frame_type & 1)) { ret = -22; goto done; }   /* intrabc: key / intra-only frames (common/frame.h:42) */
         const int sbrow = s->by4 >> f->sb_shift;
         if (s->tile != cur_tile || sbrow != cur_sbrow) {
             if (cur_tile >= 0) {            /* decode.c:2677: end of a tile's superblock row */
@@ -234,7 +236,7 @@ EXPORT int SUFFIX(oracle_recon_frame)(const OracleReconFrame *const fr) {
             Av1Block b;
             memset(&b, 0, sizeof(b));
             b.bs = bs; b.intra = 0; b.skip = s->skip; b.uvtx = s->uvtx;
-            b.comp_type = s->comp_kind == DAV1D_CUDA_MC_PUT || s->comp_kind == 255 ? COMP_INTER_NONE :
+            b.comp_type = s->comp_kind == DAV1D_CUDA_MC_PUT || s->comp_kind >= 254 ? COMP_INTER_NONE :
                           s->comp_kind == DAV1D_CUDA_MC_AVG ? COMP_INTER_AVG :
                           s->comp_kind == DAV1D_CUDA_MC_W_AVG ? COMP_INTER_WEIGHTED_AVG :
                           s->comp_kind == DAV1D_CUDA_MC_MASK ? COMP_INTER_WEDGE : COMP_INTER_SEG;

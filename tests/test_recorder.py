@@ -70,7 +70,7 @@ def record_frame(hf):
     return ops, out[:r.n_intra]
 
 
-@pytest.mark.parametrize("name", [n for n in R.CASES if not n.startswith(("inter_", "obmc_", "scaled_", "wedge_", "ii_", "warp_"))])
+@pytest.mark.parametrize("name", [n for n in R.CASES if not n.startswith(("inter_", "obmc_", "scaled_", "wedge_", "ii_", "warp_", "ibc_"))])
 def test_recorder_emits_the_generators_descriptors(name):
     hf, _ = R.make(name)
     want, got = record_frame(hf)
@@ -134,7 +134,7 @@ TXR = np.dtype([("coef_off", "u4"), ("eob", "i2"), ("txtp", "u1"), ("cw4", "u1")
 WARP = np.dtype([("x", "u2"), ("y", "u2"), ("sx", "i4"), ("sy", "i4"), ("mx", "i4"), ("my", "i4"), ("abcd", "i2", 4),
                  ("plane", "u1"), ("ref", "u1"), ("pad", "u2")])
 # generator's compound kind (enum Dav1dCudaMcKind; 255 = a warped single-reference block) -> enum CompInterType
-COMP_TYPE = {0: 0, 1: 2, 2: 1, 4: 3, 255: 0}
+COMP_TYPE = {0: 0, 1: 2, 2: 1, 4: 3, 255: 0, 254: 0}        # 254: an intrabc block of a key frame
 
 
 # generator's compound kind 3 (DAV1D_CUDA_MC_MASK on a real-block frame) = COMP_INTER_WEDGE
@@ -187,6 +187,7 @@ def record_inter_frame(hf, mask_tab=None):
     r.intra = C.pointer(ri)
     warps = np.zeros(cap, dtype=WARP)
     r.warp, r.cap_warp = warps.ctypes.data, cap
+    r.intrabc = int(np.any((blocks["intra"] == 0) & (blocks["comp_kind"] == 254)))      # IS_KEY_OR_INTRA(f->frame_hdr)
     for s in blocks:
         r.tile_col_start, r.tile_row_start = int(s["tile_rect"][0]), int(s["tile_rect"][1])
         if s["intra"]:
@@ -252,7 +253,7 @@ def _normalise_edge_bits(a):
     return a
 
 
-@pytest.mark.parametrize("name", [n for n in R.CASES if n.startswith(("inter_", "obmc_", "scaled_", "wedge_", "ii_", "warp_"))])
+@pytest.mark.parametrize("name", [n for n in R.CASES if n.startswith(("inter_", "obmc_", "scaled_", "wedge_", "ii_", "warp_", "ibc_"))])
 def test_inter_recorder_emits_the_generators_descriptors(name):
     """dav1d_cuda_record_b_inter over the Av1Block-style records == the descriptor arrays the generator wrote
     for the same blocks (which reproduce dav1d_recon_b_inter's pixels bit for bit, tests/test_reference_driver.py).

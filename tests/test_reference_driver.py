@@ -78,6 +78,13 @@ CASES = {
                                                                "mv_range": 300, "p_warp": 0.6}),
     "warp_luma_10b_tiles_2x2": (384, 256, 0x3ff, 114, {"warps": 1, "no_chroma": 1, "tile_cols": 2, "tile_rows": 2,
                                                       "p_intra": 0.3, "p_warp": 0.5}),
+    # intrabc blocks of key frames: dav1d_recon_b_inter's IS_KEY_OR_INTRA branch, mc() from the picture being decoded
+    # (integer and half-pel chroma vectors, sources past the right frame edge, residual trees)
+    "ibc_420_10b_cfl": (320, 256, 0x3ff, 121, {"p_ibc": 0.4, "p_cfl": 0.3}),
+    "ibc_444_8b": (256, 192, 0xff, 122, {"p_ibc": 0.5, "ss_hor": 0, "ss_ver": 0}),
+    "ibc_422_12b_pal_ragged": (264, 200, 0xfff, 123, {"p_ibc": 0.5, "ss_hor": 1, "ss_ver": 0, "p_palette": 0.1}),
+    "ibc_420_10b_tiles_2x2": (384, 256, 0x3ff, 124, {"p_ibc": 0.5, "tile_cols": 2, "tile_rows": 2}),
+    "ibc_luma_8b": (256, 256, 0xff, 125, {"p_ibc": 0.5, "no_chroma": 1}),
     # references of another size: the scaled branch of mc() with f->svc as decode.c:3517-3524 sets it
     "scaled_420_10b_half_and_same": (320, 256, 0x3ff, 51, {"ref_w": [160, 0], "ref_h": [128, 0], "p_intra": 0.2, "p_avg": 0.2,
                                                            "p_w_avg": 0.1, "p_seg": 0.15, "p_obmc": 0.3}),
