@@ -717,9 +717,12 @@ struct Gen {
         if (is_warp && P.real_blocks && !(WT && P.n_warp_tab > 0)) is_warp = false;
         D1SynthWarp wm;
         memset(&wm, 0, sizeof(wm));
+        int warp_global = 0;
         if (is_warp && P.real_blocks) {
             // one of the caller's models, translated so that the block lands where its vector points
-            wm = WT[rng.range(P.n_warp_tab)];
+            const int wk = rng.range(P.n_warp_tab);
+            wm = WT[wk];
+            warp_global = wk & 1;      // odd entries: coded as GLOBALMV with the model as the reference's global motion
             const int cx = bx4 * 4 + w4 * 2, cy = by4 * 4 + h4 * 2;
             wm.matrix[0] = mvx[0] * 8192 - (int32_t)(((int64_t)(wm.matrix[2] - 0x10000) * cx + (int64_t)wm.matrix[3] * cy));
             wm.matrix[1] = mvy[0] * 8192 - (int32_t)(((int64_t)wm.matrix[4] * cx + (int64_t)(wm.matrix[5] - 0x10000) * cy));
@@ -936,6 +939,7 @@ struct Gen {
             rec_inter.pad[0] = do_obmc ? 1 : 0;                 // b->motion_mode == MM_OBMC
             if (kind == DAV1D_CUDA_MC_MASK) rec_inter.pad[1] = (uint8_t)wedge_idx;   // b->wedge_idx
             rec_inter.warp = wm;
+            if (is_warp) rec_inter.pad[1] = (uint8_t)warp_global;      // 1: inter_mode == GLOBALMV + gmv_warp_allowed, 0: MM_WARP
             blocks.push_back(rec_inter);
             nb_set(bx4, by4, w4, h4, 1, ref[0], mvx[0], mvy[0], filter);
         }

@@ -242,12 +242,27 @@ EXPORT int SUFFIX(oracle_recon_frame)(const OracleReconFrame *const fr) {
                           s->comp_kind == DAV1D_CUDA_MC_MASK ? COMP_INTER_WEDGE : COMP_INTER_SEG;
             b.wedge_idx = s->pad[1];
             b.inter_mode = 0; b.motion_mode = s->pad[0] ? MM_OBMC : MM_TRANSLATION;
-            if (s->comp_kind == 255) {      /* local warp: what decode_b() leaves in t->warpmv (decode.c:1828-1860) */
-                b.motion_mode = MM_WARP;
+            if (s->comp_kind == 255) {
+                /* local warp (pad[1] == 0): what decode_b() leaves in t->warpmv (decode.c:1828-1860); global
+                 * motion (pad[1] == 1): a GLOBALMV block whose reference carries the model in the frame header
+                 * (recon_tmpl.c:1641-1649; the header's model is set right before the call - the records give
+                 * every block its own) */
+                Dav1dWarpedMotionParams wm;
+                memset(&wm, 0, sizeof(wm));
+                wm.type = DAV1D_WM_TYPE_AFFINE;
+                for (int k = 0; k < 6; k++) wm.matrix[k] = s->warp.matrix[k];
+                for (int k = 0; k < 4; k++) wm.u.abcd[k] = s->warp.abcd[k];
                 memset(&t->warpmv, 0, sizeof(t->warpmv));
-                t->warpmv.type = DAV1D_WM_TYPE_AFFINE;
-                for (int k = 0; k < 6; k++) t->warpmv.matrix[k] = s->warp.matrix[k];
-                for (int k = 0; k < 4; k++) t->warpmv.u.abcd[k] = s->warp.abcd[k];
+                memset(f->gmv_warp_allowed, 0, sizeof(f->gmv_warp_allowed));
+                b.wedge_idx = 0;
+                if (s->pad[1]) {
+                    b.inter_mode = GLOBALMV;
+                    hdr.gmv[s->ref[0]] = wm;
+                    f->gmv_warp_allowed[s->ref[0]] = 1;
+                } else {
+                    b.motion_mode = MM_WARP;
+                    t->warpmv = wm;
+                }
             }
             b.interintra_type = s->pad[2] & 3; b.interintra_mode = s->pad[2] >> 2;     /* INTER_INTRA_BLEND / _WEDGE + II_*_PRED */
             for (int r = 0; r < 32 + 5; r++)
