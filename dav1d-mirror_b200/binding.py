@@ -110,7 +110,7 @@ class InterRecorder(C.Structure):
                 ("itx", C.c_void_p), ("n_itx", C.c_int32), ("cap_itx", C.c_int32), ("masks_bytes", C.c_uint32),
                 ("cap_masks", C.c_uint32), ("masks", C.c_void_p), ("intra", C.POINTER(Recorder)),
                 ("warp", C.c_void_p), ("n_warp", C.c_int32), ("cap_warp", C.c_int32),
-                ("intrabc", C.c_int32), ("pad3", C.c_int32)]
+                ("intrabc", C.c_int32), ("pad3", C.c_int32), ("sub8", NbMv * 4), ("sub8_x", C.c_int32), ("sub8_y", C.c_int32)]
 
 
 class Plane(C.Structure):

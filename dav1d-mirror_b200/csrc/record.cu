@@ -295,6 +295,16 @@ struct RecInter {
 void nb_splat(Dav1dCudaInterRecorder *r, const int bx, const int by, const int bw4, const int bh4, const Dav1dCudaNbMv &n) {
     for (int x = bx; x < imin(bx + bw4, r->bw4); x++) r->above[x] = n;
     for (int y = by; y < imin(by + bh4, r->bh4); y++) r->left[y] = n;
+    // the 4x4 cells of the block's 8x8 (the sub8x8 chroma of a later block of the same 8x8 reads them)
+    if (r->sub8_x != (bx & ~1) || r->sub8_y != (by & ~1)) {
+        r->sub8_x = bx & ~1; r->sub8_y = by & ~1;
+        Dav1dCudaNbMv none;
+        memset(&none, 0, sizeof(none));
+        none.ref = -1;
+        for (int k = 0; k < 4; k++) r->sub8[k] = none;
+    }
+    for (int y = by & 1; y < imin((by & 1) + bh4, 2); y++)
+        for (int x = bx & 1; x < imin((bx & 1) + bw4, 2); x++) r->sub8[y * 2 + x] = n;
 }
 
 }  // namespace
@@ -334,7 +344,10 @@ extern "C" int dav1d_cuda_record_b_inter(Dav1dCudaInterRecorder *r, const Dav1dC
     if ((ii || wedge) && (bw4 < 2 || bh4 < 2 || bw4 > 8 || bh4 > 8)) return -22;          // BS_8x8 .. BS_32x32 (wedge.h:37)
     if (ii && (!r->intra || !r->intra->intra)) return -22;
     if (wedge && (!r->masks || !b->wedge_mask[0] || (has_chroma && (!b->wedge_mask[1] || !b->wedge_mask[2])))) return -22;
-    if (has_chroma && (bw4 == ss_hor || bh4 == ss_ver)) return -38;
+    // chroma of a 4-px-wide / -high block: predicted part by part with the partners' vectors when they are inter
+    // blocks (:1685-1751), else as one block with this block's vector from the 8x8's origin (:1764-1769)
+    const bool narrow = has_chroma && (bw4 == ss_hor || bh4 == ss_ver);
+    if (narrow && (ibc || comp || warp || ii || b->motion_mode)) return ibc ? -38 : -22;
     if (b->motion_mode == 1 && (comp || (bx & 1) || (by & 1))) return -22;     // obmc(): assert(!(t->bx & 1) && !(t->by & 1))
 
     RecInter R;
@@ -376,6 +389,38 @@ extern "C" int dav1d_cuda_record_b_inter(Dav1dCudaInterRecorder *r, const Dav1dC
                     o->my = (((int)wy & 0xffff) - b->warp_abcd[2] * 4 - b->warp_abcd[3] * 4) & ~0x3f;
                     memcpy(o->abcd, b->warp_abcd, sizeof(o->abcd));
                 }
+            }
+            continue;
+        }
+        if (!comp && pl && narrow) {
+            if (pl == 2) continue;                                             // both chroma planes are emitted at pl == 1
+            const Dav1dCudaNbMv &L = r->sub8[(by & 1) * 2], &T = r->sub8[bx & 1], &TL = r->sub8[0];
+            bool sub = r->sub8_x == (bx & ~1) && r->sub8_y == (by & ~1);
+            if (bw4 == 1) sub = sub && L.ref >= 0;
+            if (bh4 == ss_ver) sub = sub && T.ref >= 0;
+            if (bw4 == 1 && bh4 == ss_ver) sub = sub && TL.ref >= 0;
+            const int cx0 = ((bx & ~ss_hor) * 4) >> ss_hor, cy0 = ((by & ~ss_ver) * 4) >> ss_ver;
+            auto part = [&](const int nbx, const int nby, const int ref, const int mvx, const int mvy, const int filter,
+                            const int ox, const int oy, const int w, const int h) {
+                for (int p2 = 1; p2 <= 2; p2++) {
+                    Dav1dCudaMcDesc c;
+                    memset(&c, 0, sizeof(c));
+                    c.plane = (uint8_t)p2; c.kind = DAV1D_CUDA_MC_PUT;
+                    c.x = (uint16_t)(cx0 + ox); c.y = (uint16_t)(cy0 + oy); c.w = (uint8_t)w; c.h = (uint8_t)h;
+                    c.src[0] = R.src_of(p2, nbx, nby, ref, mvx, mvy, filter);
+                    R.emit_mc(c, r->put, r->n_put, r->cap_put, 0);
+                }
+            };
+            if (sub) {
+                const int cw = (bw4 * 4) >> ss_hor, ch = (bh4 * 4) >> ss_ver;
+                int h_off = 0, v_off = 0;
+                if (bw4 == 1 && bh4 == ss_ver) { part(bx - 1, by - 1, TL.ref, TL.mvx, TL.mvy, TL.filter2d, 0, 0, cw, ch); v_off = 2; h_off = 2; }
+                if (bw4 == 1) { part(bx - 1, by, L.ref, L.mvx, L.mvy, L.filter2d, 0, v_off, cw, ch); h_off = 2; }
+                if (bh4 == ss_ver) { part(bx, by - 1, T.ref, T.mvx, T.mvy, T.filter2d, h_off, 0, cw, ch); v_off = 2; }
+                part(bx, by, b->ref[0], b->mvx[0], b->mvy[0], b->filter2d, h_off, v_off, cw, ch);
+            } else {
+                part(bx & ~ss_hor, by & ~ss_ver, b->ref[0], b->mvx[0], b->mvy[0], b->filter2d, 0, 0,
+                     ((bw4 << (bw4 == ss_hor)) * 4) >> ss_hor, ((bh4 << (bh4 == ss_ver)) * 4) >> ss_ver);
             }
             continue;
         }

@@ -58,6 +58,9 @@ typedef struct D1SynthParams {
     uint64_t warp_tab;              // real_blocks: address of n_warp_tab D1SynthWarp entries - valid local-warp models
     int32_t n_warp_tab;             // (matrix + the shear parameters the decoder derives from it: the tests make them
                                     // with the reference's dav1d_get_shear_params); 0 = no warped blocks in real-block mode
+    float p_sub8x8;                 // real_blocks, 4:2:0: share of the 8x8 partitions split into 8x4 / 4x8 / 4x4 blocks
+                                    // (the chroma of such inter blocks is predicted with the vectors of up to three
+                                    // neighbours, recon_tmpl.c:1683-1751)
 } D1SynthParams;
 // Dav1dWarpedMotionParams as recon_b_inter hands it to warp_affine (t->warpmv of an MM_WARP block)
 typedef struct D1SynthWarp {
@@ -942,6 +945,7 @@ struct Gen {
             if (is_warp) rec_inter.pad[1] = (uint8_t)warp_global;      // 1: inter_mode == GLOBALMV + gmv_warp_allowed, 0: MM_WARP
             blocks.push_back(rec_inter);
             nb_set(bx4, by4, w4, h4, 1, ref[0], mvx[0], mvy[0], filter);
+            grid_set(bx4, by4, w4, h4, Nb{ 1, (uint8_t)ref[0], (uint8_t)filter, (uint8_t)w4, (uint8_t)h4, (int16_t)mvx[0], (int16_t)mvy[0] });
         }
         for (int pl = 0; pl < nplanes(); pl++) {
             const int sh = pl ? P.ss_hor : 0, sv = pl ? P.ss_ver : 0;
@@ -954,9 +958,10 @@ struct Gen {
         luma_px += 16.0 * w4 * h4;
         if (rng.chance(P.p_intra)) {
             intra_block(bx4, by4, w4, h4);
-            if (P.real_blocks) nb_set(bx4, by4, w4, h4, 0, 0, 0, 0, 0);
+            if (P.real_blocks) { nb_set(bx4, by4, w4, h4, 0, 0, 0, 0, 0); grid_set(bx4, by4, w4, h4, Nb{ 0, 0, 0, (uint8_t)w4, (uint8_t)h4, 0, 0 }); }
         } else {
-            inter_block(bx4, by4, w4, h4);
+            if (P.real_blocks && (w4 == 1 || h4 == 1)) inter_block_sub8x8(bx4, by4, w4, h4);
+            else inter_block(bx4, by4, w4, h4);
             if (P.real_blocks) {            // decode.c:810-830: intra = 0, uvmode = DC_PRED
                 const bool hc = (w4 > P.ss_hor || (bx4 & 1)) && (h4 > P.ss_ver || (by4 & 1));
                 ctx_set(bx4, by4, w4, h4, 0, 0, hc, 0);
@@ -969,8 +974,10 @@ struct Gen {
         if (bx4 >= bw4 || by4 >= bh4) return;
         const bool fits = bx4 + s4 <= bw4 && by4 + s4 <= bh4;
         int choice;   // 0 NONE 1 H 2 V 3 SPLIT 4 H4 5 V4
-        if (!fits) choice = 3;
-        else if (s4 == 2) choice = 0;
+        const bool sub_ok = P.real_blocks && P.p_sub8x8 > 0.f && P.ss_hor && P.ss_ver && !P.no_chroma;
+        if (s4 <= 1) choice = 0;
+        else if (!fits) choice = 3;
+        else if (s4 == 2) choice = (sub_ok && rng.chance(P.p_sub8x8)) ? 1 + rng.range(3) : 0;
         else {
             const int r = rng.range(100);
             if (s4 == 16) choice = r < 8 ? 0 : r < 16 ? 1 : r < 24 ? 2 : r < 28 ? 4 : r < 32 ? 5 : 3;
@@ -1031,6 +1038,85 @@ struct Gen {
     // what the refmvs rows and the filter contexts tell obmc() about the block above a column / left of a row
     struct Nb { uint8_t inter, ref, filter, w4, h4; int16_t mvx, mvy; };
     std::vector<Nb> nb_above, nb_left;
+    std::vector<Nb> nb_grid;            // per 4x4 of the frame: what the refmvs rows / f->frame_thread.b hold (sub8x8 chroma)
+    void grid_set(int bx4, int by4, int w4, int h4, const Nb &n) {
+        if (nb_grid.empty()) return;
+        for (int y = by4; y < std::min(by4 + h4, bh4); y++)
+            for (int x = bx4; x < std::min(bx4 + w4, bw4); x++) nb_grid[(size_t)y * bw4 + x] = n;
+    }
+
+    // A 4-px-wide and / or 4-px-high inter block of a 4:2:0 frame (recon_tmpl.c:1638-1657 luma, :1683-1751 chroma):
+    // single reference, translation.  The block at the odd position of its 8x8 carries the chroma of the whole
+    // 8x8: when the other blocks of the 8x8 it looks at are inter blocks too, every 2x2 / 2x4 / 4x2 chroma part is
+    // predicted with the vector, reference and filter of the luma block above it; otherwise the whole 4x4 chroma
+    // block with this block's vector.
+    void inter_block_sub8x8(int bx4, int by4, int w4, int h4) {
+        const int R = P.mv_range * 8;
+        const int filter = rng.range(10), ref = rng.range(P.n_refs);
+        int mvx = rng.irange(-R, R), mvy = rng.irange(-R, R);
+        if (rng.chance(0.1f)) mvx &= ~7;
+        if (rng.chance(0.1f)) mvy &= ~7;
+        const bool hc = (w4 > 1 || (bx4 & 1)) && (h4 > 1 || (by4 & 1));
+        D1SynthBlock rec;
+        memset(&rec, 0, sizeof(rec));
+        rec.bx4 = (uint16_t)bx4; rec.by4 = (uint16_t)by4; rec.w4 = (uint8_t)w4; rec.h4 = (uint8_t)h4;
+        rec.intra = 0; rec.has_chroma = hc ? 1 : 0; rec.skip = 1; rec.tile = (uint8_t)tile_no;
+        rec.tile_x0 = (uint16_t)tile_x0; rec.tile_y0 = (uint16_t)tile_y0;
+        rec.tile_x1 = (uint16_t)std::min(tile_x1, bw4); rec.tile_y1 = (uint16_t)std::min(tile_y1, bh4);
+        rec.mvx[0] = (int16_t)mvx; rec.mvy[0] = (int16_t)mvy; rec.ref[0] = (uint8_t)ref;
+        rec.comp_kind = DAV1D_CUDA_MC_PUT; rec.filter2d = (uint8_t)filter;
+        rec.max_ytx = (uint8_t)tx_from_dims(w4, h4); rec.uvtx = 0;          // TX_4X4 chroma
+        rec.first_tx = (uint32_t)tx_recs.size();
+        auto put_desc = [&](int pl, int x, int y, int w, int h, const Dav1dCudaMcSrc &src) {
+            Dav1dCudaMcDesc d;
+            memset(&d, 0, sizeof(d));
+            d.x = (uint16_t)x; d.y = (uint16_t)y; d.w = (uint8_t)w; d.h = (uint8_t)h;
+            d.plane = (uint8_t)pl; d.kind = DAV1D_CUDA_MC_PUT;
+            d.src[0] = src;
+            add_bytes(0, 2.0 * Bp * w * h);
+            if (!route_scaled(d, 0)) { order.push_back({ 0, (uint32_t)put.size() }); put.push_back(d); }
+        };
+        put_desc(0, bx4 * 4, by4 * 4, w4 * 4, h4 * 4, make_src(0, bx4, by4, ref, mvx, mvy, filter));
+        if (hc) {
+            const Nb own = { 1, (uint8_t)ref, (uint8_t)filter, (uint8_t)w4, (uint8_t)h4, (int16_t)mvx, (int16_t)mvy };
+            auto at = [&](int x, int y) -> const Nb & { return nb_grid[(size_t)y * bw4 + x]; };
+            bool sub = true;
+            if (w4 == 1) sub = sub && at(bx4 - 1, by4).inter;
+            if (h4 == 1) sub = sub && at(bx4, by4 - 1).inter;
+            if (w4 == 1 && h4 == 1) sub = sub && at(bx4 - 1, by4 - 1).inter;
+            const int cx0 = (bx4 >> 1) * 4, cy0 = (by4 >> 1) * 4, cw = w4 * 2, ch = h4 * 2;
+            if (sub) {
+                int h_off = 0, v_off = 0;
+                auto part = [&](int nbx, int nby, const Nb &n, int ox, int oy) {
+                    for (int pl = 1; pl <= 2; pl++)
+                        put_desc(pl, cx0 + ox, cy0 + oy, cw, ch, make_src(pl, nbx, nby, n.ref, n.mvx, n.mvy, n.filter));
+                };
+                if (w4 == 1 && h4 == 1) { part(bx4 - 1, by4 - 1, at(bx4 - 1, by4 - 1), 0, 0); v_off = 2; h_off = 2; }
+                if (w4 == 1) { part(bx4 - 1, by4, at(bx4 - 1, by4), 0, v_off); h_off = 2; }
+                if (h4 == 1) { part(bx4, by4 - 1, at(bx4, by4 - 1), h_off, 0); v_off = 2; }
+                part(bx4, by4, own, h_off, v_off);
+            } else {
+                for (int pl = 1; pl <= 2; pl++)
+                    put_desc(pl, cx0, cy0, 4, 4, make_src(pl, bx4 & ~1, by4 & ~1, ref, mvx, mvy, filter));
+            }
+        }
+        if (rng.chance(P.p_residual)) {
+            int tw4 = w4, th4 = h4;
+            rec.skip = 0;
+            if (tw4 != th4 && rng.chance(P.p_tx_split)) { split_tx(tw4, th4); rec.tx_split = 1; }
+            const int tx = tx_from_dims(tw4, th4);
+            for (int y = 0; y < h4; y += th4)
+                for (int x = 0; x < w4; x += tw4) add_itx(0, bx4 + x, by4 + y, tx);
+            if (hc)
+                for (int pl = 1; pl <= 2; pl++) add_itx(pl, bx4 >> 1, by4 >> 1, 0);
+        }
+        rec.n_tx = (uint32_t)tx_recs.size() - rec.first_tx;
+        blocks.push_back(rec);
+        nb_set(bx4, by4, w4, h4, 1, ref, mvx, mvy, filter);
+        grid_set(bx4, by4, w4, h4, Nb{ 1, (uint8_t)ref, (uint8_t)filter, (uint8_t)w4, (uint8_t)h4, (int16_t)mvx, (int16_t)mvy });
+        mark(0, bx4, by4, w4, h4);
+        if (hc) { mark(1, bx4 >> 1, by4 >> 1, 1, 1); mark(2, bx4 >> 1, by4 >> 1, 1, 1); }
+    }
     void nb_set(int bx4, int by4, int w4, int h4, int inter, int ref, int mvx, int mvy, int filter) {
         const Nb n = { (uint8_t)inter, (uint8_t)ref, (uint8_t)filter, (uint8_t)w4, (uint8_t)h4, (int16_t)mvx, (int16_t)mvy };
         for (int x = bx4; x < std::min(bx4 + w4, bw4); x++) nb_above[x] = n;
@@ -1043,6 +1129,7 @@ struct Gen {
         a_intra.assign(bw4 + 1, 0); a_mode.assign(bw4 + 1, 0); a_uvmode.assign(bw4 + 1, 0);
         l_intra.assign(bh4 + 1, 0); l_mode.assign(bh4 + 1, 0); l_uvmode.assign(bh4 + 1, 0);
         nb_above.assign(bw4 + 2, Nb{ 0, 0, 0, 1, 1, 0, 0 }); nb_left.assign(bh4 + 2, Nb{ 0, 0, 0, 1, 1, 0, 0 });
+        if (P.real_blocks && P.p_sub8x8 > 0.f) nb_grid.assign((size_t)bw4 * bh4, Nb{ 0, 0, 0, 1, 1, 0, 0 });
     }
     void ctx_reset_above() {
         for (int x = tile_x0; x < std::min(tile_x1, bw4); x++) { a_intra[x] = 0; a_mode[x] = 0; }
@@ -1088,7 +1175,7 @@ __attribute__((visibility("default"))) void d1synth_default_params(D1SynthParams
     p->p_avg = 0.2f; p->p_w_avg = 0.1f; p->p_wedge = 0.1f; p->p_seg = 0.05f; p->p_warp = 0.05f;
     p->mv_range = 128; p->n_refs = 2; p->edge_filter = 1; p->only_tx = -1; p->only_txtp = -1; p->eob_class = -1; p->dense_coefs = 0; p->p_obmc = 0.f; p->p_ii = 0.f; p->p_ibc = 0.f; p->tile_cols = 1; p->tile_rows = 1; p->real_blocks = 0;
     for (int i = 0; i < 7; i++) p->ref_w[i] = p->ref_h[i] = 0;
-    p->mask_tab = 0; p->warp_tab = 0; p->n_warp_tab = 0;
+    p->mask_tab = 0; p->warp_tab = 0; p->n_warp_tab = 0; p->p_sub8x8 = 0.f;
 }
 
 __attribute__((visibility("default"))) int d1synth_generate(const D1SynthParams *p, D1SynthFrame *f) {

@@ -25,7 +25,7 @@ class SynthParams(C.Structure):
                 ("dense_coefs", C.c_int32), ("p_obmc", C.c_float), ("p_ii", C.c_float), ("p_ibc", C.c_float),
                 ("tile_cols", C.c_int32), ("tile_rows", C.c_int32), ("real_blocks", C.c_int32),
                 ("ref_w", C.c_int32 * 7), ("ref_h", C.c_int32 * 7), ("mask_tab", C.c_uint64),
-                ("warp_tab", C.c_uint64), ("n_warp_tab", C.c_int32)]
+                ("warp_tab", C.c_uint64), ("n_warp_tab", C.c_int32), ("p_sub8x8", C.c_float)]
 
 
 BLOCK_REC_BYTES = 120          # sizeof(D1SynthBlock)

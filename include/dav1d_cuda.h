@@ -348,8 +348,9 @@ DAV1D_CUDA_API int dav1d_cuda_record_b_intra(Dav1dCudaRecorder *r, const Dav1dCu
  * the WEDGE compound, inter-intra blocks (the intra prediction + blend and the block's residuals become
  * intra-class operations appended through `intra`), from references of any size, with their residual
  * transform trees, warped blocks (local warp and global motion: warp_affine(), :1134-1193, as one
- * Dav1dCudaWarpDesc per 8x8) and the intrabc blocks of key / intra-only frames.  The 4-MV chroma of sub-8x8 blocks (:1685-1751) is NOT transcribed yet: the call
- * returns -ENOSYS for such a block and records nothing. */
+ * Dav1dCudaWarpDesc per 8x8), the intrabc blocks of key / intra-only frames and the chroma of 4xN / Nx4 blocks
+ * (:1685-1751: up to four predictions with the partners' vectors).  An intrabc block that narrow (its chroma spans
+ * two luma blocks) is the one case not transcribed: -ENOSYS, nothing recorded. */
 typedef struct Dav1dCudaNbMv {          /* what obmc() reads of a neighbour (refmvs rows + filter contexts) */
     int16_t mvx, mvy;                   /* r->mv.mv[0] */
     int8_t  ref;                        /* r->ref.ref[0] - 1: reference index, -1 = intra */
@@ -414,6 +415,11 @@ typedef struct Dav1dCudaInterRecorder {
                                            intrabc block (recon_tmpl.c:1624-1637) - its prediction (bilinear mc() from the
                                            picture being decoded) and residuals become intra-class operations through `intra` */
     int32_t pad3;
+    /* the blocks of the 8x8 being decoded, per 4x4 (index (y & 1) * 2 + (x & 1)): what the refmvs rows and
+     * f->frame_thread.b still hold of the left / top / top-left partner when the chroma of a 4xN / Nx4 block is
+     * predicted (recon_tmpl.c:1685-1751) - kept by the recorder itself, zero-initialised by the caller */
+    Dav1dCudaNbMv sub8[4];
+    int32_t sub8_x, sub8_y;             /* origin of that 8x8 (4-px units) */
 } Dav1dCudaInterRecorder;
 /* Appends the block's descriptors; returns how many, or a negative errno (-ENOSPC: an array is full, -EINVAL,
  * -ENOSYS: see above).  On error nothing of the block is kept.  `tx`: the block's cbi / cf entries in

@@ -203,12 +203,16 @@ EXPORT int SUFFIX(oracle_recon_frame)(const OracleReconFrame *const fr) {
     const int rstride = f->b4_stride + 32;
     refmvs_block *const rmv = calloc((size_t)(f->bh + 64 + 5) * rstride, sizeof(*rmv));
 
+    /* pass 2 reads the filter of a sub8x8 block's neighbours from the frame's Av1Block array (recon_tmpl.c:1710,1726,1741) */
+    Av1Block *const fb = calloc((size_t)f->b4_stride * (f->bh + 32), sizeof(*fb));
+    f->frame_thread.b = fb;
+
     /* per-block streams: pass 1 leaves cbi / cf / pal_idx as consecutive runs; a block's share is
      * built right before the call */
     int16_t cbi[3 * 256 + 8];
     coef *const cfbuf = aligned_alloc(64, sizeof(coef) * 64 * 1024);
     uint8_t *const idxbuf = aligned_alloc(64, 8192);
-    if (!edge_buf || !f->frame_thread.pal || !a || !cfbuf || !idxbuf || !rmv) { ret = -12; goto done; }
+    if (!edge_buf || !f->frame_thread.pal || !a || !cfbuf || !idxbuf || !rmv || !fb) { ret = -12; goto done; }
 
     int cur_tile = -1, cur_sbrow = -1;
     for (int i = 0; i < fr->n_blocks; i++) {
@@ -294,6 +298,8 @@ EXPORT int SUFFIX(oracle_recon_frame)(const OracleReconFrame *const fr) {
                     rb->ref.ref[0] = b.ref[0] + 1;
                     rb->ref.ref[1] = b.comp_type == COMP_INTER_NONE ? -1 : b.ref[1] + 1;
                     rb->bs = bs; rb->mf = 0;
+                    if (fb && s->by4 + y < f->bh + 32 && s->bx4 + x < f->b4_stride)
+                        fb[(size_t)(s->by4 + y) * f->b4_stride + s->bx4 + x].filter2d = b.filter2d;
                 }
             /* decode.c:808-830: filters, intra = 0, uvmode = DC_PRED into the contexts */
             const int bx4 = s->bx4 & 31, by4 = s->by4 & 31;
@@ -376,7 +382,7 @@ EXPORT int SUFFIX(oracle_recon_frame)(const OracleReconFrame *const fr) {
         }
     }
 done:
-    free(rmv); free(idxbuf); free(cfbuf); free(a); free(f->frame_thread.pal); free(edge_buf);
+    free(rmv); free(f->frame_thread.b); free(idxbuf); free(cfbuf); free(a); free(f->frame_thread.pal); free(edge_buf);
     free(t); free(ts); free(f);
     return ret;
 }

@@ -70,7 +70,7 @@ def record_frame(hf):
     return ops, out[:r.n_intra]
 
 
-@pytest.mark.parametrize("name", [n for n in R.CASES if not n.startswith(("inter_", "obmc_", "scaled_", "wedge_", "ii_", "warp_", "ibc_"))])
+@pytest.mark.parametrize("name", [n for n in R.CASES if not n.startswith(("inter_", "obmc_", "scaled_", "wedge_", "ii_", "warp_", "ibc_", "sub8x8_"))])
 def test_recorder_emits_the_generators_descriptors(name):
     hf, _ = R.make(name)
     want, got = record_frame(hf)
@@ -253,7 +253,7 @@ def _normalise_edge_bits(a):
     return a
 
 
-@pytest.mark.parametrize("name", [n for n in R.CASES if n.startswith(("inter_", "obmc_", "scaled_", "wedge_", "ii_", "warp_", "ibc_"))])
+@pytest.mark.parametrize("name", [n for n in R.CASES if n.startswith(("inter_", "obmc_", "scaled_", "wedge_", "ii_", "warp_", "ibc_", "sub8x8_"))])
 def test_inter_recorder_emits_the_generators_descriptors(name):
     """dav1d_cuda_record_b_inter over the Av1Block-style records == the descriptor arrays the generator wrote
     for the same blocks (which reproduce dav1d_recon_b_inter's pixels bit for bit, tests/test_reference_driver.py).

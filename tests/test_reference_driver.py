@@ -85,6 +85,14 @@ CASES = {
     "ibc_422_12b_pal_ragged": (264, 200, 0xfff, 123, {"p_ibc": 0.5, "ss_hor": 1, "ss_ver": 0, "p_palette": 0.1}),
     "ibc_420_10b_tiles_2x2": (384, 256, 0x3ff, 124, {"p_ibc": 0.5, "tile_cols": 2, "tile_rows": 2}),
     "ibc_luma_8b": (256, 256, 0xff, 125, {"p_ibc": 0.5, "no_chroma": 1}),
+    # 8x4 / 4x8 / 4x4 blocks in 4:2:0: the chroma of the block at the odd position of its 8x8 is predicted part by part
+    # with the vectors of its partners (recon_tmpl.c:1685-1751) or, next to an intra partner, with its own
+    "sub8x8_420_10b_all_inter": (320, 256, 0x3ff, 131, {"p_sub8x8": 0.6, "p_intra": 0.0}),
+    "sub8x8_420_8b_mixed_cfl": (256, 192, 0xff, 132, {"p_sub8x8": 0.5, "p_intra": 0.3, "p_cfl": 0.3}),
+    "sub8x8_420_12b_long_vectors_ragged": (264, 200, 0xfff, 133, {"p_sub8x8": 0.7, "p_intra": 0.2, "mv_range": 300}),
+    "sub8x8_420_10b_tiles_2x2_obmc": (384, 256, 0x3ff, 134, {"p_sub8x8": 0.5, "p_intra": 0.3, "tile_cols": 2, "tile_rows": 2,
+                                                            "p_obmc": 0.4}),
+    "sub8x8_420_8b_scaled": (256, 192, 0xff, 135, {"p_sub8x8": 0.6, "p_intra": 0.1, "ref_w": [384, 0], "ref_h": [288, 0]}),
     # references of another size: the scaled branch of mc() with f->svc as decode.c:3517-3524 sets it
     "scaled_420_10b_half_and_same": (320, 256, 0x3ff, 51, {"ref_w": [160, 0], "ref_h": [128, 0], "p_intra": 0.2, "p_avg": 0.2,
                                                            "p_w_avg": 0.1, "p_seg": 0.15, "p_obmc": 0.3}),
