@@ -974,10 +974,10 @@ struct Gen {
         if (bx4 >= bw4 || by4 >= bh4) return;
         const bool fits = bx4 + s4 <= bw4 && by4 + s4 <= bh4;
         int choice;   // 0 NONE 1 H 2 V 3 SPLIT 4 H4 5 V4
-        const bool sub_ok = P.real_blocks && P.p_sub8x8 > 0.f && P.ss_hor && P.ss_ver && !P.no_chroma;
+        const bool sub_ok = P.real_blocks && P.p_sub8x8 > 0.f && P.ss_hor && !P.no_chroma;
         if (s4 <= 1) choice = 0;
         else if (!fits) choice = 3;
-        else if (s4 == 2) choice = (sub_ok && rng.chance(P.p_sub8x8)) ? 1 + rng.range(3) : 0;
+        else if (s4 == 2) choice = (sub_ok && rng.chance(P.p_sub8x8)) ? (P.ss_ver ? 1 + rng.range(3) : 1 + 2 * rng.range(2)) : 0;   // 4:2:2: 8x4 or 4x4
         else {
             const int r = rng.range(100);
             if (s4 == 16) choice = r < 8 ? 0 : r < 16 ? 1 : r < 24 ? 2 : r < 28 ? 4 : r < 32 ? 5 : 3;
@@ -1045,7 +1045,7 @@ struct Gen {
             for (int x = bx4; x < std::min(bx4 + w4, bw4); x++) nb_grid[(size_t)y * bw4 + x] = n;
     }
 
-    // A 4-px-wide and / or 4-px-high inter block of a 4:2:0 frame (recon_tmpl.c:1638-1657 luma, :1683-1751 chroma):
+    // A 4-px-wide and / or 4-px-high inter block of a 4:2:0 / 4:2:2 frame (recon_tmpl.c:1638-1657 luma, :1683-1751 chroma):
     // single reference, translation.  The block at the odd position of its 8x8 carries the chroma of the whole
     // 8x8: when the other blocks of the 8x8 it looks at are inter blocks too, every 2x2 / 2x4 / 4x2 chroma part is
     // predicted with the vector, reference and filter of the luma block above it; otherwise the whole 4x4 chroma
@@ -1056,7 +1056,12 @@ struct Gen {
         int mvx = rng.irange(-R, R), mvy = rng.irange(-R, R);
         if (rng.chance(0.1f)) mvx &= ~7;
         if (rng.chance(0.1f)) mvy &= ~7;
-        const bool hc = (w4 > 1 || (bx4 & 1)) && (h4 > 1 || (by4 & 1));
+        const int sv = P.ss_ver;
+        const bool hc = (w4 > 1 || (bx4 & 1)) && (h4 > sv || (by4 & 1));
+        if (hc && !(w4 == 1 || h4 == sv)) {          // nothing special about its chroma (4:2:2: an 8x4 block)
+            inter_block(bx4, by4, w4, h4);
+            return;
+        }
         D1SynthBlock rec;
         memset(&rec, 0, sizeof(rec));
         rec.bx4 = (uint16_t)bx4; rec.by4 = (uint16_t)by4; rec.w4 = (uint8_t)w4; rec.h4 = (uint8_t)h4;
@@ -1082,24 +1087,28 @@ struct Gen {
             auto at = [&](int x, int y) -> const Nb & { return nb_grid[(size_t)y * bw4 + x]; };
             bool sub = true;
             if (w4 == 1) sub = sub && at(bx4 - 1, by4).inter;
-            if (h4 == 1) sub = sub && at(bx4, by4 - 1).inter;
-            if (w4 == 1 && h4 == 1) sub = sub && at(bx4 - 1, by4 - 1).inter;
-            const int cx0 = (bx4 >> 1) * 4, cy0 = (by4 >> 1) * 4, cw = w4 * 2, ch = h4 * 2;
+            if (h4 == sv) sub = sub && at(bx4, by4 - 1).inter;
+            if (w4 == 1 && h4 == sv) sub = sub && at(bx4 - 1, by4 - 1).inter;
+            const int cx0 = (bx4 >> 1) * 4, cy0 = ((by4 & ~sv) * 4) >> sv, cw = w4 * 2, ch = (h4 * 4) >> sv;
             if (sub) {
                 int h_off = 0, v_off = 0;
                 auto part = [&](int nbx, int nby, const Nb &n, int ox, int oy) {
                     for (int pl = 1; pl <= 2; pl++)
                         put_desc(pl, cx0 + ox, cy0 + oy, cw, ch, make_src(pl, nbx, nby, n.ref, n.mvx, n.mvy, n.filter));
                 };
-                if (w4 == 1 && h4 == 1) { part(bx4 - 1, by4 - 1, at(bx4 - 1, by4 - 1), 0, 0); v_off = 2; h_off = 2; }
+                if (w4 == 1 && h4 == sv) { part(bx4 - 1, by4 - 1, at(bx4 - 1, by4 - 1), 0, 0); v_off = 2; h_off = 2; }
                 if (w4 == 1) { part(bx4 - 1, by4, at(bx4 - 1, by4), 0, v_off); h_off = 2; }
-                if (h4 == 1) { part(bx4, by4 - 1, at(bx4, by4 - 1), h_off, 0); v_off = 2; }
+                if (h4 == sv) { part(bx4, by4 - 1, at(bx4, by4 - 1), h_off, 0); v_off = 2; }
                 part(bx4, by4, own, h_off, v_off);
             } else {
                 for (int pl = 1; pl <= 2; pl++)
-                    put_desc(pl, cx0, cy0, 4, 4, make_src(pl, bx4 & ~1, by4 & ~1, ref, mvx, mvy, filter));
+                    put_desc(pl, cx0, cy0, ((w4 << (w4 == 1)) * 4) >> 1, ((h4 << (h4 == sv)) * 4) >> sv,
+                             make_src(pl, bx4 & ~1, by4 & ~sv, ref, mvx, mvy, filter));
             }
         }
+        const int cbh4 = (h4 + sv) >> sv;                 // the chroma block of the odd partner: 4 px wide, 4 * cbh4 high
+        const int uvtx = tx_from_dims(1, cbh4);
+        rec.uvtx = (uint8_t)uvtx;
         if (rng.chance(P.p_residual)) {
             int tw4 = w4, th4 = h4;
             rec.skip = 0;
@@ -1108,14 +1117,14 @@ struct Gen {
             for (int y = 0; y < h4; y += th4)
                 for (int x = 0; x < w4; x += tw4) add_itx(0, bx4 + x, by4 + y, tx);
             if (hc)
-                for (int pl = 1; pl <= 2; pl++) add_itx(pl, bx4 >> 1, by4 >> 1, 0);
+                for (int pl = 1; pl <= 2; pl++) add_itx(pl, bx4 >> 1, by4 >> sv, uvtx);
         }
         rec.n_tx = (uint32_t)tx_recs.size() - rec.first_tx;
         blocks.push_back(rec);
         nb_set(bx4, by4, w4, h4, 1, ref, mvx, mvy, filter);
         grid_set(bx4, by4, w4, h4, Nb{ 1, (uint8_t)ref, (uint8_t)filter, (uint8_t)w4, (uint8_t)h4, (int16_t)mvx, (int16_t)mvy });
         mark(0, bx4, by4, w4, h4);
-        if (hc) { mark(1, bx4 >> 1, by4 >> 1, 1, 1); mark(2, bx4 >> 1, by4 >> 1, 1, 1); }
+        if (hc) { mark(1, bx4 >> 1, by4 >> sv, 1, (h4 + sv) >> sv); mark(2, bx4 >> 1, by4 >> sv, 1, (h4 + sv) >> sv); }
     }
     void nb_set(int bx4, int by4, int w4, int h4, int inter, int ref, int mvx, int mvy, int filter) {
         const Nb n = { (uint8_t)inter, (uint8_t)ref, (uint8_t)filter, (uint8_t)w4, (uint8_t)h4, (int16_t)mvx, (int16_t)mvy };

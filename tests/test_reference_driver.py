@@ -93,6 +93,9 @@ CASES = {
     "sub8x8_420_10b_tiles_2x2_obmc": (384, 256, 0x3ff, 134, {"p_sub8x8": 0.5, "p_intra": 0.3, "tile_cols": 2, "tile_rows": 2,
                                                             "p_obmc": 0.4}),
     "sub8x8_420_8b_scaled": (256, 192, 0xff, 135, {"p_sub8x8": 0.6, "p_intra": 0.1, "ref_w": [384, 0], "ref_h": [288, 0]}),
+    # 4:2:2: 4x4 blocks (chroma 2x4 parts with the left partner's vector) and 8x4 blocks
+    "sub8x8_422_10b_all_inter": (320, 256, 0x3ff, 141, {"p_sub8x8": 0.6, "p_intra": 0.0, "ss_hor": 1, "ss_ver": 0}),
+    "sub8x8_422_8b_mixed_obmc_ragged": (264, 200, 0xff, 142, {"p_sub8x8": 0.6, "p_intra": 0.3, "ss_hor": 1, "ss_ver": 0, "p_obmc": 0.3}),
     # references of another size: the scaled branch of mc() with f->svc as decode.c:3517-3524 sets it
     "scaled_420_10b_half_and_same": (320, 256, 0x3ff, 51, {"ref_w": [160, 0], "ref_h": [128, 0], "p_intra": 0.2, "p_avg": 0.2,
                                                            "p_w_avg": 0.1, "p_seg": 0.15, "p_obmc": 0.3}),
