@@ -150,7 +150,7 @@ def test_descriptors_mean_what_the_reference_driver_means(ref, name):
 
 def test_random_frames_against_the_reference_drivers(ref):
     rng = np.random.default_rng(20261019)
-    for k in range(16):
+    for k in range(48):
         lay = [(1, 1), (1, 0), (0, 0)][rng.integers(3)]
         kw = dict(ss_hor=lay[0], ss_ver=lay[1], p_cfl=float(rng.choice([0, 0.5])), p_palette=float(rng.choice([0, 0.15])),
                   p_intra=float(rng.choice([1.0, 0.5, 0.2, 0.0])), p_wedge=0.0, p_warp=0.0,
@@ -163,6 +163,7 @@ def test_random_frames_against_the_reference_drivers(ref):
         bd = [0xff, 0x3ff, 0xfff][rng.integers(3)]
         kw["p_wedge"] = float(rng.choice([0, 0.3]))
         kw["p_warp"] = float(rng.choice([0, 0.3]))
+        kw["p_sub8x8"] = float(rng.choice([0, 0.5]))          # takes effect in 4:2:0 / 4:2:2
         hf = F.HostFrame(w, h, bd, 500 + k, real_blocks=1, mask_tab=refframe.reference_mask_tab(ref),
                          warp_tab=refframe.reference_warp_tab(ref), **kw)
         init = F.random_planes(hf, 9000 + k)
