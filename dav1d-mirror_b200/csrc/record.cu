@@ -347,7 +347,7 @@ extern "C" int dav1d_cuda_record_b_inter(Dav1dCudaInterRecorder *r, const Dav1dC
     // chroma of a 4-px-wide / -high block: predicted part by part with the partners' vectors when they are inter
     // blocks (:1685-1751), else as one block with this block's vector from the 8x8's origin (:1764-1769)
     const bool narrow = has_chroma && (bw4 == ss_hor || bh4 == ss_ver);
-    if (narrow && (ibc || comp || warp || ii || b->motion_mode)) return ibc ? -38 : -22;
+    if (narrow && !ibc && (comp || warp || ii || b->motion_mode)) return -22;
     if (b->motion_mode == 1 && (comp || (bx & 1) || (by & 1))) return -22;     // obmc(): assert(!(t->bx & 1) && !(t->by & 1))
 
     RecInter R;
@@ -479,8 +479,9 @@ extern "C" int dav1d_cuda_record_b_inter(Dav1dCudaInterRecorder *r, const Dav1dC
             const int sh = pl ? ss_hor : 0, sv = pl ? ss_ver : 0;
             const int sx = ((bx & ~sh) * 4 >> sh) + (b->mvx[0] >> (3 + sh)), sy = ((by & ~sv) * 4 >> sv) + (b->mvy[0] >> (3 + sv));
             const int mx = b->mvx[0] & (15 >> !sh), my = b->mvy[0] & (15 >> !sv);
-            RI.emit(pl, bx >> sh, by >> sv, bw4 >> sh, bh4 >> sv, DAV1D_CUDA_INTRA_IBC, mx, my, 0, false, 0,
-                    (uint32_t)(sx & 0xffff) | ((uint32_t)(sy & 0xffff) << 16), 0);
+            // chroma: bw4 << (bw4 == ss_hor), bh4 << (bh4 == ss_ver) (:1631-1635) - the whole 8x8 for a 4-px-wide / -high block
+            RI.emit(pl, bx >> sh, by >> sv, pl ? (bw4 + sh) >> sh : bw4, pl ? (bh4 + sv) >> sv : bh4, DAV1D_CUDA_INTRA_IBC, mx, my, 0,
+                    false, 0, (uint32_t)(sx & 0xffff) | ((uint32_t)(sy & 0xffff) << 16), 0);
         }
     }
     if ((ii || ibc) && !R.err) {

@@ -351,12 +351,17 @@ struct Gen {
     // right edge, which the reference pads with emu_edge), residuals as residual-only operations
     bool ibc_block(int bx4, int by4, int w4, int h4) {
         const int sb_top = (by4 & ~15) * 4 - tile_y0 * 4, wpx = w4 * 4, hpx = h4 * 4;   // rows of the tile above this SB row
-        if (w4 < 2 || h4 < 2 || w4 > 16 || h4 > 16 || sb_top < hpx + 2) return false;
+        // 4-px-wide / -high blocks (real-block mode with p_sub8x8): the block at the odd position of its 8x8 predicts
+        // the chroma of the whole 8x8 with its own vector (recon_tmpl.c:1631-1635: bw4 << (bw4 == ss_hor) from t->bx & ~ss_hor)
+        const bool narrow = (w4 < 2 || h4 < 2);
+        if (narrow && !(P.real_blocks && P.p_sub8x8 > 0.f && P.ss_hor && !P.no_chroma)) return false;
+        const int pad = narrow ? 4 : 0;                    // the widened chroma source stays inside the tile / above the SB row
+        if (w4 > 16 || h4 > 16 || sb_top < hpx + 2 + 2 * pad) return false;
         const int W = std::min(tile_x1, bw4) * 4 - tile_x0 * 4;                      // the source stays inside the tile
-        if (W < wpx + 8) return false;
+        if (W < wpx + 8 + 2 * pad) return false;
         const bool one_tile = tile_x0 == 0 && tile_x1 >= bw4;
-        const int sxl = tile_x0 * 4 + ((one_tile && rng.chance(0.1f)) ? W - wpx + 2 * rng.range(4) : 2 * rng.range((W - wpx) / 2 + 1));
-        const int syl = tile_y0 * 4 + 2 * rng.range((sb_top - hpx - 2) / 2 + 1);
+        const int sxl = tile_x0 * 4 + pad + ((!narrow && one_tile && rng.chance(0.1f)) ? W - wpx + 2 * rng.range(4) : 2 * rng.range((W - wpx - 2 * pad) / 2 + 1));
+        const int syl = tile_y0 * 4 + pad + 2 * rng.range((sb_top - hpx - 2 - 2 * pad) / 2 + 1);
         const bool half = rng.chance(0.5f);          // odd luma vector components: half-pel chroma
         n_intra_blocks++;
         // real-block mode: the block record dav1d_recon_b_inter reads for an intrabc block of a key / intra-only
@@ -364,7 +369,8 @@ struct Gen {
         D1SynthBlock rec;
         memset(&rec, 0, sizeof(rec));
         rec.bx4 = (uint16_t)bx4; rec.by4 = (uint16_t)by4; rec.w4 = (uint8_t)w4; rec.h4 = (uint8_t)h4;
-        rec.intra = 0; rec.has_chroma = P.no_chroma ? 0 : 1; rec.skip = 1; rec.tile = (uint8_t)tile_no;
+        const bool hc = !P.no_chroma && (w4 > P.ss_hor || (bx4 & 1)) && (h4 > P.ss_ver || (by4 & 1));
+        rec.intra = 0; rec.has_chroma = hc ? 1 : 0; rec.skip = 1; rec.tile = (uint8_t)tile_no;
         rec.tile_x0 = (uint16_t)tile_x0; rec.tile_y0 = (uint16_t)tile_y0;
         rec.tile_x1 = (uint16_t)std::min(tile_x1, bw4); rec.tile_y1 = (uint16_t)std::min(tile_y1, bh4);
         rec.comp_kind = 254; rec.filter2d = 9;
@@ -378,6 +384,9 @@ struct Gen {
             fit_tx(ua, ub);
             rec.uvtx = (uint8_t)tx_from_dims(ua, ub);
         }
+        // chroma block of the (odd) block: the widened one of a narrow block
+        const int cbw4 = (w4 + P.ss_hor) >> P.ss_hor, cbh4 = (h4 + P.ss_ver) >> P.ss_ver;
+        if (narrow) rec.uvtx = (uint8_t)tx_from_dims(cbw4, cbh4);
         auto rec_tx = [&]() {                             // the cbi / cf entry of the residual-only operation just added
             if (!P.real_blocks) return;
             const Dav1dCudaIntraDesc &o = intra.back();
@@ -386,24 +395,32 @@ struct Gen {
             t.coef_off = o.coef_off; t.eob = o.eob; t.txtp = o.txtp; t.cw4 = o.cw4; t.ch4 = o.ch4; t.tx = o.tx; t.plane = o.plane;
             tx_recs.push_back(t);
         };
-        for (int pl = 0; pl < nplanes(); pl++) {
+        for (int pl = 0; pl < (narrow ? (hc ? 3 : 1) : nplanes()); pl++) {
             const int sh = pl ? P.ss_hor : 0, sv = pl ? P.ss_ver : 0;
-            const int lx = sxl + (half ? 1 : 0), ly = syl + (half ? 1 : 0);
+            // chroma of a narrow block: from the 8x8's origin (t->bx & ~ss_hor, t->by & ~ss_ver)
+            const int lx = sxl + (half ? 1 : 0) - (narrow && pl ? 4 * (bx4 & sh) : 0);
+            const int ly = syl + (half ? 1 : 0) - (narrow && pl ? 4 * (by4 & sv) : 0);
             const int sx = lx >> sh, sy = ly >> sv;
             const int mx = (sh && (lx & 1)) ? 8 : 0, my = (sv && (ly & 1)) ? 8 : 0;
-            add_intra(pl, bx4 >> sh, by4 >> sv, w4 >> sh, h4 >> sv, DAV1D_CUDA_INTRA_IBC, mx, my, false,
-                      (uint32_t)(sx & 0xffff) | ((uint32_t)(sy & 0xffff) << 16));
+            add_intra(pl, bx4 >> sh, by4 >> sv, narrow && pl ? cbw4 : w4 >> sh, narrow && pl ? cbh4 : h4 >> sv,
+                      DAV1D_CUDA_INTRA_IBC, mx, my, false, (uint32_t)(sx & 0xffff) | ((uint32_t)(sy & 0xffff) << 16));
         }
         if (rng.chance(P.p_residual)) {
             int tw4 = std::min(w4, 16), th4 = std::min(h4, 16);
             rec.skip = 0;
-            if (rng.chance(P.p_tx_split)) { split_tx(tw4, th4); rec.tx_split = tw4 * th4 < std::min(w4, 16) * std::min(h4, 16); }
+            if (rng.chance(P.p_tx_split) && !(narrow && tw4 == th4)) { split_tx(tw4, th4); rec.tx_split = tw4 * th4 < std::min(w4, 16) * std::min(h4, 16); }
             for (int y = 0; y < h4; y += th4)
                 for (int x = 0; x < w4; x += tw4) {
                     add_intra(0, bx4 + x, by4 + y, tw4, th4, DAV1D_CUDA_INTRA_NONE, 0, 0, true);
                     rec_tx();
                 }
-            if (!P.no_chroma) {
+            if (narrow) {
+                if (hc)
+                    for (int pl = 1; pl <= 2; pl++) {
+                        add_intra(pl, bx4 >> P.ss_hor, by4 >> P.ss_ver, cbw4, cbh4, DAV1D_CUDA_INTRA_NONE, 0, 0, true);
+                        rec_tx();
+                    }
+            } else if (!P.no_chroma) {
                 const int cw4 = w4 >> P.ss_hor, ch4 = h4 >> P.ss_ver;
                 int utw4 = std::min(cw4, 8), uth4 = std::min(ch4, 8);
                 fit_tx(utw4, uth4);

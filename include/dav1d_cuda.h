@@ -349,8 +349,9 @@ DAV1D_CUDA_API int dav1d_cuda_record_b_intra(Dav1dCudaRecorder *r, const Dav1dCu
  * intra-class operations appended through `intra`), from references of any size, with their residual
  * transform trees, warped blocks (local warp and global motion: warp_affine(), :1134-1193, as one
  * Dav1dCudaWarpDesc per 8x8), the intrabc blocks of key / intra-only frames and the chroma of 4xN / Nx4 blocks
- * (:1685-1751: up to four predictions with the partners' vectors).  An intrabc block that narrow (its chroma spans
- * two luma blocks) is the one case not transcribed: -ENOSYS, nothing recorded. */
+ * (:1685-1751: up to four predictions with the partners' vectors; an intrabc block that narrow predicts the
+ * chroma of its 8x8 with its own vector, :1631-1635).  Every branch of both drivers is transcribed; -ENOSYS is
+ * only returned for residual trees split deeper than one level inside inter-intra / intrabc blocks. */
 typedef struct Dav1dCudaNbMv {          /* what obmc() reads of a neighbour (refmvs rows + filter contexts) */
     int16_t mvx, mvy;                   /* r->mv.mv[0] */
     int8_t  ref;                        /* r->ref.ref[0] - 1: reference index, -1 = intra */

@@ -96,6 +96,11 @@ CASES = {
     # 4:2:2: 4x4 blocks (chroma 2x4 parts with the left partner's vector) and 8x4 blocks
     "sub8x8_422_10b_all_inter": (320, 256, 0x3ff, 141, {"p_sub8x8": 0.6, "p_intra": 0.0, "ss_hor": 1, "ss_ver": 0}),
     "sub8x8_422_8b_mixed_obmc_ragged": (264, 200, 0xff, 142, {"p_sub8x8": 0.6, "p_intra": 0.3, "ss_hor": 1, "ss_ver": 0, "p_obmc": 0.3}),
+    # 4-px-wide / -high intrabc blocks: the odd block predicts the chroma of its 8x8 with its own vector
+    "ibc_sub8x8_420_10b": (320, 256, 0x3ff, 151, {"p_ibc": 0.6, "p_sub8x8": 0.6}),
+    "ibc_sub8x8_422_8b": (256, 192, 0xff, 152, {"p_ibc": 0.6, "p_sub8x8": 0.7, "ss_hor": 1, "ss_ver": 0}),
+    "ibc_sub8x8_420_12b_tiles_2x2_cfl": (384, 256, 0xfff, 153, {"p_ibc": 0.6, "p_sub8x8": 0.6, "tile_cols": 2, "tile_rows": 2,
+                                                               "p_cfl": 0.3}),
     # references of another size: the scaled branch of mc() with f->svc as decode.c:3517-3524 sets it
     "scaled_420_10b_half_and_same": (320, 256, 0x3ff, 51, {"ref_w": [160, 0], "ref_h": [128, 0], "p_intra": 0.2, "p_avg": 0.2,
                                                            "p_w_avg": 0.1, "p_seg": 0.15, "p_obmc": 0.3}),
