@@ -363,6 +363,8 @@ struct Gen {
         const int sxl = tile_x0 * 4 + pad + ((!narrow && one_tile && rng.chance(0.1f)) ? W - wpx + 2 * rng.range(4) : 2 * rng.range((W - wpx - 2 * pad) / 2 + 1));
         const int syl = tile_y0 * 4 + pad + 2 * rng.range((sb_top - hpx - 2 - 2 * pad) / 2 + 1);
         const bool half = rng.chance(0.5f);          // odd luma vector components: half-pel chroma
+        // ... but never one pixel into the tile to the right, which is decoded later (a stream may not do that)
+        const bool halfx = half && (one_tile || sxl + 1 + wpx <= std::min(tile_x1, bw4) * 4);
         n_intra_blocks++;
         // real-block mode: the block record dav1d_recon_b_inter reads for an intrabc block of a key / intra-only
         // frame (b->intra == 0, integer-pel b->mv[0], FILTER_2D_BILINEAR; decode.c:1262-1330)
@@ -374,7 +376,7 @@ struct Gen {
         rec.tile_x0 = (uint16_t)tile_x0; rec.tile_y0 = (uint16_t)tile_y0;
         rec.tile_x1 = (uint16_t)std::min(tile_x1, bw4); rec.tile_y1 = (uint16_t)std::min(tile_y1, bh4);
         rec.comp_kind = 254; rec.filter2d = 9;
-        rec.mvx[0] = (int16_t)((sxl + (half ? 1 : 0) - bx4 * 4) * 8);
+        rec.mvx[0] = (int16_t)((sxl + (halfx ? 1 : 0) - bx4 * 4) * 8);
         rec.mvy[0] = (int16_t)((syl + (half ? 1 : 0) - by4 * 4) * 8);
         rec.first_tx = (uint32_t)tx_recs.size();
         {
@@ -398,7 +400,7 @@ struct Gen {
         for (int pl = 0; pl < (narrow ? (hc ? 3 : 1) : nplanes()); pl++) {
             const int sh = pl ? P.ss_hor : 0, sv = pl ? P.ss_ver : 0;
             // chroma of a narrow block: from the 8x8's origin (t->bx & ~ss_hor, t->by & ~ss_ver)
-            const int lx = sxl + (half ? 1 : 0) - (narrow && pl ? 4 * (bx4 & sh) : 0);
+            const int lx = sxl + (halfx ? 1 : 0) - (narrow && pl ? 4 * (bx4 & sh) : 0);
             const int ly = syl + (half ? 1 : 0) - (narrow && pl ? 4 * (by4 & sv) : 0);
             const int sx = lx >> sh, sy = ly >> sv;
             const int mx = (sh && (lx & 1)) ? 8 : 0, my = (sv && (ly & 1)) ? 8 : 0;
