@@ -1,3 +1,7 @@
+#!/usr/bin/env python3
+"""Where does the CUDA frame differ from the reference driver?  Runs one case of tests/test_reference_driver.py on
+the GPU (device-side and recorded levels) and prints the differing 4x4 cells per plane with the intra-class
+operation that covers the first one.  usage: tools/diff_frame_vs_driver.py <case name>"""
 import sys
 sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
 import numpy as np
