@@ -12,6 +12,9 @@
 namespace d1 {
 
 constexpr int MC_WARPS = 4;
+#ifndef D1_PUT_MINB
+#define D1_PUT_MINB 6
+#endif
 void mc_init_attrs();
 
 struct McArgs {
@@ -47,8 +50,10 @@ template <bool SMALL> struct McVar {
 // warp (group) strides over the tile list: warps are independent, so a slow tile (picture edge,
 // large window) delays only its own warp instead of holding a block's slot, and the next
 // tile's descriptor is fetched while the current tile is computed.
-template <typename pixel, bool SMALL>
-__global__ void __launch_bounds__(MC_WARPS * 32, 8) mc_put_kernel(const __grid_constant__ McArgs a) {
+// WITH_PREP = false: the descriptor list holds no PREP entries (the frame path: a.tmp == nullptr) - the kernel then
+// carries ONE instantiation of the filter code instead of two and fits the instruction caches (57 -> ~30 KB).
+template <typename pixel, bool SMALL, bool WITH_PREP>
+__global__ void __launch_bounds__(MC_WARPS * 32, D1_PUT_MINB) mc_put_kernel(const __grid_constant__ McArgs a) {
     extern __shared__ __align__(16) uint8_t mc_smem_raw[];
     typedef McVar<SMALL> V;
     const int wl = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -71,7 +76,7 @@ __global__ void __launch_bounds__(MC_WARPS * 32, 8) mc_put_kernel(const __grid_c
         const TileGeo g = tile_geo(d, tcode & 15);
         const Dav1dCudaMcSrc s = d.src[0];
         const PlaneView &ref = a.refs[s.ref].p[d.plane];
-        if (d.kind == DAV1D_CUDA_MC_PREP) {
+        if (WITH_PREP && d.kind == DAV1D_CUDA_MC_PREP) {
             int16_t *out = a.tmp + d.aux_off + g.y0 * d.w + g.x0;
             mc_tile<pixel, true, V::TMAX, V::G>(ref, s.x + g.x0, s.y + g.y0, g.tw, g.th, d.w, d.h, s.mx, s.my,
                                                 s.filter_2d, a.dst.bdmax, sm, out, d.w, lane, gmask);
@@ -89,7 +94,7 @@ __global__ void __launch_bounds__(MC_WARPS * 32, 8) mc_put_kernel(const __grid_c
 
 // ---- fused compound: two preps into shared int16 tiles, then the combine
 template <typename pixel, bool SMALL>
-__global__ void __launch_bounds__(MC_WARPS * 32, SMALL ? 6 : 5) mc_compound_kernel(const __grid_constant__ McArgs a) {
+__global__ void __launch_bounds__(MC_WARPS * 32, 5) mc_compound_kernel(const __grid_constant__ McArgs a) {
     extern __shared__ __align__(16) uint8_t mc_smem_raw[];
     typedef McVar<SMALL> V;
     const int wl = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -172,7 +177,7 @@ DEV int mc_tma_arrive(const McArgs &a, const Dav1dCudaMcDesc &d, const Dav1dCuda
     return mc_stage<pixel, MC_T, 32>(a.refs[s.ref].p[d.plane], s.x + g.x0, s.y + g.y0, g.tw, g.th, s.mx, s.my, buf, lane);
 }
 
-template <typename pixel>
+template <typename pixel, bool WITH_PREP>
 __global__ void __launch_bounds__(MC_WARPS * 32, 5) mc_put_tma_kernel(const __grid_constant__ McArgs a) {
     extern __shared__ __align__(128) uint8_t mc_smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -202,7 +207,7 @@ __global__ void __launch_bounds__(MC_WARPS * 32, 5) mc_put_tma_kernel(const __gr
         const Dav1dCudaMcSrc s = d.src[0];
         const int off = mc_tma_arrive<pixel>(a, d, s, g, cur, sm->src[b], &sm->bar[b], (par >> b) & 1u, lane);
         if (cur) par ^= 1u << b;
-        if (d.kind == DAV1D_CUDA_MC_PREP) {
+        if (WITH_PREP && d.kind == DAV1D_CUDA_MC_PREP) {
             int16_t *out = a.tmp + d.aux_off + g.y0 * d.w + g.x0;
             mc_filter<pixel, true, MC_T, 32>(sm->src[b], off, sm->mid, g.tw, g.th, d.w, d.h, s.mx, s.my, s.filter_2d,
                                              a.dst.bdmax, out, d.w, lane);
@@ -232,33 +237,34 @@ __global__ void __launch_bounds__(MC_WARPS_TC * 32, 3) mc_compound_tma_kernel(co
     Dav1dCudaMcDesc d = a.descs[tcode >> 4], nd;
     TileGeo g = tile_geo(d, tcode & 15);
     if (ti + stride < a.n_tiles) { ncode = a.tiles[ti + stride]; nd = a.descs[ncode >> 4]; }
-    unsigned par0 = 0, par1 = 0;
-    // the first source's window always lands in buffer 0, the second's in buffer 1
-    bool req0 = mc_tma_request<pixel>(a, d, d.src[0], g, sm->s.src[0], &sm->s.bar[0], lane);
+    // the first source's window always lands in buffer 0, the second's in buffer 1; bit i of `par` / `req`:
+    // phase parity of buffer i's barrier / its window was requested through TMA
+    unsigned par = 0;
+    unsigned req = mc_tma_request<pixel>(a, d, d.src[0], g, sm->s.src[0], &sm->s.bar[0], lane) ? 1u : 0u;
     for (;;) {
         const int tn = ti + stride, tnn = tn + stride;
         uint32_t nncode = 0;
         Dav1dCudaMcDesc nnd;
         if (tnn < a.n_tiles) { nncode = a.tiles[tnn]; nnd = a.descs[nncode >> 4]; }
-        const bool req1 = mc_tma_request<pixel>(a, d, d.src[1], g, sm->s.src[1], &sm->s.bar[1], lane);
-        {
-            const Dav1dCudaMcSrc s = d.src[0];
-            const int off = mc_tma_arrive<pixel>(a, d, s, g, req0, sm->s.src[0], &sm->s.bar[0], par0, lane);
-            if (req0) par0 ^= 1u;
-            mc_filter<pixel, true, MC_T, 32>(sm->s.src[0], off, sm->s.mid, g.tw, g.th, d.w, d.h, s.mx, s.my, s.filter_2d,
-                                             a.dst.bdmax, sm->ta, MC_T, lane);
-        }
         TileGeo ng = g;
-        if (tn < a.n_tiles) {
-            ng = tile_geo(nd, ncode & 15);
-            req0 = mc_tma_request<pixel>(a, nd, nd.src[0], ng, sm->s.src[0], &sm->s.bar[0], lane);
-        }
-        {
-            const Dav1dCudaMcSrc s = d.src[1];
-            const int off = mc_tma_arrive<pixel>(a, d, s, g, req1, sm->s.src[1], &sm->s.bar[1], par1, lane);
-            if (req1) par1 ^= 1u;
-            mc_filter<pixel, true, MC_T, 32>(sm->s.src[1], off, sm->s.mid, g.tw, g.th, d.w, d.h, s.mx, s.my, s.filter_2d,
-                                             a.dst.bdmax, sm->tb, MC_T, lane);
+        if (tn < a.n_tiles) ng = tile_geo(nd, ncode & 15);
+        // the two predictions through ONE copy of the filter code (the loop stays rolled: two copies do not fit the
+        // instruction caches, measured 51 instead of 40 us per frame): source i from window buffer i; before it is
+        // filtered, the request for the next window goes out - (d, 1) while i == 0, (next tile, 0) while i == 1
+#pragma unroll 1
+        for (int i = 0; i < 2; i++) {
+            const int j = i ^ 1;
+            if (i == 0 || tn < a.n_tiles) {
+                const Dav1dCudaMcDesc &pd = i ? nd : d;
+                const bool ok = mc_tma_request<pixel>(a, pd, i ? pd.src[0] : pd.src[1], i ? ng : g, sm->s.src[j], &sm->s.bar[j], lane);
+                req = (req & ~(1u << j)) | ((ok ? 1u : 0u) << j);
+            }
+            const Dav1dCudaMcSrc s = i ? d.src[1] : d.src[0];
+            const bool requested = (req >> i) & 1u;
+            const int off = mc_tma_arrive<pixel>(a, d, s, g, requested, sm->s.src[i], &sm->s.bar[i], (par >> i) & 1u, lane);
+            if (requested) par ^= 1u << i;
+            mc_filter<pixel, true, MC_T, 32>(sm->s.src[i], off, sm->s.mid, g.tw, g.th, d.w, d.h, s.mx, s.my, s.filter_2d,
+                                             a.dst.bdmax, i ? sm->tb : sm->ta, MC_T, lane);
         }
         const PlaneView &dp = a.dst.p[d.plane];
         const int dstride = (int)(dp.stride / (int)sizeof(pixel));
@@ -597,17 +603,18 @@ template <typename K> static int resident_blocks(K kernel, size_t smem, int &cac
 
 // TMA staging of the 32x32-tile kernels where the references carry tensor maps (dav1d_cuda_set_mc_tma):
 // 0 off, 1 single-reference predictions (default), 2 compound predictions as well.  Measured on B200 (4K
-// 10-bit benchmark mix, per frame): put 21.7 us with TMA vs 21.6 with cp.async (the kernel is bound by its
-// filter arithmetic, not by the staging); compound 54.5 vs 40.5 us - the second window buffer costs a
-// quarter of the resident warps (15 instead of 20 per SM) and the fixed boxes fetch more than the tile
-// needs, so compound stays on cp.async by default.
+// 10-bit benchmark mix, per frame): put 20.6 us with TMA vs 21.6 with cp.async; compound 42.3 vs 41.0 us - the
+// second window buffer costs a quarter of the resident warps (15 instead of 20 per SM), so compound stays on
+// cp.async by default.  (A first version that called the filter code twice per tile ran at 54.5 us: two copies
+// of it, 65 KB, do not fit the instruction caches - both compound kernels keep the two predictions in a rolled
+// loop, and the put kernels are instantiated without the PREP branch for the frame path.)
 static int g_mc_tma = 1;
 void mc_set_tma(int mode) { g_mc_tma = mode < 0 ? 0 : mode > 2 ? 2 : mode; }
 int mc_get_tma() { return g_mc_tma; }
 
 template <typename pixel, bool COMPOUND>
 static int launch_mc(McArgs a, cudaStream_t st) {
-    static int cap_small = 0, cap_big = 0;
+    static int cap_small = 0, cap_big = 0, cap_small_prep = 0, cap_big_prep = 0;
     const int n_small = a.n_small, n_big = a.n_tiles - a.n_small;
     const uint32_t *tiles = a.tiles;
     if (n_small > 0) {
@@ -619,8 +626,13 @@ static int launch_mc(McArgs a, cudaStream_t st) {
             mc_compound_kernel<pixel, true><<<grid, MC_WARPS * 32, smem, st>>>(a);
         } else {
             const size_t smem = MC_WARPS * 4 * sizeof(McSmem<pixel, 8>);
-            grid = std::min(grid, resident_blocks(mc_put_kernel<pixel, true>, smem, cap_small));
-            mc_put_kernel<pixel, true><<<grid, MC_WARPS * 32, smem, st>>>(a);
+            if (a.tmp) {
+                grid = std::min(grid, resident_blocks(mc_put_kernel<pixel, true, true>, smem, cap_small_prep));
+                mc_put_kernel<pixel, true, true><<<grid, MC_WARPS * 32, smem, st>>>(a);
+            } else {
+                grid = std::min(grid, resident_blocks(mc_put_kernel<pixel, true, false>, smem, cap_small));
+                mc_put_kernel<pixel, true, false><<<grid, MC_WARPS * 32, smem, st>>>(a);
+            }
         }
         count_launch();
     }
@@ -628,7 +640,7 @@ static int launch_mc(McArgs a, cudaStream_t st) {
     for (int i = 0; i < 7; i++) tma = tma && (a.tmaps[i] || !a.refs[i].p[0].data);
     if (n_big > 0 && tma) {
         // every reference carries tensor maps: TMA staging, two window buffers per warp
-        static int cap_tma = 0;
+        static int cap_tma = 0, cap_tma_prep = 0;
         a.tiles = tiles + n_small; a.n_tiles = n_big;
         if (COMPOUND) {
             const size_t smem = MC_WARPS_TC * sizeof(McSmemTmaCompound<pixel>);
@@ -637,9 +649,15 @@ static int launch_mc(McArgs a, cudaStream_t st) {
             mc_compound_tma_kernel<pixel><<<grid, MC_WARPS_TC * 32, smem, st>>>(a);
         } else {
             const size_t smem = MC_WARPS * sizeof(McSmemTma<pixel>);
-            const int grid = std::min((n_big + MC_WARPS - 1) / MC_WARPS,
-                                      resident_blocks(mc_put_tma_kernel<pixel>, smem, cap_tma, MC_WARPS * 32));
-            mc_put_tma_kernel<pixel><<<grid, MC_WARPS * 32, smem, st>>>(a);
+            if (a.tmp) {
+                const int grid = std::min((n_big + MC_WARPS - 1) / MC_WARPS,
+                                          resident_blocks(mc_put_tma_kernel<pixel, true>, smem, cap_tma_prep, MC_WARPS * 32));
+                mc_put_tma_kernel<pixel, true><<<grid, MC_WARPS * 32, smem, st>>>(a);
+            } else {
+                const int grid = std::min((n_big + MC_WARPS - 1) / MC_WARPS,
+                                          resident_blocks(mc_put_tma_kernel<pixel, false>, smem, cap_tma, MC_WARPS * 32));
+                mc_put_tma_kernel<pixel, false><<<grid, MC_WARPS * 32, smem, st>>>(a);
+            }
         }
         count_launch();
     } else if (n_big > 0) {
@@ -651,8 +669,13 @@ static int launch_mc(McArgs a, cudaStream_t st) {
             mc_compound_kernel<pixel, false><<<grid, MC_WARPS * 32, smem, st>>>(a);
         } else {
             const size_t smem = MC_WARPS * sizeof(McSmem<pixel, 32>);
-            grid = std::min(grid, resident_blocks(mc_put_kernel<pixel, false>, smem, cap_big));
-            mc_put_kernel<pixel, false><<<grid, MC_WARPS * 32, smem, st>>>(a);
+            if (a.tmp) {
+                grid = std::min(grid, resident_blocks(mc_put_kernel<pixel, false, true>, smem, cap_big_prep));
+                mc_put_kernel<pixel, false, true><<<grid, MC_WARPS * 32, smem, st>>>(a);
+            } else {
+                grid = std::min(grid, resident_blocks(mc_put_kernel<pixel, false, false>, smem, cap_big));
+                mc_put_kernel<pixel, false, false><<<grid, MC_WARPS * 32, smem, st>>>(a);
+            }
         }
         count_launch();
     }
@@ -707,9 +730,13 @@ void mc_init_attrs() {
                          (int)(MC_WARPS_TC * sizeof(McSmemTmaCompound<uint16_t>)));
     cudaFuncSetAttribute(mc_compound_tma_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)(MC_WARPS_TC * sizeof(McSmemTmaCompound<uint8_t>)));
-    cudaFuncSetAttribute(mc_put_tma_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaFuncSetAttribute(mc_put_tma_kernel<uint16_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)(MC_WARPS * sizeof(McSmemTma<uint16_t>)));
-    cudaFuncSetAttribute(mc_put_tma_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaFuncSetAttribute(mc_put_tma_kernel<uint8_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)(MC_WARPS * sizeof(McSmemTma<uint8_t>)));
+    cudaFuncSetAttribute(mc_put_tma_kernel<uint16_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)(MC_WARPS * sizeof(McSmemTma<uint16_t>)));
+    cudaFuncSetAttribute(mc_put_tma_kernel<uint8_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)(MC_WARPS * sizeof(McSmemTma<uint8_t>)));
     cudaFuncSetAttribute(mc_compound_kernel<uint16_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)(MC_WARPS * sizeof(McSmemCompound<uint16_t, 32>)));

@@ -452,8 +452,8 @@ DAV1D_CUDA_API void dav1d_cuda_picture_free(Dav1dCudaContext *c, Dav1dCudaPictur
  * measurements and tests).  With TMA a window is ONE cp.async.bulk.tensor.2d request against the reference's
  * tensor maps, completing on an mbarrier, into one of two window buffers per warp: the next window is in
  * flight while the current one is filtered.  mode 0: per-lane cp.async copies everywhere; 1 (default): TMA
- * for single-reference predictions; 2: TMA for compound predictions too (measured slower than cp.async on
- * B200: DESIGN.md section 8).  Same pixels in every mode. */
+ * for single-reference predictions (measured 5 % faster than cp.async); 2: TMA for compound predictions too
+ * (measured 3 % slower: DESIGN.md section 8).  Same pixels in every mode. */
 DAV1D_CUDA_API void dav1d_cuda_set_mc_tma(int mode);
 DAV1D_CUDA_API int  dav1d_cuda_get_mc_tma(void);
 DAV1D_CUDA_API int  dav1d_cuda_picture_upload(Dav1dCudaContext *c, const Dav1dCudaPicture *pic, int plane,
