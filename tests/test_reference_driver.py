@@ -153,9 +153,10 @@ def test_descriptors_mean_what_the_reference_driver_means(ref, name):
         assert md5_planes(want) == json.load(f)[name], name      # drift of generator / reference build
 
 
-def test_random_frames_against_the_reference_drivers(ref):
+def random_frames(ref, n, first=0):
+    """The random sweep: frame k's parameters are a function of k alone (one generator stream, drawn in order)."""
     rng = np.random.default_rng(20261019)
-    for k in range(48):
+    for k in range(n):
         lay = [(1, 1), (1, 0), (0, 0)][rng.integers(3)]
         kw = dict(ss_hor=lay[0], ss_ver=lay[1], p_cfl=float(rng.choice([0, 0.5])), p_palette=float(rng.choice([0, 0.15])),
                   p_intra=float(rng.choice([1.0, 0.5, 0.2, 0.0])), p_wedge=0.0, p_warp=0.0,
@@ -169,13 +170,34 @@ def test_random_frames_against_the_reference_drivers(ref):
         kw["p_wedge"] = float(rng.choice([0, 0.3]))
         kw["p_warp"] = float(rng.choice([0, 0.3]))
         kw["p_sub8x8"] = float(rng.choice([0, 0.5]))          # takes effect in 4:2:0 / 4:2:2
+        if k < first:
+            continue
         hf = F.HostFrame(w, h, bd, 500 + k, real_blocks=1, mask_tab=refframe.reference_mask_tab(ref),
                          warp_tab=refframe.reference_warp_tab(ref), **kw)
         init = F.random_planes(hf, 9000 + k)
         refs = [F.random_planes(hf, 9100 + 2 * k + j) for j in range(2)]
+        yield k, hf, init, refs, (w, h, hex(bd), kw)
+
+
+def test_random_frames_against_the_reference_drivers(ref):
+    for k, hf, init, refs, what in random_frames(ref, 48):
         want = refframe.run_reference_driver(ref, hf, [p.copy() for p in init], refs)
         got = refframe.run_oracle(ref, hf, [p.copy() for p in init], refs)
-        assert all(np.array_equal(a, b) for a, b in zip(want, got)), (k, w, h, hex(bd), kw)
+        assert all(np.array_equal(a, b) for a, b in zip(want, got)), (k, what)
+
+
+@pytest.mark.gpu
+def test_cuda_random_frames_against_the_reference_drivers(ref):
+    """The same sweep on the product path: CUDA == dav1d_recon_b_intra / dav1d_recon_b_inter, frame after frame."""
+    import test_frame
+    for k, hf, init, refs, what in random_frames(ref, 32):
+        want = refframe.run_reference_driver(ref, hf, [p.copy() for p in init], refs)
+        if k & 1:
+            hf.record_levels()
+        got = test_frame.run_gpu(hf, refs, init, use_graph=False)
+        for pl, (a, b) in enumerate(zip(want, got)):
+            bad = np.argwhere(a != b)
+            assert bad.size == 0, f"frame {k} {what}: plane {pl}: {len(bad)} pixels differ, first {bad[0]}"
 
 
 @pytest.mark.gpu
