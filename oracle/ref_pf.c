@@ -8,6 +8,10 @@
  * Masks and levels as oracle/ref_lf.c, CDEF fields as oracle/ref_cdef.c, restoration units drawn at random into
  * f->lf.lr_mask.  Hands out what dav1d holds when the filters start.  Compiled twice (BITDEPTH 8 / 16); this
  * repo's own code.
+ * Super-resolution (sr_w > w): frame_hdr->width[0] != width[1], f->sr_cur a second picture of the upscaled width -
+ * dav1d_filter_sbrow then runs dav1d_filter_sbrow_resize between CDEF and loop restoration (recon_tmpl.c:2104-2137,
+ * 2155-2158), dav1d_copy_lpf keeps RESIZED deblocked lines (lf_apply_tmpl.c:76-91) and the restoration units are
+ * indexed with f->sr_sb128w (lr_apply_tmpl.c:142).
  */
 #include "config.h"
 #include <stdint.h>
@@ -63,6 +67,11 @@ typedef struct OraclePfFrame {
     uint8_t *lut;                               /* Av1FilterLUT */
     void *lr_mask;                              /* Av1Restoration[sb128w * sb128h] */
     int32_t b4_stride, sb128w, sb128h, w4, h4, bw, bh, sizeof_av1filter, sizeof_av1restoration;
+    /* super-resolution: sr_w > w switches it on (in); sr_sb128w = f->sr_sb128w (out: lr_mask holds sr_sb128w * sb128h) */
+    int32_t sr_w, sr_sb128w;
+    int32_t resize_step[2], resize_start[2];    /* f->resize_step / _start (decode.c:3576-3583), in */
+    void *sr_dst[3];                            /* f->sr_cur planes (in: allocated by the caller; out: the frame) */
+    ptrdiff_t sr_stride[2];
 } OraclePfFrame;
 
 #if BITDEPTH == 8
@@ -91,6 +100,7 @@ EXPORT void SUFFIX(oracle_pf_geometry)(OraclePfFrame *const fr) {
     fr->w4 = (fr->w + 3) >> 2; fr->h4 = (fr->h + 3) >> 2;
     fr->sizeof_av1filter = (int) sizeof(Av1Filter);
     fr->sizeof_av1restoration = (int) sizeof(Av1Restoration);
+    fr->sr_sb128w = fr->sr_w > fr->w ? (fr->sr_w + 127) >> 7 : fr->sb128w;     /* decode.c:3063 */
 }
 
 EXPORT int SUFFIX(oracle_pf_frame)(OraclePfFrame *const fr) {
@@ -102,6 +112,7 @@ EXPORT int SUFFIX(oracle_pf_frame)(OraclePfFrame *const fr) {
     SUFFIX(dav1d_loop_filter_dsp_init)(&dsp.lf);
     SUFFIX(dav1d_cdef_dsp_init)(&dsp.cdef);
     SUFFIX(dav1d_loop_restoration_dsp_init)(&dsp.lr, bpc);
+    SUFFIX(dav1d_mc_dsp_init)(&dsp.mc);          /* mc.resize: dav1d_filter_sbrow_resize, backup_lpf */
     Dav1dSequenceHeader seq;
     Dav1dFrameHeader hdr;
     memset(&seq, 0, sizeof(seq));
@@ -134,22 +145,36 @@ EXPORT int SUFFIX(oracle_pf_frame)(OraclePfFrame *const fr) {
     f->cur.p.layout = fr->no_chroma ? DAV1D_PIXEL_LAYOUT_I400 :
                       fr->ss_ver ? DAV1D_PIXEL_LAYOUT_I420 : fr->ss_hor ? DAV1D_PIXEL_LAYOUT_I422 : DAV1D_PIXEL_LAYOUT_I444;
     f->sr_cur.p = f->cur;                         /* no super-resolution: the same picture */
+    const int superres = fr->sr_w > fr->w;
+    hdr.width[0] = fr->w; hdr.width[1] = superres ? fr->sr_w : fr->w;
+    hdr.super_res.enabled = superres;
+    if (superres) {                               /* decode.c:3566-3584 */
+        if (!fr->sr_dst[0] || fr->sb128w * 128 < fr->w) { free(c); free(f); free(tc); return -22; }
+        f->sr_cur.p.data[0] = fr->sr_dst[0]; f->sr_cur.p.data[1] = fr->sr_dst[1]; f->sr_cur.p.data[2] = fr->sr_dst[2];
+        f->sr_cur.p.stride[0] = fr->sr_stride[0]; f->sr_cur.p.stride[1] = fr->sr_stride[1];
+        f->sr_cur.p.p.w = fr->sr_w;
+        f->resize_step[0] = fr->resize_step[0]; f->resize_step[1] = fr->resize_step[1];
+        f->resize_start[0] = fr->resize_start[0]; f->resize_start[1] = fr->resize_start[1];
+    }
     const int ss_hor = !fr->no_chroma && fr->ss_hor, ss_ver = !fr->no_chroma && fr->ss_ver;
     f->bw = fr->bw; f->bh = fr->bh; f->w4 = fr->w4; f->h4 = fr->h4;
-    f->sb128w = f->sr_sb128w = fr->sb128w; f->sb128h = fr->sb128h;
+    f->sb128w = fr->sb128w; f->sr_sb128w = fr->sr_sb128w; f->sb128h = fr->sb128h;
     f->sb_shift = 4; f->sb_step = 16;
     f->sbh = (f->bh + f->sb_step - 1) >> f->sb_shift;
     f->b4_stride = fr->b4_stride;
-    const int n128 = f->sb128w * f->sb128h;
+    const int n128 = f->sb128w * f->sb128h, n128_sr = f->sr_sb128w * f->sb128h;
     Av1Filter *const masks = fr->masks;
     Av1Restoration *const lrm = fr->lr_mask;
     memset(masks, 0, sizeof(Av1Filter) * n128);
-    memset(lrm, 0, sizeof(Av1Restoration) * n128);
+    memset(lrm, 0, sizeof(Av1Restoration) * n128_sr);
     memset(fr->level, 0, (size_t) f->b4_stride * 32 * f->sb128h * 4);
     f->lf.mask = masks; f->lf.lr_mask = lrm;
     f->lf.level = (uint8_t (*)[4]) fr->level;
     f->lf.restore_planes = fr->do_lr ? fr->restore_planes & (fr->no_chroma ? 1 : 7) : 0;
-    for (int pl = 0; pl < 3; pl++) f->lf.p[pl] = f->lf.sr_p[pl] = fr->dst[pl];
+    for (int pl = 0; pl < 3; pl++) {
+        f->lf.p[pl] = fr->dst[pl];
+        f->lf.sr_p[pl] = superres ? fr->sr_dst[pl] : fr->dst[pl];
+    }
     dav1d_calc_eih(&f->lf.lim_lut, fr->sharpness);
     memcpy(fr->lut, &f->lf.lim_lut, sizeof(Av1FilterLUT));
     int ret = 0;
@@ -164,7 +189,7 @@ EXPORT int SUFFIX(oracle_pf_frame)(OraclePfFrame *const fr) {
     f->a = a;
     for (int i = 0; i < 9; i++) {                 /* cdef_line[2][3]: 2 rows; lr_lpf_line[3]: 12 rows (n_tc == 1) */
         const int pl = i % 3;
-        const ptrdiff_t st = f->cur.stride[!!pl];
+        const ptrdiff_t st = i < 6 ? f->cur.stride[!!pl] : f->sr_cur.p.stride[!!pl];   /* lf_apply_tmpl.c:118 */
         bufs[i] = calloc((size_t) st * (i < 6 ? 2 : 12) + 256, 1);
         if (!bufs[i]) { ret = -12; goto done; }
         if (i < 6) f->lf.cdef_line[i / 3][pl] = bufs[i];
@@ -221,12 +246,12 @@ EXPORT int SUFFIX(oracle_pf_frame)(OraclePfFrame *const fr) {
             }
         }
     }
-    for (int i = 0; i < n128; i++) {
-        for (int k = 0; k < 4; k++) {
+    for (int i = 0; i < n128 || i < n128_sr; i++) {
+        for (int k = 0; k < 4 && i < n128; k++) {
             const uint64_t r = next_u64(&rng);
             masks[i].cdef_idx[k] = (int) (r % 1000) < fr->p_unset ? -1 : (int8_t) ((r >> 20) & 7);
         }
-        for (int pl = 0; pl < 3; pl++)
+        for (int pl = 0; pl < 3 && i < n128_sr; pl++)
             for (int k = 0; k < 4; k++) {
                 Av1RestorationUnit *const u = &lrm[i].lr[pl][k];
                 const int kind = rnd_range(&rng, 0, 999);

@@ -118,15 +118,33 @@ class OraclePfFrame(C.Structure):
                 ("masks", C.c_void_p), ("level", C.c_void_p), ("lut", C.c_void_p), ("lr_mask", C.c_void_p),
                 ("b4_stride", C.c_int32), ("sb128w", C.c_int32), ("sb128h", C.c_int32), ("w4", C.c_int32),
                 ("h4", C.c_int32), ("bw", C.c_int32), ("bh", C.c_int32), ("sizeof_av1filter", C.c_int32),
-                ("sizeof_av1restoration", C.c_int32)]
+                ("sizeof_av1restoration", C.c_int32),
+                ("sr_w", C.c_int32), ("sr_sb128w", C.c_int32),
+                ("resize_step", C.c_int32 * 2), ("resize_start", C.c_int32 * 2),
+                ("sr_dst", C.c_void_p * 3), ("sr_stride", C.c_ssize_t * 2)]
+
+
+def _c_div(a, b):
+    q = abs(a) // abs(b)
+    return q if (a < 0) == (b < 0) else -q
+
+
+def resize_params(src_w, dst_w):
+    """f->resize_step / f->resize_start (decode.c:3365-3369 get_upscale_x0, :3576-3583 scale_fac)."""
+    dx = ((src_w << 14) + (dst_w >> 1)) // dst_w
+    err = dst_w * dx - (src_w << 14)
+    x0 = _c_div(-((dst_w - src_w) << 13) + (dst_w >> 1), dst_w) + 128 - _c_div(err, 2)
+    return dx, x0 & 0x3fff
 
 
 def run_reference_chain(ref, hf, planes, seed, deblock=True, cdef=True, lr=True, sharpness=0, p_zero_level=100,
                         damping=4, y_strength=(0,) * 8, uv_strength=(0,) * 8, p_unset=100, unit_size_log2=(6, 6),
-                        restore_planes=7, p_lr_none=150, run=True):
+                        restore_planes=7, p_lr_none=150, run=True, sr_w=0):
     """The reference's own post-filter chain (dav1d_filter_sbrow per superblock row) on `planes`, in place, with the
     stages switched by deblock / cdef / lr.  Returns (planes, state): masks, levels, limit table, restoration units
-    and the frame parameters the device calls take."""
+    and the frame parameters the device calls take.
+    sr_w > hf.w: super-resolution to that width - the result is f->sr_cur (new planes of the upscaled width; `planes`
+    then holds f->cur after deblocking and CDEF), state carries sr_w, sr_sb128w, resize_step / resize_start."""
     assert hf.n_block_recs > 0 and hf.w % 8 == 0 and hf.h % 8 == 0
     of = OraclePfFrame()
     for pl, a in enumerate(planes):
@@ -146,12 +164,24 @@ def run_reference_chain(ref, hf, planes, seed, deblock=True, cdef=True, lr=True,
     geo = getattr(ref.lib, "oracle_pf_geometry_" + sfx)
     geo.argtypes = [C.POINTER(OraclePfFrame)]
     geo.restype = None
+    sr_planes = None
+    if sr_w > hf.w:
+        of.sr_w = sr_w
+        sr_planes = [np.zeros((a.shape[0], sr_w if pl == 0 else (sr_w + hf.ss_hor) >> hf.ss_hor), dtype=a.dtype)
+                     for pl, a in enumerate(planes)]
+        for pl, a in enumerate(sr_planes):
+            of.sr_dst[pl] = a.ctypes.data
+        of.sr_stride[0] = sr_planes[0].strides[0]
+        of.sr_stride[1] = sr_planes[-1].strides[0]
+        in_cw, out_cw = (hf.w + hf.ss_hor) >> hf.ss_hor, (sr_w + hf.ss_hor) >> hf.ss_hor
+        (of.resize_step[0], of.resize_start[0]), (of.resize_step[1], of.resize_start[1]) = \
+            resize_params(hf.w, sr_w), resize_params(in_cw, out_cw)
     geo(C.byref(of))
     n128 = of.sb128w * of.sb128h
     masks = np.zeros(n128 * of.sizeof_av1filter, dtype=np.uint8)
     level = np.zeros(of.b4_stride * 32 * of.sb128h * 4, dtype=np.uint8)
     lut = np.zeros(144, dtype=np.uint8)
-    lr_mask = np.zeros(n128 * of.sizeof_av1restoration, dtype=np.uint8)
+    lr_mask = np.zeros(of.sr_sb128w * of.sb128h * of.sizeof_av1restoration, dtype=np.uint8)
     of.masks, of.level, of.lut, of.lr_mask = masks.ctypes.data, level.ctypes.data, lut.ctypes.data, lr_mask.ctypes.data
     fn = getattr(ref.lib, "oracle_pf_frame_" + sfx)
     fn.argtypes = [C.POINTER(OraclePfFrame)]
@@ -164,5 +194,6 @@ def run_reference_chain(ref, hf, planes, seed, deblock=True, cdef=True, lr=True,
              "damping": damping, "y_strength": list(y_strength),
              "uv_strength": [0] * 8 if hf.no_chroma else list(uv_strength),
              "unit_size_log2": tuple(unit_size_log2), "restore_planes": restore_planes & (1 if hf.no_chroma else 7),
-             "sizeof_av1restoration": of.sizeof_av1restoration}
-    return planes, state
+             "sizeof_av1restoration": of.sizeof_av1restoration, "sr_w": sr_w if sr_planes else 0,
+             "sr_sb128w": of.sr_sb128w, "resize_step": tuple(of.resize_step), "resize_start": tuple(of.resize_start)}
+    return (sr_planes if sr_planes else planes), state

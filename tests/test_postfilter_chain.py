@@ -1,5 +1,5 @@
 """Loop restoration on the device (dav1d_cuda_lr_frame) and the whole device post-filter chain (deblock in place ->
-CDEF out of place -> loop restoration out of place) against the reference's OWN chain: dav1d_filter_sbrow()
+CDEF out of place -> [super-resolution out of place] -> loop restoration out of place) against the reference's OWN chain: dav1d_filter_sbrow()
 (src/recon_tmpl.c:2149-2160) per superblock row with dav1d_copy_lpf's line backups, dav1d_cdef_brow and
 dav1d_lr_sbrow / lr_stripe / wiener_c / sgr_*_c, compiled where they lie (oracle/ref_pf.c)."""
 import ctypes as C
@@ -34,16 +34,29 @@ CASES = {
     "chain_luma_8b": (256, 256, 0xff, 95, {"no_chroma": 1, "p_intra": 1.0}, (1, 1, 1), (6, 6)),
     "chain_420_10b_no_cdef": (320, 200, 0x3ff, 96, {"p_intra": 0.3}, (1, 0, 1), (6, 6)),
     "chain_420_10b_720p": (1280, 720, 0x3ff, 97, {"p_intra": 0.3}, (1, 1, 1), (6, 6)),
+    # super-resolution (9th field: the upscaled width, frame_hdr->width[1]; denominators 9..16 of 8): the reference
+    # runs dav1d_filter_sbrow_resize between CDEF and loop restoration, backs up RESIZED deblocked lines and indexes
+    # the restoration units with f->sr_sb128w
+    "sr_chain_420_8b_d16": (128, 192, 0xff, 101, {"p_intra": 0.4}, (1, 1, 1), (6, 6), 256),
+    "sr_chain_420_10b_d11": (256, 200, 0x3ff, 102, {"p_intra": 0.3}, (1, 1, 1), (6, 5), 352),
+    "sr_chain_444_12b_d9": (320, 192, 0xfff, 103, {"ss_hor": 0, "ss_ver": 0, "p_intra": 0.5}, (1, 1, 1), (7, 7), 360),
+    "sr_chain_422_10b_d13": (192, 136, 0x3ff, 104, {"ss_hor": 1, "ss_ver": 0, "p_intra": 0.5}, (1, 1, 1), (6, 6), 312),
+    "sr_chain_luma_8b_d12": (256, 256, 0xff, 105, {"no_chroma": 1, "p_intra": 1.0}, (1, 1, 1), (8, 8), 384),
+    "sr_lr_only_420_10b_d14": (232, 184, 0x3ff, 106, {"p_intra": 0.2}, (0, 0, 1), (6, 5), 406),
+    "sr_no_cdef_420_8b_d15": (328, 200, 0xff, 107, {"p_intra": 0.3}, (1, 0, 1), (6, 6), 615),
+    "sr_no_lr_420_10b_d10": (256, 192, 0x3ff, 108, {"p_intra": 0.3}, (1, 1, 0), (6, 6), 320),
 }
 
 
 def make(name):
-    w, h, bd, seed, kw, stages, units = CASES[name]
+    w, h, bd, seed, kw, stages, units = CASES[name][:7]
     hf = F.HostFrame(w, h, bd, seed, real_blocks=1, p_wedge=0.0, p_warp=0.0, **kw)
     rng = np.random.default_rng(seed)
     par = dict(deblock=bool(stages[0]), cdef=bool(stages[1]), lr=bool(stages[2]), sharpness=int(rng.integers(8)),
                damping=3 + int(rng.integers(4)), y_strength=[int(v) for v in rng.integers(0, 64, 8)],
                uv_strength=[int(v) for v in rng.integers(0, 64, 8)], unit_size_log2=units)
+    if len(CASES[name]) > 7:
+        par["sr_w"] = CASES[name][7]
     return hf, reflf.blocky_planes(hf, seed + 1000), seed, par
 
 
@@ -59,18 +72,44 @@ def test_reference_chain_matches_golden(ref, name):
     hf, src, seed, par = make(name)
     out, st = reflf.run_reference_chain(ref, hf, [p.copy() for p in src], seed, **par)
     assert st["sizeof_av1restoration"] == 108
-    assert 0.2 < float((src[0] != out[0]).mean())
+    if out[0].shape == src[0].shape:
+        assert 0.2 < float((src[0] != out[0]).mean())
+    else:
+        assert out[0].shape == (hf.h, par["sr_w"]) and st["sr_sb128w"] == (par["sr_w"] + 127) >> 7
     with open(GOLDEN) as f:
         assert md5_planes(out) == json.load(f)[name], name
 
 
+def test_reference_superres_is_a_whole_plane_resize(ref):
+    """What the device chain relies on: dav1d_filter_sbrow_resize (recon_tmpl.c:2104-2137), one superblock row at a
+    time with its 8-row lag, leaves in f->sr_cur exactly mc.resize of every row of the filtered f->cur."""
+    name = "sr_no_lr_420_10b_d10"
+    hf, src, seed, par = make(name)
+    cur = [p.copy() for p in src]
+    out, st = reflf.run_reference_chain(ref, hf, cur, seed, **par)     # cur: deblocked + CDEF, in place
+    R = ref.bpc[hf.hbd]
+    for pl, (p, o) in enumerate(zip(cur, out)):
+        d = np.zeros_like(o)
+        args = [d.ctypes.data, d.strides[0], p.ctypes.data, p.strides[0], o.shape[1], p.shape[0], p.shape[1],
+                st["resize_step"][pl > 0], st["resize_start"][pl > 0]]
+        R.resize(*(args + ([hf.bdmax] if hf.hbd else [])))
+        assert np.array_equal(d, o), f"plane {pl}"
+        assert not np.array_equal(p, src[pl])
+
+
 def run_gpu(hf, src, st, par):
-    """deblock (in place, picture 0) -> CDEF (0 -> 1) -> loop restoration (src 1, deblocked 0 -> 2)."""
+    """deblock (in place, picture 0) -> CDEF (0 -> 1) -> loop restoration (src 1, deblocked 0 -> 2).
+    With super-resolution (st["sr_w"]): the CDEF output AND the deblocked picture are upscaled (dav1d_cuda_resize_frame,
+    1 -> 3, 0 -> 4: the reference resizes the deblocked lines it backs up row by row, lf_apply_tmpl.c:76-91, which is
+    the same as taking them from the resized deblocked picture) and loop restoration runs on pictures of the
+    upscaled width (src 3, deblocked 4 -> 2) with f->sr_sb128w."""
     L = pkg.lib()
     ctx = F.open_context(0)
-    pics = [B.Picture() for _ in range(3)]
-    for pic in pics:
-        assert L.dav1d_cuda_picture_alloc(ctx, C.byref(pic), hf.w, hf.h, hf.ss_hor, hf.ss_ver, hf.bdmax) == 0
+    sr_w = st.get("sr_w", 0)
+    pics = [B.Picture() for _ in range(5 if sr_w else 3)]
+    for k, pic in enumerate(pics):
+        pw = sr_w if sr_w and k >= 2 else hf.w
+        assert L.dav1d_cuda_picture_alloc(ctx, C.byref(pic), pw, hf.h, hf.ss_hor, hf.ss_ver, hf.bdmax) == 0
     bufs = {k: L.dav1d_cuda_malloc(st[k].nbytes) for k in ("masks", "level", "lr_mask")}
     try:
         for pl, a in enumerate(src):
@@ -95,16 +134,22 @@ def run_gpu(hf, src, st, par):
             p.masks = bufs["masks"]
             assert L.dav1d_cuda_cdef_frame(ctx, C.byref(pics[1]), C.byref(pics[0]), C.byref(p)) == 0
             cur = 1
+        if sr_w:
+            step, start = (C.c_int32 * 2)(*st["resize_step"]), (C.c_int32 * 2)(*st["resize_start"])
+            assert L.dav1d_cuda_resize_frame(ctx, C.byref(pics[3]), C.byref(pics[cur]), step, start) == 0
+            if par["lr"] and pre != cur:
+                assert L.dav1d_cuda_resize_frame(ctx, C.byref(pics[4]), C.byref(pics[pre]), step, start) == 0
+            cur, pre = 3, (4 if pre != cur else 3)
         if par["lr"]:
             q = B.LrFrame()
-            q.w, q.h, q.sb128w, q.sb128 = hf.w, hf.h, st["sb128w"], 0
+            q.w, q.h, q.sb128w, q.sb128 = sr_w or hf.w, hf.h, st["sr_sb128w"], 0
             q.unit_size_log2[0], q.unit_size_log2[1] = st["unit_size_log2"]
             q.restore_planes, q.lr_mask = st["restore_planes"], bufs["lr_mask"]
             assert L.dav1d_cuda_lr_frame(ctx, C.byref(pics[2]), C.byref(pics[cur]), C.byref(pics[pre]), C.byref(q)) == 0
             cur = 2
         out = []
         for pl, a in enumerate(src):
-            o = np.zeros_like(a)
+            o = np.zeros_like(a) if not sr_w else np.zeros((a.shape[0], sr_w if pl == 0 else (sr_w + hf.ss_hor) >> hf.ss_hor), a.dtype)
             L.dav1d_cuda_picture_download(ctx, C.byref(pics[cur]), pl, o.ctypes.data, o.strides[0])
             out.append(o)
         L.dav1d_cuda_synchronize(ctx)
