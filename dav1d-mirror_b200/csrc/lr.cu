@@ -234,7 +234,12 @@ extern "C" int dav1d_cuda_lr_frame(Dav1dCudaContext *c, const Dav1dCudaPicture *
         p->w <= 0 || p->h <= 0 || p->sb128w < (p->w + 127) / 128) return -22;
     for (int k = 0; k < 2; k++)
         if (p->unit_size_log2[k] < 5 || p->unit_size_log2[k] > 8) return -22;
-    if (p->sb128) return -38;                           // 128x128 superblocks: the unit lookup of lr_sbrow differs, not built
+    // 128x128 superblocks: lr_sbrow (lr_apply_tmpl.c:137-143) looks the unit of a whole 128-row superblock row up
+    // at its first row.  The frame header gives such streams units of at least 128 luma pixels
+    // (obu.c:944-954: unit_size[0] = 6 + sb128 ..., unit_size[1] one less only when both directions are
+    // subsampled), and then every 64-row stripe finds the same unit at its own first row: the kernel's
+    // lookup is the reference's.  Smaller units with sb128 are not a stream the reference can be handed.
+    if (p->sb128 && (p->unit_size_log2[0] < 7 || p->unit_size_log2[1] < 7 - (src->ss_ver ? 1 : 0))) return -22;
     D1_CHECK(cudaSetDevice(c->device));
     LrArgs a;
     const PicView s = pic_view(src), q = pic_view(deblocked), d = pic_view(dst);

@@ -538,7 +538,9 @@ DAV1D_CUDA_API int dav1d_cuda_cdef_frame(Dav1dCudaContext *c, const Dav1dCudaPic
  * lf_apply_tmpl.c:108-175); pass src twice when the frame has no CDEF.
  *   lr_mask = f->lf.lr_mask (device): Av1Restoration[f->sr_sb128w * f->sb128h] (src/lf_mask.h:40-46,61-63,
  *             108 bytes each); unit_size_log2 = frame_hdr->restoration.unit_size; restore_planes = f->lf.restore_planes.
- * 64x64 superblocks only (sb128 != 0: -ENOSYS).
+ * 128x128 superblocks (sb128 != 0) need units of at least 128 luma pixels, which is what the frame header gives such
+ * streams (obu.c:944-954): every 64-row stripe then finds the unit lr_sbrow looks up once per 128-row superblock
+ * row (lr_apply_tmpl.c:137-143); smaller units with sb128: -EINVAL.
  * Super-resolution (frame_hdr->width[0] != width[1]): src = dav1d_cuda_resize_frame of the CDEF output, deblocked =
  * dav1d_cuda_resize_frame of the deblocked picture (the reference resizes the lines it backs up row by row,
  * lf_apply_tmpl.c:76-91 - the same pixels), w / sb128w = the upscaled width / f->sr_sb128w; bit-exact with

@@ -72,6 +72,7 @@ typedef struct OraclePfFrame {
     int32_t resize_step[2], resize_start[2];    /* f->resize_step / _start (decode.c:3576-3583), in */
     void *sr_dst[3];                            /* f->sr_cur planes (in: allocated by the caller; out: the frame) */
     ptrdiff_t sr_stride[2];
+    int32_t sb128;                              /* seq_hdr->sb128 (in): superblock rows of 128 luma rows */
 } OraclePfFrame;
 
 #if BITDEPTH == 8
@@ -118,6 +119,7 @@ EXPORT int SUFFIX(oracle_pf_frame)(OraclePfFrame *const fr) {
     memset(&seq, 0, sizeof(seq));
     memset(&hdr, 0, sizeof(hdr));
     seq.cdef = fr->do_cdef;
+    seq.sb128 = !!fr->sb128;
     hdr.loopfilter.level_y[0] = hdr.loopfilter.level_y[1] = fr->do_deblock;
     hdr.loopfilter.level_u = hdr.loopfilter.level_v = fr->do_deblock && !fr->no_chroma;
     hdr.loopfilter.sharpness = fr->sharpness;
@@ -159,7 +161,7 @@ EXPORT int SUFFIX(oracle_pf_frame)(OraclePfFrame *const fr) {
     const int ss_hor = !fr->no_chroma && fr->ss_hor, ss_ver = !fr->no_chroma && fr->ss_ver;
     f->bw = fr->bw; f->bh = fr->bh; f->w4 = fr->w4; f->h4 = fr->h4;
     f->sb128w = fr->sb128w; f->sr_sb128w = fr->sr_sb128w; f->sb128h = fr->sb128h;
-    f->sb_shift = 4; f->sb_step = 16;
+    f->sb_shift = 4 + seq.sb128; f->sb_step = 16 << seq.sb128;        /* decode.c:3413-3414 */
     f->sbh = (f->bh + f->sb_step - 1) >> f->sb_shift;
     f->b4_stride = fr->b4_stride;
     const int n128 = f->sb128w * f->sb128h, n128_sr = f->sr_sb128w * f->sb128h;

@@ -121,7 +121,7 @@ class OraclePfFrame(C.Structure):
                 ("sizeof_av1restoration", C.c_int32),
                 ("sr_w", C.c_int32), ("sr_sb128w", C.c_int32),
                 ("resize_step", C.c_int32 * 2), ("resize_start", C.c_int32 * 2),
-                ("sr_dst", C.c_void_p * 3), ("sr_stride", C.c_ssize_t * 2)]
+                ("sr_dst", C.c_void_p * 3), ("sr_stride", C.c_ssize_t * 2), ("sb128", C.c_int32)]
 
 
 def _c_div(a, b):
@@ -139,7 +139,7 @@ def resize_params(src_w, dst_w):
 
 def run_reference_chain(ref, hf, planes, seed, deblock=True, cdef=True, lr=True, sharpness=0, p_zero_level=100,
                         damping=4, y_strength=(0,) * 8, uv_strength=(0,) * 8, p_unset=100, unit_size_log2=(6, 6),
-                        restore_planes=7, p_lr_none=150, run=True, sr_w=0):
+                        restore_planes=7, p_lr_none=150, run=True, sr_w=0, sb128=0):
     """The reference's own post-filter chain (dav1d_filter_sbrow per superblock row) on `planes`, in place, with the
     stages switched by deblock / cdef / lr.  Returns (planes, state): masks, levels, limit table, restoration units
     and the frame parameters the device calls take.
@@ -160,6 +160,7 @@ def run_reference_chain(ref, hf, planes, seed, deblock=True, cdef=True, lr=True,
         of.uv_strength[k] = 0 if hf.no_chroma else uv_strength[k]
     of.unit_size_log2[0], of.unit_size_log2[1] = unit_size_log2
     of.restore_planes, of.p_lr_none = restore_planes, p_lr_none
+    of.sb128 = sb128
     sfx = "16bpc" if hf.hbd else "8bpc"
     geo = getattr(ref.lib, "oracle_pf_geometry_" + sfx)
     geo.argtypes = [C.POINTER(OraclePfFrame)]

@@ -45,6 +45,12 @@ CASES = {
     "sr_lr_only_420_10b_d14": (232, 184, 0x3ff, 106, {"p_intra": 0.2}, (0, 0, 1), (6, 5), 406),
     "sr_no_cdef_420_8b_d15": (328, 200, 0xff, 107, {"p_intra": 0.3}, (1, 0, 1), (6, 6), 615),
     "sr_no_lr_420_10b_d10": (256, 192, 0x3ff, 108, {"p_intra": 0.3}, (1, 1, 0), (6, 6), 320),
+    # 128x128 superblocks (10th field: seq_hdr->sb128): the reference filters 128-row superblock rows and looks the
+    # restoration unit of a whole row up at its first line; units are at least 128 luma pixels then (obu.c:944-954)
+    "sb128_chain_420_10b": (384, 328, 0x3ff, 111, {"p_intra": 0.3}, (1, 1, 1), (7, 6), 0, 1),
+    "sb128_chain_444_8b_u256": (320, 264, 0xff, 112, {"ss_hor": 0, "ss_ver": 0, "p_intra": 0.5}, (1, 1, 1), (8, 8), 0, 1),
+    "sb128_chain_422_12b": (264, 200, 0xfff, 113, {"ss_hor": 1, "ss_ver": 0, "p_intra": 0.5}, (1, 1, 1), (7, 7), 0, 1),
+    "sb128_sr_chain_420_10b_d12": (256, 392, 0x3ff, 114, {"p_intra": 0.3}, (1, 1, 1), (8, 7), 384, 1),
 }
 
 
@@ -57,6 +63,8 @@ def make(name):
                uv_strength=[int(v) for v in rng.integers(0, 64, 8)], unit_size_log2=units)
     if len(CASES[name]) > 7:
         par["sr_w"] = CASES[name][7]
+    if len(CASES[name]) > 8:
+        par["sb128"] = CASES[name][8]
     return hf, reflf.blocky_planes(hf, seed + 1000), seed, par
 
 
@@ -95,6 +103,18 @@ def test_reference_superres_is_a_whole_plane_resize(ref):
         R.resize(*(args + ([hf.bdmax] if hf.hbd else [])))
         assert np.array_equal(d, o), f"plane {pl}"
         assert not np.array_equal(p, src[pl])
+
+
+@pytest.mark.gpu
+def test_lr_sb128_small_units_are_refused(ref):
+    """sb128 with 64-pixel luma units is not a stream (obu.c:944-954) and the reference's unit lookup differs
+    there (lr_apply_tmpl.c:137-143): -EINVAL, not a silently different picture."""
+    hf, src, seed, par = make("chain_420_10b")
+    _, st = reflf.run_reference_chain(ref, hf, [p.copy() for p in src], seed, run=False, **par)
+    par = dict(par, deblock=False, cdef=False, sb128=1, unit_size_log2=(6, 6))
+    st = dict(st, unit_size_log2=(6, 6))
+    with pytest.raises(AssertionError):
+        run_gpu(hf, src, st, par)
 
 
 def run_gpu(hf, src, st, par):
@@ -142,7 +162,7 @@ def run_gpu(hf, src, st, par):
             cur, pre = 3, (4 if pre != cur else 3)
         if par["lr"]:
             q = B.LrFrame()
-            q.w, q.h, q.sb128w, q.sb128 = sr_w or hf.w, hf.h, st["sr_sb128w"], 0
+            q.w, q.h, q.sb128w, q.sb128 = sr_w or hf.w, hf.h, st["sr_sb128w"], par.get("sb128", 0)
             q.unit_size_log2[0], q.unit_size_log2[1] = st["unit_size_log2"]
             q.restore_planes, q.lr_mask = st["restore_planes"], bufs["lr_mask"]
             assert L.dav1d_cuda_lr_frame(ctx, C.byref(pics[2]), C.byref(pics[cur]), C.byref(pics[pre]), C.byref(q)) == 0
