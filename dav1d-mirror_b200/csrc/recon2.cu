@@ -17,8 +17,8 @@
 //                publish their level in a second per-cell map, readers poll it: the levels spread
 //                through the frame as a dataflow wave, no barrier anywhere;
 //   3. sort      counting sort of the operations by (level, predictor class, size class);
-//   4. execute   ONE persistent launch: warps claim chunks of the sorted list with a ticket -
-//                four small operations per warp (one per octet of lanes) or one large one - wait
+//   4. execute   ONE persistent launch: CTAs claim runs of chunks of the sorted list with a ticket, a
+//                chunk per warp - four small operations per warp (one per octet of lanes) or one large one - wait
 //                until the count of every cell they read is at zero, predict, add the residual of
 //                the transform pre-pass, store, and count their own cells down.  Claims follow the
 //                level order, so whatever an operation waits for has been claimed before it by a
@@ -472,7 +472,7 @@ DEV unsigned bin_slots(const unsigned bin, const bool thin) {
 
 // control block of a group's executor (device memory, cleared before the mark launch)
 struct ExecCtl {
-    unsigned ticket;                    // next chunk of four slots to claim
+    unsigned ticket;                    // next chunk to claim (a CTA takes R_WARPS at a time)
     unsigned n_chunks;                  // written by the scan
     unsigned max_level;
     int levels_done;                    // all chunks of the levels up to this one are complete (-1: none yet)
@@ -765,17 +765,23 @@ __global__ void __launch_bounds__(R_WARPS * 32, 3) intra_exec_kernel(const __gri
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     ExecSmem<pixel> *sm = (ExecSmem<pixel> *)exec_smem_raw + warp;
     const unsigned n_chunks = __ldcg(&a.ctl->n_chunks);
-    // a warp claims one chunk (32 slots) at a time, the next claim is in flight while it works
-    unsigned nxt = 0;
-    if (lane == 0) nxt = atomicAdd(&a.ctl->ticket, 1u);
+    // a CTA claims R_WARPS consecutive chunks at a time (neighbours in the sorted list: the same size class and
+    // predictor, the same frame), warp w takes the w-th; the next claim is in flight while the CTA works
+    __shared__ unsigned s_base[2];
+    if (threadIdx.x == 0) s_base[0] = atomicAdd(&a.ctl->ticket, (unsigned)R_WARPS);
+    __syncthreads();
+    unsigned round = 0;
     const int n_lev = (int)min(__ldcg(&a.ctl->max_level) + 1u, (unsigned)MAX_LEVELS);
     int level = 0, known_done = -1;
     unsigned level_end = __ldcg(a.lvl_end);
     for (;;) {
-        const unsigned c = __shfl_sync(0xffffffffu, nxt, 0);
-        if (c >= n_chunks) break;
+        const unsigned base = s_base[round & 1u];
+        if (base >= n_chunks) break;                         // the same for every warp of the CTA
+        if (threadIdx.x == 0) s_base[(round + 1u) & 1u] = atomicAdd(&a.ctl->ticket, (unsigned)R_WARPS);
+        round++;
+        const unsigned c = base + (unsigned)warp;
+        if (c >= n_chunks) { __syncthreads(); continue; }
         const unsigned sl = __ldcg(a.slots + 32 * c + lane);
-        if (lane == 0) nxt = atomicAdd(&a.ctl->ticket, 1u);
         // the chunk's level (claims only move forward); are all lower levels complete?  Then nothing
         // the chunk's operations read can still change and they need not look at the cell counts.
         while (c >= level_end && level + 1 < n_lev) level_end = __ldcg(a.lvl_end + ++level);
@@ -813,6 +819,7 @@ __global__ void __launch_bounds__(R_WARPS * 32, 3) intra_exec_kernel(const __gri
             while (d + 1 < n_lev && ld_acquire_u32(a.lvl_left + d + 1) == 0u) d++;
             atomicMax(&a.ctl->levels_done, d);
         }
+        __syncthreads();                                     // the round is over: the next claim is visible
     }
 }
 
