@@ -213,3 +213,29 @@ def test_cuda_chain_random_frames(ref):
         want, st = reflf.run_reference_chain(ref, hf, [p.copy() for p in src], 940 + k, **par)
         got = run_gpu(hf, src, st, par)
         assert all(np.array_equal(a, b) for a, b in zip(want, got)), (k, w, h, hex(bd), lay, par)
+
+
+@pytest.mark.gpu
+def test_cuda_chain_random_superres_and_sb128(ref):
+    """Random frames with super-resolution (denominators 9..16) and / or 128x128 superblocks, every stage switched
+    at random, against dav1d_filter_sbrow of the reference."""
+    rng = np.random.default_rng(20261023)
+    for k in range(12):
+        lay = [(1, 1), (1, 0), (0, 0)][rng.integers(3)]
+        w, h = int(rng.integers(8, 48)) * 8, int(rng.integers(8, 40)) * 8
+        bd = [0xff, 0x3ff, 0xfff][rng.integers(3)]
+        hf = F.HostFrame(w, h, bd, 1740 + k, real_blocks=1, p_wedge=0.0, p_warp=0.0, ss_hor=lay[0], ss_ver=lay[1],
+                         p_intra=float(rng.choice([0.0, 0.3, 1.0])), p_residual=float(rng.choice([0.2, 0.6, 1.0])))
+        src = reflf.blocky_planes(hf, 1840 + k) if k % 3 else F.random_planes(hf, 1840 + k)
+        sb128 = int(k % 3 != 0)
+        lu = int(rng.integers(7 if sb128 else 6, 9))
+        par = dict(deblock=bool(rng.integers(2)), cdef=bool(rng.integers(2)), lr=bool(k % 4), sharpness=int(rng.integers(8)),
+                   damping=3 + int(rng.integers(4)), y_strength=[int(v) for v in rng.integers(0, 64, 8)],
+                   uv_strength=[int(v) for v in rng.integers(0, 64, 8)],
+                   unit_size_log2=(lu, lu - int(rng.integers(2)) if lay == (1, 1) else lu),
+                   restore_planes=int(rng.integers(1, 8)), p_lr_none=int(rng.choice([0, 150, 500])), sb128=sb128)
+        if k % 3 != 1:
+            par["sr_w"] = (w * int(rng.integers(9, 17)) + 4) >> 3
+        want, st = reflf.run_reference_chain(ref, hf, [p.copy() for p in src], 1940 + k, **par)
+        got = run_gpu(hf, src, st, par)
+        assert all(np.array_equal(a, b) for a, b in zip(want, got)), (k, w, h, hex(bd), lay, par)
