@@ -983,20 +983,22 @@ template <typename pixel> __global__ void __launch_bounds__(256) mc_resize_kerne
     const int mx = (int)(T & 0x3fff);
     const int src_x = -1 + (int)(T >> 14);
     const int8_t *const F = g_resize_filter + (mx >> 8) * 8;
-    int xs[8];
+    // positions and taps are the column's: in registers once, then RESIZE_ROWS rows per thread
+    int xs[8], f[8];
 #pragma unroll
-    for (int k = 0; k < 8; k++) xs[k] = iclip(src_x - 3 + k, 0, a.src_w - 1);
+    for (int k = 0; k < 8; k++) { xs[k] = iclip(src_x - 3 + k, 0, a.src_w - 1); f[k] = F[k]; }
     for (int y = blockIdx.y; y < a.h; y += gridDim.y) {
         const pixel *s = (const pixel *)a.src + y * a.sstride;
         int sum = 0;
 #pragma unroll
-        for (int k = 0; k < 8; k++) sum += F[k] * (int)s[xs[k]];
+        for (int k = 0; k < 8; k++) sum += f[k] * (int)s[xs[k]];
         ((pixel *)a.dst)[y * a.dstride + x] = (pixel)clip_px<pixel>((-sum + 64) >> 7, a.bdmax);
     }
 }
 static int resize_launch(const ResizeArgs &a, const bool hbd, cudaStream_t st) {
     if (a.dst_w <= 0 || a.h <= 0) return 0;
-    const dim3 grid((unsigned)((a.dst_w + 255) / 256), (unsigned)std::min(a.h, 4096));
+    constexpr int RESIZE_ROWS = 8;
+    const dim3 grid((unsigned)((a.dst_w + 255) / 256), (unsigned)std::min((a.h + RESIZE_ROWS - 1) / RESIZE_ROWS, 4096));
     if (hbd) mc_resize_kernel<uint16_t><<<grid, 256, 0, st>>>(a);
     else mc_resize_kernel<uint8_t><<<grid, 256, 0, st>>>(a);
     count_launch();

@@ -119,4 +119,29 @@ per = ms / (reps * len(dsts)) * 1e3
 alg = samples * 2 * 2
 print(f"lr      4K 10-bit 4:2:0: {per:.1f} us/frame, {w * h / per / 1e3:.1f} Gpix/s, {alg / per / 1e3:.0f} GB/s of "
       f"read-once / write-once picture traffic ({alg / 1e6:.1f} MB/frame); all units restored, Wiener and self-guided mixed")
+
+# super-resolution: a 2560-wide coded frame upscaled to 3840 (denominator 12), all three planes; with loop
+# restoration the deblocked picture is upscaled too (two of these per frame)
+sw = 2560
+step, start = zip(reflf.resize_params(sw, w), reflf.resize_params(sw // 2, w // 2))
+st_, sa_ = (C.c_int32 * 2)(*step), (C.c_int32 * 2)(*start)
+small = B.Picture()
+assert L.dav1d_cuda_picture_alloc(ctx, C.byref(small), sw, h, 1, 1, bd) == 0
+for pl, a in enumerate(src):
+    c_ = np.ascontiguousarray(a[:, :sw >> (1 if pl else 0)])
+    L.dav1d_cuda_picture_upload(ctx, C.byref(small), pl, c_.ctypes.data, c_.strides[0])
+for d in dsts[:2]:
+    assert L.dav1d_cuda_resize_frame(ctx, C.byref(d), C.byref(small), st_, sa_) == 0
+L.dav1d_cuda_synchronize(ctx)
+L.dav1d_cuda_event_record(ctx, e0)
+for _ in range(reps):
+    for d in dsts:
+        L.dav1d_cuda_resize_frame(ctx, C.byref(d), C.byref(small), st_, sa_)
+L.dav1d_cuda_event_record(ctx, e1)
+L.dav1d_cuda_synchronize(ctx)
+ms = L.dav1d_cuda_event_elapsed_ms(e0, e1)
+per = ms / (reps * len(dsts)) * 1e3
+alg = samples * 2 + samples * 2 * sw / w      # read the coded picture once, write the upscaled one once
+print(f"resize  2560 -> 3840 x 2160 10-bit 4:2:0: {per:.1f} us/frame, {w * h / per / 1e3:.1f} Gpix/s, "
+      f"{alg / per / 1e3:.0f} GB/s of read-once / write-once picture traffic ({alg / 1e6:.1f} MB/frame)")
 pkg.check_error()
